@@ -1,0 +1,131 @@
+/* pgc.h - C ABI of the B200-native pagmo batch-evaluation / generation engine (libpgc.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `extern "C"`, no C++/torch types.
+ * Every entry point names the reference interface it stands in for (file:line under esa/pagmo2 v2.19.1).
+ * A maintainer binds these from pagmo's C++ plugin layer - see include/pagmo_cuda/cuda_bfe.hpp for the
+ * header-only adapters (UDBFE `cuda_bfe`, CUDA-backed UDPs with `batch_fitness`) and INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns PGC_OK (0) or a negative pgc_status; the message of the last failure on the
+ *     calling thread is available from pgc_last_error().  There is NO CPU fallback: without a usable
+ *     CUDA device every compute entry point fails with PGC_ERR_CUDA.
+ *   - decision vectors are flat row-major [n x nx] doubles, fitness vectors flat row-major [n x nf]
+ *     (same layout as pagmo::bfe, reference include/pagmo/bfe.hpp:320, src/problem.cpp:383-410).
+ *   - `stream` arguments are a cudaStream_t passed as void* (NULL = the context's own stream).
+ */
+#ifndef PAGMO_CUDA_PGC_H
+#define PAGMO_CUDA_PGC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pgc_status {
+    PGC_OK = 0,
+    PGC_ERR_INVALID_ARGUMENT = -1, /* maps to std::invalid_argument in the C++ adapters (pagmo_throw) */
+    PGC_ERR_UNSUPPORTED = -2,      /* problem/operator not implemented on the device: adapters throw, no fallback */
+    PGC_ERR_CUDA = -3,             /* CUDA runtime failure / no device: std::runtime_error */
+    PGC_ERR_OUT_OF_MEMORY = -4
+} pgc_status;
+
+/* Problem families = the reference's UDPs on the hot path. */
+typedef enum pgc_family {
+    PGC_RASTRIGIN = 1,     /* src/problems/rastrigin.cpp:62-72 */
+    PGC_ACKLEY = 2,        /* src/problems/ackley.cpp:61-76 */
+    PGC_GRIEWANK = 3,      /* src/problems/griewank.cpp:60-75 */
+    PGC_SCHWEFEL = 4,      /* src/problems/schwefel.cpp:60-69 */
+    PGC_ROSENBROCK = 5,    /* src/problems/rosenbrock.cpp:59-66 */
+    PGC_CEC2014 = 6,       /* src/problems/cec2014.cpp:119-247 */
+    PGC_CEC2013 = 7,       /* src/problems/cec2013.cpp:78-197 */
+    PGC_ZDT = 8,           /* src/problems/zdt.cpp:233-356 */
+    PGC_DTLZ = 9,          /* src/problems/dtlz.cpp:258-409 */
+    PGC_WFG = 10,          /* src/problems/wfg.cpp:304-1066 */
+    PGC_LENNARD_JONES = 11 /* src/problems/lennard_jones.cpp:72-92 */
+} pgc_family;
+
+/* POD description of a UDP.  Mirrors the constructor arguments of the reference UDPs plus, for the CEC
+ * suites, the data tables the reference keeps in private members (cec2014.hpp:227-236).
+ *   prob_id : cec2014 1..30, cec2013 1..28, zdt 1..6, dtlz 1..7, wfg 1..9; ignored otherwise
+ *   dim     : nx (cec/simple), zdt `param`, dtlz/wfg number of decision variables, lennard_jones `atoms`
+ *   nobj    : dtlz `fdim`, wfg `dim_obj`; ignored otherwise
+ *   param   : dtlz `alpha`, wfg `dim_k`; ignored otherwise
+ *   rotation: cec2014 `m_rotation_matrix` (>= k*dim*dim row-major, component i at i*dim*dim, cec2014.cpp:1046)
+ *             cec2013 `m_rotation_matrix` = MD[dim] (10*dim*dim)
+ *   shift   : cec2014 `m_origin_shift` AFTER the ctor's compaction (component i at i*dim, cec2014.cpp:76-86,1046)
+ *             cec2013 `m_origin_shift` flat table (component i at i*dim, cec2013.cpp:878)
+ *   shuffle : cec2014 `m_shuffle`, 1-based (component i at i*dim, cec2014.cpp:807-809,1189)
+ * The tables are copied to the device at creation; the caller keeps ownership of the host arrays. */
+typedef struct pgc_problem_desc {
+    int32_t family;
+    uint32_t prob_id;
+    uint32_t dim;
+    uint32_t nobj;
+    uint32_t param;
+    const double *rotation;
+    size_t rotation_len;
+    const double *shift;
+    size_t shift_len;
+    const int32_t *shuffle;
+    size_t shuffle_len;
+} pgc_problem_desc;
+
+typedef struct pgc_ctx pgc_ctx;
+typedef struct pgc_problem pgc_problem;
+
+/* ---- library / context ------------------------------------------------------------------------------ */
+const char *pgc_version(void);
+const char *pgc_last_error(void);
+int pgc_device_count(int *count);
+/* One context pins one device and owns one stream plus pinned/device staging buffers.  Distinct contexts may
+ * be used concurrently from different threads (thread_safety::basic, reference threading.hpp:42). */
+int pgc_ctx_create(int device, pgc_ctx **out);
+int pgc_ctx_destroy(pgc_ctx *ctx);
+int pgc_ctx_device(const pgc_ctx *ctx, int *device);
+int pgc_ctx_stream(const pgc_ctx *ctx, void **stream);
+int pgc_ctx_synchronize(pgc_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
+int pgc_ctx_launch_count(const pgc_ctx *ctx, uint64_t *count);
+
+/* ---- problems (stand-in for pagmo::problem{UDP}, reference src/problem.cpp:154-242) ------------------ */
+int pgc_problem_create(pgc_ctx *ctx, const pgc_problem_desc *desc, pgc_problem **out);
+int pgc_problem_destroy(pgc_problem *prob);
+int pgc_problem_nx(const pgc_problem *prob, size_t *nx);     /* problem::get_nx  */
+int pgc_problem_nobj(const pgc_problem *prob, size_t *nobj); /* problem::get_nobj */
+int pgc_problem_nf(const pgc_problem *prob, size_t *nf);     /* problem::get_nf (= nobj here: no constraints) */
+int pgc_problem_bounds(const pgc_problem *prob, double *lb, double *ub); /* UDP::get_bounds */
+int pgc_problem_name(const pgc_problem *prob, char *buf, size_t buflen); /* UDP::get_name */
+/* FP64 add/mul/fma(=2) per evaluation and libm calls per evaluation, as tabulated in DESIGN.md
+ * (roofline bookkeeping for bench.py). */
+int pgc_problem_work(const pgc_problem *prob, double *flops_per_eval, double *transcendentals_per_eval,
+                     double *bytes_per_eval);
+
+/* ---- batch fitness evaluation ------------------------------------------------------------------------
+ * Stand-in for `UDBFE::operator()(const problem&, const vector_double& dvs)` (bfe.hpp:119, bfe.cpp:91-110,
+ * thread_bfe.cpp:64-144) and for `UDP::batch_fitness` (problem.cpp:413-427, member_bfe.cpp:40-45). */
+/* device-resident: d_dvs [n x nx], d_fvs [n x nf] are device pointers on the context's device; asynchronous
+ * on `stream`. */
+int pgc_eval_device(pgc_problem *prob, const double *d_dvs, size_t n, double *d_fvs, void *stream);
+/* host vectors (the pagmo::bfe contract): pageable or pinned host memory; chunked H2D -> kernel -> D2H
+ * through the context's pinned staging ring; returns when fvs is complete. */
+int pgc_eval_host(pgc_problem *prob, const double *dvs, size_t n, double *fvs);
+
+/* ---- device memory helpers (so a host-language binding needs no CUDA runtime of its own) ------------- */
+int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out);
+int pgc_free_device(pgc_ctx *ctx, void *ptr);
+int pgc_malloc_pinned(pgc_ctx *ctx, size_t bytes, void **out);
+int pgc_free_pinned(pgc_ctx *ctx, void *ptr);
+int pgc_memcpy_h2d(pgc_ctx *ctx, void *dst, const void *src, size_t bytes);
+int pgc_memcpy_d2h(pgc_ctx *ctx, void *dst, const void *src, size_t bytes);
+
+/* ---- measurement helpers ------------------------------------------------------------------------------
+ * Dependent-chain-free DFMA loop over the whole chip: the measured FP64-pipe ceiling that bench.py uses as
+ * the roofline denominator for the rotation-bound kernels (MEASURED_PEAKS.json has no FP64 figure). */
+int pgc_measure_fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAGMO_CUDA_PGC_H */

@@ -1,0 +1,38 @@
+/* oracle/oracle.h - C API of the CPU restatement (liboracle.so).  TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C restatement of the reference's algorithms on the hot path, one function per reference routine,
+ * each citing the reference file:line it follows.  It exists to CHECK the CUDA path: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.  It is itself pinned
+ * bit-exactly against the unmodified reference (oracle/_ref/libpagmo_ref.so) and against the golden vectors in
+ * tests/golden/ (see tests/test_oracle_*.py).
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORACLE_RASTRIGIN = 1, ORACLE_ACKLEY = 2, ORACLE_GRIEWANK = 3, ORACLE_SCHWEFEL = 4, ORACLE_ROSENBROCK = 5 };
+
+/* ---- simple UDPs (restate_simple.c) ---- */
+int oracle_simple_fitness(int family, size_t dim, const double *x, double *f);
+int oracle_simple_batch(int family, size_t dim, const double *xs, size_t n, double *fs);
+int oracle_simple_bounds(int family, double *lo, double *hi);
+
+/* ---- CEC2014 (restate_cec2014.c) ----
+ * Mr: rotation table (component i at i*dim*dim), Os: COMPACTED shift (component i at i*dim, i.e. what
+ * cec2014::get_origin_shift() returns, cec2014.cpp:76-86), S: 1-based shuffle (component i at i*dim). */
+int oracle_cec2014_fitness(unsigned func, unsigned dim, const double *Mr, const double *Os, const int *S,
+                           const double *x, double *f);
+/* nthreads<=1: sequential.  Static contiguous partition over individuals (thread_bfe.cpp:94-137 restated). */
+int oracle_cec2014_batch(unsigned func, unsigned dim, const double *Mr, const double *Os, const int *S,
+                         const double *xs, size_t n, double *fs, int nthreads);
+/* compaction performed by the cec2014 constructor (cec2014.cpp:76-86): keep the first dim of every 100 */
+size_t oracle_cec2014_compact_shift(const double *lines, size_t nlines, unsigned dim, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,277 @@
+"""ctypes loaders for the two checkers.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+* ``Oracle``    - oracle/liboracle.so, the plain-C restatement (oracle/restate_*.c + cec_synth.c).
+* ``Reference`` - oracle/_ref/libpagmo_ref.so, the UNMODIFIED reference sources compiled against oracle/shim
+                  (built in the authoring container only; the prebuilt .so travels to the GPU box).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ORACLE_SO = HERE / "liboracle.so"
+REF_SO = HERE / "_ref" / "libpagmo_ref.so"
+REFERENCE_ROOT = Path("/root/reference")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_size_p = C.POINTER(C.c_size_t)
+
+
+def _dp(a: np.ndarray):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a: np.ndarray):
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_int_p)
+
+
+def _sp(a: np.ndarray):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_size_p)
+
+
+def build(ref: bool = True) -> None:
+    """Compile the checkers (make -C oracle).  The reference library is only attempted when /root/reference exists."""
+    targets = ["liboracle.so"]
+    if ref and (REFERENCE_ROOT / "src" / "problem.cpp").exists():
+        targets.append("_ref/libpagmo_ref.so")
+    subprocess.run(["make", "-s", "-j8", "-C", str(HERE), *targets], check=True)
+
+
+SIMPLE = {"rastrigin": 1, "ackley": 2, "griewank": 3, "schwefel": 4, "rosenbrock": 5}
+CEC_NCOMP = 10
+
+
+class Oracle:
+    def __init__(self):
+        if not ORACLE_SO.exists():
+            build(ref=False)
+        self.lib = L = C.CDLL(str(ORACLE_SO))
+        L.oracle_cec2014_compact_shift.restype = C.c_size_t
+
+    # ---- synthetic CEC tables (cec_synth.c) ----
+    def cec2014_tables(self, func: int, dim: int):
+        """Returns (Mr[10*dim*dim], Os_lines[10*100], S[10*dim] int32) exactly as the reference ctor sees them."""
+        mr = np.empty(CEC_NCOMP * dim * dim)
+        os_ = np.empty(CEC_NCOMP * 100)
+        s = np.empty(CEC_NCOMP * dim, dtype=np.int32)
+        self.lib.cec2014_synth_rotation(C.c_uint(func), C.c_uint(dim), _dp(mr))
+        self.lib.cec2014_synth_shift(C.c_uint(func), _dp(os_))
+        self.lib.cec2014_synth_shuffle(C.c_uint(func), C.c_uint(dim), _ip(s))
+        return mr, os_, s
+
+    def cec2014_compact_shift(self, lines: np.ndarray, dim: int) -> np.ndarray:
+        out = np.empty(lines.size)
+        k = self.lib.oracle_cec2014_compact_shift(_dp(lines), C.c_size_t(lines.size // 100), C.c_uint(dim), _dp(out))
+        return out[:k].copy()
+
+    def cec2014_problem_tables(self, func: int, dim: int):
+        """(Mr, Os_compacted, S): the m_rotation_matrix / m_origin_shift / m_shuffle members of cec2014{func, dim}."""
+        mr, lines, s = self.cec2014_tables(func, dim)
+        return mr, self.cec2014_compact_shift(lines, dim), s
+
+    def cec2013_tables(self, dim: int):
+        mr = np.empty(CEC_NCOMP * dim * dim)
+        os_ = np.empty(CEC_NCOMP * 100)
+        self.lib.cec2013_synth_md(C.c_uint(dim), _dp(mr))
+        self.lib.cec2013_synth_shift(_dp(os_))
+        return mr, os_
+
+    # ---- restated evaluators ----
+    def simple(self, family: str, xs: np.ndarray) -> np.ndarray:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n, d = xs.shape
+        out = np.empty(n)
+        rc = self.lib.oracle_simple_batch(C.c_int(SIMPLE[family]), C.c_size_t(d), _dp(xs), C.c_size_t(n), _dp(out))
+        if rc:
+            raise ValueError(f"oracle_simple_batch failed rc={rc}")
+        return out
+
+    def cec2014(self, func: int, xs: np.ndarray, tables=None, nthreads: int = 1) -> np.ndarray:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n, d = xs.shape
+        mr, os_, s = tables if tables is not None else self.cec2014_problem_tables(func, d)
+        out = np.empty(n)
+        rc = self.lib.oracle_cec2014_batch(C.c_uint(func), C.c_uint(d), _dp(mr), _dp(os_), _ip(s), _dp(xs),
+                                           C.c_size_t(n), _dp(out), C.c_int(nthreads))
+        if rc:
+            raise ValueError(f"oracle_cec2014_batch failed rc={rc} (func={func}, dim={d})")
+        return out
+
+
+class RefProblem:
+    def __init__(self, ref: "Reference", handle):
+        self._ref, self._h = ref, handle
+        L = ref.lib
+        self.nx = L.ref_problem_nx(handle)
+        self.nf = L.ref_problem_nf(handle)
+        self.nobj = L.ref_problem_nobj(handle)
+
+    def __del__(self):
+        try:
+            self._ref.lib.ref_problem_destroy(self._h)
+        except Exception:
+            pass
+
+    @property
+    def name(self) -> str:
+        buf = C.create_string_buffer(256)
+        self._ref._check(self._ref.lib.ref_problem_name(self._h, buf, C.c_size_t(256)))
+        return buf.value.decode()
+
+    @property
+    def fevals(self) -> int:
+        return self._ref.lib.ref_problem_fevals(self._h)
+
+    def bounds(self):
+        lb, ub = np.empty(self.nx), np.empty(self.nx)
+        self._ref._check(self._ref.lib.ref_problem_bounds(self._h, _dp(lb), _dp(ub)))
+        return lb, ub
+
+    def fitness(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.empty(self.nf)
+        self._ref._check(self._ref.lib.ref_problem_fitness(self._h, _dp(x), _dp(f)))
+        return f
+
+    def fitness_loop(self, xs: np.ndarray) -> np.ndarray:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n = xs.size // self.nx
+        f = np.empty((n, self.nf))
+        self._ref._check(self._ref.lib.ref_problem_fitness_loop(self._h, _dp(xs), C.c_size_t(n), _dp(f)))
+        return f
+
+    def thread_bfe(self, xs: np.ndarray, nthreads: int = 0) -> np.ndarray:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n = xs.size // self.nx
+        f = np.empty((n, self.nf))
+        self._ref._check(self._ref.lib.ref_thread_bfe(self._h, _dp(xs), C.c_size_t(n), _dp(f), C.c_int(nthreads)))
+        return f
+
+    def default_bfe(self, xs: np.ndarray, nthreads: int = 0) -> np.ndarray:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n = xs.size // self.nx
+        f = np.empty((n, self.nf))
+        self._ref._check(self._ref.lib.ref_default_bfe(self._h, _dp(xs), C.c_size_t(n), _dp(f), C.c_int(nthreads)))
+        return f
+
+
+class Reference:
+    """The unmodified reference behind a C handle API (oracle/ref_capi.h)."""
+
+    @staticmethod
+    def available() -> bool:
+        return REF_SO.exists()
+
+    def __init__(self):
+        if not REF_SO.exists():
+            if (REFERENCE_ROOT / "src" / "problem.cpp").exists():
+                build(ref=True)
+            else:
+                raise FileNotFoundError(f"{REF_SO} is missing and /root/reference is not available to build it")
+        self.lib = L = C.CDLL(str(REF_SO))
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_problem_nx.restype = C.c_size_t
+        L.ref_problem_nf.restype = C.c_size_t
+        L.ref_problem_nobj.restype = C.c_size_t
+        L.ref_problem_fevals.restype = C.c_ulonglong
+        for fn in ("ref_problem_nx", "ref_problem_nf", "ref_problem_nobj", "ref_problem_fevals", "ref_problem_destroy"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+        L.ref_problem_destroy.restype = None
+        L.ref_problem_bounds.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        L.ref_problem_name.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.ref_problem_fitness.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        L.ref_problem_fitness_loop.argtypes = [C.c_void_p, c_double_p, C.c_size_t, c_double_p]
+        L.ref_thread_bfe.argtypes = [C.c_void_p, c_double_p, C.c_size_t, c_double_p, C.c_int]
+        L.ref_default_bfe.argtypes = [C.c_void_p, c_double_p, C.c_size_t, c_double_p, C.c_int]
+        L.ref_cec2014_origin_shift.argtypes = [C.c_void_p, c_double_p, C.c_size_t, c_size_p]
+
+    def _check(self, rc: int):
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+
+    def problem(self, family: str, p0=0, p1=0, p2=0, p3=0) -> RefProblem:
+        h = C.c_void_p()
+        self._check(self.lib.ref_problem_create(family.encode(), C.c_uint(p0), C.c_uint(p1), C.c_uint(p2), C.c_uint(p3),
+                                                C.byref(h)))
+        return RefProblem(self, h)
+
+    def cec2014_tables(self, func: int, dim: int):
+        mr = np.empty(CEC_NCOMP * dim * dim)
+        os_ = np.empty(CEC_NCOMP * 100)
+        s = np.empty(CEC_NCOMP * dim, dtype=np.int32)
+        self._check(self.lib.ref_cec2014_tables(C.c_uint(func), C.c_uint(dim), _dp(mr), _dp(os_), _ip(s)))
+        return mr, os_, s
+
+    def cec2014_origin_shift(self, prob: RefProblem) -> np.ndarray:
+        out = np.empty(CEC_NCOMP * 100)
+        n = C.c_size_t()
+        self._check(self.lib.ref_cec2014_origin_shift(prob._h, _dp(out), C.c_size_t(out.size), C.byref(n)))
+        return out[: n.value].copy()
+
+    # ---- multi-objective utilities ----
+    def fnds(self, f: np.ndarray, with_dom_list: bool = False):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        n, m = f.shape
+        rank = np.empty(n, dtype=np.uint64)
+        dc = np.empty(n, dtype=np.uint64)
+        fidx = np.empty(n, dtype=np.uint64)
+        foff = np.empty(n + 1, dtype=np.uint64)
+        nfr = C.c_size_t()
+        dl_off = np.empty(n + 1, dtype=np.uint64) if with_dom_list else None
+        dl_cap = n * n if with_dom_list else 0
+        dl_idx = np.empty(dl_cap, dtype=np.uint64) if with_dom_list else None
+        self._check(self.lib.ref_fnds(_dp(f), C.c_size_t(n), C.c_size_t(m), _sp(rank), _sp(dc), _sp(fidx), _sp(foff),
+                                      C.byref(nfr), _sp(dl_idx) if with_dom_list else None,
+                                      _sp(dl_off) if with_dom_list else None, C.c_size_t(dl_cap)))
+        k = nfr.value
+        fronts = [fidx[int(foff[i]):int(foff[i + 1])].astype(np.int64) for i in range(k)]
+        out = {"rank": rank.astype(np.int64), "dom_count": dc.astype(np.int64), "fronts": fronts}
+        if with_dom_list:
+            out["dom_list"] = [dl_idx[int(dl_off[i]):int(dl_off[i + 1])].astype(np.int64) for i in range(n)]
+        return out
+
+    def crowding_distance(self, f: np.ndarray) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        out = np.empty(f.shape[0])
+        self._check(self.lib.ref_crowding_distance(_dp(f), C.c_size_t(f.shape[0]), C.c_size_t(f.shape[1]), _dp(out)))
+        return out
+
+    def sort_population_mo(self, f: np.ndarray) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        out = np.empty(f.shape[0], dtype=np.uint64)
+        self._check(self.lib.ref_sort_population_mo(_dp(f), C.c_size_t(f.shape[0]), C.c_size_t(f.shape[1]), _sp(out)))
+        return out.astype(np.int64)
+
+    def select_best_N_mo(self, f: np.ndarray, N: int) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        out = np.empty(f.shape[0], dtype=np.uint64)
+        nout = C.c_size_t()
+        self._check(self.lib.ref_select_best_N_mo(_dp(f), C.c_size_t(f.shape[0]), C.c_size_t(f.shape[1]), C.c_size_t(N),
+                                                  _sp(out), C.byref(nout)))
+        return out[: nout.value].astype(np.int64)
+
+
+_ORACLE = None
+_REFERENCE = None
+
+
+def oracle() -> Oracle:
+    global _ORACLE
+    if _ORACLE is None:
+        _ORACLE = Oracle()
+    return _ORACLE
+
+
+def reference() -> Reference:
+    global _REFERENCE
+    if _REFERENCE is None:
+        _REFERENCE = Reference()
+    return _REFERENCE

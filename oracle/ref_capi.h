@@ -1,0 +1,62 @@
+/* oracle/ref_capi.h - plain-C handle API over the UNMODIFIED reference sources.  TEST INFRASTRUCTURE ONLY.
+ *
+ * oracle/_ref/libpagmo_ref.so is compiled by oracle/Makefile from /root/reference/src/... (where the
+ * files lie, never copied) against oracle/shim/, plus this wrapper.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  All functions return 0 on success,
+ * non-zero on a C++ exception (message via ref_last_error()).
+ */
+#ifndef ORACLE_REF_CAPI_H
+#define ORACLE_REF_CAPI_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ref_problem ref_problem;
+
+const char *ref_last_error(void);
+
+/* family: "rastrigin","ackley","griewank","schwefel","rosenbrock" (p0=dim),
+ *         "cec2014","cec2013" (p0=prob_id,p1=dim), "zdt" (p0=prob_id,p1=param),
+ *         "dtlz" (p0=prob_id,p1=dim,p2=fdim,p3=alpha), "wfg" (p0=prob_id,p1=dim_dvs,p2=dim_obj,p3=dim_k),
+ *         "lennard_jones" (p0=atoms).  Wraps `pagmo::problem{udp}` (problem.cpp:154-242). */
+int ref_problem_create(const char *family, unsigned p0, unsigned p1, unsigned p2, unsigned p3, ref_problem **out);
+void ref_problem_destroy(ref_problem *p);
+size_t ref_problem_nx(const ref_problem *p);
+size_t ref_problem_nf(const ref_problem *p);
+size_t ref_problem_nobj(const ref_problem *p);
+unsigned long long ref_problem_fevals(const ref_problem *p);
+int ref_problem_bounds(const ref_problem *p, double *lb, double *ub);
+int ref_problem_name(const ref_problem *p, char *buf, size_t buflen);
+/* problem::fitness (problem.cpp:353-380) */
+int ref_problem_fitness(const ref_problem *p, const double *x, double *f);
+/* n sequential problem::fitness calls on one thread (what de/de1220/sade/pso/sga do) */
+int ref_problem_fitness_loop(const ref_problem *p, const double *dvs, size_t n, double *fvs);
+/* pagmo::bfe{thread_bfe{}}(prob, dvs) (bfe.cpp:91-110 -> thread_bfe.cpp:64-144); nthreads<=0: all cores */
+int ref_thread_bfe(ref_problem *p, const double *dvs, size_t n, double *fvs, int nthreads);
+/* pagmo::bfe{} == default_bfe (default_bfe.cpp:53-68) */
+int ref_default_bfe(ref_problem *p, const double *dvs, size_t n, double *fvs, int nthreads);
+
+/* the tables the reference constructors saw (synthetic, see cec_synth.h); sizes: Mr 10*dim*dim,
+ * Os 10*100 (uncompacted lines), S 10*dim */
+int ref_cec2014_tables(unsigned func, unsigned dim, double *Mr, double *Os, int *S);
+int ref_cec2013_tables(unsigned dim, double *Mr, double *Os);
+/* cec2014::get_origin_shift() (cec2014.hpp:104): the compacted shift vector, returns its length in *n */
+int ref_cec2014_origin_shift(const ref_problem *p, double *out, size_t cap, size_t *n);
+
+/* ---- multi-objective utilities (src/utils/multi_objective.cpp) on flat row-major [n x m] ---- */
+int ref_pareto_dominance(const double *a, const double *b, size_t m, int *out);
+/* fast_non_dominated_sorting :200-257.  rank[n], dom_count[n]; fronts flattened into front_idx[n] with
+ * front_off[nfronts+1]; dom_list flattened into dl_idx[*dl_total<=cap] with dl_off[n+1] (pass NULL to skip). */
+int ref_fnds(const double *f, size_t n, size_t m, size_t *rank, size_t *dom_count, size_t *front_idx,
+             size_t *front_off, size_t *nfronts, size_t *dl_idx, size_t *dl_off, size_t dl_cap);
+int ref_crowding_distance(const double *f, size_t n, size_t m, double *out);
+int ref_sort_population_mo(const double *f, size_t n, size_t m, size_t *out);
+int ref_select_best_N_mo(const double *f, size_t n, size_t m, size_t N, size_t *out, size_t *nout);
+int ref_ideal(const double *f, size_t n, size_t m, double *out);
+int ref_nadir(const double *f, size_t n, size_t m, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

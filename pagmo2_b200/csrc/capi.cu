@@ -1,0 +1,428 @@
+// capi.cu - the extern "C" boundary of libpgc.so (declared in include/pagmo_cuda/pgc.h).
+// Contexts, problem handles, device/host batch evaluation, memory helpers, the FP64 ceiling probe.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "pgc_internal.cuh"
+
+namespace pgc
+{
+
+static thread_local std::string g_last_error;
+
+void set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) in `%s` at %s:%d", static_cast<int>(e), cudaGetErrorString(e), what, file, line);
+    return e == cudaErrorMemoryAllocation ? PGC_ERR_OUT_OF_MEMORY : PGC_ERR_CUDA;
+}
+
+int ensure_scratch(pgc_ctx *ctx, size_t bytes)
+{
+    if (ctx->scratch_bytes >= bytes) return PGC_OK;
+    // growing the scratch area must not race with kernels still using the old one
+    PGC_CUDA(cudaDeviceSynchronize());
+    if (ctx->scratch) PGC_CUDA(cudaFree(ctx->scratch));
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    PGC_CUDA(cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return PGC_OK;
+}
+
+// ---- FP64 ceiling probe: 8 independent DFMA chains per thread, every SM saturated ------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+            r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+}
+
+int fp64_peak(pgc_ctx *ctx, int iters, double *tflops)
+{
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    double *d = nullptr;
+    PGC_CUDA(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    PGC_CUDA(cudaEventCreate(&e0));
+    PGC_CUDA(cudaEventCreate(&e1));
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters / 4 + 1, 0.999999, 1e-9); // warm-up
+    PGC_CUDA(cudaEventRecord(e0, ctx->stream));
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999999, 1e-9);
+    PGC_CUDA(cudaEventRecord(e1, ctx->stream));
+    PGC_CUDA(cudaEventSynchronize(e1));
+    ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    float ms = 0;
+    PGC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 64.0 * static_cast<double>(iters) * blocks * threads;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return PGC_OK;
+}
+
+static int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t s)
+{
+    switch (p->desc.family) {
+        case PGC_RASTRIGIN:
+        case PGC_ACKLEY:
+        case PGC_GRIEWANK:
+        case PGC_SCHWEFEL:
+        case PGC_ROSENBROCK: return simple_eval(p, d_dvs, n, d_fvs, s);
+        case PGC_CEC2014: return cec2014_eval(p, d_dvs, n, d_fvs, s);
+        default: set_error("family %d has no device evaluator in this build", p->desc.family); return PGC_ERR_UNSUPPORTED;
+    }
+}
+
+} // namespace pgc
+
+using namespace pgc;
+
+extern "C" {
+
+const char *pgc_version(void) { return "pagmo2_b200 0.1.0 (sm_100a)"; }
+
+const char *pgc_last_error(void) { return g_last_error.c_str(); }
+
+int pgc_device_count(int *count)
+{
+    PGC_REQUIRE(count, "pgc_device_count: null output");
+    *count = 0;
+    PGC_CUDA(cudaGetDeviceCount(count));
+    return PGC_OK;
+}
+
+int pgc_ctx_create(int device, pgc_ctx **out)
+{
+    PGC_REQUIRE(out, "pgc_ctx_create: null output");
+    *out = nullptr;
+    int count = 0;
+    PGC_CUDA(cudaGetDeviceCount(&count));
+    PGC_REQUIRE(device >= 0 && device < count, "pgc_ctx_create: device %d out of range (%d CUDA devices visible)", device, count);
+    PGC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PGC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("pgc_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return PGC_ERR_UNSUPPORTED;
+    }
+    pgc_ctx *ctx = new (std::nothrow) pgc_ctx;
+    if (!ctx) return PGC_ERR_OUT_OF_MEMORY;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    PGC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto &s : ctx->copy_stream) PGC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (int i = 0; i < pgc_ctx::kRing; ++i) {
+        PGC_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+        PGC_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+        PGC_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+    }
+    *out = ctx;
+    return PGC_OK;
+}
+
+int pgc_ctx_destroy(pgc_ctx *ctx)
+{
+    if (!ctx) return PGC_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < pgc_ctx::kRing; ++i) {
+        if (ctx->h_in[i]) cudaFreeHost(ctx->h_in[i]);
+        if (ctx->h_out[i]) cudaFreeHost(ctx->h_out[i]);
+        if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
+        if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
+        cudaEventDestroy(ctx->ev_in[i]);
+        cudaEventDestroy(ctx->ev_k[i]);
+        cudaEventDestroy(ctx->ev_out[i]);
+    }
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    for (auto &s : ctx->copy_stream) cudaStreamDestroy(s);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PGC_OK;
+}
+
+int pgc_ctx_device(const pgc_ctx *ctx, int *device)
+{
+    PGC_REQUIRE(ctx && device, "pgc_ctx_device: null argument");
+    *device = ctx->device;
+    return PGC_OK;
+}
+
+int pgc_ctx_stream(const pgc_ctx *ctx, void **stream)
+{
+    PGC_REQUIRE(ctx && stream, "pgc_ctx_stream: null argument");
+    *stream = ctx->stream;
+    return PGC_OK;
+}
+
+int pgc_ctx_synchronize(pgc_ctx *ctx)
+{
+    PGC_REQUIRE(ctx, "pgc_ctx_synchronize: null context");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    PGC_CUDA(cudaDeviceSynchronize());
+    return PGC_OK;
+}
+
+int pgc_ctx_launch_count(const pgc_ctx *ctx, uint64_t *count)
+{
+    PGC_REQUIRE(ctx && count, "pgc_ctx_launch_count: null argument");
+    *count = ctx->launches.load(std::memory_order_relaxed);
+    return PGC_OK;
+}
+
+int pgc_problem_create(pgc_ctx *ctx, const pgc_problem_desc *desc, pgc_problem **out)
+{
+    PGC_REQUIRE(ctx && desc && out, "pgc_problem_create: null argument");
+    *out = nullptr;
+    pgc_problem *p = new (std::nothrow) pgc_problem;
+    if (!p) return PGC_ERR_OUT_OF_MEMORY;
+    p->ctx = ctx;
+    p->desc = *desc;
+    p->desc.rotation = nullptr;
+    p->desc.shift = nullptr;
+    p->desc.shuffle = nullptr;
+    int rc;
+    switch (desc->family) {
+        case PGC_RASTRIGIN:
+        case PGC_ACKLEY:
+        case PGC_GRIEWANK:
+        case PGC_SCHWEFEL:
+        case PGC_ROSENBROCK: rc = simple_create(p); break;
+        case PGC_CEC2014: rc = cec2014_create(p, desc); break;
+        default:
+            set_error("pgc_problem_create: family %d is not supported by this build (no CPU fallback)", desc->family);
+            rc = PGC_ERR_UNSUPPORTED;
+    }
+    if (rc != PGC_OK) {
+        cec2014_destroy(p);
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return PGC_OK;
+}
+
+int pgc_problem_destroy(pgc_problem *p)
+{
+    if (!p) return PGC_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaDeviceSynchronize();
+    cec2014_destroy(p);
+    delete p;
+    return PGC_OK;
+}
+
+int pgc_problem_nx(const pgc_problem *p, size_t *nx)
+{
+    PGC_REQUIRE(p && nx, "pgc_problem_nx: null argument");
+    *nx = p->nx;
+    return PGC_OK;
+}
+
+int pgc_problem_nobj(const pgc_problem *p, size_t *nobj)
+{
+    PGC_REQUIRE(p && nobj, "pgc_problem_nobj: null argument");
+    *nobj = p->nobj;
+    return PGC_OK;
+}
+
+int pgc_problem_nf(const pgc_problem *p, size_t *nf)
+{
+    PGC_REQUIRE(p && nf, "pgc_problem_nf: null argument");
+    *nf = p->nobj;
+    return PGC_OK;
+}
+
+int pgc_problem_bounds(const pgc_problem *p, double *lb, double *ub)
+{
+    PGC_REQUIRE(p && lb && ub, "pgc_problem_bounds: null argument");
+    std::copy(p->lb.begin(), p->lb.end(), lb);
+    std::copy(p->ub.begin(), p->ub.end(), ub);
+    return PGC_OK;
+}
+
+int pgc_problem_name(const pgc_problem *p, char *buf, size_t buflen)
+{
+    PGC_REQUIRE(p && buf && buflen, "pgc_problem_name: null argument");
+    std::strncpy(buf, p->name.c_str(), buflen - 1);
+    buf[buflen - 1] = 0;
+    return PGC_OK;
+}
+
+int pgc_problem_work(const pgc_problem *p, double *flops, double *transc, double *bytes)
+{
+    PGC_REQUIRE(p, "pgc_problem_work: null problem");
+    if (flops) *flops = p->flops_per_eval;
+    if (transc) *transc = p->transc_per_eval;
+    if (bytes) *bytes = 8.0 * static_cast<double>(p->nx + p->nobj);
+    return PGC_OK;
+}
+
+int pgc_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, void *stream)
+{
+    PGC_REQUIRE(p, "pgc_eval_device: null problem");
+    PGC_REQUIRE(n == 0 || (d_dvs && d_fvs), "pgc_eval_device: null device buffer");
+    PGC_CUDA(cudaSetDevice(p->ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->ctx->stream;
+    return problem_eval_device(p, d_dvs, n, d_fvs, s);
+}
+
+// Host-vector path = the pagmo::bfe contract.  The batch is cut into chunks that cycle through a ring of
+// pinned+device staging buffers: memcpy(host->pinned) | H2D | kernels | D2H | memcpy(pinned->host) overlap
+// across chunks on three streams.  PCIe-bound by construction.
+int pgc_eval_host(pgc_problem *p, const double *dvs, size_t n, double *fvs)
+{
+    PGC_REQUIRE(p, "pgc_eval_host: null problem");
+    if (n == 0) return PGC_OK;
+    PGC_REQUIRE(dvs && fvs, "pgc_eval_host: null host buffer");
+    pgc_ctx *ctx = p->ctx;
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    const size_t nx = p->nx, nf = p->nobj;
+    // chunk: ~32 MiB of decision vectors, a multiple of 16 individuals
+    size_t chunk = (32u << 20) / (nx * sizeof(double));
+    chunk = std::max<size_t>(16, chunk / 16 * 16);
+    if (chunk > n) chunk = (n + 15) / 16 * 16;
+    const size_t in_bytes = chunk * nx * sizeof(double), out_bytes = chunk * nf * sizeof(double);
+    if (ctx->ring_in_bytes < in_bytes || ctx->ring_out_bytes < out_bytes) {
+        PGC_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < pgc_ctx::kRing; ++i) {
+            if (ctx->h_in[i]) cudaFreeHost(ctx->h_in[i]);
+            if (ctx->h_out[i]) cudaFreeHost(ctx->h_out[i]);
+            if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
+            if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
+            ctx->h_in[i] = ctx->h_out[i] = ctx->d_in[i] = ctx->d_out[i] = nullptr;
+        }
+        ctx->ring_in_bytes = ctx->ring_out_bytes = 0;
+        for (int i = 0; i < pgc_ctx::kRing; ++i) {
+            PGC_CUDA(cudaMallocHost(&ctx->h_in[i], in_bytes));
+            PGC_CUDA(cudaMallocHost(&ctx->h_out[i], out_bytes));
+            PGC_CUDA(cudaMalloc(&ctx->d_in[i], in_bytes));
+            PGC_CUDA(cudaMalloc(&ctx->d_out[i], out_bytes));
+        }
+        ctx->ring_in_bytes = in_bytes;
+        ctx->ring_out_bytes = out_bytes;
+    }
+    cudaPointerAttributes attr;
+    const bool in_pinned = cudaPointerGetAttributes(&attr, dvs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    const bool out_pinned = cudaPointerGetAttributes(&attr, fvs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError(); // clear a possible "invalid value" from probing pageable memory
+
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    cudaStream_t s_in = ctx->copy_stream[0], s_out = ctx->copy_stream[1], s_k = ctx->stream;
+    struct Pending { size_t first, count; };
+    Pending pend[pgc_ctx::kRing];
+    auto drain = [&](int slot) -> int { // finish the D2H of the chunk living in `slot`
+        PGC_CUDA(cudaEventSynchronize(ctx->ev_out[slot]));
+        if (!out_pinned)
+            std::memcpy(fvs + pend[slot].first * nf, ctx->h_out[slot], pend[slot].count * nf * sizeof(double));
+        return PGC_OK;
+    };
+    for (size_t c = 0; c < nchunks; ++c) {
+        const int slot = static_cast<int>(c % pgc_ctx::kRing);
+        if (c >= static_cast<size_t>(pgc_ctx::kRing)) {
+            int rc = drain(slot);
+            if (rc != PGC_OK) return rc;
+        }
+        const size_t first = c * chunk, count = std::min(chunk, n - first);
+        pend[slot] = {first, count};
+        const double *src = dvs + first * nx;
+        if (!in_pinned) {
+            std::memcpy(ctx->h_in[slot], src, count * nx * sizeof(double));
+            src = static_cast<const double *>(ctx->h_in[slot]);
+        }
+        PGC_CUDA(cudaMemcpyAsync(ctx->d_in[slot], src, count * nx * sizeof(double), cudaMemcpyHostToDevice, s_in));
+        PGC_CUDA(cudaEventRecord(ctx->ev_in[slot], s_in));
+        PGC_CUDA(cudaStreamWaitEvent(s_k, ctx->ev_in[slot], 0));
+        int rc = problem_eval_device(p, static_cast<const double *>(ctx->d_in[slot]), count,
+                                     static_cast<double *>(ctx->d_out[slot]), s_k);
+        if (rc != PGC_OK) return rc;
+        PGC_CUDA(cudaEventRecord(ctx->ev_k[slot], s_k));
+        PGC_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_k[slot], 0));
+        double *dst = out_pinned ? fvs + first * nf : static_cast<double *>(ctx->h_out[slot]);
+        PGC_CUDA(cudaMemcpyAsync(dst, ctx->d_out[slot], count * nf * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        PGC_CUDA(cudaEventRecord(ctx->ev_out[slot], s_out));
+    }
+    const size_t tail = std::min<size_t>(nchunks, pgc_ctx::kRing);
+    for (size_t c = nchunks - tail; c < nchunks; ++c) {
+        int rc = drain(static_cast<int>(c % pgc_ctx::kRing));
+        if (rc != PGC_OK) return rc;
+    }
+    return PGC_OK;
+}
+
+int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out)
+{
+    PGC_REQUIRE(ctx && out, "pgc_malloc_device: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    PGC_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    return PGC_OK;
+}
+
+int pgc_free_device(pgc_ctx *ctx, void *ptr)
+{
+    PGC_REQUIRE(ctx, "pgc_free_device: null context");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    PGC_CUDA(cudaFree(ptr));
+    return PGC_OK;
+}
+
+int pgc_malloc_pinned(pgc_ctx *ctx, size_t bytes, void **out)
+{
+    PGC_REQUIRE(ctx && out, "pgc_malloc_pinned: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    PGC_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return PGC_OK;
+}
+
+int pgc_free_pinned(pgc_ctx *ctx, void *ptr)
+{
+    PGC_REQUIRE(ctx, "pgc_free_pinned: null context");
+    PGC_CUDA(cudaFreeHost(ptr));
+    return PGC_OK;
+}
+
+int pgc_memcpy_h2d(pgc_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    PGC_REQUIRE(ctx, "pgc_memcpy_h2d: null context");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    PGC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PGC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PGC_OK;
+}
+
+int pgc_memcpy_d2h(pgc_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    PGC_REQUIRE(ctx, "pgc_memcpy_d2h: null context");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    PGC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PGC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PGC_OK;
+}
+
+int pgc_measure_fp64_peak(pgc_ctx *ctx, int iters, double *tflops)
+{
+    PGC_REQUIRE(ctx && tflops && iters > 0, "pgc_measure_fp64_peak: bad argument");
+    return fp64_peak(ctx, iters, tflops);
+}
+
+} // extern "C"

@@ -1,0 +1,642 @@
+// eval_cec2014.cu - CEC2014 f1..f30 batch fitness on sm_100a (the headline path).
+//
+// Replaces, for a whole batch, reference pagmo::cec2014::fitness (src/problems/cec2014.cpp:119-247) as driven by
+// thread_bfe (src/batch_evaluators/thread_bfe.cpp:94-137).
+//
+// Design:
+//   * one "stage kernel" launch per recipe stage (cec2014_recipe.cpp).  A stage = sr_func (shift, scale,
+//     rotate; cec2014.cpp:1238-1274) + optional hybrid permutation (:807-809) + 1..5 primitive groups.
+//     Compositions (f23-f30) launch one stage kernel per component plus a tiny cf_cal kernel (:1319-1353).
+//   * rotation z = Mr*y is the FP64-pipe-bound part (2*D^2 flop/eval).  Persistent CTAs (one per SM, 8 warps)
+//     keep the whole matrix in shared memory, re-tiled so that an 8-lane group reads 128 contiguous bytes.
+//     Every warp is an independent worker on tiles of 16 individuals with a private shared-memory buffer:
+//     load+shift+scale -> register-tiled DFMA GEMM (4 individuals x TN outputs per lane) -> z back to the
+//     buffer -> primitive epilogue (2 lanes per individual).  Warps de-synchronise, so one warp's load /
+//     epilogue overlaps the other warps' DFMA streams; no block-level barrier inside the tile loop.
+//   * accumulation order over the rotation's inner index is the reference's (j ascending, :1231-1233); the only
+//     difference is fused multiply-add (one rounding instead of two).  The file is compiled with -fmad=false so
+//     every other expression keeps the reference's operation order and roundings.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "pgc_internal.cuh"
+
+namespace pgc
+{
+
+namespace
+{
+
+constexpr int kWarps = 8;   // workers per CTA
+constexpr int kTileInd = 16; // individuals per warp tile
+constexpr unsigned kFull = 0xffffffffu;
+
+__host__ __device__ constexpr int pad8(int d) { return (d + 7) / 8 * 8; }
+// Row stride (doubles) of a warp buffer: even (16-byte rows) and such that the 4 rows a 128-bit broadcast load
+// touches (rows q, q+4, ... differ by q=0..3) fall on disjoint bank groups: stride mod 16 in {2,6,10,14,4,12}.
+__host__ __device__ constexpr int ystride(int d)
+{
+    int s = d + 2;
+    while (!((s % 16 == 2) || (s % 16 == 6) || (s % 16 == 10) || (s % 16 == 14) || (s % 16 == 4) || (s % 16 == 12))) s += 2;
+    return s;
+}
+
+struct StageParams {
+    const double *x;    // [n x D]
+    const double *mr;   // re-tiled rotation of this component: D x DP (see retile_rotation)
+    const double *os;   // shift of this component: D
+    const int *perm;    // 0-based permutation of this component (D) or nullptr
+    const double *table; // problem constant table
+    double *out;        // final f (non-composition) or fit[stage] (composition)
+    double *wout;       // composition: w[stage]; nullptr otherwise
+    long long n;
+    double fbias;
+    int aligned16;
+    StageDesc st;
+};
+
+// cos(theta) for |theta| up to ~2^50 with a two-term 1/(2*pi): r = frac(theta/(2*pi)) to ~1e-17, then cospi.
+// Used where the reference feeds libm cos huge arguments as a matter of course (weierstrass :504,
+// grie_rosen :708); matches a correctly-rounded cos to ~1 ulp without the Payne-Hanek slow path.
+__device__ __forceinline__ double cos_big(double theta)
+{
+    const double I1 = 0x1.45f306dc9c883p-3, I2 = -0x1.6b01ec5417056p-57;
+    const double p = theta * I1;
+    const double e = fma(theta, I1, -p);
+    const double r = (p - rint(p)) + fma(theta, I2, e);
+    return cospi(2.0 * r);
+}
+
+struct Elem {
+    const double *row;
+    const int *idx; // may be nullptr
+    int off;
+    double rate;
+    __device__ __forceinline__ double operator()(int j) const
+    {
+        const int jj = idx ? idx[off + j] : off + j;
+        return row[jj] * rate;
+    }
+};
+
+__device__ __forceinline__ double pair_add(double v) { return v + __shfl_xor_sync(kFull, v, 1); }
+__device__ __forceinline__ double pair_mul(double v) { return v * __shfl_xor_sync(kFull, v, 1); }
+
+// One primitive on n coordinates, evaluated by a pair of lanes (h = 0/1 takes the lower/upper half of the
+// terms); both lanes return the full value.  Expressions follow cec2014.cpp term by term.
+__device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__restrict__ tab, int h)
+{
+    const int n = g.len;
+    const double dn = static_cast<double>(static_cast<unsigned>(n));
+    const int lo = (n * h) >> 1, hi = (n * (h + 1)) >> 1;
+    const double two_pi = 2.0 * 3.141592653589793238462643383279502884;
+    switch (g.prim) {
+        case P_ELLIPS: { // :382-384
+            double s = 0.0;
+            for (int j = lo; j < hi; ++j) {
+                const double z = v(j);
+                s += tab[g.tab_off + j] * z * z;
+            }
+            return pair_add(s);
+        }
+        case P_BENT_CIGAR: { // :395-398
+            double s = 0.0;
+            for (int j = lo; j < hi; ++j) {
+                const double z = v(j);
+                s += (j == 0) ? z * z : 1.0e6 * z * z;
+            }
+            return pair_add(s);
+        }
+        case P_DISCUS: { // :408-411
+            double s = 0.0;
+            for (int j = lo; j < hi; ++j) {
+                const double z = v(j);
+                s += (j == 0) ? 1.0e6 * z * z : z * z;
+            }
+            return pair_add(s);
+        }
+        case P_ROSENBROCK: { // :438-444
+            const int nt = n - 1;
+            const int tlo = (nt * h) >> 1, thi = (nt * (h + 1)) >> 1;
+            double s = 0.0;
+            for (int j = tlo; j < thi; ++j) {
+                const double zj = v(j) + 1.0, zn = v(j + 1) + 1.0;
+                const double t1 = zj * zj - zn, t2 = zj - 1.0;
+                s += 100.0 * t1 * t1 + t2 * t2;
+            }
+            return pair_add(s);
+        }
+        case P_ACKLEY: { // :476-482
+            double s1 = 0.0, s2 = 0.0;
+            for (int j = lo; j < hi; ++j) {
+                const double z = v(j);
+                s1 += z * z;
+                s2 += cos(two_pi * z);
+            }
+            s1 = pair_add(s1);
+            s2 = pair_add(s2);
+            s1 = -0.2 * sqrt(s1 / dn);
+            s2 /= dn;
+            return 2.718281828459045235360287471352662498 - 20.0 * exp(s1) - exp(s2) + 20.0;
+        }
+        case P_WEIERSTRASS: { // :500-509
+            const double *cj = tab + g.tab_off, *aj = cj + 21;
+            double s = 0.0;
+            for (int j = lo; j < hi; ++j) {
+                const double u = v(j) + 0.5;
+                double sum = 0.0;
+#pragma unroll 3
+                for (int k = 0; k <= 20; ++k) sum += aj[k] * cos_big(cj[k] * u);
+                s += sum;
+            }
+            return pair_add(s) - g.c0;
+        }
+        case P_GRIEWANK: { // :524-528
+            double s = 0.0, p = 1.0;
+            for (int j = lo; j < hi; ++j) {
+                const double z = v(j);
+                s += z * z;
+                p *= cos(z / tab[g.tab_off + j]);
+            }
+            s = pair_add(s);
+            p = pair_mul(p);
+            return 1.0 + s / 4000.0 - p;
+        }
+        case P_RASTRIGIN: { // :541-543
+            double s = 0.0;
+            for (int j = lo; j < hi; ++j) {
+                const double z = v(j);
+                s += (z * z - 10.0 * cos(two_pi * z) + 10.0);
+            }
+            return pair_add(s);
+        }
+        case P_SCHWEFEL: { // :575-589
+            double s = 0.0;
+            for (int j = lo; j < hi; ++j) {
+                const double z = v(j) + 4.209687462275036e+002;
+                if (z > 500.0) {
+                    const double m = 500.0 - fmod(z, 500.0);
+                    s -= m * sin(sqrt(m));
+                    const double t = (z - 500.0) / 100.0;
+                    s += t * t / dn;
+                } else if (z < -500.0) {
+                    const double fm = fmod(fabs(z), 500.0);
+                    s -= (-500.0 + fm) * sin(sqrt(500.0 - fm));
+                    const double t = (z + 500.0) / 100.0;
+                    s += t * t / dn;
+                } else {
+                    s -= z * sin(sqrt(fabs(z)));
+                }
+            }
+            return pair_add(s) + g.c0;
+        }
+        case P_KATSUURA: { // :604-614
+            double p = 1.0;
+            for (int j = lo; j < hi; ++j) {
+                const double z = v(j);
+                double temp = 0.0, t1 = 1.0, it1 = 1.0;
+#pragma unroll 4
+                for (int k = 1; k <= 32; ++k) {
+                    t1 *= 2.0;
+                    it1 *= 0.5;
+                    const double t2 = t1 * z;
+                    temp += fabs(t2 - floor(t2 + 0.5)) * it1; // "/ 2^k" == "* 2^-k" exactly
+                }
+                p *= pow(1.0 + static_cast<double>(j + 1) * temp, g.c0);
+            }
+            p = pair_mul(p);
+            return p * g.c1 - g.c1;
+        }
+        case P_HAPPYCAT: { // :751-759
+            double r2 = 0.0, sz = 0.0;
+            for (int j = lo; j < hi; ++j) {
+                const double z = v(j) - 1.0;
+                r2 += z * z;
+                sz += z;
+            }
+            r2 = pair_add(r2);
+            sz = pair_add(sz);
+            return sqrt(sqrt(fabs(r2 - dn))) + (0.5 * r2 + sz) / dn + 0.5;
+        }
+        case P_HGBAT: { // :774-782
+            double r2 = 0.0, sz = 0.0;
+            for (int j = lo; j < hi; ++j) {
+                const double z = v(j) - 1.0;
+                r2 += z * z;
+                sz += z;
+            }
+            r2 = pair_add(r2);
+            sz = pair_add(sz);
+            return sqrt(fabs(r2 * r2 - sz * sz)) + (0.5 * r2 + sz) / dn + 0.5;
+        }
+        case P_GRIE_ROSEN: { // :702-713 (cyclic last term)
+            double s = 0.0;
+            for (int j = lo; j < hi; ++j) {
+                const int jn = (j + 1 == n) ? 0 : j + 1;
+                const double zj = v(j) + 1.0, zn = v(jn) + 1.0;
+                const double t1 = zj * zj - zn, t2 = zj - 1.0;
+                const double temp = 100.0 * t1 * t1 + t2 * t2;
+                s += (temp * temp) / 4000.0 - cos_big(temp) + 1.0;
+            }
+            return pair_add(s);
+        }
+        case P_ESCAFFER6: { // :727-736 (cyclic last term)
+            double s = 0.0;
+            for (int j = lo; j < hi; ++j) {
+                const int jn = (j + 1 == n) ? 0 : j + 1;
+                const double a = v(j), b = v(jn);
+                const double ss = a * a + b * b;
+                double t1 = sin(sqrt(ss));
+                t1 = t1 * t1;
+                const double t2 = 1.0 + 0.001 * ss;
+                s += 0.5 + (t1 - 0.5) / (t2 * t2);
+            }
+            return pair_add(s);
+        }
+        default: return 0.0;
+    }
+}
+
+template <int D, bool ROT>
+__global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __grid_constant__ StageParams P)
+{
+    constexpr int DP = pad8(D);
+    constexpr int TN = DP / 8;
+    constexpr int NPAIR = TN / 2;
+    constexpr bool ODD = (TN & 1) != 0;
+    constexpr int YS = ystride(D);
+    constexpr int MR_ELEMS = ROT ? D * DP : 0;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sMr = reinterpret_cast<double *>(smem_raw);
+    double *sBuf = sMr + MR_ELEMS;
+    double *sOs = sBuf + kWarps * kTileInd * YS;
+    int *sPerm = reinterpret_cast<int *>(sOs + D);
+
+    // ---- per-CTA preload: rotation (already re-tiled on the host), shift, permutation --------------------
+    if (ROT) {
+        const double2 *src = reinterpret_cast<const double2 *>(P.mr);
+        double2 *dst = reinterpret_cast<double2 *>(sMr);
+        for (int i = threadIdx.x; i < MR_ELEMS / 2; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        sOs[i] = P.os[i];
+        sPerm[i] = P.perm ? P.perm[i] : i;
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *buf = sBuf + warp * kTileInd * YS;
+    const int *perm = P.st.permute ? sPerm : nullptr;
+    const long long ntiles = (P.n + kTileInd - 1) / kTileInd;
+    const bool need_w = P.wout != nullptr;
+    const double pre_rate = P.st.pre_rate;
+
+    for (long long tile = static_cast<long long>(blockIdx.x) * kWarps + warp; tile < ntiles;
+         tile += static_cast<long long>(gridDim.x) * kWarps) {
+        const long long t0 = tile * kTileInd;
+        const int nt = (P.n - t0 < kTileInd) ? static_cast<int>(P.n - t0) : kTileInd;
+
+        // ---- L: coalesced load, shift (x - Os) and scale (* sh_rate), cec2014.cpp:1245-1258 --------------
+        {
+            const double *src = P.x + t0 * D;
+            const double scale = need_w ? 1.0 : pre_rate; // composition: keep x-Os for the cf_cal weight first
+#pragma unroll 5
+            for (int e = 2 * lane; e < kTileInd * D; e += 64) {
+                const int t = e / D, j = e - t * D;
+                double2 xv = make_double2(0.0, 0.0);
+                if (t < nt) {
+                    if (P.aligned16) {
+                        xv = __ldcs(reinterpret_cast<const double2 *>(src + e));
+                    } else {
+                        xv.x = __ldcs(src + e);
+                        xv.y = __ldcs(src + e + 1);
+                    }
+                }
+                double2 y;
+                y.x = (xv.x - sOs[j]) * scale;
+                y.y = (xv.y - sOs[j + 1]) * scale;
+                *reinterpret_cast<double2 *>(buf + t * YS + j) = y;
+            }
+        }
+        __syncwarp();
+
+        const int et = lane >> 1, eh = lane & 1; // epilogue mapping: individual, half
+        double wacc = 0.0;
+        if (need_w) { // cf_cal weight sum_j (x_j - Os_j)^2, :1330-1332, then the deferred scale
+            double *row = buf + et * YS;
+            const int lo = (D * eh) >> 1, hi = (D * (eh + 1)) >> 1;
+            for (int j = lo; j < hi; ++j) {
+                const double d = row[j];
+                wacc += d * d;
+                row[j] = d * pre_rate;
+            }
+            wacc = pair_add(wacc);
+            __syncwarp();
+        }
+
+        // ---- G: z = Mr * y, :1224-1235.  lane = (q, o): individuals t = 4m+q, outputs i = 8c+o -------------
+        if (ROT) {
+            const int o = lane & 7, q = lane >> 3;
+            double acc[4][TN];
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int c = 0; c < TN; ++c) acc[m][c] = 0.0;
+            const double *yb = buf + q * YS;
+            const double *mb = sMr + o * 2;
+            const double *mo = sMr + NPAIR * 16 + o;
+#pragma unroll 2
+            for (int k = 0; k < D; k += 2) {
+                double2 y[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) y[m] = *reinterpret_cast<const double2 *>(yb + m * 4 * YS + k);
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    double2 b[NPAIR > 0 ? NPAIR : 1];
+                    double bo = 0.0;
+#pragma unroll
+                    for (int c2 = 0; c2 < NPAIR; ++c2)
+                        b[c2] = *reinterpret_cast<const double2 *>(mb + (k + kk) * DP + c2 * 16);
+                    if (ODD) bo = mo[(k + kk) * DP];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const double ym = kk ? y[m].y : y[m].x;
+#pragma unroll
+                        for (int c2 = 0; c2 < NPAIR; ++c2) {
+                            acc[m][2 * c2] = fma(ym, b[c2].x, acc[m][2 * c2]);
+                            acc[m][2 * c2 + 1] = fma(ym, b[c2].y, acc[m][2 * c2 + 1]);
+                        }
+                        if (ODD) acc[m][TN - 1] = fma(ym, bo, acc[m][TN - 1]);
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                double *zr = buf + (m * 4 + q) * YS + o;
+#pragma unroll
+                for (int c = 0; c < TN; ++c)
+                    if (c * 8 + o < D) zr[c * 8] = acc[m][c];
+            }
+            __syncwarp();
+        }
+
+        // ---- E: primitives on z (2 lanes per individual) ---------------------------------------------------
+        double val = 0.0;
+        {
+            Elem v;
+            v.row = buf + et * YS;
+            v.idx = perm;
+            for (int gi = 0; gi < P.st.ngroups; ++gi) {
+                const GroupDesc &g = P.st.g[gi];
+                v.off = g.off;
+                v.rate = g.rate;
+                val += eval_group(g, v, P.table, eh);
+            }
+        }
+        if (eh == 0 && et < nt) {
+            if (need_w) {
+                if (P.st.scaled) val = P.st.mul * val / P.st.div; // e.g. :1047 fit = 10000 * fit / 1e+4
+                P.out[t0 + et] = val;
+                P.wout[t0 + et] = wacc;
+            } else {
+                P.out[t0 + et] = val + P.fbias; // :126 f[0] += 100.0 * func
+            }
+        }
+        __syncwarp();
+    }
+}
+
+struct CombineParams {
+    const double *fit; // [nstages][n]
+    const double *w;   // [nstages][n]
+    double *out;
+    long long n;
+    int nstages;
+    int dim;
+    double fbias;
+    double delta[kMaxStages];
+    double cbias[kMaxStages];
+};
+
+// cf_cal, cec2014.cpp:1319-1353
+__global__ void cec14_combine_kernel(const __grid_constant__ CombineParams P)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    double w[kMaxStages], fit[kMaxStages];
+    double w_max = 0.0, w_sum = 0.0;
+    const double nx = static_cast<double>(P.dim);
+    for (int s = 0; s < P.nstages; ++s) {
+        fit[s] = P.fit[s * P.n + i] + P.cbias[s];
+        double ws = P.w[s * P.n + i];
+        if (ws != 0.0)
+            ws = sqrt(1.0 / ws) * exp(-ws / 2.0 / nx / (P.delta[s] * P.delta[s]));
+        else
+            ws = DBL_MAX;
+        if (ws > w_max) w_max = ws;
+        w[s] = ws;
+    }
+    for (int s = 0; s < P.nstages; ++s) w_sum = w_sum + w[s];
+    if (w_max == 0.0) {
+        for (int s = 0; s < P.nstages; ++s) w[s] = 1.0;
+        w_sum = P.nstages;
+    }
+    double f = 0.0;
+    for (int s = 0; s < P.nstages; ++s) f = f + w[s] / w_sum * fit[s];
+    P.out[i] = f + P.fbias;
+}
+
+template <int D, bool ROT> size_t stage_smem_bytes()
+{
+    constexpr int DP = pad8(D);
+    constexpr int YS = ystride(D);
+    return sizeof(double) * ((ROT ? D * DP : 0) + kWarps * kTileInd * YS + D) + sizeof(int) * D + 16;
+}
+
+template <int D, bool ROT> int launch_stage(pgc_ctx *ctx, const StageParams &sp, cudaStream_t stream)
+{
+    static thread_local int configured_dev = -1;
+    const size_t smem = stage_smem_bytes<D, ROT>();
+    auto kern = cec14_stage_kernel<D, ROT>;
+    if (configured_dev != ctx->device) {
+        PGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured_dev = ctx->device;
+    }
+    const long long ntiles = (sp.n + kTileInd - 1) / kTileInd;
+    long long ctas = (ntiles + kWarps - 1) / kWarps;
+    int per_sm = 1;
+    if (!ROT) { // no big matrix: several CTAs fit per SM, ask the runtime how many
+        PGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarps * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
+    const long long cap = static_cast<long long>(ctx->sm_count) * per_sm;
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    kern<<<static_cast<unsigned>(ctas), kWarps * 32, smem, stream>>>(sp);
+    PGC_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return PGC_OK;
+}
+
+template <int D> int launch_stage_d(pgc_ctx *ctx, const StageParams &sp, bool rot, cudaStream_t stream)
+{
+    return rot ? launch_stage<D, true>(ctx, sp, stream) : launch_stage<D, false>(ctx, sp, stream);
+}
+
+// Re-tile a row-major D x D rotation (Mr[i*D + j], z_i = sum_j Mr[i][j] y_j) into the shared-memory image the
+// kernel copies verbatim: for inner index k a row of DP doubles, laid out [c2][o][2] for output pairs
+// i = (2*c2 + {0,1})*8 + o followed (odd TN) by [o] for i = (TN-1)*8 + o; outputs >= D are zero.
+void retile_rotation(const double *mr, int D, double *dst)
+{
+    const int DP = pad8(D), TN = DP / 8, NPAIR = TN / 2;
+    std::memset(dst, 0, sizeof(double) * static_cast<size_t>(D) * DP);
+    for (int k = 0; k < D; ++k) {
+        double *row = dst + static_cast<size_t>(k) * DP;
+        for (int c = 0; c < TN; ++c)
+            for (int o = 0; o < 8; ++o) {
+                const int i = c * 8 + o;
+                if (i >= D) continue;
+                const double val = mr[static_cast<size_t>(i) * D + k];
+                if (c < 2 * NPAIR) row[(c / 2) * 16 + o * 2 + (c & 1)] = val;
+                else row[NPAIR * 16 + o] = val;
+            }
+    }
+}
+
+} // namespace
+
+int cec2014_create(pgc_problem *p, const pgc_problem_desc *d)
+{
+    Cec2014Recipe &r = p->cec14;
+    int rc = build_cec2014_recipe(d->prob_id, d->dim, r);
+    if (rc != PGC_OK) return rc;
+    const size_t D = d->dim;
+    int ncomp = 0;
+    bool any_rot = false, any_perm = false;
+    for (int s = 0; s < r.nstages; ++s) {
+        if (r.st[s].comp + 1 > ncomp) ncomp = r.st[s].comp + 1;
+        any_rot |= r.st[s].rotate != 0;
+        any_perm |= r.st[s].permute != 0;
+    }
+    PGC_REQUIRE(d->shift && d->shift_len >= ncomp * D,
+                "cec2014: shift table needs at least %zu values (m_origin_shift layout), got %zu", ncomp * D,
+                d->shift_len);
+    PGC_REQUIRE(!any_rot || (d->rotation && d->rotation_len >= ncomp * D * D),
+                "cec2014: rotation table needs at least %zu values, got %zu", ncomp * D * D, d->rotation_len);
+    PGC_REQUIRE(!any_perm || (d->shuffle && d->shuffle_len >= ncomp * D),
+                "cec2014: shuffle table needs at least %zu values, got %zu", ncomp * D, d->shuffle_len);
+
+    p->nx = D;
+    p->nobj = 1;
+    p->lb.assign(D, -100.0); // cec2014.cpp:103-109
+    p->ub.assign(D, 100.0);
+    static const char *names[31] = {"", "ellips_func", "bent_cigar_func", "discus_func", "rosenbrock_func", "ackley_func",
+                                    "weierstrass_func", "griewank_func", "rastrigin_func_non_rotated", "rastrigin_func",
+                                    "schwefel_func_non_rotated", "schwefel_func", "katsuura_func", "happycat_func",
+                                    "hgbat_func", "grie_rosen_func", "escaffer6_func", "hf01", "hf02", "hf03", "hf04",
+                                    "hf05", "hf06", "cf01", "cf02", "cf03", "cf04", "cf05", "cf06", "cf07", "cf08"};
+    p->name = "CEC2014 - f" + std::to_string(d->prob_id) + "(" + names[d->prob_id] + ")"; // :253-350
+    p->flops_per_eval = r.flops_per_eval;
+    p->transc_per_eval = r.transc_per_eval;
+
+    PGC_CUDA(cudaSetDevice(p->ctx->device));
+    PGC_CUDA(cudaMalloc(&p->d_shift, sizeof(double) * ncomp * D));
+    PGC_CUDA(cudaMemcpy(p->d_shift, d->shift, sizeof(double) * ncomp * D, cudaMemcpyHostToDevice));
+    if (any_rot) {
+        const size_t DP = pad8(static_cast<int>(D));
+        std::vector<double> tiled(static_cast<size_t>(ncomp) * D * DP);
+        for (int c = 0; c < ncomp; ++c) retile_rotation(d->rotation + c * D * D, static_cast<int>(D), tiled.data() + c * D * DP);
+        PGC_CUDA(cudaMalloc(&p->d_rotation, sizeof(double) * tiled.size()));
+        PGC_CUDA(cudaMemcpy(p->d_rotation, tiled.data(), sizeof(double) * tiled.size(), cudaMemcpyHostToDevice));
+    }
+    if (any_perm) {
+        std::vector<int> zero_based(ncomp * D);
+        for (size_t i = 0; i < zero_based.size(); ++i) {
+            const int s = d->shuffle[i];
+            PGC_REQUIRE(s >= 1 && s <= static_cast<int>(D), "cec2014: shuffle entry %zu = %d is not in [1, %zu]", i, s, D);
+            zero_based[i] = s - 1; // :808  m_z[S[j] - 1]
+        }
+        PGC_CUDA(cudaMalloc(&p->d_shuffle, sizeof(int) * zero_based.size()));
+        PGC_CUDA(cudaMemcpy(p->d_shuffle, zero_based.data(), sizeof(int) * zero_based.size(), cudaMemcpyHostToDevice));
+    }
+    const size_t tab = r.table.size() ? r.table.size() : 2;
+    PGC_CUDA(cudaMalloc(&p->d_table, sizeof(double) * tab));
+    if (r.table.size())
+        PGC_CUDA(cudaMemcpy(p->d_table, r.table.data(), sizeof(double) * r.table.size(), cudaMemcpyHostToDevice));
+    return PGC_OK;
+}
+
+void cec2014_destroy(pgc_problem *p)
+{
+    cudaFree(p->d_shift);
+    cudaFree(p->d_rotation);
+    cudaFree(p->d_shuffle);
+    cudaFree(p->d_table);
+    p->d_shift = p->d_rotation = p->d_table = nullptr;
+    p->d_shuffle = nullptr;
+}
+
+int cec2014_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream)
+{
+    if (n == 0) return PGC_OK;
+    const Cec2014Recipe &r = p->cec14;
+    pgc_ctx *ctx = p->ctx;
+    const size_t D = r.dim, DP = pad8(r.dim);
+    double *fit = nullptr, *w = nullptr;
+    if (r.composition) {
+        int rc = ensure_scratch(ctx, sizeof(double) * 2 * kMaxStages * n);
+        if (rc != PGC_OK) return rc;
+        fit = static_cast<double *>(ctx->scratch);
+        w = fit + kMaxStages * n;
+    }
+    for (int s = 0; s < r.nstages; ++s) {
+        StageParams sp;
+        sp.x = d_dvs;
+        sp.mr = r.st[s].rotate ? p->d_rotation + r.st[s].comp * D * DP : nullptr;
+        sp.os = p->d_shift + r.st[s].comp * D;
+        sp.perm = r.st[s].permute ? p->d_shuffle + r.st[s].comp * D : nullptr;
+        sp.table = p->d_table;
+        sp.out = r.composition ? fit + s * n : d_fvs;
+        sp.wout = r.composition ? w + s * n : nullptr;
+        sp.n = static_cast<long long>(n);
+        sp.fbias = r.fbias;
+        sp.aligned16 = (reinterpret_cast<uintptr_t>(d_dvs) & 15u) == 0;
+        sp.st = r.st[s];
+        int rc;
+        const bool rot = r.st[s].rotate != 0;
+        switch (r.dim) {
+            case 2: rc = launch_stage_d<2>(ctx, sp, rot, stream); break;
+            case 10: rc = launch_stage_d<10>(ctx, sp, rot, stream); break;
+            case 20: rc = launch_stage_d<20>(ctx, sp, rot, stream); break;
+            case 30: rc = launch_stage_d<30>(ctx, sp, rot, stream); break;
+            case 50: rc = launch_stage_d<50>(ctx, sp, rot, stream); break;
+            case 100: rc = launch_stage_d<100>(ctx, sp, rot, stream); break;
+            default: set_error("cec2014: unsupported dimension %d", r.dim); return PGC_ERR_INVALID_ARGUMENT;
+        }
+        if (rc != PGC_OK) return rc;
+    }
+    if (r.composition) {
+        CombineParams cp;
+        cp.fit = fit;
+        cp.w = w;
+        cp.out = d_fvs;
+        cp.n = static_cast<long long>(n);
+        cp.nstages = r.nstages;
+        cp.dim = r.dim;
+        cp.fbias = r.fbias;
+        for (int s = 0; s < kMaxStages; ++s) {
+            cp.delta[s] = r.delta[s];
+            cp.cbias[s] = r.cbias[s];
+        }
+        const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+        cec14_combine_kernel<<<blocks, 256, 0, stream>>>(cp);
+        PGC_CUDA(cudaGetLastError());
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return PGC_OK;
+}
+
+} // namespace pgc

@@ -1,0 +1,146 @@
+// pgc_internal.cuh - shared internals of libpgc.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/pagmo_cuda/pgc.h"
+
+namespace pgc
+{
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define PGC_CUDA(call)                                                                                                 \
+    do {                                                                                                               \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess) return ::pgc::cuda_fail(e__, #call, __FILE__, __LINE__);                               \
+    } while (0)
+
+#define PGC_REQUIRE(cond, ...)                                                                                         \
+    do {                                                                                                               \
+        if (!(cond)) {                                                                                                 \
+            ::pgc::set_error(__VA_ARGS__);                                                                             \
+            return PGC_ERR_INVALID_ARGUMENT;                                                                           \
+        }                                                                                                              \
+    } while (0)
+
+// ---- CEC2014 recipe (host built, see cec2014_recipe.cpp) ------------------------------------------------
+// Primitive ids: the 14 basic functions used by f1..f30 (reference cec2014.cpp:375-783).
+enum Prim : int {
+    P_ELLIPS = 0,
+    P_BENT_CIGAR,
+    P_DISCUS,
+    P_ROSENBROCK,
+    P_ACKLEY,
+    P_WEIERSTRASS,
+    P_GRIEWANK,
+    P_RASTRIGIN,
+    P_SCHWEFEL,
+    P_KATSUURA,
+    P_HAPPYCAT,
+    P_HGBAT,
+    P_GRIE_ROSEN,
+    P_ESCAFFER6,
+    P_COUNT
+};
+
+constexpr int kMaxGroups = 5;
+constexpr int kMaxStages = 5;
+
+// One group of a stage: a primitive applied (with its own sh_rate, s_flag=r_flag=0 semantics) to the
+// coordinate range [off, off+len) of the stage vector.
+struct GroupDesc {
+    int prim;
+    int off;
+    int len;
+    int tab_off;   // offset (doubles) into the problem's constant table: per-coordinate coefficients
+    double rate;   // post-rotation scale (1.0 for the basic functions: exact no-op)
+    double c0, c1; // primitive-specific host-precomputed constants
+};
+
+// One stage = one shift(+scale)(+rotate)(+permute) followed by 1..5 groups (cec2014.cpp sr_func + hfXX/cfXX).
+struct StageDesc {
+    int comp;       // component index i: Os offset i*D, Mr offset i*D*D, S offset i*D
+    int rotate;     // r_flag
+    int permute;    // hybrid: y[j] = z[S[j]-1]
+    int ngroups;
+    double pre_rate; // sh_rate applied before the rotation
+    int scaled;      // composition: fit = mul*fit/div
+    double mul, div;
+    GroupDesc g[kMaxGroups];
+};
+
+struct Cec2014Recipe {
+    int func;
+    int dim;
+    int nstages;
+    int composition; // cf_cal combine
+    double delta[kMaxStages];
+    double cbias[kMaxStages];
+    double fbias; // 100*func
+    StageDesc st[kMaxStages];
+    std::vector<double> table; // coefficient tables referenced by GroupDesc::tab_off
+    double flops_per_eval;
+    double transc_per_eval;
+};
+
+int build_cec2014_recipe(unsigned func, unsigned dim, Cec2014Recipe &out);
+
+} // namespace pgc
+
+// ---- opaque handle layouts -----------------------------------------------------------------------------
+struct pgc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;     // compute
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    std::atomic<uint64_t> launches{0};
+    // pinned + device staging ring for pgc_eval_host
+    static constexpr int kRing = 3;
+    void *h_in[kRing] = {};
+    void *h_out[kRing] = {};
+    void *d_in[kRing] = {};
+    void *d_out[kRing] = {};
+    size_t ring_in_bytes = 0, ring_out_bytes = 0;
+    cudaEvent_t ev_in[kRing] = {}, ev_k[kRing] = {}, ev_out[kRing] = {};
+    // scratch (composition stage outputs etc.)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+struct pgc_problem {
+    pgc_ctx *ctx = nullptr;
+    pgc_problem_desc desc{}; // table pointers nulled after the copy
+    size_t nx = 0, nobj = 1;
+    std::vector<double> lb, ub;
+    std::string name;
+    // device tables
+    double *d_rotation = nullptr; // cec: padded/retiled per component (see eval_cec2014.cu)
+    double *d_shift = nullptr;
+    int *d_shuffle = nullptr;
+    double *d_table = nullptr;
+    pgc::Cec2014Recipe cec14;
+    double flops_per_eval = 0, transc_per_eval = 0;
+};
+
+namespace pgc
+{
+int ensure_scratch(pgc_ctx *ctx, size_t bytes);
+// family back-ends: validate + upload tables (create) and launch (eval, asynchronous on `stream`)
+int simple_create(pgc_problem *p);
+int simple_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
+int cec2014_create(pgc_problem *p, const pgc_problem_desc *d);
+int cec2014_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
+void cec2014_destroy(pgc_problem *p);
+int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
+} // namespace pgc
