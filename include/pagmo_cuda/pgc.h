@@ -19,6 +19,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#if defined(__GNUC__) || defined(__clang__)
+#define PGC_API __attribute__((visibility("default")))
+#else
+#define PGC_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -76,30 +82,30 @@ typedef struct pgc_ctx pgc_ctx;
 typedef struct pgc_problem pgc_problem;
 
 /* ---- library / context ------------------------------------------------------------------------------ */
-const char *pgc_version(void);
-const char *pgc_last_error(void);
-int pgc_device_count(int *count);
+PGC_API const char *pgc_version(void);
+PGC_API const char *pgc_last_error(void);
+PGC_API int pgc_device_count(int *count);
 /* One context pins one device and owns one stream plus pinned/device staging buffers.  Distinct contexts may
  * be used concurrently from different threads (thread_safety::basic, reference threading.hpp:42). */
-int pgc_ctx_create(int device, pgc_ctx **out);
-int pgc_ctx_destroy(pgc_ctx *ctx);
-int pgc_ctx_device(const pgc_ctx *ctx, int *device);
-int pgc_ctx_stream(const pgc_ctx *ctx, void **stream);
-int pgc_ctx_synchronize(pgc_ctx *ctx);
+PGC_API int pgc_ctx_create(int device, pgc_ctx **out);
+PGC_API int pgc_ctx_destroy(pgc_ctx *ctx);
+PGC_API int pgc_ctx_device(const pgc_ctx *ctx, int *device);
+PGC_API int pgc_ctx_stream(const pgc_ctx *ctx, void **stream);
+PGC_API int pgc_ctx_synchronize(pgc_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
-int pgc_ctx_launch_count(const pgc_ctx *ctx, uint64_t *count);
+PGC_API int pgc_ctx_launch_count(const pgc_ctx *ctx, uint64_t *count);
 
 /* ---- problems (stand-in for pagmo::problem{UDP}, reference src/problem.cpp:154-242) ------------------ */
-int pgc_problem_create(pgc_ctx *ctx, const pgc_problem_desc *desc, pgc_problem **out);
-int pgc_problem_destroy(pgc_problem *prob);
-int pgc_problem_nx(const pgc_problem *prob, size_t *nx);     /* problem::get_nx  */
-int pgc_problem_nobj(const pgc_problem *prob, size_t *nobj); /* problem::get_nobj */
-int pgc_problem_nf(const pgc_problem *prob, size_t *nf);     /* problem::get_nf (= nobj here: no constraints) */
-int pgc_problem_bounds(const pgc_problem *prob, double *lb, double *ub); /* UDP::get_bounds */
-int pgc_problem_name(const pgc_problem *prob, char *buf, size_t buflen); /* UDP::get_name */
+PGC_API int pgc_problem_create(pgc_ctx *ctx, const pgc_problem_desc *desc, pgc_problem **out);
+PGC_API int pgc_problem_destroy(pgc_problem *prob);
+PGC_API int pgc_problem_nx(const pgc_problem *prob, size_t *nx);     /* problem::get_nx  */
+PGC_API int pgc_problem_nobj(const pgc_problem *prob, size_t *nobj); /* problem::get_nobj */
+PGC_API int pgc_problem_nf(const pgc_problem *prob, size_t *nf);     /* problem::get_nf (= nobj here: no constraints) */
+PGC_API int pgc_problem_bounds(const pgc_problem *prob, double *lb, double *ub); /* UDP::get_bounds */
+PGC_API int pgc_problem_name(const pgc_problem *prob, char *buf, size_t buflen); /* UDP::get_name */
 /* FP64 add/mul/fma(=2) per evaluation and libm calls per evaluation, as tabulated in DESIGN.md
  * (roofline bookkeeping for bench.py). */
-int pgc_problem_work(const pgc_problem *prob, double *flops_per_eval, double *transcendentals_per_eval,
+PGC_API int pgc_problem_work(const pgc_problem *prob, double *flops_per_eval, double *transcendentals_per_eval,
                      double *bytes_per_eval);
 
 /* ---- batch fitness evaluation ------------------------------------------------------------------------
@@ -107,23 +113,25 @@ int pgc_problem_work(const pgc_problem *prob, double *flops_per_eval, double *tr
  * thread_bfe.cpp:64-144) and for `UDP::batch_fitness` (problem.cpp:413-427, member_bfe.cpp:40-45). */
 /* device-resident: d_dvs [n x nx], d_fvs [n x nf] are device pointers on the context's device; asynchronous
  * on `stream`. */
-int pgc_eval_device(pgc_problem *prob, const double *d_dvs, size_t n, double *d_fvs, void *stream);
+PGC_API int pgc_eval_device(pgc_problem *prob, const double *d_dvs, size_t n, double *d_fvs, void *stream);
 /* host vectors (the pagmo::bfe contract): pageable or pinned host memory; chunked H2D -> kernel -> D2H
  * through the context's pinned staging ring; returns when fvs is complete. */
-int pgc_eval_host(pgc_problem *prob, const double *dvs, size_t n, double *fvs);
+PGC_API int pgc_eval_host(pgc_problem *prob, const double *dvs, size_t n, double *fvs);
 
 /* ---- device memory helpers (so a host-language binding needs no CUDA runtime of its own) ------------- */
-int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out);
-int pgc_free_device(pgc_ctx *ctx, void *ptr);
-int pgc_malloc_pinned(pgc_ctx *ctx, size_t bytes, void **out);
-int pgc_free_pinned(pgc_ctx *ctx, void *ptr);
-int pgc_memcpy_h2d(pgc_ctx *ctx, void *dst, const void *src, size_t bytes);
-int pgc_memcpy_d2h(pgc_ctx *ctx, void *dst, const void *src, size_t bytes);
+PGC_API int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out);
+PGC_API int pgc_free_device(pgc_ctx *ctx, void *ptr);
+PGC_API int pgc_malloc_pinned(pgc_ctx *ctx, size_t bytes, void **out);
+PGC_API int pgc_free_pinned(pgc_ctx *ctx, void *ptr);
+PGC_API int pgc_memcpy_h2d(pgc_ctx *ctx, void *dst, const void *src, size_t bytes);
+PGC_API int pgc_memcpy_d2h(pgc_ctx *ctx, void *dst, const void *src, size_t bytes);
 
 /* ---- measurement helpers ------------------------------------------------------------------------------
  * Dependent-chain-free DFMA loop over the whole chip: the measured FP64-pipe ceiling that bench.py uses as
  * the roofline denominator for the rotation-bound kernels (MEASURED_PEAKS.json has no FP64 figure). */
-int pgc_measure_fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
+PGC_API int pgc_measure_fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
+/* The same probe through mma.sync m8n8k4 f64 (DMMA), to decide SIMT-vs-DMMA with numbers. */
+PGC_API int pgc_measure_fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
 
 #ifdef __cplusplus
 }

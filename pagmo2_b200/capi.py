@@ -1,0 +1,233 @@
+"""ctypes binding of libpgc.so - the harness-side view of the C ABI in include/pagmo_cuda/pgc.h.
+
+This module is plumbing for tests/ and bench.py: the product is the shared library and the header-only C++
+adapters in include/pagmo_cuda/.  Nothing here computes: every call goes through the C ABI, and importing it
+without a built library (or calling it without a CUDA device) fails loudly - there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libpgc.so"
+
+PGC_OK = 0
+PGC_ERR_INVALID_ARGUMENT = -1
+PGC_ERR_UNSUPPORTED = -2
+PGC_ERR_CUDA = -3
+PGC_ERR_OUT_OF_MEMORY = -4
+
+FAMILY = {
+    "rastrigin": 1, "ackley": 2, "griewank": 3, "schwefel": 4, "rosenbrock": 5, "cec2014": 6, "cec2013": 7, "zdt": 8,
+    "dtlz": 9, "wfg": 10, "lennard_jones": 11,
+}
+
+
+class PgcError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"pgc status {status}: {msg}")
+        self.status = status
+
+
+class ProblemDesc(C.Structure):
+    _fields_ = [
+        ("family", C.c_int32), ("prob_id", C.c_uint32), ("dim", C.c_uint32), ("nobj", C.c_uint32), ("param", C.c_uint32),
+        ("rotation", C.POINTER(C.c_double)), ("rotation_len", C.c_size_t),
+        ("shift", C.POINTER(C.c_double)), ("shift_len", C.c_size_t),
+        ("shuffle", C.POINTER(C.c_int32)), ("shuffle_len", C.c_size_t),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load libpgc.so (raises if it was not built: run `python -m pagmo2_b200.build`)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(f"{LIB_PATH} not found - build it with `python -m pagmo2_b200.build`; "
+                                    "there is no CPU fallback")
+        L = C.CDLL(str(LIB_PATH))
+        L.pgc_version.restype = C.c_char_p
+        L.pgc_last_error.restype = C.c_char_p
+        vp, sz, dp = C.c_void_p, C.c_size_t, C.POINTER(C.c_double)
+        L.pgc_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.pgc_ctx_destroy.argtypes = [vp]
+        L.pgc_ctx_stream.argtypes = [vp, C.POINTER(vp)]
+        L.pgc_ctx_synchronize.argtypes = [vp]
+        L.pgc_ctx_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.pgc_problem_create.argtypes = [vp, C.POINTER(ProblemDesc), C.POINTER(vp)]
+        L.pgc_problem_destroy.argtypes = [vp]
+        for fn in ("pgc_problem_nx", "pgc_problem_nobj", "pgc_problem_nf"):
+            getattr(L, fn).argtypes = [vp, C.POINTER(sz)]
+        L.pgc_problem_bounds.argtypes = [vp, dp, dp]
+        L.pgc_problem_name.argtypes = [vp, C.c_char_p, sz]
+        L.pgc_problem_work.argtypes = [vp, dp, dp, dp]
+        L.pgc_eval_device.argtypes = [vp, vp, sz, vp, vp]
+        L.pgc_eval_host.argtypes = [vp, vp, sz, vp]
+        L.pgc_malloc_device.argtypes = [vp, sz, C.POINTER(vp)]
+        L.pgc_free_device.argtypes = [vp, vp]
+        L.pgc_malloc_pinned.argtypes = [vp, sz, C.POINTER(vp)]
+        L.pgc_free_pinned.argtypes = [vp, vp]
+        L.pgc_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+        L.pgc_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+        L.pgc_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
+        L.pgc_measure_fp64_mma_peak.argtypes = [vp, C.c_int, dp]
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != PGC_OK:
+        raise PgcError(rc, lib().pgc_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    n = C.c_int()
+    check(lib().pgc_device_count(C.byref(n)))
+    return n.value
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().pgc_ctx_create(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().pgc_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        s = C.c_void_p()
+        check(lib().pgc_ctx_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def synchronize(self):
+        check(lib().pgc_ctx_synchronize(self._h))
+
+    @property
+    def launches(self) -> int:
+        n = C.c_uint64()
+        check(lib().pgc_ctx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        check(lib().pgc_malloc_device(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, ptr: int):
+        check(lib().pgc_free_device(self._h, C.c_void_p(ptr)))
+
+    def pinned_array(self, shape, dtype=np.float64) -> np.ndarray:
+        """numpy array backed by page-locked host memory (freed when the context closes... never, tiny leak ok)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        check(lib().pgc_malloc_pinned(self._h, n, C.byref(p)))
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def to_device(self, a: np.ndarray) -> int:
+        a = np.ascontiguousarray(a)
+        d = self.malloc(a.nbytes)
+        check(lib().pgc_memcpy_h2d(self._h, C.c_void_p(d), a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return d
+
+    def from_device(self, ptr: int, shape, dtype=np.float64) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        check(lib().pgc_memcpy_d2h(self._h, out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), out.nbytes))
+        return out
+
+    def fp64_peak_tflops(self, iters: int = 4096) -> float:
+        t = C.c_double()
+        check(lib().pgc_measure_fp64_peak(self._h, iters, C.byref(t)))
+        return t.value
+
+    def fp64_mma_peak_tflops(self, iters: int = 4096) -> float:
+        t = C.c_double()
+        check(lib().pgc_measure_fp64_mma_peak(self._h, iters, C.byref(t)))
+        return t.value
+
+
+class Problem:
+    """Handle on a device-side UDP (pgc_problem).  Mirrors the accessors of pagmo::problem."""
+
+    def __init__(self, ctx: Context, family: str, prob_id: int = 0, dim: int = 0, nobj: int = 0, param: int = 0,
+                 rotation: np.ndarray | None = None, shift: np.ndarray | None = None, shuffle: np.ndarray | None = None):
+        self.ctx = ctx
+        d = ProblemDesc()
+        d.family, d.prob_id, d.dim, d.nobj, d.param = FAMILY[family], prob_id, dim, nobj, param
+        keep = []
+        if rotation is not None:
+            r = np.ascontiguousarray(rotation, dtype=np.float64); keep.append(r)
+            d.rotation, d.rotation_len = r.ctypes.data_as(C.POINTER(C.c_double)), r.size
+        if shift is not None:
+            s = np.ascontiguousarray(shift, dtype=np.float64); keep.append(s)
+            d.shift, d.shift_len = s.ctypes.data_as(C.POINTER(C.c_double)), s.size
+        if shuffle is not None:
+            p = np.ascontiguousarray(shuffle, dtype=np.int32); keep.append(p)
+            d.shuffle, d.shuffle_len = p.ctypes.data_as(C.POINTER(C.c_int32)), p.size
+        self._h = C.c_void_p()
+        check(lib().pgc_problem_create(ctx._h, C.byref(d), C.byref(self._h)))
+        n = C.c_size_t()
+        check(lib().pgc_problem_nx(self._h, C.byref(n))); self.nx = n.value
+        check(lib().pgc_problem_nobj(self._h, C.byref(n))); self.nobj = n.value
+        check(lib().pgc_problem_nf(self._h, C.byref(n))); self.nf = n.value
+
+    def close(self):
+        if self._h:
+            lib().pgc_problem_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def name(self) -> str:
+        buf = C.create_string_buffer(256)
+        check(lib().pgc_problem_name(self._h, buf, 256))
+        return buf.value.decode()
+
+    def bounds(self):
+        lb, ub = np.empty(self.nx), np.empty(self.nx)
+        dp = C.POINTER(C.c_double)
+        check(lib().pgc_problem_bounds(self._h, lb.ctypes.data_as(dp), ub.ctypes.data_as(dp)))
+        return lb, ub
+
+    def work(self):
+        """(fp64 flops, libm calls, algorithmic bytes) per evaluation."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        check(lib().pgc_problem_work(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def eval_device(self, d_dvs: int, n: int, d_fvs: int, stream: int = 0):
+        check(lib().pgc_eval_device(self._h, C.c_void_p(d_dvs), n, C.c_void_p(d_fvs), C.c_void_p(stream)))
+
+    def eval_host_into(self, dvs: np.ndarray, fvs: np.ndarray):
+        n = dvs.size // self.nx
+        check(lib().pgc_eval_host(self._h, dvs.ctypes.data_as(C.c_void_p), n, fvs.ctypes.data_as(C.c_void_p)))
+
+    def eval_host(self, dvs: np.ndarray) -> np.ndarray:
+        dvs = np.ascontiguousarray(dvs, dtype=np.float64)
+        if dvs.size % self.nx:
+            raise ValueError("decision-vector batch size is not a multiple of nx")
+        n = dvs.size // self.nx
+        fvs = np.empty((n, self.nf))
+        self.eval_host_into(dvs, fvs)
+        return fvs

@@ -54,6 +54,54 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
 }
 
+// Same probe through the legacy FP64 tensor path (mma.sync m8n8k4, "DMMA"): 8 independent accumulator chains
+// per warp.  Only used to decide, with numbers, whether DMMA could beat the SIMT DFMA rotation on this part.
+__global__ void __launch_bounds__(256) fp64_mma_peak_kernel(double *out, int iters, double a, double b)
+{
+    double c0[8], c1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        c0[i] = threadIdx.x + i;
+        c1[i] = threadIdx.x - i;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0[i]), "+d"(c1[i])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops)
+{
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    double *d = nullptr;
+    PGC_CUDA(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    PGC_CUDA(cudaEventCreate(&e0));
+    PGC_CUDA(cudaEventCreate(&e1));
+    fp64_mma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters / 4 + 1, 1e-3, 1e-3);
+    PGC_CUDA(cudaEventRecord(e0, ctx->stream));
+    fp64_mma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters, 1e-3, 1e-3);
+    PGC_CUDA(cudaEventRecord(e1, ctx->stream));
+    PGC_CUDA(cudaEventSynchronize(e1));
+    ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    float ms = 0;
+    PGC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 512.0 * 8.0 * static_cast<double>(iters) * blocks * (threads / 32);
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return PGC_OK;
+}
+
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops)
 {
     PGC_CUDA(cudaSetDevice(ctx->device));
@@ -423,6 +471,12 @@ int pgc_measure_fp64_peak(pgc_ctx *ctx, int iters, double *tflops)
 {
     PGC_REQUIRE(ctx && tflops && iters > 0, "pgc_measure_fp64_peak: bad argument");
     return fp64_peak(ctx, iters, tflops);
+}
+
+int pgc_measure_fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops)
+{
+    PGC_REQUIRE(ctx && tflops && iters > 0, "pgc_measure_fp64_mma_peak: bad argument");
+    return fp64_mma_peak(ctx, iters, tflops);
 }
 
 } // extern "C"

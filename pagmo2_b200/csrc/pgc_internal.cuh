@@ -143,4 +143,5 @@ int cec2014_create(pgc_problem *p, const pgc_problem_desc *d);
 int cec2014_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
 void cec2014_destroy(pgc_problem *p);
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
+int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
 } // namespace pgc

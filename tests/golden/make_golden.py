@@ -1,0 +1,46 @@
+"""Regenerate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libpagmo_ref.so).
+
+Run in the authoring container (needs /root/reference to build oracle/_ref):  python tests/golden/make_golden.py
+The fixtures let the oracle restatement and the CUDA path be checked against reference outputs on boxes where the
+reference itself cannot be built.  Inputs are seeded; outputs are whatever the reference code computes.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle.pyoracle import reference  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def main():
+    R = reference()
+    rng = np.random.default_rng(20141)
+    # ---- CEC2014: every function at D in {10, 30, 100}, 6 points in the box + the shift itself + origin
+    data = {}
+    for dim in (10, 30, 100):
+        for func in range(1, 31):
+            p = R.problem("cec2014", func, dim)
+            shift = R.cec2014_origin_shift(p)[:dim]
+            xs = np.vstack([rng.uniform(-100, 100, (6, dim)), shift[None, :], np.zeros((1, dim))])
+            data[f"x_f{func}_d{dim}"] = xs
+            data[f"f_f{func}_d{dim}"] = p.fitness_loop(xs)[:, 0]
+    np.savez_compressed(OUT / "cec2014_ref.npz", **data)
+    # ---- simple UDPs: random points + the known answers of the reference's own tests
+    data = {}
+    for fam in ("rastrigin", "ackley", "griewank", "schwefel", "rosenbrock"):
+        for dim in (2, 5, 10, 100):
+            p = R.problem(fam, dim)
+            lb, ub = p.bounds()
+            xs = np.vstack([rng.uniform(lb, ub, (6, dim)), np.ones((1, dim)), np.zeros((1, dim))])
+            data[f"x_{fam}_d{dim}"] = xs
+            data[f"f_{fam}_d{dim}"] = p.fitness_loop(xs)[:, 0]
+    np.savez_compressed(OUT / "simple_ref.npz", **data)
+    print("wrote", [p.name for p in OUT.glob("*.npz")])
+
+
+if __name__ == "__main__":
+    main()
