@@ -1,0 +1,324 @@
+// cuda_bfe.hpp - header-only C++ adapters that put libpgc.so behind pagmo's own plugin API.
+//
+//   pagmo_cuda::cuda_bfe        a user-defined batch fitness evaluator (UDBFE, reference include/pagmo/bfe.hpp:68-108):
+//                               `pagmo::bfe{cuda_bfe{}}`, `algo.set_bfe(...)`, `population{prob, cuda_bfe{}, n}`.
+//   pagmo_cuda::cuda_cec2014    CUDA-backed UDPs (reference include/pagmo/problem.hpp:394-411,532-553): mandatory
+//   pagmo_cuda::cuda_simple<F>  fitness()/get_bounds() plus batch_fitness(), so pagmo::default_bfe / member_bfe pick the
+//                               device path up automatically (default_bfe.cpp:56-57, member_bfe.cpp:40-45).
+//
+// Compiles against the real pagmo headers (or against oracle/shim in this repository's tests).  There is no CPU
+// fallback: a problem without a device evaluator makes cuda_bfe throw std::invalid_argument, a CUDA failure throws
+// std::runtime_error - the same exception types pagmo_throw produces (reference exceptions.hpp:112-126), so
+// island::wait_check() semantics are unchanged.
+#ifndef PAGMO_CUDA_CUDA_BFE_HPP
+#define PAGMO_CUDA_CUDA_BFE_HPP
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include <pagmo/bfe.hpp>
+#include <pagmo/exceptions.hpp>
+#include <pagmo/problem.hpp>
+#include <pagmo/problems/ackley.hpp>
+#include <pagmo/problems/griewank.hpp>
+#include <pagmo/problems/rastrigin.hpp>
+#include <pagmo/problems/rosenbrock.hpp>
+#include <pagmo/problems/schwefel.hpp>
+#include <pagmo/s11n.hpp>
+#include <pagmo/threading.hpp>
+#include <pagmo/types.hpp>
+
+#include <pagmo_cuda/pgc.h>
+
+namespace pagmo_cuda
+{
+
+namespace detail
+{
+
+[[noreturn]] inline void throw_status(int rc, const char *where)
+{
+    const std::string msg = std::string(where) + ": " + pgc_last_error();
+    if (rc == PGC_ERR_INVALID_ARGUMENT || rc == PGC_ERR_UNSUPPORTED) {
+        pagmo_throw(std::invalid_argument, msg);
+    }
+    pagmo_throw(std::runtime_error, msg);
+}
+
+inline void check(int rc, const char *where)
+{
+    if (rc != PGC_OK) throw_status(rc, where);
+}
+
+// One pgc_ctx per (process, device), shared by every adapter object that names the device; destroyed at exit.
+inline std::shared_ptr<pgc_ctx> device_context(int device)
+{
+    static std::mutex mtx;
+    static std::map<int, std::shared_ptr<pgc_ctx>> table;
+    std::lock_guard<std::mutex> lk(mtx);
+    auto it = table.find(device);
+    if (it != table.end()) return it->second;
+    pgc_ctx *raw = nullptr;
+    check(pgc_ctx_create(device, &raw), "pgc_ctx_create");
+    std::shared_ptr<pgc_ctx> sp(raw, [](pgc_ctx *c) { pgc_ctx_destroy(c); });
+    table.emplace(device, sp);
+    return sp;
+}
+
+// RAII handle on a device-side problem.  Copies of an adapter share it; calls are serialised by a mutex because
+// one pgc_problem drives one stream and one staging ring (thread_safety::basic, reference threading.hpp:42).
+class problem_handle
+{
+public:
+    problem_handle(int device, const pgc_problem_desc &desc) : m_ctx(device_context(device))
+    {
+        check(pgc_problem_create(m_ctx.get(), &desc, &m_prob), "pgc_problem_create");
+        check(pgc_problem_nx(m_prob, &m_nx), "pgc_problem_nx");
+        check(pgc_problem_nf(m_prob, &m_nf), "pgc_problem_nf");
+    }
+    ~problem_handle()
+    {
+        pgc_problem_destroy(m_prob);
+    }
+    problem_handle(const problem_handle &) = delete;
+    problem_handle &operator=(const problem_handle &) = delete;
+
+    std::size_t nx() const { return m_nx; }
+    std::size_t nf() const { return m_nf; }
+
+    pagmo::vector_double evaluate(const pagmo::vector_double &dvs) const
+    {
+        if (dvs.size() % m_nx != 0u) {
+            pagmo_throw(std::invalid_argument, "cuda evaluator: a batch of " + std::to_string(dvs.size())
+                                                   + " values is not a multiple of the problem dimension "
+                                                   + std::to_string(m_nx));
+        }
+        const std::size_t n = dvs.size() / m_nx;
+        pagmo::vector_double fvs(n * m_nf);
+        std::lock_guard<std::mutex> lk(m_mtx);
+        check(pgc_eval_host(m_prob, dvs.data(), n, fvs.data()), "pgc_eval_host");
+        return fvs;
+    }
+
+    std::pair<pagmo::vector_double, pagmo::vector_double> bounds() const
+    {
+        pagmo::vector_double lb(m_nx), ub(m_nx);
+        check(pgc_problem_bounds(m_prob, lb.data(), ub.data()), "pgc_problem_bounds");
+        return {std::move(lb), std::move(ub)};
+    }
+
+    std::string name() const
+    {
+        char buf[256];
+        check(pgc_problem_name(m_prob, buf, sizeof(buf)), "pgc_problem_name");
+        return buf;
+    }
+
+private:
+    std::shared_ptr<pgc_ctx> m_ctx;
+    pgc_problem *m_prob = nullptr;
+    std::size_t m_nx = 0, m_nf = 0;
+    mutable std::mutex m_mtx;
+};
+
+inline pgc_problem_desc make_desc(int family, unsigned prob_id, unsigned dim, unsigned nobj = 0, unsigned param = 0)
+{
+    pgc_problem_desc d{};
+    d.family = family;
+    d.prob_id = prob_id;
+    d.dim = dim;
+    d.nobj = nobj;
+    d.param = param;
+    return d;
+}
+
+} // namespace detail
+
+// Common part of the CUDA-backed UDPs: the five members pagmo looks for on a UDP.
+class cuda_udp_base
+{
+public:
+    pagmo::vector_double fitness(const pagmo::vector_double &x) const // a batch of one
+    {
+        return handle().evaluate(x);
+    }
+    pagmo::vector_double batch_fitness(const pagmo::vector_double &dvs) const
+    {
+        return handle().evaluate(dvs);
+    }
+    std::pair<pagmo::vector_double, pagmo::vector_double> get_bounds() const
+    {
+        return handle().bounds();
+    }
+    pagmo::vector_double::size_type get_nobj() const
+    {
+        return handle().nf();
+    }
+    std::string get_name() const
+    {
+        return handle().name() + " [CUDA sm_100a]";
+    }
+    pagmo::thread_safety get_thread_safety() const
+    {
+        return pagmo::thread_safety::basic;
+    }
+    int device() const { return m_device; }
+
+protected:
+    const detail::problem_handle &handle() const
+    {
+        if (!m_handle) pagmo_throw(std::runtime_error, "cuda UDP used before its device problem was created");
+        return *m_handle;
+    }
+    int m_device = 0;
+    std::shared_ptr<detail::problem_handle> m_handle;
+};
+
+// CEC2014 on the device.  The reference UDP keeps its tables private (cec2014.hpp:227-236), so the CUDA UDP takes
+// them as constructor arguments in the layout of the reference members: `rotation` = m_rotation_matrix
+// (component i at i*dim*dim), `shift` = m_origin_shift after compaction (component i at i*dim, cec2014.cpp:76-86),
+// `shuffle` = m_shuffle (1-based).
+class cuda_cec2014 : public cuda_udp_base
+{
+public:
+    cuda_cec2014() = default; // pagmo requires default-constructible UDPs; unusable until assigned
+    cuda_cec2014(unsigned prob_id, unsigned dim, std::vector<double> rotation, std::vector<double> shift,
+                 std::vector<int> shuffle = {}, int device = 0)
+        : m_prob_id(prob_id), m_dim(dim), m_rotation(std::move(rotation)), m_shift(std::move(shift)),
+          m_shuffle(std::move(shuffle))
+    {
+        m_device = device;
+        create();
+    }
+    const pagmo::vector_double &get_origin_shift() const // cec2014.hpp:104
+    {
+        return m_shift;
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_prob_id, m_dim, m_rotation, m_shift, m_shuffle, m_device);
+        // device state is rebuilt lazily after loading
+    }
+
+private:
+    void create()
+    {
+        pgc_problem_desc d = detail::make_desc(PGC_CEC2014, m_prob_id, m_dim);
+        d.rotation = m_rotation.data();
+        d.rotation_len = m_rotation.size();
+        d.shift = m_shift.data();
+        d.shift_len = m_shift.size();
+        static_assert(sizeof(int) == sizeof(int32_t), "pgc.h passes the shuffle as int32_t");
+        d.shuffle = reinterpret_cast<const int32_t *>(m_shuffle.data());
+        d.shuffle_len = m_shuffle.size();
+        m_handle = std::make_shared<detail::problem_handle>(m_device, d);
+    }
+    unsigned m_prob_id = 0, m_dim = 0;
+    std::vector<double> m_rotation, m_shift;
+    std::vector<int> m_shuffle;
+};
+
+// rastrigin / ackley / griewank / schwefel / rosenbrock on the device (same constructor argument as the
+// reference UDPs: the dimension).
+template <int Family>
+class cuda_simple : public cuda_udp_base
+{
+public:
+    explicit cuda_simple(unsigned dim = (Family == PGC_ROSENBROCK ? 2u : 1u), int device = 0) : m_dim(dim)
+    {
+        m_device = device;
+        m_handle = std::make_shared<detail::problem_handle>(m_device, detail::make_desc(Family, 0u, dim));
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_dim, m_device);
+    }
+
+private:
+    unsigned m_dim;
+};
+using cuda_rastrigin = cuda_simple<PGC_RASTRIGIN>;
+using cuda_ackley = cuda_simple<PGC_ACKLEY>;
+using cuda_griewank = cuda_simple<PGC_GRIEWANK>;
+using cuda_schwefel = cuda_simple<PGC_SCHWEFEL>;
+using cuda_rosenbrock = cuda_simple<PGC_ROSENBROCK>;
+
+// The UDBFE.  Dispatch order: (1) a CUDA-backed UDP -> its own device problem; (2) a stock pagmo UDP whose
+// parameters are recoverable from its public interface -> a cached device twin; (3) anything else -> throw.
+class cuda_bfe
+{
+public:
+    explicit cuda_bfe(int device = 0) : m_device(device), m_cache(std::make_shared<cache_t>()) {}
+
+    pagmo::vector_double operator()(const pagmo::problem &p, const pagmo::vector_double &dvs) const
+    {
+        // (1) our own UDPs: same path as member_bfe (member_bfe.cpp:40-45), fevals are bumped by pagmo::bfe
+        if (p.is<cuda_cec2014>() || p.is<cuda_rastrigin>() || p.is<cuda_ackley>() || p.is<cuda_griewank>()
+            || p.is<cuda_schwefel>() || p.is<cuda_rosenbrock>()) {
+            return pagmo::detail::prob_invoke_mem_batch_fitness(p, dvs, false);
+        }
+        // (2) stock UDPs that are fully described by (type, nx)
+        int family = 0;
+        if (p.is<pagmo::rastrigin>()) family = PGC_RASTRIGIN;
+        else if (p.is<pagmo::ackley>()) family = PGC_ACKLEY;
+        else if (p.is<pagmo::griewank>()) family = PGC_GRIEWANK;
+        else if (p.is<pagmo::schwefel>()) family = PGC_SCHWEFEL;
+        else if (p.is<pagmo::rosenbrock>()) family = PGC_ROSENBROCK;
+        if (family == 0) {
+            // (3) no device evaluator and, by design, no CPU fallback
+            pagmo_throw(std::invalid_argument,
+                        "cuda_bfe cannot evaluate the problem '" + p.get_name()
+                            + "': no CUDA evaluator exists for this UDP type (wrap it in a pagmo_cuda:: UDP, or use "
+                              "thread_bfe); there is no CPU fallback");
+        }
+        return twin(family, static_cast<unsigned>(p.get_nx())).evaluate(dvs);
+    }
+    std::string get_name() const
+    {
+        return "CUDA batch fitness evaluator (sm_100a, device " + std::to_string(m_device) + ")";
+    }
+    pagmo::thread_safety get_thread_safety() const
+    {
+        return pagmo::thread_safety::basic;
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_device);
+    }
+
+private:
+    struct cache_t {
+        std::mutex mtx;
+        std::map<std::tuple<int, unsigned>, std::shared_ptr<detail::problem_handle>> twins;
+    };
+    const detail::problem_handle &twin(int family, unsigned dim) const
+    {
+        std::lock_guard<std::mutex> lk(m_cache->mtx);
+        auto &slot = m_cache->twins[std::make_tuple(family, dim)];
+        if (!slot) slot = std::make_shared<detail::problem_handle>(m_device, detail::make_desc(family, 0u, dim));
+        return *slot;
+    }
+    int m_device;
+    std::shared_ptr<cache_t> m_cache;
+};
+
+} // namespace pagmo_cuda
+
+PAGMO_S11N_BFE_EXPORT_KEY(pagmo_cuda::cuda_bfe)
+PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_cec2014)
+PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_rastrigin)
+PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_ackley)
+PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_griewank)
+PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_schwefel)
+PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_rosenbrock)
+
+#endif

@@ -1,0 +1,166 @@
+// tests/cpp/test_adapters.cpp - the drop-in boundary exercised through pagmo's OWN type-erased classes.
+// Compiled against the unmodified reference headers (+ oracle/shim for the absent Boost/TBB) and linked with
+// oracle/_ref/libpagmo_ref.so (pagmo::problem, pagmo::bfe, pagmo::population, thread_bfe, the stock UDPs) and
+// pagmo2_b200/libpgc.so.  Mirrors the reference's bfe-equivalence tests: tests/thread_bfe.cpp:66-97,
+// tests/default_bfe.cpp, tests/bfe.cpp.  Run on the GPU box by tests/test_gpu_adapters.py.
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <pagmo/batch_evaluators/default_bfe.hpp>
+#include <pagmo/batch_evaluators/member_bfe.hpp>
+#include <pagmo/batch_evaluators/thread_bfe.hpp>
+#include <pagmo/bfe.hpp>
+#include <pagmo/population.hpp>
+#include <pagmo/problem.hpp>
+#include <pagmo/problems/cec2014.hpp>
+#include <pagmo/problems/rastrigin.hpp>
+#include <pagmo/problems/zdt.hpp>
+
+#include <pagmo_cuda/cuda_bfe.hpp>
+
+#include "cec_synth.h"
+
+namespace oracle_ref { void ensure_cec2014_tables(unsigned, unsigned); }
+
+static int g_fail = 0;
+#define CHECK(cond)                                                                                                    \
+    do {                                                                                                               \
+        if (!(cond)) {                                                                                                 \
+            std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond);                                                \
+            ++g_fail;                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+
+static double max_rel(const pagmo::vector_double &a, const pagmo::vector_double &b)
+{
+    double m = 0;
+    if (a.size() != b.size()) return 1e300;
+    for (std::size_t i = 0; i < a.size(); ++i) m = std::max(m, std::abs(a[i] - b[i]) / std::max(std::abs(b[i]), 1e-300));
+    return m;
+}
+
+static pagmo::vector_double random_batch(const pagmo::problem &p, std::size_t n, unsigned seed)
+{
+    std::mt19937 e(seed);
+    const auto lb = p.get_lb(), ub = p.get_ub();
+    pagmo::vector_double dvs(n * p.get_nx());
+    for (std::size_t i = 0; i < n; ++i)
+        for (std::size_t j = 0; j < p.get_nx(); ++j)
+            dvs[i * p.get_nx() + j] = std::uniform_real_distribution<double>(lb[j], ub[j])(e);
+    return dvs;
+}
+
+int main()
+{
+    using namespace pagmo_cuda;
+    const double tol = 1e-12;
+
+    // ---- 1. cuda_bfe as a UDBFE on a STOCK pagmo UDP (pagmo::rastrigin) -------------------------------------
+    {
+        pagmo::problem p{pagmo::rastrigin{10u}};
+        pagmo::bfe gpu{cuda_bfe{}}, cpu{pagmo::thread_bfe{}};
+        CHECK(gpu.get_name().find("CUDA") != std::string::npos);
+        CHECK(gpu.get_thread_safety() == pagmo::thread_safety::basic);
+        const auto dvs = random_batch(p, 1024, 23);
+        const auto f0 = p.get_fevals();
+        const auto fg = gpu(p, dvs);
+        CHECK(p.get_fevals() == f0 + 1024u); // bumped once, by pagmo::bfe (bfe.cpp:107)
+        const auto fc = cpu(p, dvs);
+        CHECK(max_rel(fg, fc) <= tol);
+        // the wrapper's own input validation still applies (bfe_impl.cpp:72-77)
+        bool threw = false;
+        try {
+            gpu(p, pagmo::vector_double(15));
+        } catch (const std::invalid_argument &) {
+            threw = true;
+        }
+        CHECK(threw);
+        // empty batch
+        CHECK(gpu(p, pagmo::vector_double{}).empty());
+        // copies share the device state and stay usable
+        pagmo::bfe gpu2(gpu);
+        CHECK(max_rel(gpu2(p, dvs), fc) <= tol);
+    }
+
+    // ---- 2. a UDP without a device evaluator: throw, never fall back to the CPU -------------------------------
+    {
+        pagmo::problem p{pagmo::zdt{1u, 30u}};
+        pagmo::bfe gpu{cuda_bfe{}};
+        bool threw = false;
+        try {
+            gpu(p, random_batch(p, 4, 1));
+        } catch (const std::invalid_argument &e) {
+            threw = std::string(e.what()).find("no CPU fallback") != std::string::npos;
+        }
+        CHECK(threw);
+    }
+
+    // ---- 3. CUDA-backed UDP: fitness / batch_fitness / default_bfe / member_bfe / population ------------------
+    for (unsigned func : {5u, 17u, 23u, 30u}) {
+        const unsigned dim = 30u;
+        std::vector<double> mr(10u * dim * dim), lines(1000), shift;
+        std::vector<int> shuf(10u * dim);
+        cec2014_synth_rotation(func, dim, mr.data());
+        cec2014_synth_shift(func, lines.data());
+        cec2014_synth_shuffle(func, dim, shuf.data());
+        for (unsigned i = 0; i < 1000u; ++i)
+            if (i % 100u < dim) shift.push_back(lines[i]); // cec2014.cpp:76-86
+        oracle_ref::ensure_cec2014_tables(func, dim);
+        pagmo::problem ref{pagmo::cec2014{func, dim}};
+        pagmo::problem gpu{cuda_cec2014{func, dim, mr, shift, shuf}};
+        CHECK(gpu.has_batch_fitness());
+        CHECK(gpu.get_nx() == dim && gpu.get_nobj() == 1u);
+        CHECK(gpu.get_bounds() == ref.get_bounds());
+        CHECK(gpu.get_name().find("CEC2014 - f" + std::to_string(func)) != std::string::npos);
+        CHECK(gpu.extract<cuda_cec2014>()->get_origin_shift() == ref.extract<pagmo::cec2014>()->get_origin_shift());
+        const auto dvs = random_batch(ref, 777, 100 + func);
+        const auto want = pagmo::bfe{pagmo::thread_bfe{}}(ref, dvs);
+        // single fitness
+        const pagmo::vector_double x0(dvs.begin(), dvs.begin() + dim);
+        CHECK(std::abs(gpu.fitness(x0)[0] - want[0]) <= tol * std::abs(want[0]));
+        // problem::batch_fitness (problem.cpp:413-427) counts fevals itself
+        const auto f0 = gpu.get_fevals();
+        CHECK(max_rel(gpu.batch_fitness(dvs), want) <= tol);
+        CHECK(gpu.get_fevals() == f0 + 777u);
+        // default_bfe prefers the member (default_bfe.cpp:56-57); member_bfe; cuda_bfe: all the same numbers
+        CHECK(max_rel(pagmo::bfe{}(gpu, dvs), want) <= tol);
+        CHECK(max_rel(pagmo::bfe{pagmo::member_bfe{}}(gpu, dvs), want) <= tol);
+        CHECK(max_rel(pagmo::bfe{cuda_bfe{}}(gpu, dvs), want) <= tol);
+        CHECK(gpu.get_fevals() == f0 + 4u * 777u);
+        // population constructed through the bfe (population.cpp:82-103): same seed => same decision vectors as the
+        // reference population, fitness within tolerance
+        pagmo::population pg{gpu, pagmo::bfe{cuda_bfe{}}, 64u, 42u}, pr{ref, pagmo::bfe{pagmo::thread_bfe{}}, 64u, 42u};
+        CHECK(pg.get_x() == pr.get_x());
+        double worst = 0;
+        for (std::size_t i = 0; i < 64u; ++i) worst = std::max(worst, max_rel(pg.get_f()[i], pr.get_f()[i]));
+        CHECK(worst <= tol);
+        CHECK(pg.best_idx() == pr.best_idx());
+        std::printf("cec2014 f%u D=%u via pagmo::problem/bfe/population: ok (worst rel %.2e)\n", func, dim, worst);
+    }
+
+    // ---- 4. constructor errors surface as std::invalid_argument, like the reference UDP (cec2014.cpp:51-64) ----
+    {
+        bool threw = false;
+        try {
+            cuda_cec2014 bad{29u, 2u, std::vector<double>(40), std::vector<double>(20), std::vector<int>(20, 1)};
+        } catch (const std::invalid_argument &) {
+            threw = true;
+        }
+        CHECK(threw);
+        threw = false;
+        try {
+            cuda_rosenbrock bad{1u};
+        } catch (const std::invalid_argument &) {
+            threw = true;
+        }
+        CHECK(threw);
+    }
+
+    std::printf(g_fail ? "ADAPTERS FAILED (%d)\n" : "ADAPTERS OK\n", g_fail);
+    return g_fail ? 1 : 0;
+}
