@@ -8,14 +8,19 @@
 //     rotate; cec2014.cpp:1238-1274) + optional hybrid permutation (:807-809) + 1..5 primitive groups.
 //     Compositions (f23-f30) launch one stage kernel per component plus a tiny cf_cal kernel (:1319-1353).
 //   * rotation z = Mr*y is the FP64-pipe-bound part (2*D^2 flop/eval).  Persistent CTAs (one per SM, 8 warps)
-//     keep the whole matrix in shared memory, re-tiled so that an 8-lane group reads 128 contiguous bytes.
-//     Every warp is an independent worker on tiles of 16 individuals with a private shared-memory buffer:
-//     load+shift+scale -> register-tiled DFMA GEMM (4 individuals x TN outputs per lane) -> z back to the
-//     buffer -> primitive epilogue (2 lanes per individual).  Warps de-synchronise, so one warp's load /
-//     epilogue overlaps the other warps' DFMA streams; no block-level barrier inside the tile loop.
-//   * accumulation order over the rotation's inner index is the reference's (j ascending, :1231-1233); the only
-//     difference is fused multiply-add (one rounding instead of two).  The file is compiled with -fmad=false so
-//     every other expression keeps the reference's operation order and roundings.
+//     keep the whole matrix in shared memory (row-major, padded stride).  Every warp is an independent worker
+//     on tiles of 16 individuals with a private shared-memory buffer:
+//     load+shift+scale -> FP64 GEMM on mma.sync.m8n8k4.f64 (DMMA; 2 x NT accumulator tiles per warp) -> z back
+//     to the buffer -> primitive epilogue (2 lanes per individual).  Warps de-synchronise, so one warp's load /
+//     epilogue overlaps the other warps' DMMA streams; no block-level barrier inside the tile loop.
+//     Why DMMA and not SIMT DFMA: a register-tiled DFMA version (profiles/r1a_simt_*) was shared-memory-
+//     bandwidth bound - an LDS costs (bytes per lane x 32)/128 cycles whatever the broadcast pattern, so a
+//     4x13 register tile needs 1.3x more LSU cycles than FP64-pipe cycles and stalled at 42% pipe utilisation.
+//     An m8n8k4 tile does 8 FMAs per lane per operand pair loaded (vs 3), and the measured DMMA ceiling on B200
+//     (37.0 TFLOP/s) is not below the DFMA one (34.2 TFLOP/s).
+//   * the inner-index accumulation order inside one DMMA is the hardware's; differences to the reference's
+//     sequential non-fused sum (:1231-1233) are ~1e-16 relative per term.  The file is compiled with -fmad=false
+//     so every expression outside the rotation keeps the reference's operation order and roundings.
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -33,18 +38,35 @@ constexpr int kTileInd = 16; // individuals per warp tile
 constexpr unsigned kFull = 0xffffffffu;
 
 __host__ __device__ constexpr int pad8(int d) { return (d + 7) / 8 * 8; }
-// Row stride (doubles) of a warp buffer: even (16-byte rows) and such that the 4 rows a 128-bit broadcast load
-// touches (rows q, q+4, ... differ by q=0..3) fall on disjoint bank groups: stride mod 16 in {2,6,10,14,4,12}.
+__host__ __device__ constexpr int pad4(int d) { return (d + 3) / 4 * 4; }
+// Row stride (doubles) of the row-major operand tiles - the warp's Y tile (rows = individuals) and the rotation
+// image (rows = outputs): >= the padded inner length and == 4 or 12 (mod 16), so that the 16 lanes of a half
+// warp (4 rows x 4 consecutive doubles of an m8n8k4 operand fragment) cover all 32 banks exactly once.
 __host__ __device__ constexpr int ystride(int d)
 {
-    int s = d + 2;
-    while (!((s % 16 == 2) || (s % 16 == 6) || (s % 16 == 10) || (s % 16 == 14) || (s % 16 == 4) || (s % 16 == 12))) s += 2;
+    int s = pad4(d);
+    while (s % 16 != 4 && s % 16 != 12) s += 4;
     return s;
+}
+// After the rotation the warp keeps z TRANSPOSED: zT[coordinate][individual], row stride kZS, so that the epilogue
+// (lane = individual) reads 16 consecutive doubles per coordinate: conflict-free whatever the permutation.
+constexpr int kZS = 18;
+__host__ __device__ constexpr int warp_buf_elems(int d)
+{
+    return (16 * ystride(d) > pad8(d) * kZS) ? 16 * ystride(d) : pad8(d) * kZS;
+}
+
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor path.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2*(l%4)+{0,1}].
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
 }
 
 struct StageParams {
     const double *x;    // [n x D]
-    const double *mr;   // re-tiled rotation of this component: D x DP (see retile_rotation)
+    const double *mr;   // shared-memory image of this component's rotation (see make_rotation_image)
     const double *os;   // shift of this component: D
     const int *perm;    // 0-based permutation of this component (D) or nullptr
     const double *table; // problem constant table
@@ -69,19 +91,20 @@ __device__ __forceinline__ double cos_big(double theta)
 }
 
 struct Elem {
-    const double *row;
-    const int *idx; // may be nullptr
+    const double *col; // zT + individual: coordinate c lives at col[c * kZS]
+    const int *idx;    // may be nullptr
     int off;
     double rate;
     __device__ __forceinline__ double operator()(int j) const
     {
         const int jj = idx ? idx[off + j] : off + j;
-        return row[jj] * rate;
+        return col[jj * kZS] * rate;
     }
 };
 
-__device__ __forceinline__ double pair_add(double v) { return v + __shfl_xor_sync(kFull, v, 1); }
-__device__ __forceinline__ double pair_mul(double v) { return v * __shfl_xor_sync(kFull, v, 1); }
+// the two lanes of an individual are 16 apart (lane = half * 16 + individual)
+__device__ __forceinline__ double pair_add(double v) { return v + __shfl_xor_sync(kFull, v, 16); }
+__device__ __forceinline__ double pair_mul(double v) { return v * __shfl_xor_sync(kFull, v, 16); }
 
 // One primitive on n coordinates, evaluated by a pair of lanes (h = 0/1 takes the lower/upper half of the
 // terms); both lanes return the full value.  Expressions follow cec2014.cpp term by term.
@@ -141,13 +164,34 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
             return 2.718281828459045235360287471352662498 - 20.0 * exp(s1) - exp(s2) + 20.0;
         }
         case P_WEIERSTRASS: { // :500-509
-            const double *cj = tab + g.tab_off, *aj = cj + 21;
+            // sum_k 0.5^k cos(theta_k), theta_k = fl(fl(2 pi 3^k) * u) as the reference forms it.  Every 7th term
+            // (k = 0, 7, 14) is evaluated directly from the reference's own argument (exact two-term reduction by
+            // 2 pi, then sincospi); the terms in between come from the angle-tripling map w -> w^3 on the unit
+            // circle (complex multiplication: the error grows exactly 3x per step, <= 3^6 * 1e-16 before the next
+            // restart).  ~2.5x fewer FP64 instructions than 21 range-reduced cosines per coordinate.
+            const double *cj = tab + g.tab_off;
+            const double I1 = 0x1.45f306dc9c883p-3, I2 = -0x1.6b01ec5417056p-57;
             double s = 0.0;
             for (int j = lo; j < hi; ++j) {
                 const double u = v(j) + 0.5;
-                double sum = 0.0;
-#pragma unroll 3
-                for (int k = 0; k <= 20; ++k) sum += aj[k] * cos_big(cj[k] * u);
+                double sum = 0.0, w = 1.0, sn = 0.0, cs = 1.0;
+#pragma unroll
+                for (int k = 0; k <= 20; ++k) {
+                    if (k % 7 == 0) {
+                        const double theta = cj[k] * u;
+                        const double p = theta * I1;
+                        const double e = fma(theta, I1, -p);
+                        const double r = (p - rint(p)) + fma(theta, I2, e);
+                        sincospi(2.0 * r, &sn, &cs);
+                    } else {
+                        const double c2 = fma(cs, cs, -(sn * sn)), s2 = (cs + cs) * sn; // w^2
+                        const double c3 = fma(c2, cs, -(s2 * sn)), s3 = fma(s2, cs, c2 * sn); // w^3
+                        cs = c3;
+                        sn = s3;
+                    }
+                    sum = fma(w, cs, sum); // 0.5^k * cos is an exact scaling: same value as "sum += pow(a,k)*cos"
+                    w *= 0.5;
+                }
                 s += sum;
             }
             return pair_add(s) - g.c0;
@@ -171,41 +215,59 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
             }
             return pair_add(s);
         }
-        case P_SCHWEFEL: { // :575-589
+        case P_SCHWEFEL: { // :575-589, the three branches folded into one sin(sqrt(.)) per coordinate
             double s = 0.0;
+            const double inv_n = 1.0 / dn;
             for (int j = lo; j < hi; ++j) {
                 const double z = v(j) + 4.209687462275036e+002;
-                if (z > 500.0) {
-                    const double m = 500.0 - fmod(z, 500.0);
-                    s -= m * sin(sqrt(m));
-                    const double t = (z - 500.0) / 100.0;
-                    s += t * t / dn;
-                } else if (z < -500.0) {
-                    const double fm = fmod(fabs(z), 500.0);
-                    s -= (-500.0 + fm) * sin(sqrt(500.0 - fm));
-                    const double t = (z + 500.0) / 100.0;
-                    s += t * t / dn;
-                } else {
-                    s -= z * sin(sqrt(fabs(z)));
+                const double az = fabs(z);
+                const bool big = az > 500.0;
+                double m = az, mult = z, pen = 0.0;
+                if (big) {
+                    // fm = fmod(|z|, 500) EXACTLY: q may be off by one, the fused remainder is exact, then fix up
+                    const double q = floor(az * 0.002);
+                    double fm = fma(-q, 500.0, az);
+                    if (fm < 0.0) fm += 500.0;
+                    else if (fm >= 500.0) fm -= 500.0;
+                    m = 500.0 - fm;            // z > 500: (500 - fmod(z,500)); z < -500: -(-500 + fmod(|z|,500))
+                    mult = copysign(m, z);
+                    const double t = (z - copysign(500.0, z)) * 0.01;
+                    pen = t * t * inv_n;
                 }
+                s -= mult * sin(sqrt(m));
+                s += pen;
             }
             return pair_add(s) + g.c0;
         }
         case P_KATSUURA: { // :604-614
-            double p = 1.0;
+            // |2^k z - floor(2^k z + 0.5)| is the distance to the nearest integer: same value via round-to-nearest
+            // (magic-constant add, valid for |2^k z| < 2^51).  prod_j b_j^c0 is taken as exp(c0 * sum_j log b_j).
+            double slog = 0.0;
             for (int j = lo; j < hi; ++j) {
                 const double z = v(j);
-                double temp = 0.0, t1 = 1.0, it1 = 1.0;
-#pragma unroll 4
-                for (int k = 1; k <= 32; ++k) {
-                    t1 *= 2.0;
-                    it1 *= 0.5;
-                    const double t2 = t1 * z;
-                    temp += fabs(t2 - floor(t2 + 0.5)) * it1; // "/ 2^k" == "* 2^-k" exactly
+                double temp = 0.0;
+                if (fabs(z) < 262144.0) {
+                    double t1 = 1.0, it1 = 1.0;
+#pragma unroll
+                    for (int k = 1; k <= 32; ++k) {
+                        t1 *= 2.0;
+                        it1 *= 0.5;
+                        const double t2 = t1 * z;
+                        const double r = (t2 + 6755399441055744.0) - 6755399441055744.0;
+                        temp = fma(fabs(t2 - r), it1, temp); // "/ 2^k" is an exact scaling
+                    }
+                } else {
+                    double t1 = 1.0;
+                    for (int k = 1; k <= 32; ++k) {
+                        t1 *= 2.0;
+                        const double t2 = t1 * z;
+                        temp += fabs(t2 - floor(t2 + 0.5)) / t1;
+                    }
                 }
-                p *= pow(1.0 + static_cast<double>(j + 1) * temp, g.c0);
+                slog += log(1.0 + static_cast<double>(j + 1) * temp);
             }
-            p = pair_mul(p);
+            slog = pair_add(slog);
+            const double p = exp(g.c0 * slog);
             return p * g.c1 - g.c1;
         }
         case P_HAPPYCAT: { // :751-759
@@ -261,20 +323,21 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
 template <int D, bool ROT>
 __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __grid_constant__ StageParams P)
 {
-    constexpr int DP = pad8(D);
-    constexpr int TN = DP / 8;
-    constexpr int NPAIR = TN / 2;
-    constexpr bool ODD = (TN & 1) != 0;
-    constexpr int YS = ystride(D);
-    constexpr int MR_ELEMS = ROT ? D * DP : 0;
+    constexpr int DP = pad8(D);     // padded output count (rows of the rotation image)
+    constexpr int KP = pad4(D);     // padded inner length
+    constexpr int NT = DP / 8;      // 8-wide output tiles per warp
+    constexpr int YS = ystride(D);  // row stride of Y tile and rotation image
+    constexpr int WB = warp_buf_elems(D);
+    constexpr int MR_ELEMS = ROT ? DP * YS : 0;
+    constexpr int NLOAD = (kTileInd * D + 63) / 64; // 16-byte loads per lane per tile
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sMr = reinterpret_cast<double *>(smem_raw);
     double *sBuf = sMr + MR_ELEMS;
-    double *sOs = sBuf + kWarps * kTileInd * YS;
+    double *sOs = sBuf + kWarps * WB;
     int *sPerm = reinterpret_cast<int *>(sOs + D);
 
-    // ---- per-CTA preload: rotation (already re-tiled on the host), shift, permutation --------------------
+    // ---- per-CTA preload: rotation image (built on the host), shift, permutation -----------------------------
     if (ROT) {
         const double2 *src = reinterpret_cast<const double2 *>(P.mr);
         double2 *dst = reinterpret_cast<double2 *>(sMr);
@@ -287,107 +350,114 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *buf = sBuf + warp * kTileInd * YS;
+    double *buf = sBuf + warp * WB;
     const int *perm = P.st.permute ? sPerm : nullptr;
     const long long ntiles = (P.n + kTileInd - 1) / kTileInd;
     const bool need_w = P.wout != nullptr;
     const double pre_rate = P.st.pre_rate;
+    const int et = lane & 15, eh = lane >> 4; // epilogue mapping: individual, half
 
     for (long long tile = static_cast<long long>(blockIdx.x) * kWarps + warp; tile < ntiles;
          tile += static_cast<long long>(gridDim.x) * kWarps) {
         const long long t0 = tile * kTileInd;
         const int nt = (P.n - t0 < kTileInd) ? static_cast<int>(P.n - t0) : kTileInd;
 
-        // ---- L: coalesced load, shift (x - Os) and scale (* sh_rate), cec2014.cpp:1245-1258 --------------
+        // ---- L: coalesced load (all 16-byte loads of the tile in flight at once), shift (x - Os) and scale
+        // (* sh_rate), cec2014.cpp:1245-1258.  ROT: row-major Y tile for the DMMA; otherwise straight into zT.
         {
             const double *src = P.x + t0 * D;
             const double scale = need_w ? 1.0 : pre_rate; // composition: keep x-Os for the cf_cal weight first
-#pragma unroll 5
-            for (int e = 2 * lane; e < kTileInd * D; e += 64) {
-                const int t = e / D, j = e - t * D;
-                double2 xv = make_double2(0.0, 0.0);
-                if (t < nt) {
+            double2 xv[NLOAD];
+#pragma unroll
+            for (int r = 0; r < NLOAD; ++r) {
+                const int e = 2 * lane + 64 * r;
+                const int t = e / D;
+                xv[r] = make_double2(0.0, 0.0);
+                if (e < kTileInd * D && t < nt) {
                     if (P.aligned16) {
-                        xv = __ldcs(reinterpret_cast<const double2 *>(src + e));
+                        xv[r] = __ldcs(reinterpret_cast<const double2 *>(src + e));
                     } else {
-                        xv.x = __ldcs(src + e);
-                        xv.y = __ldcs(src + e + 1);
+                        xv[r].x = __ldcs(src + e);
+                        xv[r].y = __ldcs(src + e + 1);
                     }
                 }
-                double2 y;
-                y.x = (xv.x - sOs[j]) * scale;
-                y.y = (xv.y - sOs[j + 1]) * scale;
-                *reinterpret_cast<double2 *>(buf + t * YS + j) = y;
+            }
+#pragma unroll
+            for (int r = 0; r < NLOAD; ++r) {
+                const int e = 2 * lane + 64 * r;
+                if (e < kTileInd * D) {
+                    const int t = e / D, j = e - t * D;
+                    const double y0 = (xv[r].x - sOs[j]) * scale, y1 = (xv[r].y - sOs[j + 1]) * scale;
+                    if (ROT) {
+                        *reinterpret_cast<double2 *>(buf + t * YS + j) = make_double2(y0, y1);
+                    } else {
+                        buf[j * kZS + t] = y0;
+                        buf[(j + 1) * kZS + t] = y1;
+                    }
+                }
+            }
+            if (ROT && KP > D) { // zero the inner-index padding (zT of the previous tile lived there)
+                if (lane < kTileInd)
+                    for (int j = D; j < KP; ++j) buf[lane * YS + j] = 0.0;
             }
         }
         __syncwarp();
 
-        const int et = lane >> 1, eh = lane & 1; // epilogue mapping: individual, half
         double wacc = 0.0;
         if (need_w) { // cf_cal weight sum_j (x_j - Os_j)^2, :1330-1332, then the deferred scale
-            double *row = buf + et * YS;
             const int lo = (D * eh) >> 1, hi = (D * (eh + 1)) >> 1;
             for (int j = lo; j < hi; ++j) {
-                const double d = row[j];
+                double *pd = ROT ? buf + et * YS + j : buf + j * kZS + et;
+                const double d = *pd;
                 wacc += d * d;
-                row[j] = d * pre_rate;
+                *pd = d * pre_rate;
             }
             wacc = pair_add(wacc);
             __syncwarp();
         }
 
-        // ---- G: z = Mr * y, :1224-1235.  lane = (q, o): individuals t = 4m+q, outputs i = 8c+o -------------
+        // ---- G: z = Mr * y (:1224-1235) on DMMA.  A = Y tile (rows = individuals), B = Mr^T (rows of the image =
+        // outputs); both fragments are "row g = lane/4, inner index 4u + lane%4": one 8-byte load per row and
+        // 4-deep step, 2 + NT loads feeding 2*NT independent m8n8k4 accumulator tiles.
         if (ROT) {
-            const int o = lane & 7, q = lane >> 3;
-            double acc[4][TN];
+            const int g = lane >> 2, j = lane & 3;
+            double acc[2][NT][2];
 #pragma unroll
-            for (int m = 0; m < 4; ++m)
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int c = 0; c < TN; ++c) acc[m][c] = 0.0;
-            const double *yb = buf + q * YS;
-            const double *mb = sMr + o * 2;
-            const double *mo = sMr + NPAIR * 16 + o;
+                for (int nt2 = 0; nt2 < NT; ++nt2) acc[mt][nt2][0] = acc[mt][nt2][1] = 0.0;
+            const double *ya = buf + g * YS + j;
+            const double *mb = sMr + g * YS + j;
 #pragma unroll 2
-            for (int k = 0; k < D; k += 2) {
-                double2 y[4];
+            for (int u = 0; u < KP / 4; ++u) {
+                double a[2], b[NT];
 #pragma unroll
-                for (int m = 0; m < 4; ++m) y[m] = *reinterpret_cast<const double2 *>(yb + m * 4 * YS + k);
+                for (int mt = 0; mt < 2; ++mt) a[mt] = ya[mt * 8 * YS + u * 4];
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    double2 b[NPAIR > 0 ? NPAIR : 1];
-                    double bo = 0.0;
+                for (int nt2 = 0; nt2 < NT; ++nt2) b[nt2] = mb[nt2 * 8 * YS + u * 4];
 #pragma unroll
-                    for (int c2 = 0; c2 < NPAIR; ++c2)
-                        b[c2] = *reinterpret_cast<const double2 *>(mb + (k + kk) * DP + c2 * 16);
-                    if (ODD) bo = mo[(k + kk) * DP];
+                for (int nt2 = 0; nt2 < NT; ++nt2)
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const double ym = kk ? y[m].y : y[m].x;
-#pragma unroll
-                        for (int c2 = 0; c2 < NPAIR; ++c2) {
-                            acc[m][2 * c2] = fma(ym, b[c2].x, acc[m][2 * c2]);
-                            acc[m][2 * c2 + 1] = fma(ym, b[c2].y, acc[m][2 * c2 + 1]);
-                        }
-                        if (ODD) acc[m][TN - 1] = fma(ym, bo, acc[m][TN - 1]);
-                    }
-                }
+                    for (int mt = 0; mt < 2; ++mt) dmma(acc[mt][nt2][0], acc[mt][nt2][1], a[mt], b[nt2]);
             }
             __syncwarp();
+            // accumulator tile (mt, nt): lane holds z[individual mt*8 + g][coordinate nt*8 + 2j + {0,1}] -> zT
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                double *zr = buf + (m * 4 + q) * YS + o;
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int c = 0; c < TN; ++c)
-                    if (c * 8 + o < D) zr[c * 8] = acc[m][c];
-            }
+                for (int nt2 = 0; nt2 < NT; ++nt2) {
+                    double *zc = buf + (nt2 * 8 + 2 * j) * kZS + mt * 8 + g;
+                    zc[0] = acc[mt][nt2][0];
+                    zc[kZS] = acc[mt][nt2][1];
+                }
             __syncwarp();
         }
 
-        // ---- E: primitives on z (2 lanes per individual) ---------------------------------------------------
+        // ---- E: primitives on z (2 lanes per individual, 16 lanes apart) ------------------------------------------
         double val = 0.0;
         {
             Elem v;
-            v.row = buf + et * YS;
+            v.col = buf + et;
             v.idx = perm;
             for (int gi = 0; gi < P.st.ngroups; ++gi) {
                 const GroupDesc &g = P.st.g[gi];
@@ -453,7 +523,7 @@ template <int D, bool ROT> size_t stage_smem_bytes()
 {
     constexpr int DP = pad8(D);
     constexpr int YS = ystride(D);
-    return sizeof(double) * ((ROT ? D * DP : 0) + kWarps * kTileInd * YS + D) + sizeof(int) * D + 16;
+    return sizeof(double) * ((ROT ? DP * YS : 0) + kWarps * warp_buf_elems(D) + D) + sizeof(int) * D + 16;
 }
 
 template <int D, bool ROT> int launch_stage(pgc_ctx *ctx, const StageParams &sp, cudaStream_t stream)
@@ -486,24 +556,16 @@ template <int D> int launch_stage_d(pgc_ctx *ctx, const StageParams &sp, bool ro
     return rot ? launch_stage<D, true>(ctx, sp, stream) : launch_stage<D, false>(ctx, sp, stream);
 }
 
-// Re-tile a row-major D x D rotation (Mr[i*D + j], z_i = sum_j Mr[i][j] y_j) into the shared-memory image the
-// kernel copies verbatim: for inner index k a row of DP doubles, laid out [c2][o][2] for output pairs
-// i = (2*c2 + {0,1})*8 + o followed (odd TN) by [o] for i = (TN-1)*8 + o; outputs >= D are zero.
-void retile_rotation(const double *mr, int D, double *dst)
+// Shared-memory image of a row-major D x D rotation (Mr[i*D + j], z_i = sum_j Mr[i][j] y_j): DP rows (outputs,
+// zero rows beyond D) of stride ystride(D) (zero beyond D), copied verbatim by the kernel.
+size_t rotation_image_elems(int D) { return static_cast<size_t>(pad8(D)) * ystride(D); }
+
+void make_rotation_image(const double *mr, int D, double *dst)
 {
-    const int DP = pad8(D), TN = DP / 8, NPAIR = TN / 2;
-    std::memset(dst, 0, sizeof(double) * static_cast<size_t>(D) * DP);
-    for (int k = 0; k < D; ++k) {
-        double *row = dst + static_cast<size_t>(k) * DP;
-        for (int c = 0; c < TN; ++c)
-            for (int o = 0; o < 8; ++o) {
-                const int i = c * 8 + o;
-                if (i >= D) continue;
-                const double val = mr[static_cast<size_t>(i) * D + k];
-                if (c < 2 * NPAIR) row[(c / 2) * 16 + o * 2 + (c & 1)] = val;
-                else row[NPAIR * 16 + o] = val;
-            }
-    }
+    const int YS = ystride(D);
+    std::memset(dst, 0, sizeof(double) * rotation_image_elems(D));
+    for (int i = 0; i < D; ++i)
+        for (int k = 0; k < D; ++k) dst[static_cast<size_t>(i) * YS + k] = mr[static_cast<size_t>(i) * D + k];
 }
 
 } // namespace
@@ -546,9 +608,9 @@ int cec2014_create(pgc_problem *p, const pgc_problem_desc *d)
     PGC_CUDA(cudaMalloc(&p->d_shift, sizeof(double) * ncomp * D));
     PGC_CUDA(cudaMemcpy(p->d_shift, d->shift, sizeof(double) * ncomp * D, cudaMemcpyHostToDevice));
     if (any_rot) {
-        const size_t DP = pad8(static_cast<int>(D));
-        std::vector<double> tiled(static_cast<size_t>(ncomp) * D * DP);
-        for (int c = 0; c < ncomp; ++c) retile_rotation(d->rotation + c * D * D, static_cast<int>(D), tiled.data() + c * D * DP);
+        const size_t img = rotation_image_elems(static_cast<int>(D));
+        std::vector<double> tiled(static_cast<size_t>(ncomp) * img);
+        for (int c = 0; c < ncomp; ++c) make_rotation_image(d->rotation + c * D * D, static_cast<int>(D), tiled.data() + c * img);
         PGC_CUDA(cudaMalloc(&p->d_rotation, sizeof(double) * tiled.size()));
         PGC_CUDA(cudaMemcpy(p->d_rotation, tiled.data(), sizeof(double) * tiled.size(), cudaMemcpyHostToDevice));
     }
@@ -584,7 +646,7 @@ int cec2014_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, c
     if (n == 0) return PGC_OK;
     const Cec2014Recipe &r = p->cec14;
     pgc_ctx *ctx = p->ctx;
-    const size_t D = r.dim, DP = pad8(r.dim);
+    const size_t D = r.dim, img = rotation_image_elems(r.dim);
     double *fit = nullptr, *w = nullptr;
     if (r.composition) {
         int rc = ensure_scratch(ctx, sizeof(double) * 2 * kMaxStages * n);
@@ -595,7 +657,7 @@ int cec2014_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, c
     for (int s = 0; s < r.nstages; ++s) {
         StageParams sp;
         sp.x = d_dvs;
-        sp.mr = r.st[s].rotate ? p->d_rotation + r.st[s].comp * D * DP : nullptr;
+        sp.mr = r.st[s].rotate ? p->d_rotation + r.st[s].comp * img : nullptr;
         sp.os = p->d_shift + r.st[s].comp * D;
         sp.perm = r.st[s].permute ? p->d_shuffle + r.st[s].comp * D : nullptr;
         sp.table = p->d_table;
