@@ -118,6 +118,10 @@ PGC_API int pgc_eval_device(pgc_problem *prob, const double *d_dvs, size_t n, do
  * through the context's pinned staging ring; returns when fvs is complete. */
 PGC_API int pgc_eval_host(pgc_problem *prob, const double *dvs, size_t n, double *fvs);
 
+/* Debug/profiling aid for the CEC2014 stage kernel: same evaluation with clock64() phase counters, summed over all
+ * warp-tiles and stages.  out7 = {load, weight pass, token wait, GEMM, z store, epilogue} cycles, warp-tiles. */
+PGC_API int pgc_debug_cec2014_phase_cycles(pgc_problem *prob, const double *d_dvs, size_t n, double *d_fvs, uint64_t *out7);
+
 /* ---- device memory helpers (so a host-language binding needs no CUDA runtime of its own) ------------- */
 PGC_API int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out);
 PGC_API int pgc_free_device(pgc_ctx *ctx, void *ptr);
@@ -132,6 +136,12 @@ PGC_API int pgc_memcpy_d2h(pgc_ctx *ctx, void *dst, const void *src, size_t byte
 PGC_API int pgc_measure_fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
 /* The same probe through mma.sync m8n8k4 f64 (DMMA), to decide SIMT-vs-DMMA with numbers. */
 PGC_API int pgc_measure_fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
+
+/* Design probe: one CTA of `total_warps` warps per SM; the first `dmma_warps` run 26 independent DMMA chains each
+ * (the rotation kernel's accumulator count), the others 8 independent DFMA chains.  tflops2[0] / [1] = the two groups'
+ * throughput in the same launch - answers "can one warp per sub-partition saturate DMMA" and "do DMMA and DFMA share
+ * a pipe". */
+PGC_API int pgc_debug_fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops2);
 
 #ifdef __cplusplus
 }

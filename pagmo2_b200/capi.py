@@ -69,6 +69,7 @@ def lib():
         L.pgc_problem_work.argtypes = [vp, dp, dp, dp]
         L.pgc_eval_device.argtypes = [vp, vp, sz, vp, vp]
         L.pgc_eval_host.argtypes = [vp, vp, sz, vp]
+        L.pgc_debug_cec2014_phase_cycles.argtypes = [vp, vp, sz, vp, C.POINTER(C.c_uint64)]
         L.pgc_malloc_device.argtypes = [vp, sz, C.POINTER(vp)]
         L.pgc_free_device.argtypes = [vp, vp]
         L.pgc_malloc_pinned.argtypes = [vp, sz, C.POINTER(vp)]
@@ -218,6 +219,13 @@ class Problem:
 
     def eval_device(self, d_dvs: int, n: int, d_fvs: int, stream: int = 0):
         check(lib().pgc_eval_device(self._h, C.c_void_p(d_dvs), n, C.c_void_p(d_fvs), C.c_void_p(stream)))
+
+    def phase_cycles(self, d_dvs: int, n: int, d_fvs: int) -> dict:
+        """cec2014 only: per-phase cycle totals of the stage kernel (debug aid)."""
+        out = (C.c_uint64 * 7)()
+        check(lib().pgc_debug_cec2014_phase_cycles(self._h, C.c_void_p(d_dvs), n, C.c_void_p(d_fvs), out))
+        names = ["load", "weight", "token_wait", "gemm", "store_z", "epilogue", "warp_tiles"]
+        return dict(zip(names, [int(v) for v in out]))
 
     def eval_host_into(self, dvs: np.ndarray, fvs: np.ndarray):
         n = dvs.size // self.nx

@@ -102,6 +102,76 @@ int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops)
     return PGC_OK;
 }
 
+// Probe kernel for design decisions: `dmma_warps` warps of each CTA run NACC independent DMMA chains,
+// the remaining warps run 8 independent DFMA chains.  One CTA per SM (big dynamic smem keeps others out).
+template <int NACC> __global__ void __launch_bounds__(512) fp64_mix_kernel(double *out, int iters, int dmma_warps, double a, double b)
+{
+    const int warp = threadIdx.x >> 5;
+    double s = 0;
+    if (warp < dmma_warps) {
+        double c0[NACC], c1[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) {
+            c0[i] = threadIdx.x + i;
+            c1[i] = threadIdx.x - i;
+        }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < NACC; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c0[i]), "+d"(c1[i])
+                             : "d"(a), "d"(b));
+        }
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) s += c0[i] + c1[i];
+    } else {
+        double r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = threadIdx.x + i;
+        // same FMA count per warp-iteration as the DMMA warps: NACC * 256 FMA / 32 lanes = 8*NACC per lane
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < NACC; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = fma(r[i], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += r[i];
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// tflops_out[0] = DMMA-warps' TFLOP/s, [1] = DFMA-warps' TFLOP/s, measured in the same launch
+int fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops_out)
+{
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count, threads = total_warps * 32;
+    auto kern = fp64_mix_kernel<26>;
+    const size_t smem = 120 * 1024; // one CTA per SM
+    PGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    double *d = nullptr;
+    PGC_CUDA(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    PGC_CUDA(cudaEventCreate(&e0));
+    PGC_CUDA(cudaEventCreate(&e1));
+    kern<<<blocks, threads, smem, ctx->stream>>>(d, iters / 4 + 1, dmma_warps, 1e-3, 1e-3);
+    PGC_CUDA(cudaEventRecord(e0, ctx->stream));
+    kern<<<blocks, threads, smem, ctx->stream>>>(d, iters, dmma_warps, 1e-3, 1e-3);
+    PGC_CUDA(cudaEventRecord(e1, ctx->stream));
+    PGC_CUDA(cudaEventSynchronize(e1));
+    PGC_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    float ms = 0;
+    PGC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double per_warp = 2.0 * 256.0 * 26.0 * static_cast<double>(iters);
+    tflops_out[0] = per_warp * dmma_warps * blocks / (ms * 1e-3) / 1e12;
+    tflops_out[1] = per_warp * (total_warps - dmma_warps) * blocks / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return PGC_OK;
+}
+
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops)
 {
     PGC_CUDA(cudaSetDevice(ctx->device));
@@ -418,6 +488,17 @@ int pgc_eval_host(pgc_problem *p, const double *dvs, size_t n, double *fvs)
     return PGC_OK;
 }
 
+int pgc_debug_cec2014_phase_cycles(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, uint64_t *out7)
+{
+    PGC_REQUIRE(p && d_dvs && d_fvs && out7, "pgc_debug_cec2014_phase_cycles: null argument");
+    PGC_REQUIRE(p->desc.family == PGC_CEC2014, "pgc_debug_cec2014_phase_cycles: not a cec2014 problem");
+    PGC_CUDA(cudaSetDevice(p->ctx->device));
+    unsigned long long tmp[8] = {};
+    int rc = cec2014_phase_cycles(p, d_dvs, n, d_fvs, tmp);
+    for (int i = 0; i < 7; ++i) out7[i] = tmp[i];
+    return rc;
+}
+
 int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out)
 {
     PGC_REQUIRE(ctx && out, "pgc_malloc_device: null argument");
@@ -471,6 +552,14 @@ int pgc_measure_fp64_peak(pgc_ctx *ctx, int iters, double *tflops)
 {
     PGC_REQUIRE(ctx && tflops && iters > 0, "pgc_measure_fp64_peak: bad argument");
     return fp64_peak(ctx, iters, tflops);
+}
+
+int pgc_debug_fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops2)
+{
+    PGC_REQUIRE(ctx && tflops2 && iters > 0 && total_warps >= 1 && total_warps <= 16 && dmma_warps >= 0
+                    && dmma_warps <= total_warps,
+                "pgc_debug_fp64_mix_probe: bad argument");
+    return fp64_mix_probe(ctx, iters, total_warps, dmma_warps, tflops2);
 }
 
 int pgc_measure_fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops)

@@ -69,8 +69,8 @@ void add_group(Cec2014Recipe &r, StageDesc &st, int prim, int off, int len, doub
         case P_ELLIPS: // :383  pow(10.0, 6.0 * i / (nx - 1))
             for (unsigned i = 0; i < nx; ++i) r.table.push_back(std::pow(10.0, 6.0 * i / (nx - 1)));
             break;
-        case P_GRIEWANK: // :526  sqrt(1.0 + i)
-            for (unsigned i = 0; i < nx; ++i) r.table.push_back(std::sqrt(1.0 + i));
+        case P_GRIEWANK: // :526  z / sqrt(1.0 + i), kept as a reciprocal (<= 1 ulp from the true quotient)
+            for (unsigned i = 0; i < nx; ++i) r.table.push_back(1.0 / std::sqrt(1.0 + i));
             break;
         case P_WEIERSTRASS: { // :491-509
             const double a = 0.5, b = 3.0;

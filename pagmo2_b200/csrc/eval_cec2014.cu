@@ -33,8 +33,10 @@ namespace pgc
 namespace
 {
 
-constexpr int kWarps = 8;   // workers per CTA
-constexpr int kTileInd = 16; // individuals per warp tile
+constexpr int kMT = 1;              // m8n8k4 row tiles per warp tile
+constexpr int kTileInd = 8 * kMT;   // individuals per warp tile
+constexpr int kLPI = 32 / kTileInd; // lanes per individual in the epilogue
+constexpr int kWarps = 16;          // independent workers per CTA (4 per SM sub-partition)
 constexpr unsigned kFull = 0xffffffffu;
 
 __host__ __device__ constexpr int pad8(int d) { return (d + 7) / 8 * 8; }
@@ -49,11 +51,12 @@ __host__ __device__ constexpr int ystride(int d)
     return s;
 }
 // After the rotation the warp keeps z TRANSPOSED: zT[coordinate][individual], row stride kZS, so that the epilogue
-// (lane = individual) reads 16 consecutive doubles per coordinate: conflict-free whatever the permutation.
-constexpr int kZS = 18;
+// (lane = individual + kTileInd * q) reads consecutive doubles per coordinate whatever the permutation; the +2 pad
+// makes the accumulator-tile stores conflict-free.
+constexpr int kZS = kTileInd + 2;
 __host__ __device__ constexpr int warp_buf_elems(int d)
 {
-    return (16 * ystride(d) > pad8(d) * kZS) ? 16 * ystride(d) : pad8(d) * kZS;
+    return (kTileInd * ystride(d) > pad8(d) * kZS) ? kTileInd * ystride(d) : pad8(d) * kZS;
 }
 
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor path.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2*(l%4)+{0,1}].
@@ -75,19 +78,71 @@ struct StageParams {
     long long n;
     double fbias;
     int aligned16;
+    unsigned long long *prof; // optional (pgc_debug_cec2014_phase_cycles): per-phase cycle totals, see kPh*
     StageDesc st;
 };
 
-// cos(theta) for |theta| up to ~2^50 with a two-term 1/(2*pi): r = frac(theta/(2*pi)) to ~1e-17, then cospi.
-// Used where the reference feeds libm cos huge arguments as a matter of course (weierstrass :504,
-// grie_rosen :708); matches a correctly-rounded cos to ~1 ulp without the Payne-Hanek slow path.
-__device__ __forceinline__ double cos_big(double theta)
+enum { kPhLoad = 0, kPhWeight, kPhTokenWait, kPhGemm, kPhStoreZ, kPhEpilogue, kPhTiles, kPhCount };
+
+// ---- branch-free FP64 trigonometry for the epilogues ---------------------------------------------------------
+// libdevice's sin/cos carry a data-dependent branch (Payne-Hanek slow path), which stops the compiler from
+// interleaving independent evaluations; the epilogues then run at the latency of one dependent DFMA chain per
+// coordinate.  These versions are straight-line code (selects only), ~1 ulp, valid for |theta| < 2^50, so two
+// coordinates per lane overlap.  The argument is the reference's own rounded double (e.g. fl(2*pi*z)):
+// turns = frac(theta / (2 pi)) with a two-term 1/(2 pi) (error ~1e-17 turns), then a quadrant fold to
+// [-pi/4, pi/4] and the classic minimax kernels (fdlibm k_sin.c / k_cos.c coefficients).
+__device__ __forceinline__ double round_magic(double x) // round to nearest integer, |x| < 2^51
+{
+    return (x + 6755399441055744.0) - 6755399441055744.0;
+}
+
+__device__ __forceinline__ double turns_of(double theta) // frac(theta / (2 pi)) in [-0.5, 0.5]
 {
     const double I1 = 0x1.45f306dc9c883p-3, I2 = -0x1.6b01ec5417056p-57;
     const double p = theta * I1;
     const double e = fma(theta, I1, -p);
-    const double r = (p - rint(p)) + fma(theta, I2, e);
-    return cospi(2.0 * r);
+    return (p - rint(p)) + fma(theta, I2, e);
+}
+
+// sin and cos of 2*pi*r for |r| <~ 1
+__device__ __forceinline__ void sincos_turns(double r, double &sn, double &cs)
+{
+    const double q = round_magic(4.0 * r);
+    const double f = fma(-0.25, q, r); // exact, in [-1/8, 1/8]
+    const int iq = __double2int_rn(q);
+    const double t = fma(f, 6.283185307179586232, f * 2.4492935982947064e-16); // 2*pi*f, hi + lo
+    const double z = t * t;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double st = fma(t * z, ps, t);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double ct = fma(z * z, pc, fma(-0.5, z, 1.0));
+    // angle = t + iq*pi/2
+    const bool odd = iq & 1;
+    const double s0 = odd ? ct : st, c0 = odd ? st : ct;
+    sn = (iq & 2) ? -s0 : s0;
+    cs = ((iq + 1) & 2) ? -c0 : c0;
+}
+
+__device__ __forceinline__ double cos_theta(double theta)
+{
+    double sn, cs;
+    sincos_turns(turns_of(theta), sn, cs);
+    return cs;
+}
+
+__device__ __forceinline__ double sin_theta(double theta)
+{
+    double sn, cs;
+    sincos_turns(turns_of(theta), sn, cs);
+    return sn;
 }
 
 struct Elem {
@@ -102,61 +157,73 @@ struct Elem {
     }
 };
 
-// the two lanes of an individual are 16 apart (lane = half * 16 + individual)
-__device__ __forceinline__ double pair_add(double v) { return v + __shfl_xor_sync(kFull, v, 16); }
-__device__ __forceinline__ double pair_mul(double v) { return v * __shfl_xor_sync(kFull, v, 16); }
+// the kLPI lanes of an individual are kTileInd apart (lane = q * kTileInd + individual)
+__device__ __forceinline__ double pair_add(double v)
+{
+#pragma unroll
+    for (int m = kTileInd; m < 32; m <<= 1) v = v + __shfl_xor_sync(kFull, v, m);
+    return v;
+}
+__device__ __forceinline__ double pair_mul(double v)
+{
+#pragma unroll
+    for (int m = kTileInd; m < 32; m <<= 1) v = v * __shfl_xor_sync(kFull, v, m);
+    return v;
+}
 
-// One primitive on n coordinates, evaluated by a pair of lanes (h = 0/1 takes the lower/upper half of the
-// terms); both lanes return the full value.  Expressions follow cec2014.cpp term by term.
+// Sum term(j) for j = lo, lo + kLPI, ... < hi IN ORDER (lane q of an individual takes the terms j == q mod kLPI),
+// evaluating two terms at a time so that their (independent, branch-free) dependency chains overlap.
+template <class F> __device__ __forceinline__ double ordered_sum(int lo, int hi, F term)
+{
+    double s = 0.0;
+    int j = lo;
+    for (; j + kLPI < hi; j += 2 * kLPI) {
+        const double a = term(j), b = term(j + kLPI);
+        s += a;
+        s += b;
+    }
+    if (j < hi) s += term(j);
+    return s;
+}
+
+// One primitive on n coordinates, evaluated by the kLPI lanes of an individual (lane q takes the terms
+// j == q mod kLPI); every lane returns the full value.  Expressions follow cec2014.cpp term by term.
 __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__restrict__ tab, int h)
 {
     const int n = g.len;
     const double dn = static_cast<double>(static_cast<unsigned>(n));
-    const int lo = (n * h) >> 1, hi = (n * (h + 1)) >> 1;
+    const int lo = h, hi = n;
     const double two_pi = 2.0 * 3.141592653589793238462643383279502884;
+    const double *gt = tab + g.tab_off;
     switch (g.prim) {
-        case P_ELLIPS: { // :382-384
-            double s = 0.0;
-            for (int j = lo; j < hi; ++j) {
+        case P_ELLIPS: // :382-384
+            return pair_add(ordered_sum(lo, hi, [&](int j) {
                 const double z = v(j);
-                s += tab[g.tab_off + j] * z * z;
-            }
-            return pair_add(s);
-        }
-        case P_BENT_CIGAR: { // :395-398
-            double s = 0.0;
-            for (int j = lo; j < hi; ++j) {
+                return gt[j] * z * z;
+            }));
+        case P_BENT_CIGAR: // :395-398
+            return pair_add(ordered_sum(lo, hi, [&](int j) {
                 const double z = v(j);
-                s += (j == 0) ? z * z : 1.0e6 * z * z;
-            }
-            return pair_add(s);
-        }
-        case P_DISCUS: { // :408-411
-            double s = 0.0;
-            for (int j = lo; j < hi; ++j) {
+                return (j == 0) ? z * z : 1.0e6 * z * z;
+            }));
+        case P_DISCUS: // :408-411
+            return pair_add(ordered_sum(lo, hi, [&](int j) {
                 const double z = v(j);
-                s += (j == 0) ? 1.0e6 * z * z : z * z;
-            }
-            return pair_add(s);
-        }
+                return (j == 0) ? 1.0e6 * z * z : z * z;
+            }));
         case P_ROSENBROCK: { // :438-444
-            const int nt = n - 1;
-            const int tlo = (nt * h) >> 1, thi = (nt * (h + 1)) >> 1;
-            double s = 0.0;
-            for (int j = tlo; j < thi; ++j) {
+            return pair_add(ordered_sum(h, n - 1, [&](int j) {
                 const double zj = v(j) + 1.0, zn = v(j + 1) + 1.0;
                 const double t1 = zj * zj - zn, t2 = zj - 1.0;
-                s += 100.0 * t1 * t1 + t2 * t2;
-            }
-            return pair_add(s);
+                return 100.0 * t1 * t1 + t2 * t2;
+            }));
         }
         case P_ACKLEY: { // :476-482
-            double s1 = 0.0, s2 = 0.0;
-            for (int j = lo; j < hi; ++j) {
+            double s1 = ordered_sum(lo, hi, [&](int j) {
                 const double z = v(j);
-                s1 += z * z;
-                s2 += cos(two_pi * z);
-            }
+                return z * z;
+            });
+            double s2 = ordered_sum(lo, hi, [&](int j) { return cos_theta(two_pi * v(j)); });
             s1 = pair_add(s1);
             s2 = pair_add(s2);
             s1 = -0.2 * sqrt(s1 / dn);
@@ -166,84 +233,90 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
         case P_WEIERSTRASS: { // :500-509
             // sum_k 0.5^k cos(theta_k), theta_k = fl(fl(2 pi 3^k) * u) as the reference forms it.  Every 7th term
             // (k = 0, 7, 14) is evaluated directly from the reference's own argument (exact two-term reduction by
-            // 2 pi, then sincospi); the terms in between come from the angle-tripling map w -> w^3 on the unit
-            // circle (complex multiplication: the error grows exactly 3x per step, <= 3^6 * 1e-16 before the next
-            // restart).  ~2.5x fewer FP64 instructions than 21 range-reduced cosines per coordinate.
-            const double *cj = tab + g.tab_off;
-            const double I1 = 0x1.45f306dc9c883p-3, I2 = -0x1.6b01ec5417056p-57;
-            double s = 0.0;
-            for (int j = lo; j < hi; ++j) {
-                const double u = v(j) + 0.5;
-                double sum = 0.0, w = 1.0, sn = 0.0, cs = 1.0;
+            // 2 pi); the terms in between come from the angle-tripling map w -> w^3 on the unit circle (complex
+            // multiplication: the error grows exactly 3x per step, <= 3^6 * 1e-16 before the next restart).
+            // ~2.5x fewer FP64 instructions than 21 range-reduced cosines per coordinate.
+            return pair_add(ordered_sum(lo, hi, [&](int j) {
+                       const double u = v(j) + 0.5;
+                       double sum = 0.0, w = 1.0, sn = 0.0, cs = 1.0;
 #pragma unroll
-                for (int k = 0; k <= 20; ++k) {
-                    if (k % 7 == 0) {
-                        const double theta = cj[k] * u;
-                        const double p = theta * I1;
-                        const double e = fma(theta, I1, -p);
-                        const double r = (p - rint(p)) + fma(theta, I2, e);
-                        sincospi(2.0 * r, &sn, &cs);
-                    } else {
-                        const double c2 = fma(cs, cs, -(sn * sn)), s2 = (cs + cs) * sn; // w^2
-                        const double c3 = fma(c2, cs, -(s2 * sn)), s3 = fma(s2, cs, c2 * sn); // w^3
-                        cs = c3;
-                        sn = s3;
-                    }
-                    sum = fma(w, cs, sum); // 0.5^k * cos is an exact scaling: same value as "sum += pow(a,k)*cos"
-                    w *= 0.5;
-                }
-                s += sum;
-            }
-            return pair_add(s) - g.c0;
+                       for (int k = 0; k <= 20; ++k) {
+                           if (k % 7 == 0) {
+                               sincos_turns(turns_of(gt[k] * u), sn, cs);
+                           } else {
+                               const double c2 = fma(cs, cs, -(sn * sn)), s2 = (cs + cs) * sn;       // w^2
+                               const double c3 = fma(c2, cs, -(s2 * sn)), s3 = fma(s2, cs, c2 * sn); // w^3
+                               cs = c3;
+                               sn = s3;
+                           }
+                           sum = fma(w, cs, sum); // 0.5^k * cos is an exact scaling: == "sum += pow(a,k)*cos"
+                           w *= 0.5;
+                       }
+                       return sum;
+                   }))
+                   - g.c0;
         }
-        case P_GRIEWANK: { // :524-528
-            double s = 0.0, p = 1.0;
-            for (int j = lo; j < hi; ++j) {
+        case P_GRIEWANK: { // :524-528; gt[j] = 1/sqrt(1+j) (the reference divides by sqrt(1+j): <= 1 ulp apart)
+            double s = ordered_sum(lo, hi, [&](int j) {
                 const double z = v(j);
-                s += z * z;
-                p *= cos(z / tab[g.tab_off + j]);
+                return z * z;
+            });
+            double p = 1.0;
+            int j = lo;
+            for (; j + kLPI < hi; j += 2 * kLPI) {
+                const double a = cos_theta(v(j) * gt[j]), b = cos_theta(v(j + kLPI) * gt[j + kLPI]);
+                p *= a;
+                p *= b;
             }
+            if (j < hi) p *= cos_theta(v(j) * gt[j]);
             s = pair_add(s);
             p = pair_mul(p);
             return 1.0 + s / 4000.0 - p;
         }
-        case P_RASTRIGIN: { // :541-543
-            double s = 0.0;
-            for (int j = lo; j < hi; ++j) {
+        case P_RASTRIGIN: // :541-543
+            return pair_add(ordered_sum(lo, hi, [&](int j) {
                 const double z = v(j);
-                s += (z * z - 10.0 * cos(two_pi * z) + 10.0);
-            }
-            return pair_add(s);
-        }
+                return (z * z - 10.0 * cos_theta(two_pi * z) + 10.0);
+            }));
         case P_SCHWEFEL: { // :575-589, the three branches folded into one sin(sqrt(.)) per coordinate
-            double s = 0.0;
             const double inv_n = 1.0 / dn;
-            for (int j = lo; j < hi; ++j) {
+            double s = 0.0;
+            auto term = [&](int j, double &sub, double &pen) {
                 const double z = v(j) + 4.209687462275036e+002;
                 const double az = fabs(z);
                 const bool big = az > 500.0;
-                double m = az, mult = z, pen = 0.0;
-                if (big) {
-                    // fm = fmod(|z|, 500) EXACTLY: q may be off by one, the fused remainder is exact, then fix up
-                    const double q = floor(az * 0.002);
-                    double fm = fma(-q, 500.0, az);
-                    if (fm < 0.0) fm += 500.0;
-                    else if (fm >= 500.0) fm -= 500.0;
-                    m = 500.0 - fm;            // z > 500: (500 - fmod(z,500)); z < -500: -(-500 + fmod(|z|,500))
-                    mult = copysign(m, z);
-                    const double t = (z - copysign(500.0, z)) * 0.01;
-                    pen = t * t * inv_n;
-                }
-                s -= mult * sin(sqrt(m));
-                s += pen;
+                // fm = fmod(|z|, 500) EXACTLY: q may be off by one, the fused remainder is exact, then fix up
+                const double q = floor(az * 0.002);
+                double fm = fma(-q, 500.0, az);
+                fm = (fm < 0.0) ? fm + 500.0 : ((fm >= 500.0) ? fm - 500.0 : fm);
+                // z > 500: (500 - fmod(z,500)); z < -500: -(-500 + fmod(|z|,500)); else |z|
+                const double m = big ? 500.0 - fm : az;
+                const double t = (z - copysign(500.0, z)) * 0.01;
+                sub = copysign(m, z) * sin_theta(sqrt(m));
+                pen = big ? t * t * inv_n : 0.0;
+            };
+            int j = lo;
+            for (; j + kLPI < hi; j += 2 * kLPI) {
+                double s0, p0, s1, p1;
+                term(j, s0, p0);
+                term(j + kLPI, s1, p1);
+                s -= s0;
+                s += p0;
+                s -= s1;
+                s += p1;
+            }
+            if (j < hi) {
+                double s0, p0;
+                term(j, s0, p0);
+                s -= s0;
+                s += p0;
             }
             return pair_add(s) + g.c0;
         }
         case P_KATSUURA: { // :604-614
             // |2^k z - floor(2^k z + 0.5)| is the distance to the nearest integer: same value via round-to-nearest
             // (magic-constant add, valid for |2^k z| < 2^51).  prod_j b_j^c0 is taken as exp(c0 * sum_j log b_j).
-            double slog = 0.0;
-            for (int j = lo; j < hi; ++j) {
+            double slog = ordered_sum(lo, hi, [&](int j) {
                 const double z = v(j);
                 double temp = 0.0;
                 if (fabs(z) < 262144.0) {
@@ -253,8 +326,7 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
                         t1 *= 2.0;
                         it1 *= 0.5;
                         const double t2 = t1 * z;
-                        const double r = (t2 + 6755399441055744.0) - 6755399441055744.0;
-                        temp = fma(fabs(t2 - r), it1, temp); // "/ 2^k" is an exact scaling
+                        temp = fma(fabs(t2 - round_magic(t2)), it1, temp); // "/ 2^k" is an exact scaling
                     }
                 } else {
                     double t1 = 1.0;
@@ -264,58 +336,42 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
                         temp += fabs(t2 - floor(t2 + 0.5)) / t1;
                     }
                 }
-                slog += log(1.0 + static_cast<double>(j + 1) * temp);
-            }
+                return log(1.0 + static_cast<double>(j + 1) * temp);
+            });
             slog = pair_add(slog);
             const double p = exp(g.c0 * slog);
             return p * g.c1 - g.c1;
         }
-        case P_HAPPYCAT: { // :751-759
-            double r2 = 0.0, sz = 0.0;
-            for (int j = lo; j < hi; ++j) {
+        case P_HAPPYCAT:
+        case P_HGBAT: { // :751-759, :774-782
+            double r2 = ordered_sum(lo, hi, [&](int j) {
                 const double z = v(j) - 1.0;
-                r2 += z * z;
-                sz += z;
-            }
+                return z * z;
+            });
+            double sz = ordered_sum(lo, hi, [&](int j) { return v(j) - 1.0; });
             r2 = pair_add(r2);
             sz = pair_add(sz);
-            return sqrt(sqrt(fabs(r2 - dn))) + (0.5 * r2 + sz) / dn + 0.5;
-        }
-        case P_HGBAT: { // :774-782
-            double r2 = 0.0, sz = 0.0;
-            for (int j = lo; j < hi; ++j) {
-                const double z = v(j) - 1.0;
-                r2 += z * z;
-                sz += z;
-            }
-            r2 = pair_add(r2);
-            sz = pair_add(sz);
+            if (g.prim == P_HAPPYCAT) return sqrt(sqrt(fabs(r2 - dn))) + (0.5 * r2 + sz) / dn + 0.5;
             return sqrt(fabs(r2 * r2 - sz * sz)) + (0.5 * r2 + sz) / dn + 0.5;
         }
-        case P_GRIE_ROSEN: { // :702-713 (cyclic last term)
-            double s = 0.0;
-            for (int j = lo; j < hi; ++j) {
+        case P_GRIE_ROSEN: // :702-713 (cyclic last term)
+            return pair_add(ordered_sum(lo, hi, [&](int j) {
                 const int jn = (j + 1 == n) ? 0 : j + 1;
                 const double zj = v(j) + 1.0, zn = v(jn) + 1.0;
                 const double t1 = zj * zj - zn, t2 = zj - 1.0;
                 const double temp = 100.0 * t1 * t1 + t2 * t2;
-                s += (temp * temp) / 4000.0 - cos_big(temp) + 1.0;
-            }
-            return pair_add(s);
-        }
-        case P_ESCAFFER6: { // :727-736 (cyclic last term)
-            double s = 0.0;
-            for (int j = lo; j < hi; ++j) {
+                return (temp * temp) / 4000.0 - cos_theta(temp) + 1.0;
+            }));
+        case P_ESCAFFER6: // :727-736 (cyclic last term)
+            return pair_add(ordered_sum(lo, hi, [&](int j) {
                 const int jn = (j + 1 == n) ? 0 : j + 1;
                 const double a = v(j), b = v(jn);
                 const double ss = a * a + b * b;
-                double t1 = sin(sqrt(ss));
+                double t1 = sin_theta(sqrt(ss));
                 t1 = t1 * t1;
                 const double t2 = 1.0 + 0.001 * ss;
-                s += 0.5 + (t1 - 0.5) / (t2 * t2);
-            }
-            return pair_add(s);
-        }
+                return 0.5 + (t1 - 0.5) / (t2 * t2);
+            }));
         default: return 0.0;
     }
 }
@@ -329,7 +385,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
     constexpr int YS = ystride(D);  // row stride of Y tile and rotation image
     constexpr int WB = warp_buf_elems(D);
     constexpr int MR_ELEMS = ROT ? DP * YS : 0;
-    constexpr int NLOAD = (kTileInd * D + 63) / 64; // 16-byte loads per lane per tile
+    // L phase geometry: a row (individual) is D/2 16-byte chunks, fetched by LPR lanes in PASS passes
+    constexpr int CH = D / 2;
+    constexpr int PASS = (CH + 31) / 32;
+    constexpr int LPR = (CH + PASS - 1) / PASS;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sMr = reinterpret_cast<double *>(smem_raw);
@@ -355,45 +414,72 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
     const long long ntiles = (P.n + kTileInd - 1) / kTileInd;
     const bool need_w = P.wout != nullptr;
     const double pre_rate = P.st.pre_rate;
-    const int et = lane & 15, eh = lane >> 4; // epilogue mapping: individual, half
+    const int et = lane & (kTileInd - 1), eq = lane / kTileInd; // epilogue mapping: individual, term class
+
+    // this lane's slice of the shift vector for the L phase (same columns for every row of every tile)
+    double2 osv[PASS];
+#pragma unroll
+    for (int ps = 0; ps < PASS; ++ps) {
+        const int c = ps * LPR + lane;
+        osv[ps] = (lane < LPR && c < CH) ? make_double2(sOs[2 * c], sOs[2 * c + 1]) : make_double2(0.0, 0.0);
+    }
+
+    // The four warps of an SM sub-partition share its FP64 pipe (DMMA and DFMA issue to the same pipe).  Identical
+    // warps started together stay in lock step - all loading, then all in the GEMM, then all in the epilogue - and
+    // the pipe idles in between.  A one-off stagger of a quarter period per warp keeps the phases spread for the
+    // whole launch (phase lengths are deterministic).
+    if (ROT) {
+        const long long wait = static_cast<long long>(warp >> 2) * (NT * (KP / 4) * 16 * kMT);
+        const long long t_start = clock64();
+        while (clock64() - t_start < wait) {
+        }
+    }
 
     for (long long tile = static_cast<long long>(blockIdx.x) * kWarps + warp; tile < ntiles;
          tile += static_cast<long long>(gridDim.x) * kWarps) {
         const long long t0 = tile * kTileInd;
         const int nt = (P.n - t0 < kTileInd) ? static_cast<int>(P.n - t0) : kTileInd;
+        long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tp5 = 0, tp6 = 0;
+        if (P.prof) tp0 = clock64();
 
-        // ---- L: coalesced load (all 16-byte loads of the tile in flight at once), shift (x - Os) and scale
+        // ---- L: coalesced load (every 16-byte load of the tile in flight at once), shift (x - Os) and scale
         // (* sh_rate), cec2014.cpp:1245-1258.  ROT: row-major Y tile for the DMMA; otherwise straight into zT.
         {
             const double *src = P.x + t0 * D;
             const double scale = need_w ? 1.0 : pre_rate; // composition: keep x-Os for the cf_cal weight first
-            double2 xv[NLOAD];
+            if (P.aligned16) {
+                double2 xv[kTileInd][PASS];
 #pragma unroll
-            for (int r = 0; r < NLOAD; ++r) {
-                const int e = 2 * lane + 64 * r;
-                const int t = e / D;
-                xv[r] = make_double2(0.0, 0.0);
-                if (e < kTileInd * D && t < nt) {
-                    if (P.aligned16) {
-                        xv[r] = __ldcs(reinterpret_cast<const double2 *>(src + e));
-                    } else {
-                        xv[r].x = __ldcs(src + e);
-                        xv[r].y = __ldcs(src + e + 1);
+                for (int t = 0; t < kTileInd; ++t)
+#pragma unroll
+                    for (int ps = 0; ps < PASS; ++ps) {
+                        const int c = ps * LPR + lane;
+                        xv[t][ps] = make_double2(0.0, 0.0);
+                        if (lane < LPR && c < CH && t < nt)
+                            xv[t][ps] = __ldcs(reinterpret_cast<const double2 *>(src + t * D) + c);
                     }
-                }
-            }
 #pragma unroll
-            for (int r = 0; r < NLOAD; ++r) {
-                const int e = 2 * lane + 64 * r;
-                if (e < kTileInd * D) {
+                for (int t = 0; t < kTileInd; ++t)
+#pragma unroll
+                    for (int ps = 0; ps < PASS; ++ps) {
+                        const int c = ps * LPR + lane;
+                        if (lane < LPR && c < CH) {
+                            const double y0 = (xv[t][ps].x - osv[ps].x) * scale, y1 = (xv[t][ps].y - osv[ps].y) * scale;
+                            if (ROT) {
+                                *reinterpret_cast<double2 *>(buf + t * YS + 2 * c) = make_double2(y0, y1);
+                            } else {
+                                buf[(2 * c) * kZS + t] = y0;
+                                buf[(2 * c + 1) * kZS + t] = y1;
+                            }
+                        }
+                    }
+            } else { // 8-byte aligned input only (a shard that starts mid-allocation): scalar loads
+                for (int e = lane; e < kTileInd * D; e += 32) {
                     const int t = e / D, j = e - t * D;
-                    const double y0 = (xv[r].x - sOs[j]) * scale, y1 = (xv[r].y - sOs[j + 1]) * scale;
-                    if (ROT) {
-                        *reinterpret_cast<double2 *>(buf + t * YS + j) = make_double2(y0, y1);
-                    } else {
-                        buf[j * kZS + t] = y0;
-                        buf[(j + 1) * kZS + t] = y1;
-                    }
+                    const double xj = (t < nt) ? __ldcs(src + e) : 0.0;
+                    const double y = (xj - sOs[j]) * scale;
+                    if (ROT) buf[t * YS + j] = y;
+                    else buf[j * kZS + t] = y;
                 }
             }
             if (ROT && KP > D) { // zero the inner-index padding (zT of the previous tile lived there)
@@ -402,11 +488,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
             }
         }
         __syncwarp();
+        if (P.prof) tp1 = clock64();
 
         double wacc = 0.0;
         if (need_w) { // cf_cal weight sum_j (x_j - Os_j)^2, :1330-1332, then the deferred scale
-            const int lo = (D * eh) >> 1, hi = (D * (eh + 1)) >> 1;
-            for (int j = lo; j < hi; ++j) {
+            for (int j = eq; j < D; j += kLPI) {
                 double *pd = ROT ? buf + et * YS + j : buf + j * kZS + et;
                 const double d = *pd;
                 wacc += d * d;
@@ -415,35 +501,38 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
             wacc = pair_add(wacc);
             __syncwarp();
         }
+        if (P.prof) tp2 = clock64();
 
         // ---- G: z = Mr * y (:1224-1235) on DMMA.  A = Y tile (rows = individuals), B = Mr^T (rows of the image =
         // outputs); both fragments are "row g = lane/4, inner index 4u + lane%4": one 8-byte load per row and
-        // 4-deep step, 2 + NT loads feeding 2*NT independent m8n8k4 accumulator tiles.
+        // 4-deep step, kMT + NT loads feeding kMT*NT independent m8n8k4 accumulator tiles.
         if (ROT) {
+            if (P.prof) tp3 = clock64();
             const int g = lane >> 2, j = lane & 3;
-            double acc[2][NT][2];
+            double acc[kMT][NT][2];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+            for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
                 for (int nt2 = 0; nt2 < NT; ++nt2) acc[mt][nt2][0] = acc[mt][nt2][1] = 0.0;
             const double *ya = buf + g * YS + j;
             const double *mb = sMr + g * YS + j;
 #pragma unroll 2
             for (int u = 0; u < KP / 4; ++u) {
-                double a[2], b[NT];
+                double a[kMT], b[NT];
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) a[mt] = ya[mt * 8 * YS + u * 4];
+                for (int mt = 0; mt < kMT; ++mt) a[mt] = ya[mt * 8 * YS + u * 4];
 #pragma unroll
                 for (int nt2 = 0; nt2 < NT; ++nt2) b[nt2] = mb[nt2 * 8 * YS + u * 4];
 #pragma unroll
                 for (int nt2 = 0; nt2 < NT; ++nt2)
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) dmma(acc[mt][nt2][0], acc[mt][nt2][1], a[mt], b[nt2]);
+                    for (int mt = 0; mt < kMT; ++mt) dmma(acc[mt][nt2][0], acc[mt][nt2][1], a[mt], b[nt2]);
             }
             __syncwarp();
+            if (P.prof) tp4 = clock64();
             // accumulator tile (mt, nt): lane holds z[individual mt*8 + g][coordinate nt*8 + 2j + {0,1}] -> zT
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+            for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
                 for (int nt2 = 0; nt2 < NT; ++nt2) {
                     double *zc = buf + (nt2 * 8 + 2 * j) * kZS + mt * 8 + g;
@@ -453,7 +542,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
             __syncwarp();
         }
 
-        // ---- E: primitives on z (2 lanes per individual, 16 lanes apart) ------------------------------------------
+        if (P.prof) tp5 = clock64();
+        // ---- E: primitives on z (kLPI lanes per individual) -------------------------------------------------------
         double val = 0.0;
         {
             Elem v;
@@ -463,10 +553,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
                 const GroupDesc &g = P.st.g[gi];
                 v.off = g.off;
                 v.rate = g.rate;
-                val += eval_group(g, v, P.table, eh);
+                val += eval_group(g, v, P.table, eq);
             }
         }
-        if (eh == 0 && et < nt) {
+        if (eq == 0 && et < nt) {
             if (need_w) {
                 if (P.st.scaled) val = P.st.mul * val / P.st.div; // e.g. :1047 fit = 10000 * fit / 1e+4
                 P.out[t0 + et] = val;
@@ -476,6 +566,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
             }
         }
         __syncwarp();
+        if (P.prof && lane == 0) {
+            tp6 = clock64();
+            atomicAdd(P.prof + kPhLoad, static_cast<unsigned long long>(tp1 - tp0));
+            atomicAdd(P.prof + kPhWeight, static_cast<unsigned long long>(tp2 - tp1));
+            if (ROT) {
+                atomicAdd(P.prof + kPhTokenWait, static_cast<unsigned long long>(tp3 - tp2));
+                atomicAdd(P.prof + kPhGemm, static_cast<unsigned long long>(tp4 - tp3));
+                atomicAdd(P.prof + kPhStoreZ, static_cast<unsigned long long>(tp5 - tp4));
+            }
+            atomicAdd(P.prof + kPhEpilogue, static_cast<unsigned long long>(tp6 - tp5));
+            atomicAdd(P.prof + kPhTiles, 1ull);
+        }
     }
 }
 
@@ -641,7 +743,33 @@ void cec2014_destroy(pgc_problem *p)
     p->d_shuffle = nullptr;
 }
 
+int cec2014_eval_impl(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream,
+                      unsigned long long *d_prof);
+
 int cec2014_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream)
+{
+    return cec2014_eval_impl(p, d_dvs, n, d_fvs, stream, nullptr);
+}
+
+// Debug aid: run the evaluation with per-phase cycle counters (summed over warp-tiles and stages).
+// out[0..6] = load, weight pass, token wait, GEMM, z store, epilogue cycles, warp-tiles.
+int cec2014_phase_cycles(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, unsigned long long *out)
+{
+    unsigned long long *d_prof = nullptr;
+    PGC_CUDA(cudaMalloc(&d_prof, sizeof(unsigned long long) * kPhCount));
+    PGC_CUDA(cudaMemset(d_prof, 0, sizeof(unsigned long long) * kPhCount));
+    int rc = cec2014_eval_impl(p, d_dvs, n, d_fvs, p->ctx->stream, d_prof);
+    if (rc == PGC_OK) {
+        cudaError_t e = cudaStreamSynchronize(p->ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(out, d_prof, sizeof(unsigned long long) * kPhCount, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "phase profile", __FILE__, __LINE__);
+    }
+    cudaFree(d_prof);
+    return rc;
+}
+
+int cec2014_eval_impl(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream,
+                      unsigned long long *d_prof)
 {
     if (n == 0) return PGC_OK;
     const Cec2014Recipe &r = p->cec14;
@@ -666,6 +794,7 @@ int cec2014_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, c
         sp.n = static_cast<long long>(n);
         sp.fbias = r.fbias;
         sp.aligned16 = (reinterpret_cast<uintptr_t>(d_dvs) & 15u) == 0;
+        sp.prof = d_prof;
         sp.st = r.st[s];
         int rc;
         const bool rot = r.st[s].rotate != 0;

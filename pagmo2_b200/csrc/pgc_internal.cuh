@@ -142,6 +142,8 @@ int simple_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cu
 int cec2014_create(pgc_problem *p, const pgc_problem_desc *d);
 int cec2014_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
 void cec2014_destroy(pgc_problem *p);
+int cec2014_phase_cycles(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, unsigned long long *out);
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
+int fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops_out);
 } // namespace pgc
