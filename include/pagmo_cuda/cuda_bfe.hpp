@@ -2,6 +2,7 @@
 //
 //   pagmo_cuda::cuda_bfe        a user-defined batch fitness evaluator (UDBFE, reference include/pagmo/bfe.hpp:68-108):
 //                               `pagmo::bfe{cuda_bfe{}}`, `algo.set_bfe(...)`, `population{prob, cuda_bfe{}, n}`.
+//   pagmo_cuda::cuda_zdt/_dtlz  CUDA-backed multi-objective UDPs (same constructor arguments as pagmo::zdt / dtlz)
 //   pagmo_cuda::cuda_cec2014    CUDA-backed UDPs (reference include/pagmo/problem.hpp:394-411,532-553): mandatory
 //   pagmo_cuda::cuda_simple<F>  fitness()/get_bounds() plus batch_fitness(), so pagmo::default_bfe / member_bfe pick the
 //                               device path up automatically (default_bfe.cpp:56-57, member_bfe.cpp:40-45).
@@ -26,10 +27,12 @@
 #include <pagmo/exceptions.hpp>
 #include <pagmo/problem.hpp>
 #include <pagmo/problems/ackley.hpp>
+#include <pagmo/problems/dtlz.hpp>
 #include <pagmo/problems/griewank.hpp>
 #include <pagmo/problems/rastrigin.hpp>
 #include <pagmo/problems/rosenbrock.hpp>
 #include <pagmo/problems/schwefel.hpp>
+#include <pagmo/problems/zdt.hpp>
 #include <pagmo/s11n.hpp>
 #include <pagmo/threading.hpp>
 #include <pagmo/types.hpp>
@@ -251,6 +254,51 @@ using cuda_griewank = cuda_simple<PGC_GRIEWANK>;
 using cuda_schwefel = cuda_simple<PGC_SCHWEFEL>;
 using cuda_rosenbrock = cuda_simple<PGC_ROSENBROCK>;
 
+// ZDT1-6 on the device; same constructor arguments as pagmo::zdt (zdt.hpp:145).
+class cuda_zdt : public cuda_udp_base
+{
+public:
+    explicit cuda_zdt(unsigned prob_id = 1u, unsigned param = 30u, int device = 0) : m_prob_id(prob_id), m_param(param)
+    {
+        m_device = device;
+        m_handle = std::make_shared<detail::problem_handle>(m_device, detail::make_desc(PGC_ZDT, prob_id, param));
+    }
+    pagmo::vector_double::size_type get_nix() const // zdt.cpp:126-143: zdt5 is integer valued
+    {
+        return m_prob_id == 5u ? 30u + 5u * (m_param - 1u) : 0u;
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_prob_id, m_param, m_device);
+    }
+
+private:
+    unsigned m_prob_id, m_param;
+};
+
+// DTLZ1-7 on the device; same constructor arguments as pagmo::dtlz (dtlz.hpp:105).
+class cuda_dtlz : public cuda_udp_base
+{
+public:
+    explicit cuda_dtlz(unsigned prob_id = 1u, pagmo::vector_double::size_type dim = 5u,
+                       pagmo::vector_double::size_type fdim = 3u, unsigned alpha = 100u, int device = 0)
+        : m_prob_id(prob_id), m_alpha(alpha), m_dim(static_cast<unsigned>(dim)), m_fdim(static_cast<unsigned>(fdim))
+    {
+        m_device = device;
+        m_handle = std::make_shared<detail::problem_handle>(m_device,
+                                                            detail::make_desc(PGC_DTLZ, prob_id, m_dim, m_fdim, alpha));
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_prob_id, m_dim, m_fdim, m_alpha, m_device);
+    }
+
+private:
+    unsigned m_prob_id, m_alpha, m_dim, m_fdim;
+};
+
 // The UDBFE.  Dispatch order: (1) a CUDA-backed UDP -> its own device problem; (2) a stock pagmo UDP whose
 // parameters are recoverable from its public interface -> a cached device twin; (3) anything else -> throw.
 class cuda_bfe
@@ -262,10 +310,27 @@ public:
     {
         // (1) our own UDPs: same path as member_bfe (member_bfe.cpp:40-45), fevals are bumped by pagmo::bfe
         if (p.is<cuda_cec2014>() || p.is<cuda_rastrigin>() || p.is<cuda_ackley>() || p.is<cuda_griewank>()
-            || p.is<cuda_schwefel>() || p.is<cuda_rosenbrock>()) {
+            || p.is<cuda_schwefel>() || p.is<cuda_rosenbrock>() || p.is<cuda_zdt>() || p.is<cuda_dtlz>()) {
             return pagmo::detail::prob_invoke_mem_batch_fitness(p, dvs, false);
         }
-        // (2) stock UDPs that are fully described by (type, nx)
+        // (2a) stock zdt / dtlz: the problem id is only visible through get_name() ("ZDT3", "DTLZ2": zdt.cpp:161-164,
+        // dtlz.cpp:170-173); dtlz4's alpha is private and cannot be recovered
+        if (p.is<pagmo::zdt>() || p.is<pagmo::dtlz>()) {
+            const std::string nm = p.get_name();
+            const bool is_zdt = p.is<pagmo::zdt>();
+            const unsigned id = static_cast<unsigned>(std::stoul(nm.substr(is_zdt ? 3 : 4)));
+            const unsigned nx = static_cast<unsigned>(p.get_nx());
+            if (is_zdt) {
+                const unsigned param = (id == 5u) ? (nx - 30u) / 5u + 1u : nx; // zdt.cpp:115-118
+                return twin(detail::make_desc(PGC_ZDT, id, param)).evaluate(dvs);
+            }
+            if (id == 4u) {
+                pagmo_throw(std::invalid_argument, "cuda_bfe cannot evaluate a stock pagmo::dtlz with prob_id 4: its alpha "
+                                                   "is private; construct a pagmo_cuda::cuda_dtlz instead");
+            }
+            return twin(detail::make_desc(PGC_DTLZ, id, nx, static_cast<unsigned>(p.get_nobj()), 100u)).evaluate(dvs);
+        }
+        // (2b) stock UDPs that are fully described by (type, nx)
         int family = 0;
         if (p.is<pagmo::rastrigin>()) family = PGC_RASTRIGIN;
         else if (p.is<pagmo::ackley>()) family = PGC_ACKLEY;
@@ -279,7 +344,7 @@ public:
                             + "': no CUDA evaluator exists for this UDP type (wrap it in a pagmo_cuda:: UDP, or use "
                               "thread_bfe); there is no CPU fallback");
         }
-        return twin(family, static_cast<unsigned>(p.get_nx())).evaluate(dvs);
+        return twin(detail::make_desc(family, 0u, static_cast<unsigned>(p.get_nx()))).evaluate(dvs);
     }
     std::string get_name() const
     {
@@ -298,13 +363,13 @@ public:
 private:
     struct cache_t {
         std::mutex mtx;
-        std::map<std::tuple<int, unsigned>, std::shared_ptr<detail::problem_handle>> twins;
+        std::map<std::tuple<int, unsigned, unsigned, unsigned, unsigned>, std::shared_ptr<detail::problem_handle>> twins;
     };
-    const detail::problem_handle &twin(int family, unsigned dim) const
+    const detail::problem_handle &twin(const pgc_problem_desc &d) const
     {
         std::lock_guard<std::mutex> lk(m_cache->mtx);
-        auto &slot = m_cache->twins[std::make_tuple(family, dim)];
-        if (!slot) slot = std::make_shared<detail::problem_handle>(m_device, detail::make_desc(family, 0u, dim));
+        auto &slot = m_cache->twins[std::make_tuple(d.family, d.prob_id, d.dim, d.nobj, d.param)];
+        if (!slot) slot = std::make_shared<detail::problem_handle>(m_device, d);
         return *slot;
     }
     int m_device;
@@ -320,5 +385,7 @@ PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_ackley)
 PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_griewank)
 PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_schwefel)
 PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_rosenbrock)
+PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_zdt)
+PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_dtlz)
 
 #endif

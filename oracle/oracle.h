@@ -32,6 +32,12 @@ int oracle_cec2014_batch(unsigned func, unsigned dim, const double *Mr, const do
 /* compaction performed by the cec2014 constructor (cec2014.cpp:76-86): keep the first dim of every 100 */
 size_t oracle_cec2014_compact_shift(const double *lines, size_t nlines, unsigned dim, double *out);
 
+/* ---- multi-objective UDPs (restate_mo.c) ---- */
+int oracle_zdt_fitness(unsigned id, const double *x, size_t N, double *f);
+int oracle_dtlz_fitness(unsigned id, const double *x, size_t N, size_t M, unsigned alpha, double *f);
+int oracle_zdt_batch(unsigned id, const double *xs, size_t n, size_t N, double *fs);
+int oracle_dtlz_batch(unsigned id, const double *xs, size_t n, size_t N, size_t M, unsigned alpha, double *fs);
+
 #ifdef __cplusplus
 }
 #endif

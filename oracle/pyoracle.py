@@ -94,6 +94,23 @@ class Oracle:
             raise ValueError(f"oracle_simple_batch failed rc={rc}")
         return out
 
+    def zdt(self, prob_id: int, xs: np.ndarray) -> np.ndarray:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n, d = xs.shape
+        out = np.empty((n, 2))
+        if self.lib.oracle_zdt_batch(C.c_uint(prob_id), _dp(xs), C.c_size_t(n), C.c_size_t(d), _dp(out)):
+            raise ValueError("oracle_zdt_batch failed")
+        return out
+
+    def dtlz(self, prob_id: int, xs: np.ndarray, fdim: int, alpha: int = 100) -> np.ndarray:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n, d = xs.shape
+        out = np.empty((n, fdim))
+        if self.lib.oracle_dtlz_batch(C.c_uint(prob_id), _dp(xs), C.c_size_t(n), C.c_size_t(d), C.c_size_t(fdim),
+                                      C.c_uint(alpha), _dp(out)):
+            raise ValueError("oracle_dtlz_batch failed")
+        return out
+
     def cec2014(self, func: int, xs: np.ndarray, tables=None, nthreads: int = 1) -> np.ndarray:
         xs = np.ascontiguousarray(xs, dtype=np.float64)
         n, d = xs.shape

@@ -231,17 +231,17 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
             return 2.718281828459045235360287471352662498 - 20.0 * exp(s1) - exp(s2) + 20.0;
         }
         case P_WEIERSTRASS: { // :500-509
-            // sum_k 0.5^k cos(theta_k), theta_k = fl(fl(2 pi 3^k) * u) as the reference forms it.  Every 7th term
-            // (k = 0, 7, 14) is evaluated directly from the reference's own argument (exact two-term reduction by
-            // 2 pi); the terms in between come from the angle-tripling map w -> w^3 on the unit circle (complex
-            // multiplication: the error grows exactly 3x per step, <= 3^6 * 1e-16 before the next restart).
-            // ~2.5x fewer FP64 instructions than 21 range-reduced cosines per coordinate.
+            // sum_k 0.5^k cos(theta_k), theta_k = fl(fl(2 pi 3^k) * u) as the reference forms it.  Terms k = 0 and
+            // k = 10 are evaluated directly from the reference's own argument (exact two-term reduction by 2 pi);
+            // the terms in between come from the angle-tripling map w -> w^3 on the unit circle (complex
+            // multiplication: the error grows exactly 3x per step, so term k is off by <= 3^(k mod 10) * 1e-16,
+            // and it is weighted by 0.5^k).  ~2.7x fewer FP64 instructions than 21 range-reduced cosines.
             return pair_add(ordered_sum(lo, hi, [&](int j) {
                        const double u = v(j) + 0.5;
                        double sum = 0.0, w = 1.0, sn = 0.0, cs = 1.0;
 #pragma unroll
                        for (int k = 0; k <= 20; ++k) {
-                           if (k % 7 == 0) {
+                           if (k % 10 == 0 && k < 20) {
                                sincos_turns(turns_of(gt[k] * u), sn, cs);
                            } else {
                                const double c2 = fma(cs, cs, -(sn * sn)), s2 = (cs + cs) * sn;       // w^2
@@ -285,10 +285,11 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
                 const double z = v(j) + 4.209687462275036e+002;
                 const double az = fabs(z);
                 const bool big = az > 500.0;
-                // fm = fmod(|z|, 500) EXACTLY: q may be off by one, the fused remainder is exact, then fix up
-                const double q = floor(az * 0.002);
+                // fm = fmod(|z|, 500) EXACTLY: q = nearest multiple, the fused remainder az - 500 q is exact and lies
+                // in [-250, 250]; one fix-up brings it to [0, 500)
+                const double q = round_magic(az * 0.002);
                 double fm = fma(-q, 500.0, az);
-                fm = (fm < 0.0) ? fm + 500.0 : ((fm >= 500.0) ? fm - 500.0 : fm);
+                fm = (fm < 0.0) ? fm + 500.0 : fm;
                 // z > 500: (500 - fmod(z,500)); z < -500: -(-500 + fmod(|z|,500)); else |z|
                 const double m = big ? 500.0 - fm : az;
                 const double t = (z - copysign(500.0, z)) * 0.01;
@@ -441,13 +442,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
         const int nt = (P.n - t0 < kTileInd) ? static_cast<int>(P.n - t0) : kTileInd;
         long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tp5 = 0, tp6 = 0;
         if (P.prof) tp0 = clock64();
+        double wacc = 0.0;
 
         // ---- L: coalesced load (every 16-byte load of the tile in flight at once), shift (x - Os) and scale
         // (* sh_rate), cec2014.cpp:1245-1258.  ROT: row-major Y tile for the DMMA; otherwise straight into zT.
         {
             const double *src = P.x + t0 * D;
-            const double scale = need_w ? 1.0 : pre_rate; // composition: keep x-Os for the cf_cal weight first
+            const double scale = need_w ? 1.0 : pre_rate; // unaligned path: keep x-Os for the weight pass first
             if (P.aligned16) {
+                double wrow[kTileInd];
+#pragma unroll
+                for (int t = 0; t < kTileInd; ++t) wrow[t] = 0.0;
                 double2 xv[kTileInd][PASS];
 #pragma unroll
                 for (int t = 0; t < kTileInd; ++t)
@@ -464,7 +469,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
                     for (int ps = 0; ps < PASS; ++ps) {
                         const int c = ps * LPR + lane;
                         if (lane < LPR && c < CH) {
-                            const double y0 = (xv[t][ps].x - osv[ps].x) * scale, y1 = (xv[t][ps].y - osv[ps].y) * scale;
+                            const double d0 = xv[t][ps].x - osv[ps].x, d1 = xv[t][ps].y - osv[ps].y;
+                            if (need_w) wrow[t] += d0 * d0 + d1 * d1; // cf_cal weight sum_j (x_j - Os_j)^2, :1330-1332
+                            const double y0 = d0 * pre_rate, y1 = d1 * pre_rate;
                             if (ROT) {
                                 *reinterpret_cast<double2 *>(buf + t * YS + 2 * c) = make_double2(y0, y1);
                             } else {
@@ -473,6 +480,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
                             }
                         }
                     }
+                if (need_w) {
+#pragma unroll
+                    for (int t = 0; t < kTileInd; ++t) {
+                        double w = wrow[t];
+#pragma unroll
+                        for (int m = 16; m > 0; m >>= 1) w += __shfl_xor_sync(kFull, w, m);
+                        if (t == et) wacc = w;
+                    }
+                }
             } else { // 8-byte aligned input only (a shard that starts mid-allocation): scalar loads
                 for (int e = lane; e < kTileInd * D; e += 32) {
                     const int t = e / D, j = e - t * D;
@@ -490,8 +506,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
         __syncwarp();
         if (P.prof) tp1 = clock64();
 
-        double wacc = 0.0;
-        if (need_w) { // cf_cal weight sum_j (x_j - Os_j)^2, :1330-1332, then the deferred scale
+        if (need_w && !P.aligned16) { // unaligned path: weight pass over the tile, then the deferred scale
             for (int j = eq; j < D; j += kLPI) {
                 double *pd = ROT ? buf + et * YS + j : buf + j * kZS + et;
                 const double d = *pd;

@@ -139,6 +139,8 @@ int ensure_scratch(pgc_ctx *ctx, size_t bytes);
 // family back-ends: validate + upload tables (create) and launch (eval, asynchronous on `stream`)
 int simple_create(pgc_problem *p);
 int simple_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
+int mo_create(pgc_problem *p);
+int mo_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
 int cec2014_create(pgc_problem *p, const pgc_problem_desc *d);
 int cec2014_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
 void cec2014_destroy(pgc_problem *p);

@@ -17,7 +17,10 @@
 #include <pagmo/bfe.hpp>
 #include <pagmo/population.hpp>
 #include <pagmo/problem.hpp>
+#include <pagmo/algorithms/nsga2.hpp>
 #include <pagmo/problems/cec2014.hpp>
+#include <pagmo/problems/dtlz.hpp>
+#include <pagmo/problems/lennard_jones.hpp>
 #include <pagmo/problems/rastrigin.hpp>
 #include <pagmo/problems/zdt.hpp>
 
@@ -89,7 +92,7 @@ int main()
 
     // ---- 2. a UDP without a device evaluator: throw, never fall back to the CPU -------------------------------
     {
-        pagmo::problem p{pagmo::zdt{1u, 30u}};
+        pagmo::problem p{pagmo::lennard_jones{5u}};
         pagmo::bfe gpu{cuda_bfe{}};
         bool threw = false;
         try {
@@ -141,6 +144,39 @@ int main()
         CHECK(worst <= tol);
         CHECK(pg.best_idx() == pr.best_idx());
         std::printf("cec2014 f%u D=%u via pagmo::problem/bfe/population: ok (worst rel %.2e)\n", func, dim, worst);
+    }
+
+    // ---- 3b. multi-objective: stock zdt/dtlz through cuda_bfe, CUDA UDPs, and nsga2 with set_bfe ----------------
+    {
+        pagmo::bfe gpu{cuda_bfe{}}, cpu{pagmo::thread_bfe{}};
+        for (unsigned id = 1; id <= 6u; ++id) {
+            pagmo::problem ref{pagmo::zdt{id, 13u}}, twin{cuda_zdt{id, 13u}};
+            const auto dvs = random_batch(ref, 300, 7 + id);
+            const auto want = cpu(ref, dvs);
+            CHECK(max_rel(gpu(ref, dvs), want) <= tol);       // stock UDP recognised by name
+            CHECK(max_rel(pagmo::bfe{}(twin, dvs), want) <= tol); // CUDA UDP via default_bfe
+            CHECK(twin.get_nobj() == 2u && twin.get_nix() == ref.get_nix() && twin.get_bounds() == ref.get_bounds());
+        }
+        for (unsigned id = 1; id <= 7u; ++id) {
+            pagmo::problem ref{pagmo::dtlz{id, 12u, 3u, 100u}}, twin{cuda_dtlz{id, 12u, 3u, 100u}};
+            const auto dvs = random_batch(ref, 300, 70 + id);
+            const auto want = cpu(ref, dvs);
+            if (id != 4u) CHECK(max_rel(gpu(ref, dvs), want) <= tol);
+            CHECK(max_rel(gpu(twin, dvs), want) <= tol);
+            CHECK(twin.get_nobj() == 3u);
+        }
+        // the reference's own bfe-equivalence pattern (tests/nsga2.cpp:204-232): same seed, with and without a bfe
+        pagmo::problem prob{pagmo::zdt{1u, 30u}};
+        pagmo::population pop1{prob, 40u, 23u}, pop2{prob, 40u, 23u};
+        pagmo::nsga2 a1{10u, 0.95, 10., 0.01, 50., 32u}, a2{10u, 0.95, 10., 0.01, 50., 32u};
+        a2.set_bfe(gpu);
+        pop1 = a1.evolve(pop1);
+        pop2 = a2.evolve(pop2);
+        double worst = 0;
+        for (std::size_t i = 0; i < 40u; ++i) worst = std::max(worst, max_rel(pop2.get_f()[i], pop1.get_f()[i]));
+        CHECK(pop1.get_x() == pop2.get_x()); // identical trajectories: fitness differences stay below every comparison
+        CHECK(worst <= tol);
+        std::printf("nsga2 on zdt1 with set_bfe(cuda_bfe): same final population as the sequential run (rel %.2e)\n", worst);
     }
 
     // ---- 4. constructor errors surface as std::invalid_argument, like the reference UDP (cec2014.cpp:51-64) ----

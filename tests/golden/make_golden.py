@@ -39,6 +39,22 @@ def main():
             data[f"x_{fam}_d{dim}"] = xs
             data[f"f_{fam}_d{dim}"] = p.fitness_loop(xs)[:, 0]
     np.savez_compressed(OUT / "simple_ref.npz", **data)
+    # ---- ZDT / DTLZ: random points in the box
+    data = {}
+    for pid in range(1, 7):
+        for param in (2, 11, 30):
+            p = R.problem("zdt", pid, param)
+            lb, ub = p.bounds()
+            xs = rng.uniform(lb, ub, (8, p.nx))
+            data[f"x_zdt{pid}_p{param}"] = xs
+            data[f"f_zdt{pid}_p{param}"] = p.fitness_loop(xs)
+    for pid in range(1, 8):
+        for dim, fdim in ((5, 3), (12, 3), (7, 2), (30, 5)):
+            p = R.problem("dtlz", pid, dim, fdim, 100)
+            xs = rng.uniform(0, 1, (8, dim))
+            data[f"x_dtlz{pid}_d{dim}_m{fdim}"] = xs
+            data[f"f_dtlz{pid}_d{dim}_m{fdim}"] = p.fitness_loop(xs)
+    np.savez_compressed(OUT / "mo_ref.npz", **data)
     print("wrote", [p.name for p in OUT.glob("*.npz")])
 
 

@@ -212,3 +212,44 @@ def test_full_size_properties(capi, ctx, orc):
         prob.close()
     ctx.free(d_x)
     ctx.free(d_f)
+
+
+def test_zdt_dtlz_parity(capi, ctx, orc):
+    rng = np.random.default_rng(21)
+    g = np.load(GOLD / "mo_ref.npz")
+    worst = {}
+    for pid in range(1, 7):
+        for param in (2, 11, 30, 100):
+            prob = capi.Problem(ctx, "zdt", prob_id=pid, dim=param)
+            lb, ub = prob.bounds()
+            xs = rng.uniform(lb, ub, (1001, prob.nx))
+            got, want = prob.eval_host(xs), orc.zdt(pid, xs)
+            assert got.shape == (1001, 2)
+            worst[f"zdt{pid}_p{param}"] = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-9)))
+            key = f"zdt{pid}_p{param}"
+            if "x_" + key in g.files:
+                gg = prob.eval_host(g["x_" + key])
+                assert np.all(np.abs(gg - g["f_" + key]) <= REL_TOL * np.maximum(np.abs(g["f_" + key]), 1e-9)), key
+            prob.close()
+    for pid in range(1, 8):
+        for dim, fdim, alpha in ((5, 3, 100), (12, 3, 100), (7, 2, 3), (30, 5, 100), (9, 8, 10)):
+            prob = capi.Problem(ctx, "dtlz", prob_id=pid, dim=dim, nobj=fdim, param=alpha)
+            xs = rng.uniform(0, 1, (1001, dim))
+            got, want = prob.eval_host(xs), orc.dtlz(pid, xs, fdim, alpha)
+            assert got.shape == (1001, fdim)
+            worst[f"dtlz{pid}_d{dim}_m{fdim}"] = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-9)))
+            prob.close()
+    _report["mo_max_rel_err"] = worst
+    _dump_report()
+    bad = {k: e for k, e in worst.items() if not e <= REL_TOL}
+    assert not bad, bad
+    # reference KATs, tests/zdt.cpp:67-80
+    f = capi.Problem(ctx, "zdt", prob_id=1, dim=30).eval_host(np.full((1, 30), 0.25))[0]
+    assert f[0] == 0.25 and abs(f[1] - 2.3486121811340026) <= 1e-15 * 2.35
+    for bad_args in (dict(prob_id=0, dim=30), dict(prob_id=7, dim=30), dict(prob_id=1, dim=1)):
+        with pytest.raises(capi.PgcError):
+            capi.Problem(ctx, "zdt", **bad_args)
+    for bad_args in (dict(prob_id=0, dim=5, nobj=3), dict(prob_id=8, dim=5, nobj=3), dict(prob_id=1, dim=3, nobj=3),
+                     dict(prob_id=1, dim=5, nobj=1)):
+        with pytest.raises(capi.PgcError):
+            capi.Problem(ctx, "dtlz", **bad_args)

@@ -132,3 +132,40 @@ def test_simple_restatement_is_bit_exact_vs_reference(orc, ref):
             lb, ub = p.bounds()
             xs = rng.uniform(lb, ub, (32, dim))
             assert np.array_equal(orc.simple(fam, xs), p.fitness_loop(xs)[:, 0]), (fam, dim)
+
+
+# ---------------------------------------------------------------- multi-objective UDPs
+def test_zdt_known_answers(orc):
+    # reference tests/zdt.cpp:67-120 (BOOST_CHECK_CLOSE 1e-13 %)
+    kat = {(1, 30, 0.25): (0.25, 2.3486121811340026), (1, 13, 0.33): (0.33, 2.825404001404863),
+           (2, 30, 0.25): (0.25, 3.230769230769231), (2, 13, 0.33): (0.33, 3.9425692695214107),
+           (3, 30, 0.25): (0.25, 2.0986121811340026)}
+    for (pid, n, v), (f0, f1) in kat.items():
+        f = orc.zdt(pid, np.full((1, n), v))[0]
+        assert f[0] == pytest.approx(f0, rel=1e-15) and f[1] == pytest.approx(f1, rel=1e-15)
+
+
+def test_mo_matches_golden(orc):
+    g = np.load(GOLD / "mo_ref.npz")
+    for pid in range(1, 7):
+        for param in (2, 11, 30):
+            assert np.array_equal(orc.zdt(pid, g[f"x_zdt{pid}_p{param}"]), g[f"f_zdt{pid}_p{param}"]), (pid, param)
+    for pid in range(1, 8):
+        for dim, fdim in ((5, 3), (12, 3), (7, 2), (30, 5)):
+            k = f"dtlz{pid}_d{dim}_m{fdim}"
+            assert np.array_equal(orc.dtlz(pid, g["x_" + k], fdim, 100), g["f_" + k]), k
+
+
+def test_mo_restatement_is_bit_exact_vs_reference(orc, ref):
+    rng = np.random.default_rng(5)
+    for pid in range(1, 7):
+        for param in (2, 3, 11, 30):
+            p = ref.problem("zdt", pid, param)
+            lb, ub = p.bounds()
+            xs = rng.uniform(lb, ub, (64, p.nx))
+            assert np.array_equal(p.fitness_loop(xs), orc.zdt(pid, xs)), (pid, param)
+    for pid in range(1, 8):
+        for dim, fdim, alpha in ((5, 3, 100), (12, 3, 100), (7, 2, 3), (30, 5, 100), (9, 8, 10)):
+            p = ref.problem("dtlz", pid, dim, fdim, alpha)
+            xs = rng.uniform(0, 1, (64, dim))
+            assert np.array_equal(p.fitness_loop(xs), orc.dtlz(pid, xs, fdim, alpha)), (pid, dim, fdim)
