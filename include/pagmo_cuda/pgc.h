@@ -118,6 +118,33 @@ PGC_API int pgc_eval_device(pgc_problem *prob, const double *d_dvs, size_t n, do
  * through the context's pinned staging ring; returns when fvs is complete. */
 PGC_API int pgc_eval_host(pgc_problem *prob, const double *dvs, size_t n, double *fvs);
 
+/* ---- multi-objective utilities (reference src/utils/multi_objective.cpp) ---------------------------------------------
+ * f is flat row-major [n x m] (a std::vector<vector_double> of objective vectors, flattened).  Index results are the
+ * reference's pop_size_t values: size_t in the host entry points, uint32_t on the device.
+ *
+ * fast_non_dominated_sorting (:200-257): rank[n] = non_dom_rank, dom_count[n] (may be NULL), the fronts concatenated in
+ * front_idx[n] - same order inside every front as the reference - with front k = front_idx[front_off[k] .. front_off[k+1]).
+ * The O(N^2) dom_list (tuple element 1, only consumed by tests) is not materialised.  Needs n >= 2, m <= 8. */
+PGC_API int pgc_fnds_host(pgc_ctx *ctx, const double *f, size_t n, size_t m, size_t *rank, size_t *dom_count,
+                          size_t *front_idx, size_t *front_off /* n+1 */, size_t *nfronts);
+PGC_API int pgc_fnds_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, uint32_t *d_rank, uint32_t *d_dom_count,
+                            uint32_t *d_front_idx, uint32_t *d_front_off /* n+1 */, uint32_t *nfronts, void *stream);
+/* crowding_distance (:280-315) of ONE front given as its fitness list (n >= 2, m >= 2). */
+PGC_API int pgc_crowding_distance_host(pgc_ctx *ctx, const double *f, size_t n, size_t m, double *out);
+/* crowding distance of every front of an FNDS result at once, written at the points' own indices.
+ * small_front_rule: 0 = none (fronts of size < 2 keep 0), 1 = nsga2.cpp:188-198 (size 1 or 2 -> +inf),
+ * 2 = sort_population_mo :441-443 (size 1 -> 0). */
+PGC_API int pgc_crowding_fronts_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const uint32_t *d_front_idx,
+                                       const uint32_t *d_front_off, uint32_t nfronts, int small_front_rule, double *d_cd,
+                                       void *stream);
+/* select_best_N_mo (:344-396): whole fronts while they fit, then the cut front by crowding distance descending (stable:
+ * equal distances keep front order; the reference's std::sort leaves the order of ties unspecified). */
+PGC_API int pgc_select_best_N_mo_host(pgc_ctx *ctx, const double *f, size_t n, size_t m, size_t N, size_t *out, size_t *nout);
+PGC_API int pgc_select_best_N_mo_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, size_t N, uint32_t *d_out,
+                                        uint32_t *nout, void *stream);
+/* sort_population_mo (:425-465): indices by (rank ascending, crowding distance descending), stable. */
+PGC_API int pgc_sort_population_mo_host(pgc_ctx *ctx, const double *f, size_t n, size_t m, size_t *out);
+
 /* Debug/profiling aid for the CEC2014 stage kernel: same evaluation with clock64() phase counters, summed over all
  * warp-tiles and stages.  out7 = {load, weight pass, token wait, GEMM, z store, epilogue} cycles, warp-tiles. */
 PGC_API int pgc_debug_cec2014_phase_cycles(pgc_problem *prob, const double *d_dvs, size_t n, double *d_fvs, uint64_t *out7);

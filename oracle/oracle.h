@@ -38,6 +38,14 @@ int oracle_dtlz_fitness(unsigned id, const double *x, size_t N, size_t M, unsign
 int oracle_zdt_batch(unsigned id, const double *xs, size_t n, size_t N, double *fs);
 int oracle_dtlz_batch(unsigned id, const double *xs, size_t n, size_t N, size_t M, unsigned alpha, double *fs);
 
+/* ---- multi-objective utilities (restate_mo_utils.c), f flat row-major [n x m] ---- */
+int oracle_pareto_dominance(const double *a, const double *b, size_t m);
+int oracle_fnds(const double *f, size_t n, size_t m, size_t *rank, size_t *dom_count, size_t *front_idx, size_t *front_off,
+                size_t *nfronts);
+int oracle_crowding_distance(const double *f, size_t n, size_t m, double *out);
+int oracle_select_best_N_mo(const double *f, size_t n, size_t m, size_t N, size_t *out, size_t *nout);
+int oracle_sort_population_mo(const double *f, size_t n, size_t m, size_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,6 +111,41 @@ class Oracle:
             raise ValueError("oracle_dtlz_batch failed")
         return out
 
+    # ---- multi-objective utilities (restate_mo_utils.c) ----
+    def fnds(self, f: np.ndarray):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        n, m = f.shape
+        rank, dc, fi = (np.empty(n, dtype=np.uint64) for _ in range(3))
+        fo = np.empty(n + 1, dtype=np.uint64)
+        nf = C.c_size_t()
+        if self.lib.oracle_fnds(_dp(f), C.c_size_t(n), C.c_size_t(m), _sp(rank), _sp(dc), _sp(fi), _sp(fo), C.byref(nf)):
+            raise ValueError("oracle_fnds failed")
+        fronts = [fi[int(fo[k]):int(fo[k + 1])].astype(np.int64) for k in range(nf.value)]
+        return {"rank": rank.astype(np.int64), "dom_count": dc.astype(np.int64), "fronts": fronts}
+
+    def crowding_distance(self, f: np.ndarray) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        out = np.empty(f.shape[0])
+        if self.lib.oracle_crowding_distance(_dp(f), C.c_size_t(f.shape[0]), C.c_size_t(f.shape[1]), _dp(out)):
+            raise ValueError("oracle_crowding_distance failed")
+        return out
+
+    def select_best_N_mo(self, f: np.ndarray, N: int) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        out = np.empty(max(f.shape[0], 1), dtype=np.uint64)
+        nout = C.c_size_t()
+        if self.lib.oracle_select_best_N_mo(_dp(f), C.c_size_t(f.shape[0]), C.c_size_t(f.shape[1]), C.c_size_t(N), _sp(out),
+                                            C.byref(nout)):
+            raise ValueError("oracle_select_best_N_mo failed")
+        return out[: nout.value].astype(np.int64)
+
+    def sort_population_mo(self, f: np.ndarray) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        out = np.empty(max(f.shape[0], 1), dtype=np.uint64)
+        if self.lib.oracle_sort_population_mo(_dp(f), C.c_size_t(f.shape[0]), C.c_size_t(f.shape[1]), _sp(out)):
+            raise ValueError("oracle_sort_population_mo failed")
+        return out[: f.shape[0]].astype(np.int64)
+
     def cec2014(self, func: int, xs: np.ndarray, tables=None, nthreads: int = 1) -> np.ndarray:
         xs = np.ascontiguousarray(xs, dtype=np.float64)
         n, d = xs.shape

@@ -76,6 +76,15 @@ def lib():
         L.pgc_free_pinned.argtypes = [vp, vp]
         L.pgc_memcpy_h2d.argtypes = [vp, vp, vp, sz]
         L.pgc_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+        szp = C.POINTER(C.c_size_t)
+        L.pgc_fnds_host.argtypes = [vp, vp, sz, sz, szp, szp, szp, szp, szp]
+        L.pgc_crowding_distance_host.argtypes = [vp, vp, sz, sz, dp]
+        L.pgc_select_best_N_mo_host.argtypes = [vp, vp, sz, sz, sz, szp, szp]
+        L.pgc_sort_population_mo_host.argtypes = [vp, vp, sz, sz, szp]
+        u32p = C.POINTER(C.c_uint32)
+        L.pgc_fnds_device.argtypes = [vp, vp, sz, sz, vp, vp, vp, vp, u32p, vp]
+        L.pgc_crowding_fronts_device.argtypes = [vp, vp, sz, sz, vp, vp, C.c_uint32, C.c_int, vp, vp]
+        L.pgc_select_best_N_mo_device.argtypes = [vp, vp, sz, sz, sz, vp, u32p, vp]
         L.pgc_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
         L.pgc_measure_fp64_mma_peak.argtypes = [vp, C.c_int, dp]
         _lib = L
@@ -151,6 +160,43 @@ class Context:
         out = np.empty(shape, dtype=dtype)
         check(lib().pgc_memcpy_d2h(self._h, out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), out.nbytes))
         return out
+
+    # ---- multi-objective utilities (host-vector entry points, pagmo signatures) ----
+    def fnds(self, f: np.ndarray) -> dict:
+        """fast_non_dominated_sorting -> {'rank', 'dom_count', 'fronts'} (fronts in the reference's order)."""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        n, m = f.shape
+        rank, dc, fi = (np.empty(max(n, 1), dtype=np.uint64) for _ in range(3))
+        fo = np.empty(n + 1, dtype=np.uint64)
+        nf = C.c_size_t()
+        szp = C.POINTER(C.c_size_t)
+        check(lib().pgc_fnds_host(self._h, f.ctypes.data_as(C.c_void_p), n, m, rank.ctypes.data_as(szp), dc.ctypes.data_as(szp),
+                                  fi.ctypes.data_as(szp), fo.ctypes.data_as(szp), C.byref(nf)))
+        fronts = [fi[int(fo[k]):int(fo[k + 1])].astype(np.int64) for k in range(nf.value)]
+        return {"rank": rank[:n].astype(np.int64), "dom_count": dc[:n].astype(np.int64), "fronts": fronts}
+
+    def crowding_distance(self, f: np.ndarray) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        n, m = f.shape
+        out = np.empty(max(n, 1))
+        check(lib().pgc_crowding_distance_host(self._h, f.ctypes.data_as(C.c_void_p), n, m, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out[:n]
+
+    def select_best_N_mo(self, f: np.ndarray, N: int) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        n, m = f.shape if f.ndim == 2 else (0, 0)
+        out = np.empty(max(n, 1), dtype=np.uint64)
+        nout = C.c_size_t()
+        szp = C.POINTER(C.c_size_t)
+        check(lib().pgc_select_best_N_mo_host(self._h, f.ctypes.data_as(C.c_void_p), n, m, N, out.ctypes.data_as(szp), C.byref(nout)))
+        return out[: nout.value].astype(np.int64)
+
+    def sort_population_mo(self, f: np.ndarray) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        n, m = f.shape if f.ndim == 2 else (0, 0)
+        out = np.empty(max(n, 1), dtype=np.uint64)
+        check(lib().pgc_sort_population_mo_host(self._h, f.ctypes.data_as(C.c_void_p), n, m, out.ctypes.data_as(C.POINTER(C.c_size_t))))
+        return out[:n].astype(np.int64)
 
     def fp64_peak_tflops(self, iters: int = 4096) -> float:
         t = C.c_double()

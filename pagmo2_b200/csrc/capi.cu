@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "pgc_internal.cuh"
 
@@ -215,6 +216,28 @@ static int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, do
 } // namespace pgc
 
 using namespace pgc;
+
+namespace
+{
+struct DevBuf { // RAII device buffer for the host-vector convenience entry points
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int alloc(size_t bytes)
+    {
+        PGC_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        return PGC_OK;
+    }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+} // namespace
+
+static int indices_out(DevBuf &b, size_t cnt, size_t *dst)
+{
+    std::vector<unsigned> tmp(cnt ? cnt : 1);
+    PGC_CUDA(cudaMemcpy(tmp.data(), b.p, 4 * cnt, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < cnt; ++i) dst[i] = tmp[i];
+    return PGC_OK;
+}
 
 extern "C" {
 
@@ -501,6 +524,114 @@ int pgc_debug_cec2014_phase_cycles(pgc_problem *p, const double *d_dvs, size_t n
     int rc = cec2014_phase_cycles(p, d_dvs, n, d_fvs, tmp);
     for (int i = 0; i < 7; ++i) out7[i] = tmp[i];
     return rc;
+}
+
+// ---- multi-objective utilities -----------------------------------------------------------------------------------
+int pgc_fnds_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, uint32_t *d_rank, uint32_t *d_dom_count,
+                    uint32_t *d_front_idx, uint32_t *d_front_off, uint32_t *nfronts, void *stream)
+{
+    PGC_REQUIRE(ctx && d_f && d_rank && d_front_idx && d_front_off && nfronts, "pgc_fnds_device: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return fnds_device(ctx, d_f, n, m, d_rank, d_dom_count, d_front_idx, d_front_off, nfronts,
+                       stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int pgc_crowding_fronts_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const uint32_t *d_front_idx,
+                               const uint32_t *d_front_off, uint32_t nfronts, int small_front_rule, double *d_cd, void *stream)
+{
+    PGC_REQUIRE(ctx && d_f && d_front_idx && d_front_off && d_cd, "pgc_crowding_fronts_device: null argument");
+    PGC_REQUIRE(m >= 2, "Points in the non dominated front must contain at least two objectives: %zu detected.", m);
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return crowding_device(ctx, d_f, n, m, d_front_idx, d_front_off, nfronts, small_front_rule, d_cd,
+                           stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int pgc_select_best_N_mo_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, size_t N, uint32_t *d_out, uint32_t *nout,
+                                void *stream)
+{
+    PGC_REQUIRE(ctx && nout && (n == 0 || (d_f && d_out)), "pgc_select_best_N_mo_device: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return select_best_device(ctx, d_f, n, m, N, d_out, nout, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int pgc_fnds_host(pgc_ctx *ctx, const double *f, size_t n, size_t m, size_t *rank, size_t *dom_count, size_t *front_idx,
+                  size_t *front_off, size_t *nfronts)
+{
+    PGC_REQUIRE(ctx && nfronts, "pgc_fnds_host: null argument");
+    PGC_REQUIRE(n >= 2, "At least two points are needed for fast_non_dominated_sorting: %zu detected.", n);
+    PGC_REQUIRE(f || m == 0, "pgc_fnds_host: null fitness buffer");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    DevBuf df, dr, dc, doo, dfo;
+    int rc;
+    if ((rc = df.alloc(sizeof(double) * n * m)) || (rc = dr.alloc(4 * n)) || (rc = dc.alloc(4 * n)) || (rc = doo.alloc(4 * n))
+        || (rc = dfo.alloc(4 * (n + 1))))
+        return rc;
+    if (m) PGC_CUDA(cudaMemcpyAsync(df.p, f, sizeof(double) * n * m, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned nf = 0;
+    if ((rc = fnds_device(ctx, df.as<double>(), n, m, dr.as<unsigned>(), dc.as<unsigned>(), doo.as<unsigned>(), dfo.as<unsigned>(), &nf,
+                          ctx->stream)))
+        return rc;
+    std::vector<unsigned> tmp(n + 1);
+    auto fetch = [&](DevBuf &b, size_t cnt, size_t *dst) -> int {
+        if (!dst) return PGC_OK;
+        PGC_CUDA(cudaMemcpy(tmp.data(), b.p, 4 * cnt, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < cnt; ++i) dst[i] = tmp[i];
+        return PGC_OK;
+    };
+    if ((rc = fetch(dr, n, rank)) || (rc = fetch(dc, n, dom_count)) || (rc = fetch(doo, n, front_idx)) || (rc = fetch(dfo, nf + 1, front_off)))
+        return rc;
+    *nfronts = nf;
+    return PGC_OK;
+}
+
+int pgc_crowding_distance_host(pgc_ctx *ctx, const double *f, size_t n, size_t m, double *out)
+{
+    PGC_REQUIRE(ctx && out, "pgc_crowding_distance_host: null argument");
+    PGC_REQUIRE(n >= 2, "A non dominated front must contain at least two points: %zu detected.", n);            // :283-286
+    PGC_REQUIRE(m >= 2, "Points in the non dominated front must contain at least two objectives: %zu detected.", m); // :289-292
+    PGC_REQUIRE(f, "pgc_crowding_distance_host: null fitness buffer");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    DevBuf df, dcd;
+    int rc;
+    if ((rc = df.alloc(sizeof(double) * n * m)) || (rc = dcd.alloc(sizeof(double) * n))) return rc;
+    PGC_CUDA(cudaMemcpyAsync(df.p, f, sizeof(double) * n * m, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = crowding_device(ctx, df.as<double>(), n, m, nullptr, nullptr, 1, 0, dcd.as<double>(), ctx->stream))) return rc;
+    PGC_CUDA(cudaMemcpy(out, dcd.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return PGC_OK;
+}
+
+int pgc_select_best_N_mo_host(pgc_ctx *ctx, const double *f, size_t n, size_t m, size_t N, size_t *out, size_t *nout)
+{
+    PGC_REQUIRE(ctx && nout, "pgc_select_best_N_mo_host: null argument");
+    *nout = 0;
+    if (N == 0 || n == 0) return PGC_OK;
+    PGC_REQUIRE(out && (f || m == 0), "pgc_select_best_N_mo_host: null buffer");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    DevBuf df, dout;
+    int rc;
+    if ((rc = df.alloc(sizeof(double) * n * m)) || (rc = dout.alloc(4 * n))) return rc;
+    if (m) PGC_CUDA(cudaMemcpyAsync(df.p, f, sizeof(double) * n * m, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned cnt = 0;
+    if ((rc = select_best_device(ctx, df.as<double>(), n, m, N, dout.as<unsigned>(), &cnt, ctx->stream))) return rc;
+    PGC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((rc = indices_out(dout, cnt, out))) return rc;
+    *nout = cnt;
+    return PGC_OK;
+}
+
+int pgc_sort_population_mo_host(pgc_ctx *ctx, const double *f, size_t n, size_t m, size_t *out)
+{
+    PGC_REQUIRE(ctx, "pgc_sort_population_mo_host: null context");
+    if (n == 0) return PGC_OK;
+    PGC_REQUIRE(out && (f || m == 0), "pgc_sort_population_mo_host: null buffer");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    DevBuf df, dout;
+    int rc;
+    if ((rc = df.alloc(sizeof(double) * n * m)) || (rc = dout.alloc(4 * n))) return rc;
+    if (m) PGC_CUDA(cudaMemcpyAsync(df.p, f, sizeof(double) * n * m, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = sort_population_device(ctx, df.as<double>(), n, m, dout.as<unsigned>(), ctx->stream))) return rc;
+    PGC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return indices_out(dout, n, out);
 }
 
 int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out)

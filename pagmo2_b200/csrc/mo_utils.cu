@@ -1,0 +1,621 @@
+// mo_utils.cu - multi-objective utilities on sm_100a: fast_non_dominated_sorting, crowding_distance,
+// select_best_N_mo, sort_population_mo (reference src/utils/multi_objective.cpp:97-113,200-257,280-315,344-396,425-465).
+//
+// Integer results (ranks, fronts and the ORDER inside the fronts, dominator counts) are bit-exact with the reference.
+// How the reference's front order is reproduced without its O(N^2) dom_list: front 0 is in ascending
+// index order; a point q joins front k+1 when its dominator counter reaches zero, i.e. while the reference processes the
+// LAST of q's dominators in front k's order, and dom_list[p] is ascending in q.  Hence front k+1 is ordered by
+// (position in front k of q's last dominator there, q).  The algorithm is level synchronous:
+//   count[q] = #dominators                                   one all-pairs pass  (fnds_count_kernel)
+//   repeat: for every unassigned q, c = #dominators in front k and mp = max position among them;
+//           count[q] -= c; if it hits 0: rank = k+1, key = mp, q becomes a candidate (fnds_peel_kernel)
+//           front k+1 = candidates sorted by (key, q)          (fnds_order_kernel in shared memory, CUB radix sort when big)
+// Every (dominator, dominated) pair is tested once in the count pass and once in the peel passes: 2*N^2 dominance tests
+// of M FP64 compares in total, no N^2-bit matrix in memory.  The roofline that binds is compare throughput
+// (FP64 DSETP issue), not HBM: bytes are 8*N*M in + O(N) out.
+// Crowding distances are exact IEEE (same subtraction / division per element, objectives applied in order); the sort
+// inside a front is a stable segmented radix sort, which matches the reference's std::sort whenever the objective values
+// inside a front are distinct (the reference's order of ties is unspecified: SURVEY.md F5).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <vector>
+
+#include "pgc_internal.cuh"
+
+namespace pgc
+{
+
+namespace
+{
+
+constexpr unsigned kUnassigned = 0xffffffffu;
+constexpr int kTP = 256;          // dominators per shared-memory tile / threads per block in the pair kernels
+constexpr int kMaxM = 8;          // objectives held in registers
+constexpr int kOrderCap = 4096;   // candidates the single-CTA order kernel sorts in shared memory
+constexpr int kBatch = 8;         // levels launched between two host polls
+
+struct Meta {            // device-side bookkeeping of the level loop
+    unsigned ncand;      // candidates collected by the current peel
+    unsigned front_size; // size of the front being peeled (front `level`)
+    unsigned front_off;  // its offset in `order`
+    unsigned assigned;   // points placed in fronts so far
+    unsigned level;      // index of the front being peeled
+    unsigned overflow;   // 1: ncand > kOrderCap, the host must order this level with the big path
+    unsigned nfronts;
+    unsigned pad;
+};
+
+// pareto_dominance, multi_objective.cpp:97-113 with the NaN-aware comparisons of detail/custom_comparisons.hpp:54-88
+// (NaN is placed after +inf).  a dominates b.
+template <int M, bool NANAWARE> __device__ __forceinline__ bool dominates(const double *a, const double *b)
+{
+    bool strict = false, worse = false;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        const double x = a[i], y = b[i];
+        if (NANAWARE) {
+            const bool nx = isnan(x), ny = isnan(y);
+            worse |= (nx && !ny) || (x > y);  // greater_than_f(x, y)
+            strict |= (!nx) && (ny || x < y); // less_than_f(x, y)
+        } else {
+            worse |= (x > y);
+            strict |= (x < y);
+        }
+    }
+    return strict && !worse;
+}
+
+__global__ void has_nan_kernel(const double *f, size_t len, unsigned *flag)
+{
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool any = false;
+    for (; i < len; i += static_cast<size_t>(gridDim.x) * blockDim.x) any |= isnan(f[i]);
+    if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(flag, 1u);
+}
+
+// count[q] = number of points dominating q (multi_objective.cpp:215-227, both branches of the pair loop)
+template <int M, bool NANAWARE>
+__global__ void __launch_bounds__(kTP) fnds_count_kernel(const double *__restrict__ f, unsigned n, unsigned *count,
+                                                         unsigned *dom_count)
+{
+    constexpr int m = M;
+    __shared__ double tile[kTP * (M ? M : 1)];
+    const unsigned q = blockIdx.x * kTP + threadIdx.x;
+    double fq[M ? M : 1];
+#pragma unroll
+    for (int i = 0; i < M; ++i) fq[i] = (q < n) ? f[static_cast<size_t>(q) * m + i] : 0.0;
+    unsigned c = 0;
+    for (unsigned base = 0; base < n; base += kTP) {
+        const unsigned np = min(static_cast<unsigned>(kTP), n - base);
+        for (unsigned e = threadIdx.x; e < np * m; e += kTP) tile[e] = f[static_cast<size_t>(base) * m + e];
+        __syncthreads();
+        if (q < n) {
+#pragma unroll 4
+            for (unsigned t = 0; t < np; ++t) c += dominates<M, NANAWARE>(tile + t * M, fq) ? 1u : 0u;
+        }
+        __syncthreads();
+    }
+    if (q < n) {
+        count[q] = c;
+        if (dom_count) dom_count[q] = c;
+    }
+}
+
+// one level: subtract the dominators found in front `level` from every unassigned point's counter
+template <int M, bool NANAWARE>
+__global__ void __launch_bounds__(kTP) fnds_peel_kernel(const double *__restrict__ f, unsigned n,
+                                                        const unsigned *__restrict__ order, unsigned *count, unsigned *rank,
+                                                        unsigned *key, unsigned *cand, Meta *meta)
+{
+    constexpr int m = M;
+    __shared__ double tile[kTP * (M ? M : 1)];
+    if (meta->overflow) return;
+    const unsigned fs = meta->front_size, fo = meta->front_off, level = meta->level;
+    if (fs == 0) return;
+    const unsigned q = blockIdx.x * kTP + threadIdx.x;
+    const bool active = q < n && rank[q] == kUnassigned;
+    if (!__syncthreads_or(active)) return;
+    double fq[M ? M : 1];
+#pragma unroll
+    for (int i = 0; i < M; ++i) fq[i] = active ? f[static_cast<size_t>(q) * m + i] : 0.0;
+    unsigned c = 0, mp = 0;
+    for (unsigned base = 0; base < fs; base += kTP) {
+        const unsigned np = min(static_cast<unsigned>(kTP), fs - base);
+        for (unsigned e = threadIdx.x; e < np * m; e += kTP) {
+            const unsigned t = e / m, i = e % m;
+            tile[e] = f[static_cast<size_t>(order[fo + base + t]) * m + i];
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (unsigned t = 0; t < np; ++t)
+                if (dominates<M, NANAWARE>(tile + t * M, fq)) {
+                    ++c;
+                    mp = base + t; // positions ascend: the last hit is the maximum
+                }
+        }
+        __syncthreads();
+    }
+    if (active && c) {
+        const unsigned left = count[q] - c;
+        count[q] = left;
+        if (left == 0) {
+            rank[q] = level + 1;
+            key[q] = mp;
+            cand[atomicAdd(&meta->ncand, 1u)] = q;
+        }
+    }
+}
+
+// first level: the candidates are the points with no dominator, key 0 (front 0 is in index order, :228-233)
+__global__ void fnds_front0_kernel(unsigned n, const unsigned *count, unsigned *rank, unsigned *key, unsigned *cand, Meta *meta)
+{
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    if (count[q] == 0) {
+        rank[q] = 0;
+        key[q] = 0;
+        cand[atomicAdd(&meta->ncand, 1u)] = q;
+    } else {
+        rank[q] = kUnassigned;
+    }
+}
+
+// close a level: order the candidates by (key, q) and append them to `order` as the next front
+__global__ void __launch_bounds__(1024) fnds_order_kernel(const unsigned *cand, const unsigned *key, unsigned *order,
+                                                          unsigned *front_off_out, Meta *meta, int first)
+{
+    __shared__ unsigned long long s[kOrderCap];
+    if (meta->overflow) return;
+    const unsigned C = meta->ncand;
+    if (!first && meta->front_size == 0) return; // finished earlier
+    if (C > kOrderCap) {
+        if (threadIdx.x == 0) meta->overflow = 1;
+        return;
+    }
+    unsigned P = 1;
+    while (P < C) P <<= 1;
+    for (unsigned i = threadIdx.x; i < P; i += blockDim.x)
+        s[i] = (i < C) ? ((static_cast<unsigned long long>(key[cand[i]]) << 32) | cand[i]) : ~0ull;
+    __syncthreads();
+    for (unsigned k = 2; k <= P; k <<= 1)
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = threadIdx.x; i < P; i += blockDim.x) {
+                const unsigned l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = s[i], b = s[l];
+                    if ((a > b) == up) {
+                        s[i] = b;
+                        s[l] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    const unsigned off = first ? 0u : meta->front_off + meta->front_size;
+    for (unsigned i = threadIdx.x; i < C; i += blockDim.x) order[off + i] = static_cast<unsigned>(s[i] & 0xffffffffu);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned level = first ? 0u : meta->level + 1;
+        if (C) {
+            front_off_out[level] = off;
+            front_off_out[level + 1] = off + C;
+            meta->nfronts = level + 1;
+        }
+        meta->level = level;
+        meta->front_off = off;
+        meta->front_size = C;
+        meta->assigned += C;
+        meta->ncand = 0;
+    }
+}
+
+// big path helpers (the host sorts packed (key, q) with CUB when a level has more than kOrderCap candidates)
+__global__ void pack_keys_kernel(const unsigned *cand, const unsigned *key, unsigned C, unsigned long long *out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) out[i] = (static_cast<unsigned long long>(key[cand[i]]) << 32) | cand[i];
+}
+
+__global__ void unpack_front_kernel(const unsigned long long *sorted, unsigned C, unsigned off, unsigned *order)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) order[off + i] = static_cast<unsigned>(sorted[i] & 0xffffffffu);
+}
+
+__global__ void close_big_level_kernel(unsigned *front_off_out, Meta *meta, int first)
+{
+    const unsigned C = meta->ncand;
+    const unsigned off = first ? 0u : meta->front_off + meta->front_size;
+    const unsigned level = first ? 0u : meta->level + 1;
+    front_off_out[level] = off;
+    front_off_out[level + 1] = off + C;
+    meta->nfronts = level + 1;
+    meta->level = level;
+    meta->front_off = off;
+    meta->front_size = C;
+    meta->assigned += C;
+    meta->ncand = 0;
+    meta->overflow = 0;
+}
+
+// ---- crowding distance ----------------------------------------------------------------------------------------
+__global__ void gather_objective_kernel(const double *f, int m, int obj, const unsigned *order, unsigned n, double *keys,
+                                        unsigned *vals)
+{
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) {
+        const unsigned idx = order ? order[j] : j;
+        keys[j] = f[static_cast<size_t>(idx) * m + obj] + 0.0; // -0.0 -> +0.0 so that the radix order is the numeric order
+        vals[j] = idx;
+    }
+}
+
+// multi_objective.cpp:303-313 for every front (segment) at once.  small_rule: 0 = crowding_distance semantics only
+// (segments of size < 2 untouched), 1 = nsga2.cpp:188-198 (size 1 or 2 -> inf), 2 = sort_population_mo :441-443 (size 1 -> 0)
+__global__ void crowding_accumulate_kernel(const double *keys, const unsigned *vals, const unsigned *seg_of,
+                                           const unsigned *front_off, unsigned n, double *cd)
+{
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned s = seg_of[j], b = front_off[s], e = front_off[s + 1];
+    if (e - b < 2) return;
+    const unsigned idx = vals[j];
+    if (j == b || j == e - 1) {
+        cd[idx] = INFINITY;
+    } else {
+        const double df = keys[e - 1] - keys[b];
+        cd[idx] += (keys[j + 1] - keys[j - 1]) / df;
+    }
+}
+
+__global__ void segment_ids_kernel(const unsigned *front_off, unsigned nfronts, unsigned *seg_of)
+{
+    const unsigned s = blockIdx.x;
+    if (s >= nfronts) return;
+    for (unsigned j = front_off[s] + threadIdx.x; j < front_off[s + 1]; j += blockDim.x) seg_of[j] = s;
+}
+
+__global__ void small_front_rule_kernel(const unsigned *order, const unsigned *front_off, unsigned nfronts, int rule, double *cd)
+{
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nfronts) return;
+    const unsigned b = front_off[s], sz = front_off[s + 1] - b;
+    if (rule == 1 && sz <= 2) {
+        for (unsigned i = 0; i < sz; ++i) cd[order[b + i]] = INFINITY;
+    } else if (rule == 2 && sz == 1) {
+        cd[order[b]] = 0.0;
+    }
+}
+
+__global__ void fill_double_kernel(double *p, size_t n, double v)
+{
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void iota_kernel(unsigned *p, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+__global__ void gather_double_kernel(const double *src, const unsigned *idx, unsigned n, double *dst)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
+__global__ void gather_u32_kernel(const unsigned *src, const unsigned *idx, unsigned n, unsigned *dst)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
+// descending sort keys with the reference's NaN placement (greater_than_f: NaN is "greater" than everything, so NaNs come
+// FIRST in a descending sort): map to an ascending unsigned key
+__global__ void cd_desc_key_kernel(const double *cd, const unsigned *idx, unsigned n, unsigned long long *key)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = cd[idx ? idx[i] : i] + 0.0;
+    unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+    unsigned long long asc = (bits & 0x8000000000000000ull) ? ~bits : (bits | 0x8000000000000000ull); // ascending numeric
+    if (isnan(v)) asc = ~0ull;                                                                          // NaN largest
+    key[i] = ~asc; // descending
+}
+
+__global__ void gather_rows_kernel(const double *f, const unsigned *ord, unsigned sz, int m, double *dst)
+{
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < sz * m) dst[e] = f[static_cast<size_t>(ord[e / m]) * m + e % m];
+}
+
+struct Workspace {
+    pgc_ctx *ctx;
+    std::vector<void *> owned;
+    ~Workspace()
+    {
+        for (void *p : owned) cudaFree(p);
+    }
+    template <class T> int alloc(T **out, size_t count)
+    {
+        void *p = nullptr;
+        PGC_CUDA(cudaMalloc(&p, sizeof(T) * std::max<size_t>(count, 1)));
+        owned.push_back(p);
+        *out = static_cast<T *>(p);
+        return PGC_OK;
+    }
+};
+
+inline unsigned blocks_for(size_t n, unsigned t) { return static_cast<unsigned>((n + t - 1) / t); }
+
+} // namespace
+
+// fast_non_dominated_sorting on device-resident f [n x m]; d_rank / d_order [n], d_front_off [n+1] are device outputs.
+int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned *d_rank, unsigned *d_dom_count,
+                unsigned *d_order, unsigned *d_front_off, unsigned *nfronts_out, cudaStream_t st)
+{
+    PGC_REQUIRE(n_ >= 2, "At least two points are needed for fast_non_dominated_sorting: %zu detected.", n_); // :204-207
+    PGC_REQUIRE(n_ < 0x7fffffffu, "fast_non_dominated_sorting: too many points (%zu)", n_);
+    PGC_REQUIRE(m_ <= static_cast<size_t>(kMaxM), "fast_non_dominated_sorting: at most %d objectives are supported on the device, got %zu", kMaxM, m_);
+    const unsigned n = static_cast<unsigned>(n_);
+    const int m = static_cast<int>(m_);
+    Workspace ws{ctx, {}};
+    unsigned *count, *key, *cand, *flag;
+    Meta *meta;
+    unsigned long long *pk0 = nullptr, *pk1 = nullptr;
+    void *cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    int rc;
+    if ((rc = ws.alloc(&count, n)) || (rc = ws.alloc(&key, n)) || (rc = ws.alloc(&cand, n)) || (rc = ws.alloc(&flag, 1))
+        || (rc = ws.alloc(&meta, 1)))
+        return rc;
+    PGC_CUDA(cudaMemsetAsync(meta, 0, sizeof(Meta), st));
+    PGC_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned), st));
+    bool nanaware = false;
+    if (m > 0) {
+        has_nan_kernel<<<std::min(1024u, blocks_for(n_ * m_, 256)), 256, 0, st>>>(d_f, n_ * m_, flag);
+        unsigned h = 0;
+        PGC_CUDA(cudaMemcpyAsync(&h, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        nanaware = h != 0;
+    }
+    const unsigned gb = blocks_for(n, kTP);
+    using count_fn = void (*)(const double *, unsigned, unsigned *, unsigned *);
+    using peel_fn = void (*)(const double *, unsigned, const unsigned *, unsigned *, unsigned *, unsigned *, unsigned *, Meta *);
+    count_fn count_k = nullptr;
+    peel_fn peel_k = nullptr;
+#define PGC_MO_CASE(MM)                                                                                                \
+    case MM:                                                                                                           \
+        count_k = nanaware ? fnds_count_kernel<MM, true> : fnds_count_kernel<MM, false>;                               \
+        peel_k = nanaware ? fnds_peel_kernel<MM, true> : fnds_peel_kernel<MM, false>;                                  \
+        break;
+    switch (m) {
+        PGC_MO_CASE(0) PGC_MO_CASE(1) PGC_MO_CASE(2) PGC_MO_CASE(3) PGC_MO_CASE(4) PGC_MO_CASE(5) PGC_MO_CASE(6) PGC_MO_CASE(7)
+        PGC_MO_CASE(8)
+    }
+#undef PGC_MO_CASE
+    count_k<<<gb, kTP, 0, st>>>(d_f, n, count, d_dom_count);
+    fnds_front0_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, count, d_rank, key, cand, meta);
+    ctx->launches.fetch_add(3, std::memory_order_relaxed);
+
+    auto big_order = [&](int first) -> int { // order a level with more than kOrderCap candidates through CUB
+        Meta h;
+        PGC_CUDA(cudaMemcpyAsync(&h, meta, sizeof(Meta), cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        const unsigned C = h.ncand;
+        if (!pk0) {
+            int r2;
+            if ((r2 = ws.alloc(&pk0, n)) || (r2 = ws.alloc(&pk1, n))) return r2;
+            PGC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, pk0, pk1, static_cast<int>(n), 0, 64, st));
+            PGC_CUDA(cudaMalloc(&cub_tmp, cub_bytes));
+            ws.owned.push_back(cub_tmp);
+        }
+        pack_keys_kernel<<<blocks_for(C, 256), 256, 0, st>>>(cand, key, C, pk0);
+        size_t bytes = cub_bytes;
+        PGC_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, bytes, pk0, pk1, static_cast<int>(C), 0, 64, st));
+        const unsigned off = first ? 0u : h.front_off + h.front_size;
+        unpack_front_kernel<<<blocks_for(C, 256), 256, 0, st>>>(pk1, C, off, d_order);
+        close_big_level_kernel<<<1, 1, 0, st>>>(d_front_off, meta, first);
+        ctx->launches.fetch_add(5, std::memory_order_relaxed);
+        return PGC_OK;
+    };
+
+    fnds_order_kernel<<<1, 1024, 0, st>>>(cand, key, d_order, d_front_off, meta, 1);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    Meta h;
+    PGC_CUDA(cudaMemcpyAsync(&h, meta, sizeof(Meta), cudaMemcpyDeviceToHost, st));
+    PGC_CUDA(cudaStreamSynchronize(st));
+    if (h.overflow) {
+        if ((rc = big_order(1))) return rc;
+        PGC_CUDA(cudaMemcpyAsync(&h, meta, sizeof(Meta), cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+    }
+    while (h.assigned < n) {
+        if (h.front_size == 0) {
+            set_error("fast_non_dominated_sorting: internal error, empty front with %u of %u points assigned", h.assigned, n);
+            return PGC_ERR_CUDA;
+        }
+        for (int b = 0; b < kBatch; ++b) {
+            peel_k<<<gb, kTP, 0, st>>>(d_f, n, d_order, count, d_rank, key, cand, meta);
+            fnds_order_kernel<<<1, 1024, 0, st>>>(cand, key, d_order, d_front_off, meta, 0);
+        }
+        ctx->launches.fetch_add(2 * kBatch, std::memory_order_relaxed);
+        PGC_CUDA(cudaMemcpyAsync(&h, meta, sizeof(Meta), cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        if (h.overflow) {
+            if ((rc = big_order(0))) return rc;
+            PGC_CUDA(cudaMemcpyAsync(&h, meta, sizeof(Meta), cudaMemcpyDeviceToHost, st));
+            PGC_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    PGC_CUDA(cudaGetLastError());
+    if (nfronts_out) *nfronts_out = h.nfronts;
+    return PGC_OK;
+}
+
+// Crowding distance of every front at once (segments of `d_order` delimited by `d_front_off`), written at the points'
+// own indices in d_cd.  d_order == nullptr: one segment = all n points in index order (plain crowding_distance()).
+int crowding_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, const unsigned *d_order, const unsigned *d_front_off,
+                    unsigned nfronts, int small_rule, double *d_cd, cudaStream_t st)
+{
+    const unsigned n = static_cast<unsigned>(n_);
+    const int m = static_cast<int>(m_);
+    Workspace ws{ctx, {}};
+    double *keys_in, *keys_out;
+    unsigned *vals_in, *vals_out, *seg_of, *one_off = nullptr;
+    int rc;
+    if ((rc = ws.alloc(&keys_in, n)) || (rc = ws.alloc(&keys_out, n)) || (rc = ws.alloc(&vals_in, n)) || (rc = ws.alloc(&vals_out, n))
+        || (rc = ws.alloc(&seg_of, n)))
+        return rc;
+    if (!d_order) {
+        if ((rc = ws.alloc(&one_off, 2))) return rc;
+        const unsigned h[2] = {0u, n};
+        PGC_CUDA(cudaMemcpyAsync(one_off, h, sizeof(h), cudaMemcpyHostToDevice, st));
+        d_front_off = one_off;
+        nfronts = 1;
+    }
+    fill_double_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_cd, n, 0.0);
+    segment_ids_kernel<<<nfronts, 128, 0, st>>>(d_front_off, nfronts, seg_of);
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    PGC_CUDA(cub::DeviceSegmentedSort::StableSortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n),
+                                                       static_cast<int>(nfronts), d_front_off, d_front_off + 1, st));
+    PGC_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    ws.owned.push_back(tmp);
+    for (int obj = 0; obj < m; ++obj) {
+        gather_objective_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_f, m, obj, d_order, n, keys_in, vals_in);
+        size_t bytes = tmp_bytes;
+        PGC_CUDA(cub::DeviceSegmentedSort::StableSortPairs(tmp, bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n),
+                                                           static_cast<int>(nfronts), d_front_off, d_front_off + 1, st));
+        crowding_accumulate_kernel<<<blocks_for(n, 256), 256, 0, st>>>(keys_out, vals_out, seg_of, d_front_off, n, d_cd);
+        ctx->launches.fetch_add(4, std::memory_order_relaxed);
+    }
+    if (small_rule && d_order) {
+        small_front_rule_kernel<<<blocks_for(nfronts, 128), 128, 0, st>>>(d_order, d_front_off, nfronts, small_rule, d_cd);
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    PGC_CUDA(cudaGetLastError());
+    PGC_CUDA(cudaStreamSynchronize(st)); // workspace is freed on return
+    return PGC_OK;
+}
+
+// stable sort of `count` indices (d_idx, in place) by crowding distance descending (greater_than_f order)
+static int sort_by_cd_desc(pgc_ctx *ctx, const double *d_cd, unsigned *d_idx, unsigned count, cudaStream_t st)
+{
+    if (count < 2) return PGC_OK;
+    Workspace ws{ctx, {}};
+    unsigned long long *k0, *k1;
+    unsigned *v1;
+    int rc;
+    if ((rc = ws.alloc(&k0, count)) || (rc = ws.alloc(&k1, count)) || (rc = ws.alloc(&v1, count))) return rc;
+    cd_desc_key_kernel<<<blocks_for(count, 256), 256, 0, st>>>(d_cd, d_idx, count, k0);
+    void *tmp = nullptr;
+    size_t bytes = 0;
+    PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0, k1, d_idx, v1, static_cast<int>(count), 0, 64, st));
+    PGC_CUDA(cudaMalloc(&tmp, bytes ? bytes : 1));
+    ws.owned.push_back(tmp);
+    PGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, k0, k1, d_idx, v1, static_cast<int>(count), 0, 64, st));
+    PGC_CUDA(cudaMemcpyAsync(d_idx, v1, sizeof(unsigned) * count, cudaMemcpyDeviceToDevice, st));
+    PGC_CUDA(cudaStreamSynchronize(st));
+    ctx->launches.fetch_add(3, std::memory_order_relaxed);
+    return PGC_OK;
+}
+
+// select_best_N_mo, multi_objective.cpp:344-396, on device-resident f; d_out receives min(N, n) indices
+int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, size_t N_, unsigned *d_out, unsigned *nout,
+                       cudaStream_t st)
+{
+    const unsigned n = static_cast<unsigned>(n_);
+    if (N_ == 0 || n == 0) { // :346-351
+        *nout = 0;
+        return PGC_OK;
+    }
+    if (n == 1) { // :352-354
+        const unsigned z = 0;
+        PGC_CUDA(cudaMemcpyAsync(d_out, &z, sizeof(z), cudaMemcpyHostToDevice, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        *nout = 1;
+        return PGC_OK;
+    }
+    if (N_ >= n) { // :355-359
+        iota_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_out, n);
+        *nout = n;
+        return PGC_OK;
+    }
+    const unsigned N = static_cast<unsigned>(N_);
+    Workspace ws{ctx, {}};
+    unsigned *rank, *order, *foff;
+    int rc;
+    if ((rc = ws.alloc(&rank, n)) || (rc = ws.alloc(&order, n)) || (rc = ws.alloc(&foff, n + 1))) return rc;
+    unsigned nfronts = 0;
+    if ((rc = fnds_device(ctx, d_f, n, m_, rank, nullptr, order, foff, &nfronts, st))) return rc;
+    std::vector<unsigned> hoff(nfronts + 1);
+    PGC_CUDA(cudaMemcpyAsync(hoff.data(), foff, sizeof(unsigned) * (nfronts + 1), cudaMemcpyDeviceToHost, st));
+    PGC_CUDA(cudaStreamSynchronize(st));
+    unsigned front_id = 0, taken = 0; // whole fronts while they fit, :365-377
+    while (front_id < nfronts && taken + (hoff[front_id + 1] - hoff[front_id]) <= N) {
+        taken += hoff[front_id + 1] - hoff[front_id];
+        ++front_id;
+    }
+    PGC_CUDA(cudaMemcpyAsync(d_out, order, sizeof(unsigned) * taken, cudaMemcpyDeviceToDevice, st));
+    if (taken < N) { // the cut front, by crowding distance descending, :378-394
+        const unsigned b = hoff[front_id], sz = hoff[front_id + 1] - b;
+        double *cd, *fsub;
+        unsigned *idx;
+        if ((rc = ws.alloc(&cd, sz)) || (rc = ws.alloc(&fsub, static_cast<size_t>(sz) * m_)) || (rc = ws.alloc(&idx, sz))) return rc;
+        // crowding_distance() of the front's own fitness list (local indices 0..sz-1 in front order)
+        gather_rows_kernel<<<blocks_for(static_cast<size_t>(sz) * m_, 256), 256, 0, st>>>(d_f, order + b, sz, static_cast<int>(m_), fsub);
+        if ((rc = crowding_device(ctx, fsub, sz, m_, nullptr, nullptr, 1, 0, cd, st))) return rc;
+        iota_kernel<<<blocks_for(sz, 256), 256, 0, st>>>(idx, sz);
+        if ((rc = sort_by_cd_desc(ctx, cd, idx, sz, st))) return rc;
+        gather_u32_kernel<<<blocks_for(N - taken, 256), 256, 0, st>>>(order + b, idx, N - taken, d_out + taken);
+    }
+    PGC_CUDA(cudaGetLastError());
+    PGC_CUDA(cudaStreamSynchronize(st));
+    *nout = N;
+    return PGC_OK;
+}
+
+// sort_population_mo, multi_objective.cpp:425-465: indices by (rank ascending, crowding distance descending)
+int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned *d_out, cudaStream_t st)
+{
+    const unsigned n = static_cast<unsigned>(n_);
+    if (n == 0) return PGC_OK;
+    if (n == 1) {
+        const unsigned z = 0;
+        PGC_CUDA(cudaMemcpyAsync(d_out, &z, sizeof(z), cudaMemcpyHostToDevice, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        return PGC_OK;
+    }
+    Workspace ws{ctx, {}};
+    unsigned *rank, *order, *foff, *rk_in, *rk_out, *v_out;
+    double *cd;
+    int rc;
+    if ((rc = ws.alloc(&rank, n)) || (rc = ws.alloc(&order, n)) || (rc = ws.alloc(&foff, n + 1)) || (rc = ws.alloc(&cd, n))
+        || (rc = ws.alloc(&rk_in, n)) || (rc = ws.alloc(&rk_out, n)) || (rc = ws.alloc(&v_out, n)))
+        return rc;
+    unsigned nfronts = 0;
+    if ((rc = fnds_device(ctx, d_f, n, m_, rank, nullptr, order, foff, &nfronts, st))) return rc;
+    if ((rc = crowding_device(ctx, d_f, n, m_, order, foff, nfronts, 2, cd, st))) return rc;
+    iota_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_out, n);
+    if ((rc = sort_by_cd_desc(ctx, cd, d_out, n, st))) return rc;
+    gather_u32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(rank, d_out, n, rk_in);
+    void *tmp = nullptr;
+    size_t bytes = 0;
+    PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, rk_in, rk_out, d_out, v_out, static_cast<int>(n), 0, 32, st));
+    PGC_CUDA(cudaMalloc(&tmp, bytes ? bytes : 1));
+    ws.owned.push_back(tmp);
+    PGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, rk_in, rk_out, d_out, v_out, static_cast<int>(n), 0, 32, st));
+    PGC_CUDA(cudaMemcpyAsync(d_out, v_out, sizeof(unsigned) * n, cudaMemcpyDeviceToDevice, st));
+    PGC_CUDA(cudaStreamSynchronize(st));
+    return PGC_OK;
+}
+
+} // namespace pgc

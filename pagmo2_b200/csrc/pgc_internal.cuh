@@ -145,6 +145,12 @@ int cec2014_create(pgc_problem *p, const pgc_problem_desc *d);
 int cec2014_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
 void cec2014_destroy(pgc_problem *p);
 int cec2014_phase_cycles(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, unsigned long long *out);
+int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, unsigned *d_rank, unsigned *d_dom_count, unsigned *d_order,
+                unsigned *d_front_off, unsigned *nfronts_out, cudaStream_t st);
+int crowding_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const unsigned *d_order, const unsigned *d_front_off,
+                    unsigned nfronts, int small_rule, double *d_cd, cudaStream_t st);
+int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, size_t N, unsigned *d_out, unsigned *nout, cudaStream_t st);
+int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, unsigned *d_out, cudaStream_t st);
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops_out);

@@ -1,0 +1,113 @@
+"""GPU parity of the multi-objective utilities (fast_non_dominated_sorting, crowding_distance, select_best_N_mo,
+sort_population_mo) through the C ABI against the oracle: ranks, dominator counts and fronts INCLUDING the order inside
+every front must be bit-exact; crowding distances bit-exact on tie-free fronts; selections exact on distinct keys
+(the reference leaves the order of equal keys unspecified)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+EX1 = np.array([[0, 7], [1, 5], [2, 3], [4, 2], [7, 1], [10, 0], [2, 6], [4, 4], [10, 2], [6, 6], [9, 5]], dtype=float)
+
+
+def same_fnds(a, b):
+    return (np.array_equal(a["rank"], b["rank"]) and np.array_equal(a["dom_count"], b["dom_count"])
+            and len(a["fronts"]) == len(b["fronts"]) and all(np.array_equal(x, y) for x, y in zip(a["fronts"], b["fronts"])))
+
+
+def test_reference_known_answers(ctx):
+    # reference tests/multi_objective.cpp:96-209
+    r = ctx.fnds(EX1)
+    assert [list(x) for x in r["fronts"]] == [[0, 1, 2, 3, 4, 5], [6, 7, 8], [9, 10]]
+    assert list(r["dom_count"]) == [0, 0, 0, 0, 0, 0, 2, 2, 3, 5, 5] and list(r["rank"]) == [0, 0, 0, 0, 0, 0, 1, 1, 1, 2, 2]
+    r = ctx.fnds(np.array([[1, 2, 3], [-2, 3, 7], [-1, -2, -3], [0, 0, 0]], dtype=float))
+    assert [list(x) for x in r["fronts"]] == [[1, 2], [3], [0]] and list(r["rank"]) == [2, 0, 0, 1]
+    r = ctx.fnds(np.empty((4, 0)))  # {{}, {}, {}, {}}: everything in front 0
+    assert [list(x) for x in r["fronts"]] == [[0, 1, 2, 3]]
+    inf = np.inf
+    assert list(ctx.crowding_distance(np.array([[0, 0], [-1, 1], [2, -2]], dtype=float))) == [2, inf, inf]
+    assert list(ctx.crowding_distance(np.array([[0.25, 0.25, 0.25], [-1, 1, 2], [2, -2, -2]], dtype=float))) == [3, inf, inf]
+    assert list(ctx.crowding_distance(np.array([[0, 0], [1, -1], [2, -2], [4, -4]], dtype=float))) == [inf, 1.0, 1.5, inf]
+    assert list(ctx.crowding_distance(np.zeros((2, 2)))) == [inf, inf]
+    assert list(ctx.sort_population_mo(np.array([[0.25, 0.25], [-1, 1], [2, -2]]))) == [1, 2, 0]
+    assert list(ctx.sort_population_mo(EX1)) == [0, 5, 4, 3, 1, 2, 6, 8, 7, 9, 10]
+    assert list(ctx.sort_population_mo(np.arange(11, dtype=float)[:, None])) == list(range(11))
+    assert list(ctx.sort_population_mo(np.array([[1.0, 5, 2, 3]]))) == [0] and len(ctx.sort_population_mo(np.empty((0, 2)))) == 0
+
+
+def test_errors(ctx):
+    from pagmo2_b200 import capi
+    for bad in (np.zeros((1, 3)), np.empty((0, 2))):
+        with pytest.raises(capi.PgcError):
+            ctx.fnds(bad)
+    for bad in (np.zeros((1, 2)), np.zeros((2, 1)), np.empty((2, 0))):
+        with pytest.raises(capi.PgcError):
+            ctx.crowding_distance(bad)
+
+
+@pytest.mark.parametrize("n,m", [(2, 2), (17, 2), (255, 2), (256, 3), (257, 3), (1000, 2), (5000, 2), (4096, 3), (3000, 4), (2000, 8),
+                                 (300, 1)])
+def test_fnds_bit_exact_vs_oracle(ctx, orc, n, m):
+    rng = np.random.default_rng(n * 10 + m)
+    f = rng.uniform(0, 1, (n, m))
+    assert same_fnds(ctx.fnds(f), orc.fnds(f))
+    # duplicated points and shared coordinates (ties in single objectives) change nothing about exactness
+    g = np.round(f * 8) / 8
+    assert same_fnds(ctx.fnds(g), orc.fnds(g))
+    # NaN-aware dominance (custom_comparisons.hpp:54-88)
+    h = f.copy()
+    h[rng.integers(0, n, max(1, n // 50)), rng.integers(0, m, max(1, n // 50))] = np.nan
+    assert same_fnds(ctx.fnds(h), orc.fnds(h))
+
+
+def test_fnds_converged_population_big_fronts(ctx, orc):
+    """A population sitting on two fronts (the NSGA-II end game): fronts larger than the shared-memory sort."""
+    rng = np.random.default_rng(77)
+    n = 12000
+    t = rng.uniform(0, 1, n)
+    f = np.stack([t, 1 - t], axis=1)
+    f[n // 2:] += 0.25
+    assert same_fnds(ctx.fnds(f), orc.fnds(f))
+
+
+@pytest.mark.parametrize("n,m", [(3, 2), (100, 2), (1000, 3), (5000, 2)])
+def test_crowding_select_sort_vs_oracle(ctx, orc, n, m):
+    rng = np.random.default_rng(n + m)
+    f = rng.uniform(0, 1, (n, m))
+    assert np.array_equal(ctx.crowding_distance(f), orc.crowding_distance(f))  # tie-free keys: bit exact
+    ro = orc.fnds(f)
+    cd = np.zeros(n)
+    for fi in ro["fronts"]:
+        cd[fi] = 0.0 if len(fi) == 1 else orc.crowding_distance(f[fi])
+    so, sg = orc.sort_population_mo(f), ctx.sort_population_mo(f)
+    assert np.array_equal(sg, so)  # both stable: identical, including the +inf ties
+    for N in (0, 1, n // 3, n // 2, n - 1, n, n + 3):
+        assert np.array_equal(ctx.select_best_N_mo(f, N), orc.select_best_N_mo(f, N)), N
+
+
+def test_nsga2_scale_population(ctx, orc):
+    """BASELINE cfg3 scale (2N = 131072 points would take the O(N^2) CPU oracle minutes): check 65536 points through
+    size-independent properties and a 8192-point prefix against the oracle."""
+    rng = np.random.default_rng(31)
+    n, m = 65536, 2
+    f = rng.uniform(0, 1, (n, m))
+    r = ctx.fnds(f)
+    rank = r["rank"]
+    assert sorted(np.concatenate(r["fronts"]).tolist()) == list(range(n))            # fronts partition the population
+    assert all((rank[fr] == k).all() for k, fr in enumerate(r["fronts"]))             # ranks agree with fronts
+    assert np.array_equal(r["fronts"][0], np.flatnonzero(r["dom_count"] == 0))        # front 0 ascending, no dominators
+    # nobody inside a front dominates anybody else there (sampled), and every point of front k>0 has a dominator in k-1
+    for k in (0, 1, len(r["fronts"]) // 2):
+        fr = r["fronts"][k][:400]
+        a = f[fr]
+        dom = (a[:, None, :] <= a[None, :, :]).all(-1) & (a[:, None, :] < a[None, :, :]).any(-1)
+        assert not dom.any()
+        if k:
+            prev = f[r["fronts"][k - 1]]
+            for q in fr[:50]:
+                assert ((prev <= f[q]).all(-1) & (prev < f[q]).any(-1)).any()
+    sub = f[:8192]
+    assert same_fnds(ctx.fnds(sub), orc.fnds(sub))
+    best = ctx.select_best_N_mo(f, n // 2)
+    assert len(best) == n // 2 and len(set(best.tolist())) == n // 2
+    assert rank[best].max() <= rank[np.setdiff1d(np.arange(n), best)].min()           # no worse rank kept over a better one

@@ -169,3 +169,43 @@ def test_mo_restatement_is_bit_exact_vs_reference(orc, ref):
             p = ref.problem("dtlz", pid, dim, fdim, alpha)
             xs = rng.uniform(0, 1, (64, dim))
             assert np.array_equal(p.fitness_loop(xs), orc.dtlz(pid, xs, fdim, alpha)), (pid, dim, fdim)
+
+
+# ---------------------------------------------------------------- multi-objective utilities
+FNDS_EX1 = np.array([[0, 7], [1, 5], [2, 3], [4, 2], [7, 1], [10, 0], [2, 6], [4, 4], [10, 2], [6, 6], [9, 5]], dtype=float)
+
+
+def test_mo_utils_known_answers(orc):
+    # reference tests/multi_objective.cpp:96-120 (fronts, dom_count, ranks), :160-176 (crowding), :193-201 (sorting)
+    r = orc.fnds(FNDS_EX1)
+    assert [list(x) for x in r["fronts"]] == [[0, 1, 2, 3, 4, 5], [6, 7, 8], [9, 10]]
+    assert list(r["dom_count"]) == [0, 0, 0, 0, 0, 0, 2, 2, 3, 5, 5]
+    assert list(r["rank"]) == [0, 0, 0, 0, 0, 0, 1, 1, 1, 2, 2]
+    r = orc.fnds(np.array([[1, 2, 3], [-2, 3, 7], [-1, -2, -3], [0, 0, 0]], dtype=float))
+    assert [list(x) for x in r["fronts"]] == [[1, 2], [3], [0]] and list(r["dom_count"]) == [2, 0, 0, 1]
+    inf = np.inf
+    assert list(orc.crowding_distance(np.array([[0, 0], [-1, 1], [2, -2]], dtype=float))) == [2, inf, inf]
+    assert list(orc.crowding_distance(np.array([[0, 0, 0], [-1, 1, 2], [2, -2, -2]], dtype=float))) == [3, inf, inf]
+    assert list(orc.crowding_distance(np.array([[0, 0], [1, -1], [2, -2], [4, -4]], dtype=float))) == [inf, 1.0, 1.5, inf]
+    assert list(orc.crowding_distance(np.zeros((2, 2)))) == [inf, inf]
+    assert list(orc.sort_population_mo(np.array([[0.25, 0.25], [-1, 1], [2, -2]]))) == [1, 2, 0]
+    assert list(orc.sort_population_mo(FNDS_EX1)) == [0, 5, 4, 3, 1, 2, 6, 8, 7, 9, 10]
+    assert list(orc.sort_population_mo(np.arange(11, dtype=float)[:, None])) == list(range(11))
+
+
+def test_mo_utils_restatement_vs_reference(orc, ref):
+    rng = np.random.default_rng(3)
+    for n, m in ((11, 2), (200, 2), (500, 3), (300, 4), (64, 1), (1000, 2)):
+        f = rng.uniform(0, 1, (n, m))
+        if n == 300:
+            f[::7] = f[3]  # duplicated points: never dominate each other, same front
+        a, b = orc.fnds(f), ref.fnds(f)
+        assert np.array_equal(a["rank"], b["rank"]) and np.array_equal(a["dom_count"], b["dom_count"])
+        assert len(a["fronts"]) == len(b["fronts"]) and all(np.array_equal(x, y) for x, y in zip(a["fronts"], b["fronts"]))
+        if m >= 2 and n != 300:
+            assert np.array_equal(orc.crowding_distance(f), ref.crowding_distance(f))
+            so, sr = orc.sort_population_mo(f), ref.sort_population_mo(f)
+            assert sorted(so) == list(range(n)) and np.array_equal(b["rank"][so], b["rank"][sr])
+            for N in (1, n // 3, n // 2, n - 1, n, n + 5):
+                x, y = orc.select_best_N_mo(f, N), ref.select_best_N_mo(f, N)
+                assert len(x) == len(y) and np.array_equal(b["rank"][x], b["rank"][y])
