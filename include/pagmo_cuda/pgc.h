@@ -145,6 +145,27 @@ PGC_API int pgc_select_best_N_mo_device(pgc_ctx *ctx, const double *d_f, size_t 
 /* sort_population_mo (:425-465): indices by (rank ascending, crowding distance descending), stable. */
 PGC_API int pgc_sort_population_mo_host(pgc_ctx *ctx, const double *f, size_t n, size_t m, size_t *out);
 
+/* ---- generation operators on a counter-based Philox stream --------------------------------------------------------
+ * Every random draw is u01(seed, tag, generation, index, slot) = Philox4x32-10 with counter {slot, index, generation, tag}
+ * and key {seed}; (word1:word0 >> 11) * 2^-53.  Tags: 1/2 = the two NSGA-II shuffles, 3 = NSGA-II variation (index = group
+ * of 4), 4 = DE family, 5 = PSO, 6 = sga, 7 = population init.  A CPU restatement consuming the same values reproduces the
+ * device results (tests/: "parity on injected draws"). */
+PGC_API int pgc_philox_u01(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot, double *out);
+/* permutation of 0..n-1: stable argsort of the keys u64(seed, tag, generation, i, 0) (stands in for std::shuffle,
+ * nsga2.cpp:180-181) */
+PGC_API int pgc_philox_permutation_device(pgc_ctx *ctx, size_t n, uint64_t seed, uint32_t tag, uint32_t generation,
+                                          uint32_t *d_perm, void *stream);
+/* nsga2.cpp:215-239: per group of 4, tournament x2 + SBX + polynomial mutation x2 on each shuffle; children [NP x nx].
+ * (genetic_operators.cpp:71-144,148-197,200-211).  Continuous decision variables only. */
+PGC_API int pgc_nsga2_variation_device(pgc_ctx *ctx, const double *d_x, const uint32_t *d_rank, const double *d_cd, size_t NP,
+                                       size_t nx, const double *d_lb, const double *d_ub, const uint32_t *d_shuffle1,
+                                       const uint32_t *d_shuffle2, double cr, double eta_c, double m, double eta_m, uint64_t seed,
+                                       uint32_t generation, double *d_children, void *stream);
+/* nsga2::evolve (nsga2.cpp:91-307) on a device-resident population: `gens` generations of shuffle, FNDS + crowding,
+ * variation, batch evaluation, select_best_N_mo; d_x [NP x nx] and d_f [NP x nobj] are updated in place. */
+PGC_API int pgc_nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP, unsigned gens, double cr, double eta_c,
+                                    double m, double eta_m, uint64_t seed, uint32_t first_generation, void *stream);
+
 /* Debug/profiling aid for the CEC2014 stage kernel: same evaluation with clock64() phase counters, summed over all
  * warp-tiles and stages.  out7 = {load, weight pass, token wait, GEMM, z store, epilogue} cycles, warp-tiles. */
 PGC_API int pgc_debug_cec2014_phase_cycles(pgc_problem *prob, const double *d_dvs, size_t n, double *d_fvs, uint64_t *out7);

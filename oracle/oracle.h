@@ -46,6 +46,18 @@ int oracle_crowding_distance(const double *f, size_t n, size_t m, double *out);
 int oracle_select_best_N_mo(const double *f, size_t n, size_t m, size_t N, size_t *out, size_t *nout);
 int oracle_sort_population_mo(const double *f, size_t n, size_t m, size_t *out);
 
+/* ---- Philox draws and NSGA-II generation operators (philox.h, restate_nsga2.c) ---- */
+void oracle_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+double oracle_philox_u01_at(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot);
+int oracle_philox_perm(size_t n, uint64_t seed, uint32_t tag, uint32_t generation, size_t *perm);
+int oracle_nsga2_variation(const double *x, const size_t *rank, const double *cd, size_t NP, size_t nx, const double *lb,
+                           const double *ub, const size_t *sh1, const size_t *sh2, double cr, double eta_c, double m, double eta_m,
+                           uint64_t seed, uint32_t generation, double *children);
+int oracle_nsga2_rank_crowding(const double *f, size_t NP, size_t nobj, size_t *rank, double *cd);
+int oracle_nsga2_evolve(int family, unsigned prob_id, size_t nx, size_t nobj, unsigned alpha, const double *lb, const double *ub,
+                        double *x, double *f, size_t NP, unsigned gens, double cr, double eta_c, double m, double eta_m, uint64_t seed,
+                        uint32_t first_generation);
+
 #ifdef __cplusplus
 }
 #endif

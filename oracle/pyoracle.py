@@ -146,6 +146,55 @@ class Oracle:
             raise ValueError("oracle_sort_population_mo failed")
         return out[: f.shape[0]].astype(np.int64)
 
+    # ---- Philox draws and NSGA-II operators (restate_nsga2.c) ----
+    def philox_raw(self, ctr, key):
+        c = (C.c_uint32 * 4)(*ctr)
+        k = (C.c_uint32 * 2)(*key)
+        o = (C.c_uint32 * 4)()
+        self.lib.oracle_philox_raw(c, k, o)
+        return list(o)
+
+    def philox_u01(self, seed, tag, generation, index, slot) -> float:
+        self.lib.oracle_philox_u01_at.restype = C.c_double
+        return self.lib.oracle_philox_u01_at(C.c_uint64(seed), C.c_uint32(tag), C.c_uint32(generation), C.c_uint32(index), C.c_uint32(slot))
+
+    def philox_perm(self, n, seed, tag, generation) -> np.ndarray:
+        out = np.empty(max(n, 1), dtype=np.uint64)
+        self.lib.oracle_philox_perm(C.c_size_t(n), C.c_uint64(seed), C.c_uint32(tag), C.c_uint32(generation), _sp(out))
+        return out[:n].astype(np.int64)
+
+    def nsga2_rank_crowding(self, f):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        rank = np.empty(f.shape[0], dtype=np.uint64)
+        cd = np.empty(f.shape[0])
+        if self.lib.oracle_nsga2_rank_crowding(_dp(f), C.c_size_t(f.shape[0]), C.c_size_t(f.shape[1]), _sp(rank), _dp(cd)):
+            raise ValueError("oracle_nsga2_rank_crowding failed")
+        return rank.astype(np.int64), cd
+
+    def nsga2_variation(self, x, rank, cd, lb, ub, sh1, sh2, cr, eta_c, m, eta_m, seed, generation):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        NP, nx = x.shape
+        r = np.ascontiguousarray(rank, dtype=np.uint64)
+        s1, s2 = np.ascontiguousarray(sh1, dtype=np.uint64), np.ascontiguousarray(sh2, dtype=np.uint64)
+        cd, lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (cd, lb, ub))
+        out = np.empty((NP, nx))
+        if self.lib.oracle_nsga2_variation(_dp(x), _sp(r), _dp(cd), C.c_size_t(NP), C.c_size_t(nx), _dp(lb), _dp(ub), _sp(s1), _sp(s2),
+                                           C.c_double(cr), C.c_double(eta_c), C.c_double(m), C.c_double(eta_m), C.c_uint64(seed),
+                                           C.c_uint32(generation), _dp(out)):
+            raise ValueError("oracle_nsga2_variation failed")
+        return out
+
+    def nsga2_evolve(self, family, prob_id, nobj, alpha, lb, ub, x, f, gens, cr, eta_c, m, eta_m, seed, first_generation=0):
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C")
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        fam = {"zdt": 8, "dtlz": 9}[family]
+        if self.lib.oracle_nsga2_evolve(C.c_int(fam), C.c_uint(prob_id), C.c_size_t(x.shape[1]), C.c_size_t(nobj), C.c_uint(alpha), _dp(lb),
+                                        _dp(ub), _dp(x), _dp(f), C.c_size_t(x.shape[0]), C.c_uint(gens), C.c_double(cr), C.c_double(eta_c),
+                                        C.c_double(m), C.c_double(eta_m), C.c_uint64(seed), C.c_uint32(first_generation)):
+            raise ValueError("oracle_nsga2_evolve failed")
+        return x, f
+
     def cec2014(self, func: int, xs: np.ndarray, tables=None, nthreads: int = 1) -> np.ndarray:
         xs = np.ascontiguousarray(xs, dtype=np.float64)
         n, d = xs.shape
@@ -206,6 +255,22 @@ class RefProblem:
         f = np.empty((n, self.nf))
         self._ref._check(self._ref.lib.ref_thread_bfe(self._h, _dp(xs), C.c_size_t(n), _dp(f), C.c_int(nthreads)))
         return f
+
+    def evolve(self, algo: str, pop_size: int, gens: int, pop_seed: int = 1, algo_seed: int = 2, use_bfe: bool = False,
+               nthreads: int = 0):
+        """Unmodified reference algorithm on a fresh population: returns (seconds of evolve(), x, f, fevals)."""
+        import os
+        x = np.empty((pop_size, self.nx))
+        f = np.empty((pop_size, self.nf))
+        secs = C.c_double()
+        fe = C.c_ulonglong()
+        if nthreads > 0:
+            os.environ["ORACLE_TBB_THREADS"] = str(nthreads)
+        self._ref.lib.ref_evolve.argtypes = [C.c_void_p, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_int,
+                                             C.POINTER(C.c_double), c_double_p, c_double_p, C.POINTER(C.c_ulonglong)]
+        self._ref._check(self._ref.lib.ref_evolve(self._h, algo.encode(), pop_size, gens, pop_seed, algo_seed, int(use_bfe),
+                                                  C.byref(secs), _dp(x), _dp(f), C.byref(fe)))
+        return secs.value, x, f, fe.value
 
     def default_bfe(self, xs: np.ndarray, nthreads: int = 0) -> np.ndarray:
         xs = np.ascontiguousarray(xs, dtype=np.float64)

@@ -73,6 +73,8 @@ struct threads_env_guard {
     ~threads_env_guard() { unsetenv("ORACLE_TBB_THREADS"); }
 };
 
+extern "C" void ref_set_error(const char *msg) { g_err = msg; }
+
 extern "C" {
 
 const char *ref_last_error(void) { return g_err.c_str(); }

@@ -56,6 +56,12 @@ int ref_select_best_N_mo(const double *f, size_t n, size_t m, size_t N, size_t *
 int ref_ideal(const double *f, size_t n, size_t m, double *out);
 int ref_nadir(const double *f, size_t n, size_t m, double *out);
 
+/* ---- unmodified reference algorithms (ref_algos.cpp): evolve a fresh population(prob, pop_size, pop_seed) for `gens`
+ * generations with reference default parameters; returns the wall time of evolve() and the final population.
+ * algo: "nsga2" (nsga2.cpp:91-307; thread_bfe when use_bfe), "de", "de1220", "sade", "pso", "pso_gen". */
+int ref_evolve(ref_problem *p, const char *algo, unsigned pop_size, unsigned gens, unsigned pop_seed, unsigned algo_seed,
+               int use_bfe, double *seconds, double *x_out, double *f_out, unsigned long long *fevals);
+
 #ifdef __cplusplus
 }
 #endif

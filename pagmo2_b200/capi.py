@@ -85,6 +85,12 @@ def lib():
         L.pgc_fnds_device.argtypes = [vp, vp, sz, sz, vp, vp, vp, vp, u32p, vp]
         L.pgc_crowding_fronts_device.argtypes = [vp, vp, sz, sz, vp, vp, C.c_uint32, C.c_int, vp, vp]
         L.pgc_select_best_N_mo_device.argtypes = [vp, vp, sz, sz, sz, vp, u32p, vp]
+        L.pgc_philox_u01.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, dp]
+        L.pgc_philox_permutation_device.argtypes = [vp, sz, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp]
+        L.pgc_nsga2_variation_device.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double,
+                                                 C.c_double, C.c_uint64, C.c_uint32, vp, vp]
+        L.pgc_nsga2_evolve_device.argtypes = [vp, vp, vp, sz, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64,
+                                              C.c_uint32, vp]
         L.pgc_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
         L.pgc_measure_fp64_mma_peak.argtypes = [vp, C.c_int, dp]
         _lib = L
@@ -198,6 +204,30 @@ class Context:
         check(lib().pgc_sort_population_mo_host(self._h, f.ctypes.data_as(C.c_void_p), n, m, out.ctypes.data_as(C.POINTER(C.c_size_t))))
         return out[:n].astype(np.int64)
 
+    # ---- generation operators ----
+    def philox_permutation(self, n: int, seed: int, tag: int, generation: int) -> np.ndarray:
+        d = self.malloc(4 * max(n, 1))
+        check(lib().pgc_philox_permutation_device(self._h, n, seed, tag, generation, C.c_void_p(d), None))
+        out = self.from_device(d, (n,), dtype=np.uint32)
+        self.free(d)
+        return out.astype(np.int64)
+
+    def nsga2_variation(self, x, rank, cd, lb, ub, sh1, sh2, cr, eta_c, m, eta_m, seed, generation) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        NP, nx = x.shape
+        bufs = [self.to_device(x), self.to_device(np.ascontiguousarray(rank, dtype=np.uint32)),
+                self.to_device(np.ascontiguousarray(cd, dtype=np.float64)), self.to_device(np.ascontiguousarray(lb, dtype=np.float64)),
+                self.to_device(np.ascontiguousarray(ub, dtype=np.float64)), self.to_device(np.ascontiguousarray(sh1, dtype=np.uint32)),
+                self.to_device(np.ascontiguousarray(sh2, dtype=np.uint32)), self.malloc(8 * NP * nx)]
+        try:
+            check(lib().pgc_nsga2_variation_device(self._h, bufs[0], bufs[1], bufs[2], NP, nx, bufs[3], bufs[4], bufs[5], bufs[6], cr, eta_c,
+                                                   m, eta_m, seed, generation, bufs[7], None))
+            self.synchronize()
+            return self.from_device(bufs[7], (NP, nx))
+        finally:
+            for b in bufs:
+                self.free(b)
+
     def fp64_peak_tflops(self, iters: int = 4096) -> float:
         t = C.c_double()
         check(lib().pgc_measure_fp64_peak(self._h, iters, C.byref(t)))
@@ -272,6 +302,19 @@ class Problem:
         check(lib().pgc_debug_cec2014_phase_cycles(self._h, C.c_void_p(d_dvs), n, C.c_void_p(d_fvs), out))
         names = ["load", "weight", "token_wait", "gemm", "store_z", "epilogue", "warp_tiles"]
         return dict(zip(names, [int(v) for v in out]))
+
+    def nsga2_evolve(self, x: np.ndarray, f: np.ndarray, gens: int, cr=0.95, eta_c=10., m=0.01, eta_m=50., seed=0, first_generation=0):
+        """nsga2::evolve on the device: returns the evolved (x, f)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        NP = x.shape[0]
+        dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
+        try:
+            check(lib().pgc_nsga2_evolve_device(self._h, dx, df, NP, gens, cr, eta_c, m, eta_m, seed, first_generation, None))
+            return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape)
+        finally:
+            self.ctx.free(dx)
+            self.ctx.free(df)
 
     def eval_host_into(self, dvs: np.ndarray, fvs: np.ndarray):
         n = dvs.size // self.nx

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "pgc_internal.cuh"
+#include "philox.cuh"
 
 namespace pgc
 {
@@ -198,7 +199,7 @@ int fp64_peak(pgc_ctx *ctx, int iters, double *tflops)
     return PGC_OK;
 }
 
-static int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t s)
+int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t s)
 {
     switch (p->desc.family) {
         case PGC_RASTRIGIN:
@@ -273,6 +274,12 @@ int pgc_ctx_create(int device, pgc_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     PGC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    { // keep the stream-ordered pool warm: scratch of the level loops comes from cudaMallocAsync
+        cudaMemPool_t pool;
+        PGC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;
+        PGC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     for (auto &s : ctx->copy_stream) PGC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (int i = 0; i < pgc_ctx::kRing; ++i) {
         PGC_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
@@ -632,6 +639,44 @@ int pgc_sort_population_mo_host(pgc_ctx *ctx, const double *f, size_t n, size_t 
     if ((rc = sort_population_device(ctx, df.as<double>(), n, m, dout.as<unsigned>(), ctx->stream))) return rc;
     PGC_CUDA(cudaStreamSynchronize(ctx->stream));
     return indices_out(dout, n, out);
+}
+
+// ---- generation operators ------------------------------------------------------------------------------------------
+int pgc_philox_u01(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot, double *out)
+{
+    PGC_REQUIRE(out, "pgc_philox_u01: null output");
+    *out = philox_u01(seed, tag, generation, index, slot);
+    return PGC_OK;
+}
+
+int pgc_philox_permutation_device(pgc_ctx *ctx, size_t n, uint64_t seed, uint32_t tag, uint32_t generation, uint32_t *d_perm, void *stream)
+{
+    PGC_REQUIRE(ctx && (d_perm || n == 0), "pgc_philox_permutation_device: null argument");
+    if (n == 0) return PGC_OK;
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return philox_permutation_device(ctx, static_cast<unsigned>(n), seed, tag, generation, d_perm,
+                                     stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int pgc_nsga2_variation_device(pgc_ctx *ctx, const double *d_x, const uint32_t *d_rank, const double *d_cd, size_t NP, size_t nx,
+                               const double *d_lb, const double *d_ub, const uint32_t *d_shuffle1, const uint32_t *d_shuffle2,
+                               double cr, double eta_c, double m, double eta_m, uint64_t seed, uint32_t generation,
+                               double *d_children, void *stream)
+{
+    PGC_REQUIRE(ctx && d_x && d_rank && d_cd && d_lb && d_ub && d_shuffle1 && d_shuffle2 && d_children, "pgc_nsga2_variation_device: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return nsga2_variation_device(ctx, d_x, d_rank, d_cd, static_cast<unsigned>(NP), static_cast<unsigned>(nx), d_lb, d_ub, d_shuffle1,
+                                  d_shuffle2, cr, eta_c, m, eta_m, seed, generation, d_children,
+                                  stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int pgc_nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP, unsigned gens, double cr, double eta_c, double m,
+                            double eta_m, uint64_t seed, uint32_t first_generation, void *stream)
+{
+    PGC_REQUIRE(prob && d_x && d_f, "pgc_nsga2_evolve_device: null argument");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    return nsga2_evolve_device(prob, d_x, d_f, static_cast<unsigned>(NP), gens, cr, eta_c, m, eta_m, seed, first_generation,
+                               problem_eval_device, stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
 }
 
 int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out)

@@ -336,20 +336,31 @@ __global__ void gather_rows_kernel(const double *f, const unsigned *ord, unsigne
     if (e < sz * m) dst[e] = f[static_cast<size_t>(ord[e / m]) * m + e % m];
 }
 
+// Stream-ordered scratch from the device's memory pool (kept warm: pgc_ctx_create sets the release threshold to
+// "never"), so the level loop does not pay cudaMalloc / cudaFree (tens of ms each on a busy box) per call.
 struct Workspace {
     pgc_ctx *ctx;
+    cudaStream_t st;
     std::vector<void *> owned;
+    Workspace(pgc_ctx *c, cudaStream_t s) : ctx(c), st(s) {}
     ~Workspace()
     {
-        for (void *p : owned) cudaFree(p);
+        for (void *p : owned) cudaFreeAsync(p, st);
+    }
+    int alloc_bytes(void **out, size_t bytes)
+    {
+        void *p = nullptr;
+        PGC_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, st));
+        owned.push_back(p);
+        *out = p;
+        return PGC_OK;
     }
     template <class T> int alloc(T **out, size_t count)
     {
         void *p = nullptr;
-        PGC_CUDA(cudaMalloc(&p, sizeof(T) * std::max<size_t>(count, 1)));
-        owned.push_back(p);
+        int rc = alloc_bytes(&p, sizeof(T) * std::max<size_t>(count, 1));
         *out = static_cast<T *>(p);
-        return PGC_OK;
+        return rc;
     }
 };
 
@@ -366,7 +377,7 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
     PGC_REQUIRE(m_ <= static_cast<size_t>(kMaxM), "fast_non_dominated_sorting: at most %d objectives are supported on the device, got %zu", kMaxM, m_);
     const unsigned n = static_cast<unsigned>(n_);
     const int m = static_cast<int>(m_);
-    Workspace ws{ctx, {}};
+    Workspace ws(ctx, st);
     unsigned *count, *key, *cand, *flag;
     Meta *meta;
     unsigned long long *pk0 = nullptr, *pk1 = nullptr;
@@ -414,8 +425,7 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
             int r2;
             if ((r2 = ws.alloc(&pk0, n)) || (r2 = ws.alloc(&pk1, n))) return r2;
             PGC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, pk0, pk1, static_cast<int>(n), 0, 64, st));
-            PGC_CUDA(cudaMalloc(&cub_tmp, cub_bytes));
-            ws.owned.push_back(cub_tmp);
+            if ((r2 = ws.alloc_bytes(&cub_tmp, cub_bytes))) return r2;
         }
         pack_keys_kernel<<<blocks_for(C, 256), 256, 0, st>>>(cand, key, C, pk0);
         size_t bytes = cub_bytes;
@@ -467,7 +477,7 @@ int crowding_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, const
 {
     const unsigned n = static_cast<unsigned>(n_);
     const int m = static_cast<int>(m_);
-    Workspace ws{ctx, {}};
+    Workspace ws(ctx, st);
     double *keys_in, *keys_out;
     unsigned *vals_in, *vals_out, *seg_of, *one_off = nullptr;
     int rc;
@@ -487,8 +497,7 @@ int crowding_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, const
     size_t tmp_bytes = 0;
     PGC_CUDA(cub::DeviceSegmentedSort::StableSortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n),
                                                        static_cast<int>(nfronts), d_front_off, d_front_off + 1, st));
-    PGC_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
-    ws.owned.push_back(tmp);
+    if ((rc = ws.alloc_bytes(&tmp, tmp_bytes))) return rc;
     for (int obj = 0; obj < m; ++obj) {
         gather_objective_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_f, m, obj, d_order, n, keys_in, vals_in);
         size_t bytes = tmp_bytes;
@@ -510,7 +519,7 @@ int crowding_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, const
 static int sort_by_cd_desc(pgc_ctx *ctx, const double *d_cd, unsigned *d_idx, unsigned count, cudaStream_t st)
 {
     if (count < 2) return PGC_OK;
-    Workspace ws{ctx, {}};
+    Workspace ws(ctx, st);
     unsigned long long *k0, *k1;
     unsigned *v1;
     int rc;
@@ -519,8 +528,7 @@ static int sort_by_cd_desc(pgc_ctx *ctx, const double *d_cd, unsigned *d_idx, un
     void *tmp = nullptr;
     size_t bytes = 0;
     PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0, k1, d_idx, v1, static_cast<int>(count), 0, 64, st));
-    PGC_CUDA(cudaMalloc(&tmp, bytes ? bytes : 1));
-    ws.owned.push_back(tmp);
+    if ((rc = ws.alloc_bytes(&tmp, bytes))) return rc;
     PGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, k0, k1, d_idx, v1, static_cast<int>(count), 0, 64, st));
     PGC_CUDA(cudaMemcpyAsync(d_idx, v1, sizeof(unsigned) * count, cudaMemcpyDeviceToDevice, st));
     PGC_CUDA(cudaStreamSynchronize(st));
@@ -550,7 +558,7 @@ int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, si
         return PGC_OK;
     }
     const unsigned N = static_cast<unsigned>(N_);
-    Workspace ws{ctx, {}};
+    Workspace ws(ctx, st);
     unsigned *rank, *order, *foff;
     int rc;
     if ((rc = ws.alloc(&rank, n)) || (rc = ws.alloc(&order, n)) || (rc = ws.alloc(&foff, n + 1))) return rc;
@@ -594,7 +602,7 @@ int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_
         PGC_CUDA(cudaStreamSynchronize(st));
         return PGC_OK;
     }
-    Workspace ws{ctx, {}};
+    Workspace ws(ctx, st);
     unsigned *rank, *order, *foff, *rk_in, *rk_out, *v_out;
     double *cd;
     int rc;
@@ -610,8 +618,7 @@ int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_
     void *tmp = nullptr;
     size_t bytes = 0;
     PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, rk_in, rk_out, d_out, v_out, static_cast<int>(n), 0, 32, st));
-    PGC_CUDA(cudaMalloc(&tmp, bytes ? bytes : 1));
-    ws.owned.push_back(tmp);
+    if ((rc = ws.alloc_bytes(&tmp, bytes))) return rc;
     PGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, rk_in, rk_out, d_out, v_out, static_cast<int>(n), 0, 32, st));
     PGC_CUDA(cudaMemcpyAsync(d_out, v_out, sizeof(unsigned) * n, cudaMemcpyDeviceToDevice, st));
     PGC_CUDA(cudaStreamSynchronize(st));

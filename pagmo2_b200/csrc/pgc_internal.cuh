@@ -151,6 +151,16 @@ int crowding_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const u
                     unsigned nfronts, int small_rule, double *d_cd, cudaStream_t st);
 int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, size_t N, unsigned *d_out, unsigned *nout, cudaStream_t st);
 int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, unsigned *d_out, cudaStream_t st);
+int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t s);
+int philox_permutation_device(pgc_ctx *ctx, unsigned n, unsigned long long seed, unsigned tag, unsigned generation, unsigned *d_perm,
+                              cudaStream_t st);
+int nsga2_variation_device(pgc_ctx *ctx, const double *d_x, const unsigned *d_rank, const double *d_cd, unsigned NP, unsigned nx,
+                           const double *d_lb, const double *d_ub, const unsigned *d_sh1, const unsigned *d_sh2, double cr,
+                           double eta_c, double m, double eta_m, unsigned long long seed, unsigned generation, double *d_children,
+                           cudaStream_t st);
+int nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double cr, double eta_c, double m,
+                        double eta_m, unsigned long long seed, unsigned first_generation,
+                        int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops_out);
