@@ -166,6 +166,15 @@ PGC_API int pgc_nsga2_variation_device(pgc_ctx *ctx, const double *d_x, const ui
 PGC_API int pgc_nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP, unsigned gens, double cr, double eta_c,
                                     double m, double eta_m, uint64_t seed, uint32_t first_generation, void *stream);
 
+/* pso_gen::evolve (pso_gen.cpp:120-530) on a device-resident swarm: variants 1-5, topologies 1 (gbest) and 2 (lbest ring).
+ * In: d_x [n x nx] positions, d_f [n] fitness, d_v velocities or NULL (then drawn as pso_gen.cpp:187-196).
+ * Out: d_x / d_f = the particles' best positions / fitness (what evolve() writes back, :524-527), d_v = final velocities,
+ * d_xcur (optional) = final current positions.  Reference defaults: omega 0.7298, eta1 = eta2 = 2.05, max_vel 0.5,
+ * variant 5, neighb_type 2, neighb_param 4. */
+PGC_API int pgc_pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, double *d_xcur, size_t n, unsigned gens,
+                                  double omega, double eta1, double eta2, double max_vel, unsigned variant, unsigned neighb_type,
+                                  unsigned neighb_param, uint64_t seed, uint32_t first_generation, void *stream);
+
 /* Debug/profiling aid for the CEC2014 stage kernel: same evaluation with clock64() phase counters, summed over all
  * warp-tiles and stages.  out7 = {load, weight pass, token wait, GEMM, z store, epilogue} cycles, warp-tiles. */
 PGC_API int pgc_debug_cec2014_phase_cycles(pgc_problem *prob, const double *d_dvs, size_t n, double *d_fvs, uint64_t *out7);

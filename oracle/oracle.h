@@ -38,6 +38,10 @@ int oracle_dtlz_fitness(unsigned id, const double *x, size_t N, size_t M, unsign
 int oracle_zdt_batch(unsigned id, const double *xs, size_t n, size_t N, double *fs);
 int oracle_dtlz_batch(unsigned id, const double *xs, size_t n, size_t N, size_t M, unsigned alpha, double *fs);
 
+/* ---- Lennard-Jones (restate_lj.c) ---- */
+int oracle_lj_fitness(unsigned atoms, const double *x, double *f);
+int oracle_lj_batch(unsigned atoms, const double *xs, size_t n, double *fs);
+
 /* ---- multi-objective utilities (restate_mo_utils.c), f flat row-major [n x m] ---- */
 int oracle_pareto_dominance(const double *a, const double *b, size_t m);
 int oracle_fnds(const double *f, size_t n, size_t m, size_t *rank, size_t *dom_count, size_t *front_idx, size_t *front_off,
@@ -45,6 +49,19 @@ int oracle_fnds(const double *f, size_t n, size_t m, size_t *rank, size_t *dom_c
 int oracle_crowding_distance(const double *f, size_t n, size_t m, double *out);
 int oracle_select_best_N_mo(const double *f, size_t n, size_t m, size_t N, size_t *out, size_t *nout);
 int oracle_sort_population_mo(const double *f, size_t n, size_t m, size_t *out);
+
+/* ---- generic problem handle for the restated algorithms (restate_pso.c, restate_de.c) ----
+ * family ids = pgc_family (1-5 simple, 6 cec2014, 8 zdt, 9 dtlz, 11 lennard_jones: dim = atoms) */
+typedef struct oracle_problem {
+    int family;
+    unsigned prob_id, dim, nobj, param;
+    const double *rotation, *shift;
+    const int *shuffle;
+} oracle_problem;
+int oracle_problem_eval(const oracle_problem *p, const double *xs, size_t n, double *fs);
+int oracle_pso_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, double *v, double *xcur,
+                      size_t n, size_t dim, unsigned gens, double omega, double eta1, double eta2, double max_vel, unsigned variant,
+                      unsigned neighb_type, unsigned neighb_param, uint64_t seed, uint32_t first_generation);
 
 /* ---- Philox draws and NSGA-II generation operators (philox.h, restate_nsga2.c) ---- */
 void oracle_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -49,6 +49,15 @@ SIMPLE = {"rastrigin": 1, "ackley": 2, "griewank": 3, "schwefel": 4, "rosenbrock
 CEC_NCOMP = 10
 
 
+class OracleProblem(C.Structure):
+    _fields_ = [("family", C.c_int), ("prob_id", C.c_uint), ("dim", C.c_uint), ("nobj", C.c_uint), ("param", C.c_uint),
+                ("rotation", c_double_p), ("shift", c_double_p), ("shuffle", c_int_p)]
+
+
+FAMILY_ID = {"rastrigin": 1, "ackley": 2, "griewank": 3, "schwefel": 4, "rosenbrock": 5, "cec2014": 6, "zdt": 8, "dtlz": 9,
+             "lennard_jones": 11}
+
+
 class Oracle:
     def __init__(self):
         if not ORACLE_SO.exists():
@@ -111,6 +120,13 @@ class Oracle:
             raise ValueError("oracle_dtlz_batch failed")
         return out
 
+    def lennard_jones(self, atoms: int, xs: np.ndarray) -> np.ndarray:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        out = np.empty(xs.shape[0])
+        if self.lib.oracle_lj_batch(C.c_uint(atoms), _dp(xs), C.c_size_t(xs.shape[0]), _dp(out)):
+            raise ValueError("oracle_lj_batch failed")
+        return out
+
     # ---- multi-objective utilities (restate_mo_utils.c) ----
     def fnds(self, f: np.ndarray):
         f = np.ascontiguousarray(f, dtype=np.float64)
@@ -145,6 +161,35 @@ class Oracle:
         if self.lib.oracle_sort_population_mo(_dp(f), C.c_size_t(f.shape[0]), C.c_size_t(f.shape[1]), _sp(out)):
             raise ValueError("oracle_sort_population_mo failed")
         return out[: f.shape[0]].astype(np.int64)
+
+    def problem(self, family, prob_id=0, dim=0, nobj=1, param=0, tables=None):
+        """oracle_problem handle (keeps the table arrays alive)."""
+        p = OracleProblem(FAMILY_ID[family], prob_id, dim, nobj, param, None, None, None)
+        p._keep = tables
+        if tables is not None:
+            p.rotation, p.shift, p.shuffle = _dp(tables[0]), _dp(tables[1]), _ip(tables[2])
+        return p
+
+    def pso_evolve(self, prob, lb, ub, x, f, v=None, gens=1, omega=0.7298, eta1=2.05, eta2=2.05, max_vel=0.5, variant=5, neighb_type=2,
+                   neighb_param=4, seed=0, first_generation=1):
+        """restated pso_gen::evolve: returns (lbX, lbfit, V, Xcur)."""
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C").reshape(-1)
+        n, dim = x.shape
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        vv = None if v is None else np.array(v, dtype=np.float64, order="C")
+        vout = vv if vv is not None else np.empty((n, dim))
+        xcur = np.empty((n, dim))
+        if vv is None:
+            # velocities are drawn inside; fetch them by a second identical call is wasteful - expose through xcur only
+            pass
+        rc = self.lib.oracle_pso_evolve(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), _dp(vv) if vv is not None else None, _dp(xcur),
+                                        C.c_size_t(n), C.c_size_t(dim), C.c_uint(gens), C.c_double(omega), C.c_double(eta1),
+                                        C.c_double(eta2), C.c_double(max_vel), C.c_uint(variant), C.c_uint(neighb_type),
+                                        C.c_uint(neighb_param), C.c_uint64(seed), C.c_uint32(first_generation))
+        if rc:
+            raise ValueError("oracle_pso_evolve failed")
+        return x, f, (vv if vv is not None else None), xcur
 
     # ---- Philox draws and NSGA-II operators (restate_nsga2.c) ----
     def philox_raw(self, ctr, key):

@@ -1,0 +1,129 @@
+/* oracle/restate_pso.c - plain-C restatement of pagmo::pso_gen::evolve (generational PSO).  TEST INFRASTRUCTURE ONLY.
+ * Follows reference src/algorithms/pso_gen.cpp: velocity update :231-327 (variants 1-5), clamp/move/box correction :329-363,
+ * evaluation :417-440, memory update :445-459, best neighbour :593-623, lbest ring :679-698, gbest :644-664.
+ * PARITY UNPINNED for the random stream (the reference's mt19937 draws are not pinned by any reference test; tests/pso_gen.cpp
+ * checks determinism and bfe-equivalence only): every draw is the Philox value the device consumes at the same
+ * (generation, particle, slot) - see oracle/philox.h and pagmo2_b200/csrc/pso.cu.  The arithmetic is the reference's.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "oracle.h"
+#include "philox.h"
+
+static int less_f(double a, double b) { return !isnan(a) && (isnan(b) || a < b); }
+static int equal_f(double a, double b) { return (isnan(a) && isnan(b)) || a == b; }
+static int leq_f(double a, double b) { return less_f(a, b) || equal_f(a, b); }
+
+/* generic problem evaluation for the restated algorithms */
+int oracle_problem_eval(const oracle_problem *p, const double *xs, size_t n, double *fs)
+{
+    switch (p->family) {
+        case 1: case 2: case 3: case 4: case 5: return oracle_simple_batch(p->family, p->dim, xs, n, fs);
+        case 6: return oracle_cec2014_batch(p->prob_id, p->dim, p->rotation, p->shift, p->shuffle, xs, n, fs, 1);
+        case 8: return oracle_zdt_batch(p->prob_id, xs, n, p->dim, fs);
+        case 9: return oracle_dtlz_batch(p->prob_id, xs, n, p->dim, p->nobj, p->param, fs);
+        case 11: return oracle_lj_batch(p->dim, xs, n, fs);
+        default: return -1;
+    }
+}
+
+int oracle_pso_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x /* in: X, out: lbX */,
+                      double *f /* in: fit, out: lbfit */, double *v /* in/out or NULL */, double *xcur /* out or NULL */, size_t n,
+                      size_t dim, unsigned gens, double omega, double eta1, double eta2, double max_vel, unsigned variant,
+                      unsigned neighb_type, unsigned neighb_param, uint64_t seed, uint32_t first_generation)
+{
+    if (variant < 1 || variant > 5 || neighb_type < 1 || neighb_type > 2 || n == 0) return -1;
+    double *X = (double *)malloc(n * dim * sizeof(double)), *V = (double *)malloc(n * dim * sizeof(double)),
+           *fit = (double *)malloc(n * sizeof(double));
+    double *lbX = x, *lbfit = f;
+    memcpy(X, x, n * dim * sizeof(double));
+    memcpy(fit, f, n * sizeof(double));
+    if (v) memcpy(V, v, n * dim * sizeof(double));
+    else
+        for (size_t p = 0; p < n; ++p)
+            for (size_t d = 0; d < dim; ++d) {
+                const double vwidth = (ub[d] - lb[d]) * max_vel, minv = -1. * vwidth, maxv = vwidth;
+                const double u = oracle_philox_u01(seed, ORACLE_TAG_INIT, first_generation, (uint32_t)p, (uint32_t)d);
+                V[p * dim + d] = (minv == maxv) ? minv : (maxv - minv) * u + minv;
+            }
+    size_t gbest = 0;
+    double gbest_fit = 0;
+    if (neighb_type == 1) { /* pop.best_idx(): first minimum */
+        gbest = 0;
+        for (size_t p = 1; p < n; ++p)
+            if (less_f(lbfit[p], lbfit[gbest])) gbest = p;
+        gbest_fit = lbfit[gbest];
+    }
+    const size_t radius = neighb_param / 2u;
+    int rc = 0;
+    for (unsigned g = 0; g < gens && !rc; ++g) {
+        const uint32_t generation = first_generation + g;
+        for (size_t p = 0; p < n; ++p) {
+            size_t b = gbest;
+            if (neighb_type == 2) { /* lbest ring + particle__get_best_neighbor */
+                int first = 1;
+                for (size_t j = radius; j > 0u; --j) {
+                    const size_t q = (p < j) ? p - j + n : p - j;
+                    if (first || leq_f(lbfit[q], lbfit[b])) b = q;
+                    first = 0;
+                }
+                for (size_t j = 1u; j <= radius; ++j) {
+                    const size_t q = (p + j >= n) ? p + j - n : p + j;
+                    if (first || leq_f(lbfit[q], lbfit[b])) b = q;
+                    first = 0;
+                }
+            }
+            const double *best_neighb = lbX + b * dim;
+            double r1 = 0, r2 = 0;
+            if (variant == 3 || variant == 4) {
+                r1 = oracle_philox_u01(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, 0);
+                r2 = oracle_philox_u01(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, 1);
+            }
+            for (size_t d = 0; d < dim; ++d) {
+                double *Vp = &V[p * dim + d];
+                const double Xp = X[p * dim + d], lbXp = lbX[p * dim + d];
+                if (variant == 1 || variant == 5) {
+                    r1 = oracle_philox_u01(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, (uint32_t)(2 * d));
+                    r2 = oracle_philox_u01(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, (uint32_t)(2 * d + 1));
+                } else if (variant == 2) {
+                    r1 = oracle_philox_u01(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, (uint32_t)d);
+                }
+                switch (variant) {
+                    case 1: case 3: *Vp = omega * *Vp + eta1 * r1 * (lbXp - Xp) + eta2 * r2 * (best_neighb[d] - Xp); break;
+                    case 2: case 4: *Vp = omega * *Vp + eta1 * r1 * (lbXp - Xp) + eta2 * r1 * (best_neighb[d] - Xp); break;
+                    default: *Vp = omega * (*Vp + eta1 * r1 * (lbXp - Xp) + eta2 * r2 * (best_neighb[d] - Xp));
+                }
+            }
+        }
+        /* NOTE: the reference finishes ALL velocity updates before moving any particle (two loops); best_neighb only reads lbX,
+         * which does not change here, so fusing is equivalent - kept as two loops anyway */
+        for (size_t p = 0; p < n; ++p)
+            for (size_t d = 0; d < dim; ++d) {
+                const double vwidth = (ub[d] - lb[d]) * max_vel, minv = -1. * vwidth, maxv = vwidth;
+                double *Vp = &V[p * dim + d];
+                if (*Vp > maxv) *Vp = maxv;
+                else if (*Vp < minv) *Vp = minv;
+                double new_x = X[p * dim + d] + *Vp;
+                if (new_x < lb[d]) { new_x = lb[d]; *Vp = 0.; }
+                else if (new_x > ub[d]) { new_x = ub[d]; *Vp = 0.; }
+                X[p * dim + d] = new_x;
+            }
+        rc = oracle_problem_eval(prob, X, n, fit);
+        for (size_t p = 0; p < n && !rc; ++p) {
+            if (leq_f(fit[p], lbfit[p])) {
+                lbfit[p] = fit[p];
+                memcpy(lbX + p * dim, X + p * dim, dim * sizeof(double));
+                if (neighb_type == 1 && leq_f(fit[p], gbest_fit)) {
+                    gbest = p;
+                    gbest_fit = fit[p];
+                }
+            }
+        }
+    }
+    if (v) memcpy(v, V, n * dim * sizeof(double));
+    if (xcur) memcpy(xcur, X, n * dim * sizeof(double));
+    free(X); free(V); free(fit);
+    return rc;
+}

@@ -91,6 +91,8 @@ def lib():
                                                  C.c_double, C.c_uint64, C.c_uint32, vp, vp]
         L.pgc_nsga2_evolve_device.argtypes = [vp, vp, vp, sz, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64,
                                               C.c_uint32, vp]
+        L.pgc_pso_evolve_device.argtypes = [vp, vp, vp, vp, vp, sz, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint,
+                                            C.c_uint, C.c_uint, C.c_uint64, C.c_uint32, vp]
         L.pgc_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
         L.pgc_measure_fp64_mma_peak.argtypes = [vp, C.c_int, dp]
         _lib = L
@@ -315,6 +317,24 @@ class Problem:
         finally:
             self.ctx.free(dx)
             self.ctx.free(df)
+
+    def pso_evolve(self, x, f, v=None, gens=1, omega=0.7298, eta1=2.05, eta2=2.05, max_vel=0.5, variant=5, neighb_type=2, neighb_param=4,
+                   seed=0, first_generation=1):
+        """pso_gen::evolve on the device: returns (lbX, lbfit, V or None, Xcur)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        n = x.shape[0]
+        dx, df, dc = self.ctx.to_device(x), self.ctx.to_device(f), self.ctx.malloc(x.nbytes)
+        dv = self.ctx.to_device(np.ascontiguousarray(v, dtype=np.float64)) if v is not None else None
+        try:
+            check(lib().pgc_pso_evolve_device(self._h, dx, df, dv, dc, n, gens, omega, eta1, eta2, max_vel, variant, neighb_type,
+                                              neighb_param, seed, first_generation, None))
+            return (self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape),
+                    self.ctx.from_device(dv, x.shape) if dv else None, self.ctx.from_device(dc, x.shape))
+        finally:
+            for b in (dx, df, dc, dv):
+                if b:
+                    self.ctx.free(b)
 
     def eval_host_into(self, dvs: np.ndarray, fvs: np.ndarray):
         n = dvs.size // self.nx

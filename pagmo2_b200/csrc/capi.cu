@@ -210,6 +210,7 @@ int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d
         case PGC_CEC2014: return cec2014_eval(p, d_dvs, n, d_fvs, s);
         case PGC_ZDT:
         case PGC_DTLZ: return mo_eval(p, d_dvs, n, d_fvs, s);
+        case PGC_LENNARD_JONES: return lj_eval(p, d_dvs, n, d_fvs, s);
         default: set_error("family %d has no device evaluator in this build", p->desc.family); return PGC_ERR_UNSUPPORTED;
     }
 }
@@ -361,6 +362,7 @@ int pgc_problem_create(pgc_ctx *ctx, const pgc_problem_desc *desc, pgc_problem *
         case PGC_CEC2014: rc = cec2014_create(p, desc); break;
         case PGC_ZDT:
         case PGC_DTLZ: rc = mo_create(p); break;
+        case PGC_LENNARD_JONES: rc = lj_create(p); break;
         default:
             set_error("pgc_problem_create: family %d is not supported by this build (no CPU fallback)", desc->family);
             rc = PGC_ERR_UNSUPPORTED;
@@ -677,6 +679,17 @@ int pgc_nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t 
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return nsga2_evolve_device(prob, d_x, d_f, static_cast<unsigned>(NP), gens, cr, eta_c, m, eta_m, seed, first_generation,
                                problem_eval_device, stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
+}
+
+int pgc_pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, double *d_xcur, size_t n, unsigned gens, double omega,
+                          double eta1, double eta2, double max_vel, unsigned variant, unsigned neighb_type, unsigned neighb_param,
+                          uint64_t seed, uint32_t first_generation, void *stream)
+{
+    PGC_REQUIRE(prob && d_x && d_f, "pgc_pso_evolve_device: null argument");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    return pso_evolve_device(prob, d_x, d_f, d_v, d_xcur, static_cast<unsigned>(n), gens, omega, eta1, eta2, max_vel, variant, neighb_type,
+                             neighb_param, seed, first_generation, problem_eval_device,
+                             stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
 }
 
 int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out)

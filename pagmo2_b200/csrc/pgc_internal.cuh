@@ -139,6 +139,8 @@ int ensure_scratch(pgc_ctx *ctx, size_t bytes);
 // family back-ends: validate + upload tables (create) and launch (eval, asynchronous on `stream`)
 int simple_create(pgc_problem *p);
 int simple_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
+int lj_create(pgc_problem *p);
+int lj_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
 int mo_create(pgc_problem *p);
 int mo_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
 int cec2014_create(pgc_problem *p, const pgc_problem_desc *d);
@@ -161,6 +163,10 @@ int nsga2_variation_device(pgc_ctx *ctx, const double *d_x, const unsigned *d_ra
 int nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double cr, double eta_c, double m,
                         double eta_m, unsigned long long seed, unsigned first_generation,
                         int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
+int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, double *d_xcur, unsigned n, unsigned gens, double omega,
+                      double eta1, double eta2, double max_vel, unsigned variant, unsigned neighb_type, unsigned neighb_param,
+                      unsigned long long seed, unsigned first_generation,
+                      int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops_out);

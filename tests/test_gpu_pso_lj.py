@@ -1,0 +1,73 @@
+"""GPU parity: Lennard-Jones batch energy and the generational PSO (pso_gen) against the oracle with injected Philox draws."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from pagmo2_b200 import capi as m
+    return m
+
+
+@pytest.mark.parametrize("atoms", [3, 4, 7, 38, 150])
+def test_lennard_jones_parity(capi, ctx, orc, atoms):
+    rng = np.random.default_rng(atoms)
+    prob = capi.Problem(ctx, "lennard_jones", dim=atoms)
+    assert prob.nx == 3 * atoms - 6 and prob.name == f"Lennard Jones Cluster ({atoms} atoms)"
+    lb, ub = prob.bounds()
+    xs = rng.uniform(lb, ub, (515, prob.nx))
+    got, want = prob.eval_host(xs)[:, 0], orc.lennard_jones(atoms, xs)
+    assert np.max(np.abs(got - want) / np.abs(want)) <= REL_TOL
+    if atoms == 3:  # reference tests/lennard_jones.cpp:59-60
+        f = prob.eval_host(np.array([[1.12, -0.33, 2.34], [1.23, -1.23, 0.33]]))[:, 0]
+        assert np.allclose(f, [-1.7633355813175688, -1.833100934753864], rtol=1e-13)
+        lb3, ub3 = prob.bounds()
+        assert list(lb3) == [-3, -3, -3] and list(ub3) == [3, 3, 3]
+    if atoms >= 4:  # coincident atoms: the reference assigns DBL_MAX, keeps summing, multiplies by 4 -> +inf (:81-91)
+        x = xs[0].copy()
+        x[3:6] = [0.0, x[1], x[2]]  # atom 3 on top of atom 2
+        assert prob.eval_host(x[None, :])[0, 0] == orc.lennard_jones(atoms, x[None, :])[0] == np.inf
+    with pytest.raises(capi.PgcError):
+        capi.Problem(ctx, "lennard_jones", dim=2)
+    prob.close()
+
+
+@pytest.mark.parametrize("variant,ntype", [(5, 2), (5, 1), (1, 2), (2, 1), (3, 2), (4, 1)])
+def test_pso_matches_oracle(capi, ctx, orc, variant, ntype):
+    """Same Philox draws => same trajectories.  Positions are compared with a tolerance (fitness values differ by ulps,
+    which can only matter through the <= comparisons of the memory update)."""
+    rng = np.random.default_rng(variant * 10 + ntype)
+    n, dim = 64, 10
+    prob = capi.Problem(ctx, "rastrigin", dim=dim)
+    op = orc.problem("rastrigin", dim=dim)
+    lb, ub = prob.bounds()
+    x = rng.uniform(lb, ub, (n, dim))
+    f = orc.simple("rastrigin", x)
+    kw = dict(gens=8, variant=variant, neighb_type=ntype, seed=42, first_generation=1)
+    xo, fo, _, co = orc.pso_evolve(op, lb, ub, x, f, **kw)
+    xg, fg, _, cg = prob.pso_evolve(x, f, **kw)
+    assert np.allclose(cg, co, rtol=1e-9, atol=1e-12) and np.allclose(xg, xo, rtol=1e-9, atol=1e-12)
+    assert np.allclose(fg, fo, rtol=1e-9)
+    assert (fg <= f + 1e-12).all() and fg.min() < f.min()  # memories never get worse; the swarm improves
+    assert (xg >= lb).all() and (xg <= ub).all()
+    prob.close()
+
+
+def test_pso_on_lennard_jones_and_argument_checks(capi, ctx, orc):
+    rng = np.random.default_rng(3)
+    atoms, n = 13, 256
+    prob = capi.Problem(ctx, "lennard_jones", dim=atoms)
+    lb, ub = prob.bounds()
+    x = rng.uniform(lb, ub, (n, prob.nx))
+    f = prob.eval_host(x)[:, 0]
+    xg, fg, _, _ = prob.pso_evolve(x, f, gens=40, seed=1)
+    assert np.isfinite(fg).all() and fg.min() < f.min() and np.allclose(prob.eval_host(xg)[:, 0], fg, rtol=1e-12)
+    for bad in (dict(omega=1.5), dict(eta1=5.0), dict(max_vel=0.0), dict(variant=7), dict(neighb_type=5), dict(variant=6), dict(neighb_type=3)):
+        with pytest.raises(capi.PgcError):
+            prob.pso_evolve(x, f, gens=1, **bad)
+    mo = capi.Problem(ctx, "zdt", prob_id=1, dim=5)
+    with pytest.raises(capi.PgcError):
+        mo.pso_evolve(np.zeros((8, 5)), np.zeros(8), gens=1)
