@@ -175,6 +175,17 @@ PGC_API int pgc_pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, d
                                   double omega, double eta1, double eta2, double max_vel, unsigned variant, unsigned neighb_type,
                                   unsigned neighb_param, uint64_t seed, uint32_t first_generation, void *stream);
 
+/* Differential evolution family as a generational device loop (trial vectors for all individuals -> one batch evaluation ->
+ * selection): algo 0 = de (de.cpp:76-345; variant 1..10, F, CR), 1 = sade (sade.cpp:78-560; variant 1..18, variant_adptv 1 = jDE,
+ * 2 = iDE), 2 = de1220 (de1220.cpp:80-600; allowed_variants, variant_adptv).  d_x [NP x nx], d_f [NP] updated in place; d_F / d_CR /
+ * d_variant = per-individual self-adaptation memory (NULL: initialised as the reference does without memory).  Stops early on
+ * the reference's xtol / ftol exits; *gens_done = generations run.  Reference defaults: de(F 0.8, CR 0.9, variant 2), sade(variant 2,
+ * adptv 1), de1220(allowed {2,3,7,10,13,14,15,16}, adptv 1), ftol = xtol = 1e-6. */
+PGC_API int pgc_de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP, unsigned gens, unsigned algo, unsigned variant,
+                                 unsigned variant_adptv, double F, double CR, const uint32_t *allowed_variants, unsigned n_allowed,
+                                 double ftol, double xtol, double *d_F, double *d_CR, uint32_t *d_variant, uint64_t seed,
+                                 uint32_t first_generation, unsigned *gens_done, void *stream);
+
 /* Debug/profiling aid for the CEC2014 stage kernel: same evaluation with clock64() phase counters, summed over all
  * warp-tiles and stages.  out7 = {load, weight pass, token wait, GEMM, z store, epilogue} cycles, warp-tiles. */
 PGC_API int pgc_debug_cec2014_phase_cycles(pgc_problem *prob, const double *d_dvs, size_t n, double *d_fvs, uint64_t *out7);

@@ -63,6 +63,11 @@ int oracle_pso_evolve(const oracle_problem *prob, const double *lb, const double
                       size_t n, size_t dim, unsigned gens, double omega, double eta1, double eta2, double max_vel, unsigned variant,
                       unsigned neighb_type, unsigned neighb_param, uint64_t seed, uint32_t first_generation);
 
+int oracle_de_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim,
+                     unsigned gens, unsigned algo, unsigned variant, unsigned variant_adptv, double F, double CR,
+                     const unsigned *allowed, unsigned n_allowed, double ftol, double xtol, uint64_t seed, uint32_t first_generation,
+                     unsigned *gens_done, double *F_state, double *CR_state, unsigned *variant_state);
+
 /* ---- Philox draws and NSGA-II generation operators (philox.h, restate_nsga2.c) ---- */
 void oracle_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double oracle_philox_u01_at(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot);

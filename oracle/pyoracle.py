@@ -191,6 +191,26 @@ class Oracle:
             raise ValueError("oracle_pso_evolve failed")
         return x, f, (vv if vv is not None else None), xcur
 
+    def de_evolve(self, prob, lb, ub, x, f, gens=1, algo="de1220", variant=2, variant_adptv=1, F=0.8, CR=0.9,
+                  allowed=(2, 3, 7, 10, 13, 14, 15, 16), ftol=1e-6, xtol=1e-6, seed=0, first_generation=1):
+        """restated generational de / sade / de1220: returns (x, f, gens_done, F, CR, variant)."""
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C").reshape(-1)
+        NP, dim = x.shape
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        al = np.ascontiguousarray(allowed, dtype=np.uint32)
+        Fs, Cs, Vs = np.zeros(NP), np.zeros(NP), np.zeros(NP, dtype=np.uint32)
+        done = C.c_uint()
+        code = {"de": 0, "sade": 1, "de1220": 2}[algo]
+        rc = self.lib.oracle_de_evolve(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), C.c_size_t(NP), C.c_size_t(dim), C.c_uint(gens),
+                                       C.c_uint(code), C.c_uint(variant), C.c_uint(variant_adptv), C.c_double(F), C.c_double(CR),
+                                       al.ctypes.data_as(C.POINTER(C.c_uint)), C.c_uint(al.size), C.c_double(ftol), C.c_double(xtol),
+                                       C.c_uint64(seed), C.c_uint32(first_generation), C.byref(done), _dp(Fs), _dp(Cs),
+                                       Vs.ctypes.data_as(C.POINTER(C.c_uint)))
+        if rc:
+            raise ValueError("oracle_de_evolve failed")
+        return x, f, done.value, Fs, Cs, Vs
+
     # ---- Philox draws and NSGA-II operators (restate_nsga2.c) ----
     def philox_raw(self, ctr, key):
         c = (C.c_uint32 * 4)(*ctr)

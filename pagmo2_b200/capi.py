@@ -93,6 +93,8 @@ def lib():
                                               C.c_uint32, vp]
         L.pgc_pso_evolve_device.argtypes = [vp, vp, vp, vp, vp, sz, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint,
                                             C.c_uint, C.c_uint, C.c_uint64, C.c_uint32, vp]
+        L.pgc_de_evolve_device.argtypes = [vp, vp, vp, sz, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_double, vp, C.c_uint,
+                                           C.c_double, C.c_double, vp, vp, vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint), vp]
         L.pgc_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
         L.pgc_measure_fp64_mma_peak.argtypes = [vp, C.c_int, dp]
         _lib = L
@@ -335,6 +337,25 @@ class Problem:
             for b in (dx, df, dc, dv):
                 if b:
                     self.ctx.free(b)
+
+    def de_evolve(self, x, f, gens=1, algo="de1220", variant=2, variant_adptv=1, F=0.8, CR=0.9, allowed=(2, 3, 7, 10, 13, 14, 15, 16),
+                  ftol=1e-6, xtol=1e-6, seed=0, first_generation=1):
+        """generational de / sade / de1220 on the device: returns (x, f, gens_done, F, CR, variant)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        NP = x.shape[0]
+        al = np.ascontiguousarray(allowed, dtype=np.uint32)
+        code = {"de": 0, "sade": 1, "de1220": 2}[algo]
+        dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
+        dF, dC, dV = None, None, None
+        done = C.c_uint()
+        try:
+            check(lib().pgc_de_evolve_device(self._h, dx, df, NP, gens, code, variant, variant_adptv, F, CR, al.ctypes.data_as(C.c_void_p),
+                                             al.size, ftol, xtol, dF, dC, dV, seed, first_generation, C.byref(done), None))
+            return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), done.value
+        finally:
+            self.ctx.free(dx)
+            self.ctx.free(df)
 
     def eval_host_into(self, dvs: np.ndarray, fvs: np.ndarray):
         n = dvs.size // self.nx

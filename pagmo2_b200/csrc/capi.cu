@@ -692,6 +692,18 @@ int pgc_pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d
                              stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
 }
 
+int pgc_de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP, unsigned gens, unsigned algo, unsigned variant,
+                         unsigned variant_adptv, double F, double CR, const uint32_t *allowed_variants, unsigned n_allowed, double ftol,
+                         double xtol, double *d_F, double *d_CR, uint32_t *d_variant, uint64_t seed, uint32_t first_generation,
+                         unsigned *gens_done, void *stream)
+{
+    PGC_REQUIRE(prob && d_x && d_f, "pgc_de_evolve_device: null argument");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    return de_evolve_device(prob, d_x, d_f, static_cast<unsigned>(NP), gens, algo, variant, variant_adptv, F, CR, allowed_variants, n_allowed,
+                            ftol, xtol, d_F, d_CR, d_variant, seed, first_generation, gens_done, problem_eval_device,
+                            stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
+}
+
 int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out)
 {
     PGC_REQUIRE(ctx && out, "pgc_malloc_device: null argument");

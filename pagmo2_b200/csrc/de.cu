@@ -1,0 +1,436 @@
+// de.cu - differential evolution family (de, sade, de1220) as a GENERATIONAL device loop.
+//
+// Reference: src/algorithms/de.cpp:76-345 (10 variants :154-275, selection :277-299, exit :302-321),
+// src/algorithms/sade.cpp:78-560 and src/algorithms/de1220.cpp:80-600 (18 variants :199-505, F/CR initialisation :147-165,
+// jDE adaptation :193-197, iDE adaptation inside every variant, feasibility :507-513, selection :515-536).
+//
+// The reference evaluates `prob.fitness(tmp)` one individual at a time inside the population loop (no bfe hook).
+// Its trial vectors only read `popold` and `gbIter` (the previous generation), so building all NP trials first, evaluating
+// them as one batch and then applying the selection is the same algorithm, with two documented differences: the self-adapted
+// F/CR/variant of individuals accepted earlier IN THE SAME generation are not yet visible to later individuals (iDE reads
+// m_F[r[k]]), and the global best (gbX, gbF, gbCR) is updated once per generation with the reference's tie rule (`<=`, so the
+// last of equal minima wins).
+// Draws: individual i owns the Philox substream (seed, kTagDe, generation, i) and consumes it in the reference's order:
+// 7 (de: 5) Durstenfeld index picks, [de1220: variant gate], [jDE: F gate (+1), CR gate (+1)] | [iDE: normals, Box-Muller],
+// start gene, crossover draws, one draw per out-of-bounds gene.  uniform_int(a, b) = a + floor(u * (b - a + 1)).
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+#include "pgc_internal.cuh"
+#include "philox.cuh"
+
+namespace pgc
+{
+
+namespace
+{
+
+struct DeConfig {
+    unsigned algo;          // 0 = de, 1 = sade, 2 = de1220
+    unsigned variant;       // de / sade: mutation variant
+    unsigned variant_adptv; // sade / de1220: 1 = jDE, 2 = iDE
+    double F, CR;           // de
+    unsigned n_allowed;
+    unsigned allowed[18];
+};
+
+struct TrialParams {
+    const double *popold; // [NP x dim]
+    const double *gbIter; // [dim]
+    const double *lb, *ub;
+    const double *F_in, *CR_in;     // per individual (sade / de1220)
+    const unsigned *variant_in;     // per individual (de1220)
+    const double *gbIterF, *gbIterCR; // device scalars
+    double *trial;                  // [NP x dim]
+    double *F_out, *CR_out;
+    unsigned *variant_out;
+    unsigned NP, dim;
+    unsigned long long seed;
+    unsigned generation;
+    DeConfig cfg;
+};
+
+__device__ __forceinline__ double normal01(PhiloxStream &rs) // Box-Muller on two uniforms
+{
+    const double u1 = 1.0 - rs.next();
+    const double u2 = rs.next();
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+__device__ __forceinline__ unsigned uint_below(PhiloxStream &rs, unsigned n) // uniform in [0, n)
+{
+    const unsigned v = static_cast<unsigned>(rs.next() * static_cast<double>(n));
+    return v < n ? v : n - 1;
+}
+
+// mutation formulas.  de.cpp and de1220/sade.cpp share variants 1-3 / 6-8; 4,5,9,10 differ in form (de: one product).
+__device__ __forceinline__ double mutate(unsigned algo, unsigned base, double t, double gb, const double *p, double pi, double F)
+{
+    // p[k] = popold[r[k]][n], pi = popold[i][n], t = tmp[n] (== pi)
+    switch (base) {
+        case 1: return gb + F * (p[1] - p[2]);
+        case 2: return p[0] + F * (p[1] - p[2]);
+        case 3: return t + F * (gb - t) + F * (p[0] - p[1]);
+        case 4: return algo == 0 ? gb + (p[0] + p[1] - p[2] - p[3]) * F : gb + (p[0] - p[1]) * F + (p[2] - p[3]) * F;
+        case 5: return algo == 0 ? p[4] + (p[0] + p[1] - p[2] - p[3]) * F : p[4] + (p[0] - p[1]) * F + (p[2] - p[3]) * F;
+        case 6: return p[0] + (p[1] - p[2]) * F + (p[3] - p[4]) * F + (p[5] - p[6]) * F; // variants 11/12
+        case 7: return gb + (p[1] - p[2]) * F + (p[3] - p[4]) * F + (p[5] - p[6]) * F;   // 13/14
+        case 8: return p[0] + (p[1] - pi) * F + (p[2] - p[3]) * F;                       // 15/16
+        default: return p[0] + (p[1] - pi) * F - (p[2] - gb) * F;                        // 17/18
+    }
+}
+
+// variant -> (formula id, exponential crossover?)
+__device__ __forceinline__ void decode_variant(unsigned v, unsigned &base, bool &expo)
+{
+    if (v <= 10u) {
+        expo = v <= 5u;
+        base = expo ? v : v - 5u;
+    } else {
+        expo = (v & 1u) != 0u; // 11, 13, 15, 17 exponential; 12, 14, 16, 18 binomial
+        base = 6u + (v - 11u) / 2u;
+    }
+}
+
+// one thread per individual
+__global__ void de_trial_kernel(const TrialParams P)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.NP) return;
+    const unsigned NP = P.NP, dim = P.dim;
+    PhiloxStream rs(P.seed, kTagDe, P.generation, i);
+    // Durstenfeld partial shuffle of 0..NP-1 (de.cpp:143-149, de1220.cpp:181-187) on a virtual array: only the picked
+    // positions are ever overwritten (with the value of the current last position)
+    const unsigned npick = P.cfg.algo == 0 ? 5u : 7u;
+    unsigned r[7], pos[7], val[7];
+    for (unsigned j = 0; j < npick; ++j) {
+        const unsigned last = NP - 1u - j;
+        const unsigned idx = uint_below(rs, NP - j);
+        unsigned at_idx = idx, at_last = last;
+        for (unsigned k = 0; k < j; ++k) {
+            if (pos[k] == idx) at_idx = val[k];
+            if (pos[k] == last) at_last = val[k];
+        }
+        r[j] = at_idx;
+        pos[j] = idx;
+        val[j] = at_last;
+    }
+    for (unsigned j = npick; j < 7u; ++j) r[j] = 0;
+
+    double F = P.cfg.F, CR = P.cfg.CR;
+    unsigned variant = P.cfg.variant;
+    if (P.cfg.algo == 2u) { // de1220.cpp:192
+        variant = (rs.next() < 0.9) ? P.variant_in[i] : P.cfg.allowed[uint_below(rs, P.cfg.n_allowed)];
+    }
+    if (P.cfg.algo != 0u && P.cfg.variant_adptv == 1u) { // jDE, de1220.cpp:193-196 / sade.cpp:178-182
+        F = (rs.next() < 0.9) ? P.F_in[i] : rs.next() * 0.9 + 0.1;
+        CR = (rs.next() < 0.9) ? P.CR_in[i] : rs.next();
+    }
+    unsigned base;
+    bool expo;
+    decode_variant(variant, base, expo);
+    if (P.cfg.algo != 0u && P.cfg.variant_adptv == 2u) { // iDE: the per-variant F/CR formulas (e.g. de1220.cpp:201-202)
+        // the normal draws are taken in the order they appear in the reference's expressions, F first then CR (the C++
+        // evaluation order inside one expression is unspecified, so it is fixed here explicitly)
+        const double *mF = P.F_in, *mC = P.CR_in;
+        const double gF = *P.gbIterF, gC = *P.gbIterCR;
+        double a1, a2, a3, c1, c2;
+        switch (base) {
+            case 1:
+                a1 = normal01(rs); c1 = normal01(rs);
+                F = gF + a1 * 0.5 * (mF[r[1]] - mF[r[2]]);
+                CR = gC + c1 * 0.5 * (mC[r[1]] - mC[r[2]]);
+                break;
+            case 2:
+                a1 = normal01(rs); c1 = normal01(rs);
+                F = mF[r[0]] + a1 * 0.5 * (mF[r[1]] - mF[r[2]]);
+                CR = mC[r[0]] + c1 * 0.5 * (mC[r[1]] - mC[r[2]]);
+                break;
+            case 3:
+                a1 = normal01(rs); a2 = normal01(rs); c1 = normal01(rs); c2 = normal01(rs);
+                F = mF[i] + a1 * 0.5 * (gF - mF[i]) + a2 * 0.5 * (mF[r[0]] - mF[r[1]]);
+                CR = mC[i] + c1 * 0.5 * (gC - mC[i]) + c2 * 0.5 * (mC[r[0]] - mC[r[1]]);
+                break;
+            case 4:
+                a1 = normal01(rs); a2 = normal01(rs); c1 = normal01(rs); c2 = normal01(rs);
+                F = gF + a1 * 0.5 * (mF[r[0]] - mF[r[1]]) + a2 * 0.5 * (mF[r[2]] - mF[r[3]]);
+                CR = gC + c1 * 0.5 * (mC[r[0]] - mC[r[1]]) + c2 * 0.5 * (mC[r[2]] - mC[r[3]]);
+                break;
+            case 5:
+                a1 = normal01(rs); a2 = normal01(rs); c1 = normal01(rs); c2 = normal01(rs);
+                F = mF[r[4]] + a1 * 0.5 * (mF[r[0]] - mF[r[1]]) + a2 * 0.5 * (mF[r[2]] - mF[r[3]]);
+                CR = mC[r[4]] + c1 * 0.5 * (mC[r[0]] - mC[r[1]]) + c2 * 0.5 * (mC[r[2]] - mC[r[3]]);
+                break;
+            case 6:
+                a1 = normal01(rs); a2 = normal01(rs); a3 = normal01(rs); c1 = normal01(rs);
+                F = mF[r[0]] + a1 * 0.5 * (mF[r[1]] - mF[r[2]]) + a2 * 0.5 * (mF[r[3]] - mF[r[4]]) + a3 * 0.5 * (mF[r[5]] - mF[r[6]]);
+                CR = mC[r[4]] + c1 * 0.5 * (mC[r[0]] + mC[r[1]] - mC[r[2]] - mC[r[3]]);
+                break;
+            case 7:
+                a1 = normal01(rs); a2 = normal01(rs); a3 = normal01(rs); c1 = normal01(rs);
+                F = gF + a1 * 0.5 * (mF[r[1]] - mF[r[2]]) + a2 * 0.5 * (mF[r[3]] - mF[r[4]]) + a3 * 0.5 * (mF[r[5]] - mF[r[6]]);
+                CR = gC + c1 * 0.5 * (mC[r[0]] + mC[r[1]] - mC[r[2]] - mC[r[3]]);
+                break;
+            case 8:
+                a1 = normal01(rs); a2 = normal01(rs); c1 = normal01(rs); c2 = normal01(rs);
+                F = mF[r[0]] + a1 * 0.5 * (mF[r[1]] - mF[i]) + a2 * 0.5 * (mF[r[3]] - mF[r[4]]);
+                CR = mC[r[0]] + c1 * 0.5 * (mC[r[1]] - mC[i]) + c2 * 0.5 * (mC[r[3]] - mC[r[4]]);
+                break;
+            default:
+                a1 = normal01(rs); a2 = normal01(rs); c1 = normal01(rs); c2 = normal01(rs);
+                F = mF[r[0]] + a1 * 0.5 * (mF[r[1]] - mF[i]) - a2 * 0.5 * (mF[r[2]] - gF);
+                CR = mC[r[0]] + c1 * 0.5 * (mC[r[1]] - mC[i]) - c2 * 0.5 * (mC[r[3]] - gC);
+        }
+    }
+
+    const double *xi = P.popold + static_cast<size_t>(i) * dim;
+    double *tmp = P.trial + static_cast<size_t>(i) * dim;
+    for (unsigned d = 0; d < dim; ++d) tmp[d] = xi[d];
+    unsigned n = uint_below(rs, dim); // c_idx(m_e)
+    auto gene = [&](unsigned nn) {
+        double p[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) p[k] = P.popold[static_cast<size_t>(r[k]) * dim + nn];
+        return mutate(P.cfg.algo, base, tmp[nn], P.gbIter[nn], p, xi[nn], F);
+    };
+    if (expo) {
+        unsigned L = 0u;
+        do {
+            tmp[n] = gene(n);
+            n = (n + 1u) % dim;
+            ++L;
+        } while ((rs.next() < CR) && (L < dim));
+    } else {
+        for (unsigned L = 0u; L < dim; ++L) {
+            if ((rs.next() < CR) || L + 1u == dim) tmp[n] = gene(n);
+            n = (n + 1u) % dim;
+        }
+    }
+    // feasibility: out-of-bounds genes are resampled uniformly, de1220.cpp:507-513 / force_bounds_random generic.hpp:403-412
+    for (unsigned j = 0; j < dim; ++j) {
+        if ((tmp[j] < P.lb[j]) || (tmp[j] > P.ub[j])) {
+            const double lo = P.lb[j], hi = P.ub[j];
+            tmp[j] = (lo == hi) ? lo : (hi - lo) * rs.next() + lo;
+        }
+    }
+    if (P.F_out) {
+        P.F_out[i] = F;
+        P.CR_out[i] = CR;
+    }
+    if (P.variant_out) P.variant_out[i] = variant;
+}
+
+// selection, de.cpp:281-299 / de1220.cpp:515-536
+__global__ void de_select_kernel(const double *trial, const double *ftrial, double *x, double *f, unsigned NP, unsigned dim,
+                                 unsigned char *accepted, const double *F_try, const double *CR_try, const unsigned *var_try,
+                                 double *F, double *CR, unsigned *variant)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NP) return;
+    const bool ok = ftrial[i] <= f[i];
+    accepted[i] = ok;
+    if (ok) {
+        f[i] = ftrial[i];
+        if (F) {
+            F[i] = F_try[i];
+            CR[i] = CR_try[i];
+        }
+        if (variant) variant[i] = var_try[i];
+    }
+}
+
+__global__ void de_copy_accepted_kernel(const double *trial, double *x, const unsigned char *accepted, unsigned NP, unsigned dim)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e < static_cast<size_t>(NP) * dim && accepted[e / dim]) x[e] = trial[e];
+}
+
+struct DeGlobal { // device-side global best + exit-condition data
+    double gbfit, gbF, gbCR;
+    unsigned gbidx, gbvariant;
+    unsigned best_idx, worst_idx;
+    double dx, df;
+};
+
+// sequential "if accepted and f <= gbfit: gb = i" over ascending i == smallest accepted fitness, last index on ties, if <= gbfit;
+// plus pop.best_idx() / worst_idx() (first min / first max) and the exit quantities dx, df (de.cpp:302-316).  Single CTA.
+__global__ void de_global_kernel(const double *x, const double *f, const unsigned char *accepted, unsigned NP, unsigned dim,
+                                 const double *F, const double *CR, const unsigned *variant, double *gbX, DeGlobal *G, int init)
+{
+    __shared__ double sfa[256], sfb[256], sfw[256];
+    __shared__ unsigned sia[256], sib[256], siw[256];
+    const unsigned t = threadIdx.x;
+    double fa = 0, fb = 0, fw = 0;
+    unsigned ia = 0xffffffffu, ib = 0xffffffffu, iw = 0xffffffffu;
+    for (unsigned i = t; i < NP; i += blockDim.x) {
+        const double v = f[i];
+        if (ib == 0xffffffffu || v < fb) { fb = v; ib = i; }
+        if (iw == 0xffffffffu || v > fw) { fw = v; iw = i; }
+        if (!init && accepted[i] && (ia == 0xffffffffu || v <= fa)) { fa = v; ia = i; }
+    }
+    sfa[t] = fa; sia[t] = ia; sfb[t] = fb; sib[t] = ib; sfw[t] = fw; siw[t] = iw;
+    __syncthreads();
+    if (t == 0) {
+        for (unsigned k = 1; k < blockDim.x; ++k) {
+            if (sib[k] != 0xffffffffu && (ib == 0xffffffffu || sfb[k] < fb || (sfb[k] == fb && sib[k] < ib))) { fb = sfb[k]; ib = sib[k]; }
+            if (siw[k] != 0xffffffffu && (iw == 0xffffffffu || sfw[k] > fw || (sfw[k] == fw && siw[k] < iw))) { fw = sfw[k]; iw = siw[k]; }
+            if (sia[k] != 0xffffffffu && (ia == 0xffffffffu || sfa[k] < fa || (sfa[k] == fa && sia[k] > ia))) { fa = sfa[k]; ia = sia[k]; }
+        }
+        G->best_idx = ib;
+        G->worst_idx = iw;
+        if (init) {
+            G->gbidx = ib;
+            G->gbfit = fb;
+            G->gbF = F ? F[0] : 0.0;   // "initialization to the 0 ind, will soon be forgotten", de1220.cpp:168-170
+            G->gbCR = CR ? CR[0] : 0.0;
+            G->gbvariant = variant ? variant[0] : 0u;
+        } else if (ia != 0xffffffffu && fa <= G->gbfit) {
+            G->gbidx = ia;
+            G->gbfit = fa;
+            if (F) { G->gbF = F[ia]; G->gbCR = CR[ia]; }
+            if (variant) G->gbvariant = variant[ia];
+        }
+        G->df = fabs(f[iw] - f[ib]);
+    }
+    __syncthreads();
+    // gbX <- x[gbidx]: the individual holding the global best can only be replaced by a trial that is itself <= gbfit, in
+    // which case gbidx moved with it, so x[gbidx] always equals the reference's gbX.  dx = sum |x_worst - x_best|.
+    const unsigned gi = G->gbidx;
+    for (unsigned d = t; d < dim; d += blockDim.x) gbX[d] = x[static_cast<size_t>(gi) * dim + d];
+    double part = 0;
+    for (unsigned d = t; d < dim; d += blockDim.x) part += fabs(x[static_cast<size_t>(G->worst_idx) * dim + d] - x[static_cast<size_t>(G->best_idx) * dim + d]);
+    sfa[t] = part;
+    __syncthreads();
+    if (t == 0) {
+        double s = 0;
+        for (unsigned k = 0; k < blockDim.x; ++k) s += sfa[k];
+        G->dx = s;
+    }
+}
+
+__global__ void de_init_adapt_kernel(double *F, double *CR, unsigned *variant, unsigned NP, DeConfig cfg, unsigned long long seed,
+                                     unsigned generation)
+{ // de1220.cpp:147-165 / sade.cpp:137-156
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NP) return;
+    PhiloxStream rs(seed, kTagInit, generation, i);
+    if (cfg.variant_adptv == 1u) {
+        const double c = rs.next();
+        const double f = rs.next();
+        CR[i] = c;
+        F[i] = f * 0.9 + 0.1;
+    } else {
+        const double c = normal01(rs);
+        const double f = normal01(rs);
+        CR[i] = c * 0.15 + 0.5;
+        F[i] = f * 0.15 + 0.5;
+    }
+    if (variant) variant[i] = cfg.allowed[uint_below(rs, cfg.n_allowed)];
+}
+
+inline unsigned nblk(size_t n, unsigned t) { return static_cast<unsigned>((n + t - 1) / t); }
+
+} // namespace
+
+// gens generations of de / sade / de1220 on a device-resident population (d_x, d_f updated in place).
+// d_F / d_CR / d_variant: per-individual self-adaptation state (sade, de1220); nullptr = initialise as the reference does when
+// it has no memory.  *gens_done receives the generations actually run (the xtol / ftol exits of de.cpp:302-321).
+int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, unsigned algo, unsigned variant,
+                     unsigned variant_adptv, double F, double CR, const unsigned *allowed, unsigned n_allowed, double ftol, double xtol,
+                     double *d_F, double *d_CR, unsigned *d_variant, unsigned long long seed, unsigned first_generation,
+                     unsigned *gens_done, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st)
+{
+    pgc_ctx *ctx = prob->ctx;
+    const unsigned dim = static_cast<unsigned>(prob->nx);
+    if (gens_done) *gens_done = 0;
+    PGC_REQUIRE(algo <= 2u, "de_evolve: algo must be 0 (de), 1 (sade) or 2 (de1220)");
+    PGC_REQUIRE(prob->nobj == 1, "Multiple objectives detected in %s instance. Differential evolution cannot deal with them", prob->name.c_str());
+    if (gens == 0) return PGC_OK;
+    const unsigned min_np = algo == 0 ? 5u : 7u; // de.cpp:107-110, sade.cpp:109-112, de1220.cpp:111-114
+    PGC_REQUIRE(NP >= min_np, "differential evolution needs at least %u individuals in the population, %u detected", min_np, NP);
+    DeConfig cfg{};
+    cfg.algo = algo;
+    cfg.variant = variant;
+    cfg.variant_adptv = variant_adptv;
+    cfg.F = F;
+    cfg.CR = CR;
+    if (algo == 0u) {
+        PGC_REQUIRE(variant >= 1u && variant <= 10u, "The Differential Evolution variant must be in [1, .., 10], while a value of %u was detected.", variant);
+        PGC_REQUIRE(F >= 0. && F <= 1. && CR >= 0. && CR <= 1., "The F and CR parameters must be in the [0,1] range");
+    } else {
+        PGC_REQUIRE(variant_adptv >= 1u && variant_adptv <= 2u, "The variant for self-adaptation must be in [1,2], while a value of %u was detected.", variant_adptv);
+        if (algo == 1u) PGC_REQUIRE(variant >= 1u && variant <= 18u, "The Differential Evolution mutation variant must be in [1, .., 18], while a value of %u was detected.", variant);
+        if (algo == 2u) {
+            PGC_REQUIRE(allowed && n_allowed >= 1u && n_allowed <= 18u, "de1220 needs between 1 and 18 allowed mutation variants");
+            for (unsigned k = 0; k < n_allowed; ++k) {
+                PGC_REQUIRE(allowed[k] >= 1u && allowed[k] <= 18u, "All mutation variants considered must be in [1, .., 18], while a value of %u was detected.", allowed[k]);
+                cfg.allowed[k] = allowed[k];
+            }
+            cfg.n_allowed = n_allowed;
+        }
+    }
+    struct Buf {
+        cudaStream_t st;
+        std::vector<void *> owned;
+        ~Buf()
+        {
+            for (void *p : owned) cudaFreeAsync(p, st);
+        }
+        int get(void **out, size_t bytes)
+        {
+            PGC_CUDA(cudaMallocAsync(out, bytes ? bytes : 1, st));
+            owned.push_back(*out);
+            return PGC_OK;
+        }
+    } buf{st, {}};
+    const size_t nd = static_cast<size_t>(NP) * dim;
+    double *trial, *ftrial, *gbX, *lb, *ub, *Fs = d_F, *CRs = d_CR, *Ftry = nullptr, *CRtry = nullptr;
+    unsigned *vars = d_variant, *vtry = nullptr;
+    unsigned char *accepted;
+    DeGlobal *G;
+    int rc;
+    if ((rc = buf.get(reinterpret_cast<void **>(&trial), 8 * nd)) || (rc = buf.get(reinterpret_cast<void **>(&ftrial), 8 * NP))
+        || (rc = buf.get(reinterpret_cast<void **>(&gbX), 8 * dim)) || (rc = buf.get(reinterpret_cast<void **>(&lb), 8 * dim))
+        || (rc = buf.get(reinterpret_cast<void **>(&ub), 8 * dim)) || (rc = buf.get(reinterpret_cast<void **>(&accepted), NP))
+        || (rc = buf.get(reinterpret_cast<void **>(&G), sizeof(DeGlobal))))
+        return rc;
+    PGC_CUDA(cudaMemcpyAsync(lb, prob->lb.data(), 8 * dim, cudaMemcpyHostToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(ub, prob->ub.data(), 8 * dim, cudaMemcpyHostToDevice, st));
+    if (algo != 0u) {
+        const bool fresh = !(d_F && d_CR && (algo == 1u || d_variant));
+        if ((rc = buf.get(reinterpret_cast<void **>(&Ftry), 8 * NP)) || (rc = buf.get(reinterpret_cast<void **>(&CRtry), 8 * NP))) return rc;
+        if (algo == 2u && (rc = buf.get(reinterpret_cast<void **>(&vtry), 4 * NP))) return rc;
+        if (fresh) {
+            if (!Fs && (rc = buf.get(reinterpret_cast<void **>(&Fs), 8 * NP))) return rc;
+            if (!CRs && (rc = buf.get(reinterpret_cast<void **>(&CRs), 8 * NP))) return rc;
+            if (algo == 2u && !vars && (rc = buf.get(reinterpret_cast<void **>(&vars), 4 * NP))) return rc;
+            de_init_adapt_kernel<<<nblk(NP, 128), 128, 0, st>>>(Fs, CRs, algo == 2u ? vars : nullptr, NP, cfg, seed, first_generation);
+        }
+    }
+    de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, nullptr, NP, dim, Fs, CRs, algo == 2u ? vars : nullptr, gbX, G, 1);
+    unsigned done = 0;
+    for (unsigned g = 0; g < gens; ++g) {
+        TrialParams tp{d_x, gbX, lb, ub, Fs, CRs, algo == 2u ? vars : nullptr, &G->gbF, &G->gbCR, trial, Ftry, CRtry, vtry, NP, dim, seed,
+                       first_generation + g, cfg};
+        de_trial_kernel<<<nblk(NP, 64), 64, 0, st>>>(tp);
+        if ((rc = eval(prob, trial, NP, ftrial, st))) return rc;
+        de_select_kernel<<<nblk(NP, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, NP, dim, accepted, Ftry, CRtry, vtry, algo ? Fs : nullptr,
+                                                        algo ? CRs : nullptr, algo == 2u ? vars : nullptr);
+        de_copy_accepted_kernel<<<nblk(nd, 256), 256, 0, st>>>(trial, d_x, accepted, NP, dim);
+        de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, accepted, NP, dim, algo ? Fs : nullptr, algo ? CRs : nullptr, algo == 2u ? vars : nullptr,
+                                            gbX, G, 0);
+        ctx->launches.fetch_add(4, std::memory_order_relaxed);
+        ++done;
+        DeGlobal h;
+        PGC_CUDA(cudaMemcpyAsync(&h, G, sizeof(DeGlobal), cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        if (h.dx < xtol || h.df < ftol) break; // de.cpp:308,316
+    }
+    if (gens_done) *gens_done = done;
+    PGC_CUDA(cudaGetLastError());
+    PGC_CUDA(cudaStreamSynchronize(st));
+    return PGC_OK;
+}
+
+} // namespace pgc

@@ -167,6 +167,10 @@ int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, 
                       double eta1, double eta2, double max_vel, unsigned variant, unsigned neighb_type, unsigned neighb_param,
                       unsigned long long seed, unsigned first_generation,
                       int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
+int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, unsigned algo, unsigned variant,
+                     unsigned variant_adptv, double F, double CR, const unsigned *allowed, unsigned n_allowed, double ftol, double xtol,
+                     double *d_F, double *d_CR, unsigned *d_variant, unsigned long long seed, unsigned first_generation,
+                     unsigned *gens_done, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops_out);
