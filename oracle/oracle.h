@@ -29,6 +29,9 @@ int oracle_cec2014_fitness(unsigned func, unsigned dim, const double *Mr, const 
 /* nthreads<=1: sequential.  Static contiguous partition over individuals (thread_bfe.cpp:94-137 restated). */
 int oracle_cec2014_batch(unsigned func, unsigned dim, const double *Mr, const double *Os, const int *S,
                          const double *xs, size_t n, double *fs, int nthreads);
+/* ---- CEC2013 (restate_cec2013.c): Mr = MD[dim] (10 matrices), Os = shift_data (10 lines of 100, addressed at i*dim) ---- */
+int oracle_cec2013_fitness(unsigned func, unsigned dim, const double *Mr, const double *Os, const double *x, double *f);
+int oracle_cec2013_batch(unsigned func, unsigned dim, const double *Mr, const double *Os, const double *xs, size_t n, double *fs);
 /* compaction performed by the cec2014 constructor (cec2014.cpp:76-86): keep the first dim of every 100 */
 size_t oracle_cec2014_compact_shift(const double *lines, size_t nlines, unsigned dim, double *out);
 

@@ -272,6 +272,16 @@ class Oracle:
         return out
 
 
+    def cec2013(self, func: int, xs: np.ndarray, tables=None) -> np.ndarray:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n, d = xs.shape
+        mr, os_ = tables if tables is not None else self.cec2013_tables(d)
+        out = np.empty(n)
+        if self.lib.oracle_cec2013_batch(C.c_uint(func), C.c_uint(d), _dp(mr), _dp(os_), _dp(xs), C.c_size_t(n), _dp(out)):
+            raise ValueError(f"oracle_cec2013_batch failed (func={func}, dim={d})")
+        return out
+
+
 class RefProblem:
     def __init__(self, ref: "Reference", handle):
         self._ref, self._h = ref, handle
@@ -391,6 +401,14 @@ class Reference:
         s = np.empty(CEC_NCOMP * dim, dtype=np.int32)
         self._check(self.lib.ref_cec2014_tables(C.c_uint(func), C.c_uint(dim), _dp(mr), _dp(os_), _ip(s)))
         return mr, os_, s
+
+    def cec2013_tables(self, dim: int):
+        """(MD[dim], shift_data) as the reference constructors saw them."""
+        mr = np.empty(CEC_NCOMP * dim * dim)
+        os_ = np.empty(CEC_NCOMP * 100)
+        self.lib.ref_cec2013_tables.argtypes = [C.c_uint, c_double_p, c_double_p]
+        self._check(self.lib.ref_cec2013_tables(C.c_uint(dim), _dp(mr), _dp(os_)))
+        return mr, os_
 
     def cec2014_origin_shift(self, prob: RefProblem) -> np.ndarray:
         out = np.empty(CEC_NCOMP * 100)

@@ -208,6 +208,7 @@ int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d
         case PGC_SCHWEFEL:
         case PGC_ROSENBROCK: return simple_eval(p, d_dvs, n, d_fvs, s);
         case PGC_CEC2014: return cec2014_eval(p, d_dvs, n, d_fvs, s);
+        case PGC_CEC2013: return cec2013_eval(p, d_dvs, n, d_fvs, s);
         case PGC_ZDT:
         case PGC_DTLZ: return mo_eval(p, d_dvs, n, d_fvs, s);
         case PGC_LENNARD_JONES: return lj_eval(p, d_dvs, n, d_fvs, s);
@@ -360,6 +361,7 @@ int pgc_problem_create(pgc_ctx *ctx, const pgc_problem_desc *desc, pgc_problem *
         case PGC_SCHWEFEL:
         case PGC_ROSENBROCK: rc = simple_create(p); break;
         case PGC_CEC2014: rc = cec2014_create(p, desc); break;
+        case PGC_CEC2013: rc = cec2013_create(p, desc); break;
         case PGC_ZDT:
         case PGC_DTLZ: rc = mo_create(p); break;
         case PGC_LENNARD_JONES: rc = lj_create(p); break;
@@ -368,6 +370,7 @@ int pgc_problem_create(pgc_ctx *ctx, const pgc_problem_desc *desc, pgc_problem *
             rc = PGC_ERR_UNSUPPORTED;
     }
     if (rc != PGC_OK) {
+        cec2013_destroy(p);
         cec2014_destroy(p);
         delete p;
         return rc;
@@ -381,6 +384,7 @@ int pgc_problem_destroy(pgc_problem *p)
     if (!p) return PGC_OK;
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
+    cec2013_destroy(p);
     cec2014_destroy(p);
     delete p;
     return PGC_OK;

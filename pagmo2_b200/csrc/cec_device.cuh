@@ -1,0 +1,127 @@
+// pagmo2_b200/csrc/cec_device.cuh - device helpers shared by the CEC2014 and CEC2013 evaluators: operand-tile geometry for
+// the FP64 tensor path (mma.sync.m8n8k4.f64), branch-free trigonometry, and the "4 lanes per individual" ordered reductions
+// of the epilogues (8-individual warp tiles).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pgc
+{
+namespace cecdev
+{
+
+constexpr int kTileInd = 8;         // individuals per warp tile (one m8n8k4 row tile)
+constexpr int kLPI = 32 / kTileInd; // lanes per individual in the epilogue
+constexpr unsigned kFull = 0xffffffffu;
+
+__host__ __device__ constexpr int pad8(int d) { return (d + 7) / 8 * 8; }
+__host__ __device__ constexpr int pad4(int d) { return (d + 3) / 4 * 4; }
+// Row stride (doubles) of the row-major operand tiles - the warp's Y tile (rows = individuals) and the rotation
+// image (rows = outputs): >= the padded inner length and == 4 or 12 (mod 16), so that the 16 lanes of a half
+// warp (4 rows x 4 consecutive doubles of an m8n8k4 operand fragment) cover all 32 banks exactly once.
+__host__ __device__ constexpr int ystride(int d)
+{
+    int s = pad4(d);
+    while (s % 16 != 4 && s % 16 != 12) s += 4;
+    return s;
+}
+
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor path.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2*(l%4)+{0,1}].
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- branch-free FP64 trigonometry for the epilogues ---------------------------------------------------------
+// libdevice's sin/cos carry a data-dependent branch (Payne-Hanek slow path), which stops the compiler from
+// interleaving independent evaluations; the epilogues then run at the latency of one dependent DFMA chain per
+// coordinate.  These versions are straight-line code (selects only), ~1 ulp, valid for |theta| < 2^50, so two
+// coordinates per lane overlap.  The argument is the reference's own rounded double (e.g. fl(2*pi*z)):
+// turns = frac(theta / (2 pi)) with a two-term 1/(2 pi) (error ~1e-17 turns), then a quadrant fold to
+// [-pi/4, pi/4] and the classic minimax kernels (fdlibm k_sin.c / k_cos.c coefficients).
+__device__ __forceinline__ double round_magic(double x) // round to nearest integer, |x| < 2^51
+{
+    return (x + 6755399441055744.0) - 6755399441055744.0;
+}
+
+__device__ __forceinline__ double turns_of(double theta) // frac(theta / (2 pi)) in [-0.5, 0.5]
+{
+    const double I1 = 0x1.45f306dc9c883p-3, I2 = -0x1.6b01ec5417056p-57;
+    const double p = theta * I1;
+    const double e = fma(theta, I1, -p);
+    return (p - rint(p)) + fma(theta, I2, e);
+}
+
+// sin and cos of 2*pi*r for |r| <~ 1
+__device__ __forceinline__ void sincos_turns(double r, double &sn, double &cs)
+{
+    const double q = round_magic(4.0 * r);
+    const double f = fma(-0.25, q, r); // exact, in [-1/8, 1/8]
+    const int iq = __double2int_rn(q);
+    const double t = fma(f, 6.283185307179586232, f * 2.4492935982947064e-16); // 2*pi*f, hi + lo
+    const double z = t * t;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double st = fma(t * z, ps, t);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double ct = fma(z * z, pc, fma(-0.5, z, 1.0));
+    // angle = t + iq*pi/2
+    const bool odd = iq & 1;
+    const double s0 = odd ? ct : st, c0 = odd ? st : ct;
+    sn = (iq & 2) ? -s0 : s0;
+    cs = ((iq + 1) & 2) ? -c0 : c0;
+}
+
+__device__ __forceinline__ double cos_theta(double theta)
+{
+    double sn, cs;
+    sincos_turns(turns_of(theta), sn, cs);
+    return cs;
+}
+
+__device__ __forceinline__ double sin_theta(double theta)
+{
+    double sn, cs;
+    sincos_turns(turns_of(theta), sn, cs);
+    return sn;
+}
+
+// the kLPI lanes of an individual are kTileInd apart (lane = q * kTileInd + individual)
+__device__ __forceinline__ double pair_add(double v)
+{
+#pragma unroll
+    for (int m = kTileInd; m < 32; m <<= 1) v = v + __shfl_xor_sync(kFull, v, m);
+    return v;
+}
+__device__ __forceinline__ double pair_mul(double v)
+{
+#pragma unroll
+    for (int m = kTileInd; m < 32; m <<= 1) v = v * __shfl_xor_sync(kFull, v, m);
+    return v;
+}
+
+// Sum term(j) for j = lo, lo + kLPI, ... < hi IN ORDER (lane q of an individual takes the terms j == q mod kLPI),
+// evaluating two terms at a time so that their (independent, branch-free) dependency chains overlap.
+template <class F> __device__ __forceinline__ double ordered_sum(int lo, int hi, F term)
+{
+    double s = 0.0;
+    int j = lo;
+    for (; j + kLPI < hi; j += 2 * kLPI) {
+        const double a = term(j), b = term(j + kLPI);
+        s += a;
+        s += b;
+    }
+    if (j < hi) s += term(j);
+    return s;
+}
+
+} // namespace cecdev
+} // namespace pgc

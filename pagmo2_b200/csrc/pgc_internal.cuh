@@ -95,6 +95,8 @@ struct Cec2014Recipe {
 
 int build_cec2014_recipe(unsigned func, unsigned dim, Cec2014Recipe &out);
 
+struct Cec2013Plan; // eval_cec2013.cu
+
 } // namespace pgc
 
 // ---- opaque handle layouts -----------------------------------------------------------------------------
@@ -130,6 +132,7 @@ struct pgc_problem {
     int *d_shuffle = nullptr;
     double *d_table = nullptr;
     pgc::Cec2014Recipe cec14;
+    pgc::Cec2013Plan *cec13 = nullptr;
     double flops_per_eval = 0, transc_per_eval = 0;
 };
 
@@ -146,6 +149,9 @@ int mo_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaSt
 int cec2014_create(pgc_problem *p, const pgc_problem_desc *d);
 int cec2014_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
 void cec2014_destroy(pgc_problem *p);
+int cec2013_create(pgc_problem *p, const pgc_problem_desc *d);
+int cec2013_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
+void cec2013_destroy(pgc_problem *p);
 int cec2014_phase_cycles(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, unsigned long long *out);
 int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, unsigned *d_rank, unsigned *d_dom_count, unsigned *d_order,
                 unsigned *d_front_off, unsigned *nfronts_out, cudaStream_t st);

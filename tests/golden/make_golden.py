@@ -16,8 +16,26 @@ from oracle.pyoracle import reference  # noqa: E402
 OUT = Path(__file__).resolve().parent
 
 
+def cec2013_fixture(R):
+    # ---- CEC2013: every function at D in {10, 30, 50}: 4 points in the box, 3 near the component-0 shift, the shift, origin
+    data = {}
+    rng13 = np.random.default_rng(20131)
+    for dim in (10, 30, 50):
+        _, os13 = R.cec2013_tables(dim)
+        for func in range(1, 29):
+            p = R.problem("cec2013", func, dim)
+            xs = np.vstack([rng13.uniform(-100, 100, (4, dim)), os13[:dim] + rng13.normal(0, 1.0, (3, dim)), os13[None, :dim],
+                            np.zeros((1, dim))])
+            data[f"x_f{func}_d{dim}"] = xs
+            data[f"f_f{func}_d{dim}"] = p.fitness_loop(xs)[:, 0]
+    np.savez_compressed(OUT / "cec2013_ref.npz", **data)
+
+
 def main():
     R = reference()
+    cec2013_fixture(R)
+    if "--cec2013-only" in sys.argv:  # add this fixture without rewriting the others
+        return
     rng = np.random.default_rng(20141)
     # ---- CEC2014: every function at D in {10, 30, 100}, 6 points in the box + the shift itself + origin
     data = {}

@@ -75,6 +75,13 @@ def test_cec2014_matches_golden(orc):
             assert np.array_equal(got, g[f"f_f{func}_d{dim}"]), (func, dim)
 
 
+def test_cec2013_matches_golden(orc):
+    g = np.load(GOLD / "cec2013_ref.npz")
+    for dim in (10, 30, 50):
+        for func in range(1, 29):
+            assert np.array_equal(orc.cec2013(func, g[f"x_f{func}_d{dim}"]), g[f"f_f{func}_d{dim}"]), (func, dim)
+
+
 def test_simple_matches_golden(orc):
     g = np.load(GOLD / "simple_ref.npz")
     for fam in ("rastrigin", "ackley", "griewank", "schwefel", "rosenbrock"):
@@ -96,6 +103,27 @@ def test_cec2014_restatement_is_bit_exact_vs_reference(orc, ref, dim):
         assert np.array_equal(orc.cec2014_problem_tables(func, dim)[1], ref.cec2014_origin_shift(p))
         xs = np.vstack([rng.uniform(-100, 100, (24, dim)), rng.normal(0, 1e-3, (4, dim)), np.zeros((1, dim))])
         assert np.array_equal(orc.cec2014(func, xs), p.fitness_loop(xs)[:, 0]), (func, dim)
+
+
+@pytest.mark.parametrize("dim", (2, 5, 10, 20, 30, 40, 50, 60, 70, 80, 90, 100))
+def test_cec2013_restatement_is_bit_exact_vs_reference(orc, ref, dim):
+    """all 28 functions; points in the box, near the optimum, exactly on the shift and with single zero coordinates (the oszfunc /
+    asyfunc / cf_cal special cases).  cec2013 has no value test in the reference (tests/cec2013.cpp:50-68): this pins the restatement."""
+    rng = np.random.default_rng(300 + dim)
+    for a, b in zip(orc.cec2013_tables(dim), ref.cec2013_tables(dim)):
+        assert np.array_equal(a, b)
+    _, os_ = orc.cec2013_tables(dim)
+    for func in range(1, 29):
+        p = ref.problem("cec2013", func, dim)
+        xs = np.vstack([rng.uniform(-100, 100, (12, dim)), os_[:dim] + rng.normal(0, 1.0, (4, dim)), os_[None, :dim], np.zeros((1, dim)),
+                        rng.uniform(-100, 100, (2, dim))])
+        xs[-1, 0] = os_[0]
+        xs[-2, dim - 1] = os_[dim - 1]
+        assert np.array_equal(orc.cec2013(func, xs), p.fitness_loop(xs)[:, 0]), (func, dim)
+    with pytest.raises(ValueError):
+        orc.cec2013(29, np.zeros((1, dim)))
+    with pytest.raises(ValueError):
+        orc.cec2013(1, np.zeros((1, 3)))
 
 
 def test_reference_thread_bfe_equals_sequential_fitness(ref):
