@@ -186,6 +186,55 @@ PGC_API int pgc_de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, si
                                  double ftol, double xtol, double *d_F, double *d_CR, uint32_t *d_variant, uint64_t seed,
                                  uint32_t first_generation, unsigned *gens_done, void *stream);
 
+/* ---- algorithms behind one descriptor (pagmo::algorithm::evolve(pop), src/algorithm.cpp) ------------------------------- */
+typedef enum pgc_algo {
+    PGC_ALGO_DE = 1,      /* src/algorithms/de.cpp:76-345 */
+    PGC_ALGO_SADE = 2,    /* src/algorithms/sade.cpp:78-560 */
+    PGC_ALGO_DE1220 = 3,  /* src/algorithms/de1220.cpp:80-600 */
+    PGC_ALGO_PSO_GEN = 4, /* src/algorithms/pso_gen.cpp:120-590 */
+    PGC_ALGO_NSGA2 = 5    /* src/algorithms/nsga2.cpp:91-307 */
+} pgc_algo;
+
+/* Constructor arguments of the reference UDAs; pgc_algo_defaults() fills in the reference's default values
+ * (de.hpp:119, sade.hpp:138, de1220.hpp:158, pso_gen.hpp:127, nsga2.hpp:103). */
+typedef struct pgc_algo_desc {
+    int32_t algo;
+    uint32_t gens;
+    uint32_t variant, variant_adptv;      /* de family; pso_gen variant */
+    uint32_t neighb_type, neighb_param;   /* pso_gen */
+    uint32_t n_allowed;
+    uint32_t allowed_variants[18];        /* de1220 */
+    double F, CR, ftol, xtol;             /* de family */
+    double omega, eta1, eta2, max_vel;    /* pso_gen */
+    double cr, eta_c, m, eta_m;           /* nsga2 */
+    uint64_t seed;
+} pgc_algo_desc;
+
+PGC_API int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out);
+/* algorithm::evolve on a device-resident population (d_x [n x nx], d_f [n x nobj], in place).  `first_generation` offsets the
+ * Philox generation counter so that successive calls continue the random stream; *gens_done (optional) = generations run. */
+PGC_API int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *algo, double *d_x, double *d_f, size_t n,
+                                   uint32_t first_generation, unsigned *gens_done, void *stream);
+
+/* ---- populations and migration (island.cpp:428-652) ------------------------------------------------------------------- */
+/* population(prob, bfe, n, seed) (population.cpp:82-103, generic.hpp:326-389): n uniform random decision vectors in the bounds,
+ * one batch evaluation, random 64-bit IDs.  d_f and d_ids may be NULL. */
+PGC_API int pgc_population_init_device(pgc_problem *prob, size_t n, uint64_t seed, double *d_x, double *d_f, uint64_t *d_ids,
+                                       void *stream);
+/* select_best::select (select_best.cpp:63-171): the best `rate` individuals (absolute count, or a fraction of n when
+ * rate_is_frac) of the group (ids, x, f); outputs sized for n rows; *n_out = rows written.  Unconstrained problems. */
+PGC_API int pgc_select_best_device(pgc_ctx *ctx, const uint64_t *d_ids, const double *d_x, const double *d_f, size_t n, size_t nx,
+                                   size_t nobj, int rate_is_frac, double rate, uint64_t *d_ids_out, double *d_x_out, double *d_f_out,
+                                   size_t *n_out, void *stream);
+/* fair_replace::replace (fair_replace.cpp:63-221): merge the best min(rate, nm) migrants into the group and keep its best n, IN
+ * PLACE and in sorted order, as the reference returns it.  Unconstrained problems. */
+PGC_API int pgc_fair_replace_device(pgc_ctx *ctx, uint64_t *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nobj,
+                                    int rate_is_frac, double rate, const uint64_t *d_mids, const double *d_mx, const double *d_mf,
+                                    size_t nm, void *stream);
+/* topology::get_connections(i) for kind 0 = unconnected, 1 = ring (ring.cpp:74-116), 2 = fully_connected
+ * (fully_connected.cpp:86-115) with n vertices: sources of the edges into i and their weights; buffers sized n. */
+PGC_API int pgc_topology_connections(int kind, size_t n, size_t i, double weight, size_t *idx_out, double *w_out, size_t *count);
+
 /* Debug/profiling aid for the CEC2014 stage kernel: same evaluation with clock64() phase counters, summed over all
  * warp-tiles and stages.  out7 = {load, weight pass, token wait, GEMM, z store, epilogue} cycles, warp-tiles. */
 PGC_API int pgc_debug_cec2014_phase_cycles(pgc_problem *prob, const double *d_dvs, size_t n, double *d_fvs, uint64_t *out7);

@@ -71,6 +71,15 @@ int oracle_de_evolve(const oracle_problem *prob, const double *lb, const double 
                      const unsigned *allowed, unsigned n_allowed, double ftol, double xtol, uint64_t seed, uint32_t first_generation,
                      unsigned *gens_done, double *F_state, double *CR_state, unsigned *variant_state);
 
+/* ---- migration (restate_migration.c): select_best / fair_replace on flat groups, topology in-edge lists ---- */
+int oracle_select_best(const uint64_t *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac, double rate,
+                       uint64_t *ids_out, double *x_out, double *f_out, size_t *n_out);
+int oracle_fair_replace(const uint64_t *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac, double rate,
+                        const uint64_t *mids, const double *mx, const double *mf, size_t nm, uint64_t *ids_out, double *x_out, double *f_out);
+int oracle_ring_connections(size_t n, size_t i, size_t *out, size_t *count);
+int oracle_fully_connected_connections(size_t n, size_t i, size_t *out, size_t *count);
+int oracle_population_init(const double *lb, const double *ub, size_t n, size_t nx, uint64_t seed, double *x, uint64_t *ids);
+
 /* ---- Philox draws and NSGA-II generation operators (philox.h, restate_nsga2.c) ---- */
 void oracle_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double oracle_philox_u01_at(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot);

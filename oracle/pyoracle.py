@@ -54,7 +54,7 @@ class OracleProblem(C.Structure):
                 ("rotation", c_double_p), ("shift", c_double_p), ("shuffle", c_int_p)]
 
 
-FAMILY_ID = {"rastrigin": 1, "ackley": 2, "griewank": 3, "schwefel": 4, "rosenbrock": 5, "cec2014": 6, "zdt": 8, "dtlz": 9,
+FAMILY_ID = {"rastrigin": 1, "ackley": 2, "griewank": 3, "schwefel": 4, "rosenbrock": 5, "cec2014": 6, "cec2013": 7, "zdt": 8, "dtlz": 9,
              "lennard_jones": 11}
 
 
@@ -167,7 +167,9 @@ class Oracle:
         p = OracleProblem(FAMILY_ID[family], prob_id, dim, nobj, param, None, None, None)
         p._keep = tables
         if tables is not None:
-            p.rotation, p.shift, p.shuffle = _dp(tables[0]), _dp(tables[1]), _ip(tables[2])
+            p.rotation, p.shift = _dp(tables[0]), _dp(tables[1])
+            if len(tables) > 2:
+                p.shuffle = _ip(tables[2])
         return p
 
     def pso_evolve(self, prob, lb, ub, x, f, v=None, gens=1, omega=0.7298, eta1=2.05, eta2=2.05, max_vel=0.5, variant=5, neighb_type=2,
@@ -210,6 +212,56 @@ class Oracle:
         if rc:
             raise ValueError("oracle_de_evolve failed")
         return x, f, done.value, Fs, Cs, Vs
+
+    # ---- migration (restate_migration.c) ----
+    @staticmethod
+    def _group(ids, x, f, nf=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = x.shape[0]
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = f.reshape(n, -1) if n else f.reshape(0, nf if nf is not None else (f.shape[1] if f.ndim == 2 else 1))
+        return np.ascontiguousarray(ids, dtype=np.uint64), x, f
+
+    def select_best(self, ids, x, f, rate):
+        """select_best{rate}.select: (ids, x, f) of the selected individuals; float rate = fractional."""
+        ids, x, f = self._group(ids, x, f)
+        n, nx, nf = x.shape[0], x.shape[1], f.shape[1]
+        io, xo, fo = np.empty(max(n, 1), dtype=np.uint64), np.empty((max(n, 1), nx)), np.empty((max(n, 1), nf))
+        k = C.c_size_t()
+        u64p = C.POINTER(C.c_uint64)
+        if self.lib.oracle_select_best(ids.ctypes.data_as(u64p), _dp(x), _dp(f), C.c_size_t(n), C.c_size_t(nx), C.c_size_t(nf),
+                                       C.c_int(isinstance(rate, float)), C.c_double(rate), io.ctypes.data_as(u64p), _dp(xo), _dp(fo), C.byref(k)):
+            raise ValueError("oracle_select_best: invalid migration rate")
+        return io[:k.value], xo[:k.value], fo[:k.value]
+
+    def fair_replace(self, ids, x, f, rate, mids, mx, mf):
+        """fair_replace{rate}.replace: the new (ids, x, f) of the island."""
+        ids, x, f = self._group(ids, x, f)
+        n, nx, nf = x.shape[0], x.shape[1], f.shape[1]
+        mids, mx, mf = self._group(mids, np.asarray(mx, dtype=np.float64).reshape(-1, nx), mf, nf)
+        io, xo, fo = np.empty(max(n, 1), dtype=np.uint64), np.empty((max(n, 1), nx)), np.empty((max(n, 1), nf))
+        u64p = C.POINTER(C.c_uint64)
+        if self.lib.oracle_fair_replace(ids.ctypes.data_as(u64p), _dp(x), _dp(f), C.c_size_t(n), C.c_size_t(nx), C.c_size_t(nf),
+                                        C.c_int(isinstance(rate, float)), C.c_double(rate), mids.ctypes.data_as(u64p), _dp(mx), _dp(mf),
+                                        C.c_size_t(mx.shape[0]), io.ctypes.data_as(u64p), _dp(xo), _dp(fo)):
+            raise ValueError("oracle_fair_replace: invalid migration rate")
+        return io[:n], xo[:n], fo[:n]
+
+    def connections(self, kind: str, n: int, i: int) -> np.ndarray:
+        out = np.empty(max(n, 1), dtype=np.uint64)
+        cnt = C.c_size_t()
+        fn = {"ring": self.lib.oracle_ring_connections, "fully_connected": self.lib.oracle_fully_connected_connections}[kind]
+        if fn(C.c_size_t(n), C.c_size_t(i), out.ctypes.data_as(C.POINTER(C.c_size_t)), C.byref(cnt)):
+            raise ValueError("invalid vertex index")
+        return out[:cnt.value].astype(np.int64)
+
+    def population_init(self, lb, ub, n: int, seed: int):
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        x, ids = np.empty((n, lb.size)), np.empty(n, dtype=np.uint64)
+        if self.lib.oracle_population_init(_dp(lb), _dp(ub), C.c_size_t(n), C.c_size_t(lb.size), C.c_uint64(seed), _dp(x),
+                                           ids.ctypes.data_as(C.POINTER(C.c_uint64))):
+            raise ValueError("Cannot generate a random real if the bounds are not finite")
+        return x, ids
 
     # ---- Philox draws and NSGA-II operators (restate_nsga2.c) ----
     def philox_raw(self, ctr, key):
@@ -409,6 +461,32 @@ class Reference:
         self.lib.ref_cec2013_tables.argtypes = [C.c_uint, c_double_p, c_double_p]
         self._check(self.lib.ref_cec2013_tables(C.c_uint(dim), _dp(mr), _dp(os_)))
         return mr, os_
+
+    def fair_replace(self, ids, x, f, rate, mids, mx, mf):
+        """unmodified fair_replace{rate}.replace on flat groups."""
+        ids, x, f = Oracle._group(ids, x, f)
+        n, nx, nf = x.shape[0], x.shape[1], f.shape[1]
+        mids, mx, mf = Oracle._group(mids, np.asarray(mx, dtype=np.float64).reshape(-1, nx), mf, nf)
+        io, xo, fo = np.empty(max(n, 1), dtype=np.uint64), np.empty((max(n, 1), nx)), np.empty((max(n, 1), nf))
+        u64p = C.POINTER(C.c_ulonglong)
+        self.lib.ref_fair_replace.argtypes = [u64p, c_double_p, c_double_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_double, u64p,
+                                              c_double_p, c_double_p, C.c_size_t, u64p, c_double_p, c_double_p]
+        self._check(self.lib.ref_fair_replace(ids.ctypes.data_as(u64p), _dp(x), _dp(f), n, nx, nf, int(isinstance(rate, float)), float(rate),
+                                              mids.ctypes.data_as(u64p), _dp(mx), _dp(mf), mx.shape[0], io.ctypes.data_as(u64p), _dp(xo),
+                                              _dp(fo)))
+        return io[:n], xo[:n], fo[:n]
+
+    def select_best(self, ids, x, f, rate):
+        ids, x, f = Oracle._group(ids, x, f)
+        n, nx, nf = x.shape[0], x.shape[1], f.shape[1]
+        io, xo, fo = np.empty(max(n, 1), dtype=np.uint64), np.empty((max(n, 1), nx)), np.empty((max(n, 1), nf))
+        k = C.c_size_t()
+        u64p = C.POINTER(C.c_ulonglong)
+        self.lib.ref_select_best.argtypes = [u64p, c_double_p, c_double_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_double, u64p,
+                                             c_double_p, c_double_p, C.POINTER(C.c_size_t)]
+        self._check(self.lib.ref_select_best(ids.ctypes.data_as(u64p), _dp(x), _dp(f), n, nx, nf, int(isinstance(rate, float)), float(rate),
+                                             io.ctypes.data_as(u64p), _dp(xo), _dp(fo), C.byref(k)))
+        return io[:k.value], xo[:k.value], fo[:k.value]
 
     def cec2014_origin_shift(self, prob: RefProblem) -> np.ndarray:
         out = np.empty(CEC_NCOMP * 100)

@@ -62,6 +62,15 @@ int ref_nadir(const double *f, size_t n, size_t m, double *out);
 int ref_evolve(ref_problem *p, const char *algo, unsigned pop_size, unsigned gens, unsigned pop_seed, unsigned algo_seed,
                int use_bfe, double *seconds, double *x_out, double *f_out, unsigned long long *fevals);
 
+/* ---- unmodified reference migration policies (ref_policies.cpp) on flat row-major groups (ids[n], x[n x nx], f[n x nobj]);
+ * unconstrained problems (nec = nic = 0).  fair_replace::replace fair_replace.cpp:63-221, select_best::select select_best.cpp:63-171.
+ * rate: absolute count, or a fraction of n when rate_is_frac. */
+int ref_fair_replace(const unsigned long long *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac,
+                     double rate, const unsigned long long *mids, const double *mx, const double *mf, size_t nm, unsigned long long *ids_out,
+                     double *x_out, double *f_out);
+int ref_select_best(const unsigned long long *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac,
+                    double rate, unsigned long long *ids_out, double *x_out, double *f_out, size_t *n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,71 @@
+// oracle/ref_policies.cpp - C entry points over the UNMODIFIED reference migration policies (fair_replace, select_best).
+// TEST INFRASTRUCTURE ONLY; see ref_capi.h.
+#include <cstring>
+#include <stdexcept>
+#include <tuple>
+#include <vector>
+
+#include <pagmo/r_policies/fair_replace.hpp>
+#include <pagmo/s_policies/select_best.hpp>
+#include <pagmo/types.hpp>
+
+#include "ref_capi.h"
+
+extern "C" void ref_set_error(const char *what);
+
+namespace
+{
+pagmo::individuals_group_t group_of(const unsigned long long *ids, const double *x, const double *f, size_t n, size_t nx, size_t nf)
+{
+    pagmo::individuals_group_t g;
+    for (size_t i = 0; i < n; ++i) {
+        std::get<0>(g).push_back(ids[i]);
+        std::get<1>(g).emplace_back(x + i * nx, x + (i + 1) * nx);
+        std::get<2>(g).emplace_back(f + i * nf, f + (i + 1) * nf);
+    }
+    return g;
+}
+size_t flatten(const pagmo::individuals_group_t &g, unsigned long long *ids, double *x, double *f, size_t nx, size_t nf)
+{
+    const size_t n = std::get<0>(g).size();
+    for (size_t i = 0; i < n; ++i) {
+        ids[i] = std::get<0>(g)[i];
+        std::memcpy(x + i * nx, std::get<1>(g)[i].data(), nx * sizeof(double));
+        std::memcpy(f + i * nf, std::get<2>(g)[i].data(), nf * sizeof(double));
+    }
+    return n;
+}
+} // namespace
+
+extern "C" {
+
+// fair_replace{rate}.replace(inds, nx, 0, nobj, 0, 0, {}, mig) (fair_replace.cpp:63-221).  rate_is_frac: fractional rate.
+int ref_fair_replace(const unsigned long long *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac,
+                     double rate, const unsigned long long *mids, const double *mx, const double *mf, size_t nm, unsigned long long *ids_out,
+                     double *x_out, double *f_out)
+{
+    try {
+        const auto pol = rate_is_frac ? pagmo::fair_replace(rate) : pagmo::fair_replace(static_cast<pagmo::pop_size_t>(rate));
+        const auto out = pol.replace(group_of(ids, x, f, n, nx, nobj), nx, 0, nobj, 0, 0, {}, group_of(mids, mx, mf, nm, nx, nobj));
+        if (flatten(out, ids_out, x_out, f_out, nx, nobj) != n) throw std::runtime_error("fair_replace changed the population size");
+        return 0;
+    } catch (const std::exception &e) {
+        ref_set_error(e.what());
+        return 1;
+    }
+}
+
+// select_best{rate}.select(inds, nx, 0, nobj, 0, 0, {}) (select_best.cpp:63-171); outputs sized n
+int ref_select_best(const unsigned long long *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac,
+                    double rate, unsigned long long *ids_out, double *x_out, double *f_out, size_t *n_out)
+{
+    try {
+        const auto pol = rate_is_frac ? pagmo::select_best(rate) : pagmo::select_best(static_cast<pagmo::pop_size_t>(rate));
+        *n_out = flatten(pol.select(group_of(ids, x, f, n, nx, nobj), nx, 0, nobj, 0, 0, {}), ids_out, x_out, f_out, nx, nobj);
+        return 0;
+    } catch (const std::exception &e) {
+        ref_set_error(e.what());
+        return 1;
+    }
+}
+}

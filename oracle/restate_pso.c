@@ -22,6 +22,7 @@ int oracle_problem_eval(const oracle_problem *p, const double *xs, size_t n, dou
     switch (p->family) {
         case 1: case 2: case 3: case 4: case 5: return oracle_simple_batch(p->family, p->dim, xs, n, fs);
         case 6: return oracle_cec2014_batch(p->prob_id, p->dim, p->rotation, p->shift, p->shuffle, xs, n, fs, 1);
+        case 7: return oracle_cec2013_batch(p->prob_id, p->dim, p->rotation, p->shift, xs, n, fs);
         case 8: return oracle_zdt_batch(p->prob_id, xs, n, p->dim, fs);
         case 9: return oracle_dtlz_batch(p->prob_id, xs, n, p->dim, p->nobj, p->param, fs);
         case 11: return oracle_lj_batch(p->dim, xs, n, fs);

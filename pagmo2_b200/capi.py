@@ -41,6 +41,53 @@ class ProblemDesc(C.Structure):
     ]
 
 
+class AlgoDesc(C.Structure):
+    """pgc_algo_desc: constructor arguments of the reference UDAs."""
+    _fields_ = [
+        ("algo", C.c_int32), ("gens", C.c_uint32), ("variant", C.c_uint32), ("variant_adptv", C.c_uint32), ("neighb_type", C.c_uint32),
+        ("neighb_param", C.c_uint32), ("n_allowed", C.c_uint32), ("allowed_variants", C.c_uint32 * 18),
+        ("F", C.c_double), ("CR", C.c_double), ("ftol", C.c_double), ("xtol", C.c_double),
+        ("omega", C.c_double), ("eta1", C.c_double), ("eta2", C.c_double), ("max_vel", C.c_double),
+        ("cr", C.c_double), ("eta_c", C.c_double), ("m", C.c_double), ("eta_m", C.c_double), ("seed", C.c_uint64),
+    ]
+
+
+ALGO = {"de": 1, "sade": 2, "de1220": 3, "pso_gen": 4, "nsga2": 5}
+TOPOLOGY = {"unconnected": 0, "ring": 1, "fully_connected": 2}
+
+
+def algo_desc(name: str, gens: int = 1, seed: int = 0, **overrides) -> AlgoDesc:
+    """Reference-default constructor arguments of UDA `name`, with keyword overrides (e.g. variant=7, ftol=0.)."""
+    d = AlgoDesc()
+    check(lib().pgc_algo_defaults(ALGO[name], gens, seed, C.byref(d)))
+    for k, v in overrides.items():
+        if k == "allowed_variants":
+            d.n_allowed = len(v)
+            for i, a in enumerate(v):
+                d.allowed_variants[i] = a
+        else:
+            if not hasattr(d, k):
+                raise AttributeError(f"pgc_algo_desc has no field {k!r}")
+            setattr(d, k, v)
+    return d
+
+
+def topology_connections(kind: str, n: int, i: int, weight: float = 1.0):
+    """topology::get_connections(i): (sources of the edges into i, weights)."""
+    idx = np.empty(max(n, 1), dtype=np.uint64)
+    w = np.empty(max(n, 1))
+    cnt = C.c_size_t()
+    check(lib().pgc_topology_connections(TOPOLOGY[kind], n, i, weight, idx.ctypes.data_as(C.POINTER(C.c_size_t)),
+                                         w.ctypes.data_as(C.POINTER(C.c_double)), C.byref(cnt)))
+    return idx[:cnt.value].astype(np.int64), w[:cnt.value].copy()
+
+
+def philox_u01(seed: int, tag: int, generation: int, index: int, slot: int) -> float:
+    out = C.c_double()
+    check(lib().pgc_philox_u01(seed, tag, generation, index, slot, C.byref(out)))
+    return out.value
+
+
 _lib = None
 
 
@@ -55,6 +102,7 @@ def lib():
         L.pgc_version.restype = C.c_char_p
         L.pgc_last_error.restype = C.c_char_p
         vp, sz, dp = C.c_void_p, C.c_size_t, C.POINTER(C.c_double)
+        szp = C.POINTER(C.c_size_t)
         L.pgc_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.pgc_ctx_destroy.argtypes = [vp]
         L.pgc_ctx_stream.argtypes = [vp, C.POINTER(vp)]
@@ -76,7 +124,6 @@ def lib():
         L.pgc_free_pinned.argtypes = [vp, vp]
         L.pgc_memcpy_h2d.argtypes = [vp, vp, vp, sz]
         L.pgc_memcpy_d2h.argtypes = [vp, vp, vp, sz]
-        szp = C.POINTER(C.c_size_t)
         L.pgc_fnds_host.argtypes = [vp, vp, sz, sz, szp, szp, szp, szp, szp]
         L.pgc_crowding_distance_host.argtypes = [vp, vp, sz, sz, dp]
         L.pgc_select_best_N_mo_host.argtypes = [vp, vp, sz, sz, sz, szp, szp]
@@ -95,6 +142,12 @@ def lib():
                                             C.c_uint, C.c_uint, C.c_uint64, C.c_uint32, vp]
         L.pgc_de_evolve_device.argtypes = [vp, vp, vp, sz, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_double, vp, C.c_uint,
                                            C.c_double, C.c_double, vp, vp, vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint), vp]
+        L.pgc_algo_defaults.argtypes = [C.c_int, C.c_uint, C.c_uint64, C.POINTER(AlgoDesc)]
+        L.pgc_algo_evolve_device.argtypes = [vp, C.POINTER(AlgoDesc), vp, vp, sz, C.c_uint32, C.POINTER(C.c_uint), vp]
+        L.pgc_population_init_device.argtypes = [vp, sz, C.c_uint64, vp, vp, vp, vp]
+        L.pgc_select_best_device.argtypes = [vp, vp, vp, vp, sz, sz, sz, C.c_int, C.c_double, vp, vp, vp, szp, vp]
+        L.pgc_fair_replace_device.argtypes = [vp, vp, vp, vp, sz, sz, sz, C.c_int, C.c_double, vp, vp, vp, sz, vp]
+        L.pgc_topology_connections.argtypes = [C.c_int, sz, sz, C.c_double, szp, dp, szp]
         L.pgc_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
         L.pgc_measure_fp64_mma_peak.argtypes = [vp, C.c_int, dp]
         _lib = L

@@ -708,6 +708,115 @@ int pgc_de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP,
                             stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
 }
 
+int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out)
+{
+    PGC_REQUIRE(out, "pgc_algo_defaults: null argument");
+    pgc_algo_desc d{};
+    d.algo = algo;
+    d.gens = gens;
+    d.seed = seed;
+    d.ftol = d.xtol = 1e-6;
+    d.variant_adptv = 1;
+    switch (algo) {
+        case PGC_ALGO_DE: d.F = 0.8, d.CR = 0.9, d.variant = 2; break;            // de.hpp:119
+        case PGC_ALGO_SADE: d.variant = 2; break;                                 // sade.hpp:138
+        case PGC_ALGO_DE1220: {                                                   // de1220.hpp:158, :52-53
+            static const uint32_t allowed[8] = {2u, 3u, 7u, 10u, 13u, 14u, 15u, 16u};
+            d.n_allowed = 8;
+            for (int i = 0; i < 8; ++i) d.allowed_variants[i] = allowed[i];
+            break;
+        }
+        case PGC_ALGO_PSO_GEN: // pso_gen.hpp:127
+            d.omega = 0.7298, d.eta1 = d.eta2 = 2.05, d.max_vel = 0.5, d.variant = 5, d.neighb_type = 2, d.neighb_param = 4;
+            break;
+        case PGC_ALGO_NSGA2: d.cr = 0.95, d.eta_c = 10., d.m = 0.01, d.eta_m = 50.; break; // nsga2.hpp:103
+        default: set_error("pgc_algo_defaults: unknown algorithm %d", algo); return PGC_ERR_INVALID_ARGUMENT;
+    }
+    *out = d;
+    return PGC_OK;
+}
+
+int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *a, double *d_x, double *d_f, size_t n, uint32_t first_generation,
+                           unsigned *gens_done, void *stream)
+{
+    PGC_REQUIRE(prob && a && d_x && d_f, "pgc_algo_evolve_device: null argument");
+    if (gens_done) *gens_done = a->gens;
+    switch (a->algo) {
+        case PGC_ALGO_DE:
+        case PGC_ALGO_SADE:
+        case PGC_ALGO_DE1220:
+            return pgc_de_evolve_device(prob, d_x, d_f, n, a->gens, static_cast<unsigned>(a->algo - PGC_ALGO_DE), a->variant, a->variant_adptv,
+                                        a->F, a->CR, a->allowed_variants, a->n_allowed, a->ftol, a->xtol, nullptr, nullptr, nullptr, a->seed,
+                                        first_generation, gens_done, stream);
+        case PGC_ALGO_PSO_GEN:
+            return pgc_pso_evolve_device(prob, d_x, d_f, nullptr, nullptr, n, a->gens, a->omega, a->eta1, a->eta2, a->max_vel, a->variant,
+                                         a->neighb_type, a->neighb_param, a->seed, first_generation, stream);
+        case PGC_ALGO_NSGA2:
+            return pgc_nsga2_evolve_device(prob, d_x, d_f, n, a->gens, a->cr, a->eta_c, a->m, a->eta_m, a->seed, first_generation, stream);
+        default: set_error("pgc_algo_evolve_device: unknown algorithm %d", a->algo); return PGC_ERR_INVALID_ARGUMENT;
+    }
+}
+
+int pgc_population_init_device(pgc_problem *prob, size_t n, uint64_t seed, double *d_x, double *d_f, uint64_t *d_ids, void *stream)
+{
+    PGC_REQUIRE(prob && (d_x || n == 0), "pgc_population_init_device: null argument");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    return population_init_device(prob, n, seed, d_x, d_f, reinterpret_cast<unsigned long long *>(d_ids), problem_eval_device,
+                                  stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
+}
+
+int pgc_select_best_device(pgc_ctx *ctx, const uint64_t *d_ids, const double *d_x, const double *d_f, size_t n, size_t nx, size_t nobj,
+                           int rate_is_frac, double rate, uint64_t *d_ids_out, double *d_x_out, double *d_f_out, size_t *n_out, void *stream)
+{
+    PGC_REQUIRE(ctx && n_out && (n == 0 || (d_ids && d_x && d_f && d_ids_out && d_x_out && d_f_out)), "pgc_select_best_device: null argument");
+    PGC_REQUIRE(nobj >= 1 && nx >= 1 && n < 0x7fffffffull, "pgc_select_best_device: invalid sizes");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return select_best_policy_device(ctx, reinterpret_cast<const unsigned long long *>(d_ids), d_x, d_f, n, nx, nobj, rate_is_frac, rate,
+                                     reinterpret_cast<unsigned long long *>(d_ids_out), d_x_out, d_f_out, n_out,
+                                     stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int pgc_fair_replace_device(pgc_ctx *ctx, uint64_t *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nobj, int rate_is_frac,
+                            double rate, const uint64_t *d_mids, const double *d_mx, const double *d_mf, size_t nm, void *stream)
+{
+    PGC_REQUIRE(ctx && (n == 0 || (d_ids && d_x && d_f)) && (nm == 0 || (d_mids && d_mx && d_mf)), "pgc_fair_replace_device: null argument");
+    PGC_REQUIRE(nobj >= 1 && nx >= 1 && n + nm < 0x7fffffffull, "pgc_fair_replace_device: invalid sizes");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return fair_replace_policy_device(ctx, reinterpret_cast<unsigned long long *>(d_ids), d_x, d_f, n, nx, nobj, rate_is_frac, rate,
+                                      reinterpret_cast<const unsigned long long *>(d_mids), d_mx, d_mf, nm,
+                                      stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int pgc_topology_connections(int kind, size_t n, size_t i, double weight, size_t *idx_out, double *w_out, size_t *count)
+{
+    PGC_REQUIRE(idx_out && w_out && count, "pgc_topology_connections: null argument");
+    PGC_REQUIRE(weight >= 0.0 && weight <= 1.0, "invalid weight for the edge of a topology: the value %g is not in the [0., 1.] range", weight);
+    std::vector<size_t> src;
+    switch (kind) {
+        case 0: PGC_REQUIRE(i < n, "pgc_topology_connections: vertex %zu of %zu", i, n); break; // unconnected.cpp: no edges
+        case 1: {
+            int rc = ring_connections(n, i, src);
+            if (rc != PGC_OK) return rc;
+            break;
+        }
+        case 2: // fully_connected.cpp:86-115
+            PGC_REQUIRE(i < n,
+                        "Cannot get the connections to the vertex at index %zu in a fully connected topology: the number of vertices in the "
+                        "topology is only %zu",
+                        i, n);
+            for (size_t j = 0; j < n; ++j)
+                if (j != i) src.push_back(j);
+            break;
+        default: set_error("pgc_topology_connections: unknown topology kind %d", kind); return PGC_ERR_INVALID_ARGUMENT;
+    }
+    *count = src.size();
+    for (size_t q = 0; q < src.size(); ++q) {
+        idx_out[q] = src[q];
+        w_out[q] = weight;
+    }
+    return PGC_OK;
+}
+
 int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out)
 {
     PGC_REQUIRE(ctx && out, "pgc_malloc_device: null argument");

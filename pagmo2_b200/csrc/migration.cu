@@ -1,0 +1,209 @@
+// migration.cu - the migration step of an archipelago on device-resident populations (sm_100a).
+//
+// Replaces reference select_best::select (src/s_policies/select_best.cpp:63-171) and fair_replace::replace
+// (src/r_policies/fair_replace.cpp:63-221) for unconstrained problems (every UDP of the device path), and the in-edge lists of
+// ring / fully_connected (src/topologies/ring.cpp:74-116, fully_connected.cpp:86-115) that island::evolve consults
+// (src/island.cpp:461-470).  Populations are flat row-major groups: ids[n] (u64), x[n x nx], f[n x nobj].
+//   single objective : order by fitness, NaN last (detail::less_than_f) - a stable radix sort on order-preserving u64 keys
+//   multi objective  : select_best_N_mo (mo_utils.cu)
+// The reference sorts with std::sort (order of ties unspecified); here ties keep index order, residents before migrants.
+// HBM-bound index work: bytes = 8*(n + k) keys + 8*(nx + nobj + 1) per moved row.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <vector>
+
+#include "pgc_internal.cuh"
+
+namespace pgc
+{
+
+namespace
+{
+
+__global__ void so_keys_kernel(const double *__restrict__ f, size_t stride, unsigned n, unsigned long long *keys, unsigned *idx)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = f[i * stride];
+    unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+    // order-preserving map of IEEE doubles; every NaN goes to the top (less_than_f: NaN is greater than anything)
+    b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+    keys[i] = (v != v) ? 0xffffffffffffffffull : b;
+    idx[i] = i;
+}
+
+// out row r = (r < n0 ? A : B)[sel[r]]: gathers ids / x / f rows of a merged group A (n0 rows) ++ B
+__global__ void gather_rows_kernel(const unsigned *__restrict__ sel, unsigned rows, unsigned n0, unsigned nx, unsigned nf,
+                                   const unsigned long long *idA, const double *xA, const double *fA, const unsigned long long *idB,
+                                   const double *xB, const double *fB, unsigned long long *id_out, double *x_out, double *f_out)
+{
+    const unsigned r = blockIdx.x;
+    if (r >= rows) return;
+    const unsigned s = sel ? sel[r] : r;
+    const bool a = s < n0;
+    const unsigned src = a ? s : s - n0;
+    const double *x = (a ? xA : xB) + static_cast<size_t>(src) * nx, *f = (a ? fA : fB) + static_cast<size_t>(src) * nf;
+    for (unsigned j = threadIdx.x; j < nx; j += blockDim.x) x_out[static_cast<size_t>(r) * nx + j] = x[j];
+    for (unsigned j = threadIdx.x; j < nf; j += blockDim.x) f_out[static_cast<size_t>(r) * nf + j] = f[j];
+    if (threadIdx.x == 0) id_out[r] = (a ? idA : idB)[src];
+}
+
+struct Tmp { // stream-ordered scratch
+    cudaStream_t st;
+    std::vector<void *> ptrs;
+    explicit Tmp(cudaStream_t s) : st(s) {}
+    template <class T> int get(T **out, size_t count)
+    {
+        void *p = nullptr;
+        PGC_CUDA(cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), st));
+        ptrs.push_back(p);
+        *out = static_cast<T *>(p);
+        return PGC_OK;
+    }
+    ~Tmp()
+    {
+        for (void *p : ptrs) cudaFreeAsync(p, st);
+    }
+};
+
+// d_sel[0..k) = indices of the best k rows of f [n x nobj]
+int best_indices(pgc_ctx *ctx, const double *d_f, size_t n, size_t nobj, size_t k, unsigned *d_sel, Tmp &tmp, cudaStream_t st)
+{
+    if (k == 0 || n == 0) return PGC_OK;
+    if (nobj > 1) {
+        unsigned nout = 0;
+        unsigned *full = nullptr;
+        int rc = tmp.get(&full, n);
+        if (rc != PGC_OK) return rc;
+        rc = select_best_device(ctx, d_f, n, nobj, k, full, &nout, st);
+        if (rc != PGC_OK) return rc;
+        PGC_REQUIRE(nout == k, "migration: select_best_N_mo returned %u of %zu individuals", nout, k);
+        PGC_CUDA(cudaMemcpyAsync(d_sel, full, k * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+        return PGC_OK;
+    }
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    unsigned *i0 = nullptr, *i1 = nullptr;
+    int rc;
+    if ((rc = tmp.get(&k0, n)) || (rc = tmp.get(&k1, n)) || (rc = tmp.get(&i0, n)) || (rc = tmp.get(&i1, n))) return rc;
+    const unsigned un = static_cast<unsigned>(n);
+    so_keys_kernel<<<(un + 255) / 256, 256, 0, st>>>(d_f, 1, un, k0, i0);
+    PGC_CUDA(cudaGetLastError());
+    size_t bytes = 0;
+    PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0, k1, i0, i1, static_cast<int>(n), 0, 64, st));
+    unsigned char *ws = nullptr;
+    if ((rc = tmp.get(&ws, bytes))) return rc;
+    PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, bytes, k0, k1, i0, i1, static_cast<int>(n), 0, 64, st));
+    PGC_CUDA(cudaMemcpyAsync(d_sel, i1, k * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    ctx->launches.fetch_add(3, std::memory_order_relaxed);
+    return PGC_OK;
+}
+
+int rate_count(const char *who, int rate_is_frac, double rate, size_t n, size_t *out)
+{
+    if (rate_is_frac) { // base_sr_policy.cpp:46-55
+        PGC_REQUIRE(rate >= 0.0 && rate <= 1.0 && rate == rate,
+                    "Invalid fractional migration rate specified in the constructor of a replacement/selection policy: the rate must be in "
+                    "the [0., 1.] range, but it is %g instead",
+                    rate);
+        const size_t c = static_cast<size_t>(rate * static_cast<double>(n));
+        *out = c < n ? c : n;
+        return PGC_OK;
+    }
+    PGC_REQUIRE(rate >= 0.0, "%s: negative absolute migration rate", who);
+    const size_t c = static_cast<size_t>(rate);
+    PGC_REQUIRE(c <= n, "The absolute migration rate (%zu) in a '%s' policy is larger than the number of input individuals (%zu)", c, who, n);
+    *out = c;
+    return PGC_OK;
+}
+
+} // namespace
+
+int select_best_policy_device(pgc_ctx *ctx, const unsigned long long *d_ids, const double *d_x, const double *d_f, size_t n, size_t nx,
+                              size_t nobj, int rate_is_frac, double rate, unsigned long long *d_ids_out, double *d_x_out, double *d_f_out,
+                              size_t *n_out, cudaStream_t st)
+{
+    size_t k = 0;
+    int rc = rate_count("Select best", rate_is_frac, rate, n, &k); // select_best.cpp:80-100
+    if (rc != PGC_OK) return rc;
+    *n_out = k;
+    if (k == 0) return PGC_OK;
+    Tmp tmp(st);
+    unsigned *sel = nullptr;
+    if ((rc = tmp.get(&sel, k)) || (rc = best_indices(ctx, d_f, n, nobj, k, sel, tmp, st))) return rc;
+    gather_rows_kernel<<<static_cast<unsigned>(k), 64, 0, st>>>(sel, static_cast<unsigned>(k), static_cast<unsigned>(n), static_cast<unsigned>(nx),
+                                                                static_cast<unsigned>(nobj), d_ids, d_x, d_f, d_ids, d_x, d_f, d_ids_out, d_x_out,
+                                                                d_f_out);
+    PGC_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return PGC_OK;
+}
+
+int fair_replace_policy_device(pgc_ctx *ctx, unsigned long long *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nobj,
+                               int rate_is_frac, double rate, const unsigned long long *d_mids, const double *d_mx, const double *d_mf,
+                               size_t nm, cudaStream_t st)
+{
+    size_t k = 0;
+    int rc = rate_count("fair_replace", rate_is_frac, rate, n, &k); // fair_replace.cpp:80-103
+    if (rc != PGC_OK) return rc;
+    if (k > nm) k = nm; // :105-107
+    if (n == 0) return PGC_OK;
+    Tmp tmp(st);
+    // the top k migrants (:118-123 / :191), appended to the residents (:127-132)
+    unsigned *top = nullptr, *keep = nullptr;
+    unsigned long long *gid = nullptr, *oid = nullptr;
+    double *gx = nullptr, *gf = nullptr, *ox = nullptr, *of = nullptr;
+    const size_t tot = n + k;
+    if ((rc = tmp.get(&top, k)) || (rc = tmp.get(&keep, n)) || (rc = tmp.get(&gid, k)) || (rc = tmp.get(&gx, k * nx)) || (rc = tmp.get(&gf, tot * nobj))
+        || (rc = tmp.get(&oid, n)) || (rc = tmp.get(&ox, n * nx)) || (rc = tmp.get(&of, n * nobj)))
+        return rc;
+    if (k) {
+        if ((rc = best_indices(ctx, d_mf, nm, nobj, k, top, tmp, st))) return rc;
+        // merged fitness = residents ++ chosen migrants (rows n..tot-1 of gf); chosen migrants' ids / x in gid / gx
+        gather_rows_kernel<<<static_cast<unsigned>(k), 64, 0, st>>>(top, static_cast<unsigned>(k), static_cast<unsigned>(nm), static_cast<unsigned>(nx),
+                                                                    static_cast<unsigned>(nobj), d_mids, d_mx, d_mf, d_mids, d_mx, d_mf, gid, gx,
+                                                                    gf + n * nobj);
+        PGC_CUDA(cudaGetLastError());
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    PGC_CUDA(cudaMemcpyAsync(gf, d_f, n * nobj * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // the best n of the merged group, in sorted order (:134-155 / :203-217): this REORDERS the island's population
+    if ((rc = best_indices(ctx, gf, tot, nobj, n, keep, tmp, st))) return rc;
+    gather_rows_kernel<<<static_cast<unsigned>(n), 64, 0, st>>>(keep, static_cast<unsigned>(n), static_cast<unsigned>(n), static_cast<unsigned>(nx),
+                                                                static_cast<unsigned>(nobj), d_ids, d_x, d_f, gid, gx, gf + n * nobj, oid, ox, of);
+    PGC_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    PGC_CUDA(cudaMemcpyAsync(d_ids, oid, n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(d_x, ox, n * nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(d_f, of, n * nobj * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return PGC_OK;
+}
+
+// in-edge sources of vertex i of a ring built by n push_back() calls, in base_bgl_topology::get_connections order (the in-edge
+// list of the reference's vecS/bidirectionalS graph keeps insertion order; ring.cpp:83-110 is replayed on plain vectors)
+int ring_connections(size_t n, size_t i, std::vector<size_t> &out)
+{
+    PGC_REQUIRE(i < n, "invalid vertex index in a BGL topology: the index is %zu, but the number of vertices is only %zu", i, n);
+    std::vector<std::vector<size_t>> in(n);
+    auto add = [&](size_t u, size_t v) { in[v].push_back(u); };
+    auto del = [&](size_t u, size_t v) {
+        for (size_t q = 0; q < in[v].size(); ++q)
+            if (in[v][q] == u) {
+                in[v].erase(in[v].begin() + static_cast<long>(q));
+                break;
+            }
+    };
+    for (size_t size = 1; size <= n; ++size) {
+        if (size == 2) {
+            add(0, 1), add(1, 0);
+        } else if (size == 3) {
+            add(1, 2), add(2, 1), add(2, 0), add(0, 2);
+        } else if (size > 3) {
+            del(size - 2, 0), del(0, size - 2);
+            add(size - 2, size - 1), add(size - 1, size - 2), add(0, size - 1), add(size - 1, 0);
+        }
+    }
+    out = in[i];
+    return PGC_OK;
+}
+
+} // namespace pgc

@@ -177,6 +177,15 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
                      unsigned variant_adptv, double F, double CR, const unsigned *allowed, unsigned n_allowed, double ftol, double xtol,
                      double *d_F, double *d_CR, unsigned *d_variant, unsigned long long seed, unsigned first_generation,
                      unsigned *gens_done, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
+int population_init_device(pgc_problem *prob, size_t n, unsigned long long seed, double *d_x, double *d_f, unsigned long long *d_ids,
+                           int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
+int select_best_policy_device(pgc_ctx *ctx, const unsigned long long *d_ids, const double *d_x, const double *d_f, size_t n, size_t nx,
+                              size_t nobj, int rate_is_frac, double rate, unsigned long long *d_ids_out, double *d_x_out, double *d_f_out,
+                              size_t *n_out, cudaStream_t st);
+int fair_replace_policy_device(pgc_ctx *ctx, unsigned long long *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nobj,
+                               int rate_is_frac, double rate, const unsigned long long *d_mids, const double *d_mx, const double *d_mf,
+                               size_t nm, cudaStream_t st);
+int ring_connections(size_t n, size_t i, std::vector<size_t> &out);
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops_out);

@@ -20,7 +20,8 @@ enum PhiloxTag : uint32_t { // stream tags: one per consumer so that streams nev
     kTagSga = 6,
     kTagInit = 7,
     kTagCmaes = 8,
-    kTagMigrate = 9
+    kTagMigrate = 9,
+    kTagPopulation = 10
 };
 
 struct Philox4 {

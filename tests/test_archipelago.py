@@ -1,0 +1,121 @@
+"""CPU tests of the migration path: restated policies against the compiled reference, topologies against the reference's own test
+(tests/ring.cpp:47-74, tests/fully_connected.cpp), the archipelago's host logic, and the N>1 exchange with world_size 2 over gloo."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def test_policies_restatement_vs_reference(orc, ref):
+    rng = np.random.default_rng(3)
+    for nobj in (1, 2, 3):
+        for n, nm, rate in ((20, 5, 1), (20, 5, 3), (20, 0, 2), (7, 9, 0.5), (16, 16, 1.0), (5, 3, 0), (64, 64, 0.1)):
+            ids = rng.integers(0, 2**63, n, dtype=np.uint64)
+            x, f = rng.normal(size=(n, 4)), rng.normal(size=(n, nobj))
+            mids = rng.integers(0, 2**63, nm, dtype=np.uint64)
+            mx, mf = rng.normal(size=(nm, 4)), rng.normal(size=(nm, nobj))
+            # select_best_N_mo cuts the last front by crowding distance, where the boundary points tie at +inf: the reference's
+            # std::sort leaves their order unspecified (and introsort reorders them beyond 16 elements), so multi-objective groups
+            # of that size are compared as sets of individuals
+            as_set = nobj > 1 and n + nm > 16
+
+            def same(a, b):
+                if as_set:
+                    oa, ob = np.argsort(a[0]), np.argsort(b[0])
+                    return all(np.array_equal(u[oa], v[ob]) for u, v in zip(a, b))
+                return all(np.array_equal(u, v) for u, v in zip(a, b))
+
+            assert same(orc.fair_replace(ids, x, f, rate, mids, mx, mf), ref.fair_replace(ids, x, f, rate, mids, mx, mf)), (nobj, n, nm, rate)
+            assert same(orc.select_best(ids, x, f, rate), ref.select_best(ids, x, f, rate)), (nobj, n, nm, rate)
+    # NaN fitness sorts last (detail::less_than_f); absolute rate above the population size throws (fair_replace.cpp:92-99)
+    f = np.array([[3.0], [np.nan], [1.0], [2.0]])
+    ids = np.arange(4, dtype=np.uint64)
+    for impl in (orc, ref):
+        assert list(impl.select_best(ids, np.zeros((4, 2)), f, 4)[0]) == [2, 3, 0, 1]
+        with pytest.raises(Exception):
+            impl.fair_replace(ids, np.zeros((4, 2)), f, 5, ids, np.zeros((4, 2)), f)
+        with pytest.raises(Exception):
+            impl.select_best(ids, np.zeros((4, 2)), f, 5)
+
+
+@pytest.mark.parametrize("kind", ("ring", "fully_connected"))
+def test_topologies(orc, kind):
+    from pagmo2_b200 import capi
+    for n in range(1, 12):
+        for i in range(n):
+            src, w = capi.topology_connections(kind, n, i, 0.5)
+            assert list(src) == list(orc.connections(kind, n, i)) and (w == 0.5).all()
+            if kind == "ring":  # verify_ring_topology, reference tests/ring.cpp:47-74
+                assert len(src) == (0 if n < 2 else 1 if n == 2 else 2)
+                if n >= 2:
+                    assert (i + 1) % n in src and (i - 1) % n in src
+            else:
+                assert list(src) == [j for j in range(n) if j != i]
+    with pytest.raises(capi.PgcError):
+        capi.topology_connections(kind, 3, 3)
+    with pytest.raises(capi.PgcError):
+        capi.topology_connections(kind, 3, 0, 1.5)
+    assert len(capi.topology_connections("unconnected", 4, 2)[0]) == 0
+
+
+def _archi(orc, n_islands, topology, mtype, handling, **kw):
+    from oracle_island import OracleIsland
+    from pagmo2_b200.archipelago import Archipelago
+    return Archipelago(n_islands, lambda g: OracleIsland(orc, "rastrigin", 6, 16, seed=100 + g, algo="sade", gens=2, algo_seed=7 + g, s_rate=2,
+                                                         r_rate=2, ftol=0.0, xtol=0.0),
+                       topology=topology, weight=0.75, migration_type=mtype, migrant_handling=handling, seed=5, **kw)
+
+
+def test_archipelago_host_logic(orc):
+    # unconnected islands never exchange anything and evolve exactly like stand-alone islands
+    a = _archi(orc, 3, "unconnected", "p2p", "preserve")
+    a.evolve(3)
+    from oracle_island import OracleIsland
+    solo = OracleIsland(orc, "rastrigin", 6, 16, seed=101, algo="sade", gens=2, algo_seed=8, ftol=0.0, xtol=0.0)
+    for _ in range(3):
+        solo.evolve()
+    assert np.array_equal(a.islands[1].population().x, solo.x) and not a.log
+    # ring: migrants enter, the log only holds IDs that are inside the destination afterwards, the database holds s_rate rows
+    for mtype in ("p2p", "broadcast"):
+        for handling in ("preserve", "evict"):
+            a = _archi(orc, 4, "ring", mtype, handling)
+            before = [isl.population().f.min() for isl in a.islands]
+            a.evolve(4)
+            assert a.log, (mtype, handling)
+            assert all(len(g) in (0, 2) for g in a.db) and (handling == "evict" or all(len(g) == 2 for g in a.db))
+            for e in a.log:
+                assert e.src in a.conn[e.dst][0] and e.src != e.dst
+            assert all(isl.population().f.min() <= b for isl, b in zip(a.islands, before))
+            for isl in a.islands:  # fair_replace leaves the population sorted only right after a migration; sizes never change
+                assert isl.population().x.shape == (16, 6)
+    with pytest.raises(ValueError):
+        _archi(orc, 4, "ring", "p2p", "keep")
+
+
+@pytest.mark.parametrize("mtype,handling", (("p2p", "preserve"), ("broadcast", "evict")))
+def test_world_size_2_gloo_matches_single_process(orc, tmp_path, mtype, handling):
+    """4 islands on 2 processes (2 each, gloo all_gather of the migrants database) == the same archipelago in one process."""
+    out = tmp_path / "archi"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    port = 29500 + (os.getpid() + (0 if mtype == "p2p" else 1)) % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+           str(port), str(ROOT / "tests" / "dist_archi_worker.py"), str(out), "4", "ring", mtype, handling, "3"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    single = _archi(orc, 4, "ring", mtype, handling)
+    single.evolve(3)
+    log = []
+    for rank in range(2):
+        z = np.load(f"{out}.rank{rank}.npz")
+        assert int(z["first"]) == 2 * rank
+        for i in range(2):
+            p = single.islands[2 * rank + i].population()
+            assert np.array_equal(z["x"][i], p.x) and np.array_equal(z["f"][i], p.f) and np.array_equal(z["ids"][i], p.ids)
+        log += [tuple(row) for row in z["log"]]
+    assert sorted(log) == sorted((e.round, e.id % (1 << 62), e.src, e.dst) for e in single.log) and log

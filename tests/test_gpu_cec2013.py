@@ -3,8 +3,8 @@
 Tolerance: 1e-12 relative (north_star) - EXCEPT where the reference function itself is ill-conditioned at the test point.
 asyfunc (cec2013.cpp:1053-1059) raises coordinates to powers up to ~x^8, after which schaffer_F7 / ackley / escaffer6 take
 sin/cos of arguments whose last-bit spacing exceeds the period: the reference's own value then moves by far more than 1e-12
-when an input moves by one ulp.  For such points the bound is a few times the oracle's own response to 1-ulp input
-perturbations (measured here, per point); the share of points that needed it is written to the parity report."""
+when an input moves in its last bits.  For such points the bound is 32x the oracle's own response to input perturbations of at
+most 4 ulp(100) per coordinate (measured here, per point, 8 random draws); the share of points that needed it is written to the parity report."""
 import json
 from pathlib import Path
 
@@ -31,21 +31,26 @@ def make13(capi, ctx, orc, func, dim):
     return capi.Problem(ctx, "cec2013", prob_id=func, dim=dim, rotation=mr, shift=os_)
 
 
-def noise_floor(orc, func, xs, want, rng, reps=3):
-    """|f(x~) - f(x)| of the ORACLE for x~ = x moved by one ulp per coordinate in a random direction."""
+def noise_floor(orc, func, xs, want, rng, reps=8):
+    """max |f(x~) - f(x)| of the ORACLE over `reps` inputs x~ = x + k * ulp(100), k uniform in -4..4 per coordinate: a few units of
+    the absolute resolution of the [-100, 100] box (an ulp of x itself says nothing at x = 0, where x - Os absorbs it)."""
     k = np.zeros_like(want)
     for _ in range(reps):
-        xp = np.where(rng.integers(0, 2, xs.shape) == 1, np.nextafter(xs, np.inf), np.nextafter(xs, -np.inf))
+        xp = xs + rng.integers(-4, 5, xs.shape) * np.spacing(100.0)
         k = np.maximum(k, np.abs(orc.cec2013(func, xp) - want))
     return k
 
 
 def check(orc, func, xs, got, want, rng):
     err = np.abs(got - want)
-    strict = err <= REL_TOL * np.abs(want)
+    # schwefel_func returns 418.98...*nx + (sum of terms) (cec2013.cpp:699): near its optimum the value is the difference of two numbers
+    # of that size, so the relative bound applies to that size (the same holds for the reference's own rounding)
+    scale = 4.189828872724338e+002 * xs.shape[1] if func in (14, 15, 22, 23, 24, 25, 26, 27, 28) else 0.0
+    strict = err <= REL_TOL * np.maximum(np.abs(want), scale)
     if strict.all():
         return 0.0, float((err / np.abs(want)).max())
     loose = err <= 32.0 * noise_floor(orc, func, xs, want, rng)
+    loose &= err <= 1e-6 * np.abs(want) if func not in (8, 20) else True  # hard cap; ackley / escaffer6 after asy are chaotic
     assert (strict | loose).all(), (func, xs.shape[1], float(err[~(strict | loose)].max()), want[~(strict | loose)][:3])
     return float((~strict).mean()), float((err[strict] / np.abs(want[strict])).max()) if strict.any() else 0.0
 
