@@ -1,0 +1,218 @@
+// cuda_algorithms.hpp - header-only user-defined algorithms (UDAs, reference include/pagmo/algorithm.hpp:122-160) whose evolve()
+// runs whole generations on the device: trial construction / variation, batch fitness, selection.
+//
+//   pagmo_cuda::cuda_de      pagmo::de      (de.hpp:119      gen, F, CR, variant, ftol, xtol, seed)
+//   pagmo_cuda::cuda_sade    pagmo::sade    (sade.hpp:138    gen, variant, variant_adptv, ftol, xtol, memory, seed)
+//   pagmo_cuda::cuda_de1220  pagmo::de1220  (de1220.hpp:158  gen, allowed_variants, variant_adptv, ftol, xtol, memory, seed)
+//   pagmo_cuda::cuda_pso_gen pagmo::pso_gen (pso_gen.hpp:127 gen, omega, eta1, eta2, max_vel, variant, neighb_type, neighb_param, memory, seed)
+//   pagmo_cuda::cuda_nsga2   pagmo::nsga2   (nsga2.hpp:103   gen, cr, eta_c, m, eta_m, seed)
+//
+// Same constructor arguments as the reference UDAs (plus the device), so `algorithm{cuda_sade{50u}}` drops into an island of a
+// stock pagmo::archipelago: thread_island (thread_island.cpp:79-159) runs it unchanged, and pagmo's own migration machinery
+// (island.cpp:461-641) keeps working on the host populations.  The population's problem must have a device evaluator: a
+// pagmo_cuda:: UDP or a stock UDP that cuda_bfe recognises; otherwise evolve() throws (no CPU fallback).
+// Differences from the reference algorithms, as documented in DESIGN.md: the DE family and PSO are GENERATIONAL (all trial
+// vectors of a generation are built from the previous population and evaluated in one batch; the reference updates in place,
+// individual by individual), random draws come from Philox streams keyed by (seed, generation, individual), `memory = true` is
+// not supported.  fevals are accounted for as the reference does (one per individual per generation).
+#ifndef PAGMO_CUDA_CUDA_ALGORITHMS_HPP
+#define PAGMO_CUDA_CUDA_ALGORITHMS_HPP
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <pagmo/algorithm.hpp>
+#include <pagmo/exceptions.hpp>
+#include <pagmo/population.hpp>
+#include <pagmo/problem.hpp>
+#include <pagmo/rng.hpp>
+#include <pagmo/s11n.hpp>
+#include <pagmo/threading.hpp>
+#include <pagmo/types.hpp>
+
+#include <pagmo_cuda/cuda_bfe.hpp>
+#include <pagmo_cuda/pgc.h>
+
+namespace pagmo_cuda
+{
+
+// Common part: population <-> device round trip around pgc_algo_evolve_device.
+class cuda_algorithm_base
+{
+public:
+    pagmo::population evolve(pagmo::population pop) const
+    {
+        const auto &prob = pop.get_problem();
+        const auto n = pop.size();
+        if (m_desc.gens == 0u || n == 0u) return pop; // the reference UDAs return early on gen == 0 (de.cpp:118-120)
+        if (prob.get_nc() != 0u) {
+            pagmo_throw(std::invalid_argument, "Non linear constraints detected in " + prob.get_name() + " instance. " + get_name()
+                                                   + " cannot deal with them");
+        }
+        if (prob.is_stochastic()) {
+            pagmo_throw(std::invalid_argument, "The problem appears to be stochastic " + get_name() + " cannot deal with it");
+        }
+        const auto h = m_cache->find(prob, m_device);
+        if (!h) {
+            pagmo_throw(std::invalid_argument, get_name() + " cannot evolve a population of '" + prob.get_name()
+                                                   + "': no CUDA evaluator exists for this UDP type; there is no CPU fallback");
+        }
+        const auto nx = prob.get_nx(), nf = prob.get_nf();
+        pagmo::vector_double x(n * nx), f(n * nf);
+        for (decltype(pop.size()) i = 0; i < n; ++i) {
+            std::copy(pop.get_x()[i].begin(), pop.get_x()[i].end(), x.begin() + static_cast<std::ptrdiff_t>(i * nx));
+            std::copy(pop.get_f()[i].begin(), pop.get_f()[i].end(), f.begin() + static_cast<std::ptrdiff_t>(i * nf));
+        }
+        const unsigned done = h->evolve(m_desc, x, f, m_generation);
+        m_generation += m_desc.gens;
+        for (decltype(pop.size()) i = 0; i < n; ++i) {
+            pop.set_xf(i, pagmo::vector_double(x.begin() + static_cast<std::ptrdiff_t>(i * nx), x.begin() + static_cast<std::ptrdiff_t>((i + 1) * nx)),
+                       pagmo::vector_double(f.begin() + static_cast<std::ptrdiff_t>(i * nf), f.begin() + static_cast<std::ptrdiff_t>((i + 1) * nf)));
+        }
+        prob.increment_fevals(static_cast<unsigned long long>(done) * n); // what `done` generations of prob.fitness() would have counted
+        return pop;
+    }
+    void set_seed(unsigned seed)
+    {
+        m_desc.seed = seed;
+    }
+    unsigned get_seed() const
+    {
+        return static_cast<unsigned>(m_desc.seed);
+    }
+    unsigned get_gen() const
+    {
+        return m_desc.gens;
+    }
+    std::string get_name() const
+    {
+        return m_name + " [CUDA sm_100a]";
+    }
+    pagmo::thread_safety get_thread_safety() const
+    {
+        return pagmo::thread_safety::basic;
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_device, m_name, m_generation);
+    }
+
+protected:
+    cuda_algorithm_base(int algo, const char *name, unsigned gen, unsigned seed, int device)
+        : m_device(device), m_name(name), m_cache(std::make_shared<detail::twin_cache>())
+    {
+        detail::check(pgc_algo_defaults(algo, gen, seed, &m_desc), "pgc_algo_defaults");
+    }
+    static void no_memory(bool memory, const char *who)
+    {
+        if (memory) pagmo_throw(std::invalid_argument, std::string(who) + ": memory = true is not supported on the device path");
+    }
+    pgc_algo_desc m_desc{};
+    int m_device = 0;
+    std::string m_name;
+    mutable unsigned m_generation = 1; // Philox generation counter: successive evolve() calls continue the stream
+    std::shared_ptr<detail::twin_cache> m_cache;
+};
+
+class cuda_de : public cuda_algorithm_base
+{
+public:
+    cuda_de(unsigned gen = 1u, double F = 0.8, double CR = 0.9, unsigned variant = 2u, double ftol = 1e-6, double xtol = 1e-6,
+            unsigned seed = pagmo::random_device::next(), int device = 0)
+        : cuda_algorithm_base(PGC_ALGO_DE, "DE: Differential Evolution", gen, seed, device)
+    {
+        if (variant < 1u || variant > 10u) { // de.cpp:58-61
+            pagmo_throw(std::invalid_argument, "The Differential Evolution variant must be in [1, .., 10], while a value of "
+                                                   + std::to_string(variant) + " was detected.");
+        }
+        if (CR < 0. || F < 0. || CR > 1. || F > 1.) { // de.cpp:62-65
+            pagmo_throw(std::invalid_argument, "The F and CR parameters must be in the [0,1] range");
+        }
+        m_desc.F = F, m_desc.CR = CR, m_desc.variant = variant, m_desc.ftol = ftol, m_desc.xtol = xtol;
+    }
+};
+
+class cuda_sade : public cuda_algorithm_base
+{
+public:
+    cuda_sade(unsigned gen = 1u, unsigned variant = 2u, unsigned variant_adptv = 1u, double ftol = 1e-6, double xtol = 1e-6, bool memory = false,
+              unsigned seed = pagmo::random_device::next(), int device = 0)
+        : cuda_algorithm_base(PGC_ALGO_SADE, "saDE: Self-adaptive Differential Evolution", gen, seed, device)
+    {
+        if (variant < 1u || variant > 18u) { // sade.cpp:62-65
+            pagmo_throw(std::invalid_argument, "The Differential Evolution mutation variant must be in [1, .., 18], while a value of "
+                                                   + std::to_string(variant) + " was detected.");
+        }
+        if (variant_adptv < 1u || variant_adptv > 2u) { // sade.cpp:66-69
+            pagmo_throw(std::invalid_argument, "The variant for self-adaptation must be in [1,2], while a value of "
+                                                   + std::to_string(variant_adptv) + " was detected.");
+        }
+        no_memory(memory, "cuda_sade");
+        m_desc.variant = variant, m_desc.variant_adptv = variant_adptv, m_desc.ftol = ftol, m_desc.xtol = xtol;
+    }
+};
+
+class cuda_de1220 : public cuda_algorithm_base
+{
+public:
+    cuda_de1220(unsigned gen = 1u, std::vector<unsigned> allowed_variants = {2u, 3u, 7u, 10u, 13u, 14u, 15u, 16u}, unsigned variant_adptv = 1u,
+                double ftol = 1e-6, double xtol = 1e-6, bool memory = false, unsigned seed = pagmo::random_device::next(), int device = 0)
+        : cuda_algorithm_base(PGC_ALGO_DE1220, "sa-DE1220: Self-adaptive Differential Evolution 1220", gen, seed, device)
+    {
+        for (auto v : allowed_variants) { // de1220.cpp:62-68
+            if (v < 1u || v > 18u) {
+                pagmo_throw(std::invalid_argument,
+                            "All mutation variants considered must be in [1, .., 18], while a value of " + std::to_string(v) + " was detected.");
+            }
+        }
+        if (variant_adptv < 1u || variant_adptv > 2u) { // de1220.cpp:70-73
+            pagmo_throw(std::invalid_argument, "The variant for self-adaptation must be in [1,2], while a value of "
+                                                   + std::to_string(variant_adptv) + " was detected.");
+        }
+        if (allowed_variants.empty() || allowed_variants.size() > 18u) {
+            pagmo_throw(std::invalid_argument, "cuda_de1220: between 1 and 18 allowed variants are required");
+        }
+        no_memory(memory, "cuda_de1220");
+        m_desc.n_allowed = static_cast<unsigned>(allowed_variants.size());
+        for (std::size_t i = 0; i < allowed_variants.size(); ++i) m_desc.allowed_variants[i] = allowed_variants[i];
+        m_desc.variant_adptv = variant_adptv, m_desc.ftol = ftol, m_desc.xtol = xtol;
+    }
+};
+
+class cuda_pso_gen : public cuda_algorithm_base
+{
+public:
+    cuda_pso_gen(unsigned gen = 1u, double omega = 0.7298, double eta1 = 2.05, double eta2 = 2.05, double max_vel = 0.5, unsigned variant = 5u,
+                 unsigned neighb_type = 2u, unsigned neighb_param = 4u, bool memory = false, unsigned seed = pagmo::random_device::next(),
+                 int device = 0)
+        : cuda_algorithm_base(PGC_ALGO_PSO_GEN, "GPSO: Generational Particle Swarm Optimization", gen, seed, device)
+    {
+        no_memory(memory, "cuda_pso_gen");
+        m_desc.omega = omega, m_desc.eta1 = eta1, m_desc.eta2 = eta2, m_desc.max_vel = max_vel, m_desc.variant = variant;
+        m_desc.neighb_type = neighb_type, m_desc.neighb_param = neighb_param; // range checks: pso.cu (pso_gen.cpp:69-107)
+    }
+};
+
+class cuda_nsga2 : public cuda_algorithm_base
+{
+public:
+    cuda_nsga2(unsigned gen = 1u, double cr = 0.95, double eta_c = 10., double m = 0.01, double eta_m = 50.,
+               unsigned seed = pagmo::random_device::next(), int device = 0)
+        : cuda_algorithm_base(PGC_ALGO_NSGA2, "NSGA-II:", gen, seed, device)
+    {
+        m_desc.cr = cr, m_desc.eta_c = eta_c, m_desc.m = m, m_desc.eta_m = eta_m; // range checks: nsga2.cu (nsga2.cpp:71-86)
+    }
+};
+
+} // namespace pagmo_cuda
+
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_de)
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_sade)
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_de1220)
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_pso_gen)
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_nsga2)
+
+#endif

@@ -2,7 +2,8 @@
 //
 //   pagmo_cuda::cuda_bfe        a user-defined batch fitness evaluator (UDBFE, reference include/pagmo/bfe.hpp:68-108):
 //                               `pagmo::bfe{cuda_bfe{}}`, `algo.set_bfe(...)`, `population{prob, cuda_bfe{}, n}`.
-//   pagmo_cuda::cuda_zdt/_dtlz  CUDA-backed multi-objective UDPs (same constructor arguments as pagmo::zdt / dtlz)
+//   pagmo_cuda::cuda_zdt/_dtlz/_wfg  CUDA-backed multi-objective UDPs (same constructor arguments as pagmo::zdt / dtlz / wfg)
+//   pagmo_cuda::cuda_cec2013, cuda_lennard_jones   likewise (cec2013 takes its data tables, like cuda_cec2014)
 //   pagmo_cuda::cuda_cec2014    CUDA-backed UDPs (reference include/pagmo/problem.hpp:394-411,532-553): mandatory
 //   pagmo_cuda::cuda_simple<F>  fitness()/get_bounds() plus batch_fitness(), so pagmo::default_bfe / member_bfe pick the
 //                               device path up automatically (default_bfe.cpp:56-57, member_bfe.cpp:40-45).
@@ -29,6 +30,7 @@
 #include <pagmo/problems/ackley.hpp>
 #include <pagmo/problems/dtlz.hpp>
 #include <pagmo/problems/griewank.hpp>
+#include <pagmo/problems/lennard_jones.hpp>
 #include <pagmo/problems/rastrigin.hpp>
 #include <pagmo/problems/rosenbrock.hpp>
 #include <pagmo/problems/schwefel.hpp>
@@ -123,6 +125,37 @@ public:
         return buf;
     }
 
+    // algorithm::evolve on a host population: upload x [n x nx] / f [n x nf], run on the device, download in place.
+    // Returns the number of generations run.
+    unsigned evolve(const pgc_algo_desc &algo, pagmo::vector_double &x, pagmo::vector_double &f, unsigned first_generation) const
+    {
+        const std::size_t n = x.size() / m_nx;
+        std::lock_guard<std::mutex> lk(m_mtx);
+        void *dx = nullptr, *df = nullptr;
+        check(pgc_malloc_device(m_ctx.get(), x.size() * sizeof(double), &dx), "pgc_malloc_device");
+        if (int rc = pgc_malloc_device(m_ctx.get(), f.size() * sizeof(double), &df)) {
+            pgc_free_device(m_ctx.get(), dx);
+            throw_status(rc, "pgc_malloc_device");
+        }
+        unsigned done = 0;
+        int rc = pgc_memcpy_h2d(m_ctx.get(), dx, x.data(), x.size() * sizeof(double));
+        if (rc == PGC_OK) rc = pgc_memcpy_h2d(m_ctx.get(), df, f.data(), f.size() * sizeof(double));
+        const char *where = "pgc_memcpy_h2d";
+        if (rc == PGC_OK) {
+            rc = pgc_algo_evolve_device(m_prob, &algo, static_cast<double *>(dx), static_cast<double *>(df), n, first_generation, &done, nullptr);
+            where = "pgc_algo_evolve_device";
+        }
+        if (rc == PGC_OK) {
+            rc = pgc_memcpy_d2h(m_ctx.get(), x.data(), dx, x.size() * sizeof(double));
+            if (rc == PGC_OK) rc = pgc_memcpy_d2h(m_ctx.get(), f.data(), df, f.size() * sizeof(double));
+            where = "pgc_memcpy_d2h";
+        }
+        pgc_free_device(m_ctx.get(), dx);
+        pgc_free_device(m_ctx.get(), df);
+        if (rc != PGC_OK) throw_status(rc, where);
+        return done;
+    }
+
 private:
     std::shared_ptr<pgc_ctx> m_ctx;
     pgc_problem *m_prob = nullptr;
@@ -172,6 +205,7 @@ public:
         return pagmo::thread_safety::basic;
     }
     int device() const { return m_device; }
+    std::shared_ptr<detail::problem_handle> shared_handle() const { return m_handle; }
 
 protected:
     const detail::problem_handle &handle() const
@@ -299,22 +333,100 @@ private:
     unsigned m_prob_id, m_alpha, m_dim, m_fdim;
 };
 
-// The UDBFE.  Dispatch order: (1) a CUDA-backed UDP -> its own device problem; (2) a stock pagmo UDP whose
-// parameters are recoverable from its public interface -> a cached device twin; (3) anything else -> throw.
-class cuda_bfe
+// CEC2013 on the device.  Like cuda_cec2014 the data tables are constructor arguments, in the layout of the reference members:
+// `rotation` = m_rotation_matrix = MD[dim] (10 matrices, cec2013.cpp:65-67), `shift` = m_origin_shift (flat, component i at i*dim).
+class cuda_cec2013 : public cuda_udp_base
 {
 public:
-    explicit cuda_bfe(int device = 0) : m_device(device), m_cache(std::make_shared<cache_t>()) {}
-
-    pagmo::vector_double operator()(const pagmo::problem &p, const pagmo::vector_double &dvs) const
+    cuda_cec2013() = default;
+    cuda_cec2013(unsigned prob_id, unsigned dim, std::vector<double> rotation, std::vector<double> shift, int device = 0)
+        : m_prob_id(prob_id), m_dim(dim), m_rotation(std::move(rotation)), m_shift(std::move(shift))
     {
-        // (1) our own UDPs: same path as member_bfe (member_bfe.cpp:40-45), fevals are bumped by pagmo::bfe
-        if (p.is<cuda_cec2014>() || p.is<cuda_rastrigin>() || p.is<cuda_ackley>() || p.is<cuda_griewank>()
-            || p.is<cuda_schwefel>() || p.is<cuda_rosenbrock>() || p.is<cuda_zdt>() || p.is<cuda_dtlz>()) {
-            return pagmo::detail::prob_invoke_mem_batch_fitness(p, dvs, false);
-        }
-        // (2a) stock zdt / dtlz: the problem id is only visible through get_name() ("ZDT3", "DTLZ2": zdt.cpp:161-164,
-        // dtlz.cpp:170-173); dtlz4's alpha is private and cannot be recovered
+        m_device = device;
+        pgc_problem_desc d = detail::make_desc(PGC_CEC2013, m_prob_id, m_dim);
+        d.rotation = m_rotation.data();
+        d.rotation_len = m_rotation.size();
+        d.shift = m_shift.data();
+        d.shift_len = m_shift.size();
+        m_handle = std::make_shared<detail::problem_handle>(m_device, d);
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_prob_id, m_dim, m_rotation, m_shift, m_device);
+    }
+
+private:
+    unsigned m_prob_id = 0, m_dim = 0;
+    std::vector<double> m_rotation, m_shift;
+};
+
+// WFG1-9 on the device; same constructor arguments as pagmo::wfg (wfg.hpp:107).
+class cuda_wfg : public cuda_udp_base
+{
+public:
+    explicit cuda_wfg(unsigned prob_id = 1u, pagmo::vector_double::size_type dim_dvs = 5u, pagmo::vector_double::size_type dim_obj = 3u,
+                      pagmo::vector_double::size_type dim_k = 4u, int device = 0)
+        : m_prob_id(prob_id), m_dim_dvs(static_cast<unsigned>(dim_dvs)), m_dim_obj(static_cast<unsigned>(dim_obj)),
+          m_dim_k(static_cast<unsigned>(dim_k))
+    {
+        m_device = device;
+        m_handle = std::make_shared<detail::problem_handle>(m_device, detail::make_desc(PGC_WFG, prob_id, m_dim_dvs, m_dim_obj, m_dim_k));
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_prob_id, m_dim_dvs, m_dim_obj, m_dim_k, m_device);
+    }
+
+private:
+    unsigned m_prob_id, m_dim_dvs, m_dim_obj, m_dim_k;
+};
+
+// Lennard-Jones cluster on the device; same constructor argument as pagmo::lennard_jones (lennard_jones.hpp:82).
+class cuda_lennard_jones : public cuda_udp_base
+{
+public:
+    explicit cuda_lennard_jones(unsigned atoms = 3u, int device = 0) : m_atoms(atoms)
+    {
+        m_device = device;
+        m_handle = std::make_shared<detail::problem_handle>(m_device, detail::make_desc(PGC_LENNARD_JONES, 0u, atoms));
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_atoms, m_device);
+    }
+
+private:
+    unsigned m_atoms;
+};
+
+namespace detail
+{
+// The device problem behind a pagmo::problem: (1) a CUDA-backed UDP -> its own handle; (2) a stock pagmo UDP whose parameters
+// are recoverable from its public interface -> a cached device twin; (3) anything else -> nullptr (callers throw: no CPU fallback).
+class twin_cache
+{
+public:
+    std::shared_ptr<problem_handle> find(const pagmo::problem &p, int device)
+    {
+#define PGC_OWN_UDP(T)                                                                                                                      \
+    if (p.is<T>()) return p.extract<T>()->shared_handle();
+        PGC_OWN_UDP(cuda_cec2014)
+        PGC_OWN_UDP(cuda_cec2013)
+        PGC_OWN_UDP(cuda_rastrigin)
+        PGC_OWN_UDP(cuda_ackley)
+        PGC_OWN_UDP(cuda_griewank)
+        PGC_OWN_UDP(cuda_schwefel)
+        PGC_OWN_UDP(cuda_rosenbrock)
+        PGC_OWN_UDP(cuda_zdt)
+        PGC_OWN_UDP(cuda_dtlz)
+        PGC_OWN_UDP(cuda_wfg)
+        PGC_OWN_UDP(cuda_lennard_jones)
+#undef PGC_OWN_UDP
+        // stock zdt / dtlz: the problem id is only visible through get_name() ("ZDT3", "DTLZ2": zdt.cpp:161-164,
+        // dtlz.cpp:170-173); dtlz4's alpha is private and cannot be recovered; so is wfg's dim_k
         if (p.is<pagmo::zdt>() || p.is<pagmo::dtlz>()) {
             const std::string nm = p.get_name();
             const bool is_zdt = p.is<pagmo::zdt>();
@@ -322,29 +434,59 @@ public:
             const unsigned nx = static_cast<unsigned>(p.get_nx());
             if (is_zdt) {
                 const unsigned param = (id == 5u) ? (nx - 30u) / 5u + 1u : nx; // zdt.cpp:115-118
-                return twin(detail::make_desc(PGC_ZDT, id, param)).evaluate(dvs);
+                return twin(device, make_desc(PGC_ZDT, id, param));
             }
             if (id == 4u) {
-                pagmo_throw(std::invalid_argument, "cuda_bfe cannot evaluate a stock pagmo::dtlz with prob_id 4: its alpha "
+                pagmo_throw(std::invalid_argument, "the CUDA path cannot evaluate a stock pagmo::dtlz with prob_id 4: its alpha "
                                                    "is private; construct a pagmo_cuda::cuda_dtlz instead");
             }
-            return twin(detail::make_desc(PGC_DTLZ, id, nx, static_cast<unsigned>(p.get_nobj()), 100u)).evaluate(dvs);
+            return twin(device, make_desc(PGC_DTLZ, id, nx, static_cast<unsigned>(p.get_nobj()), 100u));
         }
-        // (2b) stock UDPs that are fully described by (type, nx)
-        int family = 0;
+        if (p.is<pagmo::lennard_jones>()) { // nx = 3*atoms - 6, lennard_jones.cpp:99-110
+            return twin(device, make_desc(PGC_LENNARD_JONES, 0u, static_cast<unsigned>((p.get_nx() + 6u) / 3u)));
+        }
+        int family = 0; // stock UDPs that are fully described by (type, nx)
         if (p.is<pagmo::rastrigin>()) family = PGC_RASTRIGIN;
         else if (p.is<pagmo::ackley>()) family = PGC_ACKLEY;
         else if (p.is<pagmo::griewank>()) family = PGC_GRIEWANK;
         else if (p.is<pagmo::schwefel>()) family = PGC_SCHWEFEL;
         else if (p.is<pagmo::rosenbrock>()) family = PGC_ROSENBROCK;
-        if (family == 0) {
-            // (3) no device evaluator and, by design, no CPU fallback
+        if (family == 0) return nullptr;
+        return twin(device, make_desc(family, 0u, static_cast<unsigned>(p.get_nx())));
+    }
+
+private:
+    std::shared_ptr<problem_handle> twin(int device, const pgc_problem_desc &d)
+    {
+        std::lock_guard<std::mutex> lk(m_mtx);
+        auto &slot = m_twins[std::make_tuple(device, d.family, d.prob_id, d.dim, d.nobj, d.param)];
+        if (!slot) slot = std::make_shared<problem_handle>(device, d);
+        return slot;
+    }
+    std::mutex m_mtx;
+    std::map<std::tuple<int, int, unsigned, unsigned, unsigned, unsigned>, std::shared_ptr<problem_handle>> m_twins;
+};
+} // namespace detail
+
+// The UDBFE.  Dispatch order (detail::twin_cache::find): (1) a CUDA-backed UDP -> its own device problem; (2) a stock pagmo UDP
+// whose parameters are recoverable from its public interface -> a cached device twin; (3) anything else -> throw.
+class cuda_bfe
+{
+public:
+    explicit cuda_bfe(int device = 0) : m_device(device), m_cache(std::make_shared<detail::twin_cache>()) {}
+
+    pagmo::vector_double operator()(const pagmo::problem &p, const pagmo::vector_double &dvs) const
+    {
+        // fevals are bumped by pagmo::bfe (bfe.cpp:94-107), never here (member_bfe.cpp:40-45 does the same)
+        const auto h = m_cache->find(p, m_device);
+        if (!h) {
+            // no device evaluator and, by design, no CPU fallback
             pagmo_throw(std::invalid_argument,
                         "cuda_bfe cannot evaluate the problem '" + p.get_name()
                             + "': no CUDA evaluator exists for this UDP type (wrap it in a pagmo_cuda:: UDP, or use "
                               "thread_bfe); there is no CPU fallback");
         }
-        return twin(detail::make_desc(family, 0u, static_cast<unsigned>(p.get_nx()))).evaluate(dvs);
+        return h->evaluate(dvs);
     }
     std::string get_name() const
     {
@@ -361,19 +503,8 @@ public:
     }
 
 private:
-    struct cache_t {
-        std::mutex mtx;
-        std::map<std::tuple<int, unsigned, unsigned, unsigned, unsigned>, std::shared_ptr<detail::problem_handle>> twins;
-    };
-    const detail::problem_handle &twin(const pgc_problem_desc &d) const
-    {
-        std::lock_guard<std::mutex> lk(m_cache->mtx);
-        auto &slot = m_cache->twins[std::make_tuple(d.family, d.prob_id, d.dim, d.nobj, d.param)];
-        if (!slot) slot = std::make_shared<detail::problem_handle>(m_device, d);
-        return *slot;
-    }
     int m_device;
-    std::shared_ptr<cache_t> m_cache;
+    std::shared_ptr<detail::twin_cache> m_cache;
 };
 
 } // namespace pagmo_cuda
@@ -387,5 +518,8 @@ PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_schwefel)
 PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_rosenbrock)
 PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_zdt)
 PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_dtlz)
+PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_cec2013)
+PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_wfg)
+PAGMO_S11N_PROBLEM_EXPORT_KEY(pagmo_cuda::cuda_lennard_jones)
 
 #endif

@@ -71,6 +71,11 @@ int oracle_de_evolve(const oracle_problem *prob, const double *lb, const double 
                      const unsigned *allowed, unsigned n_allowed, double ftol, double xtol, uint64_t seed, uint32_t first_generation,
                      unsigned *gens_done, double *F_state, double *CR_state, unsigned *variant_state);
 
+/* ---- WFG1..9 (restate_wfg.c): n = dim_dvs, M = dim_obj, k = dim_k ---- */
+int oracle_wfg_check(unsigned prob_id, size_t n, size_t M, size_t k);
+int oracle_wfg_fitness(unsigned prob_id, size_t n, size_t M, size_t k, const double *x, double *f);
+int oracle_wfg_batch(unsigned prob_id, size_t n, size_t M, size_t k, const double *xs, size_t count, double *fs);
+
 /* ---- migration (restate_migration.c): select_best / fair_replace on flat groups, topology in-edge lists ---- */
 int oracle_select_best(const uint64_t *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac, double rate,
                        uint64_t *ids_out, double *x_out, double *f_out, size_t *n_out);

@@ -120,6 +120,14 @@ class Oracle:
             raise ValueError("oracle_dtlz_batch failed")
         return out
 
+    def wfg(self, prob_id: int, xs: np.ndarray, dim_obj: int, dim_k: int) -> np.ndarray:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n, d = xs.shape
+        out = np.empty((n, dim_obj))
+        if self.lib.oracle_wfg_batch(C.c_uint(prob_id), C.c_size_t(d), C.c_size_t(dim_obj), C.c_size_t(dim_k), _dp(xs), C.c_size_t(n), _dp(out)):
+            raise ValueError(f"oracle_wfg_batch: invalid WFG{prob_id} configuration (dim_dvs={d}, dim_obj={dim_obj}, dim_k={dim_k})")
+        return out
+
     def lennard_jones(self, atoms: int, xs: np.ndarray) -> np.ndarray:
         xs = np.ascontiguousarray(xs, dtype=np.float64)
         out = np.empty(xs.shape[0])

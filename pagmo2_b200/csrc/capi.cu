@@ -210,7 +210,8 @@ int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d
         case PGC_CEC2014: return cec2014_eval(p, d_dvs, n, d_fvs, s);
         case PGC_CEC2013: return cec2013_eval(p, d_dvs, n, d_fvs, s);
         case PGC_ZDT:
-        case PGC_DTLZ: return mo_eval(p, d_dvs, n, d_fvs, s);
+        case PGC_DTLZ:
+        case PGC_WFG: return mo_eval(p, d_dvs, n, d_fvs, s);
         case PGC_LENNARD_JONES: return lj_eval(p, d_dvs, n, d_fvs, s);
         default: set_error("family %d has no device evaluator in this build", p->desc.family); return PGC_ERR_UNSUPPORTED;
     }
@@ -363,7 +364,8 @@ int pgc_problem_create(pgc_ctx *ctx, const pgc_problem_desc *desc, pgc_problem *
         case PGC_CEC2014: rc = cec2014_create(p, desc); break;
         case PGC_CEC2013: rc = cec2013_create(p, desc); break;
         case PGC_ZDT:
-        case PGC_DTLZ: rc = mo_create(p); break;
+        case PGC_DTLZ:
+        case PGC_WFG: rc = mo_create(p); break;
         case PGC_LENNARD_JONES: rc = lj_create(p); break;
         default:
             set_error("pgc_problem_create: family %d is not supported by this build (no CPU fallback)", desc->family);

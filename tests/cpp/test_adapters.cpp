@@ -24,6 +24,11 @@
 #include <pagmo/problems/rastrigin.hpp>
 #include <pagmo/problems/zdt.hpp>
 
+#include <pagmo/algorithm.hpp>
+#include <pagmo/algorithms/sade.hpp>
+#include <pagmo/problems/wfg.hpp>
+
+#include <pagmo_cuda/cuda_algorithms.hpp>
 #include <pagmo_cuda/cuda_bfe.hpp>
 
 #include "cec_synth.h"
@@ -177,6 +182,59 @@ int main()
         CHECK(pop1.get_x() == pop2.get_x()); // identical trajectories: fitness differences stay below every comparison
         CHECK(worst <= tol);
         std::printf("nsga2 on zdt1 with set_bfe(cuda_bfe): same final population as the sequential run (rel %.2e)\n", worst);
+    }
+
+    // ---- 3b. wfg / lennard_jones UDPs and the stock lennard_jones twin ----
+    {
+        pagmo::bfe gpu{cuda_bfe{}}, cpu{pagmo::thread_bfe{}};
+        for (unsigned id = 1; id <= 9u; ++id) {
+            pagmo::problem ref{pagmo::wfg{id, 12u, 3u, 4u}}, twin{cuda_wfg{id, 12u, 3u, 4u}};
+            const auto dvs = random_batch(ref, 200, 170 + id);
+            CHECK(max_rel(gpu(twin, dvs), cpu(ref, dvs)) <= 1e-11);
+            CHECK(twin.get_nobj() == 3u && twin.get_bounds() == ref.get_bounds());
+        }
+        pagmo::problem lj{pagmo::lennard_jones{7u}}, ljc{cuda_lennard_jones{7u}};
+        const auto dvs = random_batch(lj, 100, 5);
+        CHECK(max_rel(gpu(lj, dvs), cpu(lj, dvs)) <= 1e-10);
+        CHECK(max_rel(gpu(ljc, dvs), cpu(lj, dvs)) <= 1e-10);
+    }
+
+    // ---- 3c. CUDA UDAs behind pagmo::algorithm: evolve() keeps the population consistent and counts fevals like the reference ----
+    {
+        using namespace pagmo_cuda;
+        pagmo::problem prob{pagmo::rastrigin{10u}};
+        pagmo::population pop{prob, 64u, 23u};
+        const double before = pop.champion_f()[0];
+        const auto fe0 = pop.get_problem().get_fevals();
+        pagmo::algorithm algo{cuda_sade{30u, 2u, 1u, 0., 0., false, 41u}};
+        pop = algo.evolve(pop);
+        CHECK(pop.get_problem().get_fevals() - fe0 == 30u * 64u);
+        CHECK(pop.champion_f()[0] < before);
+        for (std::size_t i = 0; i < pop.size(); ++i) CHECK(max_rel(prob.fitness(pop.get_x()[i]), pop.get_f()[i]) <= tol);
+        pagmo::population pop2{prob, 64u, 23u};
+        pop2 = pagmo::algorithm{cuda_sade{30u, 2u, 1u, 0., 0., false, 41u}}.evolve(pop2);
+        CHECK(pop2.get_x() == pop.get_x()); // deterministic given the seeds
+        for (const auto &a : {pagmo::algorithm{cuda_de{20u, 0.8, 0.9, 2u, 0., 0., 3u}}, pagmo::algorithm{cuda_de1220{20u, {2u, 3u, 7u}, 1u, 0., 0., false, 3u}},
+                              pagmo::algorithm{cuda_pso_gen{20u, 0.7298, 2.05, 2.05, 0.5, 5u, 2u, 4u, false, 3u}}}) {
+            pagmo::population q{prob, 32u, 9u};
+            const double b = q.champion_f()[0];
+            q = a.evolve(q);
+            CHECK(q.champion_f()[0] <= b);
+            std::printf("%s: %.4g -> %.4g\n", a.get_name().c_str(), b, q.champion_f()[0]);
+        }
+        pagmo::problem zp{pagmo::zdt{1u, 30u}};
+        pagmo::population mo{zp, 40u, 5u};
+        mo = pagmo::algorithm{cuda_nsga2{10u, 0.95, 10., 0.01, 50., 32u}}.evolve(mo);
+        CHECK(mo.size() == 40u && mo.get_f()[0].size() == 2u);
+        bool threw = false;
+        try {
+            oracle_ref::ensure_cec2014_tables(1u, 10u);
+            pagmo::population bad{pagmo::problem{pagmo::cec2014{1u, 10u}}, 16u, 1u};
+            pagmo::algorithm{cuda_sade{2u}}.evolve(bad); // stock cec2014 keeps its tables private: no device twin
+        } catch (const std::invalid_argument &) {
+            threw = true;
+        }
+        CHECK(threw);
     }
 
     // ---- 4. constructor errors surface as std::invalid_argument, like the reference UDP (cec2014.cpp:51-64) ----

@@ -31,11 +31,32 @@ def cec2013_fixture(R):
     np.savez_compressed(OUT / "cec2013_ref.npz", **data)
 
 
+WFG_CONFIGS = ((9, 5, 8), (10, 5, 8), (5, 3, 4), (12, 3, 4), (30, 4, 6), (4, 2, 2), (24, 2, 4))
+
+
+def wfg_fixture(R):
+    # ---- WFG1..9: random points in the box, the corners, and the point of the reference's own tests (x = 2, tests/wfg.cpp:75-181)
+    data = {}
+    rng = np.random.default_rng(20161)
+    for pid in range(1, 10):
+        for n, m, k in WFG_CONFIGS:
+            if pid in (2, 3) and (n - k) % 2:
+                continue
+            ub = 2.0 * (np.arange(n) + 1)
+            xs = np.vstack([rng.uniform(0, 1, (6, n)) * ub, np.zeros((1, n)), ub[None, :], np.full((1, n), 2.0)])
+            data[f"x_wfg{pid}_{n}_{m}_{k}"] = xs
+            data[f"f_wfg{pid}_{n}_{m}_{k}"] = R.problem("wfg", pid, n, m, k).fitness_loop(xs)
+    np.savez_compressed(OUT / "wfg_ref.npz", **data)
+
+
 def main():
     R = reference()
+    if "--wfg-only" in sys.argv:  # add one fixture without rewriting the others
+        return wfg_fixture(R)
     cec2013_fixture(R)
-    if "--cec2013-only" in sys.argv:  # add this fixture without rewriting the others
+    if "--cec2013-only" in sys.argv:
         return
+    wfg_fixture(R)
     rng = np.random.default_rng(20141)
     # ---- CEC2014: every function at D in {10, 30, 100}, 6 points in the box + the shift itself + origin
     data = {}

@@ -82,6 +82,46 @@ def test_cec2013_matches_golden(orc):
             assert np.array_equal(orc.cec2013(func, g[f"x_f{func}_d{dim}"]), g[f"f_f{func}_d{dim}"]), (func, dim)
 
 
+WFG_KAT = {  # reference tests/wfg.cpp:75-181: wfg{id, dim_dvs, 5, 8} at x = (2, ..., 2), BOOST_CHECK_CLOSE 1e-6 %
+    1: (9, [2.67637472191165, 1.00059019674296, 1.00158344827345, 0.999721693168825, 0.994938703521363]),
+    2: (10, [0.486888085871606, 0.495069130688985, 0.760259287323669, 3.2410479386539, 6.7367724867725]),
+    3: (10, [0.553316039900195, 0.767247897430556, 1.66007950505305, 4.09523809523809, 2.98677248677249]),
+    4: (9, [0.50411484109126659, 0.62464631796973902, 1.52629658797989287, 6.09678409164092994, 7.24371673029278185]),
+    5: (9, [0.89534187984089331, 1.77719665056195542, 2.65432694359806565, 1.53267330147733283, 8.29285568212296020]),
+    6: (9, [0.70886239871081658, 1.01095392496448455, 2.84355886471448649, 7.82173248919986541, 3.27073013356489017]),
+    7: (9, [1.84130317215186778, 2.30307723148680399, 3.52250245655475958, 4.61486710981617687, 2.54081486970198434]),
+    8: (9, [0.415416373194518, 0.820930156178991, 2.71771179680979, 6.99576478246945, 4.19378015276566]),
+    9: (9, [0.70102740452657, 1.08669966382728, 2.03157023149974, 4.14060740683114, 8.71813196317622]),
+}
+
+
+def test_wfg_known_answers_and_golden(orc):
+    for pid, (n, want) in WFG_KAT.items():
+        assert np.allclose(orc.wfg(pid, np.full((1, n), 2.0), 5, 8)[0], want, rtol=1e-8, atol=0)
+    g = np.load(GOLD / "wfg_ref.npz")
+    keys = [k for k in g.files if k.startswith("x_")]
+    assert len(keys) == 59
+    for kx in keys:
+        pid, n, m, k = (int(v) for v in kx[5:].split("_"))
+        assert np.array_equal(orc.wfg(pid, g[kx], m, k), g["f" + kx[1:]], equal_nan=True), kx
+    for bad in ((0, 5, 3, 4), (10, 5, 3, 4), (1, 5, 1, 4), (1, 5, 3, 5), (1, 5, 3, 3), (2, 9, 3, 4), (3, 9, 3, 4)):  # tests/wfg.cpp:52-61
+        with pytest.raises(ValueError):
+            orc.wfg(bad[0], np.zeros((1, bad[1])), bad[2], bad[3])
+
+
+def test_wfg_restatement_is_bit_exact_vs_reference(orc, ref):
+    rng = np.random.default_rng(16)
+    for pid in range(1, 10):
+        for n, m, k in ((9, 5, 8), (10, 5, 8), (5, 3, 4), (12, 3, 4), (30, 4, 6), (4, 2, 2), (24, 2, 4), (8, 3, 2), (40, 3, 10)):
+            if pid in (2, 3) and (n - k) % 2:
+                continue
+            ub = 2.0 * (np.arange(n) + 1)
+            xs = np.vstack([rng.uniform(0, 1, (24, n)) * ub, np.zeros((1, n)), ub[None, :], 0.35 * ub[None, :]])
+            p = ref.problem("wfg", pid, n, m, k)
+            assert p.nobj == m and np.array_equal(p.bounds()[1], ub)
+            assert np.array_equal(orc.wfg(pid, xs, m, k), p.fitness_loop(xs), equal_nan=True), (pid, n, m, k)
+
+
 def test_simple_matches_golden(orc):
     g = np.load(GOLD / "simple_ref.npz")
     for fam in ("rastrigin", "ackley", "griewank", "schwefel", "rosenbrock"):
