@@ -97,7 +97,8 @@ int main()
 
     // ---- 2. a UDP without a device evaluator: throw, never fall back to the CPU -------------------------------
     {
-        pagmo::problem p{pagmo::lennard_jones{5u}};
+        oracle_ref::ensure_cec2014_tables(3u, 10u);
+        pagmo::problem p{pagmo::cec2014{3u, 10u}}; // the stock UDP keeps its data tables private: no device twin
         pagmo::bfe gpu{cuda_bfe{}};
         bool threw = false;
         try {

@@ -17,7 +17,7 @@ def capi():
 
 def close(got, want):
     # objectives are sums of O(1) terms (f_i = t_M + 2i * shape_i): bound relative to max(|f|, 1)
-    return np.all(np.abs(got - want) <= REL_TOL * np.maximum(np.abs(want), 1.0) | (np.isnan(got) & np.isnan(want)))
+    return np.all((np.abs(got - want) <= REL_TOL * np.maximum(np.abs(want), 1.0)) | (np.isnan(got) & np.isnan(want)))
 
 
 @pytest.mark.parametrize("pid", range(1, 10))
