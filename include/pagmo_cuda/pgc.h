@@ -186,6 +186,16 @@ PGC_API int pgc_de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, si
                                  double ftol, double xtol, double *d_F, double *d_CR, uint32_t *d_variant, uint64_t seed,
                                  uint32_t first_generation, unsigned *gens_done, void *stream);
 
+/* ---- hypervolume (src/utils/hypervolume.cpp:196-330; hv2d hv_hv2d.cpp:59-148, hv3d / HyCon3D hv_hv3d.cpp:107-343) ----------------
+ * points [n x m] row-major, m = 2 or 3 (the dimensions the reference serves with hv2d / hv3d), r_point[m] on the host.
+ * compute: *hv = hypervolume(points).compute(r_point); contributions: out[n] = exclusive contribution of every point.
+ * An invalid reference point (hv_algorithm.cpp:226-258) gives PGC_ERR_INVALID_ARGUMENT. */
+PGC_API int pgc_hv_compute_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r_point, double *hv);
+PGC_API int pgc_hv_contributions_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r_point, double *out);
+/* device-resident points; d_out: n doubles (compute writes the hypervolume to d_out[0]) */
+PGC_API int pgc_hv_device(pgc_ctx *ctx, const double *d_points, size_t n, size_t m, const double *r_point, int compute, double *d_out,
+                          void *stream);
+
 /* ---- algorithms behind one descriptor (pagmo::algorithm::evolve(pop), src/algorithm.cpp) ------------------------------- */
 typedef enum pgc_algo {
     PGC_ALGO_DE = 1,      /* src/algorithms/de.cpp:76-345 */

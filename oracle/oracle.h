@@ -76,6 +76,11 @@ int oracle_wfg_check(unsigned prob_id, size_t n, size_t M, size_t k);
 int oracle_wfg_fitness(unsigned prob_id, size_t n, size_t M, size_t k, const double *x, double *f);
 int oracle_wfg_batch(unsigned prob_id, size_t n, size_t M, size_t k, const double *xs, size_t count, double *fs);
 
+/* ---- exact hypervolume for m = 2, 3 (restate_hv.c) ---- */
+int oracle_hv_check(const double *f, size_t n, size_t m, const double *r);
+int oracle_hv_compute(const double *f, size_t n, size_t m, const double *r, double *out);
+int oracle_hv_contributions(const double *f, size_t n, size_t m, const double *r, double *out);
+
 /* ---- migration (restate_migration.c): select_best / fair_replace on flat groups, topology in-edge lists ---- */
 int oracle_select_best(const uint64_t *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac, double rate,
                        uint64_t *ids_out, double *x_out, double *f_out, size_t *n_out);

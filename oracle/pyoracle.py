@@ -221,6 +221,23 @@ class Oracle:
             raise ValueError("oracle_de_evolve failed")
         return x, f, done.value, Fs, Cs, Vs
 
+    # ---- hypervolume (restate_hv.c) ----
+    def hv_compute(self, f, r) -> float:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        out = C.c_double()
+        if self.lib.oracle_hv_compute(_dp(f), C.c_size_t(f.shape[0]), C.c_size_t(r.size), _dp(r), C.byref(out)):
+            raise ValueError("Reference point is invalid, or the dimension is not 2 or 3")
+        return out.value
+
+    def hv_contributions(self, f, r) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        out = np.empty(max(f.shape[0], 1))
+        if self.lib.oracle_hv_contributions(_dp(f), C.c_size_t(f.shape[0]), C.c_size_t(r.size), _dp(r), _dp(out)):
+            raise ValueError("Reference point is invalid, or the dimension is not 2 or 3")
+        return out[:f.shape[0]]
+
     # ---- migration (restate_migration.c) ----
     @staticmethod
     def _group(ids, x, f, nf=None):
@@ -495,6 +512,22 @@ class Reference:
         self._check(self.lib.ref_select_best(ids.ctypes.data_as(u64p), _dp(x), _dp(f), n, nx, nf, int(isinstance(rate, float)), float(rate),
                                              io.ctypes.data_as(u64p), _dp(xo), _dp(fo), C.byref(k)))
         return io[:k.value], xo[:k.value], fo[:k.value]
+
+    def hv_compute(self, f, r) -> float:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        out = C.c_double()
+        self.lib.ref_hv_compute.argtypes = [c_double_p, C.c_size_t, C.c_size_t, c_double_p, C.POINTER(C.c_double)]
+        self._check(self.lib.ref_hv_compute(_dp(f), f.shape[0], r.size, _dp(r), C.byref(out)))
+        return out.value
+
+    def hv_contributions(self, f, r) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        out = np.empty(max(f.shape[0], 1))
+        self.lib.ref_hv_contributions.argtypes = [c_double_p, C.c_size_t, C.c_size_t, c_double_p, c_double_p]
+        self._check(self.lib.ref_hv_contributions(_dp(f), f.shape[0], r.size, _dp(r), _dp(out)))
+        return out[:f.shape[0]]
 
     def cec2014_origin_shift(self, prob: RefProblem) -> np.ndarray:
         out = np.empty(CEC_NCOMP * 100)

@@ -69,3 +69,39 @@ int ref_select_best(const unsigned long long *ids, const double *x, const double
     }
 }
 }
+
+// ---- hypervolume (src/utils/hypervolume.cpp, hv_algos/hv_hv2d.cpp, hv_hv3d.cpp) through pagmo::hypervolume with the reference's own
+// choice of algorithm (get_best_compute / get_best_contributions: hv2d for 2 objectives, hv3d for 3, hvwfg beyond)
+#include <pagmo/utils/hypervolume.hpp>
+namespace
+{
+std::vector<pagmo::vector_double> rows(const double *f, size_t n, size_t m)
+{
+    std::vector<pagmo::vector_double> v(n);
+    for (size_t i = 0; i < n; ++i) v[i].assign(f + i * m, f + (i + 1) * m);
+    return v;
+}
+} // namespace
+extern "C" {
+int ref_hv_compute(const double *f, size_t n, size_t m, const double *r, double *out)
+{
+    try {
+        *out = pagmo::hypervolume(rows(f, n, m), true).compute(pagmo::vector_double(r, r + m));
+        return 0;
+    } catch (const std::exception &e) {
+        ref_set_error(e.what());
+        return 1;
+    }
+}
+int ref_hv_contributions(const double *f, size_t n, size_t m, const double *r, double *out)
+{
+    try {
+        const auto c = pagmo::hypervolume(rows(f, n, m), true).contributions(pagmo::vector_double(r, r + m));
+        std::memcpy(out, c.data(), n * sizeof(double));
+        return 0;
+    } catch (const std::exception &e) {
+        ref_set_error(e.what());
+        return 1;
+    }
+}
+}

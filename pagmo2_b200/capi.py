@@ -142,6 +142,9 @@ def lib():
                                             C.c_uint, C.c_uint, C.c_uint64, C.c_uint32, vp]
         L.pgc_de_evolve_device.argtypes = [vp, vp, vp, sz, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_double, vp, C.c_uint,
                                            C.c_double, C.c_double, vp, vp, vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint), vp]
+        L.pgc_hv_compute_host.argtypes = [vp, vp, sz, sz, dp, dp]
+        L.pgc_hv_contributions_host.argtypes = [vp, vp, sz, sz, dp, dp]
+        L.pgc_hv_device.argtypes = [vp, vp, sz, sz, dp, C.c_int, vp, vp]
         L.pgc_algo_defaults.argtypes = [C.c_int, C.c_uint, C.c_uint64, C.POINTER(AlgoDesc)]
         L.pgc_algo_evolve_device.argtypes = [vp, C.POINTER(AlgoDesc), vp, vp, sz, C.c_uint32, C.POINTER(C.c_uint), vp]
         L.pgc_population_init_device.argtypes = [vp, sz, C.c_uint64, vp, vp, vp, vp]
@@ -223,6 +226,23 @@ class Context:
         out = np.empty(shape, dtype=dtype)
         check(lib().pgc_memcpy_d2h(self._h, out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), out.nbytes))
         return out
+
+    # ---- hypervolume (pagmo::hypervolume::compute / contributions for 2 and 3 objectives) ----
+    def hv_compute(self, points: np.ndarray, r_point) -> float:
+        f = np.ascontiguousarray(points, dtype=np.float64)
+        r = np.ascontiguousarray(r_point, dtype=np.float64)
+        out = C.c_double()
+        check(lib().pgc_hv_compute_host(self._h, f.ctypes.data_as(C.c_void_p), f.shape[0], r.size, r.ctypes.data_as(C.POINTER(C.c_double)),
+                                        C.byref(out)))
+        return out.value
+
+    def hv_contributions(self, points: np.ndarray, r_point) -> np.ndarray:
+        f = np.ascontiguousarray(points, dtype=np.float64)
+        r = np.ascontiguousarray(r_point, dtype=np.float64)
+        out = np.empty(max(f.shape[0], 1))
+        check(lib().pgc_hv_contributions_host(self._h, f.ctypes.data_as(C.c_void_p), f.shape[0], r.size,
+                                              r.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out[:f.shape[0]]
 
     # ---- multi-objective utilities (host-vector entry points, pagmo signatures) ----
     def fnds(self, f: np.ndarray) -> dict:

@@ -710,6 +710,42 @@ int pgc_de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP,
                             stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
 }
 
+int pgc_hv_device(pgc_ctx *ctx, const double *d_points, size_t n, size_t m, const double *r_point, int compute, double *d_out, void *stream)
+{
+    PGC_REQUIRE(ctx && r_point && d_out && (d_points || n == 0), "pgc_hv_device: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return hv_device(ctx, d_points, n, m, r_point, compute, d_out, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+static int hv_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r, int compute, double *out)
+{
+    PGC_REQUIRE(ctx && r && out && (points || n == 0), "pgc_hv_*_host: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    double *d_f = nullptr, *d_o = nullptr;
+    PGC_CUDA(cudaMalloc(&d_f, (n * m ? n * m : 1) * sizeof(double)));
+    cudaError_t e = cudaMalloc(&d_o, (n ? n : 1) * sizeof(double));
+    int rc = PGC_OK;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_f, points, n * m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = hv_device(ctx, d_f, n, m, r, compute, d_o, ctx->stream);
+    if (e == cudaSuccess && rc == PGC_OK)
+        e = cudaMemcpyAsync(out, d_o, (compute ? 1 : n) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && rc == PGC_OK) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_f);
+    cudaFree(d_o);
+    if (e != cudaSuccess) return cuda_fail(e, "pgc_hv_*_host", __FILE__, __LINE__);
+    return rc;
+}
+
+int pgc_hv_compute_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r_point, double *hv)
+{
+    return hv_host(ctx, points, n, m, r_point, 1, hv);
+}
+
+int pgc_hv_contributions_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r_point, double *out)
+{
+    return hv_host(ctx, points, n, m, r_point, 0, out);
+}
+
 int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out)
 {
     PGC_REQUIRE(out, "pgc_algo_defaults: null argument");

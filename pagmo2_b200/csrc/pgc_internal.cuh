@@ -186,6 +186,7 @@ int fair_replace_policy_device(pgc_ctx *ctx, unsigned long long *d_ids, double *
                                int rate_is_frac, double rate, const unsigned long long *d_mids, const double *d_mx, const double *d_mf,
                                size_t nm, cudaStream_t st);
 int ring_connections(size_t n, size_t i, std::vector<size_t> &out);
+int hv_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const double *r, int compute, double *d_out, cudaStream_t st);
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops_out);

@@ -49,14 +49,68 @@ def wfg_fixture(R):
     np.savez_compressed(OUT / "wfg_ref.npz", **data)
 
 
+def hv_fixture(R):
+    """(a) the reference's own hypervolume fixtures (tests/hypervolume_test_data, format: tests/hypervolume.cpp:132-163): the first fronts
+    of the 2D / 3D `compute` files, and the complete `exclusive` and `least_contributor` files for 2 and 3 objectives, with the answers
+    they carry; (b) contributions of seeded random fronts (with dominated points and duplicates) computed by the compiled reference."""
+    base = Path("/root/reference/tests/hypervolume_test_data/testcases")
+    data = {}
+
+    def parse(name, kind, limit):
+        tok = (base / name).read_text().split()
+        pos = 0
+
+        def take(k):
+            nonlocal pos
+            out = tok[pos:pos + k]
+            pos += k
+            return out
+        t = int(take(1)[0])
+        for case in range(min(t, limit)):
+            d, n = (int(v) for v in take(2))
+            r = np.array(take(d), dtype=np.float64)
+            pts = np.array(take(d * n), dtype=np.float64).reshape(n, d)
+            ans = [float(v) for v in take({"compute": 1, "exclusive": 2, "least": 1}[kind])]
+            data[f"{kind}_{name}_{case}_r"] = r
+            data[f"{kind}_{name}_{case}_p"] = pts
+            data[f"{kind}_{name}_{case}_a"] = np.array(ans)
+
+    parse("c_max_t100_d2_n128", "compute", 12)
+    parse("c_max_t100_d3_n128", "compute", 12)
+    parse("c_max_t1_d3_n2048", "compute", 1)
+    for name in ("e_max_d2", "e_max_d3"):
+        parse(name, "exclusive", 10**6)
+    for name in ("lc_max_d2", "lc_max_d3"):
+        parse(name, "least", 10**6)
+    rng = np.random.default_rng(20171)
+    for m in (2, 3):
+        for n, kind in ((1, "random"), (2, "random"), (37, "random"), (300, "random"), (300, "front"), (120, "dups")):
+            f = rng.uniform(0, 1, (n, m))
+            if kind == "front":
+                f = f / np.linalg.norm(f, axis=1, keepdims=True)
+            if kind == "dups":
+                f[1] = f[0]
+                f[2] = f[0] + 0.1
+                f[5:20, m - 1] = f[4, m - 1]  # ties in the sweep coordinate
+            r = np.full(m, 1.3)
+            key = f"ref_m{m}_n{n}_{kind}"
+            data[key + "_p"], data[key + "_r"] = f, r
+            data[key + "_hv"] = np.array([R.hv_compute(f, r)])
+            data[key + "_c"] = R.hv_contributions(f, r)
+    np.savez_compressed(OUT / "hv_ref.npz", **data)
+
+
 def main():
     R = reference()
+    if "--hv-only" in sys.argv:
+        return hv_fixture(R)
     if "--wfg-only" in sys.argv:  # add one fixture without rewriting the others
         return wfg_fixture(R)
     cec2013_fixture(R)
     if "--cec2013-only" in sys.argv:
         return
     wfg_fixture(R)
+    hv_fixture(R)
     rng = np.random.default_rng(20141)
     # ---- CEC2014: every function at D in {10, 30, 100}, 6 points in the box + the shift itself + origin
     data = {}

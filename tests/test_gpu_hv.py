@@ -1,0 +1,77 @@
+"""GPU parity of the hypervolume path (compute and exclusive contributions, 2 and 3 objectives) against the reference's own fixtures,
+golden outputs of the compiled reference (hv2d / hv3d / HyCon3D) and the restated oracle."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+REL = 1e-12
+
+
+def cases(g, prefix):
+    return sorted({k[:-2] for k in g.files if k.startswith(prefix) and k.endswith("_p")})
+
+
+def test_reference_fixtures(ctx):
+    g = np.load(GOLD / "hv_ref.npz")
+    for k in cases(g, "compute_"):  # tests/hypervolume_test_data/testcases_list.txt:23-28, eps 1e-8 there
+        assert abs(ctx.hv_compute(g[k + "_p"], g[k + "_r"]) - g[k + "_a"][0]) < 1e-8, k
+    for k in cases(g, "exclusive_"):
+        idx, want = int(g[k + "_a"][0]), g[k + "_a"][1]
+        assert abs(ctx.hv_contributions(g[k + "_p"], g[k + "_r"])[idx] - want) < 1e-8, k
+    for k in cases(g, "least_"):
+        assert int(np.argmin(ctx.hv_contributions(g[k + "_p"], g[k + "_r"]))) == int(g[k + "_a"][0]), k
+
+
+def test_golden_outputs_of_the_compiled_reference(ctx):
+    g = np.load(GOLD / "hv_ref.npz")
+    for k in cases(g, "ref_"):
+        p, r, hv, c = g[k + "_p"], g[k + "_r"], g[k + "_hv"][0], g[k + "_c"]
+        assert abs(ctx.hv_compute(p, r) - hv) <= REL * hv, k
+        got = ctx.hv_contributions(p, r)
+        # exclusive volumes are sums of positive boxes on both sides: relative agreement wherever the contribution is not ~0
+        assert np.all(np.abs(got - c) <= REL * np.maximum(np.abs(c), 1e-3 * hv / len(c))), (k, np.abs(got - c).max())
+        assert np.array_equal(got == 0.0, c == 0.0) or np.all(np.abs(got - c) <= 1e-15 * hv), k
+
+
+@pytest.mark.parametrize("m", (2, 3))
+def test_against_oracle_and_properties(ctx, orc, m):
+    rng = np.random.default_rng(60 + m)
+    for n, kind in ((1, "random"), (2, "random"), (65, "random"), (400, "front"), (400, "random"), (257, "ties")):
+        f = rng.uniform(0, 1, (n, m))
+        if kind == "front":
+            f = f / np.linalg.norm(f, axis=1, keepdims=True)
+        if kind == "ties":
+            f = np.round(f * 8) / 8  # many equal coordinates, duplicates and dominated points
+        r = np.full(m, 1.25)
+        hv, c = ctx.hv_compute(f, r), ctx.hv_contributions(f, r)
+        hv_o = orc.hv_compute(f, r)
+        assert abs(hv - hv_o) <= REL * hv_o, (n, kind)
+        assert np.abs(c - orc.hv_contributions(f, r)).max() <= 1e-14 * hv_o, (n, kind)
+        assert (c >= 0).all() and c.sum() <= hv * (1 + 1e-12)
+        # definition: removing point i loses exactly its exclusive contribution
+        for i in rng.choice(n, size=min(n, 5), replace=False):
+            if n > 1:
+                assert abs((hv - ctx.hv_compute(np.delete(f, i, axis=0), r)) - c[i]) <= 1e-13 * hv
+    # large front: permutation invariance (every point has its own sweep) and additivity of a far-away clone
+    f = rng.uniform(0, 1, (20000, m))
+    f = f / np.linalg.norm(f, axis=1, keepdims=True)
+    r = np.full(m, 1.25)
+    c = ctx.hv_contributions(f, r)
+    perm = rng.permutation(len(f))
+    assert np.allclose(ctx.hv_contributions(f[perm], r), c[perm], rtol=1e-12, atol=0)
+    assert abs(ctx.hv_compute(f[perm], r) - ctx.hv_compute(f, r)) <= 1e-12 * ctx.hv_compute(f, r)
+
+
+def test_errors_and_empty(ctx, capi=None):
+    from pagmo2_b200 import capi
+    with pytest.raises(capi.PgcError):  # hv_algorithm.cpp:226-258
+        ctx.hv_compute(np.array([[0.5, 2.0]]), [1.0, 1.0])
+    with pytest.raises(capi.PgcError):
+        ctx.hv_contributions(np.array([[1.0, 1.0]]), [1.0, 1.0])
+    with pytest.raises(capi.PgcError):
+        ctx.hv_compute(np.zeros((3, 4)), np.ones(4))  # 4 objectives: the reference switches to hvwfg, not part of the device path
+    assert ctx.hv_compute(np.zeros((0, 3)), np.ones(3)) == 0.0
+    assert ctx.hv_contributions(np.array([[0.25, 0.5, 0.0]]), np.ones(3))[0] == 0.75 * 0.5 * 1.0

@@ -122,6 +122,45 @@ def test_wfg_restatement_is_bit_exact_vs_reference(orc, ref):
             assert np.array_equal(orc.wfg(pid, xs, m, k), p.fitness_loop(xs), equal_nan=True), (pid, n, m, k)
 
 
+def hv_cases(g, prefix):
+    return sorted({k[:-2] for k in g.files if k.startswith(prefix) and k.endswith("_p")})
+
+
+def test_hypervolume_against_reference_fixtures(orc):
+    """the reference's own fixtures (tests/hypervolume_test_data/testcases_list.txt:23-43, eps 1e-8 there)."""
+    g = np.load(GOLD / "hv_ref.npz")
+    assert len(hv_cases(g, "compute_")) == 25
+    for k in hv_cases(g, "compute_"):
+        assert abs(orc.hv_compute(g[k + "_p"], g[k + "_r"]) - g[k + "_a"][0]) < 1e-8, k
+    for k in hv_cases(g, "exclusive_"):
+        idx, want = int(g[k + "_a"][0]), g[k + "_a"][1]
+        assert abs(orc.hv_contributions(g[k + "_p"], g[k + "_r"])[idx] - want) < 1e-8, k
+    for k in hv_cases(g, "least_"):
+        assert int(np.argmin(orc.hv_contributions(g[k + "_p"], g[k + "_r"]))) == int(g[k + "_a"][0]), k
+    for k in hv_cases(g, "ref_"):  # outputs of the compiled reference (hv2d / hv3d / HyCon3D)
+        hv = g[k + "_hv"][0]
+        assert orc.hv_compute(g[k + "_p"], g[k + "_r"]) == hv, k
+        assert np.abs(orc.hv_contributions(g[k + "_p"], g[k + "_r"]) - g[k + "_c"]).max() <= 4e-15 * hv, k
+
+
+def test_hypervolume_restatement_vs_reference(orc, ref):
+    rng = np.random.default_rng(8)
+    for m in (2, 3):
+        for n in (1, 2, 3, 17, 150):
+            for kind in ("random", "front"):
+                f = rng.uniform(0, 1, (n, m))
+                if kind == "front":
+                    f = f / np.linalg.norm(f, axis=1, keepdims=True)
+                r = np.full(m, 1.1)
+                hv = ref.hv_compute(f, r)
+                assert orc.hv_compute(f, r) == hv
+                assert np.abs(orc.hv_contributions(f, r) - ref.hv_contributions(f, r)).max() <= 4e-15 * hv
+    with pytest.raises(ValueError):  # hv_algorithm.cpp:226-258
+        orc.hv_compute(np.array([[0.5, 2.0]]), [1.0, 1.0])
+    with pytest.raises(ValueError):
+        orc.hv_contributions(np.array([[1.0, 1.0]]), [1.0, 1.0])
+
+
 def test_simple_matches_golden(orc):
     g = np.load(GOLD / "simple_ref.npz")
     for fam in ("rastrigin", "ackley", "griewank", "schwefel", "rosenbrock"):
