@@ -34,7 +34,9 @@ struct HvParams {
     double *out;           // per point: contribution, or its term of HV(S)
     double *sx, *sy;       // staircase scratch: [threads in this launch][cap]
     unsigned cap;
-    unsigned p0, pcount;   // points handled by this launch
+    unsigned p0, pcount;   // points handled by this launch: p0 + t, or plist[t]
+    const unsigned *plist;
+    unsigned *overflow;    // [0] = count, [1..] = points whose staircase outgrew cap (nullptr: cap is the worst case)
     int compute;           // 1: terms of HV(S)
 };
 
@@ -64,15 +66,22 @@ __global__ void hv_zkeys_kernel(const double *f, unsigned n, unsigned long long 
 struct Stair { // staircase of the points strictly inside p's quadrant: x ascending, y strictly descending
     double *x, *y;
     unsigned s;
-    __device__ void insert(double qx, double qy)
+    // returns false when the staircase would outgrow `cap` (the caller reruns this point with a full-size scratch)
+    __device__ bool insert(double qx, double qy, unsigned cap)
     {
-        unsigned i = 0;
-        while (i < s && x[i] < qx) ++i;
-        if (i > 0 && y[i - 1] <= qy) return;          // an earlier point with smaller x is at least as low
-        if (i < s && x[i] == qx && y[i] <= qy) return; // same x, not lower
+        unsigned lo = 0, hi = s; // first i with x[i] >= qx
+        while (lo < hi) {
+            const unsigned mid = (lo + hi) >> 1;
+            if (x[mid] < qx) lo = mid + 1;
+            else hi = mid;
+        }
+        const unsigned i = lo;
+        if (i > 0 && y[i - 1] <= qy) return true;          // an earlier point with smaller x is at least as low
+        if (i < s && x[i] == qx && y[i] <= qy) return true; // same x, not lower
         unsigned j = i;
-        while (j < s && y[j] >= qy) ++j;               // points q now covers: x >= qx and y >= qy
-        if (j == i) {                                  // make room
+        while (j < s && y[j] >= qy) ++j;                    // points q now covers: x >= qx and y >= qy
+        if (j == i) {                                       // make room
+            if (s == cap) return false;
             for (unsigned k = s; k > i; --k) {
                 x[k] = x[k - 1];
                 y[k] = y[k - 1];
@@ -88,6 +97,7 @@ struct Stair { // staircase of the points strictly inside p's quadrant: x ascend
         }
         x[i] = qx;
         y[i] = qy;
+        return true;
     }
     // uncovered area of [px, xr) x [py, yt) under the staircase, as a sum of positive columns
     __device__ double uncovered(double px, double py, double xr, double yt) const
@@ -108,7 +118,7 @@ __global__ void hv_sweep_kernel(const HvParams P)
 {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.pcount) return;
-    const unsigned p = P.p0 + t;
+    const unsigned p = P.plist ? P.plist[t] : P.p0 + t;
     const bool three = P.m == 3;
     const double *fp = P.f + static_cast<size_t>(p) * P.m;
     const double px = fp[0], py = fp[1], pz = three ? fp[2] : 0.0;
@@ -147,7 +157,10 @@ __global__ void hv_sweep_kernel(const HvParams P)
                 dirty = true;
             }
         } else if (qx < xr && qy < yt) {
-            st.insert(qx, qy);
+            if (!st.insert(qx, qy, P.cap)) {
+                P.overflow[1 + atomicAdd(P.overflow, 1u)] = p;
+                return;
+            }
             dirty = true;
         }
     }
@@ -217,14 +230,14 @@ int hv_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const double 
         PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, bytes, k0, k1, i0, order, static_cast<int>(n), 0, 64, st));
         ctx->launches.fetch_add(2, std::memory_order_relaxed);
     }
-    // staircase scratch: worst case n entries per point; bound one launch to ~1 GiB of it
-    const size_t budget = size_t(1) << 30;
-    size_t batch = budget / (2 * sizeof(double) * n);
-    if (batch < 64) batch = 64;
-    if (batch > n) batch = n;
+    // Staircase scratch.  First pass: every point at once with a small per-point capacity; the (rare) points whose staircase
+    // outgrows it are collected and rerun with the worst-case capacity n, in batches bounded to ~1 GiB of scratch.
+    const unsigned cap1 = un < 512u ? un : 512u;
     double *sx = nullptr, *sy = nullptr, *terms = nullptr;
-    if ((rc = tmp.get(&sx, batch * n)) || (rc = tmp.get(&sy, batch * n))) return rc;
+    unsigned *ovf = nullptr;
+    if ((rc = tmp.get(&sx, n * cap1)) || (rc = tmp.get(&sy, n * cap1)) || (rc = tmp.get(&ovf, n + 1))) return rc;
     if (compute && (rc = tmp.get(&terms, n))) return rc;
+    PGC_CUDA(cudaMemsetAsync(ovf, 0, sizeof(unsigned), st));
     HvParams P;
     P.f = d_f;
     P.order = order;
@@ -236,14 +249,37 @@ int hv_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const double 
     P.out = compute ? terms : d_out;
     P.sx = sx;
     P.sy = sy;
-    P.cap = un;
+    P.cap = cap1;
+    P.p0 = 0;
+    P.pcount = un;
+    P.plist = nullptr;
+    P.overflow = ovf;
     P.compute = compute;
-    for (size_t p0 = 0; p0 < n; p0 += batch) {
-        P.p0 = static_cast<unsigned>(p0);
-        P.pcount = static_cast<unsigned>(n - p0 < batch ? n - p0 : batch);
-        hv_sweep_kernel<<<(P.pcount + 63) / 64, 64, 0, st>>>(P);
-        PGC_CUDA(cudaGetLastError());
-        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    hv_sweep_kernel<<<(un + 63) / 64, 64, 0, st>>>(P);
+    PGC_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    if (cap1 < un) {
+        unsigned nover = 0;
+        PGC_CUDA(cudaMemcpyAsync(&nover, ovf, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        if (nover) {
+            size_t batch = (size_t(1) << 30) / (2 * sizeof(double) * n);
+            if (batch < 64) batch = 64;
+            if (batch > nover) batch = nover;
+            double *bx = nullptr, *by = nullptr;
+            if ((rc = tmp.get(&bx, batch * n)) || (rc = tmp.get(&by, batch * n))) return rc;
+            P.sx = bx;
+            P.sy = by;
+            P.cap = un;
+            P.overflow = nullptr; // cannot overflow any more
+            for (size_t o0 = 0; o0 < nover; o0 += batch) {
+                P.plist = ovf + 1 + o0;
+                P.pcount = static_cast<unsigned>(nover - o0 < batch ? nover - o0 : batch);
+                hv_sweep_kernel<<<(P.pcount + 63) / 64, 64, 0, st>>>(P);
+                PGC_CUDA(cudaGetLastError());
+                ctx->launches.fetch_add(1, std::memory_order_relaxed);
+            }
+        }
     }
     if (compute) {
         size_t bytes = 0;

@@ -31,9 +31,11 @@ def test_golden_outputs_of_the_compiled_reference(ctx):
         p, r, hv, c = g[k + "_p"], g[k + "_r"], g[k + "_hv"][0], g[k + "_c"]
         assert abs(ctx.hv_compute(p, r) - hv) <= REL * hv, k
         got = ctx.hv_contributions(p, r)
-        # exclusive volumes are sums of positive boxes on both sides: relative agreement wherever the contribution is not ~0
-        assert np.all(np.abs(got - c) <= REL * np.maximum(np.abs(c), 1e-3 * hv / len(c))), (k, np.abs(got - c).max())
-        assert np.array_equal(got == 0.0, c == 0.0) or np.all(np.abs(got - c) <= 1e-15 * hv), k
+        # non-dominated fronts: HyCon3D and the device both add positive boxes -> relative agreement per point.  With dominated points
+        # the reference switches to hvwfg (hv_hv3d.cpp:236-238), which subtracts hypervolumes: its own values carry ~1e-16 * HV.
+        nondominated = "front" in k or len(c) <= 2
+        tol = REL * np.abs(c) if nondominated else np.maximum(REL * np.abs(c), 4e-15 * hv)
+        assert np.all(np.abs(got - c) <= tol), (k, np.abs(got - c).max())
 
 
 @pytest.mark.parametrize("m", (2, 3))
@@ -63,6 +65,17 @@ def test_against_oracle_and_properties(ctx, orc, m):
     perm = rng.permutation(len(f))
     assert np.allclose(ctx.hv_contributions(f[perm], r), c[perm], rtol=1e-12, atol=0)
     assert abs(ctx.hv_compute(f[perm], r) - ctx.hv_compute(f, r)) <= 1e-12 * ctx.hv_compute(f, r)
+
+
+def test_deep_staircase_takes_the_second_pass(ctx, orc):
+    """one point that dominates, in the xy-plane, a 2D front of 699 points lying below it in z: its sweep needs a staircase deeper than
+    the first pass's per-point capacity (512), so it is rerun with the worst-case scratch."""
+    t = np.linspace(0.05, 0.95, 699)
+    f = np.vstack([np.column_stack([t, 1.0 - t, np.full_like(t, 0.1) + 1e-4 * t]), [[0.0, 0.0, 0.5]]])
+    r = np.full(3, 1.25)
+    hv_o = orc.hv_compute(f, r)
+    assert abs(ctx.hv_compute(f, r) - hv_o) <= REL * hv_o
+    assert np.abs(ctx.hv_contributions(f, r) - orc.hv_contributions(f, r)).max() <= 1e-14 * hv_o
 
 
 def test_errors_and_empty(ctx, capi=None):
