@@ -196,6 +196,19 @@ PGC_API int pgc_hv_contributions_host(pgc_ctx *ctx, const double *points, size_t
 PGC_API int pgc_hv_device(pgc_ctx *ctx, const double *d_points, size_t n, size_t m, const double *r_point, int compute, double *d_out,
                           void *stream);
 
+/* ---- dense contractions of CMA-ES / xNES (cmaes.cpp:246-253,362-380; xnes.cpp:302-305); D <= 128 ---------------------------------
+ * sampling: x_i = mean + sigma * BD * z_i, i < lambda, z ~ N(0, I) from Philox (seed, tag 8, generation, i, .); BD = B*D row-major
+ * [D x D] (the caller's eigendecomposition, cmaes.cpp:386-401, stays on the host); d_z optional (xnes keeps z). */
+PGC_API int pgc_cmaes_sample_device(pgc_ctx *ctx, const double *d_mean, const double *d_bd, double sigma, size_t lambda, size_t D,
+                                    uint64_t seed, uint32_t generation, double *d_z, double *d_x, void *stream);
+/* out[D x D] = sum_{i<k} w_i (r_i - c)(r_i - c)^T / scale_div, r_i = rows[idx ? idx[i] : i] (rank-mu: rows = population, idx =
+ * the mu best, c = old mean, scale_div = sigma^2; xnes: rows = z, idx = s_idx, c = NULL, w = u, scale_div = 1). */
+PGC_API int pgc_weighted_gram_device(pgc_ctx *ctx, const double *d_rows, const uint32_t *d_idx, const double *d_center, const double *d_w,
+                                     size_t k, size_t D, double scale_div, double *d_out, void *stream);
+/* out[D] = sum_{i<k} w_i r_i in the reference's order (cmaes.cpp:363-366) */
+PGC_API int pgc_weighted_mean_device(pgc_ctx *ctx, const double *d_rows, const uint32_t *d_idx, const double *d_w, size_t k, size_t D,
+                                     double *d_out, void *stream);
+
 /* ---- algorithms behind one descriptor (pagmo::algorithm::evolve(pop), src/algorithm.cpp) ------------------------------- */
 typedef enum pgc_algo {
     PGC_ALGO_DE = 1,      /* src/algorithms/de.cpp:76-345 */

@@ -81,6 +81,13 @@ int oracle_hv_check(const double *f, size_t n, size_t m, const double *r);
 int oracle_hv_compute(const double *f, size_t n, size_t m, const double *r, double *out);
 int oracle_hv_contributions(const double *f, size_t n, size_t m, const double *r, double *out);
 
+/* ---- CMA-ES / xNES contractions (restate_cmaes.c) ---- */
+int oracle_weighted_mean(const double *rows, const uint32_t *idx, const double *w, size_t k, size_t D, double *out);
+int oracle_weighted_gram(const double *rows, const uint32_t *idx, const double *center, const double *w, size_t k, size_t D, double scale_div,
+                         double *out);
+int oracle_cmaes_sample(const double *mean, const double *bd, double sigma, size_t lambda, size_t D, uint64_t seed, uint32_t generation,
+                        double *z, double *x);
+
 /* ---- migration (restate_migration.c): select_best / fair_replace on flat groups, topology in-edge lists ---- */
 int oracle_select_best(const uint64_t *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac, double rate,
                        uint64_t *ids_out, double *x_out, double *f_out, size_t *n_out);

@@ -221,6 +221,28 @@ class Oracle:
             raise ValueError("oracle_de_evolve failed")
         return x, f, done.value, Fs, Cs, Vs
 
+    # ---- CMA-ES / xNES contractions (restate_cmaes.c) ----
+    def weighted_gram(self, rows, w, idx=None, center=None, scale_div: float = 1.0):
+        """(sum_i w_i (r_i - c)(r_i - c)^T / scale_div, sum_i w_i r_i) in the reference's order."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        D = rows.shape[1]
+        ip = np.ascontiguousarray(idx, dtype=np.uint32).ctypes.data_as(C.POINTER(C.c_uint32)) if idx is not None else None
+        cp = _dp(np.ascontiguousarray(center, dtype=np.float64)) if center is not None else None
+        g, m = np.empty((D, D)), np.empty(D)
+        self.lib.oracle_weighted_gram(_dp(rows), ip, cp, _dp(w), C.c_size_t(w.size), C.c_size_t(D), C.c_double(scale_div), _dp(g))
+        self.lib.oracle_weighted_mean(_dp(rows), ip, _dp(w), C.c_size_t(w.size), C.c_size_t(D), _dp(m))
+        return g, m
+
+    def cmaes_sample(self, mean, bd, sigma, lam, seed, generation):
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        bd = np.ascontiguousarray(bd, dtype=np.float64)
+        D = mean.size
+        z, x = np.empty((lam, D)), np.empty((lam, D))
+        self.lib.oracle_cmaes_sample(_dp(mean), _dp(bd), C.c_double(sigma), C.c_size_t(lam), C.c_size_t(D), C.c_uint64(seed),
+                                     C.c_uint32(generation), _dp(z), _dp(x))
+        return x, z
+
     # ---- hypervolume (restate_hv.c) ----
     def hv_compute(self, f, r) -> float:
         f = np.ascontiguousarray(f, dtype=np.float64)

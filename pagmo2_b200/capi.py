@@ -145,6 +145,9 @@ def lib():
         L.pgc_hv_compute_host.argtypes = [vp, vp, sz, sz, dp, dp]
         L.pgc_hv_contributions_host.argtypes = [vp, vp, sz, sz, dp, dp]
         L.pgc_hv_device.argtypes = [vp, vp, sz, sz, dp, C.c_int, vp, vp]
+        L.pgc_cmaes_sample_device.argtypes = [vp, vp, vp, C.c_double, sz, sz, C.c_uint64, C.c_uint32, vp, vp, vp]
+        L.pgc_weighted_gram_device.argtypes = [vp, vp, vp, vp, vp, sz, sz, C.c_double, vp, vp]
+        L.pgc_weighted_mean_device.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp]
         L.pgc_algo_defaults.argtypes = [C.c_int, C.c_uint, C.c_uint64, C.POINTER(AlgoDesc)]
         L.pgc_algo_evolve_device.argtypes = [vp, C.POINTER(AlgoDesc), vp, vp, sz, C.c_uint32, C.POINTER(C.c_uint), vp]
         L.pgc_population_init_device.argtypes = [vp, sz, C.c_uint64, vp, vp, vp, vp]
@@ -226,6 +229,38 @@ class Context:
         out = np.empty(shape, dtype=dtype)
         check(lib().pgc_memcpy_d2h(self._h, out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), out.nbytes))
         return out
+
+    # ---- CMA-ES / xNES contractions (host-array convenience wrappers over the device entry points) ----
+    def cmaes_sample(self, mean, bd, sigma: float, lam: int, seed: int, generation: int):
+        """(x [lam x D], z [lam x D]): x_i = mean + sigma * BD z_i."""
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        bd = np.ascontiguousarray(bd, dtype=np.float64)
+        D = mean.size
+        dm, db = self.to_device(mean), self.to_device(bd)
+        dz, dx = self.malloc(8 * max(lam * D, 1)), self.malloc(8 * max(lam * D, 1))
+        try:
+            check(lib().pgc_cmaes_sample_device(self._h, dm, db, sigma, lam, D, seed, generation, dz, dx, None))
+            self.synchronize()
+            return self.from_device(dx, (lam, D)), self.from_device(dz, (lam, D))
+        finally:
+            for p in (dm, db, dz, dx):
+                self.free(p)
+
+    def weighted_gram(self, rows, w, idx=None, center=None, scale_div: float = 1.0):
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        D = rows.shape[1]
+        bufs = [self.to_device(rows), self.to_device(w), self.malloc(8 * D * D), self.malloc(8 * D)]
+        di = self.to_device(np.ascontiguousarray(idx, dtype=np.uint32)) if idx is not None else None
+        dc = self.to_device(np.ascontiguousarray(center, dtype=np.float64)) if center is not None else None
+        try:
+            check(lib().pgc_weighted_gram_device(self._h, bufs[0], di, dc, bufs[1], w.size, D, scale_div, bufs[2], None))
+            check(lib().pgc_weighted_mean_device(self._h, bufs[0], di, bufs[1], w.size, D, bufs[3], None))
+            self.synchronize()
+            return self.from_device(bufs[2], (D, D)), self.from_device(bufs[3], (D,))
+        finally:
+            for p in bufs + [q for q in (di, dc) if q]:
+                self.free(p)
 
     # ---- hypervolume (pagmo::hypervolume::compute / contributions for 2 and 3 objectives) ----
     def hv_compute(self, points: np.ndarray, r_point) -> float:

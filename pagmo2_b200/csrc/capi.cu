@@ -746,6 +746,30 @@ int pgc_hv_contributions_host(pgc_ctx *ctx, const double *points, size_t n, size
     return hv_host(ctx, points, n, m, r_point, 0, out);
 }
 
+int pgc_cmaes_sample_device(pgc_ctx *ctx, const double *d_mean, const double *d_bd, double sigma, size_t lambda, size_t D, uint64_t seed,
+                            uint32_t generation, double *d_z, double *d_x, void *stream)
+{
+    PGC_REQUIRE(ctx && d_mean && d_bd && (d_x || lambda == 0), "pgc_cmaes_sample_device: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return cmaes_sample_device(ctx, d_mean, d_bd, sigma, lambda, D, seed, generation, d_z, d_x, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int pgc_weighted_gram_device(pgc_ctx *ctx, const double *d_rows, const uint32_t *d_idx, const double *d_center, const double *d_w, size_t k,
+                             size_t D, double scale_div, double *d_out, void *stream)
+{
+    PGC_REQUIRE(ctx && d_rows && d_w && d_out, "pgc_weighted_gram_device: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return weighted_gram_device(ctx, d_rows, d_idx, d_center, d_w, k, D, scale_div, d_out, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int pgc_weighted_mean_device(pgc_ctx *ctx, const double *d_rows, const uint32_t *d_idx, const double *d_w, size_t k, size_t D, double *d_out,
+                             void *stream)
+{
+    PGC_REQUIRE(ctx && d_rows && d_w && d_out, "pgc_weighted_mean_device: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return weighted_mean_device(ctx, d_rows, d_idx, d_w, k, D, d_out, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
 int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out)
 {
     PGC_REQUIRE(out, "pgc_algo_defaults: null argument");

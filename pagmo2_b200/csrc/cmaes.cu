@@ -1,0 +1,265 @@
+// cmaes.cu - the dense FP64 contractions of CMA-ES / xNES on the FP64 tensor path (sm_100a).
+//
+// Replaces, for a whole generation, reference
+//   cmaes::evolve sampling  x_i = mean + sigma * B * D * z_i          src/algorithms/cmaes.cpp:246-253   (lambda x D times D x D)
+//   cmaes::evolve rank-mu   C = sum_i w_i (e_i - m)(e_i - m)^T / s^2  src/algorithms/cmaes.cpp:375-380   (D x mu times mu x D)
+//   cmaes::evolve mean      m = sum_i w_i e_i                          src/algorithms/cmaes.cpp:362-366
+//   xnes::evolve            cov_grad = sum_i u_i (z_i z_i^T - I)       src/algorithms/xnes.cpp:302-305    (same weighted Gram matrix)
+// The eigendecomposition of C (cmaes.cpp:386-401, O(D^3) on a D x D matrix every ~lambda/(10 D (c1+cmu)) generations) stays on the
+// host, as SURVEY.md 8(a22) says; the caller hands in B*D.
+// Both contractions run on mma.sync.m8n8k4.f64 with operands staged in shared memory in bank-conflict-free strides:
+//   * weighted Gram: a CTA owns chunks of 32 individuals (centred rows in shared memory, stride == 8 mod 16), warp `a` owns
+//     the 8-row block `a` of the output and all its column tiles (<= 16 accumulator tiles); per-CTA partial sums go to scratch and
+//     are added in CTA order by a second kernel, so the result does not depend on scheduling (no FP64 atomics).
+//   * sampling: B*D resident in shared memory (stride == 4 mod 16), a warp owns tiles of 8 individuals: normals from Philox
+//     (seed, kTagCmaes, generation, i, 2j / 2j+1) by Box-Muller, DMMA, + mean, coalesced store.
+// D <= 128 (one column group of 16 tiles); larger dimensions are rejected (PGC_ERR_UNSUPPORTED), not sent to the CPU.
+// FP64-pipe bound: 2*mu*D^2 resp. 2*lambda*D^2 flop against 8*(mu*D + D*D) resp. 8*lambda*D bytes.
+#include <cmath>
+#include <vector>
+
+#include "cec_device.cuh"
+#include "pgc_internal.cuh"
+#include "philox.cuh"
+
+namespace pgc
+{
+
+namespace
+{
+
+using cecdev::dmma;
+using cecdev::pad4;
+using cecdev::pad8;
+constexpr int kMaxD = 128, kMaxNT = kMaxD / 8;
+constexpr int kGramWarps = 16, kGramChunk = 32;
+
+__host__ __device__ inline int stride_mod16(int d, int want) // smallest s >= d with s % 16 == want
+{
+    int s = d;
+    while (s % 16 != want) ++s;
+    return s;
+}
+
+struct GramParams {
+    const double *rows;    // [n x D]
+    const unsigned *idx;   // optional gather: row i = rows[idx[i]]
+    const double *center;  // optional [D]
+    const double *w;       // [k]
+    unsigned k, D;
+    double *partial;       // [gridDim.x][DP x DP]
+};
+
+__global__ void __launch_bounds__(kGramWarps * 32, 1) gram_partial_kernel(const GramParams P)
+{
+    const int D = static_cast<int>(P.D), DP = pad8(D), NT = DP / 8, S = stride_mod16(DP, 8);
+    extern __shared__ __align__(16) double smem[];
+    double *d = smem;                    // [kGramChunk][S]
+    double *sw = d + kGramChunk * S;     // [kGramChunk]
+    double *sc = sw + kGramChunk;        // [DP]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, j = lane & 3;
+    for (int a = threadIdx.x; a < DP; a += blockDim.x) sc[a] = (P.center && a < D) ? P.center[a] : 0.0;
+    double acc[kMaxNT][2];
+#pragma unroll
+    for (int t = 0; t < kMaxNT; ++t) acc[t][0] = acc[t][1] = 0.0;
+    const unsigned nchunks = (P.k + kGramChunk - 1) / kGramChunk;
+    for (unsigned c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < kGramChunk * DP; e += blockDim.x) {
+            const int r = e / DP, a = e - r * DP;
+            const unsigned i = c * kGramChunk + r;
+            double v = 0.0;
+            if (i < P.k && a < D) {
+                const size_t row = P.idx ? P.idx[i] : i;
+                v = P.rows[row * D + a] - sc[a];
+            }
+            d[r * S + a] = v;
+        }
+        for (int r = threadIdx.x; r < kGramChunk; r += blockDim.x) {
+            const unsigned i = c * kGramChunk + r;
+            sw[r] = i < P.k ? P.w[i] : 0.0;
+        }
+        __syncthreads();
+        if (warp < NT) { // warp = 8-row block of the output; A[row a][k i] = w_i d_ia, B[k i][col b] = d_ib
+            const double *pa = d + j * S + warp * 8 + g;
+            const double *pb = d + j * S + g;
+#pragma unroll 2
+            for (int k0 = 0; k0 < kGramChunk; k0 += 4) {
+                const double a = pa[k0 * S] * sw[k0 + j];
+#pragma unroll
+                for (int t = 0; t < kMaxNT; ++t)
+                    if (t < NT) dmma(acc[t][0], acc[t][1], a, pb[k0 * S + t * 8]);
+            }
+        }
+    }
+    if (warp < NT) {
+        double *out = P.partial + static_cast<size_t>(blockIdx.x) * DP * DP;
+#pragma unroll
+        for (int t = 0; t < kMaxNT; ++t)
+            if (t < NT) {
+                double *o = out + (warp * 8 + g) * DP + t * 8 + 2 * j;
+                o[0] = acc[t][0];
+                o[1] = acc[t][1];
+            }
+    }
+}
+
+__global__ void gram_reduce_kernel(const double *partial, unsigned nparts, unsigned D, unsigned DP, double scale_div, double *out)
+{
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D * D) return;
+    const unsigned a = e / D, b = e - a * D;
+    double s = 0.0;
+    for (unsigned p = 0; p < nparts; ++p) s += partial[static_cast<size_t>(p) * DP * DP + a * DP + b];
+    out[e] = s / scale_div; // cmaes.cpp:380  C /= sigma * sigma
+}
+
+// mean = e_0 w_0; mean += e_i w_i (cmaes.cpp:363-366), one thread per coordinate, same order and roundings as the reference
+__global__ void weighted_mean_kernel(const double *rows, const unsigned *idx, const double *w, unsigned k, unsigned D, double *out)
+{
+    const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= D) return;
+    double m = 0.0;
+    for (unsigned i = 0; i < k; ++i) {
+        const size_t row = idx ? idx[i] : i;
+        const double term = rows[row * D + a] * w[i];
+        m = (i == 0) ? term : m + term;
+    }
+    out[a] = m;
+}
+
+struct SampleParams {
+    const double *mean; // [D]
+    const double *bd;   // [D x D] row-major: (B*D)[a][j]
+    double sigma;
+    unsigned lambda, D;
+    unsigned long long seed;
+    unsigned generation;
+    double *z; // optional [lambda x D]
+    double *x; // [lambda x D]
+};
+
+__device__ __forceinline__ double normal_at(unsigned long long seed, unsigned generation, unsigned i, unsigned j)
+{
+    const double u1 = 1.0 - philox_u01(seed, kTagCmaes, generation, i, 2 * j);
+    const double u2 = philox_u01(seed, kTagCmaes, generation, i, 2 * j + 1);
+    return sqrt(-2.0 * log(u1)) * cos(2.0 * 3.141592653589793238462643383279502884 * u2);
+}
+
+constexpr int kSampleWarps = 8;
+
+__global__ void __launch_bounds__(kSampleWarps * 32, 1) cmaes_sample_kernel(const SampleParams P)
+{
+    const int D = static_cast<int>(P.D), DP = pad8(D), KP = pad4(D), NT = DP / 8, S = stride_mod16(KP, 4);
+    extern __shared__ __align__(16) double smem[];
+    double *sB = smem;              // [DP][S]: row a = output coordinate, column j
+    double *sZ = sB + DP * S;       // [warps][8][S]
+    double *sM = sZ + kSampleWarps * 8 * S;
+    for (int e = threadIdx.x; e < DP * S; e += blockDim.x) {
+        const int a = e / S, jj = e - a * S;
+        sB[e] = (a < D && jj < D) ? P.bd[a * D + jj] : 0.0;
+    }
+    for (int a = threadIdx.x; a < DP; a += blockDim.x) sM[a] = a < D ? P.mean[a] : 0.0;
+    for (int e = threadIdx.x; e < kSampleWarps * 8 * S; e += blockDim.x) sZ[e] = 0.0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, j = lane & 3;
+    double *zt = sZ + warp * 8 * S;
+    const unsigned ntiles = (P.lambda + 7) / 8;
+    for (unsigned tile = blockIdx.x * kSampleWarps + warp; tile < ntiles; tile += gridDim.x * kSampleWarps) {
+        const unsigned i0 = tile * 8;
+        for (int e = lane; e < 8 * D; e += 32) {
+            const int t = e / D, jj = e - t * D;
+            const unsigned i = i0 + t;
+            const double z = i < P.lambda ? normal_at(P.seed, P.generation, i, jj) : 0.0;
+            zt[t * S + jj] = z;
+            if (P.z && i < P.lambda) P.z[static_cast<size_t>(i) * D + jj] = z;
+        }
+        __syncwarp();
+        double acc[kMaxNT][2];
+#pragma unroll
+        for (int t = 0; t < kMaxNT; ++t) acc[t][0] = acc[t][1] = 0.0;
+        const double *pa = zt + g * S + j;  // A[row individual g][k j]
+        const double *pb = sB + g * S + j;  // B[k j][col a] = BD[a][j]: row a0 + g, column k0 + j
+#pragma unroll 2
+        for (int k0 = 0; k0 < KP; k0 += 4) {
+            const double a = pa[k0];
+#pragma unroll
+            for (int t = 0; t < kMaxNT; ++t)
+                if (t < NT) dmma(acc[t][0], acc[t][1], a, pb[t * 8 * S + k0]);
+        }
+        __syncwarp();
+        // accumulator tile t: lane holds y[individual g][coordinate t*8 + 2j + {0,1}]; x = mean + sigma * y
+        const unsigned i = i0 + g;
+#pragma unroll
+        for (int t = 0; t < kMaxNT; ++t)
+            if (t < NT && i < P.lambda) {
+                const int c = t * 8 + 2 * j;
+                if (c < D) P.x[static_cast<size_t>(i) * D + c] = sM[c] + P.sigma * acc[t][0];
+                if (c + 1 < D) P.x[static_cast<size_t>(i) * D + c + 1] = sM[c + 1] + P.sigma * acc[t][1];
+            }
+        __syncwarp();
+    }
+}
+
+} // namespace
+
+int weighted_gram_device(pgc_ctx *ctx, const double *d_rows, const unsigned *d_idx, const double *d_center, const double *d_w, size_t k,
+                         size_t D, double scale_div, double *d_out, cudaStream_t st)
+{
+    PGC_REQUIRE(D >= 1 && k >= 1, "weighted Gram matrix: empty input");
+    if (D > static_cast<size_t>(kMaxD)) {
+        set_error("weighted Gram matrix (cmaes rank-mu / xnes): dimension %zu > %d is not implemented on the device yet", D, kMaxD);
+        return PGC_ERR_UNSUPPORTED;
+    }
+    const int DP = pad8(static_cast<int>(D)), S = stride_mod16(DP, 8);
+    const size_t smem = sizeof(double) * (kGramChunk * S + kGramChunk + DP);
+    const unsigned nchunks = static_cast<unsigned>((k + kGramChunk - 1) / kGramChunk);
+    unsigned grid = nchunks < static_cast<unsigned>(ctx->sm_count) ? nchunks : static_cast<unsigned>(ctx->sm_count);
+    double *partial = nullptr;
+    PGC_CUDA(cudaMallocAsync(&partial, sizeof(double) * grid * DP * DP, st));
+    GramParams P{d_rows, d_idx, d_center, d_w, static_cast<unsigned>(k), static_cast<unsigned>(D), partial};
+    PGC_CUDA(cudaFuncSetAttribute(gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    gram_partial_kernel<<<grid, kGramWarps * 32, smem, st>>>(P);
+    PGC_CUDA(cudaGetLastError());
+    const unsigned dd = static_cast<unsigned>(D * D);
+    gram_reduce_kernel<<<(dd + 255) / 256, 256, 0, st>>>(partial, grid, static_cast<unsigned>(D), static_cast<unsigned>(DP), scale_div, d_out);
+    PGC_CUDA(cudaGetLastError());
+    PGC_CUDA(cudaFreeAsync(partial, st));
+    ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    return PGC_OK;
+}
+
+int weighted_mean_device(pgc_ctx *ctx, const double *d_rows, const unsigned *d_idx, const double *d_w, size_t k, size_t D, double *d_out,
+                         cudaStream_t st)
+{
+    PGC_REQUIRE(D >= 1 && k >= 1, "weighted mean: empty input");
+    weighted_mean_kernel<<<static_cast<unsigned>((D + 127) / 128), 128, 0, st>>>(d_rows, d_idx, d_w, static_cast<unsigned>(k),
+                                                                              static_cast<unsigned>(D), d_out);
+    PGC_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return PGC_OK;
+}
+
+int cmaes_sample_device(pgc_ctx *ctx, const double *d_mean, const double *d_bd, double sigma, size_t lambda, size_t D, unsigned long long seed,
+                        unsigned generation, double *d_z, double *d_x, cudaStream_t st)
+{
+    if (lambda == 0) return PGC_OK;
+    PGC_REQUIRE(D >= 1, "cmaes sampling: empty dimension");
+    if (D > static_cast<size_t>(kMaxD)) {
+        set_error("cmaes sampling: dimension %zu > %d is not implemented on the device yet", D, kMaxD);
+        return PGC_ERR_UNSUPPORTED;
+    }
+    const int DP = pad8(static_cast<int>(D)), KP = pad4(static_cast<int>(D)), S = stride_mod16(KP, 4);
+    const size_t smem = sizeof(double) * (static_cast<size_t>(DP) * S + kSampleWarps * 8 * S + DP);
+    PGC_CUDA(cudaFuncSetAttribute(cmaes_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const unsigned ntiles = static_cast<unsigned>((lambda + 7) / 8);
+    unsigned grid = (ntiles + kSampleWarps - 1) / kSampleWarps;
+    if (grid > static_cast<unsigned>(ctx->sm_count)) grid = static_cast<unsigned>(ctx->sm_count);
+    SampleParams P{d_mean, d_bd, sigma, static_cast<unsigned>(lambda), static_cast<unsigned>(D), seed, generation, d_z, d_x};
+    cmaes_sample_kernel<<<grid, kSampleWarps * 32, smem, st>>>(P);
+    PGC_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return PGC_OK;
+}
+
+} // namespace pgc

@@ -187,6 +187,12 @@ int fair_replace_policy_device(pgc_ctx *ctx, unsigned long long *d_ids, double *
                                size_t nm, cudaStream_t st);
 int ring_connections(size_t n, size_t i, std::vector<size_t> &out);
 int hv_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const double *r, int compute, double *d_out, cudaStream_t st);
+int weighted_gram_device(pgc_ctx *ctx, const double *d_rows, const unsigned *d_idx, const double *d_center, const double *d_w, size_t k,
+                         size_t D, double scale_div, double *d_out, cudaStream_t st);
+int weighted_mean_device(pgc_ctx *ctx, const double *d_rows, const unsigned *d_idx, const double *d_w, size_t k, size_t D, double *d_out,
+                         cudaStream_t st);
+int cmaes_sample_device(pgc_ctx *ctx, const double *d_mean, const double *d_bd, double sigma, size_t lambda, size_t D, unsigned long long seed,
+                        unsigned generation, double *d_z, double *d_x, cudaStream_t st);
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops_out);
