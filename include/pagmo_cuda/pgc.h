@@ -209,17 +209,26 @@ PGC_API int pgc_weighted_gram_device(pgc_ctx *ctx, const double *d_rows, const u
 PGC_API int pgc_weighted_mean_device(pgc_ctx *ctx, const double *d_rows, const uint32_t *d_idx, const double *d_w, size_t k, size_t D,
                                      double *d_out, void *stream);
 
+/* sga::evolve (sga.cpp:184-292) on a device-resident single-objective population, in place (the population comes back sorted by
+ * fitness, as the reference's reinsertion leaves it).  crossover: 0 exponential, 1 binomial, 2 single, 3 sbx; mutation: 0 gaussian,
+ * 1 uniform, 2 polynomial; selection: 0 tournament (param_s <= 16), 1 truncated.  Reference defaults: cr 0.9, eta_c 1, m 0.02,
+ * param_m 1, param_s 2, exponential, polynomial, tournament. */
+PGC_API int pgc_sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP, unsigned gens, double cr, double eta_c, double m,
+                                  double param_m, unsigned param_s, unsigned crossover, unsigned mutation, unsigned selection,
+                                  uint64_t seed, uint32_t first_generation, void *stream);
+
 /* ---- algorithms behind one descriptor (pagmo::algorithm::evolve(pop), src/algorithm.cpp) ------------------------------- */
 typedef enum pgc_algo {
     PGC_ALGO_DE = 1,      /* src/algorithms/de.cpp:76-345 */
     PGC_ALGO_SADE = 2,    /* src/algorithms/sade.cpp:78-560 */
     PGC_ALGO_DE1220 = 3,  /* src/algorithms/de1220.cpp:80-600 */
     PGC_ALGO_PSO_GEN = 4, /* src/algorithms/pso_gen.cpp:120-590 */
-    PGC_ALGO_NSGA2 = 5    /* src/algorithms/nsga2.cpp:91-307 */
+    PGC_ALGO_NSGA2 = 5,   /* src/algorithms/nsga2.cpp:91-307 */
+    PGC_ALGO_SGA = 6      /* src/algorithms/sga.cpp:184-292 */
 } pgc_algo;
 
 /* Constructor arguments of the reference UDAs; pgc_algo_defaults() fills in the reference's default values
- * (de.hpp:119, sade.hpp:138, de1220.hpp:158, pso_gen.hpp:127, nsga2.hpp:103). */
+ * (de.hpp:119, sade.hpp:138, de1220.hpp:158, pso_gen.hpp:127, nsga2.hpp:103, sga.hpp:166). */
 typedef struct pgc_algo_desc {
     int32_t algo;
     uint32_t gens;
@@ -229,8 +238,10 @@ typedef struct pgc_algo_desc {
     uint32_t allowed_variants[18];        /* de1220 */
     double F, CR, ftol, xtol;             /* de family */
     double omega, eta1, eta2, max_vel;    /* pso_gen */
-    double cr, eta_c, m, eta_m;           /* nsga2 */
+    double cr, eta_c, m, eta_m;           /* nsga2; sga uses cr, eta_c, m */
     uint64_t seed;
+    double param_m;                       /* sga */
+    uint32_t param_s, crossover, mutation, selection; /* sga: see pgc_sga_evolve_device */
 } pgc_algo_desc;
 
 PGC_API int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out);

@@ -97,6 +97,10 @@ int oracle_ring_connections(size_t n, size_t i, size_t *out, size_t *count);
 int oracle_fully_connected_connections(size_t n, size_t i, size_t *out, size_t *count);
 int oracle_population_init(const double *lb, const double *ub, size_t n, size_t nx, uint64_t seed, double *x, uint64_t *ids);
 
+int oracle_sga_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t nx, unsigned gens,
+                      double cr, double eta_c, double m, double param_m, unsigned param_s, unsigned crossover, unsigned mutation,
+                      unsigned selection, uint64_t seed, uint32_t first_generation);
+
 /* ---- Philox draws and NSGA-II generation operators (philox.h, restate_nsga2.c) ---- */
 void oracle_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double oracle_philox_u01_at(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot);

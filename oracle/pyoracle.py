@@ -221,6 +221,21 @@ class Oracle:
             raise ValueError("oracle_de_evolve failed")
         return x, f, done.value, Fs, Cs, Vs
 
+    def sga_evolve(self, prob, lb, ub, x, f, gens=1, cr=0.9, eta_c=1.0, m=0.02, param_m=1.0, param_s=2, crossover="exponential",
+                   mutation="polynomial", selection="tournament", seed=0, first_generation=1):
+        """restated generational sga: returns (x, f)."""
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C").reshape(-1)
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        xo = {"exponential": 0, "binomial": 1, "single": 2, "sbx": 3}[crossover]
+        mu = {"gaussian": 0, "uniform": 1, "polynomial": 2}[mutation]
+        se = {"tournament": 0, "truncated": 1}[selection]
+        if self.lib.oracle_sga_evolve(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), C.c_size_t(x.shape[0]), C.c_size_t(x.shape[1]),
+                                      C.c_uint(gens), C.c_double(cr), C.c_double(eta_c), C.c_double(m), C.c_double(param_m), C.c_uint(param_s),
+                                      C.c_uint(xo), C.c_uint(mu), C.c_uint(se), C.c_uint64(seed), C.c_uint32(first_generation)):
+            raise ValueError("oracle_sga_evolve failed")
+        return x, f
+
     # ---- CMA-ES / xNES contractions (restate_cmaes.c) ----
     def weighted_gram(self, rows, w, idx=None, center=None, scale_div: float = 1.0):
         """(sum_i w_i (r_i - c)(r_i - c)^T / scale_div, sum_i w_i r_i) in the reference's order."""

@@ -49,10 +49,14 @@ class AlgoDesc(C.Structure):
         ("F", C.c_double), ("CR", C.c_double), ("ftol", C.c_double), ("xtol", C.c_double),
         ("omega", C.c_double), ("eta1", C.c_double), ("eta2", C.c_double), ("max_vel", C.c_double),
         ("cr", C.c_double), ("eta_c", C.c_double), ("m", C.c_double), ("eta_m", C.c_double), ("seed", C.c_uint64),
+        ("param_m", C.c_double), ("param_s", C.c_uint32), ("crossover", C.c_uint32), ("mutation", C.c_uint32), ("selection", C.c_uint32),
     ]
 
 
-ALGO = {"de": 1, "sade": 2, "de1220": 3, "pso_gen": 4, "nsga2": 5}
+ALGO = {"de": 1, "sade": 2, "de1220": 3, "pso_gen": 4, "nsga2": 5, "sga": 6}
+SGA_CROSSOVER = {"exponential": 0, "binomial": 1, "single": 2, "sbx": 3}
+SGA_MUTATION = {"gaussian": 0, "uniform": 1, "polynomial": 2}
+SGA_SELECTION = {"tournament": 0, "truncated": 1}
 TOPOLOGY = {"unconnected": 0, "ring": 1, "fully_connected": 2}
 
 
@@ -460,6 +464,20 @@ class Problem:
         try:
             check(lib().pgc_de_evolve_device(self._h, dx, df, NP, gens, code, variant, variant_adptv, F, CR, al.ctypes.data_as(C.c_void_p),
                                              al.size, ftol, xtol, dF, dC, dV, seed, first_generation, C.byref(done), None))
+            return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), done.value
+        finally:
+            self.ctx.free(dx)
+            self.ctx.free(df)
+
+    def evolve(self, algo: "AlgoDesc", x, f, first_generation=1):
+        """pagmo::algorithm::evolve on host arrays: upload, `pgc_algo_evolve_device`, download.  Returns (x, f, gens_done)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(x.shape[0], -1)
+        dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
+        done = C.c_uint()
+        try:
+            check(lib().pgc_algo_evolve_device(self._h, C.byref(algo), dx, df, x.shape[0], first_generation, C.byref(done), None))
+            self.ctx.synchronize()
             return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), done.value
         finally:
             self.ctx.free(dx)

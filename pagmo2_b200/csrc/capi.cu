@@ -770,6 +770,16 @@ int pgc_weighted_mean_device(pgc_ctx *ctx, const double *d_rows, const uint32_t 
     return weighted_mean_device(ctx, d_rows, d_idx, d_w, k, D, d_out, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
 }
 
+int pgc_sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP, unsigned gens, double cr, double eta_c, double m,
+                          double param_m, unsigned param_s, unsigned crossover, unsigned mutation, unsigned selection, uint64_t seed,
+                          uint32_t first_generation, void *stream)
+{
+    PGC_REQUIRE(prob && d_x && d_f, "pgc_sga_evolve_device: null argument");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    return sga_evolve_device(prob, d_x, d_f, static_cast<unsigned>(NP), gens, cr, eta_c, m, param_m, param_s, crossover, mutation, selection,
+                             seed, first_generation, problem_eval_device, stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
+}
+
 int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out)
 {
     PGC_REQUIRE(out, "pgc_algo_defaults: null argument");
@@ -792,6 +802,9 @@ int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out
             d.omega = 0.7298, d.eta1 = d.eta2 = 2.05, d.max_vel = 0.5, d.variant = 5, d.neighb_type = 2, d.neighb_param = 4;
             break;
         case PGC_ALGO_NSGA2: d.cr = 0.95, d.eta_c = 10., d.m = 0.01, d.eta_m = 50.; break; // nsga2.hpp:103
+        case PGC_ALGO_SGA: // sga.hpp:166: exponential crossover, polynomial mutation, tournament selection
+            d.cr = 0.9, d.eta_c = 1., d.m = 0.02, d.param_m = 1., d.param_s = 2, d.crossover = 0, d.mutation = 2, d.selection = 0;
+            break;
         default: set_error("pgc_algo_defaults: unknown algorithm %d", algo); return PGC_ERR_INVALID_ARGUMENT;
     }
     *out = d;
@@ -815,6 +828,9 @@ int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *a, double *d_
                                          a->neighb_type, a->neighb_param, a->seed, first_generation, stream);
         case PGC_ALGO_NSGA2:
             return pgc_nsga2_evolve_device(prob, d_x, d_f, n, a->gens, a->cr, a->eta_c, a->m, a->eta_m, a->seed, first_generation, stream);
+        case PGC_ALGO_SGA:
+            return pgc_sga_evolve_device(prob, d_x, d_f, n, a->gens, a->cr, a->eta_c, a->m, a->param_m, a->param_s, a->crossover, a->mutation,
+                                         a->selection, a->seed, first_generation, stream);
         default: set_error("pgc_algo_evolve_device: unknown algorithm %d", a->algo); return PGC_ERR_INVALID_ARGUMENT;
     }
 }

@@ -118,6 +118,13 @@ int rate_count(const char *who, int rate_is_frac, double rate, size_t n, size_t 
 
 } // namespace
 
+// d_sel[0..k) = indices of the k smallest of the n single-objective fitness values d_f, in ascending order (NaN last, ties by index)
+int so_best_indices_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t k, unsigned *d_sel, cudaStream_t st)
+{
+    Tmp tmp(st);
+    return best_indices(ctx, d_f, n, 1, k, d_sel, tmp, st);
+}
+
 int select_best_policy_device(pgc_ctx *ctx, const unsigned long long *d_ids, const double *d_x, const double *d_f, size_t n, size_t nx,
                               size_t nobj, int rate_is_frac, double rate, unsigned long long *d_ids_out, double *d_x_out, double *d_f_out,
                               size_t *n_out, cudaStream_t st)

@@ -185,6 +185,10 @@ int select_best_policy_device(pgc_ctx *ctx, const unsigned long long *d_ids, con
 int fair_replace_policy_device(pgc_ctx *ctx, unsigned long long *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nobj,
                                int rate_is_frac, double rate, const unsigned long long *d_mids, const double *d_mx, const double *d_mf,
                                size_t nm, cudaStream_t st);
+int so_best_indices_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t k, unsigned *d_sel, cudaStream_t st);
+int sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double cr, double eta_c, double m,
+                      double param_m, unsigned param_s, unsigned crossover, unsigned mutation, unsigned selection, unsigned long long seed,
+                      unsigned first_generation, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
 int ring_connections(size_t n, size_t i, std::vector<size_t> &out);
 int hv_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const double *r, int compute, double *d_out, cudaStream_t st);
 int weighted_gram_device(pgc_ctx *ctx, const double *d_rows, const unsigned *d_idx, const double *d_center, const double *d_w, size_t k,

@@ -21,7 +21,7 @@ def test_rank_mu_and_mean(ctx, orc, D):
         d = np.abs(x[idx] - m_old)
         scale = (d.T * w) @ d / (sigma * sigma)
         assert np.all(np.abs(C - Co) <= 1e-12 * scale + 1e-300), (D, n, np.abs(C - Co).max())
-        assert np.allclose(C, C.T, rtol=1e-13, atol=1e-300)
+        assert np.all(np.abs(C - C.T) <= 1e-12 * scale + 1e-300)  # (w d_a) d_b vs (w d_b) d_a: symmetric up to rounding, like Eigen's
     # xnes form: rows = z, no centre, signed utilities
     z = rng.normal(size=(64, D))
     u = rng.normal(size=64)
