@@ -34,6 +34,7 @@ sys.path.insert(0, str(ROOT))
 DIM = 100
 FUNCS = list(range(1, 31))
 N_DEFAULT = 1 << 20
+STAGE_DRAM_BYTES = 8.467e8  # measured once with ncu (see roofline.traffic_note); per launch at the default batch
 ROTATIONS = {**{f: 1 for f in range(1, 23)}, 8: 0, 10: 0, 23: 4, 24: 2, 25: 3, 26: 5, 27: 5, 28: 5, 29: 3, 30: 3}
 
 
@@ -286,7 +287,9 @@ def run_native(args):
                 "path": "pgc_eval_host: pinned host -> chunked H2D -> kernels -> D2H -> pinned host"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp64_peak, "traffic": None,
+                     "frac": achieved / fp64_peak, "traffic": STAGE_DRAM_BYTES,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one rotated stage launch (1 Mi x 100), ncu --set full, "
+                                     "profiles/r1h_stage_kernel_ncu_full.csv; algorithmic bytes of that launch = 8*(100+1)*2^20 = 8.47e8",
                      "peak_source": "pgc_measure_fp64_peak (DFMA loop, this run); MEASURED_PEAKS.json has no FP64 figure",
                      "dmma_probe_tflops": fp64_mma_peak,
                      "rotation_only_frac": rot_flops_step / step_s_rank / 1e12 / fp64_peak,
