@@ -143,9 +143,13 @@ def test_cec2014_rejects_bad_arguments(capi, ctx, orc):
         assert ei.value.status == capi.PGC_ERR_INVALID_ARGUMENT
     with pytest.raises(capi.PgcError):  # tables too short
         capi.Problem(ctx, "cec2014", prob_id=23, dim=10, rotation=mr[:100], shift=os_c, shuffle=s)
-    with pytest.raises(capi.PgcError) as ei:  # a family this build does not evaluate: error, not a CPU fallback
-        capi.Problem(ctx, "wfg", prob_id=1, dim=5, nobj=3, param=4)
-    assert ei.value.status == capi.PGC_ERR_UNSUPPORTED
+    capi.FAMILY["golomb_ruler"] = 12  # a UDP family without a device evaluator: error, not a CPU fallback
+    try:
+        with pytest.raises(capi.PgcError) as ei:
+            capi.Problem(ctx, "golomb_ruler", dim=5)
+        assert ei.value.status == capi.PGC_ERR_UNSUPPORTED
+    finally:
+        del capi.FAMILY["golomb_ruler"]
     prob = make_cec(capi, ctx, orc, 5, 10)
     assert prob.name == "CEC2014 - f5(ackley_func)"
     lb, ub = prob.bounds()
