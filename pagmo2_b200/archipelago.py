@@ -137,6 +137,7 @@ class Archipelago:
     migrant_handling: str = "preserve"
     seed: int = 0
     group: object = None  # torch.distributed process group (None: default group when initialised, else single process)
+    distributed: bool = True  # False: ignore an initialised torch.distributed and own every island in this process
     log: list = field(default_factory=list)
 
     def __post_init__(self):
@@ -144,7 +145,7 @@ class Archipelago:
         self._dist = None
         try:
             import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
+            if self.distributed and dist.is_available() and dist.is_initialized():
                 self._dist = dist
                 self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         except ImportError:
