@@ -117,7 +117,7 @@ def run_reference(args):
     try:
         rate, per_step = cpu_reference_rate(sample, cores, steps=args.steps, warmup=args.warmup)
     except Exception as e:  # the prebuilt checker is missing: say so, never fake a number
-        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not loadable: {e}"[:200]}))
+        OUT.emit(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not loadable: {e}"[:200]}))
         return 0
     desc = f"{sample} individuals x 30 functions per step (of the 1Mi-vector workload), thread_bfe on {cores} threads"
     line = {
@@ -129,7 +129,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    OUT.emit(json.dumps(line))
     return 0
 
 
@@ -299,13 +299,32 @@ def run_native(args):
         "geomean_evals_per_s_per_gpu": geomean,
         "per_function": per_function,
     }
-    print(json.dumps(line))
+    OUT.emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
+class QuietStdout:
+    """Keep stdout to the ONE JSON line: libraries (NCCL's version banner, torchrun helpers) that print to fd 1 while the benchmark
+    runs are sent to stderr; `emit` writes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text: str):
+        sys.stdout.flush()
+        os.write(self._real, (text + "\n").encode())
+
+
+OUT = None
+
+
 def main():
+    global OUT
+    OUT = QuietStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
