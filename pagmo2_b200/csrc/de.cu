@@ -42,6 +42,7 @@ struct TrialParams {
     const double *F_in, *CR_in;     // per individual (sade / de1220)
     const unsigned *variant_in;     // per individual (de1220)
     const double *gbIterF, *gbIterCR; // device scalars
+    const unsigned *stopped;          // device flag: an exit condition fired in an earlier generation of this batch of launches
     double *trial;                  // [NP x dim]
     double *F_out, *CR_out;
     unsigned *variant_out;
@@ -97,7 +98,7 @@ __device__ __forceinline__ void decode_variant(unsigned v, unsigned &base, bool 
 __global__ void de_trial_kernel(const TrialParams P)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.NP) return;
+    if (i >= P.NP || *P.stopped) return;
     const unsigned NP = P.NP, dim = P.dim;
     PhiloxStream rs(P.seed, kTagDe, P.generation, i);
     // Durstenfeld partial shuffle of 0..NP-1 (de.cpp:143-149, de1220.cpp:181-187) on a virtual array: only the picked
@@ -224,10 +225,10 @@ __global__ void de_trial_kernel(const TrialParams P)
 // selection, de.cpp:281-299 / de1220.cpp:515-536
 __global__ void de_select_kernel(const double *trial, const double *ftrial, double *x, double *f, unsigned NP, unsigned dim,
                                  unsigned char *accepted, const double *F_try, const double *CR_try, const unsigned *var_try,
-                                 double *F, double *CR, unsigned *variant)
+                                 double *F, double *CR, unsigned *variant, const unsigned *stopped)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= NP) return;
+    if (i >= NP || *stopped) return;
     const bool ok = ftrial[i] <= f[i];
     accepted[i] = ok;
     if (ok) {
@@ -240,9 +241,11 @@ __global__ void de_select_kernel(const double *trial, const double *ftrial, doub
     }
 }
 
-__global__ void de_copy_accepted_kernel(const double *trial, double *x, const unsigned char *accepted, unsigned NP, unsigned dim)
+__global__ void de_copy_accepted_kernel(const double *trial, double *x, const unsigned char *accepted, unsigned NP, unsigned dim,
+                                        const unsigned *stopped)
 {
     const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (*stopped) return;
     if (e < static_cast<size_t>(NP) * dim && accepted[e / dim]) x[e] = trial[e];
 }
 
@@ -251,16 +254,24 @@ struct DeGlobal { // device-side global best + exit-condition data
     unsigned gbidx, gbvariant;
     unsigned best_idx, worst_idx;
     double dx, df;
+    unsigned stopped;   // set when dx < xtol or df < ftol (de.cpp:302-321): later generations already queued become no-ops
+    unsigned gens_done;
 };
 
 // sequential "if accepted and f <= gbfit: gb = i" over ascending i == smallest accepted fitness, last index on ties, if <= gbfit;
 // plus pop.best_idx() / worst_idx() (first min / first max) and the exit quantities dx, df (de.cpp:302-316).  Single CTA.
 __global__ void de_global_kernel(const double *x, const double *f, const unsigned char *accepted, unsigned NP, unsigned dim,
-                                 const double *F, const double *CR, const unsigned *variant, double *gbX, DeGlobal *G, int init)
+                                 const double *F, const double *CR, const unsigned *variant, double *gbX, DeGlobal *G, int init, double xtol,
+                                 double ftol)
 {
     __shared__ double sfa[256], sfb[256], sfw[256];
     __shared__ unsigned sia[256], sib[256], siw[256];
     const unsigned t = threadIdx.x;
+    if (!init && G->stopped) return; // uniform: written only by this kernel, at the end of an earlier launch
+    if (init && t == 0) {
+        G->stopped = 0;
+        G->gens_done = 0;
+    }
     double fa = 0, fb = 0, fw = 0;
     unsigned ia = 0xffffffffu, ib = 0xffffffffu, iw = 0xffffffffu;
     for (unsigned i = t; i < NP; i += blockDim.x) {
@@ -306,6 +317,10 @@ __global__ void de_global_kernel(const double *x, const double *f, const unsigne
         double s = 0;
         for (unsigned k = 0; k < blockDim.x; ++k) s += sfa[k];
         G->dx = s;
+        if (!init) {
+            G->gens_done += 1;
+            if (s < xtol || G->df < ftol) G->stopped = 1; // de.cpp:308,316
+        }
     }
 }
 
@@ -408,24 +423,30 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
             de_init_adapt_kernel<<<nblk(NP, 128), 128, 0, st>>>(Fs, CRs, algo == 2u ? vars : nullptr, NP, cfg, seed, first_generation);
         }
     }
-    de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, nullptr, NP, dim, Fs, CRs, algo == 2u ? vars : nullptr, gbX, G, 1);
+    de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, nullptr, NP, dim, Fs, CRs, algo == 2u ? vars : nullptr, gbX, G, 1, xtol, ftol);
+    // The exit conditions live on the device (DeGlobal::stopped): once one fires, the generations already queued return
+    // immediately, and the host only looks every kPoll generations - a sync per generation made small populations
+    // latency-bound on the host round trip.
+    constexpr unsigned kPoll = 16;
     unsigned done = 0;
+    DeGlobal h{};
     for (unsigned g = 0; g < gens; ++g) {
-        TrialParams tp{d_x, gbX, lb, ub, Fs, CRs, algo == 2u ? vars : nullptr, &G->gbF, &G->gbCR, trial, Ftry, CRtry, vtry, NP, dim, seed,
-                       first_generation + g, cfg};
+        TrialParams tp{d_x, gbX, lb, ub, Fs, CRs, algo == 2u ? vars : nullptr, &G->gbF, &G->gbCR, &G->stopped, trial, Ftry, CRtry, vtry, NP, dim,
+                       seed, first_generation + g, cfg};
         de_trial_kernel<<<nblk(NP, 64), 64, 0, st>>>(tp);
         if ((rc = eval(prob, trial, NP, ftrial, st))) return rc;
         de_select_kernel<<<nblk(NP, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, NP, dim, accepted, Ftry, CRtry, vtry, algo ? Fs : nullptr,
-                                                        algo ? CRs : nullptr, algo == 2u ? vars : nullptr);
-        de_copy_accepted_kernel<<<nblk(nd, 256), 256, 0, st>>>(trial, d_x, accepted, NP, dim);
+                                                        algo ? CRs : nullptr, algo == 2u ? vars : nullptr, &G->stopped);
+        de_copy_accepted_kernel<<<nblk(nd, 256), 256, 0, st>>>(trial, d_x, accepted, NP, dim, &G->stopped);
         de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, accepted, NP, dim, algo ? Fs : nullptr, algo ? CRs : nullptr, algo == 2u ? vars : nullptr,
-                                            gbX, G, 0);
+                                            gbX, G, 0, xtol, ftol);
         ctx->launches.fetch_add(4, std::memory_order_relaxed);
-        ++done;
-        DeGlobal h;
-        PGC_CUDA(cudaMemcpyAsync(&h, G, sizeof(DeGlobal), cudaMemcpyDeviceToHost, st));
-        PGC_CUDA(cudaStreamSynchronize(st));
-        if (h.dx < xtol || h.df < ftol) break; // de.cpp:308,316
+        if ((g + 1) % kPoll == 0 || g + 1 == gens) {
+            PGC_CUDA(cudaMemcpyAsync(&h, G, sizeof(DeGlobal), cudaMemcpyDeviceToHost, st));
+            PGC_CUDA(cudaStreamSynchronize(st));
+            done = h.gens_done;
+            if (h.stopped) break;
+        }
     }
     if (gens_done) *gens_done = done;
     PGC_CUDA(cudaGetLastError());

@@ -23,6 +23,39 @@ KEEP = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum", "sm__cycles_elapsed.max"]
 
+KEEP += ["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
+         "l1tex__t_sector_hit_rate.pct", "smsp__thread_inst_executed_per_inst_executed.ratio"]
+
+# secondary kernels: gpurun_out/<tag>_sec_<name>.ncu-rep -> profiles/<tag>_sec_kernels_ncu_full.csv (one column per kernel)
+sec = sorted((ROOT / "gpurun_out").glob(f"{tag}_sec_*.ncu-rep"))
+if sec:
+    cols = {}
+    for repf in sec:
+        raw = subprocess.run(["ncu", "-i", str(repf), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        if len(rows) < 3:
+            continue
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        cols[repf.stem.replace(f"{tag}_sec_", "")] = (hdr, units, data[0])
+    if cols:
+        stall_all = sorted({h for hdr, _, _ in cols.values() for h in hdr if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h})
+        with open(out / f"{tag}_sec_kernels_ncu_full.csv", "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["metric", "unit"] + list(cols))
+            for k in KEEP + stall_all:
+                unit, vals = "", []
+                for hdr, units, row in cols.values():
+                    if k in hdr:
+                        i = hdr.index(k)
+                        unit = units[i]
+                        vals.append(row[i])
+                    else:
+                        vals.append("")
+                if any(vals):
+                    w.writerow([k, unit] + vals)
+        print("wrote", out / f"{tag}_sec_kernels_ncu_full.csv")
+
 rep = ROOT / "gpurun_out" / f"{tag}_prof.ncu-rep"
 if rep.exists():
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
