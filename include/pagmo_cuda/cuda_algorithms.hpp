@@ -6,6 +6,7 @@
 //   pagmo_cuda::cuda_de1220  pagmo::de1220  (de1220.hpp:158  gen, allowed_variants, variant_adptv, ftol, xtol, memory, seed)
 //   pagmo_cuda::cuda_pso_gen pagmo::pso_gen (pso_gen.hpp:127 gen, omega, eta1, eta2, max_vel, variant, neighb_type, neighb_param, memory, seed)
 //   pagmo_cuda::cuda_nsga2   pagmo::nsga2   (nsga2.hpp:103   gen, cr, eta_c, m, eta_m, seed)
+//   pagmo_cuda::cuda_sga     pagmo::sga     (sga.hpp:166     gen, cr, eta_c, m, param_m, param_s, crossover, mutation, selection, seed)
 //
 // Same constructor arguments as the reference UDAs (plus the device), so `algorithm{cuda_sade{50u}}` drops into an island of a
 // stock pagmo::archipelago: thread_island (thread_island.cpp:79-159) runs it unchanged, and pagmo's own migration machinery
@@ -207,8 +208,33 @@ public:
     }
 };
 
+class cuda_sga : public cuda_algorithm_base
+{
+public:
+    cuda_sga(unsigned gen = 1u, double cr = .90, double eta_c = 1., double m = 0.02, double param_m = 1., unsigned param_s = 2u,
+             std::string crossover = "exponential", std::string mutation = "polynomial", std::string selection = "tournament",
+             unsigned seed = pagmo::random_device::next(), int device = 0)
+        : cuda_algorithm_base(PGC_ALGO_SGA, "SGA: Genetic Algorithm", gen, seed, device)
+    {
+        // the string -> strategy maps of sga.cpp:78-108; the numeric range checks (sga.cpp:116-160) are made by pgc_sga_evolve_device
+        const auto pick = [](const std::string &what, const std::string &v, std::initializer_list<const char *> names) -> unsigned {
+            unsigned k = 0;
+            for (const char *n : names) {
+                if (v == n) return k;
+                ++k;
+            }
+            pagmo_throw(std::invalid_argument, "The " + what + " type is unknown: " + v); // sga.cpp:138-155
+        };
+        m_desc.crossover = pick("crossover", crossover, {"exponential", "binomial", "single", "sbx"});
+        m_desc.mutation = pick("mutation", mutation, {"gaussian", "uniform", "polynomial"});
+        m_desc.selection = pick("selection", selection, {"tournament", "truncated"});
+        m_desc.cr = cr, m_desc.eta_c = eta_c, m_desc.m = m, m_desc.param_m = param_m, m_desc.param_s = param_s;
+    }
+};
+
 } // namespace pagmo_cuda
 
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_sga)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_de)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_sade)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_de1220)

@@ -5,7 +5,7 @@
 // (arithmetic intensity ~60 flop/B at D = 444).  One warp per individual: the atom coordinates are staged in shared
 // memory (SoA), the pair list (i, j) - in the reference's loop order - is linearised and strided over the lanes, lane
 // partial sums are combined with shuffles (row i broadcast, 32 consecutive j per step).  Differences to the reference: summation order (lane-strided instead of
-// sequential) and 1/(d*d*d) instead of libm pow(d, -3): ~1e-15 relative.  A coincident pair makes the reference assign
+// sequential), fused multiply-adds in the distance, and a Newton reciprocal of d*d*d instead of libm pow(d, -3): ~1e-15 relative.  A coincident pair makes the reference assign
 // DBL_MAX and keep summing, then multiply by 4 (:81-91): the result is +inf, reproduced explicitly.
 #include <cfloat>
 #include <cmath>
@@ -20,6 +20,18 @@ namespace
 {
 
 constexpr int kLjWarps = 8;
+
+// 1/d for a normal, positive d: hardware seed (rcp.approx.ftz.f64, ~2^-20) + two Newton steps (quadratic: 2^-40, 2^-80) - about
+// 1 ulp, no special-case branch.  d = 0 gives +inf (the caller flags coincident atoms separately).
+__device__ __forceinline__ double fast_rcp(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
 
 __global__ void __launch_bounds__(kLjWarps * 32) lj_kernel(const double *__restrict__ x, double *__restrict__ f, long long n, int atoms,
                                                            const ushort2 *__restrict__ pairs, int npairs)
@@ -56,22 +68,21 @@ __global__ void __launch_bounds__(kLjWarps * 32) lj_kernel(const double *__restr
         double s = 0.0;
         bool coincident = false;
         // pairs (i, j > i): atom i is a broadcast read, the lanes take consecutive j (conflict-free), 32 at a time starting
-        // at the chunk that contains i + 1; ~18 FP64-pipe instructions per pair (3 sub, mul + 2 fma, 2 mul, reciprocal, fma, add)
+        // at the chunk that contains i + 1.  ~14 FP64-pipe instructions per pair: 3 sub, mul + 2 fma, 2 mul, reciprocal
+        // (seed + 2 Newton steps = 4 fma), fma, add; a coincident pair only raises a flag (its inf - inf term is discarded).
         for (int i = 0; i + 1 < atoms; ++i) {
             const double xi0 = px[i], yi0 = py[i], zi0 = pz[i];
 #pragma unroll 2
-            for (int j0 = (i + 1) & ~31; j0 < atoms; j0 += 32) {
+            for (int j0 = (i + 1) & ~31; j0 < atoms; j0 += 32) { // straight-line body: masked lanes redo pair (i, i+1) and drop it
                 const int j = j0 + lane;
-                if (j > i && j < atoms) {
-                    const double dx = xi0 - px[j], dy = yi0 - py[j], dz = zi0 - pz[j];
-                    const double dist = dx * dx + dy * dy + dz * dz; // rij^2, :78-80
-                    if (dist == 0.0) {
-                        coincident = true;
-                    } else {
-                        const double sixth = __drcp_rn(dist * dist * dist); // rij^-6, :84
-                        s += (sixth * sixth - sixth);                         // :85
-                    }
-                }
+                const bool valid = j > i && j < atoms;
+                const int jj = valid ? j : i + 1;
+                const double dx = xi0 - px[jj], dy = yi0 - py[jj], dz = zi0 - pz[jj];
+                const double dist = fma(dz, dz, fma(dy, dy, dx * dx)); // rij^2, :78-80
+                coincident |= valid && dist == 0.0;
+                const double sixth = fast_rcp(dist * dist * dist);     // rij^-6, :84
+                const double term = fma(sixth, sixth, -sixth);         // :85
+                s += valid ? term : 0.0;
             }
         }
 #pragma unroll
