@@ -15,7 +15,9 @@
 // Work is O(n^2) point visits + staircase updates - compare/min throughput bound, no atomics; bytes = 8*n*m in, 8*n out.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
+#include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <vector>
 
 #include "pgc_internal.cuh"
@@ -175,6 +177,397 @@ __global__ void hv_sweep_kernel(const HvParams P)
     P.out[p] = V;
 }
 
+
+// ---- first pass: one WARP per point ------------------------------------------------------------------------------------------
+// The 32 lanes look at 32 consecutive points of the z-order at once.  Most of them change nothing (a left / below point only
+// matters when it beats the running minimum, an interior point only when the staircase does not already cover it - each lane
+// checks that on its own, with a binary search in the warp's shared-memory staircase), so the lanes vote and the warp steps
+// only through the few EVENTS of the chunk, in z order: integrate the slab since the last event, apply the event, and
+// recompute the uncovered area co-operatively (lanes strided over the staircase).  The staircase keeps only its live range
+// [lo, hi): a smaller yt retires entries from the front, a smaller xr from the back, without moving data.
+constexpr int kHvWarps = 8, kHvCap = 512;
+
+struct HvWarpParams {
+    const double *pts;     // [n][3] sorted by z (2 objectives: z = 0, input order)
+    const double *ptsx;    // [n][4] the same points by ascending (x, y): x, y, z, position in the z-order
+    const unsigned *order; // sorted position -> original index (nullptr: identity)
+    unsigned n;
+    double rx, ry, rz;
+    double *out;
+    unsigned *overflow;    // [0] = count, [1..] = ORIGINAL indices to rerun with the full-size scratch
+    int compute;
+};
+
+struct WarpStair {
+    double *x, *y; // shared memory, capacity kHvCap
+    int lo, hi;    // live range (uniform across the warp)
+
+    // is (qx, qy) covered by a live staircase point?  (called per lane, independently)
+    __device__ bool covers(double qx, double qy) const
+    {
+        int a = lo, b = hi; // first i in [lo, hi) with x[i] >= qx
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (x[mid] < qx) a = mid + 1;
+            else b = mid;
+        }
+        if (a > lo && y[a - 1] <= qy) return true;
+        return a < hi && x[a] == qx && y[a] <= qy;
+    }
+    // warp-uniform insert; returns 0 = already covered, 1 = inserted, -1 = out of capacity
+    __device__ int insert(double qx, double qy, int lane)
+    {
+        int a = lo, b = hi;
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (x[mid] < qx) a = mid + 1;
+            else b = mid;
+        }
+        const int i = a;
+        if (i > lo && y[i - 1] <= qy) return 0;
+        if (i < hi && x[i] == qx && y[i] <= qy) return 0;
+        a = i, b = hi; // first j >= i with y[j] < qy (y descends): [i, j) are the entries q covers
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (y[mid] >= qy) a = mid + 1;
+            else b = mid;
+        }
+        const int j = a;
+        if (j == i) { // grow by one: shift [i, hi) right
+            if (hi == kHvCap) {
+                if (lo == 0) return -1;
+                for (int base = lo; base < hi; base += 32) { // compact to the front first (reads run ahead of the writes)
+                    const int k = base + lane;
+                    double vx = 0, vy = 0;
+                    if (k < hi) {
+                        vx = x[k];
+                        vy = y[k];
+                    }
+                    __syncwarp();
+                    if (k < hi) {
+                        x[k - lo] = vx;
+                        y[k - lo] = vy;
+                    }
+                    __syncwarp();
+                }
+                const int shift = lo;
+                hi -= shift;
+                lo = 0;
+                return insert_at(i - shift, i - shift, qx, qy, lane);
+            }
+            return insert_at(i, j, qx, qy, lane);
+        }
+        return insert_at(i, j, qx, qy, lane);
+    }
+    __device__ int insert_at(int i, int j, double qx, double qy, int lane)
+    {
+        if (j == i) {
+            for (int top = hi; top > i; top -= 32) { // chunks from the back so nothing is overwritten before it is read
+                const int k = top - 1 - lane;
+                double vx = 0, vy = 0;
+                if (k >= i) {
+                    vx = x[k];
+                    vy = y[k];
+                }
+                __syncwarp();
+                if (k >= i) {
+                    x[k + 1] = vx;
+                    y[k + 1] = vy;
+                }
+                __syncwarp();
+            }
+            ++hi;
+        } else if (j > i + 1) {
+            const int gone = j - i - 1;
+            for (int base = j; base < hi; base += 32) {
+                const int k = base + lane;
+                double vx = 0, vy = 0;
+                if (k < hi) {
+                    vx = x[k];
+                    vy = y[k];
+                }
+                __syncwarp();
+                if (k < hi) {
+                    x[k - gone] = vx;
+                    y[k - gone] = vy;
+                }
+                __syncwarp();
+            }
+            hi -= gone;
+        }
+        if (lane == 0) {
+            x[i] = qx;
+            y[i] = qy;
+        }
+        __syncwarp();
+        return 1;
+    }
+    // retire entries outside the clip: y >= yt at the front, x >= xr at the back
+    __device__ void trim(double xr, double yt)
+    {
+        int a = lo, b = hi;
+        while (a < b) { // first i with y[i] < yt
+            const int mid = (a + b) >> 1;
+            if (y[mid] >= yt) a = mid + 1;
+            else b = mid;
+        }
+        lo = a;
+        a = lo, b = hi;
+        while (a < b) { // first i with x[i] >= xr
+            const int mid = (a + b) >> 1;
+            if (x[mid] < xr) a = mid + 1;
+            else b = mid;
+        }
+        hi = a;
+    }
+    // uncovered area of [px, xr) x [py, yt) under the live staircase, all lanes get the sum (positive columns only)
+    __device__ double uncovered(double px, double py, double xr, double yt, int lane) const
+    {
+        double part = 0.0;
+        for (int i = lo + lane; i < hi; i += 32) {
+            const double prevx = i == lo ? px : x[i - 1], h = i == lo ? yt : y[i - 1];
+            part += (x[i] - prevx) * (h - py);
+        }
+        if (lane == 0) {
+            const double lastx = hi > lo ? x[hi - 1] : px, h = hi > lo ? y[hi - 1] : yt;
+            part += (xr - lastx) * (h - py);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+        return part;
+    }
+};
+
+__global__ void __launch_bounds__(kHvWarps * 32) hv_warp_kernel(const HvWarpParams P)
+{
+    extern __shared__ double s_stair_raw[]; // [kHvWarps][2][kHvCap]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned pp = blockIdx.x * kHvWarps + warp; // position of this warp's point in the z-order
+    if (pp >= P.n) return;
+    const double px = P.pts[3 * pp], py = P.pts[3 * pp + 1], pz = P.pts[3 * pp + 2];
+    WarpStair st{s_stair_raw + static_cast<size_t>(warp) * 2 * kHvCap, s_stair_raw + static_cast<size_t>(warp) * 2 * kHvCap + kHvCap, 0, 0};
+    const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+    const unsigned kFullMask = 0xffffffffu;
+    double xr = P.rx, yt = P.ry;
+    bool covered = false, overflow = false;
+
+    // ---- phase 1: everything at or below p's height (compute: everything sorted before p).  No volume is swept yet, so the
+    // order is free: the points are visited by ascending (x, y), which makes the staircase APPEND-ONLY - an interior point
+    // joins iff its y beats every earlier one - and the whole chunk is handled with votes and prefix minima, no serial events.
+    {
+        double ymin = kInf; // y of the last staircase entry
+        int hi = 0;
+        for (unsigned base = 0; base < P.n && !covered; base += 32) {
+            const unsigned k = base + lane;
+            double qx = 0, qy = 0, qz = 0;
+            unsigned qpos = pp;
+            if (k < P.n) {
+                const double2 v0 = reinterpret_cast<const double2 *>(P.ptsx)[2 * static_cast<size_t>(k)];
+                const double2 v1 = reinterpret_cast<const double2 *>(P.ptsx)[2 * static_cast<size_t>(k) + 1];
+                qx = v0.x;
+                qy = v0.y;
+                qz = v1.x;
+                qpos = static_cast<unsigned>(v1.y);
+            }
+            const bool in1 = qpos != pp && (P.compute ? qpos < pp : qz <= pz);
+            const bool lefty = qx <= px;
+            if (__any_sync(kFullMask, in1 && lefty && qy <= py)) { // p's quadrant is covered from its own height on
+                covered = true;
+                break;
+            }
+            // the reductions below are skipped for the (vast majority of) chunks that cannot change the state
+            if (__any_sync(kFullMask, in1 && lefty && qy < yt)) {
+                double cy = (in1 && lefty) ? qy : kInf;
+#pragma unroll
+                for (int m = 16; m > 0; m >>= 1) cy = fmin(cy, __shfl_xor_sync(kFullMask, cy, m));
+                yt = fmin(yt, cy);
+            }
+            if (__any_sync(kFullMask, in1 && !lefty && qy <= py && qx < xr)) {
+                double cx = (in1 && !lefty && qy <= py) ? qx : kInf;
+#pragma unroll
+                for (int m = 16; m > 0; m >>= 1) cx = fmin(cx, __shfl_xor_sync(kFullMask, cx, m));
+                xr = fmin(xr, cx);
+            }
+            const bool inter = in1 && !lefty && qy > py && qx < xr && qy < yt && qy < ymin;
+            if (!__any_sync(kFullMask, inter)) continue;
+            // exclusive prefix minimum of the interior y's in lane (= x) order, seeded with the staircase's last y
+            const double v = inter ? qy : kInf;
+            double pm = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double o = __shfl_up_sync(kFullMask, pm, d);
+                if (lane >= d) pm = fmin(pm, o);
+            }
+            double ex = __shfl_up_sync(kFullMask, pm, 1);
+            ex = lane == 0 ? ymin : fmin(ex, ymin);
+            const bool rec = inter && qy < ex;
+            const unsigned m = __ballot_sync(kFullMask, rec);
+            if (m) {
+                const int at = hi + __popc(m & ((1u << lane) - 1u));
+                if (rec && at < kHvCap) {
+                    st.x[at] = qx;
+                    st.y[at] = qy;
+                }
+                hi += __popc(m);
+                if (hi > kHvCap) {
+                    overflow = true;
+                    break;
+                }
+                ymin = fmin(ymin, __shfl_sync(kFullMask, pm, 31));
+            }
+        }
+        __syncwarp();
+        st.lo = 0;
+        st.hi = hi;
+        if (!covered && !overflow) st.trim(xr, yt);
+    }
+
+    // ---- phase 2 (contributions only): the points above p in ascending z.  Each chunk of 32 is pre-filtered in parallel; the few
+    // EVENTS that change the state are stepped through in z order: integrate the slab since the last event, apply the event.
+    double V = 0.0, cur_z = pz, E = 0.0;
+    bool dirty = true;
+    if (!P.compute && !covered && !overflow) {
+        unsigned a = pp + 1, b = P.n; // first position with z > pz (z ascending; ties with p belong to phase 1)
+        while (a < b) {
+            const unsigned mid = (a + b) >> 1;
+            if (P.pts[3 * mid + 2] <= pz) a = mid + 1;
+            else b = mid;
+        }
+        for (unsigned base = a; base < P.n && !covered && !overflow; base += 32) {
+            const unsigned k = base + lane;
+            const bool act = k < P.n;
+            double qx = 0, qy = 0, qz = 0;
+            if (act) {
+                qx = P.pts[3 * k];
+                qy = P.pts[3 * k + 1];
+                qz = P.pts[3 * k + 2];
+            }
+            int type = 0; // 1 cover, 2 left, 3 below, 4 interior; pre-filter against the state at the start of the chunk
+            if (act) {
+                if (qx <= px) type = (qy <= py) ? 1 : (qy < yt ? 2 : 0);
+                else if (qy <= py) type = (qx < xr) ? 3 : 0;
+                else if (qx < xr && qy < yt && !st.covers(qx, qy)) type = 4;
+            }
+            unsigned mask = __ballot_sync(kFullMask, type != 0);
+            while (mask) {
+                const int l = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int et = __shfl_sync(kFullMask, type, l);
+                const double ex = __shfl_sync(kFullMask, qx, l), ey = __shfl_sync(kFullMask, qy, l), ez = __shfl_sync(kFullMask, qz, l);
+                // an earlier event of this chunk may have made this one irrelevant
+                if ((et == 2 && !(ey < yt)) || (et == 3 && !(ex < xr)) || (et == 4 && !(ex < xr && ey < yt))) continue;
+                if (ez > cur_z) { // a slab ends here
+                    if (dirty) {
+                        E = st.uncovered(px, py, xr, yt, lane);
+                        dirty = false;
+                    }
+                    V += E * (ez - cur_z);
+                    cur_z = ez;
+                }
+                if (et == 1) {
+                    covered = true;
+                    break;
+                }
+                if (et == 2) {
+                    yt = ey;
+                    st.trim(xr, yt);
+                    dirty = true;
+                } else if (et == 3) {
+                    xr = ex;
+                    st.trim(xr, yt);
+                    dirty = true;
+                } else {
+                    const int r = st.insert(ex, ey, lane);
+                    if (r < 0) {
+                        overflow = true;
+                        break;
+                    }
+                    dirty |= r > 0;
+                }
+            }
+        }
+    }
+    const unsigned orig = P.order ? P.order[pp] : pp;
+    if (overflow) {
+        if (lane == 0) P.overflow[1 + atomicAdd(P.overflow, 1u)] = orig;
+        return;
+    }
+    double res;
+    if (P.compute) {
+        res = covered ? 0.0 : st.uncovered(px, py, xr, yt, lane) * (P.rz - pz);
+    } else {
+        // `covered` from phase 1 means a point at or below p's height dominates it: nothing is exclusive.  In phase 2 it only ends
+        // the sweep (the slab up to the covering point has been added).
+        if (!covered || cur_z > pz) {
+            if (!covered) {
+                if (dirty) E = st.uncovered(px, py, xr, yt, lane);
+                V += E * (P.rz - cur_z);
+            }
+        }
+        res = V;
+    }
+    if (lane == 0) P.out[orig] = res;
+}
+
+__global__ void hv_gather_sorted_kernel(const double *f, const unsigned *order, unsigned n, unsigned m, double *pts)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t q = order ? order[k] : k;
+    pts[3 * k] = f[q * m];
+    pts[3 * k + 1] = f[q * m + 1];
+    pts[3 * k + 2] = m == 3 ? f[q * m + 2] : 0.0;
+}
+
+// keys of one coordinate of the z-sorted points (for the (x, y) ordering of phase 1), and the final gather
+__global__ void hv_coord_keys_kernel(const double *pts, unsigned n, int coord, const unsigned *idx_in, unsigned long long *keys, unsigned *idx)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned src = idx_in ? idx_in[i] : i;
+    unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(pts[3 * static_cast<size_t>(src) + coord]));
+    keys[i] = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+    idx[i] = src;
+}
+
+__global__ void hv_gather_xorder_kernel(const double *pts, const unsigned *xorder, unsigned n, double *ptsx)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned q = xorder[k]; // position in the z-order
+    ptsx[4 * k] = pts[3 * static_cast<size_t>(q)];
+    ptsx[4 * k + 1] = pts[3 * static_cast<size_t>(q) + 1];
+    ptsx[4 * k + 2] = pts[3 * static_cast<size_t>(q) + 2];
+    ptsx[4 * k + 3] = static_cast<double>(q);
+}
+
+// ---- 2 objectives, indicator only: the reference's own sweep (hv2d::compute, hv_hv2d.cpp:59-84) is a sort by y, a running
+// maximum of the width r.x - x and a sum - i.e. a radix sort, an inclusive max-scan and a reduction.
+__global__ void hv2d_ykeys_kernel(const double *f, unsigned n, unsigned long long *keys, unsigned *idx)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(f[2 * static_cast<size_t>(i) + 1]));
+    keys[i] = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+    idx[i] = i;
+}
+__global__ void hv2d_width_kernel(const double *f, const unsigned *order, unsigned n, double rx, double *w)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = rx - f[2 * static_cast<size_t>(order[i])];
+}
+__global__ void hv2d_terms_kernel(const double *f, const unsigned *order, const double *wmax, unsigned n, double ry, double *terms)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double y = f[2 * static_cast<size_t>(order[i]) + 1];
+    const double ynext = i + 1 < n ? f[2 * static_cast<size_t>(order[i + 1]) + 1] : ry;
+    terms[i] = (ynext - y) * wmax[i]; // :75-80
+}
+struct MaxOp {
+    __device__ __forceinline__ double operator()(double a, double b) const { return fmax(a, b); }
+};
+
 struct Scratch {
     cudaStream_t st;
     std::vector<void *> ptrs;
@@ -216,6 +609,29 @@ int hv_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const double 
     PGC_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     PGC_CUDA(cudaStreamSynchronize(st));
     PGC_REQUIRE(!bad, "Reference point is invalid: another point seems to be outside the reference point boundary, or be equal to it");
+    if (m == 2 && compute) {
+        unsigned long long *k0 = nullptr, *k1 = nullptr;
+        unsigned *i0 = nullptr, *ord = nullptr;
+        double *w = nullptr, *wmax = nullptr, *terms2 = nullptr;
+        if ((rc = tmp.get(&k0, n)) || (rc = tmp.get(&k1, n)) || (rc = tmp.get(&i0, n)) || (rc = tmp.get(&ord, n)) || (rc = tmp.get(&w, n))
+            || (rc = tmp.get(&wmax, n)) || (rc = tmp.get(&terms2, n)))
+            return rc;
+        hv2d_ykeys_kernel<<<(un + 255) / 256, 256, 0, st>>>(d_f, un, k0, i0);
+        size_t b1 = 0, b2 = 0, b3 = 0;
+        PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b1, k0, k1, i0, ord, static_cast<int>(n), 0, 64, st));
+        PGC_CUDA(cub::DeviceScan::InclusiveScan(nullptr, b2, w, wmax, MaxOp(), static_cast<int>(n), st));
+        PGC_CUDA(cub::DeviceReduce::Sum(nullptr, b3, terms2, d_out, static_cast<int>(n), st));
+        unsigned char *ws = nullptr;
+        if ((rc = tmp.get(&ws, std::max(b1, std::max(b2, b3))))) return rc;
+        PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, b1, k0, k1, i0, ord, static_cast<int>(n), 0, 64, st));
+        hv2d_width_kernel<<<(un + 255) / 256, 256, 0, st>>>(d_f, ord, un, r[0], w);
+        PGC_CUDA(cub::DeviceScan::InclusiveScan(ws, b2, w, wmax, MaxOp(), static_cast<int>(n), st));
+        hv2d_terms_kernel<<<(un + 255) / 256, 256, 0, st>>>(d_f, ord, wmax, un, r[1], terms2);
+        PGC_CUDA(cub::DeviceReduce::Sum(ws, b3, terms2, d_out, static_cast<int>(n), st));
+        PGC_CUDA(cudaGetLastError());
+        ctx->launches.fetch_add(6, std::memory_order_relaxed);
+        return PGC_OK;
+    }
     unsigned *order = nullptr;
     if (m == 3) {
         unsigned long long *k0 = nullptr, *k1 = nullptr;
@@ -230,14 +646,40 @@ int hv_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const double 
         PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, bytes, k0, k1, i0, order, static_cast<int>(n), 0, 64, st));
         ctx->launches.fetch_add(2, std::memory_order_relaxed);
     }
-    // Staircase scratch.  First pass: every point at once with a small per-point capacity; the (rare) points whose staircase
-    // outgrows it are collected and rerun with the worst-case capacity n, in batches bounded to ~1 GiB of scratch.
-    const unsigned cap1 = un < 512u ? un : 512u;
-    double *sx = nullptr, *sy = nullptr, *terms = nullptr;
+    // First pass: one warp per point with the staircase in shared memory (hv_warp_kernel).  The (rare) points whose staircase
+    // outgrows it are collected and rerun by the one-thread-per-point kernel with the worst-case capacity n in global memory,
+    // in batches bounded to ~1 GiB of scratch.
+    const unsigned cap1 = 0; // the second pass, when needed, always uses cap = n
+    double *pts = nullptr, *terms = nullptr;
     unsigned *ovf = nullptr;
-    if ((rc = tmp.get(&sx, n * cap1)) || (rc = tmp.get(&sy, n * cap1)) || (rc = tmp.get(&ovf, n + 1))) return rc;
+    if ((rc = tmp.get(&pts, 3 * n)) || (rc = tmp.get(&ovf, n + 1))) return rc;
     if (compute && (rc = tmp.get(&terms, n))) return rc;
     PGC_CUDA(cudaMemsetAsync(ovf, 0, sizeof(unsigned), st));
+    hv_gather_sorted_kernel<<<(un + 255) / 256, 256, 0, st>>>(d_f, order, un, static_cast<unsigned>(m), pts);
+    double *ptsx = nullptr;
+    {   // (x, y) lexicographic order of the z-sorted points: stable radix sort by y, then by x
+        unsigned long long *ka = nullptr, *kb = nullptr;
+        unsigned *ia = nullptr, *ib = nullptr, *ic = nullptr;
+        if ((rc = tmp.get(&ptsx, 4 * n)) || (rc = tmp.get(&ka, n)) || (rc = tmp.get(&kb, n)) || (rc = tmp.get(&ia, n)) || (rc = tmp.get(&ib, n))
+            || (rc = tmp.get(&ic, n)))
+            return rc;
+        size_t bytes = 0;
+        PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ka, kb, ia, ib, static_cast<int>(n), 0, 64, st));
+        unsigned char *ws = nullptr;
+        if ((rc = tmp.get(&ws, bytes))) return rc;
+        hv_coord_keys_kernel<<<(un + 255) / 256, 256, 0, st>>>(pts, un, 1, nullptr, ka, ia);
+        PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, bytes, ka, kb, ia, ib, static_cast<int>(n), 0, 64, st));
+        hv_coord_keys_kernel<<<(un + 255) / 256, 256, 0, st>>>(pts, un, 0, ib, ka, ia);
+        PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, bytes, ka, kb, ia, ic, static_cast<int>(n), 0, 64, st));
+        hv_gather_xorder_kernel<<<(un + 255) / 256, 256, 0, st>>>(pts, ic, un, ptsx);
+        ctx->launches.fetch_add(5, std::memory_order_relaxed);
+    }
+    HvWarpParams W{pts, ptsx, order, un, r[0], r[1], rz, compute ? terms : d_out, ovf, compute};
+    constexpr size_t kStairBytes = sizeof(double) * kHvWarps * 2 * kHvCap;
+    PGC_CUDA(cudaFuncSetAttribute(hv_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kStairBytes)));
+    hv_warp_kernel<<<(un + kHvWarps - 1) / kHvWarps, kHvWarps * 32, kStairBytes, st>>>(W);
+    PGC_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(2, std::memory_order_relaxed);
     HvParams P;
     P.f = d_f;
     P.order = order;
@@ -247,17 +689,7 @@ int hv_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const double 
     P.ry = r[1];
     P.rz = rz;
     P.out = compute ? terms : d_out;
-    P.sx = sx;
-    P.sy = sy;
-    P.cap = cap1;
-    P.p0 = 0;
-    P.pcount = un;
-    P.plist = nullptr;
-    P.overflow = ovf;
     P.compute = compute;
-    hv_sweep_kernel<<<(un + 63) / 64, 64, 0, st>>>(P);
-    PGC_CUDA(cudaGetLastError());
-    ctx->launches.fetch_add(1, std::memory_order_relaxed);
     if (cap1 < un) {
         unsigned nover = 0;
         PGC_CUDA(cudaMemcpyAsync(&nover, ovf, sizeof(unsigned), cudaMemcpyDeviceToHost, st));

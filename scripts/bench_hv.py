@@ -18,7 +18,7 @@ stream = torch.cuda.ExternalStream(ctx.stream)
 out = {}
 rng = np.random.default_rng(1)
 for m in (2, 3):
-    for n in (1024, 8192, 32768):
+    for n in (1024, 8192, 65536):
         f = rng.uniform(0, 1, (n, m))
         f = f / np.linalg.norm(f, axis=1, keepdims=True)
         r = np.full(m, 1.25)
