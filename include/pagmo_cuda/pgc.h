@@ -146,9 +146,10 @@ PGC_API int pgc_select_best_N_mo_device(pgc_ctx *ctx, const double *d_f, size_t 
 PGC_API int pgc_sort_population_mo_host(pgc_ctx *ctx, const double *f, size_t n, size_t m, size_t *out);
 
 /* ---- generation operators on a counter-based Philox stream --------------------------------------------------------
- * Every random draw is u01(seed, tag, generation, index, slot) = Philox4x32-10 with counter {slot, index, generation, tag}
- * and key {seed}; (word1:word0 >> 11) * 2^-53.  Tags: 1/2 = the two NSGA-II shuffles, 3 = NSGA-II variation (index = group
- * of 4), 4 = DE family, 5 = PSO, 6 = sga, 7 = population init.  A CPU restatement consuming the same values reproduces the
+ * Every random draw is u01(seed, tag, generation, index, slot) = Philox4x32-10 with counter {slot / 2, index, generation, tag}
+ * and key {seed}; u64 = word1:word0 for an even slot, word3:word2 for the odd slot after it; u01 = (u64 >> 11) * 2^-53.
+ * Tags: 1/2 = the two NSGA-II shuffles, 3 = NSGA-II variation (index = group of 4), 4 = DE family, 5 = PSO, 6 = sga,
+ * 7 = DE self-adaptation init, 8 = cmaes normals, 9 = migration decisions, 10 = population init.  A CPU restatement consuming the same values reproduces the
  * device results (tests/: "parity on injected draws"). */
 PGC_API int pgc_philox_u01(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot, double *out);
 /* permutation of 0..n-1: stable argsort of the keys u64(seed, tag, generation, i, 0) (stands in for std::shuffle,

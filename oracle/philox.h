@@ -2,7 +2,8 @@
  * TEST INFRASTRUCTURE ONLY.  Restated from the published algorithm (Salmon, Moraes, Dror, Shaw, SC'11; Random123
  * known-answer vectors are checked in tests/test_oracle.py); it must produce the same draws as the device-side
  * pagmo2_b200/csrc/philox.cuh for the "parity on injected draws" tests.
- *   counter = {slot, index, generation, tag}, key = {seed lo, seed hi};  u01 = (word1:word0 >> 11) * 2^-53
+ *   counter = {slot / 2, index, generation, tag}, key = {seed lo, seed hi};  u64 = word1:word0 (even slot) or word3:word2 (odd slot);
+ *   u01 = (u64 >> 11) * 2^-53
  */
 #ifndef ORACLE_PHILOX_H
 #define ORACLE_PHILOX_H
@@ -26,10 +27,11 @@ static inline void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t ke
 
 static inline uint64_t oracle_philox_u64(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot)
 {
-    const uint32_t ctr[4] = {slot, index, generation, tag}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    /* one Philox call serves two consecutive slots: words 1:0 for the even slot, 3:2 for the odd one (csrc/philox.cuh) */
+    const uint32_t ctr[4] = {slot >> 1, index, generation, tag}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t o[4];
     oracle_philox4x32_10(ctr, key, o);
-    return ((uint64_t)o[1] << 32) | o[0];
+    return (slot & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
 }
 
 static inline double oracle_philox_u01(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot)

@@ -222,31 +222,29 @@ __global__ void de_trial_kernel(const TrialParams P)
     if (P.variant_out) P.variant_out[i] = variant;
 }
 
-// selection, de.cpp:281-299 / de1220.cpp:515-536
+// selection, de.cpp:281-299 / de1220.cpp:515-536: one warp per individual - lane 0 decides, the lanes copy the accepted trial
 __global__ void de_select_kernel(const double *trial, const double *ftrial, double *x, double *f, unsigned NP, unsigned dim,
                                  unsigned char *accepted, const double *F_try, const double *CR_try, const unsigned *var_try,
                                  double *F, double *CR, unsigned *variant, const unsigned *stopped)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= NP || *stopped) return;
     const bool ok = ftrial[i] <= f[i];
-    accepted[i] = ok;
+    __syncwarp();
     if (ok) {
-        f[i] = ftrial[i];
-        if (F) {
-            F[i] = F_try[i];
-            CR[i] = CR_try[i];
-        }
-        if (variant) variant[i] = var_try[i];
+        for (unsigned d = lane; d < dim; d += 32) x[static_cast<size_t>(i) * dim + d] = trial[static_cast<size_t>(i) * dim + d];
     }
-}
-
-__global__ void de_copy_accepted_kernel(const double *trial, double *x, const unsigned char *accepted, unsigned NP, unsigned dim,
-                                        const unsigned *stopped)
-{
-    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (*stopped) return;
-    if (e < static_cast<size_t>(NP) * dim && accepted[e / dim]) x[e] = trial[e];
+    if (lane == 0) {
+        accepted[i] = ok;
+        if (ok) {
+            f[i] = ftrial[i];
+            if (F) {
+                F[i] = F_try[i];
+                CR[i] = CR_try[i];
+            }
+            if (variant) variant[i] = var_try[i];
+        }
+    }
 }
 
 struct DeGlobal { // device-side global best + exit-condition data
@@ -272,22 +270,29 @@ __global__ void de_global_kernel(const double *x, const double *f, const unsigne
         G->stopped = 0;
         G->gens_done = 0;
     }
+    const unsigned kNone = 0xffffffffu;
     double fa = 0, fb = 0, fw = 0;
-    unsigned ia = 0xffffffffu, ib = 0xffffffffu, iw = 0xffffffffu;
+    unsigned ia = kNone, ib = kNone, iw = kNone;
     for (unsigned i = t; i < NP; i += blockDim.x) {
         const double v = f[i];
-        if (ib == 0xffffffffu || v < fb) { fb = v; ib = i; }
-        if (iw == 0xffffffffu || v > fw) { fw = v; iw = i; }
-        if (!init && accepted[i] && (ia == 0xffffffffu || v <= fa)) { fa = v; ia = i; }
+        if (ib == kNone || v < fb) { fb = v; ib = i; }
+        if (iw == kNone || v > fw) { fw = v; iw = i; }
+        if (!init && accepted[i] && (ia == kNone || v <= fa)) { fa = v; ia = i; }
     }
     sfa[t] = fa; sia[t] = ia; sfb[t] = fb; sib[t] = ib; sfw[t] = fw; siw[t] = iw;
     __syncthreads();
-    if (t == 0) {
-        for (unsigned k = 1; k < blockDim.x; ++k) {
-            if (sib[k] != 0xffffffffu && (ib == 0xffffffffu || sfb[k] < fb || (sfb[k] == fb && sib[k] < ib))) { fb = sfb[k]; ib = sib[k]; }
-            if (siw[k] != 0xffffffffu && (iw == 0xffffffffu || sfw[k] > fw || (sfw[k] == fw && siw[k] < iw))) { fw = sfw[k]; iw = siw[k]; }
-            if (sia[k] != 0xffffffffu && (ia == 0xffffffffu || sfa[k] < fa || (sfa[k] == fa && sia[k] > ia))) { fa = sfa[k]; ia = sia[k]; }
+    // tree reduction with the reference's tie rules: best = first minimum, worst = first maximum, accepted = LAST minimum
+    for (unsigned h = blockDim.x >> 1; h > 0; h >>= 1) {
+        if (t < h) {
+            const unsigned o = t + h;
+            if (sib[o] != kNone && (sib[t] == kNone || sfb[o] < sfb[t] || (sfb[o] == sfb[t] && sib[o] < sib[t]))) { sfb[t] = sfb[o]; sib[t] = sib[o]; }
+            if (siw[o] != kNone && (siw[t] == kNone || sfw[o] > sfw[t] || (sfw[o] == sfw[t] && siw[o] < siw[t]))) { sfw[t] = sfw[o]; siw[t] = siw[o]; }
+            if (sia[o] != kNone && (sia[t] == kNone || sfa[o] < sfa[t] || (sfa[o] == sfa[t] && sia[o] > sia[t]))) { sfa[t] = sfa[o]; sia[t] = sia[o]; }
         }
+        __syncthreads();
+    }
+    if (t == 0) {
+        fa = sfa[0]; ia = sia[0]; fb = sfb[0]; ib = sib[0]; fw = sfw[0]; iw = siw[0];
         G->best_idx = ib;
         G->worst_idx = iw;
         if (init) {
@@ -435,12 +440,12 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
                        seed, first_generation + g, cfg};
         de_trial_kernel<<<nblk(NP, 64), 64, 0, st>>>(tp);
         if ((rc = eval(prob, trial, NP, ftrial, st))) return rc;
-        de_select_kernel<<<nblk(NP, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, NP, dim, accepted, Ftry, CRtry, vtry, algo ? Fs : nullptr,
-                                                        algo ? CRs : nullptr, algo == 2u ? vars : nullptr, &G->stopped);
-        de_copy_accepted_kernel<<<nblk(nd, 256), 256, 0, st>>>(trial, d_x, accepted, NP, dim, &G->stopped);
+        de_select_kernel<<<nblk(static_cast<size_t>(NP) * 32, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, NP, dim, accepted, Ftry, CRtry, vtry,
+                                                                                  algo ? Fs : nullptr, algo ? CRs : nullptr,
+                                                                                  algo == 2u ? vars : nullptr, &G->stopped);
         de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, accepted, NP, dim, algo ? Fs : nullptr, algo ? CRs : nullptr, algo == 2u ? vars : nullptr,
                                             gbX, G, 0, xtol, ftol);
-        ctx->launches.fetch_add(4, std::memory_order_relaxed);
+        ctx->launches.fetch_add(3, std::memory_order_relaxed);
         if ((g + 1) % kPoll == 0 || g + 1 == gens) {
             PGC_CUDA(cudaMemcpyAsync(&h, G, sizeof(DeGlobal), cudaMemcpyDeviceToHost, st));
             PGC_CUDA(cudaStreamSynchronize(st));

@@ -3,8 +3,9 @@
 // algorithm (e.g. nsga2.cpp:180-233); a counter-based stream gives every (generation, individual, slot) its own draw, so
 // the operators parallelise without changing their per-individual logic, and a CPU restatement consuming the same
 // (seed, tag, generation, index, slot) values reproduces the device results ("parity on injected draws").
-//   counter = {slot, index, generation, stream tag}, key = {seed lo, seed hi}
-//   u01     = (u64 >> 11) * 2^-53 in [0, 1), u64 = word1:word0 of the Philox output
+//   counter = {slot / 2, index, generation, stream tag}, key = {seed lo, seed hi}: one Philox call serves TWO consecutive slots
+//   u64     = word1:word0 of the output for an even slot, word3:word2 for the odd slot that follows
+//   u01     = (u64 >> 11) * 2^-53 in [0, 1)
 #pragma once
 #include <cstdint>
 
@@ -47,8 +48,8 @@ __host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 
 __host__ __device__ inline uint64_t philox_u64(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot)
 {
-    const Philox4 r = philox4x32_10(slot, index, generation, tag, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-    return (static_cast<uint64_t>(r.v[1]) << 32) | r.v[0];
+    const Philox4 r = philox4x32_10(slot >> 1, index, generation, tag, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    return (slot & 1u) ? ((static_cast<uint64_t>(r.v[3]) << 32) | r.v[2]) : ((static_cast<uint64_t>(r.v[1]) << 32) | r.v[0]);
 }
 
 __host__ __device__ inline double philox_u01(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot)
@@ -56,13 +57,25 @@ __host__ __device__ inline double philox_u01(uint64_t seed, uint32_t tag, uint32
     return static_cast<double>(philox_u64(seed, tag, generation, index, slot) >> 11) * (1.0 / 9007199254740992.0);
 }
 
-// sequential view of one (tag, generation, index) substream
+// sequential view of one (tag, generation, index) substream: every second draw comes out of the previous call's upper half
 struct PhiloxStream {
-    uint64_t seed;
+    uint64_t seed, spare;
     uint32_t tag, generation, index, slot;
-    __host__ __device__ PhiloxStream(uint64_t s, uint32_t t, uint32_t g, uint32_t i) : seed(s), tag(t), generation(g), index(i), slot(0) {}
-    __host__ __device__ double next() { return philox_u01(seed, tag, generation, index, slot++); }
-    __host__ __device__ uint64_t next_u64() { return philox_u64(seed, tag, generation, index, slot++); }
+    __host__ __device__ PhiloxStream(uint64_t s, uint32_t t, uint32_t g, uint32_t i) : seed(s), spare(0), tag(t), generation(g), index(i), slot(0) {}
+    __host__ __device__ uint64_t next_u64()
+    {
+        uint64_t out;
+        if (slot & 1u) {
+            out = spare;
+        } else {
+            const Philox4 r = philox4x32_10(slot >> 1, index, generation, tag, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+            out = (static_cast<uint64_t>(r.v[1]) << 32) | r.v[0];
+            spare = (static_cast<uint64_t>(r.v[3]) << 32) | r.v[2];
+        }
+        ++slot;
+        return out;
+    }
+    __host__ __device__ double next() { return static_cast<double>(next_u64() >> 11) * (1.0 / 9007199254740992.0); }
 };
 
 } // namespace pgc
