@@ -111,3 +111,24 @@ def test_nsga2_scale_population(ctx, orc):
     best = ctx.select_best_N_mo(f, n // 2)
     assert len(best) == n // 2 and len(set(best.tolist())) == n // 2
     assert rank[best].max() <= rank[np.setdiff1d(np.arange(n), best)].min()           # no worse rank kept over a better one
+
+
+@pytest.mark.parametrize("m", (2, 3))
+def test_duplicate_points_follow_the_stable_restatement(ctx, orc, m):
+    """clones of existing individuals (an offspring that escaped crossover and mutation) tie in every comparison: fronts, crowding
+    distances and the truncated selection must still agree with the restated (stable) reference semantics."""
+    rng = np.random.default_rng(70 + m)
+    for n in (12, 64, 512):
+        f = rng.uniform(0, 1, (n, m))
+        f[n // 2] = f[1]          # a clone inside the same front
+        f[n - 1] = f[n // 3]      # another one
+        f[3] = f[2] + 0.0         # and a third
+        f[3, 0] = f[2, 0]
+        got, want = ctx.fnds(f), orc.fnds(f)
+        assert np.array_equal(got["rank"], want["rank"]) and len(got["fronts"]) == len(want["fronts"])
+        for a, b in zip(got["fronts"], want["fronts"]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(ctx.crowding_distance(f[got["fronts"][0]]), orc.crowding_distance(f[got["fronts"][0]]))
+        for N in (1, n // 4, n // 2, n - 1):
+            assert np.array_equal(ctx.select_best_N_mo(f, N), orc.select_best_N_mo(f, N)), (n, N)
+        assert np.array_equal(ctx.sort_population_mo(f), orc.sort_population_mo(f))
