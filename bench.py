@@ -136,7 +136,7 @@ def run_reference(args):
 def workload_config(n, gpus):
     return {"workload": "cec2014 f1-f30 shifted/rotated/hybrid/composition, D=100, one pass of the batch per function",
             "individuals_per_gpu": n, "global_batch": n * gpus, "dim": DIM, "functions": 30,
-            "tables": "synthetic seeded (oracle/cec_synth.c): orthogonal Mr, Os~U[-80,80), random shuffles",
+            "tables": "synthetic seeded: orthogonal Mr, Os~U[-80,80), random shuffles (pagmo2_b200/synth.py on the native arm, oracle/cec_synth.c on the reference arm)",
             "inputs": "x~U[-100,100), seed 20141+rank; 839 MB per GPU (> 126 MB L2, no flush needed)",
             "parallelism": f"shard-by-individual x{gpus}, no collective"}
 
@@ -157,11 +157,10 @@ def run_native(args):
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     n = args.n
 
-    from oracle.pyoracle import oracle  # only for the synthetic tables (data) and the cpu_baseline leg
-    O = oracle()
+    from pagmo2_b200 import synth  # seeded synthetic data tables (numpy); nothing under oracle/ is touched on this arm's GPU path
     probs = []
     for f in FUNCS:
-        mr, os_c, s = O.cec2014_problem_tables(f, DIM)
+        mr, os_c, s = synth.cec2014_tables(f, DIM)
         probs.append(capi.Problem(ctx, "cec2014", prob_id=f, dim=DIM, rotation=mr, shift=os_c, shuffle=s))
     work = [p.work() for p in probs]  # (flops, transcendentals, bytes) per eval
 

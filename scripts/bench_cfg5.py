@@ -14,11 +14,10 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from pagmo2_b200 import capi  # noqa: E402
 from pagmo2_b200.archipelago import Archipelago, DeviceIsland  # noqa: E402
-from oracle.pyoracle import oracle  # noqa: E402  (synthetic data tables only)
+from pagmo2_b200 import synth  # noqa: E402  (synthetic data tables)
 
 D, ISLANDS, POP, GENS, ROUNDS = 50, 8, 1024, 50, 4
-orc = oracle()
-mr, os_ = orc.cec2013_tables(D)
+mr, os_ = synth.cec2013_tables(D)
 out = {"config": {"dim": D, "islands": ISLANDS, "pop_per_island": POP, "gens_per_round": GENS, "rounds": ROUNDS, "topology": "ring(1.0)",
                   "algo": "sade defaults, ftol = xtol = 0"}}
 for func in (12, 28):

@@ -15,12 +15,12 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from pagmo2_b200 import capi  # noqa: E402
 from pagmo2_b200.archipelago import Archipelago, DeviceIsland  # noqa: E402
-from oracle.pyoracle import oracle  # noqa: E402  (synthetic data tables only)
+from pagmo2_b200 import synth  # noqa: E402  (synthetic data tables)
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-mr, os_ = oracle().cec2013_tables(50)
+mr, os_ = synth.cec2013_tables(50)
 ISLANDS, ROUNDS = 8, 4
 
 

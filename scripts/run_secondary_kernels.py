@@ -10,14 +10,14 @@ import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from pagmo2_b200 import capi  # noqa: E402
-from oracle.pyoracle import oracle  # noqa: E402  (synthetic data tables only)
+from pagmo2_b200 import synth  # noqa: E402  (synthetic data tables)
 
 which = sys.argv[1]
 ctx = capi.Context(0)
 lib = capi.lib()
 g = torch.Generator(device="cuda:0").manual_seed(1)
 if which == "cec13":
-    mr, os_ = oracle().cec2013_tables(50)
+    mr, os_ = synth.cec2013_tables(50)
     prob = capi.Problem(ctx, "cec2013", prob_id=12, dim=50, rotation=mr, shift=os_)
     n = 1 << 20
     x = torch.rand((n, 50), dtype=torch.float64, device="cuda:0", generator=g) * 200 - 100
