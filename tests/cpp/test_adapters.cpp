@@ -30,6 +30,10 @@
 
 #include <pagmo_cuda/cuda_algorithms.hpp>
 #include <pagmo_cuda/cuda_bfe.hpp>
+#include <pagmo_cuda/cuda_hypervolume.hpp>
+#include <pagmo/utils/hypervolume.hpp>
+#include <pagmo/utils/hv_algos/hv_hv2d.hpp>
+#include <pagmo/utils/hv_algos/hv_hv3d.hpp>
 
 #include "cec_synth.h"
 
@@ -237,6 +241,37 @@ int main()
             threw = true;
         }
         CHECK(threw);
+    }
+
+    // ---- 3d. cuda_hv behind pagmo::hypervolume (reference tests/hypervolume.cpp pattern: same answers as hv2d / hv3d) ----
+    {
+        std::mt19937 e(77);
+        std::uniform_real_distribution<double> u(0., 1.);
+        for (unsigned m : {2u, 3u}) {
+            std::vector<pagmo::vector_double> pts(200, pagmo::vector_double(m));
+            for (auto &p : pts) {
+                double nrm = 0;
+                for (auto &v : p) {
+                    v = u(e);
+                    nrm += v * v;
+                }
+                for (auto &v : p) v /= std::sqrt(nrm);
+            }
+            const pagmo::vector_double r(m, 1.2);
+            pagmo::hypervolume hv{pts, true};
+            pagmo_cuda::cuda_hv gpu_algo;
+            pagmo::hv2d a2;
+            pagmo::hv3d a3;
+            pagmo::hv_algorithm &cpu_algo = (m == 2u) ? static_cast<pagmo::hv_algorithm &>(a2) : static_cast<pagmo::hv_algorithm &>(a3);
+            const double want = hv.compute(r, cpu_algo), got = hv.compute(r, gpu_algo);
+            CHECK(std::abs(got - want) <= 1e-12 * want);
+            const auto cw = hv.contributions(r, cpu_algo), cg = hv.contributions(r, gpu_algo);
+            CHECK(max_rel(cg, cw) <= 1e-9);
+            CHECK(hv.least_contributor(r, gpu_algo) == hv.least_contributor(r, cpu_algo));
+            CHECK(hv.greatest_contributor(r, gpu_algo) == hv.greatest_contributor(r, cpu_algo));
+            CHECK(std::abs(hv.exclusive(5u, r, gpu_algo) - cw[5]) <= 1e-9 * std::max(cw[5], 1e-300));
+            std::printf("cuda_hv m=%u: hv %.15g (cpu %.15g)\n", m, got, want);
+        }
     }
 
     // ---- 4. constructor errors surface as std::invalid_argument, like the reference UDP (cec2014.cpp:51-64) ----
