@@ -46,6 +46,8 @@ struct Meta {            // device-side bookkeeping of the level loop
     unsigned level;      // index of the front being peeled
     unsigned overflow;   // 1: ncand > kOrderCap, the host must order this level with the big path
     unsigned nfronts;
+    unsigned stop_after; // 0: peel everything; else stop once this many points sit in closed fronts (select_best_N_mo needs no more)
+    unsigned done;
     unsigned pad;
 };
 
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(kTP) fnds_peel_kernel(const double *__restrict
 {
     constexpr int m = M;
     __shared__ double tile[kTP * (M ? M : 1)];
-    if (meta->overflow) return;
+    if (meta->overflow || meta->done) return;
     const unsigned fs = meta->front_size, fo = meta->front_off, level = meta->level;
     if (fs == 0) return;
     const unsigned q = blockIdx.x * kTP + threadIdx.x;
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(1024) fnds_order_kernel(const unsigned *cand, 
                                                           unsigned *front_off_out, Meta *meta, int first)
 {
     __shared__ unsigned long long s[kOrderCap];
-    if (meta->overflow) return;
+    if (meta->overflow || meta->done) return;
     const unsigned C = meta->ncand;
     if (!first && meta->front_size == 0) return; // finished earlier
     if (C > kOrderCap) {
@@ -212,6 +214,7 @@ __global__ void __launch_bounds__(1024) fnds_order_kernel(const unsigned *cand, 
         meta->front_size = C;
         meta->assigned += C;
         meta->ncand = 0;
+        if (meta->stop_after && meta->assigned >= meta->stop_after) meta->done = 1;
     }
 }
 
@@ -242,6 +245,7 @@ __global__ void close_big_level_kernel(unsigned *front_off_out, Meta *meta, int 
     meta->assigned += C;
     meta->ncand = 0;
     meta->overflow = 0;
+    if (meta->stop_after && meta->assigned >= meta->stop_after) meta->done = 1;
 }
 
 // ---- crowding distance ----------------------------------------------------------------------------------------
@@ -370,7 +374,8 @@ inline unsigned blocks_for(size_t n, unsigned t) { return static_cast<unsigned>(
 
 // fast_non_dominated_sorting on device-resident f [n x m]; d_rank / d_order [n], d_front_off [n+1] are device outputs.
 int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned *d_rank, unsigned *d_dom_count,
-                unsigned *d_order, unsigned *d_front_off, unsigned *nfronts_out, cudaStream_t st)
+                unsigned *d_order, unsigned *d_front_off, unsigned *nfronts_out, cudaStream_t st, unsigned stop_after,
+                unsigned *d_key_out)
 {
     PGC_REQUIRE(n_ >= 2, "At least two points are needed for fast_non_dominated_sorting: %zu detected.", n_); // :204-207
     PGC_REQUIRE(n_ < 0x7fffffffu, "fast_non_dominated_sorting: too many points (%zu)", n_);
@@ -384,10 +389,15 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
     void *cub_tmp = nullptr;
     size_t cub_bytes = 0;
     int rc;
-    if ((rc = ws.alloc(&count, n)) || (rc = ws.alloc(&key, n)) || (rc = ws.alloc(&cand, n)) || (rc = ws.alloc(&flag, 1))
-        || (rc = ws.alloc(&meta, 1)))
-        return rc;
-    PGC_CUDA(cudaMemsetAsync(meta, 0, sizeof(Meta), st));
+    if ((rc = ws.alloc(&count, n)) || (rc = ws.alloc(&cand, n)) || (rc = ws.alloc(&flag, 1)) || (rc = ws.alloc(&meta, 1))) return rc;
+    key = d_key_out; // the ordering keys (position of the last dominator in the previous front) stay with the caller if it asks
+    if (!key && (rc = ws.alloc(&key, n))) return rc;
+    {
+        Meta m0{};
+        m0.stop_after = stop_after;
+        PGC_CUDA(cudaMemcpyAsync(meta, &m0, sizeof(Meta), cudaMemcpyHostToDevice, st));
+        PGC_CUDA(cudaStreamSynchronize(st)); // m0 is a stack object
+    }
     PGC_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned), st));
     bool nanaware = false;
     if (m > 0) {
@@ -447,7 +457,7 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
         PGC_CUDA(cudaMemcpyAsync(&h, meta, sizeof(Meta), cudaMemcpyDeviceToHost, st));
         PGC_CUDA(cudaStreamSynchronize(st));
     }
-    while (h.assigned < n) {
+    while (h.assigned < n && !h.done) {
         if (h.front_size == 0) {
             set_error("fast_non_dominated_sorting: internal error, empty front with %u of %u points assigned", h.assigned, n);
             return PGC_ERR_CUDA;
@@ -537,9 +547,21 @@ static int sort_by_cd_desc(pgc_ctx *ctx, const double *d_cd, unsigned *d_idx, un
 }
 
 // select_best_N_mo, multi_objective.cpp:344-396, on device-resident f; d_out receives min(N, n) indices
-int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, size_t N_, unsigned *d_out, unsigned *nout,
-                       cudaStream_t st)
+__global__ void add_offset_kernel(const unsigned *in, unsigned n, unsigned off, unsigned *out)
 {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] + off;
+}
+
+// `ranking` (optional): fast_non_dominated_sorting of the SELECTED individuals, indexed by their position in d_out, derived
+// from this run instead of a second sort.  Why it is exact: a survivor's dominators all sit in lower fronts, which survive
+// whole, so ranks carry over; whole fronts keep their member sequence (d_out lists them in front order, and the order inside
+// a front is (position of the last dominator in the previous front, index) - positions are unchanged and the new indices
+// ascend in the old order); only the cut front must be re-ordered, by (its old keys, new index).
+int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, size_t N_, unsigned *d_out, unsigned *nout,
+                       cudaStream_t st, SelectedRanking *ranking)
+{
+    if (ranking) ranking->valid = false;
     const unsigned n = static_cast<unsigned>(n_);
     if (N_ == 0 || n == 0) { // :346-351
         *nout = 0;
@@ -559,11 +581,12 @@ int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, si
     }
     const unsigned N = static_cast<unsigned>(N_);
     Workspace ws(ctx, st);
-    unsigned *rank, *order, *foff;
+    unsigned *rank, *order, *foff, *key;
     int rc;
-    if ((rc = ws.alloc(&rank, n)) || (rc = ws.alloc(&order, n)) || (rc = ws.alloc(&foff, n + 1))) return rc;
+    if ((rc = ws.alloc(&rank, n)) || (rc = ws.alloc(&order, n)) || (rc = ws.alloc(&foff, n + 1)) || (rc = ws.alloc(&key, n))) return rc;
     unsigned nfronts = 0;
-    if ((rc = fnds_device(ctx, d_f, n, m_, rank, nullptr, order, foff, &nfronts, st))) return rc;
+    // only the fronts that hold the best N are needed: the level loop stops once N points sit in closed fronts
+    if ((rc = fnds_device(ctx, d_f, n, m_, rank, nullptr, order, foff, &nfronts, st, N, key))) return rc;
     std::vector<unsigned> hoff(nfronts + 1);
     PGC_CUDA(cudaMemcpyAsync(hoff.data(), foff, sizeof(unsigned) * (nfronts + 1), cudaMemcpyDeviceToHost, st));
     PGC_CUDA(cudaStreamSynchronize(st));
@@ -584,6 +607,31 @@ int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, si
         iota_kernel<<<blocks_for(sz, 256), 256, 0, st>>>(idx, sz);
         if ((rc = sort_by_cd_desc(ctx, cd, idx, sz, st))) return rc;
         gather_u32_kernel<<<blocks_for(N - taken, 256), 256, 0, st>>>(order + b, idx, N - taken, d_out + taken);
+    }
+    if (ranking) {
+        // whole fronts: position i of d_out is new individual i, fronts keep their offsets
+        const unsigned nf_new = front_id + (taken < N ? 1u : 0u);
+        std::vector<unsigned> noff(hoff.begin(), hoff.begin() + front_id + 1);
+        if (taken < N) noff.push_back(N);
+        PGC_CUDA(cudaMemcpyAsync(ranking->front_off, noff.data(), sizeof(unsigned) * noff.size(), cudaMemcpyHostToDevice, st));
+        iota_kernel<<<blocks_for(N, 256), 256, 0, st>>>(ranking->order, N);
+        segment_ids_kernel<<<nf_new, 256, 0, st>>>(ranking->front_off, nf_new, ranking->rank);
+        if (taken < N && front_id > 0) { // the cut front: stable sort of its survivors by their old keys
+            const unsigned c = N - taken;
+            unsigned *k0, *k1, *j0, *j1;
+            if ((rc = ws.alloc(&k0, c)) || (rc = ws.alloc(&k1, c)) || (rc = ws.alloc(&j0, c)) || (rc = ws.alloc(&j1, c))) return rc;
+            gather_u32_kernel<<<blocks_for(c, 256), 256, 0, st>>>(key, d_out + taken, c, k0);
+            iota_kernel<<<blocks_for(c, 256), 256, 0, st>>>(j0, c);
+            size_t bytes = 0;
+            void *tmp = nullptr;
+            PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0, k1, j0, j1, static_cast<int>(c), 0, 32, st));
+            if ((rc = ws.alloc_bytes(&tmp, bytes))) return rc;
+            PGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, k0, k1, j0, j1, static_cast<int>(c), 0, 32, st));
+            add_offset_kernel<<<blocks_for(c, 256), 256, 0, st>>>(j1, c, taken, ranking->order + taken);
+        }
+        PGC_CUDA(cudaStreamSynchronize(st)); // noff is a host vector
+        ranking->nfronts = nf_new;
+        ranking->valid = true;
     }
     PGC_CUDA(cudaGetLastError());
     PGC_CUDA(cudaStreamSynchronize(st));

@@ -258,6 +258,8 @@ int nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double, std::milli>(b - a).count();
     };
+    SelectedRanking carried{rank, order, foff, 0, false};
+    unsigned nfronts = 0;
     for (unsigned g = 0; g < gens; ++g) {
         const unsigned generation = first_generation + g;
         const auto t0 = now();
@@ -266,9 +268,11 @@ int nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP
         PGC_CUDA(cudaMemcpyAsync(f2, d_f, sizeof(double) * NP * nobj, cudaMemcpyDeviceToDevice, st));
         if ((rc = philox_permutation_device(ctx, NP, seed, kTagShuffle1, generation, sh1, st))) return rc;
         if ((rc = philox_permutation_device(ctx, NP, seed, kTagShuffle2, generation, sh2, st))) return rc;
-        unsigned nfronts = 0;
         const auto t1 = now();
-        if ((rc = fnds_device(ctx, d_f, NP, nobj, rank, nullptr, order, foff, &nfronts, st))) return rc;
+        // ranks and fronts of the current population: sorted from scratch for the first generation only, afterwards they come
+        // with the previous generation's select_best_N_mo (see select_best_device)
+        if (!carried.valid && (rc = fnds_device(ctx, d_f, NP, nobj, rank, nullptr, order, foff, &nfronts, st))) return rc;
+        if (carried.valid) nfronts = carried.nfronts;
         const auto t2 = now();
         if ((rc = crowding_device(ctx, d_f, NP, nobj, order, foff, nfronts, 1, cd, st))) return rc;
         const auto t3 = now();
@@ -278,7 +282,7 @@ int nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP
         if ((rc = eval(prob, x2 + static_cast<size_t>(NP) * nx, NP, f2 + static_cast<size_t>(NP) * nobj, st))) return rc;
         unsigned nsel = 0;
         const auto t4 = now();
-        if ((rc = select_best_device(ctx, f2, 2 * NP, nobj, NP, sel, &nsel, st))) return rc;
+        if ((rc = select_best_device(ctx, f2, 2 * NP, nobj, NP, sel, &nsel, st, &carried))) return rc;
         const auto t5 = now();
         if (trace)
             std::fprintf(stderr, "[pgc nsga2] gen %u: shuffles %.2f ms, fnds(N) %.2f (%u fronts), crowding %.2f, variation+eval %.2f, select(2N) %.2f\n",

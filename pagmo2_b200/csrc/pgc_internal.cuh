@@ -154,10 +154,16 @@ int cec2013_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, c
 void cec2013_destroy(pgc_problem *p);
 int cec2014_phase_cycles(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, unsigned long long *out);
 int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, unsigned *d_rank, unsigned *d_dom_count, unsigned *d_order,
-                unsigned *d_front_off, unsigned *nfronts_out, cudaStream_t st);
+                unsigned *d_front_off, unsigned *nfronts_out, cudaStream_t st, unsigned stop_after = 0, unsigned *d_key_out = nullptr);
+struct SelectedRanking { // fast_non_dominated_sorting of the individuals select_best_device picked, in their new numbering
+    unsigned *rank, *order, *front_off; // device, N / N / N + 1 entries (caller-owned)
+    unsigned nfronts;
+    bool valid;
+};
 int crowding_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const unsigned *d_order, const unsigned *d_front_off,
                     unsigned nfronts, int small_rule, double *d_cd, cudaStream_t st);
-int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, size_t N, unsigned *d_out, unsigned *nout, cudaStream_t st);
+int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, size_t N, unsigned *d_out, unsigned *nout, cudaStream_t st,
+                       SelectedRanking *ranking = nullptr);
 int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, unsigned *d_out, cudaStream_t st);
 int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t s);
 int philox_permutation_device(pgc_ctx *ctx, unsigned n, unsigned long long seed, unsigned tag, unsigned generation, unsigned *d_perm,

@@ -81,3 +81,25 @@ def test_evolve_converges_and_checks_arguments(capi, ctx, orc):
     so = capi.Problem(ctx, "rastrigin", dim=5)  # single objective: nsga2.cpp:117-120
     with pytest.raises(capi.PgcError):
         so.nsga2_evolve(np.zeros((8, 5)), np.zeros((8, 1)), gens=1)
+
+
+def test_carried_ranking_equals_fresh_sorting(capi, ctx, orc):
+    """From the second generation on, the ranks / fronts of the population are derived from the previous generation's
+    select_best_N_mo instead of a new fast_non_dominated_sorting.  Five generations in one call (carried ranking) must give exactly
+    the population of five one-generation calls (fresh sorting every time), and follow the restated reference loop."""
+    rng = np.random.default_rng(12)
+    for fam, pid, nx, nobj, NP in (("zdt", 1, 30, 2, 256), ("zdt", 3, 10, 2, 1000), ("dtlz", 2, 12, 3, 512), ("dtlz", 1, 7, 3, 64)):
+        prob = capi.Problem(ctx, fam, prob_id=pid, dim=nx, nobj=nobj, param=100)
+        lb, ub = prob.bounds()
+        x = rng.uniform(lb, ub, (NP, nx))
+        f = prob.eval_host(x)
+        kw = dict(cr=0.9, eta_c=10, m=0.05, eta_m=50, seed=5)
+        xa, fa = prob.nsga2_evolve(x, f, gens=5, first_generation=0, **kw)
+        xb, fb = x, f
+        for g in range(5):
+            xb, fb = prob.nsga2_evolve(xb, fb, gens=1, first_generation=g, **kw)
+        assert np.array_equal(xa, xb) and np.array_equal(fa, fb), (fam, pid)
+        if fam == "zdt" and pid == 1:  # zdt1 is evaluated bit-exactly on the device: the restated loop must agree over 5 generations
+            xo, fo = orc.nsga2_evolve(fam, pid, nobj, 100, lb, ub, x, orc.zdt(pid, x), gens=5, first_generation=0, **kw)
+            assert np.allclose(xa, xo, rtol=1e-12, atol=1e-14) and np.allclose(fa, fo, rtol=1e-12, atol=1e-14)
+        prob.close()
