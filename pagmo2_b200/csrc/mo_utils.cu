@@ -107,6 +107,71 @@ __global__ void __launch_bounds__(kTP) fnds_count_kernel(const double *__restric
     }
 }
 
+// The same count on points SORTED by their first objective: p can dominate q only if f0[p] <= f0[q], i.e. only if p sits at or
+// before the end of q's run of equal f0 in the sorted order - the CTA of sorted positions [b*kTP, (b+1)*kTP) scans the tiles up
+// to the last position with f0 <= (largest f0 in the CTA) and skips the rest: half of the pair tests.  CTAs are issued largest
+// first.  fs: points in sorted order [n x M]; src: sorted position -> original index.  (NaN-free inputs only.)
+template <int M>
+__global__ void __launch_bounds__(kTP) fnds_count_sorted_kernel(const double *__restrict__ fs, const unsigned *__restrict__ src, unsigned n,
+                                                                unsigned *count, unsigned *dom_count)
+{
+    constexpr int m = M;
+    __shared__ double tile[kTP * (M ? M : 1)];
+    __shared__ unsigned s_limit;
+    const unsigned b = gridDim.x - 1 - blockIdx.x;
+    const unsigned q = b * kTP + threadIdx.x;
+    if (threadIdx.x == 0) {
+        const unsigned last = min(n, (b + 1) * kTP) - 1;
+        const double top = fs[static_cast<size_t>(last) * m];
+        unsigned lo = last + 1, hi = n; // first position with f0 > top
+        while (lo < hi) {
+            const unsigned mid = (lo + hi) >> 1;
+            if (fs[static_cast<size_t>(mid) * m] <= top) lo = mid + 1;
+            else hi = mid;
+        }
+        s_limit = lo;
+    }
+    double fq[M ? M : 1];
+#pragma unroll
+    for (int i = 0; i < M; ++i) fq[i] = (q < n) ? fs[static_cast<size_t>(q) * m + i] : 0.0;
+    __syncthreads();
+    const unsigned limit = s_limit;
+    unsigned c = 0;
+    for (unsigned base = 0; base < limit; base += kTP) {
+        const unsigned np = min(static_cast<unsigned>(kTP), limit - base);
+        for (unsigned e = threadIdx.x; e < np * m; e += kTP) tile[e] = fs[static_cast<size_t>(base) * m + e];
+        __syncthreads();
+        if (q < n) {
+#pragma unroll 4
+            for (unsigned t = 0; t < np; ++t) c += dominates<M, false>(tile + t * M, fq) ? 1u : 0u;
+        }
+        __syncthreads();
+    }
+    if (q < n) {
+        const unsigned o = src[q];
+        count[o] = c;
+        if (dom_count) dom_count[o] = c;
+    }
+}
+
+__global__ void f0_keys_kernel(const double *f, unsigned n, int m, unsigned long long *keys, unsigned *idx)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = f[static_cast<size_t>(i) * m] + 0.0; // -0.0 -> +0.0: the radix order must be the numeric order
+    const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+    keys[i] = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+    idx[i] = i;
+}
+
+__global__ void gather_rows_m_kernel(const double *f, const unsigned *src, unsigned n, int m, double *out)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(n) * m) return;
+    const unsigned r = static_cast<unsigned>(e / m), c = static_cast<unsigned>(e - static_cast<size_t>(r) * m);
+    out[e] = f[static_cast<size_t>(src[r]) * m + c];
+}
+
 // one level: subtract the dominators found in front `level` from every unassigned point's counter
 template <int M, bool NANAWARE>
 __global__ void __launch_bounds__(kTP) fnds_peel_kernel(const double *__restrict__ f, unsigned n,
@@ -422,7 +487,30 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
         PGC_MO_CASE(8)
     }
 #undef PGC_MO_CASE
-    count_k<<<gb, kTP, 0, st>>>(d_f, n, count, d_dom_count);
+    if (!nanaware && m >= 1 && n >= 4096) { // sorted count pass (half the pair tests); small inputs are launch-bound anyway
+        unsigned long long *k0, *k1;
+        unsigned *i0, *src;
+        double *fs;
+        if ((rc = ws.alloc(&k0, n)) || (rc = ws.alloc(&k1, n)) || (rc = ws.alloc(&i0, n)) || (rc = ws.alloc(&src, n))
+            || (rc = ws.alloc(&fs, static_cast<size_t>(n) * m)))
+            return rc;
+        f0_keys_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_f, n, m, k0, i0);
+        size_t bytes = 0;
+        void *tmp = nullptr;
+        PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0, k1, i0, src, static_cast<int>(n), 0, 64, st));
+        if ((rc = ws.alloc_bytes(&tmp, bytes))) return rc;
+        PGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, k0, k1, i0, src, static_cast<int>(n), 0, 64, st));
+        gather_rows_m_kernel<<<blocks_for(static_cast<size_t>(n) * m, 256), 256, 0, st>>>(d_f, src, n, m, fs);
+        switch (m) {
+#define PGC_MO_SORTED(MM) case MM: fnds_count_sorted_kernel<MM><<<gb, kTP, 0, st>>>(fs, src, n, count, d_dom_count); break;
+            PGC_MO_SORTED(1) PGC_MO_SORTED(2) PGC_MO_SORTED(3) PGC_MO_SORTED(4) PGC_MO_SORTED(5) PGC_MO_SORTED(6) PGC_MO_SORTED(7)
+            PGC_MO_SORTED(8)
+#undef PGC_MO_SORTED
+        }
+        ctx->launches.fetch_add(3, std::memory_order_relaxed);
+    } else {
+        count_k<<<gb, kTP, 0, st>>>(d_f, n, count, d_dom_count);
+    }
     fnds_front0_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, count, d_rank, key, cand, meta);
     ctx->launches.fetch_add(3, std::memory_order_relaxed);
 
