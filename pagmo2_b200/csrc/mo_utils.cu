@@ -17,6 +17,7 @@
 // inside a front is a stable segmented radix sort, which matches the reference's std::sort whenever the objective values
 // inside a front are distinct (the reference's order of ties is unspecified: SURVEY.md F5).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
@@ -107,71 +108,6 @@ __global__ void __launch_bounds__(kTP) fnds_count_kernel(const double *__restric
     }
 }
 
-// The same count on points SORTED by their first objective: p can dominate q only if f0[p] <= f0[q], i.e. only if p sits at or
-// before the end of q's run of equal f0 in the sorted order - the CTA of sorted positions [b*kTP, (b+1)*kTP) scans the tiles up
-// to the last position with f0 <= (largest f0 in the CTA) and skips the rest: half of the pair tests.  CTAs are issued largest
-// first.  fs: points in sorted order [n x M]; src: sorted position -> original index.  (NaN-free inputs only.)
-template <int M>
-__global__ void __launch_bounds__(kTP) fnds_count_sorted_kernel(const double *__restrict__ fs, const unsigned *__restrict__ src, unsigned n,
-                                                                unsigned *count, unsigned *dom_count)
-{
-    constexpr int m = M;
-    __shared__ double tile[kTP * (M ? M : 1)];
-    __shared__ unsigned s_limit;
-    const unsigned b = gridDim.x - 1 - blockIdx.x;
-    const unsigned q = b * kTP + threadIdx.x;
-    if (threadIdx.x == 0) {
-        const unsigned last = min(n, (b + 1) * kTP) - 1;
-        const double top = fs[static_cast<size_t>(last) * m];
-        unsigned lo = last + 1, hi = n; // first position with f0 > top
-        while (lo < hi) {
-            const unsigned mid = (lo + hi) >> 1;
-            if (fs[static_cast<size_t>(mid) * m] <= top) lo = mid + 1;
-            else hi = mid;
-        }
-        s_limit = lo;
-    }
-    double fq[M ? M : 1];
-#pragma unroll
-    for (int i = 0; i < M; ++i) fq[i] = (q < n) ? fs[static_cast<size_t>(q) * m + i] : 0.0;
-    __syncthreads();
-    const unsigned limit = s_limit;
-    unsigned c = 0;
-    for (unsigned base = 0; base < limit; base += kTP) {
-        const unsigned np = min(static_cast<unsigned>(kTP), limit - base);
-        for (unsigned e = threadIdx.x; e < np * m; e += kTP) tile[e] = fs[static_cast<size_t>(base) * m + e];
-        __syncthreads();
-        if (q < n) {
-#pragma unroll 4
-            for (unsigned t = 0; t < np; ++t) c += dominates<M, false>(tile + t * M, fq) ? 1u : 0u;
-        }
-        __syncthreads();
-    }
-    if (q < n) {
-        const unsigned o = src[q];
-        count[o] = c;
-        if (dom_count) dom_count[o] = c;
-    }
-}
-
-__global__ void f0_keys_kernel(const double *f, unsigned n, int m, unsigned long long *keys, unsigned *idx)
-{
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double v = f[static_cast<size_t>(i) * m] + 0.0; // -0.0 -> +0.0: the radix order must be the numeric order
-    const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
-    keys[i] = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-    idx[i] = i;
-}
-
-__global__ void gather_rows_m_kernel(const double *f, const unsigned *src, unsigned n, int m, double *out)
-{
-    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= static_cast<size_t>(n) * m) return;
-    const unsigned r = static_cast<unsigned>(e / m), c = static_cast<unsigned>(e - static_cast<size_t>(r) * m);
-    out[e] = f[static_cast<size_t>(src[r]) * m + c];
-}
-
 // one level: subtract the dominators found in front `level` from every unassigned point's counter
 template <int M, bool NANAWARE>
 __global__ void __launch_bounds__(kTP) fnds_peel_kernel(const double *__restrict__ f, unsigned n,
@@ -216,6 +152,139 @@ __global__ void __launch_bounds__(kTP) fnds_peel_kernel(const double *__restrict
             cand[atomicAdd(&meta->ncand, 1u)] = q;
         }
     }
+}
+
+// ---- the same two kernels on integer RANKS -------------------------------------------------------------------------------
+// For large inputs every objective value is first replaced by its dense rank among the n values of that objective (equal
+// values share a rank; NaNs, which the reference orders after everything - detail::less_than_f - get the last rank).  Pareto
+// dominance only compares values of the same objective, so it is unchanged, but a pair test becomes M 32-bit integer compares
+// on 4-byte operands instead of 2*M FP64 compares on 8-byte operands: the FP64 pipe (64 lanes/clk/SM) is no longer the limit.
+template <int M> __device__ __forceinline__ bool dominates_rank(const unsigned *a, const unsigned *b)
+{
+    bool strict = false, worse = false;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        worse |= a[i] > b[i];
+        strict |= a[i] < b[i];
+    }
+    return strict && !worse;
+}
+
+// count pass on points sorted by the rank of their first objective: only positions up to the end of the run of equal first
+// ranks can hold dominators (half of the pair tests); CTAs issued largest first.  rs: ranks in sorted order, src: sorted -> original
+template <int M>
+__global__ void __launch_bounds__(kTP) fnds_count_rank_kernel(const unsigned *__restrict__ rs, const unsigned *__restrict__ src, unsigned n,
+                                                              unsigned *count, unsigned *dom_count)
+{
+    constexpr int m = M;
+    __shared__ unsigned tile[kTP * (M ? M : 1)];
+    __shared__ unsigned s_limit;
+    const unsigned b = gridDim.x - 1 - blockIdx.x;
+    const unsigned q = b * kTP + threadIdx.x;
+    if (threadIdx.x == 0) {
+        const unsigned last = min(n, (b + 1) * kTP) - 1;
+        const unsigned top = rs[static_cast<size_t>(last) * m];
+        unsigned lo = last + 1, hi = n; // first position with a larger first rank
+        while (lo < hi) {
+            const unsigned mid = (lo + hi) >> 1;
+            if (rs[static_cast<size_t>(mid) * m] <= top) lo = mid + 1;
+            else hi = mid;
+        }
+        s_limit = lo;
+    }
+    unsigned rq[M ? M : 1];
+#pragma unroll
+    for (int i = 0; i < M; ++i) rq[i] = (q < n) ? rs[static_cast<size_t>(q) * m + i] : 0u;
+    __syncthreads();
+    const unsigned limit = s_limit;
+    unsigned c = 0;
+    for (unsigned base = 0; base < limit; base += kTP) {
+        const unsigned np = min(static_cast<unsigned>(kTP), limit - base);
+        for (unsigned e = threadIdx.x; e < np * m; e += kTP) tile[e] = rs[static_cast<size_t>(base) * m + e];
+        __syncthreads();
+        if (q < n) {
+#pragma unroll 8
+            for (unsigned t = 0; t < np; ++t) c += dominates_rank<M>(tile + t * M, rq) ? 1u : 0u;
+        }
+        __syncthreads();
+    }
+    if (q < n) {
+        const unsigned o = src[q];
+        count[o] = c;
+        if (dom_count) dom_count[o] = c;
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(kTP) fnds_peel_rank_kernel(const unsigned *__restrict__ r, unsigned n, const unsigned *__restrict__ order,
+                                                             unsigned *count, unsigned *rank, unsigned *key, unsigned *cand, Meta *meta)
+{
+    constexpr int m = M;
+    __shared__ unsigned tile[kTP * (M ? M : 1)];
+    if (meta->overflow || meta->done) return;
+    const unsigned fs = meta->front_size, fo = meta->front_off, level = meta->level;
+    if (fs == 0) return;
+    const unsigned q = blockIdx.x * kTP + threadIdx.x;
+    const bool active = q < n && rank[q] == kUnassigned;
+    if (!__syncthreads_or(active)) return;
+    unsigned rq[M ? M : 1];
+#pragma unroll
+    for (int i = 0; i < M; ++i) rq[i] = active ? r[static_cast<size_t>(q) * m + i] : 0u;
+    unsigned c = 0, mp = 0;
+    for (unsigned base = 0; base < fs; base += kTP) {
+        const unsigned np = min(static_cast<unsigned>(kTP), fs - base);
+        for (unsigned e = threadIdx.x; e < np * m; e += kTP) {
+            const unsigned t = e / m, i = e % m;
+            tile[e] = r[static_cast<size_t>(order[fo + base + t]) * m + i];
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (unsigned t = 0; t < np; ++t)
+                if (dominates_rank<M>(tile + t * M, rq)) {
+                    ++c;
+                    mp = base + t; // positions ascend: the last hit is the maximum
+                }
+        }
+        __syncthreads();
+    }
+    if (active && c) {
+        const unsigned left = count[q] - c;
+        count[q] = left;
+        if (left == 0) {
+            rank[q] = level + 1;
+            key[q] = mp;
+            cand[atomicAdd(&meta->ncand, 1u)] = q;
+        }
+    }
+}
+
+// dense ranks of one objective: order-preserving keys (NaN last, -0 == +0), sorted, flag the value changes, scan, scatter
+__global__ void objective_keys_kernel(const double *f, unsigned n, int m, int obj, unsigned long long *keys, unsigned *idx)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = f[static_cast<size_t>(i) * m + obj] + 0.0;
+    const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+    keys[i] = (v != v) ? ~0ull : ((b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull));
+    idx[i] = i;
+}
+__global__ void key_change_flags_kernel(const unsigned long long *sorted, unsigned n, unsigned *flags)
+{
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) flags[j] = (j > 0 && sorted[j] != sorted[j - 1]) ? 1u : 0u;
+}
+__global__ void scatter_ranks_kernel(const unsigned *sorted_idx, const unsigned *dense, unsigned n, int m, int obj, unsigned *r)
+{
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) r[static_cast<size_t>(sorted_idx[j]) * m + obj] = dense[j];
+}
+__global__ void gather_rows_u32m_kernel(const unsigned *r, const unsigned *src, unsigned n, int m, unsigned *out)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(n) * m) return;
+    const unsigned row = static_cast<unsigned>(e / m), c = static_cast<unsigned>(e - static_cast<size_t>(row) * m);
+    out[e] = r[static_cast<size_t>(src[row]) * m + c];
 }
 
 // first level: the candidates are the points with no dominator, key 0 (front 0 is in index order, :228-233)
@@ -487,27 +556,34 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
         PGC_MO_CASE(8)
     }
 #undef PGC_MO_CASE
-    if (!nanaware && m >= 1 && n >= 4096) { // sorted count pass (half the pair tests); small inputs are launch-bound anyway
+    unsigned *ranks = nullptr; // [n x m] dense ranks per objective (large inputs): the level loop then runs on integers
+    if (m >= 1 && n >= 4096) {
         unsigned long long *k0, *k1;
-        unsigned *i0, *src;
-        double *fs;
-        if ((rc = ws.alloc(&k0, n)) || (rc = ws.alloc(&k1, n)) || (rc = ws.alloc(&i0, n)) || (rc = ws.alloc(&src, n))
-            || (rc = ws.alloc(&fs, static_cast<size_t>(n) * m)))
+        unsigned *i0, *i1, *src, *flags, *dense, *rs;
+        if ((rc = ws.alloc(&k0, n)) || (rc = ws.alloc(&k1, n)) || (rc = ws.alloc(&i0, n)) || (rc = ws.alloc(&i1, n)) || (rc = ws.alloc(&src, n))
+            || (rc = ws.alloc(&flags, n)) || (rc = ws.alloc(&dense, n)) || (rc = ws.alloc(&ranks, static_cast<size_t>(n) * m))
+            || (rc = ws.alloc(&rs, static_cast<size_t>(n) * m)))
             return rc;
-        f0_keys_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_f, n, m, k0, i0);
-        size_t bytes = 0;
+        size_t b1 = 0, b2 = 0;
         void *tmp = nullptr;
-        PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0, k1, i0, src, static_cast<int>(n), 0, 64, st));
-        if ((rc = ws.alloc_bytes(&tmp, bytes))) return rc;
-        PGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, k0, k1, i0, src, static_cast<int>(n), 0, 64, st));
-        gather_rows_m_kernel<<<blocks_for(static_cast<size_t>(n) * m, 256), 256, 0, st>>>(d_f, src, n, m, fs);
-        switch (m) {
-#define PGC_MO_SORTED(MM) case MM: fnds_count_sorted_kernel<MM><<<gb, kTP, 0, st>>>(fs, src, n, count, d_dom_count); break;
-            PGC_MO_SORTED(1) PGC_MO_SORTED(2) PGC_MO_SORTED(3) PGC_MO_SORTED(4) PGC_MO_SORTED(5) PGC_MO_SORTED(6) PGC_MO_SORTED(7)
-            PGC_MO_SORTED(8)
-#undef PGC_MO_SORTED
+        PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b1, k0, k1, i0, i1, static_cast<int>(n), 0, 64, st));
+        PGC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, b2, flags, dense, static_cast<int>(n), st));
+        if ((rc = ws.alloc_bytes(&tmp, std::max(b1, b2)))) return rc;
+        for (int obj = 0; obj < m; ++obj) {
+            unsigned *sorted_idx = obj == 0 ? src : i1;
+            objective_keys_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_f, n, m, obj, k0, i0);
+            PGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, b1, k0, k1, i0, sorted_idx, static_cast<int>(n), 0, 64, st));
+            key_change_flags_kernel<<<blocks_for(n, 256), 256, 0, st>>>(k1, n, flags);
+            PGC_CUDA(cub::DeviceScan::InclusiveSum(tmp, b2, flags, dense, static_cast<int>(n), st));
+            scatter_ranks_kernel<<<blocks_for(n, 256), 256, 0, st>>>(sorted_idx, dense, n, m, obj, ranks);
         }
-        ctx->launches.fetch_add(3, std::memory_order_relaxed);
+        gather_rows_u32m_kernel<<<blocks_for(static_cast<size_t>(n) * m, 256), 256, 0, st>>>(ranks, src, n, m, rs);
+        switch (m) {
+#define PGC_MO_RANK(MM) case MM: fnds_count_rank_kernel<MM><<<gb, kTP, 0, st>>>(rs, src, n, count, d_dom_count); break;
+            PGC_MO_RANK(1) PGC_MO_RANK(2) PGC_MO_RANK(3) PGC_MO_RANK(4) PGC_MO_RANK(5) PGC_MO_RANK(6) PGC_MO_RANK(7) PGC_MO_RANK(8)
+#undef PGC_MO_RANK
+        }
+        ctx->launches.fetch_add(5 * m + 2, std::memory_order_relaxed);
     } else {
         count_k<<<gb, kTP, 0, st>>>(d_f, n, count, d_dom_count);
     }
@@ -551,7 +627,15 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
             return PGC_ERR_CUDA;
         }
         for (int b = 0; b < kBatch; ++b) {
-            peel_k<<<gb, kTP, 0, st>>>(d_f, n, d_order, count, d_rank, key, cand, meta);
+            if (ranks) {
+                switch (m) {
+#define PGC_MO_PEEL(MM) case MM: fnds_peel_rank_kernel<MM><<<gb, kTP, 0, st>>>(ranks, n, d_order, count, d_rank, key, cand, meta); break;
+                    PGC_MO_PEEL(1) PGC_MO_PEEL(2) PGC_MO_PEEL(3) PGC_MO_PEEL(4) PGC_MO_PEEL(5) PGC_MO_PEEL(6) PGC_MO_PEEL(7) PGC_MO_PEEL(8)
+#undef PGC_MO_PEEL
+                }
+            } else {
+                peel_k<<<gb, kTP, 0, st>>>(d_f, n, d_order, count, d_rank, key, cand, meta);
+            }
             fnds_order_kernel<<<1, 1024, 0, st>>>(cand, key, d_order, d_front_off, meta, 0);
         }
         ctx->launches.fetch_add(2 * kBatch, std::memory_order_relaxed);
