@@ -197,7 +197,7 @@ PGC_API int pgc_hv_contributions_host(pgc_ctx *ctx, const double *points, size_t
 PGC_API int pgc_hv_device(pgc_ctx *ctx, const double *d_points, size_t n, size_t m, const double *r_point, int compute, double *d_out,
                           void *stream);
 
-/* ---- dense contractions of CMA-ES / xNES (cmaes.cpp:246-253,362-380; xnes.cpp:302-305); D <= 128 ---------------------------------
+/* ---- dense contractions of CMA-ES / xNES (cmaes.cpp:246-253,362-380; xnes.cpp:302-305) ------------------------------------------
  * sampling: x_i = mean + sigma * BD * z_i, i < lambda, z ~ N(0, I) from Philox (seed, tag 8, generation, i, .); BD = B*D row-major
  * [D x D] (the caller's eigendecomposition, cmaes.cpp:386-401, stays on the host); d_z optional (xnes keeps z). */
 PGC_API int pgc_cmaes_sample_device(pgc_ctx *ctx, const double *d_mean, const double *d_bd, double sigma, size_t lambda, size_t D,

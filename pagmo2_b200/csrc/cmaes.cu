@@ -13,7 +13,8 @@
 //     are added in CTA order by a second kernel, so the result does not depend on scheduling (no FP64 atomics).
 //   * sampling: B*D resident in shared memory (stride == 4 mod 16), a warp owns tiles of 8 individuals: normals from Philox
 //     (seed, kTagCmaes, generation, i, 2j / 2j+1) by Box-Muller, DMMA, + mean, coalesced store.
-// D <= 128 (one column group of 16 tiles); larger dimensions are rejected (PGC_ERR_UNSUPPORTED), not sent to the CPU.
+// D <= 128 takes the resident-matrix kernels above; larger D the *_big_kernel variants (column groups of 16 tiles, B*D streamed in
+// blocks).  The Gram kernels keep a 32-row chunk of full rows in shared memory, which bounds D to ~850 (PGC_ERR_UNSUPPORTED beyond).
 // FP64-pipe bound: 2*mu*D^2 resp. 2*lambda*D^2 flop against 8*(mu*D + D*D) resp. 8*lambda*D bytes.
 #include <cmath>
 #include <vector>
@@ -101,6 +102,65 @@ __global__ void __launch_bounds__(kGramWarps * 32, 1) gram_partial_kernel(const 
                 o[0] = acc[t][0];
                 o[1] = acc[t][1];
             }
+    }
+}
+
+// D > 128: the output has more than 16 column tiles per 8-row block, so a warp's work item is (row block, group of 16 column
+// tiles) and the CTA walks over the items in passes of kGramWarps, re-reading its chunks of individuals in every pass.
+__global__ void __launch_bounds__(kGramWarps * 32, 1) gram_partial_big_kernel(const GramParams P)
+{
+    const int D = static_cast<int>(P.D), DP = pad8(D), NT = DP / 8, S = stride_mod16(DP, 8), NCG = (NT + kMaxNT - 1) / kMaxNT;
+    extern __shared__ __align__(16) double smem[];
+    double *d = smem, *sw = d + kGramChunk * S, *sc = sw + kGramChunk;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, j = lane & 3;
+    for (int a = threadIdx.x; a < DP; a += blockDim.x) sc[a] = (P.center && a < D) ? P.center[a] : 0.0;
+    const unsigned nchunks = (P.k + kGramChunk - 1) / kGramChunk;
+    const int items = NT * NCG;
+    double *out = P.partial + static_cast<size_t>(blockIdx.x) * DP * DP;
+    for (int first = 0; first < items; first += kGramWarps) {
+        const int item = first + warp, ra = item / NCG, cg = item - ra * NCG;
+        const bool valid = item < items;
+        double acc[kMaxNT][2];
+#pragma unroll
+        for (int t = 0; t < kMaxNT; ++t) acc[t][0] = acc[t][1] = 0.0;
+        for (unsigned c = blockIdx.x; c < nchunks; c += gridDim.x) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < kGramChunk * DP; e += blockDim.x) {
+                const int r = e / DP, a = e - r * DP;
+                const unsigned i = c * kGramChunk + r;
+                double v = 0.0;
+                if (i < P.k && a < D) {
+                    const size_t row = P.idx ? P.idx[i] : i;
+                    v = P.rows[row * D + a] - sc[a];
+                }
+                d[r * S + a] = v;
+            }
+            for (int r = threadIdx.x; r < kGramChunk; r += blockDim.x) {
+                const unsigned i = c * kGramChunk + r;
+                sw[r] = i < P.k ? P.w[i] : 0.0;
+            }
+            __syncthreads();
+            if (valid) {
+                const double *pa = d + j * S + ra * 8 + g;
+                const double *pb = d + j * S + cg * kMaxNT * 8 + g;
+#pragma unroll 2
+                for (int k0 = 0; k0 < kGramChunk; k0 += 4) {
+                    const double a = pa[k0 * S] * sw[k0 + j];
+#pragma unroll
+                    for (int t = 0; t < kMaxNT; ++t)
+                        if (cg * kMaxNT + t < NT) dmma(acc[t][0], acc[t][1], a, pb[k0 * S + t * 8]);
+                }
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int t = 0; t < kMaxNT; ++t)
+                if (cg * kMaxNT + t < NT) {
+                    double *o = out + (ra * 8 + g) * DP + (cg * kMaxNT + t) * 8 + 2 * j;
+                    o[0] = acc[t][0];
+                    o[1] = acc[t][1];
+                }
+        }
     }
 }
 
@@ -201,25 +261,85 @@ __global__ void __launch_bounds__(kSampleWarps * 32, 1) cmaes_sample_kernel(cons
     }
 }
 
+// D > 128: B*D no longer fits in shared memory and an individual has more than 16 output tiles.  The CTA takes 8 tiles of
+// individuals at a time (one per warp) and walks, in lock step, over groups of 128 output coordinates and blocks of kSampleKC
+// inner indices: the block of B*D is staged co-operatively, every warp regenerates the matching slice of its normals (Philox
+// makes z_ij a pure function of (i, j)) and accumulates.
+constexpr int kSampleKC = 64;
+
+__global__ void __launch_bounds__(kSampleWarps * 32, 1) cmaes_sample_big_kernel(const SampleParams P)
+{
+    const int D = static_cast<int>(P.D), DP = pad8(D), KP = pad4(D), NT = DP / 8, NCG = (NT + kMaxNT - 1) / kMaxNT;
+    constexpr int S = kSampleKC + 4; // == 4 (mod 16)
+    extern __shared__ __align__(16) double smem[];
+    double *sB = smem;                          // [128][S]: rows = output coordinates of the group, columns = inner block
+    double *sZ = sB + kMaxD * S;                // [warps][8][S]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, j = lane & 3;
+    double *zt = sZ + warp * 8 * S;
+    const unsigned ntiles = (P.lambda + 7) / 8;
+    for (unsigned t0 = blockIdx.x * kSampleWarps; t0 < ntiles; t0 += gridDim.x * kSampleWarps) {
+        const unsigned tile = t0 + warp, i0 = tile * 8;
+        for (int cg = 0; cg < NCG; ++cg) {
+            double acc[kMaxNT][2];
+#pragma unroll
+            for (int t = 0; t < kMaxNT; ++t) acc[t][0] = acc[t][1] = 0.0;
+            for (int kc = 0; kc < KP; kc += kSampleKC) {
+                __syncthreads();
+                for (int e = threadIdx.x; e < kMaxD * kSampleKC; e += blockDim.x) {
+                    const int r = e / kSampleKC, c = e - r * kSampleKC, a = cg * kMaxD + r, jj = kc + c;
+                    sB[r * S + c] = (a < D && jj < D) ? P.bd[static_cast<size_t>(a) * D + jj] : 0.0;
+                }
+                for (int e = lane; e < 8 * kSampleKC; e += 32) {
+                    const int t = e / kSampleKC, c = e - t * kSampleKC, jj = kc + c;
+                    const unsigned i = i0 + t;
+                    const double z = (i < P.lambda && jj < D) ? normal_at(P.seed, P.generation, i, jj) : 0.0;
+                    zt[t * S + c] = z;
+                    if (P.z && cg == 0 && i < P.lambda && jj < D) P.z[static_cast<size_t>(i) * D + jj] = z;
+                }
+                __syncthreads();
+                const double *pa = zt + g * S + j, *pb = sB + g * S + j;
+                const int kn = min(kSampleKC, KP - kc);
+#pragma unroll 2
+                for (int k0 = 0; k0 < kn; k0 += 4) {
+                    const double a = pa[k0];
+#pragma unroll
+                    for (int t = 0; t < kMaxNT; ++t)
+                        if (cg * kMaxNT + t < NT) dmma(acc[t][0], acc[t][1], a, pb[t * 8 * S + k0]);
+                }
+            }
+            const unsigned i = i0 + g;
+#pragma unroll
+            for (int t = 0; t < kMaxNT; ++t)
+                if (cg * kMaxNT + t < NT && i < P.lambda) {
+                    const int c = (cg * kMaxNT + t) * 8 + 2 * j;
+                    if (c < D) P.x[static_cast<size_t>(i) * D + c] = P.mean[c] + P.sigma * acc[t][0];
+                    if (c + 1 < D) P.x[static_cast<size_t>(i) * D + c + 1] = P.mean[c + 1] + P.sigma * acc[t][1];
+                }
+        }
+    }
+}
+
 } // namespace
 
 int weighted_gram_device(pgc_ctx *ctx, const double *d_rows, const unsigned *d_idx, const double *d_center, const double *d_w, size_t k,
                          size_t D, double scale_div, double *d_out, cudaStream_t st)
 {
     PGC_REQUIRE(D >= 1 && k >= 1, "weighted Gram matrix: empty input");
-    if (D > static_cast<size_t>(kMaxD)) {
-        set_error("weighted Gram matrix (cmaes rank-mu / xnes): dimension %zu > %d is not implemented on the device yet", D, kMaxD);
-        return PGC_ERR_UNSUPPORTED;
-    }
     const int DP = pad8(static_cast<int>(D)), S = stride_mod16(DP, 8);
     const size_t smem = sizeof(double) * (kGramChunk * S + kGramChunk + DP);
+    if (smem > ctx->smem_optin) {
+        set_error("weighted Gram matrix (cmaes rank-mu / xnes): dimension %zu needs %zu bytes of shared memory per CTA, the device offers %zu",
+                  D, smem, ctx->smem_optin);
+        return PGC_ERR_UNSUPPORTED;
+    }
     const unsigned nchunks = static_cast<unsigned>((k + kGramChunk - 1) / kGramChunk);
     unsigned grid = nchunks < static_cast<unsigned>(ctx->sm_count) ? nchunks : static_cast<unsigned>(ctx->sm_count);
     double *partial = nullptr;
     PGC_CUDA(cudaMallocAsync(&partial, sizeof(double) * grid * DP * DP, st));
     GramParams P{d_rows, d_idx, d_center, d_w, static_cast<unsigned>(k), static_cast<unsigned>(D), partial};
-    PGC_CUDA(cudaFuncSetAttribute(gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    gram_partial_kernel<<<grid, kGramWarps * 32, smem, st>>>(P);
+    auto kern = D > static_cast<size_t>(kMaxD) ? gram_partial_big_kernel : gram_partial_kernel;
+    PGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, kGramWarps * 32, smem, st>>>(P);
     PGC_CUDA(cudaGetLastError());
     const unsigned dd = static_cast<unsigned>(D * D);
     gram_reduce_kernel<<<(dd + 255) / 256, 256, 0, st>>>(partial, grid, static_cast<unsigned>(D), static_cast<unsigned>(DP), scale_div, d_out);
@@ -245,9 +365,17 @@ int cmaes_sample_device(pgc_ctx *ctx, const double *d_mean, const double *d_bd, 
 {
     if (lambda == 0) return PGC_OK;
     PGC_REQUIRE(D >= 1, "cmaes sampling: empty dimension");
+    const unsigned ntiles_all = static_cast<unsigned>((lambda + 7) / 8);
     if (D > static_cast<size_t>(kMaxD)) {
-        set_error("cmaes sampling: dimension %zu > %d is not implemented on the device yet", D, kMaxD);
-        return PGC_ERR_UNSUPPORTED;
+        const size_t smem_big = sizeof(double) * (static_cast<size_t>(kMaxD) * (kSampleKC + 4) + kSampleWarps * 8 * (kSampleKC + 4));
+        PGC_CUDA(cudaFuncSetAttribute(cmaes_sample_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_big)));
+        unsigned grid_big = (ntiles_all + kSampleWarps - 1) / kSampleWarps;
+        if (grid_big > static_cast<unsigned>(ctx->sm_count)) grid_big = static_cast<unsigned>(ctx->sm_count);
+        SampleParams PB{d_mean, d_bd, sigma, static_cast<unsigned>(lambda), static_cast<unsigned>(D), seed, generation, d_z, d_x};
+        cmaes_sample_big_kernel<<<grid_big, kSampleWarps * 32, smem_big, st>>>(PB);
+        PGC_CUDA(cudaGetLastError());
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        return PGC_OK;
     }
     const int DP = pad8(static_cast<int>(D)), KP = pad4(static_cast<int>(D)), S = stride_mod16(KP, 4);
     const size_t smem = sizeof(double) * (static_cast<size_t>(DP) * S + kSampleWarps * 8 * S + DP);

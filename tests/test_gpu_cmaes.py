@@ -5,10 +5,10 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("D", (1, 2, 7, 10, 30, 50, 100, 128))
+@pytest.mark.parametrize("D", (1, 2, 7, 10, 30, 50, 100, 128, 129, 200, 444))
 def test_rank_mu_and_mean(ctx, orc, D):
     rng = np.random.default_rng(D)
-    for n, mu in ((8, 4), (200, 100), (4099, 2049), (65536, 32768 if D <= 50 else 4096)):
+    for n, mu in ((8, 4), (200, 100), (4099, 2049), (65536, 32768 if D <= 50 else 4096))[: 4 if D <= 128 else 3]:
         x = rng.normal(size=(n, D)) * rng.uniform(0.1, 10, D)
         idx = rng.permutation(n)[:mu]
         w = np.log(mu + 0.5) - np.log(np.arange(mu) + 1.0)  # cmaes.cpp:166-169
@@ -30,13 +30,13 @@ def test_rank_mu_and_mean(ctx, orc, D):
     assert G.shape == (D, D)
 
 
-@pytest.mark.parametrize("D", (1, 5, 10, 50, 100, 128))
+@pytest.mark.parametrize("D", (1, 5, 10, 50, 100, 128, 130, 444))
 def test_sampling(ctx, orc, D):
     rng = np.random.default_rng(100 + D)
     q, _ = np.linalg.qr(rng.normal(size=(D, D)))
     bd = q * rng.uniform(0.5, 20, D)  # B * D
     mean = rng.normal(size=D) * 10
-    for lam in (1, 9, 1000, 65536 if D <= 50 else 5000):
+    for lam in (1, 9, 1000, 65536 if D <= 50 else (5000 if D <= 128 else 700)):
         x, z = ctx.cmaes_sample(mean, bd, 0.5, lam, seed=9, generation=3)
         xo, zo = orc.cmaes_sample(mean, bd, 0.5, lam, 9, 3)
         assert np.allclose(z, zo, rtol=1e-13, atol=1e-15)  # log / cos / sqrt differ by ulps between libdevice and glibc
@@ -47,7 +47,5 @@ def test_sampling(ctx, orc, D):
 
 def test_unsupported_dimension_fails_loudly(ctx):
     from pagmo2_b200 import capi
-    with pytest.raises(capi.PgcError):
-        ctx.weighted_gram(np.zeros((4, 129)), np.ones(4))
-    with pytest.raises(capi.PgcError):
-        ctx.cmaes_sample(np.zeros(200), np.eye(200), 1.0, 8, 1, 1)
+    with pytest.raises(capi.PgcError):  # a 32-row chunk of full rows no longer fits in shared memory
+        ctx.weighted_gram(np.zeros((4, 2000)), np.ones(4))
