@@ -93,6 +93,64 @@ __global__ void __launch_bounds__(kLjWarps * 32) lj_kernel(const double *__restr
     }
 }
 
+
+// Register-tiled variant for clusters of up to 32*NC atoms: lane l keeps atoms l, l+32, ... (NC of them) in registers for the
+// whole individual, row atom i is a broadcast read, and the chunks that lie entirely at or below i are skipped by a warp-uniform
+// test - no per-pair address arithmetic, no shared-memory traffic for the j side.  ~16 FP64-pipe instructions per pair slot.
+template <int NC>
+__global__ void __launch_bounds__(kLjWarps * 32) lj_reg_kernel(const double *__restrict__ x, double *__restrict__ f, long long n, int atoms)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *px = smem + static_cast<size_t>(warp) * 3 * atoms, *py = px + atoms, *pz = py + atoms;
+    const int D = 3 * atoms - 6;
+    for (long long ind = static_cast<long long>(blockIdx.x) * kLjWarps + warp; ind < n; ind += static_cast<long long>(gridDim.x) * kLjWarps) {
+        const double *xi = x + ind * D;
+        double xj[NC], yj[NC], zj[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { // coordinate map _r, :132-151; atoms beyond the cluster are parked far away, one per slot
+            const int a = c * 32 + lane;
+            double cx = 1.0e8 * (a + 1), cy = 0.0, cz = 0.0;
+            if (a < atoms) {
+                cx = (a >= 3) ? xi[3 * (a - 2)] : 0.0;
+                cy = (a >= 3) ? xi[3 * (a - 2) + 1] : (a == 2 ? xi[1] : 0.0);
+                cz = (a >= 3) ? xi[3 * (a - 2) + 2] : (a == 2 ? xi[2] : (a == 1 ? xi[0] : 0.0));
+                px[a] = cx;
+                py[a] = cy;
+                pz[a] = cz;
+            }
+            xj[c] = cx;
+            yj[c] = cy;
+            zj[c] = cz;
+        }
+        __syncwarp();
+        double s = 0.0;
+        bool coincident = false;
+        for (int i = 0; i + 1 < atoms; ++i) {
+            const double xi0 = px[i], yi0 = py[i], zi0 = pz[i];
+            const int cmin = (i + 1) >> 5; // chunks below hold only j <= i
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                if (c >= cmin) {
+                    const int j = c * 32 + lane;
+                    const bool valid = j > i && j < atoms;
+                    const double dx = xi0 - xj[c], dy = yi0 - yj[c], dz = zi0 - zj[c];
+                    const double dist = fma(dz, dz, fma(dy, dy, dx * dx)); // rij^2, :78-80
+                    coincident |= valid && dist == 0.0;
+                    const double sixth = fast_rcp(dist * dist * dist);     // rij^-6, :84
+                    const double term = fma(sixth, sixth, -sixth);         // :85
+                    s += valid ? term : 0.0;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+        coincident = __any_sync(0xffffffffu, coincident);
+        if (lane == 0) f[ind] = coincident ? INFINITY : 4 * s; // :90
+        __syncwarp();
+    }
+}
+
 } // namespace
 
 int lj_create(pgc_problem *p)
@@ -134,14 +192,33 @@ int lj_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaSt
     const int npairs = atoms * (atoms - 1) / 2;
     const size_t smem = sizeof(double) * 3 * atoms * kLjWarps;
     PGC_REQUIRE(smem <= 200 * 1024, "Lennard-Jones device evaluator: %d atoms do not fit the shared-memory tile", atoms);
-    PGC_CUDA(cudaFuncSetAttribute(lj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    int per_sm = 1;
-    PGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lj_kernel, kLjWarps * 32, smem));
-    if (per_sm < 1) per_sm = 1;
+    using reg_fn = void (*)(const double *, double *, long long, int);
+    reg_fn reg = nullptr;
+    switch ((atoms + 31) / 32) { // register-tiled kernel up to 256 atoms
+        case 1: reg = lj_reg_kernel<1>; break;
+        case 2: reg = lj_reg_kernel<2>; break;
+        case 3: reg = lj_reg_kernel<3>; break;
+        case 4: reg = lj_reg_kernel<4>; break;
+        case 5: reg = lj_reg_kernel<5>; break;
+        case 6: reg = lj_reg_kernel<6>; break;
+        case 7: reg = lj_reg_kernel<7>; break;
+        case 8: reg = lj_reg_kernel<8>; break;
+        default: break;
+    }
     long long blocks = (static_cast<long long>(n) + kLjWarps - 1) / kLjWarps;
-    blocks = std::min<long long>(blocks, static_cast<long long>(p->ctx->sm_count) * per_sm);
-    lj_kernel<<<static_cast<unsigned>(blocks), kLjWarps * 32, smem, stream>>>(d_dvs, d_fvs, static_cast<long long>(n), atoms,
-                                                                              reinterpret_cast<const ushort2 *>(p->d_shuffle), npairs);
+    int per_sm = 1;
+    if (reg) {
+        PGC_CUDA(cudaFuncSetAttribute(reg, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        PGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reg, kLjWarps * 32, smem));
+        blocks = std::min<long long>(blocks, static_cast<long long>(p->ctx->sm_count) * std::max(per_sm, 1));
+        reg<<<static_cast<unsigned>(blocks), kLjWarps * 32, smem, stream>>>(d_dvs, d_fvs, static_cast<long long>(n), atoms);
+    } else {
+        PGC_CUDA(cudaFuncSetAttribute(lj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        PGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lj_kernel, kLjWarps * 32, smem));
+        blocks = std::min<long long>(blocks, static_cast<long long>(p->ctx->sm_count) * std::max(per_sm, 1));
+        lj_kernel<<<static_cast<unsigned>(blocks), kLjWarps * 32, smem, stream>>>(d_dvs, d_fvs, static_cast<long long>(n), atoms,
+                                                                                  reinterpret_cast<const ushort2 *>(p->d_shuffle), npairs);
+    }
     PGC_CUDA(cudaGetLastError());
     p->ctx->launches.fetch_add(1, std::memory_order_relaxed);
     return PGC_OK;

@@ -12,7 +12,7 @@ def capi():
     return m
 
 
-@pytest.mark.parametrize("atoms", [3, 4, 7, 38, 150])
+@pytest.mark.parametrize("atoms", [3, 4, 7, 33, 38, 150, 256, 300])
 def test_lennard_jones_parity(capi, ctx, orc, atoms):
     rng = np.random.default_rng(atoms)
     prob = capi.Problem(ctx, "lennard_jones", dim=atoms)
