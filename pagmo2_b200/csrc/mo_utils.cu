@@ -313,6 +313,19 @@ __global__ void __launch_bounds__(1024) fnds_order_kernel(const unsigned *cand, 
         if (threadIdx.x == 0) meta->overflow = 1;
         return;
     }
+    const unsigned off = first ? 0u : meta->front_off + meta->front_size;
+    if (C <= 1024u) {
+        // small levels (the common case): rank sort - every candidate counts the candidates that precede it; C*C/1024 compares
+        // per thread and two barriers, instead of the ~50 barriers of a bitonic network
+        for (unsigned i = threadIdx.x; i < C; i += blockDim.x) s[i] = (static_cast<unsigned long long>(key[cand[i]]) << 32) | cand[i];
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < C; i += blockDim.x) {
+            const unsigned long long mine = s[i];
+            unsigned before = 0;
+            for (unsigned j = 0; j < C; ++j) before += s[j] < mine ? 1u : 0u; // (key, index) pairs are distinct
+            order[off + before] = static_cast<unsigned>(mine & 0xffffffffu);
+        }
+    } else {
     unsigned P = 1;
     while (P < C) P <<= 1;
     for (unsigned i = threadIdx.x; i < P; i += blockDim.x)
@@ -333,8 +346,8 @@ __global__ void __launch_bounds__(1024) fnds_order_kernel(const unsigned *cand, 
             }
             __syncthreads();
         }
-    const unsigned off = first ? 0u : meta->front_off + meta->front_size;
     for (unsigned i = threadIdx.x; i < C; i += blockDim.x) order[off + i] = static_cast<unsigned>(s[i] & 0xffffffffu);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned level = first ? 0u : meta->level + 1;
