@@ -176,6 +176,17 @@ PGC_API int pgc_pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, d
                                   double omega, double eta1, double eta2, double max_vel, unsigned variant, unsigned neighb_type,
                                   unsigned neighb_param, uint64_t seed, uint32_t first_generation, void *stream);
 
+/* One generation of ONE SHARD of a pso_gen swarm with the lbest ring topology (pso_gen.cpp:679-698), for swarms spread over several
+ * GPUs.  The shard holds n_loc consecutive particles, global indices index_offset .. index_offset + n_loc - 1.  d_X / d_V: current
+ * positions / velocities [n_loc x nx]; d_lbX_ext [(n_loc + 2 radius) x nx] and d_lbfit_ext [n_loc + 2 radius]: best positions and
+ * fitness with `radius` HALO rows at each end (radius = neighb_param / 2), the shard's own rows in the middle.  The caller fills the
+ * halos from the neighbouring shards before every step (pagmo2_b200/swarm.py does it with one all_gather).  init_velocity = 1:
+ * only draw the initial velocities (pso_gen.cpp:187-196).  Draws are addressed by the global particle index, so a sharded swarm
+ * moves exactly like pgc_pso_evolve_device on one device. */
+PGC_API int pgc_pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_V, double *d_lbX_ext, double *d_lbfit_ext, size_t n_loc,
+                                      unsigned radius, unsigned index_offset, double omega, double eta1, double eta2, double max_vel,
+                                      unsigned variant, uint64_t seed, uint32_t generation, int init_velocity, void *stream);
+
 /* Differential evolution family as a generational device loop (trial vectors for all individuals -> one batch evaluation ->
  * selection): algo 0 = de (de.cpp:76-345; variant 1..10, F, CR), 1 = sade (sade.cpp:78-560; variant 1..18, variant_adptv 1 = jDE,
  * 2 = iDE), 2 = de1220 (de1220.cpp:80-600; allowed_variants, variant_adptv).  d_x [NP x nx], d_f [NP] updated in place; d_F / d_CR /

@@ -170,9 +170,154 @@ __global__ void pso_gbest_kernel(const double *fit, const unsigned char *improve
     }
 }
 
+// ---- one swarm sharded over several GPUs (contiguous blocks of particles) ---------------------------------------------------
+// The lbest ring couples a particle with `radius` neighbours on each side, so a shard needs the best positions / fitness of
+// `radius` particles beyond each of its ends.  They live in HALO rows of extended arrays: lbX_ext [(n_loc + 2 radius) x dim],
+// lbfit_ext [n_loc + 2 radius], the shard's own particles at rows [radius, radius + n_loc); the caller fills the halos (from
+// the neighbouring shards, or from its own other end when there is one shard) before every step.  Neighbour indices are in
+// extended coordinates, no wrap-around; Philox substreams are addressed by the GLOBAL particle index, so a sharded swarm
+// moves exactly like the same swarm on one device.
+__global__ void pso_lbest_ext_kernel(const double *lbfit_ext, unsigned n_loc, unsigned radius, unsigned *bn)
+{
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_loc) return;
+    const unsigned c = p + radius; // own row in extended coordinates
+    unsigned best = 0;
+    bool first = true;
+    for (unsigned j = radius; j > 0u; --j) { // same visiting order as pso_lbest_kernel: p-radius .. p-1, p+1 .. p+radius
+        const unsigned q = c - j;
+        if (first || leq_f(lbfit_ext[q], lbfit_ext[best])) best = q;
+        first = false;
+    }
+    for (unsigned j = 1u; j <= radius; ++j) {
+        const unsigned q = c + j;
+        if (first || leq_f(lbfit_ext[q], lbfit_ext[best])) best = q;
+        first = false;
+    }
+    bn[p] = best;
+}
+
+struct ShardMoveParams {
+    double *X, *V;           // [n_loc x dim]
+    const double *lbX_ext;   // [(n_loc + 2 radius) x dim]
+    const unsigned *bn;      // best neighbour, extended row index
+    const double *lb, *ub;
+    unsigned n_loc, dim, radius, index_offset;
+    double omega, eta1, eta2, max_vel;
+    unsigned variant;
+    unsigned long long seed;
+    unsigned generation;
+};
+
+__global__ void pso_move_shard_kernel(const ShardMoveParams P)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(P.n_loc) * P.dim) return;
+    const unsigned p = static_cast<unsigned>(e / P.dim), d = static_cast<unsigned>(e % P.dim);
+    const unsigned gp = P.index_offset + p; // global particle index: the draw address
+    const double x = P.X[e], lbx = P.lbX_ext[static_cast<size_t>(p + P.radius) * P.dim + d], bnx = P.lbX_ext[static_cast<size_t>(P.bn[p]) * P.dim + d];
+    double v = P.V[e], r1, r2;
+    switch (P.variant) { // pso_gen.cpp:242-306, as pso_move_kernel
+        case 1:
+            r1 = philox_u01(P.seed, kTagPso, P.generation, gp, 2 * d);
+            r2 = philox_u01(P.seed, kTagPso, P.generation, gp, 2 * d + 1);
+            v = P.omega * v + P.eta1 * r1 * (lbx - x) + P.eta2 * r2 * (bnx - x);
+            break;
+        case 2:
+            r1 = philox_u01(P.seed, kTagPso, P.generation, gp, d);
+            v = P.omega * v + P.eta1 * r1 * (lbx - x) + P.eta2 * r1 * (bnx - x);
+            break;
+        case 3:
+            r1 = philox_u01(P.seed, kTagPso, P.generation, gp, 0);
+            r2 = philox_u01(P.seed, kTagPso, P.generation, gp, 1);
+            v = P.omega * v + P.eta1 * r1 * (lbx - x) + P.eta2 * r2 * (bnx - x);
+            break;
+        case 4:
+            r1 = philox_u01(P.seed, kTagPso, P.generation, gp, 0);
+            v = P.omega * v + P.eta1 * r1 * (lbx - x) + P.eta2 * r1 * (bnx - x);
+            break;
+        default: // 5
+            r1 = philox_u01(P.seed, kTagPso, P.generation, gp, 2 * d);
+            r2 = philox_u01(P.seed, kTagPso, P.generation, gp, 2 * d + 1);
+            v = P.omega * (v + P.eta1 * r1 * (lbx - x) + P.eta2 * r2 * (bnx - x));
+    }
+    const double vwidth = (P.ub[d] - P.lb[d]) * P.max_vel, minv = -1. * vwidth, maxv = vwidth; // :329-363
+    if (v > maxv) v = maxv;
+    else if (v < minv) v = minv;
+    double new_x = x + v;
+    if (new_x < P.lb[d]) {
+        new_x = P.lb[d];
+        v = 0.;
+    } else if (new_x > P.ub[d]) {
+        new_x = P.ub[d];
+        v = 0.;
+    }
+    P.X[e] = new_x;
+    P.V[e] = v;
+}
+
+__global__ void pso_init_velocity_shard_kernel(double *V, const double *lb, const double *ub, unsigned n_loc, unsigned dim, unsigned index_offset,
+                                               double max_vel, unsigned long long seed, unsigned generation)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(n_loc) * dim) return;
+    const unsigned p = static_cast<unsigned>(e / dim), d = static_cast<unsigned>(e % dim);
+    const double vwidth = (ub[d] - lb[d]) * max_vel, minv = -1. * vwidth, maxv = vwidth; // :179-183
+    const double u = philox_u01(seed, kTagInit, generation, index_offset + p, d);
+    V[e] = (minv == maxv) ? minv : (maxv - minv) * u + minv;
+}
+
 inline unsigned nblk(size_t n, unsigned t) { return static_cast<unsigned>((n + t - 1) / t); }
 
 } // namespace
+
+// One generation of a shard (lbest ring).  d_V == nullptr on entry is not allowed: call with init_velocity = 1 once to draw them.
+int pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_V, double *d_lbX_ext, double *d_lbfit_ext, unsigned n_loc, unsigned radius,
+                          unsigned index_offset, double omega, double eta1, double eta2, double max_vel, unsigned variant,
+                          unsigned long long seed, unsigned generation, int init_velocity,
+                          int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st)
+{
+    pgc_ctx *ctx = prob->ctx;
+    const unsigned dim = static_cast<unsigned>(prob->nx);
+    PGC_REQUIRE(omega >= 0. && omega <= 1., "The particles' inertia (or the constriction factor) must be in the [0,1] range, while a value of %g was detected", omega);
+    PGC_REQUIRE(eta1 >= 0. && eta2 >= 0. && eta1 <= 4. && eta2 <= 4., "The eta parameters must be in the [0,4] range, while eta1 = %g, eta2 = %g was detected", eta1, eta2);
+    PGC_REQUIRE(max_vel > 0. && max_vel <= 1., "The maximum particle velocity (as a fraction of the bounds) should be in the (0,1] range, while a value of %g was detected", max_vel);
+    PGC_REQUIRE(variant >= 1u && variant <= 5u, "pso shards implement variants 1-5, while a value of %u was detected", variant);
+    PGC_REQUIRE(prob->nobj == 1, "Multiple objectives detected in %s instance. PSO cannot deal with them", prob->name.c_str());
+    PGC_REQUIRE(n_loc >= 1 && radius >= 1, "pso shard: empty shard or zero radius");
+    const size_t nd = static_cast<size_t>(n_loc) * dim;
+    double *lb = nullptr, *fit = nullptr;
+    unsigned *bn = nullptr;
+    unsigned char *improved = nullptr;
+    PGC_CUDA(cudaMallocAsync(&lb, 16 * dim, st));
+    PGC_CUDA(cudaMallocAsync(&fit, 8 * static_cast<size_t>(n_loc), st));
+    PGC_CUDA(cudaMallocAsync(&bn, 4 * static_cast<size_t>(n_loc), st));
+    PGC_CUDA(cudaMallocAsync(&improved, n_loc, st));
+    double *ub = lb + dim;
+    PGC_CUDA(cudaMemcpyAsync(lb, prob->lb.data(), 8 * dim, cudaMemcpyHostToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(ub, prob->ub.data(), 8 * dim, cudaMemcpyHostToDevice, st));
+    int rc = PGC_OK;
+    if (init_velocity) {
+        pso_init_velocity_shard_kernel<<<nblk(nd, 256), 256, 0, st>>>(d_V, lb, ub, n_loc, dim, index_offset, max_vel, seed, generation);
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+        pso_lbest_ext_kernel<<<nblk(n_loc, 256), 256, 0, st>>>(d_lbfit_ext, n_loc, radius, bn);
+        ShardMoveParams mp{d_X, d_V, d_lbX_ext, bn, lb, ub, n_loc, dim, radius, index_offset, omega, eta1, eta2, max_vel, variant, seed, generation};
+        pso_move_shard_kernel<<<nblk(nd, 256), 256, 0, st>>>(mp);
+        rc = eval(prob, d_X, n_loc, fit, st);
+        if (rc == PGC_OK) {
+            pso_memory_flag_kernel<<<nblk(n_loc, 256), 256, 0, st>>>(fit, d_lbfit_ext + radius, n_loc, improved);
+            pso_memory_copy_kernel<<<nblk(nd, 256), 256, 0, st>>>(d_X, d_lbX_ext + static_cast<size_t>(radius) * dim, improved, n_loc, dim);
+            ctx->launches.fetch_add(4, std::memory_order_relaxed);
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(st); // lb / ub came from pageable host vectors
+    for (void *p : {static_cast<void *>(lb), static_cast<void *>(fit), static_cast<void *>(bn), static_cast<void *>(improved)}) cudaFreeAsync(p, st);
+    if (rc != PGC_OK) return rc;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "pso_shard_step_device", __FILE__, __LINE__);
+    return PGC_OK;
+}
 
 // pso_gen::evolve on a device-resident swarm.  In: d_x = positions, d_f = their fitness, d_v = velocities (or nullptr: drawn
 // as in :187-196).  Out: d_x / d_f = the particles' best positions lbX / lbfit (what evolve() puts back into the population,

@@ -119,3 +119,46 @@ def test_world_size_2_gloo_matches_single_process(orc, tmp_path, mtype, handling
             assert np.array_equal(z["x"][i], p.x) and np.array_equal(z["f"][i], p.f) and np.array_equal(z["ids"][i], p.ids)
         log += [tuple(row) for row in z["log"]]
     assert sorted(log) == sorted((e.round, e.id % (1 << 62), e.src, e.dst) for e in single.log) and log
+
+
+def test_swarm_halo_wiring():
+    """ring wiring of the sharded PSO swarm's halo exchange (pagmo2_b200/swarm.py): shard r gets the LAST rows of shard r-1 and the
+    FIRST rows of shard r+1, with wrap-around; one shard wraps onto itself."""
+    from pagmo2_b200.swarm import halo_rows
+    radius, world = 2, 3
+    blocks = np.stack([np.array([[10 * r + 0], [10 * r + 1], [10 * r + 8], [10 * r + 9]], dtype=float) for r in range(world)])
+    for r in range(world):
+        left, right = halo_rows(blocks, r, world, radius)
+        assert left[:, 0].tolist() == [10 * ((r - 1) % world) + 8, 10 * ((r - 1) % world) + 9]
+        assert right[:, 0].tolist() == [10 * ((r + 1) % world) + 0, 10 * ((r + 1) % world) + 1]
+    left, right = halo_rows(blocks[:1], 0, 1, radius)
+    assert left[:, 0].tolist() == [8, 9] and right[:, 0].tolist() == [0, 1]
+
+
+def test_swarm_exchange_world_size_2_gloo(tmp_path):
+    """the all_gather of boundary rows over gloo: two fake shards (no device) must end up with each other's rows as halos."""
+    worker = tmp_path / "w.py"
+    worker.write_text('''
+import sys, numpy as np, torch.distributed as dist
+sys.path.insert(0, %r)
+from pagmo2_b200.swarm import ShardedSwarm
+class Fake:
+    radius = 2
+    def __init__(self, r): self.r, self.halos = r, None
+    def boundary(self): return np.array([[self.r, 0.], [self.r, 1.], [self.r, 8.], [self.r, 9.]])
+    def set_halos(self, left, right): self.halos = (left.copy(), right.copy())
+    def step(self, p, generation, init_velocity=False): pass
+dist.init_process_group("gloo")
+s = ShardedSwarm(Fake(dist.get_rank()))
+s.evolve(2)
+other = 1 - dist.get_rank()
+left, right = s.shard.halos
+assert left.tolist() == [[other, 8.], [other, 9.]] and right.tolist() == [[other, 0.], [other, 1.]], (left, right)
+assert s.generation == 3
+dist.barrier(); dist.destroy_process_group()
+''' % str(ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+           str(31500 + os.getpid() % 2000), str(worker)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]

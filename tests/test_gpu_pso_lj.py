@@ -71,3 +71,35 @@ def test_pso_on_lennard_jones_and_argument_checks(capi, ctx, orc):
     mo = capi.Problem(ctx, "zdt", prob_id=1, dim=5)
     with pytest.raises(capi.PgcError):
         mo.pso_evolve(np.zeros((8, 5)), np.zeros(8), gens=1)
+
+
+@pytest.mark.parametrize("variant", (1, 2, 3, 4, 5))
+def test_sharded_swarm_one_shard_equals_evolve(capi, ctx, variant):
+    """pagmo2_b200.swarm with a single shard (its halos wrap onto itself) must move exactly like pgc_pso_evolve_device; with two
+    shards in one process (halos swapped by hand) too - the multi-process version only replaces the swap by an all_gather."""
+    from pagmo2_b200.swarm import DeviceShard, ShardedSwarm, halo_rows
+    rng = np.random.default_rng(variant)
+    prob = capi.Problem(ctx, "rastrigin", dim=7)
+    lb, ub = prob.bounds()
+    n = 96
+    x = rng.uniform(lb, ub, (n, 7))
+    f = prob.eval_host(x)[:, 0]
+    want_x, want_f, _, _ = prob.pso_evolve(x, f, gens=5, variant=variant, seed=3, first_generation=1)
+    one = ShardedSwarm(DeviceShard(ctx, prob, x, f, 0, 2), variant=variant, seed=3, first_generation=1)
+    one.evolve(5)
+    bx, bf = one.shard.best()
+    assert np.array_equal(bx, want_x) and np.array_equal(bf, want_f)
+    # two shards of 48 particles, exchanged by hand
+    shards = [DeviceShard(ctx, prob, x[i * 48:(i + 1) * 48], f[i * 48:(i + 1) * 48], i * 48, 2) for i in range(2)]
+    p = dict(omega=0.7298, eta1=2.05, eta2=2.05, max_vel=0.5, variant=variant, seed=3)
+    for s in shards:
+        s.step(p, 1, init_velocity=True)
+    for g in range(1, 6):
+        blocks = np.stack([s.boundary() for s in shards])
+        for r, s in enumerate(shards):
+            s.set_halos(*halo_rows(blocks, r, 2, 2))
+        for s in shards:
+            s.step(p, g)
+    got = np.vstack([s.best()[0] for s in shards])
+    assert np.array_equal(got, want_x)
+    prob.close()
