@@ -319,6 +319,11 @@ def run_native(args):
                      "rotation_only_frac": rot_flops_step / step_s_rank / 1e12 / fp64_peak,
                      "hbm_gbs_achieved": sum(w[2] for w in work) * n / step_s_rank / 1e9, "hbm_peak_gbs": hbm_peak,
                      "note": "aggregate over the 54 launches of one step; per-function split in per_function"},
+        # the same step against the driver-measured HBM copy bandwidth (MEASURED_PEAKS.json), in the contract's own vocabulary:
+        # far below 1 because the step is bound by the FP64 pipe, not by memory (roofline above)
+        "roofline_hbm": {"bound": "hbm", "achieved": sum(w[2] for w in work) * n / step_s_rank / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": sum(w[2] for w in work) * n / step_s_rank / 1e9 / hbm_peak, "traffic": STAGE_DRAM_BYTES,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks.get("hbm_gbs") else "of fallback 6650 GB/s"},
         "cpu_baseline": cpu,
         "secondary": secondary,
         "geomean_evals_per_s_per_gpu": geomean,
