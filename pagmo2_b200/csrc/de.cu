@@ -15,6 +15,7 @@
 // start gene, crossover draws, one draw per out-of-bounds gene.  uniform_int(a, b) = a + floor(u * (b - a + 1)).
 #include <cfloat>
 #include <cmath>
+#include <algorithm>
 #include <vector>
 
 #include "pgc_internal.cuh"
@@ -256,11 +257,47 @@ struct DeGlobal { // device-side global best + exit-condition data
     unsigned gens_done;
 };
 
+struct DePartial { // per-CTA result of the scan below (large populations: de_global_partial_kernel)
+    double fa, fb, fw;
+    unsigned ia, ib, iw;
+};
+
+// Large populations: the scan over f is spread over many CTAs; de_global_kernel then only combines their partial results.
+__global__ void de_global_partial_kernel(const double *f, const unsigned char *accepted, unsigned NP, int init, const unsigned *stopped,
+                                         DePartial *out)
+{
+    __shared__ double sfa[256], sfb[256], sfw[256];
+    __shared__ unsigned sia[256], sib[256], siw[256];
+    if (!init && *stopped) return;
+    const unsigned t = threadIdx.x, kNone = 0xffffffffu;
+    double fa = 0, fb = 0, fw = 0;
+    unsigned ia = kNone, ib = kNone, iw = kNone;
+    const unsigned per = (NP + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * per, hi = min(NP, lo + per);
+    for (unsigned i = lo + t; i < hi; i += blockDim.x) {
+        const double v = f[i];
+        if (ib == kNone || v < fb) { fb = v; ib = i; }
+        if (iw == kNone || v > fw) { fw = v; iw = i; }
+        if (!init && accepted[i] && (ia == kNone || v <= fa)) { fa = v; ia = i; }
+    }
+    sfa[t] = fa; sia[t] = ia; sfb[t] = fb; sib[t] = ib; sfw[t] = fw; siw[t] = iw;
+    __syncthreads();
+    for (unsigned h = blockDim.x >> 1; h > 0; h >>= 1) {
+        if (t < h) {
+            const unsigned o = t + h;
+            if (sib[o] != kNone && (sib[t] == kNone || sfb[o] < sfb[t] || (sfb[o] == sfb[t] && sib[o] < sib[t]))) { sfb[t] = sfb[o]; sib[t] = sib[o]; }
+            if (siw[o] != kNone && (siw[t] == kNone || sfw[o] > sfw[t] || (sfw[o] == sfw[t] && siw[o] < siw[t]))) { sfw[t] = sfw[o]; siw[t] = siw[o]; }
+            if (sia[o] != kNone && (sia[t] == kNone || sfa[o] < sfa[t] || (sfa[o] == sfa[t] && sia[o] > sia[t]))) { sfa[t] = sfa[o]; sia[t] = sia[o]; }
+        }
+        __syncthreads();
+    }
+    if (t == 0) out[blockIdx.x] = DePartial{sfa[0], sfb[0], sfw[0], sia[0], sib[0], siw[0]};
+}
+
 // sequential "if accepted and f <= gbfit: gb = i" over ascending i == smallest accepted fitness, last index on ties, if <= gbfit;
 // plus pop.best_idx() / worst_idx() (first min / first max) and the exit quantities dx, df (de.cpp:302-316).  Single CTA.
 __global__ void de_global_kernel(const double *x, const double *f, const unsigned char *accepted, unsigned NP, unsigned dim,
                                  const double *F, const double *CR, const unsigned *variant, double *gbX, DeGlobal *G, int init, double xtol,
-                                 double ftol)
+                                 double ftol, const DePartial *partials, unsigned nparts)
 {
     __shared__ double sfa[256], sfb[256], sfw[256];
     __shared__ unsigned sia[256], sib[256], siw[256];
@@ -273,11 +310,20 @@ __global__ void de_global_kernel(const double *x, const double *f, const unsigne
     const unsigned kNone = 0xffffffffu;
     double fa = 0, fb = 0, fw = 0;
     unsigned ia = kNone, ib = kNone, iw = kNone;
-    for (unsigned i = t; i < NP; i += blockDim.x) {
-        const double v = f[i];
-        if (ib == kNone || v < fb) { fb = v; ib = i; }
-        if (iw == kNone || v > fw) { fw = v; iw = i; }
-        if (!init && accepted[i] && (ia == kNone || v <= fa)) { fa = v; ia = i; }
+    if (partials) { // combine the per-CTA scans (slices ascend with the CTA index, so the same tie rules apply)
+        for (unsigned k = t; k < nparts; k += blockDim.x) {
+            const DePartial q = partials[k];
+            if (q.ib != kNone && (ib == kNone || q.fb < fb)) { fb = q.fb; ib = q.ib; }
+            if (q.iw != kNone && (iw == kNone || q.fw > fw)) { fw = q.fw; iw = q.iw; }
+            if (q.ia != kNone && (ia == kNone || q.fa <= fa)) { fa = q.fa; ia = q.ia; }
+        }
+    } else {
+        for (unsigned i = t; i < NP; i += blockDim.x) {
+            const double v = f[i];
+            if (ib == kNone || v < fb) { fb = v; ib = i; }
+            if (iw == kNone || v > fw) { fw = v; iw = i; }
+            if (!init && accepted[i] && (ia == kNone || v <= fa)) { fa = v; ia = i; }
+        }
     }
     sfa[t] = fa; sia[t] = ia; sfb[t] = fb; sib[t] = ib; sfw[t] = fw; siw[t] = iw;
     __syncthreads();
@@ -428,7 +474,12 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
             de_init_adapt_kernel<<<nblk(NP, 128), 128, 0, st>>>(Fs, CRs, algo == 2u ? vars : nullptr, NP, cfg, seed, first_generation);
         }
     }
-    de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, nullptr, NP, dim, Fs, CRs, algo == 2u ? vars : nullptr, gbX, G, 1, xtol, ftol);
+    // large populations: the fitness scan of the global-best kernel is spread over `nparts` CTAs
+    const unsigned nparts = NP >= 16384u ? std::min(1024u, NP / 4096u) : 0u;
+    DePartial *parts = nullptr;
+    if (nparts && (rc = buf.get(reinterpret_cast<void **>(&parts), sizeof(DePartial) * nparts))) return rc;
+    if (nparts) de_global_partial_kernel<<<nparts, 256, 0, st>>>(d_f, nullptr, NP, 1, &G->stopped, parts);
+    de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, nullptr, NP, dim, Fs, CRs, algo == 2u ? vars : nullptr, gbX, G, 1, xtol, ftol, parts, nparts);
     // The exit conditions live on the device (DeGlobal::stopped): once one fires, the generations already queued return
     // immediately, and the host only looks every kPoll generations - a sync per generation made small populations
     // latency-bound on the host round trip.
@@ -443,8 +494,9 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
         de_select_kernel<<<nblk(static_cast<size_t>(NP) * 32, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, NP, dim, accepted, Ftry, CRtry, vtry,
                                                                                   algo ? Fs : nullptr, algo ? CRs : nullptr,
                                                                                   algo == 2u ? vars : nullptr, &G->stopped);
+        if (nparts) de_global_partial_kernel<<<nparts, 256, 0, st>>>(d_f, accepted, NP, 0, &G->stopped, parts);
         de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, accepted, NP, dim, algo ? Fs : nullptr, algo ? CRs : nullptr, algo == 2u ? vars : nullptr,
-                                            gbX, G, 0, xtol, ftol);
+                                            gbX, G, 0, xtol, ftol, parts, nparts);
         ctx->launches.fetch_add(3, std::memory_order_relaxed);
         if ((g + 1) % kPoll == 0 || g + 1 == gens) {
             PGC_CUDA(cudaMemcpyAsync(&h, G, sizeof(DeGlobal), cudaMemcpyDeviceToHost, st));

@@ -54,3 +54,23 @@ def test_cfg1_de1220_rastrigin(capi, ctx, orc):
             prob.de_evolve(x, f, gens=1, **bad)
     with pytest.raises(capi.PgcError):
         prob.de_evolve(x[:4], f[:4], gens=1, algo="de")
+
+
+def test_large_population_path_matches_oracle(capi, ctx, orc):
+    """populations of 16384 and more spread the global-best scan over many CTAs: same trajectory as the restated loop."""
+    rng = np.random.default_rng(99)
+    NP, dim = 16384, 6
+    prob = capi.Problem(ctx, "rastrigin", dim=dim)
+    op = orc.problem("rastrigin", dim=dim)
+    lb, ub = prob.bounds()
+    x = rng.uniform(lb, ub, (NP, dim))
+    x[5000] = x[77]  # ties in the fitness: best / worst / accepted tie rules across CTA slices
+    x[16000] = x[77]
+    f = orc.simple("rastrigin", x)
+    for algo, kw in (("de", dict(variant=1)), ("sade", dict(variant=3, variant_adptv=2)), ("de1220", dict(variant_adptv=1))):
+        args = dict(gens=3, algo=algo, seed=5, first_generation=1, ftol=0.0, xtol=0.0, **kw)
+        xo, fo, go, *_ = orc.de_evolve(op, lb, ub, x, f, **args)
+        xg, fg, gg = prob.de_evolve(x, f, **args)
+        assert gg == go == 3
+        assert np.allclose(xg, xo, rtol=1e-9, atol=1e-12) and np.allclose(fg, fo, rtol=1e-9), algo
+    prob.close()
