@@ -250,6 +250,7 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
     double *sMr = reinterpret_cast<double *>(smem_raw);
     double *sBuf = sMr + (rot ? DP * YS : 0);
     double *sOs = sBuf + W * 2 * kTileInd * YS;
+    unsigned short *sList = reinterpret_cast<unsigned short *>(sOs + D); // [W][TILE]: positions of the positive inputs of asyfunc
 
     if (rot) {
         const double2 *src = reinterpret_cast<const double2 *>(P.mr);
@@ -262,6 +263,7 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *bufs[2] = {sBuf + warp * 2 * kTileInd * YS, sBuf + warp * 2 * kTileInd * YS + kTileInd * YS};
+    unsigned short *list = sList + warp * TILE;
     const long long ntiles = (P.n + kTileInd - 1) / kTileInd;
     const int et = lane & (kTileInd - 1), eq = lane / kTileInd;
     const double *tab = P.table;
@@ -345,13 +347,32 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
                         if (fabs(v) > 0.5) out[a] = floor(2. * v + 0.5) / 2.;
                     }
                     break;
-                case O_ASY: // :1053-1059: only positive inputs are written
-                    for (int e = lane; e < TILE; e += 32) {
-                        const int t = e / D, i = e - t * D, a = t * YS + i;
+                case O_ASY: { // :1053-1059: only positive inputs are written
+                    // about half of the inputs are positive; their positions are first compacted into a list (warp votes) so that
+                    // the pow() below runs with full warps instead of half-empty ones
+                    int cnt = 0;
+                    for (int e0 = 0; e0 < TILE; e0 += 32) {
+                        const int e = e0 + lane;
+                        bool pos = false;
+                        int a = 0, i = 0;
+                        if (e < TILE) {
+                            const int t = e / D;
+                            i = e - t * D;
+                            a = t * YS + i;
+                            pos = in[a] > 0;
+                        }
+                        const unsigned m = __ballot_sync(kFull, pos);
+                        if (pos) list[cnt + __popc(m & ((1u << lane) - 1u))] = static_cast<unsigned short>(a);
+                        cnt += __popc(m);
+                    }
+                    __syncwarp();
+                    for (int k = lane; k < cnt; k += 32) {
+                        const int a = list[k], i = a - (a / YS) * YS;
                         const double v = in[a];
-                        if (v > 0) out[a] = pow(v, 1.0 + tab[s.tab + i] * sqrt(v));
+                        out[a] = pow(v, 1.0 + tab[s.tab + i] * sqrt(v));
                     }
                     break;
+                }
                 case O_OSZ: { // :1061-1089: end coordinates transformed, the rest copied
                     for (int e = lane; e < TILE; e += 32) {
                         const int t = e / D, i = e - t * D, a = t * YS + i;
@@ -482,7 +503,7 @@ template <int D> int launch13(pgc_ctx *ctx, const Params13 &pp, cudaStream_t str
         configured_dev = ctx->device;
     }
     const size_t fixed = sizeof(double) * ((pp.L.rot >= 0 ? DP * YS : 0) + D) + 16;
-    const size_t per_warp = sizeof(double) * 2 * kTileInd * YS;
+    const size_t per_warp = sizeof(double) * 2 * kTileInd * YS + sizeof(unsigned short) * kTileInd * D;
     int fit = static_cast<int>((ctx->smem_optin - fixed) / per_warp);
     if (fit > kMaxWarps13) fit = kMaxWarps13;
     PGC_REQUIRE(fit >= 1, "cec2013: shared memory too small for dimension %d", D);
