@@ -15,11 +15,13 @@
 #ifndef PAGMO_CUDA_CUDA_BFE_HPP
 #define PAGMO_CUDA_CUDA_BFE_HPP
 
+#include <exception>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <utility>
 #include <vector>
@@ -81,9 +83,16 @@ inline std::shared_ptr<pgc_ctx> device_context(int device)
 class problem_handle
 {
 public:
-    problem_handle(int device, const pgc_problem_desc &desc) : m_ctx(device_context(device))
+    problem_handle(int device, const pgc_problem_desc &desc) : m_ctx(device_context(device)), m_device(device), m_desc(desc)
     {
-        check(pgc_problem_create(m_ctx.get(), &desc, &m_prob), "pgc_problem_create");
+        // the handle keeps its own copy of the description (tables included), so that it can be re-created on another device
+        if (desc.rotation) m_rotation.assign(desc.rotation, desc.rotation + desc.rotation_len);
+        if (desc.shift) m_shift.assign(desc.shift, desc.shift + desc.shift_len);
+        if (desc.shuffle) m_shuffle.assign(desc.shuffle, desc.shuffle + desc.shuffle_len);
+        m_desc.rotation = m_rotation.empty() ? nullptr : m_rotation.data();
+        m_desc.shift = m_shift.empty() ? nullptr : m_shift.data();
+        m_desc.shuffle = m_shuffle.empty() ? nullptr : m_shuffle.data();
+        check(pgc_problem_create(m_ctx.get(), &m_desc, &m_prob), "pgc_problem_create");
         check(pgc_problem_nx(m_prob, &m_nx), "pgc_problem_nx");
         check(pgc_problem_nf(m_prob, &m_nf), "pgc_problem_nf");
     }
@@ -96,6 +105,23 @@ public:
 
     std::size_t nx() const { return m_nx; }
     std::size_t nf() const { return m_nf; }
+    int device() const { return m_device; }
+
+    // the same problem on another device (created on first use, then shared)
+    std::shared_ptr<problem_handle> twin_on(int device) const
+    {
+        std::lock_guard<std::mutex> lk(m_twin_mtx);
+        auto &slot = m_twins[device];
+        if (!slot) slot = std::make_shared<problem_handle>(device, m_desc);
+        return slot;
+    }
+
+    // n decision vectors at dvs -> n fitness vectors at fvs (plain pointers: used for the shards of a multi-device batch)
+    void evaluate_raw(const double *dvs, std::size_t n, double *fvs) const
+    {
+        std::lock_guard<std::mutex> lk(m_mtx);
+        check(pgc_eval_host(m_prob, dvs, n, fvs), "pgc_eval_host");
+    }
 
     pagmo::vector_double evaluate(const pagmo::vector_double &dvs) const
     {
@@ -158,9 +184,14 @@ public:
 
 private:
     std::shared_ptr<pgc_ctx> m_ctx;
+    int m_device = 0;
+    pgc_problem_desc m_desc{};
+    std::vector<double> m_rotation, m_shift;
+    std::vector<int32_t> m_shuffle;
     pgc_problem *m_prob = nullptr;
     std::size_t m_nx = 0, m_nf = 0;
-    mutable std::mutex m_mtx;
+    mutable std::mutex m_mtx, m_twin_mtx;
+    mutable std::map<int, std::shared_ptr<problem_handle>> m_twins;
 };
 
 inline pgc_problem_desc make_desc(int family, unsigned prob_id, unsigned dim, unsigned nobj = 0, unsigned param = 0)
@@ -473,7 +504,15 @@ private:
 class cuda_bfe
 {
 public:
-    explicit cuda_bfe(int device = 0) : m_device(device), m_cache(std::make_shared<detail::twin_cache>()) {}
+    explicit cuda_bfe(int device = 0) : m_device(device), m_devices{device}, m_cache(std::make_shared<detail::twin_cache>()) {}
+    // several devices: the batch is split into contiguous shards of individuals, one per device, evaluated concurrently (the
+    // problem's tables are replicated; no communication between the devices - SURVEY 8e).  Each device has its own PCIe link, so
+    // the host-vector path scales with the number of devices.
+    explicit cuda_bfe(std::vector<int> devices)
+        : m_device(devices.empty() ? 0 : devices.front()), m_devices(std::move(devices)), m_cache(std::make_shared<detail::twin_cache>())
+    {
+        if (m_devices.empty()) pagmo_throw(std::invalid_argument, "cuda_bfe: the list of devices is empty");
+    }
 
     pagmo::vector_double operator()(const pagmo::problem &p, const pagmo::vector_double &dvs) const
     {
@@ -486,11 +525,39 @@ public:
                             + "': no CUDA evaluator exists for this UDP type (wrap it in a pagmo_cuda:: UDP, or use "
                               "thread_bfe); there is no CPU fallback");
         }
-        return h->evaluate(dvs);
+        if (m_devices.size() == 1u) return h->evaluate(dvs);
+        const std::size_t nx = h->nx(), nf = h->nf();
+        if (dvs.size() % nx != 0u) {
+            pagmo_throw(std::invalid_argument, "cuda evaluator: a batch of " + std::to_string(dvs.size())
+                                                   + " values is not a multiple of the problem dimension " + std::to_string(nx));
+        }
+        const std::size_t n = dvs.size() / nx, G = m_devices.size();
+        pagmo::vector_double fvs(n * nf);
+        std::vector<std::shared_ptr<detail::problem_handle>> hs(G);
+        for (std::size_t g = 0; g < G; ++g) hs[g] = (m_devices[g] == h->device()) ? h : h->twin_on(m_devices[g]);
+        std::vector<std::thread> workers;
+        std::vector<std::exception_ptr> errors(G);
+        for (std::size_t g = 0; g < G; ++g) {
+            const std::size_t lo = n * g / G, hi = n * (g + 1) / G; // contiguous shard of individuals
+            if (hi == lo) continue;
+            workers.emplace_back([&, g, lo, hi]() {
+                try {
+                    hs[g]->evaluate_raw(dvs.data() + lo * nx, hi - lo, fvs.data() + lo * nf);
+                } catch (...) {
+                    errors[g] = std::current_exception();
+                }
+            });
+        }
+        for (auto &w : workers) w.join();
+        for (auto &e : errors)
+            if (e) std::rethrow_exception(e);
+        return fvs;
     }
     std::string get_name() const
     {
-        return "CUDA batch fitness evaluator (sm_100a, device " + std::to_string(m_device) + ")";
+        std::string devs;
+        for (int d : m_devices) devs += (devs.empty() ? "" : ",") + std::to_string(d);
+        return "CUDA batch fitness evaluator (sm_100a, device " + devs + ")";
     }
     pagmo::thread_safety get_thread_safety() const
     {
@@ -499,11 +566,12 @@ public:
     template <typename Archive>
     void serialize(Archive &ar, unsigned)
     {
-        pagmo::detail::archive(ar, m_device);
+        pagmo::detail::archive(ar, m_device, m_devices);
     }
 
 private:
     int m_device;
+    std::vector<int> m_devices;
     std::shared_ptr<detail::twin_cache> m_cache;
 };
 

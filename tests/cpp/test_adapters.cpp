@@ -274,6 +274,31 @@ int main()
         }
     }
 
+    // ---- 3e. one batch sharded over several devices (here: every visible device, or device 0 twice): same values as one device ----
+    {
+        int ndev = 0;
+        pgc_device_count(&ndev);
+        std::vector<int> devs = ndev >= 2 ? std::vector<int>{0, 1} : std::vector<int>{0, 0};
+        pagmo::bfe multi{cuda_bfe{devs}}, single{cuda_bfe{0}};
+        const unsigned dim = 30u;
+        std::vector<double> Mr(10u * dim * dim), Os(10u * 100u);
+        std::vector<int> S(10u * dim);
+        cec2014_synth_rotation(27u, dim, Mr.data());
+        cec2014_synth_shift(27u, Os.data());
+        cec2014_synth_shuffle(27u, dim, S.data());
+        std::vector<double> Osc; // compaction of the ctor, cec2014.cpp:76-86
+        for (unsigned k = 0; k < 10u; ++k) Osc.insert(Osc.end(), Os.begin() + 100u * k, Os.begin() + 100u * k + dim);
+        pagmo::problem p{cuda_cec2014{27u, dim, Mr, Osc, S}};
+        for (std::size_t n : {std::size_t(0), std::size_t(1), std::size_t(1001)}) {
+            const auto dvs = random_batch(p, n, 11);
+            CHECK(multi(p, dvs) == single(p, dvs));
+        }
+        pagmo::problem r{pagmo::rastrigin{9u}};
+        const auto dvs = random_batch(r, 4097, 12);
+        CHECK(multi(r, dvs) == single(r, dvs));
+        std::printf("cuda_bfe over devices {%d,%d}: identical to one device\n", devs[0], devs[1]);
+    }
+
     // ---- 4. constructor errors surface as std::invalid_argument, like the reference UDP (cec2014.cpp:51-64) ----
     {
         bool threw = false;
