@@ -248,6 +248,34 @@ __global__ void de_select_kernel(const double *trial, const double *ftrial, doub
     }
 }
 
+// Large populations: the same selection as two element-parallel kernels (a warp per individual wastes most lanes on short rows)
+__global__ void de_accept_kernel(const double *ftrial, const double *f, unsigned NP, unsigned char *accepted, const double *F_try,
+                                 const double *CR_try, const unsigned *var_try, double *F, double *CR, unsigned *variant, const unsigned *stopped)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NP || *stopped) return;
+    const bool ok = ftrial[i] <= f[i];
+    accepted[i] = ok;
+    if (ok) {
+        if (F) {
+            F[i] = F_try[i];
+            CR[i] = CR_try[i];
+        }
+        if (variant) variant[i] = var_try[i];
+    }
+}
+__global__ void de_copy_accepted_kernel(const double *trial, const double *ftrial, double *x, double *f, const unsigned char *accepted, unsigned NP,
+                                        unsigned dim, const unsigned *stopped)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (*stopped || e >= static_cast<size_t>(NP) * dim) return;
+    const unsigned i = static_cast<unsigned>(e / dim);
+    if (accepted[i]) {
+        x[e] = trial[e];
+        if (e == static_cast<size_t>(i) * dim) f[i] = ftrial[i];
+    }
+}
+
 struct DeGlobal { // device-side global best + exit-condition data
     double gbfit, gbF, gbCR;
     unsigned gbidx, gbvariant;
@@ -491,9 +519,15 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
                        seed, first_generation + g, cfg};
         de_trial_kernel<<<nblk(NP, 64), 64, 0, st>>>(tp);
         if ((rc = eval(prob, trial, NP, ftrial, st))) return rc;
-        de_select_kernel<<<nblk(static_cast<size_t>(NP) * 32, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, NP, dim, accepted, Ftry, CRtry, vtry,
-                                                                                  algo ? Fs : nullptr, algo ? CRs : nullptr,
-                                                                                  algo == 2u ? vars : nullptr, &G->stopped);
+        if (nparts && dim < 32u) { // large population of short rows: element-parallel selection
+            de_accept_kernel<<<nblk(NP, 256), 256, 0, st>>>(ftrial, d_f, NP, accepted, Ftry, CRtry, vtry, algo ? Fs : nullptr, algo ? CRs : nullptr,
+                                                            algo == 2u ? vars : nullptr, &G->stopped);
+            de_copy_accepted_kernel<<<nblk(nd, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, accepted, NP, dim, &G->stopped);
+        } else {
+            de_select_kernel<<<nblk(static_cast<size_t>(NP) * 32, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, NP, dim, accepted, Ftry, CRtry, vtry,
+                                                                                      algo ? Fs : nullptr, algo ? CRs : nullptr,
+                                                                                      algo == 2u ? vars : nullptr, &G->stopped);
+        }
         if (nparts) de_global_partial_kernel<<<nparts, 256, 0, st>>>(d_f, accepted, NP, 0, &G->stopped, parts);
         de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, accepted, NP, dim, algo ? Fs : nullptr, algo ? CRs : nullptr, algo == 2u ? vars : nullptr,
                                             gbX, G, 0, xtol, ftol, parts, nparts);
