@@ -5,6 +5,7 @@
 //   pagmo_cuda::cuda_sade    pagmo::sade    (sade.hpp:138    gen, variant, variant_adptv, ftol, xtol, memory, seed)
 //   pagmo_cuda::cuda_de1220  pagmo::de1220  (de1220.hpp:158  gen, allowed_variants, variant_adptv, ftol, xtol, memory, seed)
 //   pagmo_cuda::cuda_pso_gen pagmo::pso_gen (pso_gen.hpp:127 gen, omega, eta1, eta2, max_vel, variant, neighb_type, neighb_param, memory, seed)
+//   pagmo_cuda::cuda_pso     pagmo::pso     (pso.hpp:110     same arguments; batched per generation like pso_gen)
 //   pagmo_cuda::cuda_nsga2   pagmo::nsga2   (nsga2.hpp:103   gen, cr, eta_c, m, eta_m, seed)
 //   pagmo_cuda::cuda_sga     pagmo::sga     (sga.hpp:166     gen, cr, eta_c, m, param_m, param_s, crossover, mutation, selection, seed)
 //
@@ -197,6 +198,18 @@ public:
     }
 };
 
+// pagmo::pso (pso.hpp:110, same constructor arguments as pso_gen): the reference's pso updates the swarm particle by particle
+// (pso.cpp:115-443); on the device every generation is batched, i.e. it runs as pso_gen does.
+class cuda_pso : public cuda_pso_gen
+{
+public:
+    using cuda_pso_gen::cuda_pso_gen;
+    std::string get_name() const
+    {
+        return "PSO: Particle Swarm Optimization [CUDA sm_100a, generational]";
+    }
+};
+
 class cuda_nsga2 : public cuda_algorithm_base
 {
 public:
@@ -239,6 +252,7 @@ PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_de)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_sade)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_de1220)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_pso_gen)
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_pso)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_nsga2)
 
 #endif
