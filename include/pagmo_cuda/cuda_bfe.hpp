@@ -78,8 +78,21 @@ inline std::shared_ptr<pgc_ctx> device_context(int device)
     return sp;
 }
 
-// RAII handle on a device-side problem.  Copies of an adapter share it; calls are serialised by a mutex because
-// one pgc_problem drives one stream and one staging ring (thread_safety::basic, reference threading.hpp:42).
+// One mutex per (process, device): a pgc_ctx owns one stream and one staging ring, so every call that goes through the shared
+// context of a device is serialised - also between DIFFERENT problems living on that device (e.g. two islands of an archipelago
+// evaluating on device 0 from their own threads).
+inline std::mutex &device_mutex(int device)
+{
+    static std::mutex mtx;
+    static std::map<int, std::unique_ptr<std::mutex>> table;
+    std::lock_guard<std::mutex> lk(mtx);
+    auto &slot = table[device];
+    if (!slot) slot.reset(new std::mutex);
+    return *slot;
+}
+
+// RAII handle on a device-side problem.  Copies of an adapter share it; calls are serialised by the device's mutex because
+// one pgc_ctx drives one stream and one staging ring (thread_safety::basic, reference threading.hpp:42).
 class problem_handle
 {
 public:
@@ -119,7 +132,7 @@ public:
     // n decision vectors at dvs -> n fitness vectors at fvs (plain pointers: used for the shards of a multi-device batch)
     void evaluate_raw(const double *dvs, std::size_t n, double *fvs) const
     {
-        std::lock_guard<std::mutex> lk(m_mtx);
+        std::lock_guard<std::mutex> lk(device_mutex(m_device));
         check(pgc_eval_host(m_prob, dvs, n, fvs), "pgc_eval_host");
     }
 
@@ -132,7 +145,7 @@ public:
         }
         const std::size_t n = dvs.size() / m_nx;
         pagmo::vector_double fvs(n * m_nf);
-        std::lock_guard<std::mutex> lk(m_mtx);
+        std::lock_guard<std::mutex> lk(device_mutex(m_device));
         check(pgc_eval_host(m_prob, dvs.data(), n, fvs.data()), "pgc_eval_host");
         return fvs;
     }
@@ -156,7 +169,7 @@ public:
     unsigned evolve(const pgc_algo_desc &algo, pagmo::vector_double &x, pagmo::vector_double &f, unsigned first_generation) const
     {
         const std::size_t n = x.size() / m_nx;
-        std::lock_guard<std::mutex> lk(m_mtx);
+        std::lock_guard<std::mutex> lk(device_mutex(m_device));
         void *dx = nullptr, *df = nullptr;
         check(pgc_malloc_device(m_ctx.get(), x.size() * sizeof(double), &dx), "pgc_malloc_device");
         if (int rc = pgc_malloc_device(m_ctx.get(), f.size() * sizeof(double), &df)) {
@@ -190,7 +203,7 @@ private:
     std::vector<int32_t> m_shuffle;
     pgc_problem *m_prob = nullptr;
     std::size_t m_nx = 0, m_nf = 0;
-    mutable std::mutex m_mtx, m_twin_mtx;
+    mutable std::mutex m_twin_mtx;
     mutable std::map<int, std::shared_ptr<problem_handle>> m_twins;
 };
 

@@ -37,6 +37,7 @@ public:
     {
         const auto flat = flatten(points, r_point.size());
         double hv = 0.0;
+        std::lock_guard<std::mutex> lk(detail::device_mutex(m_device));
         detail::check(pgc_hv_compute_host(m_ctx.get(), flat.data(), points.size(), r_point.size(), r_point.data(), &hv), "pgc_hv_compute_host");
         return hv;
     }
@@ -44,6 +45,7 @@ public:
     {
         const auto flat = flatten(points, r_point.size());
         std::vector<double> c(points.size());
+        std::lock_guard<std::mutex> lk(detail::device_mutex(m_device));
         detail::check(pgc_hv_contributions_host(m_ctx.get(), flat.data(), points.size(), r_point.size(), r_point.data(), c.data()),
                       "pgc_hv_contributions_host");
         return c;

@@ -9,6 +9,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <pagmo/batch_evaluators/default_bfe.hpp>
@@ -298,6 +299,29 @@ int main()
         const auto dvs = random_batch(r, 4097, 12);
         CHECK(multi(r, dvs) == single(r, dvs));
         std::printf("cuda_bfe over devices {%d,%d}: identical to one device\n", devs[0], devs[1]);
+    }
+
+    // ---- 3f. island threads: different problems on the same device, evaluated concurrently from their own threads ----
+    {
+        const unsigned dims[4] = {5u, 17u, 30u, 64u};
+        std::vector<pagmo::problem> probs;
+        std::vector<pagmo::vector_double> batches, wants;
+        pagmo::bfe gpu{cuda_bfe{}};
+        for (unsigned d : dims) {
+            probs.emplace_back(cuda_rastrigin{d});
+            batches.push_back(random_batch(probs.back(), 3000, d));
+            wants.push_back(gpu(probs.back(), batches.back()));
+        }
+        std::vector<int> bad(4, 0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < 4; ++t)
+            th.emplace_back([&, t]() {
+                pagmo::bfe mine{cuda_bfe{}};
+                for (int rep = 0; rep < 25; ++rep)
+                    if (mine(probs[t], batches[t]) != wants[t]) ++bad[t];
+            });
+        for (auto &x : th) x.join();
+        CHECK(bad[0] + bad[1] + bad[2] + bad[3] == 0);
     }
 
     // ---- 4. constructor errors surface as std::invalid_argument, like the reference UDP (cec2014.cpp:51-64) ----
