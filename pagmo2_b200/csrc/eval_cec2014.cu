@@ -81,6 +81,32 @@ struct Elem {
 };
 
 
+// ---- per-coordinate terms shared by the tile epilogue (eval_group) and the separable fast path ----------------------
+__device__ __forceinline__ double rastrigin_term(double z) // cec2014.cpp:541-543
+{
+    const double two_pi = 2.0 * 3.141592653589793238462643383279502884;
+    return (z * z - 10.0 * cos_theta(two_pi * z) + 10.0);
+}
+
+// schwefel, cec2014.cpp:575-589, the three branches folded into one sin(sqrt(.)): f -= sub; f += pen
+__device__ __forceinline__ void schwefel_term(double zin, double inv_n, double &sub, double &pen)
+{
+    const double z = zin + 4.209687462275036e+002;
+    const double az = fabs(z);
+    const bool big = az > 500.0;
+    // fm = fmod(|z|, 500) EXACTLY: q = nearest multiple, the fused remainder az - 500 q is exact and lies
+    // in [-250, 250]; one fix-up brings it to [0, 500)
+    const double q = round_magic(az * 0.002);
+    double fm = fma(-q, 500.0, az);
+    fm = (fm < 0.0) ? fm + 500.0 : fm;
+    // z > 500: (500 - fmod(z,500)); z < -500: -(-500 + fmod(|z|,500)); else |z|
+    const double m = big ? 500.0 - fm : az;
+    const double t = (z - copysign(500.0, z)) * 0.01;
+    sub = copysign(m, z) * sin_theta(sqrt(m));
+    pen = big ? t * t * inv_n : 0.0;
+}
+
+
 // One primitive on n coordinates, evaluated by the kLPI lanes of an individual (lane q takes the terms
 // j == q mod kLPI); every lane returns the full value.  Expressions follow cec2014.cpp term by term.
 __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__restrict__ tab, int h)
@@ -139,8 +165,9 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
                            if (k % 10 == 0 && k < 20) {
                                sincos_turns(turns_of(gt[k] * u), sn, cs);
                            } else {
-                               const double c2 = fma(cs, cs, -(sn * sn)), s2 = (cs + cs) * sn;       // w^2
-                               const double c3 = fma(c2, cs, -(s2 * sn)), s3 = fma(s2, cs, c2 * sn); // w^3
+                               // w^3 = c (c^2 - 3 s^2) + i s (3 c^2 - s^2): six FP64 instructions
+                               const double cc = cs * cs, ss = sn * sn;
+                               const double c3 = cs * fma(-3.0, ss, cc), s3 = sn * fma(3.0, cc, -ss);
                                cs = c3;
                                sn = s3;
                            }
@@ -169,28 +196,11 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
             return 1.0 + s / 4000.0 - p;
         }
         case P_RASTRIGIN: // :541-543
-            return pair_add(ordered_sum(lo, hi, [&](int j) {
-                const double z = v(j);
-                return (z * z - 10.0 * cos_theta(two_pi * z) + 10.0);
-            }));
+            return pair_add(ordered_sum(lo, hi, [&](int j) { return rastrigin_term(v(j)); }));
         case P_SCHWEFEL: { // :575-589, the three branches folded into one sin(sqrt(.)) per coordinate
             const double inv_n = 1.0 / dn;
             double s = 0.0;
-            auto term = [&](int j, double &sub, double &pen) {
-                const double z = v(j) + 4.209687462275036e+002;
-                const double az = fabs(z);
-                const bool big = az > 500.0;
-                // fm = fmod(|z|, 500) EXACTLY: q = nearest multiple, the fused remainder az - 500 q is exact and lies
-                // in [-250, 250]; one fix-up brings it to [0, 500)
-                const double q = round_magic(az * 0.002);
-                double fm = fma(-q, 500.0, az);
-                fm = (fm < 0.0) ? fm + 500.0 : fm;
-                // z > 500: (500 - fmod(z,500)); z < -500: -(-500 + fmod(|z|,500)); else |z|
-                const double m = big ? 500.0 - fm : az;
-                const double t = (z - copysign(500.0, z)) * 0.01;
-                sub = copysign(m, z) * sin_theta(sqrt(m));
-                pen = big ? t * t * inv_n : 0.0;
-            };
+            auto term = [&](int j, double &sub, double &pen) { schwefel_term(v(j), inv_n, sub, pen); };
             int j = lo;
             for (; j + kLPI < hi; j += 2 * kLPI) {
                 double s0, p0, s1, p1;
@@ -216,13 +226,15 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
                 const double z = v(j);
                 double temp = 0.0;
                 if (fabs(z) < 262144.0) {
-                    double t1 = 1.0, it1 = 1.0;
+                    // d_k = dist(2^k z, Z) obeys the tent map d_{k+1} = 1/2 - |2 d_k - 1/2|, every step exact in FP64
+                    const double t2 = z + z;
+                    double d = fabs(t2 - round_magic(t2)), it1 = 0.5;
+                    temp = d * it1;
 #pragma unroll
-                    for (int k = 1; k <= 32; ++k) {
-                        t1 *= 2.0;
+                    for (int k = 2; k <= 32; ++k) {
                         it1 *= 0.5;
-                        const double t2 = t1 * z;
-                        temp = fma(fabs(t2 - round_magic(t2)), it1, temp); // "/ 2^k" is an exact scaling
+                        d = 0.5 - fabs(fma(2.0, d, -0.5));
+                        temp = fma(d, it1, temp); // "/ 2^k" is an exact scaling
                     }
                 } else {
                     double t1 = 1.0;
@@ -491,6 +503,142 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
     }
 }
 
+// ---- separable fast path --------------------------------------------------------------------------------------------
+// Un-rotated, un-permuted single-group stages whose primitive is a plain sum over coordinates (f8 rastrigin, f10 and
+// cf02[0] schwefel, cf01[4] ellips): nothing needs the tile in shared memory.  G lanes share a row (individual): lane
+// cl of the group takes the 16-byte chunks cl, cl + G, ... of the row straight from global memory, evaluates its
+// coordinates in registers and the G partial sums are added in lane order - the same order for every row, so a
+// result does not depend on the row's position in the batch.  HBM / FP64-instruction bound, no barriers.
+__host__ __device__ constexpr int sep_lanes(int d)
+{
+    // lanes per row: maximise (used lanes / 32) x (used chunk slots / issued chunk slots) with at most 8 chunks per
+    // lane (they are all in flight at once, in registers); ties -> wider group
+    const int ch = d / 2;
+    int best = 32;
+    long long best_num = 0, best_den = 1;
+    for (int g = 1; g <= 32; ++g) {
+        const int rows = 32 / g, pass = (ch + g - 1) / g;
+        if (pass > 8) continue;
+        const long long num = static_cast<long long>(rows) * g * ch, den = 32LL * g * pass;
+        if (num * best_den >= best_num * den) {
+            best = g;
+            best_num = num;
+            best_den = den;
+        }
+    }
+    return best;
+}
+
+constexpr int kSepThreads = 256;
+
+template <int D> __global__ void __launch_bounds__(kSepThreads) cec14_sep_kernel(const __grid_constant__ StageParams P)
+{
+    static_assert(D % 2 == 0, "rows are fetched in 16-byte chunks");
+    constexpr int CH = D / 2, G = sep_lanes(D), ROWS = 32 / G, PASS = (CH + G - 1) / G;
+    const int lane = threadIdx.x & 31;
+    const int r = lane / G, cl = lane - r * G;
+    const bool lane_ok = r < ROWS;
+    const GroupDesc &g = P.st.g[0];
+    const double *__restrict__ gt = P.table + g.tab_off;
+    const bool need_w = P.wout != nullptr;
+    const double pre_rate = P.st.pre_rate, rate = g.rate;
+    const double inv_n = 1.0 / static_cast<double>(D);
+    const int prim = g.prim;
+
+    double2 osv[PASS], cf[PASS];
+#pragma unroll
+    for (int ps = 0; ps < PASS; ++ps) {
+        const int c = ps * G + cl;
+        const bool ok = lane_ok && c < CH;
+        osv[ps] = ok ? make_double2(P.os[2 * c], P.os[2 * c + 1]) : make_double2(0.0, 0.0);
+        cf[ps] = (ok && prim == P_ELLIPS) ? make_double2(gt[2 * c], gt[2 * c + 1]) : make_double2(0.0, 0.0);
+    }
+
+    const long long ntiles = (P.n + ROWS - 1) / ROWS;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long tile = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; tile < ntiles; tile += nwarps) {
+        const long long row = tile * ROWS + r;
+        const bool active = lane_ok && row < P.n;
+        const double2 *src = reinterpret_cast<const double2 *>(P.x + (active ? row : 0) * D);
+        double2 xv[PASS];
+#pragma unroll
+        for (int ps = 0; ps < PASS; ++ps) {
+            const int c = ps * G + cl;
+            xv[ps] = (active && c < CH) ? __ldcs(src + c) : make_double2(0.0, 0.0);
+        }
+        double s = 0.0, w = 0.0;
+#pragma unroll
+        for (int ps = 0; ps < PASS; ++ps) {
+            const int c = ps * G + cl;
+            if (c < CH) {
+                const double d0 = xv[ps].x - osv[ps].x, d1 = xv[ps].y - osv[ps].y; // :1245-1258
+                w += d0 * d0 + d1 * d1;                                             // cf_cal weight, :1330-1332
+                const double z0 = d0 * pre_rate * rate, z1 = d1 * pre_rate * rate;
+                if (prim == P_RASTRIGIN) {
+                    const double a = rastrigin_term(z0), b = rastrigin_term(z1);
+                    s += a;
+                    s += b;
+                } else if (prim == P_SCHWEFEL) {
+                    double s0, p0, s1, p1;
+                    schwefel_term(z0, inv_n, s0, p0);
+                    schwefel_term(z1, inv_n, s1, p1);
+                    s -= s0;
+                    s += p0;
+                    s -= s1;
+                    s += p1;
+                } else { // P_ELLIPS, :382-384
+                    s += cf[ps].x * z0 * z0;
+                    s += cf[ps].y * z1 * z1;
+                }
+            }
+        }
+        // the row's G partial sums, added in lane order
+        double val = 0.0, wsum = 0.0;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const int from = (lane_ok ? r * G : 0) + k;
+            val += __shfl_sync(kFull, s, from);
+            if (need_w) wsum += __shfl_sync(kFull, w, from);
+        }
+        if (prim == P_SCHWEFEL) val = val + g.c0;
+        if (active && cl == 0) {
+            if (need_w) {
+                if (P.st.scaled) val = P.st.mul * val / P.st.div;
+                P.out[row] = val;
+                P.wout[row] = wsum;
+            } else {
+                P.out[row] = val + P.fbias;
+            }
+        }
+    }
+}
+
+template <int D> int launch_sep(pgc_ctx *ctx, const StageParams &sp, cudaStream_t stream)
+{
+    constexpr int ROWS = 32 / sep_lanes(D);
+    auto kern = cec14_sep_kernel<D>;
+    int per_sm = 1;
+    PGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSepThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    const long long ntiles = (sp.n + ROWS - 1) / ROWS;
+    long long ctas = (ntiles + kSepThreads / 32 - 1) / (kSepThreads / 32);
+    const long long cap = static_cast<long long>(ctx->sm_count) * per_sm;
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    kern<<<static_cast<unsigned>(ctas), kSepThreads, 0, stream>>>(sp);
+    PGC_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return PGC_OK;
+}
+
+inline bool stage_is_separable(const StageDesc &st, int dim)
+{
+    if (st.rotate || st.permute || st.ngroups != 1) return false;
+    const GroupDesc &g = st.g[0];
+    if (g.off != 0 || g.len != dim) return false;
+    return g.prim == P_ELLIPS || g.prim == P_RASTRIGIN || g.prim == P_SCHWEFEL;
+}
+
 struct CombineParams {
     const double *fit; // [nstages][n]
     const double *w;   // [nstages][n]
@@ -708,6 +856,19 @@ int cec2014_eval_impl(pgc_problem *p, const double *d_dvs, size_t n, double *d_f
         sp.st = r.st[s];
         int rc;
         const bool rot = r.st[s].rotate != 0;
+        if (!d_prof && sp.aligned16 && stage_is_separable(r.st[s], r.dim)) {
+            switch (r.dim) {
+                case 2: rc = launch_sep<2>(ctx, sp, stream); break;
+                case 10: rc = launch_sep<10>(ctx, sp, stream); break;
+                case 20: rc = launch_sep<20>(ctx, sp, stream); break;
+                case 30: rc = launch_sep<30>(ctx, sp, stream); break;
+                case 50: rc = launch_sep<50>(ctx, sp, stream); break;
+                case 100: rc = launch_sep<100>(ctx, sp, stream); break;
+                default: set_error("cec2014: unsupported dimension %d", r.dim); return PGC_ERR_INVALID_ARGUMENT;
+            }
+            if (rc != PGC_OK) return rc;
+            continue;
+        }
         switch (r.dim) {
             case 2: rc = launch_stage_d<2>(ctx, sp, rot, stream); break;
             case 10: rc = launch_stage_d<10>(ctx, sp, rot, stream); break;
