@@ -7,12 +7,14 @@ without a built library (or calling it without a CUDA device) fails loudly - the
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libpgc.so"
+# PGC_LIBRARY_PATH: another build of the same library (kernel-variant experiments, scripts/build_variants.py)
+LIB_PATH = Path(os.environ.get("PGC_LIBRARY_PATH") or HERE / "libpgc.so")
 
 PGC_OK = 0
 PGC_ERR_INVALID_ARGUMENT = -1

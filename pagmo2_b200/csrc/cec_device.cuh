@@ -85,28 +85,45 @@ __device__ __forceinline__ void sincos_turns(double r, double &sn, double &cs)
 // from scripts/gen_cos_turns_poly.py) and the sign (-1)^q taken from the parity bit the rounding constant leaves in the
 // low word.  12 FP64 instructions, no conversion, no select; ABSOLUTE error ~3e-16 (not a relative bound near the zeros,
 // which the sums and products of the primitives do not need).
-__device__ __forceinline__ double cos_turns(double r)
+// CM = true reads the coefficients from constant memory: in the issue-bound separable kernel the literals were
+// re-materialised with two integer moves per use (46 of 86 instructions per coordinate, ncu r1m_sep_f8).  The tile kernel
+// keeps literals (CM = false): there the issue slots are idle, and the constant-memory build measured 1.5-3 % slower.
+static __constant__ double kCosTurns[9] = {0x1.0000000000000p+0,  -0x1.3bd3cc9be45dbp+4, 0x1.03c1f081b5992p+6,
+                                           -0x1.55d3c7e3bfbf5p+6, 0x1.e1f506813a321p+5,  -0x1.a6d1efc8c38bep+4,
+                                           0x1.f9d254582ac30p+2,  -0x1.b6957b54dd389p+0, 0x1.1678f9078a9b3p-2};
+
+template <bool CM = false> __device__ __forceinline__ double cos_turns(double r)
 {
     const double t = fma(2.0, r, 6755399441055744.0);
     const double q = t - 6755399441055744.0;
     const double f = fma(-0.5, q, r);
     const double u = f * f;
-    double p = fma(u, 0x1.1678f9078a9b3p-2, -0x1.b6957b54dd389p+0);
-    p = fma(u, p, 0x1.f9d254582ac30p+2);
-    p = fma(u, p, -0x1.a6d1efc8c38bep+4);
-    p = fma(u, p, 0x1.e1f506813a321p+5);
-    p = fma(u, p, -0x1.55d3c7e3bfbf5p+6);
-    p = fma(u, p, 0x1.03c1f081b5992p+6);
-    p = fma(u, p, -0x1.3bd3cc9be45dbp+4);
-    p = fma(u, p, 0x1.0000000000000p+0);
+    double p;
+    if (CM) {
+        p = fma(u, kCosTurns[8], kCosTurns[7]);
+#pragma unroll
+        for (int k = 6; k >= 0; --k) p = fma(u, p, kCosTurns[k]);
+    } else {
+        p = fma(u, 0x1.1678f9078a9b3p-2, -0x1.b6957b54dd389p+0);
+        p = fma(u, p, 0x1.f9d254582ac30p+2);
+        p = fma(u, p, -0x1.a6d1efc8c38bep+4);
+        p = fma(u, p, 0x1.e1f506813a321p+5);
+        p = fma(u, p, -0x1.55d3c7e3bfbf5p+6);
+        p = fma(u, p, 0x1.03c1f081b5992p+6);
+        p = fma(u, p, -0x1.3bd3cc9be45dbp+4);
+        p = fma(u, p, 1.0);
+    }
     const int flip = __double2loint(t) << 31;
     return __hiloint2double(__double2hiint(p) ^ flip, __double2loint(p));
 }
 
-__device__ __forceinline__ double cos_theta(double theta) { return cos_turns(turns_of(theta)); }
+template <bool CM = false> __device__ __forceinline__ double cos_theta(double theta) { return cos_turns<CM>(turns_of(theta)); }
 
 // sin(2 pi r) = cos(2 pi (r - 1/4)); the shift costs at most 2^-54 turns
-__device__ __forceinline__ double sin_theta(double theta) { return cos_turns(turns_of(theta) - 0.25); }
+template <bool CM = false> __device__ __forceinline__ double sin_theta(double theta)
+{
+    return cos_turns<CM>(turns_of(theta) - 0.25);
+}
 
 // the kLPI lanes of an individual are kTileInd apart (lane = q * kTileInd + individual)
 __device__ __forceinline__ double pair_add(double v)
@@ -135,6 +152,20 @@ template <class F> __device__ __forceinline__ double ordered_sum(int lo, int hi,
     }
     if (j < hi) s += term(j);
     return s;
+}
+
+// Product of term(j) over the same index set, same two-at-a-time evaluation.
+template <class F> __device__ __forceinline__ double ordered_prod(int lo, int hi, F term)
+{
+    double p = 1.0;
+    int j = lo;
+    for (; j + kLPI < hi; j += 2 * kLPI) {
+        const double a = term(j), b = term(j + kLPI);
+        p *= a;
+        p *= b;
+    }
+    if (j < hi) p *= term(j);
+    return p;
 }
 
 } // namespace cecdev

@@ -38,12 +38,22 @@ using namespace cecdev;
 
 constexpr int kMT = 1;              // m8n8k4 row tiles per warp tile
 static_assert(kMT == 1 && cecdev::kTileInd == 8 * kMT, "warp tile = one m8n8k4 row tile");
-constexpr int kWarps = 16;          // independent workers per CTA (4 per SM sub-partition)
+#ifndef PGC_WARPS
+#define PGC_WARPS 16
+#endif
+#ifndef PGC_GEMM_UNROLL
+#define PGC_GEMM_UNROLL 2
+#endif
+constexpr int kGemmUnroll = PGC_GEMM_UNROLL; // 4-deep steps of the rotation unrolled together
+constexpr int kWarps = PGC_WARPS;   // independent workers per CTA (kWarps / 4 per SM sub-partition)
 
 // After the rotation the warp keeps z TRANSPOSED: zT[coordinate][individual], row stride kZS, so that the epilogue
 // (lane = individual + kTileInd * q) reads consecutive doubles per coordinate whatever the permutation; the +2 pad
 // makes the accumulator-tile stores conflict-free.
+// (An un-padded, XOR-swizzled zT that makes room for 20 warps was measured: 0.80 ms per rotated launch with 16 warps and
+// 0.87 ms with 20 warps at 96 registers, against 0.755 ms for this layout - profiles/r1o_variants.txt.)
 constexpr int kZS = kTileInd + 2;
+__device__ __forceinline__ int zt_index(int c, int ind) { return c * kZS + ind; }
 __host__ __device__ constexpr int warp_buf_elems(int d)
 {
     return (kTileInd * ystride(d) > pad8(d) * kZS) ? kTileInd * ystride(d) : pad8(d) * kZS;
@@ -69,27 +79,28 @@ enum { kPhLoad = 0, kPhWeight, kPhTokenWait, kPhGemm, kPhStoreZ, kPhEpilogue, kP
 
 
 struct Elem {
-    const double *col; // zT + individual: coordinate c lives at col[c * kZS]
+    const double *zt;  // the warp's zT tile
+    int ind;           // this lane's individual
     const int *idx;    // may be nullptr
     int off;
     double rate;
     __device__ __forceinline__ double operator()(int j) const
     {
         const int jj = idx ? idx[off + j] : off + j;
-        return col[jj * kZS] * rate;
+        return zt[zt_index(jj, ind)] * rate;
     }
 };
 
 
 // ---- per-coordinate terms shared by the tile epilogue (eval_group) and the separable fast path ----------------------
-__device__ __forceinline__ double rastrigin_term(double z) // cec2014.cpp:541-543
+template <bool CM = false> __device__ __forceinline__ double rastrigin_term(double z) // cec2014.cpp:541-543
 {
     const double two_pi = 2.0 * 3.141592653589793238462643383279502884;
-    return (z * z - 10.0 * cos_theta(two_pi * z) + 10.0);
+    return (z * z - 10.0 * cos_theta<CM>(two_pi * z) + 10.0);
 }
 
 // schwefel, cec2014.cpp:575-589, the three branches folded into one sin(sqrt(.)): f -= sub; f += pen
-__device__ __forceinline__ void schwefel_term(double zin, double inv_n, double &sub, double &pen)
+template <bool CM = false> __device__ __forceinline__ void schwefel_term(double zin, double inv_n, double &sub, double &pen)
 {
     const double z = zin + 4.209687462275036e+002;
     const double az = fabs(z);
@@ -102,7 +113,7 @@ __device__ __forceinline__ void schwefel_term(double zin, double inv_n, double &
     // z > 500: (500 - fmod(z,500)); z < -500: -(-500 + fmod(|z|,500)); else |z|
     const double m = big ? 500.0 - fm : az;
     const double t = (z - copysign(500.0, z)) * 0.01;
-    sub = copysign(m, z) * sin_theta(sqrt(m));
+    sub = copysign(m, z) * sin_theta<CM>(sqrt(m));
     pen = big ? t * t * inv_n : 0.0;
 }
 
@@ -152,17 +163,20 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
             return 2.718281828459045235360287471352662498 - 20.0 * exp(s1) - exp(s2) + 20.0;
         }
         case P_WEIERSTRASS: { // :500-509
-            // sum_k 0.5^k cos(theta_k), theta_k = fl(fl(2 pi 3^k) * u) as the reference forms it.  Terms k = 0 and
-            // k = 10 are evaluated directly from the reference's own argument (exact two-term reduction by 2 pi);
-            // the terms in between come from the angle-tripling map w -> w^3 on the unit circle (complex
-            // multiplication: the error grows exactly 3x per step, so term k is off by <= 3^(k mod 10) * 1e-16,
-            // and it is weighted by 0.5^k).  ~2.7x fewer FP64 instructions than 21 range-reduced cosines.
+            // sum_k 0.5^k cos(theta_k), theta_k = fl(fl(2 pi 3^k) * u) as the reference forms it.  Term k = 0 is
+            // evaluated directly from the reference's own argument (exact two-term reduction by 2 pi); the others come
+            // from the angle-tripling map w -> w^3 on the unit circle (complex multiplication: errors grow exactly 3x
+            // per step, so term k is off by ~3^k * 3e-16 and is weighted by 0.5^k: <= 1e-12 per coordinate at
+            // k = 20).  That is below what separates ANY evaluation from the reference's: its theta_20 ~ 2e10 carries a
+            // rounding error of ~2e-6 rad of its own, i.e. 2.4e-12 in the weighted term.  A second direct evaluation
+            // at k = 10 (used until r1n) bought nothing measurable and cost 23 instructions per coordinate.
+            // ~3.5x fewer FP64 instructions than 21 range-reduced cosines.
             return pair_add(ordered_sum(lo, hi, [&](int j) {
                        const double u = v(j) + 0.5;
                        double sum = 0.0, w = 1.0, sn = 0.0, cs = 1.0;
 #pragma unroll
                        for (int k = 0; k <= 20; ++k) {
-                           if (k % 10 == 0 && k < 20) {
+                           if (k == 0) {
                                sincos_turns(turns_of(gt[k] * u), sn, cs);
                            } else {
                                // w^3 = c (c^2 - 3 s^2) + i s (3 c^2 - s^2): six FP64 instructions
@@ -221,8 +235,9 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
         }
         case P_KATSUURA: { // :604-614
             // |2^k z - floor(2^k z + 0.5)| is the distance to the nearest integer: same value via round-to-nearest
-            // (magic-constant add, valid for |2^k z| < 2^51).  prod_j b_j^c0 is taken as exp(c0 * sum_j log b_j).
-            double slog = ordered_sum(lo, hi, [&](int j) {
+            // (magic-constant add, valid for |2^k z| < 2^51).  prod_j b_j^c0 is taken as exp(c0 * log(prod_j b_j)): each
+            // lane multiplies its own factors b_j in [1, 1 + n/2] (at most 25 of them: <= 5e42) and takes ONE log.
+            double prod = ordered_prod(lo, hi, [&](int j) {
                 const double z = v(j);
                 double temp = 0.0;
                 if (fabs(z) < 262144.0) {
@@ -244,9 +259,9 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
                         temp += fabs(t2 - floor(t2 + 0.5)) / t1;
                     }
                 }
-                return log(1.0 + static_cast<double>(j + 1) * temp);
+                return 1.0 + static_cast<double>(j + 1) * temp;
             });
-            slog = pair_add(slog);
+            double slog = pair_add(log(prod));
             const double p = exp(g.c0 * slog);
             return p * g.c1 - g.c1;
         }
@@ -382,8 +397,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
                             if (ROT) {
                                 *reinterpret_cast<double2 *>(buf + t * YS + 2 * c) = make_double2(y0, y1);
                             } else {
-                                buf[(2 * c) * kZS + t] = y0;
-                                buf[(2 * c + 1) * kZS + t] = y1;
+                                buf[zt_index(2 * c, t)] = y0;
+                                buf[zt_index(2 * c + 1, t)] = y1;
                             }
                         }
                     }
@@ -402,7 +417,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
                     const double xj = (t < nt) ? __ldcs(src + e) : 0.0;
                     const double y = (xj - sOs[j]) * scale;
                     if (ROT) buf[t * YS + j] = y;
-                    else buf[j * kZS + t] = y;
+                    else buf[zt_index(j, t)] = y;
                 }
             }
             if (ROT && KP > D) { // zero the inner-index padding (zT of the previous tile lived there)
@@ -415,7 +430,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
 
         if (need_w && !P.aligned16) { // unaligned path: weight pass over the tile, then the deferred scale
             for (int j = eq; j < D; j += kLPI) {
-                double *pd = ROT ? buf + et * YS + j : buf + j * kZS + et;
+                double *pd = ROT ? buf + et * YS + j : buf + zt_index(j, et);
                 const double d = *pd;
                 wacc += d * d;
                 *pd = d * pre_rate;
@@ -438,7 +453,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
                 for (int nt2 = 0; nt2 < NT; ++nt2) acc[mt][nt2][0] = acc[mt][nt2][1] = 0.0;
             const double *ya = buf + g * YS + j;
             const double *mb = sMr + g * YS + j;
-#pragma unroll 2
+#pragma unroll kGemmUnroll
             for (int u = 0; u < KP / 4; ++u) {
                 double a[kMT], b[NT];
 #pragma unroll
@@ -457,9 +472,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
             for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
                 for (int nt2 = 0; nt2 < NT; ++nt2) {
-                    double *zc = buf + (nt2 * 8 + 2 * j) * kZS + mt * 8 + g;
-                    zc[0] = acc[mt][nt2][0];
-                    zc[kZS] = acc[mt][nt2][1];
+                    const int c0 = nt2 * 8 + 2 * j;
+                    buf[zt_index(c0, mt * 8 + g)] = acc[mt][nt2][0];
+                    buf[zt_index(c0 + 1, mt * 8 + g)] = acc[mt][nt2][1];
                 }
             __syncwarp();
         }
@@ -469,7 +484,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
         double val = 0.0;
         {
             Elem v;
-            v.col = buf + et;
+            v.zt = buf;
+            v.ind = et;
             v.idx = perm;
             for (int gi = 0; gi < P.st.ngroups; ++gi) {
                 const GroupDesc &g = P.st.g[gi];
@@ -531,7 +547,10 @@ __host__ __device__ constexpr int sep_lanes(int d)
 
 constexpr int kSepThreads = 256;
 
-template <int D> __global__ void __launch_bounds__(kSepThreads) cec14_sep_kernel(const __grid_constant__ StageParams P)
+#ifndef PGC_SEP_MINB
+#define PGC_SEP_MINB 2
+#endif
+template <int D> __global__ void __launch_bounds__(kSepThreads, PGC_SEP_MINB) cec14_sep_kernel(const __grid_constant__ StageParams P)
 {
     static_assert(D % 2 == 0, "rows are fetched in 16-byte chunks");
     constexpr int CH = D / 2, G = sep_lanes(D), ROWS = 32 / G, PASS = (CH + G - 1) / G;
@@ -575,13 +594,13 @@ template <int D> __global__ void __launch_bounds__(kSepThreads) cec14_sep_kernel
                 w += d0 * d0 + d1 * d1;                                             // cf_cal weight, :1330-1332
                 const double z0 = d0 * pre_rate * rate, z1 = d1 * pre_rate * rate;
                 if (prim == P_RASTRIGIN) {
-                    const double a = rastrigin_term(z0), b = rastrigin_term(z1);
+                    const double a = rastrigin_term<true>(z0), b = rastrigin_term<true>(z1);
                     s += a;
                     s += b;
                 } else if (prim == P_SCHWEFEL) {
                     double s0, p0, s1, p1;
-                    schwefel_term(z0, inv_n, s0, p0);
-                    schwefel_term(z1, inv_n, s1, p1);
+                    schwefel_term<true>(z0, inv_n, s0, p0);
+                    schwefel_term<true>(z1, inv_n, s1, p1);
                     s -= s0;
                     s += p0;
                     s -= s1;
