@@ -83,11 +83,10 @@ struct Elem {
     int ind;           // this lane's individual
     const int *idx;    // may be nullptr
     int off;
-    double rate;
-    __device__ __forceinline__ double operator()(int j) const
+    __device__ __forceinline__ double operator()(int j) const // zT already carries the group's own sh_rate
     {
         const int jj = idx ? idx[off + j] : off + j;
-        return zt[zt_index(jj, ind)] * rate;
+        return zt[zt_index(jj, ind)];
     }
 };
 
@@ -283,17 +282,17 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
                 const double zj = v(j) + 1.0, zn = v(jn) + 1.0;
                 const double t1 = zj * zj - zn, t2 = zj - 1.0;
                 const double temp = 100.0 * t1 * t1 + t2 * t2;
-                return (temp * temp) / 4000.0 - cos_theta(temp) + 1.0;
+                return (temp * temp) * 2.5e-4 - cos_theta(temp) + 1.0; // "/ 4000.0" as a multiplication (<= 1 ulp apart)
             }));
         case P_ESCAFFER6: // :727-736 (cyclic last term)
             return pair_add(ordered_sum(lo, hi, [&](int j) {
                 const int jn = (j + 1 == n) ? 0 : j + 1;
                 const double a = v(j), b = v(jn);
                 const double ss = a * a + b * b;
-                double t1 = sin_theta(sqrt(ss));
-                t1 = t1 * t1;
+                // sin^2(w) - 0.5 = -0.5 cos(2 w), 2 w = sqrt(4 ss); the quotient through a Newton reciprocal (~1 ulp)
+                const double c2 = cos_theta(sqrt(4.0 * ss));
                 const double t2 = 1.0 + 0.001 * ss;
-                return 0.5 + (t1 - 0.5) / (t2 * t2);
+                return 0.5 - (0.5 * c2) * fast_rcp(t2 * t2);
             }));
         default: return 0.0;
     }
@@ -317,7 +316,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
     double *sMr = reinterpret_cast<double *>(smem_raw);
     double *sBuf = sMr + MR_ELEMS;
     double *sOs = sBuf + kWarps * WB;
-    int *sPerm = reinterpret_cast<int *>(sOs + D);
+    double *sRate = sOs + D; // per coordinate of z: the sh_rate of the group that reads it (hybrids; 1.0 otherwise)
+    int *sPerm = reinterpret_cast<int *>(sRate + DP);
 
     // ---- per-CTA preload: rotation image (built on the host), shift, permutation -----------------------------
     if (ROT) {
@@ -329,7 +329,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
         sOs[i] = P.os[i];
         sPerm[i] = P.perm ? P.perm[i] : i;
     }
+    bool unit_rate = true; // every group scale is 1.0 (all basic functions): skip the multiplies altogether
+    for (int gi = 0; gi < P.st.ngroups; ++gi) unit_rate = unit_rate && P.st.g[gi].rate == 1.0;
+    for (int i = threadIdx.x; i < DP; i += blockDim.x) sRate[i] = 1.0;
     __syncthreads();
+    if (!unit_rate) {
+        for (int gi = 0; gi < P.st.ngroups; ++gi) {
+            const GroupDesc &g = P.st.g[gi];
+            for (int j = threadIdx.x; j < g.len; j += blockDim.x) sRate[P.st.permute ? sPerm[g.off + j] : g.off + j] = g.rate;
+        }
+        __syncthreads();
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *buf = sBuf + warp * WB;
@@ -473,12 +483,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
 #pragma unroll
                 for (int nt2 = 0; nt2 < NT; ++nt2) {
                     const int c0 = nt2 * 8 + 2 * j;
-                    buf[zt_index(c0, mt * 8 + g)] = acc[mt][nt2][0];
-                    buf[zt_index(c0 + 1, mt * 8 + g)] = acc[mt][nt2][1];
+                    double z0 = acc[mt][nt2][0], z1 = acc[mt][nt2][1];
+                    if (!unit_rate) { // the primitive's own sh_rate inside a hybrid (:381 etc. with s_flag = r_flag = 0)
+                        z0 *= sRate[c0];
+                        z1 *= sRate[c0 + 1];
+                    }
+                    buf[zt_index(c0, mt * 8 + g)] = z0;
+                    buf[zt_index(c0 + 1, mt * 8 + g)] = z1;
                 }
             __syncwarp();
         }
 
+        if (!ROT && !unit_rate) { // un-rotated hybrid (not in the CEC2014 recipes; kept for completeness)
+            for (int j = eq; j < D; j += kLPI) buf[zt_index(j, et)] *= sRate[j];
+            __syncwarp();
+        }
         if (P.prof) tp5 = clock64();
         // ---- E: primitives on z (kLPI lanes per individual) -------------------------------------------------------
         double val = 0.0;
@@ -490,7 +509,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
             for (int gi = 0; gi < P.st.ngroups; ++gi) {
                 const GroupDesc &g = P.st.g[gi];
                 v.off = g.off;
-                v.rate = g.rate;
                 val += eval_group(g, v, P.table, eq);
             }
         }
@@ -702,7 +720,7 @@ template <int D, bool ROT> size_t stage_smem_bytes()
 {
     constexpr int DP = pad8(D);
     constexpr int YS = ystride(D);
-    return sizeof(double) * ((ROT ? DP * YS : 0) + kWarps * warp_buf_elems(D) + D) + sizeof(int) * D + 16;
+    return sizeof(double) * ((ROT ? DP * YS : 0) + kWarps * warp_buf_elems(D) + D + DP) + sizeof(int) * D + 16;
 }
 
 template <int D, bool ROT> int launch_stage(pgc_ctx *ctx, const StageParams &sp, cudaStream_t stream)
