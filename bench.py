@@ -313,12 +313,12 @@ def run_native(args):
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": STAGE_DRAM_BYTES,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one rotated stage launch (1 Mi x 100), ncu --set full, "
-                                     "profiles/r1h_stage_kernel_ncu_full.csv; algorithmic bytes of that launch = 8*(100+1)*2^20 = 8.47e8",
+                                     "profiles/r1r_stage_kernel_ncu_full.csv (839.0 MB read + 6.3-7.4 MB written); algorithmic bytes of that launch = 8*(100+1)*2^20 = 8.47e8",
                      "peak_source": "pgc_measure_fp64_peak (DFMA loop, this run); MEASURED_PEAKS.json has no FP64 figure",
                      "dmma_probe_tflops": fp64_mma_peak,
                      "rotation_only_frac": rot_flops_step / step_s_rank / 1e12 / fp64_peak,
                      "hbm_gbs_achieved": sum(w[2] for w in work) * n / step_s_rank / 1e9, "hbm_peak_gbs": hbm_peak,
-                     "note": "aggregate over the 54 launches of one step; per-function split in per_function"},
+                     "note": "aggregate over the 62 launches of one step (50 rotated stage + 4 separable + 8 combine); per-function split in per_function"},
         # the same step against the driver-measured HBM copy bandwidth (MEASURED_PEAKS.json), in the contract's own vocabulary:
         # far below 1 because the step is bound by the FP64 pipe, not by memory (roofline above)
         "roofline_hbm": {"bound": "hbm", "achieved": sum(w[2] for w in work) * n / step_s_rank / 1e9, "peak": hbm_peak, "unit": "GB/s",

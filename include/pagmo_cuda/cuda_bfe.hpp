@@ -109,9 +109,31 @@ public:
         check(pgc_problem_nx(m_prob, &m_nx), "pgc_problem_nx");
         check(pgc_problem_nf(m_prob, &m_nf), "pgc_problem_nf");
     }
+    // meta-problem over another device problem (pgc_problem_translate / pgc_problem_decompose): kind = PGC_TRANSLATE with
+    // a = translation, or PGC_DECOMPOSE with a = weight, b = reference point.  The wrapper keeps the inner handle alive.
+    problem_handle(std::shared_ptr<problem_handle> inner, int kind, pagmo::vector_double a, pagmo::vector_double b, int method)
+        : m_ctx(inner->m_ctx), m_device(inner->m_device), m_inner(std::move(inner)), m_meta_kind(kind), m_meta_a(std::move(a)),
+          m_meta_b(std::move(b)), m_meta_method(method)
+    {
+        std::lock_guard<std::mutex> lk(device_mutex(m_device));
+        if (kind == PGC_TRANSLATE) {
+            check(pgc_problem_translate(m_inner->m_prob, m_meta_a.data(), m_meta_a.size(), &m_prob), "pgc_problem_translate");
+        } else {
+            if (m_meta_b.size() != m_meta_a.size()) {
+                pagmo_throw(std::invalid_argument,
+                            "Reference point size must be equal to the number of objectives. The size of the reference point is "
+                                + std::to_string(m_meta_b.size()) + " while the problem has " + std::to_string(m_inner->nf())
+                                + " objectives");
+            }
+            check(pgc_problem_decompose(m_inner->m_prob, m_meta_a.data(), m_meta_b.data(), m_meta_a.size(), method, 0, &m_prob),
+                  "pgc_problem_decompose");
+        }
+        check(pgc_problem_nx(m_prob, &m_nx), "pgc_problem_nx");
+        check(pgc_problem_nf(m_prob, &m_nf), "pgc_problem_nf");
+    }
     ~problem_handle()
     {
-        pgc_problem_destroy(m_prob);
+        pgc_problem_destroy(m_prob); // a wrapper first, then (member order) its inner handle
     }
     problem_handle(const problem_handle &) = delete;
     problem_handle &operator=(const problem_handle &) = delete;
@@ -125,7 +147,10 @@ public:
     {
         std::lock_guard<std::mutex> lk(m_twin_mtx);
         auto &slot = m_twins[device];
-        if (!slot) slot = std::make_shared<problem_handle>(device, m_desc);
+        if (!slot) {
+            slot = m_inner ? std::make_shared<problem_handle>(m_inner->twin_on(device), m_meta_kind, m_meta_a, m_meta_b, m_meta_method)
+                           : std::make_shared<problem_handle>(device, m_desc);
+        }
         return slot;
     }
 
@@ -201,6 +226,10 @@ private:
     pgc_problem_desc m_desc{};
     std::vector<double> m_rotation, m_shift;
     std::vector<int32_t> m_shuffle;
+    std::shared_ptr<problem_handle> m_inner; // meta-problems only
+    int m_meta_kind = 0;
+    pagmo::vector_double m_meta_a, m_meta_b;
+    int m_meta_method = 0;
     pgc_problem *m_prob = nullptr;
     std::size_t m_nx = 0, m_nf = 0;
     mutable std::mutex m_twin_mtx;
@@ -446,6 +475,64 @@ private:
     unsigned m_atoms;
 };
 
+// pagmo::translate on the device (reference include/pagmo/problems/translate.hpp, src/problems/translate.cpp:100-153): the
+// inner problem is one of the CUDA UDPs above (or another cuda_translate); fitness(x) = inner.fitness(x - translation), bounds
+// = inner bounds + translation.  The stock pagmo::translate{cuda_udp, t} works too (it de-shifts on the host and calls the inner
+// batch_fitness); this one keeps the de-shifting on the device, so a device-resident generation loop never leaves it.
+class cuda_translate : public cuda_udp_base
+{
+public:
+    cuda_translate() = default; // like every UDP: default-constructible; unusable until assigned from a constructed one
+    template <typename T>
+    cuda_translate(const T &inner, const pagmo::vector_double &translation) : m_translation(translation)
+    {
+        m_device = inner.device();
+        m_handle = std::make_shared<detail::problem_handle>(inner.shared_handle(), static_cast<int>(PGC_TRANSLATE), translation,
+                                                            pagmo::vector_double{}, 0);
+    }
+    const pagmo::vector_double &get_translation() const // translate.hpp: get_translation()
+    {
+        return m_translation;
+    }
+
+private:
+    pagmo::vector_double m_translation;
+};
+
+// pagmo::decompose on the device (reference include/pagmo/problems/decompose.hpp, src/problems/decompose.cpp:66-154;
+// decompose_objectives, src/utils/multi_objective.cpp:582-638).  Same constructor arguments and checks as the reference;
+// adapt_ideal = true is refused: the reference moves z after every single fitness call, in call order.
+class cuda_decompose : public cuda_udp_base
+{
+public:
+    cuda_decompose() = default;
+    template <typename T>
+    cuda_decompose(const T &inner, const pagmo::vector_double &weight, const pagmo::vector_double &z,
+                   const std::string &method = "weighted", bool adapt_ideal = false)
+        : m_weight(weight), m_z(z), m_method(method)
+    {
+        if (method != "weighted" && method != "tchebycheff" && method != "bi") { // decompose.cpp:80-83
+            pagmo_throw(std::invalid_argument, "Decomposition method requested is: " + method
+                                                   + " while only one of ['weighted', 'tchebycheff', 'bi'] are allowed");
+        }
+        if (adapt_ideal) {
+            pagmo_throw(std::invalid_argument, "cuda_decompose: adapt_ideal is a sequential semantic (decompose.cpp:143-149: z moves "
+                                               "after every fitness call); it is not available on the batch path");
+        }
+        m_device = inner.device();
+        const int code = method == "weighted" ? PGC_DECOMPOSE_WEIGHTED : method == "tchebycheff" ? PGC_DECOMPOSE_TCHEBYCHEFF : PGC_DECOMPOSE_BI;
+        m_handle = std::make_shared<detail::problem_handle>(inner.shared_handle(), static_cast<int>(PGC_DECOMPOSE), weight, z, code);
+    }
+    pagmo::vector_double get_z() const // decompose.cpp:208-211
+    {
+        return m_z;
+    }
+
+private:
+    pagmo::vector_double m_weight, m_z;
+    std::string m_method;
+};
+
 namespace detail
 {
 // The device problem behind a pagmo::problem: (1) a CUDA-backed UDP -> its own handle; (2) a stock pagmo UDP whose parameters
@@ -468,6 +555,8 @@ public:
         PGC_OWN_UDP(cuda_dtlz)
         PGC_OWN_UDP(cuda_wfg)
         PGC_OWN_UDP(cuda_lennard_jones)
+        PGC_OWN_UDP(cuda_translate)
+        PGC_OWN_UDP(cuda_decompose)
 #undef PGC_OWN_UDP
         // stock zdt / dtlz: the problem id is only visible through get_name() ("ZDT3", "DTLZ2": zdt.cpp:161-164,
         // dtlz.cpp:170-173); dtlz4's alpha is private and cannot be recovered; so is wfg's dim_k

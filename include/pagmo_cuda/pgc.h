@@ -49,8 +49,14 @@ typedef enum pgc_family {
     PGC_ZDT = 8,           /* src/problems/zdt.cpp:233-356 */
     PGC_DTLZ = 9,          /* src/problems/dtlz.cpp:258-409 */
     PGC_WFG = 10,          /* src/problems/wfg.cpp:304-1066 */
-    PGC_LENNARD_JONES = 11 /* src/problems/lennard_jones.cpp:72-92 */
+    PGC_LENNARD_JONES = 11, /* src/problems/lennard_jones.cpp:72-92 */
+    /* meta-problems: created by pgc_problem_translate / pgc_problem_decompose only */
+    PGC_TRANSLATE = 12, /* src/problems/translate.cpp:100-153 */
+    PGC_DECOMPOSE = 13  /* src/problems/decompose.cpp:139-154 */
 } pgc_family;
+
+/* decompose_objectives methods (src/utils/multi_objective.cpp:603-632) */
+typedef enum pgc_decompose_method { PGC_DECOMPOSE_WEIGHTED = 0, PGC_DECOMPOSE_TCHEBYCHEFF = 1, PGC_DECOMPOSE_BI = 2 } pgc_decompose_method;
 
 /* POD description of a UDP.  Mirrors the constructor arguments of the reference UDPs plus, for the CEC
  * suites, the data tables the reference keeps in private members (cec2014.hpp:227-236).
@@ -107,6 +113,18 @@ PGC_API int pgc_problem_name(const pgc_problem *prob, char *buf, size_t buflen);
  * (roofline bookkeeping for bench.py). */
 PGC_API int pgc_problem_work(const pgc_problem *prob, double *flops_per_eval, double *transcendentals_per_eval,
                      double *bytes_per_eval);
+
+/* Meta-problems over an existing device problem.  `inner` is borrowed and must outlive the wrapper; the
+ * wrapper evaluates through every entry point that takes a pgc_problem (pgc_eval_*, pgc_*_evolve_*, ...).
+ *   translate (src/problems/translate.cpp:83-87,100-153,175-181): fitness(x) = inner.fitness(x - translation); the bounds
+ *     are the inner bounds + translation; len must equal inner nx ("Length of shift vector is: ...").
+ *   decompose (src/problems/decompose.cpp:66-124,139-154; decompose_objectives, src/utils/multi_objective.cpp:582-638):
+ *     one objective = weighted / tchebycheff / bi decomposition of the inner objectives; the constructor's checks (>= 2
+ *     objectives, sizes, finite values, weights >= 0 summing to 1 within 1e-8) fail with PGC_ERR_INVALID_ARGUMENT and the
+ *     reference's messages.  adapt_ideal != 0 is refused (PGC_ERR_UNSUPPORTED): the reference adapts z call by call. */
+PGC_API int pgc_problem_translate(pgc_problem *inner, const double *translation, size_t len, pgc_problem **out);
+PGC_API int pgc_problem_decompose(pgc_problem *inner, const double *weight, const double *z, size_t len, int method /* pgc_decompose_method */,
+                                  int adapt_ideal, pgc_problem **out);
 
 /* ---- batch fitness evaluation ------------------------------------------------------------------------
  * Stand-in for `UDBFE::operator()(const problem&, const vector_double& dvs)` (bfe.hpp:119, bfe.cpp:91-110,

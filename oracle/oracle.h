@@ -41,6 +41,11 @@ int oracle_dtlz_fitness(unsigned id, const double *x, size_t N, size_t M, unsign
 int oracle_zdt_batch(unsigned id, const double *xs, size_t n, size_t N, double *fs);
 int oracle_dtlz_batch(unsigned id, const double *xs, size_t n, size_t N, size_t M, unsigned alpha, double *fs);
 
+/* ---- meta-problems (restate_meta.c): translate.cpp:137-150, multi_objective.cpp:582-638 (method 0 weighted, 1 tchebycheff, 2 bi) ---- */
+int oracle_translate_rows(const double *xs, size_t n, size_t nx, const double *t, double *out);
+int oracle_decompose_objectives(const double *f, size_t m, const double *weight, const double *ref_point, int method, double *out);
+int oracle_decompose_rows(const double *fs, size_t n, size_t m, const double *weight, const double *ref_point, int method, double *out);
+
 /* ---- Lennard-Jones (restate_lj.c) ---- */
 int oracle_lj_fitness(unsigned atoms, const double *x, double *f);
 int oracle_lj_batch(unsigned atoms, const double *xs, size_t n, double *fs);

@@ -128,6 +128,25 @@ class Oracle:
             raise ValueError(f"oracle_wfg_batch: invalid WFG{prob_id} configuration (dim_dvs={d}, dim_obj={dim_obj}, dim_k={dim_k})")
         return out
 
+    def translate_rows(self, xs: np.ndarray, t: np.ndarray) -> np.ndarray:
+        """translate::batch_fitness de-shifting (translate.cpp:137-150)."""
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        out = np.empty_like(xs)
+        self.lib.oracle_translate_rows(_dp(xs), C.c_size_t(xs.shape[0]), C.c_size_t(xs.shape[1]), _dp(t), _dp(out))
+        return out
+
+    def decompose_rows(self, fs: np.ndarray, weight, z, method: str) -> np.ndarray:
+        """decompose_objectives per row (multi_objective.cpp:582-638)."""
+        fs = np.ascontiguousarray(fs, dtype=np.float64)
+        w = np.ascontiguousarray(weight, dtype=np.float64)
+        zz = np.ascontiguousarray(z, dtype=np.float64)
+        out = np.empty(fs.shape[0])
+        if self.lib.oracle_decompose_rows(_dp(fs), C.c_size_t(fs.shape[0]), C.c_size_t(fs.shape[1]), _dp(w), _dp(zz),
+                                          C.c_int({"weighted": 0, "tchebycheff": 1, "bi": 2}[method]), _dp(out)):
+            raise ValueError("oracle_decompose_rows failed")
+        return out
+
     def lennard_jones(self, atoms: int, xs: np.ndarray) -> np.ndarray:
         xs = np.ascontiguousarray(xs, dtype=np.float64)
         out = np.empty(xs.shape[0])
@@ -492,6 +511,9 @@ class Reference:
             getattr(L, fn).argtypes = [C.c_void_p]
         L.ref_problem_destroy.restype = None
         L.ref_problem_bounds.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        L.ref_problem_translate.argtypes = [C.c_void_p, c_double_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.ref_problem_decompose.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_size_t, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.ref_decompose_objectives.argtypes = [c_double_p, c_double_p, c_double_p, C.c_size_t, C.c_char_p, C.POINTER(C.c_double)]
         L.ref_problem_name.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.ref_problem_fitness.argtypes = [C.c_void_p, c_double_p, c_double_p]
         L.ref_problem_fitness_loop.argtypes = [C.c_void_p, c_double_p, C.c_size_t, c_double_p]
@@ -508,6 +530,30 @@ class Reference:
         self._check(self.lib.ref_problem_create(family.encode(), C.c_uint(p0), C.c_uint(p1), C.c_uint(p2), C.c_uint(p3),
                                                 C.byref(h)))
         return RefProblem(self, h)
+
+    def translate(self, inner: RefProblem, t) -> RefProblem:
+        """pagmo::problem{pagmo::translate{inner, t}}"""
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        h = C.c_void_p()
+        self._check(self.lib.ref_problem_translate(inner._h, _dp(t), C.c_size_t(t.size), C.byref(h)))
+        return RefProblem(self, h)
+
+    def decompose(self, inner: RefProblem, weight, z, method: str = "weighted", adapt_ideal: bool = False) -> RefProblem:
+        """pagmo::problem{pagmo::decompose{inner, weight, z, method, adapt_ideal}}"""
+        w = np.ascontiguousarray(weight, dtype=np.float64)
+        zz = np.ascontiguousarray(z, dtype=np.float64)
+        h = C.c_void_p()
+        self._check(self.lib.ref_problem_decompose(inner._h, _dp(w), _dp(zz), C.c_size_t(w.size), method.encode(),
+                                                   C.c_int(int(adapt_ideal)), C.byref(h)))
+        return RefProblem(self, h)
+
+    def decompose_objectives(self, f, weight, z, method: str) -> float:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        w = np.ascontiguousarray(weight, dtype=np.float64)
+        zz = np.ascontiguousarray(z, dtype=np.float64)
+        out = C.c_double()
+        self._check(self.lib.ref_decompose_objectives(_dp(f), _dp(w), _dp(zz), C.c_size_t(f.size), method.encode(), C.byref(out)))
+        return out.value
 
     def cec2014_tables(self, func: int, dim: int):
         mr = np.empty(CEC_NCOMP * dim * dim)

@@ -14,12 +14,14 @@
 #include <pagmo/problems/ackley.hpp>
 #include <pagmo/problems/cec2013.hpp>
 #include <pagmo/problems/cec2014.hpp>
+#include <pagmo/problems/decompose.hpp>
 #include <pagmo/problems/dtlz.hpp>
 #include <pagmo/problems/griewank.hpp>
 #include <pagmo/problems/lennard_jones.hpp>
 #include <pagmo/problems/rastrigin.hpp>
 #include <pagmo/problems/rosenbrock.hpp>
 #include <pagmo/problems/schwefel.hpp>
+#include <pagmo/problems/translate.hpp>
 #include <pagmo/problems/wfg.hpp>
 #include <pagmo/problems/zdt.hpp>
 #include <pagmo/types.hpp>
@@ -103,6 +105,28 @@ int ref_problem_create(const char *family, unsigned p0, unsigned p1, unsigned p2
         else if (fam == "lennard_jones") pr = pagmo::problem{pagmo::lennard_jones{p0}};
         else throw std::invalid_argument("ref_problem_create: unknown family '" + fam + "'");
         *out = new ref_problem{std::move(pr)};
+    });
+}
+
+int ref_problem_translate(const ref_problem *inner, const double *t, size_t len, ref_problem **out)
+{
+    return guarded([&] { *out = new ref_problem{pagmo::problem{pagmo::translate{inner->prob, pagmo::vector_double(t, t + len)}}}; });
+}
+
+int ref_problem_decompose(const ref_problem *inner, const double *w, const double *z, size_t len, const char *method, int adapt_ideal,
+                          ref_problem **out)
+{
+    return guarded([&] {
+        *out = new ref_problem{pagmo::problem{pagmo::decompose{inner->prob, pagmo::vector_double(w, w + len),
+                                                               pagmo::vector_double(z, z + len), method, adapt_ideal != 0}}};
+    });
+}
+
+int ref_decompose_objectives(const double *f, const double *w, const double *z, size_t m, const char *method, double *out)
+{
+    return guarded([&] {
+        *out = pagmo::decompose_objectives(pagmo::vector_double(f, f + m), pagmo::vector_double(w, w + m),
+                                           pagmo::vector_double(z, z + m), method)[0];
     });
 }
 

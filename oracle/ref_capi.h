@@ -21,6 +21,13 @@ const char *ref_last_error(void);
  *         "dtlz" (p0=prob_id,p1=dim,p2=fdim,p3=alpha), "wfg" (p0=prob_id,p1=dim_dvs,p2=dim_obj,p3=dim_k),
  *         "lennard_jones" (p0=atoms).  Wraps `pagmo::problem{udp}` (problem.cpp:154-242). */
 int ref_problem_create(const char *family, unsigned p0, unsigned p1, unsigned p2, unsigned p3, ref_problem **out);
+/* pagmo::problem{pagmo::translate{inner, t}} (translate.hpp) and pagmo::problem{pagmo::decompose{inner, w, z, method, adapt_ideal}}
+ * (decompose.hpp); the inner problem is copied, as the reference's meta-problems do. */
+int ref_problem_translate(const ref_problem *inner, const double *t, size_t len, ref_problem **out);
+int ref_problem_decompose(const ref_problem *inner, const double *w, const double *z, size_t len, const char *method, int adapt_ideal,
+                          ref_problem **out);
+/* pagmo::decompose_objectives (utils/multi_objective.cpp:582-638) */
+int ref_decompose_objectives(const double *f, const double *w, const double *z, size_t m, const char *method, double *out);
 void ref_problem_destroy(ref_problem *p);
 size_t ref_problem_nx(const ref_problem *p);
 size_t ref_problem_nf(const ref_problem *p);

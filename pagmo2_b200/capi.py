@@ -116,6 +116,8 @@ def lib():
         L.pgc_ctx_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.pgc_problem_create.argtypes = [vp, C.POINTER(ProblemDesc), C.POINTER(vp)]
         L.pgc_problem_destroy.argtypes = [vp]
+        L.pgc_problem_translate.argtypes = [vp, dp, sz, C.POINTER(vp)]
+        L.pgc_problem_decompose.argtypes = [vp, dp, dp, sz, C.c_int, C.c_int, C.POINTER(vp)]
         for fn in ("pgc_problem_nx", "pgc_problem_nobj", "pgc_problem_nf"):
             getattr(L, fn).argtypes = [vp, C.POINTER(sz)]
         L.pgc_problem_bounds.argtypes = [vp, dp, dp]
@@ -359,6 +361,9 @@ class Context:
         return t.value
 
 
+DECOMPOSE_METHODS = {"weighted": 0, "tchebycheff": 1, "bi": 2}
+
+
 class Problem:
     """Handle on a device-side UDP (pgc_problem).  Mirrors the accessors of pagmo::problem."""
 
@@ -379,10 +384,44 @@ class Problem:
             d.shuffle, d.shuffle_len = p.ctypes.data_as(C.POINTER(C.c_int32)), p.size
         self._h = C.c_void_p()
         check(lib().pgc_problem_create(ctx._h, C.byref(d), C.byref(self._h)))
+        self._inner = None
+        self._read_sizes()
+
+    def _read_sizes(self):
         n = C.c_size_t()
         check(lib().pgc_problem_nx(self._h, C.byref(n))); self.nx = n.value
         check(lib().pgc_problem_nobj(self._h, C.byref(n))); self.nobj = n.value
         check(lib().pgc_problem_nf(self._h, C.byref(n))); self.nf = n.value
+
+    @classmethod
+    def _wrap(cls, inner: "Problem", handle) -> "Problem":
+        p = cls.__new__(cls)
+        p.ctx, p._h, p._inner = inner.ctx, handle, inner  # the wrapper borrows the inner problem: keep it alive
+        p._read_sizes()
+        return p
+
+    def translate(self, translation) -> "Problem":
+        """pagmo::translate{self, translation} on the device (translate.cpp:100-153)."""
+        t = np.ascontiguousarray(translation, dtype=np.float64)
+        h = C.c_void_p()
+        check(lib().pgc_problem_translate(self._h, t.ctypes.data_as(C.POINTER(C.c_double)), t.size, C.byref(h)))
+        return Problem._wrap(self, h)
+
+    def decompose(self, weight, z, method: str = "weighted", adapt_ideal: bool = False) -> "Problem":
+        """pagmo::decompose{self, weight, z, method, adapt_ideal} on the device (decompose.cpp:66-154)."""
+        if method not in DECOMPOSE_METHODS:
+            raise PgcError(-1, f"Decomposition method requested is: {method} while only one of ['weighted', 'tchebycheff', 'bi'] "
+                               "are allowed")
+        w = np.ascontiguousarray(weight, dtype=np.float64)
+        zz = np.ascontiguousarray(z, dtype=np.float64)
+        if zz.size != w.size:
+            raise PgcError(-1, "Reference point size must be equal to the number of objectives. The size of the reference point is "
+                               f"{zz.size} while the problem has {self.nobj} objectives")
+        h = C.c_void_p()
+        dp = C.POINTER(C.c_double)
+        check(lib().pgc_problem_decompose(self._h, w.ctypes.data_as(dp), zz.ctypes.data_as(dp), w.size, DECOMPOSE_METHODS[method],
+                                          int(adapt_ideal), C.byref(h)))
+        return Problem._wrap(self, h)
 
     def close(self):
         if self._h:

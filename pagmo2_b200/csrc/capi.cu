@@ -213,6 +213,8 @@ int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d
         case PGC_DTLZ:
         case PGC_WFG: return mo_eval(p, d_dvs, n, d_fvs, s);
         case PGC_LENNARD_JONES: return lj_eval(p, d_dvs, n, d_fvs, s);
+        case PGC_TRANSLATE:
+        case PGC_DECOMPOSE: return meta_eval(p, d_dvs, n, d_fvs, s);
         default: set_error("family %d has no device evaluator in this build", p->desc.family); return PGC_ERR_UNSUPPORTED;
     }
 }
@@ -386,10 +388,31 @@ int pgc_problem_destroy(pgc_problem *p)
     if (!p) return PGC_OK;
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
+    if (p->inner) { // meta-problem: its tables are the wrapped problem's
+        meta_destroy(p);
+        delete p;
+        return PGC_OK;
+    }
     cec2013_destroy(p);
     cec2014_destroy(p);
     delete p;
     return PGC_OK;
+}
+
+int pgc_problem_translate(pgc_problem *inner, const double *translation, size_t len, pgc_problem **out)
+{
+    return meta_create(inner, PGC_TRANSLATE, translation, nullptr, len, 0, out);
+}
+
+int pgc_problem_decompose(pgc_problem *inner, const double *weight, const double *z, size_t len, int method, int adapt_ideal,
+                          pgc_problem **out)
+{
+    if (adapt_ideal) {
+        set_error("pgc_problem_decompose: ideal-point adaptation updates z after every single fitness call in call order "
+                  "(decompose.cpp:143-149); the batch path does not reproduce that and there is no CPU fallback");
+        return PGC_ERR_UNSUPPORTED;
+    }
+    return meta_create(inner, PGC_DECOMPOSE, weight, z, len, method, out);
 }
 
 int pgc_problem_nx(const pgc_problem *p, size_t *nx)

@@ -134,6 +134,10 @@ struct pgc_problem {
     pgc::Cec2014Recipe cec14;
     pgc::Cec2013Plan *cec13 = nullptr;
     double flops_per_eval = 0, transc_per_eval = 0;
+    // meta-problems (meta.cu): the wrapped problem (borrowed), translation | weight+z on the device, decomposition method
+    pgc_problem *inner = nullptr;
+    double *d_meta = nullptr;
+    int meta_method = 0;
 };
 
 namespace pgc
@@ -152,6 +156,9 @@ void cec2014_destroy(pgc_problem *p);
 int cec2013_create(pgc_problem *p, const pgc_problem_desc *d);
 int cec2013_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
 void cec2013_destroy(pgc_problem *p);
+int meta_create(pgc_problem *inner, int family, const double *a, const double *b, size_t len, int method, pgc_problem **out);
+int meta_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t s);
+void meta_destroy(pgc_problem *p);
 int cec2014_phase_cycles(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, unsigned long long *out);
 int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, unsigned *d_rank, unsigned *d_dom_count, unsigned *d_order,
                 unsigned *d_front_off, unsigned *nfronts_out, cudaStream_t st, unsigned stop_after = 0, unsigned *d_key_out = nullptr);

@@ -20,6 +20,8 @@
 #include <pagmo/problem.hpp>
 #include <pagmo/algorithms/nsga2.hpp>
 #include <pagmo/problems/cec2014.hpp>
+#include <pagmo/problems/decompose.hpp>
+#include <pagmo/problems/translate.hpp>
 #include <pagmo/problems/dtlz.hpp>
 #include <pagmo/problems/lennard_jones.hpp>
 #include <pagmo/problems/rastrigin.hpp>
@@ -203,6 +205,50 @@ int main()
         const auto dvs = random_batch(lj, 100, 5);
         CHECK(max_rel(gpu(lj, dvs), cpu(lj, dvs)) <= 1e-10);
         CHECK(max_rel(gpu(ljc, dvs), cpu(lj, dvs)) <= 1e-10);
+    }
+
+    // ---- 3b'. meta-problems: cuda_translate / cuda_decompose against the stock pagmo::translate / pagmo::decompose ------------
+    {
+        pagmo::bfe gpu{cuda_bfe{}}, cpu{pagmo::thread_bfe{}};
+        const pagmo::vector_double t{0.1, -0.2, 0.3, 0.4, -0.5};
+        pagmo::problem ref{pagmo::translate{pagmo::rastrigin{5u}, t}}, twin{cuda_translate{cuda_simple<PGC_RASTRIGIN>{5u}, t}};
+        CHECK(twin.get_bounds() == ref.get_bounds());
+        CHECK(twin.get_name().find("[translated]") != std::string::npos);
+        const auto dvs = random_batch(ref, 300, 77);
+        CHECK(max_rel(gpu(twin, dvs), cpu(ref, dvs)) <= tol);
+        CHECK(max_rel(twin.batch_fitness(dvs), cpu(ref, dvs)) <= tol);
+        // the stock meta-problem over a CUDA UDP also runs (host de-shift + device batch_fitness, translate.cpp:118-153)
+        pagmo::problem mixed{pagmo::translate{cuda_simple<PGC_RASTRIGIN>{5u}, t}};
+        CHECK(max_rel(mixed.batch_fitness(dvs), cpu(ref, dvs)) <= tol);
+        bool threw = false;
+        try {
+            cuda_translate{cuda_simple<PGC_RASTRIGIN>{5u}, {1., 2.}};
+        } catch (const std::invalid_argument &) {
+            threw = true; // translate.cpp:83-87
+        }
+        CHECK(threw);
+        for (const char *method : {"weighted", "tchebycheff", "bi"}) {
+            const pagmo::vector_double w{0.3, 0.7}, z{0.1, -0.2};
+            pagmo::problem dref{pagmo::decompose{pagmo::zdt{1u, 30u}, w, z, method, false}};
+            pagmo::problem dtwin{cuda_decompose{cuda_zdt{1u, 30u}, w, z, method, false}};
+            CHECK(dtwin.get_nobj() == 1u && dtwin.get_bounds() == dref.get_bounds());
+            const auto xs = random_batch(dref, 200, 78);
+            CHECK(max_rel(gpu(dtwin, xs), cpu(dref, xs)) <= tol);
+        }
+        threw = false;
+        try {
+            cuda_decompose{cuda_zdt{1u, 30u}, {0.5, 0.6}, {0., 0.}};
+        } catch (const std::invalid_argument &) {
+            threw = true; // decompose.cpp:109-115
+        }
+        CHECK(threw);
+        threw = false;
+        try {
+            cuda_decompose{cuda_simple<PGC_RASTRIGIN>{5u}, {0.5, 0.5}, {0., 0.}};
+        } catch (const std::invalid_argument &) {
+            threw = true; // decompose.cpp:70-72
+        }
+        CHECK(threw);
     }
 
     // ---- 3c. CUDA UDAs behind pagmo::algorithm: evolve() keeps the population consistent and counts fevals like the reference ----

@@ -345,3 +345,50 @@ def test_nsga2_restatement_behaves(orc):
     assert x2.shape == x.shape and (x2 >= lb).all() and (x2 <= ub).all()
     assert np.array_equal(orc.zdt(1, x2), f2)
     assert g1.mean() < 0.5 * g0.mean()
+
+
+# ---------------------------------------------------------------- meta-problems: translate, decompose
+def test_decompose_objectives_known_answers(orc):
+    # tests/multi_objective.cpp:385-405 (BOOST_CHECK_CLOSE 1e-8 %)
+    w, z, f = np.array([0.5, 0.5]), np.zeros(2), np.array([[1.234, -1.345]])
+    assert orc.decompose_rows(f, w, z, "weighted")[0] == pytest.approx(f[0, 0] * 0.5 + f[0, 1] * 0.5, rel=1e-10)
+    assert orc.decompose_rows(f, w, z, "tchebycheff")[0] == pytest.approx(max(0.5 * abs(f[0, 0]), 0.5 * abs(f[0, 1])), rel=1e-10)
+    lnorm = np.sqrt(0.5)
+    il = w / lnorm
+    d1 = f[0] @ il
+    d2 = np.sqrt(np.sum((f[0] - d1 * il) ** 2))
+    assert orc.decompose_rows(f, w, z, "bi")[0] == pytest.approx(d1 + 5.0 * d2, rel=1e-10)
+
+
+def test_meta_restatement_is_bit_exact_vs_reference(orc, ref):
+    rng = np.random.default_rng(77)
+    # decompose_objectives on random objective vectors, incl. a zero weight (tchebycheff's 1e-4 substitution, :610)
+    for m in (2, 3, 5):
+        f = rng.normal(0, 3, (64, m))
+        z = rng.normal(0, 1, m)
+        for w in (rng.dirichlet(np.ones(m)), np.eye(m)[0]):
+            for method in ("weighted", "tchebycheff", "bi"):
+                got = orc.decompose_rows(f, w, z, method)
+                want = np.array([ref.decompose_objectives(fi, w, z, method) for fi in f])
+                assert np.array_equal(got, want), (m, method)
+    # decompose{zdt1} and decompose{dtlz2}: restated inner fitness + restated decomposition == reference fitness, bit for bit
+    xs = rng.uniform(0, 1, (32, 30))
+    inner = ref.problem("zdt", 1, 30)
+    for method in ("weighted", "tchebycheff", "bi"):
+        p = ref.decompose(inner, [0.3, 0.7], [0.1, -0.2], method)
+        assert p.nobj == 1 and p.nx == 30 and p.name.endswith("[decomposed]")
+        assert np.array_equal(p.fitness_loop(xs)[:, 0], orc.decompose_rows(orc.zdt(1, xs), [0.3, 0.7], [0.1, -0.2], method))
+    # translate{rastrigin}, translate{zdt1}: bounds move with the problem, fitness(x) = inner(x - t)
+    t = rng.uniform(-1, 1, 10)
+    inner = ref.problem("rastrigin", 10)
+    p = ref.translate(inner, t)
+    lb, ub = inner.bounds()
+    plb, pub = p.bounds()
+    assert np.array_equal(plb, lb + t) and np.array_equal(pub, ub + t) and p.name.endswith("[translated]")
+    xs = rng.uniform(-5, 5, (40, 10))
+    assert np.array_equal(p.fitness_loop(xs)[:, 0], orc.simple("rastrigin", orc.translate_rows(xs, t)))
+    assert np.array_equal(p.thread_bfe(xs, 2).reshape(-1), orc.simple("rastrigin", orc.translate_rows(xs, t)))
+    with pytest.raises(RuntimeError, match="Length of shift vector is: 2 while the problem dimension is: 10"):
+        ref.translate(inner, [1.0, 2.0])
+    with pytest.raises(RuntimeError, match="multi-objective"):
+        ref.decompose(inner, [0.5, 0.5], [0.0, 0.0])
