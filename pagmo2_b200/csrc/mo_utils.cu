@@ -16,12 +16,14 @@
 // Crowding distances are exact IEEE (same subtraction / division per element, objectives applied in order); the sort
 // inside a front is a stable segmented radix sort, which matches the reference's std::sort whenever the objective values
 // inside a front are distinct (the reference's order of ties is unspecified: SURVEY.md F5).
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 #include <vector>
 
@@ -170,93 +172,355 @@ template <int M> __device__ __forceinline__ bool dominates_rank(const unsigned *
     return strict && !worse;
 }
 
-// count pass on points sorted by the rank of their first objective: only positions up to the end of the run of equal first
-// ranks can hold dominators (half of the pair tests); CTAs issued largest first.  rs: ranks in sorted order, src: sorted -> original
+// ---- the level loop in SORTED space ----------------------------------------------------------------------------------------
+// The points are sorted by the dense rank of their first objective (stable: ties in index order) and the whole loop runs on
+// sorted positions; results go back to original indices at the end.  Two things follow:
+//   * a point at position p can only be dominated from positions up to the end of its own run of equal first ranks, so
+//     both the count pass and every peel pass stop there (half of the pair tests);
+//   * for a dominator candidate that lies BEFORE the run that holds the first point of the thread block, the first
+//     objective is already known to be strictly smaller: the pair test shrinks to "the other M-1 ranks are <=" - one
+//     compare for two objectives - and only the tiles that overlap the block's own runs pay for the full test.
+// To make whole tiles classifiable, every front is kept twice: in the reference's order (`order`, the output) and sorted
+// by position with each member's index in the front beside it (`pm_pos`, `pm_fpos`; the key of a point that joins the next
+// front is the largest such index among its dominators).
+struct SortedView {
+    const unsigned *rs;        // [n x m] dense ranks, rows in sorted order
+    const unsigned *src;       // sorted position -> original index
+    const unsigned *inv;       // original index -> sorted position
+    const unsigned *blk_lo;    // per block of kTP positions: start of the run of equal first ranks that holds its first point
+    const unsigned *blk_limit; //                             end (exclusive) of the run that holds its last point
+    unsigned *count, *rank, *key; // per sorted position
+    unsigned *cand;            // candidates of the level under construction (sorted positions) ...
+    unsigned long long *cand_key; // ... their ordering keys (key << 32 | original index) and rank rows, written by the thread that
+    unsigned *cand_rows;       //     found them, so that closing a level needs no dependent gathers
+    unsigned *order;           // fronts in the reference's order, as sorted positions
+    unsigned *pm_pos, *pm_fpos; // the same fronts, each sorted by position: position | index in the front
+    unsigned *pm_rows;         //   and the members' rank rows in that sequence: a peel tile is one coalesced load
+    unsigned *front_off;       // [n + 1] (output)
+    Meta *meta;
+    unsigned n;
+    int m;
+};
+// A level is a chain of dependent global-memory round trips (~1 us each) around very little arithmetic - with 300-400
+// fronts per sort that chain, not the pair tests, was the run time (20 us per peel launch, 10 us per order launch in
+// profiles/r1s_fnds_launches.txt).  Hence the redundant arrays above: every phase reads what it needs with independent,
+// coalesced loads, and `count != 0` doubles as "not yet in a front".
+
+template <int M> __device__ __forceinline__ bool dominates_tail(const unsigned *a, const unsigned *b) // a[0] < b[0] is known
+{
+    bool ok = true;
+#pragma unroll
+    for (int i = 1; i < M; ++i) ok &= a[i] <= b[i];
+    return ok;
+}
+
+template <int M> __global__ void block_runs_kernel(const unsigned *__restrict__ rs, unsigned n, unsigned *blk_lo, unsigned *blk_limit)
+{
+    const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned nblocks = (n + kTP - 1) / kTP;
+    if (b >= nblocks) return;
+    const unsigned first = b * kTP, last = min(n, (b + 1) * kTP) - 1;
+    const unsigned bottom = rs[static_cast<size_t>(first) * M], top = rs[static_cast<size_t>(last) * M];
+    unsigned lo = 0, hi = first; // first position whose first rank is >= bottom
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (rs[static_cast<size_t>(mid) * M] < bottom) lo = mid + 1;
+        else hi = mid;
+    }
+    blk_lo[b] = lo;
+    lo = last + 1, hi = n; // first position with a larger first rank than top
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (rs[static_cast<size_t>(mid) * M] <= top) lo = mid + 1;
+        else hi = mid;
+    }
+    blk_limit[b] = lo;
+}
+
+// count pass: count[p] = dominators of the point at position p; CTAs issued largest first
 template <int M>
-__global__ void __launch_bounds__(kTP) fnds_count_rank_kernel(const unsigned *__restrict__ rs, const unsigned *__restrict__ src, unsigned n,
-                                                              unsigned *count, unsigned *dom_count)
+__global__ void __launch_bounds__(kTP) fnds_count_sorted_kernel(SortedView V, unsigned *dom_count)
 {
     constexpr int m = M;
-    __shared__ unsigned tile[kTP * (M ? M : 1)];
-    __shared__ unsigned s_limit;
+    __shared__ unsigned tile[kTP * M];
     const unsigned b = gridDim.x - 1 - blockIdx.x;
     const unsigned q = b * kTP + threadIdx.x;
-    if (threadIdx.x == 0) {
-        const unsigned last = min(n, (b + 1) * kTP) - 1;
-        const unsigned top = rs[static_cast<size_t>(last) * m];
-        unsigned lo = last + 1, hi = n; // first position with a larger first rank
-        while (lo < hi) {
-            const unsigned mid = (lo + hi) >> 1;
-            if (rs[static_cast<size_t>(mid) * m] <= top) lo = mid + 1;
-            else hi = mid;
-        }
-        s_limit = lo;
-    }
-    unsigned rq[M ? M : 1];
+    const unsigned lo = V.blk_lo[b], limit = V.blk_limit[b];
+    unsigned rq[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) rq[i] = (q < n) ? rs[static_cast<size_t>(q) * m + i] : 0u;
-    __syncthreads();
-    const unsigned limit = s_limit;
+    for (int i = 0; i < M; ++i) rq[i] = (q < V.n) ? V.rs[static_cast<size_t>(q) * m + i] : 0u;
     unsigned c = 0;
     for (unsigned base = 0; base < limit; base += kTP) {
         const unsigned np = min(static_cast<unsigned>(kTP), limit - base);
-        for (unsigned e = threadIdx.x; e < np * m; e += kTP) tile[e] = rs[static_cast<size_t>(base) * m + e];
+        for (unsigned e = threadIdx.x; e < np * m; e += kTP) tile[e] = V.rs[static_cast<size_t>(base) * m + e];
         __syncthreads();
-        if (q < n) {
+        if (q < V.n) {
+            if (base + np <= lo) {
 #pragma unroll 8
-            for (unsigned t = 0; t < np; ++t) c += dominates_rank<M>(tile + t * M, rq) ? 1u : 0u;
+                for (unsigned t = 0; t < np; ++t) c += dominates_tail<M>(tile + t * M, rq) ? 1u : 0u;
+            } else {
+#pragma unroll 8
+                for (unsigned t = 0; t < np; ++t) c += dominates_rank<M>(tile + t * M, rq) ? 1u : 0u;
+            }
         }
         __syncthreads();
     }
-    if (q < n) {
-        const unsigned o = src[q];
-        count[o] = c;
-        if (dom_count) dom_count[o] = c;
+    if (q < V.n) {
+        V.count[q] = c;
+        if (dom_count) dom_count[V.src[q]] = c;
     }
 }
 
+// first level: the points without dominators, key 0 (front 0 is in index order, :228-233)
+__global__ void fnds_front0_sorted_kernel(SortedView V)
+{
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= V.n) return;
+    if (V.count[q] == 0) {
+        V.rank[q] = 0;
+        V.key[q] = 0;
+        const unsigned slot = atomicAdd(&V.meta->ncand, 1u);
+        V.cand[slot] = q;
+        V.cand_key[slot] = V.src[q];
+        for (int i = 0; i < V.m; ++i) V.cand_rows[static_cast<size_t>(slot) * V.m + i] = V.rs[static_cast<size_t>(q) * V.m + i];
+    } else {
+        V.rank[q] = kUnassigned;
+    }
+}
+
+// one block of kTP positions against front `level` (fs members at offset fo).  Data other CTAs wrote in the previous phase
+// is read with ld.global.cg (the cooperative kernel below keeps CTAs alive across levels).
 template <int M>
-__global__ void __launch_bounds__(kTP) fnds_peel_rank_kernel(const unsigned *__restrict__ r, unsigned n, const unsigned *__restrict__ order,
-                                                             unsigned *count, unsigned *rank, unsigned *key, unsigned *cand, Meta *meta)
+__device__ __forceinline__ void peel_block(const SortedView &V, unsigned b, unsigned fs, unsigned fo, unsigned level, unsigned *tileR,
+                                           unsigned *tileF)
 {
     constexpr int m = M;
-    __shared__ unsigned tile[kTP * (M ? M : 1)];
-    if (meta->overflow || meta->done) return;
-    const unsigned fs = meta->front_size, fo = meta->front_off, level = meta->level;
-    if (fs == 0) return;
-    const unsigned q = blockIdx.x * kTP + threadIdx.x;
-    const bool active = q < n && rank[q] == kUnassigned;
-    if (!__syncthreads_or(active)) return;
-    unsigned rq[M ? M : 1];
+    const unsigned q = b * kTP + threadIdx.x;
+    const unsigned left0 = q < V.n ? V.count[q] : 0u; // dominators not yet in a closed front; 0 = the point sits in a front
+    const unsigned lo = V.blk_lo[b], limit = V.blk_limit[b];
+    const unsigned srcq = q < V.n ? V.src[q] : 0u;
+    unsigned rq[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) rq[i] = active ? r[static_cast<size_t>(q) * m + i] : 0u;
+    for (int i = 0; i < M; ++i) rq[i] = q < V.n ? V.rs[static_cast<size_t>(q) * m + i] : 0u;
+    const bool active = left0 != 0;
+    if (!__syncthreads_or(active)) return;
     unsigned c = 0, mp = 0;
     for (unsigned base = 0; base < fs; base += kTP) {
         const unsigned np = min(static_cast<unsigned>(kTP), fs - base);
-        for (unsigned e = threadIdx.x; e < np * m; e += kTP) {
-            const unsigned t = e / m, i = e % m;
-            tile[e] = r[static_cast<size_t>(order[fo + base + t]) * m + i];
-        }
+        if (__ldcg(V.pm_pos + fo + base) >= limit) break; // this member and all later ones lie beyond the block's last run
+        const unsigned last_pos = __ldcg(V.pm_pos + fo + base + np - 1);
+        for (unsigned e = threadIdx.x; e < np * m; e += kTP) tileR[e] = __ldcg(V.pm_rows + static_cast<size_t>(fo + base) * m + e);
+        for (unsigned t = threadIdx.x; t < np; t += kTP) tileF[t] = __ldcg(V.pm_fpos + fo + base + t);
         __syncthreads();
         if (active) {
+            if (last_pos < lo) {
 #pragma unroll 4
-            for (unsigned t = 0; t < np; ++t)
-                if (dominates_rank<M>(tile + t * M, rq)) {
-                    ++c;
-                    mp = base + t; // positions ascend: the last hit is the maximum
-                }
+                for (unsigned t = 0; t < np; ++t)
+                    if (dominates_tail<M>(tileR + t * M, rq)) {
+                        ++c;
+                        mp = max(mp, tileF[t]);
+                    }
+            } else {
+#pragma unroll 4
+                for (unsigned t = 0; t < np; ++t)
+                    if (dominates_rank<M>(tileR + t * M, rq)) {
+                        ++c;
+                        mp = max(mp, tileF[t]);
+                    }
+            }
         }
         __syncthreads();
     }
     if (active && c) {
-        const unsigned left = count[q] - c;
-        count[q] = left;
+        const unsigned left = left0 - c;
+        V.count[q] = left;
         if (left == 0) {
-            rank[q] = level + 1;
-            key[q] = mp;
-            cand[atomicAdd(&meta->ncand, 1u)] = q;
+            V.rank[q] = level + 1;
+            V.key[q] = mp;
+            const unsigned slot = atomicAdd(&V.meta->ncand, 1u);
+            V.cand[slot] = q;
+            V.cand_key[slot] = (static_cast<unsigned long long>(mp) << 32) | srcq;
+#pragma unroll
+            for (int i = 0; i < M; ++i) V.cand_rows[static_cast<size_t>(slot) * m + i] = rq[i];
         }
     }
+}
+
+// close a level (one CTA): the candidates ordered by (key, original index) become the next front, stored in that order and,
+// beside it, sorted by position.  s_sort: kOrderCap entries, s_pos: 1024 entries of shared memory.
+__device__ void order_level(const SortedView &V, int first, unsigned long long *s_sort, unsigned *s_pos)
+{
+    Meta *meta = V.meta;
+    const unsigned C = __ldcg(&meta->ncand);
+    if (C > kOrderCap) {
+        if (threadIdx.x == 0) meta->overflow = 1;
+        return;
+    }
+    const unsigned fo = __ldcg(&meta->front_off), fs = __ldcg(&meta->front_size), lvl = __ldcg(&meta->level);
+    const unsigned off = first ? 0u : fo + fs;
+    if (C <= 1024u) {
+        // small levels (the common case): rank sorts - every candidate counts the candidates that precede it in either order
+        const int m = V.m;
+        for (unsigned i = threadIdx.x; i < C; i += blockDim.x) {
+            s_pos[i] = __ldcg(V.cand + i);
+            s_sort[i] = __ldcg(V.cand_key + i);
+        }
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < C; i += blockDim.x) {
+            const unsigned long long mine = s_sort[i];
+            const unsigned myp = s_pos[i];
+            unsigned row[kMaxM];
+            for (int k = 0; k < m; ++k) row[k] = __ldcg(V.cand_rows + static_cast<size_t>(i) * m + k);
+            unsigned before = 0, bp = 0;
+            for (unsigned j = 0; j < C; ++j) {
+                before += s_sort[j] < mine ? 1u : 0u; // (key, index) pairs are distinct
+                bp += s_pos[j] < myp ? 1u : 0u;
+            }
+            V.order[off + before] = myp;
+            V.pm_pos[off + bp] = myp;
+            V.pm_fpos[off + bp] = before;
+            for (int k = 0; k < m; ++k) V.pm_rows[static_cast<size_t>(off + bp) * m + k] = row[k];
+        }
+    } else {
+        unsigned P = 1;
+        while (P < C) P <<= 1;
+        auto bitonic = [&]() {
+            for (unsigned k = 2; k <= P; k <<= 1)
+                for (unsigned j = k >> 1; j > 0; j >>= 1) {
+                    for (unsigned i = threadIdx.x; i < P; i += blockDim.x) {
+                        const unsigned l = i ^ j;
+                        if (l > i) {
+                            const bool up = (i & k) == 0;
+                            const unsigned long long a = s_sort[i], bb = s_sort[l];
+                            if ((a > bb) == up) {
+                                s_sort[i] = bb;
+                                s_sort[l] = a;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+        };
+        for (unsigned i = threadIdx.x; i < P; i += blockDim.x) {
+            s_sort[i] = i < C ? __ldcg(V.cand_key + i) : ~0ull;
+        }
+        __syncthreads();
+        bitonic();
+        for (unsigned i = threadIdx.x; i < C; i += blockDim.x) {
+            const unsigned sp = V.inv[static_cast<unsigned>(s_sort[i] & 0xffffffffu)];
+            V.order[off + i] = sp;
+            s_sort[i] = (static_cast<unsigned long long>(sp) << 32) | i;
+        }
+        __syncthreads();
+        bitonic(); // the padding (~0) stays at the end
+        for (unsigned i = threadIdx.x; i < C; i += blockDim.x) {
+            const unsigned pos = static_cast<unsigned>(s_sort[i] >> 32);
+            V.pm_pos[off + i] = pos;
+            V.pm_fpos[off + i] = static_cast<unsigned>(s_sort[i] & 0xffffffffu);
+            for (int k = 0; k < V.m; ++k) V.pm_rows[static_cast<size_t>(off + i) * V.m + k] = V.rs[static_cast<size_t>(pos) * V.m + k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned level = first ? 0u : lvl + 1;
+        if (C) {
+            V.front_off[level] = off;
+            V.front_off[level + 1] = off + C;
+            meta->nfronts = level + 1;
+        }
+        const unsigned assigned = __ldcg(&meta->assigned) + C;
+        meta->level = level;
+        meta->front_off = off;
+        meta->front_size = C;
+        meta->assigned = assigned;
+        meta->ncand = 0;
+        const unsigned stop = __ldcg(&meta->stop_after);
+        if (stop && assigned >= stop) meta->done = 1;
+    }
+}
+
+template <int M> __global__ void __launch_bounds__(kTP) fnds_peel_sorted_kernel(SortedView V)
+{
+    __shared__ unsigned tileR[kTP * M], tileF[kTP];
+    const Meta *meta = V.meta;
+    if (meta->overflow || meta->done) return;
+    const unsigned fs = meta->front_size;
+    if (fs == 0) return;
+    peel_block<M>(V, blockIdx.x, fs, meta->front_off, meta->level, tileR, tileF);
+}
+
+__global__ void __launch_bounds__(1024) fnds_order_sorted_kernel(SortedView V, int first)
+{
+    __shared__ unsigned long long s_sort[kOrderCap];
+    __shared__ unsigned s_pos[1024];
+    const Meta *meta = V.meta;
+    if (meta->overflow || meta->done) return;
+    if (!first && meta->front_size == 0) return; // finished earlier
+    order_level(V, first, s_sort, s_pos);
+}
+
+// The whole remaining level loop in ONE cooperative launch: a co-resident grid, peel | grid.sync | CTA 0 closes the level |
+// grid.sync.  Every CTA owns the same position blocks at every level (b = blockIdx.x, + gridDim.x, ...), so rank[] / count[]
+// stay coherent in its L1.  Returns when all points are assigned, `stop_after` is reached or a level overflows kOrderCap.
+template <int M> __global__ void __launch_bounds__(kTP) fnds_levels_sorted_kernel(SortedView V)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned tileR[kTP * M], tileF[kTP];
+    __shared__ unsigned long long s_sort[kOrderCap];
+    __shared__ unsigned s_pos[1024];
+    const unsigned nblocks = (V.n + kTP - 1) / kTP;
+    Meta *meta = V.meta;
+    for (;;) {
+        const unsigned fs = __ldcg(&meta->front_size), fo = __ldcg(&meta->front_off), level = __ldcg(&meta->level);
+        if (__ldcg(&meta->overflow) || __ldcg(&meta->done) || __ldcg(&meta->assigned) >= V.n || fs == 0) break;
+        for (unsigned b = blockIdx.x; b < nblocks; b += gridDim.x) peel_block<M>(V, b, fs, fo, level, tileR, tileF);
+        grid.sync();
+        if (blockIdx.x == 0) order_level(V, 0, s_sort, s_pos);
+        grid.sync();
+    }
+}
+
+// big levels (more than kOrderCap candidates): the host sorts packed keys with CUB
+__global__ void pack_level_keys_kernel(SortedView V, unsigned C, unsigned long long *out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) out[i] = V.cand_key[i];
+}
+__global__ void unpack_level_order_kernel(SortedView V, const unsigned long long *sorted, unsigned C, unsigned off, unsigned long long *next)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) {
+        const unsigned sp = V.inv[static_cast<unsigned>(sorted[i] & 0xffffffffu)];
+        V.order[off + i] = sp;
+        next[i] = (static_cast<unsigned long long>(sp) << 32) | i;
+    }
+}
+__global__ void unpack_level_pos_kernel(SortedView V, const unsigned long long *sorted, unsigned C, unsigned off)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) {
+        const unsigned pos = static_cast<unsigned>(sorted[i] >> 32);
+        V.pm_pos[off + i] = pos;
+        V.pm_fpos[off + i] = static_cast<unsigned>(sorted[i] & 0xffffffffu);
+        for (int k = 0; k < V.m; ++k) V.pm_rows[static_cast<size_t>(off + i) * V.m + k] = V.rs[static_cast<size_t>(pos) * V.m + k];
+    }
+}
+
+// back to original indices
+__global__ void invert_perm_kernel(const unsigned *src, unsigned n, unsigned *inv)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[src[i]] = i;
+}
+__global__ void fnds_unsort_kernel(SortedView V, unsigned *rank_out, unsigned *key_out, unsigned *order_out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V.n) return;
+    const unsigned o = V.src[i];
+    rank_out[o] = V.rank[i];
+    if (key_out) key_out[o] = V.key[i];
+    if (i < V.meta->assigned) order_out[i] = V.src[V.order[i]];
 }
 
 // dense ranks of one objective: order-preserving keys (NaN last, -0 == +0), sorted, flag the value changes, scan, scatter
@@ -569,19 +833,25 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
         PGC_MO_CASE(8)
     }
 #undef PGC_MO_CASE
-    unsigned *ranks = nullptr; // [n x m] dense ranks per objective (large inputs): the level loop then runs on integers
     if (m >= 1 && n >= 4096) {
+        // ---- large inputs: dense integer ranks per objective, then the level loop in sorted space (see SortedView) ----
         unsigned long long *k0, *k1;
-        unsigned *i0, *i1, *src, *flags, *dense, *rs;
+        unsigned *i0, *i1, *src, *flags, *dense, *ranks, *rs, *inv, *blk_lo, *blk_limit, *rank_s, *key_s, *order_s, *pm_pos, *pm_fpos, *cand_rows, *pm_rows;
+        unsigned long long *cand_key;
         if ((rc = ws.alloc(&k0, n)) || (rc = ws.alloc(&k1, n)) || (rc = ws.alloc(&i0, n)) || (rc = ws.alloc(&i1, n)) || (rc = ws.alloc(&src, n))
             || (rc = ws.alloc(&flags, n)) || (rc = ws.alloc(&dense, n)) || (rc = ws.alloc(&ranks, static_cast<size_t>(n) * m))
-            || (rc = ws.alloc(&rs, static_cast<size_t>(n) * m)))
+            || (rc = ws.alloc(&rs, static_cast<size_t>(n) * m)) || (rc = ws.alloc(&inv, n)) || (rc = ws.alloc(&blk_lo, gb))
+            || (rc = ws.alloc(&blk_limit, gb)) || (rc = ws.alloc(&rank_s, n)) || (rc = ws.alloc(&key_s, n)) || (rc = ws.alloc(&order_s, n))
+            || (rc = ws.alloc(&pm_pos, n)) || (rc = ws.alloc(&pm_fpos, n)) || (rc = ws.alloc(&cand_rows, static_cast<size_t>(n) * m))
+            || (rc = ws.alloc(&pm_rows, static_cast<size_t>(n) * m)) || (rc = ws.alloc(&cand_key, n)))
             return rc;
-        size_t b1 = 0, b2 = 0;
+        size_t b1 = 0, b2 = 0, b3 = 0;
         void *tmp = nullptr;
         PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b1, k0, k1, i0, i1, static_cast<int>(n), 0, 64, st));
         PGC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, b2, flags, dense, static_cast<int>(n), st));
-        if ((rc = ws.alloc_bytes(&tmp, std::max(b1, b2)))) return rc;
+        PGC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, b3, k0, k1, static_cast<int>(n), 0, 64, st));
+        const size_t tmp_bytes = std::max(b1, std::max(b2, b3));
+        if ((rc = ws.alloc_bytes(&tmp, tmp_bytes))) return rc;
         for (int obj = 0; obj < m; ++obj) {
             unsigned *sorted_idx = obj == 0 ? src : i1;
             objective_keys_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_f, n, m, obj, k0, i0);
@@ -591,15 +861,92 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
             scatter_ranks_kernel<<<blocks_for(n, 256), 256, 0, st>>>(sorted_idx, dense, n, m, obj, ranks);
         }
         gather_rows_u32m_kernel<<<blocks_for(static_cast<size_t>(n) * m, 256), 256, 0, st>>>(ranks, src, n, m, rs);
+        invert_perm_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, n, inv);
+        SortedView V{rs,      src,    inv,     blk_lo,      blk_limit, count, rank_s, key_s, cand, cand_key, cand_rows, order_s,
+                     pm_pos,  pm_fpos, pm_rows, d_front_off, meta,      n,     m};
+        void *levels_fn = nullptr;
         switch (m) {
-#define PGC_MO_RANK(MM) case MM: fnds_count_rank_kernel<MM><<<gb, kTP, 0, st>>>(rs, src, n, count, d_dom_count); break;
-            PGC_MO_RANK(1) PGC_MO_RANK(2) PGC_MO_RANK(3) PGC_MO_RANK(4) PGC_MO_RANK(5) PGC_MO_RANK(6) PGC_MO_RANK(7) PGC_MO_RANK(8)
-#undef PGC_MO_RANK
+#define PGC_MO_SORTED(MM)                                                                                              \
+    case MM:                                                                                                           \
+        block_runs_kernel<MM><<<blocks_for(gb, 256), 256, 0, st>>>(rs, n, blk_lo, blk_limit);                          \
+        fnds_count_sorted_kernel<MM><<<gb, kTP, 0, st>>>(V, d_dom_count);                                              \
+        levels_fn = reinterpret_cast<void *>(fnds_levels_sorted_kernel<MM>);                                           \
+        break;
+            PGC_MO_SORTED(1) PGC_MO_SORTED(2) PGC_MO_SORTED(3) PGC_MO_SORTED(4) PGC_MO_SORTED(5) PGC_MO_SORTED(6) PGC_MO_SORTED(7)
+            PGC_MO_SORTED(8)
+#undef PGC_MO_SORTED
         }
-        ctx->launches.fetch_add(5 * m + 2, std::memory_order_relaxed);
-    } else {
-        count_k<<<gb, kTP, 0, st>>>(d_f, n, count, d_dom_count);
+        fnds_front0_sorted_kernel<<<blocks_for(n, 256), 256, 0, st>>>(V);
+        fnds_order_sorted_kernel<<<1, 1024, 0, st>>>(V, 1);
+        ctx->launches.fetch_add(5 * m + 6, std::memory_order_relaxed);
+
+        Meta h;
+        auto poll = [&]() -> int {
+            PGC_CUDA(cudaMemcpyAsync(&h, meta, sizeof(Meta), cudaMemcpyDeviceToHost, st));
+            PGC_CUDA(cudaStreamSynchronize(st));
+            return PGC_OK;
+        };
+        auto big_level = [&](int first) -> int { // a level with more than kOrderCap candidates: both orders through CUB
+            const unsigned C = h.ncand;
+            const unsigned off = first ? 0u : h.front_off + h.front_size;
+            size_t bytes = tmp_bytes;
+            pack_level_keys_kernel<<<blocks_for(C, 256), 256, 0, st>>>(V, C, k0);
+            PGC_CUDA(cub::DeviceRadixSort::SortKeys(tmp, bytes, k0, k1, static_cast<int>(C), 0, 64, st));
+            unpack_level_order_kernel<<<blocks_for(C, 256), 256, 0, st>>>(V, k1, C, off, k0);
+            bytes = tmp_bytes;
+            PGC_CUDA(cub::DeviceRadixSort::SortKeys(tmp, bytes, k0, k1, static_cast<int>(C), 0, 64, st));
+            unpack_level_pos_kernel<<<blocks_for(C, 256), 256, 0, st>>>(V, k1, C, off);
+            close_big_level_kernel<<<1, 1, 0, st>>>(d_front_off, meta, first);
+            ctx->launches.fetch_add(8, std::memory_order_relaxed);
+            return poll();
+        };
+        if ((rc = poll())) return rc;
+        if (h.overflow && (rc = big_level(1))) return rc;
+        int coop_attr = 0;
+        PGC_CUDA(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, ctx->device));
+        // PGC_FNDS_COOP=1 selects the single cooperative launch instead of two launches per level (A/B switch; results are
+        // identical).  Measured at pop 65 536 (profiles/r1s_bench_mo_65536.json): equal on ZDT1 (410 fronts of ~320), 30 % slower
+        // on DTLZ2 (83 fronts of ~1600: its 256-thread CTA sorts big levels slower than the 1024-thread order kernel), so the
+        // launch-per-level loop stays the default.
+        const char *coop_env = std::getenv("PGC_FNDS_COOP");
+        const bool coop = coop_attr != 0 && coop_env && coop_env[0] == '1';
+        unsigned coop_grid = 0;
+        while (h.assigned < n && !h.done) {
+            if (h.front_size == 0) {
+                set_error("fast_non_dominated_sorting: internal error, empty front with %u of %u points assigned", h.assigned, n);
+                return PGC_ERR_CUDA;
+            }
+            if (coop) {
+                if (coop_grid == 0) {
+                    int per_sm = 0;
+                    PGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, levels_fn, kTP, 0));
+                    coop_grid = std::min<unsigned>(gb, static_cast<unsigned>(ctx->sm_count * std::max(1, per_sm)));
+                }
+                void *args[] = {&V};
+                PGC_CUDA(cudaLaunchCooperativeKernel(levels_fn, dim3(coop_grid), dim3(kTP), args, 0, st));
+                ctx->launches.fetch_add(1, std::memory_order_relaxed);
+            } else {
+                for (int b = 0; b < kBatch; ++b) {
+                    switch (m) {
+#define PGC_MO_PEEL(MM) case MM: fnds_peel_sorted_kernel<MM><<<gb, kTP, 0, st>>>(V); break;
+                        PGC_MO_PEEL(1) PGC_MO_PEEL(2) PGC_MO_PEEL(3) PGC_MO_PEEL(4) PGC_MO_PEEL(5) PGC_MO_PEEL(6) PGC_MO_PEEL(7) PGC_MO_PEEL(8)
+#undef PGC_MO_PEEL
+                    }
+                    fnds_order_sorted_kernel<<<1, 1024, 0, st>>>(V, 0);
+                }
+                ctx->launches.fetch_add(2 * kBatch, std::memory_order_relaxed);
+            }
+            if ((rc = poll())) return rc;
+            if (h.overflow && (rc = big_level(0))) return rc;
+        }
+        fnds_unsort_kernel<<<blocks_for(n, 256), 256, 0, st>>>(V, d_rank, d_key_out, d_order);
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        PGC_CUDA(cudaGetLastError());
+        PGC_CUDA(cudaStreamSynchronize(st)); // the workspace is released on return
+        if (nfronts_out) *nfronts_out = h.nfronts;
+        return PGC_OK;
     }
+    count_k<<<gb, kTP, 0, st>>>(d_f, n, count, d_dom_count);
     fnds_front0_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, count, d_rank, key, cand, meta);
     ctx->launches.fetch_add(3, std::memory_order_relaxed);
 
@@ -640,15 +987,7 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
             return PGC_ERR_CUDA;
         }
         for (int b = 0; b < kBatch; ++b) {
-            if (ranks) {
-                switch (m) {
-#define PGC_MO_PEEL(MM) case MM: fnds_peel_rank_kernel<MM><<<gb, kTP, 0, st>>>(ranks, n, d_order, count, d_rank, key, cand, meta); break;
-                    PGC_MO_PEEL(1) PGC_MO_PEEL(2) PGC_MO_PEEL(3) PGC_MO_PEEL(4) PGC_MO_PEEL(5) PGC_MO_PEEL(6) PGC_MO_PEEL(7) PGC_MO_PEEL(8)
-#undef PGC_MO_PEEL
-                }
-            } else {
-                peel_k<<<gb, kTP, 0, st>>>(d_f, n, d_order, count, d_rank, key, cand, meta);
-            }
+            peel_k<<<gb, kTP, 0, st>>>(d_f, n, d_order, count, d_rank, key, cand, meta);
             fnds_order_kernel<<<1, 1024, 0, st>>>(cand, key, d_order, d_front_off, meta, 0);
         }
         ctx->launches.fetch_add(2 * kBatch, std::memory_order_relaxed);
