@@ -205,6 +205,17 @@ PGC_API int pgc_pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_
                                       unsigned radius, unsigned index_offset, double omega, double eta1, double eta2, double max_vel,
                                       unsigned variant, uint64_t seed, uint32_t generation, int init_velocity, void *stream);
 
+/* The same for the gbest topology (pso_gen.cpp:644-677: every particle's best neighbour is the swarm's best particle; tracking rule
+ * :452-457).  The extended arrays carry ONE row at each end: row 0 = the swarm's current best position / fitness, kept up to date by
+ * the caller; rows 1 .. n_loc = the shard's own particles; the last row is unused.  After the step d_cand (device, 2 doubles) holds the
+ * shard's candidate for the next best: [fitness, local index] of the particle that improved to the smallest fitness (last index on
+ * ties), or [+inf, -1].  The caller reduces the candidates of all shards (smallest fitness, largest GLOBAL index on ties, accepted if
+ * <= the current best) and writes the winner's row into row 0 everywhere: pagmo2_b200/swarm.py (GbestSwarm) does it with one
+ * all_gather of nx + 2 doubles per shard and generation. */
+PGC_API int pgc_pso_shard_step_gbest_device(pgc_problem *prob, double *d_X, double *d_V, double *d_lbX_ext, double *d_lbfit_ext, size_t n_loc,
+                                            unsigned index_offset, double omega, double eta1, double eta2, double max_vel, unsigned variant,
+                                            uint64_t seed, uint32_t generation, int init_velocity, double *d_cand, void *stream);
+
 /* Differential evolution family as a generational device loop (trial vectors for all individuals -> one batch evaluation ->
  * selection): algo 0 = de (de.cpp:76-345; variant 1..10, F, CR), 1 = sade (sade.cpp:78-560; variant 1..18, variant_adptv 1 = jDE,
  * 2 = iDE), 2 = de1220 (de1220.cpp:80-600; allowed_variants, variant_adptv).  d_x [NP x nx], d_f [NP] updated in place; d_F / d_CR /

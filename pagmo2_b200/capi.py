@@ -150,6 +150,8 @@ def lib():
                                             C.c_uint, C.c_uint, C.c_uint64, C.c_uint32, vp]
         L.pgc_pso_shard_step_device.argtypes = [vp, vp, vp, vp, vp, sz, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double,
                                                 C.c_uint, C.c_uint64, C.c_uint32, C.c_int, vp]
+        L.pgc_pso_shard_step_gbest_device.argtypes = [vp, vp, vp, vp, vp, sz, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                      C.c_uint, C.c_uint64, C.c_uint32, C.c_int, vp, vp]
         L.pgc_de_evolve_device.argtypes = [vp, vp, vp, sz, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_double, vp, C.c_uint,
                                            C.c_double, C.c_double, vp, vp, vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint), vp]
         L.pgc_hv_compute_host.argtypes = [vp, vp, sz, sz, dp, dp]

@@ -732,6 +732,17 @@ int pgc_pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_V, doubl
                                  stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
 }
 
+int pgc_pso_shard_step_gbest_device(pgc_problem *prob, double *d_X, double *d_V, double *d_lbX_ext, double *d_lbfit_ext, size_t n_loc,
+                                    unsigned index_offset, double omega, double eta1, double eta2, double max_vel, unsigned variant,
+                                    uint64_t seed, uint32_t generation, int init_velocity, double *d_cand, void *stream)
+{
+    PGC_REQUIRE(prob && d_V && d_cand && (init_velocity || (d_X && d_lbX_ext && d_lbfit_ext)), "pgc_pso_shard_step_gbest_device: null argument");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    return pso_shard_step_device(prob, d_X, d_V, d_lbX_ext, d_lbfit_ext, static_cast<unsigned>(n_loc), 1u, index_offset, omega, eta1, eta2,
+                                 max_vel, variant, seed, generation, init_velocity, problem_eval_device,
+                                 stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream, d_cand);
+}
+
 int pgc_de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP, unsigned gens, unsigned algo, unsigned variant,
                          unsigned variant_adptv, double F, double CR, const uint32_t *allowed_variants, unsigned n_allowed, double ftol,
                          double xtol, double *d_F, double *d_CR, uint32_t *d_variant, uint64_t seed, uint32_t first_generation,

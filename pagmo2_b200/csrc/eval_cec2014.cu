@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
     const long long ntiles = (P.n + kTileInd - 1) / kTileInd;
     const bool need_w = P.wout != nullptr;
     const double pre_rate = P.st.pre_rate;
+    const bool unit_pre = pre_rate == 1.0;
     const int et = lane & (kTileInd - 1), eq = lane / kTileInd; // epilogue mapping: individual, term class
 
     // this lane's slice of the shift vector for the L phase (same columns for every row of every tile)
@@ -403,7 +404,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) cec14_stage_kernel(const __gri
                         if (lane < LPR && c < CH) {
                             const double d0 = xv[t][ps].x - osv[ps].x, d1 = xv[t][ps].y - osv[ps].y;
                             if (need_w) wrow[t] += d0 * d0 + d1 * d1; // cf_cal weight sum_j (x_j - Os_j)^2, :1330-1332
-                            const double y0 = d0 * pre_rate, y1 = d1 * pre_rate;
+                            // sh_rate = 1 (ellips, bent_cigar, discus, ackley, escaffer6, the hybrids): x * 1.0 is x, skip the multiply
+                            double y0 = d0, y1 = d1;
+                            if (!unit_pre) {
+                                y0 = d0 * pre_rate;
+                                y1 = d1 * pre_rate;
+                            }
                             if (ROT) {
                                 *reinterpret_cast<double2 *>(buf + t * YS + 2 * c) = make_double2(y0, y1);
                             } else {

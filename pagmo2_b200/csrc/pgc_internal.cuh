@@ -189,7 +189,7 @@ int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, 
 int pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_V, double *d_lbX_ext, double *d_lbfit_ext, unsigned n_loc, unsigned radius,
                           unsigned index_offset, double omega, double eta1, double eta2, double max_vel, unsigned variant,
                           unsigned long long seed, unsigned generation, int init_velocity,
-                          int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
+                          int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st, double *d_cand = nullptr);
 int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, unsigned algo, unsigned variant,
                      unsigned variant_adptv, double F, double CR, const unsigned *allowed, unsigned n_allowed, double ftol, double xtol,
                      double *d_F, double *d_CR, unsigned *d_variant, unsigned long long seed, unsigned first_generation,

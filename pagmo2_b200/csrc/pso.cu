@@ -267,15 +267,57 @@ __global__ void pso_init_velocity_shard_kernel(double *V, const double *lb, cons
     V[e] = (minv == maxv) ? minv : (maxv - minv) * u + minv;
 }
 
+// gbest topology on a shard: every particle's best neighbour is the swarm's best particle, whose row the caller keeps in
+// extended row 0
+__global__ void pso_fill_u32_kernel(unsigned *p, unsigned n, unsigned v)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// the shard's candidate for the swarm's new best (:452-457 restricted to this shard): among the particles that improved in
+// this generation the smallest fitness, the LAST index on ties.  cand[0] = fitness (+inf if none), cand[1] = local index (-1).
+__global__ void pso_shard_candidate_kernel(const double *fit, const unsigned char *improved, unsigned n, double *cand)
+{
+    __shared__ double sf[256];
+    __shared__ unsigned si[256];
+    double bf = 0.;
+    unsigned bi = 0xffffffffu;
+    for (unsigned p = threadIdx.x; p < n; p += blockDim.x) {
+        if (!improved[p]) continue;
+        const double f = fit[p];
+        if (bi == 0xffffffffu || less_f(f, bf) || equal_f(f, bf)) {
+            bf = f;
+            bi = p;
+        }
+    }
+    sf[threadIdx.x] = bf;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned t = 1; t < blockDim.x; ++t) {
+            if (si[t] == 0xffffffffu) continue;
+            if (bi == 0xffffffffu || less_f(sf[t], bf) || (equal_f(sf[t], bf) && si[t] > bi)) {
+                bf = sf[t];
+                bi = si[t];
+            }
+        }
+        cand[0] = bi == 0xffffffffu ? INFINITY : bf;
+        cand[1] = bi == 0xffffffffu ? -1.0 : static_cast<double>(bi);
+    }
+}
+
 inline unsigned nblk(size_t n, unsigned t) { return static_cast<unsigned>((n + t - 1) / t); }
 
 } // namespace
 
-// One generation of a shard (lbest ring).  d_V == nullptr on entry is not allowed: call with init_velocity = 1 once to draw them.
+// One generation of a shard.  d_cand == nullptr: lbest ring; d_cand != nullptr: gbest topology (radius must be 1, extended row 0 =
+// the swarm's best row, d_cand receives the shard's candidate for the next best).  d_V == nullptr on entry is not allowed: call
+// with init_velocity = 1 once to draw them.
 int pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_V, double *d_lbX_ext, double *d_lbfit_ext, unsigned n_loc, unsigned radius,
                           unsigned index_offset, double omega, double eta1, double eta2, double max_vel, unsigned variant,
                           unsigned long long seed, unsigned generation, int init_velocity,
-                          int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st)
+                          int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st, double *d_cand)
 {
     pgc_ctx *ctx = prob->ctx;
     const unsigned dim = static_cast<unsigned>(prob->nx);
@@ -285,6 +327,7 @@ int pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_V, double *d
     PGC_REQUIRE(variant >= 1u && variant <= 5u, "pso shards implement variants 1-5, while a value of %u was detected", variant);
     PGC_REQUIRE(prob->nobj == 1, "Multiple objectives detected in %s instance. PSO cannot deal with them", prob->name.c_str());
     PGC_REQUIRE(n_loc >= 1 && radius >= 1, "pso shard: empty shard or zero radius");
+    PGC_REQUIRE(!d_cand || radius == 1, "pso shard, gbest topology: the extended arrays carry one row at each end (radius 1), got %u", radius);
     const size_t nd = static_cast<size_t>(n_loc) * dim;
     double *lb = nullptr, *fit = nullptr;
     unsigned *bn = nullptr;
@@ -301,14 +344,16 @@ int pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_V, double *d
         pso_init_velocity_shard_kernel<<<nblk(nd, 256), 256, 0, st>>>(d_V, lb, ub, n_loc, dim, index_offset, max_vel, seed, generation);
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
     } else {
-        pso_lbest_ext_kernel<<<nblk(n_loc, 256), 256, 0, st>>>(d_lbfit_ext, n_loc, radius, bn);
+        if (d_cand) pso_fill_u32_kernel<<<nblk(n_loc, 256), 256, 0, st>>>(bn, n_loc, 0u);
+        else pso_lbest_ext_kernel<<<nblk(n_loc, 256), 256, 0, st>>>(d_lbfit_ext, n_loc, radius, bn);
         ShardMoveParams mp{d_X, d_V, d_lbX_ext, bn, lb, ub, n_loc, dim, radius, index_offset, omega, eta1, eta2, max_vel, variant, seed, generation};
         pso_move_shard_kernel<<<nblk(nd, 256), 256, 0, st>>>(mp);
         rc = eval(prob, d_X, n_loc, fit, st);
         if (rc == PGC_OK) {
             pso_memory_flag_kernel<<<nblk(n_loc, 256), 256, 0, st>>>(fit, d_lbfit_ext + radius, n_loc, improved);
             pso_memory_copy_kernel<<<nblk(nd, 256), 256, 0, st>>>(d_X, d_lbX_ext + static_cast<size_t>(radius) * dim, improved, n_loc, dim);
-            ctx->launches.fetch_add(4, std::memory_order_relaxed);
+            if (d_cand) pso_shard_candidate_kernel<<<1, 256, 0, st>>>(fit, improved, n_loc, d_cand);
+            ctx->launches.fetch_add(d_cand ? 5 : 4, std::memory_order_relaxed);
         }
     }
     cudaError_t e = cudaStreamSynchronize(st); // lb / ub came from pageable host vectors

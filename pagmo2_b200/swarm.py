@@ -97,3 +97,107 @@ class ShardedSwarm:
             self.exchange()
             self.shard.step(self.params, self.generation)
             self.generation += 1
+
+
+# ---- gbest topology (pso_gen.cpp:644-677; tracking rule :452-457) -----------------------------------------------------------------
+# Every particle's best neighbour is the swarm's best particle.  A shard keeps that particle's best position in row 0 of its extended
+# arrays; after every generation each shard publishes its candidate - the particle that improved to the smallest fitness, last index
+# on ties - and all shards apply the reference's rule to the gathered candidates: smallest fitness, largest global index on ties,
+# accepted if <= the current best.  One all_gather of nx + 2 doubles per shard and generation.
+
+def pick_initial_best(cands: np.ndarray):
+    """cands[r] = [fitness, global index, row...] of shard r's first minimum.  pop.best_idx(): the FIRST minimum of the swarm."""
+    order = np.lexsort((cands[:, 1], cands[:, 0]))
+    return cands[order[0]]
+
+
+def pick_next_best(cands: np.ndarray, current_fit: float):
+    """cands[r] = [fitness, global index or -1, row...].  Returns the winning candidate row or None (the best stays)."""
+    live = cands[cands[:, 1] >= 0]
+    if live.shape[0] == 0:
+        return None
+    order = np.lexsort((-live[:, 1], live[:, 0]))  # smallest fitness, LARGEST index on ties (the sequential scan keeps the last)
+    best = live[order[0]]
+    return best if best[0] <= current_fit else None
+
+
+class GbestShard:
+    """n_loc particles of a gbest swarm on one GPU: extended row 0 = the swarm's best, rows 1..n_loc = own particles."""
+    radius = 1
+
+    def __init__(self, ctx: capi.Context, prob: capi.Problem, x: np.ndarray, f: np.ndarray, index_offset: int):
+        self.ctx, self.prob, self.n, self.nx, self.offset = ctx, prob, x.shape[0], x.shape[1], index_offset
+        f = np.asarray(f, dtype=np.float64).reshape(-1)
+        ext = np.zeros((self.n + 2, self.nx))
+        ext[1:1 + self.n] = x
+        fext = np.zeros(self.n + 2)
+        fext[1:1 + self.n] = f
+        self.d_X, self.d_V = ctx.to_device(np.ascontiguousarray(x, dtype=np.float64)), ctx.malloc(8 * self.n * self.nx)
+        self.d_lbX, self.d_lbf, self.d_cand = ctx.to_device(ext), ctx.to_device(fext), ctx.malloc(16)
+        i = int(np.argmin(f))  # first minimum
+        self._initial = np.concatenate([[f[i], index_offset + i], x[i]])
+
+    def initial_candidate(self) -> np.ndarray:
+        return self._initial
+
+    def candidate(self) -> np.ndarray:
+        """[fitness, global index or -1, best position of that particle] after a step."""
+        fit, idx = self.ctx.from_device(self.d_cand, (2,))
+        if idx < 0:
+            return np.concatenate([[np.inf, -1.0], np.zeros(self.nx)])
+        row = self.ctx.from_device(self.d_lbX + 8 * (1 + int(idx)) * self.nx, (self.nx,))
+        return np.concatenate([[fit, self.offset + idx], row])
+
+    def set_best(self, cand: np.ndarray):
+        x, f = np.ascontiguousarray(cand[2:]), np.ascontiguousarray(cand[:1])
+        lib = capi.lib()
+        capi.check(lib.pgc_memcpy_h2d(self.ctx._h, self.d_lbX, x.ctypes.data, x.nbytes))
+        capi.check(lib.pgc_memcpy_h2d(self.ctx._h, self.d_lbf, f.ctypes.data, f.nbytes))
+
+    def step(self, p: dict, generation: int, init_velocity: bool = False):
+        capi.check(capi.lib().pgc_pso_shard_step_gbest_device(self.prob._h, self.d_X, self.d_V, self.d_lbX, self.d_lbf, self.n, self.offset,
+                                                              p["omega"], p["eta1"], p["eta2"], p["max_vel"], p["variant"], p["seed"],
+                                                              generation, int(init_velocity), self.d_cand, None))
+
+    def best(self):
+        rows = self.ctx.from_device(self.d_lbX + 8 * self.nx, (self.n, self.nx))
+        return rows, self.ctx.from_device(self.d_lbf + 8, (self.n,))
+
+
+class GbestSwarm:
+    """The shard of this process plus the per-generation reduction of the shards' candidates.  `shard` needs initial_candidate() /
+    candidate() / set_best() / step()."""
+
+    def __init__(self, shard, omega=0.7298, eta1=2.05, eta2=2.05, max_vel=0.5, variant=5, seed=0, first_generation=1, group=None):
+        self.shard, self.group, self.generation = shard, group, first_generation
+        self.params = dict(omega=omega, eta1=eta1, eta2=eta2, max_vel=max_vel, variant=variant, seed=seed)
+        self.rank, self.world, self._dist = 0, 1, None
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self._dist, self.rank, self.world = dist, dist.get_rank(group), dist.get_world_size(group)
+        except ImportError:
+            pass
+        shard.step(self.params, first_generation, init_velocity=True)  # velocities, pso_gen.cpp:187-196
+        self.current = pick_initial_best(self._gather(shard.initial_candidate()))  # best_fit / best_neighb, :215-224
+        shard.set_best(self.current)
+
+    def _gather(self, mine: np.ndarray) -> np.ndarray:
+        if self.world == 1:
+            return mine[None]
+        import torch
+        dist = self._dist
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(np.ascontiguousarray(mine)).to(dev)
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t, group=self.group)
+        return np.stack([q.cpu().numpy() for q in parts])
+
+    def evolve(self, gens: int):
+        for _ in range(gens):
+            self.shard.step(self.params, self.generation)
+            winner = pick_next_best(self._gather(self.shard.candidate()), self.current[0])
+            if winner is not None:
+                self.current = winner
+                self.shard.set_best(winner)
+            self.generation += 1
