@@ -162,3 +162,50 @@ dist.barrier(); dist.destroy_process_group()
            str(31500 + os.getpid() % 2000), str(worker)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_gbest_reduction_rules():
+    """pick_initial_best = pop.best_idx() (first minimum); pick_next_best = the sequential scan of pso_gen.cpp:452-457 over the
+    gathered candidates: smallest fitness, LAST global index on ties, accepted if <= the current best."""
+    from pagmo2_b200.swarm import pick_initial_best, pick_next_best
+    c = np.array([[3.0, 40, 1.0], [1.0, 70, 2.0], [1.0, 10, 3.0]])
+    assert pick_initial_best(c).tolist() == [1.0, 10, 3.0]
+    assert pick_next_best(c, 5.0).tolist() == [1.0, 70, 2.0]
+    assert pick_next_best(c, 1.0).tolist() == [1.0, 70, 2.0]  # equal fitness replaces (<=)
+    assert pick_next_best(c, 0.5) is None
+    none = np.array([[np.inf, -1, 0.0], [np.inf, -1, 0.0]])
+    assert pick_next_best(none, 5.0) is None
+    mixed = np.array([[np.inf, -1, 0.0], [2.0, 5, 9.0]])
+    assert pick_next_best(mixed, 2.5).tolist() == [2.0, 5, 9.0]
+
+
+def test_gbest_swarm_world_size_2_gloo(tmp_path):
+    """GbestSwarm over gloo with fake shards: both ranks must agree on the swarm's best after every generation."""
+    worker = tmp_path / "w.py"
+    worker.write_text('''
+import sys, numpy as np, torch.distributed as dist
+sys.path.insert(0, %r)
+from pagmo2_b200.swarm import GbestSwarm
+class Fake:
+    def __init__(self, r): self.r, self.seen, self.g = r, [], 0
+    def initial_candidate(self): return np.array([10.0 - self.r, 100 * self.r + 3, float(self.r)])
+    def candidate(self):
+        # generation 1: only rank 0 improves (to 5); generation 2: both reach 4 -> the larger global index (rank 1) wins; 3: nobody
+        if self.g == 1: return np.array([5.0, 7, 0.5]) if self.r == 0 else np.array([np.inf, -1, 0.0])
+        if self.g == 2: return np.array([4.0, 100 * self.r + 1, 10.0 + self.r])
+        return np.array([np.inf, -1, 0.0])
+    def set_best(self, cand): self.seen.append(cand.tolist())
+    def step(self, p, generation, init_velocity=False):
+        if not init_velocity: self.g += 1
+dist.init_process_group("gloo")
+s = GbestSwarm(Fake(dist.get_rank()))
+s.evolve(3)
+assert s.shard.seen == [[9.0, 103, 1.0], [5.0, 7, 0.5], [4.0, 101, 11.0]], s.shard.seen
+assert s.generation == 4
+dist.barrier(); dist.destroy_process_group()
+''' % str(ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+           str(33500 + os.getpid() % 2000), str(worker)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]

@@ -103,3 +103,40 @@ def test_sharded_swarm_one_shard_equals_evolve(capi, ctx, variant):
     got = np.vstack([s.best()[0] for s in shards])
     assert np.array_equal(got, want_x)
     prob.close()
+
+
+@pytest.mark.parametrize("variant", (1, 3, 5))
+def test_sharded_gbest_swarm_equals_evolve(capi, ctx, variant):
+    """gbest topology (pso_gen.cpp:644-677, tracking :452-457) sharded: one shard, and three shards in one process whose candidates
+    are reduced by hand with the same functions GbestSwarm uses after its all_gather, must move exactly like pgc_pso_evolve_device."""
+    from pagmo2_b200.swarm import GbestShard, GbestSwarm, pick_initial_best, pick_next_best
+    rng = np.random.default_rng(10 + variant)
+    prob = capi.Problem(ctx, "rastrigin", dim=6)
+    lb, ub = prob.bounds()
+    n, gens = 90, 8
+    x = rng.uniform(lb, ub, (n, 6))
+    f = prob.eval_host(x)[:, 0]
+    want_x, want_f, _, _ = prob.pso_evolve(x, f, gens=gens, variant=variant, neighb_type=1, seed=5, first_generation=1)
+    one = GbestSwarm(GbestShard(ctx, prob, x, f, 0), variant=variant, seed=5, first_generation=1)
+    one.evolve(gens)
+    bx, bf = one.shard.best()
+    assert np.array_equal(bx, want_x) and np.array_equal(bf, want_f)
+    shards = [GbestShard(ctx, prob, x[i * 30:(i + 1) * 30], f[i * 30:(i + 1) * 30], i * 30) for i in range(3)]
+    p = dict(omega=0.7298, eta1=2.05, eta2=2.05, max_vel=0.5, variant=variant, seed=5)
+    for s in shards:
+        s.step(p, 1, init_velocity=True)
+    current = pick_initial_best(np.stack([s.initial_candidate() for s in shards]))
+    for s in shards:
+        s.set_best(current)
+    for g in range(1, gens + 1):
+        for s in shards:
+            s.step(p, g)
+        winner = pick_next_best(np.stack([s.candidate() for s in shards]), current[0])
+        if winner is not None:
+            current = winner
+            for s in shards:
+                s.set_best(current)
+    assert np.array_equal(np.vstack([s.best()[0] for s in shards]), want_x)
+    assert np.array_equal(np.concatenate([s.best()[1] for s in shards]), want_f)
+    assert current[0] == want_f.min()
+    prob.close()
