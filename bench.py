@@ -47,44 +47,62 @@ def env_int(name, default):
 
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi sampler for one GPU during the timed region (recipe: B200_PROFILING.md, clocks line)."""
+    """SM clock / throttle-reason sampler for one GPU during the timed region (recipe: B200_PROFILING.md, clocks line).
+    NVML in-process (nvidia_ml_py), one sample every 10 ms - a freshly spawned `nvidia-smi -lms` needs longer to print its first
+    line than a 0.3 s timed region lasts, more so on an 8-GPU box; nvidia-smi stays as the fallback when NVML is not importable."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self._stop_evt = index, [], None, threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            N = self.nvml
+            reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop_evt.is_set():
+                try:
+                    sm = float(N.nvmlDeviceGetClockInfo(self.handle, N.NVML_CLOCK_SM))
+                    mask = int(reasons_fn(self.handle))
+                    self.rows.append([sm, self.max_sm, mask])
+                except Exception:
+                    pass
+                self._stop_evt.wait(0.01)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                c = [x.strip() for x in line.split(",")]
+                mask = sum(bit for (nm, bit), v in zip(self.REASONS.items(), c[3:7]) if v.lower().startswith("active"))
+                self.rows.append([float(c[0]), float(c[1]), mask])
         except Exception:
             pass
 
     def stop(self):
+        self._stop_evt.set()
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except (ValueError, IndexError):
-                continue
-        # the sampler also sees idle moments before/after; "under load" = the upper half of the samples
+        sm = [r[0] for r in self.rows]
+        mx = max([r[1] for r in self.rows], default=0)
+        reasons = sorted(nm for nm, bit in self.REASONS.items() if any(r[2] & bit for r in self.rows))
+        # the sampler also sees idle moments at the edges; "under load" = the upper half of the samples
         sm_load = sorted(sm)[len(sm) // 2:] if sm else []
         return {"sm_mhz": statistics.median(sm_load) if sm_load else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
