@@ -171,6 +171,15 @@ def run_native(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    if world > 1:
+        # one process per GPU: run (and first-touch the pinned e2e buffers) on the cores next to this GPU, so that eight host->device
+        # streams do not cross the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        except Exception:
+            pass
     ctx = capi.Context(local)  # raises if there is no device: no CPU fallback
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     n = args.n
