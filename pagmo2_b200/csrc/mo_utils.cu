@@ -16,9 +16,10 @@
 // Crowding distances are exact IEEE (same subtraction / division per element, objectives applied in order); the sort
 // inside a front is a stable segmented radix sort, which matches the reference's std::sort whenever the objective values
 // inside a front are distinct (the reference's order of ties is unspecified: SURVEY.md F5).
-#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
@@ -40,6 +41,7 @@ constexpr int kTP = 256;          // dominators per shared-memory tile / threads
 constexpr int kMaxM = 8;          // objectives held in registers
 constexpr int kOrderCap = 4096;   // candidates the single-CTA order kernel sorts in shared memory
 constexpr int kBatch = 8;         // levels launched between two host polls
+constexpr unsigned kFusedCap = 1024; // largest level the last thread block of a fused peel pass orders itself
 
 struct Meta {            // device-side bookkeeping of the level loop
     unsigned ncand;      // candidates collected by the current peel
@@ -47,11 +49,13 @@ struct Meta {            // device-side bookkeeping of the level loop
     unsigned front_off;  // its offset in `order`
     unsigned assigned;   // points placed in fronts so far
     unsigned level;      // index of the front being peeled
-    unsigned overflow;   // 1: ncand > kOrderCap, the host must order this level with the big path
+    unsigned overflow;   // 1: ncand > kOrderCap, the host must order this level with the big path; 2: a fused pass met a level of
+                         //    more than kFusedCap candidates, the host closes it with the 1024-thread order kernel
     unsigned nfronts;
     unsigned stop_after; // 0: peel everything; else stop once this many points sit in closed fronts (select_best_N_mo needs no more)
     unsigned done;
-    unsigned pad;
+    unsigned nact;       // sorted-space loop: live length of the active list
+    unsigned tickets;    // fused levels: thread blocks of the current peel pass that have finished (the last one closes the level)
 };
 
 // pareto_dominance, multi_objective.cpp:97-113 with the NaN-aware comparisons of detail/custom_comparisons.hpp:54-88
@@ -183,12 +187,20 @@ template <int M> __device__ __forceinline__ bool dominates_rank(const unsigned *
 // To make whole tiles classifiable, every front is kept twice: in the reference's order (`order`, the output) and sorted
 // by position with each member's index in the front beside it (`pm_pos`, `pm_fpos`; the key of a point that joins the next
 // front is the largest such index among its dominators).
+struct StillActive { // predicate of the active-list compaction
+    const unsigned *count;
+    __device__ __forceinline__ bool operator()(const unsigned &pos) const { return count[pos] != 0u; }
+};
+
 struct SortedView {
     const unsigned *rs;        // [n x m] dense ranks, rows in sorted order
     const unsigned *src;       // sorted position -> original index
     const unsigned *inv;       // original index -> sorted position
-    const unsigned *blk_lo;    // per block of kTP positions: start of the run of equal first ranks that holds its first point
-    const unsigned *blk_limit; //                             end (exclusive) of the run that holds its last point
+    const unsigned *run_lo;    // per position: start of its run of equal first ranks
+    const unsigned *run_end;   //               end (exclusive) of that run
+    const unsigned *act;       // positions not yet in a front, ascending: the list the peel passes walk.  Re-compacted every few
+    unsigned nact_cap;         //   levels (compact_active below); nact_cap = its length at the last compaction (grid size), the
+                               //   live length is meta->nact
     unsigned *count, *rank, *key; // per sorted position
     unsigned *cand;            // candidates of the level under construction (sorted positions) ...
     unsigned long long *cand_key; // ... their ordering keys (key << 32 | original index) and rank rows, written by the thread that
@@ -214,27 +226,25 @@ template <int M> __device__ __forceinline__ bool dominates_tail(const unsigned *
     return ok;
 }
 
-template <int M> __global__ void block_runs_kernel(const unsigned *__restrict__ rs, unsigned n, unsigned *blk_lo, unsigned *blk_limit)
+template <int M> __global__ void run_bounds_kernel(const unsigned *__restrict__ rs, unsigned n, unsigned *run_lo, unsigned *run_end)
 {
-    const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned nblocks = (n + kTP - 1) / kTP;
-    if (b >= nblocks) return;
-    const unsigned first = b * kTP, last = min(n, (b + 1) * kTP) - 1;
-    const unsigned bottom = rs[static_cast<size_t>(first) * M], top = rs[static_cast<size_t>(last) * M];
-    unsigned lo = 0, hi = first; // first position whose first rank is >= bottom
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const unsigned mine = rs[static_cast<size_t>(p) * M];
+    unsigned lo = 0, hi = p; // first position whose first rank is >= mine
     while (lo < hi) {
         const unsigned mid = (lo + hi) >> 1;
-        if (rs[static_cast<size_t>(mid) * M] < bottom) lo = mid + 1;
+        if (rs[static_cast<size_t>(mid) * M] < mine) lo = mid + 1;
         else hi = mid;
     }
-    blk_lo[b] = lo;
-    lo = last + 1, hi = n; // first position with a larger first rank than top
+    run_lo[p] = lo;
+    lo = p + 1, hi = n; // first position with a larger first rank
     while (lo < hi) {
         const unsigned mid = (lo + hi) >> 1;
-        if (rs[static_cast<size_t>(mid) * M] <= top) lo = mid + 1;
+        if (rs[static_cast<size_t>(mid) * M] <= mine) lo = mid + 1;
         else hi = mid;
     }
-    blk_limit[b] = lo;
+    run_end[p] = lo;
 }
 
 // count pass: count[p] = dominators of the point at position p; CTAs issued largest first
@@ -245,7 +255,7 @@ __global__ void __launch_bounds__(kTP) fnds_count_sorted_kernel(SortedView V, un
     __shared__ unsigned tile[kTP * M];
     const unsigned b = gridDim.x - 1 - blockIdx.x;
     const unsigned q = b * kTP + threadIdx.x;
-    const unsigned lo = V.blk_lo[b], limit = V.blk_limit[b];
+    const unsigned lo = V.run_lo[b * kTP], limit = V.run_end[min(V.n, (b + 1) * kTP) - 1];
     unsigned rq[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) rq[i] = (q < V.n) ? V.rs[static_cast<size_t>(q) * m + i] : 0u;
@@ -288,69 +298,23 @@ __global__ void fnds_front0_sorted_kernel(SortedView V)
     }
 }
 
-// one block of kTP positions against front `level` (fs members at offset fo).  Data other CTAs wrote in the previous phase
-// is read with ld.global.cg (the cooperative kernel below keeps CTAs alive across levels).
-template <int M>
-__device__ __forceinline__ void peel_block(const SortedView &V, unsigned b, unsigned fs, unsigned fo, unsigned level, unsigned *tileR,
-                                           unsigned *tileF)
-{
-    constexpr int m = M;
-    const unsigned q = b * kTP + threadIdx.x;
-    const unsigned left0 = q < V.n ? V.count[q] : 0u; // dominators not yet in a closed front; 0 = the point sits in a front
-    const unsigned lo = V.blk_lo[b], limit = V.blk_limit[b];
-    const unsigned srcq = q < V.n ? V.src[q] : 0u;
-    unsigned rq[M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) rq[i] = q < V.n ? V.rs[static_cast<size_t>(q) * m + i] : 0u;
-    const bool active = left0 != 0;
-    if (!__syncthreads_or(active)) return;
-    unsigned c = 0, mp = 0;
-    for (unsigned base = 0; base < fs; base += kTP) {
-        const unsigned np = min(static_cast<unsigned>(kTP), fs - base);
-        if (__ldcg(V.pm_pos + fo + base) >= limit) break; // this member and all later ones lie beyond the block's last run
-        const unsigned last_pos = __ldcg(V.pm_pos + fo + base + np - 1);
-        for (unsigned e = threadIdx.x; e < np * m; e += kTP) tileR[e] = __ldcg(V.pm_rows + static_cast<size_t>(fo + base) * m + e);
-        for (unsigned t = threadIdx.x; t < np; t += kTP) tileF[t] = __ldcg(V.pm_fpos + fo + base + t);
-        __syncthreads();
-        if (active) {
-            if (last_pos < lo) {
-#pragma unroll 4
-                for (unsigned t = 0; t < np; ++t)
-                    if (dominates_tail<M>(tileR + t * M, rq)) {
-                        ++c;
-                        mp = max(mp, tileF[t]);
-                    }
-            } else {
-#pragma unroll 4
-                for (unsigned t = 0; t < np; ++t)
-                    if (dominates_rank<M>(tileR + t * M, rq)) {
-                        ++c;
-                        mp = max(mp, tileF[t]);
-                    }
-            }
-        }
-        __syncthreads();
-    }
-    if (active && c) {
-        const unsigned left = left0 - c;
-        V.count[q] = left;
-        if (left == 0) {
-            V.rank[q] = level + 1;
-            V.key[q] = mp;
-            const unsigned slot = atomicAdd(&V.meta->ncand, 1u);
-            V.cand[slot] = q;
-            V.cand_key[slot] = (static_cast<unsigned long long>(mp) << 32) | srcq;
-#pragma unroll
-            for (int i = 0; i < M; ++i) V.cand_rows[static_cast<size_t>(slot) * m + i] = rq[i];
-        }
-    }
-}
-
+// one block of kTP entries of the active list against front `level` (fs members at offset fo).  The list is ascending, so
+// the block's dominators end at the run of its last entry and tiles before the run of its first entry need the tail test only.
+// Entries whose point joined a front since the last compaction are skipped (count == 0); compaction keeps warps densely
+// active - without it every warp kept a few live lanes until late and a pass cost N x |front| whatever was left.
 // close a level (one CTA): the candidates ordered by (key, original index) become the next front, stored in that order and,
 // beside it, sorted by position.  s_sort: kOrderCap entries, s_pos: 1024 entries of shared memory.
 __device__ void order_level(const SortedView &V, int first, unsigned long long *s_sort, unsigned *s_pos)
 {
     Meta *meta = V.meta;
+    // speculative loads for the common small level (thread i owns candidate i): issued before the bookkeeping is known, so the
+    // two round trips overlap; entries beyond ncand are stale and ignored (the arrays have n >= 4096 entries)
+    const int mm = V.m;
+    const unsigned spec_pos = __ldcg(V.cand + threadIdx.x);
+    const unsigned long long spec_key = __ldcg(V.cand_key + threadIdx.x);
+    unsigned spec_row[kMaxM];
+#pragma unroll
+    for (int k = 0; k < kMaxM; ++k) spec_row[k] = k < mm ? __ldcg(V.cand_rows + static_cast<size_t>(threadIdx.x) * mm + k) : 0u;
     const unsigned C = __ldcg(&meta->ncand);
     if (C > kOrderCap) {
         if (threadIdx.x == 0) meta->overflow = 1;
@@ -361,16 +325,17 @@ __device__ void order_level(const SortedView &V, int first, unsigned long long *
     if (C <= 1024u) {
         // small levels (the common case): rank sorts - every candidate counts the candidates that precede it in either order
         const int m = V.m;
+        const bool spec = blockDim.x >= 1024u; // thread i == candidate i
         for (unsigned i = threadIdx.x; i < C; i += blockDim.x) {
-            s_pos[i] = __ldcg(V.cand + i);
-            s_sort[i] = __ldcg(V.cand_key + i);
+            s_pos[i] = spec ? spec_pos : __ldcg(V.cand + i);
+            s_sort[i] = spec ? spec_key : __ldcg(V.cand_key + i);
         }
         __syncthreads();
         for (unsigned i = threadIdx.x; i < C; i += blockDim.x) {
             const unsigned long long mine = s_sort[i];
             const unsigned myp = s_pos[i];
             unsigned row[kMaxM];
-            for (int k = 0; k < m; ++k) row[k] = __ldcg(V.cand_rows + static_cast<size_t>(i) * m + k);
+            for (int k = 0; k < m; ++k) row[k] = spec ? spec_row[k] : __ldcg(V.cand_rows + static_cast<size_t>(i) * m + k);
             unsigned before = 0, bp = 0;
             for (unsigned j = 0; j < C; ++j) {
                 before += s_sort[j] < mine ? 1u : 0u; // (key, index) pairs are distinct
@@ -439,14 +404,88 @@ __device__ void order_level(const SortedView &V, int first, unsigned long long *
     }
 }
 
-template <int M> __global__ void __launch_bounds__(kTP) fnds_peel_sorted_kernel(SortedView V)
+// FUSED: the last thread block to finish a pass closes the level itself (order_level), so a level is ONE launch instead of two -
+// at 300-400 levels per sort the launches, not the work inside them, were most of a level (ncu: ~4 us active of a ~10 us peel
+// launch, ~5 of ~8.5 us for the order launch; profiles/r1x_fnds_variants.txt).
+template <int M, bool FUSED> __global__ void __launch_bounds__(kTP) fnds_peel_sorted_kernel(SortedView V)
 {
+    constexpr int m = M;
     __shared__ unsigned tileR[kTP * M], tileF[kTP];
+    __shared__ unsigned long long s_sort[FUSED ? kOrderCap : 1];
+    __shared__ unsigned s_pos[FUSED ? 1024 : 1];
+    __shared__ bool s_last;
+    // A level is latency: every dependent global round trip is ~1 us against ~2 us of arithmetic.  So the loads are issued in
+    // two independent chains before anything waits: (list entry -> its count / ranks / run bounds) and (bookkeeping -> tile 0).
+    const unsigned nact = V.nact_cap; // == meta->nact: the list only changes in compact_active, after which the host re-reads it
+    const unsigned first = blockIdx.x * kTP, idx = first + threadIdx.x;
+    const bool in = idx < nact;
+    const unsigned q = V.act[in ? idx : first];
+    const unsigned q_first = V.act[first], q_last = V.act[min(nact, first + kTP) - 1];
     const Meta *meta = V.meta;
-    if (meta->overflow || meta->done) return;
-    const unsigned fs = meta->front_size;
-    if (fs == 0) return;
-    peel_block<M>(V, blockIdx.x, fs, meta->front_off, meta->level, tileR, tileF);
+    const unsigned m_overflow = meta->overflow, m_done = meta->done, fs = meta->front_size, fo = meta->front_off, level = meta->level;
+    const unsigned left0 = in ? V.count[q] : 0u; // dominators not yet in a closed front; 0 = the point sits in a front
+    const unsigned lo = V.run_lo[q_first], limit = V.run_end[q_last];
+    const unsigned srcq = V.src[q];
+    unsigned rq[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) rq[i] = V.rs[static_cast<size_t>(q) * m + i];
+    if (m_overflow || m_done || fs == 0) return; // nobody takes a ticket: the level loop is over or waits for the host
+    const bool active = left0 != 0;
+    const bool work = __syncthreads_or(active);
+    unsigned c = 0, mp = 0;
+    for (unsigned base = 0; work && base < fs; base += kTP) {
+        const unsigned np = min(static_cast<unsigned>(kTP), fs - base);
+        const unsigned first_pos = __ldcg(V.pm_pos + fo + base), last_pos = __ldcg(V.pm_pos + fo + base + np - 1);
+        for (unsigned e = threadIdx.x; e < np * m; e += kTP) tileR[e] = __ldcg(V.pm_rows + static_cast<size_t>(fo + base) * m + e);
+        for (unsigned t = threadIdx.x; t < np; t += kTP) tileF[t] = __ldcg(V.pm_fpos + fo + base + t);
+        if (first_pos >= limit) break; // this member and all later ones lie beyond the run of the block's last entry
+        __syncthreads();
+        if (active) {
+            if (last_pos < lo) {
+#pragma unroll 4
+                for (unsigned t = 0; t < np; ++t)
+                    if (dominates_tail<M>(tileR + t * M, rq)) {
+                        ++c;
+                        mp = max(mp, tileF[t]);
+                    }
+            } else {
+#pragma unroll 4
+                for (unsigned t = 0; t < np; ++t)
+                    if (dominates_rank<M>(tileR + t * M, rq)) {
+                        ++c;
+                        mp = max(mp, tileF[t]);
+                    }
+            }
+        }
+        __syncthreads();
+    }
+    if (active && c) {
+        const unsigned left = left0 - c;
+        V.count[q] = left;
+        if (left == 0) {
+            V.rank[q] = level + 1;
+            V.key[q] = mp;
+            const unsigned slot = atomicAdd(&V.meta->ncand, 1u);
+            V.cand[slot] = q;
+            V.cand_key[slot] = (static_cast<unsigned long long>(mp) << 32) | srcq;
+#pragma unroll
+            for (int i = 0; i < M; ++i) V.cand_rows[static_cast<size_t>(slot) * m + i] = rq[i];
+        }
+    }
+    if (FUSED) {
+        __threadfence(); // this block's candidates are visible before its ticket is
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&V.meta->tickets, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            if (threadIdx.x == 0) V.meta->tickets = 0;
+            if (__ldcg(&V.meta->ncand) > kFusedCap) {
+                if (threadIdx.x == 0) V.meta->overflow = 2; // too big for 256 threads: the host launches the order kernel
+            } else {
+                order_level(V, 0, s_sort, s_pos);
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(1024) fnds_order_sorted_kernel(SortedView V, int first)
@@ -457,28 +496,6 @@ __global__ void __launch_bounds__(1024) fnds_order_sorted_kernel(SortedView V, i
     if (meta->overflow || meta->done) return;
     if (!first && meta->front_size == 0) return; // finished earlier
     order_level(V, first, s_sort, s_pos);
-}
-
-// The whole remaining level loop in ONE cooperative launch: a co-resident grid, peel | grid.sync | CTA 0 closes the level |
-// grid.sync.  Every CTA owns the same position blocks at every level (b = blockIdx.x, + gridDim.x, ...), so rank[] / count[]
-// stay coherent in its L1.  Returns when all points are assigned, `stop_after` is reached or a level overflows kOrderCap.
-template <int M> __global__ void __launch_bounds__(kTP) fnds_levels_sorted_kernel(SortedView V)
-{
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    __shared__ unsigned tileR[kTP * M], tileF[kTP];
-    __shared__ unsigned long long s_sort[kOrderCap];
-    __shared__ unsigned s_pos[1024];
-    const unsigned nblocks = (V.n + kTP - 1) / kTP;
-    Meta *meta = V.meta;
-    for (;;) {
-        const unsigned fs = __ldcg(&meta->front_size), fo = __ldcg(&meta->front_off), level = __ldcg(&meta->level);
-        if (__ldcg(&meta->overflow) || __ldcg(&meta->done) || __ldcg(&meta->assigned) >= V.n || fs == 0) break;
-        for (unsigned b = blockIdx.x; b < nblocks; b += gridDim.x) peel_block<M>(V, b, fs, fo, level, tileR, tileF);
-        grid.sync();
-        if (blockIdx.x == 0) order_level(V, 0, s_sort, s_pos);
-        grid.sync();
-    }
 }
 
 // big levels (more than kOrderCap candidates): the host sorts packed keys with CUB
@@ -836,21 +853,25 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
     if (m >= 1 && n >= 4096) {
         // ---- large inputs: dense integer ranks per objective, then the level loop in sorted space (see SortedView) ----
         unsigned long long *k0, *k1;
-        unsigned *i0, *i1, *src, *flags, *dense, *ranks, *rs, *inv, *blk_lo, *blk_limit, *rank_s, *key_s, *order_s, *pm_pos, *pm_fpos, *cand_rows, *pm_rows;
+        unsigned *i0, *i1, *src, *flags, *dense, *ranks, *rs, *inv, *run_lo, *run_end, *act_a, *act_b, *rank_s, *key_s, *order_s, *pm_pos, *pm_fpos, *cand_rows, *pm_rows;
         unsigned long long *cand_key;
         if ((rc = ws.alloc(&k0, n)) || (rc = ws.alloc(&k1, n)) || (rc = ws.alloc(&i0, n)) || (rc = ws.alloc(&i1, n)) || (rc = ws.alloc(&src, n))
             || (rc = ws.alloc(&flags, n)) || (rc = ws.alloc(&dense, n)) || (rc = ws.alloc(&ranks, static_cast<size_t>(n) * m))
-            || (rc = ws.alloc(&rs, static_cast<size_t>(n) * m)) || (rc = ws.alloc(&inv, n)) || (rc = ws.alloc(&blk_lo, gb))
-            || (rc = ws.alloc(&blk_limit, gb)) || (rc = ws.alloc(&rank_s, n)) || (rc = ws.alloc(&key_s, n)) || (rc = ws.alloc(&order_s, n))
+            || (rc = ws.alloc(&rs, static_cast<size_t>(n) * m)) || (rc = ws.alloc(&inv, n)) || (rc = ws.alloc(&run_lo, n))
+            || (rc = ws.alloc(&run_end, n)) || (rc = ws.alloc(&act_a, n)) || (rc = ws.alloc(&act_b, n)) || (rc = ws.alloc(&rank_s, n)) || (rc = ws.alloc(&key_s, n)) || (rc = ws.alloc(&order_s, n))
             || (rc = ws.alloc(&pm_pos, n)) || (rc = ws.alloc(&pm_fpos, n)) || (rc = ws.alloc(&cand_rows, static_cast<size_t>(n) * m))
             || (rc = ws.alloc(&pm_rows, static_cast<size_t>(n) * m)) || (rc = ws.alloc(&cand_key, n)))
             return rc;
-        size_t b1 = 0, b2 = 0, b3 = 0;
+        size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
         void *tmp = nullptr;
+        const StillActive still_active{count};
+        cub::CountingInputIterator<unsigned> all_positions(0u);
+        PGC_CUDA(cub::DeviceSelect::If(nullptr, b4, all_positions, act_a, &meta->nact, static_cast<int>(n), still_active, st));
+        PGC_CUDA(cub::DeviceSelect::If(nullptr, b5, act_a, act_b, &meta->nact, static_cast<int>(n), still_active, st));
         PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b1, k0, k1, i0, i1, static_cast<int>(n), 0, 64, st));
         PGC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, b2, flags, dense, static_cast<int>(n), st));
         PGC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, b3, k0, k1, static_cast<int>(n), 0, 64, st));
-        const size_t tmp_bytes = std::max(b1, std::max(b2, b3));
+        const size_t tmp_bytes = std::max(std::max(b1, b2), std::max(b3, std::max(b4, b5)));
         if ((rc = ws.alloc_bytes(&tmp, tmp_bytes))) return rc;
         for (int obj = 0; obj < m; ++obj) {
             unsigned *sorted_idx = obj == 0 ? src : i1;
@@ -862,15 +883,13 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
         }
         gather_rows_u32m_kernel<<<blocks_for(static_cast<size_t>(n) * m, 256), 256, 0, st>>>(ranks, src, n, m, rs);
         invert_perm_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, n, inv);
-        SortedView V{rs,      src,    inv,     blk_lo,      blk_limit, count, rank_s, key_s, cand, cand_key, cand_rows, order_s,
-                     pm_pos,  pm_fpos, pm_rows, d_front_off, meta,      n,     m};
-        void *levels_fn = nullptr;
+        SortedView V{rs,    src,      inv,       run_lo,  run_end, act_a,   0u,      count,       rank_s, key_s, cand,
+                     cand_key, cand_rows, order_s, pm_pos,  pm_fpos, pm_rows, d_front_off, meta,   n,     m};
         switch (m) {
 #define PGC_MO_SORTED(MM)                                                                                              \
     case MM:                                                                                                           \
-        block_runs_kernel<MM><<<blocks_for(gb, 256), 256, 0, st>>>(rs, n, blk_lo, blk_limit);                          \
+        run_bounds_kernel<MM><<<blocks_for(n, 256), 256, 0, st>>>(rs, n, run_lo, run_end);                             \
         fnds_count_sorted_kernel<MM><<<gb, kTP, 0, st>>>(V, d_dom_count);                                              \
-        levels_fn = reinterpret_cast<void *>(fnds_levels_sorted_kernel<MM>);                                           \
         break;
             PGC_MO_SORTED(1) PGC_MO_SORTED(2) PGC_MO_SORTED(3) PGC_MO_SORTED(4) PGC_MO_SORTED(5) PGC_MO_SORTED(6) PGC_MO_SORTED(7)
             PGC_MO_SORTED(8)
@@ -878,7 +897,11 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
         }
         fnds_front0_sorted_kernel<<<blocks_for(n, 256), 256, 0, st>>>(V);
         fnds_order_sorted_kernel<<<1, 1024, 0, st>>>(V, 1);
-        ctx->launches.fetch_add(5 * m + 6, std::memory_order_relaxed);
+        {   // the active list: every position that still has dominators outside the closed fronts
+            size_t bytes = tmp_bytes;
+            PGC_CUDA(cub::DeviceSelect::If(tmp, bytes, all_positions, act_a, &meta->nact, static_cast<int>(n), still_active, st));
+        }
+        ctx->launches.fetch_add(5 * m + 8, std::memory_order_relaxed);
 
         Meta h;
         auto poll = [&]() -> int {
@@ -902,41 +925,45 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
         };
         if ((rc = poll())) return rc;
         if (h.overflow && (rc = big_level(1))) return rc;
-        int coop_attr = 0;
-        PGC_CUDA(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, ctx->device));
-        // PGC_FNDS_COOP=1 selects the single cooperative launch instead of two launches per level (A/B switch; results are
-        // identical).  Measured at pop 65 536 (profiles/r1s_bench_mo_65536.json): equal on ZDT1 (410 fronts of ~320), 30 % slower
-        // on DTLZ2 (83 fronts of ~1600: its 256-thread CTA sorts big levels slower than the 1024-thread order kernel), so the
-        // launch-per-level loop stays the default.
-        const char *coop_env = std::getenv("PGC_FNDS_COOP");
-        const bool coop = coop_attr != 0 && coop_env && coop_env[0] == '1';
-        unsigned coop_grid = 0;
+        const char *fuse_env = std::getenv("PGC_FNDS_FUSE"); // PGC_FNDS_FUSE=0: always two launches per level (A/B switch)
+        const bool fuse_ok = !(fuse_env && fuse_env[0] == '0');
+        const char *batch_env = std::getenv("PGC_FNDS_BATCH"); // levels launched between two host polls (experiments)
+        const int batch = batch_env ? std::max(1, std::atoi(batch_env)) : kBatch;
         while (h.assigned < n && !h.done) {
             if (h.front_size == 0) {
                 set_error("fast_non_dominated_sorting: internal error, empty front with %u of %u points assigned", h.assigned, n);
                 return PGC_ERR_CUDA;
             }
-            if (coop) {
-                if (coop_grid == 0) {
-                    int per_sm = 0;
-                    PGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, levels_fn, kTP, 0));
-                    coop_grid = std::min<unsigned>(gb, static_cast<unsigned>(ctx->sm_count * std::max(1, per_sm)));
-                }
-                void *args[] = {&V};
-                PGC_CUDA(cudaLaunchCooperativeKernel(levels_fn, dim3(coop_grid), dim3(kTP), args, 0, st));
-                ctx->launches.fetch_add(1, std::memory_order_relaxed);
-            } else {
-                for (int b = 0; b < kBatch; ++b) {
-                    switch (m) {
-#define PGC_MO_PEEL(MM) case MM: fnds_peel_sorted_kernel<MM><<<gb, kTP, 0, st>>>(V); break;
-                        PGC_MO_PEEL(1) PGC_MO_PEEL(2) PGC_MO_PEEL(3) PGC_MO_PEEL(4) PGC_MO_PEEL(5) PGC_MO_PEEL(6) PGC_MO_PEEL(7) PGC_MO_PEEL(8)
+            const unsigned grid = std::max(1u, blocks_for(h.nact, kTP)); // h.nact: length of the list at the last compaction
+            V.nact_cap = h.nact;
+            // small fronts: one fused launch per level; a front above kFusedCap switches the next batches to two launches
+            const bool fused = fuse_ok && h.front_size <= kFusedCap;
+            for (int b = 0; b < batch; ++b) {
+                switch (m) {
+#define PGC_MO_PEEL(MM)                                                                                                \
+    case MM:                                                                                                           \
+        if (fused) fnds_peel_sorted_kernel<MM, true><<<grid, kTP, 0, st>>>(V);                                         \
+        else fnds_peel_sorted_kernel<MM, false><<<grid, kTP, 0, st>>>(V);                                              \
+        break;
+                    PGC_MO_PEEL(1) PGC_MO_PEEL(2) PGC_MO_PEEL(3) PGC_MO_PEEL(4) PGC_MO_PEEL(5) PGC_MO_PEEL(6) PGC_MO_PEEL(7) PGC_MO_PEEL(8)
 #undef PGC_MO_PEEL
-                    }
-                    fnds_order_sorted_kernel<<<1, 1024, 0, st>>>(V, 0);
                 }
-                ctx->launches.fetch_add(2 * kBatch, std::memory_order_relaxed);
+                if (!fused) fnds_order_sorted_kernel<<<1, 1024, 0, st>>>(V, 0);
             }
+            {   // drop the points that joined a front during this batch (order is kept: the list stays ascending)
+                unsigned *next = V.act == act_a ? act_b : act_a;
+                size_t bytes = tmp_bytes;
+                PGC_CUDA(cub::DeviceSelect::If(tmp, bytes, V.act, next, &meta->nact, static_cast<int>(h.nact), still_active, st));
+                V.act = next;
+            }
+            ctx->launches.fetch_add((fused ? 1 : 2) * batch + 2, std::memory_order_relaxed);
             if ((rc = poll())) return rc;
+            if (h.overflow == 2) { // a fused pass left a level of more than kFusedCap candidates open
+                PGC_CUDA(cudaMemsetAsync(&meta->overflow, 0, sizeof(unsigned), st));
+                fnds_order_sorted_kernel<<<1, 1024, 0, st>>>(V, 0);
+                ctx->launches.fetch_add(1, std::memory_order_relaxed);
+                if ((rc = poll())) return rc;
+            }
             if (h.overflow && (rc = big_level(0))) return rc;
         }
         fnds_unsort_kernel<<<blocks_for(n, 256), 256, 0, st>>>(V, d_rank, d_key_out, d_order);
