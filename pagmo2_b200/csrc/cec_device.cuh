@@ -134,6 +134,23 @@ __device__ __forceinline__ double fast_rcp(double d)
     return fma(r, fma(e, e, e), r);
 }
 
+// sqrt(x) for x >= 0 without the IEEE routine's special-case branch: hardware seed (rsqrt.approx.ftz.f64), two coupled
+// Goldschmidt steps on (g ~ sqrt x, h ~ 1 / (2 sqrt x)) and one residual correction - <= 1 ulp on normal inputs; x = 0 (and
+// denormals) are lifted to the smallest magnitudes whose root the callers multiply by x anyway.
+__device__ __forceinline__ double sqrt_nobranch(double x)
+{
+    const double xs = fmax(x, 1.0e-300);
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(xs));
+    double g = xs * r, h = 0.5 * r;
+    double e = fma(-h, g, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    e = fma(-h, g, 0.5);
+    g = fma(g, e, g);
+    return fma(fma(-g, g, xs), h, g);
+}
+
 // the kLPI lanes of an individual are kTileInd apart (lane = q * kTileInd + individual)
 __device__ __forceinline__ double pair_add(double v)
 {

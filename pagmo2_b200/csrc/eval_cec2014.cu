@@ -112,7 +112,9 @@ template <bool CM = false> __device__ __forceinline__ void schwefel_term(double 
     // z > 500: (500 - fmod(z,500)); z < -500: -(-500 + fmod(|z|,500)); else |z|
     const double m = big ? 500.0 - fm : az;
     const double t = (z - copysign(500.0, z)) * 0.01;
-    sub = copysign(m, z) * sin_theta<CM>(sqrt(m));
+    // the separable kernel (CM) takes a branch-free square root so that the evaluations of a lane's coordinates interleave;
+    // the IEEE sqrt's slow-path branch kept them in separate basic blocks (FP64 pipe 60 % busy, issue slots 61 %: latency bound)
+    sub = copysign(m, z) * sin_theta<CM>(CM ? sqrt_nobranch(m) : sqrt(m));
     pen = big ? t * t * inv_n : 0.0;
 }
 
@@ -610,10 +612,11 @@ template <int D> __global__ void __launch_bounds__(kSepThreads, PGC_SEP_MINB) ce
             xv[ps] = (active && c < CH) ? __ldcs(src + c) : make_double2(0.0, 0.0);
         }
         double s = 0.0, w = 0.0;
+        constexpr bool FULL = CH % G == 0; // every pass is complete: no per-pass branch, one basic block for all coordinates
 #pragma unroll
         for (int ps = 0; ps < PASS; ++ps) {
             const int c = ps * G + cl;
-            if (c < CH) {
+            if (FULL || c < CH) {
                 const double d0 = xv[ps].x - osv[ps].x, d1 = xv[ps].y - osv[ps].y; // :1245-1258
                 w += d0 * d0 + d1 * d1;                                             // cf_cal weight, :1330-1332
                 const double z0 = d0 * pre_rate * rate, z1 = d1 * pre_rate * rate;
