@@ -151,6 +151,44 @@ __device__ __forceinline__ double sqrt_nobranch(double x)
     return fma(fma(-g, g, xs), h, g);
 }
 
+// katsuura's inner sum  sum_{k=1..32} |2^k z - floor(2^k z + 0.5)| / 2^k  (cec2014.cpp:604-611, cec2013.cpp:726-735).
+// |2^k z - floor(2^k z + 0.5)| is the distance d_k of 2^k z to the nearest integer; it obeys the tent map
+// d_{k+1} = 1/2 - |2 d_k - 1/2|, every step exact in FP64 for |z| >~ 2^-10 (below that a step may round by <= 2^-55, far
+// inside the tolerance), and "/ 2^k" is an exact scaling: three instructions per term instead of a multiply, a rounding, a
+// subtraction and a division.  Huge |z| (>= 2^18, outside every CEC domain) keeps the reference's own loop.
+__device__ __forceinline__ double katsuura_inner(double z)
+{
+    double temp = 0.0;
+    if (fabs(z) < 262144.0) {
+        const double t2 = z + z;
+        double d = fabs(t2 - round_magic(t2)), it1 = 0.5;
+        temp = d * it1;
+#pragma unroll
+        for (int k = 2; k <= 32; ++k) {
+            it1 *= 0.5;
+            d = 0.5 - fabs(fma(2.0, d, -0.5));
+            temp = fma(d, it1, temp);
+        }
+    } else {
+        double t1 = 1.0;
+        for (int k = 1; k <= 32; ++k) {
+            t1 *= 2.0;
+            const double t2 = t1 * z;
+            temp += fabs(t2 - floor(t2 + 0.5)) / t1;
+        }
+    }
+    return temp;
+}
+
+// one angle-tripling step w -> w^3 on the unit circle, w = cs + i sn: c (c^2 - 3 s^2) + i s (3 c^2 - s^2), six FP64 instructions
+__device__ __forceinline__ void triple_angle(double &sn, double &cs)
+{
+    const double cc = cs * cs, ss = sn * sn;
+    const double c3 = cs * fma(-3.0, ss, cc), s3 = sn * fma(3.0, cc, -ss);
+    cs = c3;
+    sn = s3;
+}
+
 // the kLPI lanes of an individual are kTileInd apart (lane = q * kTileInd + individual)
 __device__ __forceinline__ double pair_add(double v)
 {

@@ -146,10 +146,7 @@ __device__ double reduce13(const Params13 &P, const Row &v, int h, const double 
                            if (k % 10 == 0 && k < 20) {
                                sincos_turns(turns_of(gt[k] * u), sn, cs);
                            } else {
-                               const double c2 = fma(cs, cs, -(sn * sn)), s2 = (cs + cs) * sn;
-                               const double c3 = fma(c2, cs, -(s2 * sn)), s3 = fma(s2, cs, c2 * sn);
-                               cs = c3;
-                               sn = s3;
+                               triple_angle(sn, cs);
                            }
                            sum = fma(w, cs, sum);
                            w *= 0.5;
@@ -185,18 +182,10 @@ __device__ double reduce13(const Params13 &P, const Row &v, int h, const double 
             }
             return 4.189828872724338e+002 * dn + pair_add(s);
         }
-        case R_KATS: { // :726-738; prod_j b_j^c0 = exp(c0 * sum_j log b_j)
-            double slog = ordered_sum(h, n, [&](int j) {
-                const double z = v(j);
-                double temp = 0.0, t1 = 1.0;
-                for (int k = 1; k <= 32; ++k) {
-                    t1 *= 2.0;
-                    const double t2 = t1 * z;
-                    temp += fabs(t2 - floor(t2 + 0.5)) / t1;
-                }
-                return log(1.0 + static_cast<double>(j + 1) * temp);
-            });
-            slog = pair_add(slog);
+        case R_KATS: { // :726-738; prod_j b_j^c0 = exp(c0 * log(prod_j b_j)): every lane multiplies its own factors (each in
+                       // [1, 1 + n/2], at most 25 of them) and takes one log - as eval_cec2014.cu
+            const double prod = ordered_prod(h, n, [&](int j) { return 1.0 + static_cast<double>(j + 1) * katsuura_inner(v(j)); });
+            double slog = pair_add(log(prod));
             return exp(P.kats_c0 * slog) * P.kats_c1 - P.kats_c1;
         }
         case R_BIRAS: { // :779-797; tmpx is rebuilt from x (:751-763): y = (x-Os)*0.1, tmpx = +-2y + mu0

@@ -180,11 +180,7 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
                            if (k == 0) {
                                sincos_turns(turns_of(gt[k] * u), sn, cs);
                            } else {
-                               // w^3 = c (c^2 - 3 s^2) + i s (3 c^2 - s^2): six FP64 instructions
-                               const double cc = cs * cs, ss = sn * sn;
-                               const double c3 = cs * fma(-3.0, ss, cc), s3 = sn * fma(3.0, cc, -ss);
-                               cs = c3;
-                               sn = s3;
+                               triple_angle(sn, cs);
                            }
                            sum = fma(w, cs, sum); // 0.5^k * cos is an exact scaling: == "sum += pow(a,k)*cos"
                            w *= 0.5;
@@ -239,27 +235,7 @@ __device__ double eval_group(const GroupDesc &g, const Elem &v, const double *__
             // (magic-constant add, valid for |2^k z| < 2^51).  prod_j b_j^c0 is taken as exp(c0 * log(prod_j b_j)): each
             // lane multiplies its own factors b_j in [1, 1 + n/2] (at most 25 of them: <= 5e42) and takes ONE log.
             double prod = ordered_prod(lo, hi, [&](int j) {
-                const double z = v(j);
-                double temp = 0.0;
-                if (fabs(z) < 262144.0) {
-                    // d_k = dist(2^k z, Z) obeys the tent map d_{k+1} = 1/2 - |2 d_k - 1/2|, every step exact in FP64
-                    const double t2 = z + z;
-                    double d = fabs(t2 - round_magic(t2)), it1 = 0.5;
-                    temp = d * it1;
-#pragma unroll
-                    for (int k = 2; k <= 32; ++k) {
-                        it1 *= 0.5;
-                        d = 0.5 - fabs(fma(2.0, d, -0.5));
-                        temp = fma(d, it1, temp); // "/ 2^k" is an exact scaling
-                    }
-                } else {
-                    double t1 = 1.0;
-                    for (int k = 1; k <= 32; ++k) {
-                        t1 *= 2.0;
-                        const double t2 = t1 * z;
-                        temp += fabs(t2 - floor(t2 + 0.5)) / t1;
-                    }
-                }
+                const double temp = katsuura_inner(v(j));
                 return 1.0 + static_cast<double>(j + 1) * temp;
             });
             double slog = pair_add(log(prod));
