@@ -132,3 +132,26 @@ def test_duplicate_points_follow_the_stable_restatement(ctx, orc, m):
         for N in (1, n // 4, n // 2, n - 1):
             assert np.array_equal(ctx.select_best_N_mo(f, N), orc.select_best_N_mo(f, N)), (n, N)
         assert np.array_equal(ctx.sort_population_mo(f), orc.sort_population_mo(f))
+
+
+def test_fnds_sorted_space_degenerate_inputs(ctx, orc):
+    """inputs that stress the large-input (sorted-space) level loop: every point identical (one front, nothing left to peel), two
+    distinct points repeated (two fronts larger than the shared-memory sort, runs of equal first ranks spanning many blocks), a
+    total order (one point per front: thousands of levels, the compacted list shrinking by one per level), and select_best_N_mo
+    stopping inside such a sort."""
+    n = 4608
+    same = np.full((n, 2), 0.25)
+    assert same_fnds(ctx.fnds(same), orc.fnds(same))
+    two = np.where((np.arange(n) % 2 == 0)[:, None], np.array([[0.1, 0.2]]), np.array([[0.3, 0.4]]))
+    assert same_fnds(ctx.fnds(two), orc.fnds(two))
+    chain = np.stack([np.arange(n, dtype=float), np.arange(n, dtype=float)[::-1].copy()[::-1]], axis=1)  # point i dominates i + 1
+    rng = np.random.default_rng(5)
+    chain = chain[rng.permutation(n)]
+    got = ctx.fnds(chain)
+    assert same_fnds(got, orc.fnds(chain)) and len(got["fronts"]) == n
+    for N in (1, 100, n // 2):
+        assert np.array_equal(ctx.select_best_N_mo(chain, N), orc.select_best_N_mo(chain, N))
+    # three objectives, half the points cloned
+    f = rng.uniform(0, 1, (n, 3))
+    f[n // 2:] = f[:n // 2]
+    assert same_fnds(ctx.fnds(f), orc.fnds(f))
