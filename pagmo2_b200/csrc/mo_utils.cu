@@ -42,6 +42,10 @@ constexpr int kMaxM = 8;          // objectives held in registers
 constexpr int kOrderCap = 4096;   // candidates the single-CTA order kernel sorts in shared memory
 constexpr int kBatch = 8;         // levels launched between two host polls
 constexpr unsigned kFusedCap = 1024; // largest level the last thread block of a fused peel pass orders itself
+#ifndef PGC_PEEL_THREADS
+#define PGC_PEEL_THREADS 256
+#endif
+constexpr int kPT = PGC_PEEL_THREADS; // threads (= list entries) per thread block of the sorted-space peel pass; tiles stay kTP wide
 
 struct Meta {            // device-side bookkeeping of the level loop
     unsigned ncand;      // candidates collected by the current peel
@@ -407,7 +411,7 @@ __device__ void order_level(const SortedView &V, int first, unsigned long long *
 // FUSED: the last thread block to finish a pass closes the level itself (order_level), so a level is ONE launch instead of two -
 // at 300-400 levels per sort the launches, not the work inside them, were most of a level (ncu: ~4 us active of a ~10 us peel
 // launch, ~5 of ~8.5 us for the order launch; profiles/r1x_fnds_variants.txt).
-template <int M, bool FUSED> __global__ void __launch_bounds__(kTP) fnds_peel_sorted_kernel(SortedView V)
+template <int M, bool FUSED> __global__ void __launch_bounds__(kPT) fnds_peel_sorted_kernel(SortedView V)
 {
     constexpr int m = M;
     __shared__ unsigned tileR[kTP * M], tileF[kTP];
@@ -417,10 +421,10 @@ template <int M, bool FUSED> __global__ void __launch_bounds__(kTP) fnds_peel_so
     // A level is latency: every dependent global round trip is ~1 us against ~2 us of arithmetic.  So the loads are issued in
     // two independent chains before anything waits: (list entry -> its count / ranks / run bounds) and (bookkeeping -> tile 0).
     const unsigned nact = V.nact_cap; // == meta->nact: the list only changes in compact_active, after which the host re-reads it
-    const unsigned first = blockIdx.x * kTP, idx = first + threadIdx.x;
+    const unsigned first = blockIdx.x * kPT, idx = first + threadIdx.x;
     const bool in = idx < nact;
     const unsigned q = V.act[in ? idx : first];
-    const unsigned q_first = V.act[first], q_last = V.act[min(nact, first + kTP) - 1];
+    const unsigned q_first = V.act[first], q_last = V.act[min(nact, first + kPT) - 1];
     const Meta *meta = V.meta;
     const unsigned m_overflow = meta->overflow, m_done = meta->done, fs = meta->front_size, fo = meta->front_off, level = meta->level;
     const unsigned left0 = in ? V.count[q] : 0u; // dominators not yet in a closed front; 0 = the point sits in a front
@@ -436,8 +440,8 @@ template <int M, bool FUSED> __global__ void __launch_bounds__(kTP) fnds_peel_so
     for (unsigned base = 0; work && base < fs; base += kTP) {
         const unsigned np = min(static_cast<unsigned>(kTP), fs - base);
         const unsigned first_pos = __ldcg(V.pm_pos + fo + base), last_pos = __ldcg(V.pm_pos + fo + base + np - 1);
-        for (unsigned e = threadIdx.x; e < np * m; e += kTP) tileR[e] = __ldcg(V.pm_rows + static_cast<size_t>(fo + base) * m + e);
-        for (unsigned t = threadIdx.x; t < np; t += kTP) tileF[t] = __ldcg(V.pm_fpos + fo + base + t);
+        for (unsigned e = threadIdx.x; e < np * m; e += kPT) tileR[e] = __ldcg(V.pm_rows + static_cast<size_t>(fo + base) * m + e);
+        for (unsigned t = threadIdx.x; t < np; t += kPT) tileF[t] = __ldcg(V.pm_fpos + fo + base + t);
         if (first_pos >= limit) break; // this member and all later ones lie beyond the run of the block's last entry
         __syncthreads();
         if (active) {
@@ -934,7 +938,7 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
                 set_error("fast_non_dominated_sorting: internal error, empty front with %u of %u points assigned", h.assigned, n);
                 return PGC_ERR_CUDA;
             }
-            const unsigned grid = std::max(1u, blocks_for(h.nact, kTP)); // h.nact: length of the list at the last compaction
+            const unsigned grid = std::max(1u, blocks_for(h.nact, kPT)); // h.nact: length of the list at the last compaction
             V.nact_cap = h.nact;
             // small fronts: one fused launch per level; a front above kFusedCap switches the next batches to two launches
             const bool fused = fuse_ok && h.front_size <= kFusedCap;
@@ -942,8 +946,8 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
                 switch (m) {
 #define PGC_MO_PEEL(MM)                                                                                                \
     case MM:                                                                                                           \
-        if (fused) fnds_peel_sorted_kernel<MM, true><<<grid, kTP, 0, st>>>(V);                                         \
-        else fnds_peel_sorted_kernel<MM, false><<<grid, kTP, 0, st>>>(V);                                              \
+        if (fused) fnds_peel_sorted_kernel<MM, true><<<grid, kPT, 0, st>>>(V);                                         \
+        else fnds_peel_sorted_kernel<MM, false><<<grid, kPT, 0, st>>>(V);                                              \
         break;
                     PGC_MO_PEEL(1) PGC_MO_PEEL(2) PGC_MO_PEEL(3) PGC_MO_PEEL(4) PGC_MO_PEEL(5) PGC_MO_PEEL(6) PGC_MO_PEEL(7) PGC_MO_PEEL(8)
 #undef PGC_MO_PEEL
