@@ -577,42 +577,78 @@ template <int D> __global__ void __launch_bounds__(kSepThreads, PGC_SEP_MINB) ce
 
     const long long ntiles = (P.n + ROWS - 1) / ROWS;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-    for (long long tile = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; tile < ntiles; tile += nwarps) {
+    // the loads of tile t + 1 are issued before tile t is evaluated (register double buffer): ncu showed the HBM round trip of a
+    // tile exposed with only ~4 warps per scheduler (long-scoreboard stalls 2.2 per issued instruction)
+    auto fetch = [&](long long tile, double2(&dst)[PASS]) {
+        const long long row = tile * ROWS + r;
+        const bool act = lane_ok && tile < ntiles && row < P.n;
+        const double2 *src = reinterpret_cast<const double2 *>(P.x + (act ? row : 0) * D);
+#pragma unroll
+        for (int ps = 0; ps < PASS; ++ps) {
+            const int c = ps * G + cl;
+            dst[ps] = (act && c < CH) ? __ldcs(src + c) : make_double2(0.0, 0.0);
+        }
+    };
+    const long long tile0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    double2 xnext[PASS];
+    fetch(tile0, xnext);
+    for (long long tile = tile0; tile < ntiles; tile += nwarps) {
         const long long row = tile * ROWS + r;
         const bool active = lane_ok && row < P.n;
-        const double2 *src = reinterpret_cast<const double2 *>(P.x + (active ? row : 0) * D);
         double2 xv[PASS];
 #pragma unroll
-        for (int ps = 0; ps < PASS; ++ps) {
-            const int c = ps * G + cl;
-            xv[ps] = (active && c < CH) ? __ldcs(src + c) : make_double2(0.0, 0.0);
-        }
+        for (int ps = 0; ps < PASS; ++ps) xv[ps] = xnext[ps];
+        fetch(tile + nwarps, xnext);
         double s = 0.0, w = 0.0;
-        constexpr bool FULL = CH % G == 0; // every pass is complete: no per-pass branch, one basic block for all coordinates
+        constexpr bool FULL = CH % G == 0; // every pass is complete: no per-pass branch
+        double z0[PASS], z1[PASS];
 #pragma unroll
         for (int ps = 0; ps < PASS; ++ps) {
             const int c = ps * G + cl;
-            if (FULL || c < CH) {
-                const double d0 = xv[ps].x - osv[ps].x, d1 = xv[ps].y - osv[ps].y; // :1245-1258
-                w += d0 * d0 + d1 * d1;                                             // cf_cal weight, :1330-1332
-                const double z0 = d0 * pre_rate * rate, z1 = d1 * pre_rate * rate;
-                if (prim == P_RASTRIGIN) {
-                    const double a = rastrigin_term<true>(z0), b = rastrigin_term<true>(z1);
-                    s += a;
-                    s += b;
-                } else if (prim == P_SCHWEFEL) {
-                    double s0, p0, s1, p1;
-                    schwefel_term<true>(z0, inv_n, s0, p0);
-                    schwefel_term<true>(z1, inv_n, s1, p1);
-                    s -= s0;
-                    s += p0;
-                    s -= s1;
-                    s += p1;
-                } else { // P_ELLIPS, :382-384
-                    s += cf[ps].x * z0 * z0;
-                    s += cf[ps].y * z1 * z1;
-                }
+            const bool ok = FULL || c < CH;
+            const double d0 = xv[ps].x - osv[ps].x, d1 = xv[ps].y - osv[ps].y; // :1245-1258
+            if (ok) w += d0 * d0 + d1 * d1;                                      // cf_cal weight, :1330-1332
+            z0[ps] = d0 * pre_rate * rate;
+            z1[ps] = d1 * pre_rate * rate;
+        }
+        // the primitive is chosen OUTSIDE the pass loop: each branch is one straight-line block over all of the lane's coordinates,
+        // so their (independent) evaluations interleave - with the switch inside the loop every pass was its own basic block and
+        // the kernel ran at the latency of one FP64 dependency chain (ncu: FP64 pipe 56-60 % busy, issue slots 47-61 %)
+        if (prim == P_RASTRIGIN) {
+            double ta[PASS], tb[PASS];
+#pragma unroll
+            for (int ps = 0; ps < PASS; ++ps) {
+                ta[ps] = rastrigin_term<true>(z0[ps]);
+                tb[ps] = rastrigin_term<true>(z1[ps]);
             }
+#pragma unroll
+            for (int ps = 0; ps < PASS; ++ps)
+                if (FULL || ps * G + cl < CH) {
+                    s += ta[ps];
+                    s += tb[ps];
+                }
+        } else if (prim == P_SCHWEFEL) {
+            double s0[PASS], p0[PASS], s1[PASS], p1[PASS];
+#pragma unroll
+            for (int ps = 0; ps < PASS; ++ps) {
+                schwefel_term<true>(z0[ps], inv_n, s0[ps], p0[ps]);
+                schwefel_term<true>(z1[ps], inv_n, s1[ps], p1[ps]);
+            }
+#pragma unroll
+            for (int ps = 0; ps < PASS; ++ps)
+                if (FULL || ps * G + cl < CH) {
+                    s -= s0[ps];
+                    s += p0[ps];
+                    s -= s1[ps];
+                    s += p1[ps];
+                }
+        } else { // P_ELLIPS, :382-384
+#pragma unroll
+            for (int ps = 0; ps < PASS; ++ps)
+                if (FULL || ps * G + cl < CH) {
+                    s += cf[ps].x * z0[ps] * z0[ps];
+                    s += cf[ps].y * z1[ps] * z1[ps];
+                }
         }
         // the row's G partial sums, added in lane order
         double val = 0.0, wsum = 0.0;
