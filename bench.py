@@ -340,7 +340,7 @@ def run_native(args):
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": STAGE_DRAM_BYTES,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one rotated stage launch (1 Mi x 100), ncu --set full, "
-                                     "profiles/r1y_stage_kernel_ncu_full.csv (839.0 MB read + 6-8 MB written); algorithmic bytes of that launch = 8*(100+1)*2^20 = 8.47e8",
+                                     "profiles/r1z_stage_kernel_ncu_full.csv (839.0 MB read + 6-8 MB written); algorithmic bytes of that launch = 8*(100+1)*2^20 = 8.47e8",
                      "peak_source": "pgc_measure_fp64_peak (DFMA loop, this run); MEASURED_PEAKS.json has no FP64 figure",
                      "dmma_probe_tflops": fp64_mma_peak,
                      "rotation_only_frac": rot_flops_step / step_s_rank / 1e12 / fp64_peak,

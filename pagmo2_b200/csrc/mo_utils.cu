@@ -19,7 +19,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
@@ -869,7 +869,7 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
         size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
         void *tmp = nullptr;
         const StillActive still_active{count};
-        cub::CountingInputIterator<unsigned> all_positions(0u);
+        thrust::counting_iterator<unsigned> all_positions(0u);
         PGC_CUDA(cub::DeviceSelect::If(nullptr, b4, all_positions, act_a, &meta->nact, static_cast<int>(n), still_active, st));
         PGC_CUDA(cub::DeviceSelect::If(nullptr, b5, act_a, act_b, &meta->nact, static_cast<int>(n), still_active, st));
         PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b1, k0, k1, i0, i1, static_cast<int>(n), 0, 64, st));
