@@ -60,6 +60,8 @@ struct Meta {            // device-side bookkeeping of the level loop
     unsigned done;
     unsigned nact;       // sorted-space loop: live length of the active list
     unsigned tickets;    // fused levels: thread blocks of the current peel pass that have finished (the last one closes the level)
+    unsigned level_pub;  // persistent loop: `level`, stored LAST when a level is closed - the flag the other thread blocks spin on
+    unsigned stuck;      // persistent loop: a thread block gave up waiting (watchdog); the host reports an internal error
 };
 
 // pareto_dominance, multi_objective.cpp:97-113 with the NaN-aware comparisons of detail/custom_comparisons.hpp:54-88
@@ -405,6 +407,8 @@ __device__ void order_level(const SortedView &V, int first, unsigned long long *
         meta->ncand = 0;
         const unsigned stop = __ldcg(&meta->stop_after);
         if (stop && assigned >= stop) meta->done = 1;
+        __threadfence();
+        *reinterpret_cast<volatile unsigned *>(&meta->level_pub) = level; // after everything else of the new level is visible
     }
 }
 
@@ -490,6 +494,168 @@ template <int M, bool FUSED> __global__ void __launch_bounds__(kPT) fnds_peel_so
             }
         }
     }
+}
+
+// ---- the level loop as ONE resident kernel -----------------------------------------------------------------------------------
+// On this system a dependent kernel launch costs ~10 us end to end whatever it does, and a sort has 300-400 levels.  Here the grid
+// stays resident for the whole loop (cooperative launch: one 1024-thread block per SM, all co-resident): thread t of block b owns
+// sorted position b * slice + t for the entire sort and keeps its point - ranks, remaining dominator count, original index - in
+// REGISTERS, so a level reads nothing on the point side.  A level: every block peels the current front (tiles of its members
+// through shared memory, cut at the end of the block's last run), appends its new candidates, fences and takes a ticket; the block
+// that takes the last ticket closes the level (order_level, 1024 threads) and publishes meta->level_pub; the others spin on that
+// word.  The loop leaves the kernel for the host only when a level has more than kOrderCap candidates (CUB path), writing the
+// counts back first so that any path can resume.  A watchdog on the spin (never seen firing) turns a lost wake-up into an error
+// instead of a hung device.
+constexpr int kPersistThreads = 1024;
+constexpr unsigned kSpinLimit = 1u << 26;
+
+template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persistent_kernel(SortedView V, unsigned slice)
+{
+    constexpr int m = M;
+    __shared__ unsigned tileR[kTP * M], tileF[kTP], tileP[kTP];
+    __shared__ unsigned long long s_sort[kOrderCap];
+    __shared__ unsigned s_pos[1024];
+    __shared__ unsigned s_flag[2]; // [0]: exit code seen by thread 0 (0 go on, 1 leave), [1]: this block took the last ticket
+    Meta *meta = V.meta;
+    // Warp w of block b owns the 32 consecutive positions of chunk b + w * gridDim.x: a point at a high position has more of a
+    // front before it than one at a low position, so contiguous slices per block left the last blocks with 4-5x the work of the
+    // first (measured with clock64: 21 k against 4.6 k cycles per level) and a level lasts as long as its slowest block.
+    // Chunks dealt round-robin give every block the same mix; the cut-offs are per warp.
+    (void)slice;
+    const unsigned chunk = blockIdx.x + (threadIdx.x >> 5) * gridDim.x;
+    const unsigned q = chunk * 32u + (threadIdx.x & 31u);
+    const bool in = q < V.n;
+    unsigned left = in ? V.count[q] : 0u;
+    const unsigned srcq = in ? V.src[q] : 0u;
+    unsigned rq[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) rq[i] = in ? V.rs[static_cast<size_t>(q) * m + i] : 0u;
+    const bool nonempty = chunk * 32u < V.n;
+    const unsigned lo = nonempty ? V.run_lo[chunk * 32u] : 0u, limit = nonempty ? V.run_end[min(V.n, chunk * 32u + 32u) - 1] : 0u;
+    unsigned expect = __ldcg(&meta->level); // the front to peel next; nothing changes it before the first publication below
+#ifdef PGC_FNDS_TIMING
+    long long tw = 0, tp = 0, tt = 0, to = 0, nl = 0, norder = 0, t0 = clock64(), t1;
+#define PGC_TICK(acc) t1 = clock64(); acc += t1 - t0; t0 = t1;
+#else
+#define PGC_TICK(acc)
+#endif
+    for (;;) {
+        // ---- wait until front `expect` is published, then read the bookkeeping of this level
+        if (threadIdx.x == 0) {
+            unsigned spins = 0;
+            while (*reinterpret_cast<volatile unsigned *>(&meta->level_pub) != expect && ++spins < kSpinLimit) {
+            }
+            __threadfence();
+            unsigned code = 0;
+            if (spins >= kSpinLimit) {
+                meta->stuck = 1;
+                code = 1;
+            }
+            if (__ldcg(&meta->overflow) || __ldcg(&meta->done) || __ldcg(&meta->stuck) || __ldcg(&meta->assigned) >= V.n
+                || __ldcg(&meta->front_size) == 0)
+                code = 1;
+            s_flag[0] = code;
+        }
+        __syncthreads();
+        PGC_TICK(tw)
+        if (s_flag[0]) break;
+        const unsigned fs = __ldcg(&meta->front_size), fo = __ldcg(&meta->front_off), level = expect;
+        // ---- peel
+        const bool active = left != 0;
+        const bool warp_work = __any_sync(0xffffffffu, active);
+        const bool work = __syncthreads_or(active);
+        unsigned c = 0, mp = 0;
+        for (unsigned base = 0; work && base < fs; base += kTP) {
+            const unsigned np = min(static_cast<unsigned>(kTP), fs - base);
+            for (unsigned e = threadIdx.x; e < np * m; e += kPersistThreads) tileR[e] = __ldcg(V.pm_rows + static_cast<size_t>(fo + base) * m + e);
+            for (unsigned t = threadIdx.x; t < np; t += kPersistThreads) {
+                tileF[t] = __ldcg(V.pm_fpos + fo + base + t);
+                tileP[t] = __ldcg(V.pm_pos + fo + base + t);
+            }
+            __syncthreads();
+            const unsigned first_pos = tileP[0], last_pos = tileP[np - 1]; // one round trip for the whole tile
+            if (warp_work && first_pos < limit) {
+                // the tile is sorted by position: members [0, ta) lie before the run of the warp's first position (first objective
+                // strictly smaller: tail test), [ta, tb) inside the warp's runs (full test), [tb, np) after them (cannot dominate)
+                unsigned ta = 0, tb = np;
+                if (last_pos >= lo) {
+                    unsigned l = 0, h2 = np;
+                    while (l < h2) {
+                        const unsigned mid = (l + h2) >> 1;
+                        if (tileP[mid] < lo) l = mid + 1;
+                        else h2 = mid;
+                    }
+                    ta = l;
+                    h2 = np;
+                    while (l < h2) {
+                        const unsigned mid = (l + h2) >> 1;
+                        if (tileP[mid] < limit) l = mid + 1;
+                        else h2 = mid;
+                    }
+                    tb = l;
+                } else {
+                    ta = np;
+                }
+                if (active) {
+#pragma unroll 8
+                    for (unsigned t = 0; t < ta; ++t) { // branch-free: a data-dependent branch per pair costs issue slots
+                        const bool hit = dominates_tail<M>(tileR + t * M, rq);
+                        c += hit ? 1u : 0u;
+                        mp = max(mp, hit ? tileF[t] : 0u);
+                    }
+#pragma unroll 4
+                    for (unsigned t = ta; t < tb; ++t) {
+                        const bool hit = dominates_rank<M>(tileR + t * M, rq);
+                        c += hit ? 1u : 0u;
+                        mp = max(mp, hit ? tileF[t] : 0u);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (active && c) {
+            left -= c;
+            if (left == 0) {
+                V.rank[q] = level + 1;
+                V.key[q] = mp;
+                const unsigned slot = atomicAdd(&meta->ncand, 1u);
+                V.cand[slot] = q;
+                V.cand_key[slot] = (static_cast<unsigned long long>(mp) << 32) | srcq;
+#pragma unroll
+                for (int i = 0; i < M; ++i) V.cand_rows[static_cast<size_t>(slot) * m + i] = rq[i];
+            }
+        }
+        // ---- the block that takes the last ticket closes the level and publishes the next one
+        __threadfence();
+        __syncthreads();
+        PGC_TICK(tp)
+        if (threadIdx.x == 0) s_flag[1] = atomicAdd(&meta->tickets, 1u) == gridDim.x - 1 ? 1u : 0u;
+        __syncthreads();
+        PGC_TICK(tt)
+        if (s_flag[1]) {
+            if (threadIdx.x == 0) meta->tickets = 0;
+            __threadfence();
+            order_level(V, 0, s_sort, s_pos); // sets meta->overflow instead when the level is too big for shared memory ...
+            if (threadIdx.x == 0 && __ldcg(&meta->overflow)) { // ... and then the waiting blocks are released to leave as well
+                __threadfence();
+                *reinterpret_cast<volatile unsigned *>(&meta->level_pub) = expect + 1;
+            }
+#ifdef PGC_FNDS_TIMING
+            ++norder;
+#endif
+            PGC_TICK(to)
+        }
+        ++expect;
+#ifdef PGC_FNDS_TIMING
+        ++nl;
+#endif
+    }
+#ifdef PGC_FNDS_TIMING
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 70 || blockIdx.x == 147) && nl > 20)
+        printf("blk %3d: %lld levels  wait %lld  peel %lld  ticket %lld  order %lld (closed %lld) cycles per level\n", blockIdx.x, nl, tw / nl, tp / nl,
+               tt / nl, norder ? to / norder : 0, norder);
+#endif
+    if (in) V.count[q] = left; // any path can resume from here
 }
 
 __global__ void __launch_bounds__(1024) fnds_order_sorted_kernel(SortedView V, int first)
@@ -672,6 +838,7 @@ __global__ void close_big_level_kernel(unsigned *front_off_out, Meta *meta, int 
     front_off_out[level + 1] = off + C;
     meta->nfronts = level + 1;
     meta->level = level;
+    meta->level_pub = level;
     meta->front_off = off;
     meta->front_size = C;
     meta->assigned += C;
@@ -933,10 +1100,38 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
         const bool fuse_ok = !(fuse_env && fuse_env[0] == '0');
         const char *batch_env = std::getenv("PGC_FNDS_BATCH"); // levels launched between two host polls (experiments)
         const int batch = batch_env ? std::max(1, std::atoi(batch_env)) : kBatch;
+        // resident level loop (fnds_persistent_kernel) when every position gets its own thread of a one-block-per-SM grid;
+        // PGC_FNDS_PERSIST=0 selects the launch-per-level loop below (A/B switch; results are identical)
+        int coop_attr = 0;
+        PGC_CUDA(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, ctx->device));
+        const char *persist_env = std::getenv("PGC_FNDS_PERSIST");
+        const unsigned pgrid = static_cast<unsigned>(ctx->sm_count);
+        const unsigned slice = (n + pgrid - 1) / pgrid;
+        const bool persist = coop_attr != 0 && slice <= static_cast<unsigned>(kPersistThreads) && !(persist_env && persist_env[0] == '0');
         while (h.assigned < n && !h.done) {
             if (h.front_size == 0) {
                 set_error("fast_non_dominated_sorting: internal error, empty front with %u of %u points assigned", h.assigned, n);
                 return PGC_ERR_CUDA;
+            }
+            if (persist) {
+                void *fn = nullptr;
+                switch (m) {
+#define PGC_MO_PERSIST(MM) case MM: fn = reinterpret_cast<void *>(fnds_persistent_kernel<MM>); break;
+                    PGC_MO_PERSIST(1) PGC_MO_PERSIST(2) PGC_MO_PERSIST(3) PGC_MO_PERSIST(4) PGC_MO_PERSIST(5) PGC_MO_PERSIST(6)
+                    PGC_MO_PERSIST(7) PGC_MO_PERSIST(8)
+#undef PGC_MO_PERSIST
+                }
+                unsigned slice_arg = slice;
+                void *args[] = {&V, &slice_arg};
+                PGC_CUDA(cudaLaunchCooperativeKernel(fn, dim3(pgrid), dim3(kPersistThreads), args, 0, st));
+                ctx->launches.fetch_add(1, std::memory_order_relaxed);
+                if ((rc = poll())) return rc;
+                if (h.stuck) {
+                    set_error("fast_non_dominated_sorting: internal error, the resident level loop lost a wake-up at level %u", h.level);
+                    return PGC_ERR_CUDA;
+                }
+                if (h.overflow && (rc = big_level(0))) return rc;
+                continue;
             }
             const unsigned grid = std::max(1u, blocks_for(h.nact, kPT)); // h.nact: length of the list at the last compaction
             V.nact_cap = h.nact;
