@@ -336,16 +336,44 @@ __device__ void order_level(const SortedView &V, int first, unsigned long long *
             s_pos[i] = spec ? spec_pos : __ldcg(V.cand + i);
             s_sort[i] = spec ? spec_key : __ldcg(V.cand_key + i);
         }
+        // With 1024 threads and C candidates the scan of a candidate is split over `parts` threads (thread t: candidate t % Cr,
+        // part t / Cr); the partial counts meet in shared-memory counters kept in the unused upper part of s_sort.
+        unsigned *cnt = reinterpret_cast<unsigned *>(s_sort + 1024); // [0, 1024): before | [1024, 2048): bp
+        const unsigned Cr = (C + 31u) & ~31u;
+        const unsigned parts = (spec && Cr) ? blockDim.x / Cr : 1u;
+        if (parts > 1u)
+            for (unsigned i = threadIdx.x; i < 2048u; i += blockDim.x) cnt[i] = 0u;
         __syncthreads();
+        if (parts > 1u) {
+            const unsigned i = threadIdx.x % Cr, part = threadIdx.x / Cr;
+            if (i < C && part < parts) {
+                const unsigned long long mine = s_sort[i];
+                const unsigned myp = s_pos[i];
+                const unsigned per = (C + parts - 1u) / parts, j0 = part * per, j1 = min(C, j0 + per);
+                unsigned before = 0, bp = 0;
+                for (unsigned j = j0; j < j1; ++j) {
+                    before += s_sort[j] < mine ? 1u : 0u; // (key, index) pairs are distinct
+                    bp += s_pos[j] < myp ? 1u : 0u;
+                }
+                atomicAdd(cnt + i, before);
+                atomicAdd(cnt + 1024 + i, bp);
+            }
+            __syncthreads();
+        }
         for (unsigned i = threadIdx.x; i < C; i += blockDim.x) {
             const unsigned long long mine = s_sort[i];
             const unsigned myp = s_pos[i];
             unsigned row[kMaxM];
             for (int k = 0; k < m; ++k) row[k] = spec ? spec_row[k] : __ldcg(V.cand_rows + static_cast<size_t>(i) * m + k);
             unsigned before = 0, bp = 0;
-            for (unsigned j = 0; j < C; ++j) {
-                before += s_sort[j] < mine ? 1u : 0u; // (key, index) pairs are distinct
-                bp += s_pos[j] < myp ? 1u : 0u;
+            if (parts > 1u) {
+                before = cnt[i];
+                bp = cnt[1024 + i];
+            } else {
+                for (unsigned j = 0; j < C; ++j) {
+                    before += s_sort[j] < mine ? 1u : 0u;
+                    bp += s_pos[j] < myp ? 1u : 0u;
+                }
             }
             V.order[off + before] = myp;
             V.pm_pos[off + bp] = myp;
