@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 #include <limits>
 #include <vector>
@@ -60,9 +61,12 @@ struct Meta {            // device-side bookkeeping of the level loop
     unsigned done;
     unsigned nact;       // sorted-space loop: live length of the active list
     unsigned tickets;    // fused levels: thread blocks of the current peel pass that have finished (the last one closes the level)
-    unsigned level_pub;  // persistent loop: `level`, stored LAST when a level is closed - the flag the other thread blocks spin on
     unsigned stuck;      // persistent loop: a thread block gave up waiting (watchdog); the host reports an internal error
+    // the two words the waiting thread blocks poll, adjacent and 8-byte aligned so that one load reads both
+    unsigned level_pub;  // persistent loop: `level`, stored LAST when a level is closed
+    unsigned big_pub;    // persistent loop: index of a level that ALL thread blocks close together (see distributed_close)
 };
+static_assert(offsetof(Meta, level_pub) % 8 == 0 && offsetof(Meta, big_pub) == offsetof(Meta, level_pub) + 4, "polled pair");
 
 // pareto_dominance, multi_objective.cpp:97-113 with the NaN-aware comparisons of detail/custom_comparisons.hpp:54-88
 // (NaN is placed after +inf).  a dominates b.
@@ -536,8 +540,44 @@ template <int M, bool FUSED> __global__ void __launch_bounds__(kPT) fnds_peel_so
 // instead of a hung device.
 constexpr int kPersistThreads = 1024;
 constexpr unsigned kSpinLimit = 1u << 26;
+constexpr unsigned kBigInKernel = 16384; // largest level the resident grid orders together (rank sort, O(C^2 / threads)); above, CUB
 
-template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persistent_kernel(SortedView V, unsigned slice)
+// A level of 1024 < C <= kBigInKernel candidates is closed by ALL blocks of the resident grid: block b ranks its share of the
+// candidates (C / gridDim of them) against all C in both orders, the scan of one candidate split over 1024 / share threads, partial
+// counts meeting in shared-memory counters.  ~40 us at C = 9 000 against ~150 us for leaving the kernel, two CUB sorts and a
+// cooperative relaunch.  Returns with everything stored; the caller fences, takes a ticket and the last block publishes the level.
+__device__ void distributed_close(const SortedView &V, unsigned C, unsigned off, unsigned *cnt)
+{
+    const unsigned per = (C + gridDim.x - 1) / gridDim.x, i0 = min(C, blockIdx.x * per), nloc = min(C, i0 + per) - i0;
+    const unsigned Cr = max(32u, (nloc + 31u) & ~31u), parts = blockDim.x / Cr;
+    for (unsigned i = threadIdx.x; i < 2048u; i += blockDim.x) cnt[i] = 0u;
+    __syncthreads();
+    const unsigned li = threadIdx.x % Cr, part = threadIdx.x / Cr;
+    if (li < nloc && part < parts) {
+        const unsigned long long mine = __ldcg(V.cand_key + i0 + li);
+        const unsigned myp = __ldcg(V.cand + i0 + li);
+        const unsigned perj = (C + parts - 1) / parts, j0 = part * perj, j1 = min(C, j0 + perj);
+        unsigned before = 0, bp = 0;
+#pragma unroll 4
+        for (unsigned j = j0; j < j1; ++j) {
+            before += __ldcg(V.cand_key + j) < mine ? 1u : 0u; // (key, index) pairs are distinct
+            bp += __ldcg(V.cand + j) < myp ? 1u : 0u;
+        }
+        atomicAdd(cnt + li, before);
+        atomicAdd(cnt + 1024 + li, bp);
+    }
+    __syncthreads();
+    if (threadIdx.x < nloc) {
+        const unsigned before = cnt[threadIdx.x], bp = cnt[1024 + threadIdx.x], myp = __ldcg(V.cand + i0 + threadIdx.x);
+        V.order[off + before] = myp;
+        V.pm_pos[off + bp] = myp;
+        V.pm_fpos[off + bp] = before;
+        for (int k = 0; k < V.m; ++k)
+            V.pm_rows[static_cast<size_t>(off + bp) * V.m + k] = __ldcg(V.cand_rows + static_cast<size_t>(i0 + threadIdx.x) * V.m + k);
+    }
+}
+
+template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persistent_kernel(SortedView V, unsigned big_inkernel)
 {
     constexpr int m = M;
     __shared__ unsigned tileR[kTP * M], tileF[kTP], tileP[kTP];
@@ -549,7 +589,6 @@ template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persist
     // front before it than one at a low position, so contiguous slices per block left the last blocks with 4-5x the work of the
     // first (measured with clock64: 21 k against 4.6 k cycles per level) and a level lasts as long as its slowest block.
     // Chunks dealt round-robin give every block the same mix; the cut-offs are per warp.
-    (void)slice;
     const unsigned chunk = blockIdx.x + (threadIdx.x >> 5) * gridDim.x;
     const unsigned q = chunk * 32u + (threadIdx.x & 31u);
     const bool in = q < V.n;
@@ -561,6 +600,7 @@ template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persist
     const bool nonempty = chunk * 32u < V.n;
     const unsigned lo = nonempty ? V.run_lo[chunk * 32u] : 0u, limit = nonempty ? V.run_end[min(V.n, chunk * 32u + 32u) - 1] : 0u;
     unsigned expect = __ldcg(&meta->level); // the front to peel next; nothing changes it before the first publication below
+    unsigned did_big = 0xffffffffu;         // last level this block helped to close in distributed_close
 #ifdef PGC_FNDS_TIMING
     long long tw = 0, tp = 0, tt = 0, to = 0, nl = 0, norder = 0, t0 = clock64(), t1;
 #define PGC_TICK(acc) t1 = clock64(); acc += t1 - t0; t0 = t1;
@@ -570,23 +610,54 @@ template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persist
     for (;;) {
         // ---- wait until front `expect` is published, then read the bookkeeping of this level
         if (threadIdx.x == 0) {
-            unsigned spins = 0;
-            while (*reinterpret_cast<volatile unsigned *>(&meta->level_pub) != expect && ++spins < kSpinLimit) {
+            unsigned spins = 0, code = 0;
+            for (;;) {
+                const unsigned long long both = *reinterpret_cast<volatile unsigned long long *>(&meta->level_pub);
+                if (static_cast<unsigned>(both) == expect) break;
+                if (did_big != expect && static_cast<unsigned>(both >> 32) == expect) {
+                    code = 2; // level `expect` is being closed by all blocks together (this block has not done its share yet)
+                    break;
+                }
+                if (++spins >= kSpinLimit) {
+                    meta->stuck = 1;
+                    break;
+                }
             }
             __threadfence();
-            unsigned code = 0;
-            if (spins >= kSpinLimit) {
-                meta->stuck = 1;
-                code = 1;
-            }
-            if (__ldcg(&meta->overflow) || __ldcg(&meta->done) || __ldcg(&meta->stuck) || __ldcg(&meta->assigned) >= V.n
+            if (__ldcg(&meta->overflow) || __ldcg(&meta->done) || __ldcg(&meta->stuck) || (code == 0 && __ldcg(&meta->assigned) >= V.n)
                 || __ldcg(&meta->front_size) == 0)
                 code = 1;
             s_flag[0] = code;
         }
         __syncthreads();
         PGC_TICK(tw)
-        if (s_flag[0]) break;
+        if (s_flag[0] == 1) break;
+        if (s_flag[0] == 2) { // ---- close level `expect` together; meta still describes the front that was just peeled
+            const unsigned C = __ldcg(&meta->ncand), off = __ldcg(&meta->front_off) + __ldcg(&meta->front_size);
+            distributed_close(V, C, off, reinterpret_cast<unsigned *>(s_sort + 1024));
+            did_big = expect;
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) s_flag[1] = atomicAdd(&meta->tickets, 1u) == gridDim.x - 1 ? 1u : 0u;
+            __syncthreads();
+            if (s_flag[1] && threadIdx.x == 0) { // the last block publishes the level (as the tail of order_level does)
+                meta->tickets = 0;
+                V.front_off[expect] = off;
+                V.front_off[expect + 1] = off + C;
+                meta->nfronts = expect + 1;
+                const unsigned assigned = __ldcg(&meta->assigned) + C;
+                meta->level = expect;
+                meta->front_off = off;
+                meta->front_size = C;
+                meta->assigned = assigned;
+                meta->ncand = 0;
+                const unsigned stop = __ldcg(&meta->stop_after);
+                if (stop && assigned >= stop) meta->done = 1;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned *>(&meta->level_pub) = expect;
+            }
+            continue; // back to the wait: level_pub == expect now (or soon)
+        }
         const unsigned fs = __ldcg(&meta->front_size), fo = __ldcg(&meta->front_off), level = expect;
         // ---- peel
         const bool active = left != 0;
@@ -663,6 +734,10 @@ template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persist
         if (s_flag[1]) {
             if (threadIdx.x == 0) meta->tickets = 0;
             __threadfence();
+            const unsigned Cnow = __ldcg(&meta->ncand);
+            if (big_inkernel && Cnow > 1024u && Cnow <= kBigInKernel) { // all blocks close this level together
+                if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(&meta->big_pub) = expect + 1;
+            } else
             order_level(V, 0, s_sort, s_pos); // sets meta->overflow instead when the level is too big for shared memory ...
             if (threadIdx.x == 0 && __ldcg(&meta->overflow)) { // ... and then the waiting blocks are released to leave as well
                 __threadfence();
@@ -1022,6 +1097,7 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
     {
         Meta m0{};
         m0.stop_after = stop_after;
+        m0.big_pub = 0xffffffffu;
         PGC_CUDA(cudaMemcpyAsync(meta, &m0, sizeof(Meta), cudaMemcpyHostToDevice, st));
         PGC_CUDA(cudaStreamSynchronize(st)); // m0 is a stack object
     }
@@ -1149,8 +1225,9 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
                     PGC_MO_PERSIST(7) PGC_MO_PERSIST(8)
 #undef PGC_MO_PERSIST
                 }
-                unsigned slice_arg = slice;
-                void *args[] = {&V, &slice_arg};
+                const char *big_env = std::getenv("PGC_FNDS_BIG_INKERNEL"); // 0: big levels always through the host / CUB path
+                unsigned big_arg = (big_env && big_env[0] == '0') ? 0u : 1u;
+                void *args[] = {&V, &big_arg};
                 PGC_CUDA(cudaLaunchCooperativeKernel(fn, dim3(pgrid), dim3(kPersistThreads), args, 0, st));
                 ctx->launches.fetch_add(1, std::memory_order_relaxed);
                 if ((rc = poll())) return rc;
