@@ -13,6 +13,11 @@
 // Every (dominator, dominated) pair is tested once in the count pass and once in the peel passes: 2*N^2 dominance tests
 // of M FP64 compares in total, no N^2-bit matrix in memory.  The roofline that binds is compare throughput
 // (FP64 DSETP issue), not HBM: bytes are 8*N*M in + O(N) out.
+// That describes the kernels used for small inputs (n < 4096).  Large inputs run on dense integer ranks, in sorted space
+// (SortedView): position cut-offs halve the pair tests, most of the rest shrink to M-1 integer compares, and the level loop is
+// ONE resident cooperative kernel (fnds_persistent_kernel: point state in registers, levels separated by a ticket counter and a
+// published level word, big levels closed by all blocks together) with a launch-per-level loop as the fallback for inputs
+// above one thread per position (profiles/r1x_fnds_variants.txt).
 // Crowding distances are exact IEEE (same subtraction / division per element, objectives applied in order); the sort
 // inside a front is a stable segmented radix sort, which matches the reference's std::sort whenever the objective values
 // inside a front are distinct (the reference's order of ties is unspecified: SURVEY.md F5).
