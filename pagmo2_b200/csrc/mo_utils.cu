@@ -1216,7 +1216,7 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
         const char *persist_env = std::getenv("PGC_FNDS_PERSIST");
         const unsigned pgrid = static_cast<unsigned>(ctx->sm_count);
         const unsigned slice = (n + pgrid - 1) / pgrid;
-        const bool persist = coop_attr != 0 && slice <= static_cast<unsigned>(kPersistThreads) && !(persist_env && persist_env[0] == '0');
+        bool persist = coop_attr != 0 && slice <= static_cast<unsigned>(kPersistThreads) && !(persist_env && persist_env[0] == '0');
         while (h.assigned < n && !h.done) {
             if (h.front_size == 0) {
                 set_error("fast_non_dominated_sorting: internal error, empty front with %u of %u points assigned", h.assigned, n);
@@ -1233,7 +1233,11 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
                 const char *big_env = std::getenv("PGC_FNDS_BIG_INKERNEL"); // 0: big levels always through the host / CUB path
                 unsigned big_arg = (big_env && big_env[0] == '0') ? 0u : 1u;
                 void *args[] = {&V, &big_arg};
-                PGC_CUDA(cudaLaunchCooperativeKernel(fn, dim3(pgrid), dim3(kPersistThreads), args, 0, st));
+                if (cudaLaunchCooperativeKernel(fn, dim3(pgrid), dim3(kPersistThreads), args, 0, st) != cudaSuccess) {
+                    cudaGetLastError(); // the grid cannot be co-resident here (e.g. a partitioned device): launch-per-level loop instead
+                    persist = false;
+                    continue;
+                }
                 ctx->launches.fetch_add(1, std::memory_order_relaxed);
                 if ((rc = poll())) return rc;
                 if (h.stuck) {
