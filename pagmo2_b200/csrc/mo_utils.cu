@@ -588,7 +588,8 @@ template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persist
     __shared__ unsigned tileR[kTP * M], tileF[kTP], tileP[kTP];
     __shared__ unsigned long long s_sort[kOrderCap];
     __shared__ unsigned s_pos[1024];
-    __shared__ unsigned s_flag[2]; // [0]: exit code seen by thread 0 (0 go on, 1 leave), [1]: this block took the last ticket
+    __shared__ unsigned s_flag[4]; // [0]: code seen by thread 0 (0 peel, 1 leave, 2 close together), [1]: this block took the last
+                                   // ticket, [2], [3]: front_size, front_off of the level
     Meta *meta = V.meta;
     // Warp w of block b owns the 32 consecutive positions of chunk b + w * gridDim.x: a point at a high position has more of a
     // front before it than one at a low position, so contiguous slices per block left the last blocks with 4-5x the work of the
@@ -629,10 +630,13 @@ template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persist
                 }
             }
             __threadfence();
+            const unsigned m_fs = __ldcg(&meta->front_size), m_fo = __ldcg(&meta->front_off);
             if (__ldcg(&meta->overflow) || __ldcg(&meta->done) || __ldcg(&meta->stuck) || (code == 0 && __ldcg(&meta->assigned) >= V.n)
-                || __ldcg(&meta->front_size) == 0)
+                || m_fs == 0)
                 code = 1;
             s_flag[0] = code;
+            s_flag[2] = m_fs; // the level's bookkeeping reaches the other threads through shared memory: one round trip less
+            s_flag[3] = m_fo;
         }
         __syncthreads();
         PGC_TICK(tw)
@@ -663,7 +667,7 @@ template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persist
             }
             continue; // back to the wait: level_pub == expect now (or soon)
         }
-        const unsigned fs = __ldcg(&meta->front_size), fo = __ldcg(&meta->front_off), level = expect;
+        const unsigned fs = s_flag[2], fo = s_flag[3], level = expect;
         // ---- peel
         const bool active = left != 0;
         const bool warp_work = __any_sync(0xffffffffu, active);
