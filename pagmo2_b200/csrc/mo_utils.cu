@@ -296,6 +296,63 @@ __global__ void __launch_bounds__(kTP) fnds_count_sorted_kernel(SortedView V, un
     }
 }
 
+// ---- two objectives: the count pass in O(N (N / B) log B) instead of O(N^2) ---------------------------------------------------
+// In sorted space a point p at a position before the run of q (first rank strictly smaller) dominates q iff its second rank
+// is <= q's.  Blocks of kCB positions get their second ranks sorted once (count2_sort_blocks_kernel); the dominators of q in all
+// blocks that end before q's run are then one upper_bound per block, and only the positions from the start of the block that
+// holds the run's first position to the end of the run are tested pair by pair (at most kCB + the run).
+constexpr int kCB = 1024;
+
+__global__ void __launch_bounds__(kCB / 2) count2_sort_blocks_kernel(const unsigned *__restrict__ rs, unsigned n, unsigned *sorted)
+{
+    __shared__ unsigned s[kCB];
+    const unsigned base = blockIdx.x * kCB;
+    for (unsigned i = threadIdx.x; i < kCB; i += blockDim.x) s[i] = base + i < n ? rs[static_cast<size_t>(base + i) * 2 + 1] : 0xffffffffu;
+    __syncthreads();
+    for (unsigned k = 2; k <= kCB; k <<= 1)
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = threadIdx.x; i < kCB; i += blockDim.x) {
+                const unsigned l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned a = s[i], b = s[l];
+                    if ((a > b) == up) {
+                        s[i] = b;
+                        s[l] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (unsigned i = threadIdx.x; i < kCB; i += blockDim.x) sorted[base + i] = s[i];
+}
+
+__global__ void __launch_bounds__(256) fnds_count2_kernel(SortedView V, const unsigned *__restrict__ sorted, unsigned *dom_count)
+{
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= V.n) return;
+    const unsigned q0 = V.rs[static_cast<size_t>(q) * 2], q1 = V.rs[static_cast<size_t>(q) * 2 + 1];
+    const unsigned lo = V.run_lo[q], end = V.run_end[q];
+    const unsigned full_blocks = lo / kCB; // blocks that end at or before the start of q's run: first rank strictly smaller
+    unsigned c = 0;
+    for (unsigned b = 0; b < full_blocks; ++b) {
+        const unsigned *blk = sorted + static_cast<size_t>(b) * kCB;
+        unsigned l = 0, h = kCB; // upper_bound(q1): number of second ranks <= q1
+        while (l < h) {
+            const unsigned mid = (l + h) >> 1;
+            if (blk[mid] <= q1) l = mid + 1;
+            else h = mid;
+        }
+        c += l;
+    }
+    for (unsigned p = full_blocks * kCB; p < end; ++p) { // the rest pair by pair (pareto_dominance on ranks)
+        const unsigned p0 = V.rs[static_cast<size_t>(p) * 2], p1 = V.rs[static_cast<size_t>(p) * 2 + 1];
+        c += (p0 <= q0 && p1 <= q1 && (p0 < q0 || p1 < q1)) ? 1u : 0u;
+    }
+    V.count[q] = c;
+    if (dom_count) dom_count[V.src[q]] = c;
+}
+
 // first level: the points without dominators, key 0 (front 0 is in index order, :228-233)
 __global__ void fnds_front0_sorted_kernel(SortedView V)
 {
@@ -1167,13 +1224,23 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
         }
         gather_rows_u32m_kernel<<<blocks_for(static_cast<size_t>(n) * m, 256), 256, 0, st>>>(ranks, src, n, m, rs);
         invert_perm_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, n, inv);
+        // two objectives: sort-based dominance count (PGC_FNDS_COUNT2=0: the all-pairs pass)
+        const char *count2_env = std::getenv("PGC_FNDS_COUNT2");
+        const bool count2_ok = m == 2 && !(count2_env && count2_env[0] == '0');
+        unsigned *c2sorted = nullptr; // per-block sorted second ranks, padded to whole blocks
+        if (count2_ok && (rc = ws.alloc(&c2sorted, static_cast<size_t>(blocks_for(n, kCB)) * kCB))) return rc;
         SortedView V{rs,    src,      inv,       run_lo,  run_end, act_a,   0u,      count,       rank_s, key_s, cand,
                      cand_key, cand_rows, order_s, pm_pos,  pm_fpos, pm_rows, d_front_off, meta,   n,     m};
         switch (m) {
 #define PGC_MO_SORTED(MM)                                                                                              \
     case MM:                                                                                                           \
         run_bounds_kernel<MM><<<blocks_for(n, 256), 256, 0, st>>>(rs, n, run_lo, run_end);                             \
-        fnds_count_sorted_kernel<MM><<<gb, kTP, 0, st>>>(V, d_dom_count);                                              \
+        if (MM == 2 && count2_ok) {                                                                                    \
+            count2_sort_blocks_kernel<<<blocks_for(n, kCB), kCB / 2, 0, st>>>(rs, n, c2sorted);                        \
+            fnds_count2_kernel<<<blocks_for(n, 256), 256, 0, st>>>(V, c2sorted, d_dom_count);                          \
+        } else {                                                                                                       \
+            fnds_count_sorted_kernel<MM><<<gb, kTP, 0, st>>>(V, d_dom_count);                                          \
+        }                                                                                                              \
         break;
             PGC_MO_SORTED(1) PGC_MO_SORTED(2) PGC_MO_SORTED(3) PGC_MO_SORTED(4) PGC_MO_SORTED(5) PGC_MO_SORTED(6) PGC_MO_SORTED(7)
             PGC_MO_SORTED(8)

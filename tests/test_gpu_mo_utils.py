@@ -46,7 +46,7 @@ def test_errors(ctx):
 
 
 @pytest.mark.parametrize("n,m", [(2, 2), (17, 2), (255, 2), (256, 3), (257, 3), (1000, 2), (5000, 2), (4096, 3), (3000, 4), (2000, 8),
-                                 (300, 1), (9000, 3), (6000, 5), (4500, 1)])
+                                 (300, 1), (9000, 3), (6000, 5), (4500, 1), (4096, 2), (8192, 2)])  # the last two: sort-based count pass (n % 1024 == 0, m == 2)
 def test_fnds_bit_exact_vs_oracle(ctx, orc, n, m):
     rng = np.random.default_rng(n * 10 + m)
     f = rng.uniform(0, 1, (n, m))
