@@ -118,6 +118,35 @@ int oracle_nsga2_evolve(int family, unsigned prob_id, size_t nx, size_t nobj, un
                         double *x, double *f, size_t NP, unsigned gens, double cr, double eta_c, double m, double eta_m, uint64_t seed,
                         uint32_t first_generation);
 
+
+/* ---- the same restatements on the REFERENCE's draw stream (sequential std::mt19937 + libstdc++ distributions, mt19937.h):
+ * these are what tests/test_oracle_pin.py compares bit for bit with the compiled reference (ref_capi.h: ref_*_from) ---- */
+/* 1: index sorts in libstdc++ std::sort order (ties as the compiled reference leaves them), 0 (default): stable */
+void oracle_set_sort_mode(int libstdcxx);
+int oracle_std_argsort(const double *keys, size_t n, int desc, size_t *out);
+int oracle_mt_sequence(uint32_t seed, int kind, uint64_t a, uint64_t b, size_t n, double *out_real, uint64_t *out_int);
+int oracle_mt_shuffles(uint32_t seed, size_t n, size_t rounds, size_t *perm);
+int oracle_genetic_operators_mt(const double *p1, const double *p2, size_t nx, const double *lb, const double *ub, double p_cr, double eta_c,
+                                double p_m, double eta_m, const size_t *rank, const double *cd, size_t n_pairs, uint32_t seed, double *c1,
+                                double *c2, size_t *winners);
+int oracle_population_init_mt(const double *lb, const double *ub, size_t n, size_t nx, uint32_t seed, double *x, uint64_t *ids);
+int oracle_sga_evolve_mt(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t nx,
+                         unsigned gens, double cr, double eta_c, double m, double param_m, unsigned param_s, unsigned crossover,
+                         unsigned mutation, unsigned selection, uint32_t seed);
+int oracle_mt_binomial_sequence(uint32_t seed, uint64_t t, double p, size_t n, uint64_t *out);
+int oracle_de_evolve_sequential(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim,
+                                unsigned gens, unsigned algo, unsigned variant, unsigned variant_adptv, double F, double CR,
+                                const unsigned *allowed, unsigned n_allowed, double ftol, double xtol, uint64_t seed,
+                                uint32_t first_generation, unsigned *gens_done, double *F_state, double *CR_state, unsigned *variant_state);
+int oracle_de_evolve_mt(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim,
+                        unsigned gens, unsigned algo, unsigned variant, unsigned variant_adptv, double F, double CR,
+                        const unsigned *allowed, unsigned n_allowed, double ftol, double xtol, uint32_t seed, unsigned *gens_done);
+int oracle_pso_evolve_mt(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t n, size_t dim,
+                         unsigned gens, double omega, double eta1, double eta2, double max_vel, unsigned variant, unsigned neighb_type,
+                         unsigned neighb_param, uint32_t seed);
+int oracle_nsga2_evolve_mt(int family, unsigned prob_id, size_t nx, size_t nobj, unsigned alpha, const double *lb, const double *ub,
+                           double *x, double *f, size_t NP, unsigned gens, double cr, double eta_c, double m, double eta_m, uint32_t seed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,8 @@
  */
 #ifndef ORACLE_PHILOX_H
 #define ORACLE_PHILOX_H
+#include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 
 enum { ORACLE_TAG_SHUFFLE1 = 1, ORACLE_TAG_SHUFFLE2 = 2, ORACLE_TAG_NSGA2_VAR = 3, ORACLE_TAG_DE = 4, ORACLE_TAG_PSO = 5,
@@ -39,7 +41,47 @@ static inline double oracle_philox_u01(uint64_t seed, uint32_t tag, uint32_t gen
     return (double)(oracle_philox_u64(seed, tag, generation, index, slot) >> 11) * (1.0 / 9007199254740992.0);
 }
 
+/* ---- draw source ------------------------------------------------------------------------------------------------------------
+ * Two modes.  Philox (default): every draw is addressed by (seed, tag, generation, index, slot) - what the device consumes.
+ * Sequential mt19937 (oracle_mt_active != NULL, set by the *_mt entry points): the address is ignored and the draw is the NEXT
+ * value of the reference's own generator through the libstdc++ distribution the reference uses at that statement (mt19937.h),
+ * so a restated loop written in the reference's statement order reproduces the compiled reference bit for bit.  The arithmetic
+ * around the draws is shared by both modes - that is what the pin tests (tests/test_oracle_pin.py) certify. */
+#include "mt19937.h"
+#include "std_sort.h"
+extern _Thread_local oracle_mt *oracle_mt_active;
+/* "be the reference": its random stream and its std::sort tie order, for the duration of one *_mt entry point */
+#define ORACLE_MT_BEGIN(seed32)          \
+    oracle_mt oracle_mt_local_;          \
+    oracle_mt_seed(&oracle_mt_local_, (seed32)); \
+    oracle_mt_active = &oracle_mt_local_; \
+    const int oracle_sort_saved_ = oracle_sort_libstdcxx; \
+    oracle_sort_libstdcxx = 1
+#define ORACLE_MT_END()       \
+    oracle_mt_active = NULL;  \
+    oracle_sort_libstdcxx = oracle_sort_saved_
+
 typedef struct { uint64_t seed; uint32_t tag, generation, index, slot; } oracle_stream;
-static inline double oracle_next(oracle_stream *s) { return oracle_philox_u01(s->seed, s->tag, s->generation, s->index, s->slot++); }
+/* uniform_real_distribution<double>(0,1) */
+static inline double oracle_u01_at(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot)
+{
+    return oracle_mt_active ? oracle_mt_u01(oracle_mt_active) : oracle_philox_u01(seed, tag, generation, index, slot);
+}
+static inline double oracle_next(oracle_stream *s) { return oracle_u01_at(s->seed, s->tag, s->generation, s->index, s->slot++); }
+/* uniform_int_distribution(0, n-1): Philox mode = floor(u * n) */
+static inline size_t oracle_next_below(oracle_stream *s, size_t n)
+{
+    if (oracle_mt_active) return (size_t)oracle_mt_below(oracle_mt_active, n);
+    const size_t v = (size_t)(oracle_next(s) * (double)n);
+    return v < n ? v : n - 1;
+}
+/* normal_distribution(0,1): Philox mode = Box-Muller on two draws */
+static inline double oracle_next_normal(oracle_stream *s)
+{
+    if (oracle_mt_active) return oracle_mt_normal(oracle_mt_active, 0., 1.);
+    const double u1 = 1.0 - oracle_next(s);
+    const double u2 = oracle_next(s);
+    return sqrt(-2.0 * log(u1)) * cos(2.0 * 3.141592653589793238462643383279502884 * u2);
+}
 
 #endif

@@ -221,8 +221,9 @@ class Oracle:
         return x, f, (vv if vv is not None else None), xcur
 
     def de_evolve(self, prob, lb, ub, x, f, gens=1, algo="de1220", variant=2, variant_adptv=1, F=0.8, CR=0.9,
-                  allowed=(2, 3, 7, 10, 13, 14, 15, 16), ftol=1e-6, xtol=1e-6, seed=0, first_generation=1):
-        """restated generational de / sade / de1220: returns (x, f, gens_done, F, CR, variant)."""
+                  allowed=(2, 3, 7, 10, 13, 14, 15, 16), ftol=1e-6, xtol=1e-6, seed=0, first_generation=1, sequential=False):
+        """restated generational de / sade / de1220: returns (x, f, gens_done, F, CR, variant).
+        sequential=True: same Philox draws, the reference's evaluate-and-select-one-at-a-time order."""
         x = np.array(x, dtype=np.float64, order="C")
         f = np.array(f, dtype=np.float64, order="C").reshape(-1)
         NP, dim = x.shape
@@ -231,7 +232,8 @@ class Oracle:
         Fs, Cs, Vs = np.zeros(NP), np.zeros(NP), np.zeros(NP, dtype=np.uint32)
         done = C.c_uint()
         code = {"de": 0, "sade": 1, "de1220": 2}[algo]
-        rc = self.lib.oracle_de_evolve(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), C.c_size_t(NP), C.c_size_t(dim), C.c_uint(gens),
+        fn = self.lib.oracle_de_evolve_sequential if sequential else self.lib.oracle_de_evolve
+        rc = fn(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), C.c_size_t(NP), C.c_size_t(dim), C.c_uint(gens),
                                        C.c_uint(code), C.c_uint(variant), C.c_uint(variant_adptv), C.c_double(F), C.c_double(CR),
                                        al.ctypes.data_as(C.POINTER(C.c_uint)), C.c_uint(al.size), C.c_double(ftol), C.c_double(xtol),
                                        C.c_uint64(seed), C.c_uint32(first_generation), C.byref(done), _dp(Fs), _dp(Cs),
@@ -392,6 +394,112 @@ class Oracle:
                                         C.c_double(m), C.c_double(eta_m), C.c_uint64(seed), C.c_uint32(first_generation)):
             raise ValueError("oracle_nsga2_evolve failed")
         return x, f
+
+    # ---- sequential-mt19937 mode: the restatements on the reference's own draw stream (mt19937.h) ----
+    def mt_sequence(self, seed: int, kind: str, n: int, a: int = 0, b: int = 0):
+        k = {"raw": 0, "u01": 1, "int": 2, "normal": 3, "real": 4}[kind]
+        r, i = np.empty(n), np.empty(n, dtype=np.uint64)
+        if self.lib.oracle_mt_sequence(C.c_uint32(seed), C.c_int(k), C.c_uint64(a), C.c_uint64(b), C.c_size_t(n), _dp(r),
+                                       i.ctypes.data_as(C.POINTER(C.c_uint64))):
+            raise ValueError("oracle_mt_sequence failed")
+        return i if k in (0, 2) else r
+
+    def set_sort_mode(self, libstdcxx: bool) -> None:
+        """True: index sorts leave ties as libstdc++'s std::sort does (= the compiled reference); False (default): stable."""
+        self.lib.oracle_set_sort_mode(C.c_int(1 if libstdcxx else 0))
+
+    def std_argsort(self, keys, desc: bool = False) -> np.ndarray:
+        keys = np.ascontiguousarray(keys, dtype=np.float64)
+        out = np.empty(max(keys.size, 1), dtype=np.uint64)
+        self.lib.oracle_std_argsort(_dp(keys), C.c_size_t(keys.size), C.c_int(int(desc)), _sp(out))
+        return out[:keys.size].astype(np.int64)
+
+    def mt_shuffles(self, seed: int, n: int, rounds: int = 1) -> np.ndarray:
+        out = np.empty(max(n, 1), dtype=np.uint64)
+        self.lib.oracle_mt_shuffles(C.c_uint32(seed), C.c_size_t(n), C.c_size_t(rounds), _sp(out))
+        return out[:n].astype(np.int64)
+
+    def mt_binomial(self, seed: int, t: int, p: float, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.uint64)
+        if self.lib.oracle_mt_binomial_sequence(C.c_uint32(seed), C.c_uint64(t), C.c_double(p), C.c_size_t(n),
+                                                out.ctypes.data_as(C.POINTER(C.c_uint64))):
+            raise ValueError("oracle_mt_binomial_sequence: t*p >= 8 is not restated")
+        return out
+
+    def genetic_operators_mt(self, p1, p2, lb, ub, p_cr, eta_c, p_m, eta_m, rank, cd, seed):
+        p1, p2, lb, ub, cd = (np.ascontiguousarray(a, dtype=np.float64) for a in (p1, p2, lb, ub, cd))
+        rank = np.ascontiguousarray(rank, dtype=np.uint64)
+        npairs = rank.size // 2
+        c1, c2, w = np.empty_like(p1), np.empty_like(p1), np.empty(max(npairs, 1), dtype=np.uint64)
+        self.lib.oracle_genetic_operators_mt(_dp(p1), _dp(p2), C.c_size_t(p1.size), _dp(lb), _dp(ub), C.c_double(p_cr), C.c_double(eta_c),
+                                             C.c_double(p_m), C.c_double(eta_m), _sp(rank), _dp(cd), C.c_size_t(npairs), C.c_uint32(seed),
+                                             _dp(c1), _dp(c2), _sp(w))
+        return c1, c2, w[:npairs].astype(np.int64)
+
+    def nsga2_evolve_mt(self, family, prob_id, nobj, alpha, lb, ub, x, f, gens, cr, eta_c, m, eta_m, seed):
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C")
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        fam = {"zdt": 8, "dtlz": 9}[family]
+        if self.lib.oracle_nsga2_evolve_mt(C.c_int(fam), C.c_uint(prob_id), C.c_size_t(x.shape[1]), C.c_size_t(nobj), C.c_uint(alpha), _dp(lb),
+                                           _dp(ub), _dp(x), _dp(f), C.c_size_t(x.shape[0]), C.c_uint(gens), C.c_double(cr), C.c_double(eta_c),
+                                           C.c_double(m), C.c_double(eta_m), C.c_uint32(seed)):
+            raise ValueError("oracle_nsga2_evolve_mt failed")
+        return x, f
+
+    def pso_evolve_mt(self, prob, lb, ub, x, f, gens=1, omega=0.7298, eta1=2.05, eta2=2.05, max_vel=0.5, variant=5, neighb_type=2,
+                      neighb_param=4, seed=0):
+        """restated pso_gen::evolve on the mt19937 stream: returns (lbX, lbfit)."""
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C").reshape(-1)
+        n, dim = x.shape
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        if self.lib.oracle_pso_evolve_mt(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), C.c_size_t(n), C.c_size_t(dim), C.c_uint(gens),
+                                         C.c_double(omega), C.c_double(eta1), C.c_double(eta2), C.c_double(max_vel), C.c_uint(variant),
+                                         C.c_uint(neighb_type), C.c_uint(neighb_param), C.c_uint32(seed)):
+            raise ValueError("oracle_pso_evolve_mt failed")
+        return x, f
+
+    def de_evolve_mt(self, prob, lb, ub, x, f, gens=1, algo="de1220", variant=2, variant_adptv=1, F=0.8, CR=0.9,
+                     allowed=(2, 3, 7, 10, 13, 14, 15, 16), ftol=1e-6, xtol=1e-6, seed=0):
+        """restated de / sade / de1220 on the mt19937 stream, in the reference's one-at-a-time order: returns (x, f, gens_done)."""
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C").reshape(-1)
+        NP, dim = x.shape
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        al = np.ascontiguousarray(allowed, dtype=np.uint32)
+        done = C.c_uint()
+        code = {"de": 0, "sade": 1, "de1220": 2}[algo]
+        rc = self.lib.oracle_de_evolve_mt(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), C.c_size_t(NP), C.c_size_t(dim), C.c_uint(gens),
+                                          C.c_uint(code), C.c_uint(variant), C.c_uint(variant_adptv), C.c_double(F), C.c_double(CR),
+                                          al.ctypes.data_as(C.POINTER(C.c_uint)), C.c_uint(al.size), C.c_double(ftol), C.c_double(xtol),
+                                          C.c_uint32(seed), C.byref(done))
+        if rc:
+            raise ValueError("oracle_de_evolve_mt failed")
+        return x, f, done.value
+
+    def sga_evolve_mt(self, prob, lb, ub, x, f, gens=1, cr=0.9, eta_c=1.0, m=0.02, param_m=1.0, param_s=2, crossover="exponential",
+                      mutation="polynomial", selection="tournament", seed=0):
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C").reshape(-1)
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        xo = {"exponential": 0, "binomial": 1, "single": 2, "sbx": 3}[crossover]
+        mu = {"gaussian": 0, "uniform": 1, "polynomial": 2}[mutation]
+        se = {"tournament": 0, "truncated": 1}[selection]
+        if self.lib.oracle_sga_evolve_mt(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), C.c_size_t(x.shape[0]), C.c_size_t(x.shape[1]),
+                                         C.c_uint(gens), C.c_double(cr), C.c_double(eta_c), C.c_double(m), C.c_double(param_m), C.c_uint(param_s),
+                                         C.c_uint(xo), C.c_uint(mu), C.c_uint(se), C.c_uint32(seed)):
+            raise ValueError("oracle_sga_evolve_mt failed")
+        return x, f
+
+    def population_init_mt(self, lb, ub, n: int, seed: int):
+        """population(prob, n, seed)'s decision vectors and ids on the mt19937 stream (population.cpp:62-80, 570-596)."""
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        x, ids = np.empty((n, lb.size)), np.empty(n, dtype=np.uint64)
+        if self.lib.oracle_population_init_mt(_dp(lb), _dp(ub), C.c_size_t(n), C.c_size_t(lb.size), C.c_uint32(seed), _dp(x),
+                                              ids.ctypes.data_as(C.POINTER(C.c_uint64))):
+            raise ValueError("oracle_population_init_mt failed")
+        return x, ids
 
     def cec2014(self, func: int, xs: np.ndarray, tables=None, nthreads: int = 1) -> np.ndarray:
         xs = np.ascontiguousarray(xs, dtype=np.float64)
@@ -569,6 +677,60 @@ class Reference:
         self.lib.ref_cec2013_tables.argtypes = [C.c_uint, c_double_p, c_double_p]
         self._check(self.lib.ref_cec2013_tables(C.c_uint(dim), _dp(mr), _dp(os_)))
         return mr, os_
+
+    # ---- pin entry points (ref_pin.cpp) ----
+    def std_sequence(self, seed: int, kind: str, n: int, a: int = 0, b: int = 0):
+        k = {"raw": 0, "u01": 1, "int": 2, "normal": 3, "real": 4}[kind]
+        r, i = np.empty(n), np.empty(n, dtype=np.uint64)
+        self._check(self.lib.ref_std_sequence(C.c_uint(seed), C.c_int(k), C.c_ulonglong(a), C.c_ulonglong(b), C.c_size_t(n), _dp(r),
+                                              i.ctypes.data_as(C.POINTER(C.c_ulonglong))))
+        return i if k in (0, 2) else r
+
+    def std_argsort(self, keys, desc: bool = False) -> np.ndarray:
+        keys = np.ascontiguousarray(keys, dtype=np.float64)
+        out = np.empty(max(keys.size, 1), dtype=np.uint64)
+        self._check(self.lib.ref_std_argsort(_dp(keys), C.c_size_t(keys.size), C.c_int(int(desc)), _sp(out)))
+        return out[:keys.size].astype(np.int64)
+
+    def std_shuffles(self, seed: int, n: int, rounds: int = 1) -> np.ndarray:
+        out = np.empty(max(n, 1), dtype=np.uint64)
+        self._check(self.lib.ref_std_shuffles(C.c_uint(seed), C.c_size_t(n), C.c_size_t(rounds), _sp(out)))
+        return out[:n].astype(np.int64)
+
+    def std_binomial(self, seed: int, t: int, p: float, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.uint64)
+        self._check(self.lib.ref_std_binomial(C.c_uint(seed), C.c_ulonglong(t), C.c_double(p), C.c_size_t(n),
+                                              out.ctypes.data_as(C.POINTER(C.c_ulonglong))))
+        return out
+
+    def genetic_operators(self, p1, p2, lb, ub, p_cr, eta_c, p_m, eta_m, rank, cd, seed):
+        """sbx_crossover_impl, polynomial_mutation_impl x2, mo_tournament_selection_impl on pairs - one engine."""
+        p1, p2, lb, ub, cd = (np.ascontiguousarray(a, dtype=np.float64) for a in (p1, p2, lb, ub, cd))
+        rank = np.ascontiguousarray(rank, dtype=np.uint64)
+        npairs = rank.size // 2
+        c1, c2, w = np.empty_like(p1), np.empty_like(p1), np.empty(max(npairs, 1), dtype=np.uint64)
+        self._check(self.lib.ref_genetic_operators(_dp(p1), _dp(p2), C.c_size_t(p1.size), _dp(lb), _dp(ub), C.c_double(p_cr), C.c_double(eta_c),
+                                                   C.c_double(p_m), C.c_double(eta_m), _sp(rank), _dp(cd), C.c_size_t(npairs), C.c_uint(seed),
+                                                   _dp(c1), _dp(c2), _sp(w)))
+        return c1, c2, w[:npairs].astype(np.int64)
+
+    def evolve_from(self, prob: "RefProblem", algo: str, par, x0, gens: int, seed: int, strategies: str | None = None):
+        """The unmodified reference UDA on the population with decision vectors x0: returns (x, f)."""
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        par = np.ascontiguousarray(par, dtype=np.float64)
+        n = x0.shape[0]
+        x, f = np.empty((n, prob.nx)), np.empty((n, prob.nf))
+        self.lib.ref_evolve_from.argtypes = [C.c_void_p, C.c_char_p, c_double_p, C.c_size_t, C.c_char_p, c_double_p, C.c_size_t, C.c_uint,
+                                             C.c_uint, c_double_p, c_double_p]
+        self._check(self.lib.ref_evolve_from(prob._h, algo.encode(), _dp(par), par.size, strategies.encode() if strategies else None, _dp(x0), n,
+                                             gens, seed, _dp(x), _dp(f)))
+        return x, f
+
+    def population_init(self, prob: "RefProblem", n: int, seed: int):
+        x, ids = np.empty((n, prob.nx)), np.empty(n, dtype=np.uint64)
+        self.lib.ref_population_init.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, c_double_p, C.POINTER(C.c_ulonglong)]
+        self._check(self.lib.ref_population_init(prob._h, n, seed, _dp(x), ids.ctypes.data_as(C.POINTER(C.c_ulonglong))))
+        return x, ids
 
     def fair_replace(self, ids, x, f, rate, mids, mx, mf):
         """unmodified fair_replace{rate}.replace on flat groups."""

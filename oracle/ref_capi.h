@@ -82,6 +82,26 @@ int ref_select_best(const unsigned long long *ids, const double *x, const double
 int ref_hv_compute(const double *f, size_t n, size_t m, const double *r, double *out);
 int ref_hv_contributions(const double *f, size_t n, size_t m, const double *r, double *out);
 
+/* ---- pinning the restatements to the reference's own random stream (ref_pin.cpp) ----
+ * The real std::mt19937 + libstdc++ distributions (what oracle/mt19937.h restates): kind 0 raw words, 1 uniform_real(0,1),
+ * 2 uniform_int<size_t>(a,b), 3 one normal_distribution(0,1) object, 4 uniform_real(-a,b). */
+int ref_std_sequence(unsigned seed, int kind, unsigned long long a, unsigned long long b, size_t n, double *out_real,
+                     unsigned long long *out_int);
+int ref_std_shuffles(unsigned seed, size_t n, size_t rounds, size_t *perm);
+int ref_std_argsort(const double *keys, size_t n, int desc, size_t *out);
+int ref_std_binomial(unsigned seed, unsigned long long t, double p, size_t n, unsigned long long *out);
+/* detail::sbx_crossover_impl + polynomial_mutation_impl (both children) + n_pairs mo_tournament_selection_impl((2i,2i+1)) on one
+ * engine seeded with `seed` (genetic_operators.cpp:71-211) */
+int ref_genetic_operators(const double *p1, const double *p2, size_t nx, const double *lb, const double *ub, double p_cr, double eta_c,
+                          double p_m, double eta_m, const size_t *rank, const double *cd, size_t n_pairs, unsigned seed, double *c1,
+                          double *c2, size_t *winners);
+/* an unmodified reference UDA ("nsga2", "pso_gen", "de", "sade", "de1220", "sga") evolving the population with decision vectors
+ * x0 [n x nx] for `gens` generations with algorithm seed `seed`; par[] = the constructor's arguments between gen and seed */
+int ref_evolve_from(ref_problem *p, const char *algo, const double *par, size_t npar, const char *strategies, const double *x0, size_t n,
+                    unsigned gens, unsigned seed, double *x_out, double *f_out);
+/* population(prob, n, seed): its decision vectors and ids (population.cpp:62-80) */
+int ref_population_init(ref_problem *p, size_t n, unsigned seed, double *x_out, unsigned long long *ids_out);
+
 #ifdef __cplusplus
 }
 #endif

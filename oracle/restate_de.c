@@ -3,11 +3,17 @@
  * index selection (Durstenfeld, de1220.cpp:181-187), variant / F / CR adaptation (:192-197 and the per-variant iDE formulas),
  * the 18 mutation + crossover variants (:199-505; de.cpp:154-275 for de's own forms of variants 4,5,9,10), feasibility
  * (:507-513), selection and global-best bookkeeping (:515-536), exit conditions (de.cpp:302-321).
- * PARITY UNPINNED for the random stream and for the intra-generation ordering: the reference evaluates and selects one individual
- * at a time with mt19937 draws (tests/de1220.cpp:72-98 only check determinism); this restatement builds all trials from the previous
- * generation, evaluates them, then selects and takes every draw from the Philox substream
- * (seed, TAG_DE, generation, i) in the reference's per-individual order.  uniform_int(a,b) = a + floor(u*(b-a+1)); normal =
- * Box-Muller; the order of the normal draws inside one reference expression is fixed left-to-right, F before CR.
+ * Two modes of the SAME statements:
+ *  - oracle_de_evolve_mt: the reference's sequential mt19937 stream and its one-individual-at-a-time order (evaluate and select
+ *    inside the loop, so the adapted F / CR / variant of an individual are visible to the ones after it, sade.cpp:504-516).
+ *    PINNED: reproduces the compiled de / sade / de1220 ::evolve bit for bit (tests/test_oracle_pin.py).
+ *  - oracle_de_evolve (what the device is compared with): the GENERATIONAL loop - all trials are built from the previous
+ *    generation, evaluated in one batch, then selected - with every draw taken from the Philox substream
+ *    (seed, TAG_DE, generation, i) in the reference's per-individual order; uniform_int(0,n-1) = floor(u*n), normal = Box-Muller.
+ *    For de, and for sade / de1220 with variant_adptv = 1, the two loops are the same function of the draws (a trial reads only
+ *    the previous generation and its own F / CR); with variant_adptv = 2 the generational loop reads the other individuals'
+ *    F / CR as they were at the start of the generation.
+ * The normal draws inside one reference expression are evaluated left to right, F before CR (GCC's order; pinned by the test).
  */
 #include <math.h>
 #include <stdlib.h>
@@ -16,18 +22,8 @@
 #include "oracle.h"
 #include "philox.h"
 
-static double normal01(oracle_stream *rs)
-{
-    const double u1 = 1.0 - oracle_next(rs);
-    const double u2 = oracle_next(rs);
-    return sqrt(-2.0 * log(u1)) * cos(2.0 * 3.141592653589793238462643383279502884 * u2);
-}
-
-static unsigned uint_below(oracle_stream *rs, unsigned n)
-{
-    const unsigned v = (unsigned)(oracle_next(rs) * (double)n);
-    return v < n ? v : n - 1;
-}
+#define normal01(rs) oracle_next_normal(rs)
+#define uint_below(rs, n) ((unsigned)oracle_next_below((rs), (n)))
 
 static double mutate(unsigned algo, unsigned base, double t, double gb, const double *p, double pi, double F)
 {
@@ -44,10 +40,10 @@ static double mutate(unsigned algo, unsigned base, double t, double gb, const do
     }
 }
 
-int oracle_de_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim,
-                     unsigned gens, unsigned algo, unsigned variant_in, unsigned variant_adptv, double F0, double CR0,
-                     const unsigned *allowed, unsigned n_allowed, double ftol, double xtol, uint64_t seed, uint32_t first_generation,
-                     unsigned *gens_done, double *F_state, double *CR_state, unsigned *variant_state)
+static int de_evolve_impl(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim,
+                          unsigned gens, unsigned algo, unsigned variant_in, unsigned variant_adptv, double F0, double CR0,
+                          const unsigned *allowed, unsigned n_allowed, double ftol, double xtol, uint64_t seed, uint32_t first_generation,
+                          unsigned *gens_done, double *F_state, double *CR_state, unsigned *variant_state, int sequential)
 {
     if (gens_done) *gens_done = 0;
     if (gens == 0) return 0;
@@ -57,20 +53,26 @@ int oracle_de_evolve(const oracle_problem *prob, const double *lb, const double 
     double *mF = (double *)malloc(NP * sizeof(double)), *mC = (double *)malloc(NP * sizeof(double));
     double *Ftry = (double *)malloc(NP * sizeof(double)), *Ctry = (double *)malloc(NP * sizeof(double));
     unsigned *mV = (unsigned *)malloc(NP * sizeof(unsigned)), *Vtry = (unsigned *)malloc(NP * sizeof(unsigned));
-    if (algo != 0) { /* de1220.cpp:147-165 (no memory) */
+    double *xnew = sequential ? (double *)malloc(NP * dim * sizeof(double)) : NULL;
+    if (algo != 0) { /* de1220.cpp:147-165 (no memory): F / CR of every individual first, then (de1220) every variant */
+        oracle_stream *irs = (oracle_stream *)malloc(NP * sizeof(oracle_stream));
         for (size_t i = 0; i < NP; ++i) {
-            oracle_stream rs = {seed, ORACLE_TAG_INIT, first_generation, (uint32_t)i, 0};
+            const oracle_stream rs0 = {seed, ORACLE_TAG_INIT, first_generation, (uint32_t)i, 0};
+            oracle_stream *rs = &irs[i];
+            *rs = rs0;
             if (variant_adptv == 1) {
-                const double c = oracle_next(&rs), ff = oracle_next(&rs);
+                const double c = oracle_next(rs), ff = oracle_next(rs);
                 mC[i] = c;
                 mF[i] = ff * 0.9 + 0.1;
             } else {
-                const double c = normal01(&rs), ff = normal01(&rs);
+                const double c = normal01(rs), ff = normal01(rs);
                 mC[i] = c * 0.15 + 0.5;
                 mF[i] = ff * 0.15 + 0.5;
             }
-            if (algo == 2) mV[i] = allowed[uint_below(&rs, n_allowed)];
         }
+        if (algo == 2)
+            for (size_t i = 0; i < NP; ++i) mV[i] = allowed[uint_below(&irs[i], n_allowed)];
+        free(irs);
     }
     /* global best: pop.best_idx() = first minimum */
     size_t gbidx = 0;
@@ -80,6 +82,23 @@ int oracle_de_evolve(const oracle_problem *prob, const double *lb, const double 
     memcpy(gbIter, x + gbidx * dim, dim * sizeof(double));
     int rc = 0;
     unsigned done = 0;
+    if (sequential) memcpy(xnew, x, NP * dim * sizeof(double));
+/* de.cpp:281-297, sade.cpp:504-521, de1220.cpp:515-536; dst = the array of the NEW generation */
+#define SELECT(i, dst)                                                                                                 \
+    do {                                                                                                               \
+        if (ftrial[i] <= f[i]) {                                                                                       \
+            f[i] = ftrial[i];                                                                                          \
+            memcpy((dst) + (i) * dim, trial + (i) * dim, dim * sizeof(double));                                        \
+            if (algo) { mC[i] = Ctry[i]; mF[i] = Ftry[i]; }                                                            \
+            if (algo == 2) mV[i] = Vtry[i];                                                                            \
+            if (ftrial[i] <= gbfit) {                                                                                  \
+                gbfit = ftrial[i];                                                                                     \
+                gbidx = (i);                                                                                           \
+                gbF = Ftry[i];                                                                                         \
+                gbCR = Ctry[i];                                                                                        \
+            }                                                                                                          \
+        }                                                                                                              \
+    } while (0)
     for (unsigned g = 0; g < gens && !rc; ++g) {
         const uint32_t generation = first_generation + g;
         const double gbIterF = gbF, gbIterCR = gbCR;
@@ -169,21 +188,17 @@ int oracle_de_evolve(const oracle_problem *prob, const double *lb, const double 
             Ftry[i] = F;
             Ctry[i] = CR;
             Vtry[i] = VARIANT;
-        }
-        if ((rc = oracle_problem_eval(prob, trial, NP, ftrial))) break;
-        for (size_t i = 0; i < NP; ++i) {
-            if (ftrial[i] <= f[i]) {
-                f[i] = ftrial[i];
-                memcpy(x + i * dim, trial + i * dim, dim * sizeof(double));
-                if (algo) { mC[i] = Ctry[i]; mF[i] = Ftry[i]; }
-                if (algo == 2) mV[i] = Vtry[i];
-                if (ftrial[i] <= gbfit) {
-                    gbfit = ftrial[i];
-                    gbidx = i;
-                    gbF = Ftry[i];
-                    gbCR = Ctry[i];
-                }
+            if (sequential) { /* the reference: evaluate and select before the next individual is built (de.cpp:281-297) */
+                if ((rc = oracle_problem_eval(prob, tmp, 1, ftrial + i))) break;
+                SELECT(i, xnew);
             }
+        }
+        if (!sequential) {
+            if ((rc = oracle_problem_eval(prob, trial, NP, ftrial))) break;
+            for (size_t i = 0; i < NP; ++i) SELECT(i, x);
+        } else {
+            if (rc) break;
+            memcpy(x, xnew, NP * dim * sizeof(double)); /* std::swap(popold, popnew) */
         }
         memcpy(gbIter, x + gbidx * dim, dim * sizeof(double));
         ++done;
@@ -201,6 +216,37 @@ int oracle_de_evolve(const oracle_problem *prob, const double *lb, const double 
     if (F_state && algo) memcpy(F_state, mF, NP * sizeof(double));
     if (CR_state && algo) memcpy(CR_state, mC, NP * sizeof(double));
     if (variant_state && algo == 2) memcpy(variant_state, mV, NP * sizeof(unsigned));
-    free(trial); free(ftrial); free(gbIter); free(mF); free(mC); free(Ftry); free(Ctry); free(mV); free(Vtry);
+    free(trial); free(ftrial); free(gbIter); free(mF); free(mC); free(Ftry); free(Ctry); free(mV); free(Vtry); free(xnew);
+    return rc;
+}
+
+int oracle_de_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim,
+                     unsigned gens, unsigned algo, unsigned variant_in, unsigned variant_adptv, double F0, double CR0,
+                     const unsigned *allowed, unsigned n_allowed, double ftol, double xtol, uint64_t seed, uint32_t first_generation,
+                     unsigned *gens_done, double *F_state, double *CR_state, unsigned *variant_state)
+{
+    return de_evolve_impl(prob, lb, ub, x, f, NP, dim, gens, algo, variant_in, variant_adptv, F0, CR0, allowed, n_allowed, ftol, xtol, seed,
+                          first_generation, gens_done, F_state, CR_state, variant_state, 0);
+}
+
+/* Philox draws, but the reference's one-individual-at-a-time order (for the generational == sequential equivalence test) */
+int oracle_de_evolve_sequential(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim,
+                                unsigned gens, unsigned algo, unsigned variant_in, unsigned variant_adptv, double F0, double CR0,
+                                const unsigned *allowed, unsigned n_allowed, double ftol, double xtol, uint64_t seed,
+                                uint32_t first_generation, unsigned *gens_done, double *F_state, double *CR_state, unsigned *variant_state)
+{
+    return de_evolve_impl(prob, lb, ub, x, f, NP, dim, gens, algo, variant_in, variant_adptv, F0, CR0, allowed, n_allowed, ftol, xtol, seed,
+                          first_generation, gens_done, F_state, CR_state, variant_state, 1);
+}
+
+/* de::evolve / sade::evolve / de1220::evolve on the reference's own stream and in its own order */
+int oracle_de_evolve_mt(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim,
+                        unsigned gens, unsigned algo, unsigned variant_in, unsigned variant_adptv, double F0, double CR0,
+                        const unsigned *allowed, unsigned n_allowed, double ftol, double xtol, uint32_t seed, unsigned *gens_done)
+{
+    ORACLE_MT_BEGIN(seed);
+    const int rc = de_evolve_impl(prob, lb, ub, x, f, NP, dim, gens, algo, variant_in, variant_adptv, F0, CR0, allowed, n_allowed, ftol, xtol,
+                                  0, 0, gens_done, NULL, NULL, NULL, 1);
+    ORACLE_MT_END();
     return rc;
 }

@@ -159,7 +159,8 @@ int oracle_fully_connected_connections(size_t n, size_t i, size_t *out, size_t *
 /* population(prob, bfe, n, seed): batch_random_decision_vector (include/pagmo/utils/generic.hpp:326-389, continuous part :376-381;
  * libstdc++ uniform_real_distribution = (b - a) * canonical + a) and one random 64-bit ID per individual (population.cpp:155-160),
  * with the device's Philox addressing: gene j of individual i = draw (seed, TAG_POPULATION, 0, i, j), ID = (seed, TAG_POPULATION, 1, i, 0).
- * PARITY UNPINNED for the random stream itself (the reference draws from a sequential mt19937). */
+ * The Philox form below is what the device is compared with; oracle_population_init_mt restates the same constructor on the
+ * reference's sequential mt19937 and is PINNED bit for bit to population(prob, n, seed) (tests/test_oracle_pin.py). */
 #include "philox.h"
 int oracle_population_init(const double *lb, const double *ub, size_t n, size_t nx, uint64_t seed, double *x, uint64_t *ids)
 {
@@ -169,6 +170,25 @@ int oracle_population_init(const double *lb, const double *ub, size_t n, size_t 
             x[i * nx + j] = (lb[j] == ub[j]) ? lb[j] : (ub[j] - lb[j]) * oracle_philox_u01(seed, ORACLE_TAG_POPULATION, 0, (uint32_t)i, (uint32_t)j) + lb[j];
         }
         if (ids) ids[i] = oracle_philox_u64(seed, ORACLE_TAG_POPULATION, 1, (uint32_t)i, 0);
+    }
+    return 0;
+}
+
+/* population::population(prob, n, seed) (population.cpp:62-80): n decision vectors drawn first - uniform_real_from_range per
+ * gene, generic.hpp:98-104 - then one id per push_back, std::uniform_int_distribution<unsigned long long>() (population.cpp:592),
+ * which for a 32-bit engine is two words, high word first */
+int oracle_population_init_mt(const double *lb, const double *ub, size_t n, size_t nx, uint32_t seed, double *x, uint64_t *ids)
+{
+    oracle_mt mt;
+    oracle_mt_seed(&mt, seed);
+    for (size_t i = 0; i < n; ++i)
+        for (size_t j = 0; j < nx; ++j) {
+            if (!isfinite(lb[j]) || !isfinite(ub[j])) return -1;
+            x[i * nx + j] = (lb[j] == ub[j]) ? lb[j] : oracle_mt_real(&mt, lb[j], ub[j]);
+        }
+    for (size_t i = 0; i < n && ids; ++i) {
+        const uint64_t hi = oracle_mt_u32(&mt);
+        ids[i] = (hi << 32) + oracle_mt_u32(&mt);
     }
     return 0;
 }

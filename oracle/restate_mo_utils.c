@@ -3,15 +3,18 @@
  * Follows reference src/utils/multi_objective.cpp: pareto_dominance :97-113, fast_non_dominated_sorting :200-257,
  * crowding_distance :280-315, select_best_N_mo :344-396, sort_population_mo :425-465, with the NaN-aware comparisons of
  * include/pagmo/detail/custom_comparisons.hpp:54-88.
- * Sorting: the reference uses std::sort (unstable); this restatement uses a STABLE merge sort, so it is bit-identical to
- * the reference whenever the sort keys are distinct, and on the reference's own known answers (tests/multi_objective.cpp:
- * 81-209, inputs of <= 16 elements, where libstdc++'s std::sort is an insertion sort).  Pinned by tests/test_oracle.py.
+ * Sorting: the reference uses std::sort (unstable).  By default this restatement uses a STABLE merge sort (what the device is
+ * compared with): bit-identical to the reference whenever the sort keys are distinct, and on the reference's own known answers
+ * (tests/multi_objective.cpp:81-209, inputs of <= 16 elements, where libstdc++'s std::sort is an insertion sort).  With
+ * oracle_set_sort_mode(1) the sorts follow libstdc++'s introsort (std_sort.h) and the results equal the compiled reference's
+ * also where keys tie.  Pinned by tests/test_oracle.py and tests/test_oracle_pin.py.
  */
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "oracle.h"
+#include "std_sort.h"
 
 static int less_f(double a, double b) /* less_than_f<double, true> */
 {
@@ -95,20 +98,8 @@ int oracle_fnds(const double *f, size_t n, size_t m, size_t *rank, size_t *dom_c
     return 0;
 }
 
-/* stable merge sort of idx[0..n) by a key comparison */
-typedef int (*before_fn)(size_t a, size_t b, const void *ctx);
-static void msort(size_t *idx, size_t *tmp, size_t n, before_fn before, const void *ctx)
-{
-    if (n < 2) return;
-    const size_t h = n / 2;
-    msort(idx, tmp, h, before, ctx);
-    msort(idx + h, tmp, n - h, before, ctx);
-    size_t i = 0, j = h, k = 0;
-    while (i < h && j < n) tmp[k++] = before(idx[j], idx[i], ctx) ? idx[j++] : idx[i++];
-    while (i < h) tmp[k++] = idx[i++];
-    while (j < n) tmp[k++] = idx[j++];
-    memcpy(idx, tmp, n * sizeof(size_t));
-}
+/* index sorts: stable merge sort by default, libstdc++'s std::sort order when oracle_sort_libstdcxx is set (std_sort.h) */
+#define msort oracle_sort_indices
 
 struct objkey { const double *f; size_t m, obj; };
 static int before_obj(size_t a, size_t b, const void *c)

@@ -2,11 +2,11 @@
  * TEST INFRASTRUCTURE ONLY: the checker the CUDA path is compared against; never linked into the product.
  * Follows reference src/utils/genetic_operators.cpp:49-57 (sbx_betaq), :71-144 (sbx_crossover_impl), :148-197
  * (polynomial_mutation_impl), :200-211 (mo_tournament_selection_impl) and src/algorithms/nsga2.cpp:176-304.
- * PARITY UNPINNED for the random stream: the reference draws from std::mt19937 through libstdc++ distributions, which no
- * reference test pins to values (tests/genetic_operators.cpp only checks throw/no-throw, tests/nsga2.cpp determinism);
- * here every draw is the Philox value (oracle/philox.h) the device consumes at the same (generation, group, slot), and a
- * shuffle is the stable argsort of Philox keys.  The operator arithmetic itself is the reference's, statement by
- * statement; continuous decision variables only (nix = 0).
+ * PINNED (tests/test_oracle_pin.py): with the draw source in sequential-mt19937 mode (philox.h) these functions reproduce the
+ * compiled reference - sbx_crossover_impl, polynomial_mutation_impl, mo_tournament_selection_impl and whole nsga2::evolve runs -
+ * bit for bit.  In the default Philox mode the SAME statements take the draw the device consumes at the same
+ * (generation, group, slot), and a shuffle is the stable argsort of Philox keys (the reference re-shuffles one persistent
+ * index vector with std::shuffle, nsga2.cpp:138-139,180-181).  Continuous decision variables only (nix = 0).
  */
 #include <math.h>
 #include <stdlib.h>
@@ -162,12 +162,18 @@ int oracle_nsga2_evolve(int family, unsigned prob_id, size_t nx, size_t nobj, un
     size_t *rank = (size_t *)malloc(NP * sizeof(size_t)), *sh1 = (size_t *)malloc(NP * sizeof(size_t)),
            *sh2 = (size_t *)malloc(NP * sizeof(size_t)), *sel = (size_t *)malloc(2 * NP * sizeof(size_t)), nsel = 0;
     int rc = 0;
+    for (size_t i = 0; i < NP; ++i) sh1[i] = sh2[i] = i; /* nsga2.cpp:138-139 */
     for (unsigned g = 0; g < gens && !rc; ++g) {
         const uint32_t generation = first_generation + g;
         memcpy(x2, x, NP * nx * sizeof(double));
         memcpy(f2, f, NP * nobj * sizeof(double));
-        oracle_philox_perm(NP, seed, ORACLE_TAG_SHUFFLE1, generation, sh1);
-        oracle_philox_perm(NP, seed, ORACLE_TAG_SHUFFLE2, generation, sh2);
+        if (oracle_mt_active) { /* nsga2.cpp:180-181: the index vectors persist across generations */
+            oracle_mt_shuffle(oracle_mt_active, sh1, NP);
+            oracle_mt_shuffle(oracle_mt_active, sh2, NP);
+        } else {
+            oracle_philox_perm(NP, seed, ORACLE_TAG_SHUFFLE1, generation, sh1);
+            oracle_philox_perm(NP, seed, ORACLE_TAG_SHUFFLE2, generation, sh2);
+        }
         if ((rc = oracle_nsga2_rank_crowding(f, NP, nobj, rank, cd))) break;
         if ((rc = oracle_nsga2_variation(x, rank, cd, NP, nx, lb, ub, sh1, sh2, cr, eta_c, m, eta_m, seed, generation, x2 + NP * nx))) break;
         rc = (family == 8) ? oracle_zdt_batch(prob_id, x2 + NP * nx, NP, nx, f2 + NP * nobj)
@@ -181,4 +187,57 @@ int oracle_nsga2_evolve(int family, unsigned prob_id, size_t nx, size_t nobj, un
     }
     free(x2); free(f2); free(cd); free(rank); free(sh1); free(sh2); free(sel);
     return rc;
+}
+
+/* ---- sequential-mt19937 entry points: the draws of a std::mt19937 seeded with `seed`, as the reference consumes them ---- */
+_Thread_local oracle_mt *oracle_mt_active = NULL;
+
+int oracle_nsga2_evolve_mt(int family, unsigned prob_id, size_t nx, size_t nobj, unsigned alpha, const double *lb, const double *ub,
+                           double *x, double *f, size_t NP, unsigned gens, double cr, double eta_c, double m, double eta_m, uint32_t seed)
+{
+    ORACLE_MT_BEGIN(seed);
+    const int rc = oracle_nsga2_evolve(family, prob_id, nx, nobj, alpha, lb, ub, x, f, NP, gens, cr, eta_c, m, eta_m, 0, 0);
+    ORACLE_MT_END();
+    return rc;
+}
+
+/* one sbx_crossover_impl call followed by polynomial_mutation_impl on both children, then `n_tournaments` tournaments of
+ * (i, i+1) pairs - all on ONE engine, so the draw position carries from one operator into the next */
+int oracle_genetic_operators_mt(const double *p1, const double *p2, size_t nx, const double *lb, const double *ub, double p_cr, double eta_c,
+                                double p_m, double eta_m, const size_t *rank, const double *cd, size_t n_pairs, uint32_t seed, double *c1,
+                                double *c2, size_t *winners)
+{
+    ORACLE_MT_BEGIN(seed);
+    oracle_stream rs = {0, 0, 0, 0, 0};
+    sbx(p1, p2, c1, c2, nx, lb, ub, p_cr, eta_c, &rs);
+    polymut(c1, nx, lb, ub, p_m, eta_m, &rs);
+    polymut(c2, nx, lb, ub, p_m, eta_m, &rs);
+    for (size_t i = 0; i < n_pairs; ++i) winners[i] = tournament(2 * i, 2 * i + 1, rank, cd, &rs);
+    ORACLE_MT_END();
+    return 0;
+}
+
+/* the helpers of mt19937.h, exported so that they can be compared with the real std:: classes (ref_std_*, ref_capi.h) */
+int oracle_mt_sequence(uint32_t seed, int kind, uint64_t a, uint64_t b, size_t n, double *out_real, uint64_t *out_int)
+{
+    oracle_mt mt;
+    oracle_mt_seed(&mt, seed);
+    for (size_t i = 0; i < n; ++i) switch (kind) {
+            case 0: out_int[i] = oracle_mt_u32(&mt); break;
+            case 1: out_real[i] = oracle_mt_u01(&mt); break;
+            case 2: out_int[i] = oracle_mt_int(&mt, a, b); break;
+            case 3: out_real[i] = oracle_mt_normal(&mt, 0., 1.); break;
+            case 4: out_real[i] = oracle_mt_real(&mt, -(double)a, (double)b); break;
+            default: return -1;
+        }
+    return 0;
+}
+
+int oracle_mt_shuffles(uint32_t seed, size_t n, size_t rounds, size_t *perm)
+{
+    oracle_mt mt;
+    oracle_mt_seed(&mt, seed);
+    for (size_t i = 0; i < n; ++i) perm[i] = i;
+    for (size_t r = 0; r < rounds; ++r) oracle_mt_shuffle(&mt, perm, n);
+    return 0;
 }

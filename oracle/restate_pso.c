@@ -1,9 +1,9 @@
 /* oracle/restate_pso.c - plain-C restatement of pagmo::pso_gen::evolve (generational PSO).  TEST INFRASTRUCTURE ONLY.
  * Follows reference src/algorithms/pso_gen.cpp: velocity update :231-327 (variants 1-5), clamp/move/box correction :329-363,
  * evaluation :417-440, memory update :445-459, best neighbour :593-623, lbest ring :679-698, gbest :644-664.
- * PARITY UNPINNED for the random stream (the reference's mt19937 draws are not pinned by any reference test; tests/pso_gen.cpp
- * checks determinism and bfe-equivalence only): every draw is the Philox value the device consumes at the same
- * (generation, particle, slot) - see oracle/philox.h and pagmo2_b200/csrc/pso.cu.  The arithmetic is the reference's.
+ * PINNED (tests/test_oracle_pin.py): oracle_pso_evolve_mt - these statements on the reference's sequential mt19937 stream -
+ * reproduces the compiled pso_gen::evolve bit for bit (variants 1-5, gbest and lbest).  In the default Philox mode every draw
+ * is the value the device consumes at the same (generation, particle, slot) - see oracle/philox.h and pagmo2_b200/csrc/pso.cu.
  */
 #include <math.h>
 #include <stdlib.h>
@@ -46,8 +46,9 @@ int oracle_pso_evolve(const oracle_problem *prob, const double *lb, const double
         for (size_t p = 0; p < n; ++p)
             for (size_t d = 0; d < dim; ++d) {
                 const double vwidth = (ub[d] - lb[d]) * max_vel, minv = -1. * vwidth, maxv = vwidth;
-                const double u = oracle_philox_u01(seed, ORACLE_TAG_INIT, first_generation, (uint32_t)p, (uint32_t)d);
-                V[p * dim + d] = (minv == maxv) ? minv : (maxv - minv) * u + minv;
+                /* uniform_real_from_range (generic.hpp:98-104): no draw when the range is empty */
+                V[p * dim + d] = (minv == maxv) ? minv
+                                                : oracle_u01_at(seed, ORACLE_TAG_INIT, first_generation, (uint32_t)p, (uint32_t)d) * (maxv - minv) + minv;
             }
     size_t gbest = 0;
     double gbest_fit = 0;
@@ -79,17 +80,17 @@ int oracle_pso_evolve(const oracle_problem *prob, const double *lb, const double
             const double *best_neighb = lbX + b * dim;
             double r1 = 0, r2 = 0;
             if (variant == 3 || variant == 4) {
-                r1 = oracle_philox_u01(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, 0);
-                r2 = oracle_philox_u01(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, 1);
+                r1 = oracle_u01_at(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, 0);
+                if (variant == 3) r2 = oracle_u01_at(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, 1); /* variant 4 draws r1 only, :274 */
             }
             for (size_t d = 0; d < dim; ++d) {
                 double *Vp = &V[p * dim + d];
                 const double Xp = X[p * dim + d], lbXp = lbX[p * dim + d];
                 if (variant == 1 || variant == 5) {
-                    r1 = oracle_philox_u01(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, (uint32_t)(2 * d));
-                    r2 = oracle_philox_u01(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, (uint32_t)(2 * d + 1));
+                    r1 = oracle_u01_at(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, (uint32_t)(2 * d));
+                    r2 = oracle_u01_at(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, (uint32_t)(2 * d + 1));
                 } else if (variant == 2) {
-                    r1 = oracle_philox_u01(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, (uint32_t)d);
+                    r1 = oracle_u01_at(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, (uint32_t)d);
                 }
                 switch (variant) {
                     case 1: case 3: *Vp = omega * *Vp + eta1 * r1 * (lbXp - Xp) + eta2 * r2 * (best_neighb[d] - Xp); break;
@@ -126,5 +127,17 @@ int oracle_pso_evolve(const oracle_problem *prob, const double *lb, const double
     if (v) memcpy(v, V, n * dim * sizeof(double));
     if (xcur) memcpy(xcur, X, n * dim * sizeof(double));
     free(X); free(V); free(fit);
+    return rc;
+}
+
+/* pso_gen::evolve on the reference's own stream: std::mt19937(seed), velocities drawn inside (memory = false, :193-201) */
+int oracle_pso_evolve_mt(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t n, size_t dim,
+                         unsigned gens, double omega, double eta1, double eta2, double max_vel, unsigned variant, unsigned neighb_type,
+                         unsigned neighb_param, uint32_t seed)
+{
+    ORACLE_MT_BEGIN(seed);
+    const int rc = oracle_pso_evolve(prob, lb, ub, x, f, NULL, NULL, n, dim, gens, omega, eta1, eta2, max_vel, variant, neighb_type,
+                                     neighb_param, 0, 0);
+    ORACLE_MT_END();
     return rc;
 }
