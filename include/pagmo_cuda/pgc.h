@@ -105,6 +105,7 @@ PGC_API int pgc_ctx_launch_count(const pgc_ctx *ctx, uint64_t *count);
 PGC_API int pgc_problem_create(pgc_ctx *ctx, const pgc_problem_desc *desc, pgc_problem **out);
 PGC_API int pgc_problem_destroy(pgc_problem *prob);
 PGC_API int pgc_problem_nx(const pgc_problem *prob, size_t *nx);     /* problem::get_nx  */
+PGC_API int pgc_problem_nix(const pgc_problem *prob, size_t *nix);   /* problem::get_nix: integer genes at the end (zdt5) */
 PGC_API int pgc_problem_nobj(const pgc_problem *prob, size_t *nobj); /* problem::get_nobj */
 PGC_API int pgc_problem_nf(const pgc_problem *prob, size_t *nf);     /* problem::get_nf (= nobj here: no constraints) */
 PGC_API int pgc_problem_bounds(const pgc_problem *prob, double *lb, double *ub); /* UDP::get_bounds */
@@ -293,7 +294,8 @@ PGC_API int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *algo,
 
 /* ---- populations and migration (island.cpp:428-652) ------------------------------------------------------------------- */
 /* population(prob, bfe, n, seed) (population.cpp:82-103, generic.hpp:326-389): n uniform random decision vectors in the bounds,
- * one batch evaluation, random 64-bit IDs.  d_f and d_ids may be NULL. */
+ * one batch evaluation, random 64-bit IDs; the last nix genes are drawn as integers in [lb, ub] (generic.hpp:289-295).  d_f and
+ * d_ids may be NULL.  The generation operators (pgc_*_evolve_device) refuse problems with integer genes (PGC_ERR_UNSUPPORTED). */
 PGC_API int pgc_population_init_device(pgc_problem *prob, size_t n, uint64_t seed, double *d_x, double *d_f, uint64_t *d_ids,
                                        void *stream);
 /* select_best::select (select_best.cpp:63-171): the best `rate` individuals (absolute count, or a fraction of n when

@@ -54,6 +54,9 @@ int oracle_lj_batch(unsigned atoms, const double *xs, size_t n, double *fs);
 int oracle_pareto_dominance(const double *a, const double *b, size_t m);
 int oracle_fnds(const double *f, size_t n, size_t m, size_t *rank, size_t *dom_count, size_t *front_idx, size_t *front_off,
                 size_t *nfronts);
+/* same results as oracle_fnds, O(n) memory and OpenMP-parallel dominance tests: the full-size checker */
+int oracle_fnds_nolist(const double *f, size_t n, size_t m, size_t *rank, size_t *dom_count, size_t *front_idx, size_t *front_off,
+                       size_t *nfronts);
 int oracle_crowding_distance(const double *f, size_t n, size_t m, double *out);
 int oracle_select_best_N_mo(const double *f, size_t n, size_t m, size_t N, size_t *out, size_t *nout);
 int oracle_sort_population_mo(const double *f, size_t n, size_t m, size_t *out);

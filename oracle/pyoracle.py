@@ -155,13 +155,15 @@ class Oracle:
         return out
 
     # ---- multi-objective utilities (restate_mo_utils.c) ----
-    def fnds(self, f: np.ndarray):
+    def fnds(self, f: np.ndarray, nolist: bool = False):
+        """fast_non_dominated_sorting; nolist=True: the O(n)-memory, OpenMP form for full-size inputs (same results)."""
         f = np.ascontiguousarray(f, dtype=np.float64)
         n, m = f.shape
         rank, dc, fi = (np.empty(n, dtype=np.uint64) for _ in range(3))
         fo = np.empty(n + 1, dtype=np.uint64)
         nf = C.c_size_t()
-        if self.lib.oracle_fnds(_dp(f), C.c_size_t(n), C.c_size_t(m), _sp(rank), _sp(dc), _sp(fi), _sp(fo), C.byref(nf)):
+        fn = self.lib.oracle_fnds_nolist if nolist else self.lib.oracle_fnds
+        if fn(_dp(f), C.c_size_t(n), C.c_size_t(m), _sp(rank), _sp(dc), _sp(fi), _sp(fo), C.byref(nf)):
             raise ValueError("oracle_fnds failed")
         fronts = [fi[int(fo[k]):int(fo[k + 1])].astype(np.int64) for k in range(nf.value)]
         return {"rank": rank.astype(np.int64), "dom_count": dc.astype(np.int64), "fronts": fronts}

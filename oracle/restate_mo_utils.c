@@ -43,6 +43,7 @@ int oracle_fnds(const double *f, size_t n, size_t m, size_t *rank, size_t *dom_c
                 size_t *nfronts)
 {
     if (n < 2) return -1;
+    if (n > 8192) return oracle_fnds_nolist(f, n, m, rank, dom_count, front_idx, front_off, nfronts); /* same results, O(n) memory */
     size_t *dl_len = (size_t *)calloc(n, sizeof(size_t)), *dl_cap = (size_t *)calloc(n, sizeof(size_t));
     size_t **dl = (size_t **)calloc(n, sizeof(size_t *));
     size_t *cnt = (size_t *)calloc(n, sizeof(size_t));
@@ -95,6 +96,93 @@ int oracle_fnds(const double *f, size_t n, size_t m, size_t *rank, size_t *dom_c
     *nfronts = nf;
     for (size_t i = 0; i < n; ++i) free(dl[i]);
     free(dl); free(dl_len); free(dl_cap); free(cnt);
+    return 0;
+}
+
+/* fast_non_dominated_sorting without the O(n^2)-memory dom_list, for the full-size (65 536 / 131 072 point) parity tests.
+ * The reference appends j to dom_list[i] in ascending j (multi_objective.cpp:215-227: entries below i during outer iteration
+ * i, entries above i in later outer iterations), and while peeling walks front k in order and, per member p, its dom_list in
+ * order (:235-254).  So "for p in front order: for q ascending: if p dominates q: if --count[q] == 0: append q" is the same
+ * sequence of appends; the list lookup is replaced by the dominance test itself.  The ascending q scan of one p is split over
+ * OpenMP threads in contiguous chunks whose appends are concatenated in chunk order - the order is unchanged.
+ * Pinned against oracle_fnds and the compiled reference in tests/test_oracle.py. */
+int oracle_fnds_nolist(const double *f, size_t n, size_t m, size_t *rank, size_t *dom_count, size_t *front_idx, size_t *front_off,
+                       size_t *nfronts)
+{
+    if (n < 2) return -1;
+    size_t *cnt = (size_t *)calloc(n, sizeof(size_t));
+    size_t *alive = (size_t *)malloc(n * sizeof(size_t)); /* ascending indices not yet in a front */
+    size_t *freed = (size_t *)malloc(n * sizeof(size_t));
+#pragma omp parallel for schedule(dynamic, 64)
+    for (size_t j = 0; j < n; ++j) {
+        size_t c = 0;
+        for (size_t i = 0; i < n; ++i)
+            if (i != j && oracle_pareto_dominance(f + i * m, f + j * m, m)) ++c;
+        cnt[j] = c;
+    }
+    size_t nf = 1, filled = 0, nalive = 0;
+    front_off[0] = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (dom_count) dom_count[i] = cnt[i];
+        if (cnt[i] == 0) {
+            rank[i] = 0;
+            front_idx[filled++] = i;
+        } else
+            alive[nalive++] = i;
+    }
+    front_off[1] = filled;
+    size_t cur_b = 0, cur_e = filled;
+    enum { MAXT = 64 };
+    while (cur_e > cur_b && nalive) {
+        const size_t next_b = filled;
+        for (size_t p = cur_b; p < cur_e; ++p) {
+            const double *fp = f + front_idx[p] * m;
+            size_t napp[MAXT] = {0};
+            int nt = 1;
+#pragma omp parallel
+            {
+                int t = 0, T = 1;
+#ifdef _OPENMP
+                extern int omp_get_thread_num(void);
+                extern int omp_get_num_threads(void);
+                t = omp_get_thread_num();
+                T = omp_get_num_threads();
+                if (T > MAXT) T = MAXT;
+#endif
+                if (t < T) {
+                    if (t == 0) nt = T;
+                    const size_t lo = nalive * (size_t)t / (size_t)T, hi = nalive * (size_t)(t + 1) / (size_t)T;
+                    size_t k = 0;
+                    /* members whose count reaches zero go to freed[lo..lo+k) in order and leave a hole in alive[] */
+                    for (size_t a = lo; a < hi; ++a) {
+                        const size_t q = alive[a];
+                        if (oracle_pareto_dominance(fp, f + q * m, m) && --cnt[q] == 0) {
+                            freed[lo + k++] = q;
+                            alive[a] = (size_t)-1;
+                        }
+                    }
+                    napp[t] = k;
+                }
+            }
+            /* append the chunks' newly freed points in chunk order, then compact `alive` */
+            size_t w = 0;
+            for (int t = 0; t < nt; ++t) {
+                const size_t lo = nalive * (size_t)t / (size_t)nt, hi = nalive * (size_t)(t + 1) / (size_t)nt;
+                for (size_t a = lo; a < lo + napp[t]; ++a) {
+                    rank[freed[a]] = nf;
+                    front_idx[filled++] = freed[a];
+                }
+                for (size_t a = lo; a < hi; ++a)
+                    if (alive[a] != (size_t)-1) alive[w++] = alive[a];
+            }
+            nalive = w;
+        }
+        cur_b = next_b;
+        cur_e = filled;
+        if (cur_e > cur_b) front_off[++nf] = filled;
+    }
+    *nfronts = nf;
+    free(cnt); free(alive); free(freed);
     return 0;
 }
 

@@ -245,6 +245,18 @@ static int indices_out(DevBuf &b, size_t cnt, size_t *dst)
     return PGC_OK;
 }
 
+// The device generation operators treat every gene as continuous (the integer tails of sbx / polynomial mutation,
+// genetic_operators.cpp:125-142,187-195, and sga's integer mutation are not built): refuse instead of silently running another algorithm.
+#define PGC_NO_INTEGER_GENES(prob, who)                                                                                \
+    do {                                                                                                               \
+        if ((prob)->nix != 0) {                                                                                        \
+            set_error("%s: '%s' has %zu integer decision variables; the device generation operators handle continuous " \
+                      "genes only (no CPU fallback)",                                                                  \
+                      who, (prob)->name.c_str(), (prob)->nix);                                                         \
+            return PGC_ERR_UNSUPPORTED;                                                                                \
+        }                                                                                                              \
+    } while (0)
+
 extern "C" {
 
 const char *pgc_version(void) { return "pagmo2_b200 0.1.0 (sm_100a)"; }
@@ -419,6 +431,13 @@ int pgc_problem_nx(const pgc_problem *p, size_t *nx)
 {
     PGC_REQUIRE(p && nx, "pgc_problem_nx: null argument");
     *nx = p->nx;
+    return PGC_OK;
+}
+
+int pgc_problem_nix(const pgc_problem *p, size_t *nix)
+{
+    PGC_REQUIRE(p && nix, "pgc_problem_nix: null argument");
+    *nix = p->nix;
     return PGC_OK;
 }
 
@@ -705,6 +724,7 @@ int pgc_nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t 
                             double eta_m, uint64_t seed, uint32_t first_generation, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_nsga2_evolve_device: null argument");
+    PGC_NO_INTEGER_GENES(prob, "pgc_nsga2_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return nsga2_evolve_device(prob, d_x, d_f, static_cast<unsigned>(NP), gens, cr, eta_c, m, eta_m, seed, first_generation,
                                problem_eval_device, stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
@@ -715,6 +735,7 @@ int pgc_pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d
                           uint64_t seed, uint32_t first_generation, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_pso_evolve_device: null argument");
+    PGC_NO_INTEGER_GENES(prob, "pgc_pso_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return pso_evolve_device(prob, d_x, d_f, d_v, d_xcur, static_cast<unsigned>(n), gens, omega, eta1, eta2, max_vel, variant, neighb_type,
                              neighb_param, seed, first_generation, problem_eval_device,
@@ -749,6 +770,7 @@ int pgc_de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP,
                          unsigned *gens_done, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_de_evolve_device: null argument");
+    PGC_NO_INTEGER_GENES(prob, "pgc_de_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return de_evolve_device(prob, d_x, d_f, static_cast<unsigned>(NP), gens, algo, variant, variant_adptv, F, CR, allowed_variants, n_allowed,
                             ftol, xtol, d_F, d_CR, d_variant, seed, first_generation, gens_done, problem_eval_device,
@@ -820,6 +842,7 @@ int pgc_sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP
                           uint32_t first_generation, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_sga_evolve_device: null argument");
+    PGC_NO_INTEGER_GENES(prob, "pgc_sga_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return sga_evolve_device(prob, d_x, d_f, static_cast<unsigned>(NP), gens, cr, eta_c, m, param_m, param_s, crossover, mutation, selection,
                              seed, first_generation, problem_eval_device, stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);

@@ -335,6 +335,7 @@ int mo_create(pgc_problem *p)
                     "ZDT test suite contains six (prob_id=[1 ... 6]) problems, prob_id=%u was detected", d.prob_id);
         const size_t D = (d.prob_id == 5u) ? 30u + 5u * (param - 1u) : param; // :115-118
         p->nx = D;
+        p->nix = d.prob_id == 5u ? D : 0u; // zdt.cpp:126-143: zdt5 is integer valued
         p->nobj = 2;
         p->lb.assign(D, 0.);
         p->ub.assign(D, 1.);

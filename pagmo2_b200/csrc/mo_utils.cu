@@ -674,6 +674,9 @@ template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persist
         // ---- wait until front `expect` is published, then read the bookkeeping of this level
         if (threadIdx.x == 0) {
             unsigned spins = 0, code = 0;
+            // fault injection (bit 1 of big_inkernel, tests only): block 0 drops out as if its wake-up had been lost; the other
+            // blocks then wait for a ticket that never comes until THEIR watchdog fires
+            if ((big_inkernel & 2u) && blockIdx.x == 0) meta->stuck = 1;
             for (;;) {
                 const unsigned long long both = *reinterpret_cast<volatile unsigned long long *>(&meta->level_pub);
                 if (static_cast<unsigned>(both) == expect) break;
@@ -801,7 +804,7 @@ template <int M> __global__ void __launch_bounds__(kPersistThreads) fnds_persist
             if (threadIdx.x == 0) meta->tickets = 0;
             __threadfence();
             const unsigned Cnow = __ldcg(&meta->ncand);
-            if (big_inkernel && Cnow > 1024u && Cnow <= kBigInKernel) { // all blocks close this level together
+            if ((big_inkernel & 1u) && Cnow > 1024u && Cnow <= kBigInKernel) { // all blocks close this level together
                 if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(&meta->big_pub) = expect + 1;
             } else
             order_level(V, 0, s_sort, s_pos); // sets meta->overflow instead when the level is too big for shared memory ...
@@ -1303,8 +1306,13 @@ int fnds_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned 
                 }
                 const char *big_env = std::getenv("PGC_FNDS_BIG_INKERNEL"); // 0: big levels always through the host / CUB path
                 unsigned big_arg = (big_env && big_env[0] == '0') ? 0u : 1u;
+                // test hooks: PGC_FNDS_INJECT_STUCK=1 makes block 0 report a lost wake-up (the watchdog path must surface as an
+                // error, not a hang); PGC_FNDS_FORCE_NOCOOP=1 behaves as if the cooperative launch had been refused
+                const char *stuck_env = std::getenv("PGC_FNDS_INJECT_STUCK"), *nocoop_env = std::getenv("PGC_FNDS_FORCE_NOCOOP");
+                if (stuck_env && stuck_env[0] == '1') big_arg |= 2u;
+                const bool refuse = nocoop_env && nocoop_env[0] == '1';
                 void *args[] = {&V, &big_arg};
-                if (cudaLaunchCooperativeKernel(fn, dim3(pgrid), dim3(kPersistThreads), args, 0, st) != cudaSuccess) {
+                if (refuse || cudaLaunchCooperativeKernel(fn, dim3(pgrid), dim3(kPersistThreads), args, 0, st) != cudaSuccess) {
                     cudaGetLastError(); // the grid cannot be co-resident here (e.g. a partitioned device): launch-per-level loop instead
                     persist = false;
                     continue;

@@ -124,6 +124,7 @@ struct pgc_problem {
     pgc_ctx *ctx = nullptr;
     pgc_problem_desc desc{}; // table pointers nulled after the copy
     size_t nx = 0, nobj = 1;
+    size_t nix = 0; // integer dimension (the last nix genes, problem::get_nix): zdt5 only; a meta-problem inherits its inner one's
     std::vector<double> lb, ub;
     std::string name;
     // device tables

@@ -155,3 +155,75 @@ def test_fnds_sorted_space_degenerate_inputs(ctx, orc):
     f = rng.uniform(0, 1, (n, 3))
     f[n // 2:] = f[:n // 2]
     assert same_fnds(ctx.fnds(f), orc.fnds(f))
+
+
+# ---------------------------------------------------------------- BASELINE cfg3 at its own size, in full
+def _cfg3_points(orc, kind, n, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "zdt1":      # ZDT1 objectives of a random population, nx = 30: ~300-400 small fronts
+        return orc.zdt(1, rng.uniform(0, 1, (n, 30)))
+    if kind == "dtlz2":     # DTLZ2, three objectives, nx = 12: ~80 big fronts
+        return orc.dtlz(2, rng.uniform(0, 1, (n, 12)), 3, 100)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind,n", [("zdt1", 65536), ("dtlz2", 65536), ("zdt1", 131072), ("dtlz2", 131072)])
+def test_fnds_full_size_bit_exact_vs_oracle(ctx, orc, kind, n):
+    """The sort NSGA-II runs every generation at pop 65 536 (N for the tournament ranking, 2N = 131 072 for select_best_N_mo):
+    ranks, dominator counts, and every front in the reference's order, compared IN FULL with the restated reference
+    (oracle_fnds_nolist: the same append order without the O(N^2) list, ~10-50 s on 8 host cores)."""
+    f = _cfg3_points(orc, kind, n, n % 1000 + len(kind))
+    assert same_fnds(ctx.fnds(f), orc.fnds(f))
+
+
+@pytest.mark.parametrize("switch", ["PGC_FNDS_PERSIST", "PGC_FNDS_COUNT2", "PGC_FNDS_BIG_INKERNEL", "PGC_FNDS_FUSE"])
+@pytest.mark.parametrize("kind", ["zdt1", "dtlz2"])
+def test_fnds_fallback_paths_equal_default_path(ctx, orc, monkeypatch, switch, kind):
+    """Every A/B switch of the large-input FNDS is product code: launch-per-level loop instead of the resident kernel
+    (PERSIST=0, alone and with FUSE=0), all-pairs count pass (COUNT2=0), big levels through the host / CUB path
+    (BIG_INKERNEL=0).  Each must give the default path's result bit for bit at the cfg3 size, and the oracle's at 12 288 points."""
+    n = 65536
+    f = _cfg3_points(orc, kind, n, 7)
+    small = f[:12288]
+    want_small = orc.fnds(small)
+    default = ctx.fnds(f)
+    monkeypatch.setenv(switch, "0")
+    if switch == "PGC_FNDS_FUSE":
+        monkeypatch.setenv("PGC_FNDS_PERSIST", "0")   # FUSE only exists in the launch-per-level loop
+    assert same_fnds(ctx.fnds(f), default)
+    assert same_fnds(ctx.fnds(small), want_small)
+    sel = ctx.select_best_N_mo(f, n // 2)
+    monkeypatch.delenv(switch)
+    monkeypatch.delenv("PGC_FNDS_PERSIST", raising=False)
+    assert np.array_equal(sel, ctx.select_best_N_mo(f, n // 2))
+
+
+def test_fnds_without_cooperative_launch(ctx, orc, monkeypatch):
+    """A device that refuses the cooperative launch (partitioned / MIG): the driver falls back to the launch-per-level loop."""
+    f = _cfg3_points(orc, "zdt1", 65536, 9)
+    default = ctx.fnds(f)
+    monkeypatch.setenv("PGC_FNDS_FORCE_NOCOOP", "1")
+    assert same_fnds(ctx.fnds(f), default)
+    g = f[:9000]
+    assert same_fnds(ctx.fnds(g), orc.fnds(g))
+
+
+def test_fnds_above_resident_capacity(ctx, orc):
+    """More points than one thread per position of the resident grid (148 x 1024 = 151 552): the launch-per-level loop is the
+    only path; full compare with the oracle."""
+    n = 155648
+    f = _cfg3_points(orc, "zdt1", n, 3)
+    assert same_fnds(ctx.fnds(f), orc.fnds(f))
+
+
+def test_fnds_watchdog_surfaces_as_error(ctx, orc, monkeypatch):
+    """A lost wake-up in the resident level loop must end as PGC_ERR_CUDA with a message, not as a hung device: block 0 is made to
+    drop out (PGC_FNDS_INJECT_STUCK=1), the other blocks' spin watchdogs fire, the host reports it, and the context stays usable."""
+    from pagmo2_b200 import capi
+    f = _cfg3_points(orc, "zdt1", 65536, 4)
+    monkeypatch.setenv("PGC_FNDS_INJECT_STUCK", "1")
+    with pytest.raises(capi.PgcError, match="lost a wake-up"):
+        ctx.fnds(f)
+    monkeypatch.delenv("PGC_FNDS_INJECT_STUCK")
+    g = f[:20000]
+    assert same_fnds(ctx.fnds(g), orc.fnds(g))

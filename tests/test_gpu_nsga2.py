@@ -103,3 +103,24 @@ def test_carried_ranking_equals_fresh_sorting(capi, ctx, orc):
             xo, fo = orc.nsga2_evolve(fam, pid, nobj, 100, lb, ub, x, orc.zdt(pid, x), gens=5, first_generation=0, **kw)
             assert np.allclose(xa, xo, rtol=1e-12, atol=1e-14) and np.allclose(fa, fo, rtol=1e-12, atol=1e-14)
         prob.close()
+
+
+@pytest.mark.parametrize("fam,pid,nx,nobj", [("zdt", 1, 30, 2), ("dtlz", 2, 12, 3)])
+def test_generation_at_cfg3_size_matches_restated_reference(capi, ctx, orc, fam, pid, nx, nobj):
+    """BASELINE cfg3 at its own size: ONE whole nsga2 generation at pop 65 536 (ranking of N, tournament + SBX + mutation, batch
+    evaluation, select_best_N_mo over 2N = 131 072) against the restated reference loop on the same Philox draws - the same
+    survivors in the same order.  The restated loop is the one pinned bit for bit to nsga2.cpp (tests/test_oracle_pin.py);
+    ~1 minute of host time per case for its two O(N^2) sorts."""
+    rng = np.random.default_rng(65536 + pid)
+    NP = 65536
+    prob = capi.Problem(ctx, fam, prob_id=pid, dim=nx, nobj=nobj, param=100)
+    lb, ub = prob.bounds()
+    x = rng.uniform(lb, ub, (NP, nx))
+    f = orc.zdt(pid, x) if fam == "zdt" else orc.dtlz(pid, x, nobj, 100)
+    kw = dict(gens=1, cr=0.95, eta_c=10, m=1.0 / nx, eta_m=50, seed=23)
+    xo, fo = orc.nsga2_evolve(fam, pid, nobj, 100, lb, ub, x, f, **kw)
+    xg, fg = prob.nsga2_evolve(x, prob.eval_host(x), **kw)
+    assert np.allclose(xg, xo, rtol=1e-12, atol=1e-14) and np.allclose(fg, fo, rtol=1e-12, atol=1e-14)
+    # survivors that are untouched parents or unmutated clones must be bit-identical rows in the same positions
+    assert (xg == xo).all(axis=1).mean() > 0.3
+    prob.close()
