@@ -88,6 +88,23 @@ public:
     {
         return m_desc.gens;
     }
+    // what a device-resident island (cuda_island.hpp) needs to run this algorithm on ITS copy of the population
+    const pgc_algo_desc &descriptor() const
+    {
+        return m_desc;
+    }
+    unsigned generation() const
+    {
+        return m_generation;
+    }
+    void advance_generation(unsigned gens) const
+    {
+        m_generation += gens;
+    }
+    int device() const
+    {
+        return m_device;
+    }
     std::string get_name() const
     {
         return m_name + " [CUDA sm_100a]";
@@ -99,7 +116,15 @@ public:
     template <typename Archive>
     void serialize(Archive &ar, unsigned)
     {
-        pagmo::detail::archive(ar, m_device, m_name, m_generation);
+        // every constructor argument lives in m_desc: pagmo default-constructs a UDA before loading it (island / archipelago
+        // save + load, pygmo pickling), so anything left out here would silently come back as a default
+        std::vector<unsigned> allowed(m_desc.allowed_variants, m_desc.allowed_variants + 18);
+        pagmo::detail::archive(ar, m_device, m_name, m_generation, m_desc.algo, m_desc.gens, m_desc.variant, m_desc.variant_adptv,
+                               m_desc.neighb_type, m_desc.neighb_param, m_desc.n_allowed, allowed, m_desc.F, m_desc.CR, m_desc.ftol,
+                               m_desc.xtol, m_desc.omega, m_desc.eta1, m_desc.eta2, m_desc.max_vel, m_desc.cr, m_desc.eta_c, m_desc.m,
+                               m_desc.eta_m, m_desc.seed, m_desc.param_m, m_desc.param_s, m_desc.crossover, m_desc.mutation,
+                               m_desc.selection);
+        for (std::size_t i = 0; i < 18u && i < allowed.size(); ++i) m_desc.allowed_variants[i] = allowed[i]; // no-op when saving
     }
 
 protected:

@@ -96,7 +96,10 @@ inline std::mutex &device_mutex(int device)
 class problem_handle
 {
 public:
-    problem_handle(int device, const pgc_problem_desc &desc) : m_ctx(device_context(device)), m_device(device), m_desc(desc)
+    // ctx = nullptr: the device's shared context (calls serialised by device_mutex); a private context (own stream, see
+    // private_on) belongs to one owner - e.g. one island of a cuda_archipelago - which then calls raw() from its own thread only
+    problem_handle(int device, const pgc_problem_desc &desc, std::shared_ptr<pgc_ctx> ctx = nullptr)
+        : m_ctx(ctx ? std::move(ctx) : device_context(device)), m_device(device), m_desc(desc)
     {
         // the handle keeps its own copy of the description (tables included), so that it can be re-created on another device
         if (desc.rotation) m_rotation.assign(desc.rotation, desc.rotation + desc.rotation_len);
@@ -141,6 +144,18 @@ public:
     std::size_t nx() const { return m_nx; }
     std::size_t nf() const { return m_nf; }
     int device() const { return m_device; }
+    pgc_problem *raw() const { return m_prob; }
+    pgc_ctx *context() const { return m_ctx.get(); }
+
+    // the same problem on `device` behind a NEW private context (own stream): islands that share a GPU overlap on it like the
+    // reference's island threads share a CPU
+    std::shared_ptr<problem_handle> private_on(int device) const
+    {
+        pgc_ctx *raw_ctx = nullptr;
+        check(pgc_ctx_create(device, &raw_ctx), "pgc_ctx_create");
+        std::shared_ptr<pgc_ctx> ctx(raw_ctx, [](pgc_ctx *c) { pgc_ctx_destroy(c); });
+        return private_with(device, ctx);
+    }
 
     // the same problem on another device (created on first use, then shared)
     std::shared_ptr<problem_handle> twin_on(int device) const
@@ -221,6 +236,11 @@ public:
     }
 
 private:
+    std::shared_ptr<problem_handle> private_with(int device, const std::shared_ptr<pgc_ctx> &ctx) const
+    {
+        if (!m_inner) return std::make_shared<problem_handle>(device, m_desc, ctx);
+        return std::make_shared<problem_handle>(m_inner->private_with(device, ctx), m_meta_kind, m_meta_a, m_meta_b, m_meta_method);
+    }
     std::shared_ptr<pgc_ctx> m_ctx;
     int m_device = 0;
     pgc_problem_desc m_desc{};
@@ -542,8 +562,12 @@ class twin_cache
 public:
     std::shared_ptr<problem_handle> find(const pagmo::problem &p, int device)
     {
+        // a CUDA-backed UDP carries its own handle; asked for another device, its twin there (created once, then shared)
 #define PGC_OWN_UDP(T)                                                                                                                      \
-    if (p.is<T>()) return p.extract<T>()->shared_handle();
+    if (p.is<T>()) {                                                                                                                        \
+        auto own = p.extract<T>()->shared_handle();                                                                                         \
+        return own->device() == device ? own : own->twin_on(device);                                                                        \
+    }
         PGC_OWN_UDP(cuda_cec2014)
         PGC_OWN_UDP(cuda_cec2013)
         PGC_OWN_UDP(cuda_rastrigin)

@@ -312,6 +312,61 @@ PGC_API int pgc_fair_replace_device(pgc_ctx *ctx, uint64_t *d_ids, double *d_x, 
  * (fully_connected.cpp:86-115) with n vertices: sources of the edges into i and their weights; buffers sized n. */
 PGC_API int pgc_topology_connections(int kind, size_t n, size_t i, double weight, size_t *idx_out, double *w_out, size_t *count);
 
+/* ---- device-resident islands (island.cpp:428-652, thread_island.cpp:79-132) -----------------------------------------------
+ * A pgc_island keeps one island's population (ids | x | f) in HBM between calls, so that successive evolve() calls, selection
+ * and replacement never cross PCIe.  It also owns a migration OUTBOX (what select_best published last: the island's entry in the
+ * archipelago's migrants database, archipelago.cpp:658-714) and `max_in_edges` INBOX slots (what arrived along in-edges), each a
+ * packed group of at most `max_migrants` individuals.  Calls on one island are ordered on its context's stream.  `prob` is
+ * borrowed and must outlive the island. */
+typedef struct pgc_island pgc_island;
+PGC_API int pgc_island_create(pgc_problem *prob, size_t n, size_t max_migrants, size_t max_in_edges, pgc_island **out);
+PGC_API int pgc_island_destroy(pgc_island *isl);
+PGC_API int pgc_island_size(const pgc_island *isl, size_t *n, size_t *nx, size_t *nf);
+PGC_API int pgc_island_pointers(pgc_island *isl, uint64_t **d_ids, double **d_x, double **d_f);
+/* island::set_population / get_population: host <-> device (the only PCIe traffic of an island) */
+PGC_API int pgc_island_upload(pgc_island *isl, const uint64_t *ids, const double *x, const double *f);
+PGC_API int pgc_island_download(pgc_island *isl, uint64_t *ids, double *x, double *f);
+/* population(prob, bfe, n, seed) directly on the device (pgc_population_init_device) */
+PGC_API int pgc_island_init(pgc_island *isl, uint64_t seed);
+/* algorithm::evolve on the resident population; the island keeps the Philox generation counter (successive calls continue the
+ * random stream; pgc_island_generation / pgc_island_set_generation read and set it) */
+PGC_API int pgc_island_evolve(pgc_island *isl, const pgc_algo_desc *algo, unsigned *gens_done);
+PGC_API int pgc_island_generation(const pgc_island *isl, uint32_t *generation);
+PGC_API int pgc_island_set_generation(pgc_island *isl, uint32_t generation);
+/* s_policy: select_best::select (select_best.cpp:63-171) into the outbox; *k = individuals published */
+PGC_API int pgc_island_select(pgc_island *isl, int rate_is_frac, double rate, size_t *k);
+PGC_API int pgc_island_clear_outbox(pgc_island *isl); /* archipelago::extract_migrants (migrant_handling::evict) */
+PGC_API int pgc_island_outbox_download(pgc_island *isl, uint64_t *ids, double *x, double *f, size_t *k);
+/* host migrants into inbox slot `slot` (a pagmo archipelago's host-side migrants database feeding a GPU island) */
+PGC_API int pgc_island_inbox_upload(pgc_island *isl, size_t slot, const uint64_t *ids, const double *x, const double *f, size_t k);
+/* r_policy: fair_replace::replace (fair_replace.cpp:63-221) of the population with the rows of inbox slots [0, n_slots).
+ * accepted_ids / accepted_slot (optional, max_migrants * max_in_edges entries): the immigrants that are in the population
+ * afterwards and the slot each came through - the rows of archipelago::get_migration_log() (island.cpp:525-536). */
+PGC_API int pgc_island_replace(pgc_island *isl, int rate_is_frac, double rate, size_t n_slots, uint64_t *accepted_ids,
+                               uint32_t *accepted_slot, size_t *n_accepted);
+/* population::champion_x / champion_f (single objective) */
+PGC_API int pgc_island_champion(pgc_island *isl, double *x, double *f);
+
+/* ---- migration over NCCL (the exchange step of SURVEY.md 8e: migrants travel device to device along topology edges) --------
+ * NCCL is bound at run time (libnccl.so.2, or $PGC_NCCL_LIBRARY); without it these return PGC_ERR_UNSUPPORTED.
+ *   pgc_comm_init        one process driving several GPUs: rank g = devices[g]                      (ncclCommInitAll)
+ *   pgc_comm_unique_id / pgc_comm_init_rank   one process per GPU: rank 0 creates the 128-byte id, the host application
+ *                        distributes it (MPI, torch.distributed, a file), every rank joins            (ncclCommInitRank) */
+typedef struct pgc_comm pgc_comm;
+PGC_API int pgc_comm_nccl_version(int *version);
+PGC_API int pgc_comm_init(int ndev, const int *devices, pgc_comm **out);
+PGC_API int pgc_comm_unique_id(void *id, size_t len /* >= 128 */);
+PGC_API int pgc_comm_init_rank(int device, int nranks, int rank, const void *id, size_t len, pgc_comm **out);
+PGC_API int pgc_comm_destroy(pgc_comm *comm);
+PGC_API int pgc_comm_size(const pgc_comm *comm, int *nranks, int *nlocal);
+/* One migration step (island.cpp:461-620 decides the edges, this moves the rows): for every edge e the OUTBOX of island
+ * edge_src[e] is delivered into inbox slot edge_slot[e] of island edge_dst[e] - ncclSend / ncclRecv in one group between GPUs, a
+ * device-to-device copy inside one GPU.  islands[i] is NULL for an island owned by another process, owner_rank[i] is the
+ * communicator rank of the GPU holding island i; every process passes the same edge list in the same order.  Asynchronous on
+ * the islands' streams (after the source's select, before the destination's replace).  comm may be NULL when no edge leaves a GPU. */
+PGC_API int pgc_migrate(pgc_comm *comm, pgc_island *const *islands, const int *owner_rank, size_t n_islands, const uint32_t *edge_src,
+                        const uint32_t *edge_dst, const uint32_t *edge_slot, size_t n_edges);
+
 /* Debug/profiling aid for the CEC2014 stage kernel: same evaluation with clock64() phase counters, summed over all
  * warp-tiles and stages.  out7 = {load, weight pass, token wait, GEMM, z store, epilogue} cycles, warp-tiles. */
 PGC_API int pgc_debug_cec2014_phase_cycles(pgc_problem *prob, const double *d_dvs, size_t n, double *d_fvs, uint64_t *out7);

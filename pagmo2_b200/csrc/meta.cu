@@ -138,6 +138,7 @@ int meta_create(pgc_problem *inner, int family, const double *a, const double *b
     p->inner = inner;
     p->meta_method = method;
     p->nx = inner->nx;
+    p->nix = inner->nix; // translate.cpp:169-172 / decompose.cpp:180-183: get_nix forwards to the inner problem
     p->lb = inner->lb;
     p->ub = inner->ub;
     p->flops_per_eval = inner->flops_per_eval;

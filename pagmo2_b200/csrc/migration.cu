@@ -118,6 +118,9 @@ int rate_count(const char *who, int rate_is_frac, double rate, size_t n, size_t 
 
 } // namespace
 
+// number of individuals a policy with this rate moves for a group of n (base_sr_policy.cpp:46-55, select_best.cpp:80-100)
+int policy_rate_count(const char *who, int rate_is_frac, double rate, size_t n, size_t *out) { return rate_count(who, rate_is_frac, rate, n, out); }
+
 // d_sel[0..k) = indices of the k smallest of the n single-objective fitness values d_f, in ascending order (NaN last, ties by index)
 int so_best_indices_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t k, unsigned *d_sel, cudaStream_t st)
 {

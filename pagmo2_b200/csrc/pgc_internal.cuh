@@ -203,6 +203,7 @@ int select_best_policy_device(pgc_ctx *ctx, const unsigned long long *d_ids, con
 int fair_replace_policy_device(pgc_ctx *ctx, unsigned long long *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nobj,
                                int rate_is_frac, double rate, const unsigned long long *d_mids, const double *d_mx, const double *d_mf,
                                size_t nm, cudaStream_t st);
+int policy_rate_count(const char *who, int rate_is_frac, double rate, size_t n, size_t *out);
 int so_best_indices_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t k, unsigned *d_sel, cudaStream_t st);
 int sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double cr, double eta_c, double m,
                       double param_m, unsigned param_s, unsigned crossover, unsigned mutation, unsigned selection, unsigned long long seed,

@@ -8,10 +8,11 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 BIN = ROOT / "tests" / "cpp" / "_bin" / "test_adapters"
+BIN_ISLANDS = ROOT / "tests" / "cpp" / "_bin" / "test_islands"
 
 
 def _ensure_binary():
-    if not BIN.exists():
+    if not BIN.exists() or not BIN_ISLANDS.exists():
         if Path("/root/reference/include/pagmo/problem.hpp").exists():
             subprocess.run(["make", "-s", "-C", str(ROOT / "tests" / "cpp")], check=True)
         else:
@@ -39,3 +40,29 @@ def test_adapters_on_device():
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ADAPTERS OK" in r.stdout
+
+
+def test_islands_fail_loudly_without_a_device():
+    from pagmo2_b200 import capi
+    import ctypes
+    n = ctypes.c_int(0)
+    if capi.lib().pgc_device_count(ctypes.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a CUDA device is visible here")
+    _ensure_binary()
+    r = subprocess.run([str(BIN_ISLANDS)], capture_output=True, text=True)
+    assert r.returncode != 0 and "ISLANDS OK" not in r.stdout
+    assert "pgc_ctx_create" in (r.stderr + r.stdout)
+
+
+@pytest.mark.gpu
+def test_islands_on_device():
+    """cuda_island inside pagmo's own island / archipelago{ring} (the reference's island.cpp, archipelago.cpp, ring.cpp compiled
+    unmodified into oracle/_ref) and the device-resident cuda_archipelago; with two or more GPUs visible the migrants travel over
+    NCCL and the run must equal the one-GPU run bit for bit."""
+    import torch
+    _ensure_binary()
+    ndev = min(torch.cuda.device_count(), 8)
+    r = subprocess.run([str(BIN_ISLANDS), "--devices", str(ndev)], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ISLANDS OK" in r.stdout
