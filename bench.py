@@ -10,6 +10,12 @@ on the launching stream, max over ranks.  `e2e` = the same metric through pgc_ev
 host vectors in, host vectors out), pinned host buffers, H2D and D2H inside the timed region.
 Multi-GPU: the batch shards by individual with no data-path collective (weak scaling, n per GPU fixed).
 
+--workload cfg5 measures BASELINE config 5 instead (8 GPU islands running sade on CEC2013 D=50, ring migration through
+pgc_migrate: ncclSend / ncclRecv between GPUs): island-generations/s and migrations/s, strong scaling (the 8 islands are spread
+over the ranks).  The default workload (cfg2, the configuration BASELINE.json's metric is quoted on) also reports, on rank 0 and
+after its timed region, BASELINE's second headline (NSGA-II generations/s at pop 65 536) and one-GPU figures for cfg1 / cfg4 / cfg5
+under "secondary" - the LAST key of the line, mirrored in config.secondary.
+
 --impl reference times the reference's own CPU path (pagmo::thread_bfe over the unmodified cec2014 UDP, compiled
 from the reference sources into oracle/_ref/libpagmo_ref.so) on all host cores, on a bounded sample of the same
 workload.  The oracle is only ever used here as the CPU baseline / checker, never on the measured GPU path.
@@ -159,6 +165,210 @@ def workload_config(n, gpus):
             "parallelism": f"shard-by-individual x{gpus}, no collective"}
 
 
+
+# ----------------------------------------------------------------------------------------------------------------
+def _timed(fn, sync):
+    sync()
+    t0 = time.perf_counter()
+    fn()
+    sync()
+    return time.perf_counter() - t0
+
+
+def measure_secondary(ctx, capi, device):
+    """One-GPU figures for the other BASELINE configs, each guarded on its own: a failure is reported, never hidden."""
+    import ctypes as C
+    L = capi.lib()
+    out = {"metric": "NSGA-II generations/sec (pop 65536)", "unit": "generations/s"}
+
+    def guarded(key, fn):
+        try:
+            out[key] = fn()
+        except Exception as e:  # noqa: BLE001
+            out[key] = {"unavailable": str(e)[:200]}
+
+    def nsga2():
+        r = {"generations_timed": 5, "what": "nsga2::evolve on the device: shuffles, FNDS + crowding of N, tournament + SBX + mutation, batch "
+                                             "evaluation, select_best_N_mo over 2N (nsga2.cpp:91-307)"}
+        ref = {}
+        try:
+            ref = json.loads((ROOT / "profiles" / "r2_ref_nsga2_timing.json").read_text())["cases"]
+        except Exception:
+            pass
+        for name, kw in (("zdt1_nx30", dict(family="zdt", prob_id=1, dim=30)), ("dtlz2_nx12_m3", dict(family="dtlz", prob_id=2, dim=12, nobj=3, param=100))):
+            p2 = capi.Problem(ctx, **kw)
+            NP = 65536
+            d_x2, d_f2 = ctx.malloc(8 * NP * p2.nx), ctx.malloc(8 * NP * p2.nf)
+            capi.check(L.pgc_population_init_device(p2._h, NP, 31, d_x2, d_f2, None, None))
+            capi.check(L.pgc_nsga2_evolve_device(p2._h, d_x2, d_f2, NP, 2, 0.95, 10.0, 0.01, 50.0, 7, 0, None))
+            dt = _timed(lambda: capi.check(L.pgc_nsga2_evolve_device(p2._h, d_x2, d_f2, NP, 5, 0.95, 10.0, 0.01, 50.0, 7, 2, None)), ctx.synchronize)
+            fronts = len(ctx.fnds(ctx.from_device(d_f2, (NP, p2.nf)))["fronts"])
+            r[name] = {"generations_per_s": 5.0 / dt, "ms_per_generation": dt / 5 * 1e3, "fronts_in_population": fronts,
+                       # latency model: the select_best_N_mo sort of 2N points peels about this many levels per generation
+                       "us_per_level": dt / 5 * 1e6 / max(fronts, 1)}
+            if name in ref:
+                r[name]["cpu_reference_generations_per_s"] = ref[name]["extrapolated_generations_per_s_at_65536"]
+                r[name]["cpu_reference_note"] = ("unmodified nsga2::evolve on one core, measured at pop 2048-16384 and extrapolated with the "
+                                                 f"fitted exponent {ref[name]['fitted_exponent']:.2f} (profiles/r2_ref_nsga2_timing.json)")
+            ctx.free(d_x2)
+            ctx.free(d_f2)
+            p2.close()
+        return r
+
+    def cfg1():  # Rastrigin D=10, pop 1024, de1220, 100 generations
+        p = capi.Problem(ctx, "rastrigin", dim=10)
+        NP = 1024
+        d_x, d_f = ctx.malloc(8 * NP * 10), ctx.malloc(8 * NP)
+        a = capi.algo_desc("de1220", gens=100, seed=41, ftol=0.0, xtol=0.0)
+        capi.check(L.pgc_population_init_device(p._h, NP, 23, d_x, d_f, None, None))
+        capi.check(L.pgc_algo_evolve_device(p._h, C.byref(a), d_x, d_f, NP, 1, None, None))
+        reps = 5
+        dt = _timed(lambda: [capi.check(L.pgc_algo_evolve_device(p._h, C.byref(a), d_x, d_f, NP, 101 + 100 * k, None, None)) for k in range(reps)],
+                    ctx.synchronize)
+        ctx.free(d_x)
+        ctx.free(d_f)
+        p.close()
+        return {"what": "cfg1: rastrigin D=10, pop 1024, de1220, 100 generations per evolve()", "generations_per_s": 100 * reps / dt,
+                "evals_per_s": 100 * reps * NP / dt, "us_per_generation": dt / (100 * reps) * 1e6}
+
+    def cfg4():  # Lennard-Jones 150 atoms, pairwise-energy kernel
+        import torch
+        p = capi.Problem(ctx, "lennard_jones", dim=150)
+        NP = 65536
+        x = torch.rand((NP, p.nx), dtype=torch.float64, device=f"cuda:{device}") * 6 - 3
+        f = torch.empty(NP, dtype=torch.float64, device=f"cuda:{device}")
+        p.eval_device(x.data_ptr(), NP, f.data_ptr(), ctx.stream)
+        dt = _timed(lambda: [p.eval_device(x.data_ptr(), NP, f.data_ptr(), ctx.stream) for _ in range(5)], ctx.synchronize)
+        p.close()
+        pairs = 150 * 149 // 2
+        return {"what": "cfg4 kernel: lennard_jones 150 atoms (D=444), 65536 individuals resident", "evals_per_s": 5 * NP / dt,
+                "fp64_tflops_14_per_pair": 5 * NP * pairs * 14 / dt / 1e12}
+
+    def cfg5():
+        return measure_cfg5(capi, [device], rank=0, world=1, comm=None, rounds=4)
+
+    guarded("nsga2_pop65536", nsga2)
+    guarded("cfg1_de1220", cfg1)
+    guarded("cfg4_lennard_jones", cfg4)
+    guarded("cfg5_islands", cfg5)
+    v = out.get("nsga2_pop65536", {}).get("zdt1_nx30", {})
+    out["value"] = v.get("generations_per_s") if isinstance(v, dict) else None
+    return out
+
+
+def secondary_summary(sec):
+    """the headline numbers of `secondary`, short enough to live inside `config`"""
+    def g(*path):
+        d = sec
+        for k in path:
+            d = d.get(k) if isinstance(d, dict) else None
+        return round(d, 3) if isinstance(d, (int, float)) else d
+    return {"nsga2_pop65536_zdt1_gens_per_s": g("nsga2_pop65536", "zdt1_nx30", "generations_per_s"),
+            "nsga2_pop65536_dtlz2_gens_per_s": g("nsga2_pop65536", "dtlz2_nx12_m3", "generations_per_s"),
+            "nsga2_cpu_reference_zdt1_gens_per_s": g("nsga2_pop65536", "zdt1_nx30", "cpu_reference_generations_per_s"),
+            "cfg1_de1220_gens_per_s": g("cfg1_de1220", "generations_per_s"),
+            "cfg4_lj150_evals_per_s": g("cfg4_lennard_jones", "evals_per_s"),
+            "cfg5_island_gens_per_s": g("cfg5_islands", "island_generations_per_s"),
+            "cfg5_evals_per_s": g("cfg5_islands", "evals_per_s"), "cfg5_migrations_per_s": g("cfg5_islands", "migrations_per_s")}
+
+
+CFG5 = {"islands": 8, "pop": 1024, "dim": 50, "func": 12, "gens_per_round": 50}
+
+
+def measure_cfg5(capi, devices, rank, world, comm, rounds, warm_rounds=1, log=True):
+    """BASELINE cfg5: 8 islands (one per GPU when 8 ranks run) x sade on CEC2013 D=50, ring topology, one migration per 50
+    generations through pgc_migrate.  This process materialises the islands of its rank(s)."""
+    from pagmo2_b200 import synth
+    from pagmo2_b200.archipelago import ResidentArchipelago
+    c = CFG5
+    mr, os_ = synth.cec2013_tables(c["dim"])
+    per = c["islands"] // world
+    spec = []
+    for g in range(c["islands"]):
+        owner = g // per
+        spec.append(dict(device=devices[(g % per) % len(devices)] if world > 1 else devices[g % len(devices)], family="cec2013",
+                         problem_kw=dict(prob_id=c["func"], dim=c["dim"], rotation=mr, shift=os_),
+                         algo=capi.algo_desc("sade", gens=c["gens_per_round"], seed=11 + g, ftol=0.0, xtol=0.0), pop_size=c["pop"], seed=200 + g,
+                         r_rate=1, s_rate=1, owner=owner if world > 1 else 0))
+    a = ResidentArchipelago(spec, topology="ring", seed=1, comm=comm, my_ranks=(rank,), log=log)
+    a.evolve(warm_rounds)
+    a.synchronize()
+    l0 = sum(a.ctx[g].launches for g in a.local)
+    m0 = len(a.log)
+    t0 = time.perf_counter()
+    a.evolve(rounds)
+    a.synchronize()
+    dt = time.perf_counter() - t0
+    gens = rounds * c["gens_per_round"]
+    return {"what": f"cfg5: {c['islands']} islands x sade (defaults, ftol = xtol = 0) on cec2013 f{c['func']} D={c['dim']}, pop {c['pop']} per island, "
+                    f"ring(1.0), 1 migrant per edge every {c['gens_per_round']} generations; device-resident islands (pgc_island) and "
+                    "pgc_migrate (NCCL send/recv between GPUs, device copy inside one)",
+            "seconds": dt, "rounds": rounds, "local_islands": len(a.local),
+            "island_generations_per_s": gens * c["islands"] / dt, "evals_per_s": gens * c["pop"] * c["islands"] / dt,
+            "migrations_per_s": (len(a.log) - m0) * (c["islands"] / max(len(a.local), 1)) / dt, "migrations_logged_locally": len(a.log) - m0,
+            "launches_per_generation_per_island": (sum(a.ctx[g].launches for g in a.local) - l0) / gens / max(len(a.local), 1),
+            "champions_f_local": a.champions_f().tolist()}
+
+
+def measure_adapter_e2e(n):
+    """The same batch through the COMPILED plugin call - pagmo::bfe{cuda_bfe{}}(problem{cuda_cec2014}, std::vector<double>) on a
+    pageable vector, returning a fresh vector (tests/cpp/test_adapters --bench) - next to e2e's ctypes + pinned-buffer path."""
+    exe = ROOT / "tests" / "cpp" / "_bin" / "test_adapters"
+    if not exe.exists():
+        return None
+    try:
+        r = subprocess.run([str(exe), "--bench", str(n)], capture_output=True, text=True, timeout=300)
+        for ln in r.stdout.splitlines():
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": (r.stdout + r.stderr)[-200:]}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
+
+
+def run_cfg5(args):
+    """--workload cfg5 (run by hand / gpurun --gpus N; the driver's default is cfg2)."""
+    import torch
+    from pagmo2_b200 import capi
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    comm, dist = None, None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        box = [capi.Comm.unique_id() if rank == 0 else None]  # the 128-byte NCCL id travels through the application's own channel
+        dist.broadcast_object_list(box, src=0)
+        comm = capi.Comm.from_unique_id(local, world, rank, box[0])
+    sampler = ClockSampler(local)
+    sampler.start()
+    res = measure_cfg5(capi, [local], rank, world, comm, rounds=max(args.steps, 1), warm_rounds=max(args.warmup, 1))
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor([res["seconds"], float(res["migrations_logged_locally"])], dtype=torch.float64, device=f"cuda:{local}")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        secs, migr = float(tmax[0].item()), float(t[1].item())
+    else:
+        secs, migr = res["seconds"], float(res["migrations_logged_locally"])
+    if rank == 0:
+        c = CFG5
+        gens = res["rounds"] * c["gens_per_round"]
+        line = {"metric": "island generations/sec (cfg5: 8 GPU islands, sade, CEC2013 D=50, ring migration)", "value": gens * c["islands"] / secs,
+                "unit": "island-generations/s", "n_gpus": world, "steps": res["rounds"], "warmup": max(args.warmup, 1),
+                "ms_per_step": secs / res["rounds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": res["what"], **c, "parallelism": f"{c['islands']} islands over {world} GPU(s), "
+                                                "migrants over pgc_migrate (ncclSend/ncclRecv)"},
+                "evals_per_s": gens * c["pop"] * c["islands"] / secs, "migrations_per_s": migr / secs, "migrations": migr, "clocks": clocks,
+                "launches_per_generation_per_island": res["launches_per_generation_per_island"], "rank0": res}
+        OUT.emit(json.dumps(line))
+    if comm is not None:
+        torch.cuda.synchronize()
+        comm.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
 # ----------------------------------------------------------------------------------------------------------------
 def run_native(args):
     import torch
@@ -221,6 +431,10 @@ def run_native(args):
     fp64_peak = ctx.fp64_peak_tflops(2048)
     fp64_peak = max(fp64_peak, ctx.fp64_peak_tflops(8192))
     fp64_mma_peak = ctx.fp64_mma_peak_tflops(4096)
+    fp64_dfma_peak = fp64_peak
+    # the rotation issues DMMA and the epilogues DFMA; both go through ONE pipe (profiles/r1_probe_fp64_dmma_dfma_share_pipe.json),
+    # so the roofline denominator is the higher of the two probes of that pipe
+    fp64_peak = max(fp64_dfma_peak, fp64_mma_peak)
 
     for _ in range(args.warmup):
         one_step()
@@ -283,37 +497,18 @@ def run_native(args):
     per_function = []
     for f, ms, w in zip(FUNCS, per_func_ms, work):
         per_function.append({
-            "f": f, "ms": round(ms, 4), "evals_per_s": n / (ms * 1e-3),
-            "fp64_tflops": (w[0] + w[1]) * n / (ms * 1e-3) / 1e12,
-            "rotation_frac_of_fp64_peak": ROTATIONS[f] * 2.0 * DIM * DIM * n / (ms * 1e-3) / 1e12 / fp64_peak,
-            "hbm_gbs": w[2] * n / (ms * 1e-3) / 1e9,
+            "f": f, "ms": round(ms, 4), "evals_per_s": round(n / (ms * 1e-3)),
+            "fp64_tflops": round((w[0] + w[1]) * n / (ms * 1e-3) / 1e12, 3),
+            "rotation_frac_of_fp64_peak": round(ROTATIONS[f] * 2.0 * DIM * DIM * n / (ms * 1e-3) / 1e12 / fp64_peak, 4),
+            "hbm_gbs": round(w[2] * n / (ms * 1e-3) / 1e9, 1),
         })
     geomean = float(np.exp(np.mean([np.log(p["evals_per_s"]) for p in per_function])))
 
-    # ---- BASELINE.json's second headline metric, measured in the same run on rank 0's GPU: NSGA-II generations/s at pop 65 536
-    # (whole generations on the device: shuffles, FNDS + crowding, variation, batch evaluation, select_best_N_mo; nsga2.cpp:91-307)
+    # ---- BASELINE.json's second headline metric (NSGA-II generations/s at pop 65 536) and one-GPU figures of the other configs,
+    # measured in the same run on rank 0's GPU after the timed region
     secondary = None
     if not args.no_secondary:
-        try:
-            import ctypes as C
-            secondary = {"metric": "NSGA-II generations/sec (pop 65536)", "unit": "generations/s", "generations_timed": 5}
-            for name, kw in (("zdt1_nx30", dict(family="zdt", prob_id=1, dim=30)), ("dtlz2_nx12_m3", dict(family="dtlz", prob_id=2, dim=12, nobj=3, param=100))):
-                p2 = capi.Problem(ctx, **kw)
-                NP = 65536
-                d_x2, d_f2 = ctx.malloc(8 * NP * p2.nx), ctx.malloc(8 * NP * p2.nf)
-                capi.check(capi.lib().pgc_population_init_device(p2._h, NP, 31, d_x2, d_f2, None, None))
-                capi.check(capi.lib().pgc_nsga2_evolve_device(p2._h, d_x2, d_f2, NP, 2, 0.95, 10.0, 0.01, 50.0, 7, 0, None))
-                ctx.synchronize()
-                t0 = time.perf_counter()
-                capi.check(capi.lib().pgc_nsga2_evolve_device(p2._h, d_x2, d_f2, NP, 5, 0.95, 10.0, 0.01, 50.0, 7, 2, None))
-                ctx.synchronize()
-                secondary[name] = 5.0 / (time.perf_counter() - t0)
-                ctx.free(d_x2)
-                ctx.free(d_f2)
-                p2.close()
-            secondary["value"] = secondary["zdt1_nx30"]
-        except Exception as e:  # noqa: BLE001
-            secondary = {"metric": "NSGA-II generations/sec (pop 65536)", "unavailable": str(e)[:200]}
+        secondary = measure_secondary(ctx, capi, local)
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -341,8 +536,9 @@ def run_native(args):
                      "frac": achieved / fp64_peak, "traffic": STAGE_DRAM_BYTES,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one rotated stage launch (1 Mi x 100), ncu --set full, "
                                      "profiles/r1z_stage_kernel_ncu_full.csv (839.0 MB read + 6-8 MB written); algorithmic bytes of that launch = 8*(100+1)*2^20 = 8.47e8",
-                     "peak_source": "pgc_measure_fp64_peak (DFMA loop, this run); MEASURED_PEAKS.json has no FP64 figure",
-                     "dmma_probe_tflops": fp64_mma_peak,
+                     "peak_source": "max(DFMA probe, DMMA probe) of the FP64 pipe, both measured in this run (pgc_measure_fp64_peak / "
+                                    "pgc_measure_fp64_mma_peak); MEASURED_PEAKS.json has no FP64 figure",
+                     "dfma_probe_tflops": fp64_dfma_peak, "dmma_probe_tflops": fp64_mma_peak,
                      "rotation_only_frac": rot_flops_step / step_s_rank / 1e12 / fp64_peak,
                      "hbm_gbs_achieved": sum(w[2] for w in work) * n / step_s_rank / 1e9, "hbm_peak_gbs": hbm_peak,
                      "note": "aggregate over the 62 launches of one step (50 rotated stage + 4 separable + 8 combine); per-function split in per_function"},
@@ -352,10 +548,15 @@ def run_native(args):
                          "frac": sum(w[2] for w in work) * n / step_s_rank / 1e9 / hbm_peak, "traffic": STAGE_DRAM_BYTES,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks.get("hbm_gbs") else "of fallback 6650 GB/s"},
         "cpu_baseline": cpu,
-        "secondary": secondary,
         "geomean_evals_per_s_per_gpu": geomean,
         "per_function": per_function,
+        "secondary": secondary,  # LAST key: survives in the tail of a truncated record
     }
+    if secondary:
+        line["config"]["secondary"] = secondary_summary(secondary)
+    adapter = measure_adapter_e2e(n)
+    if adapter:
+        line["e2e"]["adapter"] = adapter
     OUT.emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -391,11 +592,14 @@ def main():
     ap.add_argument("--n", type=int, default=N_DEFAULT, help="individuals per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=["cfg2", "cfg5"], default="cfg2")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "cfg5":
+        return run_cfg5(args)
     return run_native(args)
 
 

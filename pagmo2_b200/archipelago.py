@@ -243,3 +243,96 @@ class Archipelago:
     def champions_f(self) -> np.ndarray:
         """archipelago::get_champions_f() of the LOCAL islands (single objective): best fitness per island."""
         return np.array([isl.population().f[:, 0].min() for isl in self.islands])
+
+
+class ResidentArchipelago:
+    """The harness-side twin of pagmo_cuda::cuda_archipelago (include/pagmo_cuda/cuda_island.hpp): islands are pgc_island objects
+    (population, outbox, inbox in HBM) and the migrants travel device to device through pgc_migrate - ncclSend / ncclRecv along the
+    topology's edges between GPUs, a device copy inside one GPU.  No torch.distributed collective, no host copy of any migrant.
+
+    islands: list of dicts {device, family, problem_kw, algo (capi.AlgoDesc), pop_size, seed, r_rate, s_rate, owner} in GLOBAL
+    island order; every process passes the same list and materialises the islands whose owner rank is one of its own.
+    comm: capi.Comm (None when every island sits on one GPU); my_ranks: the communicator ranks this process drives."""
+
+    def __init__(self, islands, topology="ring", weight=1.0, migration_type="p2p", migrant_handling="preserve", seed=0, comm=None,
+                 my_ranks=(0,), log=True):
+        if migration_type not in ("p2p", "broadcast") or migrant_handling not in ("preserve", "evict"):
+            raise ValueError("migration_type must be 'p2p' or 'broadcast', migrant_handling 'preserve' or 'evict'")
+        self.spec, self.comm, self.seed, self.round = islands, comm, seed, 0
+        self.migration_type, self.migrant_handling, self.log_on, self.log = migration_type, migrant_handling, log, []
+        G = len(islands)
+        self.conn = [capi.topology_connections(topology, G, g, weight) for g in range(G)]
+        self.k_out = [min(int(s["s_rate"] * s["pop_size"]) if isinstance(s["s_rate"], float) else int(s["s_rate"]), s["pop_size"]) for s in islands]
+        cap, max_in = max(self.k_out + [1]), max([len(c[0]) for c in self.conn] + [1])
+        self.owner = [int(s.get("owner", 0)) for s in islands]
+        self.isl, self.ctx, self.prob = [None] * G, [None] * G, [None] * G
+        for g, s in enumerate(islands):
+            if self.owner[g] not in my_ranks:
+                continue
+            self.ctx[g] = capi.Context(s["device"])  # own context = own stream: islands sharing a GPU overlap on it
+            self.prob[g] = capi.Problem(self.ctx[g], s["family"], **s.get("problem_kw", {}))
+            self.isl[g] = capi.Island(self.prob[g], s["pop_size"], cap, max_in)
+            self.isl[g].init(s["seed"])
+        self.published = [False] * G
+        self.local = [g for g in range(G) if self.isl[g] is not None]
+        self._pool = ThreadPoolExecutor(max_workers=max(len(self.local), 1))
+
+    def _u(self, g, slot):
+        return capi.philox_u01(self.seed, TAG_MIGRATE, self.round, g, slot)
+
+    def _step(self, g, replace, sources):
+        isl, s = self.isl[g], self.spec[g]
+        entries = []
+        if replace:
+            for a_id, slot in isl.replace(s["r_rate"], len(sources), log=self.log_on):
+                entries.append(MigrationEntry(self.round, a_id, sources[slot][0], g))
+        isl.evolve(s["algo"])
+        isl.select(s["s_rate"])
+        return entries
+
+    def evolve(self, rounds: int = 1):
+        G = len(self.spec)
+        for _ in range(rounds):
+            pulls, edges = [(False, []) for _ in range(G)], []
+            for g in range(G):  # island.cpp:461-575, replicated on every process in island order
+                src, w = self.conn[g]
+                if len(src) == 0:
+                    continue
+                sources = []
+
+                def take(s):
+                    had = self.published[s]
+                    if self.migrant_handling == "evict":
+                        self.published[s] = False
+                    sources.append((int(s), had))
+                if self.migration_type == "p2p":
+                    j = min(int(self._u(g, 0) * len(src)), len(src) - 1)
+                    if not self._u(g, 1) < w[j]:
+                        continue
+                    take(int(src[j]))
+                else:
+                    for j, s in enumerate(src):
+                        if self._u(g, j) < w[j]:
+                            take(int(s))
+                pulls[g] = (True, sources)
+                edges += [(s, g, q) for q, (s, had) in enumerate(sources) if had]
+            for g in self.local:
+                for q, (s, had) in enumerate(pulls[g][1]):
+                    if not had:
+                        self.isl[g].inbox_upload(q, np.empty(0, np.uint64), np.empty((0, self.isl[g].nx)), np.empty((0, self.isl[g].nf)))
+            capi.migrate(self.comm, self.isl, self.owner, edges)
+            futs = [self._pool.submit(self._step, g, *pulls[g]) for g in self.local]
+            for f in futs:
+                self.log.extend(f.result())
+            self.published = [k > 0 for k in self.k_out]
+            self.round += 1
+
+    def synchronize(self):
+        for g in self.local:
+            self.ctx[g].synchronize()
+
+    def champions_f(self) -> np.ndarray:
+        return np.array([self.isl[g].champion()[1] for g in self.local])
+
+    def populations(self):
+        return {g: self.isl[g].download() for g in self.local}

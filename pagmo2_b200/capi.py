@@ -166,6 +166,30 @@ def lib():
         L.pgc_select_best_device.argtypes = [vp, vp, vp, vp, sz, sz, sz, C.c_int, C.c_double, vp, vp, vp, szp, vp]
         L.pgc_fair_replace_device.argtypes = [vp, vp, vp, vp, sz, sz, sz, C.c_int, C.c_double, vp, vp, vp, sz, vp]
         L.pgc_topology_connections.argtypes = [C.c_int, sz, sz, C.c_double, szp, dp, szp]
+        u64p = C.POINTER(C.c_uint64)
+        L.pgc_island_create.argtypes = [vp, sz, sz, sz, C.POINTER(vp)]
+        L.pgc_island_destroy.argtypes = [vp]
+        L.pgc_island_size.argtypes = [vp, szp, szp, szp]
+        L.pgc_island_upload.argtypes = [vp, vp, vp, vp]
+        L.pgc_island_download.argtypes = [vp, vp, vp, vp]
+        L.pgc_island_init.argtypes = [vp, C.c_uint64]
+        L.pgc_island_evolve.argtypes = [vp, C.POINTER(AlgoDesc), C.POINTER(C.c_uint)]
+        L.pgc_island_generation.argtypes = [vp, u32p]
+        L.pgc_island_set_generation.argtypes = [vp, C.c_uint32]
+        L.pgc_island_select.argtypes = [vp, C.c_int, C.c_double, szp]
+        L.pgc_island_clear_outbox.argtypes = [vp]
+        L.pgc_island_outbox_download.argtypes = [vp, vp, vp, vp, szp]
+        L.pgc_island_inbox_upload.argtypes = [vp, sz, vp, vp, vp, sz]
+        L.pgc_island_replace.argtypes = [vp, C.c_int, C.c_double, sz, vp, vp, szp]
+        L.pgc_island_champion.argtypes = [vp, vp, vp]
+        L.pgc_island_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        L.pgc_comm_nccl_version.argtypes = [C.POINTER(C.c_int)]
+        L.pgc_comm_init.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
+        L.pgc_comm_unique_id.argtypes = [vp, sz]
+        L.pgc_comm_init_rank.argtypes = [C.c_int, C.c_int, C.c_int, vp, sz, C.POINTER(vp)]
+        L.pgc_comm_destroy.argtypes = [vp]
+        L.pgc_comm_size.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.pgc_migrate.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int), sz, u32p, u32p, u32p, sz]
         L.pgc_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
         L.pgc_measure_fp64_mma_peak.argtypes = [vp, C.c_int, dp]
         _lib = L
@@ -540,3 +564,131 @@ class Problem:
         fvs = np.empty((n, self.nf))
         self.eval_host_into(dvs, fvs)
         return fvs
+
+
+def _rate(rate):
+    """migration rate as the C ABI takes it: (is_fraction, value) - a float is a fraction of the group, an int a count."""
+    return (1, float(rate)) if isinstance(rate, float) else (0, float(rate))
+
+
+class Island:
+    """pgc_island: one island's population, migration outbox and inbox, resident on the problem's device (island.cu)."""
+
+    def __init__(self, prob: "Problem", n: int, max_migrants: int = 1, max_in_edges: int = 1):
+        self.prob, self.n, self.nx, self.nf = prob, n, prob.nx, prob.nf
+        self.cap, self.slots = max(max_migrants, 1), max(max_in_edges, 1)
+        h = C.c_void_p()
+        check(lib().pgc_island_create(prob._h, n, max_migrants, max_in_edges, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pgc_island_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self, seed: int):
+        check(lib().pgc_island_init(self._h, seed))
+
+    def upload(self, ids, x, f):
+        ids, x, f = np.ascontiguousarray(ids, np.uint64), np.ascontiguousarray(x, np.float64), np.ascontiguousarray(f, np.float64)
+        check(lib().pgc_island_upload(self._h, ids.ctypes.data, x.ctypes.data, f.ctypes.data))
+
+    def download(self):
+        ids, x, f = np.empty(self.n, np.uint64), np.empty((self.n, self.nx)), np.empty((self.n, self.nf))
+        check(lib().pgc_island_download(self._h, ids.ctypes.data, x.ctypes.data, f.ctypes.data))
+        return ids, x, f
+
+    def evolve(self, algo: AlgoDesc) -> int:
+        done = C.c_uint()
+        check(lib().pgc_island_evolve(self._h, C.byref(algo), C.byref(done)))
+        return done.value
+
+    def select(self, rate) -> int:
+        k = C.c_size_t()
+        frac, r = _rate(rate)
+        check(lib().pgc_island_select(self._h, frac, r, C.byref(k)))
+        return k.value
+
+    def outbox(self):
+        ids, x, f, k = np.empty(self.cap, np.uint64), np.empty((self.cap, self.nx)), np.empty((self.cap, self.nf)), C.c_size_t()
+        check(lib().pgc_island_outbox_download(self._h, ids.ctypes.data, x.ctypes.data, f.ctypes.data, C.byref(k)))
+        return ids[:k.value], x[:k.value], f[:k.value]
+
+    def inbox_upload(self, slot: int, ids, x, f):
+        ids, x, f = np.ascontiguousarray(ids, np.uint64), np.ascontiguousarray(x, np.float64), np.ascontiguousarray(f, np.float64)
+        k = ids.shape[0]
+        check(lib().pgc_island_inbox_upload(self._h, slot, ids.ctypes.data if k else None, x.ctypes.data if k else None,
+                                            f.ctypes.data if k else None, k))
+
+    def replace(self, rate, n_slots: int, log: bool = True):
+        """fair_replace with the rows of inbox slots [0, n_slots); returns [(migrant id, slot)] of the immigrants now in the population."""
+        frac, r = _rate(rate)
+        if not log:
+            check(lib().pgc_island_replace(self._h, frac, r, n_slots, None, None, None))
+            return []
+        m = max(self.cap * self.slots, 1)
+        ids, slot, na = np.empty(m, np.uint64), np.empty(m, np.uint32), C.c_size_t()
+        check(lib().pgc_island_replace(self._h, frac, r, n_slots, ids.ctypes.data, slot.ctypes.data, C.byref(na)))
+        return [(int(ids[i]), int(slot[i])) for i in range(na.value)]
+
+    def champion(self):
+        x, f = np.empty(self.nx), np.empty(1)
+        check(lib().pgc_island_champion(self._h, x.ctypes.data, f.ctypes.data))
+        return x, float(f[0])
+
+
+class Comm:
+    """pgc_comm: NCCL communicator(s) of this process.  Comm.all_local(devices): one process, several GPUs;
+    Comm.from_unique_id(...): one process per GPU (rank 0 calls Comm.unique_id() and the application distributes the bytes)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def nccl_version() -> int:
+        v = C.c_int()
+        check(lib().pgc_comm_nccl_version(C.byref(v)))
+        return v.value
+
+    @staticmethod
+    def all_local(devices) -> "Comm":
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        check(lib().pgc_comm_init(len(devices), arr, C.byref(h)))
+        return Comm(h)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib().pgc_comm_unique_id(buf, 128))
+        return buf.raw
+
+    @staticmethod
+    def from_unique_id(device: int, nranks: int, rank: int, uid: bytes) -> "Comm":
+        h = C.c_void_p()
+        buf = C.create_string_buffer(uid, 128)
+        check(lib().pgc_comm_init_rank(device, nranks, rank, buf, 128, C.byref(h)))
+        return Comm(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pgc_comm_destroy(self._h)
+            self._h = None
+
+
+def migrate(comm, islands, owner_rank, edges):
+    """pgc_migrate: islands = list with None for islands of other processes; edges = [(src, dst, slot)]."""
+    n = len(islands)
+    ptrs = (C.c_void_p * n)(*[(i._h if i is not None else None) for i in islands])
+    own = (C.c_int * n)(*owner_rank)
+    m = len(edges)
+    es = (C.c_uint32 * max(m, 1))(*[e[0] for e in edges])
+    ed = (C.c_uint32 * max(m, 1))(*[e[1] for e in edges])
+    el = (C.c_uint32 * max(m, 1))(*[e[2] for e in edges])
+    check(lib().pgc_migrate(comm._h if comm is not None else None, ptrs, own, n, es, ed, el, m))

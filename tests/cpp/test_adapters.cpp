@@ -3,8 +3,10 @@
 // oracle/_ref/libpagmo_ref.so (pagmo::problem, pagmo::bfe, pagmo::population, thread_bfe, the stock UDPs) and
 // pagmo2_b200/libpgc.so.  Mirrors the reference's bfe-equivalence tests: tests/thread_bfe.cpp:66-97,
 // tests/default_bfe.cpp, tests/bfe.cpp.  Run on the GPU box by tests/test_gpu_adapters.py.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
 #include <random>
 #include <stdexcept>
@@ -70,10 +72,54 @@ static pagmo::vector_double random_batch(const pagmo::problem &p, std::size_t n,
     return dvs;
 }
 
-int main()
+// --bench N: the headline batch (N decision vectors, D = 100) through the COMPILED plugin call a pagmo user makes -
+// pagmo::bfe{cuda_bfe{}}(problem, dvs) with a pageable std::vector<double> in and a fresh std::vector<double> out - for a
+// sample of the 30 functions; prints one JSON line (bench.py: e2e.adapter).
+static int bench_adapter(std::size_t n)
+{
+    using namespace pagmo_cuda;
+    const unsigned dim = 100u;
+    const unsigned funcs[] = {1u, 8u, 17u, 23u, 28u};
+    std::vector<double> dvs(n * dim);
+    {
+        std::mt19937_64 e(20141);
+        std::uniform_real_distribution<double> u(-100., 100.);
+        for (auto &v : dvs) v = u(e);
+    }
+    pagmo::bfe b{cuda_bfe{}};
+    double secs = 0., checksum = 0.;
+    std::size_t evals = 0;
+    for (unsigned func : funcs) {
+        std::vector<double> mr(10u * dim * dim), lines(1000), shift;
+        std::vector<int> shuf(10u * dim);
+        cec2014_synth_rotation(func, dim, mr.data());
+        cec2014_synth_shift(func, lines.data());
+        cec2014_synth_shuffle(func, dim, shuf.data());
+        for (unsigned i = 0; i < 1000u; ++i)
+            if (i % 100u < dim) shift.push_back(lines[i]);
+        pagmo::problem p{cuda_cec2014{func, dim, mr, shift, shuf}};
+        {
+            const std::vector<double> warm(dvs.begin(), dvs.begin() + 4096 * dim);
+            (void)b(p, warm);
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        const auto fvs = b(p, dvs);
+        secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        evals += fvs.size();
+        checksum += fvs[0] + fvs[fvs.size() - 1];
+    }
+    std::printf("{\"value\": %.6g, \"unit\": \"evals/s\", \"path\": \"pagmo::bfe{cuda_bfe{}}(problem{cuda_cec2014}, pageable std::vector<double>) -> "
+                "fresh std::vector<double>, incl. pagmo's two size-check passes\", \"functions\": [1, 8, 17, 23, 28], \"individuals\": %zu, "
+                "\"seconds\": %.4f, \"checksum\": %.17g}\n",
+                static_cast<double>(evals) / secs, n, secs, checksum);
+    return 0;
+}
+
+int main(int argc, char **argv)
 {
     using namespace pagmo_cuda;
     const double tol = 1e-12;
+    if (argc >= 3 && std::string(argv[1]) == "--bench") return bench_adapter(static_cast<std::size_t>(std::atoll(argv[2])));
 
     // ---- 1. cuda_bfe as a UDBFE on a STOCK pagmo UDP (pagmo::rastrigin) -------------------------------------
     {
