@@ -22,7 +22,8 @@ enum PhiloxTag : uint32_t { // stream tags: one per consumer so that streams nev
     kTagInit = 7,
     kTagCmaes = 8,
     kTagMigrate = 9,
-    kTagPopulation = 10
+    kTagPopulation = 10,
+    kTagPsoTopology = 11 // adaptive-random swarm topology: informant draws (pso_gen.cpp:772-796)
 };
 
 struct Philox4 {

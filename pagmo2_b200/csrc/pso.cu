@@ -7,7 +7,9 @@
 // The arithmetic is the reference's expression by expression.  Draws: particle p owns the Philox substream
 // (seed, kTagPso, generation, p); slot 2d / 2d+1 are r1 / r2 of coordinate d (variants 1, 5), slot d is r1 (variant 2),
 // slots 0 / 1 are the per-particle r1 / r2 (variants 3, 4); initial velocities use (seed, kTagInit, generation, p, d).
-// FIPS (variant 6) and the von-Neumann / adaptive-random topologies (3, 4) are not on the device.
+// Topologies: 1 gbest, 2 lbest ring, 3 von Neumann lattice (:719-744), 4 adaptive random graph (:772-796: particle p informs itself and
+// neighb_param - 1 particles drawn from (seed, kTagPsoTopology, generation, p, j); re-drawn after every generation that did not
+// improve the swarm's best, :462).  FIPS (variant 6) is not on the device.
 #include <cfloat>
 #include <cmath>
 #include <vector>
@@ -43,6 +45,68 @@ __global__ void pso_lbest_kernel(const double *lbfit, unsigned n, unsigned radiu
         first = false;
     }
     bn[p] = best;
+}
+
+// von Neumann lattice, pso_gen.cpp:719-744: rows = the largest divisor of n not above sqrt(n); neighbours W, E, N, S with wrap-around,
+// best neighbour :608-621 (a later neighbour wins ties)
+__global__ void pso_von_kernel(const double *lbfit, unsigned n, int rows, int cols, unsigned *bn)
+{
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int p_x = static_cast<int>(p) % cols, p_y = static_cast<int>(p) / cols;
+    const int dx[4] = {-1, 1, 0, 0}, dy[4] = {0, 0, -1, 1};
+    unsigned best = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int n_x = (p_x + dx[k]) % cols, n_y = (p_y + dy[k]) % rows;
+        if (n_x < 0) n_x = cols + n_x;
+        if (n_y < 0) n_y = rows + n_y;
+        const unsigned q = static_cast<unsigned>(n_y * cols + n_x);
+        if (k == 0 || leq_f(lbfit[q], lbfit[best])) best = q;
+    }
+    bn[p] = best;
+}
+
+// ---- adaptive random topology (:772-796) ------------------------------------------------------------------------------------
+// targets[p * K + j], j >= 1: the particles p informs (j = 0 is p itself, implicit).  The reference stores, per particle q, the list
+// of its informants in ascending order of the informant's index and picks the best with "a later entry wins ties" (:608-621), i.e.
+// the informant of smallest fitness and, among equals, of LARGEST index - an order-free rule, evaluated here with two atomic passes.
+__device__ __forceinline__ unsigned long long fit_key(double v) // order-preserving, every NaN last (less_than_f)
+{
+    unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+    b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+    return (v != v) ? 0xffffffffffffffffull : b;
+}
+
+// re-draws the informants unless *keep != 0 (the swarm's best improved in the generation that just ended, :462)
+__global__ void pso_rewire_kernel(unsigned *targets, unsigned n, unsigned K, unsigned long long seed, unsigned gen_key, const int *keep)
+{
+    if (keep && *keep) return;
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(n) * K) return;
+    const unsigned p = static_cast<unsigned>(e / K), j = static_cast<unsigned>(e % K);
+    unsigned t = p;
+    if (j) {
+        t = static_cast<unsigned>(philox_u01(seed, kTagPsoTopology, gen_key, p, j) * static_cast<double>(n));
+        if (t >= n) t = n - 1u;
+    }
+    targets[e] = t;
+}
+
+__global__ void pso_ar_min_kernel(const double *lbfit, const unsigned *targets, unsigned n, unsigned K, unsigned long long *key)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(n) * K) return;
+    atomicMin(&key[targets[e]], fit_key(lbfit[e / K]));
+}
+
+__global__ void pso_ar_arg_kernel(const double *lbfit, const unsigned *targets, unsigned n, unsigned K, const unsigned long long *key,
+                                  unsigned *bn)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(n) * K) return;
+    const unsigned p = static_cast<unsigned>(e / K), q = targets[e];
+    if (fit_key(lbfit[p]) == key[q]) atomicMax(&bn[q], p);
 }
 
 struct MoveParams {
@@ -136,7 +200,8 @@ __global__ void pso_memory_copy_kernel(const double *X, double *lbX, const unsig
 
 // gbest tracking (:452-457): sequential "if improved and fit <= best: best = p" over ascending p == among the improved
 // particles the smallest fitness, the LAST index on ties, accepted if <= the previous best.  Single CTA.
-__global__ void pso_gbest_kernel(const double *fit, const unsigned char *improved, unsigned n, unsigned *gbest, double *gbest_fit, int init)
+__global__ void pso_gbest_kernel(const double *fit, const unsigned char *improved, unsigned n, unsigned *gbest, double *gbest_fit, int init,
+                                 int *best_improved = nullptr)
 {
     __shared__ double sf[256];
     __shared__ unsigned si[256];
@@ -163,10 +228,12 @@ __global__ void pso_gbest_kernel(const double *fit, const unsigned char *improve
                 bi = si[t];
             }
         }
-        if (bi != 0xffffffffu && (init || leq_f(bf, *gbest_fit))) {
+        const bool take = bi != 0xffffffffu && (init || leq_f(bf, *gbest_fit));
+        if (take) {
             *gbest = bi;
             *gbest_fit = bf;
         }
+        if (best_improved) *best_improved = take ? 1 : 0; // best_fit_improved, :447-459
     }
 }
 
@@ -383,8 +450,8 @@ int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, 
     PGC_REQUIRE(neighb_param >= 1u, "The neighborhood parameter must be in (0, inf), while a value of %u was detected", neighb_param);
     PGC_REQUIRE(prob->nobj == 1, "Multiple objectives detected in %s instance. PSO cannot deal with them", prob->name.c_str());
     PGC_REQUIRE(n > 0, "PSO does not work on an empty population");
-    if (variant == 6u || neighb_type > 2u) {
-        set_error("pso on the device implements variants 1-5 and the gbest / lbest topologies (variant %u, topology %u requested)", variant, neighb_type);
+    if (variant == 6u) {
+        set_error("pso on the device implements variants 1-5 (the fully informed swarm, variant 6, was requested)");
         return PGC_ERR_UNSUPPORTED;
     }
     struct Buf {
@@ -402,10 +469,17 @@ int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, 
         }
     } buf{st, {}};
     double *X, *V, *fit, *lb, *ub, *gfit;
-    unsigned *bn, *gbest;
+    unsigned *bn, *gbest, *targets = nullptr;
+    unsigned long long *arkey = nullptr;
+    int *keep = nullptr;
     unsigned char *improved;
     const size_t nd = static_cast<size_t>(n) * dim;
+    const unsigned K = neighb_param; // adaptive random: out-degree including the particle itself
     int rc;
+    if (neighb_type == 4u
+        && ((rc = buf.get(reinterpret_cast<void **>(&targets), 4 * static_cast<size_t>(n) * K)) || (rc = buf.get(reinterpret_cast<void **>(&arkey), 8 * static_cast<size_t>(n)))
+            || (rc = buf.get(reinterpret_cast<void **>(&keep), 4))))
+        return rc;
     if ((rc = buf.get(reinterpret_cast<void **>(&X), 8 * nd)) || (rc = buf.get(reinterpret_cast<void **>(&V), 8 * nd))
         || (rc = buf.get(reinterpret_cast<void **>(&fit), 8 * n)) || (rc = buf.get(reinterpret_cast<void **>(&lb), 8 * dim))
         || (rc = buf.get(reinterpret_cast<void **>(&ub), 8 * dim)) || (rc = buf.get(reinterpret_cast<void **>(&gfit), 8))
@@ -419,19 +493,37 @@ int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, 
     PGC_CUDA(cudaMemcpyAsync(fit, d_f, 8 * n, cudaMemcpyDeviceToDevice, st));
     if (d_v) PGC_CUDA(cudaMemcpyAsync(V, d_v, 8 * nd, cudaMemcpyDeviceToDevice, st));
     else pso_init_velocity_kernel<<<nblk(nd, 256), 256, 0, st>>>(V, lb, ub, n, dim, max_vel, seed, first_generation);
-    if (neighb_type == 1u) pso_gbest_kernel<<<1, 256, 0, st>>>(d_f, nullptr, n, gbest, gfit, 1);
+    if (neighb_type == 1u || neighb_type == 4u) pso_gbest_kernel<<<1, 256, 0, st>>>(d_f, nullptr, n, gbest, gfit, 1);
+    int von_rows = 1, von_cols = 1;
+    if (neighb_type == 3u) { // :724-727
+        von_rows = static_cast<int>(std::sqrt(static_cast<double>(n)));
+        while (static_cast<int>(n) % von_rows != 0) von_rows -= 1;
+        von_cols = static_cast<int>(n) / von_rows;
+    }
+    if (neighb_type == 4u) pso_rewire_kernel<<<nblk(static_cast<size_t>(n) * K, 256), 256, 0, st>>>(targets, n, K, seed, first_generation, nullptr);
     const unsigned radius = neighb_param / 2u;
     PGC_REQUIRE(neighb_type != 2u || (radius >= 1u && 2u * radius < n), "lbest topology: neighb_param / 2 = %u must be in [1, (swarm size - 1) / 2]", radius);
     for (unsigned g = 0; g < gens; ++g) {
         const unsigned generation = first_generation + g;
         if (neighb_type == 2u) pso_lbest_kernel<<<nblk(n, 256), 256, 0, st>>>(d_f, n, radius, bn);
-        MoveParams mp{X, V, d_x, neighb_type == 2u ? bn : nullptr, gbest, lb, ub, n, dim, omega, eta1, eta2, max_vel, variant, seed, generation};
+        else if (neighb_type == 3u) pso_von_kernel<<<nblk(n, 256), 256, 0, st>>>(d_f, n, von_rows, von_cols, bn);
+        else if (neighb_type == 4u) {
+            PGC_CUDA(cudaMemsetAsync(arkey, 0xff, 8 * static_cast<size_t>(n), st));
+            PGC_CUDA(cudaMemsetAsync(bn, 0, 4 * static_cast<size_t>(n), st));
+            pso_ar_min_kernel<<<nblk(static_cast<size_t>(n) * K, 256), 256, 0, st>>>(d_f, targets, n, K, arkey);
+            pso_ar_arg_kernel<<<nblk(static_cast<size_t>(n) * K, 256), 256, 0, st>>>(d_f, targets, n, K, arkey, bn);
+        }
+        MoveParams mp{X, V, d_x, neighb_type != 1u ? bn : nullptr, gbest, lb, ub, n, dim, omega, eta1, eta2, max_vel, variant, seed, generation};
         pso_move_kernel<<<nblk(nd, 256), 256, 0, st>>>(mp);
         if ((rc = eval(prob, X, n, fit, st))) return rc;
         pso_memory_flag_kernel<<<nblk(n, 256), 256, 0, st>>>(fit, d_f, n, improved);
         pso_memory_copy_kernel<<<nblk(nd, 256), 256, 0, st>>>(X, d_x, improved, n, dim);
         if (neighb_type == 1u) pso_gbest_kernel<<<1, 256, 0, st>>>(fit, improved, n, gbest, gfit, 0);
-        ctx->launches.fetch_add(neighb_type == 1u ? 4 : 4, std::memory_order_relaxed);
+        if (neighb_type == 4u) { // the graph is re-drawn when the swarm's best did not improve in this generation (:462)
+            pso_gbest_kernel<<<1, 256, 0, st>>>(fit, improved, n, gbest, gfit, 0, keep);
+            pso_rewire_kernel<<<nblk(static_cast<size_t>(n) * K, 256), 256, 0, st>>>(targets, n, K, seed, generation + 1u, keep);
+        }
+        ctx->launches.fetch_add(neighb_type == 4u ? 8 : 4, std::memory_order_relaxed);
     }
     if (d_v) PGC_CUDA(cudaMemcpyAsync(d_v, V, 8 * nd, cudaMemcpyDeviceToDevice, st));
     if (d_xcur) PGC_CUDA(cudaMemcpyAsync(d_xcur, X, 8 * nd, cudaMemcpyDeviceToDevice, st));
