@@ -8,6 +8,7 @@
 //   pagmo_cuda::cuda_pso     pagmo::pso     (pso.hpp:110     same arguments; batched per generation like pso_gen)
 //   pagmo_cuda::cuda_nsga2   pagmo::nsga2   (nsga2.hpp:103   gen, cr, eta_c, m, eta_m, seed)
 //   pagmo_cuda::cuda_sga     pagmo::sga     (sga.hpp:166     gen, cr, eta_c, m, param_m, param_s, crossover, mutation, selection, seed)
+//   pagmo_cuda::cuda_cmaes   pagmo::cmaes   (cmaes.hpp:110   gen, cc, cs, c1, cmu, sigma0, ftol, xtol, memory, force_bounds, seed)
 //
 // Same constructor arguments as the reference UDAs (plus the device), so `algorithm{cuda_sade{50u}}` drops into an island of a
 // stock pagmo::archipelago: thread_island (thread_island.cpp:79-159) runs it unchanged, and pagmo's own migration machinery
@@ -123,7 +124,8 @@ public:
                                m_desc.neighb_type, m_desc.neighb_param, m_desc.n_allowed, allowed, m_desc.F, m_desc.CR, m_desc.ftol,
                                m_desc.xtol, m_desc.omega, m_desc.eta1, m_desc.eta2, m_desc.max_vel, m_desc.cr, m_desc.eta_c, m_desc.m,
                                m_desc.eta_m, m_desc.seed, m_desc.param_m, m_desc.param_s, m_desc.crossover, m_desc.mutation,
-                               m_desc.selection);
+                               m_desc.selection, m_desc.cma_cc, m_desc.cma_cs, m_desc.cma_c1, m_desc.cma_cmu, m_desc.sigma0,
+                               m_desc.force_bounds);
         for (std::size_t i = 0; i < 18u && i < allowed.size(); ++i) m_desc.allowed_variants[i] = allowed[i]; // no-op when saving
     }
 
@@ -270,8 +272,40 @@ public:
     }
 };
 
+// pagmo::cmaes (cmaes.hpp:110).  Sampling, evaluation, recombination and the rank-mu matrix run on the device; the evolution paths and
+// the eigendecomposition of C (a Jacobi solver where the reference uses Eigen) on the host: pgc_cmaes_evolve_device.
+class cuda_cmaes : public cuda_algorithm_base
+{
+public:
+    cuda_cmaes(unsigned gen = 1u, double cc = -1, double cs = -1, double c1 = -1, double cmu = -1, double sigma0 = 0.5, double ftol = 1e-6,
+               double xtol = 1e-6, bool memory = false, bool force_bounds = false, unsigned seed = pagmo::random_device::next(), int device = 0)
+        : cuda_algorithm_base(PGC_ALGO_CMAES, "CMA-ES: Covariance Matrix Adaptation Evolutionary Strategy", gen, seed, device)
+    {
+        if (((cc < 0.) || (cc > 1.)) && !(cc == -1)) { // cmaes.cpp:64-67
+            pagmo_throw(std::invalid_argument, "cc must be in [0,1] or -1 if its value has to be initialized automatically, a value of "
+                                                   + std::to_string(cc) + " was detected");
+        }
+        if (((cs < 0.) || (cs > 1.)) && !(cs == -1)) {
+            pagmo_throw(std::invalid_argument, "cs needs to be in [0,1] or -1 if its value has to be initialized automatically, a value of "
+                                                   + std::to_string(cs) + " was detected");
+        }
+        if (((c1 < 0.) || (c1 > 1.)) && !(c1 == -1)) {
+            pagmo_throw(std::invalid_argument, "c1 needs to be in [0,1] or -1 if its value has to be initialized automatically, a value of "
+                                                   + std::to_string(c1) + " was detected");
+        }
+        if (((cmu < 0.) || (cmu > 1.)) && !(cmu == -1)) {
+            pagmo_throw(std::invalid_argument, "cmu needs to be in [0,1] or -1 if its value has to be initialized automatically, a value of "
+                                                   + std::to_string(cmu) + " was detected");
+        }
+        no_memory(memory, "cuda_cmaes");
+        m_desc.cma_cc = cc, m_desc.cma_cs = cs, m_desc.cma_c1 = c1, m_desc.cma_cmu = cmu, m_desc.sigma0 = sigma0;
+        m_desc.ftol = ftol, m_desc.xtol = xtol, m_desc.force_bounds = force_bounds ? 1u : 0u;
+    }
+};
+
 } // namespace pagmo_cuda
 
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_cmaes)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_sga)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_de)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_sade)

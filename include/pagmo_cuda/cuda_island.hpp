@@ -67,6 +67,7 @@ inline const cuda_algorithm_base *find_cuda_uda(const pagmo::algorithm &a)
     PGC_TRY_UDA(cuda_pso)
     PGC_TRY_UDA(cuda_nsga2)
     PGC_TRY_UDA(cuda_sga)
+    PGC_TRY_UDA(cuda_cmaes)
 #undef PGC_TRY_UDA
     return nullptr;
 }
@@ -137,7 +138,7 @@ public:
         const auto *uda = detail::find_cuda_uda(algo);
         if (!uda) {
             pagmo_throw(std::invalid_argument, "the 'cuda_island' UDI runs the pagmo_cuda:: algorithms only (cuda_de, cuda_sade, cuda_de1220, "
-                                               "cuda_pso_gen, cuda_nsga2, cuda_sga); an algorithm of type '"
+                                               "cuda_pso_gen, cuda_nsga2, cuda_sga, cuda_cmaes); an algorithm of type '"
                                                    + algo.get_name() + "' was given and there is no CPU fallback");
         }
         const auto &prob = pop.get_problem();

@@ -110,6 +110,11 @@ PGC_API int pgc_problem_nobj(const pgc_problem *prob, size_t *nobj); /* problem:
 PGC_API int pgc_problem_nf(const pgc_problem *prob, size_t *nf);     /* problem::get_nf (= nobj here: no constraints) */
 PGC_API int pgc_problem_bounds(const pgc_problem *prob, double *lb, double *ub); /* UDP::get_bounds */
 PGC_API int pgc_problem_name(const pgc_problem *prob, char *buf, size_t buflen); /* UDP::get_name */
+/* cec2013 only.  on != 0: every rotation accumulates one product at a time in the reference's order (rotatefunc,
+ * cec2013.cpp:1046-1051) instead of on the FP64 tensor path, so the rotated vectors are bit-identical to the reference's.  Several
+ * times slower; meant for checking the functions whose sin / cos / pow of large arguments amplify the last bits of the rotation
+ * (f7, f8, f20, f28) against the reference at the 1e-12 tolerance.  Default off. */
+PGC_API int pgc_problem_set_strict(pgc_problem *prob, int on);
 /* FP64 add/mul/fma(=2) per evaluation and libm calls per evaluation, as tabulated in DESIGN.md
  * (roofline bookkeeping for bench.py). */
 PGC_API int pgc_problem_work(const pgc_problem *prob, double *flops_per_eval, double *transcendentals_per_eval,
@@ -186,7 +191,8 @@ PGC_API int pgc_nsga2_variation_device(pgc_ctx *ctx, const double *d_x, const ui
 PGC_API int pgc_nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP, unsigned gens, double cr, double eta_c,
                                     double m, double eta_m, uint64_t seed, uint32_t first_generation, void *stream);
 
-/* pso_gen::evolve (pso_gen.cpp:120-530) on a device-resident swarm: variants 1-5, topologies 1 (gbest) and 2 (lbest ring).
+/* pso_gen::evolve (pso_gen.cpp:120-530) on a device-resident swarm: variants 1-5; topologies 1 gbest, 2 lbest ring, 3 von Neumann
+ * lattice (:719-744), 4 adaptive random graph with out-degree neighb_param, re-drawn after a generation without a new best (:772-796).
  * In: d_x [n x nx] positions, d_f [n] fitness, d_v velocities or NULL (then drawn as pso_gen.cpp:187-196).
  * Out: d_x / d_f = the particles' best positions / fitness (what evolve() writes back, :524-527), d_v = final velocities,
  * d_xcur (optional) = final current positions.  Reference defaults: omega 0.7298, eta1 = eta2 = 2.05, max_vel 0.5,
@@ -251,6 +257,15 @@ PGC_API int pgc_weighted_gram_device(pgc_ctx *ctx, const double *d_rows, const u
 PGC_API int pgc_weighted_mean_device(pgc_ctx *ctx, const double *d_rows, const uint32_t *d_idx, const double *d_w, size_t k, size_t D,
                                      double *d_out, void *stream);
 
+/* cmaes::evolve (cmaes.cpp:111-407, memory = false) on a device-resident population of lambda individuals: normal draws, sampling,
+ * batch evaluation, recombination and the rank-mu matrix on the device; evolution paths, the combination of C and its
+ * eigendecomposition (a cyclic Jacobi solver where the reference calls Eigen's SelfAdjointEigenSolver) on the host.  cc, cs, c1,
+ * cmu = -1: the automatic values of :169-183.  d_x / d_f end as the LAST generation sampled (the reference replaces the
+ * population every generation); *sigma_out (optional) = final step size.  Reference defaults: sigma0 0.5, ftol = xtol = 1e-6. */
+PGC_API int pgc_cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lambda, unsigned gens, double cc, double cs, double c1,
+                                    double cmu, double sigma0, double ftol, double xtol, int force_bounds, uint64_t seed,
+                                    uint32_t first_generation, unsigned *gens_done, double *sigma_out, void *stream);
+
 /* sga::evolve (sga.cpp:184-292) on a device-resident single-objective population, in place (the population comes back sorted by
  * fitness, as the reference's reinsertion leaves it).  crossover: 0 exponential, 1 binomial, 2 single, 3 sbx; mutation: 0 gaussian,
  * 1 uniform, 2 polynomial; selection: 0 tournament (param_s <= 16), 1 truncated.  Reference defaults: cr 0.9, eta_c 1, m 0.02,
@@ -266,7 +281,8 @@ typedef enum pgc_algo {
     PGC_ALGO_DE1220 = 3,  /* src/algorithms/de1220.cpp:80-600 */
     PGC_ALGO_PSO_GEN = 4, /* src/algorithms/pso_gen.cpp:120-590 */
     PGC_ALGO_NSGA2 = 5,   /* src/algorithms/nsga2.cpp:91-307 */
-    PGC_ALGO_SGA = 6      /* src/algorithms/sga.cpp:184-292 */
+    PGC_ALGO_SGA = 6,     /* src/algorithms/sga.cpp:184-292 */
+    PGC_ALGO_CMAES = 7    /* src/algorithms/cmaes.cpp:111-407 */
 } pgc_algo;
 
 /* Constructor arguments of the reference UDAs; pgc_algo_defaults() fills in the reference's default values
@@ -284,6 +300,8 @@ typedef struct pgc_algo_desc {
     uint64_t seed;
     double param_m;                       /* sga */
     uint32_t param_s, crossover, mutation, selection; /* sga: see pgc_sga_evolve_device */
+    double cma_cc, cma_cs, cma_c1, cma_cmu, sigma0;   /* cmaes (-1: automatic), cmaes.hpp:110 */
+    uint32_t force_bounds, reserved_;
 } pgc_algo_desc;
 
 PGC_API int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out);

@@ -52,10 +52,12 @@ class AlgoDesc(C.Structure):
         ("omega", C.c_double), ("eta1", C.c_double), ("eta2", C.c_double), ("max_vel", C.c_double),
         ("cr", C.c_double), ("eta_c", C.c_double), ("m", C.c_double), ("eta_m", C.c_double), ("seed", C.c_uint64),
         ("param_m", C.c_double), ("param_s", C.c_uint32), ("crossover", C.c_uint32), ("mutation", C.c_uint32), ("selection", C.c_uint32),
+        ("cma_cc", C.c_double), ("cma_cs", C.c_double), ("cma_c1", C.c_double), ("cma_cmu", C.c_double), ("sigma0", C.c_double),
+        ("force_bounds", C.c_uint32), ("reserved_", C.c_uint32),
     ]
 
 
-ALGO = {"de": 1, "sade": 2, "de1220": 3, "pso_gen": 4, "nsga2": 5, "sga": 6}
+ALGO = {"de": 1, "sade": 2, "de1220": 3, "pso_gen": 4, "nsga2": 5, "sga": 6, "cmaes": 7}
 SGA_CROSSOVER = {"exponential": 0, "binomial": 1, "single": 2, "sbx": 3}
 SGA_MUTATION = {"gaussian": 0, "uniform": 1, "polynomial": 2}
 SGA_SELECTION = {"tournament": 0, "truncated": 1}
@@ -160,6 +162,8 @@ def lib():
         L.pgc_cmaes_sample_device.argtypes = [vp, vp, vp, C.c_double, sz, sz, C.c_uint64, C.c_uint32, vp, vp, vp]
         L.pgc_weighted_gram_device.argtypes = [vp, vp, vp, vp, vp, sz, sz, C.c_double, vp, vp]
         L.pgc_weighted_mean_device.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp]
+        L.pgc_cmaes_evolve_device.argtypes = [vp, vp, vp, sz, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                              C.c_double, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint), dp, vp]
         L.pgc_algo_defaults.argtypes = [C.c_int, C.c_uint, C.c_uint64, C.POINTER(AlgoDesc)]
         L.pgc_algo_evolve_device.argtypes = [vp, C.POINTER(AlgoDesc), vp, vp, sz, C.c_uint32, C.POINTER(C.c_uint), vp]
         L.pgc_population_init_device.argtypes = [vp, sz, C.c_uint64, vp, vp, vp, vp]
@@ -472,6 +476,11 @@ class Problem:
         check(lib().pgc_problem_bounds(self._h, lb.ctypes.data_as(dp), ub.ctypes.data_as(dp)))
         return lb, ub
 
+    def set_strict(self, on: bool = True):
+        """cec2013: rotations in the reference's summation order (pgc_problem_set_strict)."""
+        lib().pgc_problem_set_strict.argtypes = [C.c_void_p, C.c_int]
+        check(lib().pgc_problem_set_strict(self._h, int(on)))
+
     def work(self):
         """(fp64 flops, libm calls, algorithmic bytes) per evaluation."""
         a, b, c = C.c_double(), C.c_double(), C.c_double()
@@ -518,6 +527,21 @@ class Problem:
             for b in (dx, df, dc, dv):
                 if b:
                     self.ctx.free(b)
+
+    def cmaes_evolve(self, x, f, gens=1, cc=-1., cs=-1., c1=-1., cmu=-1., sigma0=0.5, ftol=1e-6, xtol=1e-6, force_bounds=False, seed=0,
+                     first_generation=1):
+        """cmaes::evolve on the device: returns (x, f, gens_done, sigma)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
+        done, sigma = C.c_uint(), C.c_double()
+        try:
+            check(lib().pgc_cmaes_evolve_device(self._h, dx, df, x.shape[0], gens, cc, cs, c1, cmu, sigma0, ftol, xtol, int(force_bounds), seed,
+                                                first_generation, C.byref(done), C.byref(sigma), None))
+            return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), done.value, sigma.value
+        finally:
+            self.ctx.free(dx)
+            self.ctx.free(df)
 
     def de_evolve(self, x, f, gens=1, algo="de1220", variant=2, variant_adptv=1, F=0.8, CR=0.9, allowed=(2, 3, 7, 10, 13, 14, 15, 16),
                   ftol=1e-6, xtol=1e-6, seed=0, first_generation=1):

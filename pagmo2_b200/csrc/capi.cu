@@ -322,6 +322,7 @@ int pgc_ctx_destroy(pgc_ctx *ctx)
         cudaEventDestroy(ctx->ev_out[i]);
     }
     if (ctx->scratch) cudaFree(ctx->scratch);
+    delete ctx->copy_pool;
     for (auto &s : ctx->copy_stream) cudaStreamDestroy(s);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -441,6 +442,17 @@ int pgc_problem_nix(const pgc_problem *p, size_t *nix)
     return PGC_OK;
 }
 
+int pgc_problem_set_strict(pgc_problem *p, int on)
+{
+    PGC_REQUIRE(p, "pgc_problem_set_strict: null problem");
+    if (p->desc.family != PGC_CEC2013) {
+        set_error("pgc_problem_set_strict: the strict summation order exists for the cec2013 suite only ('%s' given)", p->name.c_str());
+        return PGC_ERR_UNSUPPORTED;
+    }
+    p->strict = on ? 1 : 0;
+    return PGC_OK;
+}
+
 int pgc_problem_nobj(const pgc_problem *p, size_t *nobj)
 {
     PGC_REQUIRE(p && nobj, "pgc_problem_nobj: null argument");
@@ -528,6 +540,13 @@ int pgc_eval_host(pgc_problem *p, const double *dvs, size_t n, double *fvs)
     const bool in_pinned = cudaPointerGetAttributes(&attr, dvs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     const bool out_pinned = cudaPointerGetAttributes(&attr, fvs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError(); // clear a possible "invalid value" from probing pageable memory
+    if (!in_pinned && !ctx->copy_pool && n * nx * sizeof(double) >= (64u << 20)) {
+        // PGC_COPY_THREADS: helpers for staging pageable input (default: up to 7, leaving cores for the other devices' contexts)
+        const char *env = std::getenv("PGC_COPY_THREADS");
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        unsigned want = env ? static_cast<unsigned>(std::max(0, std::atoi(env))) : std::min(7u, hw > 2u ? hw / 2u - 1u : 0u);
+        ctx->copy_pool = new pgc::CopyPool(want);
+    }
 
     const size_t nchunks = (n + chunk - 1) / chunk;
     cudaStream_t s_in = ctx->copy_stream[0], s_out = ctx->copy_stream[1], s_k = ctx->stream;
@@ -549,7 +568,8 @@ int pgc_eval_host(pgc_problem *p, const double *dvs, size_t n, double *fvs)
         pend[slot] = {first, count};
         const double *src = dvs + first * nx;
         if (!in_pinned) {
-            std::memcpy(ctx->h_in[slot], src, count * nx * sizeof(double));
+            if (ctx->copy_pool) ctx->copy_pool->copy(ctx->h_in[slot], src, count * nx * sizeof(double));
+            else std::memcpy(ctx->h_in[slot], src, count * nx * sizeof(double));
             src = static_cast<const double *>(ctx->h_in[slot]);
         }
         PGC_CUDA(cudaMemcpyAsync(ctx->d_in[slot], src, count * nx * sizeof(double), cudaMemcpyHostToDevice, s_in));
@@ -848,6 +868,17 @@ int pgc_sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP
                              seed, first_generation, problem_eval_device, stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
 }
 
+int pgc_cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lambda, unsigned gens, double cc, double cs, double c1, double cmu,
+                            double sigma0, double ftol, double xtol, int force_bounds, uint64_t seed, uint32_t first_generation,
+                            unsigned *gens_done, double *sigma_out, void *stream)
+{
+    PGC_REQUIRE(prob && d_x && d_f, "pgc_cmaes_evolve_device: null argument");
+    PGC_NO_INTEGER_GENES(prob, "pgc_cmaes_evolve_device");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    return cmaes_evolve_device(prob, d_x, d_f, lambda, gens, cc, cs, c1, cmu, sigma0, ftol, xtol, force_bounds, seed, first_generation, gens_done,
+                               sigma_out, problem_eval_device, stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
+}
+
 int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out)
 {
     PGC_REQUIRE(out, "pgc_algo_defaults: null argument");
@@ -873,6 +904,7 @@ int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out
         case PGC_ALGO_SGA: // sga.hpp:166: exponential crossover, polynomial mutation, tournament selection
             d.cr = 0.9, d.eta_c = 1., d.m = 0.02, d.param_m = 1., d.param_s = 2, d.crossover = 0, d.mutation = 2, d.selection = 0;
             break;
+        case PGC_ALGO_CMAES: d.cma_cc = d.cma_cs = d.cma_c1 = d.cma_cmu = -1., d.sigma0 = 0.5; break; // cmaes.hpp:110
         default: set_error("pgc_algo_defaults: unknown algorithm %d", algo); return PGC_ERR_INVALID_ARGUMENT;
     }
     *out = d;
@@ -899,6 +931,9 @@ int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *a, double *d_
         case PGC_ALGO_SGA:
             return pgc_sga_evolve_device(prob, d_x, d_f, n, a->gens, a->cr, a->eta_c, a->m, a->param_m, a->param_s, a->crossover, a->mutation,
                                          a->selection, a->seed, first_generation, stream);
+        case PGC_ALGO_CMAES:
+            return pgc_cmaes_evolve_device(prob, d_x, d_f, n, a->gens, a->cma_cc, a->cma_cs, a->cma_c1, a->cma_cmu, a->sigma0, a->ftol, a->xtol,
+                                           static_cast<int>(a->force_bounds), a->seed, first_generation, gens_done, nullptr, stream);
         default: set_error("pgc_algo_evolve_device: unknown algorithm %d", a->algo); return PGC_ERR_INVALID_ARGUMENT;
     }
 }

@@ -20,6 +20,10 @@
 #include <vector>
 
 #include "cec_device.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 #include "pgc_internal.cuh"
 #include "philox.cuh"
 
@@ -387,6 +391,262 @@ int cmaes_sample_device(pgc_ctx *ctx, const double *d_mean, const double *d_bd, 
     cmaes_sample_kernel<<<grid, kSampleWarps * 32, smem, st>>>(P);
     PGC_CUDA(cudaGetLastError());
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return PGC_OK;
+}
+
+// ---- cmaes::evolve (src/algorithms/cmaes.cpp:111-407) around the device contractions ------------------------------------------
+// The population, the normal draws, sampling x = mean + sigma * B * D * z, the batch evaluation, the recombination and the rank-mu
+// Gram matrix run on the device; the O(D^2) bookkeeping of the evolution paths, the combination of C and its eigendecomposition
+// (cmaes.cpp:385-401; Eigen's SelfAdjointEigenSolver there, a cyclic Jacobi solver here) run on the host, as SURVEY a22 scopes it.
+namespace
+{
+__global__ void clamp_rows_kernel(double *x, size_t total, unsigned D, const double *__restrict__ lb, const double *__restrict__ ub)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const unsigned j = static_cast<unsigned>(e % D);
+    const double v = x[e];
+    if (v < lb[j]) x[e] = lb[j];
+    else if (v > ub[j]) x[e] = ub[j]; // cmaes.cpp:304-313
+}
+
+// Cyclic Jacobi eigensolver for a symmetric matrix (row-major a[D x D], destroyed): eigenvalues ascending in w, the matching
+// unit eigenvectors in the COLUMNS of v, each with its largest-magnitude component positive (the sign convention is free).
+void jacobi_eigen(std::vector<double> &a, size_t D, std::vector<double> &w, std::vector<double> &v)
+{
+    v.assign(D * D, 0.);
+    for (size_t i = 0; i < D; ++i) v[i * D + i] = 1.;
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = 0., diag = 0.;
+        for (size_t p = 0; p < D; ++p) {
+            diag += a[p * D + p] * a[p * D + p];
+            for (size_t q = p + 1; q < D; ++q) off += a[p * D + q] * a[p * D + q];
+        }
+        if (off <= 1e-32 * diag || off == 0.) break;
+        for (size_t p = 0; p + 1 < D; ++p)
+            for (size_t q = p + 1; q < D; ++q) {
+                const double apq = a[p * D + q];
+                if (apq == 0.) continue;
+                const double theta = (a[q * D + q] - a[p * D + p]) / (2. * apq);
+                const double t = (theta >= 0. ? 1. : -1.) / (std::fabs(theta) + std::sqrt(theta * theta + 1.));
+                const double c = 1. / std::sqrt(t * t + 1.), sn = t * c;
+                for (size_t k = 0; k < D; ++k) { // A <- A J (columns p, q)
+                    const double akp = a[k * D + p], akq = a[k * D + q];
+                    a[k * D + p] = c * akp - sn * akq;
+                    a[k * D + q] = sn * akp + c * akq;
+                }
+                for (size_t k = 0; k < D; ++k) { // A <- J^T A (rows p, q)
+                    const double apk = a[p * D + k], aqk = a[q * D + k];
+                    a[p * D + k] = c * apk - sn * aqk;
+                    a[q * D + k] = sn * apk + c * aqk;
+                }
+                for (size_t k = 0; k < D; ++k) { // V <- V J
+                    const double vkp = v[k * D + p], vkq = v[k * D + q];
+                    v[k * D + p] = c * vkp - sn * vkq;
+                    v[k * D + q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    std::vector<size_t> order(D);
+    for (size_t i = 0; i < D; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return a[x * D + x] < a[y * D + y]; });
+    std::vector<double> vs(D * D);
+    w.resize(D);
+    for (size_t j = 0; j < D; ++j) {
+        const size_t src = order[j];
+        w[j] = a[src * D + src];
+        size_t big = 0;
+        for (size_t k = 1; k < D; ++k)
+            if (std::fabs(v[k * D + src]) > std::fabs(v[big * D + src])) big = k;
+        const double sgn = v[big * D + src] < 0. ? -1. : 1.;
+        for (size_t k = 0; k < D; ++k) vs[k * D + j] = sgn * v[k * D + src];
+    }
+    v.swap(vs);
+}
+} // namespace
+
+int cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam, unsigned gens, double cc, double cs, double c1, double cmu,
+                        double sigma0, double ftol, double xtol, int force_bounds, unsigned long long seed, unsigned first_generation,
+                        unsigned *gens_done, double *sigma_out, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t),
+                        cudaStream_t st)
+{
+    pgc_ctx *ctx = prob->ctx;
+    const size_t D = prob->nx, mu = lam / 2u;
+    if (gens_done) *gens_done = 0;
+    // constructor checks, cmaes.cpp:64-88, and evolve's, :126-150
+    PGC_REQUIRE(((cc >= 0.) && (cc <= 1.)) || cc == -1., "cc must be in [0,1] or -1 if its value has to be initialized automatically, a value of %g was detected", cc);
+    PGC_REQUIRE(((cs >= 0.) && (cs <= 1.)) || cs == -1., "cs needs to be in [0,1] or -1 if its value has to be initialized automatically, a value of %g was detected", cs);
+    PGC_REQUIRE(((c1 >= 0.) && (c1 <= 1.)) || c1 == -1., "c1 needs to be in [0,1] or -1 if its value has to be initialized automatically, a value of %g was detected", c1);
+    PGC_REQUIRE(((cmu >= 0.) && (cmu <= 1.)) || cmu == -1., "cmu needs to be in [0,1] or -1 if its value has to be initialized automatically, a value of %g was detected", cmu);
+    PGC_REQUIRE(prob->nobj == 1, "Multiple objectives detected in %s instance. CMA-ES: Covariance Matrix Adaptation Evolutionary Strategy cannot deal with them", prob->name.c_str());
+    PGC_REQUIRE(lam >= 5u, "CMA-ES: Covariance Matrix Adaptation Evolutionary Strategy needs at least 5 individuals in the population, %zu detected", lam);
+    for (size_t j = 0; j < D; ++j)
+        PGC_REQUIRE(std::isfinite(prob->lb[j]) && std::isfinite(prob->ub[j]), "A non-finite value is detected in the bounds, CMA-ES cannot deal with it.");
+    if (gens == 0) return PGC_OK;
+    const double N = static_cast<double>(D);
+    // selection weights and adaptation constants, :160-186
+    std::vector<double> weights(mu);
+    double wsum = 0.;
+    for (size_t i = 0; i < mu; ++i) {
+        weights[i] = std::log(static_cast<double>(mu) + 0.5) - std::log(static_cast<double>(i) + 1.);
+        wsum += weights[i];
+    }
+    double w2 = 0.;
+    for (auto &w : weights) {
+        w /= wsum;
+        w2 += w * w;
+    }
+    const double mueff = 1. / w2;
+    if (cc == -1) cc = (4. + mueff / N) / (N + 4. + 2. * mueff / N);
+    if (cs == -1) cs = (mueff + 2.) / (N + mueff + 5.);
+    if (c1 == -1) c1 = 2. / ((N + 1.3) * (N + 1.3) + mueff);
+    if (cmu == -1) cmu = 2. * (mueff - 2. + 1. / mueff) / ((N + 2.) * (N + 2.) + mueff);
+    const double damps = 1. + 2. * std::max(0., std::sqrt((mueff - 1.) / (N + 1.)) - 1.) + cs;
+    const double chiN = std::sqrt(N) * (1. - 1. / (4. * N) + 1. / (21. * N * N));
+
+    // population on the host: fitness only (lam doubles per generation) - the decision vectors stay on the device
+    std::vector<double> f(lam), mean(D), meanold(D), pc(D, 0.), ps(D, 0.), dvec(D), C(D * D, 0.), Cold(D * D), Cmu(D * D), B(D * D, 0.),
+        invsqrtC(D * D, 0.), BD(D * D), zlast(D), tmp(D);
+    PGC_CUDA(cudaMemcpyAsync(f.data(), d_f, 8 * lam, cudaMemcpyDeviceToHost, st));
+    PGC_CUDA(cudaStreamSynchronize(st));
+    auto best_worst = [&](size_t &b, size_t &w) { // population::best_idx / worst_idx: first minimum / first maximum
+        b = w = 0;
+        for (size_t i = 1; i < lam; ++i) {
+            if (f[i] < f[b]) b = i;
+            if (f[i] > f[w]) w = i;
+        }
+    };
+    size_t ib, iw;
+    best_worst(ib, iw);
+    double sigma = sigma0; // :196-225 (memory = false)
+    PGC_CUDA(cudaMemcpyAsync(mean.data(), d_x + ib * D, 8 * D, cudaMemcpyDeviceToHost, st));
+    PGC_CUDA(cudaStreamSynchronize(st));
+    for (size_t j = 0; j < D; ++j) {
+        dvec[j] = std::max(prob->ub[j] - prob->lb[j], 1e-6);
+        B[j * D + j] = 1.;
+        C[j * D + j] = dvec[j] * dvec[j];
+        invsqrtC[j * D + j] = 1. / dvec[j];
+    }
+    unsigned long long counteval = 0, eigeneval = 0;
+
+    struct Buf {
+        cudaStream_t st;
+        std::vector<void *> owned;
+        ~Buf()
+        {
+            for (void *p : owned) cudaFreeAsync(p, st);
+        }
+        int get(void **out, size_t bytes)
+        {
+            PGC_CUDA(cudaMallocAsync(out, bytes ? bytes : 8, st));
+            owned.push_back(*out);
+            return PGC_OK;
+        }
+    } buf{st, {}};
+    double *d_mean, *d_meanold, *d_bd, *d_z, *d_xn, *d_fn, *d_w, *d_C, *d_b;
+    unsigned *d_idx;
+    int rc;
+    if ((rc = buf.get(reinterpret_cast<void **>(&d_mean), 8 * D)) || (rc = buf.get(reinterpret_cast<void **>(&d_meanold), 8 * D))
+        || (rc = buf.get(reinterpret_cast<void **>(&d_bd), 8 * D * D)) || (rc = buf.get(reinterpret_cast<void **>(&d_z), 8 * lam * D))
+        || (rc = buf.get(reinterpret_cast<void **>(&d_xn), 8 * lam * D)) || (rc = buf.get(reinterpret_cast<void **>(&d_fn), 8 * lam))
+        || (rc = buf.get(reinterpret_cast<void **>(&d_w), 8 * mu)) || (rc = buf.get(reinterpret_cast<void **>(&d_C), 8 * D * D))
+        || (rc = buf.get(reinterpret_cast<void **>(&d_b), 16 * D)) || (rc = buf.get(reinterpret_cast<void **>(&d_idx), 4 * mu)))
+        return rc;
+    PGC_CUDA(cudaMemcpyAsync(d_w, weights.data(), 8 * mu, cudaMemcpyHostToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(d_b, prob->lb.data(), 8 * D, cudaMemcpyHostToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(d_b + D, prob->ub.data(), 8 * D, cudaMemcpyHostToDevice, st));
+    std::vector<unsigned> order(lam), idx(mu);
+    unsigned done = 0;
+    for (unsigned g = 0; g < gens; ++g) {
+        const unsigned generation = first_generation + g;
+        // 1 - lam new individuals: x_i = mean + sigma * B * D * z_i, :246-253
+        for (size_t a = 0; a < D; ++a)
+            for (size_t j = 0; j < D; ++j) BD[a * D + j] = B[a * D + j] * dvec[j];
+        PGC_CUDA(cudaMemcpyAsync(d_mean, mean.data(), 8 * D, cudaMemcpyHostToDevice, st));
+        PGC_CUDA(cudaMemcpyAsync(d_bd, BD.data(), 8 * D * D, cudaMemcpyHostToDevice, st));
+        if ((rc = cmaes_sample_device(ctx, d_mean, d_bd, sigma, lam, D, seed, generation, d_z, d_xn, st))) return rc;
+        // 1bis - exit conditions, :257-273: the step of the LAST sampled individual, the spread of the current population
+        PGC_CUDA(cudaMemcpyAsync(zlast.data(), d_z + (lam - 1) * D, 8 * D, cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        double nrm = 0.;
+        for (size_t a = 0; a < D; ++a) {
+            double y = 0.;
+            for (size_t j = 0; j < D; ++j) y += BD[a * D + j] * zlast[j];
+            nrm += (sigma * y) * (sigma * y);
+        }
+        if (std::sqrt(nrm) < xtol) break;
+        best_worst(ib, iw);
+        if (std::fabs(f[ib] - f[iw]) < ftol) break;
+        // 2 - bounds, :301-315
+        if (force_bounds) {
+            clamp_rows_kernel<<<static_cast<unsigned>((lam * D + 255) / 256), 256, 0, st>>>(d_xn, lam * D, static_cast<unsigned>(D), d_b, d_b + D);
+            ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        // 3 - evaluation and reinsertion (the new generation REPLACES the population, :323-350)
+        if ((rc = eval(prob, d_xn, lam, d_fn, st))) return rc;
+        PGC_CUDA(cudaMemcpyAsync(d_x, d_xn, 8 * lam * D, cudaMemcpyDeviceToDevice, st));
+        PGC_CUDA(cudaMemcpyAsync(d_f, d_fn, 8 * lam, cudaMemcpyDeviceToDevice, st));
+        PGC_CUDA(cudaMemcpyAsync(f.data(), d_fn, 8 * lam, cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        counteval += lam;
+        ++done;
+        // 4 - the elite: the mu best by fitness, NaN last (:352-361; std::sort there, a stable sort here)
+        for (size_t i = 0; i < lam; ++i) order[i] = static_cast<unsigned>(i);
+        std::stable_sort(order.begin(), order.end(), [&](unsigned x, unsigned y) {
+            const double a = f[x], b = f[y];
+            return !std::isnan(a) && (std::isnan(b) || a < b);
+        });
+        for (size_t i = 0; i < mu; ++i) idx[i] = order[i];
+        PGC_CUDA(cudaMemcpyAsync(d_idx, idx.data(), 4 * mu, cudaMemcpyHostToDevice, st));
+        // 5 - new mean, :363-367; 7a - rank-mu matrix around the OLD mean, :375-380
+        meanold = mean;
+        PGC_CUDA(cudaMemcpyAsync(d_meanold, meanold.data(), 8 * D, cudaMemcpyHostToDevice, st));
+        if ((rc = weighted_mean_device(ctx, d_xn, d_idx, d_w, mu, D, d_mean, st))) return rc;
+        if ((rc = weighted_gram_device(ctx, d_xn, d_idx, d_meanold, d_w, mu, D, sigma * sigma, d_C, st))) return rc;
+        PGC_CUDA(cudaMemcpyAsync(mean.data(), d_mean, 8 * D, cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaMemcpyAsync(Cmu.data(), d_C, 8 * D * D, cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        // 6 - evolution paths, :369-374
+        for (size_t a = 0; a < D; ++a) {
+            double y = 0.;
+            for (size_t j = 0; j < D; ++j) y += invsqrtC[a * D + j] * (mean[j] - meanold[j]);
+            tmp[a] = y;
+        }
+        double ps2 = 0.;
+        for (size_t a = 0; a < D; ++a) {
+            ps[a] = (1. - cs) * ps[a] + std::sqrt(cs * (2. - cs) * mueff) * tmp[a] / sigma;
+            ps2 += ps[a] * ps[a];
+        }
+        const double hsig = (ps2 / N / (1. - std::pow((1. - cs), (2. * static_cast<double>(counteval) / static_cast<double>(lam))))) < (2. + 4. / (N + 1.)) ? 1. : 0.;
+        for (size_t a = 0; a < D; ++a) pc[a] = (1. - cc) * pc[a] + hsig * std::sqrt(cc * (2. - cc) * mueff) * (mean[a] - meanold[a]) / sigma;
+        // 7b - covariance matrix, :381
+        Cold = C;
+        for (size_t a = 0; a < D; ++a)
+            for (size_t b = 0; b < D; ++b)
+                C[a * D + b] = (1. - c1 - cmu) * Cold[a * D + b] + cmu * Cmu[a * D + b]
+                               + c1 * ((pc[a] * pc[b]) + (1. - hsig) * cc * (2. - cc) * Cold[a * D + b]);
+        // 8 - step size, :383
+        sigma *= std::exp(std::min(0.6, (cs / damps) * (std::sqrt(ps2) / chiN - 1.)));
+        // 9 - eigendecomposition every O(N) evaluations, :385-401
+        if (static_cast<double>(counteval - eigeneval) > (static_cast<double>(lam) / (c1 + cmu) / N / 10.)) {
+            eigeneval = counteval;
+            for (size_t a = 0; a < D; ++a)
+                for (size_t b = a + 1; b < D; ++b) C[a * D + b] = C[b * D + a] = (C[a * D + b] + C[b * D + a]) / 2.;
+            std::vector<double> work(C), w, V;
+            jacobi_eigen(work, D, w, V);
+            B = V;
+            for (size_t j = 0; j < D; ++j) dvec[j] = std::sqrt(std::max(1e-20, w[j]));
+            for (size_t a = 0; a < D; ++a)
+                for (size_t b = 0; b < D; ++b) {
+                    double y = 0.;
+                    for (size_t j = 0; j < D; ++j) y += B[a * D + j] * (1. / dvec[j]) * B[b * D + j];
+                    invsqrtC[a * D + b] = y;
+                }
+        }
+    }
+    if (gens_done) *gens_done = done;
+    if (sigma_out) *sigma_out = sigma;
+    PGC_CUDA(cudaStreamSynchronize(st));
     return PGC_OK;
 }
 

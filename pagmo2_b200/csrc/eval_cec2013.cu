@@ -85,6 +85,7 @@ struct Params13 {
     double fbias;
     double weier_c0, kats_c0, kats_c1, bi_s, bi_mu1;
     int tell, tdif, tgri, twei;
+    int strict; // rotations accumulate one product at a time in the reference's j order (pgc_problem_set_strict)
     Launch13 L;
 };
 
@@ -391,6 +392,19 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
                     break;
                 case O_ROT: { // rotatefunc :1046-1051 on the FP64 tensor path (fragments as in eval_cec2014.cu)
                     __syncwarp();
+                    if (P.strict) {
+                        // the reference's own summation: xrot[i] = xrot[i] + x[j] * Mr[i * nx + j], j ascending, one rounding per
+                        // multiply and per add (the library is built with -fmad=false) - bit-identical rotated vectors, for the
+                        // functions whose later sin / cos / pow amplify the last bits (f7, f8, f20, f28)
+                        for (int e = lane; e < TILE; e += 32) {
+                            const int t = e / D, i = e - t * D;
+                            const double *y = in + t * YS, *m = sMr + i * YS;
+                            double acc = 0.;
+                            for (int k = 0; k < D; ++k) acc = acc + y[k] * m[k];
+                            out[t * YS + i] = acc;
+                        }
+                        break;
+                    }
                     const int g = lane >> 2, j = lane & 3;
                     double acc[NT][2];
 #pragma unroll
@@ -777,6 +791,7 @@ int cec2013_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, c
         pp.tdif = pl.tdif;
         pp.tgri = pl.tgri;
         pp.twei = pl.twei;
+        pp.strict = p->strict;
         pp.L = L;
         int rc;
         switch (pl.dim) {

@@ -3,11 +3,16 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pagmo_cuda/pgc.h"
@@ -99,6 +104,87 @@ struct Cec2013Plan; // eval_cec2013.cu
 
 } // namespace pgc
 
+// ---- host-side helper: a few threads that copy one buffer together ------------------------------------------
+// pgc_eval_host stages PAGEABLE caller memory (a std::vector<double> coming through pagmo::bfe) in pinned chunks; one thread's
+// memcpy runs at ~10 GB/s, a fifth of what the PCIe link behind it takes, so the chunk is copied by several threads at once.
+namespace pgc
+{
+class CopyPool
+{
+public:
+    explicit CopyPool(unsigned nthreads)
+    {
+        for (unsigned t = 0; t < nthreads; ++t) m_threads.emplace_back([this, t, nthreads] { worker(t, nthreads); });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_mtx);
+            m_stop = true;
+            ++m_epoch;
+        }
+        m_cv.notify_all();
+        for (auto &t : m_threads) t.join();
+    }
+    // dst[0, bytes) = src[0, bytes), split into one contiguous piece per helper plus one for the caller
+    void copy(void *dst, const void *src, size_t bytes)
+    {
+        const size_t parts = m_threads.size() + 1;
+        if (bytes < (4u << 20) || m_threads.empty()) {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_mtx);
+            m_dst = static_cast<char *>(dst);
+            m_src = static_cast<const char *>(src);
+            m_bytes = bytes;
+            m_pending = static_cast<unsigned>(m_threads.size());
+            ++m_epoch;
+        }
+        m_cv.notify_all();
+        piece(parts - 1, parts);
+        std::unique_lock<std::mutex> lk(m_mtx);
+        m_done.wait(lk, [this] { return m_pending == 0; });
+    }
+
+private:
+    void piece(size_t i, size_t parts) const
+    {
+        const size_t unit = ((m_bytes + parts - 1) / parts + 4095) & ~static_cast<size_t>(4095);
+        const size_t lo = std::min(m_bytes, i * unit), hi = std::min(m_bytes, lo + unit);
+        if (hi > lo) std::memcpy(m_dst + lo, m_src + lo, hi - lo);
+    }
+    void worker(unsigned t, unsigned nthreads)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_mtx);
+                m_cv.wait(lk, [&] { return m_epoch != seen; });
+                seen = m_epoch;
+                if (m_stop) return;
+            }
+            piece(t, nthreads + 1u);
+            {
+                std::lock_guard<std::mutex> lk(m_mtx);
+                --m_pending;
+            }
+            m_done.notify_one();
+        }
+    }
+    std::vector<std::thread> m_threads;
+    std::mutex m_mtx;
+    std::condition_variable m_cv, m_done;
+    char *m_dst = nullptr;
+    const char *m_src = nullptr;
+    size_t m_bytes = 0;
+    unsigned m_pending = 0;
+    unsigned long long m_epoch = 0;
+    bool m_stop = false;
+};
+} // namespace pgc
+
 // ---- opaque handle layouts -----------------------------------------------------------------------------
 struct pgc_ctx {
     int device = 0;
@@ -118,6 +204,7 @@ struct pgc_ctx {
     // scratch (composition stage outputs etc.)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    pgc::CopyPool *copy_pool = nullptr; // created on the first pageable pgc_eval_host call
 };
 
 struct pgc_problem {
@@ -135,6 +222,7 @@ struct pgc_problem {
     pgc::Cec2014Recipe cec14;
     pgc::Cec2013Plan *cec13 = nullptr;
     double flops_per_eval = 0, transc_per_eval = 0;
+    int strict = 0; // pgc_problem_set_strict: reference summation order in the rotations (cec2013)
     // meta-problems (meta.cu): the wrapped problem (borrowed), translation | weight+z on the device, decomposition method
     pgc_problem *inner = nullptr;
     double *d_meta = nullptr;
@@ -216,6 +304,10 @@ int weighted_mean_device(pgc_ctx *ctx, const double *d_rows, const unsigned *d_i
                          cudaStream_t st);
 int cmaes_sample_device(pgc_ctx *ctx, const double *d_mean, const double *d_bd, double sigma, size_t lambda, size_t D, unsigned long long seed,
                         unsigned generation, double *d_z, double *d_x, cudaStream_t st);
+int cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam, unsigned gens, double cc, double cs, double c1, double cmu,
+                        double sigma0, double ftol, double xtol, int force_bounds, unsigned long long seed, unsigned first_generation,
+                        unsigned *gens_done, double *sigma_out, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t),
+                        cudaStream_t st);
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops_out);

@@ -133,6 +133,10 @@ int main(int argc, char **argv)
         cuda_pso_gen g(3u, 0.6, 1.9, 2.1, 0.4, 3u, 1u, 6u, false, 5u, 0);
         const auto h = round_trip(g);
         CHECK(h.descriptor().omega == 0.6 && h.descriptor().eta2 == 2.1 && h.descriptor().neighb_type == 1u && h.descriptor().neighb_param == 6u);
+        cuda_cmaes cm(9u, 0.3, 0.4, -1, 0.2, 0.25, 1e-7, 1e-9, false, true, 77u, 0);
+        const auto cm2 = round_trip(cm);
+        CHECK(cm2.descriptor().cma_cc == 0.3 && cm2.descriptor().cma_cs == 0.4 && cm2.descriptor().cma_c1 == -1 && cm2.descriptor().cma_cmu == 0.2
+              && cm2.descriptor().sigma0 == 0.25 && cm2.descriptor().force_bounds == 1u && cm2.descriptor().xtol == 1e-9);
         // same results before and after the round trip
         pagmo::population pop{pagmo::problem{pagmo::rastrigin{10u}}, 32u, 5u};
         CHECK(same_population(pagmo::algorithm{a}.evolve(pop), pagmo::algorithm{b}.evolve(pop)));
@@ -161,6 +165,18 @@ int main(int argc, char **argv)
         }
         CHECK(a.get_population().get_problem().get_fevals() == b.get_population().get_problem().get_fevals());
         CHECK(a.get_name().find("CUDA island") != std::string::npos);
+        // cuda_cmaes through a plain pagmo::algorithm and through a cuda_island: the same population, and it gets better
+        {
+            pagmo::population p2{pagmo::problem{pagmo::rastrigin{8u}}, 24u, 3u};
+            const double before = p2.get_f()[p2.best_idx()][0];
+            const auto direct = pagmo::algorithm{cuda_cmaes{60u, -1, -1, -1, -1, 0.5, 0., 0., false, false, 9u}}.evolve(p2);
+            pagmo::island ci{cuda_island{0}, pagmo::algorithm{cuda_cmaes{60u, -1, -1, -1, -1, 0.5, 0., 0., false, false, 9u}}, p2};
+            ci.evolve();
+            ci.wait_check();
+            CHECK(same_population(ci.get_population(), direct));
+            CHECK(direct.get_f()[direct.best_idx()][0] < before);
+            std::printf("cuda_cmaes: best %g -> %g\n", before, direct.get_f()[direct.best_idx()][0]);
+        }
         // a stock CPU algorithm is refused (no CPU fallback)
         pagmo::island c{cuda_island{0}, pagmo::algorithm{pagmo::de{5u}}, pop};
         c.evolve();

@@ -136,3 +136,39 @@ def test_cec2013_metadata_and_bad_arguments(capi, ctx, orc):
         capi.Problem(ctx, "cec2013", prob_id=3, dim=10, rotation=mr[:100], shift=os_)  # needs 2 matrices
     with pytest.raises(capi.PgcError):
         capi.Problem(ctx, "cec2013", prob_id=21, dim=10, rotation=mr, shift=os_[:10])  # needs 5 shifts
+
+
+@pytest.mark.parametrize("dim", (10, 30, 50, 100))
+def test_cec2013_strict_mode_meets_the_tolerance_on_ill_conditioned_functions(capi, ctx, orc, dim):
+    """pgc_problem_set_strict: the rotations accumulate in the reference's own order (rotatefunc, cec2013.cpp:1046-1051), so the
+    rotated vectors are bit-identical and only libdevice-vs-glibc ulps remain.  Then f7 (schaffer_F7), f8 (ackley), f20 (escaffer6)
+    and f28 (cf08) - the functions that need the noise-floor bound on the tensor path - are held to a HARD cap on every point,
+    the ill-conditioned ones included; the measured worst case goes into the parity report.  cfg5 runs this suite at D = 50."""
+    rng = np.random.default_rng(1400 + dim)
+    _, os_ = orc.cec2013_tables(dim)
+    n = 403
+    xs = np.vstack([rng.uniform(-100, 100, (n - 103, dim)), os_[:dim] + rng.normal(0, 1.0, (100, dim)), os_[None, :dim], np.zeros((1, dim)),
+                    rng.uniform(-100, 100, (1, dim))])
+    worst = {}
+    for func in (7, 8, 20, 28, 3, 12, 16, 23):   # the four ill-conditioned ones and a few others: strict mode is a mode of every function
+        prob = make13(capi, ctx, orc, func, dim)
+        want = orc.cec2013(func, xs)
+        loose = prob.eval_host(xs)[:, 0]
+        prob.set_strict(True)
+        got = prob.eval_host(xs)[:, 0]
+        prob.set_strict(False)
+        assert np.array_equal(prob.eval_host(xs)[:, 0], loose)   # the switch is a switch
+        scale = 4.189828872724338e+002 * dim if func in (23, 28) else 0.0
+        rel = np.abs(got - want) / np.maximum(np.abs(want), scale)
+        worst[func] = float(rel.max())
+        assert rel.max() <= REL_TOL, (func, dim, float(rel.max()))
+        prob.close()
+    _report[f"cec2013_strict_d{dim}"] = worst
+    try:
+        OUT.mkdir(exist_ok=True)
+        (OUT / "parity_report_cec2013.json").write_text(json.dumps(_report, indent=1, sort_keys=True))
+    except OSError:
+        pass
+    other = capi.Problem(ctx, "rastrigin", dim=5)
+    with pytest.raises(capi.PgcError):
+        other.set_strict(True)

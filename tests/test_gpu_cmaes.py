@@ -49,3 +49,49 @@ def test_unsupported_dimension_fails_loudly(ctx):
     from pagmo2_b200 import capi
     with pytest.raises(capi.PgcError):  # a 32-row chunk of full rows no longer fits in shared memory
         ctx.weighted_gram(np.zeros((4, 2000)), np.ones(4))
+
+
+@pytest.mark.parametrize("fam,dim,lam", [("rosenbrock", 8, 20), ("rastrigin", 10, 32), ("ackley", 30, 64)])
+def test_cmaes_evolve_follows_the_restated_loop(ctx, orc, fam, dim, lam):
+    """cmaes::evolve (cmaes.cpp:111-407): the device loop (sampling, evaluation, recombination, rank-mu on the GPU; paths and
+    Jacobi eigendecomposition on the host) against the triple-loop restatement consuming the same Philox normals.  The two
+    Gram matrices differ by DMMA summation order (<= 1e-12 of the summed terms), which the adaptation feeds back every
+    generation: the trajectories are compared over the first generations, the convergence over a long run."""
+    from pagmo2_b200 import capi
+    rng = np.random.default_rng(dim)
+    prob = capi.Problem(ctx, fam, dim=dim)
+    op = orc.problem(fam, dim=dim)
+    lb, ub = prob.bounds()
+    x = rng.uniform(lb, ub, (lam, dim))
+    f = orc.simple(fam, x)
+    kw = dict(sigma0=0.5, ftol=0.0, xtol=0.0, seed=11, first_generation=1)
+    for gens, tol in ((1, 1e-11), (3, 1e-9), (8, 1e-6)):
+        xg, fg, dg, sg = prob.cmaes_evolve(x, f, gens=gens, **kw)
+        xo, fo, do, so = orc.cmaes_evolve(op, lb, ub, x, f, gens=gens, **kw)
+        assert dg == do == gens
+        scale = np.abs(xo).max()
+        assert np.abs(xg - xo).max() <= tol * scale, (gens, np.abs(xg - xo).max())
+        assert abs(sg - so) <= tol * so
+        assert np.allclose(prob.eval_host(xg)[:, 0], fg, rtol=1e-12)
+    # force_bounds keeps every sample inside the box (cmaes.cpp:301-315)
+    xb, fb, _, _ = prob.cmaes_evolve(x, f, gens=5, force_bounds=True, **kw)
+    assert (xb >= lb).all() and (xb <= ub).all()
+    # a long run converges like the restated one does
+    xg, fg, dg, sg = prob.cmaes_evolve(x, f, gens=400, sigma0=0.5, ftol=1e-10, xtol=1e-10, seed=11)
+    xo, fo, do, so = orc.cmaes_evolve(op, lb, ub, x, f, gens=400, sigma0=0.5, ftol=1e-10, xtol=1e-10, seed=11)
+    assert fg.min() < 0.05 * f.min() and (fg.min() <= 10 * max(fo.min(), 1e-8) or fam != "rosenbrock")
+    prob.close()
+
+
+def test_cmaes_argument_checks(ctx):
+    from pagmo2_b200 import capi
+    prob = capi.Problem(ctx, "rastrigin", dim=5)
+    x, f = np.zeros((8, 5)), np.zeros(8)
+    for bad in (dict(cc=1.5), dict(cs=-0.5), dict(c1=2.0), dict(cmu=-2.0)):   # cmaes.cpp:64-88
+        with pytest.raises(capi.PgcError):
+            prob.cmaes_evolve(x, f, gens=1, **bad)
+    with pytest.raises(capi.PgcError):                                         # :140-143: at least 5 individuals
+        prob.cmaes_evolve(x[:4], f[:4], gens=1)
+    mo = capi.Problem(ctx, "zdt", prob_id=1, dim=5)
+    with pytest.raises(capi.PgcError):
+        mo.cmaes_evolve(np.zeros((8, 5)), np.zeros(8), gens=1)

@@ -117,8 +117,9 @@ def test_pso_gen_evolve_bit_exact(orc, ref, fam, dim):
     lb, ub = rp.bounds()
     op = orc.problem(fam, dim=dim)
     for variant in (1, 2, 3, 4, 5):
-        for nt, npar in ((1, 4), (2, 4), (2, 2), (2, 7)):
-            n, gens, seed = 23, 12, variant * 10 + nt
+        # gbest, lbest rings, von Neumann lattice (24 = 4 x 6; 23 is prime: one row), adaptive random graphs (out-degree 3, 1, 4)
+        for nt, npar, n in ((1, 4, 23), (2, 4, 23), (2, 2, 23), (2, 7, 23), (3, 4, 24), (3, 4, 23), (4, 3, 23), (4, 1, 12), (4, 4, 40)):
+            gens, seed = 12, variant * 10 + nt
             x0 = rng.uniform(lb, ub, (n, dim))
             xr, fr = ref.evolve_from(rp, "pso_gen", [0.7298, 2.05, 2.05, 0.5, variant, nt, npar], x0, gens, seed)
             f0 = np.array([rp.fitness(x) for x in x0])[:, 0]
