@@ -389,6 +389,17 @@ PGC_API int pgc_migrate(pgc_comm *comm, pgc_island *const *islands, const int *o
  * warp-tiles and stages.  out7 = {load, weight pass, token wait, GEMM, z store, epilogue} cycles, warp-tiles. */
 PGC_API int pgc_debug_cec2014_phase_cycles(pgc_problem *prob, const double *d_dvs, size_t n, double *d_fvs, uint64_t *out7);
 
+/* Debug / measurement aid for the tensor-core rotation (rot_i8.cu): z = M * ((x - os) * rate) for n device-resident rows of D (even,
+ * <= 128) doubles through tcgen05.mma kind::i8 on exact digit planes (Ozaki scheme), FP64-accurate.  coef == NULL: d_out = z [n x D];
+ * otherwise d_out = f [n] = sum_j coef[j] * z_j^2 + fbias.  M (D x D row-major), os, coef are host arrays.  reps > 1: the kernel is
+ * launched reps + 1 times and *ms_per_launch (optional) receives the CUDA-event time of one launch. */
+PGC_API int pgc_debug_rot_i8(pgc_ctx *ctx, const double *M, size_t D, const double *os, const double *coef, double rate, double fbias,
+                             const double *d_x, size_t n, double *d_out, int reps, float *ms_per_launch, void *stream);
+
+/* Design probe: cycles per tcgen05.mma kind::i8 (M = 128, K = 32) for N = 32, 64, 128, 256 and four issue patterns (one accumulator;
+ * seven accumulators in turn; the same with collector::a reuse; fresh operand tiles); out32 = [4][4][2] doubles (issue, completion). */
+PGC_API int pgc_debug_mma_i8_probe(pgc_ctx *ctx, double *out32);
+
 /* ---- device memory helpers (so a host-language binding needs no CUDA runtime of its own) ------------- */
 PGC_API int pgc_malloc_device(pgc_ctx *ctx, size_t bytes, void **out);
 PGC_API int pgc_free_device(pgc_ctx *ctx, void *ptr);

