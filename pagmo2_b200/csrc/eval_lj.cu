@@ -9,6 +9,7 @@
 // DBL_MAX and keep summing, then multiply by 4 (:81-91): the result is +inf, reproduced explicitly.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "pgc_internal.cuh"
@@ -149,6 +150,184 @@ __global__ void __launch_bounds__(kLjWarps * 32) lj_reg_kernel(const double *__r
     }
 }
 
+// Circulant pair schedule: atom i meets atoms i + 1 ... i + (N - 1) / 2 (indices mod N; even N adds the offset N / 2 for the first
+// N / 2 atoms), so every unordered pair is computed once and, unlike the triangular i < j loop, no lane idles on the diagonal:
+// slot efficiency N / (32 NC) instead of ~75 %.  Lane l keeps its own atoms l, l + 32, ... (NC chunks) in registers.  The partner
+// side is read from a wrapped copy of the coordinates in shared memory (position k holds atom k mod N): at step dp = 1 ... N the
+// lane loads the ONE atom at position l + dp and uses it against every own chunk c whose offset (dp - 32 c) mod N lies in
+// 1 ... (N - 1) / 2 - two or three chunks at a time - so each individual costs N loads per lane instead of one per pair (shared
+// memory moves 128 B/clk/SM: at one 3 x 8 B load per pair it would run at 92 % of the FP64 pipe's time).  The live chunks are a
+// cyclic range [LO, LO + A) of the chunk ring that changes ~2 NC times per individual (the segment table is built once per
+// block); each (LO, A) is its own unrolled instance so the chunk arrays stay in registers, and the body is written stage by
+// stage across the live chunks so that their dependent FP64 chains (15 deep) interleave.
+// 13 FP64-pipe instructions per pair: 3 sub, mul + 2 fma, 2 mul, 3 fma (cubic step on the reciprocal seed), fma, add.
+template <int NC, int LO, int A>
+__device__ __forceinline__ void lj_span(const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz, int k0,
+                                        int k1, const double (&xa)[NC], const double (&ya)[NC], const double (&za)[NC], double (&s)[NC],
+                                        bool own_last)
+{
+    constexpr int U = A >= 4 ? 1 : (A == 3 ? 2 : (A == 2 ? 3 : 4)); // ~6 independent chains per warp
+#pragma unroll U
+    for (int k = k0; k < k1; ++k) {
+        const double qx = px[k], qy = py[k], qz = pz[k];
+        double dist[A], cube[A], r[A], e[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const int c = (LO + a) % NC;
+            const double dx = xa[c] - qx, dy = ya[c] - qy, dz = za[c] - qz;
+            dist[a] = fma(dz, dz, fma(dy, dy, dx * dx)); // rij^2, :78-80
+        }
+#pragma unroll
+        for (int a = 0; a < A; ++a) cube[a] = dist[a] * dist[a] * dist[a];
+#pragma unroll
+        for (int a = 0; a < A; ++a) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[a]) : "d"(cube[a]));
+#pragma unroll
+        for (int a = 0; a < A; ++a) e[a] = fma(-cube[a], r[a], 1.0);
+#pragma unroll
+        for (int a = 0; a < A; ++a) e[a] = fma(e[a], e[a], e[a]);
+#pragma unroll
+        for (int a = 0; a < A; ++a) r[a] = fma(r[a], e[a], r[a]);     // rij^-6, :84
+#pragma unroll
+        for (int a = 0; a < A; ++a) e[a] = fma(r[a], r[a], -r[a]);    // :85
+        // a coincident pair gives 1 / 0 = inf and inf * inf - inf = NaN, which poisons the lane's sum: detected once at the end
+        // instead of one FP64 compare per pair
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const int c = (LO + a) % NC;
+            if (c < NC - 1) s[c] += e[a];                             // every lane of these chunks owns a real atom
+            else s[c] += own_last ? e[a] : 0.0;
+        }
+    }
+}
+
+__host__ __device__ constexpr int lj_max_live(int nc) { return nc / 2 + 1; } // most own chunks one partner position can serve (checked for every N)
+
+template <int NC, int LO, int A = 1>
+__device__ __forceinline__ void lj_dispatch_count(int cnt, const double *__restrict__ px, const double *__restrict__ py,
+                                                  const double *__restrict__ pz, int k0, int k1, const double (&xa)[NC],
+                                                  const double (&ya)[NC], const double (&za)[NC], double (&s)[NC], bool own_last)
+{
+    if (cnt == A) {
+        lj_span<NC, LO, A>(px, py, pz, k0, k1, xa, ya, za, s, own_last);
+        return;
+    }
+    if constexpr (A < lj_max_live(NC) && A < NC) lj_dispatch_count<NC, LO, A + 1>(cnt, px, py, pz, k0, k1, xa, ya, za, s, own_last);
+}
+
+template <int NC, int LO = 0>
+__device__ __forceinline__ void lj_dispatch(int lo, int cnt, const double *__restrict__ px, const double *__restrict__ py,
+                                            const double *__restrict__ pz, int k0, int k1, const double (&xa)[NC], const double (&ya)[NC],
+                                            const double (&za)[NC], double (&s)[NC], bool own_last)
+{
+    if (lo == LO) {
+        lj_dispatch_count<NC, LO>(cnt, px, py, pz, k0, k1, xa, ya, za, s, own_last);
+        return;
+    }
+    if constexpr (LO + 1 < NC) lj_dispatch<NC, LO + 1>(lo, cnt, px, py, pz, k0, k1, xa, ya, za, s, own_last);
+}
+
+constexpr int kLjMaxSegments = 40; // the live set changes at most 2 NC + 1 times; gaps (clusters below 64 atoms) add NC more
+
+// entries of the wrapped coordinate copy one warp needs: positions up to 31 + N
+__host__ __device__ inline int lj_circ_len(int atoms) { return atoms + 32; }
+
+template <int NC>
+__global__ void __launch_bounds__(kLjWarps * 32) lj_circ_kernel(const double *__restrict__ x, double *__restrict__ f, long long n, int atoms)
+{
+    extern __shared__ double smem[];
+    __shared__ int seg_k0[kLjMaxSegments], seg_lo[kLjMaxSegments], seg_cnt[kLjMaxSegments], n_seg;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = atoms, W = lj_circ_len(N);
+    double *px = smem + static_cast<size_t>(warp) * 3 * W, *py = px + W, *pz = py + W;
+    const int D = 3 * atoms - 6;
+    const int full = (N - 1) / 2;          // offsets at which every atom has a partner
+    const bool half = (N % 2) == 0;        // even N: one more offset for the first N / 2 atoms
+    const bool own_last = (NC - 1) * 32 + lane < N;
+    if (threadIdx.x == 0) { // segments of dp = 1 ... N with a constant set of live chunks: c is live when (dp - 32 c) mod N is in [1, full]
+        int ns = 0, prev_lo = -1, prev_cnt = -1;
+        for (int dp = 1; dp <= N; ++dp) {
+            unsigned mask = 0;
+            for (int c = 0; c < NC; ++c) {
+                const int off = ((dp - 32 * c) % N + N) % N;
+                if (off >= 1 && off <= full) mask |= 1u << c;
+            }
+            const int cnt = __popc(mask);
+            int lo = 0; // first chunk of the cyclic run: live, predecessor not live
+            for (int c = 0; c < NC; ++c)
+                if ((mask >> c & 1u) && !(mask >> ((c + NC - 1) % NC) & 1u)) lo = c;
+            if (lo != prev_lo || cnt != prev_cnt) {
+                seg_k0[ns] = dp;
+                seg_lo[ns] = lo;
+                seg_cnt[ns] = cnt;
+                ++ns;
+                prev_lo = lo;
+                prev_cnt = cnt;
+            }
+        }
+        seg_k0[ns] = N + 1;
+        n_seg = ns;
+    }
+    __syncthreads();
+    const int nseg = n_seg;
+    for (long long ind = static_cast<long long>(blockIdx.x) * kLjWarps + warp; ind < n; ind += static_cast<long long>(gridDim.x) * kLjWarps) {
+        const double *xi = x + ind * D;
+        double xa[NC], ya[NC], za[NC];
+        for (int a = 2 * N + lane; a < W; a += 32) px[a] = py[a] = pz[a] = 0.0; // clusters below 32 atoms: read by parked lanes only
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { // coordinate map _r, :132-151; lanes beyond the cluster are parked far away (their terms are dropped)
+            const int a = c * 32 + lane;
+            double cx = 1.0e8 * (a + 1), cy = 0.0, cz = 0.0;
+            if (a < N) {
+                cx = (a >= 3) ? xi[3 * (a - 2)] : 0.0;
+                cy = (a >= 3) ? xi[3 * (a - 2) + 1] : (a == 2 ? xi[1] : 0.0);
+                cz = (a >= 3) ? xi[3 * (a - 2) + 2] : (a == 2 ? xi[2] : (a == 1 ? xi[0] : 0.0));
+                px[a] = cx;
+                py[a] = cy;
+                pz[a] = cz;
+                if (a + N < W) { // wrapped copy: position k holds atom k mod N
+                    px[a + N] = cx;
+                    py[a + N] = cy;
+                    pz[a + N] = cz;
+                }
+            }
+            xa[c] = cx;
+            ya[c] = cy;
+            za[c] = cz;
+        }
+        __syncwarp();
+        double s[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) s[c] = 0.0;
+        for (int g = 0; g < nseg; ++g) {
+            const int cnt = seg_cnt[g];
+            if (cnt > 0) lj_dispatch<NC>(seg_lo[g], cnt, px + lane, py + lane, pz + lane, seg_k0[g], seg_k0[g + 1], xa, ya, za, s, own_last);
+        }
+        if (half) {
+            const int d = N / 2;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                if (c * 32 < d) { // warp-uniform: chunks that hold atoms below N / 2
+                    const int i = c * 32 + lane, j = i + d;
+                    const bool valid = i < d;
+                    const double dx = xa[c] - px[j], dy = ya[c] - py[j], dz = za[c] - pz[j];
+                    const double dist = fma(dz, dz, fma(dy, dy, dx * dx));
+                    const double sixth = fast_rcp(dist * dist * dist);
+                    const double term = fma(sixth, sixth, -sixth);
+                    s[c] += valid ? term : 0.0;
+                }
+            }
+        }
+        double tot = s[0];
+#pragma unroll
+        for (int c = 1; c < NC; ++c) tot += s[c];
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, m);
+        // coincident atoms: the reference assigns DBL_MAX to the pair and the final 4 * v overflows to +inf (:81-91)
+        if (lane == 0) f[ind] = (tot != tot || isinf(tot)) ? INFINITY : 4 * tot; // :90
+        __syncwarp();
+    }
+}
+
 } // namespace
 
 int lj_create(pgc_problem *p)
@@ -203,9 +382,29 @@ int lj_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaSt
         case 8: reg = lj_reg_kernel<8>; break;
         default: break;
     }
+    reg_fn circ = nullptr;
+    switch ((atoms + 31) / 32) { // circulant schedule (default) up to 256 atoms; PGC_LJ_ROWS=1 selects the row-by-row kernel (A/B)
+        case 1: circ = lj_circ_kernel<1>; break;
+        case 2: circ = lj_circ_kernel<2>; break;
+        case 3: circ = lj_circ_kernel<3>; break;
+        case 4: circ = lj_circ_kernel<4>; break;
+        case 5: circ = lj_circ_kernel<5>; break;
+        case 6: circ = lj_circ_kernel<6>; break;
+        case 7: circ = lj_circ_kernel<7>; break;
+        case 8: circ = lj_circ_kernel<8>; break;
+        default: break;
+    }
+    const char *rows_env = std::getenv("PGC_LJ_ROWS");
+    if (rows_env && rows_env[0] == '1') circ = nullptr;
     long long blocks = (static_cast<long long>(n) + kLjWarps - 1) / kLjWarps;
     int per_sm = 1;
-    if (reg) {
+    if (circ) {
+        const size_t smem_c = sizeof(double) * 3 * static_cast<size_t>(lj_circ_len(atoms)) * kLjWarps;
+        PGC_CUDA(cudaFuncSetAttribute(circ, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_c)));
+        PGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, circ, kLjWarps * 32, smem_c));
+        blocks = std::min<long long>(blocks, static_cast<long long>(p->ctx->sm_count) * std::max(per_sm, 1));
+        circ<<<static_cast<unsigned>(blocks), kLjWarps * 32, smem_c, stream>>>(d_dvs, d_fvs, static_cast<long long>(n), atoms);
+    } else if (reg) {
         PGC_CUDA(cudaFuncSetAttribute(reg, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         PGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reg, kLjWarps * 32, smem));
         blocks = std::min<long long>(blocks, static_cast<long long>(p->ctx->sm_count) * std::max(per_sm, 1));
