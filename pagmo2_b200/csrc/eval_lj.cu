@@ -161,12 +161,19 @@ __global__ void __launch_bounds__(kLjWarps * 32) lj_reg_kernel(const double *__r
 // block); each (LO, A) is its own unrolled instance so the chunk arrays stay in registers, and the body is written stage by
 // stage across the live chunks so that their dependent FP64 chains (15 deep) interleave.
 // 13 FP64-pipe instructions per pair: 3 sub, mul + 2 fma, 2 mul, 3 fma (cubic step on the reciprocal seed), fma, add.
+#ifndef PGC_LJ_CHAINS
+#define PGC_LJ_CHAINS 6
+#endif
+#ifndef PGC_LJ_MINBLOCKS
+#define PGC_LJ_MINBLOCKS 1
+#endif
+
 template <int NC, int LO, int A>
 __device__ __forceinline__ void lj_span(const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz, int k0,
                                         int k1, const double (&xa)[NC], const double (&ya)[NC], const double (&za)[NC], double (&s)[NC],
                                         bool own_last)
 {
-    constexpr int U = A >= 4 ? 1 : (A == 3 ? 2 : (A == 2 ? 3 : 4)); // ~6 independent chains per warp
+    constexpr int U = (PGC_LJ_CHAINS + A - 1) / A; // ~PGC_LJ_CHAINS independent chains per warp
 #pragma unroll U
     for (int k = k0; k < k1; ++k) {
         const double qx = px[k], qy = py[k], qz = pz[k];
@@ -232,7 +239,7 @@ constexpr int kLjMaxSegments = 40; // the live set changes at most 2 NC + 1 time
 __host__ __device__ inline int lj_circ_len(int atoms) { return atoms + 32; }
 
 template <int NC>
-__global__ void __launch_bounds__(kLjWarps * 32) lj_circ_kernel(const double *__restrict__ x, double *__restrict__ f, long long n, int atoms)
+__global__ void __launch_bounds__(kLjWarps * 32, PGC_LJ_MINBLOCKS) lj_circ_kernel(const double *__restrict__ x, double *__restrict__ f, long long n, int atoms)
 {
     extern __shared__ double smem[];
     __shared__ int seg_k0[kLjMaxSegments], seg_lo[kLjMaxSegments], seg_cnt[kLjMaxSegments], n_seg;
