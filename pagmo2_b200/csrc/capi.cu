@@ -29,11 +29,21 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
     return e == cudaErrorMemoryAllocation ? PGC_ERR_OUT_OF_MEMORY : PGC_ERR_CUDA;
 }
 
+// Wait for the context's own streams.  Not cudaDeviceSynchronize(): a device-wide wait is an error while ANY stream of the device
+// is being captured (another island's thread recording its generation graph, de.cu), whatever the capture mode.
+int ctx_sync(pgc_ctx *ctx)
+{
+    if (ctx->stream) PGC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (cudaStream_t s : ctx->copy_stream)
+        if (s) PGC_CUDA(cudaStreamSynchronize(s));
+    return PGC_OK;
+}
+
 int ensure_scratch(pgc_ctx *ctx, size_t bytes)
 {
     if (ctx->scratch_bytes >= bytes) return PGC_OK;
     // growing the scratch area must not race with kernels still using the old one
-    PGC_CUDA(cudaDeviceSynchronize());
+    if (int rc = ctx_sync(ctx)) return rc;
     if (ctx->scratch) PGC_CUDA(cudaFree(ctx->scratch));
     ctx->scratch = nullptr;
     ctx->scratch_bytes = 0;
@@ -311,7 +321,11 @@ int pgc_ctx_destroy(pgc_ctx *ctx)
 {
     if (!ctx) return PGC_OK;
     cudaSetDevice(ctx->device);
-    cudaDeviceSynchronize();
+    // no error reporting here: at process exit the runtime (and the thread-local error string) may already be gone
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (cudaStream_t s : ctx->copy_stream)
+        if (s) cudaStreamSynchronize(s);
+    (void)cudaGetLastError();
     for (int i = 0; i < pgc_ctx::kRing; ++i) {
         if (ctx->h_in[i]) cudaFreeHost(ctx->h_in[i]);
         if (ctx->h_out[i]) cudaFreeHost(ctx->h_out[i]);
@@ -347,8 +361,7 @@ int pgc_ctx_synchronize(pgc_ctx *ctx)
 {
     PGC_REQUIRE(ctx, "pgc_ctx_synchronize: null context");
     PGC_CUDA(cudaSetDevice(ctx->device));
-    PGC_CUDA(cudaDeviceSynchronize());
-    return PGC_OK;
+    return ctx_sync(ctx);
 }
 
 int pgc_ctx_launch_count(const pgc_ctx *ctx, uint64_t *count)
@@ -400,7 +413,11 @@ int pgc_problem_destroy(pgc_problem *p)
 {
     if (!p) return PGC_OK;
     cudaSetDevice(p->ctx->device);
-    cudaDeviceSynchronize();
+    // device-wide on purpose: the handle may outlive its context's streams at process exit (static destruction order in a host
+    // application).  While another thread records a generation graph this returns an error, which is harmless here: the
+    // cudaFree calls below order themselves after the work that uses the tables.
+    if (cudaDeviceSynchronize() != cudaSuccess) (void)cudaGetLastError();
+    p->work.clear(); // cached generation-loop workspaces (graphs, scratch buffers)
     if (p->inner) { // meta-problem: its tables are the wrapped problem's
         meta_destroy(p);
         delete p;
@@ -450,6 +467,7 @@ int pgc_problem_set_strict(pgc_problem *p, int on)
         return PGC_ERR_UNSUPPORTED;
     }
     p->strict = on ? 1 : 0;
+    ++p->config_epoch; // cached generation graphs were captured with the old switch
     return PGC_OK;
 }
 
@@ -518,7 +536,7 @@ int pgc_eval_host(pgc_problem *p, const double *dvs, size_t n, double *fvs)
     if (chunk > n) chunk = (n + 15) / 16 * 16;
     const size_t in_bytes = chunk * nx * sizeof(double), out_bytes = chunk * nf * sizeof(double);
     if (ctx->ring_in_bytes < in_bytes || ctx->ring_out_bytes < out_bytes) {
-        PGC_CUDA(cudaDeviceSynchronize());
+        if (int rc = ctx_sync(ctx)) return rc;
         for (int i = 0; i < pgc_ctx::kRing; ++i) {
             if (ctx->h_in[i]) cudaFreeHost(ctx->h_in[i]);
             if (ctx->h_out[i]) cudaFreeHost(ctx->h_out[i]);

@@ -15,6 +15,9 @@
 // start gene, crossover draws, one draw per out-of-bounds gene.  uniform_int(a, b) = a + floor(u * (b - a + 1)).
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
+#include <memory>
+#include <mutex>
 #include <algorithm>
 #include <vector>
 
@@ -49,7 +52,7 @@ struct TrialParams {
     unsigned *variant_out;
     unsigned NP, dim;
     unsigned long long seed;
-    unsigned generation;
+    const unsigned *gen_base, *gens_done; // device: generation index = *gen_base + *gens_done (no per-launch parameter: graph-replayable)
     DeConfig cfg;
 };
 
@@ -95,35 +98,59 @@ __device__ __forceinline__ void decode_variant(unsigned v, unsigned &base, bool 
     }
 }
 
-// one thread per individual
-__global__ void de_trial_kernel(const TrialParams P)
+// ---- trial vector of individual i: the scalar prelude (index picks, variant gate, F / CR) -------------------------------------
+// DRAW is the individual's Philox substream read in order (next()): the thread-per-individual kernel passes the stream itself,
+// the warp-per-individual kernel a view of draws its lanes computed in parallel.
+struct TrialHead {
+    unsigned r[7];
+    double F, CR;
+    unsigned variant, base;
+    bool expo;
+};
+
+template <class DRAW>
+__device__ __forceinline__ unsigned uint_below_from(DRAW &rs, unsigned n) // uniform in [0, n)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.NP || *P.stopped) return;
-    const unsigned NP = P.NP, dim = P.dim;
-    PhiloxStream rs(P.seed, kTagDe, P.generation, i);
+    const unsigned v = static_cast<unsigned>(rs.next() * static_cast<double>(n));
+    return v < n ? v : n - 1;
+}
+
+template <class DRAW>
+__device__ __forceinline__ double normal01_from(DRAW &rs) // Box-Muller on two uniforms
+{
+    const double u1 = 1.0 - rs.next();
+    const double u2 = rs.next();
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+template <class DRAW>
+__device__ __forceinline__ TrialHead trial_head(const TrialParams &P, unsigned i, DRAW &rs)
+{
+    TrialHead H;
+    const unsigned NP = P.NP;
     // Durstenfeld partial shuffle of 0..NP-1 (de.cpp:143-149, de1220.cpp:181-187) on a virtual array: only the picked
     // positions are ever overwritten (with the value of the current last position)
     const unsigned npick = P.cfg.algo == 0 ? 5u : 7u;
-    unsigned r[7], pos[7], val[7];
+    unsigned pos[7], val[7];
     for (unsigned j = 0; j < npick; ++j) {
         const unsigned last = NP - 1u - j;
-        const unsigned idx = uint_below(rs, NP - j);
+        const unsigned idx = uint_below_from(rs, NP - j);
         unsigned at_idx = idx, at_last = last;
         for (unsigned k = 0; k < j; ++k) {
             if (pos[k] == idx) at_idx = val[k];
             if (pos[k] == last) at_last = val[k];
         }
-        r[j] = at_idx;
+        H.r[j] = at_idx;
         pos[j] = idx;
         val[j] = at_last;
     }
-    for (unsigned j = npick; j < 7u; ++j) r[j] = 0;
+    for (unsigned j = npick; j < 7u; ++j) H.r[j] = 0;
+    const unsigned *r = H.r;
 
     double F = P.cfg.F, CR = P.cfg.CR;
     unsigned variant = P.cfg.variant;
     if (P.cfg.algo == 2u) { // de1220.cpp:192
-        variant = (rs.next() < 0.9) ? P.variant_in[i] : P.cfg.allowed[uint_below(rs, P.cfg.n_allowed)];
+        variant = (rs.next() < 0.9) ? P.variant_in[i] : P.cfg.allowed[uint_below_from(rs, P.cfg.n_allowed)];
     }
     if (P.cfg.algo != 0u && P.cfg.variant_adptv == 1u) { // jDE, de1220.cpp:193-196 / sade.cpp:178-182
         F = (rs.next() < 0.9) ? P.F_in[i] : rs.next() * 0.9 + 0.1;
@@ -140,51 +167,71 @@ __global__ void de_trial_kernel(const TrialParams P)
         double a1, a2, a3, c1, c2;
         switch (base) {
             case 1:
-                a1 = normal01(rs); c1 = normal01(rs);
+                a1 = normal01_from(rs); c1 = normal01_from(rs);
                 F = gF + a1 * 0.5 * (mF[r[1]] - mF[r[2]]);
                 CR = gC + c1 * 0.5 * (mC[r[1]] - mC[r[2]]);
                 break;
             case 2:
-                a1 = normal01(rs); c1 = normal01(rs);
+                a1 = normal01_from(rs); c1 = normal01_from(rs);
                 F = mF[r[0]] + a1 * 0.5 * (mF[r[1]] - mF[r[2]]);
                 CR = mC[r[0]] + c1 * 0.5 * (mC[r[1]] - mC[r[2]]);
                 break;
             case 3:
-                a1 = normal01(rs); a2 = normal01(rs); c1 = normal01(rs); c2 = normal01(rs);
+                a1 = normal01_from(rs); a2 = normal01_from(rs); c1 = normal01_from(rs); c2 = normal01_from(rs);
                 F = mF[i] + a1 * 0.5 * (gF - mF[i]) + a2 * 0.5 * (mF[r[0]] - mF[r[1]]);
                 CR = mC[i] + c1 * 0.5 * (gC - mC[i]) + c2 * 0.5 * (mC[r[0]] - mC[r[1]]);
                 break;
             case 4:
-                a1 = normal01(rs); a2 = normal01(rs); c1 = normal01(rs); c2 = normal01(rs);
+                a1 = normal01_from(rs); a2 = normal01_from(rs); c1 = normal01_from(rs); c2 = normal01_from(rs);
                 F = gF + a1 * 0.5 * (mF[r[0]] - mF[r[1]]) + a2 * 0.5 * (mF[r[2]] - mF[r[3]]);
                 CR = gC + c1 * 0.5 * (mC[r[0]] - mC[r[1]]) + c2 * 0.5 * (mC[r[2]] - mC[r[3]]);
                 break;
             case 5:
-                a1 = normal01(rs); a2 = normal01(rs); c1 = normal01(rs); c2 = normal01(rs);
+                a1 = normal01_from(rs); a2 = normal01_from(rs); c1 = normal01_from(rs); c2 = normal01_from(rs);
                 F = mF[r[4]] + a1 * 0.5 * (mF[r[0]] - mF[r[1]]) + a2 * 0.5 * (mF[r[2]] - mF[r[3]]);
                 CR = mC[r[4]] + c1 * 0.5 * (mC[r[0]] - mC[r[1]]) + c2 * 0.5 * (mC[r[2]] - mC[r[3]]);
                 break;
             case 6:
-                a1 = normal01(rs); a2 = normal01(rs); a3 = normal01(rs); c1 = normal01(rs);
+                a1 = normal01_from(rs); a2 = normal01_from(rs); a3 = normal01_from(rs); c1 = normal01_from(rs);
                 F = mF[r[0]] + a1 * 0.5 * (mF[r[1]] - mF[r[2]]) + a2 * 0.5 * (mF[r[3]] - mF[r[4]]) + a3 * 0.5 * (mF[r[5]] - mF[r[6]]);
                 CR = mC[r[4]] + c1 * 0.5 * (mC[r[0]] + mC[r[1]] - mC[r[2]] - mC[r[3]]);
                 break;
             case 7:
-                a1 = normal01(rs); a2 = normal01(rs); a3 = normal01(rs); c1 = normal01(rs);
+                a1 = normal01_from(rs); a2 = normal01_from(rs); a3 = normal01_from(rs); c1 = normal01_from(rs);
                 F = gF + a1 * 0.5 * (mF[r[1]] - mF[r[2]]) + a2 * 0.5 * (mF[r[3]] - mF[r[4]]) + a3 * 0.5 * (mF[r[5]] - mF[r[6]]);
                 CR = gC + c1 * 0.5 * (mC[r[0]] + mC[r[1]] - mC[r[2]] - mC[r[3]]);
                 break;
             case 8:
-                a1 = normal01(rs); a2 = normal01(rs); c1 = normal01(rs); c2 = normal01(rs);
+                a1 = normal01_from(rs); a2 = normal01_from(rs); c1 = normal01_from(rs); c2 = normal01_from(rs);
                 F = mF[r[0]] + a1 * 0.5 * (mF[r[1]] - mF[i]) + a2 * 0.5 * (mF[r[3]] - mF[r[4]]);
                 CR = mC[r[0]] + c1 * 0.5 * (mC[r[1]] - mC[i]) + c2 * 0.5 * (mC[r[3]] - mC[r[4]]);
                 break;
             default:
-                a1 = normal01(rs); a2 = normal01(rs); c1 = normal01(rs); c2 = normal01(rs);
+                a1 = normal01_from(rs); a2 = normal01_from(rs); c1 = normal01_from(rs); c2 = normal01_from(rs);
                 F = mF[r[0]] + a1 * 0.5 * (mF[r[1]] - mF[i]) - a2 * 0.5 * (mF[r[2]] - gF);
                 CR = mC[r[0]] + c1 * 0.5 * (mC[r[1]] - mC[i]) - c2 * 0.5 * (mC[r[3]] - gC);
         }
     }
+    H.F = F;
+    H.CR = CR;
+    H.variant = variant;
+    H.base = base;
+    H.expo = expo;
+    return H;
+}
+
+// one thread per individual (large populations: every thread has its own long dependent chain, the SMs are full anyway)
+__global__ void de_trial_kernel(const TrialParams P)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.NP || *P.stopped) return;
+    const unsigned dim = P.dim;
+    PhiloxStream rs(P.seed, kTagDe, *P.gen_base + *P.gens_done, i);
+    const TrialHead H = trial_head(P, i, rs);
+    const unsigned *r = H.r;
+    const double F = H.F, CR = H.CR;
+    const unsigned base = H.base;
+    const bool expo = H.expo;
 
     const double *xi = P.popold + static_cast<size_t>(i) * dim;
     double *tmp = P.trial + static_cast<size_t>(i) * dim;
@@ -217,10 +264,104 @@ __global__ void de_trial_kernel(const TrialParams P)
         }
     }
     if (P.F_out) {
-        P.F_out[i] = F;
-        P.CR_out[i] = CR;
+        P.F_out[i] = H.F;
+        P.CR_out[i] = H.CR;
     }
-    if (P.variant_out) P.variant_out[i] = variant;
+    if (P.variant_out) P.variant_out[i] = H.variant;
+}
+
+// ---- one WARP per individual (launch-bound populations): the same trial vector, bit for bit, with the substream read by
+// position instead of in sequence.  Draw k of a Philox substream is addressable (block k / 2, half k % 2), so
+//   - the lanes compute draws 0..31 in one go and the scalar prelude reads them by shuffle (it needs at most 21);
+//   - binomial crossover: the draw of the L-th visited gene is draw c0 + L, one lane per gene;
+//   - exponential crossover: the run length is the first L >= 1 with draw c0 + L - 1 >= CR (a ballot), capped at dim;
+//   - feasibility: the out-of-bounds genes take the draws after the crossover in gene order (ballot + popc prefix).
+__device__ __forceinline__ double philox_draw_at(unsigned long long seed, unsigned generation, unsigned index, unsigned k)
+{
+    const Philox4 r = philox4x32_10(k >> 1, index, generation, kTagDe, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    const uint64_t bits = (k & 1u) ? ((static_cast<uint64_t>(r.v[3]) << 32) | r.v[2]) : ((static_cast<uint64_t>(r.v[1]) << 32) | r.v[0]);
+    return static_cast<double>(bits >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct WarpDraws { // the substream as the prelude sees it: draws 0..31 live one per lane
+    double mine;
+    unsigned long long seed;
+    unsigned generation, index, slot;
+    __device__ __forceinline__ double next()
+    {
+        const unsigned k = slot++;
+        if (k < 32u) return __shfl_sync(0xffffffffu, mine, static_cast<int>(k)); // k is warp-uniform
+        return philox_draw_at(seed, generation, index, k);
+    }
+};
+
+constexpr unsigned kTrialWarps = 8;
+
+__global__ void __launch_bounds__(kTrialWarps * 32) de_trial_warp_kernel(const TrialParams P)
+{
+    const unsigned i = blockIdx.x * kTrialWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (i >= P.NP || *P.stopped) return; // warp-uniform
+    const unsigned dim = P.dim, generation = *P.gen_base + *P.gens_done;
+    WarpDraws rs{philox_draw_at(P.seed, generation, i, lane), P.seed, generation, i, 0u};
+    const TrialHead H = trial_head(P, i, rs);
+    const unsigned n0 = uint_below_from(rs, dim); // c_idx(m_e)
+    const unsigned c0 = rs.slot;                  // first crossover draw
+    unsigned run = 0;                             // exponential: genes n0 .. n0 + run - 1 (mod dim) are mutated
+    unsigned used;                                // crossover draws consumed
+    if (H.expo) {
+        // do { mutate; ++L; } while (draw < CR && L < dim): iteration L = 1, 2, ... consumes draw c0 + L - 1 and is the last one
+        // when that draw is >= CR or L == dim
+        run = dim;
+        for (unsigned b = 0; b < dim; b += 32u) {
+            const unsigned L = b + lane + 1u;
+            const bool stop = L <= dim && (L == dim || !(philox_draw_at(P.seed, generation, i, c0 + L - 1u) < H.CR));
+            const unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (m) {
+                run = b + static_cast<unsigned>(__ffs(static_cast<int>(m)));
+                break;
+            }
+        }
+        used = run;
+    } else {
+        used = dim;
+    }
+    const double *xi = P.popold + static_cast<size_t>(i) * dim;
+    double *tmp = P.trial + static_cast<size_t>(i) * dim;
+    unsigned resampled = 0; // out-of-bounds genes before this chunk
+    for (unsigned b = 0; b < dim; b += 32u) {
+        const unsigned j = b + lane;
+        bool oob = false;
+        double v = 0.0, lo = 0.0, hi = 0.0;
+        if (j < dim) {
+            const unsigned L = j >= n0 ? j - n0 : j + dim - n0; // position of gene j in the visiting order n0, n0 + 1, ...
+            const bool take = H.expo ? (L < run) : (L + 1u == dim || philox_draw_at(P.seed, generation, i, c0 + L) < H.CR);
+            v = xi[j];
+            if (take) {
+                double p[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) p[k] = P.popold[static_cast<size_t>(H.r[k]) * dim + j];
+                v = mutate(P.cfg.algo, H.base, v, P.gbIter[j], p, v, H.F);
+            }
+            lo = P.lb[j];
+            hi = P.ub[j];
+            oob = (v < lo) || (v > hi);
+        }
+        // feasibility: out-of-bounds genes are resampled uniformly, de1220.cpp:507-513 / force_bounds_random generic.hpp:403-412
+        const unsigned m = __ballot_sync(0xffffffffu, oob && lo != hi);
+        if (oob) { // (a gene with lb == ub is reset without a draw)
+            const unsigned k = c0 + used + resampled + static_cast<unsigned>(__popc(m & ((1u << lane) - 1u)));
+            v = (lo == hi) ? lo : (hi - lo) * philox_draw_at(P.seed, generation, i, k) + lo;
+        }
+        resampled += static_cast<unsigned>(__popc(m));
+        if (j < dim) tmp[j] = v;
+    }
+    if (lane == 0) {
+        if (P.F_out) {
+            P.F_out[i] = H.F;
+            P.CR_out[i] = H.CR;
+        }
+        if (P.variant_out) P.variant_out[i] = H.variant;
+    }
 }
 
 // selection, de.cpp:281-299 / de1220.cpp:515-536: one warp per individual - lane 0 decides, the lanes copy the accepted trial
@@ -283,6 +424,7 @@ struct DeGlobal { // device-side global best + exit-condition data
     double dx, df;
     unsigned stopped;   // set when dx < xtol or df < ftol (de.cpp:302-321): later generations already queued become no-ops
     unsigned gens_done;
+    unsigned gen_base;  // generation counter of the first generation of this evolve() call (the Philox substream index)
 };
 
 struct DePartial { // per-CTA result of the scan below (large populations: de_global_partial_kernel)
@@ -325,7 +467,7 @@ __global__ void de_global_partial_kernel(const double *f, const unsigned char *a
 // plus pop.best_idx() / worst_idx() (first min / first max) and the exit quantities dx, df (de.cpp:302-316).  Single CTA.
 __global__ void de_global_kernel(const double *x, const double *f, const unsigned char *accepted, unsigned NP, unsigned dim,
                                  const double *F, const double *CR, const unsigned *variant, double *gbX, DeGlobal *G, int init, double xtol,
-                                 double ftol, const DePartial *partials, unsigned nparts)
+                                 double ftol, const DePartial *partials, unsigned nparts, unsigned first_generation)
 {
     __shared__ double sfa[256], sfb[256], sfw[256];
     __shared__ unsigned sia[256], sib[256], siw[256];
@@ -334,6 +476,7 @@ __global__ void de_global_kernel(const double *x, const double *f, const unsigne
     if (init && t == 0) {
         G->stopped = 0;
         G->gens_done = 0;
+        G->gen_base = first_generation;
     }
     const unsigned kNone = 0xffffffffu;
     double fa = 0, fb = 0, fw = 0;
@@ -403,6 +546,156 @@ __global__ void de_global_kernel(const double *x, const double *f, const unsigne
     }
 }
 
+// ---- launch-bound populations (NP < 16384): selection + global best + exit quantities in ONE launch ------------------------
+// Same rules as de_select_kernel followed by de_global_kernel: the trial replaces its parent when ftrial <= f; best = first
+// minimum, worst = first maximum, accepted-best = LAST minimum among the accepted trials; gb moves when that one is <= gbfit.
+// A warp per individual does the selection (8 per CTA); every CTA leaves its candidates in `parts`, and the CTA that finishes
+// last (ticket counter) combines them and updates the global state - no second launch, no single-CTA copy of the population.
+constexpr unsigned kFinishWarps = 8;
+constexpr unsigned kFinishMaxNP = 16384;
+
+struct ArgVal {
+    double v;
+    unsigned i;
+};
+
+// MODE 0: smaller value wins, ties -> smaller index; 1: larger value wins, ties -> smaller index; 2: smaller value wins, ties -> larger index
+template <int MODE> __device__ __forceinline__ ArgVal arg_combine(ArgVal a, ArgVal b)
+{
+    const unsigned kNone = 0xffffffffu;
+    if (b.i == kNone) return a;
+    if (a.i == kNone) return b;
+    const bool better = MODE == 1 ? b.v > a.v : b.v < a.v;
+    const bool tie = b.v == a.v && (MODE == 2 ? b.i > a.i : b.i < a.i);
+    return (better || tie) ? b : a;
+}
+
+template <int MODE> __device__ __forceinline__ ArgVal arg_reduce_warp(ArgVal a)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        ArgVal o;
+        o.v = __shfl_xor_sync(0xffffffffu, a.v, m);
+        o.i = __shfl_xor_sync(0xffffffffu, a.i, m);
+        a = arg_combine<MODE>(a, o);
+    }
+    return a;
+}
+
+__global__ void __launch_bounds__(kFinishWarps * 32) de_finish_kernel(const double *__restrict__ trial, const double *__restrict__ ftrial,
+                                                                      double *x, double *f, unsigned NP, unsigned dim, const double *F_try,
+                                                                      const double *CR_try, const unsigned *var_try, double *F, double *CR,
+                                                                      unsigned *variant, double *gbX, DeGlobal *G, double xtol, double ftol,
+                                                                      DePartial *parts, unsigned *ticket)
+{
+    __shared__ ArgVal s_best[kFinishWarps], s_worst[kFinishWarps], s_acc[kFinishWarps];
+    __shared__ double s_diff[kFinishWarps * 32];
+    __shared__ bool s_last;
+    const unsigned t = threadIdx.x, warp = t >> 5, lane = t & 31u, kNone = 0xffffffffu;
+    if (G->stopped) return; // uniform over the grid: written only by the last CTA of an earlier launch
+    const unsigned i = blockIdx.x * kFinishWarps + warp;
+    ArgVal best{0.0, kNone}, worst{0.0, kNone}, acc{0.0, kNone};
+    if (i < NP) { // selection, de.cpp:281-299 / de1220.cpp:515-536
+        const double ft = ftrial[i];
+        double v = f[i];
+        const bool ok = ft <= v;
+        if (ok) {
+            const double *src = trial + static_cast<size_t>(i) * dim;
+            double *dst = x + static_cast<size_t>(i) * dim;
+            for (unsigned d = lane; d < dim; d += 32u) dst[d] = src[d];
+            v = ft;
+            if (lane == 0) {
+                f[i] = ft;
+                if (F) {
+                    F[i] = F_try[i];
+                    CR[i] = CR_try[i];
+                }
+                if (variant) variant[i] = var_try[i];
+            }
+            acc = ArgVal{v, i};
+        }
+        best = worst = ArgVal{v, i};
+    }
+    if (lane == 0) {
+        s_best[warp] = best;
+        s_worst[warp] = worst;
+        s_acc[warp] = acc;
+    }
+    __syncthreads();
+    if (t == 0) {
+        for (unsigned w = 1; w < kFinishWarps; ++w) {
+            best = arg_combine<0>(best, s_best[w]);
+            worst = arg_combine<1>(worst, s_worst[w]);
+            acc = arg_combine<2>(acc, s_acc[w]);
+        }
+        parts[blockIdx.x] = DePartial{acc.v, best.v, worst.v, acc.i, best.i, worst.i};
+        __threadfence(); // this CTA's rows, fitness and candidates are visible before its ticket is
+        s_last = atomicAdd(ticket, 1u) + 1u == gridDim.x;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- the last CTA: every other CTA's writes are visible (read through L2: this SM's L1 never held those lines)
+    best = worst = acc = ArgVal{0.0, kNone};
+    for (unsigned k = t; k < gridDim.x; k += blockDim.x) {
+        const DePartial *q = parts + k;
+        best = arg_combine<0>(best, ArgVal{__ldcg(&q->fb), __ldcg(&q->ib)});
+        worst = arg_combine<1>(worst, ArgVal{__ldcg(&q->fw), __ldcg(&q->iw)});
+        acc = arg_combine<2>(acc, ArgVal{__ldcg(&q->fa), __ldcg(&q->ia)});
+    }
+    best = arg_reduce_warp<0>(best);
+    worst = arg_reduce_warp<1>(worst);
+    acc = arg_reduce_warp<2>(acc);
+    if (lane == 0) {
+        s_best[warp] = best;
+        s_worst[warp] = worst;
+        s_acc[warp] = acc;
+    }
+    __syncthreads();
+    best = s_best[0];
+    worst = s_worst[0];
+    acc = s_acc[0];
+    for (unsigned w = 1; w < kFinishWarps; ++w) {
+        best = arg_combine<0>(best, s_best[w]);
+        worst = arg_combine<1>(worst, s_worst[w]);
+        acc = arg_combine<2>(acc, s_acc[w]);
+    }
+    const bool moved = acc.i != kNone && acc.v <= G->gbfit; // every thread reads the old G before thread 0 writes it
+    const unsigned gi = moved ? acc.i : G->gbidx;
+    __syncthreads();
+    if (t == 0) {
+        G->best_idx = best.i;
+        G->worst_idx = worst.i;
+        if (moved) {
+            G->gbidx = gi;
+            G->gbfit = acc.v;
+            if (F) {
+                G->gbF = __ldcg(F + gi);
+                G->gbCR = __ldcg(CR + gi);
+            }
+            if (variant) G->gbvariant = __ldcg(variant + gi);
+        }
+        G->df = fabs(worst.v - best.v);
+        *ticket = 0u;
+    }
+    // gbX <- x[gbidx] (see de_global_kernel); dx = sum_d |x_worst[d] - x_best[d]| in ascending d (de.cpp:302-306)
+    for (unsigned d = t; d < dim; d += blockDim.x) gbX[d] = __ldcg(x + static_cast<size_t>(gi) * dim + d);
+    double dx = 0.0;
+    for (unsigned d0 = 0; d0 < dim; d0 += blockDim.x) {
+        const unsigned d = d0 + t;
+        if (d < dim) s_diff[t] = fabs(__ldcg(x + static_cast<size_t>(worst.i) * dim + d) - __ldcg(x + static_cast<size_t>(best.i) * dim + d));
+        __syncthreads();
+        if (t == 0)
+            for (unsigned k = 0; k < min(blockDim.x, dim - d0); ++k) dx += s_diff[k];
+        __syncthreads();
+    }
+    if (t == 0) {
+        G->dx = dx;
+        G->gens_done += 1;
+        if (dx < xtol || G->df < ftol) G->stopped = 1; // de.cpp:308,316
+    }
+}
+
 __global__ void de_init_adapt_kernel(double *F, double *CR, unsigned *variant, unsigned NP, DeConfig cfg, unsigned long long seed,
                                      unsigned generation)
 { // de1220.cpp:147-165 / sade.cpp:137-156
@@ -424,6 +717,104 @@ __global__ void de_init_adapt_kernel(double *F, double *CR, unsigned *variant, u
 }
 
 inline unsigned nblk(size_t n, unsigned t) { return static_cast<unsigned>((n + t - 1) / t); }
+
+// ---- cached workspace + generation graph ---------------------------------------------------------------------------------
+constexpr size_t kMaxWorkspaces = 4;            // per problem handle
+constexpr unsigned kGraphMaxGenerations = 128;  // generations recorded into one graph
+constexpr unsigned kGraphMaxPopulation = 65536; // larger populations are kernel-bound, not launch-bound
+
+bool graphs_enabled()
+{
+    const char *e = std::getenv("PGC_GRAPHS"); // PGC_GRAPHS=0: plain launches only (tests compare the two paths)
+    return !(e && e[0] == '0');
+}
+
+struct DeKey {
+    unsigned NP, dim;
+    DeConfig cfg;
+    const void *d_x, *d_f, *d_F, *d_CR, *d_variant, *eval;
+    unsigned long long seed;
+    double xtol, ftol;
+    unsigned config_epoch;
+    bool operator==(const DeKey &o) const
+    {
+        bool same = NP == o.NP && dim == o.dim && cfg.algo == o.cfg.algo && cfg.variant == o.cfg.variant
+                    && cfg.variant_adptv == o.cfg.variant_adptv && cfg.F == o.cfg.F && cfg.CR == o.cfg.CR && cfg.n_allowed == o.cfg.n_allowed
+                    && d_x == o.d_x && d_f == o.d_f && d_F == o.d_F && d_CR == o.d_CR && d_variant == o.d_variant && eval == o.eval
+                    && seed == o.seed && xtol == o.xtol && ftol == o.ftol && config_epoch == o.config_epoch;
+        for (unsigned k = 0; same && k < cfg.n_allowed; ++k) same = cfg.allowed[k] == o.cfg.allowed[k];
+        return same;
+    }
+};
+
+struct DeWork : LoopWorkspace {
+    DeKey key{};
+    int device = 0;
+    double *trial = nullptr, *ftrial = nullptr, *gbX = nullptr, *lb = nullptr, *ub = nullptr, *Ftry = nullptr, *CRtry = nullptr, *Fs = nullptr,
+           *CRs = nullptr;
+    unsigned *vars = nullptr, *vtry = nullptr;
+    unsigned char *accepted = nullptr;
+    DeGlobal *G = nullptr;
+    DePartial *parts = nullptr;
+    unsigned *ticket = nullptr; // de_finish_kernel: CTAs done in the current launch
+    unsigned nparts = 0;
+    std::vector<void *> owned;
+    cudaGraphExec_t exec = nullptr;
+    unsigned graph_gens = 0, graph_launches = 0;
+    bool no_graph = false;
+    const void *scratch_at_capture = nullptr;
+    size_t scratch_bytes_at_capture = 0;
+
+    template <class T>
+    int get(T **out, size_t bytes)
+    {
+        void *p = nullptr;
+        PGC_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        owned.push_back(p);
+        *out = static_cast<T *>(p);
+        return PGC_OK;
+    }
+    int allocate(pgc_problem *prob, unsigned algo)
+    {
+        device = prob->ctx->device;
+        const unsigned NP = key.NP, dim = key.dim;
+        const size_t nd = static_cast<size_t>(NP) * dim;
+        int rc;
+        if ((rc = get(&trial, 8 * nd)) || (rc = get(&ftrial, 8 * NP)) || (rc = get(&gbX, 8 * dim)) || (rc = get(&lb, 8 * dim))
+            || (rc = get(&ub, 8 * dim)) || (rc = get(&accepted, NP)) || (rc = get(&G, sizeof(DeGlobal))))
+            return rc;
+        PGC_CUDA(cudaMemcpy(lb, prob->lb.data(), 8 * dim, cudaMemcpyHostToDevice));
+        PGC_CUDA(cudaMemcpy(ub, prob->ub.data(), 8 * dim, cudaMemcpyHostToDevice));
+        if (algo != 0u) {
+            if ((rc = get(&Ftry, 8 * NP)) || (rc = get(&CRtry, 8 * NP))) return rc;
+            if (algo == 2u && (rc = get(&vtry, 4 * NP))) return rc;
+            if (!key.d_F && (rc = get(&Fs, 8 * NP))) return rc;
+            if (!key.d_CR && (rc = get(&CRs, 8 * NP))) return rc;
+            if (algo == 2u && !key.d_variant && (rc = get(&vars, 4 * NP))) return rc;
+        }
+        // large populations: the fitness scan of the global-best kernel is spread over `nparts` CTAs
+        nparts = NP >= kFinishMaxNP ? std::min(1024u, NP / 4096u) : 0u;
+        if ((rc = get(&parts, sizeof(DePartial) * (nparts ? nparts : nblk(NP, kFinishWarps))))) return rc;
+        if ((rc = get(&ticket, sizeof(unsigned)))) return rc;
+        PGC_CUDA(cudaMemset(ticket, 0, sizeof(unsigned)));
+        return PGC_OK;
+    }
+    void drop_graph()
+    {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr;
+        graph_gens = graph_launches = 0;
+    }
+    ~DeWork() override
+    {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(device);
+        drop_graph();
+        for (void *p : owned) cudaFree(p);
+        cudaSetDevice(cur);
+    }
+};
 
 } // namespace
 
@@ -464,84 +855,150 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
             cfg.n_allowed = n_allowed;
         }
     }
-    struct Buf {
-        cudaStream_t st;
-        std::vector<void *> owned;
-        ~Buf()
-        {
-            for (void *p : owned) cudaFreeAsync(p, st);
+    // ---- workspace: scratch buffers (and, from the second call on, the instantiated graph of a batch of generations) cached on the
+    // problem handle, keyed on everything a launch parameter is derived from
+    DeKey key{};
+    key.NP = NP;
+    key.dim = dim;
+    key.cfg = cfg;
+    key.d_x = d_x;
+    key.d_f = d_f;
+    key.d_F = d_F;
+    key.d_CR = d_CR;
+    key.d_variant = d_variant;
+    key.eval = reinterpret_cast<const void *>(eval);
+    key.seed = seed;
+    key.xtol = xtol;
+    key.ftol = ftol;
+    key.config_epoch = prob->config_epoch;
+    DeWork *W = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(prob->work_mu);
+        for (auto &w : prob->work) {
+            auto *dw = dynamic_cast<DeWork *>(w.get());
+            if (dw && dw->key == key) W = dw;
         }
-        int get(void **out, size_t bytes)
-        {
-            PGC_CUDA(cudaMallocAsync(out, bytes ? bytes : 1, st));
-            owned.push_back(*out);
-            return PGC_OK;
+        if (!W) {
+            if (prob->work.size() >= kMaxWorkspaces) { // evict the least recently used one (its population is gone or idle)
+                if (int rc = ctx_sync(ctx)) return rc;
+                PGC_CUDA(cudaStreamSynchronize(st));
+                auto lru = std::min_element(prob->work.begin(), prob->work.end(),
+                                            [](const auto &a, const auto &b) { return a->last_use < b->last_use; });
+                prob->work.erase(lru);
+            }
+            auto fresh_ws = std::make_unique<DeWork>();
+            fresh_ws->key = key;
+            int rc = fresh_ws->allocate(prob, algo);
+            if (rc != PGC_OK) return rc;
+            W = fresh_ws.get();
+            prob->work.push_back(std::move(fresh_ws));
         }
-    } buf{st, {}};
-    const size_t nd = static_cast<size_t>(NP) * dim;
-    double *trial, *ftrial, *gbX, *lb, *ub, *Fs = d_F, *CRs = d_CR, *Ftry = nullptr, *CRtry = nullptr;
-    unsigned *vars = d_variant, *vtry = nullptr;
-    unsigned char *accepted;
-    DeGlobal *G;
-    int rc;
-    if ((rc = buf.get(reinterpret_cast<void **>(&trial), 8 * nd)) || (rc = buf.get(reinterpret_cast<void **>(&ftrial), 8 * NP))
-        || (rc = buf.get(reinterpret_cast<void **>(&gbX), 8 * dim)) || (rc = buf.get(reinterpret_cast<void **>(&lb), 8 * dim))
-        || (rc = buf.get(reinterpret_cast<void **>(&ub), 8 * dim)) || (rc = buf.get(reinterpret_cast<void **>(&accepted), NP))
-        || (rc = buf.get(reinterpret_cast<void **>(&G), sizeof(DeGlobal))))
-        return rc;
-    PGC_CUDA(cudaMemcpyAsync(lb, prob->lb.data(), 8 * dim, cudaMemcpyHostToDevice, st));
-    PGC_CUDA(cudaMemcpyAsync(ub, prob->ub.data(), 8 * dim, cudaMemcpyHostToDevice, st));
-    if (algo != 0u) {
-        const bool fresh = !(d_F && d_CR && (algo == 1u || d_variant));
-        if ((rc = buf.get(reinterpret_cast<void **>(&Ftry), 8 * NP)) || (rc = buf.get(reinterpret_cast<void **>(&CRtry), 8 * NP))) return rc;
-        if (algo == 2u && (rc = buf.get(reinterpret_cast<void **>(&vtry), 4 * NP))) return rc;
-        if (fresh) {
-            if (!Fs && (rc = buf.get(reinterpret_cast<void **>(&Fs), 8 * NP))) return rc;
-            if (!CRs && (rc = buf.get(reinterpret_cast<void **>(&CRs), 8 * NP))) return rc;
-            if (algo == 2u && !vars && (rc = buf.get(reinterpret_cast<void **>(&vars), 4 * NP))) return rc;
-            de_init_adapt_kernel<<<nblk(NP, 128), 128, 0, st>>>(Fs, CRs, algo == 2u ? vars : nullptr, NP, cfg, seed, first_generation);
-        }
+        W->last_use = ++prob->work_clock;
     }
-    // large populations: the fitness scan of the global-best kernel is spread over `nparts` CTAs
-    const unsigned nparts = NP >= 16384u ? std::min(1024u, NP / 4096u) : 0u;
-    DePartial *parts = nullptr;
-    if (nparts && (rc = buf.get(reinterpret_cast<void **>(&parts), sizeof(DePartial) * nparts))) return rc;
+    double *trial = W->trial, *ftrial = W->ftrial, *gbX = W->gbX, *lb = W->lb, *ub = W->ub, *Ftry = W->Ftry, *CRtry = W->CRtry;
+    double *Fs = d_F ? d_F : W->Fs, *CRs = d_CR ? d_CR : W->CRs;
+    unsigned *vars = d_variant ? d_variant : W->vars, *vtry = W->vtry;
+    unsigned char *accepted = W->accepted;
+    DeGlobal *G = W->G;
+    DePartial *parts = W->parts;
+    const unsigned nparts = W->nparts;
+    const size_t nd = static_cast<size_t>(NP) * dim;
+    if (algo != 0u && !(d_F && d_CR && (algo == 1u || d_variant))) // no memory: initialise as the reference does at every evolve()
+        de_init_adapt_kernel<<<nblk(NP, 128), 128, 0, st>>>(Fs, CRs, algo == 2u ? vars : nullptr, NP, cfg, seed, first_generation);
     if (nparts) de_global_partial_kernel<<<nparts, 256, 0, st>>>(d_f, nullptr, NP, 1, &G->stopped, parts);
-    de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, nullptr, NP, dim, Fs, CRs, algo == 2u ? vars : nullptr, gbX, G, 1, xtol, ftol, parts, nparts);
+    de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, nullptr, NP, dim, Fs, CRs, algo == 2u ? vars : nullptr, gbX, G, 1, xtol, ftol,
+                                        nparts ? parts : nullptr, nparts, first_generation);
+    // one generation: no launch parameter depends on the generation index (the kernels read it from G), so the same launches can
+    // be replayed from a graph
+    auto generation = [&]() -> int {
+        TrialParams tp{d_x, gbX, lb, ub, Fs, CRs, algo == 2u ? vars : nullptr, &G->gbF, &G->gbCR, &G->stopped, trial, Ftry, CRtry, vtry, NP, dim,
+                       seed, &G->gen_base, &G->gens_done, cfg};
+        // launch-bound populations and long rows: a warp per individual (coalesced rows, substream read by position)
+        if (dim >= 16u || NP < 65536u) de_trial_warp_kernel<<<nblk(NP, kTrialWarps), kTrialWarps * 32, 0, st>>>(tp);
+        else de_trial_kernel<<<nblk(NP, 64), 64, 0, st>>>(tp);
+        if (int rc = eval(prob, trial, NP, ftrial, st)) return rc;
+        unsigned launched = 2;
+        if (!nparts) { // NP < 16384: selection, global best and exit quantities in one launch
+            de_finish_kernel<<<nblk(NP, kFinishWarps), kFinishWarps * 32, 0, st>>>(trial, ftrial, d_x, d_f, NP, dim, Ftry, CRtry, vtry,
+                                                                                   algo ? Fs : nullptr, algo ? CRs : nullptr,
+                                                                                   algo == 2u ? vars : nullptr, gbX, G, xtol, ftol, parts,
+                                                                                   W->ticket);
+        } else {
+            if (dim < 32u) { // large population of short rows: element-parallel selection
+                de_accept_kernel<<<nblk(NP, 256), 256, 0, st>>>(ftrial, d_f, NP, accepted, Ftry, CRtry, vtry, algo ? Fs : nullptr,
+                                                                algo ? CRs : nullptr, algo == 2u ? vars : nullptr, &G->stopped);
+                de_copy_accepted_kernel<<<nblk(nd, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, accepted, NP, dim, &G->stopped);
+                ++launched;
+            } else {
+                de_select_kernel<<<nblk(static_cast<size_t>(NP) * 32, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, NP, dim, accepted, Ftry, CRtry,
+                                                                                          vtry, algo ? Fs : nullptr, algo ? CRs : nullptr,
+                                                                                          algo == 2u ? vars : nullptr, &G->stopped);
+            }
+            de_global_partial_kernel<<<nparts, 256, 0, st>>>(d_f, accepted, NP, 0, &G->stopped, parts);
+            de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, accepted, NP, dim, algo ? Fs : nullptr, algo ? CRs : nullptr,
+                                                algo == 2u ? vars : nullptr, gbX, G, 0, xtol, ftol, parts, nparts, 0u);
+            launched += 2;
+        }
+        ctx->launches.fetch_add(launched, std::memory_order_relaxed);
+        return PGC_OK;
+    };
     // The exit conditions live on the device (DeGlobal::stopped): once one fires, the generations already queued return
     // immediately, and the host only looks every kPoll generations - a sync per generation made small populations
     // latency-bound on the host round trip.
     constexpr unsigned kPoll = 16;
-    unsigned done = 0;
+    unsigned done = 0, g = 0;
     DeGlobal h{};
-    for (unsigned g = 0; g < gens; ++g) {
-        TrialParams tp{d_x, gbX, lb, ub, Fs, CRs, algo == 2u ? vars : nullptr, &G->gbF, &G->gbCR, &G->stopped, trial, Ftry, CRtry, vtry, NP, dim,
-                       seed, first_generation + g, cfg};
-        de_trial_kernel<<<nblk(NP, 64), 64, 0, st>>>(tp);
-        if ((rc = eval(prob, trial, NP, ftrial, st))) return rc;
-        if (nparts && dim < 32u) { // large population of short rows: element-parallel selection
-            de_accept_kernel<<<nblk(NP, 256), 256, 0, st>>>(ftrial, d_f, NP, accepted, Ftry, CRtry, vtry, algo ? Fs : nullptr, algo ? CRs : nullptr,
-                                                            algo == 2u ? vars : nullptr, &G->stopped);
-            de_copy_accepted_kernel<<<nblk(nd, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, accepted, NP, dim, &G->stopped);
-        } else {
-            de_select_kernel<<<nblk(static_cast<size_t>(NP) * 32, 256), 256, 0, st>>>(trial, ftrial, d_x, d_f, NP, dim, accepted, Ftry, CRtry, vtry,
-                                                                                      algo ? Fs : nullptr, algo ? CRs : nullptr,
-                                                                                      algo == 2u ? vars : nullptr, &G->stopped);
-        }
-        if (nparts) de_global_partial_kernel<<<nparts, 256, 0, st>>>(d_f, accepted, NP, 0, &G->stopped, parts);
-        de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, accepted, NP, dim, algo ? Fs : nullptr, algo ? CRs : nullptr, algo == 2u ? vars : nullptr,
-                                            gbX, G, 0, xtol, ftol, parts, nparts);
-        ctx->launches.fetch_add(3, std::memory_order_relaxed);
+    int rc = PGC_OK;
+    // (a) replay the cached graph while whole batches remain.  Launch-bound populations only: the graph removes the per-launch
+    // host cost and the gaps between dependent kernels, which is all a generation of a small population consists of.
+    const bool scratch_same = W->scratch_at_capture == ctx->scratch && W->scratch_bytes_at_capture == ctx->scratch_bytes;
+    if (W->exec && !scratch_same) W->drop_graph();
+    while (W->exec && !h.stopped && gens - g >= W->graph_gens) {
+        PGC_CUDA(cudaGraphLaunch(W->exec, st));
+        ctx->launches.fetch_add(W->graph_launches, std::memory_order_relaxed);
+        g += W->graph_gens;
+        PGC_CUDA(cudaMemcpyAsync(&h, G, sizeof(DeGlobal), cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        done = h.gens_done;
+    }
+    // (b) plain launches for the rest (and for the whole first call on a new workspace)
+    for (; g < gens && !h.stopped; ++g) {
+        if ((rc = generation())) return rc;
         if ((g + 1) % kPoll == 0 || g + 1 == gens) {
             PGC_CUDA(cudaMemcpyAsync(&h, G, sizeof(DeGlobal), cudaMemcpyDeviceToHost, st));
             PGC_CUDA(cudaStreamSynchronize(st));
             done = h.gens_done;
-            if (h.stopped) break;
         }
     }
     if (gens_done) *gens_done = done;
     PGC_CUDA(cudaGetLastError());
     PGC_CUDA(cudaStreamSynchronize(st));
+    // (c) first call on this workspace: record a batch of generations for the next call.  Every buffer the launches touch is now
+    // allocated (the evaluators size the context's scratch area on first use), so the capture sees no allocation.
+    if (!W->exec && !W->no_graph && graphs_enabled() && NP <= kGraphMaxPopulation) {
+        const unsigned batch = std::min(gens, kGraphMaxGenerations);
+        const unsigned long long l0 = ctx->launches.load(std::memory_order_relaxed);
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+        if (ok) {
+            for (unsigned b = 0; b < batch && ok; ++b) ok = generation() == PGC_OK;
+            ok = (cudaStreamEndCapture(st, &graph) == cudaSuccess) && ok && graph;
+        }
+        const unsigned long long recorded = ctx->launches.load(std::memory_order_relaxed) - l0;
+        ctx->launches.fetch_sub(recorded, std::memory_order_relaxed); // recorded, not run
+        if (ok) ok = cudaGraphInstantiate(&W->exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        if (ok) {
+            W->graph_gens = batch;
+            W->graph_launches = static_cast<unsigned>(recorded);
+            W->scratch_at_capture = ctx->scratch;
+            W->scratch_bytes_at_capture = ctx->scratch_bytes;
+        } else {
+            (void)cudaGetLastError(); // an evaluator that cannot be captured keeps the plain path
+            W->exec = nullptr;
+            W->no_graph = true;
+        }
+    }
     return PGC_OK;
 }
 

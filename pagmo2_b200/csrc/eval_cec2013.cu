@@ -86,6 +86,7 @@ struct Params13 {
     double weier_c0, kats_c0, kats_c1, bi_s, bi_mu1;
     int tell, tdif, tgri, twei;
     int strict; // rotations accumulate one product at a time in the reference's j order (pgc_problem_set_strict)
+    int ti;     // individuals per warp tile: 8, or 4 / 2 / 1 for island-sized batches (the other rows of the tile stay zero)
     Launch13 L;
 };
 
@@ -232,14 +233,16 @@ __device__ double reduce13(const Params13 &P, const Row &v, int h, const double 
 template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_kernel(const __grid_constant__ Params13 P)
 {
     constexpr int DP = pad8(D), KP = pad4(D), NT = DP / 8, YS = ystride(D);
-    constexpr int TILE = kTileInd * D;
+    // island-sized batches: fewer individuals per warp tile, so that the batch spreads over many warps - every phase of a tile is
+    // a dependent chain of one warp, and a row of the tile is computed independently of the other rows (same bits either way)
     const bool rot = P.L.rot >= 0;
     const int W = blockDim.x >> 5;
+    const int TI = P.ti, TILE = TI * D;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sMr = reinterpret_cast<double *>(smem_raw);
     double *sBuf = sMr + (rot ? DP * YS : 0);
-    double *sOs = sBuf + W * 2 * kTileInd * YS;
+    double *sOs = sBuf + W * 2 * TI * YS; // a warp's two buffers hold TI rows
     unsigned short *sList = reinterpret_cast<unsigned short *>(sOs + D); // [W][TILE]: positions of the positive inputs of asyfunc
 
     if (rot) {
@@ -247,18 +250,19 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
         double2 *dst = reinterpret_cast<double2 *>(sMr);
         for (int i = threadIdx.x; i < DP * YS / 2; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    for (int i = threadIdx.x; i < W * 2 * kTileInd * YS; i += blockDim.x) sBuf[i] = 0.0; // the inner-index padding stays 0
+    for (int i = threadIdx.x; i < W * 2 * TI * YS; i += blockDim.x) sBuf[i] = 0.0; // the inner-index padding stays 0
     for (int i = threadIdx.x; i < D; i += blockDim.x) sOs[i] = P.os[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *bufs[2] = {sBuf + warp * 2 * kTileInd * YS, sBuf + warp * 2 * kTileInd * YS + kTileInd * YS};
+    double *bufs[2] = {sBuf + warp * 2 * TI * YS, sBuf + warp * 2 * TI * YS + TI * YS};
     unsigned short *list = sList + warp * TILE;
-    const long long ntiles = (P.n + kTileInd - 1) / kTileInd;
+    const long long ntiles = (P.n + TI - 1) / TI;
     const int et = lane & (kTileInd - 1), eq = lane / kTileInd;
+    const int er = et < TI ? et : 0; // lanes of absent rows read row 0 and drop their result
     const double *tab = P.table;
 
-    if (rot && W > 4) { // spread the warps of an SM sub-partition over the phases (see eval_cec2014.cu)
+    if (rot && W > 4 && TI == kTileInd) { // spread the warps of an SM sub-partition over the phases (see eval_cec2014.cu)
         const long long wait = static_cast<long long>(warp >> 2) * (NT * (KP / 4) * 16);
         const long long t_start = clock64();
         while (clock64() - t_start < wait) {
@@ -266,8 +270,8 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
     }
 
     for (long long tile = static_cast<long long>(blockIdx.x) * W + warp; tile < ntiles; tile += static_cast<long long>(gridDim.x) * W) {
-        const long long t0 = tile * kTileInd;
-        const int nt = (P.n - t0 < kTileInd) ? static_cast<int>(P.n - t0) : kTileInd;
+        const long long t0 = tile * TI;
+        const int nt = (P.n - t0 < TI) ? static_cast<int>(P.n - t0) : TI;
         const int live = nt * D;
         double wacc = 0.0;
 
@@ -281,7 +285,7 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
                 }
                 __syncwarp();
                 if (P.L.want_w) { // cf_cal distance sum_j (x_j - Os_j)^2, :1101-1103
-                    const double *row = in + et * YS;
+                    const double *row = in + er * YS;
                     for (int j = eq; j < D; j += kLPI) wacc += row[j] * row[j];
                     wacc = pair_add(wacc);
                 }
@@ -370,7 +374,7 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
                     }
                     if (lane < 2 * kTileInd) {
                         const int t = lane & (kTileInd - 1), i = (lane < kTileInd) ? 0 : D - 1;
-                        const double v = in[t * YS + i];
+                        const double v = t < TI ? in[t * YS + i] : 0.0;
                         double r = 0.0; // v == 0: sx = 0 (the stale xx of the reference is finite, so 0 * exp(.) = 0)
                         if (v != 0) {
                             const double xx = log(fabs(v));
@@ -378,7 +382,7 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
                             r = exp(xx + 0.049 * (sin(c1 * xx) + sin(c2 * xx)));
                             r = v > 0 ? r : -r;
                         }
-                        if (lane < kTileInd || D > 1) out[t * YS + i] = r;
+                        if (t < TI && (lane < kTileInd || D > 1)) out[t * YS + i] = r;
                     }
                     break;
                 }
@@ -409,7 +413,7 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
                     double acc[NT][2];
 #pragma unroll
                     for (int nt2 = 0; nt2 < NT; ++nt2) acc[nt2][0] = acc[nt2][1] = 0.0;
-                    const double *ya = in + g * YS + j;
+                    const double *ya = in + (g < TI ? g : 0) * YS + j; // absent rows: any finite operand, result dropped
                     const double *mb = sMr + g * YS + j;
 #pragma unroll 2
                     for (int u = 0; u < KP / 4; ++u) {
@@ -424,8 +428,8 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
 #pragma unroll
                     for (int nt2 = 0; nt2 < NT; ++nt2) {
                         const int c = nt2 * 8 + 2 * j;
-                        if (c < D) out[g * YS + c] = acc[nt2][0];
-                        if (c + 1 < D) out[g * YS + c + 1] = acc[nt2][1];
+                        if (g < TI && c < D) out[g * YS + c] = acc[nt2][0];
+                        if (g < TI && c + 1 < D) out[g * YS + c + 1] = acc[nt2][1];
                     }
                     break;
                 }
@@ -442,7 +446,7 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
                 dst[e] = src[t * YS + i];
             }
         } else {
-            Row v{bufs[P.L.end_buf] + et * YS};
+            Row v{bufs[P.L.end_buf] + er * YS};
             const long long xr = (et < nt) ? t0 + et : t0;
             double val = reduce13<D>(P, v, eq, P.x + xr * D, sOs);
             if (eq == 0 && et < nt) {
@@ -506,18 +510,23 @@ template <int D> int launch13(pgc_ctx *ctx, const Params13 &pp, cudaStream_t str
         configured_dev = ctx->device;
     }
     const size_t fixed = sizeof(double) * ((pp.L.rot >= 0 ? DP * YS : 0) + D) + 16;
-    const size_t per_warp = sizeof(double) * 2 * kTileInd * YS + sizeof(unsigned short) * kTileInd * D;
+    // island-sized batches (~1000 individuals) are latency-bound: shrink the tile until there are ~4 warps per SM
+    int ti = kTileInd;
+    while (ti > 1 && (pp.n + ti - 1) / ti < static_cast<long long>(ctx->sm_count) * 4) ti >>= 1;
+    const size_t per_warp = (sizeof(double) * 2 * ti * YS + sizeof(unsigned short) * ti * D + 15) / 16 * 16;
     int fit = static_cast<int>((ctx->smem_optin - fixed) / per_warp);
     if (fit > kMaxWarps13) fit = kMaxWarps13;
     PGC_REQUIRE(fit >= 1, "cec2013: shared memory too small for dimension %d", D);
-    const long long ntiles = (pp.n + kTileInd - 1) / kTileInd;
+    const long long ntiles = (pp.n + ti - 1) / ti;
     // small batches: fewer warps per CTA so that the tiles cover the SMs
     long long w = (ntiles + ctx->sm_count - 1) / ctx->sm_count;
     if (w > fit) w = fit;
     if (w < 1) w = 1;
     long long ctas = (ntiles + w - 1) / w;
     if (ctas > ctx->sm_count) ctas = ctx->sm_count;
-    kern<<<static_cast<unsigned>(ctas), static_cast<unsigned>(w * 32), fixed + per_warp * w, stream>>>(pp);
+    Params13 launch_pp = pp;
+    launch_pp.ti = ti;
+    kern<<<static_cast<unsigned>(ctas), static_cast<unsigned>(w * 32), fixed + per_warp * w, stream>>>(launch_pp);
     PGC_CUDA(cudaGetLastError());
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     return PGC_OK;
@@ -792,6 +801,7 @@ int cec2013_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, c
         pp.tgri = pl.tgri;
         pp.twei = pl.twei;
         pp.strict = p->strict;
+        pp.ti = kTileInd; // launch13 picks the tile size from the batch size
         pp.L = L;
         int rc;
         switch (pl.dim) {

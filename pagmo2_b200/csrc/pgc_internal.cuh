@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -207,6 +208,16 @@ struct pgc_ctx {
     pgc::CopyPool *copy_pool = nullptr; // created on the first pageable pgc_eval_host call
 };
 
+namespace pgc
+{
+// A cached workspace of a generation loop bound to one population (de.cu: scratch buffers + the instantiated CUDA graph of a
+// batch of generations).  Owned by the problem handle; freed with it.
+struct LoopWorkspace {
+    virtual ~LoopWorkspace() = default;
+    unsigned long long last_use = 0;
+};
+} // namespace pgc
+
 struct pgc_problem {
     pgc_ctx *ctx = nullptr;
     pgc_problem_desc desc{}; // table pointers nulled after the copy
@@ -223,6 +234,10 @@ struct pgc_problem {
     pgc::Cec2013Plan *cec13 = nullptr;
     double flops_per_eval = 0, transc_per_eval = 0;
     int strict = 0; // pgc_problem_set_strict: reference summation order in the rotations (cec2013)
+    unsigned config_epoch = 0; // bumped by every setter that changes what the evaluation kernels are launched with
+    std::mutex work_mu;
+    std::vector<std::unique_ptr<pgc::LoopWorkspace>> work; // generation-loop workspaces, least recently used evicted (de.cu)
+    unsigned long long work_clock = 0;
     // meta-problems (meta.cu): the wrapped problem (borrowed), translation | weight+z on the device, decomposition method
     pgc_problem *inner = nullptr;
     double *d_meta = nullptr;
@@ -232,6 +247,7 @@ struct pgc_problem {
 namespace pgc
 {
 int ensure_scratch(pgc_ctx *ctx, size_t bytes);
+int ctx_sync(pgc_ctx *ctx); // the context's own streams (never the whole device: see capi.cu)
 // family back-ends: validate + upload tables (create) and launch (eval, asynchronous on `stream`)
 int simple_create(pgc_problem *p);
 int simple_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);

@@ -185,3 +185,17 @@ def test_cec2013_strict_mode_meets_the_tolerance_on_ill_conditioned_functions(ca
     other = capi.Problem(ctx, "rastrigin", dim=5)
     with pytest.raises(capi.PgcError):
         other.set_strict(True)
+
+
+@pytest.mark.parametrize("dim", (10, 50))
+def test_cec2013_value_does_not_depend_on_the_batch_size(capi, ctx, orc, dim):
+    """island-sized batches run with 1, 2 or 4 individuals per warp tile instead of 8 (launch13): an individual's fitness is the
+    same bits whatever batch it arrives in."""
+    rng = np.random.default_rng(77 + dim)
+    xs = rng.uniform(-100, 100, (5000, dim))
+    for func in (1, 7, 12, 15, 19, 23, 28):
+        prob = make13(capi, ctx, orc, func, dim)
+        full = prob.eval_host(xs)[:, 0]                      # 8 per tile
+        for n in (3000, 2000, 500, 7):                       # 4, 2, 1, 1 per tile
+            assert np.array_equal(prob.eval_host(xs[:n])[:, 0], full[:n]), (func, n)
+        prob.close()

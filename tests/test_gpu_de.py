@@ -74,3 +74,56 @@ def test_large_population_path_matches_oracle(capi, ctx, orc):
         assert gg == go == 3
         assert np.allclose(xg, xo, rtol=1e-9, atol=1e-12) and np.allclose(fg, fo, rtol=1e-9), algo
     prob.close()
+
+
+@pytest.mark.parametrize("family,algo,kw", [("rastrigin", "de1220", dict(variant_adptv=1)), ("rastrigin", "de", dict(variant=7)),
+                                            ("cec2013", "sade", dict(variant=2, variant_adptv=1))])
+def test_generation_graph_replay_equals_plain_launches(capi, ctx, orc, monkeypatch, family, algo, kw):
+    """From the second evolve() on a population the generation loop replays an instantiated CUDA graph (de.cu): three calls with
+    graphs == the same three calls with plain launches (PGC_GRAPHS=0) == the restated loop, the exit conditions included."""
+    import ctypes as C
+    rng = np.random.default_rng(4242)
+    NP, dim = 256, 10
+    if family == "cec2013":
+        mr, os_ = orc.cec2013_tables(dim)
+        make = lambda: capi.Problem(ctx, "cec2013", prob_id=12, dim=dim, rotation=mr, shift=os_)  # noqa: E731
+        op = orc.problem("cec2013", prob_id=12, dim=dim, tables=(mr, os_))
+    else:
+        make = lambda: capi.Problem(ctx, family, dim=dim)  # noqa: E731
+        op = orc.problem(family, dim=dim)
+    code = {"de": 0, "sade": 1, "de1220": 2}[algo]
+    al = np.array([2, 3, 7, 10, 13, 14, 15, 16], dtype=np.uint32)
+
+    def three_calls(graphs, ftol=0.0):
+        monkeypatch.setenv("PGC_GRAPHS", "1" if graphs else "0")
+        prob = make()
+        lb, ub = prob.bounds()
+        x = np.random.default_rng(7).uniform(lb, ub, (NP, dim))
+        f = prob.eval_host(x)[:, 0]
+        dx, df = ctx.to_device(x), ctx.to_device(f)
+        l0, gens_done = ctx.launches, []
+        for call in range(3):
+            done = C.c_uint()
+            capi.check(capi.lib().pgc_de_evolve_device(prob._h, dx, df, NP, 12, code, kw.get("variant", 2), kw.get("variant_adptv", 1), 0.8, 0.9,
+                                                       al.ctypes.data_as(C.c_void_p), al.size, ftol, 0.0, None, None, None, 31, 1 + 12 * call,
+                                                       C.byref(done), None))
+            gens_done.append(done.value)
+        out = ctx.from_device(dx, x.shape), ctx.from_device(df, f.shape), gens_done, ctx.launches - l0
+        ctx.free(dx)
+        ctx.free(df)
+        prob.close()
+        return (x, f, lb, ub) + out
+
+    x, f, lb, ub, xg, fg, gg, lg = three_calls(True)
+    _, _, _, _, xp, fp, gp, lp = three_calls(False)
+    assert gg == gp == [12, 12, 12] and lg == lp  # the replayed launches are counted like the plain ones
+    assert np.array_equal(xg, xp) and np.array_equal(fg, fp)
+    xo, fo = x, f
+    for call in range(3):
+        xo, fo, go, *_ = orc.de_evolve(op, lb, ub, xo, fo, gens=12, algo=algo, seed=31, first_generation=1 + 12 * call, ftol=0.0, xtol=0.0, **kw)
+    assert np.allclose(xg, xo, rtol=1e-9, atol=1e-12) and np.allclose(fg, fo, rtol=1e-9)
+    # an exit condition that fires inside a replayed batch: same generation count as the plain path
+    big = float(np.abs(fg.max() - fg.min()) * 4)
+    *_, g1, _ = three_calls(True, ftol=big)
+    *_, g0, _ = three_calls(False, ftol=big)
+    assert g1 == g0 and g1[-1] < 12
