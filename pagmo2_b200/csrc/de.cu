@@ -21,8 +21,13 @@
 #include <algorithm>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "pgc_internal.cuh"
 #include "philox.cuh"
+#include "simple_device.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pgc
 {
@@ -297,11 +302,10 @@ struct WarpDraws { // the substream as the prelude sees it: draws 0..31 live one
 
 constexpr unsigned kTrialWarps = 8;
 
-__global__ void __launch_bounds__(kTrialWarps * 32) de_trial_warp_kernel(const TrialParams P)
+// the trial vector of individual i, gene j = lane + 32 c written to out[j]; every lane returns the head (F, CR, variant)
+__device__ __forceinline__ TrialHead trial_warp_body(const TrialParams &P, unsigned i, unsigned generation, unsigned lane, double *out)
 {
-    const unsigned i = blockIdx.x * kTrialWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
-    if (i >= P.NP || *P.stopped) return; // warp-uniform
-    const unsigned dim = P.dim, generation = *P.gen_base + *P.gens_done;
+    const unsigned dim = P.dim;
     WarpDraws rs{philox_draw_at(P.seed, generation, i, lane), P.seed, generation, i, 0u};
     const TrialHead H = trial_head(P, i, rs);
     const unsigned n0 = uint_below_from(rs, dim); // c_idx(m_e)
@@ -326,7 +330,6 @@ __global__ void __launch_bounds__(kTrialWarps * 32) de_trial_warp_kernel(const T
         used = dim;
     }
     const double *xi = P.popold + static_cast<size_t>(i) * dim;
-    double *tmp = P.trial + static_cast<size_t>(i) * dim;
     unsigned resampled = 0; // out-of-bounds genes before this chunk
     for (unsigned b = 0; b < dim; b += 32u) {
         const unsigned j = b + lane;
@@ -353,8 +356,16 @@ __global__ void __launch_bounds__(kTrialWarps * 32) de_trial_warp_kernel(const T
             v = (lo == hi) ? lo : (hi - lo) * philox_draw_at(P.seed, generation, i, k) + lo;
         }
         resampled += static_cast<unsigned>(__popc(m));
-        if (j < dim) tmp[j] = v;
+        if (j < dim) out[j] = v;
     }
+    return H;
+}
+
+__global__ void __launch_bounds__(kTrialWarps * 32) de_trial_warp_kernel(const TrialParams P)
+{
+    const unsigned i = blockIdx.x * kTrialWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (i >= P.NP || *P.stopped) return; // warp-uniform
+    const TrialHead H = trial_warp_body(P, i, *P.gen_base + *P.gens_done, lane, P.trial + static_cast<size_t>(i) * P.dim);
     if (lane == 0) {
         if (P.F_out) {
             P.F_out[i] = H.F;
@@ -696,6 +707,164 @@ __global__ void __launch_bounds__(kFinishWarps * 32) de_finish_kernel(const doub
     }
 }
 
+// ---- RESIDENT generation loop (launch-bound populations of the simple UDPs): every generation of an evolve() call inside ONE
+// cooperative launch.  A warp builds the trial vector of its individual in shared memory, evaluates it there (the terms of
+// simple_device.cuh in parallel, folded by one lane in the reference's order: the same bits as eval_simple.cu), and applies the
+// selection into the OTHER copy of the population (x, f, F, CR, variant, accepted are double buffered, so a fast CTA can start
+// generation g + 1 while a slow one still reduces generation g).  One grid-wide barrier per generation; after it every CTA
+// reduces the whole fitness vector itself (<= 16384 values), so the global-best state needs no second barrier and no broadcast.
+struct ResidentParams {
+    double *x[2], *f[2], *F[2], *CR[2];
+    unsigned *variant[2];
+    unsigned char *accepted[2];
+    const double *lb, *ub;
+    double *gbX;
+    DeGlobal *G;
+    unsigned NP, dim, gens;
+    unsigned long long seed;
+    DeConfig cfg;
+    double xtol, ftol;
+};
+
+constexpr unsigned kResWarps = 8;
+
+template <int FAM> __global__ void __launch_bounds__(kResWarps * 32) de_resident_kernel(const ResidentParams R)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double res_smem[]; // per warp: trial row | a-terms | b-terms, dim doubles each
+    __shared__ DeGlobal sG;
+    __shared__ ArgVal s_best[kResWarps], s_worst[kResWarps], s_acc[kResWarps];
+    __shared__ double s_diff[kResWarps * 32];
+    const unsigned t = threadIdx.x, warp = t >> 5, lane = t & 31u, kNone = 0xffffffffu;
+    const unsigned NP = R.NP, dim = R.dim;
+    double *row = res_smem + static_cast<size_t>(warp) * 3 * dim, *ta = row + dim, *tb = ta + dim;
+    if (t == 0) sG = *R.G;
+    __syncthreads();
+    unsigned cur = 0;
+    for (unsigned g = 0; g < R.gens; ++g) {
+        const unsigned nxt = cur ^ 1u;
+        TrialParams P{};
+        P.popold = R.x[cur];
+        P.gbIter = R.x[cur] + static_cast<size_t>(sG.gbidx) * dim; // == gbX: the row of the global best (see de_global_kernel)
+        P.lb = R.lb;
+        P.ub = R.ub;
+        P.F_in = R.F[cur];
+        P.CR_in = R.CR[cur];
+        P.variant_in = R.variant[cur];
+        P.gbIterF = &sG.gbF;
+        P.gbIterCR = &sG.gbCR;
+        P.NP = NP;
+        P.dim = dim;
+        P.seed = R.seed;
+        P.cfg = R.cfg;
+        for (unsigned i = blockIdx.x * kResWarps + warp; i < NP; i += gridDim.x * kResWarps) {
+            const TrialHead H = trial_warp_body(P, i, sG.gen_base + g, lane, row);
+            __syncwarp();
+            for (unsigned j = lane; j < dim; j += 32u) {
+                const bool has_next = j + 1u < dim;
+                simple::acc_term<FAM>(row[j], static_cast<int>(j), has_next, has_next ? row[j + 1u] : 0.0, ta[j], tb[j]);
+            }
+            __syncwarp();
+            double ft = 0.0;
+            if (lane == 0) {
+                simple::Acc acc;
+                simple::acc_init<FAM>(acc);
+                for (unsigned j = 0; j < dim; ++j) simple::acc_fold<FAM>(acc, ta[j], tb[j], j + 1u < dim);
+                ft = simple::acc_final<FAM>(acc, static_cast<int>(dim));
+            }
+            ft = __shfl_sync(0xffffffffu, ft, 0);
+            const double fo = R.f[cur][i];
+            const bool ok = ft <= fo; // selection, de.cpp:281-299 / de1220.cpp:515-536
+            const double *old_row = R.x[cur] + static_cast<size_t>(i) * dim;
+            double *new_row = R.x[nxt] + static_cast<size_t>(i) * dim;
+            for (unsigned j = lane; j < dim; j += 32u) new_row[j] = ok ? row[j] : old_row[j];
+            if (lane == 0) {
+                R.f[nxt][i] = ok ? ft : fo;
+                R.accepted[nxt][i] = ok;
+                if (R.F[0]) {
+                    R.F[nxt][i] = ok ? H.F : R.F[cur][i];
+                    R.CR[nxt][i] = ok ? H.CR : R.CR[cur][i];
+                }
+                if (R.variant[0]) R.variant[nxt][i] = ok ? H.variant : R.variant[cur][i];
+            }
+            __syncwarp();
+        }
+        grid.sync();
+        // ---- every CTA: best = first minimum, worst = first maximum, accepted-best = LAST minimum among the accepted trials
+        ArgVal best{0.0, kNone}, worst{0.0, kNone}, acc{0.0, kNone};
+        for (unsigned i = t; i < NP; i += blockDim.x) {
+            const double v = R.f[nxt][i];
+            best = arg_combine<0>(best, ArgVal{v, i});
+            worst = arg_combine<1>(worst, ArgVal{v, i});
+            if (R.accepted[nxt][i]) acc = arg_combine<2>(acc, ArgVal{v, i});
+        }
+        best = arg_reduce_warp<0>(best);
+        worst = arg_reduce_warp<1>(worst);
+        acc = arg_reduce_warp<2>(acc);
+        if (lane == 0) {
+            s_best[warp] = best;
+            s_worst[warp] = worst;
+            s_acc[warp] = acc;
+        }
+        __syncthreads();
+        best = s_best[0];
+        worst = s_worst[0];
+        acc = s_acc[0];
+        for (unsigned w = 1; w < kResWarps; ++w) {
+            best = arg_combine<0>(best, s_best[w]);
+            worst = arg_combine<1>(worst, s_worst[w]);
+            acc = arg_combine<2>(acc, s_acc[w]);
+        }
+        double dx = 0.0; // sum_d |x_worst[d] - x_best[d]| in ascending d (de.cpp:302-306)
+        for (unsigned d0 = 0; d0 < dim; d0 += blockDim.x) {
+            const unsigned d = d0 + t;
+            if (d < dim) s_diff[t] = fabs(R.x[nxt][static_cast<size_t>(worst.i) * dim + d] - R.x[nxt][static_cast<size_t>(best.i) * dim + d]);
+            __syncthreads();
+            if (t == 0)
+                for (unsigned k = 0; k < min(blockDim.x, dim - d0); ++k) dx += s_diff[k];
+            __syncthreads();
+        }
+        if (t == 0) {
+            sG.best_idx = best.i;
+            sG.worst_idx = worst.i;
+            if (acc.i != kNone && acc.v <= sG.gbfit) {
+                sG.gbidx = acc.i;
+                sG.gbfit = acc.v;
+                if (R.F[0]) {
+                    sG.gbF = R.F[nxt][acc.i];
+                    sG.gbCR = R.CR[nxt][acc.i];
+                }
+                if (R.variant[0]) sG.gbvariant = R.variant[nxt][acc.i];
+            }
+            sG.df = fabs(worst.v - best.v);
+            sG.dx = dx;
+            sG.gens_done += 1;
+            if (dx < R.xtol || sG.df < R.ftol) sG.stopped = 1; // de.cpp:308,316
+        }
+        __syncthreads();
+        cur = nxt;
+        if (sG.stopped) break; // the same decision in every CTA
+    }
+    // the caller's buffers are copy 0
+    if (cur == 1u) {
+        for (unsigned i = blockIdx.x * kResWarps + warp; i < NP; i += gridDim.x * kResWarps) {
+            for (unsigned j = lane; j < dim; j += 32u) R.x[0][static_cast<size_t>(i) * dim + j] = R.x[1][static_cast<size_t>(i) * dim + j];
+            if (lane == 0) {
+                R.f[0][i] = R.f[1][i];
+                if (R.F[0]) {
+                    R.F[0][i] = R.F[1][i];
+                    R.CR[0][i] = R.CR[1][i];
+                }
+                if (R.variant[0]) R.variant[0][i] = R.variant[1][i];
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (unsigned d = t; d < dim; d += blockDim.x) R.gbX[d] = R.x[cur][static_cast<size_t>(sG.gbidx) * dim + d];
+        if (t == 0) *R.G = sG;
+    }
+}
+
 __global__ void de_init_adapt_kernel(double *F, double *CR, unsigned *variant, unsigned NP, DeConfig cfg, unsigned long long seed,
                                      unsigned generation)
 { // de1220.cpp:147-165 / sade.cpp:137-156
@@ -757,6 +926,10 @@ struct DeWork : LoopWorkspace {
     DeGlobal *G = nullptr;
     DePartial *parts = nullptr;
     unsigned *ticket = nullptr; // de_finish_kernel: CTAs done in the current launch
+    // resident loop: the second copy of the population state
+    double *x2 = nullptr, *f2 = nullptr, *F2 = nullptr, *CR2 = nullptr;
+    unsigned *var2 = nullptr;
+    unsigned char *acc2[2] = {nullptr, nullptr};
     unsigned nparts = 0;
     std::vector<void *> owned;
     cudaGraphExec_t exec = nullptr;
@@ -799,6 +972,17 @@ struct DeWork : LoopWorkspace {
         PGC_CUDA(cudaMemset(ticket, 0, sizeof(unsigned)));
         return PGC_OK;
     }
+    int allocate_resident(unsigned algo)
+    {
+        if (x2) return PGC_OK;
+        const unsigned NP = key.NP, dim = key.dim;
+        int rc;
+        if ((rc = get(&x2, 8 * static_cast<size_t>(NP) * dim)) || (rc = get(&f2, 8 * NP)) || (rc = get(&acc2[0], NP)) || (rc = get(&acc2[1], NP)))
+            return rc;
+        if (algo != 0u && ((rc = get(&F2, 8 * NP)) || (rc = get(&CR2, 8 * NP)))) return rc;
+        if (algo == 2u && (rc = get(&var2, 4 * NP))) return rc;
+        return PGC_OK;
+    }
     void drop_graph()
     {
         if (exec) cudaGraphExecDestroy(exec);
@@ -815,6 +999,34 @@ struct DeWork : LoopWorkspace {
         cudaSetDevice(cur);
     }
 };
+
+} // namespace
+
+namespace
+{
+
+bool resident_enabled()
+{
+    const char *e = std::getenv("PGC_DE_RESIDENT"); // PGC_DE_RESIDENT=0: one launch per phase (tests compare the two paths)
+    return !(e && e[0] == '0');
+}
+
+constexpr unsigned kResidentMaxDim = 512;
+
+template <int FAM> int launch_resident(pgc_ctx *ctx, const ResidentParams &R, cudaStream_t st)
+{
+    auto kern = de_resident_kernel<FAM>;
+    const size_t smem = sizeof(double) * 3 * R.dim * kResWarps;
+    if (smem > 48 * 1024) PGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    PGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kResWarps * 32, smem));
+    PGC_REQUIRE(per_sm >= 1, "de_evolve: the resident loop does not fit on an SM (dimension %u)", R.dim);
+    const unsigned blocks = std::min(nblk(R.NP, kResWarps), static_cast<unsigned>(per_sm * ctx->sm_count));
+    void *args[] = {const_cast<ResidentParams *>(&R)};
+    PGC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(blocks), dim3(kResWarps * 32), args, smem, st));
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return PGC_OK;
+}
 
 } // namespace
 
@@ -908,6 +1120,41 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
     if (nparts) de_global_partial_kernel<<<nparts, 256, 0, st>>>(d_f, nullptr, NP, 1, &G->stopped, parts);
     de_global_kernel<<<1, 256, 0, st>>>(d_x, d_f, nullptr, NP, dim, Fs, CRs, algo == 2u ? vars : nullptr, gbX, G, 1, xtol, ftol,
                                         nparts ? parts : nullptr, nparts, first_generation);
+    // ---- launch-bound populations of the simple UDPs: all generations in one cooperative launch (de_resident_kernel)
+    const int fam = prob->desc.family;
+    const bool simple_family = !prob->inner
+                               && (fam == PGC_RASTRIGIN || fam == PGC_ACKLEY || fam == PGC_GRIEWANK || fam == PGC_SCHWEFEL || fam == PGC_ROSENBROCK);
+    if (simple_family && eval == &problem_eval_device && NP < kFinishMaxNP && dim <= kResidentMaxDim && resident_enabled()) {
+        if (int rc = W->allocate_resident(algo)) return rc;
+        ResidentParams R{};
+        R.x[0] = d_x; R.x[1] = W->x2;
+        R.f[0] = d_f; R.f[1] = W->f2;
+        R.F[0] = algo ? Fs : nullptr; R.F[1] = algo ? W->F2 : nullptr;
+        R.CR[0] = algo ? CRs : nullptr; R.CR[1] = algo ? W->CR2 : nullptr;
+        R.variant[0] = algo == 2u ? vars : nullptr; R.variant[1] = algo == 2u ? W->var2 : nullptr;
+        R.accepted[0] = W->acc2[0]; R.accepted[1] = W->acc2[1];
+        R.lb = lb; R.ub = ub;
+        R.gbX = gbX;
+        R.G = G;
+        R.NP = NP; R.dim = dim; R.gens = gens;
+        R.seed = seed;
+        R.cfg = cfg;
+        R.xtol = xtol; R.ftol = ftol;
+        int rc;
+        switch (fam) {
+            case PGC_RASTRIGIN: rc = launch_resident<PGC_RASTRIGIN>(ctx, R, st); break;
+            case PGC_ACKLEY: rc = launch_resident<PGC_ACKLEY>(ctx, R, st); break;
+            case PGC_GRIEWANK: rc = launch_resident<PGC_GRIEWANK>(ctx, R, st); break;
+            case PGC_SCHWEFEL: rc = launch_resident<PGC_SCHWEFEL>(ctx, R, st); break;
+            default: rc = launch_resident<PGC_ROSENBROCK>(ctx, R, st); break;
+        }
+        if (rc != PGC_OK) return rc;
+        DeGlobal hres{};
+        PGC_CUDA(cudaMemcpyAsync(&hres, G, sizeof(DeGlobal), cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        if (gens_done) *gens_done = hres.gens_done;
+        return PGC_OK;
+    }
     // one generation: no launch parameter depends on the generation index (the kernels read it from G), so the same launches can
     // be replayed from a graph
     auto generation = [&]() -> int {

@@ -10,6 +10,7 @@
 #include <cmath>
 
 #include "pgc_internal.cuh"
+#include "simple_device.cuh"
 
 namespace pgc
 {
@@ -21,46 +22,10 @@ constexpr int kTile = 128;  // individuals per CTA tile == threads per CTA
 constexpr int kChunk = 32;  // coordinates staged per pass
 constexpr int kStride = kChunk + 1; // odd stride: conflict-free column walks
 
-struct Acc {
-    double a, b, prev;
-};
-
-template <int FAM> __device__ __forceinline__ void acc_init(Acc &s)
-{
-    s.a = 0.0;
-    s.b = (FAM == PGC_GRIEWANK) ? 1.0 : 0.0;
-    s.prev = 0.0;
-}
-
-// consume coordinate j (value x); `has_next`/`xn` give x[j+1] for rosenbrock
-template <int FAM> __device__ __forceinline__ void acc_step(Acc &s, double x, int j, bool has_next, double xn)
-{
-    const double omega = 2.0 * 3.141592653589793238462643383279502884;
-    if (FAM == PGC_RASTRIGIN) {
-        s.a += x * x - 10.0 * cos(omega * x);
-    } else if (FAM == PGC_ACKLEY) {
-        s.a += x * x;
-        s.b += cos(omega * x);
-    } else if (FAM == PGC_GRIEWANK) {
-        s.a += x * x;
-        s.b *= cos(x / sqrt(static_cast<double>(j) + 1.0));
-    } else if (FAM == PGC_SCHWEFEL) {
-        s.a += x * sin(sqrt(fabs(x)));
-    } else if (FAM == PGC_ROSENBROCK) {
-        if (has_next) s.a += 100.0 * (x * x - xn) * (x * x - xn) + (x - 1.0) * (x - 1.0);
-    }
-}
-
-template <int FAM> __device__ __forceinline__ double acc_final(const Acc &s, int D)
-{
-    const double n = static_cast<double>(D);
-    if (FAM == PGC_RASTRIGIN) return s.a + 10.0 * n;
-    if (FAM == PGC_ACKLEY)
-        return -20.0 * exp(-0.2 * sqrt(1.0 / n * s.a)) - exp(1.0 / n * s.b) + 20.0 + 2.718281828459045235360287471352662498; // nepero = std::exp(1.0)
-    if (FAM == PGC_GRIEWANK) return (s.a / 4000.0 - s.b + 1.0);
-    if (FAM == PGC_SCHWEFEL) return 418.9828872724338 * n - s.a;
-    return s.a;
-}
+using simple::Acc;
+using simple::acc_final;
+using simple::acc_init;
+using simple::acc_step;
 
 template <int FAM>
 __global__ void __launch_bounds__(kTile) simple_kernel(const double *__restrict__ x, double *__restrict__ f, long long n, int D)

@@ -94,6 +94,8 @@ def test_generation_graph_replay_equals_plain_launches(capi, ctx, orc, monkeypat
     code = {"de": 0, "sade": 1, "de1220": 2}[algo]
     al = np.array([2, 3, 7, 10, 13, 14, 15, 16], dtype=np.uint32)
 
+    monkeypatch.setenv("PGC_DE_RESIDENT", "0")  # the simple UDPs would otherwise take the resident loop (tested below)
+
     def three_calls(graphs, ftol=0.0):
         monkeypatch.setenv("PGC_GRAPHS", "1" if graphs else "0")
         prob = make()
@@ -127,3 +129,33 @@ def test_generation_graph_replay_equals_plain_launches(capi, ctx, orc, monkeypat
     *_, g1, _ = three_calls(True, ftol=big)
     *_, g0, _ = three_calls(False, ftol=big)
     assert g1 == g0 and g1[-1] < 12
+
+
+@pytest.mark.parametrize("family", ("rastrigin", "ackley", "griewank", "schwefel", "rosenbrock"))
+def test_resident_loop_equals_one_launch_per_phase(capi, ctx, orc, monkeypatch, family):
+    """Simple UDPs at island-sized populations run all generations of an evolve() in one cooperative launch (de_resident_kernel):
+    same population, fitness and generation count, bit for bit, as the trial / evaluate / select launches (PGC_DE_RESIDENT=0),
+    odd and even generation counts (the result lives in the second copy after an odd number), exit conditions included."""
+    NP, dim = 300, 13  # ragged: not a multiple of the 8 warps of a CTA
+    prob = capi.Problem(ctx, family, dim=dim)
+    op = orc.problem(family, dim=dim)
+    lb, ub = prob.bounds()
+    x = np.random.default_rng(3).uniform(lb, ub, (NP, dim))
+    f = prob.eval_host(x)[:, 0]
+    for algo, kw in (("de", dict(variant=2)), ("de", dict(variant=8)), ("sade", dict(variant=12, variant_adptv=1)),
+                     ("sade", dict(variant=3, variant_adptv=2)), ("de1220", dict(variant_adptv=1)), ("de1220", dict(variant_adptv=2))):
+        for gens, ftol in ((7, 0.0), (10, 0.0), (40, float(np.ptp(f)) * 1.5)):  # the last one: |worst - best| < ftol at once
+            args = dict(gens=gens, algo=algo, seed=9, first_generation=5, ftol=ftol, xtol=0.0, **kw)
+            monkeypatch.setenv("PGC_DE_RESIDENT", "1")
+            l0 = ctx.launches
+            xr, fr, gr = prob.de_evolve(x, f, **args)
+            resident_launches = ctx.launches - l0
+            monkeypatch.setenv("PGC_DE_RESIDENT", "0")
+            xp, fp, gp = prob.de_evolve(x, f, **args)
+            assert gr == gp and (ftol == 0.0) == (gr == gens), (algo, kw, gens, gr, gp)
+            assert np.array_equal(xr, xp) and np.array_equal(fr, fp), (algo, kw, gens)
+            assert resident_launches <= 3  # init (global best) + the resident loop
+            if ftol == 0.0 and gens == 7:
+                xo, fo, go, *_ = orc.de_evolve(op, lb, ub, x, f, **args)
+                assert np.allclose(xr, xo, rtol=1e-9, atol=1e-12) and np.allclose(fr, fo, rtol=1e-9)
+    prob.close()
