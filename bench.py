@@ -51,6 +51,22 @@ def env_int(name, default):
         return default
 
 
+def device_of_rank(local, world):
+    """Which GPU local rank `local` drives.  On this pool's 8-GPU boxes GPUs 0-3 and 4-7 sit behind two host bridges of ~116 GB/s
+    each (scripts/h2d_probe.py, profiles/r2j_h2d_probe.json: {0,1,2,3} copies 116 GB/s from pinned host memory, {0,1,4,5} 218), so
+    when fewer ranks than visible GPUs run, the ranks alternate between the two halves - the host-buffer (e2e) path is PCIe-bound.
+    PGC_BENCH_SPREAD=0 keeps rank r on GPU r."""
+    try:
+        import torch
+        visible = torch.cuda.device_count()
+    except Exception:
+        return local
+    if os.environ.get("PGC_BENCH_SPREAD", "1") == "0" or world <= 1 or visible < 2 * world or visible % 2:
+        return local
+    half = visible // 2
+    return (local % 2) * half + local // 2
+
+
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     """SM clock / throttle-reason sampler for one GPU during the timed region (recipe: B200_PROFILING.md, clocks line).
@@ -295,6 +311,7 @@ def measure_cfg5(capi, devices, rank, world, comm, rounds, warm_rounds=1, log=Tr
     a.synchronize()
     l0 = sum(a.ctx[g].launches for g in a.local)
     m0 = len(a.log)
+    a.phase_seconds.clear()
     t0 = time.perf_counter()
     a.evolve(rounds)
     a.synchronize()
@@ -307,7 +324,7 @@ def measure_cfg5(capi, devices, rank, world, comm, rounds, warm_rounds=1, log=Tr
             "island_generations_per_s": gens * c["islands"] / dt, "evals_per_s": gens * c["pop"] * c["islands"] / dt,
             "migrations_per_s": (len(a.log) - m0) * (c["islands"] / max(len(a.local), 1)) / dt, "migrations_logged_locally": len(a.log) - m0,
             "launches_per_generation_per_island": (sum(a.ctx[g].launches for g in a.local) - l0) / gens / max(len(a.local), 1),
-            "champions_f_local": a.champions_f().tolist()}
+            "host_seconds_per_phase": dict(a.phase_seconds), "champions_f_local": a.champions_f().tolist()}
 
 
 def measure_adapter_e2e(n):
@@ -331,6 +348,7 @@ def run_cfg5(args):
     import torch
     from pagmo2_b200 import capi
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    local = device_of_rank(local, world)
     torch.cuda.set_device(local)
     comm, dist = None, None
     if world > 1:
@@ -341,7 +359,9 @@ def run_cfg5(args):
         comm = capi.Comm.from_unique_id(local, world, rank, box[0])
     sampler = ClockSampler(local)
     sampler.start()
-    res = measure_cfg5(capi, [local], rank, world, comm, rounds=max(args.steps, 1), warm_rounds=max(args.warmup, 1))
+    # NCCL opens its send/recv channels lazily, peer by peer: the first ~8 exchanges of a ring over 8 ranks take ~100 ms each
+    # (measured: 200 ms/round with 3 warm-up rounds, 2.2 ms/round after 10), so multi-rank runs warm up for at least 10 rounds
+    res = measure_cfg5(capi, [local], rank, world, comm, rounds=max(args.steps, 1), warm_rounds=max(args.warmup, 10 if world > 1 else 1))
     clocks = sampler.stop()
     if dist is not None:
         t = torch.tensor([res["seconds"], float(res["migrations_logged_locally"])], dtype=torch.float64, device=f"cuda:{local}")
@@ -375,6 +395,7 @@ def run_native(args):
     from pagmo2_b200 import capi
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    local = device_of_rank(local, world)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -526,11 +547,15 @@ def run_native(args):
         "metric": "fitness evals/sec (CEC2014 D=100)", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(n, world),
+        "config": {**workload_config(n, world), "device_of_rank0": local,
+                   "placement": "ranks alternate between GPUs 0-3 and 4-7 when fewer ranks than visible GPUs run (device_of_rank)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": len(FUNCS) * n * DIM * 8,
                 "d2h_bytes_per_step": len(FUNCS) * n * 8, "steps": e2e_steps,
-                "path": "pgc_eval_host: pinned host -> chunked H2D -> kernels -> D2H -> pinned host"},
+                "path": "pgc_eval_host: pinned host -> chunked H2D -> kernels -> D2H -> pinned host",
+                "h2d_gbs": e2e_value * DIM * 8 / 1e9,
+                "ceiling": "host -> device copies of this box, measured by scripts/h2d_probe.py (profiles/r2j_h2d_probe.json): 55.5 GB/s for "
+                           "one GPU, 111 for two, 116 for GPUs {0,1,2,3} (one host bridge), 218 for {0,1,4,5}, 188 for all eight"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": STAGE_DRAM_BYTES,

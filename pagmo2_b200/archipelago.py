@@ -26,6 +26,8 @@ import ctypes as C
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 
+import time
+
 import numpy as np
 
 from . import capi
@@ -274,6 +276,7 @@ class ResidentArchipelago:
             self.isl[g] = capi.Island(self.prob[g], s["pop_size"], cap, max_in)
             self.isl[g].init(s["seed"])
         self.published = [False] * G
+        self.phase_seconds = {}  # host wall time per phase of evolve(), summed over rounds
         self.local = [g for g in range(G) if self.isl[g] is not None]
         self._pool = ThreadPoolExecutor(max_workers=max(len(self.local), 1))
 
@@ -316,14 +319,20 @@ class ResidentArchipelago:
                             take(int(s))
                 pulls[g] = (True, sources)
                 edges += [(s, g, q) for q, (s, had) in enumerate(sources) if had]
+            t0 = time.perf_counter()
             for g in self.local:
                 for q, (s, had) in enumerate(pulls[g][1]):
                     if not had:
                         self.isl[g].inbox_upload(q, np.empty(0, np.uint64), np.empty((0, self.isl[g].nx)), np.empty((0, self.isl[g].nf)))
+            t1 = time.perf_counter()
             capi.migrate(self.comm, self.isl, self.owner, edges)
+            t2 = time.perf_counter()
             futs = [self._pool.submit(self._step, g, *pulls[g]) for g in self.local]
             for f in futs:
                 self.log.extend(f.result())
+            t3 = time.perf_counter()
+            for k, dt in (("empty_inbox_upload", t1 - t0), ("migrate_enqueue", t2 - t1), ("replace_evolve_select", t3 - t2)):
+                self.phase_seconds[k] = self.phase_seconds.get(k, 0.0) + dt
             self.published = [k > 0 for k in self.k_out]
             self.round += 1
 
