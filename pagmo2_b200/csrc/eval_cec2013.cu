@@ -21,6 +21,7 @@
 // composition reads its shift at Os[i*nx] and its second rotation at Mr[(i+1)*nx*nx]; cf_cal's zero-distance weight is 1e99.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -73,10 +74,12 @@ namespace
 using namespace cecdev;
 constexpr int kMaxWarps13 = 16;
 
+constexpr int kMaxMerge = 3; // sub-launches of one kernel launch (island-sized batches: all matrices of a chain in shared memory)
+
 struct Params13 {
     const double *x;
     double *state;
-    const double *mr;    // rotation image of this launch
+    const double *mr[kMaxMerge]; // rotation image of every sub-launch
     const double *os;    // component shift
     const double *table;
     double *out;
@@ -87,7 +90,8 @@ struct Params13 {
     int tell, tdif, tgri, twei;
     int strict; // rotations accumulate one product at a time in the reference's j order (pgc_problem_set_strict)
     int ti;     // individuals per warp tile: 8, or 4 / 2 / 1 for island-sized batches (the other rows of the tile stay zero)
-    Launch13 L;
+    int nl;     // sub-launches executed back to back on a tile (the vector stays in the warp's buffers between them)
+    Launch13 L[kMaxMerge];
 };
 
 struct Row { // one individual's row of a buffer
@@ -97,13 +101,14 @@ struct Row { // one individual's row of a buffer
 
 // reductions of cec2013.cpp on the finished vector v (4 lanes per individual, lane q takes terms j == q mod 4)
 template <int D>
-__device__ double reduce13(const Params13 &P, const Row &v, int h, const double *__restrict__ xrow, const double *__restrict__ sOs)
+__device__ double reduce13(const Params13 &P, const Launch13 &L, const Row &v, int h, const double *__restrict__ xrow,
+                           const double *__restrict__ sOs)
 {
     constexpr int n = D;
     const double dn = static_cast<double>(n);
     const double two_pi = 2.0 * 3.141592653589793238462643383279502884;
     const double *tab = P.table;
-    switch (P.L.red) {
+    switch (L.red) {
         case R_SPHERE: // :329-331
             return pair_add(ordered_sum(h, n, [&](int j) { return v(j) * v(j); }));
         case R_ELLIPS: // :345-348
@@ -230,24 +235,30 @@ __device__ double reduce13(const Params13 &P, const Row &v, int h, const double 
     }
 }
 
-template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_kernel(const __grid_constant__ Params13 P)
+// SMALL = island-sized batches: run-time tile size (P.ti individuals per warp) and up to kMaxMerge sub-launches per launch; the
+// throughput instance keeps both as compile-time constants (8 individuals, one sub-launch)
+template <int D, bool SMALL> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_kernel(const __grid_constant__ Params13 P)
 {
     constexpr int DP = pad8(D), KP = pad4(D), NT = DP / 8, YS = ystride(D);
     // island-sized batches: fewer individuals per warp tile, so that the batch spreads over many warps - every phase of a tile is
     // a dependent chain of one warp, and a row of the tile is computed independently of the other rows (same bits either way)
-    const bool rot = P.L.rot >= 0;
+    const int TI = SMALL ? P.ti : kTileInd, TILE = TI * D;
+    const int NL = SMALL ? P.nl : 1;
+    bool rot = false; // any sub-launch rotates
+    for (int q = 0; q < NL; ++q) rot = rot || P.L[q].rot >= 0;
+    const int mslots = rot ? NL : 0; // one matrix slot per sub-launch
     const int W = blockDim.x >> 5;
-    const int TI = P.ti, TILE = TI * D;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sMr = reinterpret_cast<double *>(smem_raw);
-    double *sBuf = sMr + (rot ? DP * YS : 0);
+    double *sBuf = sMr + mslots * DP * YS;
     double *sOs = sBuf + W * 2 * TI * YS; // a warp's two buffers hold TI rows
     unsigned short *sList = reinterpret_cast<unsigned short *>(sOs + D); // [W][TILE]: positions of the positive inputs of asyfunc
 
-    if (rot) {
-        const double2 *src = reinterpret_cast<const double2 *>(P.mr);
-        double2 *dst = reinterpret_cast<double2 *>(sMr);
+    for (int q = 0; q < NL; ++q) {
+        if (P.L[q].rot < 0) continue;
+        const double2 *src = reinterpret_cast<const double2 *>(P.mr[q]);
+        double2 *dst = reinterpret_cast<double2 *>(sMr + q * DP * YS);
         for (int i = threadIdx.x; i < DP * YS / 2; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     for (int i = threadIdx.x; i < W * 2 * TI * YS; i += blockDim.x) sBuf[i] = 0.0; // the inner-index padding stays 0
@@ -274,17 +285,30 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
         const int nt = (P.n - t0 < TI) ? static_cast<int>(P.n - t0) : TI;
         const int live = nt * D;
         double wacc = 0.0;
+        int prev_end = 0;
 
+        for (int q = 0; q < NL; ++q) {
+        const Launch13 &L = P.L[q];
+        const double *sM = sMr + q * DP * YS;
         { // ---- load: the 8 rows of a tile are one contiguous block of the input
-            double *in = bufs[P.L.in_buf];
-            if (P.L.from_x) {
+            double *in = bufs[L.in_buf];
+            if (q > 0 && !L.from_x) { // merged launch: the previous sub-launch left the vector in one of the warp's buffers
+                if (prev_end != L.in_buf) {
+                    const double *src = bufs[prev_end];
+                    for (int e = lane; e < TILE; e += 32) {
+                        const int t = e / D, a = t * YS + e - t * D;
+                        in[a] = src[a];
+                    }
+                }
+                __syncwarp();
+            } else if (L.from_x) {
                 const double *src = P.x + t0 * D;
                 for (int e = lane; e < TILE; e += 32) {
                     const int t = e / D, i = e - t * D;
                     in[t * YS + i] = (e < live) ? __ldg(src + e) - sOs[i] : 0.0; // shiftfunc :1038-1044
                 }
                 __syncwarp();
-                if (P.L.want_w) { // cf_cal distance sum_j (x_j - Os_j)^2, :1101-1103
+                if (L.want_w) { // cf_cal distance sum_j (x_j - Os_j)^2, :1101-1103
                     const double *row = in + er * YS;
                     for (int j = eq; j < D; j += kLPI) wacc += row[j] * row[j];
                     wacc = pair_add(wacc);
@@ -299,8 +323,8 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
             }
         }
 
-        for (int si = 0; si < P.L.nsteps; ++si) {
-            const Step13 &s = P.L.st[si];
+        for (int si = 0; si < L.nsteps; ++si) {
+            const Step13 &s = L.st[si];
             const double *in = bufs[s.src];
             double *out = bufs[s.dst];
             switch (s.op) {
@@ -402,7 +426,7 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
                         // functions whose later sin / cos / pow amplify the last bits (f7, f8, f20, f28)
                         for (int e = lane; e < TILE; e += 32) {
                             const int t = e / D, i = e - t * D;
-                            const double *y = in + t * YS, *m = sMr + i * YS;
+                            const double *y = in + t * YS, *m = sM + i * YS;
                             double acc = 0.;
                             for (int k = 0; k < D; ++k) acc = acc + y[k] * m[k];
                             out[t * YS + i] = acc;
@@ -414,7 +438,7 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
 #pragma unroll
                     for (int nt2 = 0; nt2 < NT; ++nt2) acc[nt2][0] = acc[nt2][1] = 0.0;
                     const double *ya = in + (g < TI ? g : 0) * YS + j; // absent rows: any finite operand, result dropped
-                    const double *mb = sMr + g * YS + j;
+                    const double *mb = sM + g * YS + j;
 #pragma unroll 2
                     for (int u = 0; u < KP / 4; ++u) {
                         const double a = ya[u * 4];
@@ -438,28 +462,31 @@ template <int D> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_ke
             __syncwarp();
         }
 
-        if (P.L.to_state) {
-            const double *src = bufs[P.L.end_buf];
+        if (L.to_state && q + 1 < NL) {
+            prev_end = L.end_buf; // stays in shared memory for the next sub-launch
+        } else if (L.to_state) {
+            const double *src = bufs[L.end_buf];
             double *dst = P.state + t0 * D;
             for (int e = lane; e < live; e += 32) {
                 const int t = e / D, i = e - t * D;
                 dst[e] = src[t * YS + i];
             }
         } else {
-            Row v{bufs[P.L.end_buf] + er * YS};
+            Row v{bufs[L.end_buf] + er * YS};
             const long long xr = (et < nt) ? t0 + et : t0;
-            double val = reduce13<D>(P, v, eq, P.x + xr * D, sOs);
+            double val = reduce13<D>(P, L, v, eq, P.x + xr * D, sOs);
             if (eq == 0 && et < nt) {
-                if (P.L.slot >= 0) {
-                    if (P.L.scaled) val = P.L.mul * val / P.L.div; // e.g. :877 fit = 10000 * fit / 1e+4
-                    P.out[P.L.slot * P.n + t0 + et] = val;
+                if (L.slot >= 0) {
+                    if (L.scaled) val = L.mul * val / L.div; // e.g. :877 fit = 10000 * fit / 1e+4
+                    P.out[L.slot * P.n + t0 + et] = val;
                 } else {
                     P.out[t0 + et] = val + P.fbias; // :83 f[0] += bias
                 }
             }
         }
-        if (P.L.want_w && eq == 0 && et < nt) P.wout[P.L.slot * P.n + t0 + et] = wacc;
+        if (L.want_w && eq == 0 && et < nt) P.wout[L.slot * P.n + t0 + et] = wacc;
         __syncwarp();
+        } // sub-launches
     }
 }
 
@@ -500,19 +527,35 @@ __global__ void cec13_combine_kernel(const __grid_constant__ Combine13 P)
     P.out[i] = f + P.fbias;
 }
 
+inline bool merge_enabled()
+{
+    const char *e = std::getenv("PGC_CEC13_MERGE"); // PGC_CEC13_MERGE=0: one launch per rotation at every batch size
+    return !(e && e[0] == '0');
+}
+
+// island-sized batches (~1000 individuals) are latency-bound: shrink the tile until there are ~4 warps per SM
+inline int tile_individuals(const pgc_ctx *ctx, long long n)
+{
+    int ti = kTileInd;
+    while (ti > 1 && (n + ti - 1) / ti < static_cast<long long>(ctx->sm_count) * 4) ti >>= 1;
+    return ti;
+}
+
 template <int D> int launch13(pgc_ctx *ctx, const Params13 &pp, cudaStream_t stream)
 {
     constexpr int DP = pad8(D), YS = ystride(D);
     static thread_local int configured_dev = -1;
-    auto kern = cec13_kernel<D>;
+    const int ti = tile_individuals(ctx, pp.n);
+    const bool small = ti < kTileInd || pp.nl > 1;
+    auto kern = small ? cec13_kernel<D, true> : cec13_kernel<D, false>;
     if (configured_dev != ctx->device) {
-        PGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+        PGC_CUDA(cudaFuncSetAttribute(cec13_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+        PGC_CUDA(cudaFuncSetAttribute(cec13_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
         configured_dev = ctx->device;
     }
-    const size_t fixed = sizeof(double) * ((pp.L.rot >= 0 ? DP * YS : 0) + D) + 16;
-    // island-sized batches (~1000 individuals) are latency-bound: shrink the tile until there are ~4 warps per SM
-    int ti = kTileInd;
-    while (ti > 1 && (pp.n + ti - 1) / ti < static_cast<long long>(ctx->sm_count) * 4) ti >>= 1;
+    bool any_rot = false;
+    for (int q = 0; q < pp.nl; ++q) any_rot = any_rot || pp.L[q].rot >= 0;
+    const size_t fixed = sizeof(double) * ((any_rot ? pp.nl * DP * YS : 0) + D) + 16;
     const size_t per_warp = (sizeof(double) * 2 * ti * YS + sizeof(unsigned short) * ti * D + 15) / 16 * 16;
     int fit = static_cast<int>((ctx->smem_optin - fixed) / per_warp);
     if (fit > kMaxWarps13) fit = kMaxWarps13;
@@ -780,12 +823,16 @@ int cec2013_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, c
         fit = state + state_elems;
         w = fit + 5 * n;
     }
-    for (const Launch13 &L : pl.launches) {
-        Params13 pp;
+    auto launch_group = [&](const Launch13 *Ls, int nl) -> int {
+        Params13 pp{};
         pp.x = d_dvs;
         pp.state = state;
-        pp.mr = L.rot >= 0 ? p->d_rotation + L.rot * img : nullptr;
-        pp.os = p->d_shift + L.comp * D;
+        pp.nl = nl;
+        for (int q = 0; q < nl; ++q) {
+            pp.mr[q] = Ls[q].rot >= 0 ? p->d_rotation + Ls[q].rot * img : nullptr;
+            pp.L[q] = Ls[q];
+        }
+        pp.os = p->d_shift + Ls[0].comp * D;
         pp.table = p->d_table;
         pp.out = comp ? fit : d_fvs;
         pp.wout = w;
@@ -802,24 +849,36 @@ int cec2013_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, c
         pp.twei = pl.twei;
         pp.strict = p->strict;
         pp.ti = kTileInd; // launch13 picks the tile size from the batch size
-        pp.L = L;
-        int rc;
         switch (pl.dim) {
-            case 2: rc = launch13<2>(ctx, pp, stream); break;
-            case 5: rc = launch13<5>(ctx, pp, stream); break;
-            case 10: rc = launch13<10>(ctx, pp, stream); break;
-            case 20: rc = launch13<20>(ctx, pp, stream); break;
-            case 30: rc = launch13<30>(ctx, pp, stream); break;
-            case 40: rc = launch13<40>(ctx, pp, stream); break;
-            case 50: rc = launch13<50>(ctx, pp, stream); break;
-            case 60: rc = launch13<60>(ctx, pp, stream); break;
-            case 70: rc = launch13<70>(ctx, pp, stream); break;
-            case 80: rc = launch13<80>(ctx, pp, stream); break;
-            case 90: rc = launch13<90>(ctx, pp, stream); break;
-            case 100: rc = launch13<100>(ctx, pp, stream); break;
+            case 2: return launch13<2>(ctx, pp, stream);
+            case 5: return launch13<5>(ctx, pp, stream);
+            case 10: return launch13<10>(ctx, pp, stream);
+            case 20: return launch13<20>(ctx, pp, stream);
+            case 30: return launch13<30>(ctx, pp, stream);
+            case 40: return launch13<40>(ctx, pp, stream);
+            case 50: return launch13<50>(ctx, pp, stream);
+            case 60: return launch13<60>(ctx, pp, stream);
+            case 70: return launch13<70>(ctx, pp, stream);
+            case 80: return launch13<80>(ctx, pp, stream);
+            case 90: return launch13<90>(ctx, pp, stream);
+            case 100: return launch13<100>(ctx, pp, stream);
             default: set_error("cec2013: unsupported dimension %d", pl.dim); return PGC_ERR_INVALID_ARGUMENT;
         }
+    };
+    // Island-sized batches of a single-component function whose matrices all fit in shared memory: the whole chain in ONE launch
+    // (the vector stays in the warp's buffers between the rotations instead of a round trip through the state array; same bits).
+    const size_t nl_all = pl.launches.size();
+    const size_t merged_smem = sizeof(double) * (nl_all * img + D) + 16 + 4 * (sizeof(double) * 2 * ystride(pl.dim) + sizeof(unsigned short) * D + 16);
+    const bool merge = !comp && nl_all > 1 && nl_all <= static_cast<size_t>(kMaxMerge) && tile_individuals(ctx, static_cast<long long>(n)) < kTileInd
+                       && merged_smem <= ctx->smem_optin && merge_enabled();
+    if (merge) {
+        int rc = launch_group(pl.launches.data(), static_cast<int>(nl_all));
         if (rc != PGC_OK) return rc;
+    } else {
+        for (const Launch13 &L : pl.launches) {
+            int rc = launch_group(&L, 1);
+            if (rc != PGC_OK) return rc;
+        }
     }
     if (comp) {
         Combine13 cp;
