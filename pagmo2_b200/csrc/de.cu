@@ -133,6 +133,10 @@ __device__ __forceinline__ TrialHead trial_head(const TrialParams &P, unsigned i
 {
     TrialHead H;
     const unsigned NP = P.NP;
+    // the individual's own self-adapted state: loaded before the draws decide whether it is used (latency off the chain)
+    const double own_F = (P.cfg.algo != 0u && P.cfg.variant_adptv == 1u) ? P.F_in[i] : 0.0;
+    const double own_CR = (P.cfg.algo != 0u && P.cfg.variant_adptv == 1u) ? P.CR_in[i] : 0.0;
+    const unsigned own_variant = P.cfg.algo == 2u ? P.variant_in[i] : 0u;
     // Durstenfeld partial shuffle of 0..NP-1 (de.cpp:143-149, de1220.cpp:181-187) on a virtual array: only the picked
     // positions are ever overwritten (with the value of the current last position)
     const unsigned npick = P.cfg.algo == 0 ? 5u : 7u;
@@ -155,11 +159,11 @@ __device__ __forceinline__ TrialHead trial_head(const TrialParams &P, unsigned i
     double F = P.cfg.F, CR = P.cfg.CR;
     unsigned variant = P.cfg.variant;
     if (P.cfg.algo == 2u) { // de1220.cpp:192
-        variant = (rs.next() < 0.9) ? P.variant_in[i] : P.cfg.allowed[uint_below_from(rs, P.cfg.n_allowed)];
+        variant = (rs.next() < 0.9) ? own_variant : P.cfg.allowed[uint_below_from(rs, P.cfg.n_allowed)];
     }
     if (P.cfg.algo != 0u && P.cfg.variant_adptv == 1u) { // jDE, de1220.cpp:193-196 / sade.cpp:178-182
-        F = (rs.next() < 0.9) ? P.F_in[i] : rs.next() * 0.9 + 0.1;
-        CR = (rs.next() < 0.9) ? P.CR_in[i] : rs.next();
+        F = (rs.next() < 0.9) ? own_F : rs.next() * 0.9 + 0.1;
+        CR = (rs.next() < 0.9) ? own_CR : rs.next();
     }
     unsigned base;
     bool expo;
@@ -724,9 +728,14 @@ struct ResidentParams {
     unsigned long long seed;
     DeConfig cfg;
     double xtol, ftol;
+    DePartial *parts[2];      // per-CTA (accepted-best, best, worst) candidates of a generation, double buffered like the population
+    unsigned long long *prof; // PGC_DE_PROF=1: clock64 sums of CTA 0 (trial + evaluate + select | grid barrier | reduction), else null
 };
 
-constexpr unsigned kResWarps = 8;
+#ifndef PGC_RES_WARPS
+#define PGC_RES_WARPS 8
+#endif
+constexpr unsigned kResWarps = PGC_RES_WARPS; // warps (= individuals in flight) per CTA of the resident loop
 
 template <int FAM> __global__ void __launch_bounds__(kResWarps * 32) de_resident_kernel(const ResidentParams R)
 {
@@ -741,7 +750,9 @@ template <int FAM> __global__ void __launch_bounds__(kResWarps * 32) de_resident
     if (t == 0) sG = *R.G;
     __syncthreads();
     unsigned cur = 0;
+    long long c_work = 0, c_sync = 0, c_reduce = 0;
     for (unsigned g = 0; g < R.gens; ++g) {
+        const long long c0 = clock64();
         const unsigned nxt = cur ^ 1u;
         TrialParams P{};
         P.popold = R.x[cur];
@@ -757,7 +768,9 @@ template <int FAM> __global__ void __launch_bounds__(kResWarps * 32) de_resident
         P.dim = dim;
         P.seed = R.seed;
         P.cfg = R.cfg;
+        ArgVal best{0.0, kNone}, worst{0.0, kNone}, acc{0.0, kNone}; // over this warp's individuals, after the selection
         for (unsigned i = blockIdx.x * kResWarps + warp; i < NP; i += gridDim.x * kResWarps) {
+            const double fo = R.f[cur][i]; // issued early: its latency hides behind the trial construction
             const TrialHead H = trial_warp_body(P, i, sG.gen_base + g, lane, row);
             __syncwarp();
             for (unsigned j = lane; j < dim; j += 32u) {
@@ -773,14 +786,16 @@ template <int FAM> __global__ void __launch_bounds__(kResWarps * 32) de_resident
                 ft = simple::acc_final<FAM>(acc, static_cast<int>(dim));
             }
             ft = __shfl_sync(0xffffffffu, ft, 0);
-            const double fo = R.f[cur][i];
             const bool ok = ft <= fo; // selection, de.cpp:281-299 / de1220.cpp:515-536
+            const ArgVal mine{ok ? ft : fo, i};
+            best = arg_combine<0>(best, mine);
+            worst = arg_combine<1>(worst, mine);
+            if (ok) acc = arg_combine<2>(acc, mine);
             const double *old_row = R.x[cur] + static_cast<size_t>(i) * dim;
             double *new_row = R.x[nxt] + static_cast<size_t>(i) * dim;
             for (unsigned j = lane; j < dim; j += 32u) new_row[j] = ok ? row[j] : old_row[j];
             if (lane == 0) {
                 R.f[nxt][i] = ok ? ft : fo;
-                R.accepted[nxt][i] = ok;
                 if (R.F[0]) {
                     R.F[nxt][i] = ok ? H.F : R.F[cur][i];
                     R.CR[nxt][i] = ok ? H.CR : R.CR[cur][i];
@@ -789,15 +804,33 @@ template <int FAM> __global__ void __launch_bounds__(kResWarps * 32) de_resident
             }
             __syncwarp();
         }
-        grid.sync();
-        // ---- every CTA: best = first minimum, worst = first maximum, accepted-best = LAST minimum among the accepted trials
-        ArgVal best{0.0, kNone}, worst{0.0, kNone}, acc{0.0, kNone};
-        for (unsigned i = t; i < NP; i += blockDim.x) {
-            const double v = R.f[nxt][i];
-            best = arg_combine<0>(best, ArgVal{v, i});
-            worst = arg_combine<1>(worst, ArgVal{v, i});
-            if (R.accepted[nxt][i]) acc = arg_combine<2>(acc, ArgVal{v, i});
+        if (lane == 0) {
+            s_best[warp] = best;
+            s_worst[warp] = worst;
+            s_acc[warp] = acc;
         }
+        __syncthreads();
+        if (t == 0) {
+            for (unsigned w = 1; w < kResWarps; ++w) {
+                best = arg_combine<0>(best, s_best[w]);
+                worst = arg_combine<1>(worst, s_worst[w]);
+                acc = arg_combine<2>(acc, s_acc[w]);
+            }
+            R.parts[nxt][blockIdx.x] = DePartial{acc.v, best.v, worst.v, acc.i, best.i, worst.i};
+        }
+        const long long c1 = clock64();
+        grid.sync();
+        const long long c2 = clock64();
+        // ---- every CTA combines the CTAs' candidates: best = first minimum, worst = first maximum, accepted-best = LAST minimum
+        // among the accepted trials (the rules do not depend on the order of combination)
+        best = worst = acc = ArgVal{0.0, kNone};
+        for (unsigned k = t; k < gridDim.x; k += blockDim.x) {
+            const DePartial q = R.parts[nxt][k];
+            best = arg_combine<0>(best, ArgVal{q.fb, q.ib});
+            worst = arg_combine<1>(worst, ArgVal{q.fw, q.iw});
+            acc = arg_combine<2>(acc, ArgVal{q.fa, q.ia});
+        }
+        __syncthreads(); // s_best ... are about to be reused
         best = arg_reduce_warp<0>(best);
         worst = arg_reduce_warp<1>(worst);
         acc = arg_reduce_warp<2>(acc);
@@ -815,6 +848,17 @@ template <int FAM> __global__ void __launch_bounds__(kResWarps * 32) de_resident
             worst = arg_combine<1>(worst, s_worst[w]);
             acc = arg_combine<2>(acc, s_acc[w]);
         }
+        // the new global best's self-adapted parameters: loaded now, next to the rows of the exit test
+        const bool moved = acc.i != kNone && acc.v <= sG.gbfit; // sG is written again only after the next barrier
+        double gF = 0.0, gCR = 0.0;
+        unsigned gvar = 0u;
+        if (t == 0 && moved) {
+            if (R.F[0]) {
+                gF = R.F[nxt][acc.i];
+                gCR = R.CR[nxt][acc.i];
+            }
+            if (R.variant[0]) gvar = R.variant[nxt][acc.i];
+        }
         double dx = 0.0; // sum_d |x_worst[d] - x_best[d]| in ascending d (de.cpp:302-306)
         for (unsigned d0 = 0; d0 < dim; d0 += blockDim.x) {
             const unsigned d = d0 + t;
@@ -827,14 +871,14 @@ template <int FAM> __global__ void __launch_bounds__(kResWarps * 32) de_resident
         if (t == 0) {
             sG.best_idx = best.i;
             sG.worst_idx = worst.i;
-            if (acc.i != kNone && acc.v <= sG.gbfit) {
+            if (moved) {
                 sG.gbidx = acc.i;
                 sG.gbfit = acc.v;
                 if (R.F[0]) {
-                    sG.gbF = R.F[nxt][acc.i];
-                    sG.gbCR = R.CR[nxt][acc.i];
+                    sG.gbF = gF;
+                    sG.gbCR = gCR;
                 }
-                if (R.variant[0]) sG.gbvariant = R.variant[nxt][acc.i];
+                if (R.variant[0]) sG.gbvariant = gvar;
             }
             sG.df = fabs(worst.v - best.v);
             sG.dx = dx;
@@ -842,6 +886,9 @@ template <int FAM> __global__ void __launch_bounds__(kResWarps * 32) de_resident
             if (dx < R.xtol || sG.df < R.ftol) sG.stopped = 1; // de.cpp:308,316
         }
         __syncthreads();
+        c_work += c1 - c0;
+        c_sync += c2 - c1;
+        c_reduce += clock64() - c2;
         cur = nxt;
         if (sG.stopped) break; // the same decision in every CTA
     }
@@ -862,6 +909,11 @@ template <int FAM> __global__ void __launch_bounds__(kResWarps * 32) de_resident
     if (blockIdx.x == 0) {
         for (unsigned d = t; d < dim; d += blockDim.x) R.gbX[d] = R.x[cur][static_cast<size_t>(sG.gbidx) * dim + d];
         if (t == 0) *R.G = sG;
+        if (t == 0 && R.prof) {
+            R.prof[0] = static_cast<unsigned long long>(c_work);
+            R.prof[1] = static_cast<unsigned long long>(c_sync);
+            R.prof[2] = static_cast<unsigned long long>(c_reduce);
+        }
     }
 }
 
@@ -930,6 +982,7 @@ struct DeWork : LoopWorkspace {
     double *x2 = nullptr, *f2 = nullptr, *F2 = nullptr, *CR2 = nullptr;
     unsigned *var2 = nullptr;
     unsigned char *acc2[2] = {nullptr, nullptr};
+    DePartial *res_parts = nullptr;
     unsigned nparts = 0;
     std::vector<void *> owned;
     cudaGraphExec_t exec = nullptr;
@@ -981,6 +1034,7 @@ struct DeWork : LoopWorkspace {
             return rc;
         if (algo != 0u && ((rc = get(&F2, 8 * NP)) || (rc = get(&CR2, 8 * NP)))) return rc;
         if (algo == 2u && (rc = get(&var2, 4 * NP))) return rc;
+        if ((rc = get(&res_parts, 2 * sizeof(DePartial) * ((NP + kResWarps - 1) / kResWarps)))) return rc;
         return PGC_OK;
     }
     void drop_graph()
@@ -1140,6 +1194,12 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
         R.seed = seed;
         R.cfg = cfg;
         R.xtol = xtol; R.ftol = ftol;
+        R.parts[0] = W->res_parts;
+        R.parts[1] = W->res_parts + nblk(NP, kResWarps);
+        const char *prof_env = std::getenv("PGC_DE_PROF");
+        unsigned long long *d_prof = nullptr;
+        if (prof_env && prof_env[0] == '1') PGC_CUDA(cudaMalloc(&d_prof, 3 * sizeof(unsigned long long)));
+        R.prof = d_prof;
         int rc;
         switch (fam) {
             case PGC_RASTRIGIN: rc = launch_resident<PGC_RASTRIGIN>(ctx, R, st); break;
@@ -1153,6 +1213,14 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
         PGC_CUDA(cudaMemcpyAsync(&hres, G, sizeof(DeGlobal), cudaMemcpyDeviceToHost, st));
         PGC_CUDA(cudaStreamSynchronize(st));
         if (gens_done) *gens_done = hres.gens_done;
+        if (d_prof) {
+            unsigned long long hp[3] = {};
+            cudaMemcpy(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost);
+            cudaFree(d_prof);
+            const double g = hres.gens_done ? hres.gens_done : 1;
+            std::fprintf(stderr, "[pgc de_resident] cycles per generation in CTA 0: work %.0f, grid barrier %.0f, reduction %.0f\n", hp[0] / g,
+                         hp[1] / g, hp[2] / g);
+        }
         return PGC_OK;
     }
     // one generation: no launch parameter depends on the generation index (the kernels read it from G), so the same launches can
