@@ -247,18 +247,23 @@ def measure_secondary(ctx, capi, device):
         return {"what": "cfg1: rastrigin D=10, pop 1024, de1220, 100 generations per evolve()", "generations_per_s": 100 * reps / dt,
                 "evals_per_s": 100 * reps * NP / dt, "us_per_generation": dt / (100 * reps) * 1e6}
 
-    def cfg4():  # Lennard-Jones 150 atoms, pairwise-energy kernel
+    def cfg4():  # Lennard-Jones 150 atoms (D=444), the swarm of BASELINE cfg4 (262 144 particles), pairwise-energy kernel
         import torch
         p = capi.Problem(ctx, "lennard_jones", dim=150)
-        NP = 65536
+        NP = 262144
         x = torch.rand((NP, p.nx), dtype=torch.float64, device=f"cuda:{device}") * 6 - 3
         f = torch.empty(NP, dtype=torch.float64, device=f"cuda:{device}")
         p.eval_device(x.data_ptr(), NP, f.data_ptr(), ctx.stream)
         dt = _timed(lambda: [p.eval_device(x.data_ptr(), NP, f.data_ptr(), ctx.stream) for _ in range(5)], ctx.synchronize)
         p.close()
         pairs = 150 * 149 // 2
-        return {"what": "cfg4 kernel: lennard_jones 150 atoms (D=444), 65536 individuals resident", "evals_per_s": 5 * NP / dt,
-                "fp64_tflops_14_per_pair": 5 * NP * pairs * 14 / dt / 1e12}
+        rate = 5 * NP / dt
+        # 13 FP64-pipe instructions per pair (7 of them FMAs: 20 flop): the pipe's issue ceiling at the DFMA probe's rate
+        ceiling = ctx.fp64_peak_tflops(4096) * 1e12 / 64.0 / (pairs * 13)
+        return {"what": "cfg4 kernel: lennard_jones 150 atoms (D=444), 262144 individuals resident", "evals_per_s": rate,
+                "fp64_tflops_20_per_pair": rate * pairs * 20 / 1e12,
+                "roofline": {"bound": "fp64 issue", "achieved": rate, "peak": ceiling, "unit": "evals/s", "frac": rate / ceiling,
+                             "note": "13 FP64-pipe instructions per pair; peak = DFMA probe TF/s / 2 flop / 32 lanes / (11175 pairs x 13)"}}
 
     def cfg5():
         return measure_cfg5(capi, [device], rank=0, world=1, comm=None, rounds=4)
