@@ -222,6 +222,19 @@ def measure_secondary(ctx, capi, device):
             r[name] = {"generations_per_s": 5.0 / dt, "ms_per_generation": dt / 5 * 1e3, "fronts_in_population": fronts,
                        # latency model: the select_best_N_mo sort of 2N points peels about this many levels per generation
                        "us_per_level": dt / 5 * 1e6 / max(fronts, 1)}
+            try:  # roofline of the second headline metric: the dominance relation over the 2N points of a generation
+                import torch
+                pr = torch.cuda.get_device_properties(device)
+                clock_hz = 1e3 * getattr(pr, "clock_rate", 1965000)
+                peak = pr.multi_processor_count * 64 * clock_hz  # FP64 compares (DSETP) per second: 64 lanes per SM per clock
+                tests = float(2 * NP) ** 2 * p2.nf               # objective compares of an all-pairs dominance pass over 2N points
+                r[name]["roofline"] = {"bound": "fp64 compare issue, all-pairs model", "achieved": tests / (dt / 5), "peak": peak,
+                                       "unit": "objective compares/s", "frac": tests / (dt / 5) / peak,
+                                       "note": "(2N)^2 * M compares per generation / generation time; the sort-based count (M = 2) and the "
+                                               "position ranges of the resident level loop do fewer compares than all-pairs, and the level "
+                                               "loop is latency-bound (~17 us per level), so this is an equivalent rate, not pipe utilisation"}
+            except Exception:
+                pass
             if name in ref:
                 r[name]["cpu_reference_generations_per_s"] = ref[name]["extrapolated_generations_per_s_at_65536"]
                 r[name]["cpu_reference_note"] = ("unmodified nsga2::evolve on one core, measured at pop 2048-16384 and extrapolated with the "

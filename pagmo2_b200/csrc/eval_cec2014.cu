@@ -7,11 +7,11 @@
 //   * one "stage kernel" launch per recipe stage (cec2014_recipe.cpp).  A stage = sr_func (shift, scale,
 //     rotate; cec2014.cpp:1238-1274) + optional hybrid permutation (:807-809) + 1..5 primitive groups.
 //     Compositions (f23-f30) launch one stage kernel per component plus a tiny cf_cal kernel (:1319-1353).
-//   * rotation z = Mr*y is the FP64-pipe-bound part (2*D^2 flop/eval).  Persistent CTAs (one per SM, 8 warps)
+//   * rotation z = Mr*y is the FP64-pipe-bound part (2*D^2 flop/eval).  Persistent CTAs (one per SM, 16 warps at D = 100)
 //     keep the whole matrix in shared memory (row-major, padded stride).  Every warp is an independent worker
-//     on tiles of 16 individuals with a private shared-memory buffer:
-//     load+shift+scale -> FP64 GEMM on mma.sync.m8n8k4.f64 (DMMA; 2 x NT accumulator tiles per warp) -> z back
-//     to the buffer -> primitive epilogue (2 lanes per individual).  Warps de-synchronise, so one warp's load /
+//     on tiles of 8 individuals with a private shared-memory buffer:
+//     load+shift+scale -> FP64 GEMM on mma.sync.m8n8k4.f64 (DMMA; NT accumulator tiles per warp) -> z back
+//     to the buffer -> primitive epilogue (4 lanes per individual).  Warps de-synchronise, so one warp's load /
 //     epilogue overlaps the other warps' DMMA streams; no block-level barrier inside the tile loop.
 //     Why DMMA and not SIMT DFMA: a register-tiled DFMA version (profiles/r1a_simt_*) was shared-memory-
 //     bandwidth bound - an LDS costs (bytes per lane x 32)/128 cycles whatever the broadcast pattern, so a

@@ -169,14 +169,13 @@ __global__ void __launch_bounds__(kLjWarps * 32) lj_reg_kernel(const double *__r
 #endif
 
 template <int NC, int LO, int A>
-__device__ __forceinline__ void lj_span(const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz, int k0,
-                                        int k1, const double (&xa)[NC], const double (&ya)[NC], const double (&za)[NC], double (&s)[NC],
-                                        bool own_last)
+__device__ __forceinline__ void lj_span(const double *__restrict__ pos, int k0, int k1, const double (&xa)[NC], const double (&ya)[NC],
+                                        const double (&za)[NC], double (&s)[NC])
 {
     constexpr int U = (PGC_LJ_CHAINS + A - 1) / A; // ~PGC_LJ_CHAINS independent chains per warp
 #pragma unroll U
     for (int k = k0; k < k1; ++k) {
-        const double qx = px[k], qy = py[k], qz = pz[k];
+        const double qx = pos[3 * k], qy = pos[3 * k + 1], qz = pos[3 * k + 2]; // one address register, immediate offsets
         double dist[A], cube[A], r[A], e[A];
 #pragma unroll
         for (int a = 0; a < A; ++a) {
@@ -199,38 +198,32 @@ __device__ __forceinline__ void lj_span(const double *__restrict__ px, const dou
         // a coincident pair gives 1 / 0 = inf and inf * inf - inf = NaN, which poisons the lane's sum: detected once at the end
         // instead of one FP64 compare per pair
 #pragma unroll
-        for (int a = 0; a < A; ++a) {
-            const int c = (LO + a) % NC;
-            if (c < NC - 1) s[c] += e[a];                             // every lane of these chunks owns a real atom
-            else s[c] += own_last ? e[a] : 0.0;
-        }
+        for (int a = 0; a < A; ++a) s[(LO + a) % NC] += e[a]; // (parked lanes add ~1e-48 terms to sums that are dropped at the end)
     }
 }
 
 __host__ __device__ constexpr int lj_max_live(int nc) { return nc / 2 + 1; } // most own chunks one partner position can serve (checked for every N)
 
 template <int NC, int LO, int A = 1>
-__device__ __forceinline__ void lj_dispatch_count(int cnt, const double *__restrict__ px, const double *__restrict__ py,
-                                                  const double *__restrict__ pz, int k0, int k1, const double (&xa)[NC],
-                                                  const double (&ya)[NC], const double (&za)[NC], double (&s)[NC], bool own_last)
+__device__ __forceinline__ void lj_dispatch_count(int cnt, const double *__restrict__ pos, int k0, int k1, const double (&xa)[NC],
+                                                  const double (&ya)[NC], const double (&za)[NC], double (&s)[NC])
 {
     if (cnt == A) {
-        lj_span<NC, LO, A>(px, py, pz, k0, k1, xa, ya, za, s, own_last);
+        lj_span<NC, LO, A>(pos, k0, k1, xa, ya, za, s);
         return;
     }
-    if constexpr (A < lj_max_live(NC) && A < NC) lj_dispatch_count<NC, LO, A + 1>(cnt, px, py, pz, k0, k1, xa, ya, za, s, own_last);
+    if constexpr (A < lj_max_live(NC) && A < NC) lj_dispatch_count<NC, LO, A + 1>(cnt, pos, k0, k1, xa, ya, za, s);
 }
 
 template <int NC, int LO = 0>
-__device__ __forceinline__ void lj_dispatch(int lo, int cnt, const double *__restrict__ px, const double *__restrict__ py,
-                                            const double *__restrict__ pz, int k0, int k1, const double (&xa)[NC], const double (&ya)[NC],
-                                            const double (&za)[NC], double (&s)[NC], bool own_last)
+__device__ __forceinline__ void lj_dispatch(int lo, int cnt, const double *__restrict__ pos, int k0, int k1, const double (&xa)[NC],
+                                            const double (&ya)[NC], const double (&za)[NC], double (&s)[NC])
 {
     if (lo == LO) {
-        lj_dispatch_count<NC, LO>(cnt, px, py, pz, k0, k1, xa, ya, za, s, own_last);
+        lj_dispatch_count<NC, LO>(cnt, pos, k0, k1, xa, ya, za, s);
         return;
     }
-    if constexpr (LO + 1 < NC) lj_dispatch<NC, LO + 1>(lo, cnt, px, py, pz, k0, k1, xa, ya, za, s, own_last);
+    if constexpr (LO + 1 < NC) lj_dispatch<NC, LO + 1>(lo, cnt, pos, k0, k1, xa, ya, za, s);
 }
 
 constexpr int kLjMaxSegments = 40; // the live set changes at most 2 NC + 1 times; gaps (clusters below 64 atoms) add NC more
@@ -245,11 +238,10 @@ __global__ void __launch_bounds__(kLjWarps * 32, PGC_LJ_MINBLOCKS) lj_circ_kerne
     __shared__ int seg_k0[kLjMaxSegments], seg_lo[kLjMaxSegments], seg_cnt[kLjMaxSegments], n_seg;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = atoms, W = lj_circ_len(N);
-    double *px = smem + static_cast<size_t>(warp) * 3 * W, *py = px + W, *pz = py + W;
+    double *pos = smem + static_cast<size_t>(warp) * 3 * W; // (x, y, z) of position k at pos[3 k ...]: 24-byte stride, conflict free
     const int D = 3 * atoms - 6;
     const int full = (N - 1) / 2;          // offsets at which every atom has a partner
     const bool half = (N % 2) == 0;        // even N: one more offset for the first N / 2 atoms
-    const bool own_last = (NC - 1) * 32 + lane < N;
     if (threadIdx.x == 0) { // segments of dp = 1 ... N with a constant set of live chunks: c is live when (dp - 32 c) mod N is in [1, full]
         int ns = 0, prev_lo = -1, prev_cnt = -1;
         for (int dp = 1; dp <= N; ++dp) {
@@ -279,7 +271,7 @@ __global__ void __launch_bounds__(kLjWarps * 32, PGC_LJ_MINBLOCKS) lj_circ_kerne
     for (long long ind = static_cast<long long>(blockIdx.x) * kLjWarps + warp; ind < n; ind += static_cast<long long>(gridDim.x) * kLjWarps) {
         const double *xi = x + ind * D;
         double xa[NC], ya[NC], za[NC];
-        for (int a = 2 * N + lane; a < W; a += 32) px[a] = py[a] = pz[a] = 0.0; // clusters below 32 atoms: read by parked lanes only
+        for (int a = 2 * N + lane; a < W; a += 32) pos[3 * a] = pos[3 * a + 1] = pos[3 * a + 2] = 0.0; // clusters below 32 atoms: read by parked lanes only
 #pragma unroll
         for (int c = 0; c < NC; ++c) { // coordinate map _r, :132-151; lanes beyond the cluster are parked far away (their terms are dropped)
             const int a = c * 32 + lane;
@@ -288,13 +280,13 @@ __global__ void __launch_bounds__(kLjWarps * 32, PGC_LJ_MINBLOCKS) lj_circ_kerne
                 cx = (a >= 3) ? xi[3 * (a - 2)] : 0.0;
                 cy = (a >= 3) ? xi[3 * (a - 2) + 1] : (a == 2 ? xi[1] : 0.0);
                 cz = (a >= 3) ? xi[3 * (a - 2) + 2] : (a == 2 ? xi[2] : (a == 1 ? xi[0] : 0.0));
-                px[a] = cx;
-                py[a] = cy;
-                pz[a] = cz;
+                pos[3 * a] = cx;
+                pos[3 * a + 1] = cy;
+                pos[3 * a + 2] = cz;
                 if (a + N < W) { // wrapped copy: position k holds atom k mod N
-                    px[a + N] = cx;
-                    py[a + N] = cy;
-                    pz[a + N] = cz;
+                    pos[3 * (a + N)] = cx;
+                    pos[3 * (a + N) + 1] = cy;
+                    pos[3 * (a + N) + 2] = cz;
                 }
             }
             xa[c] = cx;
@@ -307,7 +299,7 @@ __global__ void __launch_bounds__(kLjWarps * 32, PGC_LJ_MINBLOCKS) lj_circ_kerne
         for (int c = 0; c < NC; ++c) s[c] = 0.0;
         for (int g = 0; g < nseg; ++g) {
             const int cnt = seg_cnt[g];
-            if (cnt > 0) lj_dispatch<NC>(seg_lo[g], cnt, px + lane, py + lane, pz + lane, seg_k0[g], seg_k0[g + 1], xa, ya, za, s, own_last);
+            if (cnt > 0) lj_dispatch<NC>(seg_lo[g], cnt, pos + 3 * lane, seg_k0[g], seg_k0[g + 1], xa, ya, za, s);
         }
         if (half) {
             const int d = N / 2;
@@ -316,7 +308,7 @@ __global__ void __launch_bounds__(kLjWarps * 32, PGC_LJ_MINBLOCKS) lj_circ_kerne
                 if (c * 32 < d) { // warp-uniform: chunks that hold atoms below N / 2
                     const int i = c * 32 + lane, j = i + d;
                     const bool valid = i < d;
-                    const double dx = xa[c] - px[j], dy = ya[c] - py[j], dz = za[c] - pz[j];
+                    const double dx = xa[c] - pos[3 * j], dy = ya[c] - pos[3 * j + 1], dz = za[c] - pos[3 * j + 2];
                     const double dist = fma(dz, dz, fma(dy, dy, dx * dx));
                     const double sixth = fast_rcp(dist * dist * dist);
                     const double term = fma(sixth, sixth, -sixth);
@@ -324,6 +316,7 @@ __global__ void __launch_bounds__(kLjWarps * 32, PGC_LJ_MINBLOCKS) lj_circ_kerne
                 }
             }
         }
+        if ((NC - 1) * 32 + lane >= N) s[NC - 1] = 0.0; // parked lanes of the last chunk: their (tiny) terms are dropped here
         double tot = s[0];
 #pragma unroll
         for (int c = 1; c < NC; ++c) tot += s[c];
