@@ -157,4 +157,13 @@ int oracle_nsga2_evolve_mt(int family, unsigned prob_id, size_t nx, size_t nobj,
 #ifdef __cplusplus
 }
 #endif
+/* nspso::evolve (src/algorithms/nspso.cpp:84-411); diversity: 0 crowding distance, 1 niche count, 2 max min.  vel / best_x / best_f:
+ * the algorithm's memory (in/out), NULL = memory-less start (velocities drawn, archive = population) */
+int oracle_nspso_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t n, size_t dim, size_t m,
+                        unsigned gens, double omega, double c1, double c2, double chi, double v_coeff, unsigned leader_selection_range,
+                        unsigned diversity, uint64_t seed, uint32_t first_generation, double *vel, double *best_x, double *best_f);
+int oracle_nspso_evolve_mt(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t n, size_t dim, size_t m,
+                           unsigned gens, double omega, double c1, double c2, double chi, double v_coeff, unsigned leader_selection_range,
+                           unsigned diversity, uint32_t seed);
+
 #endif

@@ -476,6 +476,37 @@ class Oracle:
             raise ValueError("oracle_pso_evolve_mt failed")
         return x, f
 
+    DIVERSITY = {"crowding distance": 0, "niche count": 1, "max min": 2}
+
+    def nspso_evolve(self, prob, lb, ub, x, f, gens=1, omega=0.6, c1=2.0, c2=2.0, chi=1.0, v_coeff=0.5, leader_selection_range=60,
+                     diversity="crowding distance", seed=0, first_generation=1, vel=None, best_x=None, best_f=None, mt=False):
+        """restated nspso::evolve (Philox draws, or the mt19937 stream with mt=True): returns (x, f, vel, best_x, best_f); vel / best_*
+        are None unless the memory arrays were passed in."""
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C").reshape(x.shape[0], -1)
+        n, dim = x.shape
+        m = f.shape[1]
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        div = self.DIVERSITY[diversity]
+        if mt:
+            self.lib.oracle_nspso_evolve_mt.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_size_t, C.c_size_t,
+                                                        C.c_size_t, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                        C.c_uint, C.c_uint, C.c_uint32]
+            rc = self.lib.oracle_nspso_evolve_mt(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), n, dim, m, gens, omega, c1, c2, chi, v_coeff,
+                                                 leader_selection_range, div, seed)
+            if rc:
+                raise ValueError("oracle_nspso_evolve_mt failed")
+            return x, f, None, None, None
+        mem = [None if a is None else np.array(a, dtype=np.float64, order="C") for a in (vel, best_x, best_f)]
+        self.lib.oracle_nspso_evolve.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                 C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint, C.c_uint,
+                                                 C.c_uint64, C.c_uint32, c_double_p, c_double_p, c_double_p]
+        rc = self.lib.oracle_nspso_evolve(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), n, dim, m, gens, omega, c1, c2, chi, v_coeff,
+                                          leader_selection_range, div, seed, first_generation, *[None if a is None else _dp(a) for a in mem])
+        if rc:
+            raise ValueError("oracle_nspso_evolve failed")
+        return (x, f, *mem)
+
     def de_evolve_mt(self, prob, lb, ub, x, f, gens=1, algo="de1220", variant=2, variant_adptv=1, F=0.8, CR=0.9,
                      allowed=(2, 3, 7, 10, 13, 14, 15, 16), ftol=1e-6, xtol=1e-6, seed=0):
         """restated de / sade / de1220 on the mt19937 stream, in the reference's one-at-a-time order: returns (x, f, gens_done)."""

@@ -12,6 +12,7 @@
 #include <pagmo/algorithms/de.hpp>
 #include <pagmo/algorithms/de1220.hpp>
 #include <pagmo/algorithms/nsga2.hpp>
+#include <pagmo/algorithms/nspso.hpp>
 #include <pagmo/algorithms/pso_gen.hpp>
 #include <pagmo/algorithms/sade.hpp>
 #include <pagmo/algorithms/sga.hpp>
@@ -153,6 +154,10 @@ int ref_evolve_from(ref_problem *p, const char *algo, const double *par, size_t 
             if (c1 == std::string::npos || c2 == std::string::npos) throw std::invalid_argument("ref_evolve_from: strategies");
             alg = pagmo::algorithm{pagmo::sga(gens, par[0], par[1], par[2], par[3], static_cast<unsigned>(par[4]), s.substr(0, c1),
                                               s.substr(c1 + 1, c2 - c1 - 1), s.substr(c2 + 1), seed)};
+        } else if (a == "nspso") {
+            need(6);
+            alg = pagmo::algorithm{pagmo::nspso(gens, par[0], par[1], par[2], par[3], par[4], static_cast<unsigned>(par[5]),
+                                                std::string(strategies ? strategies : "crowding distance"), false, seed)};
         } else
             throw std::invalid_argument("ref_evolve_from: unknown algorithm '" + a + "'");
         pop = alg.evolve(pop);

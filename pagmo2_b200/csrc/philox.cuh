@@ -23,7 +23,8 @@ enum PhiloxTag : uint32_t { // stream tags: one per consumer so that streams nev
     kTagCmaes = 8,
     kTagMigrate = 9,
     kTagPopulation = 10,
-    kTagPsoTopology = 11 // adaptive-random swarm topology: informant draws (pso_gen.cpp:772-796)
+    kTagPsoTopology = 11, // adaptive-random swarm topology: informant draws (pso_gen.cpp:772-796)
+    kTagNspso = 12        // nspso: leader index (repeated while it is the particle itself), r1, r2 (nspso.cpp:304-316)
 };
 
 struct Philox4 {

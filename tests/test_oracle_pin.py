@@ -199,3 +199,26 @@ def test_population_constructor_bit_exact(orc, ref):
             xr, ir = ref.population_init(rp, n, seed)
             xo, io = orc.population_init_mt(lb, ub, n, seed)
             assert np.array_equal(xr, xo) and np.array_equal(ir, io), (fam, n)
+
+
+@pytest.mark.parametrize("fam,args,n", [("zdt", (1, 8), 24), ("zdt", (3, 6), 15), ("dtlz", (2, 7, 3, 100), 20), ("dtlz", (1, 6, 3, 100), 12)])
+def test_nspso_evolve_bit_exact(orc, ref, fam, args, n):
+    """nspso is generational in the reference itself (nspso.cpp:293-395): the restatement on the mt19937 stream must reproduce
+    nspso::evolve bit for bit - leaders (FNDS order, sort_population_mo, niche counts, max-min keys and the tie order std::sort
+    leaves), the rejection loop of the leader draw, the move, the archive of the best N of 2N."""
+    rp = ref.problem(fam, *args)
+    lb, ub = rp.bounds()
+    if fam == "zdt":
+        op = orc.problem("zdt", prob_id=args[0], dim=args[1])
+    else:
+        op = orc.problem("dtlz", prob_id=args[0], dim=args[1], nobj=args[2], param=args[3])
+    rng = np.random.default_rng(n)
+    x0 = rng.uniform(lb, ub, (n, len(lb)))
+    x0[3] = x0[1]  # duplicates: ties in every sort
+    f0 = np.array([rp.fitness(x) for x in x0])
+    for diversity in ("crowding distance", "niche count", "max min"):
+        for lsr, gens in ((60, 9), (5, 4), (100, 4)):
+            seed = lsr + gens
+            xr, fr = ref.evolve_from(rp, "nspso", [0.6, 2.0, 2.0, 1.0, 0.5, lsr], x0, gens, seed, strategies=diversity)
+            xo, fo, *_ = orc.nspso_evolve(op, lb, ub, x0, f0, gens=gens, leader_selection_range=lsr, diversity=diversity, seed=seed, mt=True)
+            assert np.array_equal(xr, xo) and np.array_equal(fr, fo), (diversity, lsr, gens)
