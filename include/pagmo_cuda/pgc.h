@@ -262,6 +262,13 @@ PGC_API int pgc_weighted_mean_device(pgc_ctx *ctx, const double *d_rows, const u
  * eigendecomposition (a cyclic Jacobi solver where the reference calls Eigen's SelfAdjointEigenSolver) on the host.  cc, cs, c1,
  * cmu = -1: the automatic values of :169-183.  d_x / d_f end as the LAST generation sampled (the reference replaces the
  * population every generation); *sigma_out (optional) = final step size.  Reference defaults: sigma0 0.5, ftol = xtol = 1e-6. */
+/* nspso::evolve (src/algorithms/nspso.cpp:84-411) on a device-resident swarm: d_x [n x nx], d_f [n x nobj] in place (the moved
+ * swarm of the last generation, as the reference returns it).  diversity: 0 "crowding distance", 1 "niche count", 2 "max min".
+ * d_vel [n x nx], d_best_x [n x nx], d_best_f [n x nobj]: the algorithm's memory (velocities and the archive m_best_dvs / m_best_fit),
+ * read and updated when given (memory = true), NULL = memory-less start (velocities drawn, archive = the population, :127-152). */
+PGC_API int pgc_nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, double omega, double c1, double c2,
+                                    double chi, double v_coeff, unsigned leader_selection_range, unsigned diversity, uint64_t seed,
+                                    uint32_t first_generation, double *d_vel, double *d_best_x, double *d_best_f, void *stream);
 PGC_API int pgc_cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lambda, unsigned gens, double cc, double cs, double c1,
                                     double cmu, double sigma0, double ftol, double xtol, int force_bounds, uint64_t seed,
                                     uint32_t first_generation, unsigned *gens_done, double *sigma_out, void *stream);
@@ -282,7 +289,8 @@ typedef enum pgc_algo {
     PGC_ALGO_PSO_GEN = 4, /* src/algorithms/pso_gen.cpp:120-590 */
     PGC_ALGO_NSGA2 = 5,   /* src/algorithms/nsga2.cpp:91-307 */
     PGC_ALGO_SGA = 6,     /* src/algorithms/sga.cpp:184-292 */
-    PGC_ALGO_CMAES = 7    /* src/algorithms/cmaes.cpp:111-407 */
+    PGC_ALGO_CMAES = 7,   /* src/algorithms/cmaes.cpp:111-407 */
+    PGC_ALGO_NSPSO = 8    /* src/algorithms/nspso.cpp:84-411 */
 } pgc_algo;
 
 /* Constructor arguments of the reference UDAs; pgc_algo_defaults() fills in the reference's default values
@@ -302,6 +310,8 @@ typedef struct pgc_algo_desc {
     uint32_t param_s, crossover, mutation, selection; /* sga: see pgc_sga_evolve_device */
     double cma_cc, cma_cs, cma_c1, cma_cmu, sigma0;   /* cmaes (-1: automatic), cmaes.hpp:110 */
     uint32_t force_bounds, reserved_;
+    double nspso_c1, nspso_c2, nspso_chi, nspso_v_coeff;       /* nspso (omega is shared with pso_gen), nspso.hpp:59-62 */
+    uint32_t leader_selection_range, diversity;               /* nspso: diversity 0 crowding distance, 1 niche count, 2 max min */
 } pgc_algo_desc;
 
 PGC_API int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out);

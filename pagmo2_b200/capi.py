@@ -54,10 +54,13 @@ class AlgoDesc(C.Structure):
         ("param_m", C.c_double), ("param_s", C.c_uint32), ("crossover", C.c_uint32), ("mutation", C.c_uint32), ("selection", C.c_uint32),
         ("cma_cc", C.c_double), ("cma_cs", C.c_double), ("cma_c1", C.c_double), ("cma_cmu", C.c_double), ("sigma0", C.c_double),
         ("force_bounds", C.c_uint32), ("reserved_", C.c_uint32),
+        ("nspso_c1", C.c_double), ("nspso_c2", C.c_double), ("nspso_chi", C.c_double), ("nspso_v_coeff", C.c_double),
+        ("leader_selection_range", C.c_uint32), ("diversity", C.c_uint32),
     ]
 
 
-ALGO = {"de": 1, "sade": 2, "de1220": 3, "pso_gen": 4, "nsga2": 5, "sga": 6, "cmaes": 7}
+ALGO = {"de": 1, "sade": 2, "de1220": 3, "pso_gen": 4, "nsga2": 5, "sga": 6, "cmaes": 7, "nspso": 8}
+NSPSO_DIVERSITY = {"crowding distance": 0, "niche count": 1, "max min": 2}
 SGA_CROSSOVER = {"exponential": 0, "binomial": 1, "single": 2, "sbx": 3}
 SGA_MUTATION = {"gaussian": 0, "uniform": 1, "polynomial": 2}
 SGA_SELECTION = {"tournament": 0, "truncated": 1}
@@ -561,6 +564,29 @@ class Problem:
         finally:
             self.ctx.free(dx)
             self.ctx.free(df)
+
+    def nspso_evolve(self, x, f, gens=1, omega=0.6, c1=2.0, c2=2.0, chi=1.0, v_coeff=0.5, leader_selection_range=60,
+                     diversity="crowding distance", seed=0, first_generation=1, vel=None, best_x=None, best_f=None):
+        """nspso::evolve on the device: returns (x, f, vel, best_x, best_f); the last three are None unless the memory arrays were given."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(x.shape[0], -1)
+        n = x.shape[0]
+        dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
+        mem = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (vel, best_x, best_f)]
+        dmem = [None if a is None else self.ctx.to_device(a) for a in mem]
+        L = lib()
+        L.pgc_nspso_evolve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_double, C.c_double, C.c_double,
+                                              C.c_double, C.c_double, C.c_uint, C.c_uint, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
+        try:
+            check(L.pgc_nspso_evolve_device(self._h, dx, df, n, gens, omega, c1, c2, chi, v_coeff, leader_selection_range,
+                                            NSPSO_DIVERSITY[diversity], seed, first_generation, *dmem, None))
+            out = [None if a is None else self.ctx.from_device(d, a.shape) for a, d in zip(mem, dmem)]
+            return (self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), *out)
+        finally:
+            for d in (dx, df, *dmem):
+                if d is not None:
+                    self.ctx.free(d)
 
     def evolve(self, algo: "AlgoDesc", x, f, first_generation=1):
         """pagmo::algorithm::evolve on host arrays: upload, `pgc_algo_evolve_device`, download.  Returns (x, f, gens_done)."""

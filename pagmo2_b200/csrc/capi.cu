@@ -815,6 +815,18 @@ int pgc_de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP,
                             stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
 }
 
+int pgc_nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, double omega, double c1, double c2, double chi,
+                            double v_coeff, unsigned leader_selection_range, unsigned diversity, uint64_t seed, uint32_t first_generation,
+                            double *d_vel, double *d_best_x, double *d_best_f, void *stream)
+{
+    PGC_REQUIRE(prob && d_x && d_f, "pgc_nspso_evolve_device: null argument");
+    PGC_NO_INTEGER_GENES(prob, "pgc_nspso_evolve_device");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    return nspso_evolve_device(prob, d_x, d_f, static_cast<unsigned>(n), gens, omega, c1, c2, chi, v_coeff, leader_selection_range, diversity, seed,
+                               first_generation, d_vel, d_best_x, d_best_f, problem_eval_device,
+                               stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
+}
+
 int pgc_hv_device(pgc_ctx *ctx, const double *d_points, size_t n, size_t m, const double *r_point, int compute, double *d_out, void *stream)
 {
     PGC_REQUIRE(ctx && r_point && d_out && (d_points || n == 0), "pgc_hv_device: null argument");
@@ -923,6 +935,9 @@ int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out
             d.cr = 0.9, d.eta_c = 1., d.m = 0.02, d.param_m = 1., d.param_s = 2, d.crossover = 0, d.mutation = 2, d.selection = 0;
             break;
         case PGC_ALGO_CMAES: d.cma_cc = d.cma_cs = d.cma_c1 = d.cma_cmu = -1., d.sigma0 = 0.5; break; // cmaes.hpp:110
+        case PGC_ALGO_NSPSO: // nspso.hpp:59-62
+            d.omega = 0.6, d.nspso_c1 = 2.0, d.nspso_c2 = 2.0, d.nspso_chi = 1.0, d.nspso_v_coeff = 0.5, d.leader_selection_range = 60, d.diversity = 0;
+            break;
         default: set_error("pgc_algo_defaults: unknown algorithm %d", algo); return PGC_ERR_INVALID_ARGUMENT;
     }
     *out = d;
@@ -952,6 +967,9 @@ int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *a, double *d_
         case PGC_ALGO_CMAES:
             return pgc_cmaes_evolve_device(prob, d_x, d_f, n, a->gens, a->cma_cc, a->cma_cs, a->cma_c1, a->cma_cmu, a->sigma0, a->ftol, a->xtol,
                                            static_cast<int>(a->force_bounds), a->seed, first_generation, gens_done, nullptr, stream);
+        case PGC_ALGO_NSPSO:
+            return pgc_nspso_evolve_device(prob, d_x, d_f, n, a->gens, a->omega, a->nspso_c1, a->nspso_c2, a->nspso_chi, a->nspso_v_coeff,
+                                           a->leader_selection_range, a->diversity, a->seed, first_generation, nullptr, nullptr, nullptr, stream);
         default: set_error("pgc_algo_evolve_device: unknown algorithm %d", a->algo); return PGC_ERR_INVALID_ARGUMENT;
     }
 }

@@ -1451,12 +1451,19 @@ int crowding_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, const
     PGC_CUDA(cub::DeviceSegmentedSort::StableSortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n),
                                                        static_cast<int>(nfronts), d_front_off, d_front_off + 1, st));
     if ((rc = ws.alloc_bytes(&tmp, tmp_bytes))) return rc;
+    unsigned *seq = nullptr; // the sequence objective `obj` is sorted from
+    if ((rc = ws.alloc(&seq, n))) return rc;
     for (int obj = 0; obj < m; ++obj) {
-        gather_objective_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_f, m, obj, d_order, n, keys_in, vals_in);
+        // The reference sorts ONE index vector objective after objective without resetting it (multi_objective.cpp:296-313), so among
+        // equal values of objective k the boundary point (and every neighbour) is decided by the order objective k - 1 left.  The
+        // sorts are stable here, so starting each one from the previous result reproduces that; objective 0 starts from the
+        // front's own order.
+        gather_objective_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_f, m, obj, obj == 0 ? d_order : seq, n, keys_in, vals_in);
         size_t bytes = tmp_bytes;
         PGC_CUDA(cub::DeviceSegmentedSort::StableSortPairs(tmp, bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n),
                                                            static_cast<int>(nfronts), d_front_off, d_front_off + 1, st));
         crowding_accumulate_kernel<<<blocks_for(n, 256), 256, 0, st>>>(keys_out, vals_out, seg_of, d_front_off, n, d_cd);
+        if (obj + 1 < m) PGC_CUDA(cudaMemcpyAsync(seq, vals_out, sizeof(unsigned) * n, cudaMemcpyDeviceToDevice, st));
         ctx->launches.fetch_add(4, std::memory_order_relaxed);
     }
     if (small_rule && d_order) {

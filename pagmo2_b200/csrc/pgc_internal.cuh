@@ -280,6 +280,10 @@ int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, 
 int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t s);
 int philox_permutation_device(pgc_ctx *ctx, unsigned n, unsigned long long seed, unsigned tag, unsigned generation, unsigned *d_perm,
                               cudaStream_t st);
+int nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double omega, double c1, double c2, double chi,
+                        double v_coeff, unsigned leader_selection_range, unsigned diversity, unsigned long long seed, unsigned first_generation,
+                        double *d_vel, double *d_best_x, double *d_best_f,
+                        int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
 int nsga2_variation_device(pgc_ctx *ctx, const double *d_x, const unsigned *d_rank, const double *d_cd, unsigned NP, unsigned nx,
                            const double *d_lb, const double *d_ub, const unsigned *d_sh1, const unsigned *d_sh2, double cr,
                            double eta_c, double m, double eta_m, unsigned long long seed, unsigned generation, double *d_children,

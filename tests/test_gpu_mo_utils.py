@@ -227,3 +227,21 @@ def test_fnds_watchdog_surfaces_as_error(ctx, orc, monkeypatch):
     monkeypatch.delenv("PGC_FNDS_INJECT_STUCK")
     g = f[:20000]
     assert same_fnds(ctx.fnds(g), orc.fnds(g))
+
+
+@pytest.mark.parametrize("m", (2, 3, 4))
+def test_crowding_ties_follow_the_carried_index_vector(ctx, orc, m):
+    """crowding_distance sorts ONE index vector objective after objective (multi_objective.cpp:296-313): among equal values of an
+    objective the order left by the previous objective decides who is the boundary point.  Quantised objectives (many exact ties,
+    DTLZ-like zeros) through crowding_distance, sort_population_mo and select_best_N_mo, device == oracle exactly."""
+    rng = np.random.default_rng(100 + m)
+    for n in (5, 64, 257, 1500):
+        f = np.round(rng.uniform(0, 1, (n, m)) * 6) / 6      # ~7 distinct values per objective
+        f[rng.integers(0, n, n // 3), m - 1] = 0.0
+        front = f[orc.fnds(f)["fronts"][0]]
+        if len(front) >= 2:
+            assert np.array_equal(ctx.crowding_distance(front), orc.crowding_distance(front), equal_nan=True), (m, n)
+        assert np.array_equal(ctx.sort_population_mo(f), orc.sort_population_mo(f)), (m, n)
+        for N in (1, n // 3, n // 2, n - 1):
+            if N >= 1:
+                assert np.array_equal(ctx.select_best_N_mo(f, N), orc.select_best_N_mo(f, N)), (m, n, N)
