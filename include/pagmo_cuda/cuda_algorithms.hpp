@@ -125,7 +125,8 @@ public:
                                m_desc.xtol, m_desc.omega, m_desc.eta1, m_desc.eta2, m_desc.max_vel, m_desc.cr, m_desc.eta_c, m_desc.m,
                                m_desc.eta_m, m_desc.seed, m_desc.param_m, m_desc.param_s, m_desc.crossover, m_desc.mutation,
                                m_desc.selection, m_desc.cma_cc, m_desc.cma_cs, m_desc.cma_c1, m_desc.cma_cmu, m_desc.sigma0,
-                               m_desc.force_bounds);
+                               m_desc.force_bounds, m_desc.nspso_c1, m_desc.nspso_c2, m_desc.nspso_chi, m_desc.nspso_v_coeff,
+                               m_desc.leader_selection_range, m_desc.diversity);
         for (std::size_t i = 0; i < 18u && i < allowed.size(); ++i) m_desc.allowed_variants[i] = allowed[i]; // no-op when saving
     }
 
@@ -303,8 +304,47 @@ public:
     }
 };
 
+// pagmo::nspso (nspso.hpp:59-62): non-dominated sorting PSO; generational in the reference itself, so this is the same algorithm on
+// Philox draws (pgc_nspso_evolve_device, nspso.cu).  memory = true (velocities and archive kept between evolve() calls) is available on
+// the C ABI (d_vel / d_best_x / d_best_f) but not through this adapter.
+class cuda_nspso : public cuda_algorithm_base
+{
+public:
+    cuda_nspso(unsigned gen = 1u, double omega = 0.6, double c1 = 2.0, double c2 = 2.0, double chi = 1.0, double v_coeff = 0.5,
+               unsigned leader_selection_range = 60u, std::string diversity_mechanism = "crowding distance", bool memory = false,
+               unsigned seed = pagmo::random_device::next(), int device = 0)
+        : cuda_algorithm_base(PGC_ALGO_NSPSO, "NSPSO", gen, seed, device)
+    {
+        if (omega < 0. || omega > 1.) { // nspso.cpp:58-62
+            pagmo_throw(std::invalid_argument, "The particles' inertia weight must be in the [0,1] range, while a value of "
+                                                   + std::to_string(omega) + " was detected");
+        }
+        if (c1 <= 0 || c2 <= 0 || chi <= 0) { // :63-66
+            pagmo_throw(std::invalid_argument, "first and second magnitude of the force "
+                                               "coefficients and velocity scaling factor should be greater than 0");
+        }
+        if (v_coeff <= 0 || v_coeff > 1) { // :67-70
+            pagmo_throw(std::invalid_argument, "velocity scaling factor should be in ]0,1] range, while a value of" + std::to_string(v_coeff)
+                                                   + " was detected");
+        }
+        if (leader_selection_range > 100) { // :71-75
+            pagmo_throw(std::invalid_argument, "leader selection range coefficient should be in the ]0,100] range, while a value of"
+                                                   + std::to_string(leader_selection_range) + " was detected");
+        }
+        unsigned div = 0;
+        if (diversity_mechanism == "crowding distance") div = 0;
+        else if (diversity_mechanism == "niche count") div = 1;
+        else if (diversity_mechanism == "max min") div = 2;
+        else pagmo_throw(std::invalid_argument, "Non existing diversity mechanism method."); // :76-80
+        no_memory(memory, "cuda_nspso");
+        m_desc.omega = omega, m_desc.nspso_c1 = c1, m_desc.nspso_c2 = c2, m_desc.nspso_chi = chi, m_desc.nspso_v_coeff = v_coeff;
+        m_desc.leader_selection_range = leader_selection_range, m_desc.diversity = div;
+    }
+};
+
 } // namespace pagmo_cuda
 
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_nspso)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_cmaes)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_sga)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_de)

@@ -1590,7 +1590,10 @@ int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, si
 }
 
 // sort_population_mo, multi_objective.cpp:425-465: indices by (rank ascending, crowding distance descending)
-int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned *d_out, cudaStream_t st)
+// `limit` (0 = everything): only d_out[0 .. limit) is needed.  The level loop then stops once `limit` points sit in closed fronts,
+// and the points of those fronts - every other point ranks behind them - are ordered exactly as the full sort would order them
+// (rank, then crowding distance descending, ties in index order); d_out receives all of them (at least `limit`, at most n).
+int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_, unsigned *d_out, cudaStream_t st, size_t limit)
 {
     const unsigned n = static_cast<unsigned>(n_);
     if (n == 0) return PGC_OK;
@@ -1600,25 +1603,40 @@ int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n_, size_t m_
         PGC_CUDA(cudaStreamSynchronize(st));
         return PGC_OK;
     }
+    const bool partial = limit > 0 && limit < n;
     Workspace ws(ctx, st);
-    unsigned *rank, *order, *foff, *rk_in, *rk_out, *v_out;
+    unsigned *rank, *order, *foff, *rk_in, *rk_out, *v_out, *key = nullptr;
     double *cd;
     int rc;
     if ((rc = ws.alloc(&rank, n)) || (rc = ws.alloc(&order, n)) || (rc = ws.alloc(&foff, n + 1)) || (rc = ws.alloc(&cd, n))
         || (rc = ws.alloc(&rk_in, n)) || (rc = ws.alloc(&rk_out, n)) || (rc = ws.alloc(&v_out, n)))
         return rc;
-    unsigned nfronts = 0;
-    if ((rc = fnds_device(ctx, d_f, n, m_, rank, nullptr, order, foff, &nfronts, st))) return rc;
-    if ((rc = crowding_device(ctx, d_f, n, m_, order, foff, nfronts, 2, cd, st))) return rc;
-    iota_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_out, n);
-    if ((rc = sort_by_cd_desc(ctx, cd, d_out, n, st))) return rc;
-    gather_u32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(rank, d_out, n, rk_in);
+    if (partial && (rc = ws.alloc(&key, n))) return rc;
+    unsigned nfronts = 0, count = n;
+    if ((rc = fnds_device(ctx, d_f, n, m_, rank, nullptr, order, foff, &nfronts, st, partial ? static_cast<unsigned>(limit) : 0u, key))) return rc;
+    if (partial) {
+        PGC_CUDA(cudaMemcpyAsync(&count, foff + nfronts, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        fill_double_kernel<<<blocks_for(n, 256), 256, 0, st>>>(cd, n, 0.0); // crowding_device clears only the entries it is given
+    }
+    if ((rc = crowding_device(ctx, d_f, count, m_, order, foff, nfronts, 2, cd, st))) return rc;
+    if (partial) { // the points of the closed fronts, in index order
+        void *tmp = nullptr;
+        size_t bytes = 0;
+        PGC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, bytes, order, d_out, static_cast<int>(count), 0, 32, st));
+        if ((rc = ws.alloc_bytes(&tmp, bytes))) return rc;
+        PGC_CUDA(cub::DeviceRadixSort::SortKeys(tmp, bytes, order, d_out, static_cast<int>(count), 0, 32, st));
+    } else {
+        iota_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_out, n);
+    }
+    if ((rc = sort_by_cd_desc(ctx, cd, d_out, count, st))) return rc;
+    gather_u32_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rank, d_out, count, rk_in);
     void *tmp = nullptr;
     size_t bytes = 0;
-    PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, rk_in, rk_out, d_out, v_out, static_cast<int>(n), 0, 32, st));
+    PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, rk_in, rk_out, d_out, v_out, static_cast<int>(count), 0, 32, st));
     if ((rc = ws.alloc_bytes(&tmp, bytes))) return rc;
-    PGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, rk_in, rk_out, d_out, v_out, static_cast<int>(n), 0, 32, st));
-    PGC_CUDA(cudaMemcpyAsync(d_out, v_out, sizeof(unsigned) * n, cudaMemcpyDeviceToDevice, st));
+    PGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, rk_in, rk_out, d_out, v_out, static_cast<int>(count), 0, 32, st));
+    PGC_CUDA(cudaMemcpyAsync(d_out, v_out, sizeof(unsigned) * count, cudaMemcpyDeviceToDevice, st));
     PGC_CUDA(cudaStreamSynchronize(st));
     return PGC_OK;
 }

@@ -281,13 +281,13 @@ int nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP
     Scratch sc(st);
     const size_t nd = static_cast<size_t>(NP) * dim, nm = static_cast<size_t>(NP) * m;
     double *lb, *ub, *minv, *maxv, *V = d_vel, *bx = d_best_x, *bf = d_best_f, *x2, *f2, *keyv, *delta;
-    unsigned *rank, *order, *foff, *sorted, *bnd, *nb, *order2, *sl;
+    unsigned *rank, *order, *foff, *sorted, *bnd, *nb, *order2, *sl, *fkey;
     int rc;
     if ((rc = sc.alloc(&lb, dim)) || (rc = sc.alloc(&ub, dim)) || (rc = sc.alloc(&minv, dim)) || (rc = sc.alloc(&maxv, dim))
         || (rc = sc.alloc(&x2, 2 * nd)) || (rc = sc.alloc(&f2, 2 * nm)) || (rc = sc.alloc(&keyv, 2 * static_cast<size_t>(NP)))
         || (rc = sc.alloc(&delta, 1)) || (rc = sc.alloc(&rank, NP)) || (rc = sc.alloc(&order, NP)) || (rc = sc.alloc(&foff, NP + 1))
         || (rc = sc.alloc(&sorted, NP)) || (rc = sc.alloc(&bnd, NP)) || (rc = sc.alloc(&nb, 1)) || (rc = sc.alloc(&order2, 2 * static_cast<size_t>(NP)))
-        || (rc = sc.alloc(&sl, NP)))
+        || (rc = sc.alloc(&sl, NP)) || (rc = sc.alloc(&fkey, NP)))
         return rc;
     if (!V && (rc = sc.alloc(&V, nd))) return rc;
     if (!bx && ((rc = sc.alloc(&bx, nd)) || (rc = sc.alloc(&bf, nm)))) return rc;
@@ -313,15 +313,18 @@ int nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP
     for (unsigned g = 0; g < gens; ++g) {
         const unsigned generation = first_generation + g;
         // 1 - the leaders
+        // only the first front is needed (its size; for the niche count its members in the reference's order, and the first member
+        // of the second front when it is a single point): the level loop stops after one (two) closed fronts
         unsigned nfronts = 0, h_foff[3] = {0, 0, 0};
-        if ((rc = fnds_device(ctx, d_f, NP, m, rank, nullptr, order, foff, &nfronts, st))) return rc; // :160
-        PGC_CUDA(cudaMemcpyAsync(h_foff, foff, sizeof(unsigned) * (nfronts >= 2 ? 3 : 2), cudaMemcpyDeviceToHost, st));
+        if ((rc = fnds_device(ctx, d_f, NP, m, rank, nullptr, order, foff, &nfronts, st, 1u, fkey))) return rc; // :160
+        PGC_CUDA(cudaMemcpyAsync(h_foff, foff, sizeof(unsigned) * 2, cudaMemcpyDeviceToHost, st));
         PGC_CUDA(cudaStreamSynchronize(st));
         const unsigned n0 = h_foff[1] - h_foff[0];
+        if (diversity == 1u && n0 == 1u && (rc = fnds_device(ctx, d_f, NP, m, rank, nullptr, order, foff, &nfronts, st, 2u, fkey))) return rc;
         unsigned h_nb = 0;
         if (diversity == 0u) {
-            if ((rc = sort_population_device(ctx, d_f, NP, m, sorted, st))) return rc;
             h_nb = n0 > 1u ? n0 : 2u;
+            if ((rc = sort_population_device(ctx, d_f, NP, m, sorted, st, h_nb))) return rc;
             PGC_CUDA(cudaMemcpyAsync(bnd, sorted, sizeof(unsigned) * h_nb, cudaMemcpyDeviceToDevice, st));
         } else if (diversity == 1u) {
             if (n0 > 1u) {
@@ -353,7 +356,7 @@ int nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP
         PGC_CUDA(cudaMemcpyAsync(x2 + nd, bx, sizeof(double) * nd, cudaMemcpyDeviceToDevice, st));
         PGC_CUDA(cudaMemcpyAsync(f2 + nm, bf, sizeof(double) * nm, cudaMemcpyDeviceToDevice, st));
         if (diversity != 2u) {
-            if ((rc = sort_population_device(ctx, f2, 2 * static_cast<size_t>(NP), m, order2, st))) return rc;
+            if ((rc = sort_population_device(ctx, f2, 2 * static_cast<size_t>(NP), m, order2, st, NP))) return rc;
         } else {
             nspso_maxmin_kernel<<<nblk(static_cast<size_t>(2 * NP) * 32, 256), 256, 0, st>>>(f2, 2 * NP, m, keyv);
             if ((rc = argsort_less_f(keyv, 2 * NP, order2, st))) return rc;

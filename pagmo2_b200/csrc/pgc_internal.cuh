@@ -276,7 +276,7 @@ int crowding_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const u
                     unsigned nfronts, int small_rule, double *d_cd, cudaStream_t st);
 int select_best_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, size_t N, unsigned *d_out, unsigned *nout, cudaStream_t st,
                        SelectedRanking *ranking = nullptr);
-int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, unsigned *d_out, cudaStream_t st);
+int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, unsigned *d_out, cudaStream_t st, size_t limit = 0);
 int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t s);
 int philox_permutation_device(pgc_ctx *ctx, unsigned n, unsigned long long seed, unsigned tag, unsigned generation, unsigned *d_perm,
                               cudaStream_t st);

@@ -326,6 +326,27 @@ int main(int argc, char **argv)
         pagmo::population mo{zp, 40u, 5u};
         mo = pagmo::algorithm{cuda_nsga2{10u, 0.95, 10., 0.01, 50., 32u}}.evolve(mo);
         CHECK(mo.size() == 40u && mo.get_f()[0].size() == 2u);
+        // cuda_nspso: the three diversity mechanisms run, fitness stays consistent with the decision vectors, fevals counted like the
+        // reference (NP per generation), the constructor rejects what nspso.cpp:58-80 rejects
+        for (const char *div : {"crowding distance", "niche count", "max min"}) {
+            pagmo::population sw{zp, 40u, 9u};
+            const auto fe0 = sw.get_problem().get_fevals();
+            sw = pagmo::algorithm{cuda_nspso{6u, 0.6, 2.0, 2.0, 1.0, 0.5, 60u, div, false, 17u}}.evolve(sw);
+            CHECK(sw.get_problem().get_fevals() - fe0 == 6u * 40u);
+            for (decltype(sw.size()) i = 0; i < sw.size(); ++i) {
+                const auto fi = zp.fitness(sw.get_x()[i]);
+                CHECK(std::abs(fi[0] - sw.get_f()[i][0]) <= 1e-12 * (1 + std::abs(fi[0])) && std::abs(fi[1] - sw.get_f()[i][1]) <= 1e-12 * (1 + std::abs(fi[1])));
+            }
+        }
+        {
+            bool bad_arg = false;
+            try {
+                cuda_nspso{1u, 0.6, 2.0, 2.0, 1.0, 0.5, 60u, "no such mechanism"};
+            } catch (const std::invalid_argument &) {
+                bad_arg = true;
+            }
+            CHECK(bad_arg);
+        }
         bool threw = false;
         try {
             oracle_ref::ensure_cec2014_tables(1u, 10u);
