@@ -1145,12 +1145,15 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
             if (dw && dw->key == key) W = dw;
         }
         if (!W) {
-            if (prob->work.size() >= kMaxWorkspaces) { // evict the least recently used one (its population is gone or idle)
-                if (int rc = ctx_sync(ctx)) return rc;
-                PGC_CUDA(cudaStreamSynchronize(st));
-                auto lru = std::min_element(prob->work.begin(), prob->work.end(),
-                                            [](const auto &a, const auto &b) { return a->last_use < b->last_use; });
-                prob->work.erase(lru);
+            if (prob->work.size() >= kMaxWorkspaces) { // evict the least recently used idle one (its population is gone or resting)
+                auto lru = prob->work.end();
+                for (auto it = prob->work.begin(); it != prob->work.end(); ++it)
+                    if ((*it)->users == 0 && (lru == prob->work.end() || (*it)->last_use < (*lru)->last_use)) lru = it;
+                if (lru != prob->work.end()) { // (every workspace busy: other threads evolve other populations of this problem - grow)
+                    if (int rc = ctx_sync(ctx)) return rc;
+                    PGC_CUDA(cudaStreamSynchronize(st));
+                    prob->work.erase(lru);
+                }
             }
             auto fresh_ws = std::make_unique<DeWork>();
             fresh_ws->key = key;
@@ -1160,7 +1163,17 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
             prob->work.push_back(std::move(fresh_ws));
         }
         W->last_use = ++prob->work_clock;
+        ++W->users;
     }
+    struct Release { // the workspace may be evicted again once this call has returned
+        pgc_problem *p;
+        DeWork *w;
+        ~Release()
+        {
+            std::lock_guard<std::mutex> lock(p->work_mu);
+            --w->users;
+        }
+    } release{prob, W};
     double *trial = W->trial, *ftrial = W->ftrial, *gbX = W->gbX, *lb = W->lb, *ub = W->ub, *Ftry = W->Ftry, *CRtry = W->CRtry;
     double *Fs = d_F ? d_F : W->Fs, *CRs = d_CR ? d_CR : W->CRs;
     unsigned *vars = d_variant ? d_variant : W->vars, *vtry = W->vtry;

@@ -215,6 +215,7 @@ namespace pgc
 struct LoopWorkspace {
     virtual ~LoopWorkspace() = default;
     unsigned long long last_use = 0;
+    int users = 0; // calls currently running on this workspace (guarded by pgc_problem::work_mu): never evicted while > 0
 };
 } // namespace pgc
 

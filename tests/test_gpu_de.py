@@ -159,3 +159,43 @@ def test_resident_loop_equals_one_launch_per_phase(capi, ctx, orc, monkeypatch, 
                 xo, fo, go, *_ = orc.de_evolve(op, lb, ub, x, f, **args)
                 assert np.allclose(xr, xo, rtol=1e-9, atol=1e-12) and np.allclose(fr, fo, rtol=1e-9)
     prob.close()
+
+
+def test_more_populations_than_cached_workspaces_on_one_problem_handle(capi, ctx, orc):
+    """Six populations evolved through ONE problem handle (four workspaces are cached per handle), from six threads at once and
+    then again one after the other: a workspace is never evicted while a call runs on it, and the results do not depend on which
+    workspaces survived."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    prob = capi.Problem(ctx, "ackley", dim=12)
+    lb, ub = prob.bounds()
+    NP, K = 200, 6
+    xs = [np.random.default_rng(40 + k).uniform(lb, ub, (NP, 12)) for k in range(K)]
+    fs = [prob.eval_host(x)[:, 0] for x in xs]
+    al = np.array([2, 3, 7, 10, 13, 14, 15, 16], dtype=np.uint32)
+
+    def run(k, dx, df):
+        for call in range(3):
+            capi.check(capi.lib().pgc_de_evolve_device(prob._h, dx, df, NP, 9, 2, 2, 1, 0.8, 0.9, al.ctypes.data_as(C.c_void_p), al.size, 0.0, 0.0,
+                                                       None, None, None, 100 + k, 1 + 9 * call, None, None))
+
+    def all_populations(parallel):
+        bufs = [(ctx.to_device(xs[k]), ctx.to_device(fs[k])) for k in range(K)]
+        if parallel:
+            with ThreadPoolExecutor(K) as pool:
+                list(pool.map(lambda k: run(k, *bufs[k]), range(K)))
+        else:
+            for k in range(K):
+                run(k, *bufs[k])
+        ctx.synchronize()
+        out = [(ctx.from_device(dx, xs[0].shape), ctx.from_device(df, fs[0].shape)) for dx, df in bufs]
+        for dx, df in bufs:
+            ctx.free(dx)
+            ctx.free(df)
+        return out
+
+    seq = all_populations(False)
+    par = all_populations(True)
+    for (xa, fa), (xb, fb), f0 in zip(seq, par, fs):
+        assert np.array_equal(xa, xb) and np.array_equal(fa, fb) and fa.min() < f0.min()
+    prob.close()
