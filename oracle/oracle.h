@@ -166,4 +166,14 @@ int oracle_nspso_evolve_mt(const oracle_problem *prob, const double *lb, const d
                            unsigned gens, double omega, double c1, double c2, double chi, double v_coeff, unsigned leader_selection_range,
                            unsigned diversity, uint32_t seed);
 
+/* moead_gen::evolve (src/algorithms/moead_gen.cpp:128-345) with the weight vectors [NP x m] and their neighbourhoods [NP x T] given;
+ * decomposition: 0 weighted, 1 tchebycheff, 2 bi */
+int oracle_moead_gen_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim, size_t m,
+                            unsigned gens, const double *weights, const size_t *neigh, size_t T, int decomposition, double CR, double F,
+                            double eta_m, double realb, unsigned limit, int preserve_diversity, uint64_t seed, uint32_t first_generation,
+                            size_t burn_draws);
+int oracle_moead_gen_evolve_mt(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim,
+                               size_t m, unsigned gens, const double *weights, const size_t *neigh, size_t T, int decomposition, double CR, double F,
+                               double eta_m, double realb, unsigned limit, int preserve_diversity, uint32_t seed, size_t burn_draws);
+
 #endif

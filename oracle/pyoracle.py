@@ -507,6 +507,31 @@ class Oracle:
             raise ValueError("oracle_nspso_evolve failed")
         return (x, f, *mem)
 
+    DECOMPOSITION = {"weighted": 0, "tchebycheff": 1, "bi": 2}
+
+    def moead_gen_evolve(self, prob, lb, ub, x, f, weights, neigh, gens=1, decomposition="tchebycheff", CR=1.0, F=0.5, eta_m=20.0, realb=0.9,
+                         limit=2, preserve_diversity=True, seed=0, first_generation=1, mt=False, burn_draws=0):
+        """restated moead_gen::evolve (Philox draws, or the mt19937 stream with mt=True) on given weight vectors [NP x m] and
+        neighbourhoods [NP x T]: returns (x, f)."""
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C").reshape(x.shape[0], -1)
+        NP, dim = x.shape
+        m = f.shape[1]
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        nb = np.ascontiguousarray(neigh, dtype=np.uint64)
+        T = nb.shape[1]
+        common = [C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), C.c_size_t(NP), C.c_size_t(dim), C.c_size_t(m), C.c_uint(gens), _dp(w),
+                  nb.ctypes.data_as(C.POINTER(C.c_size_t)), C.c_size_t(T), C.c_int(self.DECOMPOSITION[decomposition]), C.c_double(CR),
+                  C.c_double(F), C.c_double(eta_m), C.c_double(realb), C.c_uint(limit), C.c_int(1 if preserve_diversity else 0)]
+        if mt:
+            rc = self.lib.oracle_moead_gen_evolve_mt(*common, C.c_uint32(seed), C.c_size_t(burn_draws))
+        else:
+            rc = self.lib.oracle_moead_gen_evolve(*common, C.c_uint64(seed), C.c_uint32(first_generation), C.c_size_t(0))
+        if rc:
+            raise ValueError("oracle_moead_gen_evolve failed")
+        return x, f
+
     def de_evolve_mt(self, prob, lb, ub, x, f, gens=1, algo="de1220", variant=2, variant_adptv=1, F=0.8, CR=0.9,
                      allowed=(2, 3, 7, 10, 13, 14, 15, 16), ftol=1e-6, xtol=1e-6, seed=0):
         """restated de / sade / de1220 on the mt19937 stream, in the reference's one-at-a-time order: returns (x, f, gens_done)."""
@@ -772,6 +797,22 @@ class Reference:
         self._check(self.lib.ref_evolve_from(prob._h, algo.encode(), _dp(par), par.size, strategies.encode() if strategies else None, _dp(x0), n,
                                              gens, seed, _dp(x), _dp(f)))
         return x, f
+
+    def decomposition_weights(self, n_f: int, n_w: int, method: str, seed: int = 0) -> np.ndarray:
+        """pagmo::decomposition_weights with a fresh std::mt19937(seed)."""
+        out = np.empty((n_w, n_f))
+        self.lib.ref_decomposition_weights.argtypes = [C.c_size_t, C.c_size_t, C.c_char_p, C.c_uint, c_double_p]
+        self._check(self.lib.ref_decomposition_weights(n_f, n_w, method.encode(), seed, _dp(out)))
+        return out
+
+    def knn(self, points, k: int) -> np.ndarray:
+        """pagmo::kNN: [n x k] indices of the k nearest other points of every point."""
+        points = np.ascontiguousarray(points, dtype=np.float64)
+        n, m = points.shape
+        out = np.empty((n, k), dtype=np.uint64)
+        self.lib.ref_knn.argtypes = [c_double_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]
+        self._check(self.lib.ref_knn(_dp(points), n, m, k, out.ctypes.data_as(C.POINTER(C.c_size_t))))
+        return out
 
     def population_init(self, prob: "RefProblem", n: int, seed: int):
         x, ids = np.empty((n, prob.nx)), np.empty(n, dtype=np.uint64)

@@ -11,6 +11,7 @@
 #include <pagmo/algorithm.hpp>
 #include <pagmo/algorithms/de.hpp>
 #include <pagmo/algorithms/de1220.hpp>
+#include <pagmo/algorithms/moead_gen.hpp>
 #include <pagmo/algorithms/nsga2.hpp>
 #include <pagmo/algorithms/nspso.hpp>
 #include <pagmo/algorithms/pso_gen.hpp>
@@ -21,6 +22,7 @@
 #include <pagmo/rng.hpp>
 #include <pagmo/utils/generic.hpp>
 #include <pagmo/utils/genetic_operators.hpp>
+#include <pagmo/utils/multi_objective.hpp>
 
 #include "ref_capi.h"
 
@@ -154,6 +156,13 @@ int ref_evolve_from(ref_problem *p, const char *algo, const double *par, size_t 
             if (c1 == std::string::npos || c2 == std::string::npos) throw std::invalid_argument("ref_evolve_from: strategies");
             alg = pagmo::algorithm{pagmo::sga(gens, par[0], par[1], par[2], par[3], static_cast<unsigned>(par[4]), s.substr(0, c1),
                                               s.substr(c1 + 1, c2 - c1 - 1), s.substr(c2 + 1), seed)};
+        } else if (a == "moead_gen") { // strategies = "<weight generation>,<decomposition>"
+            need(7);
+            const std::string s(strategies ? strategies : "grid,tchebycheff");
+            const auto c1 = s.find(',');
+            if (c1 == std::string::npos) throw std::invalid_argument("ref_evolve_from: strategies");
+            alg = pagmo::algorithm{pagmo::moead_gen(gens, s.substr(0, c1), s.substr(c1 + 1), static_cast<unsigned>(par[0]), par[1], par[2], par[3],
+                                                    par[4], static_cast<unsigned>(par[5]), par[6] != 0., seed)};
         } else if (a == "nspso") {
             need(6);
             alg = pagmo::algorithm{pagmo::nspso(gens, par[0], par[1], par[2], par[3], par[4], static_cast<unsigned>(par[5]),
@@ -165,6 +174,26 @@ int ref_evolve_from(ref_problem *p, const char *algo, const double *par, size_t 
             if (x_out) std::memcpy(x_out + i * nx, pop.get_x()[i].data(), nx * sizeof(double));
             if (f_out) std::memcpy(f_out + i * nf, pop.get_f()[i].data(), nf * sizeof(double));
         }
+    });
+}
+
+// decomposition_weights (multi_objective.hpp:128-213) with a fresh std::mt19937(seed), and kNN of the rows (generic.cpp:107-148)
+int ref_decomposition_weights(size_t n_f, size_t n_w, const char *method, unsigned seed, double *out)
+{
+    return guarded([&] {
+        std::mt19937 e(seed);
+        const auto w = pagmo::decomposition_weights(n_f, n_w, std::string(method), e);
+        for (size_t i = 0; i < w.size(); ++i) std::memcpy(out + i * n_f, w[i].data(), n_f * sizeof(double));
+    });
+}
+int ref_knn(const double *points, size_t n, size_t m, size_t k, size_t *out)
+{
+    return guarded([&] {
+        std::vector<pagmo::vector_double> p(n);
+        for (size_t i = 0; i < n; ++i) p[i].assign(points + i * m, points + (i + 1) * m);
+        const auto r = pagmo::kNN(p, k);
+        for (size_t i = 0; i < n; ++i)
+            for (size_t j = 0; j < k; ++j) out[i * k + j] = r[i][j];
     });
 }
 

@@ -222,3 +222,30 @@ def test_nspso_evolve_bit_exact(orc, ref, fam, args, n):
             xr, fr = ref.evolve_from(rp, "nspso", [0.6, 2.0, 2.0, 1.0, 0.5, lsr], x0, gens, seed, strategies=diversity)
             xo, fo, *_ = orc.nspso_evolve(op, lb, ub, x0, f0, gens=gens, leader_selection_range=lsr, diversity=diversity, seed=seed, mt=True)
             assert np.array_equal(xr, xo) and np.array_equal(fr, fo), (diversity, lsr, gens)
+
+
+@pytest.mark.parametrize("fam,args,NP,wgen", [("zdt", (1, 8), 24, "grid"), ("zdt", (2, 6), 30, "low discrepancy"), ("zdt", (3, 7), 20, "random"),
+                                              ("dtlz", (2, 7, 3, 100), 21, "grid"), ("dtlz", (1, 6, 3, 100), 28, "low discrepancy")])
+def test_moead_gen_evolve_bit_exact(orc, ref, fam, args, NP, wgen):
+    """moead_gen::evolve (the reference's own generational MOEA/D) restated on the mt19937 stream: candidate construction (diversity
+    draw, parent rejection loop, DE operator with bound repair, polynomial mutation), batch evaluation, the sequential insertion
+    with its per-individual std::shuffle and the `limit` cut - bit for bit, for the three decompositions, with and without
+    diversity preservation.  Weights and neighbourhoods come from the compiled reference's own utilities."""
+    rp = ref.problem(fam, *args)
+    lb, ub = rp.bounds()
+    op = orc.problem("zdt", prob_id=args[0], dim=args[1]) if fam == "zdt" else orc.problem("dtlz", prob_id=args[0], dim=args[1], nobj=args[2],
+                                                                                             param=args[3])
+    m = rp.nf
+    x0 = np.random.default_rng(NP).uniform(lb, ub, (NP, len(lb)))
+    f0 = np.array([rp.fitness(x) for x in x0])
+    for decomposition in ("tchebycheff", "weighted", "bi"):
+        for T, CR, F, realb, limit, preserve, gens in ((5, 1.0, 0.5, 0.9, 2, True, 6), (8, 0.6, 0.8, 0.5, 1, True, 4), (4, 0.9, 0.5, 0.9, 2, False, 4)):
+            seed = T * 7 + gens
+            w = ref.decomposition_weights(m, NP, wgen, seed)
+            nb = ref.knn(w, T)
+            xr, fr = ref.evolve_from(rp, "moead_gen", [T, CR, F, 20.0, realb, limit, 1.0 if preserve else 0.0], x0, gens, seed,
+                                     strategies=f"{wgen},{decomposition}")
+            burn = (NP - m) * (m - 1) if wgen == "random" else 0
+            xo, fo = orc.moead_gen_evolve(op, lb, ub, x0, f0, w, nb, gens=gens, decomposition=decomposition, CR=CR, F=F, eta_m=20.0, realb=realb,
+                                          limit=limit, preserve_diversity=preserve, seed=seed, mt=True, burn_draws=burn)
+            assert np.array_equal(xr, xo) and np.array_equal(fr, fo), (decomposition, T, CR, realb, limit, preserve)
