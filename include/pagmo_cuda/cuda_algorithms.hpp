@@ -27,6 +27,8 @@
 #include <vector>
 
 #include <pagmo/algorithm.hpp>
+#include <random>
+
 #include <pagmo/exceptions.hpp>
 #include <pagmo/population.hpp>
 #include <pagmo/problem.hpp>
@@ -34,6 +36,8 @@
 #include <pagmo/s11n.hpp>
 #include <pagmo/threading.hpp>
 #include <pagmo/types.hpp>
+#include <pagmo/utils/generic.hpp>
+#include <pagmo/utils/multi_objective.hpp>
 
 #include <pagmo_cuda/cuda_bfe.hpp>
 #include <pagmo_cuda/pgc.h>
@@ -342,8 +346,130 @@ public:
     }
 };
 
+// pagmo::moead_gen (moead_gen.hpp), the reference's generational MOEA/D: the weight vectors and their neighbourhoods are computed
+// with pagmo's own decomposition_weights / kNN (on an engine seeded like the reference's, so "random" weights are the reference's),
+// candidate construction, batch evaluation and the sequential insertion run on the device (pgc_moead_gen_evolve_device, moead.cu).
+class cuda_moead_gen
+{
+public:
+    cuda_moead_gen(unsigned gen = 1u, std::string weight_generation = "grid", std::string decomposition = "tchebycheff",
+                   pagmo::population::size_type neighbours = 20u, double CR = 1.0, double F = 0.5, double eta_m = 20., double realb = 0.9,
+                   unsigned limit = 2u, bool preserve_diversity = true, unsigned seed = pagmo::random_device::next(), int device = 0)
+        : m_gen(gen), m_weight_generation(std::move(weight_generation)), m_decomposition(std::move(decomposition)), m_neighbours(neighbours),
+          m_CR(CR), m_F(F), m_eta_m(eta_m), m_realb(realb), m_limit(limit), m_preserve_diversity(preserve_diversity), m_seed(seed),
+          m_device(device), m_cache(std::make_shared<detail::twin_cache>())
+    { // moead_gen.cpp:60-104
+        if (m_weight_generation != "random" && m_weight_generation != "grid" && m_weight_generation != "low discrepancy") {
+            pagmo_throw(std::invalid_argument, "Weight generation method requested is '" + m_weight_generation
+                                                   + "', but only one of 'random', 'low discrepancy', 'grid' is allowed");
+        }
+        if (m_decomposition != "tchebycheff" && m_decomposition != "weighted" && m_decomposition != "bi") {
+            pagmo_throw(std::invalid_argument, "Weight generation method requested is '" + m_decomposition
+                                                   + "', but only one of 'tchebycheff', 'weighted', 'bi' is allowed");
+        }
+        if (CR > 1.0 || CR < 0.) {
+            pagmo_throw(std::invalid_argument,
+                        "The parameter CR (used by the differential evolution operator) needs to be in [0,1], while a value of "
+                            + std::to_string(CR) + " was detected");
+        }
+        if (F > 1.0 || F < 0.) {
+            pagmo_throw(std::invalid_argument,
+                        "The parameter F (used by the differential evolution operator) needs to be in [0,1], while a value of "
+                            + std::to_string(F) + " was detected");
+        }
+        if (eta_m < 0.) {
+            pagmo_throw(std::invalid_argument, "The distribution index for the polynomial mutation (eta_m) needs to be positive, while a value of "
+                                                   + std::to_string(eta_m) + " was detected");
+        }
+        if (realb > 1.0 || realb < 0.) {
+            pagmo_throw(std::invalid_argument, "The chance of considering a neighbourhood (realb) needs to be in [0,1], while a value of "
+                                                   + std::to_string(realb) + " was detected");
+        }
+        if (neighbours < 2) {
+            pagmo_throw(std::invalid_argument,
+                        "The size of the weight's neighborhood needs to be >= 2, while a size of " + std::to_string(neighbours) + " was detected");
+        }
+    }
+    pagmo::population evolve(pagmo::population pop) const
+    {
+        const auto &prob = pop.get_problem();
+        const auto NP = pop.size();
+        if (!NP) pagmo_throw(std::invalid_argument, get_name() + " cannot work on an empty population"); // :146-148
+        if (prob.get_nf() < 2u) {
+            pagmo_throw(std::invalid_argument, "This is a multiobjective algorithm, while number of objectives detected in " + prob.get_name()
+                                                   + " is " + std::to_string(prob.get_nf()));
+        }
+        if (prob.get_nc() != 0u) {
+            pagmo_throw(std::invalid_argument, "Non linear constraints detected in " + prob.get_name() + " instance. " + get_name()
+                                                   + " cannot deal with them");
+        }
+        if (prob.is_stochastic()) {
+            pagmo_throw(std::invalid_argument, "The problem appears to be stochastic " + get_name() + " cannot deal with it");
+        }
+        if (m_neighbours > NP - 1u) {
+            pagmo_throw(std::invalid_argument, "The neighbourhood size specified (T) is " + std::to_string(m_neighbours)
+                                                   + ": too large for the input population having size " + std::to_string(NP));
+        }
+        if (m_gen == 0u) return pop;
+        const auto h = m_cache->find(prob, m_device);
+        if (!h) {
+            pagmo_throw(std::invalid_argument, get_name() + " cannot evolve a population of '" + prob.get_name()
+                                                   + "': no CUDA evaluator exists for this UDP type; there is no CPU fallback");
+        }
+        // weights and neighbourhoods exactly as the reference computes them at the top of evolve() (:155, :168)
+        std::mt19937 engine(m_seed);
+        const auto weights = pagmo::decomposition_weights(prob.get_nf(), NP, m_weight_generation, engine);
+        const auto neigh = pagmo::kNN(weights, m_neighbours);
+        const auto nx = prob.get_nx(), nf = prob.get_nf();
+        pagmo::vector_double w(NP * nf), x(NP * nx), f(NP * nf);
+        std::vector<uint32_t> nb(NP * m_neighbours);
+        for (decltype(pop.size()) i = 0; i < NP; ++i) {
+            std::copy(weights[i].begin(), weights[i].end(), w.begin() + static_cast<std::ptrdiff_t>(i * nf));
+            for (decltype(m_neighbours) j = 0; j < m_neighbours; ++j) nb[i * m_neighbours + j] = static_cast<uint32_t>(neigh[i][j]);
+            std::copy(pop.get_x()[i].begin(), pop.get_x()[i].end(), x.begin() + static_cast<std::ptrdiff_t>(i * nx));
+            std::copy(pop.get_f()[i].begin(), pop.get_f()[i].end(), f.begin() + static_cast<std::ptrdiff_t>(i * nf));
+        }
+        const int method = m_decomposition == "weighted" ? 0 : (m_decomposition == "tchebycheff" ? 1 : 2);
+        h->on_device(x, f, "pgc_moead_gen_evolve_device", [&](double *dx, double *df, std::size_t n) {
+            return pgc_moead_gen_evolve_device(h->raw(), dx, df, n, m_gen, w.data(), nb.data(), static_cast<unsigned>(m_neighbours), method, m_CR,
+                                               m_F, m_eta_m, m_realb, m_limit, m_preserve_diversity ? 1 : 0, m_seed, m_generation, nullptr);
+        });
+        m_generation += m_gen;
+        for (decltype(pop.size()) i = 0; i < NP; ++i) {
+            pop.set_xf(i, pagmo::vector_double(x.begin() + static_cast<std::ptrdiff_t>(i * nx), x.begin() + static_cast<std::ptrdiff_t>((i + 1) * nx)),
+                       pagmo::vector_double(f.begin() + static_cast<std::ptrdiff_t>(i * nf), f.begin() + static_cast<std::ptrdiff_t>((i + 1) * nf)));
+        }
+        prob.increment_fevals(static_cast<unsigned long long>(m_gen) * NP);
+        return pop;
+    }
+    void set_seed(unsigned seed) { m_seed = seed; }
+    unsigned get_seed() const { return m_seed; }
+    unsigned get_gen() const { return m_gen; }
+    std::string get_name() const { return "MOEAD-GEN: MOEA/D - DE [CUDA sm_100a]"; }
+    pagmo::thread_safety get_thread_safety() const { return pagmo::thread_safety::basic; }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_gen, m_weight_generation, m_decomposition, m_neighbours, m_CR, m_F, m_eta_m, m_realb, m_limit,
+                               m_preserve_diversity, m_seed, m_device, m_generation);
+    }
+
+private:
+    unsigned m_gen;
+    std::string m_weight_generation, m_decomposition;
+    pagmo::population::size_type m_neighbours;
+    double m_CR, m_F, m_eta_m, m_realb;
+    unsigned m_limit;
+    bool m_preserve_diversity;
+    unsigned m_seed;
+    int m_device;
+    mutable unsigned m_generation = 1;
+    std::shared_ptr<detail::twin_cache> m_cache;
+};
+
 } // namespace pagmo_cuda
 
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_moead_gen)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_nspso)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_cmaes)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_sga)

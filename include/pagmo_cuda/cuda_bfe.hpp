@@ -208,6 +208,18 @@ public:
     // Returns the number of generations run.
     unsigned evolve(const pgc_algo_desc &algo, pagmo::vector_double &x, pagmo::vector_double &f, unsigned first_generation) const
     {
+        unsigned done = 0;
+        on_device(x, f, "pgc_algo_evolve_device", [&](double *dx, double *df, std::size_t n) {
+            return pgc_algo_evolve_device(m_prob, &algo, dx, df, n, first_generation, &done, nullptr);
+        });
+        return done;
+    }
+
+    // upload x [n x nx] / f [n x nf], run `call(d_x, d_f, n)` (a pgc_*_evolve_device entry point on this handle's problem: see raw()),
+    // download both in place; throws what the status says
+    template <typename Call>
+    void on_device(pagmo::vector_double &x, pagmo::vector_double &f, const char *what, Call call) const
+    {
         const std::size_t n = x.size() / m_nx;
         std::lock_guard<std::mutex> lk(device_mutex(m_device));
         void *dx = nullptr, *df = nullptr;
@@ -216,13 +228,12 @@ public:
             pgc_free_device(m_ctx.get(), dx);
             throw_status(rc, "pgc_malloc_device");
         }
-        unsigned done = 0;
         int rc = pgc_memcpy_h2d(m_ctx.get(), dx, x.data(), x.size() * sizeof(double));
         if (rc == PGC_OK) rc = pgc_memcpy_h2d(m_ctx.get(), df, f.data(), f.size() * sizeof(double));
         const char *where = "pgc_memcpy_h2d";
         if (rc == PGC_OK) {
-            rc = pgc_algo_evolve_device(m_prob, &algo, static_cast<double *>(dx), static_cast<double *>(df), n, first_generation, &done, nullptr);
-            where = "pgc_algo_evolve_device";
+            rc = call(static_cast<double *>(dx), static_cast<double *>(df), n);
+            where = what;
         }
         if (rc == PGC_OK) {
             rc = pgc_memcpy_d2h(m_ctx.get(), x.data(), dx, x.size() * sizeof(double));
@@ -232,7 +243,6 @@ public:
         pgc_free_device(m_ctx.get(), dx);
         pgc_free_device(m_ctx.get(), df);
         if (rc != PGC_OK) throw_status(rc, where);
-        return done;
     }
 
 private:

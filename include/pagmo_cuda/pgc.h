@@ -269,6 +269,13 @@ PGC_API int pgc_weighted_mean_device(pgc_ctx *ctx, const double *d_rows, const u
 PGC_API int pgc_nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, double omega, double c1, double c2,
                                     double chi, double v_coeff, unsigned leader_selection_range, unsigned diversity, uint64_t seed,
                                     uint32_t first_generation, double *d_vel, double *d_best_x, double *d_best_f, void *stream);
+/* moead_gen::evolve (src/algorithms/moead_gen.cpp:128-345), the reference's generational MOEA/D, on a device-resident population
+ * d_x [n x nx], d_f [n x nobj] (in place).  weights [n x nobj] and neigh [n x T] (HOST arrays): the weight vectors of the n
+ * sub-problems (pagmo::decomposition_weights) and the indices of each one's T nearest weight vectors (pagmo::kNN) - utilities
+ * outside evolve() that the caller computes.  decomposition: 0 "weighted", 1 "tchebycheff", 2 "bi". */
+PGC_API int pgc_moead_gen_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, const double *weights,
+                                        const uint32_t *neigh, unsigned T, int decomposition, double CR, double F, double eta_m, double realb,
+                                        unsigned limit, int preserve_diversity, uint64_t seed, uint32_t first_generation, void *stream);
 PGC_API int pgc_cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lambda, unsigned gens, double cc, double cs, double c1,
                                     double cmu, double sigma0, double ftol, double xtol, int force_bounds, uint64_t seed,
                                     uint32_t first_generation, unsigned *gens_done, double *sigma_out, void *stream);

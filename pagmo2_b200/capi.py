@@ -588,6 +588,28 @@ class Problem:
                 if d is not None:
                     self.ctx.free(d)
 
+    def moead_gen_evolve(self, x, f, weights, neigh, gens=1, decomposition="tchebycheff", CR=1.0, F=0.5, eta_m=20.0, realb=0.9, limit=2,
+                         preserve_diversity=True, seed=0, first_generation=1):
+        """moead_gen::evolve on the device with the given weight vectors [n x nobj] and neighbourhoods [n x T]: returns (x, f)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(x.shape[0], -1)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        nb = np.ascontiguousarray(neigh, dtype=np.uint32)
+        n = x.shape[0]
+        dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
+        L = lib()
+        L.pgc_moead_gen_evolve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint,
+                                                  C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint, C.c_int, C.c_uint64,
+                                                  C.c_uint32, C.c_void_p]
+        try:
+            check(L.pgc_moead_gen_evolve_device(self._h, dx, df, n, gens, w.ctypes.data, nb.ctypes.data, nb.shape[1],
+                                                {"weighted": 0, "tchebycheff": 1, "bi": 2}[decomposition], CR, F, eta_m, realb, limit,
+                                                1 if preserve_diversity else 0, seed, first_generation, None))
+            return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape)
+        finally:
+            self.ctx.free(dx)
+            self.ctx.free(df)
+
     def evolve(self, algo: "AlgoDesc", x, f, first_generation=1):
         """pagmo::algorithm::evolve on host arrays: upload, `pgc_algo_evolve_device`, download.  Returns (x, f, gens_done)."""
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -815,6 +815,18 @@ int pgc_de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP,
                             stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
 }
 
+int pgc_moead_gen_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, const double *weights, const uint32_t *neigh,
+                                unsigned T, int decomposition, double CR, double F, double eta_m, double realb, unsigned limit,
+                                int preserve_diversity, uint64_t seed, uint32_t first_generation, void *stream)
+{
+    PGC_REQUIRE(prob && d_x && d_f, "pgc_moead_gen_evolve_device: null argument");
+    PGC_NO_INTEGER_GENES(prob, "pgc_moead_gen_evolve_device");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    return moead_gen_evolve_device(prob, d_x, d_f, static_cast<unsigned>(n), gens, weights, neigh, T, decomposition, CR, F, eta_m, realb, limit,
+                                   preserve_diversity, seed, first_generation, problem_eval_device,
+                                   stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
+}
+
 int pgc_nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, double omega, double c1, double c2, double chi,
                             double v_coeff, unsigned leader_selection_range, unsigned diversity, uint64_t seed, uint32_t first_generation,
                             double *d_vel, double *d_best_x, double *d_best_f, void *stream)

@@ -281,6 +281,10 @@ int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, 
 int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t s);
 int philox_permutation_device(pgc_ctx *ctx, unsigned n, unsigned long long seed, unsigned tag, unsigned generation, unsigned *d_perm,
                               cudaStream_t st);
+int moead_gen_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, const double *h_weights,
+                            const unsigned *h_neigh, unsigned T, int decomposition, double CR, double F, double eta_m, double realb, unsigned limit,
+                            int preserve_diversity, unsigned long long seed, unsigned first_generation,
+                            int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
 int nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double omega, double c1, double c2, double chi,
                         double v_coeff, unsigned leader_selection_range, unsigned diversity, unsigned long long seed, unsigned first_generation,
                         double *d_vel, double *d_best_x, double *d_best_f,

@@ -24,7 +24,10 @@ enum PhiloxTag : uint32_t { // stream tags: one per consumer so that streams nev
     kTagMigrate = 9,
     kTagPopulation = 10,
     kTagPsoTopology = 11, // adaptive-random swarm topology: informant draws (pso_gen.cpp:772-796)
-    kTagNspso = 12        // nspso: leader index (repeated while it is the particle itself), r1, r2 (nspso.cpp:304-316)
+    kTagNspso = 12,       // nspso: leader index (repeated while it is the particle itself), r1, r2 (nspso.cpp:304-316)
+    kTagMoead = 13,       // moead_gen: an individual's candidate (diversity draw, parents, crossover, mutation; moead_gen.cpp:227-269)
+    kTagMoeadOrder = 14,  // moead_gen: the order of a generation (stands in for std::shuffle, :213)
+    kTagMoeadInsert = 15  // moead_gen: the shuffle of a candidate's neighbourhood at insertion (:322-324)
 };
 
 struct Philox4 {

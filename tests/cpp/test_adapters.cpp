@@ -338,6 +338,27 @@ int main(int argc, char **argv)
                 CHECK(std::abs(fi[0] - sw.get_f()[i][0]) <= 1e-12 * (1 + std::abs(fi[0])) && std::abs(fi[1] - sw.get_f()[i][1]) <= 1e-12 * (1 + std::abs(fi[1])));
             }
         }
+        // cuda_moead_gen: pagmo's own weights / neighbourhoods, evolve on the device, and the same checks as the reference's
+        for (const char *dec : {"tchebycheff", "weighted", "bi"}) {
+            pagmo::population mp{zp, 40u, 9u};
+            const auto fe0 = mp.get_problem().get_fevals();
+            mp = pagmo::algorithm{cuda_moead_gen{8u, "grid", dec, 10u, 1.0, 0.5, 20., 0.9, 2u, true, 23u}}.evolve(mp);
+            CHECK(mp.get_problem().get_fevals() - fe0 == 8u * 40u);
+            for (decltype(mp.size()) i = 0; i < mp.size(); ++i) {
+                const auto fi = zp.fitness(mp.get_x()[i]);
+                CHECK(std::abs(fi[0] - mp.get_f()[i][0]) <= 1e-12 * (1 + std::abs(fi[0])) && std::abs(fi[1] - mp.get_f()[i][1]) <= 1e-12 * (1 + std::abs(fi[1])));
+            }
+        }
+        {
+            bool threw_T = false;
+            try {
+                pagmo::population small{zp, 8u, 1u};
+                pagmo::algorithm{cuda_moead_gen{1u, "grid", "tchebycheff", 20u}}.evolve(small); // T > NP - 1, moead_gen.cpp:161-166
+            } catch (const std::invalid_argument &) {
+                threw_T = true;
+            }
+            CHECK(threw_T);
+        }
         {
             bool bad_arg = false;
             try {
