@@ -247,6 +247,31 @@ struct pgc_problem {
 
 namespace pgc
 {
+// Stream-ordered scratch from the device memory pool, released (in stream order) when it goes out of scope - whatever path leaves
+// the function, so an early return after a failed allocation or copy does not leak the buffers taken before it.
+struct StreamScratch {
+    cudaStream_t st;
+    std::vector<void *> owned;
+    explicit StreamScratch(cudaStream_t s) : st(s) {}
+    StreamScratch(const StreamScratch &) = delete;
+    StreamScratch &operator=(const StreamScratch &) = delete;
+    ~StreamScratch()
+    {
+        for (void *p : owned) cudaFreeAsync(p, st);
+    }
+    template <class T> cudaError_t get(T **out, size_t bytes)
+    {
+        void *p = nullptr;
+        const cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, st);
+        if (e == cudaSuccess) owned.push_back(p);
+        *out = static_cast<T *>(p);
+        return e;
+    }
+};
+} // namespace pgc
+
+namespace pgc
+{
 int ensure_scratch(pgc_ctx *ctx, size_t bytes);
 int ctx_sync(pgc_ctx *ctx); // the context's own streams (never the whole device: see capi.cu)
 // family back-ends: validate + upload tables (create) and launch (eval, asynchronous on `stream`)

@@ -399,10 +399,11 @@ int pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_V, double *d
     double *lb = nullptr, *fit = nullptr;
     unsigned *bn = nullptr;
     unsigned char *improved = nullptr;
-    PGC_CUDA(cudaMallocAsync(&lb, 16 * dim, st));
-    PGC_CUDA(cudaMallocAsync(&fit, 8 * static_cast<size_t>(n_loc), st));
-    PGC_CUDA(cudaMallocAsync(&bn, 4 * static_cast<size_t>(n_loc), st));
-    PGC_CUDA(cudaMallocAsync(&improved, n_loc, st));
+    StreamScratch scratch(st); // released in stream order on every path out of this function
+    PGC_CUDA(scratch.get(&lb, 16 * dim));
+    PGC_CUDA(scratch.get(&fit, 8 * static_cast<size_t>(n_loc)));
+    PGC_CUDA(scratch.get(&bn, 4 * static_cast<size_t>(n_loc)));
+    PGC_CUDA(scratch.get(&improved, n_loc));
     double *ub = lb + dim;
     PGC_CUDA(cudaMemcpyAsync(lb, prob->lb.data(), 8 * dim, cudaMemcpyHostToDevice, st));
     PGC_CUDA(cudaMemcpyAsync(ub, prob->ub.data(), 8 * dim, cudaMemcpyHostToDevice, st));
@@ -424,7 +425,6 @@ int pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_V, double *d
         }
     }
     cudaError_t e = cudaStreamSynchronize(st); // lb / ub came from pageable host vectors
-    for (void *p : {static_cast<void *>(lb), static_cast<void *>(fit), static_cast<void *>(bn), static_cast<void *>(improved)}) cudaFreeAsync(p, st);
     if (rc != PGC_OK) return rc;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "pso_shard_step_device", __FILE__, __LINE__);

@@ -250,15 +250,16 @@ int sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, 
     const unsigned nx = static_cast<unsigned>(prob->nx);
     double *d_b = nullptr, *xnew = nullptr, *fboth = nullptr, *xo = nullptr, *fo = nullptr;
     unsigned *sel = nullptr, *perm = nullptr, *order = nullptr, *keep = nullptr;
-    PGC_CUDA(cudaMallocAsync(&d_b, 2 * nx * sizeof(double), st));
-    PGC_CUDA(cudaMallocAsync(&xnew, sizeof(double) * NP * nx, st));
-    PGC_CUDA(cudaMallocAsync(&fboth, sizeof(double) * 2 * NP, st));
-    PGC_CUDA(cudaMallocAsync(&xo, sizeof(double) * NP * nx, st));
-    PGC_CUDA(cudaMallocAsync(&fo, sizeof(double) * NP, st));
-    PGC_CUDA(cudaMallocAsync(&sel, sizeof(unsigned) * NP, st));
-    PGC_CUDA(cudaMallocAsync(&perm, sizeof(unsigned) * NP, st));
-    PGC_CUDA(cudaMallocAsync(&order, sizeof(unsigned) * NP, st));
-    PGC_CUDA(cudaMallocAsync(&keep, sizeof(unsigned) * NP, st));
+    StreamScratch scratch(st); // released in stream order on every path out of this function
+    PGC_CUDA(scratch.get(&d_b, 2 * nx * sizeof(double)));
+    PGC_CUDA(scratch.get(&xnew, sizeof(double) * NP * nx));
+    PGC_CUDA(scratch.get(&fboth, sizeof(double) * 2 * NP));
+    PGC_CUDA(scratch.get(&xo, sizeof(double) * NP * nx));
+    PGC_CUDA(scratch.get(&fo, sizeof(double) * NP));
+    PGC_CUDA(scratch.get(&sel, sizeof(unsigned) * NP));
+    PGC_CUDA(scratch.get(&perm, sizeof(unsigned) * NP));
+    PGC_CUDA(scratch.get(&order, sizeof(unsigned) * NP));
+    PGC_CUDA(scratch.get(&keep, sizeof(unsigned) * NP));
     PGC_CUDA(cudaMemcpyAsync(d_b, prob->lb.data(), nx * sizeof(double), cudaMemcpyHostToDevice, st));
     PGC_CUDA(cudaMemcpyAsync(d_b + nx, prob->ub.data(), nx * sizeof(double), cudaMemcpyHostToDevice, st));
     SgaParams P{};
@@ -310,10 +311,7 @@ int sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, 
             break;
         }
     }
-    cudaStreamSynchronize(st); // lb/ub staging came from pageable host vectors; buffers are released below
-    for (void *p : {static_cast<void *>(d_b), static_cast<void *>(xnew), static_cast<void *>(fboth), static_cast<void *>(xo), static_cast<void *>(fo),
-                    static_cast<void *>(sel), static_cast<void *>(perm), static_cast<void *>(order), static_cast<void *>(keep)})
-        cudaFreeAsync(p, st);
+    cudaStreamSynchronize(st); // lb/ub staging came from pageable host vectors; the scratch is released by its destructor
     if (rc == PGC_ERR_CUDA) set_error("sga_evolve_device: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
     return rc;
 }
