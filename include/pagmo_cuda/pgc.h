@@ -330,7 +330,8 @@ PGC_API int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *algo,
 /* ---- populations and migration (island.cpp:428-652) ------------------------------------------------------------------- */
 /* population(prob, bfe, n, seed) (population.cpp:82-103, generic.hpp:326-389): n uniform random decision vectors in the bounds,
  * one batch evaluation, random 64-bit IDs; the last nix genes are drawn as integers in [lb, ub] (generic.hpp:289-295).  d_f and
- * d_ids may be NULL.  The generation operators (pgc_*_evolve_device) refuse problems with integer genes (PGC_ERR_UNSUPPORTED). */
+ * d_ids may be NULL.  The generation operators (pgc_*_evolve_device) refuse problems with integer genes (PGC_ERR_UNSUPPORTED), except pgc_nsga2_evolve_device,
+ * which applies the reference's integer operators to the last nix genes. */
 PGC_API int pgc_population_init_device(pgc_problem *prob, size_t n, uint64_t seed, double *d_x, double *d_f, uint64_t *d_ids,
                                        void *stream);
 /* select_best::select (select_best.cpp:63-171): the best `rate` individuals (absolute count, or a fraction of n when

@@ -117,6 +117,8 @@ int oracle_sga_evolve(const oracle_problem *prob, const double *lb, const double
 void oracle_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double oracle_philox_u01_at(uint64_t seed, uint32_t tag, uint32_t generation, uint32_t index, uint32_t slot);
 int oracle_philox_perm(size_t n, uint64_t seed, uint32_t tag, uint32_t generation, size_t *perm);
+/* integer alleles at the end of the chromosome (problem::get_nix()) for the NSGA-II operators below; per thread, default 0 */
+void oracle_nsga2_set_nix(size_t nix);
 int oracle_nsga2_variation(const double *x, const size_t *rank, const double *cd, size_t NP, size_t nx, const double *lb,
                            const double *ub, const size_t *sh1, const size_t *sh2, double cr, double eta_c, double m, double eta_m,
                            uint64_t seed, uint32_t generation, double *children);

@@ -476,6 +476,12 @@ class Oracle:
             raise ValueError("oracle_pso_evolve_mt failed")
         return x, f
 
+    def set_nix(self, nix: int):
+        """integer alleles at the end of the chromosome for the NSGA-II operators of this thread (problem::get_nix())."""
+        self.lib.oracle_nsga2_set_nix.argtypes = [C.c_size_t]
+        self.lib.oracle_nsga2_set_nix.restype = None
+        self.lib.oracle_nsga2_set_nix(nix)
+
     DIVERSITY = {"crowding distance": 0, "niche count": 1, "max min": 2}
 
     def nspso_evolve(self, prob, lb, ub, x, f, gens=1, omega=0.6, c1=2.0, c2=2.0, chi=1.0, v_coeff=0.5, leader_selection_range=60,

@@ -31,13 +31,25 @@ static size_t tournament(size_t i1, size_t i2, const size_t *rank, const double 
     return (oracle_next(rs) < 0.5) ? i1 : i2;
 }
 
+/* integer alleles sit at the end of the chromosome (problem::get_nix()); set per thread before calling the operators below */
+static _Thread_local size_t nsga2_nix = 0;
+void oracle_nsga2_set_nix(size_t nix) { nsga2_nix = nix; }
+
+/* uniform_integral_from_range(lb, ub) (generic.hpp:142-164): std::uniform_int_distribution<long long>; Philox mode: lb + floor(u * range) */
+static double next_integral(oracle_stream *rs, double lb, double ub)
+{
+    const long long l = (long long)lb, u = (long long)ub;
+    return (double)(l + (long long)oracle_next_below(rs, (size_t)(u - l + 1)));
+}
+
 static void sbx(const double *p1, const double *p2, double *c1, double *c2, size_t nx, const double *lb, const double *ub, double p_cr,
                 double eta_c, oracle_stream *rs)
 {
+    const size_t nix = nsga2_nix <= nx ? nsga2_nix : nx, ncx = nx - nix;
     memcpy(c1, p1, nx * sizeof(double));
     memcpy(c2, p2, nx * sizeof(double));
     if (oracle_next(rs) < p_cr) {
-        for (size_t i = 0; i < nx; i++) {
+        for (size_t i = 0; i < ncx; i++) {
             if ((oracle_next(rs) < 0.5) && (fabs(p1[i] - p2[i])) > 1e-14 && lb[i] != ub[i]) {
                 double y1, y2, yl, yu, beta, betaq, v1, v2, rand01;
                 if (p1[i] < p2[i]) { y1 = p1[i]; y2 = p2[i]; } else { y1 = p2[i]; y2 = p1[i]; }
@@ -57,12 +69,18 @@ static void sbx(const double *p1, const double *p2, double *c1, double *c2, size
                 if (oracle_next(rs) < .5) { c1[i] = v1; c2[i] = v2; } else { c1[i] = v2; c2[i] = v1; }
             }
         }
+        if (nix > 0) { /* two-point crossover of the integer part, genetic_operators.cpp:125-137 */
+            size_t site1 = ncx + oracle_next_below(rs, nix), site2 = ncx + oracle_next_below(rs, nix);
+            if (site1 > site2) { const size_t t = site1; site1 = site2; site2 = t; }
+            for (size_t j = site1; j <= site2; ++j) { c1[j] = p2[j]; c2[j] = p1[j]; }
+        }
     }
 }
 
 static void polymut(double *child, size_t nx, const double *lb, const double *ub, double p_m, double eta_m, oracle_stream *rs)
 {
-    for (size_t j = 0; j < nx; ++j) {
+    const size_t nix = nsga2_nix <= nx ? nsga2_nix : nx, ncx = nx - nix;
+    for (size_t j = 0; j < ncx; ++j) {
         if (oracle_next(rs) < p_m && lb[j] != ub[j]) {
             double y = child[j], yl = lb[j], yu = ub[j], deltaq, xy, val;
             const double delta1 = (y - yl) / (yu - yl), delta2 = (yu - y) / (yu - yl);
@@ -82,6 +100,8 @@ static void polymut(double *child, size_t nx, const double *lb, const double *ub
             child[j] = y;
         }
     }
+    for (size_t j = ncx; j < nx; ++j) /* integer mutation, genetic_operators.cpp:187-195 */
+        if (oracle_next(rs) < p_m) child[j] = next_integral(rs, lb[j], ub[j]);
 }
 
 struct kv { uint64_t k; size_t v; };

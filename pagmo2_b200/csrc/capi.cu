@@ -762,7 +762,7 @@ int pgc_nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t 
                             double eta_m, uint64_t seed, uint32_t first_generation, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_nsga2_evolve_device: null argument");
-    PGC_NO_INTEGER_GENES(prob, "pgc_nsga2_evolve_device");
+    // integer alleles (the last nix genes, e.g. ZDT5) are handled: two-point crossover + uniform integer mutation, genetic_operators.cpp:125-137, :187-195
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return nsga2_evolve_device(prob, d_x, d_f, static_cast<unsigned>(NP), gens, cr, eta_c, m, eta_m, seed, first_generation,
                                problem_eval_device, stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);

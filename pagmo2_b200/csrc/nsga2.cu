@@ -45,7 +45,7 @@ struct VarParams {
     const unsigned *sh1, *sh2;
     const double *lb, *ub; // [nx]
     double *children;      // [NP x nx]
-    unsigned NP, nx;
+    unsigned NP, nx, nix; // nix: integer alleles at the end of the chromosome (problem::get_nix())
     double cr, eta_c, m, eta_m;
     unsigned long long seed;
     unsigned generation;
@@ -62,13 +62,13 @@ __device__ __forceinline__ unsigned tournament(unsigned i1, unsigned i2, const V
 
 __device__ void sbx_and_mutate(const double *p1, const double *p2, double *c1, double *c2, const VarParams &P, PhiloxStream &rs)
 {
-    const unsigned nx = P.nx;
+    const unsigned nx = P.nx, ncx = nx - P.nix;
     for (unsigned i = 0; i < nx; ++i) { // children start as copies of the parents, :86-87
         c1[i] = p1[i];
         c2[i] = p2[i];
     }
     if (rs.next() < P.cr) { // :91
-        for (unsigned i = 0; i < nx; ++i) {
+        for (unsigned i = 0; i < ncx; ++i) {
             const double a = p1[i], b = p2[i], yl = P.lb[i], yu = P.ub[i];
             if ((rs.next() < 0.5) && (fabs(a - b)) > 1e-14 && yl != yu) { // :94
                 const double y1 = (a < b) ? a : b, y2 = (a < b) ? b : a;
@@ -92,11 +92,22 @@ __device__ void sbx_and_mutate(const double *p1, const double *p2, double *c1, d
                 }
             }
         }
+        if (P.nix > 0u) { // two-point crossover of the integer part, :125-137: uniform_int(ncx, nx - 1) twice
+            unsigned s1 = static_cast<unsigned>(rs.next() * static_cast<double>(P.nix)), s2;
+            if (s1 >= P.nix) s1 = P.nix - 1u;
+            s2 = static_cast<unsigned>(rs.next() * static_cast<double>(P.nix));
+            if (s2 >= P.nix) s2 = P.nix - 1u;
+            const unsigned site1 = ncx + min(s1, s2), site2 = ncx + max(s1, s2);
+            for (unsigned j = site1; j <= site2; ++j) {
+                c1[j] = p2[j];
+                c2[j] = p1[j];
+            }
+        }
     }
     // polynomial mutation of the first child, then of the second (nsga2.cpp:221-222), genetic_operators.cpp:164-187
     for (int k = 0; k < 2; ++k) {
         double *c = k ? c2 : c1;
-        for (unsigned j = 0; j < nx; ++j) {
+        for (unsigned j = 0; j < ncx; ++j) {
             const double yl = P.lb[j], yu = P.ub[j];
             if (rs.next() < P.m && yl != yu) {
                 double y = c[j];
@@ -117,6 +128,15 @@ __device__ void sbx_and_mutate(const double *p1, const double *p2, double *c1, d
                 if (y < yl) y = yl;
                 if (y > yu) y = yu;
                 c[j] = y;
+            }
+        }
+        for (unsigned j = ncx; j < nx; ++j) { // integer mutation, :187-195: uniform_integral_from_range(lb, ub)
+            if (rs.next() < P.m) {
+                const long long l = static_cast<long long>(P.lb[j]), u = static_cast<long long>(P.ub[j]);
+                const unsigned long long range = static_cast<unsigned long long>(u - l + 1);
+                unsigned long long v = static_cast<unsigned long long>(rs.next() * static_cast<double>(range));
+                if (v >= range) v = range - 1ull;
+                c[j] = static_cast<double>(l + static_cast<long long>(v));
             }
         }
     }
@@ -206,13 +226,14 @@ int philox_permutation_device(pgc_ctx *ctx, unsigned n, unsigned long long seed,
 int nsga2_variation_device(pgc_ctx *ctx, const double *d_x, const unsigned *d_rank, const double *d_cd, unsigned NP, unsigned nx,
                            const double *d_lb, const double *d_ub, const unsigned *d_sh1, const unsigned *d_sh2, double cr,
                            double eta_c, double m, double eta_m, unsigned long long seed, unsigned generation, double *d_children,
-                           cudaStream_t st)
+                           cudaStream_t st, unsigned nix)
 {
+    PGC_REQUIRE(nix <= nx, "nsga2 variation: %u integer alleles in a chromosome of %u", nix, nx);
     PGC_REQUIRE(NP >= 5 && NP % 4 == 0,
                 "for NSGA-II at least 5 individuals in the population are needed and the population size must be a multiple of "
                 "4. Detected input population size is: %u",
                 NP); // nsga2.cpp:121-126
-    VarParams P{d_x, d_rank, d_cd, d_sh1, d_sh2, d_lb, d_ub, d_children, NP, nx, cr, eta_c, m, eta_m, seed, generation};
+    VarParams P{d_x, d_rank, d_cd, d_sh1, d_sh2, d_lb, d_ub, d_children, NP, nx, nix, cr, eta_c, m, eta_m, seed, generation};
     nsga2_variation_kernel<<<nblk(NP / 4, 64), 64, 0, st>>>(P);
     PGC_CUDA(cudaGetLastError());
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
@@ -277,7 +298,7 @@ int nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP
         if ((rc = crowding_device(ctx, d_f, NP, nobj, order, foff, nfronts, 1, cd, st))) return rc;
         const auto t3 = now();
         if ((rc = nsga2_variation_device(ctx, d_x, rank, cd, NP, nx, lb, ub, sh1, sh2, cr, eta_c, m, eta_m, seed, generation,
-                                         x2 + static_cast<size_t>(NP) * nx, st)))
+                                         x2 + static_cast<size_t>(NP) * nx, st, static_cast<unsigned>(prob->nix))))
             return rc;
         if ((rc = eval(prob, x2 + static_cast<size_t>(NP) * nx, NP, f2 + static_cast<size_t>(NP) * nobj, st))) return rc;
         unsigned nsel = 0;

@@ -317,7 +317,7 @@ int nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP
 int nsga2_variation_device(pgc_ctx *ctx, const double *d_x, const unsigned *d_rank, const double *d_cd, unsigned NP, unsigned nx,
                            const double *d_lb, const double *d_ub, const unsigned *d_sh1, const unsigned *d_sh2, double cr,
                            double eta_c, double m, double eta_m, unsigned long long seed, unsigned generation, double *d_children,
-                           cudaStream_t st);
+                           cudaStream_t st, unsigned nix = 0);
 int nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double cr, double eta_c, double m,
                         double eta_m, unsigned long long seed, unsigned first_generation,
                         int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);

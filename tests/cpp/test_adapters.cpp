@@ -326,6 +326,22 @@ int main(int argc, char **argv)
         pagmo::population mo{zp, 40u, 5u};
         mo = pagmo::algorithm{cuda_nsga2{10u, 0.95, 10., 0.01, 50., 32u}}.evolve(mo);
         CHECK(mo.size() == 40u && mo.get_f()[0].size() == 2u);
+        { // ZDT5 is all-integer: cuda_nsga2 applies the reference's integer operators, the decision vectors stay integral
+            pagmo::problem z5{pagmo::zdt{5u, 11u}};
+            pagmo::population ip{z5, 40u, 3u};
+            ip = pagmo::algorithm{cuda_nsga2{8u, 0.95, 10., 0.05, 50., 11u}}.evolve(ip);
+            bool integral = true;
+            for (const auto &xv : ip.get_x())
+                for (double g : xv) integral = integral && g == std::floor(g) && g >= 0. && g <= 1.;
+            CHECK(integral && ip.get_problem().get_nix() == z5.get_nx());
+            bool refused = false;
+            try {
+                pagmo::algorithm{cuda_de{2u}}.evolve(pagmo::population{pagmo::problem{pagmo::decompose{pagmo::zdt{5u, 11u}, {0.5, 0.5}, {0., 0.}}}, 16u, 1u});
+            } catch (const std::invalid_argument &) {
+                refused = true; // the other device UDAs refuse integer genes (or find no twin): never a silent continuous run
+            }
+            CHECK(refused);
+        }
         // cuda_nspso: the three diversity mechanisms run, fitness stays consistent with the decision vectors, fevals counted like the
         // reference (NP per generation), the constructor rejects what nspso.cpp:58-80 rejects
         for (const char *div : {"crowding distance", "niche count", "max min"}) {

@@ -124,3 +124,28 @@ def test_generation_at_cfg3_size_matches_restated_reference(capi, ctx, orc, fam,
     # survivors that are untouched parents or unmutated clones must be bit-identical rows in the same positions
     assert (xg == xo).all(axis=1).mean() > 0.3
     prob.close()
+
+
+@pytest.mark.parametrize("param,NP", [(3, 24), (11, 64), (5, 400)])
+def test_nsga2_on_zdt5_integer_alleles(capi, ctx, orc, param, NP):
+    """ZDT5 is all-integer: the device loop applies the reference's two-point crossover and uniform integer mutation to the integer
+    alleles (genetic_operators.cpp:125-137, :187-195) - same trajectory as the restated loop (pinned to the compiled reference on
+    the mt19937 stream in tests/test_oracle_pin.py), integer decision vectors throughout; the other evolve entry points still
+    refuse integer genes."""
+    prob = capi.Problem(ctx, "zdt", prob_id=5, dim=param)
+    lb, ub = prob.bounds()
+    nx = prob.nx
+    x = np.floor(np.random.default_rng(param).uniform(lb, ub + 1, (NP, nx))).clip(lb, ub)
+    f = prob.eval_host(x)
+    orc.set_nix(nx)
+    try:
+        for cr, m, gens in ((0.95, 0.01, 6), (0.5, 0.2, 4), (0.9, 1.0 / nx, 5)):
+            xo, fo = orc.nsga2_evolve("zdt", 5, 2, 0, lb, ub, x, f, gens, cr, 10.0, m, 50.0, 17, 2)
+            xg, fg = prob.nsga2_evolve(x, f, gens, cr=cr, eta_c=10.0, m=m, eta_m=50.0, seed=17, first_generation=2)
+            assert np.array_equal(xg, xo) and np.allclose(fg, fo, rtol=1e-12, atol=0)
+            assert np.array_equal(xg, np.round(xg)) and (xg >= lb).all() and (xg <= ub).all()
+    finally:
+        orc.set_nix(0)
+    with pytest.raises(capi.PgcError):
+        prob.de_evolve(x, f[:, 0], gens=1, algo="de")
+    prob.close()

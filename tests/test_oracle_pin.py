@@ -249,3 +249,24 @@ def test_moead_gen_evolve_bit_exact(orc, ref, fam, args, NP, wgen):
             xo, fo = orc.moead_gen_evolve(op, lb, ub, x0, f0, w, nb, gens=gens, decomposition=decomposition, CR=CR, F=F, eta_m=20.0, realb=realb,
                                           limit=limit, preserve_diversity=preserve, seed=seed, mt=True, burn_draws=burn)
             assert np.array_equal(xr, xo) and np.array_equal(fr, fo), (decomposition, T, CR, realb, limit, preserve)
+
+
+@pytest.mark.parametrize("param,NP", [(3, 24), (11, 32), (5, 20)])
+def test_nsga2_on_zdt5_integer_alleles_bit_exact(orc, ref, param, NP):
+    """ZDT5 is all-integer (nix == nx): sbx_crossover_impl's two-point crossover of the integer part and polynomial_mutation_impl's
+    uniform integer redraw (genetic_operators.cpp:125-137, :187-195), inside whole nsga2::evolve runs on the mt19937 stream."""
+    rp = ref.problem("zdt", 5, param)
+    lb, ub = rp.bounds()
+    nx = len(lb)
+    x0 = np.floor(np.random.default_rng(param).uniform(lb, ub + 1, (NP, nx))).clip(lb, ub)
+    f0 = np.array([rp.fitness(x) for x in x0])
+    orc.set_nix(nx)
+    try:
+        for cr, m, gens in ((0.95, 0.01, 8), (0.5, 0.2, 5), (0.9, 1.0 / nx, 6)):
+            seed = gens + param
+            xr, fr = ref.evolve_from(rp, "nsga2", [cr, 10.0, m, 50.0], x0, gens, seed)
+            xo, fo = orc.nsga2_evolve_mt("zdt", 5, 2, 0, lb, ub, x0, f0, gens, cr, 10.0, m, 50.0, seed)
+            assert np.array_equal(xr, xo) and np.array_equal(fr, fo), (cr, m, gens)
+            assert np.array_equal(xo, np.round(xo))
+    finally:
+        orc.set_nix(0)
