@@ -16,8 +16,9 @@
 // pagmo_cuda:: UDP or a stock UDP that cuda_bfe recognises; otherwise evolve() throws (no CPU fallback).
 // Differences from the reference algorithms, as documented in DESIGN.md: the DE family and PSO are GENERATIONAL (all trial
 // vectors of a generation are built from the previous population and evaluated in one batch; the reference updates in place,
-// individual by individual), random draws come from Philox streams keyed by (seed, generation, individual), `memory = true` is
-// not supported.  fevals are accounted for as the reference does (one per individual per generation).
+// individual by individual), random draws come from Philox streams keyed by (seed, generation, individual).  `memory = true`
+// (sade, de1220, pso_gen, pso, nspso) keeps the adaptation state / velocities / archive between evolve() calls as the reference
+// does; cmaes's is not built.  fevals are accounted for as the reference does (one per individual per generation).
 #ifndef PAGMO_CUDA_CUDA_ALGORITHMS_HPP
 #define PAGMO_CUDA_CUDA_ALGORITHMS_HPP
 
@@ -72,7 +73,7 @@ public:
             std::copy(pop.get_x()[i].begin(), pop.get_x()[i].end(), x.begin() + static_cast<std::ptrdiff_t>(i * nx));
             std::copy(pop.get_f()[i].begin(), pop.get_f()[i].end(), f.begin() + static_cast<std::ptrdiff_t>(i * nf));
         }
-        const unsigned done = h->evolve(m_desc, x, f, m_generation);
+        const unsigned done = m_desc.memory ? h->evolve_memory(m_desc, x, f, m_generation, m_state) : h->evolve(m_desc, x, f, m_generation);
         m_generation += m_desc.gens;
         for (decltype(pop.size()) i = 0; i < n; ++i) {
             pop.set_xf(i, pagmo::vector_double(x.begin() + static_cast<std::ptrdiff_t>(i * nx), x.begin() + static_cast<std::ptrdiff_t>((i + 1) * nx)),
@@ -130,7 +131,8 @@ public:
                                m_desc.eta_m, m_desc.seed, m_desc.param_m, m_desc.param_s, m_desc.crossover, m_desc.mutation,
                                m_desc.selection, m_desc.cma_cc, m_desc.cma_cs, m_desc.cma_c1, m_desc.cma_cmu, m_desc.sigma0,
                                m_desc.force_bounds, m_desc.nspso_c1, m_desc.nspso_c2, m_desc.nspso_chi, m_desc.nspso_v_coeff,
-                               m_desc.leader_selection_range, m_desc.diversity);
+                               m_desc.leader_selection_range, m_desc.diversity, m_desc.memory, m_state.a, m_state.b, m_state.c, m_state.u,
+                               m_state.initialized);
         for (std::size_t i = 0; i < 18u && i < allowed.size(); ++i) m_desc.allowed_variants[i] = allowed[i]; // no-op when saving
     }
 
@@ -144,10 +146,18 @@ protected:
     {
         if (memory) pagmo_throw(std::invalid_argument, std::string(who) + ": memory = true is not supported on the device path");
     }
+    // memory = true (sade.hpp:138, de1220.hpp:158, pso_gen.hpp:127, nspso.hpp:59): F / CR / variant, the velocities, nspso's archive
+    // survive between evolve() calls.  The state is a value member (host arrays that travel with the population), so a copy of the
+    // algorithm - pagmo copies the UDA in and out of an island around every evolve - carries it like the reference's mutable members.
+    void keep_memory(bool memory)
+    {
+        m_desc.memory = memory ? 1u : 0u;
+    }
     pgc_algo_desc m_desc{};
     int m_device = 0;
     std::string m_name;
     mutable unsigned m_generation = 1; // Philox generation counter: successive evolve() calls continue the stream
+    mutable detail::problem_handle::algo_state m_state;
     std::shared_ptr<detail::twin_cache> m_cache;
 };
 
@@ -184,7 +194,7 @@ public:
             pagmo_throw(std::invalid_argument, "The variant for self-adaptation must be in [1,2], while a value of "
                                                    + std::to_string(variant_adptv) + " was detected.");
         }
-        no_memory(memory, "cuda_sade");
+        keep_memory(memory);
         m_desc.variant = variant, m_desc.variant_adptv = variant_adptv, m_desc.ftol = ftol, m_desc.xtol = xtol;
     }
 };
@@ -209,7 +219,7 @@ public:
         if (allowed_variants.empty() || allowed_variants.size() > 18u) {
             pagmo_throw(std::invalid_argument, "cuda_de1220: between 1 and 18 allowed variants are required");
         }
-        no_memory(memory, "cuda_de1220");
+        keep_memory(memory);
         m_desc.n_allowed = static_cast<unsigned>(allowed_variants.size());
         for (std::size_t i = 0; i < allowed_variants.size(); ++i) m_desc.allowed_variants[i] = allowed_variants[i];
         m_desc.variant_adptv = variant_adptv, m_desc.ftol = ftol, m_desc.xtol = xtol;
@@ -224,7 +234,7 @@ public:
                  int device = 0)
         : cuda_algorithm_base(PGC_ALGO_PSO_GEN, "GPSO: Generational Particle Swarm Optimization", gen, seed, device)
     {
-        no_memory(memory, "cuda_pso_gen");
+        keep_memory(memory);
         m_desc.omega = omega, m_desc.eta1 = eta1, m_desc.eta2 = eta2, m_desc.max_vel = max_vel, m_desc.variant = variant;
         m_desc.neighb_type = neighb_type, m_desc.neighb_param = neighb_param; // range checks: pso.cu (pso_gen.cpp:69-107)
     }
@@ -309,8 +319,7 @@ public:
 };
 
 // pagmo::nspso (nspso.hpp:59-62): non-dominated sorting PSO; generational in the reference itself, so this is the same algorithm on
-// Philox draws (pgc_nspso_evolve_device, nspso.cu).  memory = true (velocities and archive kept between evolve() calls) is available on
-// the C ABI (d_vel / d_best_x / d_best_f) but not through this adapter.
+// Philox draws (pgc_nspso_evolve_device, nspso.cu).  memory = true keeps the velocities and the archive between evolve() calls.
 class cuda_nspso : public cuda_algorithm_base
 {
 public:
@@ -340,7 +349,7 @@ public:
         else if (diversity_mechanism == "niche count") div = 1;
         else if (diversity_mechanism == "max min") div = 2;
         else pagmo_throw(std::invalid_argument, "Non existing diversity mechanism method."); // :76-80
-        no_memory(memory, "cuda_nspso");
+        keep_memory(memory);
         m_desc.omega = omega, m_desc.nspso_c1 = c1, m_desc.nspso_c2 = c2, m_desc.nspso_chi = chi, m_desc.nspso_v_coeff = v_coeff;
         m_desc.leader_selection_range = leader_selection_range, m_desc.diversity = div;
     }

@@ -215,6 +215,47 @@ public:
         return done;
     }
 
+    // the same for a UDA built with memory = true: `state` (four host arrays, pgc_algo_memory's a / b / c / u) travels with the
+    // population; initialized = false on the algorithm's first call with this population size
+    struct algo_state {
+        pagmo::vector_double a, b, c;
+        std::vector<uint32_t> u;
+        bool initialized = false;
+    };
+    unsigned evolve_memory(const pgc_algo_desc &algo, pagmo::vector_double &x, pagmo::vector_double &f, unsigned first_generation,
+                           algo_state &st) const
+    {
+        const std::size_t n = x.size() / m_nx;
+        if (!st.initialized || st.u.size() != n) { // sade.cpp:137: a population of another size restarts the adaptation
+            st.a.assign(n * m_nx, 0.), st.b.assign(n * m_nx, 0.), st.c.assign(n * m_nf, 0.), st.u.assign(n, 0u);
+            st.initialized = false;
+        }
+        unsigned done = 0;
+        on_device(x, f, "pgc_algo_evolve_memory_device", [&](double *dx, double *df, std::size_t) {
+            // (device_mutex is held by on_device)
+            void *d[4] = {nullptr, nullptr, nullptr, nullptr};
+            const void *h[4] = {st.a.data(), st.b.data(), st.c.data(), st.u.data()};
+            void *hw[4] = {st.a.data(), st.b.data(), st.c.data(), st.u.data()};
+            const std::size_t bytes[4] = {st.a.size() * sizeof(double), st.b.size() * sizeof(double), st.c.size() * sizeof(double),
+                                          st.u.size() * sizeof(uint32_t)};
+            int rc = PGC_OK;
+            for (int k = 0; k < 4 && rc == PGC_OK; ++k) {
+                rc = pgc_malloc_device(m_ctx.get(), bytes[k] ? bytes[k] : 8u, &d[k]);
+                if (rc == PGC_OK && st.initialized && bytes[k]) rc = pgc_memcpy_h2d(m_ctx.get(), d[k], h[k], bytes[k]);
+            }
+            pgc_algo_memory mem{static_cast<double *>(d[0]), static_cast<double *>(d[1]), static_cast<double *>(d[2]),
+                                static_cast<uint32_t *>(d[3]), st.initialized ? 1 : 0, 0};
+            if (rc == PGC_OK) rc = pgc_algo_evolve_memory_device(m_prob, &algo, dx, df, n, first_generation, &done, &mem, nullptr);
+            for (int k = 0; k < 4 && rc == PGC_OK; ++k)
+                if (bytes[k]) rc = pgc_memcpy_d2h(m_ctx.get(), hw[k], d[k], bytes[k]);
+            for (void *p : d)
+                if (p) pgc_free_device(m_ctx.get(), p);
+            if (rc == PGC_OK) st.initialized = true;
+            return rc;
+        });
+        return done;
+    }
+
     // upload x [n x nx] / f [n x nf], run `call(d_x, d_f, n)` (a pgc_*_evolve_device entry point on this handle's problem: see raw()),
     // download both in place; throws what the status says
     template <typename Call>

@@ -316,7 +316,8 @@ typedef struct pgc_algo_desc {
     double param_m;                       /* sga */
     uint32_t param_s, crossover, mutation, selection; /* sga: see pgc_sga_evolve_device */
     double cma_cc, cma_cs, cma_c1, cma_cmu, sigma0;   /* cmaes (-1: automatic), cmaes.hpp:110 */
-    uint32_t force_bounds, reserved_;
+    uint32_t force_bounds;
+    uint32_t memory;                      /* sade / de1220 / pso_gen / nspso: keep the adaptation state between evolve() calls (pgc_algo_memory) */
     double nspso_c1, nspso_c2, nspso_chi, nspso_v_coeff;       /* nspso (omega is shared with pso_gen), nspso.hpp:59-62 */
     uint32_t leader_selection_range, diversity;               /* nspso: diversity 0 crowding distance, 1 niche count, 2 max min */
 } pgc_algo_desc;
@@ -326,6 +327,22 @@ PGC_API int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_d
  * Philox generation counter so that successive calls continue the random stream; *gens_done (optional) = generations run. */
 PGC_API int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *algo, double *d_x, double *d_f, size_t n,
                                    uint32_t first_generation, unsigned *gens_done, void *stream);
+
+/* The state an algorithm constructed with memory = true keeps between evolve() calls (device arrays owned by the caller):
+ *   sade / de1220: a = F [n], b = CR [n], u = mutation variant [n] (de1220 only)      (sade.cpp:137-156, de1220.cpp:147-165)
+ *   pso_gen      : a = velocities [n x nx]                                            (pso_gen.cpp:193-201)
+ *   nspso        : a = velocities [n x nx], b = archive decision vectors [n x nx], c = archive fitness [n x nobj] (nspso.cpp:127-152)
+ * initialized == 0: the arrays hold nothing yet; pgc_algo_evolve_memory_device first fills them as the reference's first evolve() with
+ * memory does (drawn from the Philox streams of `first_generation`) and sets it to 1.  Other algorithms have no such state.
+ * pgc_island_evolve keeps this state in HBM inside the island when algo->memory != 0 (re-drawn if the algorithm changes, as a new
+ * reference UDA object would). */
+typedef struct pgc_algo_memory {
+    double *a, *b, *c;
+    uint32_t *u;
+    int32_t initialized, reserved_;
+} pgc_algo_memory;
+PGC_API int pgc_algo_evolve_memory_device(pgc_problem *prob, const pgc_algo_desc *algo, double *d_x, double *d_f, size_t n,
+                                          uint32_t first_generation, unsigned *gens_done, pgc_algo_memory *memory, void *stream);
 
 /* ---- populations and migration (island.cpp:428-652) ------------------------------------------------------------------- */
 /* population(prob, bfe, n, seed) (population.cpp:82-103, generic.hpp:326-389): n uniform random decision vectors in the bounds,

@@ -53,10 +53,15 @@ class AlgoDesc(C.Structure):
         ("cr", C.c_double), ("eta_c", C.c_double), ("m", C.c_double), ("eta_m", C.c_double), ("seed", C.c_uint64),
         ("param_m", C.c_double), ("param_s", C.c_uint32), ("crossover", C.c_uint32), ("mutation", C.c_uint32), ("selection", C.c_uint32),
         ("cma_cc", C.c_double), ("cma_cs", C.c_double), ("cma_c1", C.c_double), ("cma_cmu", C.c_double), ("sigma0", C.c_double),
-        ("force_bounds", C.c_uint32), ("reserved_", C.c_uint32),
+        ("force_bounds", C.c_uint32), ("memory", C.c_uint32),
         ("nspso_c1", C.c_double), ("nspso_c2", C.c_double), ("nspso_chi", C.c_double), ("nspso_v_coeff", C.c_double),
         ("leader_selection_range", C.c_uint32), ("diversity", C.c_uint32),
     ]
+
+
+class AlgoMemory(C.Structure):
+    """pgc_algo_memory: the device arrays a UDA with memory = true keeps between evolve() calls."""
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("u", C.c_void_p), ("initialized", C.c_int32), ("reserved_", C.c_int32)]
 
 
 ALGO = {"de": 1, "sade": 2, "de1220": 3, "pso_gen": 4, "nsga2": 5, "sga": 6, "cmaes": 7, "nspso": 8}
@@ -623,6 +628,31 @@ class Problem:
         finally:
             self.ctx.free(dx)
             self.ctx.free(df)
+
+    def evolve_memory(self, algo: "AlgoDesc", x, f, first_generation=1, state=None):
+        """evolve() of a UDA built with memory = true (`pgc_algo_evolve_memory_device`): `state` is what the previous call returned
+        (None: the first call, the state is drawn as the reference's first evolve() draws it).  Returns (x, f, gens_done, state),
+        state = {"a", "b", "c", "u"} host arrays (pgc_algo_memory: F / CR / variant, velocities, nspso's archive)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(x.shape[0], -1)
+        n, nx, nf = x.shape[0], x.shape[1], f.shape[1]
+        shapes = {"a": ((n, nx), np.float64), "b": ((n, nx), np.float64), "c": ((n, nf), np.float64), "u": ((n,), np.uint32)}
+        host = {k: (np.zeros(sh, dt) if state is None else np.ascontiguousarray(state[k], dtype=dt).reshape(sh)) for k, (sh, dt) in shapes.items()}
+        dev = {k: self.ctx.to_device(v) for k, v in host.items()}
+        dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
+        mem = AlgoMemory(dev["a"], dev["b"], dev["c"], dev["u"], 0 if state is None else 1, 0)
+        done = C.c_uint()
+        L = lib()
+        L.pgc_algo_evolve_memory_device.argtypes = [C.c_void_p, C.POINTER(AlgoDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
+                                                    C.POINTER(C.c_uint), C.POINTER(AlgoMemory), C.c_void_p]
+        try:
+            check(L.pgc_algo_evolve_memory_device(self._h, C.byref(algo), dx, df, n, first_generation, C.byref(done), C.byref(mem), None))
+            self.ctx.synchronize()
+            out = {k: self.ctx.from_device(dev[k], host[k].shape, dtype=host[k].dtype) for k in host}
+            return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), done.value, out
+        finally:
+            for d in (dx, df, *dev.values()):
+                self.ctx.free(d)
 
     def eval_host_into(self, dvs: np.ndarray, fvs: np.ndarray):
         n = dvs.size // self.nx

@@ -986,6 +986,55 @@ int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *a, double *d_
     }
 }
 
+int pgc_algo_evolve_memory_device(pgc_problem *prob, const pgc_algo_desc *a, double *d_x, double *d_f, size_t n, uint32_t first_generation,
+                                  unsigned *gens_done, pgc_algo_memory *mem, void *stream)
+{
+    PGC_REQUIRE(prob && a && d_x && d_f && mem, "pgc_algo_evolve_memory_device: null argument");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream;
+    const unsigned NP = static_cast<unsigned>(n);
+    if (gens_done) *gens_done = a->gens;
+    int rc;
+    switch (a->algo) {
+        case PGC_ALGO_SADE:
+        case PGC_ALGO_DE1220: {
+            const unsigned algo = static_cast<unsigned>(a->algo - PGC_ALGO_DE);
+            PGC_REQUIRE(mem->a && mem->b && (algo == 1u || mem->u), "pgc_algo_evolve_memory_device: sade / de1220 keep F, CR (and the variant)");
+            if (!mem->initialized) {
+                if ((rc = de_init_adaptation_device(NP, algo, a->variant_adptv, a->allowed_variants, a->n_allowed, a->seed, first_generation, mem->a,
+                                                    mem->b, mem->u, st)))
+                    return rc;
+                mem->initialized = 1;
+            }
+            return pgc_de_evolve_device(prob, d_x, d_f, n, a->gens, algo, a->variant, a->variant_adptv, a->F, a->CR, a->allowed_variants,
+                                        a->n_allowed, a->ftol, a->xtol, mem->a, mem->b, algo == 2u ? mem->u : nullptr, a->seed, first_generation,
+                                        gens_done, stream);
+        }
+        case PGC_ALGO_PSO_GEN:
+            PGC_REQUIRE(mem->a, "pgc_algo_evolve_memory_device: pso_gen keeps the velocities");
+            PGC_NO_INTEGER_GENES(prob, "pgc_algo_evolve_memory_device");
+            if (!mem->initialized) {
+                if ((rc = pso_init_velocity_device(prob, NP, a->max_vel, a->seed, first_generation, mem->a, st))) return rc;
+                mem->initialized = 1;
+            }
+            return pgc_pso_evolve_device(prob, d_x, d_f, mem->a, nullptr, n, a->gens, a->omega, a->eta1, a->eta2, a->max_vel, a->variant,
+                                         a->neighb_type, a->neighb_param, a->seed, first_generation, stream);
+        case PGC_ALGO_NSPSO:
+            PGC_REQUIRE(mem->a && mem->b && mem->c, "pgc_algo_evolve_memory_device: nspso keeps the velocities and the archive");
+            PGC_NO_INTEGER_GENES(prob, "pgc_algo_evolve_memory_device");
+            if (!mem->initialized) {
+                if ((rc = nspso_init_memory_device(prob, d_x, d_f, NP, a->nspso_v_coeff, a->seed, first_generation, mem->a, mem->b, mem->c, st)))
+                    return rc;
+                mem->initialized = 1;
+            }
+            return pgc_nspso_evolve_device(prob, d_x, d_f, n, a->gens, a->omega, a->nspso_c1, a->nspso_c2, a->nspso_chi, a->nspso_v_coeff,
+                                           a->leader_selection_range, a->diversity, a->seed, first_generation, mem->a, mem->b, mem->c, stream);
+        default:
+            set_error("pgc_algo_evolve_memory_device: algorithm %d keeps no state between evolve() calls", a->algo);
+            return PGC_ERR_INVALID_ARGUMENT;
+    }
+}
+
 int pgc_population_init_device(pgc_problem *prob, size_t n, uint64_t seed, double *d_x, double *d_f, uint64_t *d_ids, void *stream)
 {
     PGC_REQUIRE(prob && (d_x || n == 0), "pgc_population_init_device: null argument");

@@ -1056,6 +1056,28 @@ struct DeWork : LoopWorkspace {
 
 } // namespace
 
+// The self-adaptation state a first evolve() with memory draws (sade.cpp:137-156, de1220.cpp:147-165): F / CR per individual,
+// and de1220's mutation variant.  algo: 1 sade, 2 de1220.
+int de_init_adaptation_device(unsigned NP, unsigned algo, unsigned variant_adptv, const unsigned *allowed, unsigned n_allowed,
+                              unsigned long long seed, unsigned generation, double *d_F, double *d_CR, unsigned *d_variant, cudaStream_t st)
+{
+    PGC_REQUIRE(algo == 1u || algo == 2u, "de adaptation state: only sade (1) and de1220 (2) keep one");
+    PGC_REQUIRE(variant_adptv >= 1u && variant_adptv <= 2u, "The variant for self-adaptation must be in [1,2], while a value of %u was detected.",
+                variant_adptv);
+    PGC_REQUIRE(d_F && d_CR && (algo == 1u || d_variant), "de adaptation state: null array");
+    DeConfig cfg{};
+    cfg.algo = algo;
+    cfg.variant_adptv = variant_adptv;
+    if (algo == 2u) {
+        PGC_REQUIRE(allowed && n_allowed >= 1u && n_allowed <= 18u, "de1220 needs between 1 and 18 allowed mutation variants");
+        for (unsigned k = 0; k < n_allowed; ++k) cfg.allowed[k] = allowed[k];
+        cfg.n_allowed = n_allowed;
+    }
+    de_init_adapt_kernel<<<nblk(NP, 128), 128, 0, st>>>(d_F, d_CR, algo == 2u ? d_variant : nullptr, NP, cfg, seed, generation);
+    PGC_CUDA(cudaGetLastError());
+    return PGC_OK;
+}
+
 namespace
 {
 

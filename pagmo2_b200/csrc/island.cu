@@ -36,6 +36,9 @@ struct pgc_island {
     unsigned long long *d_mids = nullptr;
     double *d_mx = nullptr, *d_mf = nullptr;
     unsigned char *d_flags = nullptr;
+    // what an algorithm built with memory = true keeps between evolve() calls (pgc_algo_memory), resident like the population
+    pgc_algo_memory mem{};
+    int mem_algo = 0;
     double *h_heads = nullptr; // pinned: slot headers
     unsigned char *h_flags = nullptr;
     cudaEvent_t ev = nullptr;
@@ -213,7 +216,8 @@ int pgc_island_destroy(pgc_island *isl)
     cudaStreamSynchronize(isl->ctx->stream);
     for (void *p : {static_cast<void *>(isl->d_ids), static_cast<void *>(isl->d_x), static_cast<void *>(isl->d_f), static_cast<void *>(isl->d_outbox),
                     static_cast<void *>(isl->d_inbox), static_cast<void *>(isl->d_mids), static_cast<void *>(isl->d_mx),
-                    static_cast<void *>(isl->d_mf), static_cast<void *>(isl->d_flags)})
+                    static_cast<void *>(isl->d_mf), static_cast<void *>(isl->d_flags), static_cast<void *>(isl->mem.a),
+                    static_cast<void *>(isl->mem.b), static_cast<void *>(isl->mem.c), static_cast<void *>(isl->mem.u)})
         if (p) cudaFree(p);
     if (isl->h_heads) cudaFreeHost(isl->h_heads);
     if (isl->h_flags) cudaFreeHost(isl->h_flags);
@@ -288,7 +292,27 @@ int pgc_island_evolve(pgc_island *isl, const pgc_algo_desc *algo, unsigned *gens
 {
     PGC_REQUIRE(isl && algo, "pgc_island_evolve: null argument");
     unsigned done = 0;
-    const int rc = pgc_algo_evolve_device(isl->prob, algo, isl->d_x, isl->d_f, isl->n, isl->generation, &done, nullptr);
+    int rc;
+    const bool keeps_state = algo->memory
+                             && (algo->algo == PGC_ALGO_SADE || algo->algo == PGC_ALGO_DE1220 || algo->algo == PGC_ALGO_PSO_GEN
+                                 || algo->algo == PGC_ALGO_NSPSO);
+    if (keeps_state) {
+        if (isl->mem_algo != algo->algo) { // another algorithm took the island over: its first evolve() starts from nothing
+            isl->mem.initialized = 0;
+            isl->mem_algo = algo->algo;
+        }
+        if (!isl->mem.a) {
+            PGC_CUDA(cudaSetDevice(isl->ctx->device));
+            const size_t n = isl->n ? isl->n : 1u;
+            PGC_CUDA(cudaMalloc(&isl->mem.a, sizeof(double) * n * isl->nx));
+            PGC_CUDA(cudaMalloc(&isl->mem.b, sizeof(double) * n * isl->nx));
+            PGC_CUDA(cudaMalloc(&isl->mem.c, sizeof(double) * n * isl->nf));
+            PGC_CUDA(cudaMalloc(&isl->mem.u, sizeof(uint32_t) * n));
+        }
+        rc = pgc_algo_evolve_memory_device(isl->prob, algo, isl->d_x, isl->d_f, isl->n, isl->generation, &done, &isl->mem, nullptr);
+    } else {
+        rc = pgc_algo_evolve_device(isl->prob, algo, isl->d_x, isl->d_f, isl->n, isl->generation, &done, nullptr);
+    }
     if (rc != PGC_OK) return rc;
     isl->generation += algo->gens ? algo->gens : 1u;
     if (gens_done) *gens_done = done;

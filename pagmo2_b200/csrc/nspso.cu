@@ -257,6 +257,33 @@ int argsort_less_f(const double *d_v, unsigned n, unsigned *d_order_out, cudaStr
 
 } // namespace
 
+// what a first evolve() with memory sets up (nspso.cpp:127-152): velocities drawn in +-(ub - lb) * v_coeff, archive = the population
+int nspso_init_memory_device(pgc_problem *prob, const double *d_x, const double *d_f, unsigned NP, double v_coeff, unsigned long long seed,
+                             unsigned generation, double *d_vel, double *d_best_x, double *d_best_f, cudaStream_t st)
+{
+    const unsigned dim = static_cast<unsigned>(prob->nx), m = static_cast<unsigned>(prob->nobj);
+    PGC_REQUIRE(d_vel && d_best_x && d_best_f, "nspso memory: null array");
+    PGC_REQUIRE(v_coeff > 0. && v_coeff <= 1., "velocity scaling factor should be in ]0,1] range, while a value of %g was detected", v_coeff);
+    Scratch sc(st);
+    double *minv, *maxv;
+    int rc;
+    if ((rc = sc.alloc(&minv, dim)) || (rc = sc.alloc(&maxv, dim))) return rc;
+    std::vector<double> h_minv(dim), h_maxv(dim);
+    for (unsigned j = 0; j < dim; ++j) {
+        const double vwidth = (prob->ub[j] - prob->lb[j]) * v_coeff;
+        h_minv[j] = -1. * vwidth;
+        h_maxv[j] = vwidth;
+    }
+    PGC_CUDA(cudaMemcpyAsync(minv, h_minv.data(), sizeof(double) * dim, cudaMemcpyHostToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(maxv, h_maxv.data(), sizeof(double) * dim, cudaMemcpyHostToDevice, st));
+    nspso_init_velocity_kernel<<<nblk(static_cast<size_t>(NP) * dim, 256), 256, 0, st>>>(d_vel, NP, dim, minv, maxv, seed, generation);
+    PGC_CUDA(cudaMemcpyAsync(d_best_x, d_x, sizeof(double) * NP * dim, cudaMemcpyDeviceToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(d_best_f, d_f, sizeof(double) * NP * m, cudaMemcpyDeviceToDevice, st));
+    PGC_CUDA(cudaGetLastError());
+    PGC_CUDA(cudaStreamSynchronize(st));
+    return PGC_OK;
+}
+
 int nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double omega, double c1, double c2, double chi,
                         double v_coeff, unsigned leader_selection_range, unsigned diversity, unsigned long long seed, unsigned first_generation,
                         double *d_vel, double *d_best_x, double *d_best_f,

@@ -306,6 +306,12 @@ int sort_population_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, 
 int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t s);
 int philox_permutation_device(pgc_ctx *ctx, unsigned n, unsigned long long seed, unsigned tag, unsigned generation, unsigned *d_perm,
                               cudaStream_t st);
+int de_init_adaptation_device(unsigned NP, unsigned algo, unsigned variant_adptv, const unsigned *allowed, unsigned n_allowed,
+                              unsigned long long seed, unsigned generation, double *d_F, double *d_CR, unsigned *d_variant, cudaStream_t st);
+int pso_init_velocity_device(pgc_problem *prob, unsigned n, double max_vel, unsigned long long seed, unsigned generation, double *d_v,
+                             cudaStream_t st);
+int nspso_init_memory_device(pgc_problem *prob, const double *d_x, const double *d_f, unsigned NP, double v_coeff, unsigned long long seed,
+                             unsigned generation, double *d_vel, double *d_best_x, double *d_best_f, cudaStream_t st);
 int moead_gen_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, const double *h_weights,
                             const unsigned *h_neigh, unsigned T, int decomposition, double CR, double F, double eta_m, double realb, unsigned limit,
                             int preserve_diversity, unsigned long long seed, unsigned first_generation,

@@ -434,6 +434,24 @@ int pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_V, double *d
 // pso_gen::evolve on a device-resident swarm.  In: d_x = positions, d_f = their fitness, d_v = velocities (or nullptr: drawn
 // as in :187-196).  Out: d_x / d_f = the particles' best positions lbX / lbfit (what evolve() puts back into the population,
 // :524-527); d_v (if given) = the final velocities, d_xcur (if given) = the final current positions.
+// the velocities a first evolve() with memory draws (pso_gen.cpp:193-201)
+int pso_init_velocity_device(pgc_problem *prob, unsigned n, double max_vel, unsigned long long seed, unsigned generation, double *d_v,
+                             cudaStream_t st)
+{
+    const unsigned dim = static_cast<unsigned>(prob->nx);
+    PGC_REQUIRE(d_v, "pso velocities: null array");
+    PGC_REQUIRE(max_vel > 0. && max_vel <= 1., "The maximum particle velocity (as a fraction of the bounds) should be in the (0,1] range, while a value of %g was detected", max_vel);
+    StreamScratch scratch(st);
+    double *lb = nullptr;
+    PGC_CUDA(scratch.get(&lb, 16 * static_cast<size_t>(dim)));
+    PGC_CUDA(cudaMemcpyAsync(lb, prob->lb.data(), 8 * dim, cudaMemcpyHostToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(lb + dim, prob->ub.data(), 8 * dim, cudaMemcpyHostToDevice, st));
+    pso_init_velocity_kernel<<<nblk(static_cast<size_t>(n) * dim, 256), 256, 0, st>>>(d_v, lb, lb + dim, n, dim, max_vel, seed, generation);
+    PGC_CUDA(cudaGetLastError());
+    PGC_CUDA(cudaStreamSynchronize(st));
+    return PGC_OK;
+}
+
 int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, double *d_xcur, unsigned n, unsigned gens, double omega,
                       double eta1, double eta2, double max_vel, unsigned variant, unsigned neighb_type, unsigned neighb_param,
                       unsigned long long seed, unsigned first_generation,

@@ -322,6 +322,36 @@ int main(int argc, char **argv)
             CHECK(q.champion_f()[0] <= b);
             std::printf("%s: %.4g -> %.4g\n", a.get_name().c_str(), b, q.champion_f()[0]);
         }
+        { // memory = true (sade.cpp:137-156, de1220.cpp:147-165, pso_gen.cpp:193-201): the adaptation state / velocities survive
+          // between evolve() calls, so 3 + 3 generations are the uninterrupted 6; without memory the second call re-draws them
+            const auto split_equals_whole = [&](auto make) {
+                pagmo::population whole{prob, 32u, 9u}, split{prob, 32u, 9u};
+                whole = pagmo::algorithm{make(6u)}.evolve(whole);
+                pagmo::algorithm a3{make(3u)};
+                split = a3.evolve(split); // pagmo::algorithm::evolve is const: the state lives in the UDA's mutable members
+                split = a3.evolve(split);
+                return whole.get_x() == split.get_x() && whole.get_f() == split.get_f();
+            };
+            CHECK(split_equals_whole([](unsigned g) { return cuda_sade{g, 2u, 1u, 0., 0., true, 41u}; }));
+            CHECK(!split_equals_whole([](unsigned g) { return cuda_sade{g, 2u, 1u, 0., 0., false, 41u}; }));
+            CHECK(split_equals_whole([](unsigned g) { return cuda_sade{g, 7u, 2u, 0., 0., true, 41u}; }));
+            CHECK(split_equals_whole([](unsigned g) { return cuda_de1220{g, {2u, 3u, 7u, 10u}, 1u, 0., 0., true, 5u}; }));
+            CHECK(!split_equals_whole([](unsigned g) { return cuda_de1220{g, {2u, 3u, 7u, 10u}, 1u, 0., 0., false, 5u}; }));
+            CHECK(split_equals_whole([](unsigned g) { return cuda_pso_gen{g, 0.7298, 2.05, 2.05, 0.5, 5u, 2u, 4u, true, 3u}; }));
+            CHECK(!split_equals_whole([](unsigned g) { return cuda_pso_gen{g, 0.7298, 2.05, 2.05, 0.5, 5u, 2u, 4u, false, 3u}; }));
+            // a copy of the algorithm carries the state (pagmo copies the UDA in and out of an island around every evolve)
+            pagmo::population whole{prob, 32u, 9u}, split{prob, 32u, 9u};
+            whole = pagmo::algorithm{cuda_sade{6u, 2u, 1u, 0., 0., true, 41u}}.evolve(whole);
+            pagmo::algorithm first{cuda_sade{3u, 2u, 1u, 0., 0., true, 41u}};
+            split = first.evolve(split);
+            pagmo::algorithm second = first;
+            split = second.evolve(split);
+            CHECK(whole.get_x() == split.get_x());
+            // a population of another size restarts the adaptation instead of reading a stale state
+            pagmo::population other{prob, 48u, 2u};
+            other = second.evolve(other);
+            CHECK(other.size() == 48u);
+        }
         pagmo::problem zp{pagmo::zdt{1u, 30u}};
         pagmo::population mo{zp, 40u, 5u};
         mo = pagmo::algorithm{cuda_nsga2{10u, 0.95, 10., 0.01, 50., 32u}}.evolve(mo);

@@ -1,0 +1,104 @@
+"""memory = true of the reference UDAs (sade.cpp:137-156, de1220.cpp:147-165, pso_gen.cpp:193-201, nspso.cpp:127-152) behind
+`pgc_algo_evolve_memory_device` and inside a resident island (`pgc_island_evolve` with `algo.memory`): the adaptation state, the
+velocities and nspso's archive survive between evolve() calls.  The draws are keyed by (seed, generation, individual), so a run
+split into two calls must equal the uninterrupted run bit for bit when the state is kept, and must differ when it is re-drawn."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from pagmo2_b200 import capi as m
+    return m
+
+
+SO_CASES = [
+    ("sade", dict(variant=2, variant_adptv=1)),
+    ("sade", dict(variant=7, variant_adptv=2)),
+    ("de1220", dict(variant_adptv=1, allowed_variants=[2, 3, 7, 10, 13])),
+    ("de1220", dict(variant_adptv=2)),
+    ("pso_gen", dict(variant=5, neighb_type=2)),
+    ("pso_gen", dict(variant=1, neighb_type=1)),
+    ("pso_gen", dict(variant=6, neighb_type=3)),
+]
+
+
+def _so_problem(capi, ctx, n=48):
+    prob = capi.Problem(ctx, "rosenbrock", dim=9)
+    lb, ub = prob.bounds()
+    x = np.random.default_rng(3).uniform(lb, ub, (n, prob.nx))
+    return prob, x, prob.eval_host(x)
+
+
+@pytest.mark.parametrize("name,kw", SO_CASES)
+def test_split_run_with_memory_is_the_uninterrupted_run(capi, ctx, name, kw):
+    prob, x, f = _so_problem(capi, ctx)
+    tol = {} if name == "pso_gen" else dict(ftol=0.0, xtol=0.0)
+    whole = capi.algo_desc(name, gens=6, seed=17, **tol, **kw)
+    half = capi.algo_desc(name, gens=3, seed=17, **tol, **kw)
+    x6, f6, done = prob.evolve(whole, x, f, first_generation=1)
+    assert done == 6
+    xa, fa, _, st = prob.evolve_memory(half, x, f, first_generation=1)
+    xb, fb, _, st2 = prob.evolve_memory(half, xa, fa, first_generation=4, state=st)
+    assert np.array_equal(xb, x6) and np.array_equal(fb, f6)
+    # memory-less: the second call re-draws F / CR / the velocities from the streams of generation 4
+    xc, fc, _ = prob.evolve(half, xa, fa, first_generation=4)
+    assert not np.array_equal(xc, x6)
+    # the state is what the reference keeps: F in [0.1, 1], CR in [0, 1] for jDE; one velocity per gene within max_vel * width
+    if name == "pso_gen":
+        lb, ub = prob.bounds()
+        assert (np.abs(st2["a"]) <= 0.5 * (ub - lb) + 1e-12).all() and np.abs(st2["a"]).max() > 0
+    elif kw.get("variant_adptv") == 1:
+        F, CR = st2["a"].ravel()[:x.shape[0]], st2["b"].ravel()[:x.shape[0]]
+        assert (F >= 0.1).all() and (F <= 1.0).all() and (CR >= 0).all() and (CR <= 1).all()
+    if name == "de1220":
+        allowed = kw.get("allowed_variants", [2, 3, 7, 10, 13, 14, 15, 16])
+        assert set(st2["u"].tolist()) <= set(allowed)
+    prob.close()
+
+
+def test_nspso_memory_through_the_descriptor(capi, ctx):
+    prob = capi.Problem(ctx, "zdt", prob_id=1, dim=12)
+    lb, ub = prob.bounds()
+    x = np.random.default_rng(1).uniform(lb, ub, (40, prob.nx))
+    f = prob.eval_host(x)
+    whole, half = capi.algo_desc("nspso", gens=6, seed=9), capi.algo_desc("nspso", gens=3, seed=9)
+    x6, f6, _ = prob.evolve(whole, x, f, first_generation=1)
+    xa, fa, _, st = prob.evolve_memory(half, x, f, first_generation=1)
+    xb, fb, _, st = prob.evolve_memory(half, xa, fa, first_generation=4, state=st)
+    assert np.array_equal(xb, x6) and np.array_equal(fb, f6)
+    assert np.allclose(prob.eval_host(st["b"]), st["c"], rtol=1e-12, atol=1e-15)  # the archive is consistent
+    prob.close()
+
+
+@pytest.mark.parametrize("name,kw", [("sade", dict(variant_adptv=1, ftol=0.0, xtol=0.0)), ("pso_gen", dict(variant=5)),
+                                     ("de1220", dict(ftol=0.0, xtol=0.0))])
+def test_island_keeps_the_state_in_hbm(capi, ctx, name, kw):
+    prob, x, f = _so_problem(capi, ctx, n=32)
+    ids = np.arange(1, 33, dtype=np.uint64)
+    out = []
+    for memory, split in ((1, True), (1, False), (0, True)):
+        isl = capi.Island(prob, 32)
+        isl.upload(ids, x, f)
+        if split:
+            d = capi.algo_desc(name, gens=3, seed=5, memory=memory, **kw)
+            isl.evolve(d)
+            isl.evolve(d)
+        else:
+            isl.evolve(capi.algo_desc(name, gens=6, seed=5, memory=memory, **kw))
+        out.append(isl.download())
+        isl.close()
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert not np.array_equal(out[2][1], out[1][1])
+    prob.close()
+
+
+def test_memory_argument_checks(capi, ctx):
+    prob, x, f = _so_problem(capi, ctx, n=16)
+    with pytest.raises(capi.PgcError):  # de keeps no state
+        prob.evolve_memory(capi.algo_desc("de", gens=1, seed=1), x, f)
+    with pytest.raises(capi.PgcError):  # sade.cpp:66-69
+        prob.evolve_memory(capi.algo_desc("sade", gens=1, seed=1, variant_adptv=3), x, f)
+    prob.close()
