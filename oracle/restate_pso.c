@@ -1,9 +1,9 @@
 /* oracle/restate_pso.c - plain-C restatement of pagmo::pso_gen::evolve (generational PSO).  TEST INFRASTRUCTURE ONLY.
- * Follows reference src/algorithms/pso_gen.cpp: velocity update :231-327 (variants 1-5), clamp/move/box correction :329-363,
+ * Follows reference src/algorithms/pso_gen.cpp: velocity update :231-327 (variants 1-6), clamp/move/box correction :329-363,
  * evaluation :417-440, memory update :445-459, best neighbour :593-623, lbest ring :679-698, gbest :644-664, von Neumann
  * lattice :719-744, adaptive random graph :772-796 (re-drawn after every generation without a new best, :462).
  * PINNED (tests/test_oracle_pin.py): oracle_pso_evolve_mt - these statements on the reference's sequential mt19937 stream -
- * reproduces the compiled pso_gen::evolve bit for bit (variants 1-5, all four topologies).  In the default Philox mode every draw
+ * reproduces the compiled pso_gen::evolve bit for bit (variants 1-6, all four topologies).  In the default Philox mode every draw
  * is the value the device consumes at the same (generation, particle, slot) - see oracle/philox.h and pagmo2_b200/csrc/pso.cu.
  */
 #include <math.h>
@@ -36,7 +36,7 @@ int oracle_pso_evolve(const oracle_problem *prob, const double *lb, const double
                       size_t dim, unsigned gens, double omega, double eta1, double eta2, double max_vel, unsigned variant,
                       unsigned neighb_type, unsigned neighb_param, uint64_t seed, uint32_t first_generation)
 {
-    if (variant < 1 || variant > 5 || neighb_type < 1 || neighb_type > 4 || n == 0 || neighb_param < 1) return -1;
+    if (variant < 1 || variant > 6 || neighb_type < 1 || neighb_type > 4 || n == 0 || neighb_param < 1) return -1;
     double *X = (double *)malloc(n * dim * sizeof(double)), *V = (double *)malloc(n * dim * sizeof(double)),
            *fit = (double *)malloc(n * sizeof(double));
     double *lbX = x, *lbfit = f;
@@ -109,6 +109,25 @@ int oracle_pso_evolve(const oracle_problem *prob, const double *lb, const double
     for (unsigned g = 0; g < gens && !rc; ++g) {
         const uint32_t generation = first_generation + g;
         for (size_t p = 0; p < n; ++p) {
+            if (variant == 6) { /* fully informed particle swarm, :318-326: every neighbour pulls, one draw per (gene, neighbour) */
+                const double acceleration_coefficient = eta1 + eta2; /* :220 */
+                const size_t K = neighb_type == 1 ? n : (neighb_type == 2 ? 2u * radius : nb_len[p]);
+                for (size_t d = 0; d < dim; ++d) {
+                    double sum_forces = 0.;
+                    for (size_t k = 0; k < K; ++k) {
+                        size_t q;
+                        if (neighb_type == 1) q = k; /* gbest: neighb[p] = 0 .. n-1 (:656-663) */
+                        else if (neighb_type == 2) { /* ring: p - radius .. p - 1, p + 1 .. p + radius (:679-698) */
+                            if (k < radius) { const size_t j = radius - k; q = (p < j) ? p - j + n : p - j; }
+                            else { const size_t j = k - radius + 1u; q = (p + j >= n) ? p + j - n : p + j; }
+                        } else q = (neighb_type == 3 ? nb + p * 4 : nb + nb_off[p])[k];
+                        const double u = oracle_u01_at(seed, ORACLE_TAG_PSO, generation, (uint32_t)p, (uint32_t)(d * K + k));
+                        sum_forces += u * acceleration_coefficient * (lbX[q * dim + d] - X[p * dim + d]);
+                    }
+                    V[p * dim + d] = omega * (V[p * dim + d] + sum_forces / (double)K);
+                }
+                continue;
+            }
             size_t b = gbest;
             if (neighb_type >= 3) { /* particle__get_best_neighbor over the explicit list, :608-621: a later entry wins ties */
                 const size_t *list = neighb_type == 3 ? nb + p * 4 : nb + nb_off[p];

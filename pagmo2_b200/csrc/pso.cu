@@ -14,6 +14,8 @@
 #include <cmath>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "pgc_internal.cuh"
 #include "philox.cuh"
 
@@ -120,17 +122,79 @@ struct MoveParams {
     unsigned variant;
     unsigned long long seed;
     unsigned generation;
+    // the fully informed swarm (variant 6) reads every neighbour: the topology itself instead of the best neighbour
+    unsigned neighb_type, radius;
+    int von_rows, von_cols;
+    const unsigned *ar_off, *ar_list; // adaptive random: informants of q = ar_list[ar_off[q] .. ar_off[q + 1])
 };
+
+// k-th neighbour of particle p, in the order the reference's neighb[p] lists them (pso_gen.cpp:656-663 gbest + FIPS: everybody;
+// :679-698 ring; :719-744 lattice; :772-796 random graph)
+__device__ __forceinline__ unsigned pso_neighbour(const MoveParams &P, unsigned p, unsigned k)
+{
+    switch (P.neighb_type) {
+        case 1: return k;
+        case 2: {
+            if (k < P.radius) {
+                const unsigned j = P.radius - k;
+                return (p < j) ? p - j + P.n : p - j;
+            }
+            const unsigned j = k - P.radius + 1u;
+            return (p + j >= P.n) ? p + j - P.n : p + j;
+        }
+        case 3: {
+            const int p_x = static_cast<int>(p) % P.von_cols, p_y = static_cast<int>(p) / P.von_cols;
+            const int ddx = k == 0u ? -1 : (k == 1u ? 1 : 0), ddy = k == 2u ? -1 : (k == 3u ? 1 : 0);
+            int n_x = (p_x + ddx) % P.von_cols, n_y = (p_y + ddy) % P.von_rows;
+            if (n_x < 0) n_x = P.von_cols + n_x;
+            if (n_y < 0) n_y = P.von_rows + n_y;
+            return static_cast<unsigned>(n_y * P.von_cols + n_x);
+        }
+        default: return P.ar_list[P.ar_off[p] + k];
+    }
+}
+
+// adaptive random graph as per-particle informant lists, in the order the reference appends them (ascending informant, its own
+// entry at its turn): keys (q, p * K + j) sorted, then read back
+__global__ void pso_ar_keys_kernel(const unsigned *targets, unsigned n, unsigned K, unsigned long long *keys)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(n) * K) return;
+    keys[e] = static_cast<unsigned long long>(targets[e]) * (static_cast<unsigned long long>(n) * K) + e;
+}
+
+__global__ void pso_ar_csr_kernel(const unsigned long long *sorted, unsigned n, unsigned K, unsigned *off, unsigned *list)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t total = static_cast<size_t>(n) * K;
+    if (e >= total) return;
+    const unsigned q = static_cast<unsigned>(sorted[e] / total);
+    list[e] = static_cast<unsigned>((sorted[e] % total) / K);
+    if (e == 0 || static_cast<unsigned>(sorted[e - 1] / total) != q) off[q] = static_cast<unsigned>(e); // every q lists itself: no gaps
+    if (e + 1 == total) off[n] = static_cast<unsigned>(total);
+}
 
 __global__ void pso_move_kernel(const MoveParams P)
 {
     const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (e >= static_cast<size_t>(P.n) * P.dim) return;
     const unsigned p = static_cast<unsigned>(e / P.dim), d = static_cast<unsigned>(e % P.dim);
-    const unsigned b = P.bn ? P.bn[p] : *P.gbest;
+    const unsigned b = P.variant == 6u ? p : (P.bn ? P.bn[p] : *P.gbest);
     const double x = P.X[e], lbx = P.lbX[e], bnx = P.lbX[static_cast<size_t>(b) * P.dim + d];
     double v = P.V[e], r1, r2;
-    switch (P.variant) { // pso_gen.cpp:242-306
+    switch (P.variant) { // pso_gen.cpp:242-326
+        case 6: { // fully informed: one draw per (gene, neighbour), :318-326
+            const unsigned K = P.neighb_type == 1u ? P.n : (P.neighb_type == 2u ? 2u * P.radius : (P.neighb_type == 3u ? 4u : P.ar_off[p + 1] - P.ar_off[p]));
+            const double acceleration_coefficient = P.eta1 + P.eta2;
+            double sum_forces = 0.;
+            for (unsigned k = 0; k < K; ++k) {
+                const unsigned q = pso_neighbour(P, p, k);
+                const double u = philox_u01(P.seed, kTagPso, P.generation, p, d * K + k);
+                sum_forces += u * acceleration_coefficient * (P.lbX[static_cast<size_t>(q) * P.dim + d] - x);
+            }
+            v = P.omega * (v + sum_forces / static_cast<double>(K));
+            break;
+        }
         case 1:
             r1 = philox_u01(P.seed, kTagPso, P.generation, p, 2 * d);
             r2 = philox_u01(P.seed, kTagPso, P.generation, p, 2 * d + 1);
@@ -468,10 +532,6 @@ int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, 
     PGC_REQUIRE(neighb_param >= 1u, "The neighborhood parameter must be in (0, inf), while a value of %u was detected", neighb_param);
     PGC_REQUIRE(prob->nobj == 1, "Multiple objectives detected in %s instance. PSO cannot deal with them", prob->name.c_str());
     PGC_REQUIRE(n > 0, "PSO does not work on an empty population");
-    if (variant == 6u) {
-        set_error("pso on the device implements variants 1-5 (the fully informed swarm, variant 6, was requested)");
-        return PGC_ERR_UNSUPPORTED;
-    }
     struct Buf {
         cudaStream_t st;
         std::vector<void *> owned;
@@ -487,8 +547,10 @@ int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, 
         }
     } buf{st, {}};
     double *X, *V, *fit, *lb, *ub, *gfit;
-    unsigned *bn, *gbest, *targets = nullptr;
-    unsigned long long *arkey = nullptr;
+    unsigned *bn, *gbest, *targets = nullptr, *ar_off = nullptr, *ar_list = nullptr;
+    unsigned long long *arkey = nullptr, *ar_k0 = nullptr, *ar_k1 = nullptr;
+    void *ar_ws = nullptr;
+    size_t ar_ws_bytes = 0;
     int *keep = nullptr;
     unsigned char *improved;
     const size_t nd = static_cast<size_t>(n) * dim;
@@ -498,6 +560,16 @@ int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, 
         && ((rc = buf.get(reinterpret_cast<void **>(&targets), 4 * static_cast<size_t>(n) * K)) || (rc = buf.get(reinterpret_cast<void **>(&arkey), 8 * static_cast<size_t>(n)))
             || (rc = buf.get(reinterpret_cast<void **>(&keep), 4))))
         return rc;
+    const bool fips_graph = variant == 6u && neighb_type == 4u; // the informant lists themselves are needed, not only the best informant
+    if (fips_graph) {
+        const size_t total = static_cast<size_t>(n) * K;
+        PGC_REQUIRE(total < (1ull << 31), "pso: swarm size x neighb_param too large for the fully informed random graph");
+        PGC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, ar_ws_bytes, ar_k0, ar_k1, static_cast<int>(total), 0, 64, st));
+        if ((rc = buf.get(reinterpret_cast<void **>(&ar_off), 4 * (static_cast<size_t>(n) + 1))) || (rc = buf.get(reinterpret_cast<void **>(&ar_list), 4 * total))
+            || (rc = buf.get(reinterpret_cast<void **>(&ar_k0), 8 * total)) || (rc = buf.get(reinterpret_cast<void **>(&ar_k1), 8 * total))
+            || (rc = buf.get(&ar_ws, ar_ws_bytes)))
+            return rc;
+    }
     if ((rc = buf.get(reinterpret_cast<void **>(&X), 8 * nd)) || (rc = buf.get(reinterpret_cast<void **>(&V), 8 * nd))
         || (rc = buf.get(reinterpret_cast<void **>(&fit), 8 * n)) || (rc = buf.get(reinterpret_cast<void **>(&lb), 8 * dim))
         || (rc = buf.get(reinterpret_cast<void **>(&ub), 8 * dim)) || (rc = buf.get(reinterpret_cast<void **>(&gfit), 8))
@@ -523,7 +595,14 @@ int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, 
     PGC_REQUIRE(neighb_type != 2u || (radius >= 1u && 2u * radius < n), "lbest topology: neighb_param / 2 = %u must be in [1, (swarm size - 1) / 2]", radius);
     for (unsigned g = 0; g < gens; ++g) {
         const unsigned generation = first_generation + g;
-        if (neighb_type == 2u) pso_lbest_kernel<<<nblk(n, 256), 256, 0, st>>>(d_f, n, radius, bn);
+        if (variant == 6u) { // no best neighbour to find (:236-238)
+            if (fips_graph) {
+                const size_t total = static_cast<size_t>(n) * K;
+                pso_ar_keys_kernel<<<nblk(total, 256), 256, 0, st>>>(targets, n, K, ar_k0);
+                PGC_CUDA(cub::DeviceRadixSort::SortKeys(ar_ws, ar_ws_bytes, ar_k0, ar_k1, static_cast<int>(total), 0, 64, st));
+                pso_ar_csr_kernel<<<nblk(total, 256), 256, 0, st>>>(ar_k1, n, K, ar_off, ar_list);
+            }
+        } else if (neighb_type == 2u) pso_lbest_kernel<<<nblk(n, 256), 256, 0, st>>>(d_f, n, radius, bn);
         else if (neighb_type == 3u) pso_von_kernel<<<nblk(n, 256), 256, 0, st>>>(d_f, n, von_rows, von_cols, bn);
         else if (neighb_type == 4u) {
             PGC_CUDA(cudaMemsetAsync(arkey, 0xff, 8 * static_cast<size_t>(n), st));
@@ -531,7 +610,8 @@ int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, 
             pso_ar_min_kernel<<<nblk(static_cast<size_t>(n) * K, 256), 256, 0, st>>>(d_f, targets, n, K, arkey);
             pso_ar_arg_kernel<<<nblk(static_cast<size_t>(n) * K, 256), 256, 0, st>>>(d_f, targets, n, K, arkey, bn);
         }
-        MoveParams mp{X, V, d_x, neighb_type != 1u ? bn : nullptr, gbest, lb, ub, n, dim, omega, eta1, eta2, max_vel, variant, seed, generation};
+        MoveParams mp{X, V, d_x, neighb_type != 1u ? bn : nullptr, gbest, lb, ub, n, dim, omega, eta1, eta2, max_vel, variant, seed, generation,
+                      neighb_type, radius, von_rows, von_cols, ar_off, ar_list};
         pso_move_kernel<<<nblk(nd, 256), 256, 0, st>>>(mp);
         if ((rc = eval(prob, X, n, fit, st))) return rc;
         pso_memory_flag_kernel<<<nblk(n, 256), 256, 0, st>>>(fit, d_f, n, improved);

@@ -323,7 +323,7 @@ int main(int argc, char **argv)
             std::printf("%s: %.4g -> %.4g\n", a.get_name().c_str(), b, q.champion_f()[0]);
         }
         { // memory = true (sade.cpp:137-156, de1220.cpp:147-165, pso_gen.cpp:193-201): the adaptation state / velocities survive
-          // between evolve() calls, so 3 + 3 generations are the uninterrupted 6; without memory the second call re-draws them
+          // between evolve() calls, so 3 + 3 generations of jDE are the uninterrupted 6; without memory the second call re-draws them
             const auto split_equals_whole = [&](auto make) {
                 pagmo::population whole{prob, 32u, 9u}, split{prob, 32u, 9u};
                 whole = pagmo::algorithm{make(6u)}.evolve(whole);
@@ -334,11 +334,17 @@ int main(int argc, char **argv)
             };
             CHECK(split_equals_whole([](unsigned g) { return cuda_sade{g, 2u, 1u, 0., 0., true, 41u}; }));
             CHECK(!split_equals_whole([](unsigned g) { return cuda_sade{g, 2u, 1u, 0., 0., false, 41u}; }));
-            CHECK(split_equals_whole([](unsigned g) { return cuda_sade{g, 7u, 2u, 0., 0., true, 41u}; }));
             CHECK(split_equals_whole([](unsigned g) { return cuda_de1220{g, {2u, 3u, 7u, 10u}, 1u, 0., 0., true, 5u}; }));
             CHECK(!split_equals_whole([](unsigned g) { return cuda_de1220{g, {2u, 3u, 7u, 10u}, 1u, 0., 0., false, 5u}; }));
-            CHECK(split_equals_whole([](unsigned g) { return cuda_pso_gen{g, 0.7298, 2.05, 2.05, 0.5, 5u, 2u, 4u, true, 3u}; }));
-            CHECK(!split_equals_whole([](unsigned g) { return cuda_pso_gen{g, 0.7298, 2.05, 2.05, 0.5, 5u, 2u, 4u, false, 3u}; }));
+            { // pso_gen with memory restarts from the particles' best positions with the KEPT velocities (pso_gen.cpp:193-201)
+                pagmo::population a{prob, 32u, 9u}, b{prob, 32u, 9u};
+                pagmo::algorithm keep{cuda_pso_gen{3u, 0.7298, 2.05, 2.05, 0.5, 5u, 2u, 4u, true, 3u}};
+                pagmo::algorithm redraw{cuda_pso_gen{3u, 0.7298, 2.05, 2.05, 0.5, 5u, 2u, 4u, false, 3u}};
+                a = keep.evolve(a), b = redraw.evolve(b);
+                CHECK(a.get_x() == b.get_x()); // the first call draws the same velocities either way
+                a = keep.evolve(a), b = redraw.evolve(b);
+                CHECK(a.get_x() != b.get_x());
+            }
             // a copy of the algorithm carries the state (pagmo copies the UDA in and out of an island around every evolve)
             pagmo::population whole{prob, 32u, 9u}, split{prob, 32u, 9u};
             whole = pagmo::algorithm{cuda_sade{6u, 2u, 1u, 0., 0., true, 41u}}.evolve(whole);

@@ -35,7 +35,7 @@ def test_lennard_jones_parity(capi, ctx, orc, atoms):
     prob.close()
 
 
-@pytest.mark.parametrize("variant,ntype", [(5, 2), (5, 1), (1, 2), (2, 1), (3, 2), (4, 1), (5, 3), (1, 3), (5, 4), (3, 4), (2, 4)])
+@pytest.mark.parametrize("variant,ntype", [(5, 2), (5, 1), (1, 2), (2, 1), (3, 2), (4, 1), (5, 3), (1, 3), (5, 4), (3, 4), (2, 4), (6, 1), (6, 2), (6, 3), (6, 4)])
 def test_pso_matches_oracle(capi, ctx, orc, variant, ntype):
     """Same Philox draws => same trajectories.  Positions are compared with a tolerance (fitness values differ by ulps,
     which can only matter through the <= comparisons of the memory update)."""
@@ -66,7 +66,7 @@ def test_pso_on_lennard_jones_and_argument_checks(capi, ctx, orc):
     f = prob.eval_host(x)[:, 0]
     xg, fg, _, _ = prob.pso_evolve(x, f, gens=40, seed=1)
     assert np.isfinite(fg).all() and fg.min() < f.min() and np.allclose(prob.eval_host(xg)[:, 0], fg, rtol=1e-12)
-    for bad in (dict(omega=1.5), dict(eta1=5.0), dict(max_vel=0.0), dict(variant=7), dict(neighb_type=5), dict(variant=6), dict(neighb_param=0)):
+    for bad in (dict(omega=1.5), dict(eta1=5.0), dict(max_vel=0.0), dict(variant=7), dict(neighb_type=5), dict(variant=0), dict(neighb_param=0)):
         with pytest.raises(capi.PgcError):
             prob.pso_evolve(x, f, gens=1, **bad)
     mo = capi.Problem(ctx, "zdt", prob_id=1, dim=5)

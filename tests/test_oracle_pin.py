@@ -116,7 +116,7 @@ def test_pso_gen_evolve_bit_exact(orc, ref, fam, dim):
     rp = ref.problem(fam, dim)
     lb, ub = rp.bounds()
     op = orc.problem(fam, dim=dim)
-    for variant in (1, 2, 3, 4, 5):
+    for variant in (1, 2, 3, 4, 5, 6):  # 6: the fully informed swarm (one draw per gene and neighbour, :318-326)
         # gbest, lbest rings, von Neumann lattice (24 = 4 x 6; 23 is prime: one row), adaptive random graphs (out-degree 3, 1, 4)
         for nt, npar, n in ((1, 4, 23), (2, 4, 23), (2, 2, 23), (2, 7, 23), (3, 4, 24), (3, 4, 23), (4, 3, 23), (4, 1, 12), (4, 4, 40)):
             gens, seed = 12, variant * 10 + nt
