@@ -22,8 +22,11 @@
 #ifndef PAGMO_CUDA_CUDA_ALGORITHMS_HPP
 #define PAGMO_CUDA_CUDA_ALGORITHMS_HPP
 
+#include <iomanip>
+#include <iostream>
 #include <memory>
 #include <stdexcept>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -73,7 +76,22 @@ public:
             std::copy(pop.get_x()[i].begin(), pop.get_x()[i].end(), x.begin() + static_cast<std::ptrdiff_t>(i * nx));
             std::copy(pop.get_f()[i].begin(), pop.get_f()[i].end(), f.begin() + static_cast<std::ptrdiff_t>(i * nf));
         }
-        const unsigned done = m_desc.memory ? h->evolve_memory(m_desc, x, f, m_generation, m_state) : h->evolve(m_desc, x, f, m_generation);
+        unsigned done;
+        if (m_verbosity) {
+            // nspso logs the problem's absolute feval counter (nspso.cpp:191), the others the evaluations of this call
+            const double fevals0 = m_desc.algo == PGC_ALGO_NSPSO ? static_cast<double>(prob.get_fevals()) : 0.;
+            m_log_rows.clear();
+            done = h->evolve_full(m_desc, x, f, m_generation, m_desc.memory ? &m_state : nullptr, m_verbosity, &m_log_rows, &m_log_row_len);
+            for (std::size_t r = 0; m_log_row_len && r < m_log_rows.size() / m_log_row_len; ++r) {
+                double *row = m_log_rows.data() + r * m_log_row_len;
+                row[1] += fevals0;
+                if (r % 50u == 0u) std::cout << "\n" << get_name() << ": log columns as in pgc.h (pgc_algo_evolve_logged_device)\n";
+                for (std::size_t c = 0; c < m_log_row_len && c < 7u; ++c) std::cout << std::setw(c ? 15 : 7) << row[c];
+                std::cout << '\n';
+            }
+        } else {
+            done = m_desc.memory ? h->evolve_memory(m_desc, x, f, m_generation, m_state) : h->evolve(m_desc, x, f, m_generation);
+        }
         m_generation += m_desc.gens;
         for (decltype(pop.size()) i = 0; i < n; ++i) {
             pop.set_xf(i, pagmo::vector_double(x.begin() + static_cast<std::ptrdiff_t>(i * nx), x.begin() + static_cast<std::ptrdiff_t>((i + 1) * nx)),
@@ -85,6 +103,30 @@ public:
     void set_seed(unsigned seed)
     {
         m_desc.seed = seed;
+    }
+    // algorithm::set_verbosity (de.hpp:160-178): level > 0 records one log line every `level` generations (and prints it); the
+    // typed get_log() of each UDA below returns them in the reference's tuple layout
+    void set_verbosity(unsigned level)
+    {
+        const int a = m_desc.algo;
+        if (level && a != PGC_ALGO_DE && a != PGC_ALGO_SADE && a != PGC_ALGO_DE1220 && a != PGC_ALGO_PSO_GEN && a != PGC_ALGO_NSGA2
+            && a != PGC_ALGO_NSPSO) {
+            pagmo_throw(std::invalid_argument, get_name() + ": the device loop of this algorithm records no log (verbosity must be 0)");
+        }
+        m_verbosity = level;
+    }
+    unsigned get_verbosity() const
+    {
+        return m_verbosity;
+    }
+    // the log of the last evolve() as rows of get_log_row_len() doubles
+    const pagmo::vector_double &get_log_rows() const
+    {
+        return m_log_rows;
+    }
+    std::size_t get_log_row_len() const
+    {
+        return m_log_row_len;
     }
     unsigned get_seed() const
     {
@@ -132,7 +174,7 @@ public:
                                m_desc.selection, m_desc.cma_cc, m_desc.cma_cs, m_desc.cma_c1, m_desc.cma_cmu, m_desc.sigma0,
                                m_desc.force_bounds, m_desc.nspso_c1, m_desc.nspso_c2, m_desc.nspso_chi, m_desc.nspso_v_coeff,
                                m_desc.leader_selection_range, m_desc.diversity, m_desc.memory, m_state.a, m_state.b, m_state.c, m_state.u,
-                               m_state.initialized);
+                               m_state.initialized, m_verbosity, m_log_rows, m_log_row_len);
         for (std::size_t i = 0; i < 18u && i < allowed.size(); ++i) m_desc.allowed_variants[i] = allowed[i]; // no-op when saving
     }
 
@@ -158,6 +200,17 @@ protected:
     std::string m_name;
     mutable unsigned m_generation = 1; // Philox generation counter: successive evolve() calls continue the stream
     mutable detail::problem_handle::algo_state m_state;
+    unsigned m_verbosity = 0;
+    mutable pagmo::vector_double m_log_rows;
+    mutable std::size_t m_log_row_len = 0;
+    // rows -> the reference's tuple types
+    template <typename Line, typename Make>
+    std::vector<Line> typed_log(Make make) const
+    {
+        std::vector<Line> out;
+        for (std::size_t r = 0; m_log_row_len && r < m_log_rows.size() / m_log_row_len; ++r) out.push_back(make(m_log_rows.data() + r * m_log_row_len));
+        return out;
+    }
     std::shared_ptr<detail::twin_cache> m_cache;
 };
 
@@ -176,6 +229,14 @@ public:
             pagmo_throw(std::invalid_argument, "The F and CR parameters must be in the [0,1] range");
         }
         m_desc.F = F, m_desc.CR = CR, m_desc.variant = variant, m_desc.ftol = ftol, m_desc.xtol = xtol;
+    }
+    using log_line_type = std::tuple<unsigned, unsigned long long, double, double, double>; // Gen, Fevals, Best, dx, df (de.hpp:104)
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        return typed_log<log_line_type>([](const double *r) {
+            return log_line_type(static_cast<unsigned>(r[0]), static_cast<unsigned long long>(r[1]), r[2], r[3], r[4]);
+        });
     }
 };
 
@@ -196,6 +257,14 @@ public:
         }
         keep_memory(memory);
         m_desc.variant = variant, m_desc.variant_adptv = variant_adptv, m_desc.ftol = ftol, m_desc.xtol = xtol;
+    }
+    using log_line_type = std::tuple<unsigned, unsigned long long, double, double, double, double, double>; // Gen, Fevals, Best, F, CR, dx, df
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        return typed_log<log_line_type>([](const double *r) {
+            return log_line_type(static_cast<unsigned>(r[0]), static_cast<unsigned long long>(r[1]), r[2], r[3], r[4], r[5], r[6]);
+        });
     }
 };
 
@@ -224,6 +293,16 @@ public:
         for (std::size_t i = 0; i < allowed_variants.size(); ++i) m_desc.allowed_variants[i] = allowed_variants[i];
         m_desc.variant_adptv = variant_adptv, m_desc.ftol = ftol, m_desc.xtol = xtol;
     }
+    // Gen, Fevals, Best, F, CR, Variant, dx, df (de1220.hpp:142)
+    using log_line_type = std::tuple<unsigned, unsigned long long, double, double, double, unsigned, double, double>;
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        return typed_log<log_line_type>([](const double *r) {
+            return log_line_type(static_cast<unsigned>(r[0]), static_cast<unsigned long long>(r[1]), r[2], r[3], r[4], static_cast<unsigned>(r[5]),
+                                 r[6], r[7]);
+        });
+    }
 };
 
 class cuda_pso_gen : public cuda_algorithm_base
@@ -237,6 +316,15 @@ public:
         keep_memory(memory);
         m_desc.omega = omega, m_desc.eta1 = eta1, m_desc.eta2 = eta2, m_desc.max_vel = max_vel, m_desc.variant = variant;
         m_desc.neighb_type = neighb_type, m_desc.neighb_param = neighb_param; // range checks: pso.cu (pso_gen.cpp:69-107)
+    }
+    // Gen, Fevals, gbest, Mean Vel., Mean lbest, Avg. Dist. (pso_gen.hpp:111)
+    using log_line_type = std::tuple<unsigned, unsigned long long, double, double, double, double>;
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        return typed_log<log_line_type>([](const double *r) {
+            return log_line_type(static_cast<unsigned>(r[0]), static_cast<unsigned long long>(r[1]), r[2], r[3], r[4], r[5]);
+        });
     }
 };
 
@@ -260,6 +348,15 @@ public:
         : cuda_algorithm_base(PGC_ALGO_NSGA2, "NSGA-II:", gen, seed, device)
     {
         m_desc.cr = cr, m_desc.eta_c = eta_c, m_desc.m = m, m_desc.eta_m = eta_m; // range checks: nsga2.cu (nsga2.cpp:71-86)
+    }
+    using log_line_type = std::tuple<unsigned, unsigned long long, pagmo::vector_double>; // Gen, Fevals, ideal point
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        const std::size_t len = m_log_row_len;
+        return typed_log<log_line_type>([len](const double *r) {
+            return log_line_type(static_cast<unsigned>(r[0]), static_cast<unsigned long long>(r[1]), pagmo::vector_double(r + 2, r + len));
+        });
     }
 };
 
@@ -352,6 +449,15 @@ public:
         keep_memory(memory);
         m_desc.omega = omega, m_desc.nspso_c1 = c1, m_desc.nspso_c2 = c2, m_desc.nspso_chi = chi, m_desc.nspso_v_coeff = v_coeff;
         m_desc.leader_selection_range = leader_selection_range, m_desc.diversity = div;
+    }
+    using log_line_type = std::tuple<unsigned, unsigned long long, pagmo::vector_double>; // Gen, Fevals, ideal point
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        const std::size_t len = m_log_row_len;
+        return typed_log<log_line_type>([len](const double *r) {
+            return log_line_type(static_cast<unsigned>(r[0]), static_cast<unsigned long long>(r[1]), pagmo::vector_double(r + 2, r + len));
+        });
     }
 };
 

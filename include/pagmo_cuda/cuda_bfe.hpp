@@ -225,32 +225,54 @@ public:
     unsigned evolve_memory(const pgc_algo_desc &algo, pagmo::vector_double &x, pagmo::vector_double &f, unsigned first_generation,
                            algo_state &st) const
     {
+        return evolve_full(algo, x, f, first_generation, &st, 0u, nullptr, nullptr);
+    }
+    // evolve() in full: optional state (memory = true), optional log (verbosity > 0: *log = the reference's log lines as rows of
+    // *row_len doubles, pgc_algo_evolve_logged_device)
+    unsigned evolve_full(const pgc_algo_desc &algo, pagmo::vector_double &x, pagmo::vector_double &f, unsigned first_generation, algo_state *st,
+                         unsigned verbosity, pagmo::vector_double *log, std::size_t *row_len) const
+    {
         const std::size_t n = x.size() / m_nx;
-        if (!st.initialized || st.u.size() != n) { // sade.cpp:137: a population of another size restarts the adaptation
-            st.a.assign(n * m_nx, 0.), st.b.assign(n * m_nx, 0.), st.c.assign(n * m_nf, 0.), st.u.assign(n, 0u);
-            st.initialized = false;
+        if (st && (!st->initialized || st->u.size() != n)) { // sade.cpp:137: a population of another size restarts the adaptation
+            st->a.assign(n * m_nx, 0.), st->b.assign(n * m_nx, 0.), st->c.assign(n * m_nf, 0.), st->u.assign(n, 0u);
+            st->initialized = false;
+        }
+        std::size_t max_rows = 0, rl = 0;
+        if (verbosity) {
+            check(pgc_algo_log_row_len(m_prob, algo.algo, &rl), "pgc_algo_log_row_len");
+            max_rows = algo.gens ? (algo.gens - 1u) / verbosity + 1u : 0u;
+            log->assign(max_rows * rl, 0.);
+            *row_len = rl;
         }
         unsigned done = 0;
-        on_device(x, f, "pgc_algo_evolve_memory_device", [&](double *dx, double *df, std::size_t) {
+        on_device(x, f, "pgc_algo_evolve_logged_device", [&](double *dx, double *df, std::size_t) {
             // (device_mutex is held by on_device)
             void *d[4] = {nullptr, nullptr, nullptr, nullptr};
-            const void *h[4] = {st.a.data(), st.b.data(), st.c.data(), st.u.data()};
-            void *hw[4] = {st.a.data(), st.b.data(), st.c.data(), st.u.data()};
-            const std::size_t bytes[4] = {st.a.size() * sizeof(double), st.b.size() * sizeof(double), st.c.size() * sizeof(double),
-                                          st.u.size() * sizeof(uint32_t)};
+            void *h[4] = {nullptr, nullptr, nullptr, nullptr};
+            std::size_t bytes[4] = {0, 0, 0, 0};
+            if (st) {
+                h[0] = st->a.data(), h[1] = st->b.data(), h[2] = st->c.data(), h[3] = st->u.data();
+                bytes[0] = st->a.size() * sizeof(double), bytes[1] = st->b.size() * sizeof(double), bytes[2] = st->c.size() * sizeof(double);
+                bytes[3] = st->u.size() * sizeof(uint32_t);
+            }
             int rc = PGC_OK;
-            for (int k = 0; k < 4 && rc == PGC_OK; ++k) {
+            for (int k = 0; st && k < 4 && rc == PGC_OK; ++k) {
                 rc = pgc_malloc_device(m_ctx.get(), bytes[k] ? bytes[k] : 8u, &d[k]);
-                if (rc == PGC_OK && st.initialized && bytes[k]) rc = pgc_memcpy_h2d(m_ctx.get(), d[k], h[k], bytes[k]);
+                if (rc == PGC_OK && st->initialized && bytes[k]) rc = pgc_memcpy_h2d(m_ctx.get(), d[k], h[k], bytes[k]);
             }
             pgc_algo_memory mem{static_cast<double *>(d[0]), static_cast<double *>(d[1]), static_cast<double *>(d[2]),
-                                static_cast<uint32_t *>(d[3]), st.initialized ? 1 : 0, 0};
-            if (rc == PGC_OK) rc = pgc_algo_evolve_memory_device(m_prob, &algo, dx, df, n, first_generation, &done, &mem, nullptr);
-            for (int k = 0; k < 4 && rc == PGC_OK; ++k)
-                if (bytes[k]) rc = pgc_memcpy_d2h(m_ctx.get(), hw[k], d[k], bytes[k]);
+                                static_cast<uint32_t *>(d[3]), st && st->initialized ? 1 : 0, 0};
+            std::size_t n_rows = 0;
+            if (rc == PGC_OK) {
+                rc = pgc_algo_evolve_logged_device(m_prob, &algo, dx, df, n, first_generation, &done, st ? &mem : nullptr, verbosity,
+                                                   verbosity ? log->data() : nullptr, max_rows, &n_rows, nullptr);
+            }
+            for (int k = 0; st && k < 4 && rc == PGC_OK; ++k)
+                if (bytes[k]) rc = pgc_memcpy_d2h(m_ctx.get(), h[k], d[k], bytes[k]);
             for (void *p : d)
                 if (p) pgc_free_device(m_ctx.get(), p);
-            if (rc == PGC_OK) st.initialized = true;
+            if (rc == PGC_OK && st) st->initialized = true;
+            if (rc == PGC_OK && verbosity) log->resize(n_rows * rl);
             return rc;
         });
         return done;

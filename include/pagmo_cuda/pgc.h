@@ -344,6 +344,23 @@ typedef struct pgc_algo_memory {
 PGC_API int pgc_algo_evolve_memory_device(pgc_problem *prob, const pgc_algo_desc *algo, double *d_x, double *d_f, size_t n,
                                           uint32_t first_generation, unsigned *gens_done, pgc_algo_memory *memory, void *stream);
 
+/* algorithm::set_verbosity(v) + get_log() (de.hpp:160-199 and the like): evolve() that also records the log lines the reference UDA
+ * records - one every `verbosity` generations (generations 1, 1 + v, 1 + 2v, ...; every generation for v = 1), computed on the
+ * device from the resident population.  Row layouts (doubles; pgc_algo_log_row_len gives the length):
+ *   de      gen, fevals, best, dx, df                        (de.cpp:324-347)
+ *   sade    gen, fevals, best, F, CR, dx, df                 (sade.cpp:556-580)
+ *   de1220  gen, fevals, best, F, CR, variant, dx, df        (de1220.cpp:570-595)
+ *   pso_gen gen, fevals, gbest, mean velocity, mean lbest, average distance   (pso_gen.cpp:464-518)
+ *   nsga2   gen, fevals, ideal point [nobj]                  (nsga2.cpp:144-173; logged BEFORE the generation, as the reference does)
+ *   nspso   gen, fevals, ideal point of the archive [nobj]   (nspso.cpp:163-192; fevals counted from this call's start)
+ * log_rows: HOST array [max_rows x row_len]; *n_rows = lines written (the DE family stops logging at the generation whose exit test
+ * fires).  memory: NULL, or the state of an algorithm built with memory = true (pgc_algo_evolve_memory_device).  sga, cmaes: the
+ * device loops record no log (PGC_ERR_UNSUPPORTED for verbosity > 0). */
+PGC_API int pgc_algo_log_row_len(const pgc_problem *prob, int algo, size_t *row_len);
+PGC_API int pgc_algo_evolve_logged_device(pgc_problem *prob, const pgc_algo_desc *algo, double *d_x, double *d_f, size_t n,
+                                          uint32_t first_generation, unsigned *gens_done, pgc_algo_memory *memory, unsigned verbosity,
+                                          double *log_rows, size_t max_rows, size_t *n_rows, void *stream);
+
 /* ---- populations and migration (island.cpp:428-652) ------------------------------------------------------------------- */
 /* population(prob, bfe, n, seed) (population.cpp:82-103, generic.hpp:326-389): n uniform random decision vectors in the bounds,
  * one batch evaluation, random 64-bit IDs; the last nix genes are drawn as integers in [lb, ub] (generic.hpp:289-295).  d_f and

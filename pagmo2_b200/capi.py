@@ -629,6 +629,31 @@ class Problem:
             self.ctx.free(dx)
             self.ctx.free(df)
 
+    def evolve_logged(self, algo: "AlgoDesc", x, f, verbosity: int, first_generation=1):
+        """evolve() with algorithm::set_verbosity(verbosity): returns (x, f, gens_done, log [rows x row_len]) - the lines the
+        reference's get_log() would hold (`pgc_algo_evolve_logged_device`)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(x.shape[0], -1)
+        L = lib()
+        L.pgc_algo_log_row_len.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
+        L.pgc_algo_evolve_logged_device.argtypes = [C.c_void_p, C.POINTER(AlgoDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
+                                                    C.POINTER(C.c_uint), C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t,
+                                                    C.POINTER(C.c_size_t), C.c_void_p]
+        row_len = C.c_size_t()
+        check(L.pgc_algo_log_row_len(self._h, algo.algo, C.byref(row_len)))
+        max_rows = (algo.gens - 1) // max(verbosity, 1) + 1 if algo.gens else 0
+        rows = np.zeros((max(max_rows, 1), row_len.value))
+        dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
+        done, n_rows = C.c_uint(), C.c_size_t()
+        try:
+            check(L.pgc_algo_evolve_logged_device(self._h, C.byref(algo), dx, df, x.shape[0], first_generation, C.byref(done), None, verbosity,
+                                                  rows.ctypes.data, max_rows, C.byref(n_rows), None))
+            self.ctx.synchronize()
+            return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), done.value, rows[:n_rows.value]
+        finally:
+            self.ctx.free(dx)
+            self.ctx.free(df)
+
     def evolve_memory(self, algo: "AlgoDesc", x, f, first_generation=1, state=None):
         """evolve() of a UDA built with memory = true (`pgc_algo_evolve_memory_device`): `state` is what the previous call returned
         (None: the first call, the state is drawn as the reference's first evolve() draws it).  Returns (x, f, gens_done, state),

@@ -1035,6 +1035,65 @@ int pgc_algo_evolve_memory_device(pgc_problem *prob, const pgc_algo_desc *a, dou
     }
 }
 
+int pgc_algo_log_row_len(const pgc_problem *prob, int algo, size_t *row_len)
+{
+    PGC_REQUIRE(prob && row_len, "pgc_algo_log_row_len: null argument");
+    switch (algo) {
+        case PGC_ALGO_DE: *row_len = 5; return PGC_OK;
+        case PGC_ALGO_SADE: *row_len = 7; return PGC_OK;
+        case PGC_ALGO_DE1220: *row_len = 8; return PGC_OK;
+        case PGC_ALGO_PSO_GEN: *row_len = 6; return PGC_OK;
+        case PGC_ALGO_NSGA2:
+        case PGC_ALGO_NSPSO: *row_len = 2 + prob->nobj; return PGC_OK;
+        default:
+            set_error("pgc_algo_log_row_len: algorithm %d records no log on the device", algo);
+            return PGC_ERR_UNSUPPORTED;
+    }
+}
+
+int pgc_algo_evolve_logged_device(pgc_problem *prob, const pgc_algo_desc *a, double *d_x, double *d_f, size_t n, uint32_t first_generation,
+                                  unsigned *gens_done, pgc_algo_memory *memory, unsigned verbosity, double *log_rows, size_t max_rows,
+                                  size_t *n_rows, void *stream)
+{
+    PGC_REQUIRE(prob && a, "pgc_algo_evolve_logged_device: null argument");
+    if (n_rows) *n_rows = 0;
+    const auto run = [&]() {
+        return memory ? pgc_algo_evolve_memory_device(prob, a, d_x, d_f, n, first_generation, gens_done, memory, stream)
+                      : pgc_algo_evolve_device(prob, a, d_x, d_f, n, first_generation, gens_done, stream);
+    };
+    if (verbosity == 0u) return run();
+    PGC_REQUIRE(log_rows && n_rows, "pgc_algo_evolve_logged_device: verbosity > 0 needs somewhere to put the log");
+    size_t row_len = 0;
+    if (int rc = pgc_algo_log_row_len(prob, a->algo, &row_len)) return rc;
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream;
+    const size_t due = a->gens ? (a->gens - 1u) / verbosity + 1u : 0u; // generations 1, 1 + v, ... <= gens
+    const size_t rows = std::min(due, max_rows);
+    struct Dev {
+        void *p = nullptr;
+        ~Dev() { if (p) cudaFree(p); }
+    } d_rows, d_count;
+    PGC_CUDA(cudaMalloc(&d_rows.p, sizeof(double) * std::max<size_t>(rows * row_len, 1)));
+    PGC_CUDA(cudaMalloc(&d_count.p, sizeof(unsigned)));
+    PGC_CUDA(cudaMemsetAsync(d_count.p, 0, sizeof(unsigned), st));
+    LogSink sink;
+    sink.d_rows = static_cast<double *>(d_rows.p);
+    sink.d_count = static_cast<unsigned *>(d_count.p);
+    sink.verbosity = verbosity;
+    sink.max_rows = static_cast<unsigned>(rows);
+    sink.row_len = static_cast<unsigned>(row_len);
+    tls_log = &sink;
+    const int rc = run();
+    tls_log = nullptr;
+    if (rc != PGC_OK) return rc;
+    unsigned written = 0;
+    PGC_CUDA(cudaMemcpyAsync(&written, d_count.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    PGC_CUDA(cudaStreamSynchronize(st));
+    if (written) PGC_CUDA(cudaMemcpy(log_rows, d_rows.p, sizeof(double) * written * row_len, cudaMemcpyDeviceToHost));
+    *n_rows = written;
+    return PGC_OK;
+}
+
 int pgc_population_init_device(pgc_problem *prob, size_t n, uint64_t seed, double *d_x, double *d_f, uint64_t *d_ids, void *stream)
 {
     PGC_REQUIRE(prob && (d_x || n == 0), "pgc_population_init_device: null argument");

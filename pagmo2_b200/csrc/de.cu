@@ -442,6 +442,30 @@ struct DeGlobal { // device-side global best + exit-condition data
     unsigned gen_base;  // generation counter of the first generation of this evolve() call (the Philox substream index)
 };
 
+// the reference's log line of a generation (de: gen, fevals, best, dx, df; sade adds F, CR of the best; de1220 also its variant),
+// read from the quantities the exit test has just computed.  Nothing is logged for the generation whose exit test fired: the
+// reference returns before it gets there (de.cpp:308-321).
+__global__ void de_log_kernel(const DeGlobal *G, const double *f, unsigned algo, double gen, double fevals, double *rows, unsigned *count,
+                              unsigned max_rows, unsigned row_len)
+{
+    if (G->stopped) return;
+    const unsigned row = *count;
+    if (row >= max_rows) return;
+    double *o = rows + static_cast<size_t>(row) * row_len;
+    unsigned c = 0;
+    o[c++] = gen;
+    o[c++] = fevals;
+    o[c++] = f[G->best_idx];
+    if (algo >= 1u) {
+        o[c++] = G->gbF;
+        o[c++] = G->gbCR;
+    }
+    if (algo == 2u) o[c++] = static_cast<double>(G->gbvariant);
+    o[c++] = G->dx;
+    o[c++] = G->df;
+    *count = row + 1u;
+}
+
 struct DePartial { // per-CTA result of the scan below (large populations: de_global_partial_kernel)
     double fa, fb, fw;
     unsigned ia, ib, iw;
@@ -1213,7 +1237,8 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
     const int fam = prob->desc.family;
     const bool simple_family = !prob->inner
                                && (fam == PGC_RASTRIGIN || fam == PGC_ACKLEY || fam == PGC_GRIEWANK || fam == PGC_SCHWEFEL || fam == PGC_ROSENBROCK);
-    if (simple_family && eval == &problem_eval_device && NP < kFinishMaxNP && dim <= kResidentMaxDim && resident_enabled()) {
+    const bool logging = tls_log != nullptr; // log lines are appended between generations: one launch set per generation
+    if (!logging && simple_family && eval == &problem_eval_device && NP < kFinishMaxNP && dim <= kResidentMaxDim && resident_enabled()) {
         if (int rc = W->allocate_resident(algo)) return rc;
         ResidentParams R{};
         R.x[0] = d_x; R.x[1] = W->x2;
@@ -1303,7 +1328,7 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
     // host cost and the gaps between dependent kernels, which is all a generation of a small population consists of.
     const bool scratch_same = W->scratch_at_capture == ctx->scratch && W->scratch_bytes_at_capture == ctx->scratch_bytes;
     if (W->exec && !scratch_same) W->drop_graph();
-    while (W->exec && !h.stopped && gens - g >= W->graph_gens) {
+    while (!logging && W->exec && !h.stopped && gens - g >= W->graph_gens) {
         PGC_CUDA(cudaGraphLaunch(W->exec, st));
         ctx->launches.fetch_add(W->graph_launches, std::memory_order_relaxed);
         g += W->graph_gens;
@@ -1314,6 +1339,11 @@ int de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, u
     // (b) plain launches for the rest (and for the whole first call on a new workspace)
     for (; g < gens && !h.stopped; ++g) {
         if ((rc = generation())) return rc;
+        if (log_due(g + 1u)) { // de.cpp:324-347, sade.cpp:556-580, de1220.cpp:570-595
+            de_log_kernel<<<1, 1, 0, st>>>(G, d_f, algo, static_cast<double>(g + 1u), static_cast<double>(g + 1u) * static_cast<double>(NP),
+                                           tls_log->d_rows, tls_log->d_count, tls_log->max_rows, tls_log->row_len);
+            ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        }
         if ((g + 1) % kPoll == 0 || g + 1 == gens) {
             PGC_CUDA(cudaMemcpyAsync(&h, G, sizeof(DeGlobal), cudaMemcpyDeviceToHost, st));
             PGC_CUDA(cudaStreamSynchronize(st));

@@ -283,6 +283,7 @@ int nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP
     unsigned nfronts = 0;
     for (unsigned g = 0; g < gens; ++g) {
         const unsigned generation = first_generation + g;
+        if (log_due(g + 1u) && (rc = log_ideal_device(ctx, d_f, NP, nobj, g + 1u, static_cast<unsigned long long>(g) * NP, st))) return rc; // nsga2.cpp:144-173
         const auto t0 = now();
         // parents occupy the first half of the 2N buffers (popnew = pop, nsga2.cpp:177)
         PGC_CUDA(cudaMemcpyAsync(x2, d_x, sizeof(double) * NP * nx, cudaMemcpyDeviceToDevice, st));

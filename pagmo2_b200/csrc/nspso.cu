@@ -339,6 +339,7 @@ int nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP
     }
     for (unsigned g = 0; g < gens; ++g) {
         const unsigned generation = first_generation + g;
+        if (log_due(g + 1u) && (rc = log_ideal_device(ctx, bf, NP, m, g + 1u, static_cast<unsigned long long>(g) * NP, st))) return rc; // nspso.cpp:163-192
         // 1 - the leaders
         // only the first front is needed (its size; for the niche count its members in the reference's order, and the first member
         // of the second front when it is a single point): the level loop stops after one (two) closed fronts

@@ -310,6 +310,22 @@ int de_init_adaptation_device(unsigned NP, unsigned algo, unsigned variant_adptv
                               unsigned long long seed, unsigned generation, double *d_F, double *d_CR, unsigned *d_variant, cudaStream_t st);
 int pso_init_velocity_device(pgc_problem *prob, unsigned n, double max_vel, unsigned long long seed, unsigned generation, double *d_v,
                              cudaStream_t st);
+// ---- UDA logs (algo_log.cu): where the generation loops append the reference's log lines while a logged evolve() runs ------------
+struct LogSink {
+    double *d_rows = nullptr;   // [max_rows x row_len]
+    unsigned *d_count = nullptr; // rows written so far (advanced on the device, in stream order)
+    unsigned verbosity = 0, max_rows = 0, row_len = 0;
+};
+extern thread_local LogSink *tls_log;
+// generation `gen` (1-based within this evolve() call) is one the reference logs (de.cpp:327)
+inline bool log_due(unsigned gen)
+{
+    const LogSink *L = tls_log;
+    return L && L->verbosity && (gen % L->verbosity == 1u || L->verbosity == 1u);
+}
+int log_ideal_device(pgc_ctx *ctx, const double *d_f, unsigned n, unsigned m, unsigned gen, unsigned long long fevals, cudaStream_t st);
+int log_pso_device(pgc_ctx *ctx, const double *d_X, const double *d_V, const double *d_lbfit, const double *d_lb, const double *d_ub, unsigned n,
+                   unsigned dim, unsigned gen, unsigned long long fevals, cudaStream_t st);
 int nspso_init_memory_device(pgc_problem *prob, const double *d_x, const double *d_f, unsigned NP, double v_coeff, unsigned long long seed,
                              unsigned generation, double *d_vel, double *d_best_x, double *d_best_f, cudaStream_t st);
 int moead_gen_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, const double *h_weights,

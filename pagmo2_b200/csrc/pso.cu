@@ -622,6 +622,7 @@ int pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d_v, 
             pso_rewire_kernel<<<nblk(static_cast<size_t>(n) * K, 256), 256, 0, st>>>(targets, n, K, seed, generation + 1u, keep);
         }
         ctx->launches.fetch_add(neighb_type == 4u ? 8 : 4, std::memory_order_relaxed);
+        if (log_due(g + 1u) && (rc = log_pso_device(ctx, X, V, d_f, lb, ub, n, dim, g + 1u, static_cast<unsigned long long>(g + 1u) * n, st))) return rc; // pso_gen.cpp:464-518
     }
     if (d_v) PGC_CUDA(cudaMemcpyAsync(d_v, V, 8 * nd, cudaMemcpyDeviceToDevice, st));
     if (d_xcur) PGC_CUDA(cudaMemcpyAsync(d_xcur, X, 8 * nd, cudaMemcpyDeviceToDevice, st));

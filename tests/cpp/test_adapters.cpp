@@ -358,6 +358,45 @@ int main(int argc, char **argv)
             other = second.evolve(other);
             CHECK(other.size() == 48u);
         }
+        { // algorithm::set_verbosity + get_log (de.hpp:160-199): one line every `level` generations, in the reference's tuple layout
+            pagmo::algorithm a{cuda_de{10u, 0.8, 0.9, 2u, 0., 0., 3u}};
+            a.set_verbosity(3u);
+            pagmo::population q{prob, 32u, 9u}, plain{prob, 32u, 9u};
+            q = a.evolve(q);
+            plain = pagmo::algorithm{cuda_de{10u, 0.8, 0.9, 2u, 0., 0., 3u}}.evolve(plain);
+            CHECK(q.get_x() == plain.get_x()); // logging does not change the run
+            const auto log = a.extract<cuda_de>()->get_log();
+            CHECK(log.size() == 4u && std::get<0>(log[0]) == 1u && std::get<0>(log[3]) == 10u && std::get<1>(log[3]) == 10u * 32u);
+            CHECK(std::get<2>(log[3]) == q.champion_f()[0]); // the last line is the final generation here: Best = the champion
+            CHECK(std::get<2>(log[0]) >= std::get<2>(log[3]) && std::get<3>(log[3]) > 0. && std::get<4>(log[3]) > 0.);
+            pagmo::algorithm s{cuda_sade{6u, 2u, 1u, 0., 0., false, 41u}};
+            s.set_verbosity(1u);
+            pagmo::population qs{prob, 32u, 9u};
+            qs = s.evolve(qs);
+            const auto slog = s.extract<cuda_sade>()->get_log();
+            CHECK(slog.size() == 6u && std::get<3>(slog[5]) >= 0.1 && std::get<3>(slog[5]) <= 1. && std::get<4>(slog[5]) >= 0. && std::get<4>(slog[5]) <= 1.);
+            pagmo::algorithm p{cuda_pso_gen{5u, 0.7298, 2.05, 2.05, 0.5, 5u, 2u, 4u, false, 3u}};
+            p.set_verbosity(2u);
+            pagmo::population qp{prob, 32u, 9u};
+            qp = p.evolve(qp);
+            const auto plog = p.extract<cuda_pso_gen>()->get_log();
+            CHECK(plog.size() == 3u && std::get<2>(plog[2]) == qp.champion_f()[0] && std::get<5>(plog[2]) > 0.);
+            pagmo::algorithm m{cuda_nsga2{5u, 0.95, 10., 0.01, 50., 32u}};
+            m.set_verbosity(2u);
+            pagmo::population qm{pagmo::problem{pagmo::zdt{1u, 30u}}, 40u, 5u};
+            const auto ideal0 = pagmo::ideal(qm.get_f());
+            qm = m.evolve(qm);
+            const auto mlog = m.extract<cuda_nsga2>()->get_log();
+            CHECK(mlog.size() == 3u && std::get<1>(mlog[0]) == 0u && std::get<2>(mlog[0]) == ideal0 && std::get<1>(mlog[2]) == 4u * 40u);
+            bool refused = false;
+            try {
+                pagmo::algorithm g{cuda_sga{2u}};
+                g.set_verbosity(1u);
+            } catch (const std::invalid_argument &) {
+                refused = true;
+            }
+            CHECK(refused);
+        }
         pagmo::problem zp{pagmo::zdt{1u, 30u}};
         pagmo::population mo{zp, 40u, 5u};
         mo = pagmo::algorithm{cuda_nsga2{10u, 0.95, 10., 0.01, 50., 32u}}.evolve(mo);

@@ -1,0 +1,132 @@
+"""The log lines of the reference UDAs (`set_verbosity(v)` / `get_log()`) from `pgc_algo_evolve_logged_device`: every line is
+recomputed here, with the reference's formula, from the population an evolve() of exactly that many generations returns (the draws
+are keyed by generation, so a shorter run is a prefix of a longer one), and logging must not change the trajectory."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from pagmo2_b200 import capi as m
+    return m
+
+
+def _due(gens, v):
+    return [g for g in range(1, gens + 1) if g % v == 1 or v == 1]  # de.cpp:327
+
+
+def _dx_df(x, f):
+    """de.cpp:328-336: best = first minimum, worst = first maximum; dx = sum |x_worst - x_best|, df = |f_worst - f_best|."""
+    b, w = int(np.argmin(f)), int(np.argmax(f))
+    return f[b], float(np.sum(np.abs(x[w] - x[b]))), abs(f[w] - f[b])
+
+
+@pytest.mark.parametrize("name,kw,cols", [("de", dict(variant=2), 5), ("sade", dict(variant=2, variant_adptv=1), 7),
+                                          ("de1220", dict(variant_adptv=1), 8), ("sade", dict(variant=7, variant_adptv=2), 7)])
+@pytest.mark.parametrize("verbosity", (1, 4))
+def test_de_family_log(capi, ctx, name, kw, cols, verbosity):
+    prob = capi.Problem(ctx, "rastrigin", dim=8)
+    lb, ub = prob.bounds()
+    n, gens = 40, 10
+    x = np.random.default_rng(2).uniform(lb, ub, (n, prob.nx))
+    f = prob.eval_host(x)
+    algo = capi.algo_desc(name, gens=gens, seed=7, ftol=0.0, xtol=0.0, **kw)
+    xl, fl, done, log = prob.evolve_logged(algo, x, f, verbosity)
+    x0, f0, _ = prob.evolve(algo, x, f)
+    assert done == gens and np.array_equal(xl, x0) and np.array_equal(fl, f0)  # logging does not change the run
+    due = _due(gens, verbosity)
+    assert log.shape == (len(due), cols) and log[:, 0].tolist() == due and log[:, 1].tolist() == [g * n for g in due]
+    for row in log:
+        xg, fg, _ = prob.evolve(capi.algo_desc(name, gens=int(row[0]), seed=7, ftol=0.0, xtol=0.0, **kw), x, f)
+        best, dx, df = _dx_df(xg, fg[:, 0])
+        assert row[2] == best and np.isclose(row[-2], dx, rtol=1e-13) and np.isclose(row[-1], df, rtol=1e-13)
+        if name != "de":  # F and CR of the individual that last improved the global best
+            assert 0.0 < row[3] <= 1.0 + 1e-9 or kw["variant_adptv"] == 2
+            assert np.isfinite(row[4])
+        if name == "de1220":
+            assert row[5] in (2, 3, 7, 10, 13, 14, 15, 16)
+    prob.close()
+
+
+def test_de_log_stops_where_the_exit_test_fires(capi, ctx):
+    """de.cpp:308-321: the generation whose xtol / ftol test fires returns before its log line."""
+    prob = capi.Problem(ctx, "rosenbrock", dim=3)
+    lb, ub = prob.bounds()
+    x = np.random.default_rng(5).uniform(lb, ub, (20, 3))
+    f = prob.eval_host(x)
+    algo = capi.algo_desc("de", gens=2000, seed=3, ftol=1e-3, xtol=1e-3)
+    _, _, done, log = prob.evolve_logged(algo, x, f, 1)
+    assert 0 < done < 2000 and log.shape[0] == done - 1 and log[-1, 0] == done - 1
+    prob.close()
+
+
+@pytest.mark.parametrize("variant,ntype", [(5, 2), (1, 1), (6, 3)])
+def test_pso_gen_log(capi, ctx, variant, ntype):
+    """pso_gen.cpp:464-518, as written: gbest = min lbfit; the running "mean velocity" m <- (m + sum_j |V_ij / width_j|) / dim over the
+    particles; mean lbest; mean pairwise distance of the CURRENT positions in units of the box."""
+    prob = capi.Problem(ctx, "ackley", dim=6)
+    lb, ub = prob.bounds()
+    n, gens, v = 30, 7, 3
+    x = np.random.default_rng(9).uniform(lb, ub, (n, prob.nx))
+    f = prob.eval_host(x)
+    algo = capi.algo_desc("pso_gen", gens=gens, seed=11, variant=variant, neighb_type=ntype)
+    xl, fl, _, log = prob.evolve_logged(algo, x, f, v)
+    x0, f0, _ = prob.evolve(algo, x, f)
+    assert np.array_equal(xl, x0) and np.array_equal(fl, f0)
+    assert log[:, 0].tolist() == _due(gens, v) and log[:, 1].tolist() == [g * n for g in _due(gens, v)] and log.shape[1] == 6
+    for row in log:
+        g = int(row[0])
+        v0 = np.zeros_like(x)
+        # the velocities of a memory-less run: drawn inside; read them back by running with memory from the same start
+        xa, fa, _, st = prob.evolve_memory(capi.algo_desc("pso_gen", gens=g, seed=11, variant=variant, neighb_type=ntype), x, f)
+        _, _, _, xcur = prob.pso_evolve(x, f[:, 0], gens=g, seed=11, variant=variant, neighb_type=ntype)
+        V, lbfit = st["a"], fa[:, 0]
+        m = 0.0
+        for i in range(n):
+            m = (m + np.sum(np.abs(V[i] / (ub - lb)))) / prob.nx
+        d = 0.0
+        for i in range(n):
+            for j in range(i + 1, n):
+                d += np.sqrt(np.sum((xcur[i] - xcur[j]) ** 2 / (ub - lb) / (ub - lb)))
+        d /= (n - 1) * n / 2
+        assert row[2] == lbfit.min() and np.isclose(row[3], m, rtol=1e-12) and np.isclose(row[4], lbfit.sum() / n, rtol=1e-13)
+        assert np.isclose(row[5], d, rtol=1e-12)
+    prob.close()
+
+
+@pytest.mark.parametrize("name", ("nsga2", "nspso"))
+def test_mo_log_is_the_ideal_point_before_the_generation(capi, ctx, name):
+    """nsga2.cpp:144-173 / nspso.cpp:163-192: logged at the top of the loop, so line `gen` describes the population (nspso: the
+    archive, which a memory-less run starts as the population) after gen - 1 generations, with (gen - 1) * NP evaluations."""
+    prob = capi.Problem(ctx, "dtlz", prob_id=2, dim=7, nobj=3, param=100)
+    lb, ub = prob.bounds()
+    n, gens, v = 36, 9, 4
+    x = np.random.default_rng(4).uniform(lb, ub, (n, prob.nx))
+    f = prob.eval_host(x)
+    algo = capi.algo_desc(name, gens=gens, seed=13)
+    xl, fl, _, log = prob.evolve_logged(algo, x, f, v)
+    x0, f0, _ = prob.evolve(algo, x, f)
+    assert np.array_equal(xl, x0) and np.array_equal(fl, f0)
+    assert log[:, 0].tolist() == _due(gens, v) and log[:, 1].tolist() == [(g - 1) * n for g in _due(gens, v)] and log.shape[1] == 5
+    for row in log:
+        g = int(row[0]) - 1
+        if name == "nsga2":
+            fg = f if g == 0 else prob.evolve(capi.algo_desc(name, gens=g, seed=13), x, f)[1]
+        else:
+            fg = f if g == 0 else prob.evolve_memory(capi.algo_desc(name, gens=g, seed=13), x, f)[3]["c"]
+        assert np.array_equal(row[2:], fg.min(axis=0))
+    prob.close()
+
+
+def test_log_argument_checks(capi, ctx):
+    prob = capi.Problem(ctx, "rastrigin", dim=4)
+    x = np.random.default_rng(1).uniform(-5, 5, (16, 4))
+    f = prob.eval_host(x)
+    with pytest.raises(capi.PgcError):  # sga's device loop records no log
+        prob.evolve_logged(capi.algo_desc("sga", gens=2, seed=1), x, f, 1)
+    # verbosity 0: a plain evolve, no lines
+    xl, fl, _, log = prob.evolve_logged(capi.algo_desc("de", gens=3, seed=1), x, f, 0)
+    assert log.shape[0] == 0 and np.array_equal(xl, prob.evolve(capi.algo_desc("de", gens=3, seed=1), x, f)[0])
+    prob.close()
