@@ -8,8 +8,9 @@
 //     double v = hv.compute(ref_point, algo);         // replaces hv2d / hv3d (hv_hv2d.cpp:59-84, hv_hv3d.cpp:107-166)
 //     auto c   = hv.contributions(ref_point, algo);   // replaces hv2d::contributions / HyCon3D (hv_hv3d.cpp:170-343)
 //
-// 2 and 3 objectives (the dimensions the reference serves with hv2d / hv3d); other dimensions make verify_before_compute throw,
-// like hv2d / hv3d do for the wrong dimension (hv_hv3d.cpp:356-363).  No CPU fallback.
+// 2 and 3 objectives run the device versions of hv2d / hv3d, 4 to 12 objectives the device WFG (replaces hvwfg, hv_hvwfg.cpp:64-117:
+// one thread per term of the top-level sum / per (point, term) for the contributions); more make verify_before_compute throw.
+// No CPU fallback.
 #ifndef PAGMO_CUDA_CUDA_HYPERVOLUME_HPP
 #define PAGMO_CUDA_CUDA_HYPERVOLUME_HPP
 
@@ -75,8 +76,8 @@ public:
     }
     void verify_before_compute(const std::vector<pagmo::vector_double> &points, const pagmo::vector_double &r_point) const override
     {
-        if (r_point.size() != 2u && r_point.size() != 3u) {
-            pagmo_throw(std::invalid_argument, "Algorithm cuda_hv works only for 2- and 3-dimensional cases");
+        if (r_point.size() < 2u || r_point.size() > 12u) {
+            pagmo_throw(std::invalid_argument, "Algorithm cuda_hv works for 2 to 12 objectives");
         }
         hv_algorithm::assert_minimisation(points, r_point);
     }

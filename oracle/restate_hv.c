@@ -1,4 +1,4 @@
-/* oracle/restate_hv.c - plain-C restatement of pagmo's exact hypervolume for 2 and 3 objectives.  TEST INFRASTRUCTURE ONLY.
+/* oracle/restate_hv.c - plain-C restatement of pagmo's exact hypervolume (hv2d, hv3d, and WFG for 4 and more objectives).  TEST INFRASTRUCTURE ONLY.
  * Follows reference
  *   hv2d::compute  src/utils/hv_algos/hv_hv2d.cpp:59-84   (sort by the second objective, sweep with a running width)
  *   hv3d::compute  src/utils/hv_algos/hv_hv3d.cpp:107-166 (sort by the third objective, sweep plane with an ordered front; the
@@ -109,16 +109,137 @@ static double compute_skipping(const double *f, size_t n, size_t m, const double
     return v;
 }
 
+/* ---- four and more objectives: the WFG algorithm as the reference runs it (src/utils/hv_algos/hv_hvwfg.cpp) ------------------
+ * compute_hv (:227-296): one and two points by inclusion-exclusion; otherwise sort the frame by the current last objective
+ * (cmp_points, :303-313: larger first), and with that objective dropped, H = sum_p |p[last] - r[last]| * exclusive_hv(p) where
+ * exclusive_hv (:212-224) = volume_between(p, r) - hv(limitset) and limitset (:153-209) = the non-dominated subset of
+ * { max(p, q) : q after p }.  At two objectives the reference switches to hv2d (:245-248). */
+static int wfg_dom_cmp(const double *a, const double *b, size_t d) /* hv_algorithm::dom_cmp, hv_algorithm.cpp:176-209: 1 a dominates, 2 b dominates, 3 equal, 4 incomparable */
+{
+    for (size_t i = 0; i < d; ++i) {
+        if (a[i] > b[i]) {
+            for (size_t j = i + 1; j < d; ++j)
+                if (a[j] < b[j]) return 4;
+            return 2;
+        } else if (a[i] < b[i]) {
+            for (size_t j = i + 1; j < d; ++j)
+                if (a[j] > b[j]) return 4;
+            return 1;
+        }
+    }
+    return 3;
+}
+
+static double wfg_volume_between(const double *a, const double *b, size_t d)
+{
+    double v = 1.0;
+    for (size_t i = 0; i < d; ++i) v *= (a[i] - b[i]);
+    return fabs(v);
+}
+
+/* limitset of frame[p] against frame[begin ..] into `out` (row stride m); returns its size */
+static size_t wfg_limitset(const double *frame, size_t k, size_t m, size_t d, size_t begin, size_t p, double *out, int *cmp)
+{
+    size_t no = 0;
+    for (size_t idx = begin; idx < k; ++idx) {
+        if (idx == p) continue;
+        double *s = out + no * m;
+        for (size_t c = 0; c < d; ++c) s[c] = fmax(frame[idx * m + c], frame[p * m + c]);
+        int keep = 1;
+        for (size_t q = 0; q < no; ++q) {
+            cmp[q] = wfg_dom_cmp(s, out + q * m, d);
+            if (cmp[q] == 2) { keep = 0; break; }
+        }
+        if (keep) {
+            size_t prev = 0;
+            for (size_t next = 0; next < no; ++next)
+                if (cmp[next] != 1 && cmp[next] != 3) {
+                    if (prev < next) memcpy(out + prev * m, out + next * m, d * sizeof(double));
+                    ++prev;
+                }
+            if (prev < no) memmove(out + prev * m, s, d * sizeof(double));
+            no = prev + 1;
+        }
+    }
+    return no;
+}
+
+static size_t g_wfg_d, g_wfg_m;
+static int wfg_by_last_desc(const void *a, const void *b) /* cmp_points :303-313: the larger last objective first, then the earlier ones */
+{
+    const double *x = (const double *)a, *y = (const double *)b;
+    for (size_t i = g_wfg_d; i-- > 0;) {
+        if (x[i] > y[i]) return -1;
+        if (x[i] < y[i]) return 1;
+    }
+    return 0;
+}
+
+static double wfg_hv(double *frame, size_t k, size_t m, size_t d, const double *r)
+{
+    if (k == 0) return 0.0;
+    if (k == 1) return wfg_volume_between(frame, r, d);
+    if (k == 2) {
+        double isect = 1.0;
+        for (size_t i = 0; i < d; ++i) isect *= (r[i] - fmax(frame[i], frame[m + i]));
+        return wfg_volume_between(frame, r, d) + wfg_volume_between(frame + m, r, d) - isect;
+    }
+    if (d == 2) { /* hv2d on (x, y) rows */
+        double *xy = (double *)malloc(k * 2 * sizeof(double));
+        size_t *idx = (size_t *)malloc(k * sizeof(size_t));
+        for (size_t i = 0; i < k; ++i) { xy[2 * i] = frame[i * m]; xy[2 * i + 1] = frame[i * m + 1]; idx[i] = i; }
+        g_pts = xy; g_m = 2; g_key = 1;
+        qsort(idx, k, sizeof(size_t), by_key);
+        const double v = hv2d(xy, idx, k, r);
+        free(xy); free(idx);
+        return v;
+    }
+    g_wfg_d = d; g_wfg_m = m;
+    qsort(frame, k, m * sizeof(double), wfg_by_last_desc);
+    double *child = (double *)malloc(k * m * sizeof(double));
+    int *cmp = (int *)malloc(k * sizeof(int));
+    double H = 0.0;
+    for (size_t p = 0; p < k; ++p) {
+        const size_t no = wfg_limitset(frame, k, m, d - 1, p + 1, p, child, cmp);
+        double e = wfg_volume_between(frame + p * m, r, d - 1);
+        if (no == 1) e -= wfg_volume_between(child, r, d - 1);
+        else if (no > 1) e -= wfg_hv(child, no, m, d - 1, r);
+        H += fabs((frame[p * m + d - 1] - r[d - 1]) * e);
+    }
+    free(child); free(cmp);
+    return H;
+}
+
 int oracle_hv_compute(const double *f, size_t n, size_t m, const double *r, double *out)
 {
-    if ((m != 2 && m != 3) || oracle_hv_check(f, n, m, r)) return -1;
+    if (m < 2 || oracle_hv_check(f, n, m, r)) return -1;
+    if (m >= 4) {
+        double *frame = (double *)malloc((n ? n : 1) * m * sizeof(double));
+        memcpy(frame, f, n * m * sizeof(double));
+        *out = wfg_hv(frame, n, m, m, r);
+        free(frame);
+        return 0;
+    }
     *out = compute_skipping(f, n, m, r, (size_t)-1);
     return 0;
 }
 
 int oracle_hv_contributions(const double *f, size_t n, size_t m, const double *r, double *out)
 {
-    if ((m != 2 && m != 3) || oracle_hv_check(f, n, m, r)) return -1;
+    if (m < 2 || oracle_hv_check(f, n, m, r)) return -1;
+    if (m >= 4) { /* hvwfg::contributions :92-117: limitset(0, p) in the full dimension, then exclusive_hv */
+        double *child = (double *)malloc((n ? n : 1) * m * sizeof(double));
+        int *cmp = (int *)malloc((n ? n : 1) * sizeof(int));
+        for (size_t p = 0; p < n; ++p) {
+            const size_t no = wfg_limitset(f, n, m, m, 0, p, child, cmp);
+            double e = wfg_volume_between(f + p * m, r, m);
+            if (no == 1) e -= wfg_volume_between(child, r, m);
+            else if (no > 1) e -= wfg_hv(child, no, m, m, r);
+            out[p] = e;
+        }
+        free(child); free(cmp);
+        return 0;
+    }
     const double all = compute_skipping(f, n, m, r, (size_t)-1);
     for (size_t i = 0; i < n; ++i) out[i] = all - compute_skipping(f, n, m, r, i);
     return 0;

@@ -568,6 +568,221 @@ struct MaxOp {
     __device__ __forceinline__ double operator()(double a, double b) const { return fmax(a, b); }
 };
 
+// ---- four and more objectives: WFG (hv_hvwfg.cpp:153-296) ---------------------------------------------------------------------
+// hv(S) with S sorted by the last objective, larger first, is sum_i |p_i[last] - r[last]| * (vol_{d-1}(p_i) - hv_{d-1}(L_i)) where
+// L_i = the non-dominated subset of { max(p_i, p_j) : j > i } with the last objective dropped (it is p_i[last] for all of them).
+// The TERMS of that sum are independent: one thread per term, each running the recursion below it sequentially on its own frames
+// (m - 2 levels of at most `cap` rows, in global memory).  The recursion goes down to one objective, where the hypervolume of a
+// limit set is r_0 - min_j max(p_0, q_0) - no separate two-objective sweep.  hvwfg::contributions (:92-117) is the same kernel
+// over n frames: frame p = the limit set of p against every other point, contribution(p) = vol(p) - hv(frame p).
+constexpr unsigned kWfgMaxM = 12;
+
+struct WfgParams {
+    const double *frames;  // [nframes x cap x m]: each frame sorted by objective m-1, larger first
+    const unsigned *sizes; // [nframes]; nullptr: every frame holds `cap` rows
+    unsigned nframes, cap, m;
+    double r[kWfgMaxM];
+    double *arena;         // per thread of a launch: (m - 2) x cap x m doubles
+    double *terms;         // [nframes x cap]
+    unsigned long long first, count; // this launch covers the (frame, i) pairs first .. first + count - 1, numbered frame * cap + i
+};
+
+// rows of `stride` doubles; 1: a dominates-or-equals b on the first d coordinates (minimisation)
+__device__ __forceinline__ bool wfg_weakly_dominates(const double *a, const double *b, unsigned d)
+{
+    for (unsigned c = 0; c < d; ++c)
+        if (a[c] > b[c]) return false;
+    return true;
+}
+
+// limitset (:153-209): out <- non-dominated subset of { max(p, F[j]) on the first d coordinates : j in [begin, k), j != skip }
+__device__ unsigned wfg_limitset(const double *F, unsigned k, unsigned m, unsigned d, unsigned begin, unsigned skip, const double *p, double *out)
+{
+    unsigned no = 0;
+    for (unsigned j = begin; j < k; ++j) {
+        if (j == skip) continue;
+        double *s = out + static_cast<size_t>(no) * m;
+        for (unsigned c = 0; c < d; ++c) s[c] = fmax(F[static_cast<size_t>(j) * m + c], p[c]);
+        bool keep = true;
+        for (unsigned q = 0; q < no && keep; ++q) {
+            const double *g = out + static_cast<size_t>(q) * m;
+            bool g_dominates = true, equal = true;
+            for (unsigned c = 0; c < d; ++c) {
+                g_dominates = g_dominates && g[c] <= s[c];
+                equal = equal && g[c] == s[c];
+            }
+            keep = !(g_dominates && !equal); // an equal row is replaced by s below, as the reference does
+        }
+        if (!keep) continue;
+        unsigned prev = 0;
+        for (unsigned q = 0; q < no; ++q) {
+            const double *g = out + static_cast<size_t>(q) * m;
+            if (!wfg_weakly_dominates(s, g, d)) {
+                if (prev < q)
+                    for (unsigned c = 0; c < d; ++c) out[static_cast<size_t>(prev) * m + c] = g[c];
+                ++prev;
+            }
+        }
+        if (prev < no)
+            for (unsigned c = 0; c < d; ++c) out[static_cast<size_t>(prev) * m + c] = s[c];
+        no = prev + 1u;
+    }
+    return no;
+}
+
+// cmp_points (:303-313): larger objective d-1 first, ties by the earlier objectives; insertion sort (frames are short and the
+// dominance filter above is quadratic anyway)
+__device__ void wfg_sort_desc(double *F, unsigned k, unsigned m, unsigned d)
+{
+    double row[kWfgMaxM];
+    for (unsigned i = 1; i < k; ++i) {
+        for (unsigned c = 0; c < d; ++c) row[c] = F[static_cast<size_t>(i) * m + c];
+        unsigned j = i;
+        while (j > 0) {
+            const double *q = F + static_cast<size_t>(j - 1) * m;
+            bool before = false; // row sorts before q
+            for (unsigned c = d; c-- > 0;) {
+                if (row[c] > q[c]) { before = true; break; }
+                if (row[c] < q[c]) break;
+            }
+            if (!before) break;
+            for (unsigned c = 0; c < d; ++c) F[static_cast<size_t>(j) * m + c] = q[c];
+            --j;
+        }
+        if (j != i)
+            for (unsigned c = 0; c < d; ++c) F[static_cast<size_t>(j) * m + c] = row[c];
+    }
+}
+
+__device__ __forceinline__ double wfg_volume(const double *p, const double *r, unsigned d)
+{
+    double v = 1.0;
+    for (unsigned c = 0; c < d; ++c) v *= (p[c] - r[c]);
+    return fabs(v);
+}
+
+// hypervolume of the k rows at arena level 0 on their first d0 coordinates (compute_hv, :227-296), recursion unrolled on a stack
+__device__ double wfg_hv(double *arena, unsigned cap, unsigned m, const double *r, unsigned k0, unsigned d0)
+{
+    struct Level {
+        unsigned k, i;
+        double H, a, incl;
+    } st[kWfgMaxM];
+    const size_t level_stride = static_cast<size_t>(cap) * m;
+    unsigned lev = 0;
+    wfg_sort_desc(arena, k0, m, d0);
+    st[0] = {k0, 0u, 0.0, 0.0, 0.0};
+    for (;;) {
+        Level &L = st[lev];
+        const unsigned d = d0 - lev;
+        double *F = arena + lev * level_stride;
+        if (L.i == L.k) {
+            const double ret = L.H;
+            if (lev == 0u) return ret;
+            --lev;
+            Level &P = st[lev];
+            P.H += fabs(P.a * (P.incl - ret));
+            ++P.i;
+            continue;
+        }
+        const double *p = F + static_cast<size_t>(L.i) * m;
+        const double a = p[d - 1u] - r[d - 1u], incl = wfg_volume(p, r, d - 1u);
+        if (d == 1u) { // a set of numbers: r_0 - min
+            double mn = p[0];
+            for (unsigned j = 1; j < L.k; ++j) mn = fmin(mn, F[static_cast<size_t>(j) * m]);
+            L.H = r[0] - mn;
+            L.i = L.k;
+            continue;
+        }
+        if (d == 2u) { // the limit sets below are numbers: hv_1 = r_0 - min_j max(p_0, q_0)
+            double sub = 0.0;
+            if (L.i + 1u < L.k) {
+                double mn = INFINITY;
+                for (unsigned j = L.i + 1u; j < L.k; ++j) mn = fmin(mn, fmax(p[0], F[static_cast<size_t>(j) * m]));
+                sub = r[0] - mn;
+            }
+            L.H += fabs(a * (incl - sub));
+            ++L.i;
+            continue;
+        }
+        double *C = F + level_stride;
+        const unsigned no = wfg_limitset(F, L.k, m, d - 1u, L.i + 1u, 0xffffffffu, p, C);
+        if (no <= 1u) { // exclusive_hv, :212-224
+            L.H += fabs(a * (incl - (no ? wfg_volume(C, r, d - 1u) : 0.0)));
+            ++L.i;
+            continue;
+        }
+        wfg_sort_desc(C, no, m, d - 1u);
+        L.a = a;
+        L.incl = incl;
+        ++lev;
+        st[lev] = {no, 0u, 0.0, 0.0, 0.0};
+    }
+}
+
+__global__ void wfg_terms_kernel(const WfgParams P)
+{
+    const unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= P.count) return;
+    const unsigned long long e = P.first + t;
+    const unsigned fr = static_cast<unsigned>(e / P.cap), i = static_cast<unsigned>(e % P.cap);
+    const unsigned k = P.sizes ? P.sizes[fr] : P.cap;
+    if (i >= k) return;
+    const unsigned m = P.m;
+    const double *F = P.frames + static_cast<size_t>(fr) * P.cap * m;
+    const double *p = F + static_cast<size_t>(i) * m;
+    double *arena = P.arena + t * (static_cast<size_t>(m - 2u) * P.cap * m);
+    const double a = p[m - 1u] - P.r[m - 1u], incl = wfg_volume(p, P.r, m - 1u);
+    const unsigned no = wfg_limitset(F, k, m, m - 1u, i + 1u, 0xffffffffu, p, arena);
+    double sub = 0.0;
+    if (no == 1u) sub = wfg_volume(arena, P.r, m - 1u);
+    else if (no > 1u) sub = wfg_hv(arena, P.cap, m, P.r, no, m - 1u);
+    P.terms[e] = fabs(a * (incl - sub));
+}
+
+// frame p <- limit set of point p against all the others, in all m objectives, sorted for wfg_terms_kernel (:102-105)
+__global__ void wfg_contribution_frames_kernel(const double *f, unsigned n, unsigned m, double *frames, unsigned *sizes)
+{
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    double *out = frames + static_cast<size_t>(p) * n * m;
+    const unsigned no = wfg_limitset(f, n, m, m, 0u, p, f + static_cast<size_t>(p) * m, out);
+    wfg_sort_desc(out, no, m, m);
+    sizes[p] = no;
+}
+
+// sums in index order, as compute_hv accumulates them; mode 1: out[0] = hv of frame 0; mode 0: out[p] = vol(p) - hv(frame p)
+__global__ void wfg_sum_kernel(const double *terms, const unsigned *sizes, unsigned cap, unsigned nframes, const double *f, unsigned m,
+                               const WfgParams P, int compute, double *out)
+{
+    const unsigned fr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fr >= nframes) return;
+    const unsigned k = sizes ? sizes[fr] : cap;
+    double H = 0.0;
+    for (unsigned i = 0; i < k; ++i) H += terms[static_cast<size_t>(fr) * cap + i];
+    out[fr] = compute ? H : wfg_volume(f + static_cast<size_t>(fr) * m, P.r, m) - H;
+}
+
+__global__ void wfg_check_kernel(const double *f, unsigned n, const WfgParams P, int *bad)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool outside = false, all_equal = true; // assert_minimisation, hv_algorithm.cpp:226-258
+    for (unsigned c = 0; c < P.m; ++c) {
+        const double v = f[static_cast<size_t>(i) * P.m + c];
+        outside = outside || P.r[c] < v;
+        all_equal = all_equal && P.r[c] == v;
+    }
+    if (outside || all_equal) *bad = 1;
+}
+
+__global__ void wfg_copy_sorted_kernel(const double *f, unsigned n, unsigned m, double *frame)
+{ // one thread: the top-level sort (n is a front, not a population)
+    if (blockIdx.x || threadIdx.x) return;
+    for (size_t e = 0; e < static_cast<size_t>(n) * m; ++e) frame[e] = f[e];
+    wfg_sort_desc(frame, n, m, m);
+}
+
 struct Scratch {
     cudaStream_t st;
     std::vector<void *> ptrs;
@@ -588,10 +803,74 @@ struct Scratch {
 
 } // namespace
 
+int hv_wfg_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const double *r, int compute, double *d_out, cudaStream_t st)
+{
+    PGC_REQUIRE(m >= 3 && m <= kWfgMaxM, "hypervolume (WFG): between 3 and %u objectives, %zu requested", kWfgMaxM, m);
+    PGC_REQUIRE(n < 0x7fffffffull, "hypervolume: too many points");
+    if (n == 0) {
+        if (compute) PGC_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), st));
+        return PGC_OK;
+    }
+    Scratch tmp(st);
+    const unsigned un = static_cast<unsigned>(n), um = static_cast<unsigned>(m);
+    WfgParams P{};
+    P.m = um;
+    P.cap = un;
+    for (unsigned c = 0; c < um; ++c) P.r[c] = r[c];
+    int rc, *d_bad = nullptr;
+    if ((rc = tmp.get(&d_bad, 1))) return rc;
+    PGC_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    wfg_check_kernel<<<(un + 255) / 256, 256, 0, st>>>(d_f, un, P, d_bad);
+    int bad = 0;
+    PGC_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PGC_CUDA(cudaStreamSynchronize(st));
+    PGC_REQUIRE(!bad, "Reference point is invalid: another point seems to be outside the reference point boundary, or be equal to it");
+    const unsigned nframes = compute ? 1u : un;
+    double *frames = nullptr, *terms = nullptr;
+    unsigned *sizes = nullptr;
+    const size_t frame_doubles = n * m;
+    PGC_REQUIRE(static_cast<double>(nframes) * static_cast<double>(frame_doubles) * 8. < 16e9,
+                "hypervolume (WFG): %zu points in %zu objectives need more than 16 GB of frames", n, m);
+    if ((rc = tmp.get(&frames, nframes * frame_doubles)) || (rc = tmp.get(&terms, static_cast<size_t>(nframes) * n))) return rc;
+    if (compute) {
+        wfg_copy_sorted_kernel<<<1, 1, 0, st>>>(d_f, un, um, frames);
+    } else {
+        if ((rc = tmp.get(&sizes, n))) return rc;
+        wfg_contribution_frames_kernel<<<(un + 63) / 64, 64, 0, st>>>(d_f, un, um, frames, sizes);
+    }
+    PGC_CUDA(cudaGetLastError());
+    // one thread per (frame, i) term, in batches bounded by the per-thread recursion frames (~2 GiB per launch)
+    const size_t per_thread = (m - 2) * n * m; // doubles
+    const unsigned long long total = static_cast<unsigned long long>(nframes) * n;
+    unsigned long long batch = (size_t(2) << 30) / (per_thread * sizeof(double));
+    if (batch < 256) batch = 256;
+    if (batch > total) batch = total;
+    double *arena = nullptr;
+    if ((rc = tmp.get(&arena, static_cast<size_t>(batch) * per_thread))) return rc;
+    P.frames = frames;
+    P.sizes = sizes;
+    P.nframes = nframes;
+    P.arena = arena;
+    P.terms = terms;
+    unsigned launches = 3;
+    for (unsigned long long first = 0; first < total; first += batch) {
+        P.first = first;
+        P.count = std::min(batch, total - first);
+        wfg_terms_kernel<<<static_cast<unsigned>((P.count + 63) / 64), 64, 0, st>>>(P);
+        PGC_CUDA(cudaGetLastError());
+        ++launches;
+    }
+    wfg_sum_kernel<<<(nframes + 63) / 64, 64, 0, st>>>(terms, sizes, un, nframes, d_f, um, P, compute, d_out);
+    PGC_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(launches, std::memory_order_relaxed);
+    return PGC_OK;
+}
+
 // mode 0: d_out[n] = exclusive contributions; mode 1: d_out[0] = hypervolume (d_out needs n doubles of space)
 int hv_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const double *r, int compute, double *d_out, cudaStream_t st)
 {
-    PGC_REQUIRE(m == 2 || m == 3, "hypervolume: the device path implements hv2d and hv3d (2 or 3 objectives), %zu requested", m);
+    PGC_REQUIRE(m >= 2, "hypervolume: at least 2 objectives are needed, %zu requested", m);
+    if (m >= 4) return hv_wfg_device(ctx, d_f, n, m, r, compute, d_out, st); // hypervolume::get_best_compute, hypervolume.cpp:208-220
     PGC_REQUIRE(n < 0x7fffffffull, "hypervolume: too many points");
     if (n == 0) {
         if (compute) PGC_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), st));

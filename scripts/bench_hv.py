@@ -17,8 +17,9 @@ lib = capi.lib()
 stream = torch.cuda.ExternalStream(ctx.stream)
 out = {}
 rng = np.random.default_rng(1)
-for m in (2, 3):
-    for n in (1024, 8192, 65536):
+only_wfg = "--wfg" in sys.argv
+for m in (4, 5) if only_wfg else (2, 3, 4, 5):
+    for n in ((128, 512, 1024) if m >= 4 else (1024, 8192, 65536)):  # m >= 4: the device WFG against hvwfg
         f = rng.uniform(0, 1, (n, m))
         f = f / np.linalg.norm(f, axis=1, keepdims=True)
         r = np.full(m, 1.25)
@@ -48,4 +49,4 @@ for m in (2, 3):
         out[f"m{m}_n{n}"] = res
 print(json.dumps(out, indent=1))
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
-(ROOT / "gpurun_out" / "bench_hv.json").write_text(json.dumps(out, indent=1))
+(ROOT / "gpurun_out" / ("bench_hv_wfg.json" if only_wfg else "bench_hv.json")).write_text(json.dumps(out, indent=1))

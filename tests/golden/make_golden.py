@@ -49,6 +49,51 @@ def wfg_fixture(R):
     np.savez_compressed(OUT / "wfg_ref.npz", **data)
 
 
+def hv_wfg_fixture(R):
+    """four and more objectives (hvwfg): (a) the reference's own WFG fixtures (tests/hypervolume_test_data/testcases_list.txt:28,33 and
+    the 7-objective file next to them) with the answers they carry; (b) hypervolume and contributions of seeded random sets computed by
+    the compiled reference (hvwfg::compute / hvwfg::contributions)."""
+    base = Path("/root/reference/tests/hypervolume_test_data/testcases")
+    data = {}
+
+    def parse(name, kind, limit):
+        tok = (base / name).read_text().split()
+        pos = 1
+        for case in range(min(int(tok[0]), limit)):
+            d, n = int(tok[pos]), int(tok[pos + 1])
+            pos += 2
+            data[f"{kind}_{name}_{case}_r"] = np.array(tok[pos:pos + d], dtype=np.float64)
+            pos += d
+            data[f"{kind}_{name}_{case}_p"] = np.array(tok[pos:pos + d * n], dtype=np.float64).reshape(n, d)
+            pos += d * n
+            na = {"compute": 1, "exclusive": 2}[kind]
+            data[f"{kind}_{name}_{case}_a"] = np.array(tok[pos:pos + na], dtype=np.float64)
+            pos += na
+
+    parse("c_max_t1_d5_n1024", "compute", 1)
+    parse("c_max_t1_d7_n64", "compute", 1)  # not in testcases_list.txt; the answer it carries is good to ~2e-4 only
+    for name in ("c_max_t1_d5_n1024", "c_max_t1_d7_n64"):  # what the compiled hvwfg returns for them
+        data[f"compute_{name}_0_hv"] = np.array([R.hv_compute(data[f"compute_{name}_0_p"], data[f"compute_{name}_0_r"])])
+    parse("e_max_d5", "exclusive", 10**6)
+    rng = np.random.default_rng(20172)
+    for m in (4, 5, 6):
+        for n, kind in ((1, "random"), (2, "random"), (3, "random"), (37, "random"), (150, "random"), (100, "front"), (80, "dups")):
+            f = rng.uniform(0, 1, (n, m))
+            if kind == "front":
+                f = f / np.linalg.norm(f, axis=1, keepdims=True)
+            if kind == "dups":
+                f[1] = f[0]
+                f[2] = f[0] + 0.1
+                f[5:20, m - 1] = f[4, m - 1]
+                f[20:30, 0] = f[19, 0]
+            r = np.full(m, 1.3)
+            key = f"ref_m{m}_n{n}_{kind}"
+            data[key + "_p"], data[key + "_r"] = f, r
+            data[key + "_hv"] = np.array([R.hv_compute(f, r)])
+            data[key + "_c"] = R.hv_contributions(f, r)
+    np.savez_compressed(OUT / "hv_wfg_ref.npz", **data)
+
+
 def hv_fixture(R):
     """(a) the reference's own hypervolume fixtures (tests/hypervolume_test_data, format: tests/hypervolume.cpp:132-163): the first fronts
     of the 2D / 3D `compute` files, and the complete `exclusive` and `least_contributor` files for 2 and 3 objectives, with the answers
@@ -104,6 +149,8 @@ def main():
     R = reference()
     if "--hv-only" in sys.argv:
         return hv_fixture(R)
+    if "--hv-wfg-only" in sys.argv:
+        return hv_wfg_fixture(R)
     if "--wfg-only" in sys.argv:  # add one fixture without rewriting the others
         return wfg_fixture(R)
     cec2013_fixture(R)
@@ -111,6 +158,7 @@ def main():
         return
     wfg_fixture(R)
     hv_fixture(R)
+    hv_wfg_fixture(R)
     rng = np.random.default_rng(20141)
     # ---- CEC2014: every function at D in {10, 30, 100}, 6 points in the box + the shift itself + origin
     data = {}
