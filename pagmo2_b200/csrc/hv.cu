@@ -580,9 +580,10 @@ constexpr unsigned kWfgMaxM = 12;
 struct WfgParams {
     const double *frames;  // [nframes x cap x m]: each frame sorted by objective m-1, larger first
     const unsigned *sizes; // [nframes]; nullptr: every frame holds `cap` rows
-    unsigned nframes, cap, m;
+    unsigned nframes, cap, m; // m = row stride (objectives of the problem)
+    unsigned d;               // objectives the frames live in (m for contributions, m - 1 for the second level of compute)
     double r[kWfgMaxM];
-    double *arena;         // per thread of a launch: (m - 2) x cap x m doubles
+    double *arena;         // per thread of a launch: (d - 2) x cap x m doubles
     double *terms;         // [nframes x cap]
     unsigned long long first, count; // this launch covers the (frame, i) pairs first .. first + count - 1, numbered frame * cap + i
 };
@@ -728,39 +729,79 @@ __global__ void wfg_terms_kernel(const WfgParams P)
     const unsigned fr = static_cast<unsigned>(e / P.cap), i = static_cast<unsigned>(e % P.cap);
     const unsigned k = P.sizes ? P.sizes[fr] : P.cap;
     if (i >= k) return;
-    const unsigned m = P.m;
+    const unsigned m = P.m, d = P.d;
     const double *F = P.frames + static_cast<size_t>(fr) * P.cap * m;
     const double *p = F + static_cast<size_t>(i) * m;
-    double *arena = P.arena + t * (static_cast<size_t>(m - 2u) * P.cap * m);
-    const double a = p[m - 1u] - P.r[m - 1u], incl = wfg_volume(p, P.r, m - 1u);
-    const unsigned no = wfg_limitset(F, k, m, m - 1u, i + 1u, 0xffffffffu, p, arena);
+    const double a = p[d - 1u] - P.r[d - 1u], incl = wfg_volume(p, P.r, d - 1u);
     double sub = 0.0;
-    if (no == 1u) sub = wfg_volume(arena, P.r, m - 1u);
-    else if (no > 1u) sub = wfg_hv(arena, P.cap, m, P.r, no, m - 1u);
+    if (d == 2u) { // the limit set is a set of numbers
+        if (i + 1u < k) {
+            double mn = INFINITY;
+            for (unsigned j = i + 1u; j < k; ++j) mn = fmin(mn, fmax(p[0], F[static_cast<size_t>(j) * m]));
+            sub = P.r[0] - mn;
+        }
+    } else {
+        double *arena = P.arena + t * (static_cast<size_t>(d - 2u) * P.cap * m);
+        const unsigned no = wfg_limitset(F, k, m, d - 1u, i + 1u, 0xffffffffu, p, arena);
+        if (no == 1u) sub = wfg_volume(arena, P.r, d - 1u);
+        else if (no > 1u) sub = wfg_hv(arena, P.cap, m, P.r, no, d - 1u);
+    }
     P.terms[e] = fabs(a * (incl - sub));
 }
 
-// frame p <- limit set of point p against all the others, in all m objectives, sorted for wfg_terms_kernel (:102-105)
-__global__ void wfg_contribution_frames_kernel(const double *f, unsigned n, unsigned m, double *frames, unsigned *sizes)
+// frame p <- the limit set of point p, sorted for wfg_terms_kernel.  all_others != 0: against every other point, in all m objectives
+// (hvwfg::contributions, :102-105); else against the points after p in the sorted top frame, last objective dropped (compute_hv's
+// loop, :287-291)
+__global__ void wfg_frames_kernel(const double *f, unsigned n, unsigned m, int all_others, double *frames, unsigned *sizes)
 {
     const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     double *out = frames + static_cast<size_t>(p) * n * m;
-    const unsigned no = wfg_limitset(f, n, m, m, 0u, p, f + static_cast<size_t>(p) * m, out);
-    wfg_sort_desc(out, no, m, m);
+    const unsigned d = all_others ? m : m - 1u;
+    const unsigned no = wfg_limitset(f, n, m, d, all_others ? 0u : p + 1u, all_others ? p : 0xffffffffu, f + static_cast<size_t>(p) * m, out);
+    wfg_sort_desc(out, no, m, d);
     sizes[p] = no;
 }
 
-// sums in index order, as compute_hv accumulates them; mode 1: out[0] = hv of frame 0; mode 0: out[p] = vol(p) - hv(frame p)
+// per frame, in index order as compute_hv accumulates: H = sum of the frame's terms;
+// contributions: out[p] = vol_m(p) - H; compute: out[p] = |p[m-1] - r[m-1]| * (vol_{m-1}(p) - H), the top-level term of point p
 __global__ void wfg_sum_kernel(const double *terms, const unsigned *sizes, unsigned cap, unsigned nframes, const double *f, unsigned m,
                                const WfgParams P, int compute, double *out)
 {
     const unsigned fr = blockIdx.x * blockDim.x + threadIdx.x;
     if (fr >= nframes) return;
-    const unsigned k = sizes ? sizes[fr] : cap;
+    const unsigned k = sizes[fr];
     double H = 0.0;
     for (unsigned i = 0; i < k; ++i) H += terms[static_cast<size_t>(fr) * cap + i];
-    out[fr] = compute ? H : wfg_volume(f + static_cast<size_t>(fr) * m, P.r, m) - H;
+    const double *p = f + static_cast<size_t>(fr) * m;
+    out[fr] = compute ? fabs((p[m - 1u] - P.r[m - 1u]) * (wfg_volume(p, P.r, m - 1u) - H)) : wfg_volume(p, P.r, m) - H;
+}
+
+__global__ void wfg_total_kernel(const double *top_terms, unsigned n, double *out)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    double H = 0.0;
+    for (unsigned i = 0; i < n; ++i) H += top_terms[i];
+    out[0] = H;
+}
+
+// top frame: rows in decreasing order of the last objective (cmp_points; the order among equal keys does not change the sum's terms
+// beyond rounding).  keys: order-preserving bits of the last objective, flipped
+__global__ void wfg_last_keys_kernel(const double *f, unsigned n, unsigned m, unsigned long long *keys, unsigned *idx)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(f[static_cast<size_t>(i) * m + m - 1u]));
+    b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+    keys[i] = ~b;
+    idx[i] = i;
+}
+
+__global__ void wfg_gather_rows_kernel(const double *f, const unsigned *order, unsigned n, unsigned m, double *frame)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(n) * m) return;
+    frame[e] = f[static_cast<size_t>(order[e / m]) * m + e % m];
 }
 
 __global__ void wfg_check_kernel(const double *f, unsigned n, const WfgParams P, int *bad)
@@ -774,13 +815,6 @@ __global__ void wfg_check_kernel(const double *f, unsigned n, const WfgParams P,
         all_equal = all_equal && P.r[c] == v;
     }
     if (outside || all_equal) *bad = 1;
-}
-
-__global__ void wfg_copy_sorted_kernel(const double *f, unsigned n, unsigned m, double *frame)
-{ // one thread: the top-level sort (n is a front, not a population)
-    if (blockIdx.x || threadIdx.x) return;
-    for (size_t e = 0; e < static_cast<size_t>(n) * m; ++e) frame[e] = f[e];
-    wfg_sort_desc(frame, n, m, m);
 }
 
 struct Scratch {
@@ -825,23 +859,37 @@ int hv_wfg_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const dou
     PGC_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     PGC_CUDA(cudaStreamSynchronize(st));
     PGC_REQUIRE(!bad, "Reference point is invalid: another point seems to be outside the reference point boundary, or be equal to it");
-    const unsigned nframes = compute ? 1u : un;
-    double *frames = nullptr, *terms = nullptr;
+    // both modes: n frames (one per point) and one thread per (frame, term); compute works one level down (m - 1 objectives)
+    double *frames = nullptr, *terms = nullptr, *top = nullptr, *top_terms = nullptr;
     unsigned *sizes = nullptr;
     const size_t frame_doubles = n * m;
-    PGC_REQUIRE(static_cast<double>(nframes) * static_cast<double>(frame_doubles) * 8. < 16e9,
+    PGC_REQUIRE(static_cast<double>(n) * static_cast<double>(frame_doubles) * 8. < 16e9,
                 "hypervolume (WFG): %zu points in %zu objectives need more than 16 GB of frames", n, m);
-    if ((rc = tmp.get(&frames, nframes * frame_doubles)) || (rc = tmp.get(&terms, static_cast<size_t>(nframes) * n))) return rc;
+    if ((rc = tmp.get(&frames, n * frame_doubles)) || (rc = tmp.get(&terms, n * n)) || (rc = tmp.get(&sizes, n))) return rc;
+    const double *src = d_f;
+    unsigned launches = 4;
     if (compute) {
-        wfg_copy_sorted_kernel<<<1, 1, 0, st>>>(d_f, un, um, frames);
-    } else {
-        if ((rc = tmp.get(&sizes, n))) return rc;
-        wfg_contribution_frames_kernel<<<(un + 63) / 64, 64, 0, st>>>(d_f, un, um, frames, sizes);
+        unsigned long long *k0 = nullptr, *k1 = nullptr;
+        unsigned *i0 = nullptr, *order = nullptr;
+        if ((rc = tmp.get(&top, frame_doubles)) || (rc = tmp.get(&top_terms, n)) || (rc = tmp.get(&k0, n)) || (rc = tmp.get(&k1, n))
+            || (rc = tmp.get(&i0, n)) || (rc = tmp.get(&order, n)))
+            return rc;
+        wfg_last_keys_kernel<<<(un + 255) / 256, 256, 0, st>>>(d_f, un, um, k0, i0);
+        size_t bytes = 0;
+        PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0, k1, i0, order, static_cast<int>(n), 0, 64, st));
+        unsigned char *ws = nullptr;
+        if ((rc = tmp.get(&ws, bytes))) return rc;
+        PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, bytes, k0, k1, i0, order, static_cast<int>(n), 0, 64, st));
+        wfg_gather_rows_kernel<<<static_cast<unsigned>((frame_doubles + 255) / 256), 256, 0, st>>>(d_f, order, un, um, top);
+        src = top;
+        launches += 3;
     }
+    wfg_frames_kernel<<<(un + 31) / 32, 32, 0, st>>>(src, un, um, compute ? 0 : 1, frames, sizes);
     PGC_CUDA(cudaGetLastError());
-    // one thread per (frame, i) term, in batches bounded by the per-thread recursion frames (~2 GiB per launch)
-    const size_t per_thread = (m - 2) * n * m; // doubles
-    const unsigned long long total = static_cast<unsigned long long>(nframes) * n;
+    P.d = compute ? um - 1u : um;
+    // in batches bounded by the per-thread recursion frames (~2 GiB per launch)
+    const size_t per_thread = std::max<size_t>(static_cast<size_t>(P.d - 2u) * n * m, 1); // doubles
+    const unsigned long long total = static_cast<unsigned long long>(n) * n;
     unsigned long long batch = (size_t(2) << 30) / (per_thread * sizeof(double));
     if (batch < 256) batch = 256;
     if (batch > total) batch = total;
@@ -849,10 +897,9 @@ int hv_wfg_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const dou
     if ((rc = tmp.get(&arena, static_cast<size_t>(batch) * per_thread))) return rc;
     P.frames = frames;
     P.sizes = sizes;
-    P.nframes = nframes;
+    P.nframes = un;
     P.arena = arena;
     P.terms = terms;
-    unsigned launches = 3;
     for (unsigned long long first = 0; first < total; first += batch) {
         P.first = first;
         P.count = std::min(batch, total - first);
@@ -860,7 +907,8 @@ int hv_wfg_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t m, const dou
         PGC_CUDA(cudaGetLastError());
         ++launches;
     }
-    wfg_sum_kernel<<<(nframes + 63) / 64, 64, 0, st>>>(terms, sizes, un, nframes, d_f, um, P, compute, d_out);
+    wfg_sum_kernel<<<(un + 63) / 64, 64, 0, st>>>(terms, sizes, un, un, src, um, P, compute, compute ? top_terms : d_out);
+    if (compute) wfg_total_kernel<<<1, 1, 0, st>>>(top_terms, un, d_out);
     PGC_CUDA(cudaGetLastError());
     ctx->launches.fetch_add(launches, std::memory_order_relaxed);
     return PGC_OK;
