@@ -276,6 +276,20 @@ PGC_API int pgc_nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f,
 PGC_API int pgc_moead_gen_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, const double *weights,
                                         const uint32_t *neigh, unsigned T, int decomposition, double CR, double F, double eta_m, double realb,
                                         unsigned limit, int preserve_diversity, uint64_t seed, uint32_t first_generation, void *stream);
+/* gaco::evolve (src/algorithms/gaco.cpp:104-445), extended ant colony optimisation, on a device-resident population of an
+ * unconstrained single-objective problem (in place), memory = false; the problem's last nix variables are sampled as integers.
+ * Constructor arguments as gaco.hpp:104-107 (reference defaults: ker 63, q 1.0, oracle 0, acc 0.01, threshold 1, n_gen_mark 7,
+ * impstop 100000, evalstop 100000, focus 0).  The reference keeps m_oracle, m_q and its stopping counters in the algorithm object
+ * between evolve() calls: they travel in pgc_gaco_state (initialized == 0: taken from q / oracle, counters at 1; updated on return).
+ * *gens_done (optional): generations run before a stopping criterion returned. */
+typedef struct pgc_gaco_state {
+    double oracle, q;
+    uint32_t n_evalstop, n_impstop, gen_mark, initialized;
+    uint64_t fevals;
+} pgc_gaco_state;
+PGC_API int pgc_gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, unsigned ker, double q, double oracle,
+                                   double acc, unsigned threshold, unsigned n_gen_mark, unsigned impstop, unsigned evalstop, double focus,
+                                   uint64_t seed, uint32_t first_generation, pgc_gaco_state *state, unsigned *gens_done, void *stream);
 PGC_API int pgc_cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lambda, unsigned gens, double cc, double cs, double c1,
                                     double cmu, double sigma0, double ftol, double xtol, int force_bounds, uint64_t seed,
                                     uint32_t first_generation, unsigned *gens_done, double *sigma_out, void *stream);

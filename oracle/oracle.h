@@ -168,6 +168,21 @@ int oracle_nspso_evolve_mt(const oracle_problem *prob, const double *lb, const d
                            unsigned gens, double omega, double c1, double c2, double chi, double v_coeff, unsigned leader_selection_range,
                            unsigned diversity, uint32_t seed);
 
+/* gaco::evolve (src/algorithms/gaco.cpp:104-445) on an unconstrained single-objective population, memory = false; the last nix
+ * variables are integers.  The algorithm's scalar members that survive between evolve() calls travel in oracle_gaco_state. */
+typedef struct {
+    double oracle, q;
+    unsigned n_evalstop, n_impstop, gen_mark;
+    unsigned long long fevals;
+} oracle_gaco_state;
+void oracle_gaco_state_init(oracle_gaco_state *s, double q, double oracle_par);
+int oracle_gaco_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t n, size_t nx, size_t nix,
+                       unsigned gens, unsigned ker, double acc, unsigned threshold, unsigned n_gen_mark, unsigned impstop, unsigned evalstop,
+                       double focus, uint64_t seed, uint32_t first_generation, oracle_gaco_state *st, unsigned *gens_done);
+int oracle_gaco_evolve_mt(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t n, size_t nx, size_t nix,
+                          unsigned gens, unsigned ker, double q, double oracle_par, double acc, unsigned threshold, unsigned n_gen_mark,
+                          unsigned impstop, unsigned evalstop, double focus, uint32_t seed);
+
 /* moead_gen::evolve (src/algorithms/moead_gen.cpp:128-345) with the weight vectors [NP x m] and their neighbourhoods [NP x T] given;
  * decomposition: 0 weighted, 1 tchebycheff, 2 bi */
 int oracle_moead_gen_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim, size_t m,

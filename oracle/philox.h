@@ -14,7 +14,7 @@
 enum { ORACLE_TAG_SHUFFLE1 = 1, ORACLE_TAG_SHUFFLE2 = 2, ORACLE_TAG_NSGA2_VAR = 3, ORACLE_TAG_DE = 4, ORACLE_TAG_PSO = 5,
        ORACLE_TAG_SGA = 6, ORACLE_TAG_INIT = 7, ORACLE_TAG_CMAES = 8, ORACLE_TAG_MIGRATE = 9, ORACLE_TAG_POPULATION = 10,
        ORACLE_TAG_PSO_TOPOLOGY = 11, ORACLE_TAG_NSPSO = 12, ORACLE_TAG_MOEAD = 13, ORACLE_TAG_MOEAD_ORDER = 14,
-       ORACLE_TAG_MOEAD_INSERT = 15 };
+       ORACLE_TAG_MOEAD_INSERT = 15, ORACLE_TAG_GACO = 16 };
 
 static inline void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {

@@ -513,6 +513,40 @@ class Oracle:
             raise ValueError("oracle_nspso_evolve failed")
         return (x, f, *mem)
 
+    class GacoState(C.Structure):
+        _fields_ = [("oracle", C.c_double), ("q", C.c_double), ("n_evalstop", C.c_uint), ("n_impstop", C.c_uint), ("gen_mark", C.c_uint),
+                    ("fevals", C.c_ulonglong)]
+
+    def gaco_evolve(self, prob, lb, ub, x, f, nix=0, gens=1, ker=63, q=1.0, oracle=0.0, acc=0.01, threshold=1, n_gen_mark=7, impstop=100000,
+                    evalstop=100000, focus=0.0, seed=0, first_generation=1, mt=False, state=None):
+        """restated gaco::evolve (Philox draws, or the mt19937 stream with mt=True): returns (x, f, state, gens_done); `state` = the
+        scalar members that survive between evolve() calls (pass it back in to continue with the same algorithm object)."""
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C").reshape(-1)
+        n, nx = x.shape
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        if mt:
+            self.lib.oracle_gaco_evolve_mt.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_size_t, C.c_size_t,
+                                                       C.c_size_t, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_uint, C.c_uint,
+                                                       C.c_uint, C.c_uint, C.c_double, C.c_uint32]
+            if self.lib.oracle_gaco_evolve_mt(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), n, nx, nix, gens, ker, q, oracle, acc, threshold,
+                                              n_gen_mark, impstop, evalstop, focus, seed):
+                raise ValueError("oracle_gaco_evolve_mt failed")
+            return x, f, None, gens
+        st = state if state is not None else self.GacoState()
+        if state is None:
+            self.lib.oracle_gaco_state_init.argtypes = [C.c_void_p, C.c_double, C.c_double]
+            self.lib.oracle_gaco_state_init.restype = None
+            self.lib.oracle_gaco_state_init(C.byref(st), q, oracle)
+        done = C.c_uint()
+        self.lib.oracle_gaco_evolve.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                C.c_uint, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint64,
+                                                C.c_uint32, C.c_void_p, C.POINTER(C.c_uint)]
+        if self.lib.oracle_gaco_evolve(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), n, nx, nix, gens, ker, acc, threshold, n_gen_mark,
+                                       impstop, evalstop, focus, seed, first_generation, C.byref(st), C.byref(done)):
+            raise ValueError("oracle_gaco_evolve failed")
+        return x, f, st, done.value
+
     DECOMPOSITION = {"weighted": 0, "tchebycheff": 1, "bi": 2}
 
     def moead_gen_evolve(self, prob, lb, ub, x, f, weights, neigh, gens=1, decomposition="tchebycheff", CR=1.0, F=0.5, eta_m=20.0, realb=0.9,

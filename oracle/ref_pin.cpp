@@ -11,6 +11,7 @@
 #include <pagmo/algorithm.hpp>
 #include <pagmo/algorithms/de.hpp>
 #include <pagmo/algorithms/de1220.hpp>
+#include <pagmo/algorithms/gaco.hpp>
 #include <pagmo/algorithms/moead_gen.hpp>
 #include <pagmo/algorithms/nsga2.hpp>
 #include <pagmo/algorithms/nspso.hpp>
@@ -167,6 +168,11 @@ int ref_evolve_from(ref_problem *p, const char *algo, const double *par, size_t 
             need(6);
             alg = pagmo::algorithm{pagmo::nspso(gens, par[0], par[1], par[2], par[3], par[4], static_cast<unsigned>(par[5]),
                                                 std::string(strategies ? strategies : "crowding distance"), false, seed)};
+        } else if (a == "gaco") { // ker, q, oracle, acc, threshold, n_gen_mark, impstop, evalstop, focus (gaco.hpp:104-107)
+            need(9);
+            alg = pagmo::algorithm{pagmo::gaco(gens, static_cast<unsigned>(par[0]), par[1], par[2], par[3], static_cast<unsigned>(par[4]),
+                                               static_cast<unsigned>(par[5]), static_cast<unsigned>(par[6]), static_cast<unsigned>(par[7]), par[8],
+                                               false, seed)};
         } else
             throw std::invalid_argument("ref_evolve_from: unknown algorithm '" + a + "'");
         pop = alg.evolve(pop);

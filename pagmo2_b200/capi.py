@@ -59,6 +59,12 @@ class AlgoDesc(C.Structure):
     ]
 
 
+class GacoState(C.Structure):
+    """pgc_gaco_state: the scalar members pagmo::gaco keeps between evolve() calls."""
+    _fields_ = [("oracle", C.c_double), ("q", C.c_double), ("n_evalstop", C.c_uint32), ("n_impstop", C.c_uint32), ("gen_mark", C.c_uint32),
+                ("initialized", C.c_uint32), ("fevals", C.c_uint64)]
+
+
 class AlgoMemory(C.Structure):
     """pgc_algo_memory: the device arrays a UDA with memory = true keeps between evolve() calls."""
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("u", C.c_void_p), ("initialized", C.c_int32), ("reserved_", C.c_int32)]
@@ -592,6 +598,27 @@ class Problem:
             for d in (dx, df, *dmem):
                 if d is not None:
                     self.ctx.free(d)
+
+    def gaco_evolve(self, x, f, gens=1, ker=63, q=1.0, oracle=0.0, acc=0.01, threshold=1, n_gen_mark=7, impstop=100000, evalstop=100000,
+                    focus=0.0, seed=0, first_generation=1, state=None):
+        """gaco::evolve on the device: returns (x, f, state, gens_done); `state` (GacoState) = the algorithm's scalar members, pass it
+        back in to continue with the same algorithm object."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(x.shape[0], -1)
+        st = state if state is not None else GacoState()
+        dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
+        done = C.c_uint()
+        L = lib()
+        L.pgc_gaco_evolve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double,
+                                             C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint64, C.c_uint32, C.c_void_p,
+                                             C.POINTER(C.c_uint), C.c_void_p]
+        try:
+            check(L.pgc_gaco_evolve_device(self._h, dx, df, x.shape[0], gens, ker, q, oracle, acc, threshold, n_gen_mark, impstop, evalstop, focus,
+                                           seed, first_generation, C.byref(st), C.byref(done), None))
+            return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), st, done.value
+        finally:
+            self.ctx.free(dx)
+            self.ctx.free(df)
 
     def moead_gen_evolve(self, x, f, weights, neigh, gens=1, decomposition="tchebycheff", CR=1.0, F=0.5, eta_m=20.0, realb=0.9, limit=2,
                          preserve_diversity=True, seed=0, first_generation=1):

@@ -397,6 +397,25 @@ int main(int argc, char **argv)
             }
             CHECK(refused);
         }
+        { // cuda_gaco: the population comes back consistent, fevals as the reference counts them, the oracle parameter is a member
+            pagmo::algorithm g{cuda_gaco{15u, 13u, 1.0, 1e9, 0.01, 1u, 7u, 100000u, 100000u, 0., false, 5u}};
+            pagmo::population q{prob, 40u, 9u};
+            const double b = q.champion_f()[0];
+            const auto fe = q.get_problem().get_fevals();
+            q = g.evolve(q);
+            CHECK(q.get_problem().get_fevals() - fe == 15u * 40u);
+            CHECK(q.champion_f()[0] <= b);
+            for (std::size_t i = 0; i < q.size(); ++i) CHECK(max_rel(prob.fitness(q.get_x()[i]), q.get_f()[i]) <= tol);
+            CHECK(g.extract<cuda_gaco>()->get_oracle() < 1e9);
+            std::printf("%s: %.4g -> %.4g (oracle %.4g)\n", g.get_name().c_str(), b, q.champion_f()[0], g.extract<cuda_gaco>()->get_oracle());
+            bool threw = false;
+            try {
+                cuda_gaco{5u, 1u};
+            } catch (const std::invalid_argument &) {
+                threw = true; // gaco.cpp:90-93
+            }
+            CHECK(threw);
+        }
         pagmo::problem zp{pagmo::zdt{1u, 30u}};
         pagmo::population mo{zp, 40u, 5u};
         mo = pagmo::algorithm{cuda_nsga2{10u, 0.95, 10., 0.01, 50., 32u}}.evolve(mo);

@@ -224,6 +224,32 @@ def test_nspso_evolve_bit_exact(orc, ref, fam, args, n):
             assert np.array_equal(xr, xo) and np.array_equal(fr, fo), (diversity, lsr, gens)
 
 
+@pytest.mark.parametrize("fam,dim", [("rastrigin", 8), ("rosenbrock", 5), ("ackley", 6), ("griewank", 4)])
+def test_gaco_evolve_bit_exact(orc, ref, fam, dim):
+    """gaco::evolve (gaco.cpp:104-445) restated on the mt19937 stream: penalties against the oracle parameter, the archive update with
+    its accuracy filter, the kernel weights and their threshold switch, sigma from the archive's spread and the generation mark,
+    the ants (kernel choice, normal deviates with the ten redraws and the clamp), the evaluation / improvement counters and the oracle
+    update must reproduce the compiled reference bit for bit."""
+    rp = ref.problem(fam, dim)
+    lb, ub = rp.bounds()
+    op = orc.problem(fam, dim=dim)
+    rng = np.random.default_rng(dim)
+    # ker, q, oracle, acc, threshold, n_gen_mark, impstop, evalstop, focus
+    cases = [(20, (13, 1.0, 0.0, 0.01, 1, 7, 100000, 100000, 0.0), 12), (30, (30, 1.0, 1e9, 0.0, 5, 3, 100000, 100000, 0.0), 15),
+             (16, (5, 0.5, 0.0, 0.5, 3, 7, 100000, 100000, 4.0), 10), (25, (8, 1.0, 50.0, 0.01, 2, 2, 3, 100000, 0.0), 20),
+             (25, (8, 1.0, 0.0, 0.01, 1, 7, 100000, 4, 0.0), 30), (12, (2, 2.0, -5.0, 0.01, 4, 1, 100000, 100000, 100.0), 9)]
+    for n, par, gens in cases:
+        seed = n + gens
+        x0 = rng.uniform(lb, ub, (n, dim))
+        x0[3] = x0[1]  # duplicates: equal penalties in both sorts
+        f0 = np.array([rp.fitness(x) for x in x0])[:, 0]
+        xr, fr = ref.evolve_from(rp, "gaco", list(par), x0, gens, seed)
+        ker, q, oracle, acc, threshold, n_gen_mark, impstop, evalstop, focus = par
+        xo, fo, _, _ = orc.gaco_evolve(op, lb, ub, x0, f0, gens=gens, ker=ker, q=q, oracle=oracle, acc=acc, threshold=threshold,
+                                       n_gen_mark=n_gen_mark, impstop=impstop, evalstop=evalstop, focus=focus, seed=seed, mt=True)
+        assert np.array_equal(xr, xo) and np.array_equal(fr[:, 0], fo), (n, par, gens)
+
+
 @pytest.mark.parametrize("fam,args,NP,wgen", [("zdt", (1, 8), 24, "grid"), ("zdt", (2, 6), 30, "low discrepancy"), ("zdt", (3, 7), 20, "random"),
                                               ("dtlz", (2, 7, 3, 100), 21, "grid"), ("dtlz", (1, 6, 3, 100), 28, "low discrepancy")])
 def test_moead_gen_evolve_bit_exact(orc, ref, fam, args, NP, wgen):
