@@ -109,11 +109,6 @@ public:
     // typed get_log() of each UDA below returns them in the reference's tuple layout
     void set_verbosity(unsigned level)
     {
-        const int a = m_desc.algo;
-        if (level && a != PGC_ALGO_DE && a != PGC_ALGO_SADE && a != PGC_ALGO_DE1220 && a != PGC_ALGO_PSO_GEN && a != PGC_ALGO_NSGA2
-            && a != PGC_ALGO_NSPSO) {
-            pagmo_throw(std::invalid_argument, get_name() + ": the device loop of this algorithm records no log (verbosity must be 0)");
-        }
         m_verbosity = level;
     }
     unsigned get_verbosity() const
@@ -383,6 +378,14 @@ public:
         m_desc.selection = pick("selection", selection, {"tournament", "truncated"});
         m_desc.cr = cr, m_desc.eta_c = eta_c, m_desc.m = m, m_desc.param_m = param_m, m_desc.param_s = param_s;
     }
+    using log_line_type = std::tuple<unsigned, unsigned long long, double, double>; // Gen, Fevals, Best, Improvement (sga.hpp:151)
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        return typed_log<log_line_type>([](const double *r) {
+            return log_line_type(static_cast<unsigned>(r[0]), static_cast<unsigned long long>(r[1]), r[2], r[3]);
+        });
+    }
 };
 
 // pagmo::cmaes (cmaes.hpp:110).  Sampling, evaluation, recombination and the rank-mu matrix run on the device; the evolution paths and
@@ -413,6 +416,14 @@ public:
         no_memory(memory, "cuda_cmaes");
         m_desc.cma_cc = cc, m_desc.cma_cs = cs, m_desc.cma_c1 = c1, m_desc.cma_cmu = cmu, m_desc.sigma0 = sigma0;
         m_desc.ftol = ftol, m_desc.xtol = xtol, m_desc.force_bounds = force_bounds ? 1u : 0u;
+    }
+    using log_line_type = std::tuple<unsigned, unsigned long long, double, double, double, double>; // Gen, Fevals, Best, dx, df, sigma
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        return typed_log<log_line_type>([](const double *r) {
+            return log_line_type(static_cast<unsigned>(r[0]), static_cast<unsigned long long>(r[1]), r[2], r[3], r[4], r[5]);
+        });
     }
 };
 

@@ -365,11 +365,12 @@ PGC_API int pgc_algo_evolve_memory_device(pgc_problem *prob, const pgc_algo_desc
  *   sade    gen, fevals, best, F, CR, dx, df                 (sade.cpp:556-580)
  *   de1220  gen, fevals, best, F, CR, variant, dx, df        (de1220.cpp:570-595)
  *   pso_gen gen, fevals, gbest, mean velocity, mean lbest, average distance   (pso_gen.cpp:464-518)
+ *   sga     gen, fevals, best, improvement                   (sga.cpp:252-274; verbosity 1 logs only the generations that improve)
+ *   cmaes   gen, fevals, best, dx, df, sigma                 (cmaes.cpp:276-296)
  *   nsga2   gen, fevals, ideal point [nobj]                  (nsga2.cpp:144-173; logged BEFORE the generation, as the reference does)
  *   nspso   gen, fevals, ideal point of the archive [nobj]   (nspso.cpp:163-192; fevals counted from this call's start)
  * log_rows: HOST array [max_rows x row_len]; *n_rows = lines written (the DE family stops logging at the generation whose exit test
- * fires).  memory: NULL, or the state of an algorithm built with memory = true (pgc_algo_evolve_memory_device).  sga, cmaes: the
- * device loops record no log (PGC_ERR_UNSUPPORTED for verbosity > 0). */
+ * fires).  memory: NULL, or the state of an algorithm built with memory = true (pgc_algo_evolve_memory_device). */
 PGC_API int pgc_algo_log_row_len(const pgc_problem *prob, int algo, size_t *row_len);
 PGC_API int pgc_algo_evolve_logged_device(pgc_problem *prob, const pgc_algo_desc *algo, double *d_x, double *d_f, size_t n,
                                           uint32_t first_generation, unsigned *gens_done, pgc_algo_memory *memory, unsigned verbosity,

@@ -4,6 +4,8 @@
 //   sade    (gen, fevals, best, F, CR, dx, df)                  sade.cpp:556-580
 //   de1220  (gen, fevals, best, F, CR, variant, dx, df)         de1220.cpp:570-595
 //   pso_gen (gen, fevals, gbest, mean velocity, mean lbest, average distance)   pso_gen.cpp:464-518
+//   sga     (gen, fevals, best, improvement)                    sga.cpp:252-274 (verbosity 1: only the generations that improve)
+//   cmaes   (gen, fevals, best, dx, df, sigma)                  cmaes.cpp:276-296 (appended on the host: cmaes.cu runs its loop there)
 //   nsga2   (gen, fevals, ideal point)                          nsga2.cpp:144-173 (before the generation's variation)
 //   nspso   (gen, fevals, ideal point of the archive)           nspso.cpp:163-192
 // Rows are doubles, `row_len` per line, appended in the stream's order at *d_count.  The generation loops call the hooks through
@@ -123,7 +125,52 @@ __global__ void log_pso_kernel(const double *lbfit, const double *row_sum, const
     }
 }
 
+// sga.cpp:252-274: best of the children (plain <, from DBL_MAX), best of the parents (population::best_idx), their difference
+__global__ void log_sga_kernel(const double *fp, const double *fc, unsigned n, unsigned verbosity, unsigned gen, double fevals, double *rows,
+                               unsigned *count, unsigned max_rows, unsigned row_len)
+{
+    __shared__ double sp[256], sc[256];
+    double bp = NAN, bc = 1.7976931348623157e308;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const double p = fp[i], c = fc[i];
+        if (!(p != p) && ((bp != bp) || p < bp)) bp = p; // less_than_f
+        if (c < bc) bc = c;
+    }
+    sp[threadIdx.x] = bp, sc[threadIdx.x] = bc;
+    __syncthreads();
+    for (unsigned w = blockDim.x / 2; w; w >>= 1) {
+        if (threadIdx.x < w) {
+            const double p = sp[threadIdx.x + w];
+            if (!(p != p) && ((sp[threadIdx.x] != sp[threadIdx.x]) || p < sp[threadIdx.x])) sp[threadIdx.x] = p;
+            if (sc[threadIdx.x + w] < sc[threadIdx.x]) sc[threadIdx.x] = sc[threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double improvement = sp[0] - sc[0];
+        const bool due = ((gen % verbosity == 1u) && (verbosity > 1u)) || ((improvement > 0) && (verbosity == 1u));
+        const unsigned row = *count;
+        if (due && row < max_rows) {
+            double *out = rows + static_cast<size_t>(row) * row_len;
+            out[0] = gen, out[1] = fevals, out[2] = sp[0], out[3] = improvement;
+            *count = row + 1u;
+        }
+    }
+}
+
 } // namespace
+
+int log_sga_device(pgc_ctx *ctx, const double *d_f_parents, const double *d_f_children, unsigned n, unsigned gen, unsigned long long fevals,
+                   cudaStream_t st)
+{
+    LogSink *L = tls_log;
+    if (!L || !L->verbosity) return PGC_OK;
+    log_sga_kernel<<<1, 256, 0, st>>>(d_f_parents, d_f_children, n, L->verbosity, gen, static_cast<double>(fevals), L->d_rows, L->d_count,
+                                      L->max_rows, L->row_len);
+    PGC_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return PGC_OK;
+}
 
 int log_ideal_device(pgc_ctx *ctx, const double *d_f, unsigned n, unsigned m, unsigned gen, unsigned long long fevals, cudaStream_t st)
 {

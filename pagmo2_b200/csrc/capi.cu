@@ -1061,6 +1061,8 @@ int pgc_algo_log_row_len(const pgc_problem *prob, int algo, size_t *row_len)
         case PGC_ALGO_SADE: *row_len = 7; return PGC_OK;
         case PGC_ALGO_DE1220: *row_len = 8; return PGC_OK;
         case PGC_ALGO_PSO_GEN: *row_len = 6; return PGC_OK;
+        case PGC_ALGO_SGA: *row_len = 4; return PGC_OK;
+        case PGC_ALGO_CMAES: *row_len = 6; return PGC_OK;
         case PGC_ALGO_NSGA2:
         case PGC_ALGO_NSPSO: *row_len = 2 + prob->nobj; return PGC_OK;
         default:
@@ -1108,6 +1110,10 @@ int pgc_algo_evolve_logged_device(pgc_problem *prob, const pgc_algo_desc *a, dou
     PGC_CUDA(cudaMemcpyAsync(&written, d_count.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     PGC_CUDA(cudaStreamSynchronize(st));
     if (written) PGC_CUDA(cudaMemcpy(log_rows, d_rows.p, sizeof(double) * written * row_len, cudaMemcpyDeviceToHost));
+    if (!written && !sink.host_rows.empty()) { // a loop that runs on the host (cmaes) kept its lines there
+        written = static_cast<unsigned>(std::min(sink.host_rows.size() / row_len, rows));
+        std::copy(sink.host_rows.begin(), sink.host_rows.begin() + static_cast<std::ptrdiff_t>(written * row_len), log_rows);
+    }
     *n_rows = written;
     return PGC_OK;
 }

@@ -577,6 +577,11 @@ int cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam,
         if (std::sqrt(nrm) < xtol) break;
         best_worst(ib, iw);
         if (std::fabs(f[ib] - f[iw]) < ftol) break;
+        if (log_due(g + 1u)) { // 1bis - the log line, :276-296: (gen, fevals, best, dx, df, sigma)
+            const double line[6] = {static_cast<double>(g + 1u), static_cast<double>(g) * static_cast<double>(lam), f[ib], std::sqrt(nrm),
+                                    std::fabs(f[ib] - f[iw]), sigma};
+            tls_log->host_rows.insert(tls_log->host_rows.end(), line, line + 6);
+        }
         // 2 - bounds, :301-315
         if (force_bounds) {
             clamp_rows_kernel<<<static_cast<unsigned>((lam * D + 255) / 256), 256, 0, st>>>(d_xn, lam * D, static_cast<unsigned>(D), d_b, d_b + D);

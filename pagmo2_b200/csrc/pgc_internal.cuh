@@ -315,6 +315,7 @@ struct LogSink {
     double *d_rows = nullptr;   // [max_rows x row_len]
     unsigned *d_count = nullptr; // rows written so far (advanced on the device, in stream order)
     unsigned verbosity = 0, max_rows = 0, row_len = 0;
+    std::vector<double> host_rows; // loops that run on the host (cmaes) append their lines here instead
 };
 extern thread_local LogSink *tls_log;
 // generation `gen` (1-based within this evolve() call) is one the reference logs (de.cpp:327)
@@ -324,6 +325,8 @@ inline bool log_due(unsigned gen)
     return L && L->verbosity && (gen % L->verbosity == 1u || L->verbosity == 1u);
 }
 int log_ideal_device(pgc_ctx *ctx, const double *d_f, unsigned n, unsigned m, unsigned gen, unsigned long long fevals, cudaStream_t st);
+int log_sga_device(pgc_ctx *ctx, const double *d_f_parents, const double *d_f_children, unsigned n, unsigned gen, unsigned long long fevals,
+                   cudaStream_t st);
 int log_pso_device(pgc_ctx *ctx, const double *d_X, const double *d_V, const double *d_lbfit, const double *d_lb, const double *d_ub, unsigned n,
                    unsigned dim, unsigned gen, unsigned long long fevals, cudaStream_t st);
 int nspso_init_memory_device(pgc_problem *prob, const double *d_x, const double *d_f, unsigned NP, double v_coeff, unsigned long long seed,

@@ -298,6 +298,7 @@ int sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, 
         ctx->launches.fetch_add(2, std::memory_order_relaxed);
         // children's fitness into the first half of the pool, parents' into the second (:275-281)
         if ((rc = eval(prob, xnew, NP, fboth, st))) break;
+        if ((rc = log_sga_device(ctx, d_f, fboth, NP, g + 1u, static_cast<unsigned long long>(g + 1u) * NP, st))) break; // sga.cpp:252-274
         if (cudaMemcpyAsync(fboth + NP, d_f, sizeof(double) * NP, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
             rc = PGC_ERR_CUDA;
             break;

@@ -388,14 +388,19 @@ int main(int argc, char **argv)
             qm = m.evolve(qm);
             const auto mlog = m.extract<cuda_nsga2>()->get_log();
             CHECK(mlog.size() == 3u && std::get<1>(mlog[0]) == 0u && std::get<2>(mlog[0]) == ideal0 && std::get<1>(mlog[2]) == 4u * 40u);
-            bool refused = false;
-            try {
-                pagmo::algorithm g{cuda_sga{2u}};
-                g.set_verbosity(1u);
-            } catch (const std::invalid_argument &) {
-                refused = true;
-            }
-            CHECK(refused);
+            pagmo::algorithm g{cuda_sga{9u, .9, 1., 0.02, 1., 2u, "sbx", "gaussian", "truncated", 3u}};
+            g.set_verbosity(4u);
+            pagmo::population qg{prob, 32u, 9u};
+            const double parents_best = qg.champion_f()[0];
+            qg = g.evolve(qg);
+            const auto glog = g.extract<cuda_sga>()->get_log(); // generations 1, 5, 9
+            CHECK(glog.size() == 3u && std::get<0>(glog[1]) == 5u && std::get<2>(glog[0]) == parents_best);
+            pagmo::algorithm c{cuda_cmaes{6u, -1, -1, -1, -1, 0.5, 0., 0., false, false, 3u}};
+            c.set_verbosity(5u);
+            pagmo::population qc{prob, 16u, 9u};
+            qc = c.evolve(qc);
+            const auto clog = c.extract<cuda_cmaes>()->get_log(); // generations 1, 6
+            CHECK(clog.size() == 2u && std::get<5>(clog[0]) == 0.5 && std::get<1>(clog[1]) == 5u * 16u);
         }
         { // cuda_gaco: the population comes back consistent, fevals as the reference counts them, the oracle parameter is a member
             pagmo::algorithm g{cuda_gaco{15u, 13u, 1.0, 1e9, 0.01, 1u, 7u, 100000u, 100000u, 0., false, 5u}};

@@ -120,12 +120,65 @@ def test_mo_log_is_the_ideal_point_before_the_generation(capi, ctx, name):
     prob.close()
 
 
+@pytest.mark.parametrize("verbosity", (1, 3))
+def test_sga_log(capi, ctx, verbosity):
+    """sga.cpp:252-274: (gen, fevals, best of the parents, improvement = that minus the best child); verbosity 1 logs only the
+    generations whose children improve on the parents, larger values every `verbosity` generations whatever the improvement."""
+    prob = capi.Problem(ctx, "rastrigin", dim=6)
+    lb, ub = prob.bounds()
+    n, gens = 30, 12
+    x = np.random.default_rng(6).uniform(lb, ub, (n, prob.nx))
+    f = prob.eval_host(x)
+    kw = dict(seed=21, crossover=capi.SGA_CROSSOVER["sbx"], mutation=capi.SGA_MUTATION["gaussian"])
+    algo = capi.algo_desc("sga", gens=gens, **kw)
+    xl, fl, _, log = prob.evolve_logged(algo, x, f, verbosity)
+    x0, f0, _ = prob.evolve(algo, x, f)
+    assert np.array_equal(xl, x0) and np.array_equal(fl, f0) and log.shape[1] == 4
+    best = [f.min()] + [prob.evolve(capi.algo_desc("sga", gens=g, **kw), x, f)[1].min() for g in range(1, gens + 1)]
+    rows = {int(r[0]): r for r in log}
+    for g in range(1, gens + 1):
+        improved = best[g] < best[g - 1]
+        if verbosity == 1:
+            assert (g in rows) == improved, g
+        else:
+            assert (g in rows) == (g % verbosity == 1), g
+        if g in rows:
+            r = rows[g]
+            assert r[1] == g * n and r[2] == best[g - 1]
+            assert (r[3] > 0) == improved and (not improved or np.isclose(r[2] - r[3], best[g], rtol=1e-12))
+    prob.close()
+
+
+def test_cmaes_log(capi, ctx):
+    """cmaes.cpp:276-296: (gen, fevals, best, dx, df, sigma) logged after the sampling and the exit tests of a generation, i.e. on the
+    population and the step size the previous generations left."""
+    prob = capi.Problem(ctx, "rosenbrock", dim=5)
+    lb, ub = prob.bounds()
+    n, gens, v = 12, 9, 4
+    x = np.random.default_rng(3).uniform(lb, ub, (n, prob.nx))
+    f = prob.eval_host(x)
+    algo = capi.algo_desc("cmaes", gens=gens, seed=31, ftol=0.0, xtol=0.0)
+    xl, fl, _, log = prob.evolve_logged(algo, x, f, v)
+    x0, f0, _ = prob.evolve(algo, x, f)
+    assert np.array_equal(xl, x0) and np.array_equal(fl, f0)
+    assert log[:, 0].tolist() == _due(gens, v) and log[:, 1].tolist() == [(g - 1) * n for g in _due(gens, v)] and log.shape[1] == 6
+    for row in log:
+        g = int(row[0]) - 1
+        if g == 0:
+            fg, sigma = f[:, 0], 0.5
+        else:
+            _, fg, _, sigma = prob.cmaes_evolve(x, f[:, 0], gens=g, seed=31, ftol=0.0, xtol=0.0)
+        assert row[2] == fg.min() and np.isclose(row[4], fg.max() - fg.min(), rtol=1e-13) and row[5] == sigma and row[3] > 0
+    prob.close()
+
+
 def test_log_argument_checks(capi, ctx):
     prob = capi.Problem(ctx, "rastrigin", dim=4)
     x = np.random.default_rng(1).uniform(-5, 5, (16, 4))
     f = prob.eval_host(x)
-    with pytest.raises(capi.PgcError):  # sga's device loop records no log
-        prob.evolve_logged(capi.algo_desc("sga", gens=2, seed=1), x, f, 1)
+    with pytest.raises(capi.PgcError):  # verbosity > 0 needs somewhere to put the lines
+        capi.check(capi.lib().pgc_algo_evolve_logged_device(prob._h, capi.C.byref(capi.algo_desc("de", gens=2, seed=1)), None, None, 0, 1, None, None,
+                                                            1, None, 0, None, None))
     # verbosity 0: a plain evolve, no lines
     xl, fl, _, log = prob.evolve_logged(capi.algo_desc("de", gens=3, seed=1), x, f, 0)
     assert log.shape[0] == 0 and np.array_equal(xl, prob.evolve(capi.algo_desc("de", gens=3, seed=1), x, f)[0])
