@@ -10,6 +10,7 @@
 //   pagmo_cuda::cuda_sga     pagmo::sga     (sga.hpp:166     gen, cr, eta_c, m, param_m, param_s, crossover, mutation, selection, seed)
 //   pagmo_cuda::cuda_cmaes   pagmo::cmaes   (cmaes.hpp:110   gen, cc, cs, c1, cmu, sigma0, ftol, xtol, memory, force_bounds, seed)
 //   pagmo_cuda::cuda_gaco    pagmo::gaco    (gaco.hpp:104    gen, ker, q, oracle, acc, threshold, n_gen_mark, impstop, evalstop, focus, memory, seed)
+//   pagmo_cuda::cuda_maco    pagmo::maco    (maco.hpp:107    gen, ker, q, threshold, n_gen_mark, evalstop, focus, memory, seed)
 //
 // Same constructor arguments as the reference UDAs (plus the device), so `algorithm{cuda_sade{50u}}` drops into an island of a
 // stock pagmo::archipelago: thread_island (thread_island.cpp:79-159) runs it unchanged, and pagmo's own migration machinery
@@ -700,9 +701,98 @@ private:
     std::shared_ptr<detail::twin_cache> m_cache;
 };
 
+// pagmo::maco (maco.hpp:107-109), multi-objective hypervolume-based ant colony optimisation: non-dominated sorting, the hypervolume
+// contributions of the fronts, the ants and their evaluation run on the device; the host walks the fronts to rebuild the archive
+// (pgc_maco_evolve_device, gaco.cu).  memory = true is not built.
+class cuda_maco
+{
+public:
+    cuda_maco(unsigned gen = 1u, unsigned ker = 63u, double q = 1.0, unsigned threshold = 1u, unsigned n_gen_mark = 7u,
+              unsigned evalstop = 100000u, double focus = 0., bool memory = false, unsigned seed = pagmo::random_device::next(), int device = 0)
+        : m_gen(gen), m_ker(ker), m_q(q), m_threshold(threshold), m_n_gen_mark(n_gen_mark), m_evalstop(evalstop), m_focus(focus), m_seed(seed),
+          m_device(device), m_cache(std::make_shared<detail::twin_cache>())
+    { // maco.cpp:64-83
+        if (focus < 0.) {
+            pagmo_throw(std::invalid_argument, "The focus parameter must be >=0  while a value of " + std::to_string(focus) + " was detected");
+        }
+        if (memory) pagmo_throw(std::invalid_argument, "cuda_maco: memory = true is not supported on the device path");
+        if ((threshold < 1 || threshold > gen) && gen != 0) {
+            pagmo_throw(std::invalid_argument, "If memory is inactive, the threshold parameter must be either in [1,m_gen] while a value of "
+                                                   + std::to_string(threshold) + " was detected");
+        }
+    }
+    pagmo::population evolve(pagmo::population pop) const
+    {
+        const auto &prob = pop.get_problem();
+        const auto NP = pop.size();
+        if (!NP) pagmo_throw(std::invalid_argument, get_name() + " cannot work on an empty population"); // maco.cpp:126-152
+        if (prob.is_stochastic()) {
+            pagmo_throw(std::invalid_argument, "The problem appears to be stochastic " + get_name() + " cannot deal with it");
+        }
+        if (m_gen == 0u) return pop;
+        if (m_ker > NP) {
+            pagmo_throw(std::invalid_argument, get_name() + " cannot work with a solution archive bigger than the population size");
+        }
+        if (prob.get_nc() != 0u) {
+            pagmo_throw(std::invalid_argument,
+                        "Non linear constraints detected in " + prob.get_name() + " instance. " + get_name() + " cannot deal with them.");
+        }
+        if (prob.get_nf() < 2u) {
+            pagmo_throw(std::invalid_argument, "This is a multiobjective algorithm, while number of objectives detected in " + prob.get_name()
+                                                   + " is " + std::to_string(prob.get_nf()));
+        }
+        const auto h = m_cache->find(prob, m_device);
+        if (!h) {
+            pagmo_throw(std::invalid_argument, get_name() + " cannot evolve a population of '" + prob.get_name()
+                                                   + "': no CUDA evaluator exists for this UDP type; there is no CPU fallback");
+        }
+        const auto nx = prob.get_nx(), nf = prob.get_nf();
+        pagmo::vector_double x(NP * nx), f(NP * nf);
+        for (decltype(pop.size()) i = 0; i < NP; ++i) {
+            std::copy(pop.get_x()[i].begin(), pop.get_x()[i].end(), x.begin() + static_cast<std::ptrdiff_t>(i * nx));
+            std::copy(pop.get_f()[i].begin(), pop.get_f()[i].end(), f.begin() + static_cast<std::ptrdiff_t>(i * nf));
+        }
+        unsigned done = 0;
+        h->on_device(x, f, "pgc_maco_evolve_device", [&](double *dx, double *df, std::size_t n) {
+            return pgc_maco_evolve_device(h->raw(), dx, df, n, m_gen, m_ker, m_q, m_threshold, m_n_gen_mark, m_evalstop, m_focus, m_seed,
+                                          m_generation, &m_state, &done, nullptr);
+        });
+        m_generation += m_gen;
+        for (decltype(pop.size()) i = 0; i < NP; ++i) {
+            pop.set_xf(i, pagmo::vector_double(x.begin() + static_cast<std::ptrdiff_t>(i * nx), x.begin() + static_cast<std::ptrdiff_t>((i + 1) * nx)),
+                       pagmo::vector_double(f.begin() + static_cast<std::ptrdiff_t>(i * nf), f.begin() + static_cast<std::ptrdiff_t>((i + 1) * nf)));
+        }
+        prob.increment_fevals(static_cast<unsigned long long>(done) * NP);
+        return pop;
+    }
+    void set_seed(unsigned seed) { m_seed = seed; }
+    unsigned get_seed() const { return m_seed; }
+    unsigned get_gen() const { return m_gen; }
+    std::string get_name() const { return "MHACO: Multi-objective Hypervolume-based Ant Colony Optimization [CUDA sm_100a]"; }
+    pagmo::thread_safety get_thread_safety() const { return pagmo::thread_safety::basic; }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_gen, m_ker, m_q, m_threshold, m_n_gen_mark, m_evalstop, m_focus, m_seed, m_device, m_generation, m_state.q,
+                               m_state.n_evalstop, m_state.gen_mark, m_state.initialized);
+    }
+
+private:
+    unsigned m_gen, m_ker;
+    double m_q;
+    unsigned m_threshold, m_n_gen_mark, m_evalstop;
+    double m_focus;
+    unsigned m_seed;
+    int m_device;
+    mutable unsigned m_generation = 1;
+    mutable pgc_maco_state m_state{};
+    std::shared_ptr<detail::twin_cache> m_cache;
+};
+
 } // namespace pagmo_cuda
 
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_gaco)
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_maco)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_moead_gen)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_nspso)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_cmaes)

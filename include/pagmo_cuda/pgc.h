@@ -290,6 +290,17 @@ typedef struct pgc_gaco_state {
 PGC_API int pgc_gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, unsigned ker, double q, double oracle,
                                    double acc, unsigned threshold, unsigned n_gen_mark, unsigned impstop, unsigned evalstop, double focus,
                                    uint64_t seed, uint32_t first_generation, pgc_gaco_state *state, unsigned *gens_done, void *stream);
+/* maco::evolve (src/algorithms/maco.cpp:88-533), multi-objective hypervolume-based ant colony optimisation, on a device-resident
+ * population (in place), memory = false.  Constructor arguments as maco.hpp:107-109 (reference defaults: ker 63, q 1.0, threshold 1,
+ * n_gen_mark 7, evalstop 100000, focus 0).  m_q, m_n_evalstop and m_gen_mark of the algorithm object travel in pgc_maco_state
+ * (initialized == 0: q from the argument, counters as a fresh maco has them). */
+typedef struct pgc_maco_state {
+    double q;
+    uint32_t n_evalstop, gen_mark, initialized, reserved_;
+} pgc_maco_state;
+PGC_API int pgc_maco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, unsigned ker, double q,
+                                   unsigned threshold, unsigned n_gen_mark, unsigned evalstop, double focus, uint64_t seed,
+                                   uint32_t first_generation, pgc_maco_state *state, unsigned *gens_done, void *stream);
 PGC_API int pgc_cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lambda, unsigned gens, double cc, double cs, double c1,
                                     double cmu, double sigma0, double ftol, double xtol, int force_bounds, uint64_t seed,
                                     uint32_t first_generation, unsigned *gens_done, double *sigma_out, void *stream);

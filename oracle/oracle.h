@@ -183,6 +183,19 @@ int oracle_gaco_evolve_mt(const oracle_problem *prob, const double *lb, const do
                           unsigned gens, unsigned ker, double q, double oracle_par, double acc, unsigned threshold, unsigned n_gen_mark,
                           unsigned impstop, unsigned evalstop, double focus, uint32_t seed);
 
+/* maco::evolve (src/algorithms/maco.cpp:88-533), memory = false; the algorithm object's m_q, m_n_evalstop, m_gen_mark travel in the state */
+typedef struct {
+    double q;
+    unsigned n_evalstop, gen_mark;
+} oracle_maco_state;
+void oracle_maco_state_init(oracle_maco_state *s, double q);
+int oracle_maco_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t n, size_t nx, size_t nix,
+                       size_t m, unsigned gens, unsigned ker, unsigned threshold, unsigned n_gen_mark, unsigned evalstop, double focus,
+                       uint64_t seed, uint32_t first_generation, oracle_maco_state *st, unsigned *gens_done);
+int oracle_maco_evolve_mt(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t n, size_t nx, size_t nix,
+                          size_t m, unsigned gens, unsigned ker, double q, unsigned threshold, unsigned n_gen_mark, unsigned evalstop,
+                          double focus, uint32_t seed);
+
 /* moead_gen::evolve (src/algorithms/moead_gen.cpp:128-345) with the weight vectors [NP x m] and their neighbourhoods [NP x T] given;
  * decomposition: 0 weighted, 1 tchebycheff, 2 bi */
 int oracle_moead_gen_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t NP, size_t dim, size_t m,

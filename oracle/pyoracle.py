@@ -547,6 +547,39 @@ class Oracle:
             raise ValueError("oracle_gaco_evolve failed")
         return x, f, st, done.value
 
+    class MacoState(C.Structure):
+        _fields_ = [("q", C.c_double), ("n_evalstop", C.c_uint), ("gen_mark", C.c_uint)]
+
+    def maco_evolve(self, prob, lb, ub, x, f, nix=0, gens=1, ker=63, q=1.0, threshold=1, n_gen_mark=7, evalstop=100000, focus=0.0, seed=0,
+                    first_generation=1, mt=False, state=None):
+        """restated maco::evolve (Philox draws, or the mt19937 stream with mt=True): returns (x, f, state, gens_done)."""
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C").reshape(x.shape[0], -1)
+        n, nx = x.shape
+        m = f.shape[1]
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        if mt:
+            self.lib.oracle_maco_evolve_mt.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_size_t, C.c_size_t,
+                                                       C.c_size_t, C.c_size_t, C.c_uint, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint,
+                                                       C.c_double, C.c_uint32]
+            if self.lib.oracle_maco_evolve_mt(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), n, nx, nix, m, gens, ker, q, threshold, n_gen_mark,
+                                              evalstop, focus, seed):
+                raise ValueError("oracle_maco_evolve_mt failed")
+            return x, f, None, gens
+        st = state if state is not None else self.MacoState()
+        if state is None:
+            self.lib.oracle_maco_state_init.argtypes = [C.c_void_p, C.c_double]
+            self.lib.oracle_maco_state_init.restype = None
+            self.lib.oracle_maco_state_init(C.byref(st), q)
+        done = C.c_uint()
+        self.lib.oracle_maco_evolve.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint64, C.c_uint32,
+                                                C.c_void_p, C.POINTER(C.c_uint)]
+        if self.lib.oracle_maco_evolve(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), n, nx, nix, m, gens, ker, threshold, n_gen_mark, evalstop,
+                                       focus, seed, first_generation, C.byref(st), C.byref(done)):
+            raise ValueError("oracle_maco_evolve failed")
+        return x, f, st, done.value
+
     DECOMPOSITION = {"weighted": 0, "tchebycheff": 1, "bi": 2}
 
     def moead_gen_evolve(self, prob, lb, ub, x, f, weights, neigh, gens=1, decomposition="tchebycheff", CR=1.0, F=0.5, eta_m=20.0, realb=0.9,

@@ -12,6 +12,7 @@
 #include <pagmo/algorithms/de.hpp>
 #include <pagmo/algorithms/de1220.hpp>
 #include <pagmo/algorithms/gaco.hpp>
+#include <pagmo/algorithms/maco.hpp>
 #include <pagmo/algorithms/moead_gen.hpp>
 #include <pagmo/algorithms/nsga2.hpp>
 #include <pagmo/algorithms/nspso.hpp>
@@ -173,6 +174,10 @@ int ref_evolve_from(ref_problem *p, const char *algo, const double *par, size_t 
             alg = pagmo::algorithm{pagmo::gaco(gens, static_cast<unsigned>(par[0]), par[1], par[2], par[3], static_cast<unsigned>(par[4]),
                                                static_cast<unsigned>(par[5]), static_cast<unsigned>(par[6]), static_cast<unsigned>(par[7]), par[8],
                                                false, seed)};
+        } else if (a == "maco") { // ker, q, threshold, n_gen_mark, evalstop, focus (maco.hpp:107-109)
+            need(6);
+            alg = pagmo::algorithm{pagmo::maco(gens, static_cast<unsigned>(par[0]), par[1], static_cast<unsigned>(par[2]),
+                                               static_cast<unsigned>(par[3]), static_cast<unsigned>(par[4]), par[5], false, seed)};
         } else
             throw std::invalid_argument("ref_evolve_from: unknown algorithm '" + a + "'");
         pop = alg.evolve(pop);

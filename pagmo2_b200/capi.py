@@ -65,6 +65,11 @@ class GacoState(C.Structure):
                 ("initialized", C.c_uint32), ("fevals", C.c_uint64)]
 
 
+class MacoState(C.Structure):
+    """pgc_maco_state: the members pagmo::maco keeps between evolve() calls."""
+    _fields_ = [("q", C.c_double), ("n_evalstop", C.c_uint32), ("gen_mark", C.c_uint32), ("initialized", C.c_uint32), ("reserved_", C.c_uint32)]
+
+
 class AlgoMemory(C.Structure):
     """pgc_algo_memory: the device arrays a UDA with memory = true keeps between evolve() calls."""
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("u", C.c_void_p), ("initialized", C.c_int32), ("reserved_", C.c_int32)]
@@ -615,6 +620,25 @@ class Problem:
         try:
             check(L.pgc_gaco_evolve_device(self._h, dx, df, x.shape[0], gens, ker, q, oracle, acc, threshold, n_gen_mark, impstop, evalstop, focus,
                                            seed, first_generation, C.byref(st), C.byref(done), None))
+            return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), st, done.value
+        finally:
+            self.ctx.free(dx)
+            self.ctx.free(df)
+
+    def maco_evolve(self, x, f, gens=1, ker=63, q=1.0, threshold=1, n_gen_mark=7, evalstop=100000, focus=0.0, seed=0, first_generation=1,
+                    state=None):
+        """maco::evolve on the device: returns (x, f, state, gens_done); `state` (MacoState) = the algorithm object's members."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(x.shape[0], -1)
+        st = state if state is not None else MacoState()
+        dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
+        done = C.c_uint()
+        L = lib()
+        L.pgc_maco_evolve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_double, C.c_uint, C.c_uint,
+                                             C.c_uint, C.c_double, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint), C.c_void_p]
+        try:
+            check(L.pgc_maco_evolve_device(self._h, dx, df, x.shape[0], gens, ker, q, threshold, n_gen_mark, evalstop, focus, seed,
+                                           first_generation, C.byref(st), C.byref(done), None))
             return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), st, done.value
         finally:
             self.ctx.free(dx)

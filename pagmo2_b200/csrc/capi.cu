@@ -857,6 +857,23 @@ int pgc_gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n
                               stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
 }
 
+int pgc_maco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, unsigned ker, double q, unsigned threshold,
+                           unsigned n_gen_mark, unsigned evalstop, double focus, uint64_t seed, uint32_t first_generation,
+                           pgc_maco_state *state, unsigned *gens_done, void *stream)
+{
+    PGC_REQUIRE(prob && (n == 0 || (d_x && d_f)), "pgc_maco_evolve_device: null argument");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    pgc_maco_state local{};
+    pgc_maco_state *s = state ? state : &local;
+    if (!s->initialized) { // a freshly constructed pagmo::maco, maco.cpp:60-63
+        s->q = q;
+        s->n_evalstop = 0, s->gen_mark = 1;
+        s->initialized = 1;
+    }
+    return maco_evolve_device(prob, d_x, d_f, static_cast<unsigned>(n), gens, ker, threshold, n_gen_mark, evalstop, focus, seed, first_generation,
+                              s, gens_done, problem_eval_device, stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
+}
+
 int pgc_hv_device(pgc_ctx *ctx, const double *d_points, size_t n, size_t m, const double *r_point, int compute, double *d_out, void *stream)
 {
     PGC_REQUIRE(ctx && r_point && d_out && (d_points || n == 0), "pgc_hv_device: null argument");

@@ -1,5 +1,6 @@
 // gaco.cu - pagmo::gaco::evolve (extended ant colony optimisation, reference src/algorithms/gaco.cpp:104-445) on a device-resident
-// population of an unconstrained single-objective problem, memory = false.
+// population of an unconstrained single-objective problem, memory = false; and pagmo::maco::evolve (maco.cpp:88-533), its
+// multi-objective sibling, at the end of the file (same pheromone values and ants).
 //
 // One generation (the reference's own batch structure, :207-320):
 //   gaco_penalty_kernel   penalties against the oracle parameter (penalty_computation :506-549) + sort keys
@@ -17,6 +18,7 @@
 // into no-ops, and the archive is written back into the population at the end unless one fired (:408-421).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -195,11 +197,13 @@ __global__ void gaco_archive_kernel(GacoState *S, const double *x, const double 
 }
 
 // block h < nx: sigma[h]; block nx: the kernel weights (only when gen == 1 or gen == threshold)
+// (archive rows of `row` doubles with the decision vector at column `xoff`: [penalty | x | f] for gaco, [x | f] for maco)
 __global__ void gaco_pheromone_kernel(GacoState *S, const double *arch, const double *lb, const double *ub, unsigned nx, unsigned ncx,
-                                      unsigned ker, unsigned gen, unsigned threshold, double focus, double *omega, double *pc, double *sigma)
+                                      unsigned ker, unsigned gen, unsigned threshold, double focus, double *omega, double *pc, double *sigma,
+                                      unsigned row, unsigned xoff)
 {
     if (S->stopped) return;
-    const unsigned row = 1u + nx + 1u, t = threadIdx.x, T = blockDim.x;
+    const unsigned t = threadIdx.x, T = blockDim.x;
     if (blockIdx.x == nx) {
         if (t == 0 && (gen == 1u || gen == threshold)) { // :706-730
             if (gen == threshold) S->q = 0.01;
@@ -219,7 +223,7 @@ __global__ void gaco_pheromone_kernel(GacoState *S, const double *arch, const do
         }
         return;
     }
-    const unsigned h = blockIdx.x + 1u; // the archive column of variable h - 1
+    const unsigned h = blockIdx.x + xoff, v = blockIdx.x; // the archive column of variable v
     __shared__ double smin[256], smax[256];
     double d_min = fabs(arch[h] - arch[row + h]), d_max = d_min; // :759-761
     const unsigned long long pairs = static_cast<unsigned long long>(ker) * ker;
@@ -242,12 +246,12 @@ __global__ void gaco_pheromone_kernel(GacoState *S, const double *arch, const do
     }
     if (t == 0) { // :778-795
         d_min = smin[0], d_max = smax[0];
-        const double width = ub[h - 1u] - lb[h - 1u], gm = static_cast<double>(S->gen_mark);
+        const double width = ub[v] - lb[v], gm = static_cast<double>(S->gen_mark);
         double s;
         if (focus != 0. && ((d_max - d_min) / gen > width / focus)) s = width / focus;
-        else if (h <= ncx) s = (d_max - d_min) / gm;
+        else if (v < ncx) s = (d_max - d_min) / gm;
         else s = fmax(fmax((d_max - d_min) / gm, 1.0 / gm), (1.0 - 1.0 / (sqrt(static_cast<double>(nx - ncx)))));
-        sigma[h - 1u] = s;
+        sigma[v] = s;
     }
 }
 
@@ -260,11 +264,10 @@ __device__ __forceinline__ double normal01(PhiloxStream &rs) // Box-Muller on tw
 
 __global__ void gaco_ants_kernel(const GacoState *S, const double *arch, const double *pc, const double *sigma, const double *lb,
                                  const double *ub, unsigned n, unsigned nx, unsigned ncx, unsigned ker, unsigned long long seed,
-                                 unsigned generation, double *ants)
+                                 unsigned generation, double *ants, unsigned row, unsigned xoff)
 {
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n || S->stopped) return;
-    const unsigned row = 1u + nx + 1u;
     PhiloxStream rs(seed, kTagGaco, generation, j);
     const double number = rs.next();
     unsigned k_omega = 0; // :833-846
@@ -273,7 +276,7 @@ __global__ void gaco_ants_kernel(const GacoState *S, const double *arch, const d
     else
         for (unsigned k = 1; k + 1u < ker; ++k)
             if (number > pc[k - 1u] && number <= pc[k]) k_omega = k;
-    const double *mean = arch + static_cast<size_t>(k_omega) * row + 1u;
+    const double *mean = arch + static_cast<size_t>(k_omega) * row + xoff;
     for (unsigned h = 0; h < nx; ++h) { // :847-868
         const double l = lb[h], u = ub[h];
         double g_h = mean[h] + sigma[h] * normal01(rs);
@@ -389,8 +392,8 @@ int gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, 
         gaco_penalty_kernel<<<nblk(n, 256), 256, 0, st>>>(S, d_f, n, impstop, evalstop, pen, k0, i0);
         PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, ws_bytes, k0, k1, i0, sl, static_cast<int>(n), 0, 64, st));
         gaco_archive_kernel<<<1, 256, 0, st>>>(S, d_x, d_f, pen, sl, nx, ker, gen == 1u ? 1 : 0, acc, n_gen_mark, arch, tmp_arch, tp, slp, nsl, n_new);
-        gaco_pheromone_kernel<<<nx + 1u, 256, 0, st>>>(S, arch, lb, ub, nx, ncx, ker, gen, threshold, focus, omega, pc, sigma);
-        gaco_ants_kernel<<<nblk(n, 128), 128, 0, st>>>(S, arch, pc, sigma, lb, ub, n, nx, ncx, ker, seed, generation, ants);
+        gaco_pheromone_kernel<<<nx + 1u, 256, 0, st>>>(S, arch, lb, ub, nx, ncx, ker, gen, threshold, focus, omega, pc, sigma, row, 1u);
+        gaco_ants_kernel<<<nblk(n, 128), 128, 0, st>>>(S, arch, pc, sigma, lb, ub, n, nx, ncx, ker, seed, generation, ants, row, 1u);
         PGC_CUDA(cudaGetLastError());
         // (a stopped run evaluates stale ants into fnew; nothing reads them)
         if ((rc = eval(prob, ants, n, fnew, st))) return rc;
@@ -405,6 +408,233 @@ int gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, 
     state->oracle = h.oracle, state->q = h.q, state->n_evalstop = h.n_evalstop, state->n_impstop = h.n_impstop, state->gen_mark = h.gen_mark;
     state->fevals = h.fevals;
     if (gens_done) *gens_done = h.gens_done;
+    return PGC_OK;
+}
+
+
+// ---- maco (reference src/algorithms/maco.cpp:88-533) ---------------------------------------------------------------------------
+// Multi-objective hypervolume-based ant colony optimisation: gaco's pheromone values and ants on an archive that is rebuilt every
+// generation from the non-dominated fronts of (archive + population), each front ordered by DEcreasing exclusive hypervolume
+// contribution.  The device does the quadratic and the batched parts - non-dominated sorting (fnds_device), the contributions of
+// a front (hv_device: sweeps for 2 / 3 objectives, WFG above), the ants, the evaluation; the host walks the fronts: it needs
+// their sizes, a reference point per front (nadir + offset) and the order of a handful of contributions, and keeps the three
+// counters of the algorithm object.
+namespace
+{
+
+__global__ void maco_gather_rows_kernel(const double *src, const unsigned *idx, unsigned k, unsigned width, double *dst)
+{
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(k) * width) return;
+    dst[e] = src[static_cast<size_t>(idx[e / width]) * width + e % width];
+}
+
+// archive row i <- merged individual src[i]: [x | f]
+__global__ void maco_fill_archive_kernel(const double *mx, const double *mf, const unsigned *src, unsigned ker, unsigned nx, unsigned m, double *arch)
+{
+    const unsigned row = nx + m;
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(ker) * row) return;
+    const unsigned i = static_cast<unsigned>(e / row), c = static_cast<unsigned>(e % row), s = src[i];
+    arch[e] = c < nx ? mx[static_cast<size_t>(s) * nx + c] : mf[static_cast<size_t>(s) * m + (c - nx)];
+}
+
+// merged <- [archive rows ; population]
+__global__ void maco_merge_kernel(const double *arch, const double *x, const double *f, unsigned ker, unsigned n, unsigned nx, unsigned m,
+                                  double *mx, double *mf)
+{
+    const unsigned row = nx + m;
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t np = static_cast<size_t>(ker) + n;
+    if (e < np * nx) {
+        const size_t j = e / nx, c = e % nx;
+        mx[e] = j < ker ? arch[j * row + c] : x[(j - ker) * nx + c];
+    }
+    if (e < np * m) {
+        const size_t j = e / m, c = e % m;
+        mf[e] = j < ker ? arch[j * row + nx + c] : f[(j - ker) * m + c];
+    }
+}
+
+__global__ void maco_writeback_kernel(const double *arch, unsigned ker, unsigned nx, unsigned m, double *x, double *f)
+{ // :535-545
+    const unsigned row = nx + m;
+    const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<size_t>(ker) * row) return;
+    const unsigned i = static_cast<unsigned>(e / row), c = static_cast<unsigned>(e % row);
+    if (c < nx) x[static_cast<size_t>(i) * nx + c] = arch[e];
+    else f[static_cast<size_t>(i) * m + (c - nx)] = arch[e];
+}
+
+inline bool greater_than_f(double a, double b) // detail::greater_than_f
+{
+    if (!std::isnan(a)) return !std::isnan(b) ? a > b : false;
+    return !std::isnan(b);
+}
+
+} // namespace
+
+int maco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, unsigned gens, unsigned ker, unsigned threshold,
+                       unsigned n_gen_mark, unsigned evalstop, double focus, unsigned long long seed, unsigned first_generation,
+                       pgc_maco_state *state, unsigned *gens_done,
+                       int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st)
+{
+    pgc_ctx *ctx = prob->ctx;
+    const unsigned nx = static_cast<unsigned>(prob->nx), ncx = nx - static_cast<unsigned>(prob->nix), m = static_cast<unsigned>(prob->nobj);
+    if (gens_done) *gens_done = 0;
+    // constructor and evolve checks, maco.cpp:64-83,126-152
+    PGC_REQUIRE(focus >= 0., "The focus parameter must be >=0  while a value of %g was detected", focus);
+    PGC_REQUIRE(n > 0u, "MHACO: Multi-objective Hypervolume-based Ant Colony Optimization cannot work on an empty population");
+    if (gens == 0u) return PGC_OK;
+    PGC_REQUIRE(threshold >= 1u && threshold <= gens, "If memory is inactive, the threshold parameter must be either in [1,m_gen] while a value of %u was detected", threshold);
+    PGC_REQUIRE(ker <= n, "MHACO: Multi-objective Hypervolume-based Ant Colony Optimization cannot work with a solution archive bigger than the population size");
+    PGC_REQUIRE(ker >= 2u, "maco: the pheromone values need an archive of at least two solutions (ker = %u)", ker);
+    PGC_REQUIRE(m >= 2u, "This is a multiobjective algorithm, while number of objectives detected in %s is %u", prob->name.c_str(), m);
+    PGC_REQUIRE(n_gen_mark >= 1u, "maco: n_gen_mark must be at least 1");
+    const unsigned row = nx + m, np_max = ker + n;
+    Scratch sc(st);
+    GacoState *S;
+    double *arch, *mx, *mf, *lf, *contrib, *omega, *pc, *sigma, *ants, *fnew, *lb, *ub;
+    unsigned *rank, *order, *foff, *src;
+    int rc;
+    if ((rc = sc.alloc(&S, 1)) || (rc = sc.alloc(&arch, static_cast<size_t>(ker) * row)) || (rc = sc.alloc(&mx, static_cast<size_t>(np_max) * nx))
+        || (rc = sc.alloc(&mf, static_cast<size_t>(np_max) * m)) || (rc = sc.alloc(&lf, static_cast<size_t>(np_max) * m))
+        || (rc = sc.alloc(&contrib, np_max)) || (rc = sc.alloc(&omega, ker)) || (rc = sc.alloc(&pc, ker)) || (rc = sc.alloc(&sigma, nx))
+        || (rc = sc.alloc(&ants, static_cast<size_t>(n) * nx)) || (rc = sc.alloc(&fnew, static_cast<size_t>(n) * m)) || (rc = sc.alloc(&lb, nx))
+        || (rc = sc.alloc(&ub, nx)) || (rc = sc.alloc(&rank, np_max)) || (rc = sc.alloc(&order, np_max)) || (rc = sc.alloc(&foff, np_max + 1u))
+        || (rc = sc.alloc(&src, np_max)))
+        return rc;
+    PGC_CUDA(cudaMemcpyAsync(lb, prob->lb.data(), sizeof(double) * nx, cudaMemcpyHostToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(ub, prob->ub.data(), sizeof(double) * nx, cudaMemcpyHostToDevice, st));
+    std::vector<double> h_mf(static_cast<size_t>(np_max) * m), h_arch_fit(static_cast<size_t>(ker) * m, 1.0), h_contrib(np_max), ref(m), idp(m);
+    std::vector<unsigned> h_order(np_max), h_foff(np_max + 1u), h_src(ker), sl(np_max);
+    bool stopped = false;
+    unsigned done = 0;
+    for (unsigned gen = 1; gen <= gens; ++gen) {
+        const unsigned generation = first_generation + (gen - 1u);
+        // the individuals the archive is rebuilt from: the population (first generation) or archive + population (:264-284)
+        const unsigned np = gen == 1u ? n : np_max;
+        if (gen == 1u) {
+            PGC_CUDA(cudaMemcpyAsync(mx, d_x, sizeof(double) * n * nx, cudaMemcpyDeviceToDevice, st));
+            PGC_CUDA(cudaMemcpyAsync(mf, d_f, sizeof(double) * n * m, cudaMemcpyDeviceToDevice, st));
+        } else {
+            maco_merge_kernel<<<nblk(static_cast<size_t>(np) * std::max(nx, m), 256), 256, 0, st>>>(arch, d_x, d_f, ker, n, nx, m, mx, mf);
+            PGC_CUDA(cudaGetLastError());
+        }
+        PGC_CUDA(cudaMemcpyAsync(h_mf.data(), mf, sizeof(double) * np * m, cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        // rebuild the archive from the fronts (:177-262 first generation, offset 0.1; :318-410 afterwards, offset 0.01).  The first
+        // generation does it BEFORE the ideal-point test below, later ones after it - and a stop leaves the archive as it was.
+        const auto rebuild = [&](double offset, bool first) -> int {
+            unsigned nfronts = 0;
+            if (np < 2u) { // fast_non_dominated_sorting needs two points; one point is one front
+                h_order[0] = 0, h_foff[0] = 0, h_foff[1] = 1, nfronts = 1;
+            } else {
+                if (int r = fnds_device(ctx, mf, np, m, rank, nullptr, order, foff, &nfronts, st)) return r;
+                PGC_CUDA(cudaMemcpyAsync(h_order.data(), order, sizeof(unsigned) * np, cudaMemcpyDeviceToHost, st));
+                PGC_CUDA(cudaMemcpyAsync(h_foff.data(), foff, sizeof(unsigned) * (nfronts + 1u), cudaMemcpyDeviceToHost, st));
+                PGC_CUDA(cudaStreamSynchronize(st));
+            }
+            unsigned i_arch = 0;
+            for (unsigned fr = 0; fr < nfronts && i_arch < ker; ++fr) {
+                const unsigned *idxs = h_order.data() + h_foff[fr], k = h_foff[fr + 1u] - h_foff[fr];
+                for (unsigned c = 0; c < m; ++c) { // hypervolume::refpoint(offset), hypervolume.cpp:160-181
+                    double v = h_mf[static_cast<size_t>(idxs[0]) * m + c];
+                    for (unsigned i = 1; i < k; ++i) v = std::max(v, h_mf[static_cast<size_t>(idxs[i]) * m + c]);
+                    ref[c] = v + offset;
+                }
+                if (k == 1u) { // hypervolume::contributions' trivial case, hypervolume.cpp:292-297
+                    double v = 1.0;
+                    for (unsigned c = 0; c < m; ++c) v *= (h_mf[static_cast<size_t>(idxs[0]) * m + c] - ref[c]);
+                    h_contrib[0] = std::fabs(v);
+                } else {
+                    maco_gather_rows_kernel<<<nblk(static_cast<size_t>(k) * m, 256), 256, 0, st>>>(mf, order + h_foff[fr], k, m, lf);
+                    PGC_CUDA(cudaGetLastError());
+                    if (int r = hv_device(ctx, lf, k, m, ref.data(), 0, contrib, st)) return r;
+                    PGC_CUDA(cudaMemcpyAsync(h_contrib.data(), contrib, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+                    PGC_CUDA(cudaStreamSynchronize(st));
+                    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+                }
+                for (unsigned i = 0; i < k; ++i) sl[i] = i;
+                std::stable_sort(sl.begin(), sl.begin() + k, [&](unsigned a, unsigned b) { return greater_than_f(h_contrib[a], h_contrib[b]); });
+                for (unsigned i = 0; i < k && i_arch < ker; ++i, ++i_arch) {
+                    h_src[i_arch] = idxs[sl[i]];
+                    if (first) std::copy_n(h_mf.begin() + static_cast<std::ptrdiff_t>(idxs[sl[i]]) * m, m, h_arch_fit.begin() + static_cast<std::ptrdiff_t>(i_arch) * m);
+                }
+                if (i_arch >= ker && fr == 0u) { // the extremities of an overflowing first front, :231-259, as written
+                    for (unsigned c = 0; c < m; ++c) {
+                        double v = h_mf[static_cast<size_t>(idxs[0]) * m + c];
+                        for (unsigned i = 1; i < k; ++i) v = std::min(v, h_mf[static_cast<size_t>(idxs[i]) * m + c]);
+                        idp[c] = v;
+                    }
+                    std::vector<unsigned> border;
+                    for (unsigned c = 0; c < m; ++c)
+                        for (unsigned i = 0; i < k; ++i)
+                            if (h_mf[static_cast<size_t>(idxs[i]) * m + c] == idp[c]) {
+                                border.push_back(idxs[i]);
+                                break;
+                            }
+                    for (unsigned c = 0; c < m && c < ker; ++c) {
+                        h_src[ker - 1u - c] = border[c];
+                        // sol_archive_fit[ker - 1 - c] = the fitness in archive row c AT THAT MOMENT (rows ker-1-c' with c' < c are
+                        // already overwritten by their border points)
+                        const unsigned from = h_src[c];
+                        std::copy_n(h_mf.begin() + static_cast<std::ptrdiff_t>(from) * m, m, h_arch_fit.begin() + static_cast<std::ptrdiff_t>(ker - 1u - c) * m);
+                    }
+                }
+            }
+            PGC_CUDA(cudaMemcpyAsync(src, h_src.data(), sizeof(unsigned) * ker, cudaMemcpyHostToDevice, st));
+            maco_fill_archive_kernel<<<nblk(static_cast<size_t>(ker) * row, 256), 256, 0, st>>>(mx, mf, src, ker, nx, m, arch);
+            PGC_CUDA(cudaGetLastError());
+            PGC_CUDA(cudaStreamSynchronize(st)); // h_src is reused by the next call
+            ctx->launches.fetch_add(2, std::memory_order_relaxed);
+            return PGC_OK;
+        };
+        if (gen == 1u) {
+            if ((rc = rebuild(0.1, true))) return rc;
+        } else {
+            std::copy_n(h_mf.begin(), static_cast<size_t>(ker) * m, h_arch_fit.begin()); // sol_archive_fit = the archive's fitness, :267-270
+        }
+        // the ideal point of the archive against the ideal point of everything, :289-318
+        bool check = false;
+        for (unsigned c = 0; c < m && !check; ++c) {
+            double a = h_arch_fit[c], b = h_mf[c];
+            for (unsigned j = 1; j < ker; ++j) a = std::min(a, h_arch_fit[static_cast<size_t>(j) * m + c]);
+            if (gen == 1u) b = a;
+            else
+                for (unsigned j = 1; j < np; ++j) b = std::min(b, h_mf[static_cast<size_t>(j) * m + c]);
+            if (a != b) check = true;
+        }
+        if (check) ++state->n_evalstop;
+        else state->n_evalstop = 0;
+        if (state->n_evalstop == 0u || state->n_evalstop > 2u) ++state->gen_mark;
+        if (state->gen_mark > n_gen_mark) state->gen_mark = 1;
+        if (evalstop != 0u && state->n_evalstop >= evalstop) { // `return pop`, :312-317
+            stopped = true;
+            break;
+        }
+        if (gen > 1u && (rc = rebuild(0.01, false))) return rc;
+        // pheromone values and ants: gaco's kernels on rows [x | f]
+        if (gen == threshold) state->q = 0.01;
+        GacoState h{};
+        h.q = state->q, h.gen_mark = state->gen_mark;
+        PGC_CUDA(cudaMemcpyAsync(S, &h, sizeof(GacoState), cudaMemcpyHostToDevice, st));
+        gaco_pheromone_kernel<<<nx + 1u, 256, 0, st>>>(S, arch, lb, ub, nx, ncx, ker, gen, threshold, focus, omega, pc, sigma, row, 0u);
+        gaco_ants_kernel<<<nblk(n, 128), 128, 0, st>>>(S, arch, pc, sigma, lb, ub, n, nx, ncx, ker, seed, generation, ants, row, 0u);
+        PGC_CUDA(cudaGetLastError());
+        PGC_CUDA(cudaStreamSynchronize(st)); // `h` leaves scope
+        if ((rc = eval(prob, ants, n, fnew, st))) return rc;
+        PGC_CUDA(cudaMemcpyAsync(d_x, ants, sizeof(double) * n * nx, cudaMemcpyDeviceToDevice, st));
+        PGC_CUDA(cudaMemcpyAsync(d_f, fnew, sizeof(double) * n * m, cudaMemcpyDeviceToDevice, st));
+        ctx->launches.fetch_add(3, std::memory_order_relaxed);
+        ++done;
+    }
+    if (!stopped) {
+        maco_writeback_kernel<<<nblk(static_cast<size_t>(ker) * row, 256), 256, 0, st>>>(arch, ker, nx, m, d_x, d_f);
+        PGC_CUDA(cudaGetLastError());
+    }
+    PGC_CUDA(cudaStreamSynchronize(st));
+    if (gens_done) *gens_done = done;
     return PGC_OK;
 }
 

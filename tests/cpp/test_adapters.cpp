@@ -421,6 +421,16 @@ int main(int argc, char **argv)
             }
             CHECK(threw);
         }
+        { // cuda_maco: fitness consistent with the decision vectors, fevals as the reference counts them, deterministic given the seed
+            pagmo::problem z1{pagmo::zdt{1u, 30u}};
+            pagmo::population a{z1, 40u, 5u}, b{z1, 40u, 5u};
+            const auto fe = a.get_problem().get_fevals();
+            a = pagmo::algorithm{cuda_maco{8u, 12u, 1.0, 1u, 7u, 100000u, 0., false, 5u}}.evolve(a);
+            b = pagmo::algorithm{cuda_maco{8u, 12u, 1.0, 1u, 7u, 100000u, 0., false, 5u}}.evolve(b);
+            CHECK(a.get_problem().get_fevals() - fe == 8u * 40u);
+            CHECK(a.get_x() == b.get_x() && a.get_f() == b.get_f());
+            for (std::size_t i = 0; i < a.size(); ++i) CHECK(max_rel(z1.fitness(a.get_x()[i]), a.get_f()[i]) <= tol);
+        }
         pagmo::problem zp{pagmo::zdt{1u, 30u}};
         pagmo::population mo{zp, 40u, 5u};
         mo = pagmo::algorithm{cuda_nsga2{10u, 0.95, 10., 0.01, 50., 32u}}.evolve(mo);
