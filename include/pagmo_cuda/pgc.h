@@ -404,6 +404,20 @@ PGC_API int pgc_select_best_device(pgc_ctx *ctx, const uint64_t *d_ids, const do
 PGC_API int pgc_fair_replace_device(pgc_ctx *ctx, uint64_t *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nobj,
                                     int rate_is_frac, double rate, const uint64_t *d_mids, const double *d_mx, const double *d_mf,
                                     size_t nm, void *stream);
+/* The single-objective CONSTRAINED branches of the two policies (select_best.cpp:137-152, fair_replace.cpp:158-188) and the order they
+ * use, sort_population_con (constrained.cpp:180-202): rows of f are [objective | nec equality | nic inequality constraints], tol =
+ * HOST array of the nec + nic tolerances (problem::get_c_tol).  Order: more satisfied constraints first; among the feasible the smaller
+ * objective; among equally infeasible ones the smaller Euclidean norm of the violations (compare_fc measures its left argument with the
+ * sum of the equality and inequality norms instead, constrained.cpp:96-106: the same order whenever an individual violates
+ * constraints of one kind only); ties keep the input order.  d_order: device, n entries. */
+PGC_API int pgc_sort_population_con_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t nec, size_t nic, const double *tol,
+                                           uint32_t *d_order, void *stream);
+PGC_API int pgc_select_best_con_device(pgc_ctx *ctx, const uint64_t *d_ids, const double *d_x, const double *d_f, size_t n, size_t nx,
+                                       size_t nec, size_t nic, const double *tol, int rate_is_frac, double rate, uint64_t *d_ids_out,
+                                       double *d_x_out, double *d_f_out, size_t *n_out, void *stream);
+PGC_API int pgc_fair_replace_con_device(pgc_ctx *ctx, uint64_t *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nec, size_t nic,
+                                        const double *tol, int rate_is_frac, double rate, const uint64_t *d_mids, const double *d_mx,
+                                        const double *d_mf, size_t nm, void *stream);
 /* topology::get_connections(i) for kind 0 = unconnected, 1 = ring (ring.cpp:74-116), 2 = fully_connected
  * (fully_connected.cpp:86-115) with n vertices: sources of the edges into i and their weights; buffers sized n. */
 PGC_API int pgc_topology_connections(int kind, size_t n, size_t i, double weight, size_t *idx_out, double *w_out, size_t *count);

@@ -105,6 +105,13 @@ int oracle_select_best(const uint64_t *ids, const double *x, const double *f, si
                        uint64_t *ids_out, double *x_out, double *f_out, size_t *n_out);
 int oracle_fair_replace(const uint64_t *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac, double rate,
                         const uint64_t *mids, const double *mx, const double *mf, size_t nm, uint64_t *ids_out, double *x_out, double *f_out);
+/* single-objective constrained groups: rows [f | nec eq | nic ineq], tol [nec + nic] (sort_population_con, constrained.cpp:180-202) */
+int oracle_sort_population_con(const double *f, size_t n, size_t nec, size_t nic, const double *tol, size_t *out);
+int oracle_select_best_con(const uint64_t *ids, const double *x, const double *f, size_t n, size_t nx, size_t nec, size_t nic, const double *tol,
+                           int rate_is_frac, double rate, uint64_t *ids_out, double *x_out, double *f_out, size_t *n_out);
+int oracle_fair_replace_con(const uint64_t *ids, const double *x, const double *f, size_t n, size_t nx, size_t nec, size_t nic, const double *tol,
+                            int rate_is_frac, double rate, const uint64_t *mids, const double *mx, const double *mf, size_t nm,
+                            uint64_t *ids_out, double *x_out, double *f_out);
 int oracle_ring_connections(size_t n, size_t i, size_t *out, size_t *count);
 int oracle_fully_connected_connections(size_t n, size_t i, size_t *out, size_t *count);
 int oracle_population_init(const double *lb, const double *ub, size_t n, size_t nx, uint64_t seed, double *x, uint64_t *ids);

@@ -346,6 +346,41 @@ class Oracle:
             raise ValueError("oracle_fair_replace: invalid migration rate")
         return io[:n], xo[:n], fo[:n]
 
+    def sort_population_con(self, f, nec, nic, tol) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        tol = np.ascontiguousarray(tol, dtype=np.float64)
+        out = np.empty(max(f.shape[0], 1), dtype=np.uint64)
+        self.lib.oracle_sort_population_con(_dp(f), C.c_size_t(f.shape[0]), C.c_size_t(nec), C.c_size_t(nic), _dp(tol), _sp(out))
+        return out[: f.shape[0]].astype(np.int64)
+
+    def select_best_con(self, ids, x, f, rate, nec, nic, tol):
+        """the constrained branch of select_best::select (select_best.cpp:137-152): rows of f are [objective | nec eq | nic ineq]."""
+        ids, x, f = self._group(ids, x, f)
+        tol = np.ascontiguousarray(tol, dtype=np.float64)
+        n, nx, nf = x.shape[0], x.shape[1], f.shape[1]
+        io, xo, fo = np.empty(max(n, 1), dtype=np.uint64), np.empty((max(n, 1), nx)), np.empty((max(n, 1), nf))
+        k = C.c_size_t()
+        u64p = C.POINTER(C.c_uint64)
+        if self.lib.oracle_select_best_con(ids.ctypes.data_as(u64p), _dp(x), _dp(f), C.c_size_t(n), C.c_size_t(nx), C.c_size_t(nec), C.c_size_t(nic),
+                                           _dp(tol), C.c_int(isinstance(rate, float)), C.c_double(rate), io.ctypes.data_as(u64p), _dp(xo), _dp(fo),
+                                           C.byref(k)):
+            raise ValueError("oracle_select_best_con: invalid migration rate")
+        return io[:k.value], xo[:k.value], fo[:k.value]
+
+    def fair_replace_con(self, ids, x, f, rate, mids, mx, mf, nec, nic, tol):
+        """the constrained branch of fair_replace::replace (fair_replace.cpp:158-188)."""
+        ids, x, f = self._group(ids, x, f)
+        tol = np.ascontiguousarray(tol, dtype=np.float64)
+        n, nx, nf = x.shape[0], x.shape[1], f.shape[1]
+        mids, mx, mf = self._group(mids, np.asarray(mx, dtype=np.float64).reshape(-1, nx), mf, nf)
+        io, xo, fo = np.empty(max(n, 1), dtype=np.uint64), np.empty((max(n, 1), nx)), np.empty((max(n, 1), nf))
+        u64p = C.POINTER(C.c_uint64)
+        if self.lib.oracle_fair_replace_con(ids.ctypes.data_as(u64p), _dp(x), _dp(f), C.c_size_t(n), C.c_size_t(nx), C.c_size_t(nec), C.c_size_t(nic),
+                                            _dp(tol), C.c_int(isinstance(rate, float)), C.c_double(rate), mids.ctypes.data_as(u64p), _dp(mx),
+                                            _dp(mf), C.c_size_t(mx.shape[0]), io.ctypes.data_as(u64p), _dp(xo), _dp(fo)):
+            raise ValueError("oracle_fair_replace_con: invalid migration rate")
+        return io[:n], xo[:n], fo[:n]
+
     def connections(self, kind: str, n: int, i: int) -> np.ndarray:
         out = np.empty(max(n, 1), dtype=np.uint64)
         cnt = C.c_size_t()
@@ -918,6 +953,33 @@ class Reference:
         self._check(self.lib.ref_select_best(ids.ctypes.data_as(u64p), _dp(x), _dp(f), n, nx, nf, int(isinstance(rate, float)), float(rate),
                                              io.ctypes.data_as(u64p), _dp(xo), _dp(fo), C.byref(k)))
         return io[:k.value], xo[:k.value], fo[:k.value]
+
+    def select_best_con(self, ids, x, f, rate, nec, nic, tol):
+        ids, x, f = Oracle._group(ids, x, f)
+        tol = np.ascontiguousarray(tol, dtype=np.float64)
+        n, nx, nf = x.shape[0], x.shape[1], f.shape[1]
+        io, xo, fo = np.empty(max(n, 1), dtype=np.uint64), np.empty((max(n, 1), nx)), np.empty((max(n, 1), nf))
+        k = C.c_size_t()
+        u64p = C.POINTER(C.c_ulonglong)
+        self.lib.ref_select_best_con.argtypes = [u64p, c_double_p, c_double_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, c_double_p, C.c_int,
+                                                 C.c_double, u64p, c_double_p, c_double_p, C.POINTER(C.c_size_t)]
+        self._check(self.lib.ref_select_best_con(ids.ctypes.data_as(u64p), _dp(x), _dp(f), n, nx, nec, nic, _dp(tol), int(isinstance(rate, float)),
+                                                 float(rate), io.ctypes.data_as(u64p), _dp(xo), _dp(fo), C.byref(k)))
+        return io[:k.value], xo[:k.value], fo[:k.value]
+
+    def fair_replace_con(self, ids, x, f, rate, mids, mx, mf, nec, nic, tol):
+        ids, x, f = Oracle._group(ids, x, f)
+        tol = np.ascontiguousarray(tol, dtype=np.float64)
+        n, nx, nf = x.shape[0], x.shape[1], f.shape[1]
+        mids, mx, mf = Oracle._group(mids, np.asarray(mx, dtype=np.float64).reshape(-1, nx), mf, nf)
+        io, xo, fo = np.empty(max(n, 1), dtype=np.uint64), np.empty((max(n, 1), nx)), np.empty((max(n, 1), nf))
+        u64p = C.POINTER(C.c_ulonglong)
+        self.lib.ref_fair_replace_con.argtypes = [u64p, c_double_p, c_double_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, c_double_p, C.c_int,
+                                                  C.c_double, u64p, c_double_p, c_double_p, C.c_size_t, u64p, c_double_p, c_double_p]
+        self._check(self.lib.ref_fair_replace_con(ids.ctypes.data_as(u64p), _dp(x), _dp(f), n, nx, nec, nic, _dp(tol), int(isinstance(rate, float)),
+                                                  float(rate), mids.ctypes.data_as(u64p), _dp(mx), _dp(mf), mx.shape[0], io.ctypes.data_as(u64p),
+                                                  _dp(xo), _dp(fo)))
+        return io[:n], xo[:n], fo[:n]
 
     def hv_compute(self, f, r) -> float:
         f = np.ascontiguousarray(f, dtype=np.float64)

@@ -79,6 +79,11 @@ int ref_select_best(const unsigned long long *ids, const double *x, const double
                     double rate, unsigned long long *ids_out, double *x_out, double *f_out, size_t *n_out);
 
 /* ---- hypervolume::compute / contributions (hypervolume.cpp:196-330) with the reference's own algorithm choice ---- */
+int ref_fair_replace_con(const unsigned long long *ids, const double *x, const double *f, size_t n, size_t nx, size_t nec, size_t nic,
+                         const double *tol, int rate_is_frac, double rate, const unsigned long long *mids, const double *mx, const double *mf,
+                         size_t nm, unsigned long long *ids_out, double *x_out, double *f_out);
+int ref_select_best_con(const unsigned long long *ids, const double *x, const double *f, size_t n, size_t nx, size_t nec, size_t nic,
+                        const double *tol, int rate_is_frac, double rate, unsigned long long *ids_out, double *x_out, double *f_out, size_t *n_out);
 int ref_hv_compute(const double *f, size_t n, size_t m, const double *r, double *out);
 int ref_hv_contributions(const double *f, size_t n, size_t m, const double *r, double *out);
 

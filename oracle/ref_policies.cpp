@@ -55,6 +55,38 @@ int ref_fair_replace(const unsigned long long *ids, const double *x, const doubl
     }
 }
 
+// the constrained branches: rows of nf = 1 + nec + nic doubles
+int ref_fair_replace_con(const unsigned long long *ids, const double *x, const double *f, size_t n, size_t nx, size_t nec, size_t nic,
+                         const double *tol, int rate_is_frac, double rate, const unsigned long long *mids, const double *mx, const double *mf,
+                         size_t nm, unsigned long long *ids_out, double *x_out, double *f_out)
+{
+    try {
+        const size_t nf = 1 + nec + nic;
+        const auto pol = rate_is_frac ? pagmo::fair_replace(rate) : pagmo::fair_replace(static_cast<pagmo::pop_size_t>(rate));
+        const auto out = pol.replace(group_of(ids, x, f, n, nx, nf), nx, 0, 1, nec, nic, pagmo::vector_double(tol, tol + nec + nic),
+                                     group_of(mids, mx, mf, nm, nx, nf));
+        if (flatten(out, ids_out, x_out, f_out, nx, nf) != n) throw std::runtime_error("fair_replace changed the population size");
+        return 0;
+    } catch (const std::exception &e) {
+        ref_set_error(e.what());
+        return 1;
+    }
+}
+int ref_select_best_con(const unsigned long long *ids, const double *x, const double *f, size_t n, size_t nx, size_t nec, size_t nic,
+                        const double *tol, int rate_is_frac, double rate, unsigned long long *ids_out, double *x_out, double *f_out, size_t *n_out)
+{
+    try {
+        const size_t nf = 1 + nec + nic;
+        const auto pol = rate_is_frac ? pagmo::select_best(rate) : pagmo::select_best(static_cast<pagmo::pop_size_t>(rate));
+        *n_out = flatten(pol.select(group_of(ids, x, f, n, nx, nf), nx, 0, 1, nec, nic, pagmo::vector_double(tol, tol + nec + nic)), ids_out,
+                         x_out, f_out, nx, nf);
+        return 0;
+    } catch (const std::exception &e) {
+        ref_set_error(e.what());
+        return 1;
+    }
+}
+
 // select_best{rate}.select(inds, nx, 0, nobj, 0, 0, {}) (select_best.cpp:63-171); outputs sized n
 int ref_select_best(const unsigned long long *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac,
                     double rate, unsigned long long *ids_out, double *x_out, double *f_out, size_t *n_out)

@@ -1,7 +1,7 @@
 /* oracle/restate_migration.c - plain-C restatement of the migration step of pagmo's archipelago.  TEST INFRASTRUCTURE ONLY.
  * Follows reference
- *   select_best::select   src/s_policies/select_best.cpp:63-171   (unconstrained branches :116-136, :153-170)
- *   fair_replace::replace src/r_policies/fair_replace.cpp:63-221  (unconstrained branches :115-157, :189-219; n_migr :80-108)
+ *   select_best::select   src/s_policies/select_best.cpp:63-171   (all three branches)
+ *   fair_replace::replace src/r_policies/fair_replace.cpp:63-221  (all three branches; n_migr :80-108)
  *   ring                  src/topologies/ring.cpp:74-116 + base_bgl_topology::get_connections base_bgl_topology.cpp:214-230
  *   fully_connected       src/topologies/fully_connected.cpp:86-115
  * Flat row-major groups (ids[n], x[n x nx], f[n x nobj]).  The reference orders by std::sort (ties unspecified); this restatement,
@@ -20,6 +20,51 @@ static int less_f(double a, double b) /* detail::less_than_f: NaNs are greater t
     return 0;
 }
 
+/* constrained single-objective groups (select_best.cpp:137-152, fair_replace.cpp:158-188): rows are [f | nec equality | nic inequality
+ * constraints] and the order is sort_population_con's, i.e. compare_fc (src/utils/constrained.cpp:76-118) - restated as written,
+ * including its two different norms: the left argument's violation is the SUM of the equality and inequality norms, the right
+ * argument's their Euclidean combination.  The two coincide whenever an individual violates constraints of one kind only. */
+static _Thread_local struct {
+    size_t nec, nic;
+    const double *tol;
+} g_con = {0, 0, NULL};
+
+static void con_test(const double *f, size_t *nsat, double *leq, double *lineq) /* detail::test_eq_constraints / test_ineq_constraints */
+{
+    double l2 = 0.;
+    size_t n = 0;
+    for (size_t j = 0; j < g_con.nec; ++j) {
+        const double err = fmax(fabs(f[1 + j]) - g_con.tol[j], 0.);
+        l2 += err * err;
+        if (err <= 0.) ++n;
+    }
+    *leq = sqrt(l2);
+    l2 = 0.;
+    for (size_t j = 0; j < g_con.nic; ++j) {
+        const double err = fmax(f[1 + g_con.nec + j] - g_con.tol[g_con.nec + j], 0.);
+        l2 += err * err;
+        if (err <= 0.) ++n;
+    }
+    *lineq = sqrt(l2);
+    *nsat = n;
+}
+
+static int compare_fc(const double *f1, const double *f2)
+{
+    size_t n1, n2;
+    double e1, i1, e2, i2;
+    con_test(f1, &n1, &e1, &i1);
+    con_test(f2, &n2, &e2, &i2);
+    const double l1 = e1 + i1, l2 = sqrt(e2 * e2 + i2 * i2);
+    if (n1 == n2) return n1 == g_con.nec + g_con.nic ? less_f(f1[0], f2[0]) : less_f(l1, l2);
+    return n1 > n2;
+}
+
+static int row_before(const double *f, size_t nf, size_t a, size_t b)
+{
+    return (g_con.nec || g_con.nic) ? compare_fc(f + a * nf, f + b * nf) : less_f(f[a * nf], f[b * nf]);
+}
+
 /* stable argsort of f[idx][0] (insertion into a merge would be faster; n is a population) */
 static void stable_order(const double *f, size_t nobj, size_t n, size_t *idx)
 {
@@ -28,7 +73,7 @@ static void stable_order(const double *f, size_t nobj, size_t n, size_t *idx)
     for (size_t w = 1; w < n; w *= 2) {
         for (size_t lo = 0; lo < n; lo += 2 * w) {
             size_t mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n, a = lo, b = mid, k = lo;
-            while (a < mid && b < hi) tmp[k++] = less_f(f[idx[b] * nobj], f[idx[a] * nobj]) ? idx[b++] : idx[a++];
+            while (a < mid && b < hi) tmp[k++] = row_before(f, nobj, idx[b], idx[a]) ? idx[b++] : idx[a++];
             while (a < mid) tmp[k++] = idx[a++];
             while (b < hi) tmp[k++] = idx[b++];
         }
@@ -40,9 +85,9 @@ static void stable_order(const double *f, size_t nobj, size_t n, size_t *idx)
 /* indices of the best `k` of n individuals: single-objective by fitness, multi-objective by select_best_N_mo */
 static int best_indices(const double *f, size_t n, size_t nobj, size_t k, size_t *out)
 {
-    if (nobj == 1) {
+    if (nobj == 1 || g_con.nec || g_con.nic) { /* nobj = the row width: 1 + nec + nic for a constrained group */
         size_t *idx = (size_t *)malloc((n ? n : 1) * sizeof(size_t));
-        stable_order(f, 1, n, idx);
+        stable_order(f, nobj, n, idx);
         memcpy(out, idx, k * sizeof(size_t));
         free(idx);
         return 0;
@@ -115,6 +160,34 @@ int oracle_fair_replace(const uint64_t *ids, const double *x, const double *f, s
         memcpy(f_out + i * nobj, gf + keep[i] * nobj, nobj * sizeof(double));
     }
     free(top); free(gid); free(gx); free(gf); free(keep);
+    return rc;
+}
+
+/* the constrained branches: rows of nf = 1 + nec + nic doubles, tol [nec + nic] */
+int oracle_sort_population_con(const double *f, size_t n, size_t nec, size_t nic, const double *tol, size_t *out)
+{
+    g_con.nec = nec, g_con.nic = nic, g_con.tol = tol;
+    stable_order(f, 1 + nec + nic, n, out);
+    g_con.nec = g_con.nic = 0;
+    return 0;
+}
+
+int oracle_select_best_con(const uint64_t *ids, const double *x, const double *f, size_t n, size_t nx, size_t nec, size_t nic, const double *tol,
+                           int rate_is_frac, double rate, uint64_t *ids_out, double *x_out, double *f_out, size_t *n_out)
+{
+    g_con.nec = nec, g_con.nic = nic, g_con.tol = tol;
+    const int rc = oracle_select_best(ids, x, f, n, nx, 1 + nec + nic, rate_is_frac, rate, ids_out, x_out, f_out, n_out);
+    g_con.nec = g_con.nic = 0;
+    return rc;
+}
+
+int oracle_fair_replace_con(const uint64_t *ids, const double *x, const double *f, size_t n, size_t nx, size_t nec, size_t nic, const double *tol,
+                            int rate_is_frac, double rate, const uint64_t *mids, const double *mx, const double *mf, size_t nm,
+                            uint64_t *ids_out, double *x_out, double *f_out)
+{
+    g_con.nec = nec, g_con.nic = nic, g_con.tol = tol;
+    const int rc = oracle_fair_replace(ids, x, f, n, nx, 1 + nec + nic, rate_is_frac, rate, mids, mx, mf, nm, ids_out, x_out, f_out);
+    g_con.nec = g_con.nic = 0;
     return rc;
 }
 

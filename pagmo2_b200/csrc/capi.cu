@@ -1165,6 +1165,39 @@ int pgc_fair_replace_device(pgc_ctx *ctx, uint64_t *d_ids, double *d_x, double *
                                       stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
 }
 
+int pgc_sort_population_con_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t nec, size_t nic, const double *tol, uint32_t *d_order,
+                                   void *stream)
+{
+    PGC_REQUIRE(ctx && (n == 0 || (d_f && d_order)), "pgc_sort_population_con_device: null argument");
+    PGC_REQUIRE(n < 0x7fffffffull, "pgc_sort_population_con_device: too many individuals");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return sort_population_con_device(ctx, d_f, n, nec, nic, tol, d_order, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int pgc_select_best_con_device(pgc_ctx *ctx, const uint64_t *d_ids, const double *d_x, const double *d_f, size_t n, size_t nx, size_t nec,
+                               size_t nic, const double *tol, int rate_is_frac, double rate, uint64_t *d_ids_out, double *d_x_out,
+                               double *d_f_out, size_t *n_out, void *stream)
+{
+    PGC_REQUIRE(ctx && n_out && (n == 0 || (d_ids && d_x && d_f && d_ids_out && d_x_out && d_f_out)), "pgc_select_best_con_device: null argument");
+    PGC_REQUIRE(nx >= 1 && n < 0x7fffffffull, "pgc_select_best_con_device: invalid sizes");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return select_best_con_policy_device(ctx, reinterpret_cast<const unsigned long long *>(d_ids), d_x, d_f, n, nx, nec, nic, tol, rate_is_frac, rate,
+                                         reinterpret_cast<unsigned long long *>(d_ids_out), d_x_out, d_f_out, n_out,
+                                         stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int pgc_fair_replace_con_device(pgc_ctx *ctx, uint64_t *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nec, size_t nic,
+                                const double *tol, int rate_is_frac, double rate, const uint64_t *d_mids, const double *d_mx, const double *d_mf,
+                                size_t nm, void *stream)
+{
+    PGC_REQUIRE(ctx && (n == 0 || (d_ids && d_x && d_f)) && (nm == 0 || (d_mids && d_mx && d_mf)), "pgc_fair_replace_con_device: null argument");
+    PGC_REQUIRE(nx >= 1 && n + nm < 0x7fffffffull, "pgc_fair_replace_con_device: invalid sizes");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return fair_replace_con_policy_device(ctx, reinterpret_cast<unsigned long long *>(d_ids), d_x, d_f, n, nx, nec, nic, tol, rate_is_frac, rate,
+                                          reinterpret_cast<const unsigned long long *>(d_mids), d_mx, d_mf, nm,
+                                          stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
 int pgc_topology_connections(int kind, size_t n, size_t i, double weight, size_t *idx_out, double *w_out, size_t *count)
 {
     PGC_REQUIRE(idx_out && w_out && count, "pgc_topology_connections: null argument");

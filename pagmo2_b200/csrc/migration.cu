@@ -66,10 +66,82 @@ struct Tmp { // stream-ordered scratch
     }
 };
 
-// d_sel[0..k) = indices of the best k rows of f [n x nobj]
+// Constrained single-objective groups (select_best.cpp:137-152, fair_replace.cpp:158-188): rows [f | nec equality | nic inequality
+// constraints], ordered as sort_population_con orders them (compare_fc, constrained.cpp:76-118): more satisfied constraints first;
+// among the feasible, the smaller objective; among equally infeasible ones, the smaller violation norm.  The reference measures the
+// left argument's violation as the SUM of its equality and inequality norms and the right argument's as their Euclidean combination;
+// the two coincide whenever an individual violates constraints of one kind only, and the device uses the Euclidean norm throughout
+// (a strict weak order, sortable by keys).  Keys: primary = number of violated constraints, secondary = objective or norm.
+struct ConSpec {
+    size_t nec = 0, nic = 0;
+    const double *d_tol = nullptr; // device, [nec + nic]
+    bool on() const { return nec + nic > 0; }
+};
+thread_local ConSpec tls_con; // set by the *_con entry points around a policy call
+
+__global__ void con_keys_kernel(const double *__restrict__ f, unsigned n, unsigned nec, unsigned nic, const double *__restrict__ tol,
+                                unsigned long long *primary, unsigned long long *secondary, unsigned *idx)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned nf = 1u + nec + nic;
+    const double *row = f + static_cast<size_t>(i) * nf;
+    double l2e = 0., l2i = 0.;
+    unsigned nsat = 0;
+    for (unsigned j = 0; j < nec; ++j) { // detail::test_eq_constraints, constrained.hpp:49-62
+        const double err = fmax(fabs(row[1u + j]) - tol[j], 0.);
+        l2e += err * err;
+        nsat += err <= 0. ? 1u : 0u;
+    }
+    for (unsigned j = 0; j < nic; ++j) { // detail::test_ineq_constraints, :67-80
+        const double err = fmax(row[1u + nec + j] - tol[nec + j], 0.);
+        l2i += err * err;
+        nsat += err <= 0. ? 1u : 0u;
+    }
+    const double e = sqrt(l2e), q = sqrt(l2i);
+    const double v = nsat == nec + nic ? row[0] : sqrt(e * e + q * q);
+    unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+    b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+    secondary[i] = (v != v) ? 0xffffffffffffffffull : b;
+    primary[i] = nec + nic - nsat;
+    idx[i] = i;
+}
+
+__global__ void gather_keys_kernel(const unsigned long long *keys, const unsigned *idx, unsigned n, unsigned long long *out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = keys[idx[i]];
+}
+
+// d_sel[0..k) = the first k of sort_population_con(f): two stable radix passes, secondary key first
+int con_best_indices(pgc_ctx *ctx, const double *d_f, size_t n, const ConSpec &con, size_t k, unsigned *d_sel, Tmp &tmp, cudaStream_t st)
+{
+    unsigned long long *prim = nullptr, *sec = nullptr, *k1 = nullptr, *k2 = nullptr;
+    unsigned *i0 = nullptr, *i1 = nullptr, *i2 = nullptr;
+    int rc;
+    if ((rc = tmp.get(&prim, n)) || (rc = tmp.get(&sec, n)) || (rc = tmp.get(&k1, n)) || (rc = tmp.get(&k2, n)) || (rc = tmp.get(&i0, n))
+        || (rc = tmp.get(&i1, n)) || (rc = tmp.get(&i2, n)))
+        return rc;
+    const unsigned un = static_cast<unsigned>(n);
+    con_keys_kernel<<<(un + 255) / 256, 256, 0, st>>>(d_f, un, static_cast<unsigned>(con.nec), static_cast<unsigned>(con.nic), con.d_tol, prim, sec, i0);
+    PGC_CUDA(cudaGetLastError());
+    size_t bytes = 0;
+    PGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, sec, k1, i0, i1, static_cast<int>(n), 0, 64, st));
+    unsigned char *ws = nullptr;
+    if ((rc = tmp.get(&ws, bytes))) return rc;
+    PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, bytes, sec, k1, i0, i1, static_cast<int>(n), 0, 64, st));
+    gather_keys_kernel<<<(un + 255) / 256, 256, 0, st>>>(prim, i1, un, k1);
+    PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, bytes, k1, k2, i1, i2, static_cast<int>(n), 0, 32, st));
+    PGC_CUDA(cudaMemcpyAsync(d_sel, i2, k * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    ctx->launches.fetch_add(5, std::memory_order_relaxed);
+    return PGC_OK;
+}
+
+// d_sel[0..k) = indices of the best k rows of f [n x nobj] (nobj = the row width: 1 + nec + nic for a constrained group)
 int best_indices(pgc_ctx *ctx, const double *d_f, size_t n, size_t nobj, size_t k, unsigned *d_sel, Tmp &tmp, cudaStream_t st)
 {
     if (k == 0 || n == 0) return PGC_OK;
+    if (tls_con.on()) return con_best_indices(ctx, d_f, n, tls_con, k, d_sel, tmp, st);
     if (nobj > 1) {
         unsigned nout = 0;
         unsigned *full = nullptr;
@@ -186,6 +258,61 @@ int fair_replace_policy_device(pgc_ctx *ctx, unsigned long long *d_ids, double *
     PGC_CUDA(cudaMemcpyAsync(d_x, ox, n * nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
     PGC_CUDA(cudaMemcpyAsync(d_f, of, n * nobj * sizeof(double), cudaMemcpyDeviceToDevice, st));
     return PGC_OK;
+}
+
+// the constrained branches: the same policies with the group's rows ordered by sort_population_con (tol: HOST array [nec + nic])
+namespace
+{
+struct ConScope {
+    double *d_tol = nullptr;
+    int begin(size_t nec, size_t nic, const double *tol, cudaStream_t st)
+    {
+        PGC_REQUIRE(nec + nic > 0 && tol, "constrained policy: needs at least one constraint and its tolerances");
+        PGC_CUDA(cudaMalloc(&d_tol, sizeof(double) * (nec + nic)));
+        PGC_CUDA(cudaMemcpyAsync(d_tol, tol, sizeof(double) * (nec + nic), cudaMemcpyHostToDevice, st));
+        tls_con.nec = nec, tls_con.nic = nic, tls_con.d_tol = d_tol;
+        return PGC_OK;
+    }
+    ~ConScope()
+    {
+        tls_con = ConSpec{};
+        if (d_tol) cudaFree(d_tol);
+    }
+};
+} // namespace
+
+int select_best_con_policy_device(pgc_ctx *ctx, const unsigned long long *d_ids, const double *d_x, const double *d_f, size_t n, size_t nx,
+                                  size_t nec, size_t nic, const double *tol, int rate_is_frac, double rate, unsigned long long *d_ids_out,
+                                  double *d_x_out, double *d_f_out, size_t *n_out, cudaStream_t st)
+{
+    ConScope scope;
+    if (int rc = scope.begin(nec, nic, tol, st)) return rc;
+    const int rc = select_best_policy_device(ctx, d_ids, d_x, d_f, n, nx, 1 + nec + nic, rate_is_frac, rate, d_ids_out, d_x_out, d_f_out, n_out, st);
+    cudaStreamSynchronize(st); // the tolerances are freed with the scope
+    return rc;
+}
+
+int fair_replace_con_policy_device(pgc_ctx *ctx, unsigned long long *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nec, size_t nic,
+                                   const double *tol, int rate_is_frac, double rate, const unsigned long long *d_mids, const double *d_mx,
+                                   const double *d_mf, size_t nm, cudaStream_t st)
+{
+    ConScope scope;
+    if (int rc = scope.begin(nec, nic, tol, st)) return rc;
+    const int rc = fair_replace_policy_device(ctx, d_ids, d_x, d_f, n, nx, 1 + nec + nic, rate_is_frac, rate, d_mids, d_mx, d_mf, nm, st);
+    cudaStreamSynchronize(st);
+    return rc;
+}
+
+int sort_population_con_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t nec, size_t nic, const double *tol, unsigned *d_order,
+                               cudaStream_t st)
+{
+    if (n == 0) return PGC_OK;
+    ConScope scope;
+    if (int rc = scope.begin(nec, nic, tol, st)) return rc;
+    Tmp tmp(st);
+    const int rc = con_best_indices(ctx, d_f, n, tls_con, n, d_order, tmp, st);
+    cudaStreamSynchronize(st);
+    return rc;
 }
 
 // in-edge sources of vertex i of a ring built by n push_back() calls, in base_bgl_topology::get_connections order (the in-edge

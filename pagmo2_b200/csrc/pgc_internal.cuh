@@ -374,6 +374,14 @@ int select_best_policy_device(pgc_ctx *ctx, const unsigned long long *d_ids, con
 int fair_replace_policy_device(pgc_ctx *ctx, unsigned long long *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nobj,
                                int rate_is_frac, double rate, const unsigned long long *d_mids, const double *d_mx, const double *d_mf,
                                size_t nm, cudaStream_t st);
+int select_best_con_policy_device(pgc_ctx *ctx, const unsigned long long *d_ids, const double *d_x, const double *d_f, size_t n, size_t nx,
+                                  size_t nec, size_t nic, const double *tol, int rate_is_frac, double rate, unsigned long long *d_ids_out,
+                                  double *d_x_out, double *d_f_out, size_t *n_out, cudaStream_t st);
+int fair_replace_con_policy_device(pgc_ctx *ctx, unsigned long long *d_ids, double *d_x, double *d_f, size_t n, size_t nx, size_t nec, size_t nic,
+                                   const double *tol, int rate_is_frac, double rate, const unsigned long long *d_mids, const double *d_mx,
+                                   const double *d_mf, size_t nm, cudaStream_t st);
+int sort_population_con_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t nec, size_t nic, const double *tol, unsigned *d_order,
+                               cudaStream_t st);
 int policy_rate_count(const char *who, int rate_is_frac, double rate, size_t n, size_t *out);
 int so_best_indices_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t k, unsigned *d_sel, cudaStream_t st);
 int sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double cr, double eta_c, double m,

@@ -44,6 +44,48 @@ def test_policies_restatement_vs_reference(orc, ref):
             impl.select_best(ids, np.zeros((4, 2)), f, 5)
 
 
+def _constrained_group(rng, n, nec, nic, mixed):
+    """rows [f | nec equality | nic inequality constraints]: about a third feasible, the others violating a few constraints; unless
+    `mixed`, an individual violates constraints of ONE kind only (there compare_fc's two norms coincide, constrained.cpp:96-106)."""
+    f = np.empty((n, 1 + nec + nic))
+    f[:, 0] = rng.normal(size=n)
+    eq = rng.normal(scale=1e-3, size=(n, nec))          # within the tolerance of 1e-2
+    ineq = -np.abs(rng.normal(size=(n, nic)))           # satisfied
+    for i in range(n):
+        kind = rng.integers(0, 3)
+        if kind == 1 or (mixed and kind == 2):
+            if nec:
+                cols = rng.choice(nec, size=rng.integers(1, nec + 1), replace=False)
+                eq[i, cols] = rng.normal(scale=2.0, size=cols.size) + 0.5
+        if (kind == 2 or (mixed and kind == 1)) and nic:
+            cols = rng.choice(nic, size=rng.integers(1, nic + 1), replace=False)
+            ineq[i, cols] = np.abs(rng.normal(scale=2.0, size=cols.size)) + 0.05
+    f[:, 1:1 + nec] = eq
+    f[:, 1 + nec:] = ineq
+    return f
+
+
+def test_constrained_policies_restatement_vs_reference(orc, ref):
+    """the single-objective constrained branches (select_best.cpp:137-152, fair_replace.cpp:158-188, sort_population_con): the stable
+    restatement against the compiled reference on tie-free groups, with equality-only, inequality-only and both kinds of constraints."""
+    rng = np.random.default_rng(11)
+    for nec, nic in ((2, 0), (0, 3), (2, 2), (1, 4)):
+        tol = np.concatenate([np.full(nec, 1e-2), np.full(nic, 1e-2)])
+        for n, nm, rate in ((20, 5, 1), (20, 5, 3), (12, 9, 0.5), (16, 16, 1.0), (14, 6, 4)):  # <= 16 + ...: see the note on introsort above
+            ids = rng.integers(0, 2**63, n, dtype=np.uint64)
+            mids = rng.integers(0, 2**63, nm, dtype=np.uint64)
+            x, mx = rng.normal(size=(n, 3)), rng.normal(size=(nm, 3))
+            f, mf = _constrained_group(rng, n, nec, nic, False), _constrained_group(rng, nm, nec, nic, False)
+            a, b = orc.select_best_con(ids, x, f, rate, nec, nic, tol), ref.select_best_con(ids, x, f, rate, nec, nic, tol)
+            assert all(np.array_equal(u, v) for u, v in zip(a, b)), (nec, nic, n, rate)
+            a = orc.fair_replace_con(ids, x, f, rate, mids, mx, mf, nec, nic, tol)
+            b = ref.fair_replace_con(ids, x, f, rate, mids, mx, mf, nec, nic, tol)
+            assert all(np.array_equal(u, v) for u, v in zip(a, b)), (nec, nic, n, nm, rate)
+    # the order itself: feasible first by objective, then by the number of violated constraints, then by the violation norm
+    f = np.array([[5.0, 0.0, -1.0], [1.0, 0.5, -1.0], [9.0, 0.0, 2.0], [2.0, 0.0, -1.0], [0.0, 3.0, 1.0], [7.0, 0.2, -1.0]])
+    assert list(orc.sort_population_con(f, 1, 1, [1e-2, 1e-2])) == [3, 0, 5, 1, 2, 4]
+
+
 @pytest.mark.parametrize("kind", ("ring", "fully_connected"))
 def test_topologies(orc, kind):
     from pagmo2_b200 import capi

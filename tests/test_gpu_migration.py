@@ -70,6 +70,52 @@ def test_policies_match_oracle(capi, ctx, orc, nobj):
         dev_replace(capi, ctx, ids, np.zeros((4, 2)), np.zeros((4, nobj)), 1.5, ids, np.zeros((4, 2)), np.zeros((4, nobj)))
 
 
+@pytest.mark.parametrize("nec,nic", [(2, 0), (0, 3), (2, 2), (1, 4)])
+def test_constrained_policies_match_oracle(capi, ctx, orc, nec, nic):
+    """the single-objective constrained branches (select_best.cpp:137-152, fair_replace.cpp:158-188; sort_population_con): bit-exact
+    rows against the restatement, which tests/test_archipelago.py pins to the compiled reference.  Individuals violate constraints of
+    one kind only, where compare_fc's two norms coincide (pgc.h)."""
+    from test_archipelago import _constrained_group
+    rng = np.random.default_rng(70 + nec + 10 * nic)
+    tol = np.concatenate([np.full(nec, 1e-2), np.full(nic, 1e-2)])
+    L = capi.lib()
+    vp, sz = C.c_void_p, C.c_size_t
+    L.pgc_select_best_con_device.argtypes = [vp, vp, vp, vp, sz, sz, sz, sz, vp, C.c_int, C.c_double, vp, vp, vp, C.POINTER(sz), vp]
+    L.pgc_fair_replace_con_device.argtypes = [vp, vp, vp, vp, sz, sz, sz, sz, vp, C.c_int, C.c_double, vp, vp, vp, sz, vp]
+    L.pgc_sort_population_con_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
+    for n, nm, rate in ((20, 5, 1), (20, 5, 3), (12, 9, 0.5), (16, 16, 1.0), (1024, 300, 0.25), (4000, 4000, 1.0)):
+        nx, nf = 5, 1 + nec + nic
+        ids = rng.integers(0, 2**63, n, dtype=np.uint64)
+        mids = rng.integers(0, 2**63, nm, dtype=np.uint64)
+        x, mx = rng.normal(size=(n, nx)), rng.normal(size=(nm, nx))
+        f, mf = _constrained_group(rng, n, nec, nic, False), _constrained_group(rng, nm, nec, nic, False)
+        f[5] = f[2]  # a tie keeps the input order
+        d = [ctx.to_device(a) for a in (ids, x, f)]
+        o = [ctx.malloc(8 * n * w) for w in (1, nx, nf)]
+        m = [ctx.to_device(a) for a in (mids, mx, mf)]
+        dord = ctx.malloc(4 * n)
+        k = sz()
+        try:
+            capi.check(L.pgc_sort_population_con_device(ctx._h, d[2], n, nec, nic, tol.ctypes.data, dord, None))
+            assert np.array_equal(ctx.from_device(dord, (n,), np.uint32), orc.sort_population_con(f, nec, nic, tol))
+            capi.check(L.pgc_select_best_con_device(ctx._h, d[0], d[1], d[2], n, nx, nec, nic, tol.ctypes.data, int(isinstance(rate, float)),
+                                                    float(rate), o[0], o[1], o[2], C.byref(k), None))
+            got = ctx.from_device(o[0], (k.value,), np.uint64), ctx.from_device(o[1], (k.value, nx)), ctx.from_device(o[2], (k.value, nf))
+            for a, b in zip(got, orc.select_best_con(ids, x, f, rate, nec, nic, tol)):
+                assert np.array_equal(a, b), (n, rate)
+            capi.check(L.pgc_fair_replace_con_device(ctx._h, d[0], d[1], d[2], n, nx, nec, nic, tol.ctypes.data, int(isinstance(rate, float)),
+                                                     float(rate), m[0], m[1], m[2], nm, None))
+            got = ctx.from_device(d[0], (n,), np.uint64), ctx.from_device(d[1], (n, nx)), ctx.from_device(d[2], (n, nf))
+            for a, b in zip(got, orc.fair_replace_con(ids, x, f, rate, mids, mx, mf, nec, nic, tol)):
+                assert np.array_equal(a, b), (n, nm, rate)
+        finally:
+            for p in d + o + m + [dord]:
+                ctx.free(p)
+    with pytest.raises(capi.PgcError):  # no constraints: the unconstrained entry points are the ones to call
+        L.pgc_sort_population_con_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
+        capi.check(L.pgc_sort_population_con_device(ctx._h, ctx.malloc(64), 4, 0, 0, None, ctx.malloc(64), None))
+
+
 def test_population_init_matches_oracle(capi, ctx, orc):
     prob = capi.Problem(ctx, "rastrigin", dim=9)
     lb, ub = prob.bounds()
