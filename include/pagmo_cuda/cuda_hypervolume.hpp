@@ -20,6 +20,7 @@
 #include <vector>
 
 #include <pagmo/exceptions.hpp>
+#include <pagmo/rng.hpp>
 #include <pagmo/types.hpp>
 #include <pagmo/utils/hv_algos/hv_algorithm.hpp>
 
@@ -28,6 +29,19 @@
 
 namespace pagmo_cuda
 {
+
+namespace detail
+{
+inline std::vector<double> flatten_points(const std::vector<pagmo::vector_double> &points, std::size_t m)
+{
+    std::vector<double> flat(points.size() * m);
+    for (std::size_t i = 0; i < points.size(); ++i) {
+        if (points[i].size() != m) pagmo_throw(std::invalid_argument, "cuda hypervolume: a point and the reference point differ in dimension");
+        for (std::size_t d = 0; d < m; ++d) flat[i * m + d] = points[i][d];
+    }
+    return flat;
+}
+} // namespace detail
 
 class cuda_hv final : public pagmo::hv_algorithm
 {
@@ -100,6 +114,109 @@ private:
         }
         return flat;
     }
+    int m_device;
+    std::shared_ptr<pgc_ctx> m_ctx;
+};
+
+// pagmo::bf_fpras (hv_bf_fpras.hpp:63): (eps, delta) approximation of the hypervolume on the device (pgc_hv_fpras_host).  Like the
+// reference class it only computes: exclusive / least / greatest contributor throw.
+class cuda_bf_fpras final : public pagmo::hv_algorithm
+{
+public:
+    explicit cuda_bf_fpras(double eps = 1e-2, double delta = 1e-2, unsigned seed = pagmo::random_device::next(), int device = 0)
+        : m_eps(eps), m_delta(delta), m_seed(seed), m_device(device), m_ctx(detail::device_context(device))
+    {
+        if (eps <= 0 || eps > 1) pagmo_throw(std::invalid_argument, "Epsilon needs to be a probability greater then zero");
+        if (delta <= 0 || delta > 1) pagmo_throw(std::invalid_argument, "Delta needs to be a probability greater than zero");
+    }
+    double compute(std::vector<pagmo::vector_double> &points, const pagmo::vector_double &r_point) const override
+    {
+        const auto flat = detail::flatten_points(points, r_point.size());
+        double hv = 0.0;
+        std::lock_guard<std::mutex> lk(detail::device_mutex(m_device));
+        detail::check(pgc_hv_fpras_host(m_ctx.get(), flat.data(), points.size(), r_point.size(), r_point.data(), m_eps, m_delta, m_seed++, &hv),
+                      "pgc_hv_fpras_host");
+        return hv;
+    }
+    double exclusive(unsigned, std::vector<pagmo::vector_double> &, const pagmo::vector_double &) const override
+    {
+        pagmo_throw(std::invalid_argument, "This method is not supported by the bf_fpras algorithm");
+    }
+    unsigned long long least_contributor(std::vector<pagmo::vector_double> &, const pagmo::vector_double &) const override
+    {
+        pagmo_throw(std::invalid_argument, "This method is not supported by the bf_fpras algorithm");
+    }
+    unsigned long long greatest_contributor(std::vector<pagmo::vector_double> &, const pagmo::vector_double &) const override
+    {
+        pagmo_throw(std::invalid_argument, "This method is not supported by the bf_fpras algorithm");
+    }
+    std::vector<double> contributions(std::vector<pagmo::vector_double> &, const pagmo::vector_double &) const override
+    {
+        pagmo_throw(std::invalid_argument, "This method is not supported by the bf_fpras algorithm");
+    }
+    void verify_before_compute(const std::vector<pagmo::vector_double> &points, const pagmo::vector_double &r_point) const override
+    {
+        hv_algorithm::assert_minimisation(points, r_point);
+    }
+    std::shared_ptr<pagmo::hv_algorithm> clone() const override { return std::shared_ptr<pagmo::hv_algorithm>(new cuda_bf_fpras(*this)); }
+    std::string get_name() const override { return "bf_fpras algorithm (sm_100a, device " + std::to_string(m_device) + ")"; }
+
+private:
+    double m_eps, m_delta;
+    mutable unsigned m_seed; // successive calls continue like the reference's engine: a new stream each
+    int m_device;
+    std::shared_ptr<pgc_ctx> m_ctx;
+};
+
+// pagmo::bf_approx (hv_bf_approx.hpp:73): the Bringmann-Friedrich approximation of the least / greatest contributor on the device
+// (pgc_hv_approx_extreme_host).  Like the reference class it cannot compute the hypervolume itself.
+class cuda_bf_approx final : public pagmo::hv_algorithm
+{
+public:
+    explicit cuda_bf_approx(bool use_exact = true, unsigned trivial_subcase_size = 1, double eps = 1e-2, double delta = 1e-6,
+                            double delta_multiplier = 0.775, double alpha = 0.2, double initial_delta_coeff = 0.1, double gamma = 0.25,
+                            unsigned seed = pagmo::random_device::next(), int device = 0)
+        : m_use_exact(use_exact), m_trivial(trivial_subcase_size), m_eps(eps), m_delta(delta), m_delta_multiplier(delta_multiplier), m_alpha(alpha),
+          m_initial_delta_coeff(initial_delta_coeff), m_gamma(gamma), m_seed(seed), m_device(device), m_ctx(detail::device_context(device))
+    {
+        if (eps < 0 || eps > 1) pagmo_throw(std::invalid_argument, "Epsilon needs to be a probability.");
+        if (delta < 0 || delta > 1) pagmo_throw(std::invalid_argument, "Delta needs to be a probability.");
+    }
+    double compute(std::vector<pagmo::vector_double> &, const pagmo::vector_double &) const override
+    {
+        pagmo_throw(std::invalid_argument, "This algorithm can just approximate extreme contributions but not the hypervolume itself.");
+    }
+    unsigned long long least_contributor(std::vector<pagmo::vector_double> &points, const pagmo::vector_double &r_point) const override
+    {
+        return extreme(points, r_point, 0);
+    }
+    unsigned long long greatest_contributor(std::vector<pagmo::vector_double> &points, const pagmo::vector_double &r_point) const override
+    {
+        return extreme(points, r_point, 1);
+    }
+    void verify_before_compute(const std::vector<pagmo::vector_double> &points, const pagmo::vector_double &r_point) const override
+    {
+        hv_algorithm::assert_minimisation(points, r_point);
+    }
+    std::shared_ptr<pagmo::hv_algorithm> clone() const override { return std::shared_ptr<pagmo::hv_algorithm>(new cuda_bf_approx(*this)); }
+    std::string get_name() const override { return "Bringmann-Friedrich approximation method (sm_100a, device " + std::to_string(m_device) + ")"; }
+
+private:
+    unsigned long long extreme(const std::vector<pagmo::vector_double> &points, const pagmo::vector_double &r_point, int greatest) const
+    {
+        const auto flat = detail::flatten_points(points, r_point.size());
+        std::size_t idx = 0;
+        std::lock_guard<std::mutex> lk(detail::device_mutex(m_device));
+        detail::check(pgc_hv_approx_extreme_host(m_ctx.get(), flat.data(), points.size(), r_point.size(), r_point.data(), greatest,
+                                                 m_use_exact ? 1 : 0, m_trivial, m_eps, m_delta, m_delta_multiplier, m_alpha, m_initial_delta_coeff,
+                                                 m_gamma, m_seed++, &idx),
+                      "pgc_hv_approx_extreme_host");
+        return idx;
+    }
+    bool m_use_exact;
+    unsigned m_trivial;
+    double m_eps, m_delta, m_delta_multiplier, m_alpha, m_initial_delta_coeff, m_gamma;
+    mutable unsigned m_seed;
     int m_device;
     std::shared_ptr<pgc_ctx> m_ctx;
 };

@@ -243,6 +243,19 @@ PGC_API int pgc_hv_contributions_host(pgc_ctx *ctx, const double *points, size_t
 /* device-resident points; d_out: n doubles (compute writes the hypervolume to d_out[0]) */
 PGC_API int pgc_hv_device(pgc_ctx *ctx, const double *d_points, size_t n, size_t m, const double *r_point, int compute, double *d_out,
                           void *stream);
+/* bf_fpras::compute (hv_bf_fpras.cpp:91-146): (eps, delta) approximation of the hypervolume by the Karp-Luby estimator; the trial
+ * budget T = 12 log2(1 / delta) n / eps^2 is split over device threads that run whole rounds on their own Philox substreams (the same
+ * estimator T V / (n M), not the same number as the reference's mt19937 run).  Reference defaults: eps 1e-2, delta 1e-2. */
+PGC_API int pgc_hv_fpras_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r_point, double eps, double delta,
+                              uint64_t seed, double *hv);
+/* bf_approx::least_contributor / greatest_contributor (hv_bf_approx.cpp:98-112, :337-470): the Bringmann-Friedrich approximation of
+ * the extreme contributor - rounds of Monte-Carlo sampling inside every point's bounding box (all outstanding samples of a round in
+ * one launch, one CTA per point) with the reference's elimination and stopping rules, and its switch to the exact exclusive volume
+ * for small / expensive boxes (use_exact).  Reference defaults: use_exact 1, trivial_subcase_size 1, eps 1e-2, delta 1e-6,
+ * delta_multiplier 0.775, alpha 0.2, initial_delta_coeff 0.1, gamma 0.25. */
+PGC_API int pgc_hv_approx_extreme_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r_point, int greatest,
+                                       int use_exact, unsigned trivial_subcase_size, double eps, double delta, double delta_multiplier,
+                                       double alpha, double initial_delta_coeff, double gamma, uint64_t seed, size_t *idx);
 
 /* ---- dense contractions of CMA-ES / xNES (cmaes.cpp:246-253,362-380; xnes.cpp:302-305) ------------------------------------------
  * sampling: x_i = mean + sigma * BD * z_i, i < lambda, z ~ N(0, I) from Philox (seed, tag 8, generation, i, .); BD = B*D row-major

@@ -954,6 +954,24 @@ class Reference:
                                              io.ctypes.data_as(u64p), _dp(xo), _dp(fo), C.byref(k)))
         return io[:k.value], xo[:k.value], fo[:k.value]
 
+    def hv_fpras(self, f, r, eps=1e-2, delta=1e-2, seed=0) -> float:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        out = C.c_double()
+        self.lib.ref_hv_fpras.argtypes = [c_double_p, C.c_size_t, C.c_size_t, c_double_p, C.c_double, C.c_double, C.c_uint, C.POINTER(C.c_double)]
+        self._check(self.lib.ref_hv_fpras(_dp(f), f.shape[0], r.size, _dp(r), eps, delta, seed, C.byref(out)))
+        return out.value
+
+    def hv_approx_extreme(self, f, r, greatest=False, use_exact=True, eps=1e-2, delta=1e-6, seed=0) -> int:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        out = C.c_size_t()
+        self.lib.ref_hv_approx_extreme.argtypes = [c_double_p, C.c_size_t, C.c_size_t, c_double_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                   C.c_uint, C.POINTER(C.c_size_t)]
+        self._check(self.lib.ref_hv_approx_extreme(_dp(f), f.shape[0], r.size, _dp(r), int(greatest), int(use_exact), eps, delta, seed,
+                                                   C.byref(out)))
+        return out.value
+
     def select_best_con(self, ids, x, f, rate, nec, nic, tol):
         ids, x, f = Oracle._group(ids, x, f)
         tol = np.ascontiguousarray(tol, dtype=np.float64)

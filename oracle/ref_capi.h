@@ -84,6 +84,9 @@ int ref_fair_replace_con(const unsigned long long *ids, const double *x, const d
                          size_t nm, unsigned long long *ids_out, double *x_out, double *f_out);
 int ref_select_best_con(const unsigned long long *ids, const double *x, const double *f, size_t n, size_t nx, size_t nec, size_t nic,
                         const double *tol, int rate_is_frac, double rate, unsigned long long *ids_out, double *x_out, double *f_out, size_t *n_out);
+int ref_hv_fpras(const double *f, size_t n, size_t m, const double *r, double eps, double delta, unsigned seed, double *out);
+int ref_hv_approx_extreme(const double *f, size_t n, size_t m, const double *r, int greatest, int use_exact, double eps, double delta,
+                          unsigned seed, size_t *out);
 int ref_hv_compute(const double *f, size_t n, size_t m, const double *r, double *out);
 int ref_hv_contributions(const double *f, size_t n, size_t m, const double *r, double *out);
 

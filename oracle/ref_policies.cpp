@@ -104,6 +104,8 @@ int ref_select_best(const unsigned long long *ids, const double *x, const double
 
 // ---- hypervolume (src/utils/hypervolume.cpp, hv_algos/hv_hv2d.cpp, hv_hv3d.cpp) through pagmo::hypervolume with the reference's own
 // choice of algorithm (get_best_compute / get_best_contributions: hv2d for 2 objectives, hv3d for 3, hvwfg beyond)
+#include <pagmo/utils/hv_algos/hv_bf_approx.hpp>
+#include <pagmo/utils/hv_algos/hv_bf_fpras.hpp>
 #include <pagmo/utils/hypervolume.hpp>
 namespace
 {
@@ -115,6 +117,33 @@ std::vector<pagmo::vector_double> rows(const double *f, size_t n, size_t m)
 }
 } // namespace
 extern "C" {
+// the approximation algorithms through pagmo::hypervolume with an explicit algorithm object (reference defaults but eps / delta / seed)
+int ref_hv_fpras(const double *f, size_t n, size_t m, const double *r, double eps, double delta, unsigned seed, double *out)
+{
+    try {
+        pagmo::hypervolume hv(rows(f, n, m), false);
+        pagmo::bf_fpras algo(eps, delta, seed);
+        *out = hv.compute(pagmo::vector_double(r, r + m), algo);
+        return 0;
+    } catch (const std::exception &e) {
+        ref_set_error(e.what());
+        return 1;
+    }
+}
+int ref_hv_approx_extreme(const double *f, size_t n, size_t m, const double *r, int greatest, int use_exact, double eps, double delta,
+                          unsigned seed, size_t *out)
+{
+    try {
+        pagmo::hypervolume hv(rows(f, n, m), false);
+        pagmo::bf_approx algo(use_exact != 0, 1u, eps, delta, 0.775, 0.2, 0.1, 0.25, seed);
+        const pagmo::vector_double rp(r, r + m);
+        *out = static_cast<size_t>(greatest ? hv.greatest_contributor(rp, algo) : hv.least_contributor(rp, algo));
+        return 0;
+    } catch (const std::exception &e) {
+        ref_set_error(e.what());
+        return 1;
+    }
+}
 int ref_hv_compute(const double *f, size_t n, size_t m, const double *r, double *out)
 {
     try {

@@ -330,6 +330,32 @@ class Context:
                                         C.byref(out)))
         return out.value
 
+    def hv_fpras(self, f, r, eps=1e-2, delta=1e-2, seed=0) -> float:
+        """bf_fpras::compute on the device (pgc_hv_fpras_host)."""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        n, m = f.shape if f.ndim == 2 else (0, r.size)
+        out = C.c_double()
+        L = lib()
+        L.pgc_hv_fpras_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_double, C.c_double, C.c_uint64,
+                                        C.POINTER(C.c_double)]
+        check(L.pgc_hv_fpras_host(self._h, f.ctypes.data, n, m, r.ctypes.data, eps, delta, seed, C.byref(out)))
+        return out.value
+
+    def hv_approx_extreme(self, f, r, greatest=False, use_exact=True, trivial_subcase_size=1, eps=1e-2, delta=1e-6, delta_multiplier=0.775,
+                          alpha=0.2, initial_delta_coeff=0.1, gamma=0.25, seed=0) -> int:
+        """bf_approx::least_contributor / greatest_contributor on the device (pgc_hv_approx_extreme_host)."""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        out = C.c_size_t()
+        L = lib()
+        L.pgc_hv_approx_extreme_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_double,
+                                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64, C.POINTER(C.c_size_t)]
+        check(L.pgc_hv_approx_extreme_host(self._h, f.ctypes.data, f.shape[0], f.shape[1], r.ctypes.data, int(greatest), int(use_exact),
+                                           trivial_subcase_size, eps, delta, delta_multiplier, alpha, initial_delta_coeff, gamma, seed,
+                                           C.byref(out)))
+        return out.value
+
     def hv_contributions(self, points: np.ndarray, r_point) -> np.ndarray:
         f = np.ascontiguousarray(points, dtype=np.float64)
         r = np.ascontiguousarray(r_point, dtype=np.float64)

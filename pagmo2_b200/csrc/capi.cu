@@ -881,6 +881,24 @@ int pgc_hv_device(pgc_ctx *ctx, const double *d_points, size_t n, size_t m, cons
     return hv_device(ctx, d_points, n, m, r_point, compute, d_out, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
 }
 
+int pgc_hv_fpras_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r_point, double eps, double delta, uint64_t seed,
+                      double *hv)
+{
+    PGC_REQUIRE(ctx && r_point && hv && (points || n == 0), "pgc_hv_fpras_host: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return hv_fpras_host(ctx, points, n, m, r_point, eps, delta, seed, hv);
+}
+
+int pgc_hv_approx_extreme_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r_point, int greatest, int use_exact,
+                               unsigned trivial_subcase_size, double eps, double delta, double delta_multiplier, double alpha,
+                               double initial_delta_coeff, double gamma, uint64_t seed, size_t *idx)
+{
+    PGC_REQUIRE(ctx && r_point && idx && points, "pgc_hv_approx_extreme_host: null argument");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    return hv_approx_extreme_host(ctx, points, n, m, r_point, greatest, use_exact, trivial_subcase_size, eps, delta, delta_multiplier, alpha,
+                                  initial_delta_coeff, gamma, seed, idx);
+}
+
 static int hv_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r, int compute, double *out)
 {
     PGC_REQUIRE(ctx && r && out && (points || n == 0), "pgc_hv_*_host: null argument");

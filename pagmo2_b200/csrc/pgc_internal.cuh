@@ -382,6 +382,11 @@ int fair_replace_con_policy_device(pgc_ctx *ctx, unsigned long long *d_ids, doub
                                    const double *d_mf, size_t nm, cudaStream_t st);
 int sort_population_con_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t nec, size_t nic, const double *tol, unsigned *d_order,
                                cudaStream_t st);
+int hv_fpras_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r, double eps, double delta, unsigned long long seed,
+                  double *hv_out);
+int hv_approx_extreme_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const double *r, int greatest, int use_exact,
+                           unsigned trivial_subcase_size, double eps, double delta, double delta_multiplier, double alpha,
+                           double initial_delta_coeff, double gamma, unsigned long long seed, size_t *idx_out);
 int policy_rate_count(const char *who, int rate_is_frac, double rate, size_t n, size_t *out);
 int so_best_indices_device(pgc_ctx *ctx, const double *d_f, size_t n, size_t k, unsigned *d_sel, cudaStream_t st);
 int sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double cr, double eta_c, double m,

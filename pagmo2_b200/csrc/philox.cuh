@@ -28,7 +28,8 @@ enum PhiloxTag : uint32_t { // stream tags: one per consumer so that streams nev
     kTagMoead = 13,       // moead_gen: an individual's candidate (diversity draw, parents, crossover, mutation; moead_gen.cpp:227-269)
     kTagMoeadOrder = 14,  // moead_gen: the order of a generation (stands in for std::shuffle, :213)
     kTagMoeadInsert = 15, // moead_gen: the shuffle of a candidate's neighbourhood at insertion (:322-324)
-    kTagGaco = 16         // gaco: an ant's kernel choice and its normal deviates (gaco.cpp:826-868)
+    kTagGaco = 16,        // gaco: an ant's kernel choice and its normal deviates (gaco.cpp:826-868)
+    kTagHvApprox = 17     // bf_fpras / bf_approx: the Monte-Carlo samples (hv_bf_fpras.cpp:117-137, hv_bf_approx.cpp:292-320)
 };
 
 struct Philox4 {

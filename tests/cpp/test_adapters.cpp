@@ -36,6 +36,7 @@
 #include <pagmo_cuda/cuda_algorithms.hpp>
 #include <pagmo_cuda/cuda_bfe.hpp>
 #include <pagmo_cuda/cuda_hypervolume.hpp>
+#include <pagmo/utils/hv_algos/hv_hvwfg.hpp>
 #include <pagmo/utils/hypervolume.hpp>
 #include <pagmo/utils/hv_algos/hv_hv2d.hpp>
 #include <pagmo/utils/hv_algos/hv_hv3d.hpp>
@@ -533,6 +534,42 @@ int main(int argc, char **argv)
             CHECK(std::abs(hv.exclusive(5u, r, gpu_algo) - cw[5]) <= 1e-9 * std::max(cw[5], 1e-300));
             std::printf("cuda_hv m=%u: hv %.15g (cpu %.15g)\n", m, got, want);
         }
+    }
+
+    // ---- 3d'. four objectives (hvwfg's territory) and the approximation algorithms behind pagmo::hypervolume ----
+    {
+        std::mt19937 e(78);
+        std::uniform_real_distribution<double> u(0.05, 1.);
+        std::vector<pagmo::vector_double> pts(60, pagmo::vector_double(4));
+        for (auto &p : pts) {
+            double nrm = 0;
+            for (auto &v : p) {
+                v = u(e);
+                nrm += v * v;
+            }
+            for (auto &v : p) v /= std::sqrt(nrm);
+        }
+        const pagmo::vector_double r(4, 1.2);
+        pagmo::hypervolume hv{pts, true};
+        pagmo_cuda::cuda_hv gpu_algo;
+        pagmo::hvwfg wfg;
+        const double want = hv.compute(r, wfg), got = hv.compute(r, gpu_algo);
+        CHECK(std::abs(got - want) <= 1e-12 * want);
+        const auto cw = hv.contributions(r, wfg), cg = hv.contributions(r, gpu_algo);
+        CHECK(max_rel(cg, cw) <= 1e-9);
+        pagmo_cuda::cuda_bf_fpras fpras{0.02, 0.01, 5u};
+        CHECK(std::abs(hv.compute(r, fpras) - want) <= 0.02 * want);
+        pagmo_cuda::cuda_bf_approx approx{true, 1u, 0.05, 1e-4, 0.775, 0.2, 0.1, 0.25, 5u};
+        const auto lo = hv.least_contributor(r, approx), hi = hv.greatest_contributor(r, approx);
+        CHECK(cw[lo] <= 1.05 * *std::min_element(cw.begin(), cw.end()) && 1.05 * cw[hi] >= *std::max_element(cw.begin(), cw.end()));
+        bool threw = false;
+        try {
+            hv.compute(r, approx);
+        } catch (const std::invalid_argument &) {
+            threw = true; // hv_bf_approx.cpp:69-73
+        }
+        CHECK(threw);
+        std::printf("cuda_hv m=4: hv %.15g (hvwfg %.15g), fpras %.6g, least / greatest contributor %llu / %llu\n", got, want, hv.compute(r, fpras), lo, hi);
     }
 
     // ---- 3e. one batch sharded over several devices (here: every visible device, or device 0 twice): same values as one device ----

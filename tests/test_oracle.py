@@ -189,6 +189,20 @@ def test_hypervolume_wfg_against_fixtures_and_reference(orc, ref):
             assert np.abs(orc.hv_contributions(f, r) - ref.hv_contributions(f, r)).max() <= 1e-14 * hv
 
 
+def test_reference_approximations_keep_their_promise(ref):
+    """bf_fpras / bf_approx of the compiled reference on a small front: the properties tests/test_gpu_hv_approx.py asks of the device
+    versions (eps bound against the exact hypervolume; the exact extreme contributor up to 1 + eps) hold for the reference's own runs."""
+    rng = np.random.default_rng(0)
+    f = rng.uniform(0.05, 1, (40, 3))
+    f /= np.linalg.norm(f, axis=1, keepdims=True)
+    r = np.full(3, 1.2)
+    exact, c = ref.hv_compute(f, r), ref.hv_contributions(f, r)
+    assert abs(ref.hv_fpras(f, r, 0.05, 0.05, 1) - exact) <= 0.05 * exact
+    for use_exact in (True, False):
+        lo, hi = ref.hv_approx_extreme(f, r, False, use_exact, 0.05, 1e-4, 3), ref.hv_approx_extreme(f, r, True, use_exact, 0.05, 1e-4, 3)
+        assert c[lo] <= 1.05 * c.min() and 1.05 * c[hi] >= c.max()
+
+
 def test_simple_matches_golden(orc):
     g = np.load(GOLD / "simple_ref.npz")
     for fam in ("rastrigin", "ackley", "griewank", "schwefel", "rosenbrock"):
