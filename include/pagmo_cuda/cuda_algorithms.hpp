@@ -9,6 +9,7 @@
 //   pagmo_cuda::cuda_nsga2   pagmo::nsga2   (nsga2.hpp:103   gen, cr, eta_c, m, eta_m, seed)
 //   pagmo_cuda::cuda_sga     pagmo::sga     (sga.hpp:166     gen, cr, eta_c, m, param_m, param_s, crossover, mutation, selection, seed)
 //   pagmo_cuda::cuda_cmaes   pagmo::cmaes   (cmaes.hpp:110   gen, cc, cs, c1, cmu, sigma0, ftol, xtol, memory, force_bounds, seed)
+//   pagmo_cuda::cuda_xnes    pagmo::xnes    (xnes.hpp:107    gen, eta_mu, eta_sigma, eta_b, sigma0, ftol, xtol, memory, force_bounds, seed)
 //   pagmo_cuda::cuda_gaco    pagmo::gaco    (gaco.hpp:104    gen, ker, q, oracle, acc, threshold, n_gen_mark, impstop, evalstop, focus, memory, seed)
 //   pagmo_cuda::cuda_maco    pagmo::maco    (maco.hpp:107    gen, ker, q, threshold, n_gen_mark, evalstop, focus, memory, seed)
 //
@@ -428,6 +429,40 @@ public:
     }
 };
 
+// pagmo::xnes (xnes.hpp:107-108).  Sampling, evaluation and the natural-gradient contractions run on the device; the mean / A / sigma
+// updates (exp of the symmetric d_A through a Jacobi solver where the reference uses Eigen's matrix exponential) on the host:
+// pgc_xnes_evolve_device.  eta_mu, eta_sigma, eta_b travel in the descriptor's cma_cc, cma_cs, cma_c1.
+class cuda_xnes : public cuda_algorithm_base
+{
+public:
+    cuda_xnes(unsigned gen = 1u, double eta_mu = -1, double eta_sigma = -1, double eta_b = -1, double sigma0 = -1, double ftol = 1e-6,
+              double xtol = 1e-6, bool memory = false, bool force_bounds = false, unsigned seed = pagmo::random_device::next(), int device = 0)
+        : cuda_algorithm_base(PGC_ALGO_XNES, "xNES: Exponential Natural Evolution Strategies", gen, seed, device)
+    {
+        const auto check_eta = [](double v, const char *name, const char *verb) { // xnes.cpp:55-78
+            if (((v <= 0.) || (v > 1.)) && !(v == -1)) {
+                pagmo_throw(std::invalid_argument, std::string(name) + verb + " in ]0,1] or -1 if its value has to be initialized automatically, a value of "
+                                                       + std::to_string(v) + " was detected");
+            }
+        };
+        check_eta(eta_mu, "eta_mu", " must be");
+        check_eta(eta_sigma, "eta_sigma", " needs to be");
+        check_eta(eta_b, "eta_b", " needs to be");
+        check_eta(sigma0, "sigma0", " needs to be");
+        no_memory(memory, "cuda_xnes");
+        m_desc.cma_cc = eta_mu, m_desc.cma_cs = eta_sigma, m_desc.cma_c1 = eta_b, m_desc.sigma0 = sigma0;
+        m_desc.ftol = ftol, m_desc.xtol = xtol, m_desc.force_bounds = force_bounds ? 1u : 0u;
+    }
+    using log_line_type = std::tuple<unsigned, unsigned long long, double, double, double, double>; // Gen, Fevals, Best, dx, df, sigma
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        return typed_log<log_line_type>([](const double *r) {
+            return log_line_type(static_cast<unsigned>(r[0]), static_cast<unsigned long long>(r[1]), r[2], r[3], r[4], r[5]);
+        });
+    }
+};
+
 // pagmo::nspso (nspso.hpp:59-62): non-dominated sorting PSO; generational in the reference itself, so this is the same algorithm on
 // Philox draws (pgc_nspso_evolve_device, nspso.cu).  memory = true keeps the velocities and the archive between evolve() calls.
 class cuda_nspso : public cuda_algorithm_base
@@ -796,6 +831,7 @@ PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_maco)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_moead_gen)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_nspso)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_cmaes)
+PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_xnes)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_sga)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_de)
 PAGMO_S11N_ALGORITHM_EXPORT_KEY(pagmo_cuda::cuda_sade)

@@ -318,6 +318,14 @@ PGC_API int pgc_cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f,
                                     double cmu, double sigma0, double ftol, double xtol, int force_bounds, uint64_t seed,
                                     uint32_t first_generation, unsigned *gens_done, double *sigma_out, void *stream);
 
+/* xnes::evolve (src/algorithms/xnes.cpp:96-303), exponential natural evolution strategies, on a device-resident population (in place),
+ * memory = false: sampling, evaluation and the natural-gradient contractions on the device, the D x D updates on the host (exp of the
+ * symmetric d_A through a Jacobi eigendecomposition where the reference uses Eigen's matrix exponential).  Constructor arguments as
+ * xnes.hpp:107-108 (-1: automatic).  *sigma_out (optional): the step size the run ends with. */
+PGC_API int pgc_xnes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lambda, unsigned gens, double eta_mu, double eta_sigma,
+                                   double eta_b, double sigma0, double ftol, double xtol, int force_bounds, uint64_t seed,
+                                   uint32_t first_generation, unsigned *gens_done, double *sigma_out, void *stream);
+
 /* sga::evolve (sga.cpp:184-292) on a device-resident single-objective population, in place (the population comes back sorted by
  * fitness, as the reference's reinsertion leaves it).  crossover: 0 exponential, 1 binomial, 2 single, 3 sbx; mutation: 0 gaussian,
  * 1 uniform, 2 polynomial; selection: 0 tournament (param_s <= 16), 1 truncated.  Reference defaults: cr 0.9, eta_c 1, m 0.02,
@@ -335,7 +343,8 @@ typedef enum pgc_algo {
     PGC_ALGO_NSGA2 = 5,   /* src/algorithms/nsga2.cpp:91-307 */
     PGC_ALGO_SGA = 6,     /* src/algorithms/sga.cpp:184-292 */
     PGC_ALGO_CMAES = 7,   /* src/algorithms/cmaes.cpp:111-407 */
-    PGC_ALGO_NSPSO = 8    /* src/algorithms/nspso.cpp:84-411 */
+    PGC_ALGO_NSPSO = 8,   /* src/algorithms/nspso.cpp:84-411 */
+    PGC_ALGO_XNES = 9     /* src/algorithms/xnes.cpp:96-303: eta_mu, eta_sigma, eta_b travel in cma_cc, cma_cs, cma_c1 (-1: automatic) */
 } pgc_algo;
 
 /* Constructor arguments of the reference UDAs; pgc_algo_defaults() fills in the reference's default values
@@ -390,7 +399,7 @@ PGC_API int pgc_algo_evolve_memory_device(pgc_problem *prob, const pgc_algo_desc
  *   de1220  gen, fevals, best, F, CR, variant, dx, df        (de1220.cpp:570-595)
  *   pso_gen gen, fevals, gbest, mean velocity, mean lbest, average distance   (pso_gen.cpp:464-518)
  *   sga     gen, fevals, best, improvement                   (sga.cpp:252-274; verbosity 1 logs only the generations that improve)
- *   cmaes   gen, fevals, best, dx, df, sigma                 (cmaes.cpp:276-296)
+ *   cmaes   gen, fevals, best, dx, df, sigma                 (cmaes.cpp:276-296); xnes the same (xnes.cpp:238-256)
  *   nsga2   gen, fevals, ideal point [nobj]                  (nsga2.cpp:144-173; logged BEFORE the generation, as the reference does)
  *   nspso   gen, fevals, ideal point of the archive [nobj]   (nspso.cpp:163-192; fevals counted from this call's start)
  * log_rows: HOST array [max_rows x row_len]; *n_rows = lines written (the DE family stops logging at the generation whose exit test

@@ -99,6 +99,10 @@ int oracle_cmaes_sample(const double *mean, const double *bd, double sigma, size
 int oracle_cmaes_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t lam, size_t D,
                         unsigned gens, double cc, double cs, double c1, double cmu, double sigma0, double ftol, double xtol, int force_bounds,
                         uint64_t seed, uint32_t first_generation, unsigned *gens_done, double *sigma_out);
+/* xnes::evolve (xnes.cpp:96-303, memory = false) on the Philox normals; -1 = automatic for the etas and sigma0 */
+int oracle_xnes_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t lam, size_t D, unsigned gens,
+                       double eta_mu, double eta_sigma, double eta_b, double sigma0, double ftol, double xtol, int force_bounds, uint64_t seed,
+                       uint32_t first_generation, unsigned *gens_done, double *sigma_out);
 
 /* ---- migration (restate_migration.c): select_best / fair_replace on flat groups, topology in-edge lists ---- */
 int oracle_select_best(const uint64_t *ids, const double *x, const double *f, size_t n, size_t nx, size_t nobj, int rate_is_frac, double rate,

@@ -273,6 +273,20 @@ class Oracle:
             raise ValueError("oracle_cmaes_evolve failed")
         return x, f, done.value, sigma.value
 
+    def xnes_evolve(self, prob, lb, ub, x, f, gens=1, eta_mu=-1., eta_sigma=-1., eta_b=-1., sigma0=-1., ftol=1e-6, xtol=1e-6, force_bounds=False,
+                    seed=0, first_generation=1):
+        """restated xnes::evolve (memory = false) on the Philox normals: returns (x, f, gens_done, sigma)."""
+        x = np.array(x, dtype=np.float64, order="C")
+        f = np.array(f, dtype=np.float64, order="C").reshape(-1)
+        lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (lb, ub))
+        done, sigma = C.c_uint(), C.c_double()
+        if self.lib.oracle_xnes_evolve(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), C.c_size_t(x.shape[0]), C.c_size_t(x.shape[1]),
+                                       C.c_uint(gens), C.c_double(eta_mu), C.c_double(eta_sigma), C.c_double(eta_b), C.c_double(sigma0),
+                                       C.c_double(ftol), C.c_double(xtol), C.c_int(int(force_bounds)), C.c_uint64(seed),
+                                       C.c_uint32(first_generation), C.byref(done), C.byref(sigma)):
+            raise ValueError("oracle_xnes_evolve failed")
+        return x, f, done.value, sigma.value
+
     # ---- CMA-ES / xNES contractions (restate_cmaes.c) ----
     def weighted_gram(self, rows, w, idx=None, center=None, scale_div: float = 1.0):
         """(sum_i w_i (r_i - c)(r_i - c)^T / scale_div, sum_i w_i r_i) in the reference's order."""

@@ -248,3 +248,113 @@ int oracle_cmaes_evolve(const oracle_problem *prob, const double *lb, const doub
     free(z); free(xn); free(fn); free(tmp); free(work); free(wv); free(V); free(idx);
     return rc;
 }
+
+/* ---- xnes::evolve, src/algorithms/xnes.cpp:96-303 (memory = false), with the Philox normals the device draws ------------------
+ * Statement by statement after the reference: utilities u (:146-157), A = diag(max(ub - lb, 1e-6) * sigma) and the mean at the best
+ * individual (:160-175), per generation the lam samples x = mean + A z with their evaluation (pop.set_x, :196-216), the exit tests on
+ * ||A z_0|| and on the NEW population's fitness spread (:219-236), the natural gradients d_center = sum u_i z_(i), cov_grad = sum u_i
+ * (z_(i) z_(i)^T - I) over the fitness-sorted samples, and the updates mean += eta_mu A d_center, A <- A exp(d_A), sigma (:264-291).
+ * Eigen's matrix exponential (absent here) is stood in for by exp of the symmetric d_A through the Jacobi eigendecomposition above:
+ * PARITY UNPINNED for that step, like cmaes' eigendecomposition. */
+int oracle_xnes_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t lam, size_t D, unsigned gens,
+                       double eta_mu, double eta_sigma, double eta_b, double sigma0, double ftol, double xtol, int force_bounds, uint64_t seed,
+                       uint32_t first_generation, unsigned *gens_done, double *sigma_out)
+{
+    if (gens_done) *gens_done = 0;
+    if (lam < 4u) return -1;
+    if (gens == 0) return 0;
+    const double dim_d = (double)D, lam_d = (double)lam;
+    if (eta_mu == -1) eta_mu = 1.;
+    const double common_default = 0.6 * (3. + log(dim_d)) / (dim_d * sqrt(dim_d));
+    if (eta_sigma == -1) eta_sigma = common_default;
+    if (eta_b == -1) eta_b = common_default;
+    double *u = (double *)malloc(lam * sizeof(double)), sum = 0.;
+    for (size_t i = 0; i < lam; ++i) u[i] = fmax(0., log(lam_d / 2. + 1.) - log((double)(i + 1)));
+    for (size_t i = 0; i < lam; ++i) sum += u[i];
+    for (size_t i = 0; i < lam; ++i) u[i] = u[i] / sum - 1. / lam_d;
+    double sigma = sigma0 == -1 ? 0.5 : sigma0;
+    double *A = VEC(D * D), *mean = VEC(D), *z = VEC(lam * D), *xn = VEC(lam * D), *fn = VEC(lam), *dc = VEC(D), *G = VEC(D * D), *dA = VEC(D * D),
+           *work = VEC(D * D), *wv = VEC(D), *V = VEC(D * D), *E = VEC(D * D), *An = VEC(D * D), *tmp = VEC(D);
+    uint32_t *idx = (uint32_t *)malloc(lam * sizeof(uint32_t));
+    for (size_t j = 0; j < D; ++j) A[j * D + j] = fmax(ub[j] - lb[j], 1e-6) * sigma;
+    size_t ib = 0, iw = 0;
+    for (size_t i = 1; i < lam; ++i)
+        if (f[i] < f[ib]) ib = i;
+    memcpy(mean, x + ib * D, D * sizeof(double));
+    unsigned done = 0;
+    int rc = 0;
+    for (unsigned g = 0; g < gens && !rc; ++g) {
+        const uint32_t generation = first_generation + g;
+        oracle_cmaes_sample(mean, A, 1.0, lam, D, seed, generation, z, xn);
+        if (force_bounds)
+            for (size_t i = 0; i < lam; ++i)
+                for (size_t j = 0; j < D; ++j) {
+                    if (xn[i * D + j] < lb[j]) xn[i * D + j] = lb[j];
+                    else if (xn[i * D + j] > ub[j]) xn[i * D + j] = ub[j];
+                }
+        if ((rc = oracle_problem_eval(prob, xn, lam, fn))) break;
+        memcpy(x, xn, lam * D * sizeof(double));
+        memcpy(f, fn, lam * sizeof(double));
+        ++done;
+        double nrm = 0.;
+        for (size_t a = 0; a < D; ++a) {
+            double y = 0.;
+            for (size_t j = 0; j < D; ++j) y += A[a * D + j] * z[j];
+            nrm += y * y;
+        }
+        if (sqrt(nrm) < xtol) break;
+        ib = iw = 0;
+        for (size_t i = 1; i < lam; ++i) {
+            if (f[i] < f[ib]) ib = i;
+            if (f[i] > f[iw]) iw = i;
+        }
+        if (fabs(f[ib] - f[iw]) < ftol) break;
+        for (size_t i = 0; i < lam; ++i) idx[i] = (uint32_t)i;
+        for (size_t i = 1; i < lam; ++i) { /* stable insertion sort by plain < (:258-261) */
+            const uint32_t o = idx[i];
+            size_t j = i;
+            while (j > 0 && f[o] < f[idx[j - 1]]) { idx[j] = idx[j - 1]; --j; }
+            idx[j] = o;
+        }
+        oracle_weighted_mean(z, idx, u, lam, D, dc);
+        oracle_weighted_gram(z, idx, NULL, u, lam, D, 1.0, G);
+        double usum = 0.;
+        for (size_t i = 0; i < lam; ++i) usum += u[i];
+        for (size_t a = 0; a < D; ++a) G[a * D + a] -= usum; /* sum u_i (z z^T - I) */
+        double cov_trace = 0.;
+        for (size_t a = 0; a < D; ++a) cov_trace += G[a * D + a];
+        for (size_t a = 0; a < D; ++a) G[a * D + a] -= cov_trace / dim_d;
+        for (size_t a = 0; a < D; ++a)
+            for (size_t b = 0; b < D; ++b) dA[a * D + b] = 0.5 * ((a == b ? eta_sigma * cov_trace / dim_d : 0.) + eta_b * G[a * D + b]);
+        for (size_t a = 0; a < D; ++a) {
+            double y = 0.;
+            for (size_t j = 0; j < D; ++j) y += A[a * D + j] * dc[j];
+            tmp[a] = y;
+        }
+        for (size_t a = 0; a < D; ++a) mean[a] = mean[a] + eta_mu * tmp[a];
+        /* A <- A exp(d_A): d_A is symmetric, exp(d_A) = V diag(exp(w)) V^T */
+        for (size_t a = 0; a < D; ++a)
+            for (size_t b = a + 1; b < D; ++b) dA[a * D + b] = dA[b * D + a] = (dA[a * D + b] + dA[b * D + a]) / 2.;
+        memcpy(work, dA, D * D * sizeof(double));
+        jacobi_eigen(work, D, wv, V);
+        for (size_t a = 0; a < D; ++a)
+            for (size_t b = 0; b < D; ++b) {
+                double y = 0.;
+                for (size_t k = 0; k < D; ++k) y += V[a * D + k] * exp(wv[k]) * V[b * D + k];
+                E[a * D + b] = y;
+            }
+        for (size_t a = 0; a < D; ++a)
+            for (size_t b = 0; b < D; ++b) {
+                double y = 0.;
+                for (size_t k = 0; k < D; ++k) y += A[a * D + k] * E[k * D + b];
+                An[a * D + b] = y;
+            }
+        memcpy(A, An, D * D * sizeof(double));
+        sigma = sigma * exp(eta_sigma / 2. * cov_trace / dim_d);
+    }
+    if (gens_done) *gens_done = done;
+    if (sigma_out) *sigma_out = sigma;
+    free(u); free(A); free(mean); free(z); free(xn); free(fn); free(dc); free(G); free(dA); free(work); free(wv); free(V); free(E); free(An);
+    free(tmp); free(idx);
+    return rc;
+}

@@ -75,7 +75,7 @@ class AlgoMemory(C.Structure):
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("u", C.c_void_p), ("initialized", C.c_int32), ("reserved_", C.c_int32)]
 
 
-ALGO = {"de": 1, "sade": 2, "de1220": 3, "pso_gen": 4, "nsga2": 5, "sga": 6, "cmaes": 7, "nspso": 8}
+ALGO = {"de": 1, "sade": 2, "de1220": 3, "pso_gen": 4, "nsga2": 5, "sga": 6, "cmaes": 7, "nspso": 8, "xnes": 9}
 NSPSO_DIVERSITY = {"crowding distance": 0, "niche count": 1, "max min": 2}
 SGA_CROSSOVER = {"exponential": 0, "binomial": 1, "single": 2, "sbx": 3}
 SGA_MUTATION = {"gaussian": 0, "uniform": 1, "polynomial": 2}
@@ -583,6 +583,25 @@ class Problem:
         try:
             check(lib().pgc_cmaes_evolve_device(self._h, dx, df, x.shape[0], gens, cc, cs, c1, cmu, sigma0, ftol, xtol, int(force_bounds), seed,
                                                 first_generation, C.byref(done), C.byref(sigma), None))
+            return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), done.value, sigma.value
+        finally:
+            self.ctx.free(dx)
+            self.ctx.free(df)
+
+    def xnes_evolve(self, x, f, gens=1, eta_mu=-1., eta_sigma=-1., eta_b=-1., sigma0=-1., ftol=1e-6, xtol=1e-6, force_bounds=False, seed=0,
+                    first_generation=1):
+        """xnes::evolve on the device: returns (x, f, gens_done, sigma)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
+        done, sigma = C.c_uint(), C.c_double()
+        L = lib()
+        L.pgc_xnes_evolve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double,
+                                             C.c_double, C.c_double, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint), C.POINTER(C.c_double),
+                                             C.c_void_p]
+        try:
+            check(L.pgc_xnes_evolve_device(self._h, dx, df, x.shape[0], gens, eta_mu, eta_sigma, eta_b, sigma0, ftol, xtol, int(force_bounds), seed,
+                                           first_generation, C.byref(done), C.byref(sigma), None))
             return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), done.value, sigma.value
         finally:
             self.ctx.free(dx)

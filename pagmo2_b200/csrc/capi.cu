@@ -874,6 +874,17 @@ int pgc_maco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n
                               s, gens_done, problem_eval_device, stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
 }
 
+int pgc_xnes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lambda, unsigned gens, double eta_mu, double eta_sigma, double eta_b,
+                           double sigma0, double ftol, double xtol, int force_bounds, uint64_t seed, uint32_t first_generation,
+                           unsigned *gens_done, double *sigma_out, void *stream)
+{
+    PGC_REQUIRE(prob && (lambda == 0 || (d_x && d_f)), "pgc_xnes_evolve_device: null argument");
+    PGC_NO_INTEGER_GENES(prob, "pgc_xnes_evolve_device");
+    PGC_CUDA(cudaSetDevice(prob->ctx->device));
+    return xnes_evolve_device(prob, d_x, d_f, lambda, gens, eta_mu, eta_sigma, eta_b, sigma0, ftol, xtol, force_bounds, seed, first_generation,
+                              gens_done, sigma_out, problem_eval_device, stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream);
+}
+
 int pgc_hv_device(pgc_ctx *ctx, const double *d_points, size_t n, size_t m, const double *r_point, int compute, double *d_out, void *stream)
 {
     PGC_REQUIRE(ctx && r_point && d_out && (d_points || n == 0), "pgc_hv_device: null argument");
@@ -1000,6 +1011,7 @@ int pgc_algo_defaults(int algo, unsigned gens, uint64_t seed, pgc_algo_desc *out
             d.cr = 0.9, d.eta_c = 1., d.m = 0.02, d.param_m = 1., d.param_s = 2, d.crossover = 0, d.mutation = 2, d.selection = 0;
             break;
         case PGC_ALGO_CMAES: d.cma_cc = d.cma_cs = d.cma_c1 = d.cma_cmu = -1., d.sigma0 = 0.5; break; // cmaes.hpp:110
+        case PGC_ALGO_XNES: d.cma_cc = d.cma_cs = d.cma_c1 = -1., d.sigma0 = -1.; break; // xnes.hpp:107-108 (eta_mu, eta_sigma, eta_b, sigma0)
         case PGC_ALGO_NSPSO: // nspso.hpp:59-62
             d.omega = 0.6, d.nspso_c1 = 2.0, d.nspso_c2 = 2.0, d.nspso_chi = 1.0, d.nspso_v_coeff = 0.5, d.leader_selection_range = 60, d.diversity = 0;
             break;
@@ -1032,6 +1044,9 @@ int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *a, double *d_
         case PGC_ALGO_CMAES:
             return pgc_cmaes_evolve_device(prob, d_x, d_f, n, a->gens, a->cma_cc, a->cma_cs, a->cma_c1, a->cma_cmu, a->sigma0, a->ftol, a->xtol,
                                            static_cast<int>(a->force_bounds), a->seed, first_generation, gens_done, nullptr, stream);
+        case PGC_ALGO_XNES:
+            return pgc_xnes_evolve_device(prob, d_x, d_f, n, a->gens, a->cma_cc, a->cma_cs, a->cma_c1, a->sigma0, a->ftol, a->xtol,
+                                          static_cast<int>(a->force_bounds), a->seed, first_generation, gens_done, nullptr, stream);
         case PGC_ALGO_NSPSO:
             return pgc_nspso_evolve_device(prob, d_x, d_f, n, a->gens, a->omega, a->nspso_c1, a->nspso_c2, a->nspso_chi, a->nspso_v_coeff,
                                            a->leader_selection_range, a->diversity, a->seed, first_generation, nullptr, nullptr, nullptr, stream);
@@ -1097,7 +1112,8 @@ int pgc_algo_log_row_len(const pgc_problem *prob, int algo, size_t *row_len)
         case PGC_ALGO_DE1220: *row_len = 8; return PGC_OK;
         case PGC_ALGO_PSO_GEN: *row_len = 6; return PGC_OK;
         case PGC_ALGO_SGA: *row_len = 4; return PGC_OK;
-        case PGC_ALGO_CMAES: *row_len = 6; return PGC_OK;
+        case PGC_ALGO_CMAES:
+        case PGC_ALGO_XNES: *row_len = 6; return PGC_OK;
         case PGC_ALGO_NSGA2:
         case PGC_ALGO_NSPSO: *row_len = 2 + prob->nobj; return PGC_OK;
         default:

@@ -655,4 +655,158 @@ int cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam,
     return PGC_OK;
 }
 
+// xnes::evolve (reference src/algorithms/xnes.cpp:96-303, memory = false): the lam samples x = mean + A z and the two natural-gradient
+// contractions d_center = sum u_i z_(i), sum u_i z_(i) z_(i)^T run on the device (cmaes_sample_device with BD = A, sigma = 1;
+// weighted_mean_device / weighted_gram_device over all lam fitness-sorted samples); the D x D updates - mean, A <- A exp(d_A), sigma -
+// on the host, with exp of the symmetric d_A through the Jacobi eigendecomposition where the reference uses Eigen's matrix exponential.
+int xnes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam, unsigned gens, double eta_mu, double eta_sigma, double eta_b,
+                       double sigma0, double ftol, double xtol, int force_bounds, unsigned long long seed, unsigned first_generation,
+                       unsigned *gens_done, double *sigma_out, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t),
+                       cudaStream_t st)
+{
+    pgc_ctx *ctx = prob->ctx;
+    const size_t D = prob->nx;
+    if (gens_done) *gens_done = 0;
+    // constructor checks, xnes.cpp:55-78, and evolve's, :110-137
+    PGC_REQUIRE((eta_mu > 0. && eta_mu <= 1.) || eta_mu == -1., "eta_mu must be in ]0,1] or -1 if its value has to be initialized automatically, a value of %g was detected", eta_mu);
+    PGC_REQUIRE((eta_sigma > 0. && eta_sigma <= 1.) || eta_sigma == -1., "eta_sigma needs to be in ]0,1] or -1 if its value has to be initialized automatically, a value of %g was detected", eta_sigma);
+    PGC_REQUIRE((eta_b > 0. && eta_b <= 1.) || eta_b == -1., "eta_b needs to be in ]0,1] or -1 if its value has to be initialized automatically, a value of %g was detected", eta_b);
+    PGC_REQUIRE((sigma0 > 0. && sigma0 <= 1.) || sigma0 == -1., "sigma0 needs to be in ]0,1] or -1 if its value has to be initialized automatically, a value of %g was detected", sigma0);
+    PGC_REQUIRE(prob->nobj == 1, "Multiple objectives detected in %s instance. xNES: Exponential Natural Evolution Strategies cannot deal with them", prob->name.c_str());
+    PGC_REQUIRE(lam >= 4u, "xNES: Exponential Natural Evolution Strategies needs at least 5 individuals in the population, %zu detected", lam);
+    for (size_t j = 0; j < D; ++j)
+        PGC_REQUIRE(std::isfinite(prob->lb[j]) && std::isfinite(prob->ub[j]), "A non-finite value is detected in the bounds, xNES cannot deal with it.");
+    if (gens == 0) return PGC_OK;
+    const double dim_d = static_cast<double>(D), lam_d = static_cast<double>(lam);
+    if (eta_mu == -1) eta_mu = 1.;
+    const double common_default = 0.6 * (3. + std::log(dim_d)) / (dim_d * std::sqrt(dim_d)); // :143-150
+    if (eta_sigma == -1) eta_sigma = common_default;
+    if (eta_b == -1) eta_b = common_default;
+    std::vector<double> u(lam); // utilities, :151-161
+    double sum = 0.;
+    for (size_t i = 0; i < lam; ++i) u[i] = std::max(0., std::log(lam_d / 2. + 1.) - std::log(static_cast<double>(i + 1)));
+    for (size_t i = 0; i < lam; ++i) sum += u[i];
+    for (size_t i = 0; i < lam; ++i) u[i] = u[i] / sum - 1. / lam_d;
+    double usum = 0.;
+    for (size_t i = 0; i < lam; ++i) usum += u[i];
+    double sigma = sigma0 == -1 ? 0.5 : sigma0;
+    std::vector<double> f(lam), A(D * D, 0.), mean(D), z0(D), dc(D), G(D * D), dA(D * D), E(D * D), An(D * D), tmp(D);
+    for (size_t j = 0; j < D; ++j) A[j * D + j] = std::max(prob->ub[j] - prob->lb[j], 1e-6) * sigma;
+    PGC_CUDA(cudaMemcpyAsync(f.data(), d_f, 8 * lam, cudaMemcpyDeviceToHost, st));
+    PGC_CUDA(cudaStreamSynchronize(st));
+    size_t ib = 0, iw = 0;
+    for (size_t i = 1; i < lam; ++i)
+        if (f[i] < f[ib]) ib = i;
+    PGC_CUDA(cudaMemcpyAsync(mean.data(), d_x + ib * D, 8 * D, cudaMemcpyDeviceToHost, st));
+    PGC_CUDA(cudaStreamSynchronize(st));
+    struct Buf {
+        cudaStream_t st;
+        std::vector<void *> owned;
+        ~Buf()
+        {
+            for (void *p : owned) cudaFreeAsync(p, st);
+        }
+        int get(void **out, size_t bytes)
+        {
+            PGC_CUDA(cudaMallocAsync(out, bytes ? bytes : 8, st));
+            owned.push_back(*out);
+            return PGC_OK;
+        }
+    } buf{st, {}};
+    double *d_mean, *d_A, *d_z, *d_xn, *d_fn, *d_u, *d_dc, *d_G, *d_b;
+    unsigned *d_idx;
+    int rc;
+    if ((rc = buf.get(reinterpret_cast<void **>(&d_mean), 8 * D)) || (rc = buf.get(reinterpret_cast<void **>(&d_A), 8 * D * D))
+        || (rc = buf.get(reinterpret_cast<void **>(&d_z), 8 * lam * D)) || (rc = buf.get(reinterpret_cast<void **>(&d_xn), 8 * lam * D))
+        || (rc = buf.get(reinterpret_cast<void **>(&d_fn), 8 * lam)) || (rc = buf.get(reinterpret_cast<void **>(&d_u), 8 * lam))
+        || (rc = buf.get(reinterpret_cast<void **>(&d_dc), 8 * D)) || (rc = buf.get(reinterpret_cast<void **>(&d_G), 8 * D * D))
+        || (rc = buf.get(reinterpret_cast<void **>(&d_b), 16 * D)) || (rc = buf.get(reinterpret_cast<void **>(&d_idx), 4 * lam)))
+        return rc;
+    PGC_CUDA(cudaMemcpyAsync(d_u, u.data(), 8 * lam, cudaMemcpyHostToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(d_b, prob->lb.data(), 8 * D, cudaMemcpyHostToDevice, st));
+    PGC_CUDA(cudaMemcpyAsync(d_b + D, prob->ub.data(), 8 * D, cudaMemcpyHostToDevice, st));
+    std::vector<unsigned> order(lam);
+    unsigned done = 0;
+    for (unsigned g = 0; g < gens; ++g) {
+        const unsigned generation = first_generation + g;
+        // 1 - lam new individuals x_i = mean + A z_i, evaluated as they are written into the population (pop.set_x, :196-216)
+        PGC_CUDA(cudaMemcpyAsync(d_mean, mean.data(), 8 * D, cudaMemcpyHostToDevice, st));
+        PGC_CUDA(cudaMemcpyAsync(d_A, A.data(), 8 * D * D, cudaMemcpyHostToDevice, st));
+        if ((rc = cmaes_sample_device(ctx, d_mean, d_A, 1.0, lam, D, seed, generation, d_z, d_xn, st))) return rc;
+        if (force_bounds) {
+            clamp_rows_kernel<<<static_cast<unsigned>((lam * D + 255) / 256), 256, 0, st>>>(d_xn, lam * D, static_cast<unsigned>(D), d_b, d_b + D);
+            ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        if ((rc = eval(prob, d_xn, lam, d_fn, st))) return rc;
+        PGC_CUDA(cudaMemcpyAsync(d_x, d_xn, 8 * lam * D, cudaMemcpyDeviceToDevice, st));
+        PGC_CUDA(cudaMemcpyAsync(d_f, d_fn, 8 * lam, cudaMemcpyDeviceToDevice, st));
+        PGC_CUDA(cudaMemcpyAsync(f.data(), d_fn, 8 * lam, cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaMemcpyAsync(z0.data(), d_z, 8 * D, cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        ++done;
+        // 2 - exit conditions on the step of the FIRST sample and the spread of the new population, :219-236
+        double nrm = 0.;
+        for (size_t a = 0; a < D; ++a) {
+            double y = 0.;
+            for (size_t j = 0; j < D; ++j) y += A[a * D + j] * z0[j];
+            nrm += y * y;
+        }
+        if (std::sqrt(nrm) < xtol) break;
+        ib = iw = 0;
+        for (size_t i = 1; i < lam; ++i) {
+            if (f[i] < f[ib]) ib = i;
+            if (f[i] > f[iw]) iw = i;
+        }
+        if (std::fabs(f[ib] - f[iw]) < ftol) break;
+        if (log_due(g + 1u)) { // the log line, :238-256: (gen, fevals, best, dx, df, sigma)
+            const double line[6] = {static_cast<double>(g + 1u), static_cast<double>(g + 1u) * lam_d, f[ib], std::sqrt(nrm), std::fabs(f[ib] - f[iw]), sigma};
+            tls_log->host_rows.insert(tls_log->host_rows.end(), line, line + 6);
+        }
+        // 3 - the samples in order of fitness (plain <, :258-261; std::sort there, a stable sort here), the two gradients
+        for (size_t i = 0; i < lam; ++i) order[i] = static_cast<unsigned>(i);
+        std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return f[a] < f[b]; });
+        PGC_CUDA(cudaMemcpyAsync(d_idx, order.data(), 4 * lam, cudaMemcpyHostToDevice, st));
+        if ((rc = weighted_mean_device(ctx, d_z, d_idx, d_u, lam, D, d_dc, st))) return rc;               // d_center, :264-267
+        if ((rc = weighted_gram_device(ctx, d_z, d_idx, nullptr, d_u, lam, D, 1.0, d_G, st))) return rc; // sum u_i z z^T, :268-271
+        PGC_CUDA(cudaMemcpyAsync(dc.data(), d_dc, 8 * D, cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaMemcpyAsync(G.data(), d_G, 8 * D * D, cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaStreamSynchronize(st));
+        for (size_t a = 0; a < D; ++a) G[a * D + a] -= usum; // ... - sum u_i I
+        double cov_trace = 0.;
+        for (size_t a = 0; a < D; ++a) cov_trace += G[a * D + a];
+        for (size_t a = 0; a < D; ++a) G[a * D + a] -= cov_trace / dim_d; // :273
+        for (size_t a = 0; a < D; ++a)
+            for (size_t b = 0; b < D; ++b) dA[a * D + b] = 0.5 * ((a == b ? eta_sigma * cov_trace / dim_d : 0.) + eta_b * G[a * D + b]); // :274
+        // 4 - the updates, :276-291
+        for (size_t a = 0; a < D; ++a) {
+            double y = 0.;
+            for (size_t j = 0; j < D; ++j) y += A[a * D + j] * dc[j];
+            tmp[a] = y;
+        }
+        for (size_t a = 0; a < D; ++a) mean[a] = mean[a] + eta_mu * tmp[a];
+        for (size_t a = 0; a < D; ++a)
+            for (size_t b = a + 1; b < D; ++b) dA[a * D + b] = dA[b * D + a] = (dA[a * D + b] + dA[b * D + a]) / 2.;
+        std::vector<double> work(dA), w, V;
+        jacobi_eigen(work, D, w, V);
+        for (size_t a = 0; a < D; ++a)
+            for (size_t b = 0; b < D; ++b) {
+                double y = 0.;
+                for (size_t k = 0; k < D; ++k) y += V[a * D + k] * std::exp(w[k]) * V[b * D + k];
+                E[a * D + b] = y;
+            }
+        for (size_t a = 0; a < D; ++a)
+            for (size_t b = 0; b < D; ++b) {
+                double y = 0.;
+                for (size_t k = 0; k < D; ++k) y += A[a * D + k] * E[k * D + b];
+                An[a * D + b] = y;
+            }
+        A = An;
+        sigma = sigma * std::exp(eta_sigma / 2. * cov_trace / dim_d);
+    }
+    PGC_CUDA(cudaStreamSynchronize(st));
+    if (gens_done) *gens_done = done;
+    if (sigma_out) *sigma_out = sigma;
+    return PGC_OK;
+}
+
 } // namespace pgc

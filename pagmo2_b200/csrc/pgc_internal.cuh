@@ -343,6 +343,10 @@ int maco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, 
                        unsigned n_gen_mark, unsigned evalstop, double focus, unsigned long long seed, unsigned first_generation,
                        pgc_maco_state *state, unsigned *gens_done,
                        int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t), cudaStream_t st);
+int xnes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam, unsigned gens, double eta_mu, double eta_sigma, double eta_b,
+                       double sigma0, double ftol, double xtol, int force_bounds, unsigned long long seed, unsigned first_generation,
+                       unsigned *gens_done, double *sigma_out, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t),
+                       cudaStream_t st);
 int nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double omega, double c1, double c2, double chi,
                         double v_coeff, unsigned leader_selection_range, unsigned diversity, unsigned long long seed, unsigned first_generation,
                         double *d_vel, double *d_best_x, double *d_best_f,

@@ -316,7 +316,8 @@ int main(int argc, char **argv)
         for (const auto &a : {pagmo::algorithm{cuda_de{20u, 0.8, 0.9, 2u, 0., 0., 3u}}, pagmo::algorithm{cuda_de1220{20u, {2u, 3u, 7u}, 1u, 0., 0., false, 3u}},
                               pagmo::algorithm{cuda_pso_gen{20u, 0.7298, 2.05, 2.05, 0.5, 5u, 2u, 4u, false, 3u}},
                               pagmo::algorithm{cuda_sga{20u, .9, 1., 0.02, 1., 2u, "sbx", "gaussian", "truncated", 3u}},
-                              pagmo::algorithm{cuda_pso{20u, 0.7298, 2.05, 2.05, 0.5, 5u, 2u, 4u, false, 3u}}}) {
+                              pagmo::algorithm{cuda_pso{20u, 0.7298, 2.05, 2.05, 0.5, 5u, 2u, 4u, false, 3u}},
+                              pagmo::algorithm{cuda_xnes{20u, -1, -1, -1, -1, 0., 0., false, true, 3u}}}) {
             pagmo::population q{prob, 32u, 9u};
             const double b = q.champion_f()[0];
             q = a.evolve(q);

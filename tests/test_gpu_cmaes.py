@@ -97,3 +97,56 @@ def test_cmaes_argument_checks(ctx):
     mo = capi.Problem(ctx, "zdt", prob_id=1, dim=5)
     with pytest.raises(capi.PgcError):
         mo.cmaes_evolve(np.zeros((8, 5)), np.zeros(8), gens=1)
+
+
+@pytest.mark.parametrize("fam,dim,lam", [("rosenbrock", 8, 20), ("rastrigin", 10, 32), ("ackley", 30, 64)])
+def test_xnes_evolve_follows_the_restated_loop(ctx, orc, fam, dim, lam):
+    """xnes::evolve (xnes.cpp:96-303): sampling, evaluation and the natural-gradient contractions on the GPU, the D x D updates
+    (A <- A exp(d_A) through a Jacobi eigendecomposition) on the host, against the restatement consuming the same Philox normals."""
+    from pagmo2_b200 import capi
+    rng = np.random.default_rng(dim + 1)
+    prob = capi.Problem(ctx, fam, dim=dim)
+    op = orc.problem(fam, dim=dim)
+    lb, ub = prob.bounds()
+    x = rng.uniform(lb, ub, (lam, dim))
+    f = orc.simple(fam, x)
+    kw = dict(ftol=0.0, xtol=0.0, seed=13, first_generation=1)
+    for gens, tol in ((1, 1e-11), (3, 1e-9), (8, 1e-6)):
+        for extra in (dict(), dict(eta_mu=0.8, eta_sigma=0.3, eta_b=0.2, sigma0=0.3)):
+            xg, fg, dg, sg = prob.xnes_evolve(x, f, gens=gens, **kw, **extra)
+            xo, fo, do, so = orc.xnes_evolve(op, lb, ub, x, f, gens=gens, **kw, **extra)
+            assert dg == do == gens
+            scale = np.abs(xo).max()
+            assert np.abs(xg - xo).max() <= tol * scale, (gens, np.abs(xg - xo).max())
+            assert abs(sg - so) <= tol * so
+            assert np.allclose(prob.eval_host(xg)[:, 0], fg, rtol=1e-12)
+    xb, _, _, _ = prob.xnes_evolve(x, f, gens=5, force_bounds=True, **kw)
+    assert (xb >= lb).all() and (xb <= ub).all()
+    # through the descriptor (pgc_algo_evolve_device) and with the log (xnes.cpp:238-256): line `gen` = the population that generation made
+    d = capi.algo_desc("xnes", gens=6, seed=13, ftol=0.0, xtol=0.0)
+    xd, fd, done, log = prob.evolve_logged(d, x, f, 2)
+    x6, f6, _, s6 = prob.xnes_evolve(x, f, gens=6, **kw)
+    assert done == 6 and np.array_equal(xd, x6) and log[:, 0].tolist() == [1, 3, 5] and log[:, 1].tolist() == [lam, 3 * lam, 5 * lam]
+    for row in log:
+        _, fg, _, sg = prob.xnes_evolve(x, f, gens=int(row[0]), **kw)
+        _, _, _, sprev = prob.xnes_evolve(x, f, gens=int(row[0]) - 1, **kw) if row[0] > 1 else (None, None, None, 0.5)
+        assert row[2] == fg.min() and np.isclose(row[4], fg.max() - fg.min(), rtol=1e-13) and row[5] == sprev and row[3] > 0
+    # a long run converges like the restated one does
+    xg, fg, dg, sg = prob.xnes_evolve(x, f, gens=600, ftol=1e-10, xtol=1e-10, seed=13)
+    xo, fo, do, so = orc.xnes_evolve(op, lb, ub, x, f, gens=600, ftol=1e-10, xtol=1e-10, seed=13)
+    assert fg.min() < 0.5 * f.min() and fo.min() < 0.5 * f.min()
+    prob.close()
+
+
+def test_xnes_argument_checks(ctx):
+    from pagmo2_b200 import capi
+    prob = capi.Problem(ctx, "rastrigin", dim=5)
+    x, f = np.zeros((8, 5)), np.zeros(8)
+    for bad in (dict(eta_mu=1.5), dict(eta_sigma=0.0), dict(eta_b=-0.5), dict(sigma0=2.0)):   # xnes.cpp:55-78
+        with pytest.raises(capi.PgcError):
+            prob.xnes_evolve(x, f, gens=1, **bad)
+    with pytest.raises(capi.PgcError):                                                         # :120-123
+        prob.xnes_evolve(x[:3], f[:3], gens=1)
+    mo = capi.Problem(ctx, "zdt", prob_id=1, dim=5)
+    with pytest.raises(capi.PgcError):
+        mo.xnes_evolve(np.zeros((8, 5)), np.zeros(8), gens=1)
