@@ -1,7 +1,7 @@
 // hv_approx.cu - the Bringmann-Friedrich approximations of the hypervolume on the device:
 //   bf_fpras  (reference src/utils/hv_algos/hv_bf_fpras.cpp:91-146): (eps, delta) approximation of the hypervolume of a union of boxes
 //             by the Karp-Luby estimator - pick a box with probability proportional to its volume, a point in it, then draw points
-//             of the front until one dominates the sample; T * V / (n * M) with T the trial budget and M the completed rounds.
+//             of the front until one dominates the sample; T * V / (n * M) with T the trials made and M the completed rounds.
 //   bf_approx (hv_bf_approx.cpp:131-470): least / greatest contributor by rounds of Monte-Carlo sampling inside every point's
 //             bounding box, with confidence radii that eliminate candidates round by round (and the reference's switch to the exact
 //             exclusive volume for small / expensive boxes).
@@ -33,7 +33,7 @@ struct FprasParams {
     unsigned long long budget; // trials per thread
     unsigned long long seed;
     unsigned nthreads;
-    unsigned long long *rounds; // [1] completed rounds over all threads
+    unsigned long long *rounds; // [2] completed rounds and the trials they took, over all threads
 };
 
 __global__ void fpras_kernel(const FprasParams P)
@@ -57,12 +57,7 @@ __global__ void fpras_kernel(const FprasParams P)
             const double a = P.pts[static_cast<size_t>(i) * P.m + c];
             pt[c] = a + rs.next() * (P.r[c] - a);
         }
-        bool done = false;
         for (;;) { // draw points of the front until one dominates the sample, :129-137
-            if (trials >= P.budget) {
-                done = true;
-                break;
-            }
             unsigned j = static_cast<unsigned>(static_cast<double>(P.n) * rs.next());
             if (j >= P.n) j = P.n - 1u;
             ++trials;
@@ -74,10 +69,15 @@ __global__ void fpras_kernel(const FprasParams P)
             }
             if (le && lt) break;
         }
-        if (done) break;
         ++M;
+        // The reference stops in the middle of the round in which the budget runs out and divides the WHOLE budget by the completed
+        // rounds; with thousands of threads each doing that, the dropped rounds (long ones, preferentially) would bias the ratio.
+        // A thread finishes the round it is in and reports the trials it really made: trials / rounds is then a ratio of sums of
+        // whole rounds (Wald), the same estimator without the truncation.
+        if (trials >= P.budget) break;
     }
     atomicAdd(P.rounds, M);
+    atomicAdd(P.rounds + 1, trials);
 }
 
 struct ApproxParams {
@@ -208,19 +208,18 @@ int hv_fpras_host(pgc_ctx *ctx, const double *points, size_t n, size_t m, const 
     PGC_REQUIRE(static_cast<double>(P.budget) * static_cast<double>(m + 3) < 4.0e9, "bf_fpras: eps / delta ask for more draws per thread than a substream holds");
     DevBuf d_pts, d_sums, d_rounds;
     int rc;
-    if ((rc = d_pts.alloc(sizeof(double) * n * m)) || (rc = d_sums.alloc(sizeof(double) * n)) || (rc = d_rounds.alloc(sizeof(unsigned long long)))) return rc;
+    if ((rc = d_pts.alloc(sizeof(double) * n * m)) || (rc = d_sums.alloc(sizeof(double) * n)) || (rc = d_rounds.alloc(2 * sizeof(unsigned long long)))) return rc;
     PGC_CUDA(cudaMemcpyAsync(d_pts.p, points, sizeof(double) * n * m, cudaMemcpyHostToDevice, st));
     PGC_CUDA(cudaMemcpyAsync(d_sums.p, sums.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    PGC_CUDA(cudaMemsetAsync(d_rounds.p, 0, sizeof(unsigned long long), st));
+    PGC_CUDA(cudaMemsetAsync(d_rounds.p, 0, 2 * sizeof(unsigned long long), st));
     P.pts = d_pts.as<double>(), P.sums = d_sums.as<double>(), P.rounds = d_rounds.as<unsigned long long>();
     fpras_kernel<<<(P.nthreads + 127) / 128, 128, 0, st>>>(P);
     PGC_CUDA(cudaGetLastError());
-    unsigned long long M = 0;
-    PGC_CUDA(cudaMemcpyAsync(&M, d_rounds.p, sizeof(M), cudaMemcpyDeviceToHost, st));
+    unsigned long long MT[2] = {0, 0};
+    PGC_CUDA(cudaMemcpyAsync(MT, d_rounds.p, sizeof(MT), cudaMemcpyDeviceToHost, st));
     PGC_CUDA(cudaStreamSynchronize(st));
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    const double T_used = static_cast<double>(P.budget) * static_cast<double>(P.nthreads);
-    *hv_out = (T_used * V) / (static_cast<double>(n) * static_cast<double>(M)); // :131
+    *hv_out = (static_cast<double>(MT[1]) * V) / (static_cast<double>(n) * static_cast<double>(MT[0])); // T * V / (n * M), :131
     return PGC_OK;
 }
 
@@ -320,6 +319,10 @@ int hv_approx_extreme_host(pgc_ctx *ctx, const double *points, size_t n, size_t 
                 if (bp.size() <= trivial_subcase_size || static_cast<double>(no_ops[idx]) >= expected_hv_operations(bp.size(), m)) {
                     if (bp.empty()) {
                         approx_volume[idx] = box_volume[idx];
+                    } else if (bp.size() == 1u) { // one box point: what it covers of the box is a box itself
+                        double v = 1.;
+                        for (size_t c = 0; c < m; ++c) v *= (std::max(X(idx, c), X(bp[0], c)) - boxes[idx * m + c]);
+                        approx_volume[idx] = box_volume[idx] - std::fabs(v);
                     } else { // the exclusive volume itself: the box minus what the clipped box points cover, :226-243
                         sub.resize(bp.size() * m);
                         for (size_t q = 0; q < bp.size(); ++q)
