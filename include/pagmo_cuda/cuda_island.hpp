@@ -404,6 +404,12 @@ private:
                 m_comm.reset(c, [](pgc_comm *p) { pgc_comm_destroy(p); });
             }
         }
+        for (auto &e : m_islands) { // islands that share a GPU fill it together: each keeps fuller tiles (pgc_ctx_set_sharers)
+            if (!e.local) continue;
+            int sharers = 0;
+            for (const auto &o : m_islands) sharers += (o.local && o.device == e.device) ? 1 : 0;
+            detail::check(pgc_ctx_set_sharers(e.prob->context(), sharers), "pgc_ctx_set_sharers");
+        }
         for (auto &e : m_islands) {
             if (!e.local || e.isl) continue;
             e.isl = std::make_unique<detail::island_handle>(e.prob, e.n, cap, max_in);

@@ -95,6 +95,10 @@ PGC_API int pgc_device_count(int *count);
  * be used concurrently from different threads (thread_safety::basic, reference threading.hpp:42). */
 PGC_API int pgc_ctx_create(int device, pgc_ctx **out);
 PGC_API int pgc_ctx_destroy(pgc_ctx *ctx);
+/* A hint for the launch shapes of latency-bound (island-sized) batches: `n` contexts evaluate concurrently on this context's device
+ * (the islands of an archipelago that share one GPU, one context / stream each).  Alone, a small batch is spread thinly over all
+ * SMs; with sharers each context keeps fuller tiles and the sharers fill the device together.  Results do not depend on it. */
+PGC_API int pgc_ctx_set_sharers(pgc_ctx *ctx, int n);
 PGC_API int pgc_ctx_device(const pgc_ctx *ctx, int *device);
 PGC_API int pgc_ctx_stream(const pgc_ctx *ctx, void **stream);
 PGC_API int pgc_ctx_synchronize(pgc_ctx *ctx);

@@ -278,6 +278,8 @@ class ResidentArchipelago:
         self.published = [False] * G
         self.phase_seconds = {}  # host wall time per phase of evolve(), summed over rounds
         self.local = [g for g in range(G) if self.isl[g] is not None]
+        for g in self.local:  # islands that share a GPU fill it together: each keeps fuller tiles (pgc_ctx_set_sharers)
+            capi.check(capi.lib().pgc_ctx_set_sharers(self.ctx[g]._h, sum(1 for h in self.local if islands[h]["device"] == islands[g]["device"])))
         self._pool = ThreadPoolExecutor(max_workers=max(len(self.local), 1))
 
     def _u(self, g, slot):

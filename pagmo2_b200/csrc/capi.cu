@@ -317,6 +317,13 @@ int pgc_ctx_create(int device, pgc_ctx **out)
     return PGC_OK;
 }
 
+int pgc_ctx_set_sharers(pgc_ctx *ctx, int n)
+{
+    PGC_REQUIRE(ctx && n >= 1, "pgc_ctx_set_sharers: a context and a count >= 1 are needed");
+    ctx->sharers = n;
+    return PGC_OK;
+}
+
 int pgc_ctx_destroy(pgc_ctx *ctx)
 {
     if (!ctx) return PGC_OK;

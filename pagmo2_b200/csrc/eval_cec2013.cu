@@ -20,6 +20,7 @@
 // rotation is dead code (:812-820 overwrite m_z from the un-rotated m_y), so no rotation is launched for it; component i of a
 // composition reads its shift at Os[i*nx] and its second rotation at Mr[(i+1)*nx*nx]; cf_cal's zero-distance weight is 1e99.
 #include <cfloat>
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -73,6 +74,12 @@ namespace
 
 using namespace cecdev;
 constexpr int kMaxWarps13 = 16;
+// island-sized batches: several islands share the GPU (one stream each), so the SMALL instance is built to co-reside - at most 8 warps
+// per CTA and a register budget that lets kSmallMinBlocks13 CTAs of different islands sit on one SM
+#ifndef PGC_CEC13_SMALL_MINBLOCKS
+#define PGC_CEC13_SMALL_MINBLOCKS 3
+#endif
+constexpr int kSmallWarps13 = 8, kSmallMinBlocks13 = PGC_CEC13_SMALL_MINBLOCKS;
 
 constexpr int kMaxMerge = 3; // sub-launches of one kernel launch (island-sized batches: all matrices of a chain in shared memory)
 
@@ -237,7 +244,7 @@ __device__ double reduce13(const Params13 &P, const Launch13 &L, const Row &v, i
 
 // SMALL = island-sized batches: run-time tile size (P.ti individuals per warp) and up to kMaxMerge sub-launches per launch; the
 // throughput instance keeps both as compile-time constants (8 individuals, one sub-launch)
-template <int D, bool SMALL> __global__ void __launch_bounds__(kMaxWarps13 * 32, 1) cec13_kernel(const __grid_constant__ Params13 P)
+template <int D, bool SMALL> __global__ void __launch_bounds__(SMALL ? kSmallWarps13 * 32 : kMaxWarps13 * 32, SMALL ? kSmallMinBlocks13 : 1) cec13_kernel(const __grid_constant__ Params13 P)
 {
     constexpr int DP = pad8(D), KP = pad4(D), NT = DP / 8, YS = ystride(D);
     // island-sized batches: fewer individuals per warp tile, so that the batch spreads over many warps - every phase of a tile is
@@ -536,8 +543,17 @@ inline bool merge_enabled()
 // island-sized batches (~1000 individuals) are latency-bound: shrink the tile until there are ~4 warps per SM
 inline int tile_individuals(const pgc_ctx *ctx, long long n)
 {
+    // `sharers` contexts evaluate concurrently on this device (pgc_ctx_set_sharers: the islands of an archipelago that share a GPU):
+    // together they fill the SMs, so each keeps somewhat fuller tiles - an m8n8k4 tile with one individual wastes 7/8 of every DMMA,
+    // but a launch of few fat tiles is latency-bound: the target number of tiles shrinks with the square root of the sharers
+    // (measured, cfg5 on one GPU, 8 islands of 1024: tiles of 1 / 2 / 4 / 8 individuals give 6.9e4 / 7.7e4 / 7.5e4 / 5.7e4 island-generations/s)
+    const long long want = std::max(1ll, static_cast<long long>(static_cast<double>(ctx->sm_count) * 4. / std::sqrt(static_cast<double>(std::max(1, ctx->sharers)))));
     int ti = kTileInd;
-    while (ti > 1 && (n + ti - 1) / ti < static_cast<long long>(ctx->sm_count) * 4) ti >>= 1;
+    while (ti > 1 && (n + ti - 1) / ti < want) ti >>= 1;
+    if (const char *e = std::getenv("PGC_CEC13_TI")) { // experiment switch: force the tile size of island-sized batches
+        const int v = std::atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) ti = std::min(ti < kTileInd ? v : ti, kTileInd);
+    }
     return ti;
 }
 
@@ -559,6 +575,7 @@ template <int D> int launch13(pgc_ctx *ctx, const Params13 &pp, cudaStream_t str
     const size_t per_warp = (sizeof(double) * 2 * ti * YS + sizeof(unsigned short) * ti * D + 15) / 16 * 16;
     int fit = static_cast<int>((ctx->smem_optin - fixed) / per_warp);
     if (fit > kMaxWarps13) fit = kMaxWarps13;
+    if (small && fit > kSmallWarps13) fit = kSmallWarps13;
     PGC_REQUIRE(fit >= 1, "cec2013: shared memory too small for dimension %d", D);
     const long long ntiles = (pp.n + ti - 1) / ti;
     // small batches: fewer warps per CTA so that the tiles cover the SMs

@@ -206,6 +206,7 @@ struct pgc_ctx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     pgc::CopyPool *copy_pool = nullptr; // created on the first pageable pgc_eval_host call
+    int sharers = 1; // contexts expected to run concurrently on this device (pgc_ctx_set_sharers): launch-shape heuristics divide the SMs by it
 };
 
 namespace pgc
