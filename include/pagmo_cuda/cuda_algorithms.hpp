@@ -52,6 +52,24 @@
 namespace pagmo_cuda
 {
 
+namespace detail
+{
+// runs `call` with the log capture of pgc.h around it (pgc_log_capture_begin / _end) when verbosity > 0; rows: row_len doubles each
+template <typename Call>
+inline int with_log_capture(pgc_ctx *ctx, unsigned verbosity, unsigned gens, std::size_t row_len, pagmo::vector_double &rows, Call call)
+{
+    if (!verbosity) return call();
+    const std::size_t max_rows = (gens ? (gens - 1u) / verbosity + 1u : 0u) + 1u;
+    if (int rc = pgc_log_capture_begin(ctx, verbosity, max_rows, row_len)) return rc;
+    const int rc = call();
+    rows.assign(max_rows * row_len, 0.);
+    std::size_t n_rows = 0;
+    const int rc2 = pgc_log_capture_end(ctx, rows.data(), &n_rows);
+    rows.resize(n_rows * row_len);
+    return rc != PGC_OK ? rc : rc2;
+}
+} // namespace detail
+
 // Common part: population <-> device round trip around pgc_algo_evolve_device.
 class cuda_algorithm_base
 {
@@ -594,9 +612,12 @@ public:
         }
         const int method = m_decomposition == "weighted" ? 0 : (m_decomposition == "tchebycheff" ? 1 : 2);
         h->on_device(x, f, "pgc_moead_gen_evolve_device", [&](double *dx, double *df, std::size_t n) {
-            return pgc_moead_gen_evolve_device(h->raw(), dx, df, n, m_gen, w.data(), nb.data(), static_cast<unsigned>(m_neighbours), method, m_CR,
-                                               m_F, m_eta_m, m_realb, m_limit, m_preserve_diversity ? 1 : 0, m_seed, m_generation, nullptr);
+            return detail::with_log_capture(h->context(), m_verbosity, m_gen, 3u + nf, m_log_rows, [&] {
+                return pgc_moead_gen_evolve_device(h->raw(), dx, df, n, m_gen, w.data(), nb.data(), static_cast<unsigned>(m_neighbours), method, m_CR,
+                                                   m_F, m_eta_m, m_realb, m_limit, m_preserve_diversity ? 1 : 0, m_seed, m_generation, nullptr);
+            });
         });
+        m_log_row_len = 3u + nf;
         m_generation += m_gen;
         for (decltype(pop.size()) i = 0; i < NP; ++i) {
             pop.set_xf(i, pagmo::vector_double(x.begin() + static_cast<std::ptrdiff_t>(i * nx), x.begin() + static_cast<std::ptrdiff_t>((i + 1) * nx)),
@@ -609,6 +630,19 @@ public:
     unsigned get_seed() const { return m_seed; }
     unsigned get_gen() const { return m_gen; }
     std::string get_name() const { return "MOEAD-GEN: MOEA/D - DE [CUDA sm_100a]"; }
+    void set_verbosity(unsigned level) { m_verbosity = level; }
+    unsigned get_verbosity() const { return m_verbosity; }
+    using log_line_type = std::tuple<unsigned, unsigned long long, double, pagmo::vector_double>; // Gen, Fevals, ADF, ideal point (moead_gen.hpp:76)
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        log_type out;
+        for (std::size_t r = 0; m_log_row_len && r < m_log_rows.size() / m_log_row_len; ++r) {
+            const double *v = m_log_rows.data() + r * m_log_row_len;
+            out.emplace_back(static_cast<unsigned>(v[0]), static_cast<unsigned long long>(v[1]), v[2], pagmo::vector_double(v + 3, v + m_log_row_len));
+        }
+        return out;
+    }
     pagmo::thread_safety get_thread_safety() const { return pagmo::thread_safety::basic; }
     template <typename Archive>
     void serialize(Archive &ar, unsigned)
@@ -627,6 +661,9 @@ private:
     unsigned m_seed;
     int m_device;
     mutable unsigned m_generation = 1;
+    unsigned m_verbosity = 0;
+    mutable pagmo::vector_double m_log_rows;
+    mutable std::size_t m_log_row_len = 0;
     std::shared_ptr<detail::twin_cache> m_cache;
 };
 
@@ -698,8 +735,10 @@ public:
         }
         unsigned done = 0;
         h->on_device(x, f, "pgc_gaco_evolve_device", [&](double *dx, double *df, std::size_t n) {
-            return pgc_gaco_evolve_device(h->raw(), dx, df, n, m_gen, m_ker, m_q, m_oracle, m_acc, m_threshold, m_n_gen_mark, m_impstop, m_evalstop,
-                                          m_focus, m_seed, m_generation, &m_state, &done, nullptr);
+            return detail::with_log_capture(h->context(), m_verbosity, m_gen, 7u, m_log_rows, [&] {
+                return pgc_gaco_evolve_device(h->raw(), dx, df, n, m_gen, m_ker, m_q, m_oracle, m_acc, m_threshold, m_n_gen_mark, m_impstop,
+                                              m_evalstop, m_focus, m_seed, m_generation, &m_state, &done, nullptr);
+            });
         });
         m_generation += m_gen;
         for (decltype(pop.size()) i = 0; i < NP; ++i) {
@@ -714,6 +753,20 @@ public:
     unsigned get_gen() const { return m_gen; }
     // the oracle parameter as the runs so far have left it (gaco.cpp:349-402)
     double get_oracle() const { return m_state.initialized ? m_state.oracle : m_oracle; }
+    void set_verbosity(unsigned level) { m_verbosity = level; }
+    unsigned get_verbosity() const { return m_verbosity; }
+    // Gen, Fevals, Best, Kernel, Oracle, dx, dp (gaco.hpp:91)
+    using log_line_type = std::tuple<unsigned, unsigned long long, double, unsigned, double, double, double>;
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        log_type out;
+        for (std::size_t r = 0; r < m_log_rows.size() / 7u; ++r) {
+            const double *v = m_log_rows.data() + r * 7u;
+            out.emplace_back(static_cast<unsigned>(v[0]), static_cast<unsigned long long>(v[1]), v[2], static_cast<unsigned>(v[3]), v[4], v[5], v[6]);
+        }
+        return out;
+    }
     std::string get_name() const { return "GACO: Ant Colony Optimization [CUDA sm_100a]"; }
     pagmo::thread_safety get_thread_safety() const { return pagmo::thread_safety::basic; }
     template <typename Archive>
@@ -732,6 +785,8 @@ private:
     unsigned m_seed;
     int m_device;
     mutable unsigned m_generation = 1;
+    unsigned m_verbosity = 0;
+    mutable pagmo::vector_double m_log_rows;
     mutable pgc_gaco_state m_state{};
     std::shared_ptr<detail::twin_cache> m_cache;
 };
@@ -789,9 +844,12 @@ public:
         }
         unsigned done = 0;
         h->on_device(x, f, "pgc_maco_evolve_device", [&](double *dx, double *df, std::size_t n) {
-            return pgc_maco_evolve_device(h->raw(), dx, df, n, m_gen, m_ker, m_q, m_threshold, m_n_gen_mark, m_evalstop, m_focus, m_seed,
-                                          m_generation, &m_state, &done, nullptr);
+            return detail::with_log_capture(h->context(), m_verbosity, m_gen, 2u + nf, m_log_rows, [&] {
+                return pgc_maco_evolve_device(h->raw(), dx, df, n, m_gen, m_ker, m_q, m_threshold, m_n_gen_mark, m_evalstop, m_focus, m_seed,
+                                              m_generation, &m_state, &done, nullptr);
+            });
         });
+        m_log_row_len = 2u + nf;
         m_generation += m_gen;
         for (decltype(pop.size()) i = 0; i < NP; ++i) {
             pop.set_xf(i, pagmo::vector_double(x.begin() + static_cast<std::ptrdiff_t>(i * nx), x.begin() + static_cast<std::ptrdiff_t>((i + 1) * nx)),
@@ -804,6 +862,19 @@ public:
     unsigned get_seed() const { return m_seed; }
     unsigned get_gen() const { return m_gen; }
     std::string get_name() const { return "MHACO: Multi-objective Hypervolume-based Ant Colony Optimization [CUDA sm_100a]"; }
+    void set_verbosity(unsigned level) { m_verbosity = level; }
+    unsigned get_verbosity() const { return m_verbosity; }
+    using log_line_type = std::tuple<unsigned, unsigned long long, pagmo::vector_double>; // Gen, Fevals, ideal point (maco.hpp:93)
+    using log_type = std::vector<log_line_type>;
+    log_type get_log() const
+    {
+        log_type out;
+        for (std::size_t r = 0; m_log_row_len && r < m_log_rows.size() / m_log_row_len; ++r) {
+            const double *v = m_log_rows.data() + r * m_log_row_len;
+            out.emplace_back(static_cast<unsigned>(v[0]), static_cast<unsigned long long>(v[1]), pagmo::vector_double(v + 2, v + m_log_row_len));
+        }
+        return out;
+    }
     pagmo::thread_safety get_thread_safety() const { return pagmo::thread_safety::basic; }
     template <typename Archive>
     void serialize(Archive &ar, unsigned)
@@ -820,6 +891,9 @@ private:
     unsigned m_seed;
     int m_device;
     mutable unsigned m_generation = 1;
+    unsigned m_verbosity = 0;
+    mutable pagmo::vector_double m_log_rows;
+    mutable std::size_t m_log_row_len = 0;
     mutable pgc_maco_state m_state{};
     std::shared_ptr<detail::twin_cache> m_cache;
 };

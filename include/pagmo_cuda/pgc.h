@@ -413,6 +413,17 @@ PGC_API int pgc_algo_evolve_logged_device(pgc_problem *prob, const pgc_algo_desc
                                           uint32_t first_generation, unsigned *gens_done, pgc_algo_memory *memory, unsigned verbosity,
                                           double *log_rows, size_t max_rows, size_t *n_rows, void *stream);
 
+/* The same log capture for the algorithms that have their own entry point instead of a pgc_algo_desc: between pgc_log_capture_begin
+ * and pgc_log_capture_end (same thread) a pgc_gaco_ / pgc_maco_ / pgc_moead_gen_evolve_device call records the reference's lines:
+ *   gaco      gen, fevals, best, kernel, oracle, dx, dp        (gaco.cpp:254-287 inside the loop - not for the last generation -
+ *                                                               and :405-445 after it; fevals as the reference counts them, before
+ *                                                               the generation's evaluations)
+ *   maco      gen, fevals, ideal point of the archive [nobj]    (maco.cpp:415-463)
+ *   moead_gen gen, fevals, ADF, ideal point [nobj]              (moead_gen.cpp:180-211; ADF = sum of the decomposed fitnesses)
+ * row_len must be 7, 2 + nobj, 3 + nobj.  pgc_log_capture_end copies at most max_rows rows to rows_out (HOST) and ends the capture. */
+PGC_API int pgc_log_capture_begin(pgc_ctx *ctx, unsigned verbosity, size_t max_rows, size_t row_len);
+PGC_API int pgc_log_capture_end(pgc_ctx *ctx, double *rows_out, size_t *n_rows);
+
 /* ---- populations and migration (island.cpp:428-652) ------------------------------------------------------------------- */
 /* population(prob, bfe, n, seed) (population.cpp:82-103, generic.hpp:326-389): n uniform random decision vectors in the bounds,
  * one batch evaluation, random 64-bit IDs; the last nix genes are drawn as integers in [lb, ub] (generic.hpp:289-295).  d_f and

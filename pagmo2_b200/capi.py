@@ -83,6 +83,30 @@ SGA_SELECTION = {"tournament": 0, "truncated": 1}
 TOPOLOGY = {"unconnected": 0, "ring": 1, "fully_connected": 2}
 
 
+class log_capture:
+    """`with log_capture(ctx, verbosity, max_rows, row_len) as cap: prob.gaco_evolve(...)` then `cap.rows`: the reference's log lines of the
+    gaco / maco / moead_gen call made inside (pgc_log_capture_begin / _end; same thread)."""
+
+    def __init__(self, ctx, verbosity: int, max_rows: int, row_len: int):
+        self.ctx, self.v, self.max_rows, self.row_len, self.rows = ctx, verbosity, max_rows, row_len, None
+
+    def __enter__(self):
+        L = lib()
+        L.pgc_log_capture_begin.argtypes = [C.c_void_p, C.c_uint, C.c_size_t, C.c_size_t]
+        L.pgc_log_capture_end.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
+        check(L.pgc_log_capture_begin(self.ctx._h, self.v, self.max_rows, self.row_len))
+        return self
+
+    def __exit__(self, *exc):
+        buf = np.zeros((max(self.max_rows, 1), self.row_len))
+        n = C.c_size_t()
+        rc = lib().pgc_log_capture_end(self.ctx._h, buf.ctypes.data, C.byref(n))
+        if exc[0] is None:
+            check(rc)
+        self.rows = buf[:n.value]
+        return False
+
+
 def algo_desc(name: str, gens: int = 1, seed: int = 0, **overrides) -> AlgoDesc:
     """Reference-default constructor arguments of UDA `name`, with keyword overrides (e.g. variant=7, ftol=0.)."""
     d = AlgoDesc()

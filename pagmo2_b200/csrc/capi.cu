@@ -1176,6 +1176,65 @@ int pgc_algo_evolve_logged_device(pgc_problem *prob, const pgc_algo_desc *a, dou
     return PGC_OK;
 }
 
+namespace
+{
+struct Capture { // one per thread: the sink of pgc_log_capture_begin / _end
+    LogSink sink;
+    bool active = false;
+};
+thread_local Capture tls_capture;
+} // namespace
+
+int pgc_log_capture_begin(pgc_ctx *ctx, unsigned verbosity, size_t max_rows, size_t row_len)
+{
+    PGC_REQUIRE(ctx && verbosity >= 1u && row_len >= 1u, "pgc_log_capture_begin: a context, a verbosity >= 1 and a row length are needed");
+    PGC_REQUIRE(!tls_capture.active && !tls_log, "pgc_log_capture_begin: a capture is already running on this thread");
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    Capture &c = tls_capture;
+    c.sink = LogSink{};
+    PGC_CUDA(cudaMalloc(&c.sink.d_rows, sizeof(double) * std::max<size_t>(max_rows * row_len, 1)));
+    if (cudaMalloc(&c.sink.d_count, sizeof(unsigned)) != cudaSuccess) {
+        cudaFree(c.sink.d_rows);
+        set_error("pgc_log_capture_begin: out of device memory");
+        return PGC_ERR_OUT_OF_MEMORY;
+    }
+    PGC_CUDA(cudaMemsetAsync(c.sink.d_count, 0, sizeof(unsigned), ctx->stream));
+    c.sink.verbosity = verbosity, c.sink.max_rows = static_cast<unsigned>(max_rows), c.sink.row_len = static_cast<unsigned>(row_len);
+    c.active = true;
+    tls_log = &c.sink;
+    return PGC_OK;
+}
+
+int pgc_log_capture_end(pgc_ctx *ctx, double *rows_out, size_t *n_rows)
+{
+    PGC_REQUIRE(ctx && n_rows, "pgc_log_capture_end: null argument");
+    PGC_REQUIRE(tls_capture.active, "pgc_log_capture_end: no capture is running on this thread");
+    Capture &c = tls_capture;
+    tls_log = nullptr;
+    c.active = false;
+    struct Release {
+        LogSink &s;
+        ~Release()
+        {
+            cudaFree(s.d_rows);
+            cudaFree(s.d_count);
+            s = LogSink{};
+        }
+    } release{c.sink};
+    PGC_CUDA(cudaSetDevice(ctx->device));
+    unsigned written = 0;
+    PGC_CUDA(cudaMemcpyAsync(&written, c.sink.d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    PGC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t rl = c.sink.row_len;
+    if (written && rows_out) PGC_CUDA(cudaMemcpy(rows_out, c.sink.d_rows, sizeof(double) * written * rl, cudaMemcpyDeviceToHost));
+    if (!written && !c.sink.host_rows.empty()) {
+        written = static_cast<unsigned>(std::min<size_t>(c.sink.host_rows.size() / rl, c.sink.max_rows));
+        if (rows_out) std::copy(c.sink.host_rows.begin(), c.sink.host_rows.begin() + static_cast<std::ptrdiff_t>(written * rl), rows_out);
+    }
+    *n_rows = written;
+    return PGC_OK;
+}
+
 int pgc_population_init_device(pgc_problem *prob, size_t n, uint64_t seed, double *d_x, double *d_f, uint64_t *d_ids, void *stream)
 {
     PGC_REQUIRE(prob && (d_x || n == 0), "pgc_population_init_device: null argument");

@@ -331,6 +331,23 @@ __global__ void gaco_finish_kernel(GacoState *S, const double *fnew, unsigned n,
         for (unsigned r = t; r < ker; r += blockDim.x) arch[static_cast<size_t>(r) * row] = gaco_penalty(arch[static_cast<size_t>(r) * row + 1u + nx], S->oracle);
 }
 
+// the reference's log line (gaco.cpp:254-287 inside the loop, :405-445 after it): (gen, fevals, best, kernel, oracle, dx, dp) with dx / dp
+// the spread of the archive between its first and last row.  final != 0: the line after the loop, whose "best" is the population's
+// champion.  A stopped run logs nothing more.
+__global__ void gaco_log_kernel(const GacoState *S, const double *arch, unsigned nx, unsigned ker, unsigned gen, int final, double *rows,
+                                unsigned *count, unsigned max_rows, unsigned row_len)
+{
+    if (S->stopped || threadIdx.x || blockIdx.x) return;
+    const unsigned row = 1u + nx + 1u, r = *count;
+    if (r >= max_rows || row_len < 7u) return;
+    double dx = 0.;
+    for (unsigned i = 0; i < nx; ++i) dx += fabs(arch[static_cast<size_t>(ker - 1u) * row + 1u + i] - arch[1u + i]);
+    double *o = rows + static_cast<size_t>(r) * row_len;
+    o[0] = gen, o[1] = static_cast<double>(S->fevals), o[2] = final ? S->champ : arch[1u + nx], o[3] = ker, o[4] = S->oracle, o[5] = dx;
+    o[6] = fabs(arch[static_cast<size_t>(ker - 1u) * row] - arch[0]);
+    *count = r + 1u;
+}
+
 __global__ void gaco_writeback_kernel(const GacoState *S, const double *arch, unsigned nx, unsigned ker, double *x, double *f)
 { // :408-421; a stopping criterion returned the population as it was
     if (S->stopped) return;
@@ -392,6 +409,8 @@ int gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, 
         gaco_penalty_kernel<<<nblk(n, 256), 256, 0, st>>>(S, d_f, n, impstop, evalstop, pen, k0, i0);
         PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, ws_bytes, k0, k1, i0, sl, static_cast<int>(n), 0, 64, st));
         gaco_archive_kernel<<<1, 256, 0, st>>>(S, d_x, d_f, pen, sl, nx, ker, gen == 1u ? 1 : 0, acc, n_gen_mark, arch, tmp_arch, tp, slp, nsl, n_new);
+        if (gen != gens && log_due(gen)) // 3 - :254-287 (memory = false: every due generation but the last)
+            gaco_log_kernel<<<1, 32, 0, st>>>(S, arch, nx, ker, gen, 0, tls_log->d_rows, tls_log->d_count, tls_log->max_rows, tls_log->row_len);
         gaco_pheromone_kernel<<<nx + 1u, 256, 0, st>>>(S, arch, lb, ub, nx, ncx, ker, gen, threshold, focus, omega, pc, sigma, row, 1u);
         gaco_ants_kernel<<<nblk(n, 128), 128, 0, st>>>(S, arch, pc, sigma, lb, ub, n, nx, ncx, ker, seed, generation, ants, row, 1u);
         PGC_CUDA(cudaGetLastError());
@@ -402,6 +421,8 @@ int gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, 
         ctx->launches.fetch_add(7, std::memory_order_relaxed);
     }
     gaco_writeback_kernel<<<nblk(static_cast<size_t>(ker) * nx, 256), 256, 0, st>>>(S, arch, nx, ker, d_x, d_f);
+    if (tls_log && tls_log->verbosity && (gens % tls_log->verbosity == 1u || tls_log->verbosity == 1u)) // :405-445
+        gaco_log_kernel<<<1, 32, 0, st>>>(S, arch, nx, ker, gens, 1, tls_log->d_rows, tls_log->d_count, tls_log->max_rows, tls_log->row_len);
     PGC_CUDA(cudaGetLastError());
     PGC_CUDA(cudaMemcpyAsync(&h, S, sizeof(GacoState), cudaMemcpyDeviceToHost, st));
     PGC_CUDA(cudaStreamSynchronize(st));
@@ -597,13 +618,15 @@ int maco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, 
         }
         // the ideal point of the archive against the ideal point of everything, :289-318
         bool check = false;
-        for (unsigned c = 0; c < m && !check; ++c) {
+        std::vector<double> ideal_arch(m);
+        for (unsigned c = 0; c < m; ++c) {
             double a = h_arch_fit[c], b = h_mf[c];
             for (unsigned j = 1; j < ker; ++j) a = std::min(a, h_arch_fit[static_cast<size_t>(j) * m + c]);
             if (gen == 1u) b = a;
             else
                 for (unsigned j = 1; j < np; ++j) b = std::min(b, h_mf[static_cast<size_t>(j) * m + c]);
-            if (a != b) check = true;
+            ideal_arch[c] = a;
+            if (a != b && !check) check = true;
         }
         if (check) ++state->n_evalstop;
         else state->n_evalstop = 0;
@@ -614,6 +637,11 @@ int maco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, 
             break;
         }
         if (gen > 1u && (rc = rebuild(0.01, false))) return rc;
+        if (log_due(gen)) { // 2 - maco.cpp:415-463: (gen, fevals, the ideal point of the archive as the test above saw it)
+            tls_log->host_rows.push_back(gen);
+            tls_log->host_rows.push_back(static_cast<double>(gen - 1u) * n);
+            tls_log->host_rows.insert(tls_log->host_rows.end(), ideal_arch.begin(), ideal_arch.end());
+        }
         // pheromone values and ants: gaco's kernels on rows [x | f]
         if (gen == threshold) state->q = 0.01;
         GacoState h{};

@@ -323,6 +323,33 @@ __global__ void __launch_bounds__(kInsertThreads) moead_insert_kernel(const Inse
 
 } // namespace
 
+namespace
+{
+// moead_gen.cpp:180-211: (gen, fevals, ADF, ideal point); ADF = sum over the population of the decomposed fitness of individual i on
+// its own weight vector against the current ideal point
+__global__ void moead_log_kernel(const double *f, const double *w, const double *ideal, unsigned NP, unsigned m, int method, double gen,
+                                 double fevals, double *rows, unsigned *count, unsigned max_rows, unsigned row_len)
+{
+    __shared__ double s[256];
+    const unsigned r = *count;
+    if (r >= max_rows || row_len < 3u + m) return;
+    double a = 0.;
+    for (unsigned i = threadIdx.x; i < NP; i += blockDim.x) a += decompose(f + static_cast<size_t>(i) * m, m, w + static_cast<size_t>(i) * m, ideal, method);
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (unsigned k = blockDim.x / 2; k; k >>= 1) {
+        if (threadIdx.x < k) s[threadIdx.x] += s[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double *o = rows + static_cast<size_t>(r) * row_len;
+        o[0] = gen, o[1] = fevals, o[2] = s[0];
+        for (unsigned c = 0; c < m; ++c) o[3u + c] = ideal[c];
+        *count = r + 1u;
+    }
+}
+} // namespace
+
 int moead_gen_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, const double *h_weights,
                             const unsigned *h_neigh, unsigned T, int decomposition, double CR, double F, double eta_m, double realb, unsigned limit,
                             int preserve_diversity, unsigned long long seed, unsigned first_generation,
@@ -375,6 +402,9 @@ int moead_gen_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigne
     if ((rc = sc.alloc_bytes(&cub_tmp, cub_bytes))) return rc;
     for (unsigned g = 0; g < gens; ++g) {
         const unsigned generation = first_generation + g;
+        if (log_due(g + 1u))
+            moead_log_kernel<<<1, 256, 0, st>>>(d_f, w, ideal, NP, m, decomposition, static_cast<double>(g + 1u), static_cast<double>(g) * NP,
+                                                tls_log->d_rows, tls_log->d_count, tls_log->max_rows, tls_log->row_len);
         moead_order_keys_kernel<<<nblk(NP, 256), 256, 0, st>>>(NP, seed, generation, k_in, idx_in);
         size_t bytes = cub_bytes;
         PGC_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, k_in, k_out, idx_in, order, static_cast<int>(NP), 0, 64, st));

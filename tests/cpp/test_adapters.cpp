@@ -414,6 +414,16 @@ int main(int argc, char **argv)
             CHECK(q.champion_f()[0] <= b);
             for (std::size_t i = 0; i < q.size(); ++i) CHECK(max_rel(prob.fitness(q.get_x()[i]), q.get_f()[i]) <= tol);
             CHECK(g.extract<cuda_gaco>()->get_oracle() < 1e9);
+            {
+                pagmo::algorithm gl{cuda_gaco{7u, 13u, 1.0, 1e9, 0.01, 1u, 7u, 100000u, 100000u, 0., false, 5u}};
+                gl.set_verbosity(3u);
+                pagmo::population ql{prob, 40u, 9u};
+                const double b0 = ql.champion_f()[0];
+                ql = gl.evolve(ql);
+                const auto log = gl.extract<cuda_gaco>()->get_log(); // generations 1, 4 inside the loop, 7 after it (gaco.cpp:254-287, :405-445)
+                CHECK(log.size() == 3u && std::get<0>(log[2]) == 7u && std::get<1>(log[2]) == 7u * 40u && std::get<2>(log[0]) == b0);
+                CHECK(std::get<3>(log[1]) == 13u && std::get<2>(log[2]) == ql.champion_f()[0]);
+            }
             std::printf("%s: %.4g -> %.4g (oracle %.4g)\n", g.get_name().c_str(), b, q.champion_f()[0], g.extract<cuda_gaco>()->get_oracle());
             bool threw = false;
             try {
@@ -432,6 +442,19 @@ int main(int argc, char **argv)
             CHECK(a.get_problem().get_fevals() - fe == 8u * 40u);
             CHECK(a.get_x() == b.get_x() && a.get_f() == b.get_f());
             for (std::size_t i = 0; i < a.size(); ++i) CHECK(max_rel(z1.fitness(a.get_x()[i]), a.get_f()[i]) <= tol);
+            pagmo::algorithm ml{cuda_maco{5u, 12u, 1.0, 1u, 7u, 100000u, 0., false, 5u}};
+            ml.set_verbosity(2u);
+            pagmo::population c{z1, 40u, 5u};
+            const auto ideal0 = pagmo::ideal(c.get_f());
+            c = ml.evolve(c);
+            const auto mlog = ml.extract<cuda_maco>()->get_log();
+            CHECK(mlog.size() == 3u && std::get<1>(mlog[1]) == 2u * 40u && std::get<2>(mlog[0]) == ideal0);
+            pagmo::algorithm dl{cuda_moead_gen{4u, "grid", "tchebycheff", 5u, 1.0, 0.5, 20., 0.9, 2u, true, 5u}};
+            dl.set_verbosity(2u);
+            pagmo::population d{z1, 40u, 5u};
+            d = dl.evolve(d);
+            const auto dlog = dl.extract<cuda_moead_gen>()->get_log();
+            CHECK(dlog.size() == 2u && std::get<0>(dlog[1]) == 3u && std::get<3>(dlog[0]) == ideal0 && std::get<2>(dlog[0]) > 0.);
         }
         pagmo::problem zp{pagmo::zdt{1u, 30u}};
         pagmo::population mo{zp, 40u, 5u};

@@ -172,6 +172,56 @@ def test_cmaes_log(capi, ctx):
     prob.close()
 
 
+def test_gaco_maco_moead_logs(capi, ctx):
+    """the algorithms with their own entry points log through pgc_log_capture_begin / _end."""
+    # gaco (gaco.cpp:254-287, :405-445): in-loop lines for every due generation but the last, from the archive; a final line from the champion
+    prob = capi.Problem(ctx, "rastrigin", dim=6)
+    lb, ub = prob.bounds()
+    n, gens, ker = 30, 7, 8
+    x = np.random.default_rng(1).uniform(lb, ub, (n, 6))
+    f = prob.eval_host(x)[:, 0]
+    with capi.log_capture(ctx, 3, 8, 7) as cap:
+        xl, fl, st, _ = prob.gaco_evolve(x, f, gens=gens, ker=ker, oracle=1e9, seed=5)
+    x0, f0, _, _ = prob.gaco_evolve(x, f, gens=gens, ker=ker, oracle=1e9, seed=5)
+    assert np.array_equal(xl, x0) and np.array_equal(fl, f0)
+    log = cap.rows
+    assert log[:, 0].tolist() == [1, 4, 7] and log[:, 1].tolist() == [0, 3 * n, 7 * n] and (log[:, 3] == ker).all()
+    assert log[0, 2] == f.min() and log[0, 4] == 1e9            # generation 1: the archive is the best of the start, the oracle untouched
+    assert log[2, 2] == min(f.min(), log[2, 2]) and log[2, 4] == st.oracle and (log[:, 5] > 0).all() and (log[:, 6] >= 0).all()
+    xa, fa, _, _ = prob.gaco_evolve(x, f, gens=3, ker=ker, oracle=1e9, seed=5)   # the archive after 3 generations = rows 0..ker of the result
+    assert log[1, 2] <= fa[:ker, 0].min() + 1e-12
+    prob.close()
+    # maco (maco.cpp:415-463) and moead_gen (moead_gen.cpp:180-211)
+    mo = capi.Problem(ctx, "zdt", prob_id=1, dim=8)
+    lb, ub = mo.bounds()
+    n = 24
+    x = np.random.default_rng(2).uniform(lb, ub, (n, 8))
+    f = mo.eval_host(x)
+    with capi.log_capture(ctx, 2, 8, 4) as cap:
+        xl, fl, _, _ = mo.maco_evolve(x, f, gens=5, ker=10, seed=3)
+    assert np.array_equal(xl, mo.maco_evolve(x, f, gens=5, ker=10, seed=3)[0])
+    log = cap.rows
+    assert log[:, 0].tolist() == [1, 3, 5] and log[:, 1].tolist() == [0, 2 * n, 4 * n]
+    assert np.array_equal(log[0, 2:], f.min(axis=0))  # the first archive holds the whole first front: its ideal point is the population's
+    assert (log[1:, 2:] <= log[0, 2:] + 1e-15).all()
+    w = np.array([[i / (n - 1), 1 - i / (n - 1)] for i in range(n)])
+    nb = np.argsort(((w[:, None, :] - w[None, :, :]) ** 2).sum(axis=2), axis=1)[:, 1:6].astype(np.uint32)
+    with capi.log_capture(ctx, 2, 8, 5) as cap:
+        xl, fl = mo.moead_gen_evolve(x, f, w, nb, gens=4, seed=3)
+    assert np.array_equal(xl, mo.moead_gen_evolve(x, f, w, nb, gens=4, seed=3)[0])
+    log = cap.rows
+    assert log[:, 0].tolist() == [1, 3] and log[:, 1].tolist() == [0, 2 * n]
+    ideal = f.min(axis=0)
+    adf = sum(max(w[i, k] * abs(f[i, k] - ideal[k]) if w[i, k] != 0 else 1e-4 * abs(f[i, k] - ideal[k]) for k in range(2)) for i in range(n))
+    assert np.array_equal(log[0, 3:], ideal) and np.isclose(log[0, 2], adf, rtol=1e-12)  # tchebycheff, multi_objective.cpp:601-611
+    assert (log[1, 3:] <= ideal).all()
+    mo.close()
+    with pytest.raises(capi.PgcError):  # one capture per thread
+        with capi.log_capture(ctx, 1, 4, 7):
+            with capi.log_capture(ctx, 1, 4, 7):
+                pass
+
+
 def test_log_argument_checks(capi, ctx):
     prob = capi.Problem(ctx, "rastrigin", dim=4)
     x = np.random.default_rng(1).uniform(-5, 5, (16, 4))
