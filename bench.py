@@ -281,7 +281,36 @@ def measure_secondary(ctx, capi, device):
     def cfg5():
         return measure_cfg5(capi, [device], rank=0, world=1, comm=None, rounds=4)
 
+    def next_rows():  # the bfe-caller UDAs and the many-objective hypervolume, one figure each
+        import numpy as np
+        rng = np.random.default_rng(7)
+        r = {}
+        p = capi.Problem(ctx, "rastrigin", dim=30)
+        lb, ub = p.bounds()
+        x = rng.uniform(lb, ub, (65536, 30))
+        f = p.eval_host(x)
+        p.gaco_evolve(x, f, gens=2, seed=1)
+        dt = _timed(lambda: p.gaco_evolve(x, f, gens=20, seed=1), ctx.synchronize)
+        r["gaco_rastrigin30_pop65536_gens_per_s"] = 20 / dt
+        p.close()
+        p = capi.Problem(ctx, "zdt", prob_id=1, dim=30)
+        lb, ub = p.bounds()
+        x = rng.uniform(lb, ub, (16384, 30))
+        f = p.eval_host(x)
+        p.maco_evolve(x, f, gens=2, seed=1)
+        dt = _timed(lambda: p.maco_evolve(x, f, gens=10, seed=1), ctx.synchronize)
+        r["maco_zdt1_pop16384_gens_per_s"] = 10 / dt
+        p.close()
+        pts = rng.uniform(0.05, 1, (1024, 4))
+        pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+        ctx.hv_compute(pts, np.full(4, 1.25))
+        r["hv_wfg_4obj_1024pts_compute_ms"] = _timed(lambda: ctx.hv_compute(pts, np.full(4, 1.25)), ctx.synchronize) * 1e3
+        r["what"] = ("gaco (rastrigin D=30, 65536 ants) and maco (ZDT1 nx=30, 16384 ants) generations/s incl. the host round trip of the "
+                     "population per call; hypervolume of 1024 points in 4 objectives (device WFG) incl. upload")
+        return r
+
     guarded("nsga2_pop65536", nsga2)
+    guarded("next_rows", next_rows)
     guarded("cfg1_de1220", cfg1)
     guarded("cfg4_lennard_jones", cfg4)
     guarded("cfg5_islands", cfg5)
@@ -303,7 +332,10 @@ def secondary_summary(sec):
             "cfg1_de1220_gens_per_s": g("cfg1_de1220", "generations_per_s"),
             "cfg4_lj150_evals_per_s": g("cfg4_lennard_jones", "evals_per_s"),
             "cfg5_island_gens_per_s": g("cfg5_islands", "island_generations_per_s"),
-            "cfg5_evals_per_s": g("cfg5_islands", "evals_per_s"), "cfg5_migrations_per_s": g("cfg5_islands", "migrations_per_s")}
+            "cfg5_evals_per_s": g("cfg5_islands", "evals_per_s"), "cfg5_migrations_per_s": g("cfg5_islands", "migrations_per_s"),
+            "gaco_pop65536_gens_per_s": g("next_rows", "gaco_rastrigin30_pop65536_gens_per_s"),
+            "maco_pop16384_gens_per_s": g("next_rows", "maco_zdt1_pop16384_gens_per_s"),
+            "hv_wfg_4obj_1024pts_ms": g("next_rows", "hv_wfg_4obj_1024pts_compute_ms")}
 
 
 CFG5 = {"islands": 8, "pop": 1024, "dim": 50, "func": 12, "gens_per_round": 50}
@@ -571,7 +603,7 @@ def run_native(args):
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": len(FUNCS) * n * DIM * 8,
                 "d2h_bytes_per_step": len(FUNCS) * n * 8, "steps": e2e_steps,
                 "path": "pgc_eval_host: pinned host -> chunked H2D -> kernels -> D2H -> pinned host",
-                "h2d_gbs": e2e_value * DIM * 8 / 1e9,
+                "h2d_gbs": e2e_value * DIM * 8 / 1e9 if e2e_value else None,
                 "ceiling": "host -> device copies of this box, measured by scripts/h2d_probe.py (profiles/r2j_h2d_probe.json): 55.5 GB/s for "
                            "one GPU, 111 for two, 116 for GPUs {0,1,2,3} (one host bridge), 218 for {0,1,4,5}, 188 for all eight"},
         "gpu_launches": int(launches),
