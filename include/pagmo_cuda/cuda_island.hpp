@@ -68,8 +68,16 @@ inline const cuda_algorithm_base *find_cuda_uda(const pagmo::algorithm &a)
     PGC_TRY_UDA(cuda_nsga2)
     PGC_TRY_UDA(cuda_sga)
     PGC_TRY_UDA(cuda_cmaes)
+    PGC_TRY_UDA(cuda_xnes)
+    PGC_TRY_UDA(cuda_nspso)
 #undef PGC_TRY_UDA
     return nullptr;
+}
+
+// the pagmo_cuda UDAs with their own entry point (no pgc_algo_desc): an island runs them through their own evolve()
+inline bool is_standalone_cuda_uda(const pagmo::algorithm &a)
+{
+    return a.is<cuda_gaco>() || a.is<cuda_maco>() || a.is<cuda_moead_gen>();
 }
 
 // RAII pgc_island
@@ -136,9 +144,17 @@ public:
                                                    + algo.get_name() + "' does not");
         }
         const auto *uda = detail::find_cuda_uda(algo);
+        if (!uda && detail::is_standalone_cuda_uda(algo)) {
+            // cuda_gaco / cuda_maco / cuda_moead_gen keep their own state and entry point: the device work is theirs, the island only
+            // does what thread_island does around it (thread_island.cpp:118-131)
+            isl.set_population(algo.evolve(pop));
+            isl.set_algorithm(algo);
+            return;
+        }
         if (!uda) {
             pagmo_throw(std::invalid_argument, "the 'cuda_island' UDI runs the pagmo_cuda:: algorithms only (cuda_de, cuda_sade, cuda_de1220, "
-                                               "cuda_pso_gen, cuda_nsga2, cuda_sga, cuda_cmaes); an algorithm of type '"
+                                               "cuda_pso_gen, cuda_nsga2, cuda_sga, cuda_cmaes, cuda_xnes, cuda_nspso, cuda_gaco, cuda_maco, "
+                                               "cuda_moead_gen); an algorithm of type '"
                                                    + algo.get_name() + "' was given and there is no CPU fallback");
         }
         const auto &prob = pop.get_problem();

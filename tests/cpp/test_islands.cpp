@@ -177,6 +177,31 @@ int main(int argc, char **argv)
             CHECK(direct.get_f()[direct.best_idx()][0] < before);
             std::printf("cuda_cmaes: best %g -> %g\n", before, direct.get_f()[direct.best_idx()][0]);
         }
+        // the other descriptor-based UDAs (xnes, nspso), sade with memory (state resident in the island), and the UDAs with their own
+        // entry point (gaco, maco, moead_gen run through their own evolve()): an island gives what the algorithm alone gives
+        {
+            pagmo::population so{pagmo::problem{pagmo::rastrigin{8u}}, 24u, 3u}, mo{pagmo::problem{pagmo::zdt{1u, 10u}}, 24u, 3u};
+            const auto through_island = [](const pagmo::algorithm &a, const pagmo::population &p, unsigned times) {
+                pagmo::island isl{cuda_island{0}, a, p};
+                for (unsigned t = 0; t < times; ++t) {
+                    isl.evolve();
+                    isl.wait_check();
+                }
+                return isl.get_population();
+            };
+            const auto alone = [](pagmo::algorithm a, pagmo::population p, unsigned times) {
+                for (unsigned t = 0; t < times; ++t) p = a.evolve(p);
+                return p;
+            };
+            for (const auto &a : {pagmo::algorithm{cuda_xnes{10u, -1, -1, -1, -1, 0., 0., false, false, 9u}},
+                                  pagmo::algorithm{cuda_sade{6u, 2u, 1u, 0., 0., true, 9u}},
+                                  pagmo::algorithm{cuda_gaco{6u, 8u, 1.0, 1e9, 0.01, 1u, 7u, 100000u, 100000u, 0., false, 9u}}})
+                CHECK(same_population(through_island(a, so, 2u), alone(a, so, 2u)));
+            for (const auto &a : {pagmo::algorithm{cuda_nspso{5u, 0.6, 2., 2., 1., 0.5, 60u, "crowding distance", false, 9u}},
+                                  pagmo::algorithm{cuda_maco{5u, 8u, 1.0, 1u, 7u, 100000u, 0., false, 9u}},
+                                  pagmo::algorithm{cuda_moead_gen{4u, "grid", "tchebycheff", 5u, 1.0, 0.5, 20., 0.9, 2u, true, 9u}}})
+                CHECK(same_population(through_island(a, mo, 2u), alone(a, mo, 2u)));
+        }
         // a stock CPU algorithm is refused (no CPU fallback)
         pagmo::island c{cuda_island{0}, pagmo::algorithm{pagmo::de{5u}}, pop};
         c.evolve();
