@@ -20,8 +20,8 @@
 // Differences from the reference algorithms, as documented in DESIGN.md: the DE family and PSO are GENERATIONAL (all trial
 // vectors of a generation are built from the previous population and evaluated in one batch; the reference updates in place,
 // individual by individual), random draws come from Philox streams keyed by (seed, generation, individual).  `memory = true`
-// (sade, de1220, pso_gen, pso, nspso) keeps the adaptation state / velocities / archive between evolve() calls as the reference
-// does; cmaes's is not built.  fevals are accounted for as the reference does (one per individual per generation).
+// (sade, de1220, pso_gen, pso, nspso, cmaes, xnes) keeps the adaptation state / velocities / archive / distribution between evolve()
+// calls as the reference does.  fevals are accounted for as the reference does (one per individual per generation).
 #ifndef PAGMO_CUDA_CUDA_ALGORITHMS_HPP
 #define PAGMO_CUDA_CUDA_ALGORITHMS_HPP
 
@@ -190,7 +190,7 @@ public:
                                m_desc.selection, m_desc.cma_cc, m_desc.cma_cs, m_desc.cma_c1, m_desc.cma_cmu, m_desc.sigma0,
                                m_desc.force_bounds, m_desc.nspso_c1, m_desc.nspso_c2, m_desc.nspso_chi, m_desc.nspso_v_coeff,
                                m_desc.leader_selection_range, m_desc.diversity, m_desc.memory, m_state.a, m_state.b, m_state.c, m_state.u,
-                               m_state.initialized, m_verbosity, m_log_rows, m_log_row_len);
+                               m_state.initialized, m_verbosity, m_log_rows, m_log_row_len, m_state.es);
         for (std::size_t i = 0; i < 18u && i < allowed.size(); ++i) m_desc.allowed_variants[i] = allowed[i]; // no-op when saving
     }
 
@@ -433,7 +433,7 @@ public:
             pagmo_throw(std::invalid_argument, "cmu needs to be in [0,1] or -1 if its value has to be initialized automatically, a value of "
                                                    + std::to_string(cmu) + " was detected");
         }
-        no_memory(memory, "cuda_cmaes");
+        keep_memory(memory);
         m_desc.cma_cc = cc, m_desc.cma_cs = cs, m_desc.cma_c1 = c1, m_desc.cma_cmu = cmu, m_desc.sigma0 = sigma0;
         m_desc.ftol = ftol, m_desc.xtol = xtol, m_desc.force_bounds = force_bounds ? 1u : 0u;
     }
@@ -467,7 +467,7 @@ public:
         check_eta(eta_sigma, "eta_sigma", " needs to be");
         check_eta(eta_b, "eta_b", " needs to be");
         check_eta(sigma0, "sigma0", " needs to be");
-        no_memory(memory, "cuda_xnes");
+        keep_memory(memory);
         m_desc.cma_cc = eta_mu, m_desc.cma_cs = eta_sigma, m_desc.cma_c1 = eta_b, m_desc.sigma0 = sigma0;
         m_desc.ftol = ftol, m_desc.xtol = xtol, m_desc.force_bounds = force_bounds ? 1u : 0u;
     }

@@ -220,6 +220,7 @@ public:
     struct algo_state {
         pagmo::vector_double a, b, c;
         std::vector<uint32_t> u;
+        pagmo::vector_double es; // cmaes / xnes: their host-side state (pgc_es_state_len doubles)
         bool initialized = false;
     };
     unsigned evolve_memory(const pgc_algo_desc &algo, pagmo::vector_double &x, pagmo::vector_double &f, unsigned first_generation,
@@ -235,7 +236,8 @@ public:
         const std::size_t n = x.size() / m_nx;
         if (st && (!st->initialized || st->u.size() != n)) { // sade.cpp:137: a population of another size restarts the adaptation
             st->a.assign(n * m_nx, 0.), st->b.assign(n * m_nx, 0.), st->c.assign(n * m_nf, 0.), st->u.assign(n, 0u);
-            st->initialized = false;
+            // (xnes keeps its distribution whatever the population size, xnes.cpp:163; cmaes' state checks the size itself)
+            if (algo.algo != PGC_ALGO_XNES && algo.algo != PGC_ALGO_CMAES) st->initialized = false;
         }
         std::size_t max_rows = 0, rl = 0;
         if (verbosity) {
@@ -261,7 +263,14 @@ public:
                 if (rc == PGC_OK && st->initialized && bytes[k]) rc = pgc_memcpy_h2d(m_ctx.get(), d[k], h[k], bytes[k]);
             }
             pgc_algo_memory mem{static_cast<double *>(d[0]), static_cast<double *>(d[1]), static_cast<double *>(d[2]),
-                                static_cast<uint32_t *>(d[3]), st && st->initialized ? 1 : 0, 0};
+                                static_cast<uint32_t *>(d[3]), st && st->initialized ? 1 : 0, 0, nullptr, 0};
+            if (st && (algo.algo == PGC_ALGO_CMAES || algo.algo == PGC_ALGO_XNES)) {
+                std::size_t len = 0;
+                if (rc == PGC_OK) rc = pgc_es_state_len(algo.algo, m_nx, &len);
+                if (st->es.size() != len) st->es.assign(len, 0.);
+                mem.h_state = st->es.data();
+                mem.h_state_len = len;
+            }
             std::size_t n_rows = 0;
             if (rc == PGC_OK) {
                 rc = pgc_algo_evolve_logged_device(m_prob, &algo, dx, df, n, first_generation, &done, st ? &mem : nullptr, verbosity,

@@ -383,6 +383,9 @@ PGC_API int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *algo,
  *   sade / de1220: a = F [n], b = CR [n], u = mutation variant [n] (de1220 only)      (sade.cpp:137-156, de1220.cpp:147-165)
  *   pso_gen      : a = velocities [n x nx]                                            (pso_gen.cpp:193-201)
  *   nspso        : a = velocities [n x nx], b = archive decision vectors [n x nx], c = archive fitness [n x nobj] (nspso.cpp:127-152)
+ *   cmaes / xnes : h_state = HOST array of pgc_es_state_len() doubles: sigma, mean, the evolution paths and B / D / C / C^-1/2 of cmaes
+ *                  (cmaes.cpp:201-228), sigma, mean and A of xnes (xnes.cpp:163-175); kept while the dimension (and, for cmaes, the
+ *                  population size) stays the same, as in the reference
  * initialized == 0: the arrays hold nothing yet; pgc_algo_evolve_memory_device first fills them as the reference's first evolve() with
  * memory does (drawn from the Philox streams of `first_generation`) and sets it to 1.  Other algorithms have no such state.
  * pgc_island_evolve keeps this state in HBM inside the island when algo->memory != 0 (re-drawn if the algorithm changes, as a new
@@ -391,7 +394,10 @@ typedef struct pgc_algo_memory {
     double *a, *b, *c;
     uint32_t *u;
     int32_t initialized, reserved_;
+    double *h_state;      /* cmaes / xnes only (host) */
+    size_t h_state_len;
 } pgc_algo_memory;
+PGC_API int pgc_es_state_len(int algo, size_t nx, size_t *len);
 PGC_API int pgc_algo_evolve_memory_device(pgc_problem *prob, const pgc_algo_desc *algo, double *d_x, double *d_f, size_t n,
                                           uint32_t first_generation, unsigned *gens_done, pgc_algo_memory *memory, void *stream);
 

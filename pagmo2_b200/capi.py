@@ -72,7 +72,8 @@ class MacoState(C.Structure):
 
 class AlgoMemory(C.Structure):
     """pgc_algo_memory: the device arrays a UDA with memory = true keeps between evolve() calls."""
-    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("u", C.c_void_p), ("initialized", C.c_int32), ("reserved_", C.c_int32)]
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("u", C.c_void_p), ("initialized", C.c_int32), ("reserved_", C.c_int32),
+                ("h_state", C.c_void_p), ("h_state_len", C.c_size_t)]
 
 
 ALGO = {"de": 1, "sade": 2, "de1220": 3, "pso_gen": 4, "nsga2": 5, "sga": 6, "cmaes": 7, "nspso": 8, "xnes": 9}
@@ -785,7 +786,15 @@ class Problem:
         host = {k: (np.zeros(sh, dt) if state is None else np.ascontiguousarray(state[k], dtype=dt).reshape(sh)) for k, (sh, dt) in shapes.items()}
         dev = {k: self.ctx.to_device(v) for k, v in host.items()}
         dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
-        mem = AlgoMemory(dev["a"], dev["b"], dev["c"], dev["u"], 0 if state is None else 1, 0)
+        es = None
+        if algo.algo in (ALGO["cmaes"], ALGO["xnes"]):  # their state lives on the host
+            L0 = lib()
+            L0.pgc_es_state_len.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]
+            ln = C.c_size_t()
+            check(L0.pgc_es_state_len(algo.algo, nx, C.byref(ln)))
+            es = np.zeros(ln.value) if state is None else np.ascontiguousarray(state["es"], dtype=np.float64).copy()
+        mem = AlgoMemory(dev["a"], dev["b"], dev["c"], dev["u"], 0 if state is None else 1, 0, es.ctypes.data if es is not None else None,
+                         es.size if es is not None else 0)
         done = C.c_uint()
         L = lib()
         L.pgc_algo_evolve_memory_device.argtypes = [C.c_void_p, C.POINTER(AlgoDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
@@ -794,6 +803,8 @@ class Problem:
             check(L.pgc_algo_evolve_memory_device(self._h, C.byref(algo), dx, df, n, first_generation, C.byref(done), C.byref(mem), None))
             self.ctx.synchronize()
             out = {k: self.ctx.from_device(dev[k], host[k].shape, dtype=host[k].dtype) for k in host}
+            if es is not None:
+                out["es"] = es
             return self.ctx.from_device(dx, x.shape), self.ctx.from_device(df, f.shape), done.value, out
         finally:
             for d in (dx, df, *dev.values()):

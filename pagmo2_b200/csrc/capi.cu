@@ -1061,6 +1061,13 @@ int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *a, double *d_
     }
 }
 
+int pgc_es_state_len(int algo, size_t nx, size_t *len)
+{
+    PGC_REQUIRE(len && (algo == PGC_ALGO_CMAES || algo == PGC_ALGO_XNES), "pgc_es_state_len: cmaes or xnes, and somewhere to put the answer");
+    *len = es_state_doubles(algo, nx);
+    return PGC_OK;
+}
+
 int pgc_algo_evolve_memory_device(pgc_problem *prob, const pgc_algo_desc *a, double *d_x, double *d_f, size_t n, uint32_t first_generation,
                                   unsigned *gens_done, pgc_algo_memory *mem, void *stream)
 {
@@ -1104,6 +1111,22 @@ int pgc_algo_evolve_memory_device(pgc_problem *prob, const pgc_algo_desc *a, dou
             }
             return pgc_nspso_evolve_device(prob, d_x, d_f, n, a->gens, a->omega, a->nspso_c1, a->nspso_c2, a->nspso_chi, a->nspso_v_coeff,
                                            a->leader_selection_range, a->diversity, a->seed, first_generation, mem->a, mem->b, mem->c, stream);
+        case PGC_ALGO_CMAES: // the state says itself whether it is usable (dimension, population size): `initialized` is not consulted
+            PGC_REQUIRE(mem->h_state, "pgc_algo_evolve_memory_device: cmaes keeps its state in h_state (pgc_es_state_len doubles)");
+            PGC_NO_INTEGER_GENES(prob, "pgc_algo_evolve_memory_device");
+            if (!mem->initialized) mem->h_state[0] = 0.;
+            mem->initialized = 1;
+            return cmaes_evolve_device(prob, d_x, d_f, n, a->gens, a->cma_cc, a->cma_cs, a->cma_c1, a->cma_cmu, a->sigma0, a->ftol, a->xtol,
+                                       static_cast<int>(a->force_bounds), a->seed, first_generation, gens_done, nullptr, problem_eval_device, st,
+                                       mem->h_state, mem->h_state_len);
+        case PGC_ALGO_XNES:
+            PGC_REQUIRE(mem->h_state, "pgc_algo_evolve_memory_device: xnes keeps its state in h_state (pgc_es_state_len doubles)");
+            PGC_NO_INTEGER_GENES(prob, "pgc_algo_evolve_memory_device");
+            if (!mem->initialized) mem->h_state[0] = 0.;
+            mem->initialized = 1;
+            return xnes_evolve_device(prob, d_x, d_f, n, a->gens, a->cma_cc, a->cma_cs, a->cma_c1, a->sigma0, a->ftol, a->xtol,
+                                      static_cast<int>(a->force_bounds), a->seed, first_generation, gens_done, nullptr, problem_eval_device, st,
+                                      mem->h_state, mem->h_state_len);
         default:
             set_error("pgc_algo_evolve_memory_device: algorithm %d keeps no state between evolve() calls", a->algo);
             return PGC_ERR_INVALID_ARGUMENT;

@@ -465,13 +465,18 @@ void jacobi_eigen(std::vector<double> &a, size_t D, std::vector<double> &w, std:
 }
 } // namespace
 
+// doubles an evolution strategy built with memory = true keeps between evolve() calls (layouts in cmaes_evolve_device / xnes_evolve_device)
+size_t es_state_doubles(int algo, size_t D) { return algo == PGC_ALGO_XNES ? 3 + D + D * D : 6 + 4 * D + 3 * D * D; }
+
 int cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam, unsigned gens, double cc, double cs, double c1, double cmu,
                         double sigma0, double ftol, double xtol, int force_bounds, unsigned long long seed, unsigned first_generation,
                         unsigned *gens_done, double *sigma_out, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t),
-                        cudaStream_t st)
+                        cudaStream_t st, double *es_state, size_t es_state_len)
 {
     pgc_ctx *ctx = prob->ctx;
     const size_t D = prob->nx, mu = lam / 2u;
+    PGC_REQUIRE(!es_state || es_state_len >= es_state_doubles(PGC_ALGO_CMAES, D), "cmaes: the memory array holds %zu doubles, %zu are needed", es_state_len,
+                es_state_doubles(PGC_ALGO_CMAES, D));
     if (gens_done) *gens_done = 0;
     // constructor checks, cmaes.cpp:64-88, and evolve's, :126-150
     PGC_REQUIRE(((cc >= 0.) && (cc <= 1.)) || cc == -1., "cc must be in [0,1] or -1 if its value has to be initialized automatically, a value of %g was detected", cc);
@@ -528,6 +533,33 @@ int cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam,
         invsqrtC[j * D + j] = 1. / dvec[j];
     }
     unsigned long long counteval = 0, eigeneval = 0;
+    // memory = true (cmaes.cpp:201-203): a state left by an earlier call on the same dimension and population size replaces the fresh start
+    // layout: [1, D, lam, sigma, counteval, eigeneval | mean | pc | ps | dvec | B | C | invsqrtC]
+    const bool resume = es_state && es_state[0] == 1. && es_state[1] == static_cast<double>(D) && es_state[2] == static_cast<double>(lam);
+    if (resume) {
+        const double *p = es_state + 6;
+        sigma = es_state[3], counteval = static_cast<unsigned long long>(es_state[4]), eigeneval = static_cast<unsigned long long>(es_state[5]);
+        const auto take = [&](std::vector<double> &v) {
+            std::copy(p, p + v.size(), v.begin());
+            p += v.size();
+        };
+        take(mean), take(pc), take(ps), take(dvec), take(B), take(C), take(invsqrtC);
+    }
+    struct SaveState { // written back however the loop ends (an exit test leaves the state as it found it)
+        double *out;
+        const size_t &D, &lam;
+        const double &sigma;
+        const unsigned long long &counteval, &eigeneval;
+        const std::vector<double> &mean, &pc, &ps, &dvec, &B, &C, &invsqrtC;
+        ~SaveState()
+        {
+            if (!out) return;
+            out[0] = 1., out[1] = static_cast<double>(D), out[2] = static_cast<double>(lam), out[3] = sigma;
+            out[4] = static_cast<double>(counteval), out[5] = static_cast<double>(eigeneval);
+            double *p = out + 6;
+            for (const std::vector<double> *v : {&mean, &pc, &ps, &dvec, &B, &C, &invsqrtC}) p = std::copy(v->begin(), v->end(), p);
+        }
+    } save_state{es_state, D, lam, sigma, counteval, eigeneval, mean, pc, ps, dvec, B, C, invsqrtC};
 
     struct Buf {
         cudaStream_t st;
@@ -662,11 +694,13 @@ int cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam,
 int xnes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam, unsigned gens, double eta_mu, double eta_sigma, double eta_b,
                        double sigma0, double ftol, double xtol, int force_bounds, unsigned long long seed, unsigned first_generation,
                        unsigned *gens_done, double *sigma_out, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t),
-                       cudaStream_t st)
+                       cudaStream_t st, double *es_state, size_t es_state_len)
 {
     pgc_ctx *ctx = prob->ctx;
     const size_t D = prob->nx;
     if (gens_done) *gens_done = 0;
+    PGC_REQUIRE(!es_state || es_state_len >= es_state_doubles(PGC_ALGO_XNES, D), "xnes: the memory array holds %zu doubles, %zu are needed", es_state_len,
+                es_state_doubles(PGC_ALGO_XNES, D));
     // constructor checks, xnes.cpp:55-78, and evolve's, :110-137
     PGC_REQUIRE((eta_mu > 0. && eta_mu <= 1.) || eta_mu == -1., "eta_mu must be in ]0,1] or -1 if its value has to be initialized automatically, a value of %g was detected", eta_mu);
     PGC_REQUIRE((eta_sigma > 0. && eta_sigma <= 1.) || eta_sigma == -1., "eta_sigma needs to be in ]0,1] or -1 if its value has to be initialized automatically, a value of %g was detected", eta_sigma);
@@ -699,6 +733,24 @@ int xnes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam, 
         if (f[i] < f[ib]) ib = i;
     PGC_CUDA(cudaMemcpyAsync(mean.data(), d_x + ib * D, 8 * D, cudaMemcpyDeviceToHost, st));
     PGC_CUDA(cudaStreamSynchronize(st));
+    // memory = true (xnes.cpp:163): a state left by an earlier call on the same dimension replaces the fresh start.  [1, D, sigma | mean | A]
+    if (es_state && es_state[0] == 1. && es_state[1] == static_cast<double>(D)) {
+        sigma = es_state[2];
+        std::copy(es_state + 3, es_state + 3 + D, mean.begin());
+        std::copy(es_state + 3 + D, es_state + 3 + D + D * D, A.begin());
+    }
+    struct SaveState {
+        double *out;
+        const size_t &D;
+        const double &sigma;
+        const std::vector<double> &mean, &A;
+        ~SaveState()
+        {
+            if (!out) return;
+            out[0] = 1., out[1] = static_cast<double>(D), out[2] = sigma;
+            std::copy(A.begin(), A.end(), std::copy(mean.begin(), mean.end(), out + 3));
+        }
+    } save_state{es_state, D, sigma, mean, A};
     struct Buf {
         cudaStream_t st;
         std::vector<void *> owned;

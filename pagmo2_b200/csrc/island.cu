@@ -39,6 +39,7 @@ struct pgc_island {
     // what an algorithm built with memory = true keeps between evolve() calls (pgc_algo_memory), resident like the population
     pgc_algo_memory mem{};
     int mem_algo = 0;
+    std::vector<double> es_state; // cmaes / xnes with memory: their host-side state (pgc_es_state_len)
     double *h_heads = nullptr; // pinned: slot headers
     unsigned char *h_flags = nullptr;
     cudaEvent_t ev = nullptr;
@@ -295,7 +296,7 @@ int pgc_island_evolve(pgc_island *isl, const pgc_algo_desc *algo, unsigned *gens
     int rc;
     const bool keeps_state = algo->memory
                              && (algo->algo == PGC_ALGO_SADE || algo->algo == PGC_ALGO_DE1220 || algo->algo == PGC_ALGO_PSO_GEN
-                                 || algo->algo == PGC_ALGO_NSPSO);
+                                 || algo->algo == PGC_ALGO_NSPSO || algo->algo == PGC_ALGO_CMAES || algo->algo == PGC_ALGO_XNES);
     if (keeps_state) {
         if (isl->mem_algo != algo->algo) { // another algorithm took the island over: its first evolve() starts from nothing
             isl->mem.initialized = 0;
@@ -308,6 +309,16 @@ int pgc_island_evolve(pgc_island *isl, const pgc_algo_desc *algo, unsigned *gens
             PGC_CUDA(cudaMalloc(&isl->mem.b, sizeof(double) * n * isl->nx));
             PGC_CUDA(cudaMalloc(&isl->mem.c, sizeof(double) * n * isl->nf));
             PGC_CUDA(cudaMalloc(&isl->mem.u, sizeof(uint32_t) * n));
+        }
+        if (algo->algo == PGC_ALGO_CMAES || algo->algo == PGC_ALGO_XNES) {
+            size_t len = 0;
+            if ((rc = pgc_es_state_len(algo->algo, isl->nx, &len))) return rc;
+            if (isl->es_state.size() != len) {
+                isl->es_state.assign(len, 0.);
+                isl->mem.initialized = 0;
+            }
+            isl->mem.h_state = isl->es_state.data();
+            isl->mem.h_state_len = len;
         }
         rc = pgc_algo_evolve_memory_device(isl->prob, algo, isl->d_x, isl->d_f, isl->n, isl->generation, &done, &isl->mem, nullptr);
     } else {

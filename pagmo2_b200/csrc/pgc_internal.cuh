@@ -347,7 +347,7 @@ int maco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, 
 int xnes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam, unsigned gens, double eta_mu, double eta_sigma, double eta_b,
                        double sigma0, double ftol, double xtol, int force_bounds, unsigned long long seed, unsigned first_generation,
                        unsigned *gens_done, double *sigma_out, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t),
-                       cudaStream_t st);
+                       cudaStream_t st, double *es_state = nullptr, size_t es_state_len = 0);
 int nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned NP, unsigned gens, double omega, double c1, double c2, double chi,
                         double v_coeff, unsigned leader_selection_range, unsigned diversity, unsigned long long seed, unsigned first_generation,
                         double *d_vel, double *d_best_x, double *d_best_f,
@@ -408,7 +408,8 @@ int cmaes_sample_device(pgc_ctx *ctx, const double *d_mean, const double *d_bd, 
 int cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t lam, unsigned gens, double cc, double cs, double c1, double cmu,
                         double sigma0, double ftol, double xtol, int force_bounds, unsigned long long seed, unsigned first_generation,
                         unsigned *gens_done, double *sigma_out, int (*eval)(pgc_problem *, const double *, size_t, double *, cudaStream_t),
-                        cudaStream_t st);
+                        cudaStream_t st, double *es_state = nullptr, size_t es_state_len = 0);
+size_t es_state_doubles(int algo, size_t D);
 int fp64_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mma_peak(pgc_ctx *ctx, int iters, double *tflops);
 int fp64_mix_probe(pgc_ctx *ctx, int iters, int total_warps, int dmma_warps, double *tflops_out);

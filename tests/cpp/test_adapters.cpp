@@ -337,6 +337,9 @@ int main(int argc, char **argv)
             CHECK(split_equals_whole([](unsigned g) { return cuda_sade{g, 2u, 1u, 0., 0., true, 41u}; }));
             CHECK(!split_equals_whole([](unsigned g) { return cuda_sade{g, 2u, 1u, 0., 0., false, 41u}; }));
             CHECK(split_equals_whole([](unsigned g) { return cuda_de1220{g, {2u, 3u, 7u, 10u}, 1u, 0., 0., true, 5u}; }));
+            CHECK(split_equals_whole([](unsigned g) { return cuda_cmaes{g, -1, -1, -1, -1, 0.5, 0., 0., true, false, 5u}; }));
+            CHECK(!split_equals_whole([](unsigned g) { return cuda_cmaes{g, -1, -1, -1, -1, 0.5, 0., 0., false, false, 5u}; }));
+            CHECK(split_equals_whole([](unsigned g) { return cuda_xnes{g, -1, -1, -1, -1, 0., 0., true, false, 5u}; }));
             CHECK(!split_equals_whole([](unsigned g) { return cuda_de1220{g, {2u, 3u, 7u, 10u}, 1u, 0., 0., false, 5u}; }));
             { // pso_gen with memory restarts from the particles' best positions with the KEPT velocities (pso_gen.cpp:193-201)
                 pagmo::population a{prob, 32u, 9u}, b{prob, 32u, 9u};

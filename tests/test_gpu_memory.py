@@ -113,6 +113,41 @@ def test_island_keeps_the_state_in_hbm(capi, ctx, name, kw):
     prob.close()
 
 
+@pytest.mark.parametrize("name", ("cmaes", "xnes"))
+def test_evolution_strategies_keep_their_distribution(capi, ctx, name):
+    """cmaes (cmaes.cpp:201-228) and xnes (xnes.cpp:163-175) with memory = true keep sigma, the mean and the covariance factors: 3 + 3
+    generations are the uninterrupted 6 (the exit tests aside, nothing else reads the population); without memory the second call starts
+    again from the bounds' box.  cmaes restarts when the population size changes, xnes does not."""
+    prob, x, f = _so_problem(capi, ctx, n=24)
+    whole = capi.algo_desc(name, gens=6, seed=17, ftol=0.0, xtol=0.0)
+    half = capi.algo_desc(name, gens=3, seed=17, ftol=0.0, xtol=0.0)
+    x6, f6, done = prob.evolve(whole, x, f, first_generation=1)
+    assert done == 6
+    xa, fa, _, st = prob.evolve_memory(half, x, f, first_generation=1)
+    x3, f3, _ = prob.evolve(half, x, f, first_generation=1)
+    assert np.array_equal(xa, x3) and np.array_equal(fa, f3)
+    xb, fb, _, st2 = prob.evolve_memory(half, xa, fa, first_generation=4, state=st)
+    assert np.array_equal(xb, x6) and np.array_equal(fb, f6)
+    xc, _, _ = prob.evolve(half, xa, fa, first_generation=4)
+    assert not np.array_equal(xc, x6)
+    assert st2["es"][0] == 1 and st2["es"][1] == prob.nx and not np.array_equal(st2["es"], st["es"])
+    # a population of another size: cmaes starts afresh (= a memory-less call), xnes carries on
+    xs, fs = xa[:16], fa[:16]
+    xd, fd, _, _ = prob.evolve_memory(half, xs, fs, first_generation=4, state={k: (v if k == "es" else v[:16]) for k, v in st.items()})
+    xe, fe, _ = prob.evolve(half, xs, fs, first_generation=4)
+    assert np.array_equal(xd, xe) == (name == "cmaes")
+    # inside a resident island the state stays with the island
+    isl = capi.Island(prob, 24)
+    isl.upload(np.arange(1, 25, dtype=np.uint64), x, f)
+    hm = capi.algo_desc(name, gens=3, seed=17, ftol=0.0, xtol=0.0, memory=1)
+    isl.evolve(hm)
+    isl.evolve(hm)
+    _, xi, fi = isl.download()
+    isl.close()
+    assert np.array_equal(xi, x6) and np.array_equal(fi, f6)
+    prob.close()
+
+
 def test_memory_argument_checks(capi, ctx):
     prob, x, f = _so_problem(capi, ctx, n=16)
     with pytest.raises(capi.PgcError):  # de keeps no state
