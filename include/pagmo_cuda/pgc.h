@@ -368,7 +368,9 @@ typedef struct pgc_algo_desc {
     uint32_t param_s, crossover, mutation, selection; /* sga: see pgc_sga_evolve_device */
     double cma_cc, cma_cs, cma_c1, cma_cmu, sigma0;   /* cmaes (-1: automatic), cmaes.hpp:110 */
     uint32_t force_bounds;
-    uint32_t memory;                      /* sade / de1220 / pso_gen / nspso: keep the adaptation state between evolve() calls (pgc_algo_memory) */
+    uint32_t memory;                      /* sade / de1220 / pso_gen / nspso / cmaes / xnes: keep the state between evolve() calls.  Honoured where
+                                           * somebody owns that state: pgc_island_evolve (resident in the island) and the C++ adapters; through
+                                           * pgc_algo_evolve_device a call is memory-less, pgc_algo_evolve_memory_device takes the state explicitly */
     double nspso_c1, nspso_c2, nspso_chi, nspso_v_coeff;       /* nspso (omega is shared with pso_gen), nspso.hpp:59-62 */
     uint32_t leader_selection_range, diversity;               /* nspso: diversity 0 crowding distance, 1 niche count, 2 max min */
 } pgc_algo_desc;
