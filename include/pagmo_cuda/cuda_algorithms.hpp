@@ -669,8 +669,7 @@ private:
 
 // pagmo::gaco (gaco.hpp:104-107), extended ant colony optimisation: penalties, the solution archive, the pheromone values and the ants
 // of every generation are computed on the device (pgc_gaco_evolve_device, gaco.cu) - the same generational algorithm as the
-// reference's, on Philox draws.  Unconstrained single-objective problems (the ones with a device evaluator); memory = true is not
-// built.  Like the reference, the object keeps its oracle parameter, kernel width and stopping counters between evolve() calls.
+// reference's, on Philox draws.  Unconstrained single-objective problems (the ones with a device evaluator).  Like the reference, the object keeps its oracle parameter, kernel width and stopping counters between evolve() calls.
 class cuda_gaco
 {
 public:
@@ -678,7 +677,7 @@ public:
               unsigned n_gen_mark = 7u, unsigned impstop = 100000u, unsigned evalstop = 100000u, double focus = 0., bool memory = false,
               unsigned seed = pagmo::random_device::next(), int device = 0)
         : m_gen(gen), m_ker(ker), m_q(q), m_oracle(oracle), m_acc(acc), m_threshold(threshold), m_n_gen_mark(n_gen_mark), m_impstop(impstop),
-          m_evalstop(evalstop), m_focus(focus), m_seed(seed), m_device(device), m_cache(std::make_shared<detail::twin_cache>())
+          m_evalstop(evalstop), m_focus(focus), m_memory(memory), m_seed(seed), m_device(device), m_cache(std::make_shared<detail::twin_cache>())
     { // gaco.cpp:62-94
         if (acc < 0.) {
             pagmo_throw(std::invalid_argument, "The accuracy parameter must be >=0, while a value of " + std::to_string(acc) + " was detected");
@@ -686,10 +685,13 @@ public:
         if (focus < 0.) {
             pagmo_throw(std::invalid_argument, "The focus parameter must be >=0  while a value of " + std::to_string(focus) + " was detected");
         }
-        if (memory) pagmo_throw(std::invalid_argument, "cuda_gaco: memory = true is not supported on the device path");
-        if ((threshold < 1 || threshold > gen) && gen != 0) {
+        if ((threshold < 1 || threshold > gen) && gen != 0 && memory == false) {
             pagmo_throw(std::invalid_argument, "If memory is inactive, the threshold parameter must be either in [1,m_gen] while a value of "
                                                    + std::to_string(threshold) + " was detected");
+        }
+        if (threshold < 1 && gen != 0 && memory == true) {
+            pagmo_throw(std::invalid_argument,
+                        "If memory is active, the threshold parameter must be >=1 while a value of " + std::to_string(threshold) + " was detected");
         }
         if (q < 0.) {
             pagmo_throw(std::invalid_argument,
@@ -734,6 +736,19 @@ public:
             f[i] = pop.get_f()[i][0];
         }
         unsigned done = 0;
+        // the algorithm object's members travel in m_state; with memory = true also its archive (a value member: copies of the algorithm
+        // carry it).  The evalstop counter watches the POPULATION's champion (gaco.cpp:338-347), which the population brings along.
+        m_state.memory = m_memory ? 1u : 0u;
+        if (m_memory) {
+            if (m_archive.size() != static_cast<std::size_t>(m_ker) * (nx + 2u)) {
+                m_archive.assign(static_cast<std::size_t>(m_ker) * (nx + 2u), 0.);
+                m_state.counter = 0u; // another problem dimension: the archive starts again
+            }
+            m_state.h_archive = m_archive.data();
+            m_state.h_archive_len = m_archive.size();
+        }
+        m_state.has_champion = 1u;
+        m_state.champion_f = pop.champion_f()[0];
         h->on_device(x, f, "pgc_gaco_evolve_device", [&](double *dx, double *df, std::size_t n) {
             return detail::with_log_capture(h->context(), m_verbosity, m_gen, 7u, m_log_rows, [&] {
                 return pgc_gaco_evolve_device(h->raw(), dx, df, n, m_gen, m_ker, m_q, m_oracle, m_acc, m_threshold, m_n_gen_mark, m_impstop,
@@ -772,9 +787,9 @@ public:
     template <typename Archive>
     void serialize(Archive &ar, unsigned)
     {
-        pagmo::detail::archive(ar, m_gen, m_ker, m_q, m_oracle, m_acc, m_threshold, m_n_gen_mark, m_impstop, m_evalstop, m_focus, m_seed, m_device,
-                               m_generation, m_state.oracle, m_state.q, m_state.n_evalstop, m_state.n_impstop, m_state.gen_mark,
-                               m_state.initialized, m_state.fevals);
+        pagmo::detail::archive(ar, m_gen, m_ker, m_q, m_oracle, m_acc, m_threshold, m_n_gen_mark, m_impstop, m_evalstop, m_focus, m_memory, m_seed,
+                               m_device, m_generation, m_state.oracle, m_state.q, m_state.n_evalstop, m_state.n_impstop, m_state.gen_mark,
+                               m_state.initialized, m_state.fevals, m_state.counter, m_archive);
     }
 
 private:
@@ -782,11 +797,12 @@ private:
     double m_q, m_oracle, m_acc;
     unsigned m_threshold, m_n_gen_mark, m_impstop, m_evalstop;
     double m_focus;
+    bool m_memory;
     unsigned m_seed;
     int m_device;
     mutable unsigned m_generation = 1;
     unsigned m_verbosity = 0;
-    mutable pagmo::vector_double m_log_rows;
+    mutable pagmo::vector_double m_log_rows, m_archive;
     mutable pgc_gaco_state m_state{};
     std::shared_ptr<detail::twin_cache> m_cache;
 };

@@ -294,7 +294,7 @@ PGC_API int pgc_moead_gen_evolve_device(pgc_problem *prob, double *d_x, double *
                                         const uint32_t *neigh, unsigned T, int decomposition, double CR, double F, double eta_m, double realb,
                                         unsigned limit, int preserve_diversity, uint64_t seed, uint32_t first_generation, void *stream);
 /* gaco::evolve (src/algorithms/gaco.cpp:104-445), extended ant colony optimisation, on a device-resident population of an
- * unconstrained single-objective problem (in place), memory = false; the problem's last nix variables are sampled as integers.
+ * unconstrained single-objective problem (in place); the problem's last nix variables are sampled as integers.
  * Constructor arguments as gaco.hpp:104-107 (reference defaults: ker 63, q 1.0, oracle 0, acc 0.01, threshold 1, n_gen_mark 7,
  * impstop 100000, evalstop 100000, focus 0).  The reference keeps m_oracle, m_q and its stopping counters in the algorithm object
  * between evolve() calls: they travel in pgc_gaco_state (initialized == 0: taken from q / oracle, counters at 1; updated on return).
@@ -303,6 +303,16 @@ typedef struct pgc_gaco_state {
     double oracle, q;
     uint32_t n_evalstop, n_impstop, gen_mark, initialized;
     uint64_t fevals;
+    /* memory = true (gaco.cpp:106-108,223-250,732-752,778-784): the solution archive and a call counter survive between evolve() calls,
+     * the kernel weights follow the counter, and the archive is NOT written back into the population.  h_archive: HOST array of
+     * ker * (nx + 2) doubles owned by the caller. */
+    uint32_t memory, counter;
+    double *h_archive;
+    size_t h_archive_len;
+    /* the champion of the POPULATION (population.cpp:209-246, the best individual it ever held) is what the evalstop counter watches
+     * (gaco.cpp:338-347); has_champion == 0: the best of the population handed in.  Updated on return. */
+    uint32_t has_champion, reserved_;
+    double champion_f;
 } pgc_gaco_state;
 PGC_API int pgc_gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n, unsigned gens, unsigned ker, double q, double oracle,
                                    double acc, unsigned threshold, unsigned n_gen_mark, unsigned impstop, unsigned evalstop, double focus,

@@ -185,6 +185,11 @@ typedef struct {
     double oracle, q;
     unsigned n_evalstop, n_impstop, gen_mark;
     unsigned long long fevals;
+    unsigned counter;  /* m_counter: evolve() calls so far, counted only with memory */
+    int memory;        /* constructed with memory = true: the archive below survives between calls and is never written back */
+    double *archive;   /* [ker x (1 + nx + 1)], caller-owned; used with memory only */
+    int has_champion;  /* the POPULATION's champion (population.cpp:209-246: the best individual it has ever held) travels with the population */
+    double champion;   /* from call to call; 0: taken as the best of the population handed in */
 } oracle_gaco_state;
 void oracle_gaco_state_init(oracle_gaco_state *s, double q, double oracle_par);
 int oracle_gaco_evolve(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t n, size_t nx, size_t nix,
@@ -192,7 +197,7 @@ int oracle_gaco_evolve(const oracle_problem *prob, const double *lb, const doubl
                        double focus, uint64_t seed, uint32_t first_generation, oracle_gaco_state *st, unsigned *gens_done);
 int oracle_gaco_evolve_mt(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t n, size_t nx, size_t nix,
                           unsigned gens, unsigned ker, double q, double oracle_par, double acc, unsigned threshold, unsigned n_gen_mark,
-                          unsigned impstop, unsigned evalstop, double focus, uint32_t seed);
+                          unsigned impstop, unsigned evalstop, double focus, uint32_t seed, int memory, unsigned calls);
 
 /* maco::evolve (src/algorithms/maco.cpp:88-533), memory = false; the algorithm object's m_q, m_n_evalstop, m_gen_mark travel in the state */
 typedef struct {

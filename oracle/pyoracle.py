@@ -564,10 +564,11 @@ class Oracle:
 
     class GacoState(C.Structure):
         _fields_ = [("oracle", C.c_double), ("q", C.c_double), ("n_evalstop", C.c_uint), ("n_impstop", C.c_uint), ("gen_mark", C.c_uint),
-                    ("fevals", C.c_ulonglong)]
+                    ("fevals", C.c_ulonglong), ("counter", C.c_uint), ("memory", C.c_int), ("archive", C.c_void_p),
+                    ("has_champion", C.c_int), ("champion", C.c_double)]
 
     def gaco_evolve(self, prob, lb, ub, x, f, nix=0, gens=1, ker=63, q=1.0, oracle=0.0, acc=0.01, threshold=1, n_gen_mark=7, impstop=100000,
-                    evalstop=100000, focus=0.0, seed=0, first_generation=1, mt=False, state=None):
+                    evalstop=100000, focus=0.0, seed=0, first_generation=1, mt=False, state=None, memory=False, calls=1):
         """restated gaco::evolve (Philox draws, or the mt19937 stream with mt=True): returns (x, f, state, gens_done); `state` = the
         scalar members that survive between evolve() calls (pass it back in to continue with the same algorithm object)."""
         x = np.array(x, dtype=np.float64, order="C")
@@ -577,9 +578,9 @@ class Oracle:
         if mt:
             self.lib.oracle_gaco_evolve_mt.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_size_t, C.c_size_t,
                                                        C.c_size_t, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_uint, C.c_uint,
-                                                       C.c_uint, C.c_uint, C.c_double, C.c_uint32]
+                                                       C.c_uint, C.c_uint, C.c_double, C.c_uint32, C.c_int, C.c_uint]
             if self.lib.oracle_gaco_evolve_mt(C.byref(prob), _dp(lb), _dp(ub), _dp(x), _dp(f), n, nx, nix, gens, ker, q, oracle, acc, threshold,
-                                              n_gen_mark, impstop, evalstop, focus, seed):
+                                              n_gen_mark, impstop, evalstop, focus, seed, int(memory), calls):
                 raise ValueError("oracle_gaco_evolve_mt failed")
             return x, f, None, gens
         st = state if state is not None else self.GacoState()
@@ -587,6 +588,10 @@ class Oracle:
             self.lib.oracle_gaco_state_init.argtypes = [C.c_void_p, C.c_double, C.c_double]
             self.lib.oracle_gaco_state_init.restype = None
             self.lib.oracle_gaco_state_init(C.byref(st), q, oracle)
+            if memory:  # the archive lives as long as the state object does
+                st.memory = 1
+                st._archive = np.zeros(ker * (nx + 2))
+                st.archive = st._archive.ctypes.data
         done = C.c_uint()
         self.lib.oracle_gaco_evolve.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                                 C.c_uint, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint64,

@@ -131,6 +131,7 @@ int ref_evolve_from(ref_problem *p, const char *algo, const double *par, size_t 
             if (npar < k) throw std::invalid_argument("ref_evolve_from: too few parameters for '" + a + "'");
         };
         pagmo::algorithm alg;
+        unsigned calls = 1; // evolve() calls of the one algorithm object (gaco with memory)
         if (a == "nsga2") {
             need(4);
             alg = pagmo::algorithm{pagmo::nsga2(gens, par[0], par[1], par[2], par[3], seed)};
@@ -169,18 +170,20 @@ int ref_evolve_from(ref_problem *p, const char *algo, const double *par, size_t 
             need(6);
             alg = pagmo::algorithm{pagmo::nspso(gens, par[0], par[1], par[2], par[3], par[4], static_cast<unsigned>(par[5]),
                                                 std::string(strategies ? strategies : "crowding distance"), false, seed)};
-        } else if (a == "gaco") { // ker, q, oracle, acc, threshold, n_gen_mark, impstop, evalstop, focus (gaco.hpp:104-107)
-            need(9);
+        } else if (a == "gaco") { // ker, q, oracle, acc, threshold, n_gen_mark, impstop, evalstop, focus (gaco.hpp:104-107) [, memory, calls]
+            if (npar != 9 && npar != 11) throw std::invalid_argument("ref_evolve_from: gaco takes 9 or 11 parameters");
+            const bool memory = npar == 11 && par[9] != 0.;
+            if (npar == 11) calls = static_cast<unsigned>(par[10]);
             alg = pagmo::algorithm{pagmo::gaco(gens, static_cast<unsigned>(par[0]), par[1], par[2], par[3], static_cast<unsigned>(par[4]),
                                                static_cast<unsigned>(par[5]), static_cast<unsigned>(par[6]), static_cast<unsigned>(par[7]), par[8],
-                                               false, seed)};
+                                               memory, seed)};
         } else if (a == "maco") { // ker, q, threshold, n_gen_mark, evalstop, focus (maco.hpp:107-109)
             need(6);
             alg = pagmo::algorithm{pagmo::maco(gens, static_cast<unsigned>(par[0]), par[1], static_cast<unsigned>(par[2]),
                                                static_cast<unsigned>(par[3]), static_cast<unsigned>(par[4]), par[5], false, seed)};
         } else
             throw std::invalid_argument("ref_evolve_from: unknown algorithm '" + a + "'");
-        pop = alg.evolve(pop);
+        for (unsigned c = 0; c < calls; ++c) pop = alg.evolve(pop); // the same algorithm object every time: its members carry over
         for (size_t i = 0; i < n; ++i) {
             if (x_out) std::memcpy(x_out + i * nx, pop.get_x()[i].data(), nx * sizeof(double));
             if (f_out) std::memcpy(f_out + i * nf, pop.get_f()[i].data(), nf * sizeof(double));

@@ -56,6 +56,11 @@ void oracle_gaco_state_init(oracle_gaco_state *s, double q, double oracle_par)
     s->n_impstop = 1;
     s->gen_mark = 1;
     s->fevals = 0;
+    s->counter = 0;
+    s->memory = 0;
+    s->archive = NULL;
+    s->has_champion = 0;
+    s->champion = 0.;
 }
 
 /* archive rows: [penalty | x (nx) | f (1)] */
@@ -65,7 +70,10 @@ int oracle_gaco_evolve(const oracle_problem *prob, const double *lb, const doubl
 {
     if (gens_done) *gens_done = 0;
     if (n == 0 || gens == 0) return 0;
-    if (n < 2 || ker < 2 || ker > n || acc < 0. || focus < 0. || threshold < 1 || threshold > gens || st->q < 0.) return -1;
+    if (st->memory) ++st->counter; /* :106-108 */
+    if (n < 2 || ker < 2 || ker > n || acc < 0. || focus < 0. || threshold < 1 || (!st->memory && threshold > gens) || st->q < 0.) return -1;
+    const int memory = st->memory;
+    const unsigned counter = st->counter;
     const size_t row = 1 + nx + 1, ncx = nx - nix;
     double *arch = (double *)malloc(ker * row * sizeof(double)), *tmp_arch = (double *)malloc(ker * row * sizeof(double)),
            *pen = (double *)malloc(n * sizeof(double)), *sorted_pen = (double *)malloc(n * sizeof(double)),
@@ -78,6 +86,8 @@ int oracle_gaco_evolve(const oracle_problem *prob, const double *lb, const doubl
     double champ = f[0];
     for (size_t i = 1; i < n; ++i)
         if (less_f(f[i], champ)) champ = f[i];
+    if (st->has_champion && less_f(st->champion, champ)) champ = st->champion; /* the population remembers better ants than it holds */
+    if (memory && counter > 1) memcpy(arch, st->archive, ker * row * sizeof(double)); /* sol_archive = m_sol_archive, :223-225 */
     int rc = 0, stopped = 0;
     unsigned gen;
     for (gen = 1; gen <= gens && !rc; ++gen) {
@@ -93,7 +103,7 @@ int oracle_gaco_evolve(const oracle_problem *prob, const double *lb, const doubl
         for (size_t i = 0; i < n; ++i) sl[i] = i;
         key_ctx kc = {pen};
         oracle_sort_indices(sl, stmp, n, key_less, &kc); /* std::sort on the mt19937 pin, stable for the device comparison */
-        if (gen == 1) {
+        if (gen == 1 && counter < 2) {
             for (size_t i = 0; i < ker; ++i) {
                 arch[i * row] = pen[sl[i]];
                 memcpy(arch + i * row + 1, x + sl[i] * nx, nx * sizeof(double));
@@ -143,8 +153,8 @@ int oracle_gaco_evolve(const oracle_problem *prob, const double *lb, const doubl
             if (st->gen_mark > n_gen_mark) st->gen_mark = 1;
         }
         /* 4 - pheromone_computation, :690-796 */
-        if (gen == 1 || gen == threshold) {
-            if (gen == threshold) st->q = 0.01;
+        if (memory ? 1 : (gen == 1 || gen == threshold)) { /* with memory the weights are recomputed every generation, :732-752 */
+            if (memory ? counter == threshold : gen == threshold) st->q = 0.01;
             double sum_omega = 0;
             for (unsigned l = 1; l <= ker; ++l) {
                 const double omega_new = 1.0 / (st->q * ker * sqrt(2 * 3.141592653589793238462643383279502884))
@@ -166,7 +176,7 @@ int oracle_gaco_evolve(const oracle_problem *prob, const double *lb, const doubl
                     if (d < d_min) d_min = d;
                     if (d > d_max) d_max = d;
                 }
-            if (focus != 0. && ((d_max - d_min) / gen > (ub[h - 1] - lb[h - 1]) / focus)) {
+            if (focus != 0. && ((d_max - d_min) / (memory ? counter : gen) > (ub[h - 1] - lb[h - 1]) / focus)) { /* :778-784 */
                 sigma[h - 1] = (ub[h - 1] - lb[h - 1]) / focus;
             } else if (h <= ncx) {
                 sigma[h - 1] = (d_max - d_min) / st->gen_mark;
@@ -219,8 +229,11 @@ int oracle_gaco_evolve(const oracle_problem *prob, const double *lb, const doubl
         }
     }
     if (gens_done) *gens_done = gen - 1;
-    /* the archive goes back into the population, :408-421 (not when a stopping criterion returned early) */
-    if (!rc && !stopped)
+    st->champion = champ;
+    st->has_champion = 1;
+    if (memory) memcpy(st->archive, arch, ker * row * sizeof(double)); /* m_sol_archive */
+    /* the archive goes back into the population, :408-421 (memory = false only; not when a stopping criterion returned early) */
+    if (!rc && !stopped && !memory)
         for (size_t i = 0; i < ker; ++i) {
             memcpy(x + i * nx, arch + i * row + 1, nx * sizeof(double));
             f[i] = arch[i * row + 1 + nx];
@@ -230,14 +243,20 @@ int oracle_gaco_evolve(const oracle_problem *prob, const double *lb, const doubl
     return rc;
 }
 
+/* `calls` evolve() calls of ONE algorithm object on the mt19937 stream (memory != 0: constructed with memory = true) */
 int oracle_gaco_evolve_mt(const oracle_problem *prob, const double *lb, const double *ub, double *x, double *f, size_t n, size_t nx, size_t nix,
                           unsigned gens, unsigned ker, double q, double oracle_par, double acc, unsigned threshold, unsigned n_gen_mark,
-                          unsigned impstop, unsigned evalstop, double focus, uint32_t seed)
+                          unsigned impstop, unsigned evalstop, double focus, uint32_t seed, int memory, unsigned calls)
 {
     oracle_gaco_state st;
     oracle_gaco_state_init(&st, q, oracle_par);
+    st.memory = memory;
+    st.archive = (double *)calloc((size_t)ker * (nx + 2), sizeof(double));
     ORACLE_MT_BEGIN(seed);
-    const int rc = oracle_gaco_evolve(prob, lb, ub, x, f, n, nx, nix, gens, ker, acc, threshold, n_gen_mark, impstop, evalstop, focus, 0, 0, &st, NULL);
+    int rc = 0;
+    for (unsigned c = 0; c < calls && !rc; ++c)
+        rc = oracle_gaco_evolve(prob, lb, ub, x, f, n, nx, nix, gens, ker, acc, threshold, n_gen_mark, impstop, evalstop, focus, 0, 0, &st, NULL);
     ORACLE_MT_END();
+    free(st.archive);
     return rc;
 }

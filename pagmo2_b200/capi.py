@@ -62,7 +62,8 @@ class AlgoDesc(C.Structure):
 class GacoState(C.Structure):
     """pgc_gaco_state: the scalar members pagmo::gaco keeps between evolve() calls."""
     _fields_ = [("oracle", C.c_double), ("q", C.c_double), ("n_evalstop", C.c_uint32), ("n_impstop", C.c_uint32), ("gen_mark", C.c_uint32),
-                ("initialized", C.c_uint32), ("fevals", C.c_uint64)]
+                ("initialized", C.c_uint32), ("fevals", C.c_uint64), ("memory", C.c_uint32), ("counter", C.c_uint32), ("h_archive", C.c_void_p),
+                ("h_archive_len", C.c_size_t), ("has_champion", C.c_uint32), ("reserved_", C.c_uint32), ("champion_f", C.c_double)]
 
 
 class MacoState(C.Structure):
@@ -675,12 +676,16 @@ class Problem:
                     self.ctx.free(d)
 
     def gaco_evolve(self, x, f, gens=1, ker=63, q=1.0, oracle=0.0, acc=0.01, threshold=1, n_gen_mark=7, impstop=100000, evalstop=100000,
-                    focus=0.0, seed=0, first_generation=1, state=None):
-        """gaco::evolve on the device: returns (x, f, state, gens_done); `state` (GacoState) = the algorithm's scalar members, pass it
-        back in to continue with the same algorithm object."""
+                    focus=0.0, seed=0, first_generation=1, state=None, memory=False):
+        """gaco::evolve on the device: returns (x, f, state, gens_done); `state` (GacoState) = the algorithm's scalar members (and, with
+        memory=True, its archive), pass it back in to continue with the same algorithm object."""
         x = np.ascontiguousarray(x, dtype=np.float64)
         f = np.ascontiguousarray(f, dtype=np.float64).reshape(x.shape[0], -1)
         st = state if state is not None else GacoState()
+        if state is None and memory:
+            st.memory = 1
+            st._archive = np.zeros(ker * (x.shape[1] + 2))  # lives as long as the state object
+            st.h_archive, st.h_archive_len = st._archive.ctypes.data, st._archive.size
         dx, df = self.ctx.to_device(x), self.ctx.to_device(f)
         done = C.c_uint()
         L = lib()

@@ -85,8 +85,8 @@ __device__ double gaco_penalty(double fitness, double oracle)
     return penalty;
 }
 
-__global__ void gaco_init_state_kernel(GacoState *S, const double *f, unsigned n)
-{ // the population's champion: the first best individual
+__global__ void gaco_init_state_kernel(GacoState *S, const double *f, unsigned n, int has_champion, double champion)
+{ // the population's champion: the best individual it ever held (handed in), else the first best of the ones it holds
     __shared__ double s[256];
     double v = NAN;
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x)
@@ -98,7 +98,7 @@ __global__ void gaco_init_state_kernel(GacoState *S, const double *f, unsigned n
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        S->champ = s[0];
+        S->champ = (has_champion && less_f(champion, s[0])) ? champion : s[0];
         S->stopped = 0;
         S->gens_done = 0;
     }
@@ -200,13 +200,14 @@ __global__ void gaco_archive_kernel(GacoState *S, const double *x, const double 
 // (archive rows of `row` doubles with the decision vector at column `xoff`: [penalty | x | f] for gaco, [x | f] for maco)
 __global__ void gaco_pheromone_kernel(GacoState *S, const double *arch, const double *lb, const double *ub, unsigned nx, unsigned ncx,
                                       unsigned ker, unsigned gen, unsigned threshold, double focus, double *omega, double *pc, double *sigma,
-                                      unsigned row, unsigned xoff)
+                                      unsigned row, unsigned xoff, unsigned memory = 0u, unsigned counter = 0u)
 {
     if (S->stopped) return;
     const unsigned t = threadIdx.x, T = blockDim.x;
     if (blockIdx.x == nx) {
-        if (t == 0 && (gen == 1u || gen == threshold)) { // :706-730
-            if (gen == threshold) S->q = 0.01;
+        // memory = false: at generation 1 and at `threshold` (:706-730); memory = true: every generation, the switch on the call counter (:732-752)
+        if (t == 0 && (memory || gen == 1u || gen == threshold)) {
+            if (memory ? counter == threshold : gen == threshold) S->q = 0.01;
             const double q = S->q, k = static_cast<double>(ker);
             double sum_omega = 0;
             for (unsigned l = 1; l <= ker; ++l) {
@@ -248,7 +249,7 @@ __global__ void gaco_pheromone_kernel(GacoState *S, const double *arch, const do
         d_min = smin[0], d_max = smax[0];
         const double width = ub[v] - lb[v], gm = static_cast<double>(S->gen_mark);
         double s;
-        if (focus != 0. && ((d_max - d_min) / gen > width / focus)) s = width / focus;
+        if (focus != 0. && ((d_max - d_min) / (memory ? counter : gen) > width / focus)) s = width / focus; // :778-784
         else if (v < ncx) s = (d_max - d_min) / gm;
         else s = fmax(fmax((d_max - d_min) / gm, 1.0 / gm), (1.0 - 1.0 / (sqrt(static_cast<double>(nx - ncx)))));
         sigma[v] = s;
@@ -373,7 +374,16 @@ int gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, 
     // constructor and evolve checks, gaco.cpp:62-94,157-171
     PGC_REQUIRE(acc >= 0., "The accuracy parameter must be >=0, while a value of %g was detected", acc);
     PGC_REQUIRE(focus >= 0., "The focus parameter must be >=0  while a value of %g was detected", focus);
-    PGC_REQUIRE(threshold >= 1u && threshold <= gens, "If memory is inactive, the threshold parameter must be either in [1,m_gen] while a value of %u was detected", threshold);
+    const bool memory = state->memory != 0u;
+    if (memory) {
+        PGC_REQUIRE(threshold >= 1u, "If memory is active, the threshold parameter must be >=1 while a value of %u was detected", threshold);
+        PGC_REQUIRE(state->h_archive && state->h_archive_len >= static_cast<size_t>(ker) * (nx + 2u),
+                    "gaco with memory keeps its archive in h_archive: %zu doubles are needed", static_cast<size_t>(ker) * (nx + 2u));
+        ++state->counter; // :106-108
+    } else {
+        PGC_REQUIRE(threshold >= 1u && threshold <= gens, "If memory is inactive, the threshold parameter must be either in [1,m_gen] while a value of %u was detected", threshold);
+    }
+    const unsigned counter = state->counter;
     PGC_REQUIRE(state->q >= 0., "The convergence speed parameter must be >=0  while a value of %g was detected", state->q);
     PGC_REQUIRE(ker >= 2u, "The ker size parameter must be >=2  while a value of %u was detected", ker);
     PGC_REQUIRE(n >= 2u, "GACO: Ant Colony Optimization needs at least 2 individuals in the population, %u detected", n);
@@ -403,15 +413,18 @@ int gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, 
     PGC_CUDA(cudaMemcpyAsync(S, &h, sizeof(GacoState), cudaMemcpyHostToDevice, st));
     PGC_CUDA(cudaMemcpyAsync(lb, prob->lb.data(), sizeof(double) * nx, cudaMemcpyHostToDevice, st));
     PGC_CUDA(cudaMemcpyAsync(ub, prob->ub.data(), sizeof(double) * nx, cudaMemcpyHostToDevice, st));
-    gaco_init_state_kernel<<<1, 256, 0, st>>>(S, d_f, n);
+    gaco_init_state_kernel<<<1, 256, 0, st>>>(S, d_f, n, static_cast<int>(state->has_champion), state->champion_f);
+    if (memory && counter > 1u) // sol_archive = m_sol_archive, :223-225
+        PGC_CUDA(cudaMemcpyAsync(arch, state->h_archive, sizeof(double) * ker * row, cudaMemcpyHostToDevice, st));
     for (unsigned gen = 1; gen <= gens; ++gen) {
         const unsigned generation = first_generation + (gen - 1u);
         gaco_penalty_kernel<<<nblk(n, 256), 256, 0, st>>>(S, d_f, n, impstop, evalstop, pen, k0, i0);
         PGC_CUDA(cub::DeviceRadixSort::SortPairs(ws, ws_bytes, k0, k1, i0, sl, static_cast<int>(n), 0, 64, st));
-        gaco_archive_kernel<<<1, 256, 0, st>>>(S, d_x, d_f, pen, sl, nx, ker, gen == 1u ? 1 : 0, acc, n_gen_mark, arch, tmp_arch, tp, slp, nsl, n_new);
-        if (gen != gens && log_due(gen)) // 3 - :254-287 (memory = false: every due generation but the last)
+        gaco_archive_kernel<<<1, 256, 0, st>>>(S, d_x, d_f, pen, sl, nx, ker, (gen == 1u && counter < 2u) ? 1 : 0, acc, n_gen_mark, arch, tmp_arch, tp, slp, nsl,
+                                               n_new);
+        if ((gen != gens || memory) && log_due(gen)) // 3 - :254-287 (memory = false: every due generation but the last)
             gaco_log_kernel<<<1, 32, 0, st>>>(S, arch, nx, ker, gen, 0, tls_log->d_rows, tls_log->d_count, tls_log->max_rows, tls_log->row_len);
-        gaco_pheromone_kernel<<<nx + 1u, 256, 0, st>>>(S, arch, lb, ub, nx, ncx, ker, gen, threshold, focus, omega, pc, sigma, row, 1u);
+        gaco_pheromone_kernel<<<nx + 1u, 256, 0, st>>>(S, arch, lb, ub, nx, ncx, ker, gen, threshold, focus, omega, pc, sigma, row, 1u, memory ? 1u : 0u, counter);
         gaco_ants_kernel<<<nblk(n, 128), 128, 0, st>>>(S, arch, pc, sigma, lb, ub, n, nx, ncx, ker, seed, generation, ants, row, 1u);
         PGC_CUDA(cudaGetLastError());
         // (a stopped run evaluates stale ants into fnew; nothing reads them)
@@ -420,14 +433,16 @@ int gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, unsigned n, 
         gaco_finish_kernel<<<1, 256, 0, st>>>(S, fnew, n, nx, ker, arch);
         ctx->launches.fetch_add(7, std::memory_order_relaxed);
     }
-    gaco_writeback_kernel<<<nblk(static_cast<size_t>(ker) * nx, 256), 256, 0, st>>>(S, arch, nx, ker, d_x, d_f);
-    if (tls_log && tls_log->verbosity && (gens % tls_log->verbosity == 1u || tls_log->verbosity == 1u)) // :405-445
+    if (!memory) gaco_writeback_kernel<<<nblk(static_cast<size_t>(ker) * nx, 256), 256, 0, st>>>(S, arch, nx, ker, d_x, d_f); // :408-421
+    else PGC_CUDA(cudaMemcpyAsync(state->h_archive, arch, sizeof(double) * ker * row, cudaMemcpyDeviceToHost, st));            // m_sol_archive
+    if (!memory && tls_log && tls_log->verbosity && (gens % tls_log->verbosity == 1u || tls_log->verbosity == 1u)) // :405-445
         gaco_log_kernel<<<1, 32, 0, st>>>(S, arch, nx, ker, gens, 1, tls_log->d_rows, tls_log->d_count, tls_log->max_rows, tls_log->row_len);
     PGC_CUDA(cudaGetLastError());
     PGC_CUDA(cudaMemcpyAsync(&h, S, sizeof(GacoState), cudaMemcpyDeviceToHost, st));
     PGC_CUDA(cudaStreamSynchronize(st));
     state->oracle = h.oracle, state->q = h.q, state->n_evalstop = h.n_evalstop, state->n_impstop = h.n_impstop, state->gen_mark = h.gen_mark;
     state->fevals = h.fevals;
+    state->champion_f = h.champ, state->has_champion = 1u;
     if (gens_done) *gens_done = h.gens_done;
     return PGC_OK;
 }

@@ -428,6 +428,17 @@ int main(int argc, char **argv)
                 CHECK(std::get<3>(log[1]) == 13u && std::get<2>(log[2]) == ql.champion_f()[0]);
             }
             std::printf("%s: %.4g -> %.4g (oracle %.4g)\n", g.get_name().c_str(), b, q.champion_f()[0], g.extract<cuda_gaco>()->get_oracle());
+            { // memory = true: the archive lives in the algorithm object, copies carry it, and the population keeps the last ants
+                pagmo::algorithm gm{cuda_gaco{1u, 8u, 1.0, 1e9, 0.01, 3u, 7u, 100000u, 100000u, 0., true, 5u}};
+                pagmo::population qa{prob, 30u, 9u}, qb{prob, 30u, 9u};
+                for (int c = 0; c < 5; ++c) qa = gm.evolve(qa);
+                pagmo::algorithm g1{cuda_gaco{1u, 8u, 1.0, 1e9, 0.01, 3u, 7u, 100000u, 100000u, 0., true, 5u}};
+                for (int c = 0; c < 3; ++c) qb = g1.evolve(qb);
+                pagmo::algorithm g2 = g1; // a copy continues where the original stood
+                for (int c = 0; c < 2; ++c) qb = g2.evolve(qb);
+                CHECK(qa.get_x() == qb.get_x() && qa.get_f() == qb.get_f());
+                CHECK(gm.extract<cuda_gaco>()->get_oracle() < 1e9);
+            }
             bool threw = false;
             try {
                 cuda_gaco{5u, 1u};

@@ -67,6 +67,31 @@ def test_gaco_state_continues_and_stops(capi, ctx, orc):
     prob.close()
 
 
+def test_gaco_memory_follows_the_restated_loop(capi, ctx, orc):
+    """memory = true (gaco.cpp:106-108, :223-250, :732-752, :778-784): one algorithm object evolved call after call - the archive and the
+    call counter carry over, the kernel weights switch when the COUNTER reaches the threshold, the archive is never written back.  The
+    restated loop is pinned to the compiled reference in this mode too (tests/test_oracle_pin.py)."""
+    prob = capi.Problem(ctx, "rastrigin", dim=7)
+    op = orc.problem("rastrigin", dim=7)
+    lb, ub = prob.bounds()
+    rng = np.random.default_rng(4)
+    for n, gens, calls, kw in ((20, 1, 6, dict(ker=8, oracle=1e9, threshold=3)), (24, 3, 4, dict(ker=6, threshold=2, n_gen_mark=3, focus=5.0))):
+        x = rng.uniform(lb, ub, (n, 7))
+        f = prob.eval_host(x)[:, 0]
+        xg, fg, sg = x, f, None
+        xo, fo, so = x, f, None
+        for c in range(calls):
+            xg, fg, sg, _ = prob.gaco_evolve(xg, fg, gens=gens, seed=9, first_generation=1 + c * gens, state=sg, memory=True, **kw)
+            xo, fo, so, _ = orc.gaco_evolve(op, lb, ub, xo, fo, gens=gens, seed=9, first_generation=1 + c * gens, state=so, memory=True, **kw)
+            fg = fg[:, 0]
+            assert np.allclose(xg, xo, rtol=1e-9, atol=1e-12) and np.allclose(fg, fo, rtol=1e-9, atol=1e-12), (n, c)
+            assert (sg.counter, sg.n_evalstop, sg.n_impstop, sg.gen_mark, sg.q) == (so.counter, so.n_evalstop, so.n_impstop, so.gen_mark, so.q)
+            assert np.isclose(sg.champion_f, so.champion) and np.allclose(sg._archive, so._archive, rtol=1e-9, atol=1e-12)
+        # the population that comes back holds the last ants, not the archive: the champion the state tracks is the better of everything seen
+        assert sg.champion_f <= min(fg.min(), sg._archive[7 + 1]) + 1e-12
+    prob.close()
+
+
 def test_gaco_integer_tail_and_argument_checks(capi, ctx):
     """zdt5-like integer variables are rounded (:869-873) - exercised through a single-objective decomposition of zdt5; the
     reference's constructor / evolve checks (gaco.cpp:62-94, :157-171)."""

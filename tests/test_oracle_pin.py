@@ -248,6 +248,18 @@ def test_gaco_evolve_bit_exact(orc, ref, fam, dim):
         xo, fo, _, _ = orc.gaco_evolve(op, lb, ub, x0, f0, gens=gens, ker=ker, q=q, oracle=oracle, acc=acc, threshold=threshold,
                                        n_gen_mark=n_gen_mark, impstop=impstop, evalstop=evalstop, focus=focus, seed=seed, mt=True)
         assert np.array_equal(xr, xo) and np.array_equal(fr[:, 0], fo), (n, par, gens)
+    # memory = true: ONE algorithm object evolved several times (gaco.cpp:106-108, :223-250, :732-752, :778-784): the archive and the call
+    # counter carry over, the weights follow the counter, the archive is never written back into the population
+    for n, par, gens, calls in ((20, (8, 1.0, 1e9, 0.01, 3, 7, 100000, 100000, 0.0), 1, 6), (24, (6, 1.0, 0.0, 0.01, 2, 3, 100000, 100000, 5.0), 3, 4)):
+        seed = n + calls
+        x0 = rng.uniform(lb, ub, (n, dim))
+        f0 = np.array([rp.fitness(x) for x in x0])[:, 0]
+        xr, fr = ref.evolve_from(rp, "gaco", list(par) + [1, calls], x0, gens, seed)
+        ker, q, oracle, acc, threshold, n_gen_mark, impstop, evalstop, focus = par
+        xo, fo, _, _ = orc.gaco_evolve(op, lb, ub, x0, f0, gens=gens, ker=ker, q=q, oracle=oracle, acc=acc, threshold=threshold,
+                                       n_gen_mark=n_gen_mark, impstop=impstop, evalstop=evalstop, focus=focus, seed=seed, mt=True, memory=True,
+                                       calls=calls)
+        assert np.array_equal(xr, xo) and np.array_equal(fr[:, 0], fo), ("memory", n, par, gens, calls)
 
 
 @pytest.mark.parametrize("fam,args", [("zdt", (1, 8)), ("zdt", (2, 6)), ("zdt", (3, 7)), ("dtlz", (2, 7, 3, 100)), ("dtlz", (1, 6, 3, 100))])
