@@ -272,11 +272,11 @@ def measure_secondary(ctx, capi, device):
         pairs = 150 * 149 // 2
         rate = 5 * NP / dt
         # 13 FP64-pipe instructions per pair (7 of them FMAs: 20 flop): the pipe's issue ceiling at the DFMA probe's rate
-        ceiling = ctx.fp64_peak_tflops(4096) * 1e12 / 64.0 / (pairs * 13)
+        ceiling = ctx.fp64_peak_tflops(4096) * 1e12 / 2.0 / (pairs * 13)
         return {"what": "cfg4 kernel: lennard_jones 150 atoms (D=444), 262144 individuals resident", "evals_per_s": rate,
                 "fp64_tflops_20_per_pair": rate * pairs * 20 / 1e12,
                 "roofline": {"bound": "fp64 issue", "achieved": rate, "peak": ceiling, "unit": "evals/s", "frac": rate / ceiling,
-                             "note": "13 FP64-pipe instructions per pair; peak = DFMA probe TF/s / 2 flop / 32 lanes / (11175 pairs x 13)"}}
+                             "note": "13 FP64-pipe instructions per pair; peak = DFMA probe TF/s / 2 flop per thread-level DFMA / (11175 pairs x 13 thread-level instructions)"}}
 
     def cfg5():
         return measure_cfg5(capi, [device], rank=0, world=1, comm=None, rounds=4)

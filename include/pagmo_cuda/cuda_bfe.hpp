@@ -32,7 +32,9 @@
 #include <pagmo/problems/ackley.hpp>
 #include <pagmo/problems/dtlz.hpp>
 #include <pagmo/problems/griewank.hpp>
+#include <pagmo/problems/hock_schittkowski_71.hpp>
 #include <pagmo/problems/lennard_jones.hpp>
+#include <pagmo/problems/luksan_vlcek1.hpp>
 #include <pagmo/problems/rastrigin.hpp>
 #include <pagmo/problems/rosenbrock.hpp>
 #include <pagmo/problems/schwefel.hpp>
@@ -109,11 +111,11 @@ public:
         m_desc.shift = m_shift.empty() ? nullptr : m_shift.data();
         m_desc.shuffle = m_shuffle.empty() ? nullptr : m_shuffle.data();
         check(pgc_problem_create(m_ctx.get(), &m_desc, &m_prob), "pgc_problem_create");
-        check(pgc_problem_nx(m_prob, &m_nx), "pgc_problem_nx");
-        check(pgc_problem_nf(m_prob, &m_nf), "pgc_problem_nf");
+        read_sizes();
     }
-    // meta-problem over another device problem (pgc_problem_translate / pgc_problem_decompose): kind = PGC_TRANSLATE with
-    // a = translation, or PGC_DECOMPOSE with a = weight, b = reference point.  The wrapper keeps the inner handle alive.
+    // meta-problem over another device problem (pgc_problem_translate / pgc_problem_decompose / pgc_problem_unconstrain): kind =
+    // PGC_TRANSLATE with a = translation, PGC_DECOMPOSE with a = weight, b = reference point, or PGC_UNCONSTRAIN with a = weights,
+    // b = the constraint tolerances the wrapper is built with (empty: the inner problem's).  The wrapper keeps the inner handle alive.
     problem_handle(std::shared_ptr<problem_handle> inner, int kind, pagmo::vector_double a, pagmo::vector_double b, int method)
         : m_ctx(inner->m_ctx), m_device(inner->m_device), m_inner(std::move(inner)), m_meta_kind(kind), m_meta_a(std::move(a)),
           m_meta_b(std::move(b)), m_meta_method(method)
@@ -121,6 +123,17 @@ public:
         std::lock_guard<std::mutex> lk(device_mutex(m_device));
         if (kind == PGC_TRANSLATE) {
             check(pgc_problem_translate(m_inner->m_prob, m_meta_a.data(), m_meta_a.size(), &m_prob), "pgc_problem_translate");
+        } else if (kind == PGC_UNCONSTRAIN) {
+            // unconstrain copies its inner problem, tolerances included (unconstrain.cpp:155-162 reads m_problem.get_c_tol()): the
+            // device wrapper takes them at creation, so the shared inner handle gets them for the call only
+            pagmo::vector_double saved(m_inner->m_nec + m_inner->m_nic);
+            if (!m_meta_b.empty()) {
+                check(pgc_problem_c_tol(m_inner->m_prob, saved.data()), "pgc_problem_c_tol");
+                check(pgc_problem_set_c_tol(m_inner->m_prob, m_meta_b.data(), m_meta_b.size()), "pgc_problem_set_c_tol");
+            }
+            const int rc = pgc_problem_unconstrain(m_inner->m_prob, method, m_meta_a.data(), m_meta_a.size(), &m_prob);
+            if (!m_meta_b.empty()) pgc_problem_set_c_tol(m_inner->m_prob, saved.data(), saved.size());
+            check(rc, "pgc_problem_unconstrain");
         } else {
             if (m_meta_b.size() != m_meta_a.size()) {
                 pagmo_throw(std::invalid_argument,
@@ -131,8 +144,7 @@ public:
             check(pgc_problem_decompose(m_inner->m_prob, m_meta_a.data(), m_meta_b.data(), m_meta_a.size(), method, 0, &m_prob),
                   "pgc_problem_decompose");
         }
-        check(pgc_problem_nx(m_prob, &m_nx), "pgc_problem_nx");
-        check(pgc_problem_nf(m_prob, &m_nf), "pgc_problem_nf");
+        read_sizes();
     }
     ~problem_handle()
     {
@@ -142,7 +154,10 @@ public:
     problem_handle &operator=(const problem_handle &) = delete;
 
     std::size_t nx() const { return m_nx; }
-    std::size_t nf() const { return m_nf; }
+    std::size_t nf() const { return m_nf; }     // problem::get_nf: the width of a fitness row
+    std::size_t nobj() const { return m_nf - m_nec - m_nic; }
+    std::size_t nec() const { return m_nec; }
+    std::size_t nic() const { return m_nic; }
     int device() const { return m_device; }
     pgc_problem *raw() const { return m_prob; }
     pgc_ctx *context() const { return m_ctx.get(); }
@@ -318,6 +333,13 @@ public:
     }
 
 private:
+    void read_sizes()
+    {
+        check(pgc_problem_nx(m_prob, &m_nx), "pgc_problem_nx");
+        check(pgc_problem_nf(m_prob, &m_nf), "pgc_problem_nf");
+        check(pgc_problem_nec(m_prob, &m_nec), "pgc_problem_nec");
+        check(pgc_problem_nic(m_prob, &m_nic), "pgc_problem_nic");
+    }
     std::shared_ptr<problem_handle> private_with(int device, const std::shared_ptr<pgc_ctx> &ctx) const
     {
         if (!m_inner) return std::make_shared<problem_handle>(device, m_desc, ctx);
@@ -333,7 +355,7 @@ private:
     pagmo::vector_double m_meta_a, m_meta_b;
     int m_meta_method = 0;
     pgc_problem *m_prob = nullptr;
-    std::size_t m_nx = 0, m_nf = 0;
+    std::size_t m_nx = 0, m_nf = 0, m_nec = 0, m_nic = 0;
     mutable std::mutex m_twin_mtx;
     mutable std::map<int, std::shared_ptr<problem_handle>> m_twins;
 };
@@ -369,7 +391,15 @@ public:
     }
     pagmo::vector_double::size_type get_nobj() const
     {
-        return handle().nf();
+        return handle().nobj();
+    }
+    pagmo::vector_double::size_type get_nec() const // 0 but for the constrained UDPs (hock_schittkowski_71, luksan_vlcek1)
+    {
+        return handle().nec();
+    }
+    pagmo::vector_double::size_type get_nic() const
+    {
+        return handle().nic();
     }
     std::string get_name() const
     {
@@ -577,6 +607,81 @@ private:
     unsigned m_atoms;
 };
 
+// The two constrained UDPs with a device evaluator (fitness rows [objective | equalities | inequalities]); same constructor
+// arguments as pagmo::hock_schittkowski_71 (none) and pagmo::luksan_vlcek1 (luksan_vlcek1.hpp:78: the dimension, >= 3).
+class cuda_hock_schittkowski_71 : public cuda_udp_base
+{
+public:
+    explicit cuda_hock_schittkowski_71(int device = 0)
+    {
+        m_device = device;
+        m_handle = std::make_shared<detail::problem_handle>(m_device, detail::make_desc(PGC_HOCK_SCHITTKOWSKI_71, 0u, 4u));
+    }
+    pagmo::vector_double best_known() const // hock_schittkowski_71.cpp:141-144
+    {
+        return {1., 4.74299963, 3.82114998, 1.37940829};
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_device);
+    }
+};
+
+class cuda_luksan_vlcek1 : public cuda_udp_base
+{
+public:
+    explicit cuda_luksan_vlcek1(unsigned dim = 3u, int device = 0) : m_dim(dim)
+    {
+        m_device = device;
+        m_handle = std::make_shared<detail::problem_handle>(m_device, detail::make_desc(PGC_LUKSAN_VLCEK1, 0u, dim));
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_dim, m_device);
+    }
+
+private:
+    unsigned m_dim;
+};
+
+// pagmo::unconstrain on the device (reference include/pagmo/problems/unconstrain.hpp, src/problems/unconstrain.cpp:66-97,136-223):
+// the inner problem is one of the constrained CUDA UDPs above (or a cuda_translate of one); same constructor arguments, checks
+// and messages as the reference.  The reference's unconstrain wraps a pagmo::problem and reads its tolerances (problem::get_c_tol);
+// a UDP has none, so they are the optional fourth argument (empty: all zero, problem's default).  The stock
+// pagmo::unconstrain{cuda_udp, ...} works too (it penalizes on the host after the inner batch_fitness); this one keeps the penalty
+// on the device, so the device generation loops run on it.
+class cuda_unconstrain : public cuda_udp_base
+{
+public:
+    cuda_unconstrain() = default;
+    template <typename T>
+    explicit cuda_unconstrain(const T &inner, const std::string &method = "death penalty",
+                              const pagmo::vector_double &weights = pagmo::vector_double(),
+                              const pagmo::vector_double &c_tol = pagmo::vector_double())
+        : m_method(method), m_weights(weights)
+    {
+        int code = -1;
+        if (method == "death penalty") code = PGC_UNCONSTRAIN_DEATH;
+        else if (method == "kuri") code = PGC_UNCONSTRAIN_KURI;
+        else if (method == "weighted") code = PGC_UNCONSTRAIN_WEIGHTED;
+        else if (method == "ignore_c") code = PGC_UNCONSTRAIN_IGNORE_C;
+        else if (method == "ignore_o") code = PGC_UNCONSTRAIN_IGNORE_O;
+        const auto inner_handle = inner.shared_handle();
+        if (inner_handle->nec() + inner_handle->nic() != 0u && code < 0) { // unconstrain.cpp:84-88 (an unconstrained inner fails first)
+            pagmo_throw(std::invalid_argument, "The method " + method + " is not supported (did you misspell?)");
+        }
+        m_device = inner.device();
+        m_handle = std::make_shared<detail::problem_handle>(inner_handle, static_cast<int>(PGC_UNCONSTRAIN), weights, c_tol,
+                                                            code < 0 ? static_cast<int>(PGC_UNCONSTRAIN_DEATH) : code);
+    }
+
+private:
+    std::string m_method;
+    pagmo::vector_double m_weights;
+};
+
 // pagmo::translate on the device (reference include/pagmo/problems/translate.hpp, src/problems/translate.cpp:100-153): the
 // inner problem is one of the CUDA UDPs above (or another cuda_translate); fitness(x) = inner.fitness(x - translation), bounds
 // = inner bounds + translation.  The stock pagmo::translate{cuda_udp, t} works too (it de-shifts on the host and calls the inner
@@ -663,6 +768,9 @@ public:
         PGC_OWN_UDP(cuda_lennard_jones)
         PGC_OWN_UDP(cuda_translate)
         PGC_OWN_UDP(cuda_decompose)
+        PGC_OWN_UDP(cuda_hock_schittkowski_71)
+        PGC_OWN_UDP(cuda_luksan_vlcek1)
+        PGC_OWN_UDP(cuda_unconstrain)
 #undef PGC_OWN_UDP
         // stock zdt / dtlz: the problem id is only visible through get_name() ("ZDT3", "DTLZ2": zdt.cpp:161-164,
         // dtlz.cpp:170-173); dtlz4's alpha is private and cannot be recovered; so is wfg's dim_k
@@ -684,12 +792,14 @@ public:
         if (p.is<pagmo::lennard_jones>()) { // nx = 3*atoms - 6, lennard_jones.cpp:99-110
             return twin(device, make_desc(PGC_LENNARD_JONES, 0u, static_cast<unsigned>((p.get_nx() + 6u) / 3u)));
         }
+        if (p.is<pagmo::hock_schittkowski_71>()) return twin(device, make_desc(PGC_HOCK_SCHITTKOWSKI_71, 0u, 4u));
         int family = 0; // stock UDPs that are fully described by (type, nx)
         if (p.is<pagmo::rastrigin>()) family = PGC_RASTRIGIN;
         else if (p.is<pagmo::ackley>()) family = PGC_ACKLEY;
         else if (p.is<pagmo::griewank>()) family = PGC_GRIEWANK;
         else if (p.is<pagmo::schwefel>()) family = PGC_SCHWEFEL;
         else if (p.is<pagmo::rosenbrock>()) family = PGC_ROSENBROCK;
+        else if (p.is<pagmo::luksan_vlcek1>()) family = PGC_LUKSAN_VLCEK1;
         if (family == 0) return nullptr;
         return twin(device, make_desc(family, 0u, static_cast<unsigned>(p.get_nx())));
     }

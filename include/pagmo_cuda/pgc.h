@@ -52,8 +52,17 @@ typedef enum pgc_family {
     PGC_LENNARD_JONES = 11, /* src/problems/lennard_jones.cpp:72-92 */
     /* meta-problems: created by pgc_problem_translate / pgc_problem_decompose only */
     PGC_TRANSLATE = 12, /* src/problems/translate.cpp:100-153 */
-    PGC_DECOMPOSE = 13  /* src/problems/decompose.cpp:139-154 */
+    PGC_DECOMPOSE = 13, /* src/problems/decompose.cpp:139-154 */
+    /* constrained UDPs: fitness rows are [objective | nec equality | nic inequality constraints] (problem.cpp:383-410) */
+    PGC_HOCK_SCHITTKOWSKI_71 = 14, /* src/problems/hock_schittkowski_71.cpp:48-55: nx 4, 1 equality, 1 inequality */
+    PGC_LUKSAN_VLCEK1 = 15,        /* src/problems/luksan_vlcek1.cpp:60-77: dim >= 3, dim - 2 equalities */
+    PGC_UNCONSTRAIN = 16           /* src/problems/unconstrain.cpp:136-223; created by pgc_problem_unconstrain only */
 } pgc_family;
+
+/* unconstrain methods (src/problems/unconstrain.cpp:92-97): "death penalty", "kuri", "weighted", "ignore_c", "ignore_o" */
+typedef enum pgc_unconstrain_method {
+    PGC_UNCONSTRAIN_DEATH = 0, PGC_UNCONSTRAIN_KURI = 1, PGC_UNCONSTRAIN_WEIGHTED = 2, PGC_UNCONSTRAIN_IGNORE_C = 3, PGC_UNCONSTRAIN_IGNORE_O = 4
+} pgc_unconstrain_method;
 
 /* decompose_objectives methods (src/utils/multi_objective.cpp:603-632) */
 typedef enum pgc_decompose_method { PGC_DECOMPOSE_WEIGHTED = 0, PGC_DECOMPOSE_TCHEBYCHEFF = 1, PGC_DECOMPOSE_BI = 2 } pgc_decompose_method;
@@ -111,7 +120,17 @@ PGC_API int pgc_problem_destroy(pgc_problem *prob);
 PGC_API int pgc_problem_nx(const pgc_problem *prob, size_t *nx);     /* problem::get_nx  */
 PGC_API int pgc_problem_nix(const pgc_problem *prob, size_t *nix);   /* problem::get_nix: integer genes at the end (zdt5) */
 PGC_API int pgc_problem_nobj(const pgc_problem *prob, size_t *nobj); /* problem::get_nobj */
-PGC_API int pgc_problem_nf(const pgc_problem *prob, size_t *nf);     /* problem::get_nf (= nobj here: no constraints) */
+PGC_API int pgc_problem_nf(const pgc_problem *prob, size_t *nf);     /* problem::get_nf = nobj + nec + nic: the width of a fitness row */
+PGC_API int pgc_problem_nec(const pgc_problem *prob, size_t *nec);   /* problem::get_nec (hock_schittkowski_71: 1, luksan_vlcek1: dim - 2) */
+PGC_API int pgc_problem_nic(const pgc_problem *prob, size_t *nic);   /* problem::get_nic (hock_schittkowski_71: 1) */
+/* problem::set_c_tol / get_c_tol (src/problem.cpp:620-644): the nec + nic constraint tolerances (default 0) that feasibility and the
+ * unconstrain meta-problem use; wrong length, NaN or negative entries fail with the reference's messages.  A wrapper created by
+ * pgc_problem_unconstrain copies the inner problem's tolerances at creation, as unconstrain copies its inner problem. */
+PGC_API int pgc_problem_set_c_tol(pgc_problem *prob, const double *c_tol, size_t len);
+PGC_API int pgc_problem_c_tol(const pgc_problem *prob, double *c_tol);
+/* problem::feasibility_f per row (src/problem.cpp:709-721) on device rows [n x nf]: d_feasible[i] = 1 if every constraint of row i is
+ * satisfied within the tolerances, else 0. */
+PGC_API int pgc_feasibility_device(pgc_problem *prob, const double *d_f, size_t n, uint8_t *d_feasible, void *stream);
 PGC_API int pgc_problem_bounds(const pgc_problem *prob, double *lb, double *ub); /* UDP::get_bounds */
 PGC_API int pgc_problem_name(const pgc_problem *prob, char *buf, size_t buflen); /* UDP::get_name */
 /* cec2013 only.  on != 0: every rotation accumulates one product at a time in the reference's order (rotatefunc,
@@ -131,8 +150,14 @@ PGC_API int pgc_problem_work(const pgc_problem *prob, double *flops_per_eval, do
  *   decompose (src/problems/decompose.cpp:66-124,139-154; decompose_objectives, src/utils/multi_objective.cpp:582-638):
  *     one objective = weighted / tchebycheff / bi decomposition of the inner objectives; the constructor's checks (>= 2
  *     objectives, sizes, finite values, weights >= 0 summing to 1 within 1e-8) fail with PGC_ERR_INVALID_ARGUMENT and the
- *     reference's messages.  adapt_ideal != 0 is refused (PGC_ERR_UNSUPPORTED): the reference adapts z call by call. */
+ *     reference's messages.  adapt_ideal != 0 is refused (PGC_ERR_UNSUPPORTED): the reference adapts z call by call.
+ *   unconstrain (src/problems/unconstrain.cpp:66-97,136-223,269-276): the constraints of the inner problem folded into its
+ *     objectives by one of the five methods of pgc_unconstrain_method (one objective, the norm of the violation, for ignore_o); the
+ *     constructor's checks (inner problem constrained, weights only with - and exactly nec + nic of them for - "weighted") fail with
+ *     PGC_ERR_INVALID_ARGUMENT and the reference's messages.  The result has no constraints, so every algorithm entry point takes it. */
 PGC_API int pgc_problem_translate(pgc_problem *inner, const double *translation, size_t len, pgc_problem **out);
+PGC_API int pgc_problem_unconstrain(pgc_problem *inner, int method /* pgc_unconstrain_method */, const double *weights, size_t len,
+                                    pgc_problem **out);
 PGC_API int pgc_problem_decompose(pgc_problem *inner, const double *weight, const double *z, size_t len, int method /* pgc_decompose_method */,
                                   int adapt_ideal, pgc_problem **out);
 

@@ -46,6 +46,13 @@ int oracle_translate_rows(const double *xs, size_t n, size_t nx, const double *t
 int oracle_decompose_objectives(const double *f, size_t m, const double *weight, const double *ref_point, int method, double *out);
 int oracle_decompose_rows(const double *fs, size_t n, size_t m, const double *weight, const double *ref_point, int method, double *out);
 
+/* ---- constrained UDPs and the unconstrain meta-problem (restate_constrained.c): hock_schittkowski_71.cpp:48-55,
+ * luksan_vlcek1.cpp:60-77, unconstrain.cpp:136-223 (method 0 death penalty, 1 kuri, 2 weighted, 3 ignore_c, 4 ignore_o) ---- */
+int oracle_hs71_batch(const double *xs, size_t n, double *fs);
+int oracle_luksan_vlcek1_batch(size_t dim, const double *xs, size_t n, double *fs);
+int oracle_unconstrain_rows(const double *fs, size_t n, size_t nobj, size_t nec, size_t nic, const double *c_tol, int method,
+                            const double *weights, double *out);
+
 /* ---- Lennard-Jones (restate_lj.c) ---- */
 int oracle_lj_fitness(unsigned atoms, const double *x, double *f);
 int oracle_lj_batch(unsigned atoms, const double *xs, size_t n, double *fs);

@@ -49,6 +49,9 @@ SIMPLE = {"rastrigin": 1, "ackley": 2, "griewank": 3, "schwefel": 4, "rosenbrock
 CEC_NCOMP = 10
 
 
+UNCONSTRAIN_METHODS = {"death penalty": 0, "kuri": 1, "weighted": 2, "ignore_c": 3, "ignore_o": 4}
+
+
 class OracleProblem(C.Structure):
     _fields_ = [("family", C.c_int), ("prob_id", C.c_uint), ("dim", C.c_uint), ("nobj", C.c_uint), ("param", C.c_uint),
                 ("rotation", c_double_p), ("shift", c_double_p), ("shuffle", c_int_p)]
@@ -145,6 +148,34 @@ class Oracle:
         if self.lib.oracle_decompose_rows(_dp(fs), C.c_size_t(fs.shape[0]), C.c_size_t(fs.shape[1]), _dp(w), _dp(zz),
                                           C.c_int({"weighted": 0, "tchebycheff": 1, "bi": 2}[method]), _dp(out)):
             raise ValueError("oracle_decompose_rows failed")
+        return out
+
+    def hock_schittkowski_71(self, xs: np.ndarray) -> np.ndarray:
+        """hock_schittkowski_71::fitness per row: [objective | equality | inequality] (hock_schittkowski_71.cpp:48-55)."""
+        xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(-1, 4)
+        out = np.empty((xs.shape[0], 3))
+        self.lib.oracle_hs71_batch(_dp(xs), C.c_size_t(xs.shape[0]), _dp(out))
+        return out
+
+    def luksan_vlcek1(self, xs: np.ndarray) -> np.ndarray:
+        """luksan_vlcek1::fitness per row: [objective | dim - 2 equalities] (luksan_vlcek1.cpp:60-77)."""
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n, d = xs.shape
+        out = np.empty((n, d - 1))
+        if self.lib.oracle_luksan_vlcek1_batch(C.c_size_t(d), _dp(xs), C.c_size_t(n), _dp(out)):
+            raise ValueError("oracle_luksan_vlcek1_batch failed")
+        return out
+
+    def unconstrain_rows(self, fs: np.ndarray, nobj: int, nec: int, nic: int, c_tol, method: str, weights=None) -> np.ndarray:
+        """unconstrain::penalize per row (unconstrain.cpp:136-223)."""
+        fs = np.ascontiguousarray(fs, dtype=np.float64)
+        tol = np.ascontiguousarray(c_tol, dtype=np.float64)
+        w = np.ascontiguousarray(weights if weights is not None else np.zeros(nec + nic), dtype=np.float64)
+        m = UNCONSTRAIN_METHODS[method]
+        out = np.empty((fs.shape[0], 1 if m == 4 else nobj))
+        if self.lib.oracle_unconstrain_rows(_dp(fs), C.c_size_t(fs.shape[0]), C.c_size_t(nobj), C.c_size_t(nec), C.c_size_t(nic), _dp(tol),
+                                            C.c_int(m), _dp(w), _dp(out)):
+            raise ValueError("oracle_unconstrain_rows failed")
         return out
 
     def lennard_jones(self, atoms: int, xs: np.ndarray) -> np.ndarray:
@@ -729,6 +760,8 @@ class RefProblem:
         self.nx = L.ref_problem_nx(handle)
         self.nf = L.ref_problem_nf(handle)
         self.nobj = L.ref_problem_nobj(handle)
+        self.nec = L.ref_problem_nec(handle)
+        self.nic = L.ref_problem_nic(handle)
 
     def __del__(self):
         try:
@@ -745,6 +778,11 @@ class RefProblem:
     @property
     def fevals(self) -> int:
         return self._ref.lib.ref_problem_fevals(self._h)
+
+    def set_c_tol(self, tol) -> None:
+        """problem::set_c_tol (problem.cpp:620-644)"""
+        tol = np.ascontiguousarray(tol, dtype=np.float64)
+        self._ref._check(self._ref.lib.ref_problem_set_c_tol(self._h, _dp(tol), C.c_size_t(tol.size)))
 
     def bounds(self):
         lb, ub = np.empty(self.nx), np.empty(self.nx)
@@ -814,7 +852,12 @@ class Reference:
         L.ref_problem_nf.restype = C.c_size_t
         L.ref_problem_nobj.restype = C.c_size_t
         L.ref_problem_fevals.restype = C.c_ulonglong
-        for fn in ("ref_problem_nx", "ref_problem_nf", "ref_problem_nobj", "ref_problem_fevals", "ref_problem_destroy"):
+        L.ref_problem_nec.restype = C.c_size_t
+        L.ref_problem_nic.restype = C.c_size_t
+        L.ref_problem_unconstrain.argtypes = [C.c_void_p, C.c_char_p, c_double_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.ref_problem_set_c_tol.argtypes = [C.c_void_p, c_double_p, C.c_size_t]
+        for fn in ("ref_problem_nx", "ref_problem_nf", "ref_problem_nobj", "ref_problem_nec", "ref_problem_nic", "ref_problem_fevals",
+                   "ref_problem_destroy"):
             getattr(L, fn).argtypes = [C.c_void_p]
         L.ref_problem_destroy.restype = None
         L.ref_problem_bounds.argtypes = [C.c_void_p, c_double_p, c_double_p]
@@ -852,6 +895,13 @@ class Reference:
         h = C.c_void_p()
         self._check(self.lib.ref_problem_decompose(inner._h, _dp(w), _dp(zz), C.c_size_t(w.size), method.encode(),
                                                    C.c_int(int(adapt_ideal)), C.byref(h)))
+        return RefProblem(self, h)
+
+    def unconstrain(self, inner: RefProblem, method: str = "death penalty", weights=()) -> RefProblem:
+        """pagmo::problem{pagmo::unconstrain{inner, method, weights}}"""
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        h = C.c_void_p()
+        self._check(self.lib.ref_problem_unconstrain(inner._h, method.encode(), _dp(w), C.c_size_t(w.size), C.byref(h)))
         return RefProblem(self, h)
 
     def decompose_objectives(self, f, weight, z, method: str) -> float:

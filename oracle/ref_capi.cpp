@@ -17,11 +17,14 @@
 #include <pagmo/problems/decompose.hpp>
 #include <pagmo/problems/dtlz.hpp>
 #include <pagmo/problems/griewank.hpp>
+#include <pagmo/problems/hock_schittkowski_71.hpp>
 #include <pagmo/problems/lennard_jones.hpp>
+#include <pagmo/problems/luksan_vlcek1.hpp>
 #include <pagmo/problems/rastrigin.hpp>
 #include <pagmo/problems/rosenbrock.hpp>
 #include <pagmo/problems/schwefel.hpp>
 #include <pagmo/problems/translate.hpp>
+#include <pagmo/problems/unconstrain.hpp>
 #include <pagmo/problems/wfg.hpp>
 #include <pagmo/problems/zdt.hpp>
 #include <pagmo/types.hpp>
@@ -103,6 +106,8 @@ int ref_problem_create(const char *family, unsigned p0, unsigned p1, unsigned p2
         else if (fam == "dtlz") pr = pagmo::problem{pagmo::dtlz{p0, p1, p2, p3}};
         else if (fam == "wfg") pr = pagmo::problem{pagmo::wfg{p0, p1, p2, p3}};
         else if (fam == "lennard_jones") pr = pagmo::problem{pagmo::lennard_jones{p0}};
+        else if (fam == "hock_schittkowski_71") pr = pagmo::problem{pagmo::hock_schittkowski_71{}};
+        else if (fam == "luksan_vlcek1") pr = pagmo::problem{pagmo::luksan_vlcek1{p0}};
         else throw std::invalid_argument("ref_problem_create: unknown family '" + fam + "'");
         *out = new ref_problem{std::move(pr)};
     });
@@ -122,6 +127,18 @@ int ref_problem_decompose(const ref_problem *inner, const double *w, const doubl
     });
 }
 
+int ref_problem_unconstrain(const ref_problem *inner, const char *method, const double *weights, size_t len, ref_problem **out)
+{
+    return guarded([&] {
+        *out = new ref_problem{pagmo::problem{pagmo::unconstrain{inner->prob, method, pagmo::vector_double(weights, weights + len)}}};
+    });
+}
+
+int ref_problem_set_c_tol(ref_problem *p, const double *tol, size_t len)
+{
+    return guarded([&] { p->prob.set_c_tol(pagmo::vector_double(tol, tol + len)); });
+}
+
 int ref_decompose_objectives(const double *f, const double *w, const double *z, size_t m, const char *method, double *out)
 {
     return guarded([&] {
@@ -134,6 +151,8 @@ void ref_problem_destroy(ref_problem *p) { delete p; }
 size_t ref_problem_nx(const ref_problem *p) { return p->prob.get_nx(); }
 size_t ref_problem_nf(const ref_problem *p) { return p->prob.get_nf(); }
 size_t ref_problem_nobj(const ref_problem *p) { return p->prob.get_nobj(); }
+size_t ref_problem_nec(const ref_problem *p) { return p->prob.get_nec(); }
+size_t ref_problem_nic(const ref_problem *p) { return p->prob.get_nic(); }
 unsigned long long ref_problem_fevals(const ref_problem *p) { return p->prob.get_fevals(); }
 
 int ref_problem_bounds(const ref_problem *p, double *lb, double *ub)

@@ -32,6 +32,12 @@ void ref_problem_destroy(ref_problem *p);
 size_t ref_problem_nx(const ref_problem *p);
 size_t ref_problem_nf(const ref_problem *p);
 size_t ref_problem_nobj(const ref_problem *p);
+size_t ref_problem_nec(const ref_problem *p);
+size_t ref_problem_nic(const ref_problem *p);
+/* pagmo::problem{pagmo::unconstrain{inner, method, weights}} (unconstrain.hpp; methods "death penalty", "kuri", "weighted",
+ * "ignore_c", "ignore_o") and problem::set_c_tol (problem.cpp:620-644) */
+int ref_problem_unconstrain(const ref_problem *inner, const char *method, const double *weights, size_t len, ref_problem **out);
+int ref_problem_set_c_tol(ref_problem *p, const double *tol, size_t len);
 unsigned long long ref_problem_fevals(const ref_problem *p);
 int ref_problem_bounds(const ref_problem *p, double *lb, double *ub);
 int ref_problem_name(const ref_problem *p, char *buf, size_t buflen);

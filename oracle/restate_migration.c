@@ -24,6 +24,8 @@ static int less_f(double a, double b) /* detail::less_than_f: NaNs are greater t
  * constraints] and the order is sort_population_con's, i.e. compare_fc (src/utils/constrained.cpp:76-118) - restated as written,
  * including its two different norms: the left argument's violation is the SUM of the equality and inequality norms, the right
  * argument's their Euclidean combination.  The two coincide whenever an individual violates constraints of one kind only. */
+static inline double max0(double a) { return a < 0. ? 0. : a; } /* std::max(a, 0.): a NaN stays a NaN (never satisfied) */
+
 static _Thread_local struct {
     size_t nec, nic;
     const double *tol;
@@ -34,14 +36,14 @@ static void con_test(const double *f, size_t *nsat, double *leq, double *lineq) 
     double l2 = 0.;
     size_t n = 0;
     for (size_t j = 0; j < g_con.nec; ++j) {
-        const double err = fmax(fabs(f[1 + j]) - g_con.tol[j], 0.);
+        const double err = max0(fabs(f[1 + j]) - g_con.tol[j]);
         l2 += err * err;
         if (err <= 0.) ++n;
     }
     *leq = sqrt(l2);
     l2 = 0.;
     for (size_t j = 0; j < g_con.nic; ++j) {
-        const double err = fmax(f[1 + g_con.nec + j] - g_con.tol[g_con.nec + j], 0.);
+        const double err = max0(f[1 + g_con.nec + j] - g_con.tol[g_con.nec + j]);
         l2 += err * err;
         if (err <= 0.) ++n;
     }

@@ -24,8 +24,9 @@ PGC_ERR_OUT_OF_MEMORY = -4
 
 FAMILY = {
     "rastrigin": 1, "ackley": 2, "griewank": 3, "schwefel": 4, "rosenbrock": 5, "cec2014": 6, "cec2013": 7, "zdt": 8,
-    "dtlz": 9, "wfg": 10, "lennard_jones": 11,
+    "dtlz": 9, "wfg": 10, "lennard_jones": 11, "hock_schittkowski_71": 14, "luksan_vlcek1": 15,
 }
+UNCONSTRAIN_METHODS = {"death penalty": 0, "kuri": 1, "weighted": 2, "ignore_c": 3, "ignore_o": 4}
 
 
 class PgcError(RuntimeError):
@@ -165,7 +166,11 @@ def lib():
         L.pgc_problem_destroy.argtypes = [vp]
         L.pgc_problem_translate.argtypes = [vp, dp, sz, C.POINTER(vp)]
         L.pgc_problem_decompose.argtypes = [vp, dp, dp, sz, C.c_int, C.c_int, C.POINTER(vp)]
-        for fn in ("pgc_problem_nx", "pgc_problem_nobj", "pgc_problem_nf"):
+        L.pgc_problem_unconstrain.argtypes = [vp, C.c_int, dp, sz, C.POINTER(vp)]
+        L.pgc_problem_set_c_tol.argtypes = [vp, dp, sz]
+        L.pgc_problem_c_tol.argtypes = [vp, dp]
+        L.pgc_feasibility_device.argtypes = [vp, vp, sz, vp, vp]
+        for fn in ("pgc_problem_nx", "pgc_problem_nobj", "pgc_problem_nf", "pgc_problem_nec", "pgc_problem_nic"):
             getattr(L, fn).argtypes = [vp, C.POINTER(sz)]
         L.pgc_problem_bounds.argtypes = [vp, dp, dp]
         L.pgc_problem_name.argtypes = [vp, C.c_char_p, sz]
@@ -493,6 +498,8 @@ class Problem:
         check(lib().pgc_problem_nx(self._h, C.byref(n))); self.nx = n.value
         check(lib().pgc_problem_nobj(self._h, C.byref(n))); self.nobj = n.value
         check(lib().pgc_problem_nf(self._h, C.byref(n))); self.nf = n.value
+        check(lib().pgc_problem_nec(self._h, C.byref(n))); self.nec = n.value
+        check(lib().pgc_problem_nic(self._h, C.byref(n))); self.nic = n.value
 
     @classmethod
     def _wrap(cls, inner: "Problem", handle) -> "Problem":
@@ -507,6 +514,37 @@ class Problem:
         h = C.c_void_p()
         check(lib().pgc_problem_translate(self._h, t.ctypes.data_as(C.POINTER(C.c_double)), t.size, C.byref(h)))
         return Problem._wrap(self, h)
+
+    def unconstrain(self, method: str = "death penalty", weights=()) -> "Problem":
+        """pagmo::unconstrain{self, method, weights} on the device (unconstrain.cpp:66-97,136-223)."""
+        if method not in UNCONSTRAIN_METHODS:
+            raise PgcError(-1, f"The method {method} is not supported (did you misspell?)")
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        h = C.c_void_p()
+        check(lib().pgc_problem_unconstrain(self._h, UNCONSTRAIN_METHODS[method], w.ctypes.data_as(C.POINTER(C.c_double)), C.c_size_t(w.size),
+                                            C.byref(h)))
+        return Problem._wrap(self, h)
+
+    def set_c_tol(self, c_tol) -> None:
+        """problem::set_c_tol (problem.cpp:620-660): a vector of nec + nic tolerances, or one value for all."""
+        t = np.asarray(c_tol, dtype=np.float64)
+        if t.ndim == 0:
+            if np.isnan(t):
+                raise PgcError(-1, "The tolerance cannot be set to be NaN.")
+            if t < 0:
+                raise PgcError(-1, "The tolerance cannot be negative.")
+            t = np.full(self.nec + self.nic, float(t))
+        t = np.ascontiguousarray(t)
+        check(lib().pgc_problem_set_c_tol(self._h, t.ctypes.data_as(C.POINTER(C.c_double)), C.c_size_t(t.size)))
+
+    def c_tol(self) -> np.ndarray:
+        t = np.empty(self.nec + self.nic)
+        check(lib().pgc_problem_c_tol(self._h, t.ctypes.data_as(C.POINTER(C.c_double))))
+        return t
+
+    def feasibility_device(self, d_f: int, n: int, d_out: int, stream: int = 0):
+        """problem::feasibility_f per row of a device matrix [n x nf] -> n bytes (1 feasible, 0 not)."""
+        check(lib().pgc_feasibility_device(self._h, C.c_void_p(d_f), C.c_size_t(n), C.c_void_p(d_out), C.c_void_p(stream)))
 
     def decompose(self, weight, z, method: str = "weighted", adapt_ideal: bool = False) -> "Problem":
         """pagmo::decompose{self, weight, z, method, adapt_ideal} on the device (decompose.cpp:66-154)."""

@@ -223,8 +223,11 @@ int problem_eval_device(pgc_problem *p, const double *d_dvs, size_t n, double *d
         case PGC_DTLZ:
         case PGC_WFG: return mo_eval(p, d_dvs, n, d_fvs, s);
         case PGC_LENNARD_JONES: return lj_eval(p, d_dvs, n, d_fvs, s);
+        case PGC_HOCK_SCHITTKOWSKI_71:
+        case PGC_LUKSAN_VLCEK1: return constrained_eval(p, d_dvs, n, d_fvs, s);
         case PGC_TRANSLATE:
-        case PGC_DECOMPOSE: return meta_eval(p, d_dvs, n, d_fvs, s);
+        case PGC_DECOMPOSE:
+        case PGC_UNCONSTRAIN: return meta_eval(p, d_dvs, n, d_fvs, s);
         default: set_error("family %d has no device evaluator in this build", p->desc.family); return PGC_ERR_UNSUPPORTED;
     }
 }
@@ -264,6 +267,17 @@ static int indices_out(DevBuf &b, size_t cnt, size_t *dst)
                       "genes only (no CPU fallback)",                                                                  \
                       who, (prob)->name.c_str(), (prob)->nix);                                                         \
             return PGC_ERR_UNSUPPORTED;                                                                                \
+        }                                                                                                              \
+    } while (0)
+
+// The generation operators work on [n x nobj] fitness rows and rank by objectives alone.  The reference's algorithms refuse
+// constrained problems too ("Non linear constraints detected in ... instance. de cannot deal with them", de.cpp:96-99 and the same
+// check in every UDA of this path; gaco's penalty route is not built): wrap the problem in unconstrain (pgc_problem_unconstrain).
+#define PGC_NO_CONSTRAINTS(prob, who)                                                                                  \
+    do {                                                                                                               \
+        if ((prob)->nec + (prob)->nic != 0) {                                                                          \
+            set_error("Non linear constraints detected in %s instance. %s cannot deal with them", (prob)->name.c_str(), who); \
+            return PGC_ERR_INVALID_ARGUMENT;                                                                           \
         }                                                                                                              \
     } while (0)
 
@@ -402,6 +416,8 @@ int pgc_problem_create(pgc_ctx *ctx, const pgc_problem_desc *desc, pgc_problem *
         case PGC_DTLZ:
         case PGC_WFG: rc = mo_create(p); break;
         case PGC_LENNARD_JONES: rc = lj_create(p); break;
+        case PGC_HOCK_SCHITTKOWSKI_71:
+        case PGC_LUKSAN_VLCEK1: rc = constrained_create(p); break;
         default:
             set_error("pgc_problem_create: family %d is not supported by this build (no CPU fallback)", desc->family);
             rc = PGC_ERR_UNSUPPORTED;
@@ -439,6 +455,11 @@ int pgc_problem_destroy(pgc_problem *p)
 int pgc_problem_translate(pgc_problem *inner, const double *translation, size_t len, pgc_problem **out)
 {
     return meta_create(inner, PGC_TRANSLATE, translation, nullptr, len, 0, out);
+}
+
+int pgc_problem_unconstrain(pgc_problem *inner, int method, const double *weights, size_t len, pgc_problem **out)
+{
+    return meta_create(inner, PGC_UNCONSTRAIN, weights, nullptr, len, method, out);
 }
 
 int pgc_problem_decompose(pgc_problem *inner, const double *weight, const double *z, size_t len, int method, int adapt_ideal,
@@ -488,8 +509,51 @@ int pgc_problem_nobj(const pgc_problem *p, size_t *nobj)
 int pgc_problem_nf(const pgc_problem *p, size_t *nf)
 {
     PGC_REQUIRE(p && nf, "pgc_problem_nf: null argument");
-    *nf = p->nobj;
+    *nf = p->nf();
     return PGC_OK;
+}
+
+int pgc_problem_nec(const pgc_problem *p, size_t *nec)
+{
+    PGC_REQUIRE(p && nec, "pgc_problem_nec: null argument");
+    *nec = p->nec;
+    return PGC_OK;
+}
+
+int pgc_problem_nic(const pgc_problem *p, size_t *nic)
+{
+    PGC_REQUIRE(p && nic, "pgc_problem_nic: null argument");
+    *nic = p->nic;
+    return PGC_OK;
+}
+
+int pgc_problem_set_c_tol(pgc_problem *p, const double *c_tol, size_t len)
+{
+    // problem::set_c_tol, src/problem.cpp:620-644
+    PGC_REQUIRE(p && (c_tol || len == 0), "pgc_problem_set_c_tol: null argument");
+    const size_t nc = p->nec + p->nic;
+    PGC_REQUIRE(len == nc, "The tolerance vector size should be: %zu, while a size of: %zu was detected.", nc, len);
+    for (size_t i = 0; i < len; ++i) {
+        PGC_REQUIRE(!std::isnan(c_tol[i]), "The tolerance vector has a NaN value at the index %zu", i);
+        PGC_REQUIRE(!(c_tol[i] < 0.), "The tolerance vector has a negative value at the index %zu", i);
+    }
+    p->c_tol.assign(c_tol, c_tol + len);
+    return PGC_OK;
+}
+
+int pgc_problem_c_tol(const pgc_problem *p, double *c_tol)
+{
+    PGC_REQUIRE(p && (c_tol || p->c_tol.empty()), "pgc_problem_c_tol: null argument");
+    std::copy(p->c_tol.begin(), p->c_tol.end(), c_tol);
+    return PGC_OK;
+}
+
+int pgc_feasibility_device(pgc_problem *p, const double *d_f, size_t n, uint8_t *d_feasible, void *stream)
+{
+    PGC_REQUIRE(p, "pgc_feasibility_device: null problem");
+    PGC_REQUIRE(n == 0 || (d_f && d_feasible), "pgc_feasibility_device: null device buffer");
+    PGC_CUDA(cudaSetDevice(p->ctx->device));
+    return feasibility_rows(p, d_f, n, d_feasible, stream ? static_cast<cudaStream_t>(stream) : p->ctx->stream);
 }
 
 int pgc_problem_bounds(const pgc_problem *p, double *lb, double *ub)
@@ -513,7 +577,7 @@ int pgc_problem_work(const pgc_problem *p, double *flops, double *transc, double
     PGC_REQUIRE(p, "pgc_problem_work: null problem");
     if (flops) *flops = p->flops_per_eval;
     if (transc) *transc = p->transc_per_eval;
-    if (bytes) *bytes = 8.0 * static_cast<double>(p->nx + p->nobj);
+    if (bytes) *bytes = 8.0 * static_cast<double>(p->nx + p->nf());
     return PGC_OK;
 }
 
@@ -536,7 +600,7 @@ int pgc_eval_host(pgc_problem *p, const double *dvs, size_t n, double *fvs)
     PGC_REQUIRE(dvs && fvs, "pgc_eval_host: null host buffer");
     pgc_ctx *ctx = p->ctx;
     PGC_CUDA(cudaSetDevice(ctx->device));
-    const size_t nx = p->nx, nf = p->nobj;
+    const size_t nx = p->nx, nf = p->nf();
     // chunk: ~32 MiB of decision vectors, a multiple of 16 individuals
     size_t chunk = (32u << 20) / (nx * sizeof(double));
     chunk = std::max<size_t>(16, chunk / 16 * 16);
@@ -769,6 +833,7 @@ int pgc_nsga2_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t 
                             double eta_m, uint64_t seed, uint32_t first_generation, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_nsga2_evolve_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_nsga2_evolve_device");
     // integer alleles (the last nix genes, e.g. ZDT5) are handled: two-point crossover + uniform integer mutation, genetic_operators.cpp:125-137, :187-195
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return nsga2_evolve_device(prob, d_x, d_f, static_cast<unsigned>(NP), gens, cr, eta_c, m, eta_m, seed, first_generation,
@@ -780,6 +845,7 @@ int pgc_pso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, double *d
                           uint64_t seed, uint32_t first_generation, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_pso_evolve_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_pso_evolve_device");
     PGC_NO_INTEGER_GENES(prob, "pgc_pso_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return pso_evolve_device(prob, d_x, d_f, d_v, d_xcur, static_cast<unsigned>(n), gens, omega, eta1, eta2, max_vel, variant, neighb_type,
@@ -792,6 +858,7 @@ int pgc_pso_shard_step_device(pgc_problem *prob, double *d_X, double *d_V, doubl
                               uint32_t generation, int init_velocity, void *stream)
 {
     PGC_REQUIRE(prob && d_V && (init_velocity || (d_X && d_lbX_ext && d_lbfit_ext)), "pgc_pso_shard_step_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_pso_shard_step_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return pso_shard_step_device(prob, d_X, d_V, d_lbX_ext, d_lbfit_ext, static_cast<unsigned>(n_loc), radius, index_offset, omega, eta1, eta2,
                                  max_vel, variant, seed, generation, init_velocity, problem_eval_device,
@@ -803,6 +870,7 @@ int pgc_pso_shard_step_gbest_device(pgc_problem *prob, double *d_X, double *d_V,
                                     uint64_t seed, uint32_t generation, int init_velocity, double *d_cand, void *stream)
 {
     PGC_REQUIRE(prob && d_V && d_cand && (init_velocity || (d_X && d_lbX_ext && d_lbfit_ext)), "pgc_pso_shard_step_gbest_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_pso_shard_step_gbest_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return pso_shard_step_device(prob, d_X, d_V, d_lbX_ext, d_lbfit_ext, static_cast<unsigned>(n_loc), 1u, index_offset, omega, eta1, eta2,
                                  max_vel, variant, seed, generation, init_velocity, problem_eval_device,
@@ -815,6 +883,7 @@ int pgc_de_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP,
                          unsigned *gens_done, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_de_evolve_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_de_evolve_device");
     PGC_NO_INTEGER_GENES(prob, "pgc_de_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return de_evolve_device(prob, d_x, d_f, static_cast<unsigned>(NP), gens, algo, variant, variant_adptv, F, CR, allowed_variants, n_allowed,
@@ -827,6 +896,7 @@ int pgc_moead_gen_evolve_device(pgc_problem *prob, double *d_x, double *d_f, siz
                                 int preserve_diversity, uint64_t seed, uint32_t first_generation, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_moead_gen_evolve_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_moead_gen_evolve_device");
     PGC_NO_INTEGER_GENES(prob, "pgc_moead_gen_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return moead_gen_evolve_device(prob, d_x, d_f, static_cast<unsigned>(n), gens, weights, neigh, T, decomposition, CR, F, eta_m, realb, limit,
@@ -839,6 +909,7 @@ int pgc_nspso_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t 
                             double *d_vel, double *d_best_x, double *d_best_f, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_nspso_evolve_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_nspso_evolve_device");
     PGC_NO_INTEGER_GENES(prob, "pgc_nspso_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return nspso_evolve_device(prob, d_x, d_f, static_cast<unsigned>(n), gens, omega, c1, c2, chi, v_coeff, leader_selection_range, diversity, seed,
@@ -851,6 +922,7 @@ int pgc_gaco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n
                            uint32_t first_generation, pgc_gaco_state *state, unsigned *gens_done, void *stream)
 {
     PGC_REQUIRE(prob && (n == 0 || (d_x && d_f)), "pgc_gaco_evolve_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_gaco_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     pgc_gaco_state local{};
     pgc_gaco_state *s = state ? state : &local;
@@ -869,6 +941,7 @@ int pgc_maco_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t n
                            pgc_maco_state *state, unsigned *gens_done, void *stream)
 {
     PGC_REQUIRE(prob && (n == 0 || (d_x && d_f)), "pgc_maco_evolve_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_maco_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     pgc_maco_state local{};
     pgc_maco_state *s = state ? state : &local;
@@ -886,6 +959,7 @@ int pgc_xnes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t l
                            unsigned *gens_done, double *sigma_out, void *stream)
 {
     PGC_REQUIRE(prob && (lambda == 0 || (d_x && d_f)), "pgc_xnes_evolve_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_xnes_evolve_device");
     PGC_NO_INTEGER_GENES(prob, "pgc_xnes_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return xnes_evolve_device(prob, d_x, d_f, lambda, gens, eta_mu, eta_sigma, eta_b, sigma0, ftol, xtol, force_bounds, seed, first_generation,
@@ -975,6 +1049,7 @@ int pgc_sga_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t NP
                           uint32_t first_generation, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_sga_evolve_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_sga_evolve_device");
     PGC_NO_INTEGER_GENES(prob, "pgc_sga_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return sga_evolve_device(prob, d_x, d_f, static_cast<unsigned>(NP), gens, cr, eta_c, m, param_m, param_s, crossover, mutation, selection,
@@ -986,6 +1061,7 @@ int pgc_cmaes_evolve_device(pgc_problem *prob, double *d_x, double *d_f, size_t 
                             unsigned *gens_done, double *sigma_out, void *stream)
 {
     PGC_REQUIRE(prob && d_x && d_f, "pgc_cmaes_evolve_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_cmaes_evolve_device");
     PGC_NO_INTEGER_GENES(prob, "pgc_cmaes_evolve_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     return cmaes_evolve_device(prob, d_x, d_f, lambda, gens, cc, cs, c1, cmu, sigma0, ftol, xtol, force_bounds, seed, first_generation, gens_done,
@@ -1032,6 +1108,7 @@ int pgc_algo_evolve_device(pgc_problem *prob, const pgc_algo_desc *a, double *d_
                            unsigned *gens_done, void *stream)
 {
     PGC_REQUIRE(prob && a && d_x && d_f, "pgc_algo_evolve_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_algo_evolve_device");
     if (gens_done) *gens_done = a->gens;
     switch (a->algo) {
         case PGC_ALGO_DE:
@@ -1072,6 +1149,7 @@ int pgc_algo_evolve_memory_device(pgc_problem *prob, const pgc_algo_desc *a, dou
                                   unsigned *gens_done, pgc_algo_memory *mem, void *stream)
 {
     PGC_REQUIRE(prob && a && d_x && d_f && mem, "pgc_algo_evolve_memory_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_algo_evolve_memory_device");
     PGC_CUDA(cudaSetDevice(prob->ctx->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : prob->ctx->stream;
     const unsigned NP = static_cast<unsigned>(n);
@@ -1157,6 +1235,7 @@ int pgc_algo_evolve_logged_device(pgc_problem *prob, const pgc_algo_desc *a, dou
                                   size_t *n_rows, void *stream)
 {
     PGC_REQUIRE(prob && a, "pgc_algo_evolve_logged_device: null argument");
+    PGC_NO_CONSTRAINTS(prob, "pgc_algo_evolve_logged_device");
     if (n_rows) *n_rows = 0;
     const auto run = [&]() {
         return memory ? pgc_algo_evolve_memory_device(prob, a, d_x, d_f, n, first_generation, gens_done, memory, stream)

@@ -165,6 +165,9 @@ int pgc_island_create(pgc_problem *prob, size_t n, size_t max_migrants, size_t m
 {
     PGC_REQUIRE(prob && out, "pgc_island_create: null argument");
     PGC_REQUIRE(n >= 1 && n < 0xffffffffull, "pgc_island_create: population size %zu out of range", n);
+    // the resident island evolves with the device UDAs, none of which takes constraints (as in the reference): unconstrain first
+    PGC_REQUIRE(prob->nec + prob->nic == 0, "pgc_island_create: '%s' has %zu constraints; wrap it with pgc_problem_unconstrain",
+                prob->name.c_str(), prob->nec + prob->nic);
     *out = nullptr;
     pgc_island *isl = new (std::nothrow) pgc_island;
     if (!isl) return PGC_ERR_OUT_OF_MEMORY;

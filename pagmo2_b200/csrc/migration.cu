@@ -20,6 +20,8 @@ namespace pgc
 namespace
 {
 
+__device__ __forceinline__ double max0(double a) { return a < 0. ? 0. : a; } // std::max(a, 0.): a NaN stays a NaN (never satisfied)
+
 __global__ void so_keys_kernel(const double *__restrict__ f, size_t stride, unsigned n, unsigned long long *keys, unsigned *idx)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,12 +91,12 @@ __global__ void con_keys_kernel(const double *__restrict__ f, unsigned n, unsign
     double l2e = 0., l2i = 0.;
     unsigned nsat = 0;
     for (unsigned j = 0; j < nec; ++j) { // detail::test_eq_constraints, constrained.hpp:49-62
-        const double err = fmax(fabs(row[1u + j]) - tol[j], 0.);
+        const double err = max0(fabs(row[1u + j]) - tol[j]);
         l2e += err * err;
         nsat += err <= 0. ? 1u : 0u;
     }
     for (unsigned j = 0; j < nic; ++j) { // detail::test_ineq_constraints, :67-80
-        const double err = fmax(row[1u + nec + j] - tol[nec + j], 0.);
+        const double err = max0(row[1u + nec + j] - tol[nec + j]);
         l2i += err * err;
         nsat += err <= 0. ? 1u : 0u;
     }

@@ -225,6 +225,11 @@ struct pgc_problem {
     pgc_problem_desc desc{}; // table pointers nulled after the copy
     size_t nx = 0, nobj = 1;
     size_t nix = 0; // integer dimension (the last nix genes, problem::get_nix): zdt5 only; a meta-problem inherits its inner one's
+    // constraints (problem::get_nec / get_nic / get_c_tol): hock_schittkowski_71 and luksan_vlcek1 only; fitness rows are
+    // [nobj | nec | nic] wide.  Generation operators refuse nec + nic > 0, as the reference's algorithms do; unconstrain removes them.
+    size_t nec = 0, nic = 0;
+    std::vector<double> c_tol;
+    size_t nf() const { return nobj + nec + nic; }
     std::vector<double> lb, ub;
     std::string name;
     // device tables
@@ -288,6 +293,9 @@ void cec2014_destroy(pgc_problem *p);
 int cec2013_create(pgc_problem *p, const pgc_problem_desc *d);
 int cec2013_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
 void cec2013_destroy(pgc_problem *p);
+int constrained_create(pgc_problem *p);
+int constrained_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t stream);
+int feasibility_rows(pgc_problem *p, const double *d_f, size_t n, unsigned char *d_feasible, cudaStream_t stream);
 int meta_create(pgc_problem *inner, int family, const double *a, const double *b, size_t len, int method, pgc_problem **out);
 int meta_eval(pgc_problem *p, const double *d_dvs, size_t n, double *d_fvs, cudaStream_t s);
 void meta_destroy(pgc_problem *p);

@@ -24,6 +24,7 @@
 #include <pagmo/problems/cec2014.hpp>
 #include <pagmo/problems/decompose.hpp>
 #include <pagmo/problems/translate.hpp>
+#include <pagmo/problems/unconstrain.hpp>
 #include <pagmo/problems/dtlz.hpp>
 #include <pagmo/problems/lennard_jones.hpp>
 #include <pagmo/problems/rastrigin.hpp>
@@ -296,6 +297,68 @@ int main(int argc, char **argv)
             threw = true; // decompose.cpp:70-72
         }
         CHECK(threw);
+    }
+
+    // ---- 3b''. constrained UDPs and cuda_unconstrain against the stock hock_schittkowski_71 / luksan_vlcek1 / pagmo::unconstrain -------
+    {
+        pagmo::bfe gpu{cuda_bfe{}}, cpu{pagmo::thread_bfe{}};
+        pagmo::problem hs{pagmo::hock_schittkowski_71{}}, hsc{cuda_hock_schittkowski_71{}};
+        CHECK(hsc.get_nobj() == 1u && hsc.get_nec() == 1u && hsc.get_nic() == 1u && hsc.get_nf() == 3u);
+        CHECK(hsc.get_bounds() == hs.get_bounds());
+        const auto dvs = random_batch(hs, 500, 91);
+        CHECK(gpu(hsc, dvs) == cpu(hs, dvs)); // products and sums only: bit for bit
+        CHECK(gpu(hs, dvs) == cpu(hs, dvs));  // the stock UDP finds its device twin
+        CHECK(hsc.feasibility_x(pagmo::vector_double{1., 4.74299963, 3.82114998, 1.37940829}) == false); // tolerances are zero
+        hsc.set_c_tol(1e-6);
+        CHECK(hsc.feasibility_x(pagmo::vector_double{1., 4.74299963, 3.82114998, 1.37940829}) == true);
+        pagmo::problem lv{pagmo::luksan_vlcek1{12u}}, lvc{cuda_luksan_vlcek1{12u}};
+        CHECK(lvc.get_nec() == 10u && lvc.get_nic() == 0u && lvc.get_bounds() == lv.get_bounds());
+        const auto xs = random_batch(lv, 300, 92);
+        const auto a = gpu(lvc, xs), b = cpu(lv, xs), c = gpu(lv, xs);
+        double worst = 0.;
+        for (std::size_t i = 0; i < a.size(); ++i) worst = std::max({worst, std::abs(a[i] - b[i]), std::abs(c[i] - b[i])});
+        CHECK(worst <= 1e-12 * 2e5); // terms up to 5 e^10 of mixed sign: 1e-12 of their magnitude
+        const pagmo::vector_double w{3., 0.5}, ctol{2., 40.};
+        for (const char *method : {"death penalty", "kuri", "weighted", "ignore_c", "ignore_o"}) {
+            const bool wt = std::string(method) == "weighted";
+            pagmo::problem inner{pagmo::hock_schittkowski_71{}};
+            inner.set_c_tol(ctol);
+            pagmo::problem uref{pagmo::unconstrain{inner, method, wt ? w : pagmo::vector_double{}}};
+            pagmo::problem utwin{cuda_unconstrain{cuda_hock_schittkowski_71{}, method, wt ? w : pagmo::vector_double{}, ctol}};
+            CHECK(utwin.get_nobj() == 1u && utwin.get_nc() == 0u && utwin.get_bounds() == uref.get_bounds());
+            CHECK(utwin.get_name().find("[unconstrained]") != std::string::npos);
+            CHECK(gpu(utwin, dvs) == cpu(uref, dvs));
+            CHECK(utwin.batch_fitness(dvs) == cpu(uref, dvs));
+            // the stock meta-problem over the CUDA UDP: device batch_fitness, host penalty (unconstrain.cpp:244-263)
+            pagmo::problem hsc2{cuda_hock_schittkowski_71{}};
+            hsc2.set_c_tol(ctol);
+            pagmo::problem mixed{pagmo::unconstrain{hsc2, method, wt ? w : pagmo::vector_double{}}};
+            CHECK(mixed.batch_fitness(dvs) == cpu(uref, dvs));
+        }
+        const auto throws = [](auto make) {
+            try {
+                make();
+            } catch (const std::invalid_argument &) {
+                return true;
+            }
+            return false;
+        };
+        CHECK(throws([] { cuda_unconstrain{cuda_simple<PGC_RASTRIGIN>{5u}}; }));                             // unconstrain.cpp:73-77
+        CHECK(throws([] { cuda_unconstrain{cuda_hock_schittkowski_71{}, "weighted", {1.}}; }));               // :79-82
+        CHECK(throws([] { cuda_unconstrain{cuda_hock_schittkowski_71{}, "mispelled"}; }));                    // :84-88
+        CHECK(throws([] { cuda_unconstrain{cuda_hock_schittkowski_71{}, "kuri", {1., 1.}}; }));               // :90-93
+        CHECK(throws([] { cuda_luksan_vlcek1{2u}; }));                                                        // luksan_vlcek1.cpp:46-49
+        { // the device algorithms refuse constraints like the reference's do, and run on the unconstrained problem
+            using namespace pagmo_cuda;
+            pagmo::population pc{hsc, 32u, 5u};
+            CHECK(throws([&] { pagmo::algorithm{cuda_de{5u}}.evolve(pc); }));
+            pagmo::problem up{cuda_unconstrain{cuda_hock_schittkowski_71{}, "weighted", {10., 10.}, {1e-3, 1e-3}}};
+            pagmo::population pu{up, 64u, 5u};
+            const double before = pu.champion_f()[0];
+            pu = pagmo::algorithm{cuda_de{60u, 0.8, 0.9, 2u, 0., 0., 3u}}.evolve(pu);
+            CHECK(pu.champion_f()[0] < before);
+            std::printf("cuda_de on unconstrain{hs71, weighted}: %.6g -> %.6g (optimum 17.014)\n", before, pu.champion_f()[0]);
+        }
     }
 
     // ---- 3c. CUDA UDAs behind pagmo::algorithm: evolve() keeps the population consistent and counts fevals like the reference ----

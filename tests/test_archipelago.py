@@ -81,6 +81,19 @@ def test_constrained_policies_restatement_vs_reference(orc, ref):
             a = orc.fair_replace_con(ids, x, f, rate, mids, mx, mf, nec, nic, tol)
             b = ref.fair_replace_con(ids, x, f, rate, mids, mx, mf, nec, nic, tol)
             assert all(np.array_equal(u, v) for u, v in zip(a, b)), (nec, nic, n, nm, rate)
+    # NaN constraints: std::max(NaN - tol, 0.) stays NaN (constrained.hpp:55,73), so the constraint is never satisfied and the norm is NaN
+    for nec, nic in ((2, 0), (0, 3), (2, 2)):
+        tol = np.full(nec + nic, 1e-2)
+        for trial in range(10):
+            n = 14
+            ids = rng.integers(0, 2**63, n, dtype=np.uint64)
+            x = rng.normal(size=(n, 3))
+            f = _constrained_group(rng, n, nec, nic, False)
+            f[3, 1] = np.nan
+            if trial % 2:
+                f[9, nec + nic] = np.nan
+            a, b = orc.select_best_con(ids, x, f, n, nec, nic, tol), ref.select_best_con(ids, x, f, n, nec, nic, tol)
+            assert all(np.array_equal(u, v, equal_nan=True) for u, v in zip(a, b)), (nec, nic, trial)
     # the order itself: feasible first by objective, then by the number of violated constraints, then by the violation norm
     f = np.array([[5.0, 0.0, -1.0], [1.0, 0.5, -1.0], [9.0, 0.0, 2.0], [2.0, 0.0, -1.0], [0.0, 3.0, 1.0], [7.0, 0.2, -1.0]])
     assert list(orc.sort_population_con(f, 1, 1, [1e-2, 1e-2])) == [3, 0, 5, 1, 2, 4]

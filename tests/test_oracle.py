@@ -434,3 +434,53 @@ def test_meta_restatement_is_bit_exact_vs_reference(orc, ref):
         ref.translate(inner, [1.0, 2.0])
     with pytest.raises(RuntimeError, match="multi-objective"):
         ref.decompose(inner, [0.5, 0.5], [0.0, 0.0])
+
+
+# ---------------------------------------------------------------- constrained UDPs + unconstrain
+def test_constrained_udps_and_unconstrain_are_bit_exact_vs_reference(orc, ref):
+    rng = np.random.default_rng(771)
+    # hock_schittkowski_71 (1 objective, 1 equality, 1 inequality) and luksan_vlcek1 (dim - 2 equalities)
+    hs = ref.problem("hock_schittkowski_71")
+    assert (hs.nx, hs.nobj, hs.nec, hs.nic, hs.nf) == (4, 1, 1, 1, 3)
+    xs = rng.uniform(1, 5, (200, 4))
+    assert np.array_equal(hs.fitness_loop(xs), orc.hock_schittkowski_71(xs))
+    # the reference's own known answer: the optimum of HS71 (tests/hock_schittkowski_71.cpp best_known)
+    best = np.array([[1., 4.74299963, 3.82114998, 1.37940829]])
+    fb = orc.hock_schittkowski_71(best)[0]
+    assert fb[0] == pytest.approx(17.0140172, rel=1e-7) and abs(fb[1]) < 1e-6 and abs(fb[2]) < 1e-6
+    for dim in (3, 4, 10, 33):
+        lv = ref.problem("luksan_vlcek1", dim)
+        assert (lv.nx, lv.nobj, lv.nec, lv.nic) == (dim, 1, dim - 2, 0)
+        xs = rng.uniform(-5, 5, (64, dim))
+        assert np.array_equal(lv.fitness_loop(xs), orc.luksan_vlcek1(xs)), dim
+    with pytest.raises(RuntimeError, match="minimum 3 dimension"):
+        ref.problem("luksan_vlcek1", 2)
+    # unconstrain: every method, default and non-zero tolerances, rows that are feasible / partly / wholly infeasible
+    cases = [("hock_schittkowski_71", 0, lambda n: rng.uniform(1, 5, (n, 4)), orc.hock_schittkowski_71),
+             ("luksan_vlcek1", 6, lambda n: rng.uniform(-1.5, 1.5, (n, 6)), orc.luksan_vlcek1)]
+    for fam, p0, draw, inner_eval in cases:
+        for tol_scale in (0.0, 3.0, 40.0):
+            inner = ref.problem(fam, p0)
+            nc = inner.nec + inner.nic
+            tol = tol_scale * rng.uniform(0.5, 1.5, nc)
+            inner.set_c_tol(tol)
+            xs = draw(96)
+            fin = inner_eval(xs)
+            w = rng.uniform(0.1, 2.0, nc)
+            for method in ("death penalty", "kuri", "weighted", "ignore_c", "ignore_o"):
+                p = ref.unconstrain(inner, method, w if method == "weighted" else ())
+                assert p.nobj == 1 and p.nec == 0 and p.nic == 0 and p.nx == inner.nx and p.name.endswith("[unconstrained]")
+                got = orc.unconstrain_rows(fin, 1, inner.nec, inner.nic, tol, method, w)
+                assert np.array_equal(p.fitness_loop(xs), got), (fam, tol_scale, method)
+            if tol_scale == 40.0 and fam == "hock_schittkowski_71":  # large tolerances: feasible rows exist, death penalty keeps them
+                dp = orc.unconstrain_rows(fin, 1, inner.nec, inner.nic, tol, "death penalty")
+                assert (dp[:, 0] == fin[:, 0]).any() and (dp[:, 0] == np.finfo(float).max).any()
+    # constructor errors (unconstrain.cpp:68-92)
+    with pytest.raises(RuntimeError, match="can only be applied to constrained problems"):
+        ref.unconstrain(ref.problem("rastrigin", 5))
+    with pytest.raises(RuntimeError, match="Length of weight vector is: 1 while the problem constraints are: 2"):
+        ref.unconstrain(hs, "weighted", [1.0])
+    with pytest.raises(RuntimeError, match="is not supported"):
+        ref.unconstrain(hs, "mispelled")
+    with pytest.raises(RuntimeError, match="needs to be empty"):
+        ref.unconstrain(hs, "kuri", [1.0, 1.0])
