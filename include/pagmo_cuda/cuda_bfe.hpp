@@ -184,6 +184,76 @@ public:
         return slot;
     }
 
+    // Serialisation of the description this handle was built from - the UDP's constructor arguments, tables included, and for a
+    // meta-problem its own arguments followed by the wrapped problem's - so that a CUDA UDP loaded into a default-constructed
+    // object (pagmo::problem / island / archipelago save + load, pygmo pickling) re-creates the same device problem.
+    template <typename Archive>
+    static void save_chain(Archive &ar, const problem_handle *h)
+    {
+        int kind = !h ? -1 : (h->m_inner ? h->m_meta_kind : 0);
+        ar &kind;
+        if (kind < 0) return;
+        int device = h->m_device;
+        ar &device;
+        if (kind != 0) {
+            pagmo::vector_double a = h->m_meta_a, b = h->m_meta_b;
+            int method = h->m_meta_method;
+            ar &a;
+            ar &b;
+            ar &method;
+            save_chain(ar, h->m_inner.get());
+            return;
+        }
+        int family = h->m_desc.family;
+        unsigned prob_id = h->m_desc.prob_id, dim = h->m_desc.dim, nobj = h->m_desc.nobj, param = h->m_desc.param;
+        std::vector<double> rotation = h->m_rotation, shift = h->m_shift;
+        std::vector<int32_t> shuffle = h->m_shuffle;
+        ar &family;
+        ar &prob_id;
+        ar &dim;
+        ar &nobj;
+        ar &param;
+        ar &rotation;
+        ar &shift;
+        ar &shuffle;
+    }
+    template <typename Archive>
+    static std::shared_ptr<problem_handle> load_chain(Archive &ar)
+    {
+        int kind = -1, device = 0;
+        ar &kind;
+        if (kind < 0) return nullptr;
+        ar &device;
+        if (kind != 0) {
+            pagmo::vector_double a, b;
+            int method = 0;
+            ar &a;
+            ar &b;
+            ar &method;
+            auto inner = load_chain(ar);
+            if (!inner) pagmo_throw(std::invalid_argument, "cuda meta-problem archive without an inner problem");
+            return std::make_shared<problem_handle>(std::move(inner), kind, std::move(a), std::move(b), method);
+        }
+        pgc_problem_desc d{};
+        std::vector<double> rotation, shift;
+        std::vector<int32_t> shuffle;
+        ar &d.family;
+        ar &d.prob_id;
+        ar &d.dim;
+        ar &d.nobj;
+        ar &d.param;
+        ar &rotation;
+        ar &shift;
+        ar &shuffle;
+        d.rotation = rotation.empty() ? nullptr : rotation.data();
+        d.rotation_len = rotation.size();
+        d.shift = shift.empty() ? nullptr : shift.data();
+        d.shift_len = shift.size();
+        d.shuffle = shuffle.empty() ? nullptr : shuffle.data();
+        d.shuffle_len = shuffle.size();
+        return std::make_shared<problem_handle>(device, d); // the handle copies the tables
+    }
+
     // n decision vectors at dvs -> n fitness vectors at fvs (plain pointers: used for the shards of a multi-device batch)
     void evaluate_raw(const double *dvs, std::size_t n, double *fvs) const
     {
@@ -418,6 +488,18 @@ protected:
         if (!m_handle) pagmo_throw(std::runtime_error, "cuda UDP used before its device problem was created");
         return *m_handle;
     }
+    // the device problem's own description goes into the archive; a load re-creates the device problem from it (Boost archives and
+    // the test archive say which way they go through `is_loading`)
+    template <typename Archive>
+    void serialize_handle(Archive &ar)
+    {
+        ar &m_device;
+        if (Archive::is_loading::value) {
+            m_handle = detail::problem_handle::load_chain(ar);
+        } else {
+            detail::problem_handle::save_chain(ar, m_handle.get());
+        }
+    }
     int m_device = 0;
     std::shared_ptr<detail::problem_handle> m_handle;
 };
@@ -446,7 +528,7 @@ public:
     void serialize(Archive &ar, unsigned)
     {
         pagmo::detail::archive(ar, m_prob_id, m_dim, m_rotation, m_shift, m_shuffle, m_device);
-        // device state is rebuilt lazily after loading
+        serialize_handle(ar);
     }
 
 private:
@@ -482,6 +564,7 @@ public:
     void serialize(Archive &ar, unsigned)
     {
         pagmo::detail::archive(ar, m_dim, m_device);
+        serialize_handle(ar);
     }
 
 private:
@@ -510,6 +593,7 @@ public:
     void serialize(Archive &ar, unsigned)
     {
         pagmo::detail::archive(ar, m_prob_id, m_param, m_device);
+        serialize_handle(ar);
     }
 
 private:
@@ -532,6 +616,7 @@ public:
     void serialize(Archive &ar, unsigned)
     {
         pagmo::detail::archive(ar, m_prob_id, m_dim, m_fdim, m_alpha, m_device);
+        serialize_handle(ar);
     }
 
 private:
@@ -559,6 +644,7 @@ public:
     void serialize(Archive &ar, unsigned)
     {
         pagmo::detail::archive(ar, m_prob_id, m_dim, m_rotation, m_shift, m_device);
+        serialize_handle(ar);
     }
 
 private:
@@ -582,6 +668,7 @@ public:
     void serialize(Archive &ar, unsigned)
     {
         pagmo::detail::archive(ar, m_prob_id, m_dim_dvs, m_dim_obj, m_dim_k, m_device);
+        serialize_handle(ar);
     }
 
 private:
@@ -601,6 +688,7 @@ public:
     void serialize(Archive &ar, unsigned)
     {
         pagmo::detail::archive(ar, m_atoms, m_device);
+        serialize_handle(ar);
     }
 
 private:
@@ -625,6 +713,7 @@ public:
     void serialize(Archive &ar, unsigned)
     {
         pagmo::detail::archive(ar, m_device);
+        serialize_handle(ar);
     }
 };
 
@@ -640,6 +729,7 @@ public:
     void serialize(Archive &ar, unsigned)
     {
         pagmo::detail::archive(ar, m_dim, m_device);
+        serialize_handle(ar);
     }
 
 private:
@@ -676,6 +766,12 @@ public:
         m_handle = std::make_shared<detail::problem_handle>(inner_handle, static_cast<int>(PGC_UNCONSTRAIN), weights, c_tol,
                                                             code < 0 ? static_cast<int>(PGC_UNCONSTRAIN_DEATH) : code);
     }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_method, m_weights);
+        serialize_handle(ar);
+    }
 
 private:
     std::string m_method;
@@ -700,6 +796,12 @@ public:
     const pagmo::vector_double &get_translation() const // translate.hpp: get_translation()
     {
         return m_translation;
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_translation);
+        serialize_handle(ar);
     }
 
 private:
@@ -733,6 +835,12 @@ public:
     pagmo::vector_double get_z() const // decompose.cpp:208-211
     {
         return m_z;
+    }
+    template <typename Archive>
+    void serialize(Archive &ar, unsigned)
+    {
+        pagmo::detail::archive(ar, m_weight, m_z, m_method);
+        serialize_handle(ar);
     }
 
 private:

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <random>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -42,6 +43,8 @@ static int g_fail = 0;
 
 // ---- a minimal in-memory archive with Boost.Serialization's `ar & x` interface, to round-trip the adapters' serialize() ----
 struct mem_oarchive {
+    using is_loading = std::false_type; // as Boost's archives declare themselves
+    using is_saving = std::true_type;
     std::vector<unsigned char> buf;
     template <typename T, typename std::enable_if<std::is_arithmetic<T>::value || std::is_enum<T>::value, int>::type = 0>
     mem_oarchive &operator&(const T &v)
@@ -65,6 +68,8 @@ struct mem_oarchive {
     }
 };
 struct mem_iarchive {
+    using is_loading = std::true_type;
+    using is_saving = std::false_type;
     const std::vector<unsigned char> &buf;
     std::size_t pos = 0;
     template <typename T, typename std::enable_if<std::is_arithmetic<T>::value || std::is_enum<T>::value, int>::type = 0>
@@ -115,6 +120,52 @@ int main(int argc, char **argv)
     int ndev = 1;
     for (int i = 1; i + 1 < argc; ++i)
         if (std::string(argv[i]) == "--devices") ndev = std::atoi(argv[i + 1]);
+
+    // ---- 0. serialisation of the CUDA UDPs: a load into a default-constructed UDP re-creates the same device problem ----
+    {
+        const auto same_problem = [](const auto &a, const auto &b, unsigned seed) {
+            pagmo::problem pa{a}, pb{b};
+            if (pa.get_nx() != pb.get_nx() || pa.get_nf() != pb.get_nf() || pa.get_nec() != pb.get_nec() || pa.get_bounds() != pb.get_bounds()
+                || pa.get_name() != pb.get_name())
+                return false;
+            const auto lb = pa.get_lb(), ub = pa.get_ub();
+            std::mt19937 e(seed);
+            pagmo::vector_double xs(16u * pa.get_nx());
+            for (std::size_t i = 0; i < xs.size(); ++i) xs[i] = std::uniform_real_distribution<double>(lb[i % lb.size()], ub[i % lb.size()])(e);
+            return pa.batch_fitness(xs) == pb.batch_fitness(xs);
+        };
+        cuda_rastrigin r(7u);
+        CHECK(same_problem(r, round_trip(r), 1u));
+        cuda_zdt z(3u, 17u);
+        CHECK(same_problem(z, round_trip(z), 2u));
+        cuda_dtlz dz(2u, 9u, 3u, 100u);
+        CHECK(same_problem(dz, round_trip(dz), 3u));
+        cuda_lennard_jones lj(9u);
+        CHECK(same_problem(lj, round_trip(lj), 4u));
+        cuda_luksan_vlcek1 lv(8u);
+        CHECK(same_problem(lv, round_trip(lv), 5u));
+        cuda_hock_schittkowski_71 hs;
+        CHECK(same_problem(hs, round_trip(hs), 6u));
+        { // cec2014 with its tables, and the meta-problems with their chains: translate{cec2014}, unconstrain{translate{hs71}}, decompose{zdt}
+            const unsigned D = 10u;
+            std::mt19937 e(11u);
+            std::vector<double> mr(static_cast<std::size_t>(D) * D, 0.), os(D);
+            for (unsigned i = 0; i < D; ++i) mr[static_cast<std::size_t>(i) * D + (i + 3u) % D] = (i % 2u) ? -1. : 1.; // a signed permutation: orthogonal
+            for (auto &v : os) v = std::uniform_real_distribution<double>(-80., 80.)(e);
+            cuda_cec2014 c(1u, D, mr, os);
+            CHECK(same_problem(c, round_trip(c), 7u));
+            pagmo::vector_double t(D);
+            for (auto &v : t) v = std::uniform_real_distribution<double>(-1., 1.)(e);
+            cuda_translate tc(c, t);
+            const auto tc2 = round_trip(tc);
+            CHECK(same_problem(tc, tc2, 8u) && tc2.get_translation() == t);
+            cuda_unconstrain u(cuda_translate(hs, {0.5, -0.25, 0.125, 1.}), "weighted", {2., 3.}, {1e-3, 0.5});
+            CHECK(same_problem(u, round_trip(u), 9u));
+            cuda_decompose dc(z, {0.25, 0.75}, {0.1, -0.1}, "bi");
+            const auto dc2 = round_trip(dc);
+            CHECK(same_problem(dc, dc2, 10u) && dc2.get_z() == dc.get_z());
+        }
+    }
 
     // ---- 1. serialisation: every constructor argument survives save + load into a default-constructed UDA ----
     {
