@@ -145,8 +145,34 @@ def hv_fixture(R):
     np.savez_compressed(OUT / "hv_ref.npz", **data)
 
 
+def constrained_fixture(R):
+    """hock_schittkowski_71, luksan_vlcek1 and pagmo::unconstrain of both (five methods, zero and non-zero tolerances)."""
+    rng = np.random.default_rng(20171)
+    data = {}
+    for fam, p0 in (("hock_schittkowski_71", 0), ("luksan_vlcek1", 3), ("luksan_vlcek1", 10), ("luksan_vlcek1", 33)):
+        p = R.problem(fam, p0)
+        lb, ub = p.bounds()
+        xs = rng.uniform(lb, ub, (24, p.nx)) if fam != "luksan_vlcek1" else rng.uniform(-1.5, 1.5, (24, p.nx))
+        key = f"{fam}_{p0}"
+        nc = p.nec + p.nic
+        data[f"x_{key}"] = xs
+        data[f"f_{key}"] = p.fitness_loop(xs)
+        for ti, tol in enumerate((np.zeros(nc), rng.uniform(1.0, 6.0, nc))):
+            p.set_c_tol(tol)
+            w = rng.uniform(0.1, 2.0, nc)
+            data[f"tol{ti}_{key}"] = tol
+            data[f"w{ti}_{key}"] = w
+            for method in ("death penalty", "kuri", "weighted", "ignore_c", "ignore_o"):
+                u = R.unconstrain(p, method, w if method == "weighted" else ())
+                data[f"u{ti}_{method.replace(' ', '_')}_{key}"] = u.fitness_loop(xs)
+    np.savez_compressed(OUT / "constrained_ref.npz", **data)
+
+
 def main():
     R = reference()
+    if "--constrained-only" in sys.argv:
+        return constrained_fixture(R)
+    constrained_fixture(R)
     if "--hv-only" in sys.argv:
         return hv_fixture(R)
     if "--hv-wfg-only" in sys.argv:

@@ -166,3 +166,31 @@ def test_algorithms_refuse_constraints_and_run_on_the_unconstrained_problem(ctx,
     pt = hs.translate(t)
     assert (pt.nec, pt.nic, pt.nf) == (1, 1, 3)
     assert np.array_equal(pt.eval_host(x), orc.hock_schittkowski_71(orc.translate_rows(x, t)))
+
+
+def test_constrained_golden_fixture_on_device(ctx):
+    """the device path against outputs of the compiled reference itself (tests/golden/constrained_ref.npz)."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "constrained_ref.npz")
+    for key, fam, dim in (("hock_schittkowski_71_0", "hock_schittkowski_71", 0), ("luksan_vlcek1_3", "luksan_vlcek1", 3),
+                          ("luksan_vlcek1_10", "luksan_vlcek1", 10), ("luksan_vlcek1_33", "luksan_vlcek1", 33)):
+        p = capi.Problem(ctx, fam, dim=dim)
+        xs, f = g[f"x_{key}"], g[f"f_{key}"]
+        got = p.eval_host(xs)
+        if fam == "hock_schittkowski_71":
+            assert np.array_equal(got, f)
+        else:
+            assert np.all(np.abs(got[:, 0] - f[:, 0]) <= RTOL * np.abs(f[:, 0])) and np.all(np.abs(got[:, 1:] - f[:, 1:]) <= RTOL * lv_scale(xs))
+        for ti in (0, 1):
+            tol, w = g[f"tol{ti}_{key}"], g[f"w{ti}_{key}"]
+            p.set_c_tol(tol)
+            margin = np.abs(np.abs(f[:, 1:1 + p.nec]) - tol[:p.nec]).min(axis=1)  # rows whose feasibility decisions are not borderline
+            safe = margin > 1e-9
+            for method in METHODS:
+                want = g[f"u{ti}_{method.replace(' ', '_')}_{key}"]
+                out = p.unconstrain(method, w if method == "weighted" else ()).eval_host(xs)
+                if fam == "hock_schittkowski_71":
+                    assert np.array_equal(out, want), (key, ti, method)
+                else:
+                    bound = RTOL * np.maximum(1.0, np.abs(want[safe, 0])) * (1e3 + w.sum())
+                    assert safe.sum() >= 20 and np.all(np.abs(out[safe, 0] - want[safe, 0]) <= bound), (key, ti, method)

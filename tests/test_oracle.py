@@ -484,3 +484,17 @@ def test_constrained_udps_and_unconstrain_are_bit_exact_vs_reference(orc, ref):
         ref.unconstrain(hs, "mispelled")
     with pytest.raises(RuntimeError, match="needs to be empty"):
         ref.unconstrain(hs, "kuri", [1.0, 1.0])
+
+
+def test_constrained_golden_fixture(orc):
+    """the restatement against tests/golden/constrained_ref.npz (written by the compiled reference: travels to boxes without it)."""
+    g = np.load(GOLD / "constrained_ref.npz")
+    for key, eval_ in (("hock_schittkowski_71_0", orc.hock_schittkowski_71), ("luksan_vlcek1_3", orc.luksan_vlcek1),
+                       ("luksan_vlcek1_10", orc.luksan_vlcek1), ("luksan_vlcek1_33", orc.luksan_vlcek1)):
+        xs, f = g[f"x_{key}"], g[f"f_{key}"]
+        assert np.array_equal(eval_(xs), f), key
+        nec, nic = (1, 1) if key.startswith("hock") else (xs.shape[1] - 2, 0)
+        for ti in (0, 1):
+            for method in ("death penalty", "kuri", "weighted", "ignore_c", "ignore_o"):
+                want = g[f"u{ti}_{method.replace(' ', '_')}_{key}"]
+                assert np.array_equal(orc.unconstrain_rows(f, 1, nec, nic, g[f"tol{ti}_{key}"], method, g[f"w{ti}_{key}"]), want), (key, ti, method)
