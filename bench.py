@@ -305,8 +305,27 @@ def measure_secondary(ctx, capi, device):
         pts /= np.linalg.norm(pts, axis=1, keepdims=True)
         ctx.hv_compute(pts, np.full(4, 1.25))
         r["hv_wfg_4obj_1024pts_compute_ms"] = _timed(lambda: ctx.hv_compute(pts, np.full(4, 1.25)), ctx.synchronize) * 1e3
+        # 8(f) row 1: unconstrain{luksan_vlcek1 D=30} (death penalty) against its inner problem alone, 1 Mi rows resident
+        import torch
+        inner = capi.Problem(ctx, "luksan_vlcek1", dim=30)
+        inner.set_c_tol(1.0)
+        un = inner.unconstrain("death penalty")
+        n_u = 1 << 20
+        xs = torch.rand((n_u, 30), dtype=torch.float64, device=f"cuda:{device}") * 3 - 1.5
+        fi = torch.empty((n_u, inner.nf), dtype=torch.float64, device=f"cuda:{device}")
+        fu = torch.empty(n_u, dtype=torch.float64, device=f"cuda:{device}")
+        for q, o in ((inner, fi), (un, fu)):
+            q.eval_device(xs.data_ptr(), n_u, o.data_ptr(), ctx.stream)
+        ctx.synchronize()
+        r["luksan_vlcek1_d30_1Mi_ms"] = _timed(lambda: [inner.eval_device(xs.data_ptr(), n_u, fi.data_ptr(), ctx.stream) for _ in range(5)],
+                                                ctx.synchronize) / 5 * 1e3
+        r["unconstrain_luksan_vlcek1_d30_1Mi_ms"] = _timed(lambda: [un.eval_device(xs.data_ptr(), n_u, fu.data_ptr(), ctx.stream) for _ in range(5)],
+                                                            ctx.synchronize) / 5 * 1e3
+        un.close()
+        inner.close()
         r["what"] = ("gaco (rastrigin D=30, 65536 ants) and maco (ZDT1 nx=30, 16384 ants) generations/s incl. the host round trip of the "
-                     "population per call; hypervolume of 1024 points in 4 objectives (device WFG) incl. upload")
+                     "population per call; hypervolume of 1024 points in 4 objectives (device WFG) incl. upload; one batch of 1 Mi decision vectors "
+                     "through luksan_vlcek1 D=30 (1 objective + 28 equality constraints) and through unconstrain{luksan_vlcek1} (death penalty)")
         return r
 
     guarded("nsga2_pop65536", nsga2)
