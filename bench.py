@@ -687,7 +687,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", choices=["cfg2", "cfg5"], default="cfg2")
+    ap.add_argument("--cfg5-pop", type=int, default=CFG5["pop"], help="population per island of --workload cfg5 (the configuration leaves it open)")
     args = ap.parse_args()
+    CFG5["pop"] = args.cfg5_pop
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
     if args.impl == "reference":
