@@ -534,6 +534,12 @@ PGC_API int pgc_island_inbox_upload(pgc_island *isl, size_t slot, const uint64_t
  * afterwards and the slot each came through - the rows of archipelago::get_migration_log() (island.cpp:525-536). */
 PGC_API int pgc_island_replace(pgc_island *isl, int rate_is_frac, double rate, size_t n_slots, uint64_t *accepted_ids,
                                uint32_t *accepted_slot, size_t *n_accepted);
+/* The same in two halves for drivers that must not block between two evolve() calls.  enqueue: asynchronous on the island's stream;
+ * `counts` = rows in each of the n_slots inbox slots (known to a driver that replays the senders' policies), want_log != 0 also copies
+ * the acceptance flags to pinned memory behind an event.  collect: waits for that event only and returns the migration-log rows of the
+ * last enqueue (nothing when none is pending); it must be called before the next enqueue with want_log. */
+PGC_API int pgc_island_replace_enqueue(pgc_island *isl, int rate_is_frac, double rate, size_t n_slots, const size_t *counts, int want_log);
+PGC_API int pgc_island_replace_collect(pgc_island *isl, uint64_t *accepted_ids, uint32_t *accepted_slot, size_t *n_accepted);
 /* population::champion_x / champion_f (single objective) */
 PGC_API int pgc_island_champion(pgc_island *isl, double *x, double *f);
 

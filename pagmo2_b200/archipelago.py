@@ -276,6 +276,7 @@ class ResidentArchipelago:
             self.isl[g] = capi.Island(self.prob[g], s["pop_size"], cap, max_in)
             self.isl[g].init(s["seed"])
         self.published = [False] * G
+        self._pending = {}  # island -> (round, sources) of a replace whose migration-log rows have not been read back yet
         self.phase_seconds = {}  # host wall time per phase of evolve(), summed over rounds
         self.local = [g for g in range(G) if self.isl[g] is not None]
         for g in self.local:  # islands that share a GPU fill it together: each keeps fuller tiles (pgc_ctx_set_sharers)
@@ -285,12 +286,25 @@ class ResidentArchipelago:
     def _u(self, g, slot):
         return capi.philox_u01(self.seed, TAG_MIGRATE, self.round, g, slot)
 
+    def _collect(self, g):
+        """migration-log rows of island g's last replace (enqueued one round earlier): waits for that replace's log copies only"""
+        pend = self._pending.pop(g, None)
+        if pend is None:
+            return []
+        rnd, sources = pend
+        return [MigrationEntry(rnd, a_id, sources[slot][0], g) for a_id, slot in self.isl[g].replace_collect()]
+
     def _step(self, g, replace, sources):
+        # nothing here blocks on the device but _collect, whose wait ends when the PREVIOUS round's replace has run: replace, evolve and
+        # select of this round are enqueued back to back, so the GPU goes from one round's generations into the next one's without
+        # waiting for the host (the slot counts are the senders' policy counts, known to every process)
         isl, s = self.isl[g], self.spec[g]
-        entries = []
+        entries = self._collect(g)
         if replace:
-            for a_id, slot in isl.replace(s["r_rate"], len(sources), log=self.log_on):
-                entries.append(MigrationEntry(self.round, a_id, sources[slot][0], g))
+            counts = [self.k_out[src] if had else 0 for src, had in sources]
+            isl.replace_enqueue(s["r_rate"], counts, log=self.log_on)
+            if self.log_on:
+                self._pending[g] = (self.round, sources)
         isl.evolve(s["algo"])
         isl.select(s["s_rate"])
         return entries
@@ -337,6 +351,8 @@ class ResidentArchipelago:
                 self.phase_seconds[k] = self.phase_seconds.get(k, 0.0) + dt
             self.published = [k > 0 for k in self.k_out]
             self.round += 1
+        for g in self.local:  # the last round's log rows
+            self.log.extend(self._collect(g))
 
     def synchronize(self):
         for g in self.local:

@@ -938,6 +938,23 @@ class Island:
         check(lib().pgc_island_replace(self._h, frac, r, n_slots, ids.ctypes.data, slot.ctypes.data, C.byref(na)))
         return [(int(ids[i]), int(slot[i])) for i in range(na.value)]
 
+    def replace_enqueue(self, rate, counts, log: bool = True):
+        """the device half of replace(): asynchronous; `counts` = rows in each inbox slot used (known from the senders' policies)."""
+        frac, r = _rate(rate)
+        c = np.ascontiguousarray(counts, dtype=np.uint64)
+        L = lib()
+        L.pgc_island_replace_enqueue.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.c_void_p, C.c_int]
+        check(L.pgc_island_replace_enqueue(self._h, frac, r, c.size, c.ctypes.data, int(log)))
+
+    def replace_collect(self):
+        """[(migrant id, slot)] of the last replace_enqueue(log=True): waits for its log copies only; [] when nothing is pending."""
+        m = max(self.cap * self.slots, 1)
+        ids, slot, na = np.empty(m, np.uint64), np.empty(m, np.uint32), C.c_size_t()
+        L = lib()
+        L.pgc_island_replace_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
+        check(L.pgc_island_replace_collect(self._h, ids.ctypes.data, slot.ctypes.data, C.byref(na)))
+        return [(int(ids[i]), int(slot[i])) for i in range(na.value)]
+
     def champion(self):
         x, f = np.empty(self.nx), np.empty(1)
         check(lib().pgc_island_champion(self._h, x.ctypes.data, f.ctypes.data))

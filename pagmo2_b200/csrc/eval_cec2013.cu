@@ -578,8 +578,18 @@ template <int D> int launch13(pgc_ctx *ctx, const Params13 &pp, cudaStream_t str
     if (small && fit > kSmallWarps13) fit = kSmallWarps13;
     PGC_REQUIRE(fit >= 1, "cec2013: shared memory too small for dimension %d", D);
     const long long ntiles = (pp.n + ti - 1) / ti;
-    // small batches: fewer warps per CTA so that the tiles cover the SMs
-    long long w = (ntiles + ctx->sm_count - 1) / ctx->sm_count;
+    // small batches: fewer warps per CTA so that the tiles cover the SMs.  Alone, that is the lowest latency; but every CTA carries the
+    // function's rotation matrices (80 KB for three at D = 50) whatever its number of warps, so two such CTAs fill an SM's shared memory
+    // and a 128-CTA launch of 2-warp CTAs owns almost half the device: launches of different islands then queue behind each other
+    // (measured, 8 streams of 1024-row f12 D=50 evaluations: 9.4 us per launch however many streams, profiles/r2q_concurrent_parts.json).
+    // With `sharers` contexts on the device each launch takes its share of the CTA slots and fuller CTAs instead.
+    long long spread = ctx->sm_count;
+    if (small && ctx->sharers > 1) {
+        int slots_per_sm = 2;
+        if (const char *e = std::getenv("PGC_CEC13_SHARE_SLOTS")) slots_per_sm = std::max(1, std::atoi(e)); // experiment switch
+        spread = std::max(1ll, static_cast<long long>(ctx->sm_count) * slots_per_sm / ctx->sharers);
+    }
+    long long w = (ntiles + spread - 1) / spread;
     if (w > fit) w = fit;
     if (w < 1) w = 1;
     long long ctas = (ntiles + w - 1) / w;

@@ -42,7 +42,11 @@ struct pgc_island {
     std::vector<double> es_state; // cmaes / xnes with memory: their host-side state (pgc_es_state_len)
     double *h_heads = nullptr; // pinned: slot headers
     unsigned char *h_flags = nullptr;
+    unsigned long long *h_mids = nullptr; // pinned: the immigrants' ids of the last replace (migration log)
     cudaEvent_t ev = nullptr;
+    cudaEvent_t ev_log = nullptr;         // recorded after the log copies of the last replace
+    std::vector<size_t> log_cnt;          // rows per slot of the last replace whose log has not been collected yet
+    bool log_pending = false;
     size_t group_doubles() const { return 1 + cap * (1 + nx + nf); }
     unsigned long long *ids_of(double *g) const { return reinterpret_cast<unsigned long long *>(g + 1); }
     double *x_of(double *g) const { return g + 1 + cap; }
@@ -198,7 +202,9 @@ int pgc_island_create(pgc_problem *prob, size_t n, size_t max_migrants, size_t m
     dev(reinterpret_cast<void **>(&isl->d_mf), 8 * mcap * isl->nf);
     dev(reinterpret_cast<void **>(&isl->d_flags), mcap);
     if (rc == PGC_OK && (cudaMallocHost(&isl->h_heads, 8 * isl->slots) != cudaSuccess || cudaMallocHost(&isl->h_flags, mcap) != cudaSuccess
-                         || cudaEventCreateWithFlags(&isl->ev, cudaEventDisableTiming) != cudaSuccess)) {
+                         || cudaMallocHost(&isl->h_mids, 8 * mcap) != cudaSuccess
+                         || cudaEventCreateWithFlags(&isl->ev, cudaEventDisableTiming) != cudaSuccess
+                         || cudaEventCreateWithFlags(&isl->ev_log, cudaEventDisableTiming) != cudaSuccess)) {
         set_error("pgc_island_create: pinned allocation failed");
         rc = PGC_ERR_OUT_OF_MEMORY;
     }
@@ -225,7 +231,9 @@ int pgc_island_destroy(pgc_island *isl)
         if (p) cudaFree(p);
     if (isl->h_heads) cudaFreeHost(isl->h_heads);
     if (isl->h_flags) cudaFreeHost(isl->h_flags);
+    if (isl->h_mids) cudaFreeHost(isl->h_mids);
     if (isl->ev) cudaEventDestroy(isl->ev);
+    if (isl->ev_log) cudaEventDestroy(isl->ev_log);
     delete isl;
     return PGC_OK;
 }
@@ -408,21 +416,18 @@ int pgc_island_inbox_upload(pgc_island *isl, size_t slot, const uint64_t *ids, c
 
 // r_policy step: the rows of inbox slots [0, n_slots) are the immigrants of this round (island.cpp:505-517 / :577-585).
 // accepted_* (optional, sized cap * slots): ids and source slots of the immigrants that are in the population afterwards.
-int pgc_island_replace(pgc_island *isl, int rate_is_frac, double rate, size_t n_slots, uint64_t *accepted_ids, uint32_t *accepted_slot,
-                       size_t *n_accepted)
+// The two halves of a replace.  enqueue: everything that touches the device, asynchronous on the island's stream - the rows of the
+// inbox slots merged in slot order, fair_replace, and (want_log) the acceptance flags and immigrant ids copied to pinned memory behind
+// an event.  collect: wait for that event only and decode the migration-log rows.  A driver that knows the slot counts (the senders'
+// policies fix them) never blocks between the end of one evolve() and the start of the next: pgc_island_replace_enqueue, evolve,
+// select, and the log of this round read at the start of the next one (pgc_island_replace_collect).
+static int replace_enqueue(pgc_island *isl, int rate_is_frac, double rate, size_t n_slots, const size_t *cnt, bool want_log)
 {
-    PGC_REQUIRE(isl && n_slots <= isl->slots, "pgc_island_replace: %zu slots requested, the island has %zu", n_slots, isl ? isl->slots : 0);
-    if (n_accepted) *n_accepted = 0;
-    PGC_CUDA(cudaSetDevice(isl->ctx->device));
     cudaStream_t st = isl->ctx->stream;
     const size_t gd = isl->group_doubles();
-    // the counts arrive with the rows (a sender's policy fixes them, but the receiver may sit in another process)
-    PGC_CUDA(cudaMemcpy2DAsync(isl->h_heads, 8, isl->d_inbox, 8 * gd, 8, n_slots ? n_slots : 1, cudaMemcpyDeviceToHost, st));
-    PGC_CUDA(cudaStreamSynchronize(st));
+    PGC_REQUIRE(!isl->log_pending, "pgc_island_replace: the migration log of the previous replace was not collected (pgc_island_replace_collect)");
     size_t nm = 0;
-    std::vector<size_t> cnt(n_slots);
     for (size_t s = 0; s < n_slots; ++s) {
-        cnt[s] = static_cast<size_t>(isl->h_heads[s]);
         PGC_REQUIRE(cnt[s] <= isl->cap, "pgc_island_replace: corrupt inbox header in slot %zu (%zu rows, capacity %zu)", s, cnt[s], isl->cap);
         double *g = isl->d_inbox + s * gd;
         if (cnt[s]) {
@@ -435,26 +440,70 @@ int pgc_island_replace(pgc_island *isl, int rate_is_frac, double rate, size_t n_
     int rc = fair_replace_policy_device(isl->ctx, isl->d_ids, isl->d_x, isl->d_f, isl->n, isl->nx, isl->nf, rate_is_frac, rate, isl->d_mids,
                                         isl->d_mx, isl->d_mf, nm, st);
     if (rc != PGC_OK) return rc;
-    if (nm && (accepted_ids || n_accepted)) {
+    if (nm && want_log) {
         accepted_kernel<<<static_cast<unsigned>(nm), 128, 0, st>>>(isl->d_ids, static_cast<unsigned>(isl->n), isl->d_mids,
                                                                     static_cast<unsigned>(nm), isl->d_flags);
         PGC_CUDA(cudaGetLastError());
         isl->ctx->launches.fetch_add(1, std::memory_order_relaxed);
-        std::vector<uint64_t> mids(nm);
         PGC_CUDA(cudaMemcpyAsync(isl->h_flags, isl->d_flags, nm, cudaMemcpyDeviceToHost, st));
-        PGC_CUDA(cudaMemcpyAsync(mids.data(), isl->d_mids, 8 * nm, cudaMemcpyDeviceToHost, st));
-        PGC_CUDA(cudaStreamSynchronize(st));
-        size_t a = 0, j = 0;
-        for (size_t s = 0; s < n_slots; ++s)
-            for (size_t r = 0; r < cnt[s]; ++r, ++j)
-                if (isl->h_flags[j]) {
-                    if (accepted_ids) accepted_ids[a] = mids[j];
-                    if (accepted_slot) accepted_slot[a] = static_cast<uint32_t>(s);
-                    ++a;
-                }
-        if (n_accepted) *n_accepted = a;
+        PGC_CUDA(cudaMemcpyAsync(isl->h_mids, isl->d_mids, 8 * nm, cudaMemcpyDeviceToHost, st));
+        PGC_CUDA(cudaEventRecord(isl->ev_log, st));
+        isl->log_cnt.assign(cnt, cnt + n_slots);
+        isl->log_pending = true;
     }
     return PGC_OK;
+}
+
+static int replace_collect(pgc_island *isl, uint64_t *accepted_ids, uint32_t *accepted_slot, size_t *n_accepted)
+{
+    if (n_accepted) *n_accepted = 0;
+    if (!isl->log_pending) return PGC_OK;
+    PGC_CUDA(cudaEventSynchronize(isl->ev_log));
+    isl->log_pending = false;
+    size_t a = 0, j = 0;
+    for (size_t s = 0; s < isl->log_cnt.size(); ++s)
+        for (size_t r = 0; r < isl->log_cnt[s]; ++r, ++j)
+            if (isl->h_flags[j]) {
+                if (accepted_ids) accepted_ids[a] = isl->h_mids[j];
+                if (accepted_slot) accepted_slot[a] = static_cast<uint32_t>(s);
+                ++a;
+            }
+    if (n_accepted) *n_accepted = a;
+    return PGC_OK;
+}
+
+int pgc_island_replace(pgc_island *isl, int rate_is_frac, double rate, size_t n_slots, uint64_t *accepted_ids, uint32_t *accepted_slot,
+                       size_t *n_accepted)
+{
+    PGC_REQUIRE(isl && n_slots <= isl->slots, "pgc_island_replace: %zu slots requested, the island has %zu", n_slots, isl ? isl->slots : 0);
+    if (n_accepted) *n_accepted = 0;
+    PGC_CUDA(cudaSetDevice(isl->ctx->device));
+    cudaStream_t st = isl->ctx->stream;
+    const size_t gd = isl->group_doubles();
+    // the counts arrive with the rows (a sender's policy fixes them, but the receiver may sit in another process)
+    PGC_CUDA(cudaMemcpy2DAsync(isl->h_heads, 8, isl->d_inbox, 8 * gd, 8, n_slots ? n_slots : 1, cudaMemcpyDeviceToHost, st));
+    PGC_CUDA(cudaStreamSynchronize(st));
+    std::vector<size_t> cnt(n_slots);
+    for (size_t s = 0; s < n_slots; ++s) cnt[s] = static_cast<size_t>(isl->h_heads[s]);
+    const bool want_log = accepted_ids || n_accepted;
+    int rc = replace_enqueue(isl, rate_is_frac, rate, n_slots, cnt.data(), want_log);
+    if (rc != PGC_OK) return rc;
+    return want_log ? replace_collect(isl, accepted_ids, accepted_slot, n_accepted) : PGC_OK;
+}
+
+int pgc_island_replace_enqueue(pgc_island *isl, int rate_is_frac, double rate, size_t n_slots, const size_t *counts, int want_log)
+{
+    PGC_REQUIRE(isl && n_slots <= isl->slots, "pgc_island_replace_enqueue: %zu slots requested, the island has %zu", n_slots, isl ? isl->slots : 0);
+    PGC_REQUIRE(counts || n_slots == 0, "pgc_island_replace_enqueue: null counts");
+    PGC_CUDA(cudaSetDevice(isl->ctx->device));
+    return replace_enqueue(isl, rate_is_frac, rate, n_slots, counts, want_log != 0);
+}
+
+int pgc_island_replace_collect(pgc_island *isl, uint64_t *accepted_ids, uint32_t *accepted_slot, size_t *n_accepted)
+{
+    PGC_REQUIRE(isl, "pgc_island_replace_collect: null island");
+    PGC_CUDA(cudaSetDevice(isl->ctx->device));
+    return replace_collect(isl, accepted_ids, accepted_slot, n_accepted);
 }
 
 // best individual of a single-objective island (population::champion_x / champion_f of what the island holds now)
