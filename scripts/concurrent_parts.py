@@ -28,18 +28,29 @@ for mode in os.environ.get("PARTS_MODES", "eval_cec2013,loop_rastrigin,loop_cec2
             ctx = capi.Context(0)
             L.pgc_ctx_set_sharers.argtypes = [C.c_void_p, C.c_int]
             capi.check(L.pgc_ctx_set_sharers(ctx._h, K))
-            if mode == "loop_rastrigin":
+            if mode == "loop_rastrigin":  # (modes island_*: cec2013 f12 through capi.Island)
                 p = capi.Problem(ctx, "rastrigin", dim=50)
             else:
                 p = capi.Problem(ctx, "cec2013", prob_id=12, dim=50, rotation=mr, shift=os_)
             d_x, d_f = ctx.malloc(8 * NP * 50), ctx.malloc(8 * NP)
             capi.check(L.pgc_population_init_device(p._h, NP, 23 + g, d_x, d_f, None, None))
             isl.append((ctx, p, d_x, d_f, capi.algo_desc("sade", gens=GENS, seed=41 + g, ftol=0.0, xtol=0.0)))
+            if mode.startswith("island"):  # the resident island object: (select | replace + select) around every evolve call, no migrants
+                I = capi.Island(p, NP, 1, 1)
+                I.init(200 + g)
+                isl[-1] = isl[-1] + (I,)
 
         def run(i, first, reps):
-            ctx, p, d_x, d_f, a = isl[i]
+            ctx, p, d_x, d_f, a = isl[i][:5]
             for k in range(reps):
-                if mode == "eval_cec2013":
+                if mode.startswith("island"):
+                    I = isl[i][5]
+                    if mode == "island_replace_select":
+                        I.replace_enqueue(1, [0], log=False)
+                    I.evolve(a)
+                    if mode != "island_evolve":
+                        I.select(1)
+                elif mode == "eval_cec2013":
                     for _ in range(GENS):
                         p.eval_device(d_x, NP, d_f, ctx.stream)
                 else:
@@ -52,7 +63,9 @@ for mode in os.environ.get("PARTS_MODES", "eval_cec2013,loop_rastrigin,loop_cec2
             list(pool.map(lambda i: run(i, 1 + 2 * GENS, REPS), range(K)))
             dt = time.perf_counter() - t0
         out[mode][K] = {"us_per_island_step": dt / (GENS * REPS) * 1e6, "steps_per_s_all_islands": K * GENS * REPS / dt}
-        for ctx, p, d_x, d_f, a in isl:
+        for ctx, p, d_x, d_f, a, *rest in isl:
+            for I in rest:
+                I.close()
             ctx.free(d_x)
             ctx.free(d_f)
             p.close()
